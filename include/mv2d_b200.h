@@ -1,0 +1,197 @@
+/* libmv2d_b200 -- C ABI of the B200-native MV2D decoder hot path.
+ *
+ * Drop-in boundary: these entry points are what the reference's Python
+ * modules would bind (ctypes) in place of the torch / mmcv composites they run today.  Each
+ * entry cites the reference interface it replaces (paths relative to
+ * /root/reference/mmdet3d_plugin/models/).
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless the field comment says "host";
+ *   - caller owns every buffer (inputs, outputs, workspace); the library never allocates,
+ *     frees or retains a pointer past the call;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*), no host
+ *     synchronisation, no host read of device data => CUDA-graph capturable;
+ *   - return 0 = OK; <0 = argument/shape/alignment error (nothing launched);
+ *     >0 = cudaError_t of a failed launch.  Text via mv2d_last_error() (thread-local);
+ *   - float tensors are fp32, geometry is fp64 where the reference uses .double();
+ *   - feature maps are channels-last: [V, h, w, 256]; RoI tokens are [N, 49, 256].
+ */
+#ifndef MV2D_B200_H_
+#define MV2D_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define MV2D_API __attribute__((visibility("default")))
+#else
+#define MV2D_API
+#endif
+
+#define MV2D_ABI_VERSION 1
+#define MV2D_MAX_LAYERS 8
+
+MV2D_API int mv2d_abi_version(void);
+MV2D_API const char* mv2d_last_error(void);
+/* number of kernel launches this library has enqueued so far in this process */
+MV2D_API unsigned long long mv2d_launch_count(void);
+/* sizeof() of the parameter structs, so a binding can verify its mirror of this header */
+MV2D_API size_t mv2d_sizeof(int which); /* 0 Pe, 1 Qg, 2 Corr, 3 Decoder, 4 LayerWeights, 5 BranchWeights */
+
+/* ---- geometry (utils/pe.py:111; roi_heads/utils/box_correlation.py:118-122,174-178)
+ * img2lidar[v] = inv(lidar2img[v]);  trans[src][dst] = lidar2img[dst] @ img2lidar[src]  (fp64) */
+MV2D_API int mv2d_geom_prep(const double* lidar2img /*[V,16]*/, int V, double* img2lidar /*[V,16]*/,
+                   double* trans /*[V,V,16]*/, void* stream);
+
+/* NCHW [V,C,HW] -> NHWC [V,HW,C] (the FPN output layout -> this library's layout) */
+MV2D_API int mv2d_nchw_to_nhwc(const float* in, float* out, int V, int C, int HW, void* stream);
+
+/* ---- K1  PE.forward  (utils/pe.py:137-169 incl. position_encoding :84-135, SELayer :44-48,
+ * SinePositionalEncoding3D positional_encoding.py:58-96 + adapt_pos3d) */
+typedef struct Mv2dPeParams {
+    int V, h, w, depth_num, pad_h, pad_w, stride, reserved0;
+    double depth_start;
+    double position_range[6];
+    const float* feat;         /* [V,h,w,256] */
+    const double* img2lidar;   /* [V,16] from mv2d_geom_prep */
+    const uint8_t* not_mask;   /* [V,h,w] 1 = inside the un-padded image */
+    const float* dim_t;        /* [128] temperature ** (2*(i//2)/128) */
+    const float *w_pos0, *b_pos0;       /* position_encoder.0  [1024,192] */
+    const float *w_pos2, *b_pos2;       /* position_encoder.2  [256,1024] */
+    const float *w_adapt0, *b_adapt0;   /* adapt_pos3d.0       [1024,384] */
+    const float *w_adapt2, *b_adapt2;   /* adapt_pos3d.2       [256,1024] */
+    const float *w_se_reduce, *b_se_reduce; /* fpe.conv_reduce [256,256] */
+    const float *w_se_expand, *b_se_expand; /* fpe.conv_expand [256,256] */
+    const float* sine_branch_cached;    /* nullable [V*h*w,256]: adapt_pos3d(sine) computed earlier */
+    float* sine_branch_out;             /* nullable: receives adapt_pos3d(sine) */
+    float* pe;                 /* out [V,h,w,256] */
+    float* kin;                /* out, nullable: feat + pe (keys of the two-frame head) */
+    float* workspace;
+    size_t workspace_bytes;
+} Mv2dPeParams;
+MV2D_API size_t mv2d_pe3d_workspace_bytes(int V, int h, int w, int depth_num);
+MV2D_API int mv2d_pe3d(const Mv2dPeParams* p, void* stream);
+
+/* ---- K2  RoIAlign + dynamic query generator + query embedding
+ * (roi_heads/mv2d_head.py:51-72,95-101,114-134; utils/query_generator.py:333-405;
+ *  bbox_heads/cross_attention_head.py:199-200; utils/pe.py:21-33; mmcv RoIAlign avg/aligned) */
+typedef struct Mv2dQgParams {
+    int N, V, h, w, stride, reserved0;
+    float pc_range[6];
+    float intrins_feat_scale;
+    float reserved1;
+    const float* rois;          /* [N,5] (view, x1, y1, x2, y2) px */
+    const double* intrinsics;   /* [V,16] */
+    const double* extrinsics;   /* [V,16] (= lidar2cam transposed) */
+    const float* feat;          /* [V,h,w,256] */
+    const float* pe;            /* [V,h,w,256], nullable when tok_kin == NULL */
+    const float* dim_t;         /* [128] */
+    const float *w_conv, *b_conv;     /* shared_convs.0.conv repacked [256, 9*256] (tap-major K) */
+    const float *w_fc, *b_fc;         /* shared_fcs.0 [1024,256] */
+    const float *w_enc0, *b_enc0;     /* extra_enc.0 [512,1040] */
+    const float *w_enc2, *b_enc2;     /* extra_enc.2 [256,512] */
+    const float *w_center, *b_center; /* fc_center [3,256] */
+    const float *w_qe0, *b_qe0;       /* query_embedding.0 [256,384] */
+    const float *w_qe2, *b_qe2;       /* query_embedding.2 [256,256] */
+    float* tok_feat;       /* out [N,49,256] RoI-pooled image feature (bbox_feats, channels-last) */
+    float* tok_kin;        /* out, nullable [N,49,256] RoI-pooled (feat + pe) */
+    double* roi_intrinsics;/* out, nullable [N,16] K' */
+    float* center_lidar;   /* out, nullable [N,3] */
+    float* ref;            /* out [N,3] normalised reference points */
+    float* query_pos;      /* out [N,256] */
+    float* workspace;
+    size_t workspace_bytes;
+} Mv2dQgParams;
+MV2D_API size_t mv2d_roi_align_qg_workspace_bytes(int N);
+MV2D_API int mv2d_roi_align_qg(const Mv2dQgParams* p, void* stream);
+
+/* ---- K3  BoxCorrelation  (roi_heads/utils/box_correlation.py:95-398, topk_matched mode)
+ * S head: match list per RoI (self first).  T head: additionally the bit-packed per-query key
+ * mask over the [V,h,w] feature cells (bit c of word c/32, c = (v*h+y)*w+x). */
+typedef struct Mv2dCorrParams {
+    int N, V, img_h, img_w;
+    int topk, sample_size, num_depth, max_match;
+    float ratio, iou_thr, depth_start, reserved0;
+    const float* rois;        /* [N,5] */
+    const int* roi_start;     /* [V+1] first RoI of each view (RoIs are sorted by view) */
+    const double* trans;      /* [V,V,16] from mv2d_geom_prep */
+    const float* lin;         /* [sample_size] torch.linspace(0,1,S) */
+    const float* depths;      /* [num_depth] LID depth bins, fp32 */
+    int* match;               /* out [N,max_match] */
+    int* match_cnt;           /* out [N] */
+    /* two-frame head only (keymask != NULL) */
+    int h, w, stride, expand_stride;
+    const uint8_t* pad_mask;  /* nullable [V,h,w] 1 = padded-out cell (key_padding_mask) */
+    uint32_t* keymask;        /* out, nullable [N, ceil(V*h*w/32)] */
+    int* key_cnt;             /* out, nullable [N] */
+} Mv2dCorrParams;
+MV2D_API int mv2d_box_corr(const Mv2dCorrParams* p, void* stream);
+
+/* ---- K4/K5  decoder: MV2DTransformer + PETRTransformerDecoder + branches
+ * (bbox_heads/cross_attention_head.py:22-49,202-242; utils/petr_transformer.py:194-593) */
+typedef struct Mv2dLayerWeights {
+    const float *sa_in_w, *sa_in_b;     /* attentions.0.attn.in_proj [768,256] */
+    const float *sa_out_w, *sa_out_b;   /* attentions.0.attn.out_proj [256,256] */
+    const float *ca_q_w, *ca_q_b;       /* absorbed  scale*Wk_h^T Wq_h : [2048,256], [2048] */
+    const float *ca_o_w, *ca_o_b;       /* absorbed  Wo[:,h] Wv_h      : [256,2048], [256]  */
+    const float *ffn_w1, *ffn_b1;       /* ffns.0.layers.0.0 [2048,256] */
+    const float *ffn_w2, *ffn_b2;       /* ffns.0.layers.1   [256,2048] */
+    const float *ln_g[3], *ln_b[3];     /* norms.{0,1,2} */
+} Mv2dLayerWeights;
+
+typedef struct Mv2dBranchWeights {      /* stacked over layers: leading dim L */
+    const float *cls_w0, *cls_b0, *cls_g0, *cls_be0;   /* Linear [L,256,256], LN */
+    const float *cls_w1, *cls_b1, *cls_g1, *cls_be1;
+    const float *cls_w2, *cls_b2;                      /* [L,10,256] */
+    const float *reg_w0, *reg_b0, *reg_w1, *reg_b1;    /* [L,256,256] */
+    const float *reg_w2, *reg_b2;                      /* [L,10,256] */
+    const float *post_g, *post_b;                      /* decoder.post_norm */
+} Mv2dBranchWeights;
+
+typedef struct Mv2dDecoderParams {
+    int N, L, mode /*0 = RoI-token keys (S), 1 = feature-map keys (T)*/, num_rows;
+    int max_match, mask_words, reserved0, reserved1;
+    float pc_range[6];
+    float vel_dt;               /* T head: bbox_preds[..., 8:10] /= vel_dt ; 0 = off (mv2d_t_head.py:130-142) */
+    float reserved2;
+    const float* query_pos;     /* [N,256] */
+    const float* ref;           /* [N,3] */
+    const float* kin_rows;      /* [num_rows,256] key input  (memory + pos) */
+    const float* mem_rows;      /* [num_rows,256] value input (memory) */
+    const int* match;           /* mode 0: [N,max_match] RoI ids */
+    const int* match_cnt;       /* mode 0: [N] */
+    const uint32_t* keymask;    /* mode 1: [N,mask_words] */
+    const uint8_t* self_attn_mask; /* nullable [N,N] 1 = masked (DN training) */
+    const Mv2dLayerWeights* layers;   /* HOST array [L] */
+    const Mv2dBranchWeights* branches;/* HOST pointer */
+    float* cls_scores;          /* out [L,N,10] */
+    float* bbox_preds;          /* out [L,N,10] */
+    float* outs_dec;            /* out [L,N,256] post-normed intermediates */
+    float* workspace;
+    size_t workspace_bytes;
+} Mv2dDecoderParams;
+MV2D_API size_t mv2d_decoder_workspace_bytes(int N, int L);
+MV2D_API int mv2d_decoder(const Mv2dDecoderParams* p, void* stream);
+
+/* ---- low-level GEMM, exposed for tests and microbenchmarks:
+ * C[M,N] = act(A[M,K] . W[N,K]^T + bias); flags: 1 relu, 8 allow TF32 tensor cores,
+ * 16 force the tcgen05 kernel, 32 force 3xTF32 error-compensated tcgen05 */
+MV2D_API int mv2d_gemm(const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc,
+              int M, int N, int K, int flags, void* stream);
+
+/* ---- f1 (next row): NMSFreeCoder.decode_single + get_bboxes z-shift
+ * (core/bbox/coders/nms_free_coder.py:49-102; bbox_heads/cross_attention_head.py:372).
+ * Device top-k over N*10 sigmoid scores; writes max_num rows, valid[i] = inside post range. */
+MV2D_API int mv2d_nms_free_decode(const float* cls /*[N,10]*/, const float* box /*[N,10]*/, int N, int max_num,
+                         const float* post_range /*host [6]*/, float* out_boxes /*[max_num,9]*/,
+                         float* out_scores /*[max_num]*/, int* out_labels /*[max_num]*/,
+                         uint8_t* out_valid /*[max_num]*/, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MV2D_B200_H_ */

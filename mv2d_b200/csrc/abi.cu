@@ -1,0 +1,103 @@
+// extern "C" surface of libmv2d_b200 (include/mv2d_b200.h).
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include "common.cuh"
+#include "gemm_simt.cuh"
+#include "mv2d_internal.h"
+
+namespace mv2d {
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+static std::atomic<unsigned long long> g_launches{0};
+void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+}  // namespace mv2d
+
+using namespace mv2d;
+
+extern "C" {
+
+int mv2d_abi_version(void) { return MV2D_ABI_VERSION; }
+const char* mv2d_last_error(void) { return g_err; }
+unsigned long long mv2d_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+size_t mv2d_sizeof(int which) {
+    switch (which) {
+        case 0: return sizeof(Mv2dPeParams);
+        case 1: return sizeof(Mv2dQgParams);
+        case 2: return sizeof(Mv2dCorrParams);
+        case 3: return sizeof(Mv2dDecoderParams);
+        case 4: return sizeof(Mv2dLayerWeights);
+        case 5: return sizeof(Mv2dBranchWeights);
+        default: return 0;
+    }
+}
+
+#define NONNULL(p, what) MV2D_CHECK_ARG((p) != nullptr, what ": null params")
+
+int mv2d_geom_prep(const double* lidar2img, int V, double* img2lidar, double* trans, void* stream) {
+    MV2D_CHECK_ARG(lidar2img && img2lidar && trans, "geom_prep: null pointer");
+    return run_geom_prep(lidar2img, V, img2lidar, trans, (cudaStream_t)stream);
+}
+
+int mv2d_nchw_to_nhwc(const float* in, float* out, int V, int C, int HW, void* stream) {
+    MV2D_CHECK_ARG(in && out && V > 0 && C > 0 && HW > 0, "nchw_to_nhwc: bad arguments");
+    return run_nchw_to_nhwc(in, out, V, C, HW, (cudaStream_t)stream);
+}
+
+size_t mv2d_pe3d_workspace_bytes(int V, int h, int w, int depth_num) { return pe3d_workspace_bytes(V, h, w, depth_num); }
+int mv2d_pe3d(const Mv2dPeParams* p, void* stream) {
+    NONNULL(p, "pe3d");
+    MV2D_CHECK_ARG(p->feat && p->img2lidar && p->pe && p->workspace && p->dim_t && (p->not_mask || p->sine_branch_cached),
+                   "pe3d: null pointer");
+    return run_pe3d(*p, (cudaStream_t)stream);
+}
+
+size_t mv2d_roi_align_qg_workspace_bytes(int N) { return roi_align_qg_workspace_bytes(N); }
+int mv2d_roi_align_qg(const Mv2dQgParams* p, void* stream) {
+    NONNULL(p, "roi_align_qg");
+    MV2D_CHECK_ARG(p->N == 0 || (p->rois && p->intrinsics && p->extrinsics && p->feat && p->tok_feat && p->ref &&
+                                 p->query_pos && p->workspace && p->dim_t),
+                   "roi_align_qg: null pointer");
+    return run_roi_align_qg(*p, (cudaStream_t)stream);
+}
+
+int mv2d_box_corr(const Mv2dCorrParams* p, void* stream) {
+    NONNULL(p, "box_corr");
+    MV2D_CHECK_ARG(p->N == 0 || (p->rois && p->roi_start && p->trans && p->lin && p->depths && p->match && p->match_cnt),
+                   "box_corr: null pointer");
+    return run_box_corr(*p, (cudaStream_t)stream);
+}
+
+size_t mv2d_decoder_workspace_bytes(int N, int L) { return decoder_workspace_bytes(N, L); }
+int mv2d_decoder(const Mv2dDecoderParams* p, void* stream) {
+    NONNULL(p, "decoder");
+    MV2D_CHECK_ARG(p->N == 0 || (p->query_pos && p->ref && p->kin_rows && p->mem_rows && p->cls_scores &&
+                                 p->bbox_preds && p->outs_dec && p->workspace),
+                   "decoder: null pointer");
+    return run_decoder(*p, (cudaStream_t)stream);
+}
+
+int mv2d_gemm(const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc, int M, int N,
+              int K, int flags, void* stream) {
+    MV2D_CHECK_ARG(A && W && C, "gemm: null pointer");
+    GemmArgs g{};
+    g.A = A; g.lda = lda; g.W = W; g.ldw = ldw; g.C = C; g.ldc = ldc; g.bias = bias;
+    g.M = M; g.N = N; g.K = K; g.batch = 1; g.nsplit = 1; g.flags = flags;
+    return launch_gemm_tc_or_simt(g, (cudaStream_t)stream);
+}
+
+int mv2d_nms_free_decode(const float* cls, const float* box, int N, int max_num, const float* post_range,
+                         float* out_boxes, float* out_scores, int* out_labels, uint8_t* out_valid, void* stream) {
+    MV2D_CHECK_ARG(cls && box && post_range && out_boxes && out_scores && out_labels && out_valid,
+                   "nms_free_decode: null pointer");
+    return run_nms_free_decode(cls, box, N, max_num, post_range, out_boxes, out_scores, out_labels, out_valid,
+                               (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,113 @@
+// Shared device/host helpers for libmv2d_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+#define MV2D_C 256          // embed dims
+#define MV2D_HEADS 8
+#define MV2D_HD 32          // head dim
+#define MV2D_ROI 7
+#define MV2D_TOK 49         // 7x7 RoI tokens
+#define MV2D_MAXV 16        // max views per sample
+
+namespace mv2d {
+
+// thread-local last-error text, set by the host wrappers (abi.cu)
+void set_error(const char* fmt, ...);
+void note_launch();   // counts kernel launches enqueued by this library (mv2d_launch_count)
+
+#define MV2D_CHECK_ARG(cond, ...)                         \
+    do {                                                  \
+        if (!(cond)) {                                    \
+            mv2d::set_error(__VA_ARGS__);                 \
+            return -1;                                    \
+        }                                                 \
+    } while (0)
+
+#define MV2D_CHECK_LAUNCH(what)                                              \
+    do {                                                                     \
+        cudaError_t e__ = cudaGetLastError();                                \
+        mv2d::note_launch();                                                 \
+        if (e__ != cudaSuccess) {                                            \
+            mv2d::set_error("%s: %s", what, cudaGetErrorString(e__));        \
+            return (int)e__;                                                 \
+        }                                                                    \
+    } while (0)
+
+__host__ __device__ inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// ---- fp64 4x4 inverse, Gauss-Jordan with partial pivoting (what LAPACK getrf/getri amount to
+// for a 4x4; replaces np.linalg.inv pe.py:111 and torch.inverse box_correlation.py:120,176,
+// query_generator.py:339).  m and out are row-major.
+__device__ inline void inv4x4(const double* m, double* out) {
+    double a[4][8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            a[i][j] = m[i * 4 + j];
+            a[i][4 + j] = (i == j) ? 1.0 : 0.0;
+        }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        int p = c;
+        double best = fabs(a[c][c]);
+#pragma unroll
+        for (int r = c + 1; r < 4; ++r) {
+            double v = fabs(a[r][c]);
+            if (v > best) { best = v; p = r; }
+        }
+        if (p != c) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { double t = a[c][j]; a[c][j] = a[p][j]; a[p][j] = t; }
+        }
+        double inv = 1.0 / a[c][c];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[c][j] *= inv;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            if (r == c) continue;
+            double f = a[r][c];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a[r][j] -= f * a[c][j];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) out[i * 4 + j] = a[i][4 + j];
+}
+
+__device__ inline void mat4_mul(const double* a, const double* b, double* c) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            double s = 0.0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) s += a[i * 4 + k] * b[k * 4 + j];
+            c[i * 4 + j] = s;
+        }
+}
+
+__device__ inline float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ inline float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// mmdet inverse_sigmoid(x, eps=1e-5)
+__device__ inline float inverse_sigmoid_f(float x) {
+    x = fminf(fmaxf(x, 0.f), 1.f);
+    float a = fmaxf(x, 1e-5f), b = fmaxf(1.f - x, 1e-5f);
+    return logf(a / b);
+}
+__device__ inline float sigmoid_f(float x) { return 1.f / (1.f + expf(-x)); }
+
+}  // namespace mv2d

@@ -1,0 +1,522 @@
+// K4/K5: the sparse multi-view cross-attention decoder (rows a13-a19 of SURVEY.md section 8a).
+//   reference: roi_heads/bbox_heads/cross_attention_head.py:22-49,202-242;
+//              utils/petr_transformer.py:194-593 (over mmcv BaseTransformerLayer / FFN and
+//              torch.nn.MultiheadAttention)
+//
+// Cross-attention is evaluated in "absorbed" form (exact in real arithmetic): with
+//   q~_h = scale * Wk_h^T (Wq_h x + bq_h)           (256 numbers per head, one small GEMM)
+// the logits are  q~_h . (memory_k + pos_k)  (+ a per-(query,head) constant that softmax
+// cancels), and the head output is  Wv_h (sum_k p_hk memory_k) + bv_h.  So the kernel streams
+// the RAW key rows once per query -- no K/V projection of 49*N (or ~25k) keys per layer --
+// and the work per layer is bound by the bytes of the key rows it reads (HBM/L2), not flops.
+#include "common.cuh"
+#include "gemm_simt.cuh"
+#include "mv2d_internal.h"
+
+namespace mv2d {
+
+// ------------------------------------------------------------------------------------------
+// Row-wise: x = LN( sum_s partial[s] + bias + residual ) ; optional second LN (post_norm) and
+// optional "+ query_pos" copy.  One warp per row of 256.  Also used (relu=1, grouped gammas)
+// for the Linear-LN-ReLU blocks of the classification branch.
+struct LnArgs {
+    const float* partial; int nsplit; long long split_stride;
+    const float* bias; const float* residual;
+    const float* gamma; const float* beta; int rows_per_group; int group_stride;  // per-layer params
+    int relu;
+    const float* qpos;   // nullable
+    const float* gamma2; const float* beta2;  // nullable: post_norm
+    float* out; float* out_q; float* out2;
+    int rows;
+};
+
+__global__ void __launch_bounds__(256) ln_kernel(LnArgs a) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= a.rows) return;
+    const int grp = a.rows_per_group > 0 ? row / a.rows_per_group : 0;
+    const long long o = (long long)row * MV2D_C;
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int c = i * 128 + lane * 4;
+        float4 s = *reinterpret_cast<const float4*>(a.partial + o + c);
+        for (int k = 1; k < a.nsplit; ++k) {
+            float4 t = *reinterpret_cast<const float4*>(a.partial + k * a.split_stride + o + c);
+            s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+        }
+        if (a.bias) {
+            float4 t = __ldg(reinterpret_cast<const float4*>(a.bias + grp * a.group_stride + c));
+            s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+        }
+        if (a.residual) {
+            float4 t = *reinterpret_cast<const float4*>(a.residual + o + c);
+            s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+        }
+        v[i * 4 + 0] = s.x; v[i * 4 + 1] = s.y; v[i * 4 + 2] = s.z; v[i * 4 + 3] = s.w;
+    }
+    auto norm = [&](const float* g, const float* b, float* y) {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += v[i];
+        const float mean = warp_sum(s) * (1.f / MV2D_C);
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { float d = v[i] - mean; q += d * d; }
+        const float rstd = rsqrtf(warp_sum(q) * (1.f / MV2D_C) + 1e-5f);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int c = i * 128 + lane * 4;
+            float4 gg = __ldg(reinterpret_cast<const float4*>(g + c));
+            float4 bb = __ldg(reinterpret_cast<const float4*>(b + c));
+            y[i * 4 + 0] = (v[i * 4 + 0] - mean) * rstd * gg.x + bb.x;
+            y[i * 4 + 1] = (v[i * 4 + 1] - mean) * rstd * gg.y + bb.y;
+            y[i * 4 + 2] = (v[i * 4 + 2] - mean) * rstd * gg.z + bb.z;
+            y[i * 4 + 3] = (v[i * 4 + 3] - mean) * rstd * gg.w + bb.w;
+        }
+    };
+    float y[8];
+    norm(a.gamma + grp * a.group_stride, a.beta + grp * a.group_stride, y);
+    if (a.relu) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) y[i] = fmaxf(y[i], 0.f);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int c = i * 128 + lane * 4;
+        *reinterpret_cast<float4*>(a.out + o + c) = make_float4(y[i * 4], y[i * 4 + 1], y[i * 4 + 2], y[i * 4 + 3]);
+        if (a.out_q) {
+            float4 qp = *reinterpret_cast<const float4*>(a.qpos + o + c);
+            *reinterpret_cast<float4*>(a.out_q + o + c) =
+                make_float4(y[i * 4] + qp.x, y[i * 4 + 1] + qp.y, y[i * 4 + 2] + qp.z, y[i * 4 + 3] + qp.w);
+        }
+    }
+    if (a.out2) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = y[i];
+        norm(a.gamma2, a.beta2, y);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int c = i * 128 + lane * 4;
+            *reinterpret_cast<float4*>(a.out2 + o + c) = make_float4(y[i * 4], y[i * 4 + 1], y[i * 4 + 2], y[i * 4 + 3]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// FlattenMHSelfAttention core (petr_transformer.py:314-370): all N queries form ONE sequence.
+// qkv [N,768] (q | k | v, head h = channels 32h..32h+31), q already includes the bias; the
+// 1/sqrt(32) scale is applied here.  grid (ceil(N/32), 8 heads), 256 threads: warp = 4 queries
+// (one at a time), lanes = keys for QK^T, lanes = channels for PV; K/V tiles of 128 keys in smem.
+#define SA_KT 128
+__global__ void __launch_bounds__(256)
+self_attn_kernel(const float* __restrict__ qkv, const uint8_t* __restrict__ mask, int N, float* __restrict__ out) {
+    __shared__ float Ks[SA_KT][33];
+    __shared__ float Vs[SA_KT][33];
+    const int hd = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * 32 + warp * 4;
+    float q[4][32];            // q[i][d], replicated across lanes
+    float m[4], l[4], acc[4];  // running max / sum / output channel `lane`
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int qi = q0 + i;
+        m[i] = -INFINITY; l[i] = 0.f; acc[i] = 0.f;
+#pragma unroll
+        for (int d = 0; d < 32; ++d)
+            q[i][d] = (qi < N) ? __ldg(qkv + (long long)qi * 768 + hd * 32 + d) * 0.17677669529663687f : 0.f;
+    }
+    for (int k0 = 0; k0 < N; k0 += SA_KT) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < SA_KT * 32; i += 256) {
+            const int r = i >> 5, c = i & 31, k = k0 + r;
+            Ks[r][c] = (k < N) ? __ldg(qkv + (long long)k * 768 + 256 + hd * 32 + c) : 0.f;
+            Vs[r][c] = (k < N) ? __ldg(qkv + (long long)k * 768 + 512 + hd * 32 + c) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int qi = q0 + i;
+            if (qi >= N) continue;   // warp-uniform
+            for (int g = 0; g < SA_KT / 32; ++g) {
+                const int kk = g * 32 + lane, k = k0 + kk;
+                if (k0 + g * 32 >= N) break;
+                float s = 0.f;
+#pragma unroll
+                for (int d = 0; d < 32; ++d) s = fmaf(q[i][d], Ks[kk][d], s);
+                if (k >= N || (mask && mask[(long long)qi * N + k])) s = -INFINITY;
+                const float mn = fmaxf(m[i], warp_max(s));
+                if (mn == -INFINITY) continue;
+                const float alpha = __expf(m[i] - mn);   // exp(-inf) = 0 on the first tile
+                const float pj = __expf(s - mn);
+                l[i] = l[i] * alpha + warp_sum(pj);
+                float a = acc[i] * alpha;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) a = fmaf(__shfl_sync(0xffffffffu, pj, j), Vs[g * 32 + j][lane], a);
+                acc[i] = a;
+                m[i] = mn;
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int qi = q0 + i;
+        if (qi < N) out[(long long)qi * MV2D_C + hd * 32 + lane] = l[i] > 0.f ? acc[i] / l[i] : 0.f;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Sparse multi-view cross-attention core, absorbed form.  One CTA (8 warps) per query.
+//   qt   [N, 8*256]   q~ per head (scale folded in)
+//   keys: mode 0 -> RoI tokens of the matched RoIs (match list); mode 1 -> set bits of keymask
+//   kin_rows / mem_rows [num_rows, 256]
+//   ctx  [N, 8*256]   sum_k softmax_h(k) * mem_row_k
+// Keys are processed in chunks of XA_CHUNK: pass 1 (logits, warp per key, lanes along the 256
+// channels with 16-byte loads), chunk softmax with running max (warp per head), pass 2
+// (probability-weighted sum of memory rows).  Per-lane state: 8 heads x 8 channels.
+#define XA_CHUNK 512
+__device__ inline void reduce8(float (&v)[8], int lane) {
+    // transpose-reduce 8 per-lane partials over the warp: 9 shuffles instead of 40.
+    // result: every lane holds the full sum for head (lane >> 2) & 7 in v[0].
+    const bool up16 = lane & 16, up8 = lane & 8, up4 = lane & 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float send = up16 ? v[i] : v[i + 4], keep = up16 ? v[i + 4] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        float send = up8 ? v[i] : v[i + 2], keep = up8 ? v[i + 2] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    {
+        float send = up4 ? v[0] : v[1], keep = up4 ? v[1] : v[0];
+        v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+    v[0] += __shfl_xor_sync(0xffffffffu, v[0], 2);
+    v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
+struct XaArgs {
+    const float* qt; const float* kin_rows; const float* mem_rows;
+    const int* match; const int* match_cnt; int max_match;
+    const uint32_t* keymask; int mask_words;
+    int mode; int N; int klist_cap;
+    float* ctx;
+};
+
+__global__ void __launch_bounds__(256)
+cross_attn_kernel(XaArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* sc = reinterpret_cast<float*>(smem_raw);                 // [XA_CHUNK][8] logits -> probs
+    float* red = sc + XA_CHUNK * 8;                                 // [2048] cross-warp sum
+    float* stat = red + 2048;                                       // m[8], l[8], alpha[8]
+    uint16_t* klist = reinterpret_cast<uint16_t*>(stat + 24);       // [klist_cap]
+    __shared__ int nkeys_s;
+    __shared__ int grp_cnt[128];
+    const int n = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, t = threadIdx.x;
+
+    // ---- key list
+    if (t == 0) nkeys_s = 0;
+    for (int i = t; i < 2048; i += 256) red[i] = 0.f;
+    if (t < 8) { stat[t] = -INFINITY; stat[8 + t] = 0.f; stat[16 + t] = 1.f; }
+    __syncthreads();
+    if (a.mode == 0) {
+        const int cnt = a.match_cnt[n];
+        for (int i = t; i < cnt * MV2D_TOK; i += 256)
+            klist[i] = (uint16_t)(a.match[(long long)n * a.max_match + i / MV2D_TOK] * MV2D_TOK + i % MV2D_TOK);
+        if (t == 0) nkeys_s = cnt * MV2D_TOK;
+    } else {
+        // deterministic compaction of the set bits: per-32-word group counts, then a prefix
+        const uint32_t* km = a.keymask + (long long)n * a.mask_words;
+        const int ngroups = (a.mask_words + 31) / 32;           // host guarantees <= 128
+        for (int g = warp; g < ngroups; g += 8) {
+            const int w = g * 32 + lane;
+            const int c = __popc((w < a.mask_words) ? km[w] : 0u);
+            const int tot = __reduce_add_sync(0xffffffffu, c);
+            if (lane == 0) grp_cnt[g] = tot;
+        }
+        __syncthreads();
+        for (int g = warp; g < ngroups; g += 8) {
+            int base = 0;
+            for (int i = 0; i < g; ++i) base += grp_cnt[i];
+            const int w = g * 32 + lane;
+            const uint32_t bits = (w < a.mask_words) ? km[w] : 0u;
+            const int c = __popc(bits);
+            int incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+            int pos = base + incl - c;
+            uint32_t b = bits;
+            while (b) { const int bit = __ffs(b) - 1; b &= b - 1; klist[pos++] = (uint16_t)(w * 32 + bit); }
+            if (g == ngroups - 1 && lane == 31) nkeys_s = base + incl;
+        }
+    }
+    __syncthreads();
+    const int nkeys = nkeys_s;
+
+    // ---- q~ slice of this lane: 8 heads x channels {lane*4..+3, 128+lane*4..+3}
+    float qv[8][8];
+#pragma unroll
+    for (int h = 0; h < 8; ++h) {
+        const float4 x0 = *reinterpret_cast<const float4*>(a.qt + (long long)n * 2048 + h * 256 + lane * 4);
+        const float4 x1 = *reinterpret_cast<const float4*>(a.qt + (long long)n * 2048 + h * 256 + 128 + lane * 4);
+        qv[h][0] = x0.x; qv[h][1] = x0.y; qv[h][2] = x0.z; qv[h][3] = x0.w;
+        qv[h][4] = x1.x; qv[h][5] = x1.y; qv[h][6] = x1.z; qv[h][7] = x1.w;
+    }
+    float acc[8][8];
+#pragma unroll
+    for (int h = 0; h < 8; ++h)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[h][c] = 0.f;
+
+    for (int c0 = 0; c0 < nkeys; c0 += XA_CHUNK) {
+        const int cn = min(XA_CHUNK, nkeys - c0);
+        // pass 1: logits
+        for (int j = warp; j < cn; j += 8) {
+            const float* row = a.kin_rows + (long long)klist[c0 + j] * MV2D_C;
+            const float4 k0 = __ldg(reinterpret_cast<const float4*>(row + lane * 4));
+            const float4 k1 = __ldg(reinterpret_cast<const float4*>(row + 128 + lane * 4));
+            float s[8];
+#pragma unroll
+            for (int h = 0; h < 8; ++h) {
+                float x = qv[h][0] * k0.x;
+                x = fmaf(qv[h][1], k0.y, x); x = fmaf(qv[h][2], k0.z, x); x = fmaf(qv[h][3], k0.w, x);
+                x = fmaf(qv[h][4], k1.x, x); x = fmaf(qv[h][5], k1.y, x); x = fmaf(qv[h][6], k1.z, x);
+                x = fmaf(qv[h][7], k1.w, x);
+                s[h] = x;
+            }
+            reduce8(s, lane);
+            if ((lane & 3) == 0) sc[j * 8 + (lane >> 2)] = s[0];
+        }
+        __syncthreads();
+        // chunk softmax: warp = head
+        {
+            const int h = warp;
+            float mx = -INFINITY;
+            for (int j = lane; j < cn; j += 32) mx = fmaxf(mx, sc[j * 8 + h]);
+            mx = warp_max(mx);
+            const float m_old = stat[h], m_new = fmaxf(m_old, mx);
+            float sum = 0.f;
+            for (int j = lane; j < cn; j += 32) {
+                const float p = __expf(sc[j * 8 + h] - m_new);
+                sc[j * 8 + h] = p;
+                sum += p;
+            }
+            sum = warp_sum(sum);
+            if (lane == 0) {
+                const float alpha = (m_old == -INFINITY) ? 0.f : __expf(m_old - m_new);
+                stat[16 + h] = alpha;
+                stat[8 + h] = stat[8 + h] * alpha + sum;
+                stat[h] = m_new;
+            }
+        }
+        __syncthreads();
+        // pass 2: acc = acc*alpha + sum_k p_k * mem_k
+#pragma unroll
+        for (int h = 0; h < 8; ++h) {
+            const float al = stat[16 + h];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) acc[h][c] *= al;
+        }
+        for (int j = warp; j < cn; j += 8) {
+            const float* row = a.mem_rows + (long long)klist[c0 + j] * MV2D_C;
+            const float4 v0 = __ldg(reinterpret_cast<const float4*>(row + lane * 4));
+            const float4 v1 = __ldg(reinterpret_cast<const float4*>(row + 128 + lane * 4));
+            const float4 p0 = *reinterpret_cast<const float4*>(sc + j * 8);
+            const float4 p1 = *reinterpret_cast<const float4*>(sc + j * 8 + 4);
+            const float pp[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+#pragma unroll
+            for (int h = 0; h < 8; ++h) {
+                acc[h][0] = fmaf(pp[h], v0.x, acc[h][0]); acc[h][1] = fmaf(pp[h], v0.y, acc[h][1]);
+                acc[h][2] = fmaf(pp[h], v0.z, acc[h][2]); acc[h][3] = fmaf(pp[h], v0.w, acc[h][3]);
+                acc[h][4] = fmaf(pp[h], v1.x, acc[h][4]); acc[h][5] = fmaf(pp[h], v1.y, acc[h][5]);
+                acc[h][6] = fmaf(pp[h], v1.z, acc[h][6]); acc[h][7] = fmaf(pp[h], v1.w, acc[h][7]);
+            }
+        }
+        __syncthreads();
+    }
+    // ---- cross-warp sum, normalise, store
+#pragma unroll
+    for (int h = 0; h < 8; ++h)
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+            atomicAdd(&red[h * 256 + (c >> 2) * 128 + lane * 4 + (c & 3)], acc[h][c]);
+    __syncthreads();
+    for (int i = t; i < 2048; i += 256) {
+        const float l = stat[8 + (i >> 8)];
+        a.ctx[(long long)n * 2048 + i] = l > 0.f ? red[i] / l : 0.f;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Final 256 -> 10 heads of both branches + reference-point refinement
+// (cross_attention_head.py:221-238).  One warp per (layer, query).
+__global__ void __launch_bounds__(256)
+head10_kernel(const float* __restrict__ xc, const float* __restrict__ xr, const float* __restrict__ wc,
+              const float* __restrict__ bc, const float* __restrict__ wr, const float* __restrict__ br,
+              const float* __restrict__ ref, int L, int N, float pc0, float pc1, float pc2, float pc3,
+              float pc4, float pc5, float vel_dt, float* __restrict__ cls, float* __restrict__ box) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= L * N) return;
+    const int l = row / N, n = row % N;
+    float a[8], b[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        a[i] = xc[(long long)row * MV2D_C + i * 32 + lane];
+        b[i] = xr[(long long)row * MV2D_C + i * 32 + lane];
+    }
+    for (int o = 0; o < 10; ++o) {
+        const float* w1 = wc + ((long long)l * 10 + o) * MV2D_C;
+        const float* w2 = wr + ((long long)l * 10 + o) * MV2D_C;
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            s1 = fmaf(a[i], __ldg(w1 + i * 32 + lane), s1);
+            s2 = fmaf(b[i], __ldg(w2 + i * 32 + lane), s2);
+        }
+        s1 = warp_sum(s1) + __ldg(bc + l * 10 + o);
+        s2 = warp_sum(s2) + __ldg(br + l * 10 + o);
+        if (lane == 0) {
+            cls[(long long)row * 10 + o] = s1;
+            if (o == 0) s2 = sigmoid_f(s2 + inverse_sigmoid_f(ref[n * 3 + 0])) * (pc3 - pc0) + pc0;
+            else if (o == 1) s2 = sigmoid_f(s2 + inverse_sigmoid_f(ref[n * 3 + 1])) * (pc4 - pc1) + pc1;
+            else if (o == 4) s2 = sigmoid_f(s2 + inverse_sigmoid_f(ref[n * 3 + 2])) * (pc5 - pc2) + pc2;
+            else if (o >= 8 && vel_dt != 0.f) s2 = s2 / vel_dt;
+            box[(long long)row * 10 + o] = s2;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+static int gemm(const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc, int M, int N,
+                int K, int flags, cudaStream_t st, int nsplit = 1, long long split_stride = 0, int batch = 1,
+                long long sA = 0, long long sW = 0, long long sC = 0, long long sB = 0) {
+    GemmArgs g{};
+    g.A = A; g.lda = lda; g.W = W; g.ldw = ldw; g.C = C; g.ldc = ldc; g.bias = bias;
+    g.M = M; g.N = N; g.K = K; g.batch = batch; g.nsplit = nsplit; g.splitStride = split_stride; g.flags = flags;
+    g.strideA = sA; g.strideW = sW; g.strideC = sC; g.strideBias = sB;
+    return launch_gemm_simt(g, A_PLAIN, st);
+}
+
+static int ln(const LnArgs& a, cudaStream_t st) {
+    if (a.rows == 0) return 0;
+    ln_kernel<<<cdiv(a.rows, 8), 256, 0, st>>>(a);
+    MV2D_CHECK_LAUNCH("ln");
+    return 0;
+}
+
+#define DEC_SPLIT 4
+
+size_t decoder_workspace_bytes(int N, int L) {
+    size_t n = (size_t)(N > 0 ? N : 1), l = (size_t)(L > 0 ? L : 1);
+    // x, xq, x1, x1q, x2 (5*256) + qkv 768 + sa 256 + qt 2048 + ctx 2048 + hdn 2048 + partial 4*256
+    size_t per = 5 * MV2D_C + 768 + MV2D_C + 2048 + 2048 + 2048 + DEC_SPLIT * MV2D_C;
+    // branches: 4 x [L,N,256]
+    return (n * per + 4 * l * n * MV2D_C) * sizeof(float);
+}
+
+int run_decoder(const Mv2dDecoderParams& p, cudaStream_t st) {
+    const int N = p.N, L = p.L, C = MV2D_C;
+    MV2D_CHECK_ARG(N >= 0 && L >= 1 && L <= MV2D_MAX_LAYERS, "decoder: bad N=%d / L=%d", N, L);
+    if (N == 0) return 0;
+    MV2D_CHECK_ARG(p.num_rows > 0 && p.num_rows <= 65536, "decoder: num_rows=%d must be in (0, 65536]", p.num_rows);
+    MV2D_CHECK_ARG(p.layers && p.branches, "decoder: missing weights");
+    MV2D_CHECK_ARG(p.mode == 0 ? (p.match && p.match_cnt && p.max_match > 0) : (p.keymask && p.mask_words > 0),
+                   "decoder: key description missing for mode %d", p.mode);
+    float* ws = p.workspace;
+    float* x = ws;    ws += (size_t)N * C;
+    float* xq = ws;   ws += (size_t)N * C;
+    float* x1 = ws;   ws += (size_t)N * C;
+    float* x1q = ws;  ws += (size_t)N * C;
+    float* x2 = ws;   ws += (size_t)N * C;
+    float* qkv = ws;  ws += (size_t)N * 768;
+    float* sa = ws;   ws += (size_t)N * C;
+    float* qt = ws;   ws += (size_t)N * 2048;
+    float* ctx = ws;  ws += (size_t)N * 2048;
+    float* hdn = ws;  ws += (size_t)N * 2048;
+    float* part = ws; ws += (size_t)DEC_SPLIT * N * C;
+    float* b0 = ws;   ws += (size_t)L * N * C;
+    float* b1 = ws;   ws += (size_t)L * N * C;
+    float* b2 = ws;   ws += (size_t)L * N * C;
+    float* b3 = ws;   ws += (size_t)L * N * C;
+    MV2D_CHECK_ARG((size_t)(ws - p.workspace) * sizeof(float) <= p.workspace_bytes, "decoder: workspace too small");
+    const long long NC = (long long)N * C;
+    cudaError_t e;
+    // target = 0 ; query + query_pos = query_pos   (cross_attention_head.py:32)
+    if ((e = cudaMemsetAsync(x, 0, NC * sizeof(float), st)) != cudaSuccess ||
+        (e = cudaMemcpyAsync(xq, p.query_pos, NC * sizeof(float), cudaMemcpyDeviceToDevice, st)) != cudaSuccess) {
+        set_error("decoder: init %s", cudaGetErrorString(e));
+        return (int)e;
+    }
+    const int klist_cap = p.mode == 0 ? p.max_match * MV2D_TOK : p.mask_words * 32;
+    const size_t xa_smem = (size_t)(XA_CHUNK * 8 + 2048 + 24) * sizeof(float) + (size_t)klist_cap * sizeof(uint16_t);
+    MV2D_CHECK_ARG(xa_smem <= 227 * 1024, "decoder: key list does not fit shared memory");
+    MV2D_CHECK_ARG(p.mode == 0 || p.mask_words <= 4096, "decoder: mask_words=%d > 4096", p.mask_words);
+    if ((e = cudaFuncSetAttribute(cross_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xa_smem)) != cudaSuccess) {
+        set_error("decoder: smem attr %s", cudaGetErrorString(e));
+        return (int)e;
+    }
+    int rc;
+    const Mv2dBranchWeights& B = *p.branches;
+    for (int l = 0; l < L; ++l) {
+        const Mv2dLayerWeights& w = p.layers[l];
+        float* inter = p.outs_dec + (long long)l * NC;
+        // --- self attention: q,k from (x + qpos), v from x
+        if ((rc = gemm(xq, C, w.sa_in_w, C, w.sa_in_b, qkv, 768, N, 512, C, 0, st))) return rc;
+        if ((rc = gemm(x, C, w.sa_in_w + 512 * C, C, w.sa_in_b + 512, qkv + 512, 768, N, C, C, 0, st))) return rc;
+        self_attn_kernel<<<dim3(cdiv(N, 32), MV2D_HEADS), 256, 0, st>>>(qkv, p.self_attn_mask, N, sa);
+        MV2D_CHECK_LAUNCH("self_attn");
+        if ((rc = gemm(sa, C, w.sa_out_w, C, nullptr, part, C, N, C, C, 0, st))) return rc;
+        {
+            LnArgs a{}; a.partial = part; a.nsplit = 1; a.bias = w.sa_out_b; a.residual = x;
+            a.gamma = w.ln_g[0]; a.beta = w.ln_b[0]; a.qpos = p.query_pos; a.out = x1; a.out_q = x1q; a.rows = N;
+            if ((rc = ln(a, st))) return rc;
+        }
+        // --- sparse cross attention (absorbed)
+        if ((rc = gemm(x1q, C, w.ca_q_w, C, w.ca_q_b, qt, 2048, N, 2048, C, 0, st))) return rc;
+        {
+            XaArgs a{}; a.qt = qt; a.kin_rows = p.kin_rows; a.mem_rows = p.mem_rows; a.match = p.match;
+            a.match_cnt = p.match_cnt; a.max_match = p.max_match; a.keymask = p.keymask; a.mask_words = p.mask_words;
+            a.mode = p.mode; a.N = N; a.klist_cap = klist_cap; a.ctx = ctx;
+            cross_attn_kernel<<<N, 256, xa_smem, st>>>(a);
+            MV2D_CHECK_LAUNCH("cross_attn");
+        }
+        if ((rc = gemm(ctx, 2048, w.ca_o_w, 2048, nullptr, part, C, N, C, 2048, 0, st, DEC_SPLIT, NC))) return rc;
+        {
+            LnArgs a{}; a.partial = part; a.nsplit = DEC_SPLIT; a.split_stride = NC; a.bias = w.ca_o_b; a.residual = x1;
+            a.gamma = w.ln_g[1]; a.beta = w.ln_b[1]; a.out = x2; a.rows = N;
+            if ((rc = ln(a, st))) return rc;
+        }
+        // --- FFN
+        if ((rc = gemm(x2, C, w.ffn_w1, C, w.ffn_b1, hdn, 2048, N, 2048, C, GEMM_RELU, st))) return rc;
+        if ((rc = gemm(hdn, 2048, w.ffn_w2, 2048, nullptr, part, C, N, C, 2048, 0, st, DEC_SPLIT, NC))) return rc;
+        {
+            LnArgs a{}; a.partial = part; a.nsplit = DEC_SPLIT; a.split_stride = NC; a.bias = w.ffn_b2; a.residual = x2;
+            a.gamma = w.ln_g[2]; a.beta = w.ln_b[2]; a.qpos = p.query_pos; a.out = x; a.out_q = xq;
+            a.gamma2 = B.post_g; a.beta2 = B.post_b; a.out2 = inter; a.rows = N;
+            if ((rc = ln(a, st))) return rc;
+        }
+    }
+    // --- branches, batched over layers (cross_attention_head.py:216-231)
+    const long long CC = (long long)C * C;
+    if ((rc = gemm(p.outs_dec, C, B.cls_w0, C, nullptr, b0, C, N, C, C, 0, st, 1, 0, L, NC, CC, NC, 0))) return rc;
+    {
+        LnArgs a{}; a.partial = b0; a.nsplit = 1; a.bias = B.cls_b0; a.gamma = B.cls_g0; a.beta = B.cls_be0;
+        a.rows_per_group = N; a.group_stride = C; a.relu = 1; a.out = b1; a.rows = L * N;
+        if ((rc = ln(a, st))) return rc;
+    }
+    if ((rc = gemm(b1, C, B.cls_w1, C, nullptr, b0, C, N, C, C, 0, st, 1, 0, L, NC, CC, NC, 0))) return rc;
+    {
+        LnArgs a{}; a.partial = b0; a.nsplit = 1; a.bias = B.cls_b1; a.gamma = B.cls_g1; a.beta = B.cls_be1;
+        a.rows_per_group = N; a.group_stride = C; a.relu = 1; a.out = b1; a.rows = L * N;
+        if ((rc = ln(a, st))) return rc;
+    }
+    if ((rc = gemm(p.outs_dec, C, B.reg_w0, C, B.reg_b0, b2, C, N, C, C, GEMM_RELU, st, 1, 0, L, NC, CC, NC, C))) return rc;
+    if ((rc = gemm(b2, C, B.reg_w1, C, B.reg_b1, b3, C, N, C, C, GEMM_RELU, st, 1, 0, L, NC, CC, NC, C))) return rc;
+    head10_kernel<<<cdiv(L * N, 8), 256, 0, st>>>(b1, b3, B.cls_w2, B.cls_b2, B.reg_w2, B.reg_b2, p.ref, L, N,
+                                                 p.pc_range[0], p.pc_range[1], p.pc_range[2], p.pc_range[3],
+                                                 p.pc_range[4], p.pc_range[5], p.vel_dt, p.cls_scores, p.bbox_preds);
+    MV2D_CHECK_LAUNCH("head10");
+    return 0;
+}
+
+}  // namespace mv2d

@@ -1,0 +1,21 @@
+// Internal declarations shared by the translation units of libmv2d_b200.
+#pragma once
+#include <cuda_runtime.h>
+#include "../../include/mv2d_b200.h"
+
+namespace mv2d {
+
+int run_geom_prep(const double* lidar2img, int V, double* img2lidar, double* trans, cudaStream_t st);
+int run_nchw_to_nhwc(const float* in, float* out, int V, int C, int HW, cudaStream_t st);
+int run_pe3d(const Mv2dPeParams& p, cudaStream_t st);
+size_t pe3d_workspace_bytes(int V, int h, int w, int depth_num);
+int run_roi_align_qg(const Mv2dQgParams& p, cudaStream_t st);
+size_t roi_align_qg_workspace_bytes(int N);
+int run_box_corr(const Mv2dCorrParams& p, cudaStream_t st);
+int run_decoder(const Mv2dDecoderParams& p, cudaStream_t st);
+size_t decoder_workspace_bytes(int N, int L);
+int run_nms_free_decode(const float* cls, const float* box, int N, int max_num, const float* post_range,
+                        float* out_boxes, float* out_scores, int* out_labels, uint8_t* out_valid,
+                        cudaStream_t st);
+
+}  // namespace mv2d

@@ -1,0 +1,207 @@
+// K1: 3D position embedding (rows a1-a3 of SURVEY.md section 8a).
+//   reference: mmdet3d_plugin/models/utils/pe.py:84-169, positional_encoding.py:58-96
+// Layout: everything channels-last, pixel p = (v*h + y)*w + x, row p of a [P, C] matrix.
+#include "common.cuh"
+#include "gemm_simt.cuh"
+#include "mv2d_internal.h"
+
+namespace mv2d {
+
+// ---- geometry prep: img2lidar[v] = inv(lidar2img[v]); trans[src][dst] = lidar2img[dst] @ img2lidar[src]
+// (pe.py:111; box_correlation.py:118-122).  One block, V*V threads.
+__global__ void geom_prep_kernel(const double* __restrict__ lidar2img, int V,
+                                 double* __restrict__ img2lidar, double* __restrict__ trans) {
+    __shared__ double inv_s[MV2D_MAXV][16];
+    int t = threadIdx.x;
+    if (t < V) {
+        double out[16];
+        inv4x4(lidar2img + t * 16, out);
+        for (int i = 0; i < 16; ++i) { inv_s[t][i] = out[i]; img2lidar[t * 16 + i] = out[i]; }
+    }
+    __syncthreads();
+    if (t < V * V) {
+        int src = t / V, dst = t % V;
+        double out[16];
+        mat4_mul(lidar2img + dst * 16, inv_s[src], out);
+        for (int i = 0; i < 16; ++i) trans[(src * V + dst) * 16 + i] = out[i];
+    }
+}
+
+// ---- NCHW -> NHWC (the FPN hands us NCHW; every kernel below wants C contiguous)
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, float* __restrict__ out, int C, int HW) {
+    __shared__ float tile[32][33];
+    const int v = blockIdx.z;
+    const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const float* src = in + (long long)v * C * HW;
+    float* dst = out + (long long)v * C * HW;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        int c = c0 + i, p = p0 + threadIdx.x;
+        tile[i][threadIdx.x] = (c < C && p < HW) ? src[(long long)c * HW + p] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        int p = p0 + i, c = c0 + threadIdx.x;
+        if (c < C && p < HW) dst[(long long)p * C + c] = tile[threadIdx.x][i];
+    }
+}
+
+// ---- frustum coordinates -> [P, 3*D] (pe.py:93-130).  fp64 geometry as in the reference.
+// thread = (pixel, depth); 3 consecutive floats per thread => a warp writes 384 contiguous bytes.
+__global__ void pe_coords_kernel(const double* __restrict__ img2lidar, float* __restrict__ out,
+                                 int V, int h, int w, int D, double pad_h, double pad_w,
+                                 double depth_start, double pr0, double pr1, double pr2,
+                                 double pr3, double pr4, double pr5) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)V * h * w * D;
+    if (gid >= total) return;
+    const int d = (int)(gid % D);
+    const long long p = gid / D;
+    const int x = (int)(p % w), y = (int)((p / w) % h), v = (int)(p / ((long long)w * h));
+    const double cw = ((double)x + 0.5) * pad_w / (double)w - 0.5;
+    const double ch = ((double)y + 0.5) * pad_h / (double)h - 0.5;
+    const double bin = (pr3 - depth_start) / ((double)D * (1.0 + (double)D));
+    const double cd = depth_start + bin * (double)d * ((double)d + 1.0);
+    const double s = fmax(cd, 1e-3);
+    const double c0 = cw * s, c1 = ch * s;
+    const double* m = img2lidar + v * 16;
+    const double lo[3] = {pr0, pr1, pr2}, hi[3] = {pr3, pr4, pr5};
+    float r[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        double c = m[i * 4 + 0] * c0 + m[i * 4 + 1] * c1 + m[i * 4 + 2] * cd + m[i * 4 + 3];
+        c = (c - lo[i]) / (hi[i] - lo[i]);
+        c = fmin(fmax(c, 0.0), 1.0);                       // inverse_sigmoid, fp64 then .float()
+        r[i] = (float)log(fmax(c, 1e-5) / fmax(1.0 - c, 1e-5));
+    }
+    float* o = out + p * (3 * D) + d * 3;
+    o[0] = r[0]; o[1] = r[1]; o[2] = r[2];
+}
+
+// ---- SinePositionalEncoding3D, normalize=True (positional_encoding.py:58-96).
+// Step 1: per pixel the three normalised embeds (view, y, x) from the not-mask cumsums.
+__global__ void sine_prep_kernel(const uint8_t* __restrict__ not_mask, float* __restrict__ emb,
+                                 int V, int h, int w, float stride, float scale, float eps) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= V * h * w) return;
+    const int x = p % w, y = (p / w) % h, v = p / (w * h);
+    float n = 0.f, nl = 0.f, ye = 0.f, yl = 0.f, xe = 0.f, xl = 0.f;
+    for (int i = 0; i < V; ++i) {
+        float m = (float)not_mask[(i * h + y) * w + x];
+        nl += m;
+        if (i <= v) n += m;
+    }
+    for (int i = 0; i < h; ++i) {
+        float m = (float)not_mask[(v * h + i) * w + x];
+        yl += m;
+        if (i <= y) ye += m;
+    }
+    for (int i = 0; i < w; ++i) {
+        float m = (float)not_mask[(v * h + y) * w + i];
+        xl += m;
+        if (i <= x) xe += m;
+    }
+    if (stride > 0.f) {
+        ye = (ye - 0.5f) * stride; yl = (yl - 0.5f) * stride;
+        xe = (xe - 0.5f) * stride; xl = (xl - 0.5f) * stride;
+    }
+    emb[p * 3 + 0] = n / (nl + eps) * scale;
+    emb[p * 3 + 1] = ye / (yl + eps) * scale;
+    emb[p * 3 + 2] = xe / (xl + eps) * scale;
+}
+
+// Step 2: [P, 384] = per embed (n, y, x): 64 sines of even dim_t then 64 cosines of odd dim_t.
+__global__ void sine_embed_kernel(const float* __restrict__ emb, const float* __restrict__ dim_t,
+                                  float* __restrict__ out, int P) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)P * 384) return;
+    const int c = (int)(gid % 384);
+    const long long p = gid / 384;
+    const int e = c >> 7, i = c & 127;
+    const float val = emb[p * 3 + e];
+    float r;
+    if (i < 64) r = sinf(val / __ldg(dim_t + 2 * i));
+    else        r = cosf(val / __ldg(dim_t + 2 * (i - 64) + 1));
+    out[gid] = r;
+}
+
+static int gemm(const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc,
+                int M, int N, int K, int flags, cudaStream_t st, const float* gx = nullptr,
+                const float* gs = nullptr, const float* gfeat = nullptr, float* kin = nullptr) {
+    GemmArgs g{};
+    g.A = A; g.lda = lda; g.W = W; g.ldw = ldw; g.C = C; g.ldc = ldc; g.bias = bias;
+    g.M = M; g.N = N; g.K = K; g.batch = 1; g.nsplit = 1; g.flags = flags;
+    g.gx = gx; g.gs = gs; g.gfeat = gfeat; g.kin = kin;
+    return launch_gemm_tc_or_simt(g, st);
+}
+
+int run_geom_prep(const double* lidar2img, int V, double* img2lidar, double* trans, cudaStream_t st) {
+    MV2D_CHECK_ARG(V >= 1 && V <= MV2D_MAXV, "geom_prep: V=%d out of range", V);
+    geom_prep_kernel<<<1, V * V, 0, st>>>(lidar2img, V, img2lidar, trans);
+    MV2D_CHECK_LAUNCH("geom_prep");
+    return 0;
+}
+
+int run_nchw_to_nhwc(const float* in, float* out, int V, int C, int HW, cudaStream_t st) {
+    dim3 grid(cdiv(HW, 32), cdiv(C, 32), V), block(32, 8);
+    nchw_to_nhwc_kernel<<<grid, block, 0, st>>>(in, out, C, HW);
+    MV2D_CHECK_LAUNCH("nchw_to_nhwc");
+    return 0;
+}
+
+// PE.forward.  feat is NHWC [P,256].  Outputs pe [P,256] and (optional) kin = feat + pe.
+int run_pe3d(const Mv2dPeParams& p, cudaStream_t st) {
+    const int P = p.V * p.h * p.w, D = p.depth_num, C = MV2D_C;
+    MV2D_CHECK_ARG(p.V >= 1 && p.V <= MV2D_MAXV && P > 0, "pe3d: bad V/h/w");
+    MV2D_CHECK_ARG((3 * D) % 16 == 0, "pe3d: 3*depth_num must be a multiple of 16");
+    float* ws = p.workspace;
+    float* A1 = ws;                      ws += (size_t)P * 3 * D;
+    float* Hd = ws;                      ws += (size_t)P * 4 * C;
+    float* X  = ws;                      ws += (size_t)P * C;
+    float* G1 = ws;                      ws += (size_t)P * C;
+    float* S  = ws;                      ws += (size_t)P * 384;
+    float* SB = ws;                      ws += (size_t)P * C;
+    float* EM = ws;                      ws += (size_t)P * 3;
+    MV2D_CHECK_ARG((size_t)(ws - p.workspace) * sizeof(float) <= p.workspace_bytes,
+                   "pe3d: workspace too small (%zu needed)", (size_t)(ws - p.workspace) * sizeof(float));
+    int rc;
+    {
+        long long total = (long long)P * D;
+        pe_coords_kernel<<<(unsigned)cdiv((int)total, 256), 256, 0, st>>>(
+            p.img2lidar, A1, p.V, p.h, p.w, D, (double)p.pad_h, (double)p.pad_w, p.depth_start,
+            p.position_range[0], p.position_range[1], p.position_range[2], p.position_range[3],
+            p.position_range[4], p.position_range[5]);
+        MV2D_CHECK_LAUNCH("pe_coords");
+    }
+    // position_encoder: 192 -> 1024 -> 256
+    if ((rc = gemm(A1, 3 * D, p.w_pos0, 3 * D, p.b_pos0, Hd, 4 * C, P, 4 * C, 3 * D, GEMM_RELU | GEMM_TF32_OK, st))) return rc;
+    if ((rc = gemm(Hd, 4 * C, p.w_pos2, 4 * C, p.b_pos2, X, C, P, C, 4 * C, GEMM_TF32_OK, st))) return rc;
+    // sine branch: 384 -> 1024 -> 256  (input-independent given masks + weights; recomputed here)
+    if (!p.sine_branch_cached) {
+        sine_prep_kernel<<<cdiv(P, 128), 128, 0, st>>>(p.not_mask, EM, p.V, p.h, p.w, (float)p.stride,
+                                                      6.283185307179586f, 1e-6f);
+        MV2D_CHECK_LAUNCH("sine_prep");
+        sine_embed_kernel<<<(unsigned)(((long long)P * 384 + 255) / 256), 256, 0, st>>>(EM, p.dim_t, S, P);
+        MV2D_CHECK_LAUNCH("sine_embed");
+        if ((rc = gemm(S, 384, p.w_adapt0, 384, p.b_adapt0, Hd, 4 * C, P, 4 * C, 384, GEMM_RELU | GEMM_TF32_OK, st))) return rc;
+        if ((rc = gemm(Hd, 4 * C, p.w_adapt2, 4 * C, p.b_adapt2, SB, C, P, C, 4 * C, GEMM_TF32_OK, st))) return rc;
+    } else {
+        SB = const_cast<float*>(p.sine_branch_cached);
+    }
+    // SE gate on the image feature, fused combine: pe = X * sigmoid(gate) + SB ; kin = pe + feat
+    if ((rc = gemm(p.feat, C, p.w_se_reduce, C, p.b_se_reduce, G1, C, P, C, C, GEMM_RELU | GEMM_TF32_OK, st))) return rc;
+    if ((rc = gemm(G1, C, p.w_se_expand, C, p.b_se_expand, p.pe, C, P, C, C, GEMM_GATE | GEMM_TF32_OK, st, X, SB,
+                   p.feat, p.kin))) return rc;
+    if (p.sine_branch_out && !p.sine_branch_cached) {
+        cudaError_t e = cudaMemcpyAsync(p.sine_branch_out, SB, (size_t)P * C * sizeof(float),
+                                        cudaMemcpyDeviceToDevice, st);
+        if (e != cudaSuccess) { set_error("pe3d: memcpy %s", cudaGetErrorString(e)); return (int)e; }
+    }
+    return 0;
+}
+
+size_t pe3d_workspace_bytes(int V, int h, int w, int depth_num) {
+    size_t P = (size_t)V * h * w;
+    return P * (3 * depth_num + 4 * MV2D_C + MV2D_C + MV2D_C + 384 + MV2D_C + 3) * sizeof(float);
+}
+
+}  // namespace mv2d

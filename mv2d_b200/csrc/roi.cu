@@ -1,0 +1,368 @@
+// K2 (RoIAlign + query generator) and K3 (box correlation).  This translation unit is compiled
+// with -fmad=false: the fp32/fp64 geometry below feeds discontinuous decisions (hit tests,
+// IoU>0, top-k) and must round exactly like the reference's un-fused torch ops.
+//   reference: roi_heads/mv2d_head.py:51-72,95-101; roi_heads/utils/query_generator.py:333-405;
+//              roi_heads/utils/box_correlation.py:95-398; mmcv RoIAlign
+#include "common.cuh"
+#include "gemm_simt.cuh"
+#include "mv2d_internal.h"
+
+namespace mv2d {
+
+// ------------------------------------------------------------------------------------------
+// RoIAlign (avg, aligned=True, adaptive sampling grid) on channels-last maps.
+// grid (49, N), 64 threads: thread = one float4 of the 256 channels => a warp reads 512
+// contiguous bytes per bilinear corner.  Writes tok_feat and (optionally) tok_kin = feat + pe
+// tokens (RoIAlign is linear, so pooling feat+pe equals pooling them separately).
+__global__ void __launch_bounds__(64)
+roi_align_tokens_kernel(const float* __restrict__ rois, const float* __restrict__ feat,
+                        const float* __restrict__ pe, int h, int w, float spatial_scale,
+                        float* __restrict__ tok_feat, float* __restrict__ tok_kin) {
+    const int n = blockIdx.y, bin = blockIdx.x;
+    const int ph = bin / MV2D_ROI, pw = bin % MV2D_ROI;
+    const float* r = rois + n * 5;
+    const int v = (int)r[0];
+    const float x1 = r[1] * spatial_scale - 0.5f, y1 = r[2] * spatial_scale - 0.5f;
+    const float x2 = r[3] * spatial_scale - 0.5f, y2 = r[4] * spatial_scale - 0.5f;
+    const float rw = x2 - x1, rh = y2 - y1;
+    const float bw = rw / (float)MV2D_ROI, bh = rh / (float)MV2D_ROI;
+    const int gh = (int)ceilf(rh / (float)MV2D_ROI), gw = (int)ceilf(rw / (float)MV2D_ROI);
+    const float count = (float)max(gh * gw, 1);
+    const float4* f4 = reinterpret_cast<const float4*>(feat) + (long long)v * h * w * 64 + threadIdx.x;
+    const float4* p4 = pe ? reinterpret_cast<const float4*>(pe) + (long long)v * h * w * 64 + threadIdx.x : nullptr;
+    float4 af = make_float4(0.f, 0.f, 0.f, 0.f), ap = af;
+    for (int iy = 0; iy < gh; ++iy) {
+        float y = y1 + (float)ph * bh + ((float)iy + 0.5f) * bh / (float)gh;
+        for (int ix = 0; ix < gw; ++ix) {
+            float x = x1 + (float)pw * bw + ((float)ix + 0.5f) * bw / (float)gw;
+            if (y < -1.f || y > (float)h || x < -1.f || x > (float)w) continue;
+            float yy = fmaxf(y, 0.f), xx = fmaxf(x, 0.f);
+            int yl = (int)yy, xl = (int)xx, yh, xh;
+            if (yl >= h - 1) { yh = yl = h - 1; yy = (float)yl; } else yh = yl + 1;
+            if (xl >= w - 1) { xh = xl = w - 1; xx = (float)xl; } else xh = xl + 1;
+            const float ly = yy - (float)yl, lx = xx - (float)xl, hy = 1.f - ly, hx = 1.f - lx;
+            const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
+            const int o1 = (yl * w + xl) * 64, o2 = (yl * w + xh) * 64, o3 = (yh * w + xl) * 64,
+                      o4 = (yh * w + xh) * 64;
+            float4 a = __ldg(f4 + o1), b = __ldg(f4 + o2), c = __ldg(f4 + o3), d = __ldg(f4 + o4);
+            af.x += w1 * a.x + w2 * b.x + w3 * c.x + w4 * d.x;
+            af.y += w1 * a.y + w2 * b.y + w3 * c.y + w4 * d.y;
+            af.z += w1 * a.z + w2 * b.z + w3 * c.z + w4 * d.z;
+            af.w += w1 * a.w + w2 * b.w + w3 * c.w + w4 * d.w;
+            if (p4) {
+                a = __ldg(p4 + o1); b = __ldg(p4 + o2); c = __ldg(p4 + o3); d = __ldg(p4 + o4);
+                ap.x += w1 * a.x + w2 * b.x + w3 * c.x + w4 * d.x;
+                ap.y += w1 * a.y + w2 * b.y + w3 * c.y + w4 * d.y;
+                ap.z += w1 * a.z + w2 * b.z + w3 * c.z + w4 * d.z;
+                ap.w += w1 * a.w + w2 * b.w + w3 * c.w + w4 * d.w;
+            }
+        }
+    }
+    af.x /= count; af.y /= count; af.z /= count; af.w /= count;
+    const long long o = ((long long)n * MV2D_TOK + bin) * 64 + threadIdx.x;
+    reinterpret_cast<float4*>(tok_feat)[o] = af;
+    if (tok_kin) {
+        ap.x /= count; ap.y /= count; ap.z /= count; ap.w /= count;
+        reinterpret_cast<float4*>(tok_kin)[o] = make_float4(af.x + ap.x, af.y + ap.y, af.z + ap.z, af.w + ap.w);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Per-RoI camera parameters (mv2d_head.py:51-72,95-101 + query_generator.py:338-339):
+// K' = RoI-frame intrinsics (fp64), feature = clamp(float(K')*scale), M = float(inv(K' E^T)).
+__global__ void box_params_kernel(const float* __restrict__ rois, const double* __restrict__ intrinsics,
+                                  const double* __restrict__ extrinsics, int N, float feat_scale,
+                                  float* __restrict__ cat /*[N,1040]*/, float* __restrict__ m_roi /*[N,16]*/,
+                                  double* __restrict__ k_out /*nullable [N,16]*/) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const float* r = rois + n * 5;
+    const int v = (int)r[0];
+    double K[16], E[16], L[16], Li[16];
+    for (int i = 0; i < 16; ++i) { K[i] = intrinsics[v * 16 + i]; E[i] = extrinsics[v * 16 + i]; }
+    const float wx = r[3] - r[1], wy = r[4] - r[2];
+    const float sx = 7.0f / wx, sy = 7.0f / wy;
+    K[2] = K[2] - (double)r[1] - (double)(0.5f / sx);
+    K[6] = K[6] - (double)r[2] - (double)(0.5f / sy);
+    for (int j = 0; j < 4; ++j) { K[j] = K[j] * (double)sx; K[4 + j] = K[4 + j] * (double)sy; }
+    const bool invalid = (wx < 4.f) || (wy < 4.f);
+    for (int i = 0; i < 16; ++i) {
+        float f = invalid ? 0.f : (float)K[i] * feat_scale;
+        cat[(long long)n * 1040 + 1024 + i] = fminf(fmaxf(f, -5e3f), 5e3f);
+        if (k_out) k_out[n * 16 + i] = K[i];
+    }
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) {
+            double s = 0.0;
+            for (int k = 0; k < 4; ++k) s += K[i * 4 + k] * E[j * 4 + k];
+            L[i * 4 + j] = s;
+        }
+    inv4x4(L, Li);
+    for (int i = 0; i < 16; ++i) m_roi[n * 16 + i] = (float)Li[i];
+}
+
+// AvgPool2d(7) over the ReLU'd conv output: [N,49,256] -> [N,256]
+__global__ void avgpool49_kernel(const float* __restrict__ x, float* __restrict__ out, int N) {
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= N * MV2D_C) return;
+    const int n = gid / MV2D_C, c = gid % MV2D_C;
+    float s = 0.f;
+    for (int t = 0; t < MV2D_TOK; ++t) s += x[((long long)n * MV2D_TOK + t) * MV2D_C + c];
+    out[gid] = s / 49.0f;
+}
+
+// fc_center + center2lidar + normalisation + pos2posemb3d  (query_generator.py:333-341,400-403;
+// mv2d_s_head.py:147-152; utils/pe.py:21-33).  One warp per RoI.
+__global__ void qg_tail_kernel(const float* __restrict__ enc, const float* __restrict__ w_center,
+                               const float* __restrict__ b_center, const float* __restrict__ m_roi,
+                               const float* __restrict__ dim_t, int N, float pc0, float pc1, float pc2,
+                               float pc3, float pc4, float pc5, float* __restrict__ ref,
+                               float* __restrict__ center_lidar, float* __restrict__ posemb) {
+    const int n = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+    const int lane = threadIdx.x & 31;
+    if (n >= N) return;
+    float c[3];
+#pragma unroll
+    for (int o = 0; o < 3; ++o) {
+        float s = 0.f;
+        for (int k = lane; k < MV2D_C; k += 32) s = fmaf(enc[(long long)n * MV2D_C + k], __ldg(w_center + o * MV2D_C + k), s);
+        c[o] = warp_sum(s) + __ldg(b_center + o);
+    }
+    const float hom[4] = {c[0] * c[2], c[1] * c[2], c[2], 1.0f};
+    const float* m = m_roi + n * 16;
+    float xyz[3], p[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+        xyz[i] = m[i * 4 + 0] * hom[0] + m[i * 4 + 1] * hom[1] + m[i * 4 + 2] * hom[2] + m[i * 4 + 3] * hom[3];
+    p[0] = (xyz[0] - pc0) / (pc3 - pc0);
+    p[1] = (xyz[1] - pc1) / (pc4 - pc1);
+    p[2] = (xyz[2] - pc2) / (pc5 - pc2);
+    if (lane < 3) {
+        ref[n * 3 + lane] = p[lane];
+        if (center_lidar) center_lidar[n * 3 + lane] = xyz[lane];
+    }
+    // posemb = cat(emb(y), emb(x), emb(z)), interleaved sin/cos
+    for (int idx = lane; idx < 384; idx += 32) {
+        const int part = idx >> 7, i = idx & 127;
+        const float pos = (part == 0 ? p[1] : (part == 1 ? p[0] : p[2])) * 6.283185307179586f;
+        const float a = pos / __ldg(dim_t + i);
+        posemb[(long long)n * 384 + idx] = (i & 1) ? cosf(a) : sinf(a);
+    }
+}
+
+static int gemm(const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc,
+                int M, int N, int K, int flags, int amode, cudaStream_t st) {
+    GemmArgs g{};
+    g.A = A; g.lda = lda; g.W = W; g.ldw = ldw; g.C = C; g.ldc = ldc; g.bias = bias;
+    g.M = M; g.N = N; g.K = K; g.batch = 1; g.nsplit = 1; g.flags = flags;
+    return launch_gemm_simt(g, amode, st);
+}
+
+size_t roi_align_qg_workspace_bytes(int N) {
+    size_t n = (size_t)(N > 0 ? N : 1);
+    return n * ((size_t)MV2D_TOK * MV2D_C + MV2D_C + 1040 + 512 + MV2D_C + 16 + 384 + MV2D_C) * sizeof(float);
+}
+
+int run_roi_align_qg(const Mv2dQgParams& p, cudaStream_t st) {
+    const int N = p.N, C = MV2D_C;
+    MV2D_CHECK_ARG(N >= 0 && p.V >= 1 && p.V <= MV2D_MAXV, "roi_align_qg: bad N/V");
+    if (N == 0) return 0;
+    MV2D_CHECK_ARG(p.tok_kin == nullptr || p.pe != nullptr, "roi_align_qg: tok_kin needs pe");
+    float* ws = p.workspace;
+    float* conv = ws;   ws += (size_t)N * MV2D_TOK * C;
+    float* pool = ws;   ws += (size_t)N * C;
+    float* cat = ws;    ws += (size_t)N * 1040;
+    float* e0 = ws;     ws += (size_t)N * 512;
+    float* enc = ws;    ws += (size_t)N * C;
+    float* mroi = ws;   ws += (size_t)N * 16;
+    float* pemb = ws;   ws += (size_t)N * 384;
+    float* qh = ws;     ws += (size_t)N * C;
+    MV2D_CHECK_ARG((size_t)(ws - p.workspace) * sizeof(float) <= p.workspace_bytes, "roi_align_qg: workspace too small");
+    int rc;
+    roi_align_tokens_kernel<<<dim3(MV2D_TOK, N), 64, 0, st>>>(p.rois, p.feat, p.tok_kin ? p.pe : nullptr, p.h, p.w,
+                                                            1.0f / (float)p.stride, p.tok_feat, p.tok_kin);
+    MV2D_CHECK_LAUNCH("roi_align_tokens");
+    box_params_kernel<<<cdiv(N, 64), 64, 0, st>>>(p.rois, p.intrinsics, p.extrinsics, N, p.intrins_feat_scale, cat,
+                                                  mroi, p.roi_intrinsics);
+    MV2D_CHECK_LAUNCH("box_params");
+    // shared conv 3x3 (+ReLU) as implicit GEMM over the tokens, avg-pool, FC chain
+    if ((rc = gemm(p.tok_feat, C, p.w_conv, 9 * C, p.b_conv, conv, C, N * MV2D_TOK, C, 9 * C, GEMM_RELU,
+                   A_IM2COL3X3, st))) return rc;
+    avgpool49_kernel<<<cdiv(N * C, 256), 256, 0, st>>>(conv, pool, N);
+    MV2D_CHECK_LAUNCH("avgpool49");
+    if ((rc = gemm(pool, C, p.w_fc, C, p.b_fc, cat, 1040, N, 1024, C, GEMM_RELU | GEMM_CLAMP5E3, A_PLAIN, st))) return rc;
+    if ((rc = gemm(cat, 1040, p.w_enc0, 1040, p.b_enc0, e0, 512, N, 512, 1040, GEMM_RELU, A_PLAIN, st))) return rc;
+    if ((rc = gemm(e0, 512, p.w_enc2, 512, p.b_enc2, enc, C, N, C, 512, GEMM_RELU, A_PLAIN, st))) return rc;
+    qg_tail_kernel<<<cdiv(N, 4), 128, 0, st>>>(enc, p.w_center, p.b_center, mroi, p.dim_t, N, p.pc_range[0],
+                                               p.pc_range[1], p.pc_range[2], p.pc_range[3], p.pc_range[4],
+                                               p.pc_range[5], p.ref, p.center_lidar, pemb);
+    MV2D_CHECK_LAUNCH("qg_tail");
+    // query_embedding: 384 -> 256 (ReLU) -> 256
+    if ((rc = gemm(pemb, 384, p.w_qe0, 384, p.b_qe0, qh, C, N, C, 384, GEMM_RELU, A_PLAIN, st))) return rc;
+    if ((rc = gemm(qh, C, p.w_qe2, C, p.b_qe2, p.query_pos, C, N, C, C, 0, A_PLAIN, st))) return rc;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// K3 box correlation.  One CTA (128 threads = 16 sample points x 8 depths) per RoI.
+// For every other view: project the samples (fp64), test them against that view's RoIs,
+// and when any valid sample lands in any RoI, IoU-match the samples' bounding box against the
+// view's RoIs and keep the top-k with IoU > 0  (box_correlation.py:260-382).
+__device__ inline float block_min128(float v, float* red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float r = fminf(fminf(red[0], red[1]), fminf(red[2], red[3]));
+    __syncthreads();
+    return r;
+}
+
+#define CORR_MAXR 256  // max RoIs per view handled by the smem IoU table
+
+__global__ void __launch_bounds__(128)
+box_corr_kernel(Mv2dCorrParams p) {
+    __shared__ float red[4];
+    __shared__ float iou_s[CORR_MAXR];
+    __shared__ int cnt_s, kept_s;
+    const int n = blockIdx.x, t = threadIdx.x;
+    const float* r = p.rois + n * 5;
+    const int src = (int)r[0];
+    const int S = p.sample_size, Dn = p.num_depth;
+    const int pt = t / Dn, d = t % Dn;          // host guarantees S*S*Dn == 128
+    const int iy = pt / S, ix = pt % S;
+    const float wx = r[3] - r[1], wy = r[4] - r[2];
+    const float px = r[1] + wx * __ldg(p.lin + ix);
+    const float py = r[2] + wy * __ldg(p.lin + iy);
+    const double dep = (double)__ldg(p.depths + d);
+    const double hx = (double)px * dep, hy = (double)py * dep;
+    int* match = p.match + (long long)n * p.max_match;
+    if (t == 0) { match[0] = n; cnt_s = 1; }
+    __syncthreads();
+    for (int v = 0; v < p.V; ++v) {
+        const int rs = p.roi_start[v], nv = p.roi_start[v + 1] - rs;
+        if (v == src || nv == 0) continue;      // block-uniform
+        const double* T = p.trans + ((long long)src * p.V + v) * 16;
+        const double cx = T[0] * hx + T[1] * hy + T[2] * dep + T[3];
+        const double cy = T[4] * hx + T[5] * hy + T[6] * dep + T[7];
+        const double cz = T[8] * hx + T[9] * hy + T[10] * dep + T[11];
+        const double zc = fmax(cz, 1e-2);
+        const double tx = cx / zc, ty = cy / zc;
+        bool valid = !(cz < (double)p.depth_start);
+        valid = valid && (0.0 <= tx) && (tx <= (double)(p.img_w - 1)) && (0.0 <= ty) && (ty <= (double)(p.img_h - 1));
+        const float fx = (float)tx, fy = (float)ty;
+        bool hit = false;
+        if (valid) {
+            for (int j = 0; j < nv; ++j) {
+                const float* q = p.rois + (rs + j) * 5;
+                hit = hit || (q[1] <= fx && fx <= q[3] && q[2] <= fy && fy <= q[4]);
+            }
+        }
+        if (!__syncthreads_or(hit ? 1 : 0)) continue;
+        // bounding box of the valid samples in view v (1e4 / -1e4 sentinels as the reference)
+        const float xmin = block_min128(valid ? fx : 1e4f, red);
+        const float ymin = block_min128(valid ? fy : 1e4f, red);
+        const float xmax = -block_min128(valid ? -fx : 1e4f, red);
+        const float ymax = -block_min128(valid ? -fy : 1e4f, red);
+        const float area_a = (xmax - xmin) * (ymax - ymin);
+        if (t == 0) kept_s = 0;
+        for (int j = t; j < nv && j < CORR_MAXR; j += 128) {
+            const float* q = p.rois + (rs + j) * 5;
+            const float iw = fmaxf(fminf(xmax, q[3]) - fmaxf(xmin, q[1]), 0.f);
+            const float ih = fmaxf(fminf(ymax, q[4]) - fmaxf(ymin, q[2]), 0.f);
+            const float inter = iw * ih;
+            const float area_b = (q[3] - q[1]) * (q[4] - q[2]);
+            const float uni = area_a + area_b - inter;
+            iou_s[j] = inter / (uni + 1e-4f);
+        }
+        __syncthreads();
+        const int nvc = min(nv, CORR_MAXR);
+        float mx = 0.f;
+        for (int j = 0; j < nvc; ++j) mx = fmaxf(mx, iou_s[j]);
+        const int base = cnt_s;
+        int kept_local = 0;
+        for (int j = t; j < nvc; j += 128) {
+            const float me = iou_s[j];
+            if (!(me > 0.f)) continue;
+            int rank = 0;   // position in the descending-IoU order (ties: lower index first)
+            for (int k = 0; k < nvc; ++k) {
+                const float o = iou_s[k];
+                rank += (o > me) || (o == me && k < j);
+            }
+            // kept entries form a prefix of the ranking (the condition is monotone in IoU)
+            const bool keep = rank < p.topk && ((me > p.ratio * mx) || (me > p.iou_thr));
+            if (keep && base + rank < p.max_match) { match[base + rank] = rs + j; kept_local++; }
+        }
+        if (kept_local) atomicAdd(&kept_s, kept_local);
+        __syncthreads();
+        if (t == 0) cnt_s = min(base + kept_s, p.max_match);
+        __syncthreads();
+    }
+    if (t == 0) p.match_cnt[n] = cnt_s;
+}
+
+// T head: per-query key mask = OR of the (expanded) own-view cell rectangles of all matched
+// RoIs, minus padded-out cells (box_correlation.py:102-115,147-157; mv2d_t_head.py:67-88).
+__global__ void __launch_bounds__(256)
+key_mask_kernel(Mv2dCorrParams p, int words) {
+    extern __shared__ uint32_t bits[];
+    __shared__ int total;
+    const int n = blockIdx.x, t = threadIdx.x;
+    for (int i = t; i < words; i += blockDim.x) bits[i] = 0u;
+    if (t == 0) total = 0;
+    __syncthreads();
+    const int cnt = p.match_cnt[n];
+    const int* match = p.match + (long long)n * p.max_match;
+    const float st = (float)p.stride;
+    const float margin1 = 0.5f * st, margin2 = (float)p.expand_stride * st;
+    for (int i = 0; i < cnt; ++i) {
+        const float* q = p.rois + match[i] * 5;
+        const int v = (int)q[0];
+        // candidate cell window (generous), exact fp32 test per cell as the reference does
+        int cx0 = max((int)floorf((q[1] - margin1 - margin2) / st) - 1, 0);
+        int cx1 = min((int)ceilf((q[3] + margin1 + margin2) / st) + 1, p.w - 1);
+        int cy0 = max((int)floorf((q[2] - margin1 - margin2) / st) - 1, 0);
+        int cy1 = min((int)ceilf((q[4] + margin1 + margin2) / st) + 1, p.h - 1);
+        const int ww = cx1 - cx0 + 1, hh = cy1 - cy0 + 1;
+        for (int c = t; c < ww * hh; c += blockDim.x) {
+            const int x = cx0 + c % ww, y = cy0 + c / ww;
+            const float xs = ((float)x + 0.5f) * st - 0.5f, ys = ((float)y + 0.5f) * st - 0.5f;
+            const bool in = (xs + margin1 + margin2 >= q[1]) && (xs - margin1 - margin2 <= q[3]) &&
+                            (ys + margin1 + margin2 >= q[2]) && (ys - margin1 - margin2 <= q[4]);
+            if (in) {
+                const int cell = (v * p.h + y) * p.w + x;
+                if (!(p.pad_mask && p.pad_mask[cell])) atomicOr(&bits[cell >> 5], 1u << (cell & 31));
+            }
+        }
+    }
+    __syncthreads();
+    int local = 0;
+    for (int i = t; i < words; i += blockDim.x) {
+        const uint32_t b = bits[i];
+        p.keymask[(long long)n * words + i] = b;
+        local += __popc(b);
+    }
+    if (p.key_cnt) {
+        atomicAdd(&total, local);
+        __syncthreads();
+        if (t == 0) p.key_cnt[n] = total;
+    }
+}
+
+int run_box_corr(const Mv2dCorrParams& p, cudaStream_t st) {
+    MV2D_CHECK_ARG(p.N >= 0 && p.V >= 1 && p.V <= MV2D_MAXV, "box_corr: bad N/V");
+    MV2D_CHECK_ARG(p.sample_size * p.sample_size * p.num_depth == 128,
+                   "box_corr: sample_size^2*num_depth must be 128 (got %d)", p.sample_size * p.sample_size * p.num_depth);
+    MV2D_CHECK_ARG(p.max_match >= 1 && p.topk >= 1, "box_corr: bad max_match/topk");
+    if (p.N == 0) return 0;
+    box_corr_kernel<<<p.N, 128, 0, st>>>(p);
+    MV2D_CHECK_LAUNCH("box_corr");
+    if (p.keymask) {
+        const int words = cdiv(p.V * p.h * p.w, 32);
+        key_mask_kernel<<<p.N, 256, words * sizeof(uint32_t), st>>>(p, words);
+        MV2D_CHECK_LAUNCH("key_mask");
+    }
+    return 0;
+}
+
+}  // namespace mv2d

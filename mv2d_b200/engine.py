@@ -1,0 +1,313 @@
+"""Host-side driver of the hot path: owns the device buffers, marshals the per-sample metadata
+and enqueues the five C-ABI stages (geom_prep, pe3d, roi_align_qg, box_corr, decoder) on the
+current CUDA stream.  No arithmetic of the path happens in Python/torch; torch supplies device
+memory, streams and (optionally) CUDA-graph capture.
+
+Mirrors ``MV2DHead.simple_test`` minus decode
+(reference roi_heads/mv2d_head.py:249-261 -> mv2d_s_head.py:122-211 / mv2d_t_head.py:26-142).
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import lib
+from .pack import PackedWeights
+
+DEFAULTS = dict(
+    pc_range=[-51.2, -51.2, -5.0, 51.2, 51.2, 3.0],
+    position_range=[-61.2, -61.2, -10.0, 61.2, 61.2, 10.0],
+    depth_num=64, depth_start=1.0, stride=16, intrins_feat_scale=0.1,
+    sample_size=4, corr_num_depth=8, corr_depth_start=0.5, corr_depth_end=70.0,
+    topk=1, iou_thr=0.0, ratio=0.0, expand_stride=0, num_views_per_frame=6,
+)
+
+
+def feat_pad_mask(img_metas, h, w):
+    """[V,h,w] uint8, 1 = cell lies in the padded border (utils/pe.py:146-155,
+    mv2d_t_head.py:68-76): ones outside img_shape, nearest F.interpolate to (h, w).  The mask
+    is separable, so the interpolation runs on two tiny 1-D tensors."""
+    pad_h, pad_w, _ = img_metas[0]['pad_shape']
+    out = np.zeros((len(img_metas), h, w), dtype=np.uint8)
+    for v, m in enumerate(img_metas):
+        ih, iw, _ = m['img_shape']
+        rows = torch.ones(1, 1, pad_h, 1)
+        rows[:, :, :ih] = 0
+        cols = torch.ones(1, 1, 1, pad_w)
+        cols[..., :iw] = 0
+        r = F.interpolate(rows, size=(h, 1)).bool().view(h, 1).numpy()
+        c = F.interpolate(cols, size=(1, w)).bool().view(1, w).numpy()
+        out[v] = (r | c).astype(np.uint8)
+    return out
+
+
+class HotPath:
+    """MV2D-S ('S') / MV2D-T ('T') decoder hot path on one GPU."""
+
+    def __init__(self, state_dict, mode='S', device='cuda', cache_sine_branch=False, **cfg):
+        if not torch.cuda.is_available():
+            raise RuntimeError('mv2d_b200.HotPath needs a CUDA device (there is no CPU fallback)')
+        self.lib = lib.load()
+        self.mode = mode
+        self.device = torch.device(device)
+        self.cfg = dict(DEFAULTS)
+        if mode == 'T':
+            self.cfg.update(topk=20, expand_stride=2)
+        self.cfg.update(cfg)
+        self.w = PackedWeights(state_dict, self.device)
+        self.L = self.w.num_layers
+        self.cache_sine_branch = cache_sine_branch
+        self._sine_cache = {}
+        self._mask_cache = {}
+        self._buf = {}
+        c = self.cfg
+        S, Dn = c['sample_size'], c['corr_num_depth']
+        idx = torch.arange(Dn).float()
+        bin_size = (c['corr_depth_end'] - c['corr_depth_start']) / (Dn * (1 + Dn))
+        # box_correlation.py:198, 221-225 -- same torch CPU ops, so the tables are bit-identical
+        self.lin = torch.linspace(0, 1, S).to(self.device)
+        self.depths = (c['corr_depth_start'] + bin_size * idx * (idx + 1)).to(self.device)
+
+    def launch_count(self):
+        """Kernel launches enqueued by libmv2d_b200 in this process (counted inside the library)."""
+        return int(self.lib.mv2d_launch_count())
+
+    # ------------------------------------------------------------------ buffers
+    def _get(self, name, shape, dtype=torch.float32):
+        n = int(np.prod(shape))
+        t = self._buf.get(name)
+        if t is None or t.numel() < n or t.dtype != dtype:
+            t = torch.empty(max(n, 1), dtype=dtype, device=self.device)
+            self._buf[name] = t
+        return t[:n].view(*shape) if n > 0 else t[:0].view(*shape)
+
+    def _masks(self, img_metas, h, w):
+        key = (tuple(tuple(m['img_shape']) for m in img_metas), tuple(img_metas[0]['pad_shape']), h, w)
+        ent = self._mask_cache.get(key)
+        if ent is None:
+            pad = feat_pad_mask(img_metas, h, w)
+            ent = (key, torch.from_numpy(pad).to(self.device), torch.from_numpy(1 - pad).to(self.device),
+                   bool(pad.any()))
+            self._mask_cache[key] = ent
+        return ent
+
+    # ------------------------------------------------------------------ stages
+    def _upload_cams(self, img_metas):
+        V = len(img_metas)
+        cams = np.empty((3, V, 16), dtype=np.float64)
+        for v, m in enumerate(img_metas):
+            cams[0, v] = np.asarray(m['lidar2img'], dtype=np.float64).reshape(16)
+            cams[1, v] = np.asarray(m['intrinsics'], dtype=np.float64).reshape(16)
+            cams[2, v] = np.asarray(m['extrinsics'], dtype=np.float64).reshape(16)
+        d = self._get('cams', (3, V, 16), torch.float64)
+        d.copy_(torch.from_numpy(cams), non_blocking=True)
+        return d
+
+    def _upload_rois(self, proposal_list):
+        if sum(len(p) for p in proposal_list) == 0:   # mv2d_s_head.py:124-127
+            p0 = torch.tensor([[0, 50, 50, 100, 100, 0]], dtype=torch.float32, device=proposal_list[0].device)
+            proposal_list = [p0] + list(proposal_list[1:])
+        counts = [int(p.shape[0]) for p in proposal_list]
+        N = sum(counts)
+        starts = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+        rois = self._get('rois', (N, 5))
+        if proposal_list[0].is_cuda:   # bbox2roi on the device the detections live on
+            view = torch.repeat_interleave(torch.arange(len(counts), device=self.device, dtype=torch.float32),
+                                           torch.tensor(counts, device=self.device))
+            rois[:, 0] = view
+            rois[:, 1:] = torch.cat([p[:, :4].float() for p in proposal_list], 0)
+        else:
+            host = np.empty((N, 5), dtype=np.float32)
+            o = 0
+            for v, p in enumerate(proposal_list):
+                n = counts[v]
+                host[o:o + n, 0] = v
+                host[o:o + n, 1:] = p[:, :4].float().numpy()
+                o += n
+            rois.copy_(torch.from_numpy(host), non_blocking=True)
+        roi_start = self._get('roi_start', (len(counts) + 1,), torch.int32)
+        roi_start.copy_(torch.from_numpy(starts), non_blocking=True)
+        return rois, roi_start, counts, N
+
+    def geom_prep(self, cams):
+        V = cams.shape[1]
+        i2l = self._get('img2lidar', (V, 16), torch.float64)
+        trans = self._get('trans', (V, V, 16), torch.float64)
+        lib.check(self.lib.mv2d_geom_prep(cams[0].data_ptr(), V, i2l.data_ptr(), trans.data_ptr(),
+                                          lib.stream_ptr()), 'mv2d_geom_prep')
+        return i2l, trans
+
+    def to_nhwc(self, feat_nchw):
+        V, Cc, h, w = feat_nchw.shape
+        out = self._get('feat_nhwc', (V, h, w, Cc))
+        lib.check(self.lib.mv2d_nchw_to_nhwc(lib.ptr(feat_nchw), out.data_ptr(), V, Cc, h * w, lib.stream_ptr()),
+                  'mv2d_nchw_to_nhwc')
+        return out
+
+    def pe3d(self, feat_nhwc, img2lidar, img_metas):
+        """PE.forward (utils/pe.py:137-169) -> (pe [V,h,w,256], kin = feat + pe or None)."""
+        V, h, w, _ = feat_nhwc.shape
+        c, W = self.cfg, self.w
+        key, pad_mask, not_mask, _ = self._masks(img_metas, h, w)
+        pe = self._get('pe', (V, h, w, 256))
+        kin = self._get('kin', (V, h, w, 256)) if self.mode == 'T' else None
+        ws_bytes = self.lib.mv2d_pe3d_workspace_bytes(V, h, w, c['depth_num'])
+        ws = self._get('pe_ws', (ws_bytes // 4,))
+        p = lib.PeParams()
+        p.V, p.h, p.w, p.depth_num = V, h, w, c['depth_num']
+        p.pad_h, p.pad_w = int(img_metas[0]['pad_shape'][0]), int(img_metas[0]['pad_shape'][1])
+        p.stride = c['stride']
+        p.depth_start = c['depth_start']
+        p.position_range = (C.c_double * 6)(*c['position_range'])
+        p.feat, p.img2lidar, p.not_mask, p.dim_t = feat_nhwc.data_ptr(), img2lidar.data_ptr(), not_mask.data_ptr(), W.p('dim_t')
+        for f in ('w_pos0', 'b_pos0', 'w_pos2', 'b_pos2', 'w_adapt0', 'b_adapt0', 'w_adapt2', 'b_adapt2',
+                  'w_se_reduce', 'b_se_reduce', 'w_se_expand', 'b_se_expand'):
+            setattr(p, f, W.p(f))
+        cached = self._sine_cache.get(key) if self.cache_sine_branch else None
+        if cached is not None:
+            p.sine_branch_cached = cached.data_ptr()
+        elif self.cache_sine_branch:
+            self._sine_cache[key] = torch.empty((V * h * w, 256), device=self.device)
+            p.sine_branch_out = self._sine_cache[key].data_ptr()
+        p.pe = pe.data_ptr()
+        p.kin = kin.data_ptr() if kin is not None else None
+        p.workspace, p.workspace_bytes = ws.data_ptr(), ws_bytes
+        lib.check(self.lib.mv2d_pe3d(C.byref(p), lib.stream_ptr()), 'mv2d_pe3d')
+        return pe, kin
+
+    def roi_align_qg(self, rois, cams, feat_nhwc, pe_nhwc, N):
+        V, h, w, _ = feat_nhwc.shape
+        c, W = self.cfg, self.w
+        tok_feat = self._get('tok_feat', (N, 49, 256))
+        tok_kin = self._get('tok_kin', (N, 49, 256)) if self.mode == 'S' else None
+        kroi = self._get('roi_intrinsics', (N, 16), torch.float64)
+        center = self._get('center_lidar', (N, 3))
+        ref = self._get('ref', (N, 3))
+        qpos = self._get('query_pos', (N, 256))
+        ws_bytes = self.lib.mv2d_roi_align_qg_workspace_bytes(N)
+        ws = self._get('qg_ws', (ws_bytes // 4,))
+        p = lib.QgParams()
+        p.N, p.V, p.h, p.w, p.stride = N, V, h, w, c['stride']
+        p.pc_range = (C.c_float * 6)(*c['pc_range'])
+        p.intrins_feat_scale = c['intrins_feat_scale']
+        p.rois, p.intrinsics, p.extrinsics = rois.data_ptr(), cams[1].data_ptr(), cams[2].data_ptr()
+        p.feat = feat_nhwc.data_ptr()
+        p.pe = pe_nhwc.data_ptr() if tok_kin is not None else None
+        p.dim_t = W.p('dim_t')
+        for f in ('w_conv', 'b_conv', 'w_fc', 'b_fc', 'w_enc0', 'b_enc0', 'w_enc2', 'b_enc2', 'w_center',
+                  'b_center', 'w_qe0', 'b_qe0', 'w_qe2', 'b_qe2'):
+            setattr(p, f, W.p(f))
+        p.tok_feat = tok_feat.data_ptr()
+        p.tok_kin = tok_kin.data_ptr() if tok_kin is not None else None
+        p.roi_intrinsics, p.center_lidar = kroi.data_ptr(), center.data_ptr()
+        p.ref, p.query_pos = ref.data_ptr(), qpos.data_ptr()
+        p.workspace, p.workspace_bytes = ws.data_ptr(), ws_bytes
+        lib.check(self.lib.mv2d_roi_align_qg(C.byref(p), lib.stream_ptr()), 'mv2d_roi_align_qg')
+        return dict(tok_feat=tok_feat, tok_kin=tok_kin, roi_intrinsics=kroi, center_lidar=center, ref=ref,
+                    query_pos=qpos)
+
+    def box_corr(self, rois, roi_start, trans, N, V, img_metas, h, w):
+        c = self.cfg
+        max_match = 1 + (V - 1) * c['topk']
+        match = self._get('match', (N, max_match), torch.int32)
+        cnt = self._get('match_cnt', (N,), torch.int32)
+        p = lib.CorrParams()
+        p.N, p.V = N, V
+        p.img_h, p.img_w = int(img_metas[0]['pad_shape'][0]), int(img_metas[0]['pad_shape'][1])
+        p.topk, p.sample_size, p.num_depth, p.max_match = c['topk'], c['sample_size'], c['corr_num_depth'], max_match
+        p.ratio, p.iou_thr, p.depth_start = c['ratio'], c['iou_thr'], c['corr_depth_start']
+        p.rois, p.roi_start, p.trans = rois.data_ptr(), roi_start.data_ptr(), trans.data_ptr()
+        p.lin, p.depths = self.lin.data_ptr(), self.depths.data_ptr()
+        p.match, p.match_cnt = match.data_ptr(), cnt.data_ptr()
+        out = dict(match=match, match_cnt=cnt, max_match=max_match)
+        if self.mode == 'T':
+            words = (V * h * w + 31) // 32
+            keymask = self._get('keymask', (N, words), torch.int32)
+            key_cnt = self._get('key_cnt', (N,), torch.int32)
+            _, pad_mask, _, has_pad = self._masks(img_metas, h, w)
+            p.h, p.w, p.stride, p.expand_stride = h, w, c['stride'], c['expand_stride']
+            p.pad_mask = pad_mask.data_ptr() if has_pad else None
+            p.keymask, p.key_cnt = keymask.data_ptr(), key_cnt.data_ptr()
+            out.update(keymask=keymask, key_cnt=key_cnt, mask_words=words)
+        lib.check(self.lib.mv2d_box_corr(C.byref(p), lib.stream_ptr()), 'mv2d_box_corr')
+        return out
+
+    def decoder(self, qg, corr, kin_rows, mem_rows, N, vel_dt=0.0, self_attn_mask=None):
+        c, W, L = self.cfg, self.w, self.L
+        cls = self._get('cls_scores', (L, N, 10))
+        box = self._get('bbox_preds', (L, N, 10))
+        outs = self._get('outs_dec', (L, N, 256))
+        ws_bytes = self.lib.mv2d_decoder_workspace_bytes(N, L)
+        ws = self._get('dec_ws', (ws_bytes // 4,))
+        p = lib.DecoderParams()
+        p.N, p.L = N, L
+        p.mode = 0 if self.mode == 'S' else 1
+        p.num_rows = kin_rows.shape[0]
+        p.pc_range = (C.c_float * 6)(*c['pc_range'])
+        p.vel_dt = vel_dt
+        p.query_pos, p.ref = qg['query_pos'].data_ptr(), qg['ref'].data_ptr()
+        p.kin_rows, p.mem_rows = kin_rows.data_ptr(), mem_rows.data_ptr()
+        if self.mode == 'S':
+            p.match, p.match_cnt, p.max_match = corr['match'].data_ptr(), corr['match_cnt'].data_ptr(), corr['max_match']
+        else:
+            p.keymask, p.mask_words = corr['keymask'].data_ptr(), corr['mask_words']
+        p.self_attn_mask = self_attn_mask.data_ptr() if self_attn_mask is not None else None
+        p.layers, p.branches = W.layers_ptr(), W.branches_ptr()
+        p.cls_scores, p.bbox_preds, p.outs_dec = cls.data_ptr(), box.data_ptr(), outs.data_ptr()
+        p.workspace, p.workspace_bytes = ws.data_ptr(), ws_bytes
+        lib.check(self.lib.mv2d_decoder(C.byref(p), lib.stream_ptr()), 'mv2d_decoder')
+        return cls, box, outs
+
+    # ------------------------------------------------------------------ whole path
+    @torch.no_grad()
+    def forward(self, feat_nchw, proposal_list, img_metas, feat_is_nhwc=False):
+        """feat [V,256,h,w] fp32 on the device (NCHW as the FPN emits it), proposal_list: V
+        tensors [n_v, >=4] (device or host), img_metas: V dicts.  Returns a dict with
+        cls_scores / bbox_preds [L,N,10] and the stage tensors (views of reused buffers)."""
+        V = len(img_metas)
+        feat_nchw = feat_nchw.to(self.device, torch.float32)
+        if feat_is_nhwc:
+            feat = feat_nchw.contiguous()
+            _, h, w, _ = feat.shape
+        else:
+            _, _, h, w = feat_nchw.shape
+            feat = self.to_nhwc(feat_nchw.contiguous())
+        cams = self._upload_cams(img_metas)
+        rois, roi_start, counts, N = self._upload_rois(proposal_list)
+        i2l, trans = self.geom_prep(cams)
+        pe, kin = self.pe3d(feat, i2l, img_metas)
+        qg = self.roi_align_qg(rois, cams, feat, pe, N)
+        corr = self.box_corr(rois, roi_start, trans, N, V, img_metas, h, w)
+        if self.mode == 'S':
+            cls, box, outs = self.decoder(qg, corr, qg['tok_kin'].view(-1, 256), qg['tok_feat'].view(-1, 256), N)
+        else:
+            nvf = self.cfg['num_views_per_frame']
+            vel_dt = 0.0
+            if V > nvf:   # mv2d_t_head.py:131-132
+                ts = np.array([m['timestamp'] for m in img_metas], dtype=np.float64)
+                vel_dt = float(ts[nvf:].mean() - ts[:nvf].mean())
+            cls, box, outs = self.decoder(qg, corr, kin.view(-1, 256), feat.view(-1, 256), N, vel_dt=vel_dt)
+        out = dict(cls_scores=cls, bbox_preds=box, outs_dec=outs, rois=rois, pe=pe, feat_nhwc=feat, N=N,
+                   num_per_view=counts)
+        out.update(qg)
+        out.update(corr)
+        return out
+
+    @torch.no_grad()
+    def decode(self, cls_scores, bbox_preds, max_num=300):
+        """NMSFreeCoder.decode_single + z-shift on the device (next row f1)."""
+        N = cls_scores.shape[0]
+        boxes = torch.empty((max_num, 9), device=self.device)
+        scores = torch.empty((max_num,), device=self.device)
+        labels = torch.empty((max_num,), dtype=torch.int32, device=self.device)
+        valid = torch.empty((max_num,), dtype=torch.uint8, device=self.device)
+        post = (C.c_float * 6)(*self.cfg['position_range'])
+        lib.check(self.lib.mv2d_nms_free_decode(lib.ptr(cls_scores.contiguous()), lib.ptr(bbox_preds.contiguous()),
+                                                N, max_num, post, boxes.data_ptr(), scores.data_ptr(),
+                                                labels.data_ptr(), valid.data_ptr(), lib.stream_ptr()),
+                  'mv2d_nms_free_decode')
+        k = min(max_num, N * 10)
+        m = valid[:k].bool()
+        return boxes[:k][m], scores[:k][m], labels[:k][m].long()

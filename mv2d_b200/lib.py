@@ -1,0 +1,161 @@
+"""ctypes binding of ``libmv2d_b200.so`` (C ABI declared in ``include/mv2d_b200.h``).
+
+The product path has NO fallback: if the shared library is missing or a call fails this module
+raises.  The structures below mirror the header field by field; ``_check_layout`` compares
+their sizes with ``mv2d_sizeof`` at load time so a drifted mirror fails loudly.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'lib', 'libmv2d_b200.so')
+ABI_VERSION = 1
+MAX_LAYERS = 8
+
+c_f = C.c_void_p  # device pointers travel as integers (tensor.data_ptr())
+
+
+class PeParams(C.Structure):
+    _fields_ = [
+        ('V', C.c_int), ('h', C.c_int), ('w', C.c_int), ('depth_num', C.c_int),
+        ('pad_h', C.c_int), ('pad_w', C.c_int), ('stride', C.c_int), ('reserved0', C.c_int),
+        ('depth_start', C.c_double), ('position_range', C.c_double * 6),
+        ('feat', c_f), ('img2lidar', c_f), ('not_mask', c_f), ('dim_t', c_f),
+        ('w_pos0', c_f), ('b_pos0', c_f), ('w_pos2', c_f), ('b_pos2', c_f),
+        ('w_adapt0', c_f), ('b_adapt0', c_f), ('w_adapt2', c_f), ('b_adapt2', c_f),
+        ('w_se_reduce', c_f), ('b_se_reduce', c_f), ('w_se_expand', c_f), ('b_se_expand', c_f),
+        ('sine_branch_cached', c_f), ('sine_branch_out', c_f),
+        ('pe', c_f), ('kin', c_f), ('workspace', c_f), ('workspace_bytes', C.c_size_t),
+    ]
+
+
+class QgParams(C.Structure):
+    _fields_ = [
+        ('N', C.c_int), ('V', C.c_int), ('h', C.c_int), ('w', C.c_int), ('stride', C.c_int),
+        ('reserved0', C.c_int),
+        ('pc_range', C.c_float * 6), ('intrins_feat_scale', C.c_float), ('reserved1', C.c_float),
+        ('rois', c_f), ('intrinsics', c_f), ('extrinsics', c_f), ('feat', c_f), ('pe', c_f),
+        ('dim_t', c_f),
+        ('w_conv', c_f), ('b_conv', c_f), ('w_fc', c_f), ('b_fc', c_f),
+        ('w_enc0', c_f), ('b_enc0', c_f), ('w_enc2', c_f), ('b_enc2', c_f),
+        ('w_center', c_f), ('b_center', c_f), ('w_qe0', c_f), ('b_qe0', c_f),
+        ('w_qe2', c_f), ('b_qe2', c_f),
+        ('tok_feat', c_f), ('tok_kin', c_f), ('roi_intrinsics', c_f), ('center_lidar', c_f),
+        ('ref', c_f), ('query_pos', c_f), ('workspace', c_f), ('workspace_bytes', C.c_size_t),
+    ]
+
+
+class CorrParams(C.Structure):
+    _fields_ = [
+        ('N', C.c_int), ('V', C.c_int), ('img_h', C.c_int), ('img_w', C.c_int),
+        ('topk', C.c_int), ('sample_size', C.c_int), ('num_depth', C.c_int), ('max_match', C.c_int),
+        ('ratio', C.c_float), ('iou_thr', C.c_float), ('depth_start', C.c_float),
+        ('reserved0', C.c_float),
+        ('rois', c_f), ('roi_start', c_f), ('trans', c_f), ('lin', c_f), ('depths', c_f),
+        ('match', c_f), ('match_cnt', c_f),
+        ('h', C.c_int), ('w', C.c_int), ('stride', C.c_int), ('expand_stride', C.c_int),
+        ('pad_mask', c_f), ('keymask', c_f), ('key_cnt', c_f),
+    ]
+
+
+class LayerWeights(C.Structure):
+    _fields_ = [
+        ('sa_in_w', c_f), ('sa_in_b', c_f), ('sa_out_w', c_f), ('sa_out_b', c_f),
+        ('ca_q_w', c_f), ('ca_q_b', c_f), ('ca_o_w', c_f), ('ca_o_b', c_f),
+        ('ffn_w1', c_f), ('ffn_b1', c_f), ('ffn_w2', c_f), ('ffn_b2', c_f),
+        ('ln_g', c_f * 3), ('ln_b', c_f * 3),
+    ]
+
+
+class BranchWeights(C.Structure):
+    _fields_ = [
+        ('cls_w0', c_f), ('cls_b0', c_f), ('cls_g0', c_f), ('cls_be0', c_f),
+        ('cls_w1', c_f), ('cls_b1', c_f), ('cls_g1', c_f), ('cls_be1', c_f),
+        ('cls_w2', c_f), ('cls_b2', c_f),
+        ('reg_w0', c_f), ('reg_b0', c_f), ('reg_w1', c_f), ('reg_b1', c_f),
+        ('reg_w2', c_f), ('reg_b2', c_f),
+        ('post_g', c_f), ('post_b', c_f),
+    ]
+
+
+class DecoderParams(C.Structure):
+    _fields_ = [
+        ('N', C.c_int), ('L', C.c_int), ('mode', C.c_int), ('num_rows', C.c_int),
+        ('max_match', C.c_int), ('mask_words', C.c_int), ('reserved0', C.c_int),
+        ('reserved1', C.c_int),
+        ('pc_range', C.c_float * 6), ('vel_dt', C.c_float), ('reserved2', C.c_float),
+        ('query_pos', c_f), ('ref', c_f), ('kin_rows', c_f), ('mem_rows', c_f),
+        ('match', c_f), ('match_cnt', c_f), ('keymask', c_f), ('self_attn_mask', c_f),
+        ('layers', C.POINTER(LayerWeights)), ('branches', C.POINTER(BranchWeights)),
+        ('cls_scores', c_f), ('bbox_preds', c_f), ('outs_dec', c_f),
+        ('workspace', c_f), ('workspace_bytes', C.c_size_t),
+    ]
+
+
+_STRUCTS = [PeParams, QgParams, CorrParams, DecoderParams, LayerWeights, BranchWeights]
+
+# every symbol include/mv2d_b200.h declares: (name, restype, argtypes)
+SYMBOLS = [
+    ('mv2d_abi_version', C.c_int, []),
+    ('mv2d_last_error', C.c_char_p, []),
+    ('mv2d_launch_count', C.c_ulonglong, []),
+    ('mv2d_sizeof', C.c_size_t, [C.c_int]),
+    ('mv2d_geom_prep', C.c_int, [c_f, C.c_int, c_f, c_f, c_f]),
+    ('mv2d_nchw_to_nhwc', C.c_int, [c_f, c_f, C.c_int, C.c_int, C.c_int, c_f]),
+    ('mv2d_pe3d_workspace_bytes', C.c_size_t, [C.c_int] * 4),
+    ('mv2d_pe3d', C.c_int, [C.POINTER(PeParams), c_f]),
+    ('mv2d_roi_align_qg_workspace_bytes', C.c_size_t, [C.c_int]),
+    ('mv2d_roi_align_qg', C.c_int, [C.POINTER(QgParams), c_f]),
+    ('mv2d_box_corr', C.c_int, [C.POINTER(CorrParams), c_f]),
+    ('mv2d_decoder_workspace_bytes', C.c_size_t, [C.c_int, C.c_int]),
+    ('mv2d_decoder', C.c_int, [C.POINTER(DecoderParams), c_f]),
+    ('mv2d_gemm', C.c_int, [c_f, C.c_int, c_f, C.c_int, c_f, c_f, C.c_int, C.c_int, C.c_int, C.c_int,
+                            C.c_int, c_f]),
+    ('mv2d_nms_free_decode', C.c_int, [c_f, c_f, C.c_int, C.c_int, C.POINTER(C.c_float), c_f, c_f, c_f,
+                                       c_f, c_f]),
+]
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once).  Raises if it is missing -- there is no CPU fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f'{LIB_PATH} not found: build it with `python -c "import __graft_entry__ as g; g.build()"` '
+            f'or `make -C mv2d_b200/csrc`.  mv2d_b200 has no CPU fallback.')
+    lib = C.CDLL(LIB_PATH)
+    for name, res, args in SYMBOLS:
+        fn = getattr(lib, name)  # AttributeError if the .so does not export it
+        fn.restype = res
+        fn.argtypes = args
+    if lib.mv2d_abi_version() != ABI_VERSION:
+        raise RuntimeError(f'libmv2d_b200 ABI {lib.mv2d_abi_version()} != binding {ABI_VERSION}')
+    for i, st in enumerate(_STRUCTS):
+        if lib.mv2d_sizeof(i) != C.sizeof(st):
+            raise RuntimeError(f'{st.__name__}: python mirror is {C.sizeof(st)} bytes, '
+                               f'library says {lib.mv2d_sizeof(i)}')
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().mv2d_last_error().decode(errors='replace')
+        raise RuntimeError(f'{what} failed (rc={rc}): {msg}')
+
+
+def ptr(t):
+    """Device pointer of a contiguous torch tensor (None -> NULL)."""
+    if t is None:
+        return None
+    assert t.is_contiguous(), 'libmv2d_b200 needs contiguous tensors'
+    return t.data_ptr()
+
+
+def stream_ptr():
+    import torch
+    return torch.cuda.current_stream().cuda_stream

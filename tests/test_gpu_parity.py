@@ -1,0 +1,145 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (mv2d_b200.engine ->
+ctypes -> libmv2d_b200.so), against (1) the golden vectors written by the reference's own
+Python and (2) the oracle on fresh seeded inputs.
+
+Tolerance (north star): |out - ref| <= 1e-3 + 1e-3*|ref| on cls_scores / bbox_preds of all
+layers.  Integer / index work (RoI match lists, key masks) must be bit-exact.
+"""
+import json
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_path
+from mv2d_b200 import synth
+
+pytestmark = pytest.mark.gpu
+PE_SUB = 251
+ATOL = RTOL = 1e-3
+
+
+def load_golden(name):
+    g = dict(np.load(golden_path(name)))
+    spec = json.loads(bytes(g.pop('spec')).decode())
+    return spec, g
+
+
+def assert_close(a, b, atol=ATOL, rtol=RTOL, what=''):
+    a = np.asarray(a.detach().cpu() if torch.is_tensor(a) else a, dtype=np.float64)
+    b = np.asarray(b.detach().cpu() if torch.is_tensor(b) else b, dtype=np.float64)
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    assert np.isfinite(a).all(), f'{what}: non-finite values'
+    bad = np.abs(a - b) > atol + rtol * np.abs(b)
+    assert not bad.any(), f'{what}: {bad.sum()}/{bad.size} out of tol, max |d| = {np.abs(a - b).max():.3e}'
+
+
+_ENGINES = {}
+
+
+def engine(mode, num_layers, state_dicts):
+    from mv2d_b200.engine import HotPath
+    key = (mode, num_layers)
+    if key not in _ENGINES:
+        _ENGINES[key] = HotPath(state_dicts(num_layers), mode=mode)
+    return _ENGINES[key]
+
+
+def match_sets(out):
+    m, c = out['match'].cpu().numpy(), out['match_cnt'].cpu().numpy()
+    return [set(int(x) for x in m[i, :c[i]]) for i in range(len(c))]
+
+
+@pytest.mark.parametrize('name', list(synth.CASES))
+def test_cuda_path_matches_reference_golden(name, state_dicts):
+    spec, g = load_golden(name)
+    eng = engine(spec['mode'], spec['num_layers'], state_dicts)
+    feat, boxes, metas = synth.case_inputs(spec)
+    out = eng.forward(feat.cuda(), [b.cuda() for b in boxes], metas)
+    torch.cuda.synchronize()
+    N = out['N']
+    assert N == g['rois'].shape[0]
+    assert np.array_equal(out['rois'].cpu().numpy(), g['rois'])
+    # ---- stage level
+    pe = out['pe'].permute(0, 3, 1, 2).contiguous()          # back to NCHW for the comparison
+    assert_close(pe.flatten()[::PE_SUB], g['pe_sub'], 3e-3, 1e-3, 'pe')     # TF32-tolerant stage
+    tok = out['tok_feat'].view(N, 7, 7, 256).permute(0, 3, 1, 2).contiguous()
+    assert_close(tok.flatten()[::PE_SUB], g['roi_feat_sub'], 1e-5, 1e-5, 'roi_feat')
+    assert_close(out['center_lidar'], g['center_lidar'], 1e-3, 1e-4, 'center_lidar')
+    if 'intrinsics' in g:
+        assert_close(out['roi_intrinsics'].view(N, 4, 4), g['intrinsics'], 1e-9, 1e-12, 'roi_intrinsics')
+        assert_close(out['query_pos'], g['query_pos'], 1e-3, 1e-3, 'query_pos')
+        assert_close(out['outs_dec'], g['outs_dec'], 1e-3, 1e-3, 'outs_dec')
+    if spec['mode'] == 'S':
+        ref_sets = [set(int(c) for c, m in zip(cr, mr) if m) for cr, mr in zip(g['corr'], g['corr_mask'])]
+        assert match_sets(out) == ref_sets, 'RoI match lists differ'
+    else:
+        words = out['keymask'].cpu().numpy().view(np.uint32)
+        bits = np.unpackbits(words.view(np.uint8), axis=1, bitorder='little')[:, :g['key_mask_packed'].shape[1] * 8]
+        ref_bits = np.unpackbits(g['key_mask_packed'], axis=1)
+        assert np.array_equal(bits[:, :ref_bits.shape[1]], ref_bits), 'per-query key masks differ'
+    # ---- the parity gate
+    assert_close(out['cls_scores'], g['cls_scores'], what='cls_scores')
+    assert_close(out['bbox_preds'], g['bbox_preds'], what='bbox_preds')
+    # ---- next row f1: decode on the device
+    b, s, l = eng.decode(torch.from_numpy(g['cls_scores'][-1]).cuda(), torch.from_numpy(g['bbox_preds'][-1]).cuda())
+    assert_close(s, g['dec_scores'], 1e-6, 0, 'decode scores')
+    assert_close(b, g['dec_boxes'], 1e-4, 1e-5, 'decode boxes')
+    assert np.array_equal(l.cpu().numpy(), g['dec_labels'])
+
+
+@pytest.mark.parametrize('mode,V,n,seed', [('S', 6, 7, 31), ('S', 6, 12, 32), ('T', 12, 5, 33)])
+def test_cuda_path_matches_oracle_on_fresh_inputs(mode, V, n, seed, state_dicts):
+    """Jittered cameras, different seeds: CUDA vs the oracle run here on the host CPU."""
+    from oracle import mv2d_oracle as O
+    eng = engine(mode, 6, state_dicts)
+    feat, boxes, metas = synth.make_sample(seed, V, n, cam_jitter_deg=4.0)
+    fn = O.mv2d_s_forward if mode == 'S' else O.mv2d_t_forward
+    with torch.no_grad():
+        cls, box, st = fn(state_dicts(6), feat, boxes, metas, O.make_cfg(mode), return_stages=True)
+    out = eng.forward(feat.cuda(), boxes, metas)      # host-resident boxes: the other upload path
+    assert_close(out['ref'], st['ref'], 1e-5, 1e-4, 'ref')
+    assert_close(out['cls_scores'], cls, what='cls_scores')
+    assert_close(out['bbox_preds'], box, what='bbox_preds')
+
+
+def test_gemm_kernel_vs_torch_fp32():
+    """The FFMA GEMM against torch fp32 (fp64-accumulated reference for the bound)."""
+    import ctypes as C
+    from mv2d_b200 import lib
+    h = lib.load()
+    g = torch.Generator().manual_seed(0)
+    for (M, N, K, flags) in [(300, 256, 256, 0), (300, 2048, 256, 1), (37, 512, 1040, 1), (14700, 256, 2048, 0),
+                             (1, 256, 384, 1), (16896, 1024, 192, 1), (129, 768, 256, 0)]:
+        A = torch.randn(M, K, generator=g).cuda()
+        W = (torch.randn(N, K, generator=g) / K ** 0.5).cuda()
+        b = torch.randn(N, generator=g).cuda()
+        Cc = torch.empty(M, N, device='cuda')
+        lib.check(h.mv2d_gemm(A.data_ptr(), K, W.data_ptr(), K, b.data_ptr(), Cc.data_ptr(), N, M, N, K, flags,
+                              lib.stream_ptr()), 'mv2d_gemm')
+        ref = A.double() @ W.double().T + b.double()
+        if flags & 1:
+            ref = ref.relu()
+        assert_close(Cc, ref, 2e-5, 2e-5, f'gemm {M}x{N}x{K}')
+
+
+def test_full_size_properties(state_dicts):
+    """Size-independent properties at BASELINE config 2 (N=300): determinism (bitwise), and
+    equivariance under a permutation of the proposals inside each view."""
+    eng = engine('S', 6, state_dicts)
+    spec = synth.CASES['s_cfg2']
+    feat, boxes, metas = synth.case_inputs(spec)
+    featc = feat.cuda()
+    o1 = eng.forward(featc, boxes, metas)
+    c1, b1 = o1['cls_scores'].clone(), o1['bbox_preds'].clone()
+    o2 = eng.forward(featc, boxes, metas)
+    assert torch.equal(c1, o2['cls_scores']) and torch.equal(b1, o2['bbox_preds']), 'non-deterministic'
+    rng = np.random.default_rng(0)
+    perms = [torch.from_numpy(rng.permutation(len(b))) for b in boxes]
+    o3 = eng.forward(featc, [b[p] for b, p in zip(boxes, perms)], metas)
+    starts = np.concatenate([[0], np.cumsum([len(b) for b in boxes])])
+    gperm = torch.cat([p + int(s) for p, s in zip(perms, starts[:-1])]).cuda()
+    assert_close(o3['cls_scores'], c1[:, gperm], 2e-4, 2e-4, 'permuted cls')
+    assert_close(o3['bbox_preds'], b1[:, gperm], 2e-4, 2e-4, 'permuted box')
+    # every query attends at least to its own RoI
+    assert int(o1['match_cnt'].min()) >= 1 and bool((o1['match'][:, 0].cpu() == torch.arange(300)).all())
