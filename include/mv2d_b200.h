@@ -47,8 +47,9 @@ MV2D_API size_t mv2d_sizeof(int which); /* 0 Pe, 1 Qg, 2 Corr, 3 Decoder, 4 Laye
 MV2D_API int mv2d_geom_prep(const double* lidar2img /*[V,16]*/, int V, double* img2lidar /*[V,16]*/,
                    double* trans /*[V,V,16]*/, void* stream);
 
-/* NCHW [V,C,HW] -> NHWC [V,HW,C] (the FPN output layout -> this library's layout) */
-MV2D_API int mv2d_nchw_to_nhwc(const float* in, float* out, int V, int C, int HW, void* stream);
+/* NCHW [V,C,HW] -> NHWC [V,HW,C] (the FPN output layout -> this library's layout).
+ * out_tf32 (nullable) receives a copy rounded to TF32 (operand of the single-pass tensor-core SE gate GEMM). */
+MV2D_API int mv2d_nchw_to_nhwc(const float* in, float* out, float* out_tf32, int V, int C, int HW, void* stream);
 
 /* ---- K1  PE.forward  (utils/pe.py:137-169 incl. position_encoding :84-135, SELayer :44-48,
  * SinePositionalEncoding3D positional_encoding.py:58-96 + adapt_pos3d) */
@@ -57,9 +58,12 @@ typedef struct Mv2dPeParams {
     double depth_start;
     double position_range[6];
     const float* feat;         /* [V,h,w,256] */
+    const float* feat_tf32;    /* nullable: feat rounded to TF32 (from mv2d_nchw_to_nhwc); NULL = use feat */
     const double* img2lidar;   /* [V,16] from mv2d_geom_prep */
     const uint8_t* not_mask;   /* [V,h,w] 1 = inside the un-padded image */
     const float* dim_t;        /* [128] temperature ** (2*(i//2)/128) */
+    /* the six weight matrices below must be pre-rounded to TF32 (mv2d_b200/pack.py does it):
+     * the PE MLPs run as single-pass tcgen05 kind::tf32 GEMMs (inside the gate) */
     const float *w_pos0, *b_pos0;       /* position_encoder.0  [1024,192] */
     const float *w_pos2, *b_pos2;       /* position_encoder.2  [256,1024] */
     const float *w_adapt0, *b_adapt0;   /* adapt_pos3d.0       [1024,384] */
@@ -90,7 +94,8 @@ typedef struct Mv2dQgParams {
     const float* feat;          /* [V,h,w,256] */
     const float* pe;            /* [V,h,w,256], nullable when tok_kin == NULL */
     const float* dim_t;         /* [128] */
-    const float *w_conv, *b_conv;     /* shared_convs.0.conv repacked [256, 9*256] (tap-major K) */
+    const float *w_conv, *b_conv;     /* shared_convs.0.conv repacked [256, 9*256] (tap-major K), TF32 "hi" part */
+    const float *w_conv_lo;           /* TF32 "lo" part: w = hi + lo (3xTF32 error-compensated tcgen05 GEMM) */
     const float *w_fc, *b_fc;         /* shared_fcs.0 [1024,256] */
     const float *w_enc0, *b_enc0;     /* extra_enc.0 [512,1040] */
     const float *w_enc2, *b_enc2;     /* extra_enc.2 [256,512] */
@@ -179,9 +184,17 @@ MV2D_API int mv2d_decoder(const Mv2dDecoderParams* p, void* stream);
 
 /* ---- low-level GEMM, exposed for tests and microbenchmarks:
  * C[M,N] = act(A[M,K] . W[N,K]^T + bias); flags: 1 relu, 8 allow TF32 tensor cores,
- * 16 force the tcgen05 kernel, 32 force 3xTF32 error-compensated tcgen05 */
+ * 16 force the single-pass tcgen05 kernel (operands should be TF32-representable), 64 round C to TF32 */
 MV2D_API int mv2d_gemm(const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc,
               int M, int N, int K, int flags, void* stream);
+
+/* x -> hi = tf32(x), lo = tf32(x - hi): the operand split of the 3xTF32 GEMM */
+MV2D_API int mv2d_split_tf32(const float* x, float* hi, float* lo, long long n, void* stream);
+/* error-compensated 3xTF32 tcgen05 GEMM: C = act((A_hi+A_lo) . (W_hi+W_lo)^T + bias), fp32-grade.
+ * flags: 1 relu, 128 A is the implicit 3x3 im2col of [M/49,7,7,256] RoI tokens (K = 2304) */
+MV2D_API int mv2d_gemm_3xtf32(const float* A_hi, const float* A_lo, int lda, const float* W_hi, const float* W_lo,
+                              int ldw, const float* bias, float* C, int ldc, int M, int N, int K, int flags,
+                              void* stream);
 
 /* ---- f1 (next row): NMSFreeCoder.decode_single + get_bboxes z-shift
  * (core/bbox/coders/nms_free_coder.py:49-102; bbox_heads/cross_attention_head.py:372).

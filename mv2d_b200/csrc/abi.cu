@@ -4,6 +4,7 @@
 #include <cstdio>
 #include "common.cuh"
 #include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
 #include "mv2d_internal.h"
 
 namespace mv2d {
@@ -45,9 +46,24 @@ int mv2d_geom_prep(const double* lidar2img, int V, double* img2lidar, double* tr
     return run_geom_prep(lidar2img, V, img2lidar, trans, (cudaStream_t)stream);
 }
 
-int mv2d_nchw_to_nhwc(const float* in, float* out, int V, int C, int HW, void* stream) {
+int mv2d_nchw_to_nhwc(const float* in, float* out, float* out_tf32, int V, int C, int HW, void* stream) {
     MV2D_CHECK_ARG(in && out && V > 0 && C > 0 && HW > 0, "nchw_to_nhwc: bad arguments");
-    return run_nchw_to_nhwc(in, out, V, C, HW, (cudaStream_t)stream);
+    return run_nchw_to_nhwc(in, out, out_tf32, V, C, HW, (cudaStream_t)stream);
+}
+
+int mv2d_split_tf32(const float* x, float* hi, float* lo, long long n, void* stream) {
+    MV2D_CHECK_ARG(x && hi && lo && n >= 0, "split_tf32: bad arguments");
+    return launch_split_tf32(x, hi, lo, n, (cudaStream_t)stream);
+}
+
+int mv2d_gemm_3xtf32(const float* A_hi, const float* A_lo, int lda, const float* W_hi, const float* W_lo, int ldw,
+                     const float* bias, float* C, int ldc, int M, int N, int K, int flags, void* stream) {
+    MV2D_CHECK_ARG(A_hi && A_lo && W_hi && W_lo && C, "gemm_3xtf32: null pointer");
+    TcGemm t{};
+    t.A = A_hi; t.A_lo = A_lo; t.lda = lda; t.W = W_hi; t.W_lo = W_lo; t.ldw = ldw; t.bias = bias;
+    t.C = C; t.ldc = ldc; t.M = M; t.N = N; t.K = K; t.passes = 3; t.im2col = (flags & 128) ? 1 : 0;
+    t.flags = flags & GEMM_RELU;
+    return launch_gemm_tc(t, (cudaStream_t)stream);
 }
 
 size_t mv2d_pe3d_workspace_bytes(int V, int h, int w, int depth_num) { return pe3d_workspace_bytes(V, h, w, depth_num); }

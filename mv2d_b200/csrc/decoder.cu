@@ -335,12 +335,17 @@ cross_attn_kernel(XaArgs a) {
         __syncthreads();
     }
     // ---- cross-warp sum, normalise, store
+    // (fixed warp order => bitwise reproducible)
+    for (int wv = 0; wv < 8; ++wv) {
+        if (warp == wv) {
 #pragma unroll
-    for (int h = 0; h < 8; ++h)
+            for (int h = 0; h < 8; ++h)
 #pragma unroll
-        for (int c = 0; c < 8; ++c)
-            atomicAdd(&red[h * 256 + (c >> 2) * 128 + lane * 4 + (c & 3)], acc[h][c]);
-    __syncthreads();
+                for (int c = 0; c < 8; ++c)
+                    red[h * 256 + (c >> 2) * 128 + lane * 4 + (c & 3)] += acc[h][c];
+        }
+        __syncthreads();
+    }
     for (int i = t; i < 2048; i += 256) {
         const float l = stat[8 + (i >> 8)];
         a.ctx[(long long)n * 2048 + i] = l > 0.f ? red[i] / l : 0.f;

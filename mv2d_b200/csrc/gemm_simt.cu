@@ -34,15 +34,3 @@ int launch_gemm_simt(const GemmArgs& g, int amode, cudaStream_t stream) {
 }
 
 }  // namespace mv2d
-
-namespace mv2d {
-// v1: everything on the FFMA kernel.  gemm_tc.cu overrides the routing for TF32-tolerant
-// problems once the tcgen05 kernel is linked in (MV2D_HAVE_TC).
-#ifndef MV2D_HAVE_TC
-int launch_gemm_tc_or_simt(const GemmArgs& g, cudaStream_t stream) {
-    GemmArgs h = g;
-    h.flags &= ~GEMM_TF32_OK;
-    return launch_gemm_simt(h, A_PLAIN, stream);
-}
-#endif
-}  // namespace mv2d

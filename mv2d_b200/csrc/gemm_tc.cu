@@ -1,0 +1,375 @@
+// tcgen05 / TMEM / TMA GEMM for sm_100a:  C[M,N] = epi( A[M,K] . W[N,K]^T )
+//   * operands are fp32 in HBM, K-contiguous; TMA (cp.async.bulk.tensor) stages 128-byte-swizzled
+//     [rows x 32 floats] boxes into shared memory, one elected thread issues
+//     tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=BN, K=8), the accumulator tile lives in TMEM
+//     and is read back with tcgen05.ld by four epilogue warps.
+//   * PASSES = 1: single-pass TF32 (operands pre-rounded to TF32 by their producers) -- used for
+//     the PE MLPs only, where SURVEY.md App. E shows TF32 is inside the parity gate.
+//   * PASSES = 3: error-compensated 3xTF32 (a = a_hi + a_lo, both exactly TF32-representable;
+//     acc += a_hi*w_hi + a_hi*w_lo + a_lo*w_hi) -- fp32-grade accuracy for the query-generator
+//     3x3 conv, whose result feeds the precision-critical reference points.
+//   * IM2COL: the A operand is the implicit im2col of the [N,7,7,256] RoI tokens: a 4-D tensor
+//     map with box (32 ch, 7, 7, 1) loaded at (c0, dx-1, dy-1, roi); TMA zero-fills the halo.
+//     Two RoIs share one 128-row tile (rows 0..48 and 64..112).
+// Warp roles (192 threads): warp 0 TMA producer, warp 1 TMEM alloc + MMA issue, warps 2..5
+// epilogue (TMEM lane quadrant = warp_idx % 4).  One output tile per CTA; several CTAs per SM
+// overlap each other's prologue/epilogue.
+#include <cuda.h>
+#include "common.cuh"
+#include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
+
+namespace mv2d {
+
+static constexpr int TC_BM = 128;
+static constexpr int TC_BK = 32;            // floats = 128 bytes = one swizzle row
+static constexpr int TC_UMMA_K = 8;         // tf32: 32 bytes per MMA K-slice
+static constexpr int TC_THREADS = 192;
+
+// ---------------------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tmap_prefetch(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
+}
+// K-major, 128-byte swizzle smem descriptor (cute::UMMA::SmemDescriptor, version 1 = sm_100):
+// start>>4 [0,14), LBO>>4 [16,30) (=1, unused for swizzled K-major), SBO>>4 [32,46) = 1024 B
+// between 8-row groups, layout_type [61,64) = 2 (SWIZZLE_128B).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct TcArgs {
+    float* C; int ldc;
+    const float* bias;
+    int M, N, K;
+    int flags;
+    int n_rois;                                                        // IM2COL: number of RoIs
+    const float* gx; const float* gs; const float* gfeat; float* kin;  // GEMM_GATE extras
+};
+
+template <int BN, int PASSES, bool IM2COL, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
+               const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmWlo, TcArgs g) {
+    constexpr int A_BYTES = TC_BM * TC_BK * 4;      // 16 KB
+    constexpr int W_BYTES = BN * TC_BK * 4;
+    constexpr int NOP = PASSES == 3 ? 2 : 1;        // hi (+ lo) copies of each operand
+    constexpr int STAGE_BYTES = NOP * (A_BYTES + W_BYTES);
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // 1024-byte alignment is required by the 128B swizzle atoms
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tmem_full_bar = empty_bar + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m_tile = blockIdx.y, n0 = blockIdx.x * BN;
+    const int nkb = g.K / TC_BK;
+
+    if (warp == 0 && lane == 0) {
+        tmap_prefetch(&tmA); tmap_prefetch(&tmW);
+        if (PASSES == 3) { tmap_prefetch(&tmAlo); tmap_prefetch(&tmWlo); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(BN));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % STAGES, ph = (kb / STAGES) & 1;
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                uint8_t* st = smem + s * STAGE_BYTES;
+                // bytes TMA will deliver: an im2col box is 49 rows x 128 B per RoI, not a full 64-row half tile
+                constexpr int A_TX = IM2COL ? 2 * MV2D_TOK * TC_BK * 4 : A_BYTES;
+                mbar_expect_tx(&full_bar[s], NOP * (A_TX + W_BYTES));
+                if (IM2COL) {
+                    const int tap = kb / (MV2D_C / TC_BK), c0 = (kb % (MV2D_C / TC_BK)) * TC_BK;
+                    const int dx = tap % 3 - 1, dy = tap / 3 - 1;
+#pragma unroll
+                    for (int r = 0; r < 2; ++r) {   // two RoIs per 128-row tile, 64 rows apart
+                        tma_load_4d(&tmA, &full_bar[s], st + r * (A_BYTES / 2), c0, dx, dy, m_tile * 2 + r);
+                        if (PASSES == 3)
+                            tma_load_4d(&tmAlo, &full_bar[s], st + A_BYTES + r * (A_BYTES / 2), c0, dx, dy, m_tile * 2 + r);
+                    }
+                } else {
+                    tma_load_2d(&tmA, &full_bar[s], st, kb * TC_BK, m_tile * TC_BM);
+                    if (PASSES == 3) tma_load_2d(&tmAlo, &full_bar[s], st + A_BYTES, kb * TC_BK, m_tile * TC_BM);
+                }
+                tma_load_2d(&tmW, &full_bar[s], st + NOP * A_BYTES, kb * TC_BK, n0);
+                if (PASSES == 3) tma_load_2d(&tmWlo, &full_bar[s], st + NOP * A_BYTES + W_BYTES, kb * TC_BK, n0);
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        // instruction descriptor: c=F32 [4,6), a=b=TF32 [7,10)/[10,13), K-major both, N>>3 [17,23), M>>4 [24,29)
+        constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+        if (lane == 0) {
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % STAGES, ph = (kb / STAGES) & 1;
+                mbar_wait(&full_bar[s], ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+                const uint64_t a_hi = make_desc(sa), a_lo = make_desc(sa + A_BYTES);
+                const uint64_t w_hi = make_desc(sa + NOP * A_BYTES), w_lo = make_desc(sa + NOP * A_BYTES + W_BYTES);
+#pragma unroll
+                for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
+                    const uint64_t adv = (uint64_t)((k * TC_UMMA_K * 4) >> 4);   // advance start address inside the swizzle row
+                    umma_tf32(tmem_base, a_hi + adv, w_hi + adv, idesc, (kb | k) != 0);
+                    if (PASSES == 3) {
+                        umma_tf32(tmem_base, a_hi + adv, w_lo + adv, idesc, 1);
+                        umma_tf32(tmem_base, a_lo + adv, w_hi + adv, idesc, 1);
+                    }
+                }
+                umma_commit(&empty_bar[s]);               // frees the smem slot when these MMAs retire
+            }
+            umma_commit(tmem_full_bar);                   // accumulator complete
+        }
+    } else {
+        // ================= epilogue: TMEM -> registers -> global =================
+        mbar_wait(tmem_full_bar, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int q = warp & 3;                           // TMEM lane quadrant this warp may access
+        const int r = q * 32 + lane;                      // row inside the tile
+        long long orow;
+        bool row_ok;
+        if (IM2COL) {
+            const int roi = m_tile * 2 + (r >> 6), tok = r & 63;
+            row_ok = tok < MV2D_TOK && roi < g.n_rois;
+            orow = (long long)roi * MV2D_TOK + tok;
+        } else {
+            orow = (long long)m_tile * TC_BM + r;
+            row_ok = orow < g.M;
+        }
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+            uint32_t v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+            if (!row_ok) continue;
+            const int n = n0 + c * 32;
+            const long long o = orow * g.ldc + n;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                float x[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    x[i] = __uint_as_float(v[j + i]);
+                    if (g.bias) x[i] += __ldg(g.bias + n + j + i);
+                    if (g.flags & GEMM_RELU) x[i] = fmaxf(x[i], 0.f);
+                }
+                if (g.flags & GEMM_GATE) {
+                    const float4 xx = __ldg(reinterpret_cast<const float4*>(g.gx + o + j));
+                    const float4 ss = __ldg(reinterpret_cast<const float4*>(g.gs + o + j));
+                    x[0] = xx.x * sigmoid_f(x[0]) + ss.x; x[1] = xx.y * sigmoid_f(x[1]) + ss.y;
+                    x[2] = xx.z * sigmoid_f(x[2]) + ss.z; x[3] = xx.w * sigmoid_f(x[3]) + ss.w;
+                    if (g.kin) {
+                        const float4 ff = __ldg(reinterpret_cast<const float4*>(g.gfeat + o + j));
+                        *reinterpret_cast<float4*>(g.kin + o + j) = make_float4(x[0] + ff.x, x[1] + ff.y, x[2] + ff.z, x[3] + ff.w);
+                    }
+                }
+                if (g.flags & GEMM_ROUND_TF32) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) x[i] = round_tf32(x[i]);
+                }
+                *reinterpret_cast<float4*>(g.C + o + j) = make_float4(x[0], x[1], x[2], x[3]);
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN));
+    }
+}
+
+// ---------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// 2-D K-contiguous operand [rows, K] with leading dimension ld (floats); box = [32 floats, box_rows]
+static int make_map_2d(CUtensorMap* m, const float* base, int rows, int K, int ld, int box_rows) {
+    EncodeTiledFn enc = get_encode();
+    MV2D_CHECK_ARG(enc != nullptr, "gemm_tc: cuTensorMapEncodeTiled not available");
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MV2D_CHECK_ARG(r == CUDA_SUCCESS, "gemm_tc: cuTensorMapEncodeTiled(2d) failed with %d", (int)r);
+    return 0;
+}
+
+// 4-D RoI tokens [n_rois, 7, 7, 256]; box = [32 ch, 7, 7, 1]
+static int make_map_tokens(CUtensorMap* m, const float* base, int n_rois) {
+    EncodeTiledFn enc = get_encode();
+    MV2D_CHECK_ARG(enc != nullptr, "gemm_tc: cuTensorMapEncodeTiled not available");
+    cuuint64_t dims[4] = {MV2D_C, MV2D_ROI, MV2D_ROI, (cuuint64_t)n_rois};
+    cuuint64_t strides[3] = {MV2D_C * 4, MV2D_ROI * MV2D_C * 4, MV2D_TOK * MV2D_C * 4};
+    cuuint32_t box[4] = {TC_BK, MV2D_ROI, MV2D_ROI, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)base, dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MV2D_CHECK_ARG(r == CUDA_SUCCESS, "gemm_tc: cuTensorMapEncodeTiled(4d) failed with %d", (int)r);
+    return 0;
+}
+
+template <int BN, int PASSES, bool IM2COL, int STAGES>
+static int launch_tc(const CUtensorMap& a, const CUtensorMap& alo, const CUtensorMap& w, const CUtensorMap& wlo,
+                     const TcArgs& g, int m_tiles, cudaStream_t st) {
+    constexpr int NOP = PASSES == 3 ? 2 : 1;
+    constexpr size_t smem = (size_t)STAGES * NOP * (TC_BM * TC_BK * 4 + BN * TC_BK * 4) + 1024 + 256;
+    auto kern = gemm_tc_kernel<BN, PASSES, IM2COL, STAGES>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_error("gemm_tc: smem attr: %s", cudaGetErrorString(e)); return (int)e; }
+        attr_set = true;
+    }
+    dim3 grid(g.N / BN, m_tiles, 1);
+    kern<<<grid, TC_THREADS, smem, st>>>(a, alo, w, wlo, g);
+    MV2D_CHECK_LAUNCH("gemm_tc");
+    return 0;
+}
+
+int launch_gemm_tc(const TcGemm& t, cudaStream_t st) {
+    MV2D_CHECK_ARG(t.M > 0 && t.N % 128 == 0 && t.K % TC_BK == 0, "gemm_tc: need N%%128==0 and K%%32==0 (N=%d K=%d)", t.N, t.K);
+    MV2D_CHECK_ARG((t.ldc & 3) == 0 && ((uintptr_t)t.C & 15) == 0, "gemm_tc: C must be 16-byte aligned");
+    MV2D_CHECK_ARG(t.passes == 1 || (t.A_lo && t.W_lo), "gemm_tc: 3xTF32 needs the lo operands");
+    CUtensorMap a, alo, w, wlo;
+    int rc;
+    TcArgs g{};
+    g.C = t.C; g.ldc = t.ldc; g.bias = t.bias; g.M = t.M; g.N = t.N; g.K = t.K; g.flags = t.flags;
+    g.gx = t.gx; g.gs = t.gs; g.gfeat = t.gfeat; g.kin = t.kin;
+    int m_tiles;
+    if (t.im2col) {
+        MV2D_CHECK_ARG(t.K == 9 * MV2D_C && t.passes == 3, "gemm_tc: im2col expects K=2304, 3 passes");
+        g.n_rois = t.M / MV2D_TOK;
+        m_tiles = cdiv(g.n_rois, 2);
+        if ((rc = make_map_tokens(&a, t.A, g.n_rois))) return rc;
+        if ((rc = make_map_tokens(&alo, t.A_lo, g.n_rois))) return rc;
+    } else {
+        m_tiles = cdiv(t.M, TC_BM);
+        if ((rc = make_map_2d(&a, t.A, t.M, t.K, t.lda, TC_BM))) return rc;
+        if ((rc = make_map_2d(&alo, t.passes == 3 ? t.A_lo : t.A, t.M, t.K, t.lda, TC_BM))) return rc;
+    }
+    if ((rc = make_map_2d(&w, t.W, t.N, t.K, t.ldw, 128))) return rc;
+    if ((rc = make_map_2d(&wlo, t.passes == 3 ? t.W_lo : t.W, t.N, t.K, t.ldw, 128))) return rc;
+    if (t.im2col) return launch_tc<128, 3, true, 3>(a, alo, w, wlo, g, m_tiles, st);
+    if (t.passes == 3) return launch_tc<128, 3, false, 3>(a, alo, w, wlo, g, m_tiles, st);
+    return launch_tc<128, 1, false, 3>(a, alo, w, wlo, g, m_tiles, st);
+}
+
+__global__ void split_tf32_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float v = x[i], h = round_tf32(v);
+    hi[i] = h;
+    lo[i] = round_tf32(v - h);
+}
+
+int launch_split_tf32(const float* x, float* hi, float* lo, long long n, cudaStream_t st) {
+    if (n <= 0) return 0;
+    split_tf32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, hi, lo, n);
+    MV2D_CHECK_LAUNCH("split_tf32");
+    return 0;
+}
+
+// Routing used by the stage code: single-pass tcgen05 for big TF32-tolerant problems, FFMA otherwise.
+int launch_gemm_tc_or_simt(const GemmArgs& g, cudaStream_t stream) {
+    const bool shape_ok = g.N % 128 == 0 && g.K % TC_BK == 0 && g.batch == 1 && g.nsplit == 1 && !(g.flags & GEMM_CLAMP5E3);
+    const bool want = (g.flags & GEMM_FORCE_TC) || ((g.flags & GEMM_TF32_OK) && g.M >= 512);
+    if (shape_ok && want) {
+        TcGemm t{};
+        t.A = g.A; t.lda = g.lda; t.W = g.W; t.ldw = g.ldw; t.C = g.C; t.ldc = g.ldc; t.bias = g.bias;
+        t.M = g.M; t.N = g.N; t.K = g.K; t.passes = 1; t.im2col = 0;
+        t.flags = g.flags & (GEMM_RELU | GEMM_GATE | GEMM_ROUND_TF32);
+        t.gx = g.gx; t.gs = g.gs; t.gfeat = g.gfeat; t.kin = g.kin;
+        return launch_gemm_tc(t, stream);
+    }
+    GemmArgs h = g;
+    h.flags &= ~(GEMM_TF32_OK | GEMM_FORCE_TC | GEMM_ROUND_TF32);
+    return launch_gemm_simt(h, A_PLAIN, stream);
+}
+
+}  // namespace mv2d

@@ -1,0 +1,36 @@
+// Host interface of the tcgen05 GEMM (gemm_tc.cu).
+#pragma once
+#include "common.cuh"
+
+namespace mv2d {
+
+enum GemmTcFlags : int {
+    GEMM_FORCE_TC = 16,       // mv2d_gemm: run the single-pass tcgen05 kernel whatever the shape heuristics say
+    GEMM_ROUND_TF32 = 64,     // epilogue rounds the result to TF32 (it feeds a single-pass TF32 GEMM)
+};
+
+// round-to-nearest (ties away) fp32 -> tf32, kept in an fp32 container
+__device__ __forceinline__ float round_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+struct TcGemm {
+    const float* A; const float* A_lo; int lda;     // A_lo only for passes == 3
+    const float* W; const float* W_lo; int ldw;
+    float* C; int ldc;
+    const float* bias;
+    int M, N, K;
+    int passes;        // 1 = single-pass TF32 (operands already TF32-representable), 3 = 3xTF32
+    int im2col;        // A = [n_rois,7,7,256] tokens, M = 49*n_rois, K = 2304 ordered (tap, c_in)
+    int flags;         // GEMM_RELU | GEMM_GATE | GEMM_ROUND_TF32
+    const float* gx; const float* gs; const float* gfeat; float* kin;
+};
+
+int launch_gemm_tc(const TcGemm& t, cudaStream_t st);
+
+// x -> hi = rna_tf32(x), lo = rna_tf32(x - hi)   (both exactly TF32-representable)
+int launch_split_tf32(const float* x, float* hi, float* lo, long long n, cudaStream_t st);
+
+}  // namespace mv2d

@@ -6,7 +6,7 @@
 namespace mv2d {
 
 int run_geom_prep(const double* lidar2img, int V, double* img2lidar, double* trans, cudaStream_t st);
-int run_nchw_to_nhwc(const float* in, float* out, int V, int C, int HW, cudaStream_t st);
+int run_nchw_to_nhwc(const float* in, float* out, float* out_tf32, int V, int C, int HW, cudaStream_t st);
 int run_pe3d(const Mv2dPeParams& p, cudaStream_t st);
 size_t pe3d_workspace_bytes(int V, int h, int w, int depth_num);
 int run_roi_align_qg(const Mv2dQgParams& p, cudaStream_t st);

@@ -3,6 +3,7 @@
 // Layout: everything channels-last, pixel p = (v*h + y)*w + x, row p of a [P, C] matrix.
 #include "common.cuh"
 #include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
 #include "mv2d_internal.h"
 
 namespace mv2d {
@@ -28,7 +29,7 @@ __global__ void geom_prep_kernel(const double* __restrict__ lidar2img, int V,
 }
 
 // ---- NCHW -> NHWC (the FPN hands us NCHW; every kernel below wants C contiguous)
-__global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, float* __restrict__ out, int C, int HW) {
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, float* __restrict__ out, float* __restrict__ out_tf32, int C, int HW) {
     __shared__ float tile[32][33];
     const int v = blockIdx.z;
     const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -41,7 +42,11 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, float* __restr
     __syncthreads();
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
         int p = p0 + i, c = c0 + threadIdx.x;
-        if (c < C && p < HW) dst[(long long)p * C + c] = tile[threadIdx.x][i];
+        if (c < C && p < HW) {
+            const float val = tile[threadIdx.x][i];
+            dst[(long long)p * C + c] = val;
+            if (out_tf32) out_tf32[(long long)v * C * HW + (long long)p * C + c] = round_tf32(val);
+        }
     }
 }
 
@@ -71,7 +76,7 @@ __global__ void pe_coords_kernel(const double* __restrict__ img2lidar, float* __
         double c = m[i * 4 + 0] * c0 + m[i * 4 + 1] * c1 + m[i * 4 + 2] * cd + m[i * 4 + 3];
         c = (c - lo[i]) / (hi[i] - lo[i]);
         c = fmin(fmax(c, 0.0), 1.0);                       // inverse_sigmoid, fp64 then .float()
-        r[i] = (float)log(fmax(c, 1e-5) / fmax(1.0 - c, 1e-5));
+        r[i] = round_tf32((float)log(fmax(c, 1e-5) / fmax(1.0 - c, 1e-5)));   // operand of a TF32 GEMM
     }
     float* o = out + p * (3 * D) + d * 3;
     o[0] = r[0]; o[1] = r[1]; o[2] = r[2];
@@ -121,7 +126,7 @@ __global__ void sine_embed_kernel(const float* __restrict__ emb, const float* __
     float r;
     if (i < 64) r = sinf(val / __ldg(dim_t + 2 * i));
     else        r = cosf(val / __ldg(dim_t + 2 * (i - 64) + 1));
-    out[gid] = r;
+    out[gid] = round_tf32(r);   // operand of a TF32 GEMM
 }
 
 static int gemm(const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc,
@@ -141,9 +146,9 @@ int run_geom_prep(const double* lidar2img, int V, double* img2lidar, double* tra
     return 0;
 }
 
-int run_nchw_to_nhwc(const float* in, float* out, int V, int C, int HW, cudaStream_t st) {
+int run_nchw_to_nhwc(const float* in, float* out, float* out_tf32, int V, int C, int HW, cudaStream_t st) {
     dim3 grid(cdiv(HW, 32), cdiv(C, 32), V), block(32, 8);
-    nchw_to_nhwc_kernel<<<grid, block, 0, st>>>(in, out, C, HW);
+    nchw_to_nhwc_kernel<<<grid, block, 0, st>>>(in, out, out_tf32, C, HW);
     MV2D_CHECK_LAUNCH("nchw_to_nhwc");
     return 0;
 }
@@ -173,7 +178,7 @@ int run_pe3d(const Mv2dPeParams& p, cudaStream_t st) {
         MV2D_CHECK_LAUNCH("pe_coords");
     }
     // position_encoder: 192 -> 1024 -> 256
-    if ((rc = gemm(A1, 3 * D, p.w_pos0, 3 * D, p.b_pos0, Hd, 4 * C, P, 4 * C, 3 * D, GEMM_RELU | GEMM_TF32_OK, st))) return rc;
+    if ((rc = gemm(A1, 3 * D, p.w_pos0, 3 * D, p.b_pos0, Hd, 4 * C, P, 4 * C, 3 * D, GEMM_RELU | GEMM_TF32_OK | GEMM_ROUND_TF32, st))) return rc;
     if ((rc = gemm(Hd, 4 * C, p.w_pos2, 4 * C, p.b_pos2, X, C, P, C, 4 * C, GEMM_TF32_OK, st))) return rc;
     // sine branch: 384 -> 1024 -> 256  (input-independent given masks + weights; recomputed here)
     if (!p.sine_branch_cached) {
@@ -182,13 +187,14 @@ int run_pe3d(const Mv2dPeParams& p, cudaStream_t st) {
         MV2D_CHECK_LAUNCH("sine_prep");
         sine_embed_kernel<<<(unsigned)(((long long)P * 384 + 255) / 256), 256, 0, st>>>(EM, p.dim_t, S, P);
         MV2D_CHECK_LAUNCH("sine_embed");
-        if ((rc = gemm(S, 384, p.w_adapt0, 384, p.b_adapt0, Hd, 4 * C, P, 4 * C, 384, GEMM_RELU | GEMM_TF32_OK, st))) return rc;
+        if ((rc = gemm(S, 384, p.w_adapt0, 384, p.b_adapt0, Hd, 4 * C, P, 4 * C, 384, GEMM_RELU | GEMM_TF32_OK | GEMM_ROUND_TF32, st))) return rc;
         if ((rc = gemm(Hd, 4 * C, p.w_adapt2, 4 * C, p.b_adapt2, SB, C, P, C, 4 * C, GEMM_TF32_OK, st))) return rc;
     } else {
         SB = const_cast<float*>(p.sine_branch_cached);
     }
     // SE gate on the image feature, fused combine: pe = X * sigmoid(gate) + SB ; kin = pe + feat
-    if ((rc = gemm(p.feat, C, p.w_se_reduce, C, p.b_se_reduce, G1, C, P, C, C, GEMM_RELU | GEMM_TF32_OK, st))) return rc;
+    if ((rc = gemm(p.feat_tf32 ? p.feat_tf32 : p.feat, C, p.w_se_reduce, C, p.b_se_reduce, G1, C, P, C, C,
+                   GEMM_RELU | GEMM_TF32_OK | GEMM_ROUND_TF32, st))) return rc;
     if ((rc = gemm(G1, C, p.w_se_expand, C, p.b_se_expand, p.pe, C, P, C, C, GEMM_GATE | GEMM_TF32_OK, st, X, SB,
                    p.feat, p.kin))) return rc;
     if (p.sine_branch_out && !p.sine_branch_cached) {

@@ -5,6 +5,7 @@
 //              roi_heads/utils/box_correlation.py:95-398; mmcv RoIAlign
 #include "common.cuh"
 #include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
 #include "mv2d_internal.h"
 
 namespace mv2d {
@@ -17,7 +18,8 @@ namespace mv2d {
 __global__ void __launch_bounds__(64)
 roi_align_tokens_kernel(const float* __restrict__ rois, const float* __restrict__ feat,
                         const float* __restrict__ pe, int h, int w, float spatial_scale,
-                        float* __restrict__ tok_feat, float* __restrict__ tok_kin) {
+                        float* __restrict__ tok_feat, float* __restrict__ tok_kin,
+                        float* __restrict__ tok_hi, float* __restrict__ tok_lo) {
     const int n = blockIdx.y, bin = blockIdx.x;
     const int ph = bin / MV2D_ROI, pw = bin % MV2D_ROI;
     const float* r = rois + n * 5;
@@ -61,6 +63,12 @@ roi_align_tokens_kernel(const float* __restrict__ rois, const float* __restrict_
     af.x /= count; af.y /= count; af.z /= count; af.w /= count;
     const long long o = ((long long)n * MV2D_TOK + bin) * 64 + threadIdx.x;
     reinterpret_cast<float4*>(tok_feat)[o] = af;
+    {   // TF32 hi/lo split of the pooled feature: operands of the 3xTF32 conv GEMM
+        float4 hi = make_float4(round_tf32(af.x), round_tf32(af.y), round_tf32(af.z), round_tf32(af.w));
+        reinterpret_cast<float4*>(tok_hi)[o] = hi;
+        reinterpret_cast<float4*>(tok_lo)[o] = make_float4(round_tf32(af.x - hi.x), round_tf32(af.y - hi.y),
+                                                          round_tf32(af.z - hi.z), round_tf32(af.w - hi.w));
+    }
     if (tok_kin) {
         ap.x /= count; ap.y /= count; ap.z /= count; ap.w /= count;
         reinterpret_cast<float4*>(tok_kin)[o] = make_float4(af.x + ap.x, af.y + ap.y, af.z + ap.z, af.w + ap.w);
@@ -160,7 +168,7 @@ static int gemm(const float* A, int lda, const float* W, int ldw, const float* b
 
 size_t roi_align_qg_workspace_bytes(int N) {
     size_t n = (size_t)(N > 0 ? N : 1);
-    return n * ((size_t)MV2D_TOK * MV2D_C + MV2D_C + 1040 + 512 + MV2D_C + 16 + 384 + MV2D_C) * sizeof(float);
+    return n * ((size_t)3 * MV2D_TOK * MV2D_C + MV2D_C + 1040 + 512 + MV2D_C + 16 + 384 + MV2D_C) * sizeof(float);
 }
 
 int run_roi_align_qg(const Mv2dQgParams& p, cudaStream_t st) {
@@ -170,6 +178,8 @@ int run_roi_align_qg(const Mv2dQgParams& p, cudaStream_t st) {
     MV2D_CHECK_ARG(p.tok_kin == nullptr || p.pe != nullptr, "roi_align_qg: tok_kin needs pe");
     float* ws = p.workspace;
     float* conv = ws;   ws += (size_t)N * MV2D_TOK * C;
+    float* thi = ws;    ws += (size_t)N * MV2D_TOK * C;
+    float* tlo = ws;    ws += (size_t)N * MV2D_TOK * C;
     float* pool = ws;   ws += (size_t)N * C;
     float* cat = ws;    ws += (size_t)N * 1040;
     float* e0 = ws;     ws += (size_t)N * 512;
@@ -180,14 +190,18 @@ int run_roi_align_qg(const Mv2dQgParams& p, cudaStream_t st) {
     MV2D_CHECK_ARG((size_t)(ws - p.workspace) * sizeof(float) <= p.workspace_bytes, "roi_align_qg: workspace too small");
     int rc;
     roi_align_tokens_kernel<<<dim3(MV2D_TOK, N), 64, 0, st>>>(p.rois, p.feat, p.tok_kin ? p.pe : nullptr, p.h, p.w,
-                                                            1.0f / (float)p.stride, p.tok_feat, p.tok_kin);
+                                                            1.0f / (float)p.stride, p.tok_feat, p.tok_kin, thi, tlo);
     MV2D_CHECK_LAUNCH("roi_align_tokens");
     box_params_kernel<<<cdiv(N, 64), 64, 0, st>>>(p.rois, p.intrinsics, p.extrinsics, N, p.intrins_feat_scale, cat,
                                                   mroi, p.roi_intrinsics);
     MV2D_CHECK_LAUNCH("box_params");
     // shared conv 3x3 (+ReLU) as implicit GEMM over the tokens, avg-pool, FC chain
-    if ((rc = gemm(p.tok_feat, C, p.w_conv, 9 * C, p.b_conv, conv, C, N * MV2D_TOK, C, 9 * C, GEMM_RELU,
-                   A_IM2COL3X3, st))) return rc;
+    {   // tcgen05 3xTF32, A staged by 4-D TMA boxes straight from the token tensor
+        TcGemm t{};
+        t.A = thi; t.A_lo = tlo; t.lda = C; t.W = p.w_conv; t.W_lo = p.w_conv_lo; t.ldw = 9 * C; t.bias = p.b_conv;
+        t.C = conv; t.ldc = C; t.M = N * MV2D_TOK; t.N = C; t.K = 9 * C; t.passes = 3; t.im2col = 1; t.flags = GEMM_RELU;
+        if ((rc = launch_gemm_tc(t, st))) return rc;
+    }
     avgpool49_kernel<<<cdiv(N * C, 256), 256, 0, st>>>(conv, pool, N);
     MV2D_CHECK_LAUNCH("avgpool49");
     if ((rc = gemm(pool, C, p.w_fc, C, p.b_fc, cat, 1040, N, 1024, C, GEMM_RELU | GEMM_CLAMP5E3, A_PLAIN, st))) return rc;

@@ -142,11 +142,12 @@ class HotPath:
     def to_nhwc(self, feat_nchw):
         V, Cc, h, w = feat_nchw.shape
         out = self._get('feat_nhwc', (V, h, w, Cc))
-        lib.check(self.lib.mv2d_nchw_to_nhwc(lib.ptr(feat_nchw), out.data_ptr(), V, Cc, h * w, lib.stream_ptr()),
-                  'mv2d_nchw_to_nhwc')
-        return out
+        out_tf32 = self._get('feat_tf32', (V, h, w, Cc))
+        lib.check(self.lib.mv2d_nchw_to_nhwc(lib.ptr(feat_nchw), out.data_ptr(), out_tf32.data_ptr(), V, Cc, h * w,
+                                             lib.stream_ptr()), 'mv2d_nchw_to_nhwc')
+        return out, out_tf32
 
-    def pe3d(self, feat_nhwc, img2lidar, img_metas):
+    def pe3d(self, feat_nhwc, img2lidar, img_metas, feat_tf32=None):
         """PE.forward (utils/pe.py:137-169) -> (pe [V,h,w,256], kin = feat + pe or None)."""
         V, h, w, _ = feat_nhwc.shape
         c, W = self.cfg, self.w
@@ -161,6 +162,7 @@ class HotPath:
         p.stride = c['stride']
         p.depth_start = c['depth_start']
         p.position_range = (C.c_double * 6)(*c['position_range'])
+        p.feat_tf32 = feat_tf32.data_ptr() if feat_tf32 is not None else None
         p.feat, p.img2lidar, p.not_mask, p.dim_t = feat_nhwc.data_ptr(), img2lidar.data_ptr(), not_mask.data_ptr(), W.p('dim_t')
         for f in ('w_pos0', 'b_pos0', 'w_pos2', 'b_pos2', 'w_adapt0', 'b_adapt0', 'w_adapt2', 'b_adapt2',
                   'w_se_reduce', 'b_se_reduce', 'w_se_expand', 'b_se_expand'):
@@ -196,7 +198,7 @@ class HotPath:
         p.feat = feat_nhwc.data_ptr()
         p.pe = pe_nhwc.data_ptr() if tok_kin is not None else None
         p.dim_t = W.p('dim_t')
-        for f in ('w_conv', 'b_conv', 'w_fc', 'b_fc', 'w_enc0', 'b_enc0', 'w_enc2', 'b_enc2', 'w_center',
+        for f in ('w_conv', 'b_conv', 'w_conv_lo', 'w_fc', 'b_fc', 'w_enc0', 'b_enc0', 'w_enc2', 'b_enc2', 'w_center',
                   'b_center', 'w_qe0', 'b_qe0', 'w_qe2', 'b_qe2'):
             setattr(p, f, W.p(f))
         p.tok_feat = tok_feat.data_ptr()
@@ -268,16 +270,17 @@ class HotPath:
         cls_scores / bbox_preds [L,N,10] and the stage tensors (views of reused buffers)."""
         V = len(img_metas)
         feat_nchw = feat_nchw.to(self.device, torch.float32)
+        feat_tf32 = None
         if feat_is_nhwc:
             feat = feat_nchw.contiguous()
             _, h, w, _ = feat.shape
         else:
             _, _, h, w = feat_nchw.shape
-            feat = self.to_nhwc(feat_nchw.contiguous())
+            feat, feat_tf32 = self.to_nhwc(feat_nchw.contiguous())
         cams = self._upload_cams(img_metas)
         rois, roi_start, counts, N = self._upload_rois(proposal_list)
         i2l, trans = self.geom_prep(cams)
-        pe, kin = self.pe3d(feat, i2l, img_metas)
+        pe, kin = self.pe3d(feat, i2l, img_metas, feat_tf32)
         qg = self.roi_align_qg(rois, cams, feat, pe, N)
         corr = self.box_corr(rois, roi_start, trans, N, V, img_metas, h, w)
         if self.mode == 'S':

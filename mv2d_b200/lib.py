@@ -20,7 +20,7 @@ class PeParams(C.Structure):
         ('V', C.c_int), ('h', C.c_int), ('w', C.c_int), ('depth_num', C.c_int),
         ('pad_h', C.c_int), ('pad_w', C.c_int), ('stride', C.c_int), ('reserved0', C.c_int),
         ('depth_start', C.c_double), ('position_range', C.c_double * 6),
-        ('feat', c_f), ('img2lidar', c_f), ('not_mask', c_f), ('dim_t', c_f),
+        ('feat', c_f), ('feat_tf32', c_f), ('img2lidar', c_f), ('not_mask', c_f), ('dim_t', c_f),
         ('w_pos0', c_f), ('b_pos0', c_f), ('w_pos2', c_f), ('b_pos2', c_f),
         ('w_adapt0', c_f), ('b_adapt0', c_f), ('w_adapt2', c_f), ('b_adapt2', c_f),
         ('w_se_reduce', c_f), ('b_se_reduce', c_f), ('w_se_expand', c_f), ('b_se_expand', c_f),
@@ -36,7 +36,7 @@ class QgParams(C.Structure):
         ('pc_range', C.c_float * 6), ('intrins_feat_scale', C.c_float), ('reserved1', C.c_float),
         ('rois', c_f), ('intrinsics', c_f), ('extrinsics', c_f), ('feat', c_f), ('pe', c_f),
         ('dim_t', c_f),
-        ('w_conv', c_f), ('b_conv', c_f), ('w_fc', c_f), ('b_fc', c_f),
+        ('w_conv', c_f), ('b_conv', c_f), ('w_conv_lo', c_f), ('w_fc', c_f), ('b_fc', c_f),
         ('w_enc0', c_f), ('b_enc0', c_f), ('w_enc2', c_f), ('b_enc2', c_f),
         ('w_center', c_f), ('b_center', c_f), ('w_qe0', c_f), ('b_qe0', c_f),
         ('w_qe2', c_f), ('b_qe2', c_f),
@@ -101,7 +101,10 @@ SYMBOLS = [
     ('mv2d_launch_count', C.c_ulonglong, []),
     ('mv2d_sizeof', C.c_size_t, [C.c_int]),
     ('mv2d_geom_prep', C.c_int, [c_f, C.c_int, c_f, c_f, c_f]),
-    ('mv2d_nchw_to_nhwc', C.c_int, [c_f, c_f, C.c_int, C.c_int, C.c_int, c_f]),
+    ('mv2d_nchw_to_nhwc', C.c_int, [c_f, c_f, c_f, C.c_int, C.c_int, C.c_int, c_f]),
+    ('mv2d_split_tf32', C.c_int, [c_f, c_f, c_f, C.c_longlong, c_f]),
+    ('mv2d_gemm_3xtf32', C.c_int, [c_f, c_f, C.c_int, c_f, c_f, C.c_int, c_f, c_f, C.c_int, C.c_int, C.c_int,
+                                   C.c_int, C.c_int, c_f]),
     ('mv2d_pe3d_workspace_bytes', C.c_size_t, [C.c_int] * 4),
     ('mv2d_pe3d', C.c_int, [C.POINTER(PeParams), c_f]),
     ('mv2d_roi_align_qg_workspace_bytes', C.c_size_t, [C.c_int]),

@@ -50,6 +50,19 @@ def absorb_cross_attention(in_w, in_b, out_w, out_b):
     return ca_q_w.float(), ca_q_b.float(), ca_o_w.float(), ca_o_b.float()
 
 
+def round_tf32(t):
+    """Round-to-nearest (ties away from zero) fp32 -> TF32, kept in fp32: what cvt.rna.tf32.f32 does."""
+    bits = t.detach().float().contiguous().view(torch.int32)
+    return ((bits + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+def split_tf32(t):
+    """w = hi + lo with both parts exactly TF32-representable (operands of the 3xTF32 GEMM)."""
+    t = t.detach().float()
+    hi = round_tf32(t)
+    return hi, round_tf32(t - hi)
+
+
 class PackedWeights:
     """Device-resident weights + the host-side ctypes structs that point at them."""
 
@@ -67,8 +80,8 @@ class PackedWeights:
             self.t[name] = tensor.detach().float().contiguous().to(device)
             return self.t[name]
 
-        def conv1x1(key):
-            return sd[key].reshape(sd[key].shape[0], -1)
+        def conv1x1(key):   # PE MLPs run as single-pass TF32 tensor-core GEMMs: weights pre-rounded
+            return round_tf32(sd[key].reshape(sd[key].shape[0], -1))
 
         pe = 'position_encoding.'
         put('w_pos0', conv1x1(pe + 'position_encoder.0.weight')); put('b_pos0', sd[pe + 'position_encoder.0.bias'])
@@ -79,7 +92,9 @@ class PackedWeights:
         put('w_se_expand', conv1x1(pe + 'fpe.conv_expand.weight')); put('b_se_expand', sd[pe + 'fpe.conv_expand.bias'])
         qg = 'query_generator.'
         wc = sd[qg + 'shared_convs.0.conv.weight']           # [co, ci, ky, kx]
-        put('w_conv', wc.permute(0, 2, 3, 1).reshape(wc.shape[0], -1))  # [co, (ky,kx,ci)]
+        wc_hi, wc_lo = split_tf32(wc.permute(0, 2, 3, 1).reshape(wc.shape[0], -1))  # [co, (ky,kx,ci)]
+        put('w_conv', wc_hi)
+        put('w_conv_lo', wc_lo)
         put('b_conv', sd[qg + 'shared_convs.0.conv.bias'])
         put('w_fc', sd[qg + 'shared_fcs.0.weight']); put('b_fc', sd[qg + 'shared_fcs.0.bias'])
         put('w_enc0', sd[qg + 'extra_enc.0.weight']); put('b_enc0', sd[qg + 'extra_enc.0.bias'])

@@ -77,7 +77,12 @@ def test_cuda_path_matches_reference_golden(name, state_dicts):
         words = out['keymask'].cpu().numpy().view(np.uint32)
         bits = np.unpackbits(words.view(np.uint8), axis=1, bitorder='little')[:, :g['key_mask_packed'].shape[1] * 8]
         ref_bits = np.unpackbits(g['key_mask_packed'], axis=1)
-        assert np.array_equal(bits[:, :ref_bits.shape[1]], ref_bits), 'per-query key masks differ'
+        # the library folds the key_padding_mask (padded-out cells, mv2d_t_head.py:68-76) into
+        # the per-query mask; the reference applies it separately inside MultiheadAttention
+        from mv2d_b200.engine import feat_pad_mask
+        h, w = feat.shape[-2:]
+        keep = 1 - feat_pad_mask(metas, h, w).reshape(1, -1)
+        assert np.array_equal(bits[:, :ref_bits.shape[1]], ref_bits * keep), 'per-query key masks differ'
     # ---- the parity gate
     assert_close(out['cls_scores'], g['cls_scores'], what='cls_scores')
     assert_close(out['bbox_preds'], g['bbox_preds'], what='bbox_preds')
@@ -121,6 +126,64 @@ def test_gemm_kernel_vs_torch_fp32():
         if flags & 1:
             ref = ref.relu()
         assert_close(Cc, ref, 2e-5, 2e-5, f'gemm {M}x{N}x{K}')
+
+
+def test_tcgen05_gemm_single_pass_tf32():
+    """tcgen05 kind::tf32 kernel: with TF32-representable operands every product is exact, so the
+    result must match an fp64 matmul of the same operands to fp32-accumulation accuracy."""
+    from mv2d_b200 import lib
+    from mv2d_b200.pack import round_tf32
+    h = lib.load()
+    g = torch.Generator().manual_seed(1)
+    for (M, N, K, flags) in [(128, 128, 32, 16), (256, 128, 64, 16), (16896, 1024, 192, 16 | 1), (1000, 256, 1024, 16),
+                             (16896, 256, 1024, 16), (300, 256, 256, 16 | 1)]:
+        A = round_tf32(torch.randn(M, K, generator=g)).cuda()
+        W = round_tf32(torch.randn(N, K, generator=g) / K ** 0.5).cuda()
+        b = torch.randn(N, generator=g).cuda()
+        Cc = torch.full((M, N), float('nan'), device='cuda')
+        lib.check(h.mv2d_gemm(A.data_ptr(), K, W.data_ptr(), K, b.data_ptr(), Cc.data_ptr(), N, M, N, K, flags,
+                              lib.stream_ptr()), 'mv2d_gemm(tc)')
+        ref = A.double() @ W.double().T + b.double()
+        if flags & 1:
+            ref = ref.relu()
+        assert_close(Cc, ref, 2e-5, 2e-5, f'gemm_tc {M}x{N}x{K}')
+
+
+def test_tcgen05_gemm_3xtf32_and_im2col(state_dicts):
+    """Error-compensated 3xTF32: fp32-grade on arbitrary fp32 operands; and the TMA-im2col form
+    against torch conv2d (fp64)."""
+    import torch.nn.functional as F
+    from mv2d_b200 import lib
+    h = lib.load()
+    g = torch.Generator().manual_seed(2)
+
+    def split(x):
+        hi, lo = torch.empty_like(x), torch.empty_like(x)
+        lib.check(h.mv2d_split_tf32(x.data_ptr(), hi.data_ptr(), lo.data_ptr(), x.numel(), lib.stream_ptr()), 'split')
+        return hi, lo
+
+    for (M, N, K) in [(128, 128, 32), (777, 256, 2304), (14700, 256, 512)]:
+        A = torch.randn(M, K, generator=g).cuda()
+        W = (torch.randn(N, K, generator=g) / K ** 0.5).cuda()
+        b = torch.randn(N, generator=g).cuda()
+        (ah, al), (wh, wl) = split(A), split(W)
+        Cc = torch.full((M, N), float('nan'), device='cuda')
+        lib.check(h.mv2d_gemm_3xtf32(ah.data_ptr(), al.data_ptr(), K, wh.data_ptr(), wl.data_ptr(), K, b.data_ptr(),
+                                     Cc.data_ptr(), N, M, N, K, 0, lib.stream_ptr()), 'gemm_3xtf32')
+        assert_close(Cc, A.double() @ W.double().T + b.double(), 2e-5, 2e-5, f'3xtf32 {M}x{N}x{K}')
+    for n_rois in (1, 2, 7, 300):
+        x = torch.randn(n_rois, 256, 7, 7, generator=g).cuda()
+        w = (torch.randn(256, 256, 3, 3, generator=g) / 48).cuda()
+        b = torch.randn(256, generator=g).cuda()
+        tok = x.permute(0, 2, 3, 1).contiguous()
+        wk = w.permute(0, 2, 3, 1).reshape(256, -1).contiguous()
+        (th, tl), (wh, wl) = split(tok), split(wk)
+        out = torch.full((n_rois * 49, 256), float('nan'), device='cuda')
+        lib.check(h.mv2d_gemm_3xtf32(th.data_ptr(), tl.data_ptr(), 256, wh.data_ptr(), wl.data_ptr(), 2304,
+                                     b.data_ptr(), out.data_ptr(), 256, n_rois * 49, 256, 2304, 1 | 128,
+                                     lib.stream_ptr()), 'gemm_3xtf32(im2col)')
+        ref = F.conv2d(x.double(), w.double(), b.double(), padding=1).relu().permute(0, 2, 3, 1).reshape(-1, 256)
+        assert_close(out, ref, 3e-5, 3e-5, f'im2col conv n={n_rois}')
 
 
 def test_full_size_properties(state_dicts):

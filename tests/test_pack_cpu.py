@@ -36,6 +36,6 @@ def test_conv_repack_matches_conv2d(state_dicts):
                    sd['query_generator.shared_convs.0.conv.bias'], padding=1)
     tok = F.pad(x, (1, 1, 1, 1)).permute(0, 2, 3, 1)            # [n, 9, 9, c]
     cols = torch.stack([tok[:, ky:ky + 7, kx:kx + 7] for ky in range(3) for kx in range(3)], 3)  # [n,7,7,9,c]
-    out = cols.reshape(3, 49, 9 * 256) @ w.t['w_conv'].T + w.t['b_conv']
+    out = cols.reshape(3, 49, 9 * 256) @ (w.t['w_conv'] + w.t['w_conv_lo']).T + w.t['b_conv']   # hi + lo = w
     assert (out.view(3, 7, 7, 256).permute(0, 3, 1, 2) - ref).abs().max() < 2e-4
     assert w.num_layers == 1 and w.t['br.cls_w2'].shape == (1, 10, 256)
