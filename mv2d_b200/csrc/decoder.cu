@@ -105,25 +105,20 @@ __global__ void __launch_bounds__(256) ln_kernel(LnArgs a) {
 // ------------------------------------------------------------------------------------------
 // FlattenMHSelfAttention core (petr_transformer.py:314-370): all N queries form ONE sequence.
 // qkv [N,768] (q | k | v, head h = channels 32h..32h+31), q already includes the bias; the
-// 1/sqrt(32) scale is applied here.  grid (ceil(N/32), 8 heads), 256 threads: warp = 4 queries
-// (one at a time), lanes = keys for QK^T, lanes = channels for PV; K/V tiles of 128 keys in smem.
+// 1/sqrt(32) scale is applied here.  grid (ceil(N/8), 8 heads), 256 threads: one query per warp;
+// lanes = keys for QK^T (two independent 32-key groups in flight), lanes = channels for PV;
+// K/V tiles of 128 keys staged in padded shared memory; online softmax across tiles.
 #define SA_KT 128
 __global__ void __launch_bounds__(256)
 self_attn_kernel(const float* __restrict__ qkv, const uint8_t* __restrict__ mask, int N, float* __restrict__ out) {
     __shared__ float Ks[SA_KT][33];
     __shared__ float Vs[SA_KT][33];
+    __shared__ float Qs[8][32];
     const int hd = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int q0 = blockIdx.x * 32 + warp * 4;
-    float q[4][32];            // q[i][d], replicated across lanes
-    float m[4], l[4], acc[4];  // running max / sum / output channel `lane`
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int qi = q0 + i;
-        m[i] = -INFINITY; l[i] = 0.f; acc[i] = 0.f;
-#pragma unroll
-        for (int d = 0; d < 32; ++d)
-            q[i][d] = (qi < N) ? __ldg(qkv + (long long)qi * 768 + hd * 32 + d) * 0.17677669529663687f : 0.f;
-    }
+    const int qi = blockIdx.x * 8 + warp;
+    const bool qok = qi < N;
+    Qs[warp][lane] = qok ? __ldg(qkv + (long long)qi * 768 + hd * 32 + lane) * 0.17677669529663687f : 0.f;
+    float m = -INFINITY, l = 0.f, acc = 0.f;
     for (int k0 = 0; k0 < N; k0 += SA_KT) {
         __syncthreads();
         for (int i = threadIdx.x; i < SA_KT * 32; i += 256) {
@@ -132,47 +127,62 @@ self_attn_kernel(const float* __restrict__ qkv, const uint8_t* __restrict__ mask
             Vs[r][c] = (k < N) ? __ldg(qkv + (long long)k * 768 + 512 + hd * 32 + c) : 0.f;
         }
         __syncthreads();
+        if (!qok) continue;
+        const int ng = min(SA_KT, N - k0);
+        float s[SA_KT / 32];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int qi = q0 + i;
-            if (qi >= N) continue;   // warp-uniform
-            for (int g = 0; g < SA_KT / 32; ++g) {
-                const int kk = g * 32 + lane, k = k0 + kk;
-                if (k0 + g * 32 >= N) break;
-                float s = 0.f;
+        for (int g = 0; g < SA_KT / 32; ++g) s[g] = 0.f;
 #pragma unroll
-                for (int d = 0; d < 32; ++d) s = fmaf(q[i][d], Ks[kk][d], s);
-                if (k >= N || (mask && mask[(long long)qi * N + k])) s = -INFINITY;
-                const float mn = fmaxf(m[i], warp_max(s));
-                if (mn == -INFINITY) continue;
-                const float alpha = __expf(m[i] - mn);   // exp(-inf) = 0 on the first tile
-                const float pj = __expf(s - mn);
-                l[i] = l[i] * alpha + warp_sum(pj);
-                float a = acc[i] * alpha;
+        for (int d = 0; d < 32; ++d) {
+            const float qd = Qs[warp][d];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) a = fmaf(__shfl_sync(0xffffffffu, pj, j), Vs[g * 32 + j][lane], a);
-                acc[i] = a;
-                m[i] = mn;
-            }
+            for (int g = 0; g < SA_KT / 32; ++g) s[g] = fmaf(qd, Ks[g * 32 + lane][d], s[g]);
         }
-    }
+        float mx = -INFINITY;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int qi = q0 + i;
-        if (qi < N) out[(long long)qi * MV2D_C + hd * 32 + lane] = l[i] > 0.f ? acc[i] / l[i] : 0.f;
+        for (int g = 0; g < SA_KT / 32; ++g) {
+            const int kk = g * 32 + lane;
+            if (kk >= ng || (mask && mask[(long long)qi * N + k0 + kk])) s[g] = -INFINITY;
+            mx = fmaxf(mx, s[g]);
+        }
+        const float mn = fmaxf(m, warp_max(mx));
+        if (mn == -INFINITY) continue;
+        const float alpha = __expf(m - mn);      // exp(-inf) = 0 on the first tile
+        float psum = 0.f;
+#pragma unroll
+        for (int g = 0; g < SA_KT / 32; ++g) { s[g] = __expf(s[g] - mn); psum += s[g]; }
+        l = l * alpha + warp_sum(psum);
+        float a0 = acc * alpha, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            a0 = fmaf(__shfl_sync(0xffffffffu, s[0], j), Vs[j][lane], a0);
+            a1 = fmaf(__shfl_sync(0xffffffffu, s[1], j), Vs[32 + j][lane], a1);
+            a2 = fmaf(__shfl_sync(0xffffffffu, s[2], j), Vs[64 + j][lane], a2);
+            a3 = fmaf(__shfl_sync(0xffffffffu, s[3], j), Vs[96 + j][lane], a3);
+        }
+        acc = (a0 + a1) + (a2 + a3);
+        m = mn;
     }
+    if (qok) out[(long long)qi * MV2D_C + hd * 32 + lane] = l > 0.f ? acc / l : 0.f;
 }
 
 // ------------------------------------------------------------------------------------------
 // Sparse multi-view cross-attention core, absorbed form.  One CTA (8 warps) per query.
 //   qt   [N, 8*256]   q~ per head (scale folded in)
 //   keys: mode 0 -> RoI tokens of the matched RoIs (match list); mode 1 -> set bits of keymask
-//   kin_rows / mem_rows [num_rows, 256]
+//   kin_rows / mem_rows [num_rows, 256]   key input (memory + pos) / value input (memory)
 //   ctx  [N, 8*256]   sum_k softmax_h(k) * mem_row_k
-// Keys are processed in chunks of XA_CHUNK: pass 1 (logits, warp per key, lanes along the 256
-// channels with 16-byte loads), chunk softmax with running max (warp per head), pass 2
-// (probability-weighted sum of memory rows).  Per-lane state: 8 heads x 8 channels.
-#define XA_CHUNK 512
+// The key rows of a query are streamed through shared memory in chunks of XA_CH keys with
+// cp.async (16-byte copies, all 64 KB of a chunk in flight at once, double buffered so the next
+// chunk loads while this one is consumed).  Per chunk: logits (warp per key, lanes along the
+// 256 channels, warp-shuffle transpose-reduce over 8 heads), online softmax (warp per head,
+// lane per key), probability-weighted sum of the memory rows.  Per-lane state: 8 heads x 8 ch.
+#define XA_CH 32
+__device__ __forceinline__ void xa_cp16(void* smem, const void* gmem) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
+
 __device__ inline void reduce8(float (&v)[8], int lane) {
     // transpose-reduce 8 per-lane partials over the warp: 9 shuffles instead of 40.
     // result: every lane holds the full sum for head (lane >> 2) & 7 in v[0].
@@ -206,8 +216,10 @@ struct XaArgs {
 __global__ void __launch_bounds__(256)
 cross_attn_kernel(XaArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float* sc = reinterpret_cast<float*>(smem_raw);                 // [XA_CHUNK][8] logits -> probs
-    float* red = sc + XA_CHUNK * 8;                                 // [2048] cross-warp sum
+    float* kbuf = reinterpret_cast<float*>(smem_raw);               // [2][XA_CH][256] key-input rows
+    float* vbuf = kbuf + 2 * XA_CH * MV2D_C;                        // [2][XA_CH][256] memory rows
+    float* sc = vbuf + 2 * XA_CH * MV2D_C;                          // [XA_CH][8] logits -> probs
+    float* red = sc + XA_CH * 8;                                    // [2048] cross-warp sum
     float* stat = red + 2048;                                       // m[8], l[8], alpha[8]
     uint16_t* klist = reinterpret_cast<uint16_t*>(stat + 24);       // [klist_cap]
     __shared__ int nkeys_s;
@@ -252,6 +264,20 @@ cross_attn_kernel(XaArgs a) {
     }
     __syncthreads();
     const int nkeys = nkeys_s;
+    const int nchunks = (nkeys + XA_CH - 1) / XA_CH;
+
+    // stage chunk c into buffer c&1: 32 keys x (1 KB + 1 KB) = 4096 16-byte copies, 16 per thread
+    auto stage = [&](int c) {
+        const int base = c * XA_CH, cn = min(XA_CH, nkeys - base), buf = c & 1;
+        for (int i = t; i < cn * 64; i += 256) {
+            const int j = i >> 6, q4 = i & 63;
+            const long long row = (long long)klist[base + j] * MV2D_C + q4 * 4;
+            xa_cp16(kbuf + (buf * XA_CH + j) * MV2D_C + q4 * 4, a.kin_rows + row);
+            xa_cp16(vbuf + (buf * XA_CH + j) * MV2D_C + q4 * 4, a.mem_rows + row);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if (nchunks > 0) stage(0);
 
     // ---- q~ slice of this lane: 8 heads x channels {lane*4..+3, 128+lane*4..+3}
     float qv[8][8];
@@ -268,13 +294,16 @@ cross_attn_kernel(XaArgs a) {
 #pragma unroll
         for (int c = 0; c < 8; ++c) acc[h][c] = 0.f;
 
-    for (int c0 = 0; c0 < nkeys; c0 += XA_CHUNK) {
-        const int cn = min(XA_CHUNK, nkeys - c0);
-        // pass 1: logits
+    for (int c = 0; c < nchunks; ++c) {
+        const int cn = min(XA_CH, nkeys - c * XA_CH), buf = c & 1;
+        if (c + 1 < nchunks) { stage(c + 1); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        // pass 1: logits of 4 keys per warp
         for (int j = warp; j < cn; j += 8) {
-            const float* row = a.kin_rows + (long long)klist[c0 + j] * MV2D_C;
-            const float4 k0 = __ldg(reinterpret_cast<const float4*>(row + lane * 4));
-            const float4 k1 = __ldg(reinterpret_cast<const float4*>(row + 128 + lane * 4));
+            const float* row = kbuf + (buf * XA_CH + j) * MV2D_C;
+            const float4 k0 = *reinterpret_cast<const float4*>(row + lane * 4);
+            const float4 k1 = *reinterpret_cast<const float4*>(row + 128 + lane * 4);
             float s[8];
 #pragma unroll
             for (int h = 0; h < 8; ++h) {
@@ -288,20 +317,14 @@ cross_attn_kernel(XaArgs a) {
             if ((lane & 3) == 0) sc[j * 8 + (lane >> 2)] = s[0];
         }
         __syncthreads();
-        // chunk softmax: warp = head
+        // online softmax: warp = head, lane = key
         {
             const int h = warp;
-            float mx = -INFINITY;
-            for (int j = lane; j < cn; j += 32) mx = fmaxf(mx, sc[j * 8 + h]);
-            mx = warp_max(mx);
-            const float m_old = stat[h], m_new = fmaxf(m_old, mx);
-            float sum = 0.f;
-            for (int j = lane; j < cn; j += 32) {
-                const float p = __expf(sc[j * 8 + h] - m_new);
-                sc[j * 8 + h] = p;
-                sum += p;
-            }
-            sum = warp_sum(sum);
+            const float sv = lane < cn ? sc[lane * 8 + h] : -INFINITY;
+            const float m_old = stat[h], m_new = fmaxf(m_old, warp_max(sv));
+            const float p = lane < cn ? __expf(sv - m_new) : 0.f;
+            if (lane < cn) sc[lane * 8 + h] = p;
+            const float sum = warp_sum(p);
             if (lane == 0) {
                 const float alpha = (m_old == -INFINITY) ? 0.f : __expf(m_old - m_new);
                 stat[16 + h] = alpha;
@@ -315,12 +338,12 @@ cross_attn_kernel(XaArgs a) {
         for (int h = 0; h < 8; ++h) {
             const float al = stat[16 + h];
 #pragma unroll
-            for (int c = 0; c < 8; ++c) acc[h][c] *= al;
+            for (int cc = 0; cc < 8; ++cc) acc[h][cc] *= al;
         }
         for (int j = warp; j < cn; j += 8) {
-            const float* row = a.mem_rows + (long long)klist[c0 + j] * MV2D_C;
-            const float4 v0 = __ldg(reinterpret_cast<const float4*>(row + lane * 4));
-            const float4 v1 = __ldg(reinterpret_cast<const float4*>(row + 128 + lane * 4));
+            const float* row = vbuf + (buf * XA_CH + j) * MV2D_C;
+            const float4 v0 = *reinterpret_cast<const float4*>(row + lane * 4);
+            const float4 v1 = *reinterpret_cast<const float4*>(row + 128 + lane * 4);
             const float4 p0 = *reinterpret_cast<const float4*>(sc + j * 8);
             const float4 p1 = *reinterpret_cast<const float4*>(sc + j * 8 + 4);
             const float pp[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
@@ -332,10 +355,9 @@ cross_attn_kernel(XaArgs a) {
                 acc[h][6] = fmaf(pp[h], v1.z, acc[h][6]); acc[h][7] = fmaf(pp[h], v1.w, acc[h][7]);
             }
         }
-        __syncthreads();
+        __syncthreads();   // everyone done with buffer `buf` and `sc` before they are refilled
     }
-    // ---- cross-warp sum, normalise, store
-    // (fixed warp order => bitwise reproducible)
+    // ---- cross-warp sum (fixed warp order => bitwise reproducible), normalise, store
     for (int wv = 0; wv < 8; ++wv) {
         if (warp == wv) {
 #pragma unroll
@@ -453,7 +475,7 @@ int run_decoder(const Mv2dDecoderParams& p, cudaStream_t st) {
         return (int)e;
     }
     const int klist_cap = p.mode == 0 ? p.max_match * MV2D_TOK : p.mask_words * 32;
-    const size_t xa_smem = (size_t)(XA_CHUNK * 8 + 2048 + 24) * sizeof(float) + (size_t)klist_cap * sizeof(uint16_t);
+    const size_t xa_smem = (size_t)(4 * XA_CH * MV2D_C + XA_CH * 8 + 2048 + 24) * sizeof(float) + (size_t)klist_cap * sizeof(uint16_t);
     MV2D_CHECK_ARG(xa_smem <= 227 * 1024, "decoder: key list does not fit shared memory");
     MV2D_CHECK_ARG(p.mode == 0 || p.mask_words <= 4096, "decoder: mask_words=%d > 4096", p.mask_words);
     if ((e = cudaFuncSetAttribute(cross_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xa_smem)) != cudaSuccess) {
@@ -466,9 +488,13 @@ int run_decoder(const Mv2dDecoderParams& p, cudaStream_t st) {
         const Mv2dLayerWeights& w = p.layers[l];
         float* inter = p.outs_dec + (long long)l * NC;
         // --- self attention: q,k from (x + qpos), v from x
-        if ((rc = gemm(xq, C, w.sa_in_w, C, w.sa_in_b, qkv, 768, N, 512, C, 0, st))) return rc;
-        if ((rc = gemm(x, C, w.sa_in_w + 512 * C, C, w.sa_in_b + 512, qkv + 512, 768, N, C, C, 0, st))) return rc;
-        self_attn_kernel<<<dim3(cdiv(N, 32), MV2D_HEADS), 256, 0, st>>>(qkv, p.self_attn_mask, N, sa);
+        {
+            GemmArgs g{};
+            g.A = xq; g.lda = C; g.W = w.sa_in_w; g.ldw = C; g.C = qkv; g.ldc = 768; g.bias = w.sa_in_b;
+            g.M = N; g.N = 768; g.K = C; g.batch = 1; g.nsplit = 1;
+            if ((rc = launch_gemm_small(g, x, 512, st))) return rc;
+        }
+        self_attn_kernel<<<dim3(cdiv(N, 8), MV2D_HEADS), 256, 0, st>>>(qkv, p.self_attn_mask, N, sa);
         MV2D_CHECK_LAUNCH("self_attn");
         if ((rc = gemm(sa, C, w.sa_out_w, C, nullptr, part, C, N, C, C, 0, st))) return rc;
         {

@@ -2,6 +2,115 @@
 
 namespace mv2d {
 
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    const int sz = valid ? 16 : 0;   // src-size 0 => zero fill
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+#define GS_BM 32
+#define GS_BN 32
+#define GS_BK 32
+#define GS_STAGES 4
+
+__global__ void __launch_bounds__(64)
+gemm_small_kernel(GemmSmallArgs a) {
+    const GemmArgs& g = a.g;
+    __shared__ __align__(16) float As[GS_STAGES][GS_BM][GS_BK];
+    __shared__ __align__(16) float Ws[GS_STAGES][GS_BN][GS_BK];
+    const int tid = threadIdx.x, tx = tid & 7, ty = tid >> 3;
+    const int b = blockIdx.z / g.nsplit, split = blockIdx.z % g.nsplit;
+    const int m0 = blockIdx.y * GS_BM, n0 = blockIdx.x * GS_BN;
+    const int Ks = g.K / g.nsplit, kbeg = split * Ks, nk = Ks / GS_BK;
+    const float* __restrict__ A = ((a.A2 && n0 >= a.n_switch) ? a.A2 : g.A) + b * g.strideA;
+    const float* __restrict__ W = g.W + b * g.strideW;
+
+    // each thread copies 4 chunks of A and 4 of W per k-tile: chunk id f = tid + 64*i -> (row = f/8, kc = f%8)
+    auto issue = [&](int kt, int stage) {
+        const int k0 = kbeg + kt * GS_BK;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int f = tid + 64 * i, row = f >> 3, kc = f & 7, sw = kc ^ ((row >> 2) & 7);
+            const int m = m0 + row, n = n0 + row;
+            cp_async16(&As[stage][row][sw * 4], A + (long long)min(m, g.M - 1) * g.lda + k0 + kc * 4, m < g.M);
+            cp_async16(&Ws[stage][row][sw * 4], W + (long long)min(n, g.N - 1) * g.ldw + k0 + kc * 4, n < g.N);
+        }
+    };
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+#pragma unroll
+    for (int s = 0; s < GS_STAGES - 1; ++s) {
+        if (s < nk) issue(s, s);
+        cp_async_commit();
+    }
+    for (int kt = 0; kt < nk; ++kt) {
+        cp_async_wait<GS_STAGES - 2>();
+        __syncthreads();
+        if (kt + GS_STAGES - 1 < nk) issue(kt + GS_STAGES - 1, (kt + GS_STAGES - 1) % GS_STAGES);
+        cp_async_commit();
+        const int st = kt % GS_STAGES;
+#pragma unroll
+        for (int kc = 0; kc < 8; ++kc) {
+            float4 av[4], wv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int ra = ty * 4 + i, rw = tx * 4 + i;
+                av[i] = *reinterpret_cast<const float4*>(&As[st][ra][(kc ^ ((ra >> 2) & 7)) * 4]);
+                wv[i] = *reinterpret_cast<const float4*>(&Ws[st][rw][(kc ^ ((rw >> 2) & 7)) * 4]);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    acc[i][j] = fmaf(av[i].x, wv[j].x, acc[i][j]);
+                    acc[i][j] = fmaf(av[i].y, wv[j].y, acc[i][j]);
+                    acc[i][j] = fmaf(av[i].z, wv[j].z, acc[i][j]);
+                    acc[i][j] = fmaf(av[i].w, wv[j].w, acc[i][j]);
+                }
+        }
+    }
+    cp_async_wait<0>();
+
+    const bool raw = g.nsplit > 1;
+    float* __restrict__ C = g.C + (raw ? split * g.splitStride : 0) + b * g.strideC;
+    const float* __restrict__ bias = (g.bias && !raw) ? g.bias + b * g.strideBias : nullptr;
+    const int n = n0 + tx * 4;
+    if (n >= g.N) return;
+    const bool vec = ((g.N & 3) == 0) && ((g.ldc & 3) == 0);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + ty * 4 + i;
+        if (m >= g.M) continue;
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float x = acc[i][j];
+            if (bias && n + j < g.N) x += __ldg(bias + n + j);
+            if (!raw) {
+                if (g.flags & GEMM_RELU) x = fmaxf(x, 0.f);
+                if (g.flags & GEMM_CLAMP5E3) x = fminf(x, 5e3f);
+            }
+            v[j] = x;
+        }
+        const long long o = (long long)m * g.ldc + n;
+        if (vec) {
+            *reinterpret_cast<float4*>(C + o) = make_float4(v[0], v[1], v[2], v[3]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (n + j < g.N) C[o + j] = v[j];
+        }
+    }
+}
+
+
+
 template <int BM, int BN, int BK, int RM, int RN>
 static int launch_cfg(const GemmArgs& g, int amode, cudaStream_t stream) {
     constexpr int NT = (BM / (4 * RM)) * (BN / (4 * RN));
@@ -29,8 +138,24 @@ int launch_gemm_simt(const GemmArgs& g, int amode, cudaStream_t stream) {
         MV2D_CHECK_ARG(g.K == 9 * MV2D_C && g.M % MV2D_TOK == 0, "gemm: im2col expects K=2304, M=49*n");
     const long long tiles_big = (long long)cdiv(g.M, 128) * cdiv(g.N, 128) * g.batch * g.nsplit;
     if (g.M >= 1024 && g.N >= 128 && tiles_big >= 96) return launch_cfg<128, 128, 8, 2, 2>(g, amode, stream);
-    if (g.M >= 512) return launch_cfg<64, 64, 16, 1, 1>(g, amode, stream);
-    return launch_cfg<32, 64, 16, 1, 1>(g, amode, stream);
+    if (g.M >= 1024 || amode != A_PLAIN || (g.flags & GEMM_GATE) || (g.K / g.nsplit) % GS_BK != 0)
+        return launch_cfg<64, 64, 16, 1, 1>(g, amode, stream);
+    return launch_gemm_small(g, nullptr, 0, stream);
+}
+
+int launch_gemm_small(const GemmArgs& g, const float* A2, int n_switch, cudaStream_t stream) {
+    MV2D_CHECK_ARG(g.M >= 0 && g.N > 0 && g.K > 0 && g.nsplit >= 1 && g.batch >= 1, "gemm_small: bad dims");
+    if (g.M == 0) return 0;
+    MV2D_CHECK_ARG(g.K % g.nsplit == 0 && (g.K / g.nsplit) % GS_BK == 0, "gemm_small: K=%d / nsplit=%d must be a multiple of 32", g.K, g.nsplit);
+    MV2D_CHECK_ARG((g.lda & 3) == 0 && (g.ldw & 3) == 0, "gemm_small: lda/ldw must be multiples of 4");
+    MV2D_CHECK_ARG(!(g.flags & GEMM_GATE), "gemm_small: gate epilogue not supported");
+    MV2D_CHECK_ARG(A2 == nullptr || n_switch % GS_BN == 0, "gemm_small: n_switch must be a multiple of 32");
+    GemmSmallArgs a{};
+    a.g = g; a.A2 = A2; a.n_switch = n_switch;
+    dim3 grid(cdiv(g.N, GS_BN), cdiv(g.M, GS_BM), g.batch * g.nsplit);
+    gemm_small_kernel<<<grid, 64, 0, stream>>>(a);
+    MV2D_CHECK_LAUNCH("gemm_small");
+    return 0;
 }
 
 }  // namespace mv2d

@@ -204,8 +204,24 @@ gemm_simt_kernel(GemmArgs g) {
         }
 }
 
+// ------------------------------------------------------------------------------------------
+// Small-M variant (M ~ 300: every decoder / query-generator GEMM).  These problems are latency
+// bound, not FLOP bound: one 32x32 tile per CTA (64 threads, 4x4 outputs each) so that even a
+// [300,256]x[256,256] product spreads over 80 CTAs, and a 4-stage cp.async pipeline with
+// BK = 32 keeps three 8 KB k-tiles in flight per CTA.  Shared tiles are stored [row][k] with
+// the 16-byte chunks XOR-swizzled by (row >> 2) & 7, so both the cp.async stores and the
+// LDS.128 reads (4 consecutive k per thread) are bank-conflict free.
+// A may switch to a second matrix (A2) for output columns >= n_switch: the self-attention
+// in-projection takes q,k from (x + query_pos) and v from x in ONE launch.
+struct GemmSmallArgs {
+    GemmArgs g;
+    const float* A2; int n_switch;    // A2 == nullptr: unused
+};
+
 // host-side launchers (gemm_simt.cu / gemm_tc.cu)
 int launch_gemm_simt(const GemmArgs& g, int amode, cudaStream_t stream);
+// small-M kernel with the optional second A operand
+int launch_gemm_small(const GemmArgs& g, const float* A2, int n_switch, cudaStream_t stream);
 // routes big TF32-tolerant problems to the tcgen05 kernel, everything else to the FFMA kernel
 int launch_gemm_tc_or_simt(const GemmArgs& g, cudaStream_t stream);
 

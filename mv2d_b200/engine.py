@@ -62,6 +62,9 @@ class HotPath:
         self._sine_cache = {}
         self._mask_cache = {}
         self._buf = {}
+        self._pin = {}
+        self._graphs = {}
+        self.graph_launches = 0
         c = self.cfg
         S, Dn = c['sample_size'], c['corr_num_depth']
         idx = torch.arange(Dn).float()
@@ -71,8 +74,9 @@ class HotPath:
         self.depths = (c['corr_depth_start'] + bin_size * idx * (idx + 1)).to(self.device)
 
     def launch_count(self):
-        """Kernel launches enqueued by libmv2d_b200 in this process (counted inside the library)."""
-        return int(self.lib.mv2d_launch_count())
+        """Kernel launches of libmv2d_b200 in this process: counted inside the library for eager
+        calls, plus (kernels captured in a graph) x (replays) for CUDA-graph replays."""
+        return int(self.lib.mv2d_launch_count()) + self.graph_launches
 
     # ------------------------------------------------------------------ buffers
     def _get(self, name, shape, dtype=torch.float32):
@@ -94,15 +98,24 @@ class HotPath:
         return ent
 
     # ------------------------------------------------------------------ stages
+    def _pinned(self, name, shape, dtype):
+        n = int(np.prod(shape))
+        t = self._pin.get(name)
+        if t is None or t.numel() < n or t.dtype != dtype:
+            t = torch.empty(max(n, 1), dtype=dtype).pin_memory()
+            self._pin[name] = t
+        return t[:n].view(*shape)
+
     def _upload_cams(self, img_metas):
         V = len(img_metas)
-        cams = np.empty((3, V, 16), dtype=np.float64)
+        cams_t = self._pinned('cams', (3, V, 16), torch.float64)
+        cams = cams_t.numpy()
         for v, m in enumerate(img_metas):
             cams[0, v] = np.asarray(m['lidar2img'], dtype=np.float64).reshape(16)
             cams[1, v] = np.asarray(m['intrinsics'], dtype=np.float64).reshape(16)
             cams[2, v] = np.asarray(m['extrinsics'], dtype=np.float64).reshape(16)
         d = self._get('cams', (3, V, 16), torch.float64)
-        d.copy_(torch.from_numpy(cams), non_blocking=True)
+        d.copy_(cams_t, non_blocking=True)
         return d
 
     def _upload_rois(self, proposal_list):
@@ -119,16 +132,19 @@ class HotPath:
             rois[:, 0] = view
             rois[:, 1:] = torch.cat([p[:, :4].float() for p in proposal_list], 0)
         else:
-            host = np.empty((N, 5), dtype=np.float32)
+            host_t = self._pinned('rois', (N, 5), torch.float32)
+            host = host_t.numpy()
             o = 0
             for v, p in enumerate(proposal_list):
                 n = counts[v]
                 host[o:o + n, 0] = v
                 host[o:o + n, 1:] = p[:, :4].float().numpy()
                 o += n
-            rois.copy_(torch.from_numpy(host), non_blocking=True)
+            rois.copy_(host_t, non_blocking=True)
         roi_start = self._get('roi_start', (len(counts) + 1,), torch.int32)
-        roi_start.copy_(torch.from_numpy(starts), non_blocking=True)
+        starts_t = self._pinned('roi_start', (len(counts) + 1,), torch.int32)
+        starts_t.copy_(torch.from_numpy(starts))
+        roi_start.copy_(starts_t, non_blocking=True)
         return rois, roi_start, counts, N
 
     def geom_prep(self, cams):
@@ -263,22 +279,23 @@ class HotPath:
         return cls, box, outs
 
     # ------------------------------------------------------------------ whole path
-    @torch.no_grad()
-    def forward(self, feat_nchw, proposal_list, img_metas, feat_is_nhwc=False):
-        """feat [V,256,h,w] fp32 on the device (NCHW as the FPN emits it), proposal_list: V
-        tensors [n_v, >=4] (device or host), img_metas: V dicts.  Returns a dict with
-        cls_scores / bbox_preds [L,N,10] and the stage tensors (views of reused buffers)."""
+    def _vel_dt(self, img_metas):
+        nvf = self.cfg['num_views_per_frame']
+        if self.mode != 'T' or len(img_metas) <= nvf:
+            return 0.0
+        ts = np.array([m['timestamp'] for m in img_metas], dtype=np.float64)   # mv2d_t_head.py:131-132
+        return float(ts[nvf:].mean() - ts[:nvf].mean())
+
+    def _enqueue(self, feat_in, feat_is_nhwc, cams, rois, roi_start, counts, N, img_metas):
+        """Enqueue every stage of the path on the current stream (capturable: no host sync)."""
         V = len(img_metas)
-        feat_nchw = feat_nchw.to(self.device, torch.float32)
         feat_tf32 = None
         if feat_is_nhwc:
-            feat = feat_nchw.contiguous()
+            feat = feat_in
             _, h, w, _ = feat.shape
         else:
-            _, _, h, w = feat_nchw.shape
-            feat, feat_tf32 = self.to_nhwc(feat_nchw.contiguous())
-        cams = self._upload_cams(img_metas)
-        rois, roi_start, counts, N = self._upload_rois(proposal_list)
+            _, _, h, w = feat_in.shape
+            feat, feat_tf32 = self.to_nhwc(feat_in)
         i2l, trans = self.geom_prep(cams)
         pe, kin = self.pe3d(feat, i2l, img_metas, feat_tf32)
         qg = self.roi_align_qg(rois, cams, feat, pe, N)
@@ -286,16 +303,55 @@ class HotPath:
         if self.mode == 'S':
             cls, box, outs = self.decoder(qg, corr, qg['tok_kin'].view(-1, 256), qg['tok_feat'].view(-1, 256), N)
         else:
-            nvf = self.cfg['num_views_per_frame']
-            vel_dt = 0.0
-            if V > nvf:   # mv2d_t_head.py:131-132
-                ts = np.array([m['timestamp'] for m in img_metas], dtype=np.float64)
-                vel_dt = float(ts[nvf:].mean() - ts[:nvf].mean())
-            cls, box, outs = self.decoder(qg, corr, kin.view(-1, 256), feat.view(-1, 256), N, vel_dt=vel_dt)
+            cls, box, outs = self.decoder(qg, corr, kin.view(-1, 256), feat.view(-1, 256), N,
+                                          vel_dt=self._vel_dt(img_metas))
         out = dict(cls_scores=cls, bbox_preds=box, outs_dec=outs, rois=rois, pe=pe, feat_nhwc=feat, N=N,
                    num_per_view=counts)
         out.update(qg)
         out.update(corr)
+        return out
+
+    @torch.no_grad()
+    def forward(self, feat, proposal_list, img_metas, feat_is_nhwc=False, use_graph=False):
+        """feat [V,256,h,w] fp32 (NCHW as the FPN emits it; device, or pinned host memory),
+        proposal_list: V tensors [n_v, >=4] (device or host), img_metas: V dicts.  Returns a dict
+        with cls_scores / bbox_preds [L,N,10] and the stage tensors (views of reused buffers).
+
+        use_graph=True replays a CUDA graph of the whole path captured for this (N, V, h, w,
+        masks) signature: inputs are copied into the graph's static buffers, then one launch."""
+        if not use_graph:
+            feat = feat.to(self.device, torch.float32, non_blocking=True).contiguous()
+            cams = self._upload_cams(img_metas)
+            rois, roi_start, counts, N = self._upload_rois(proposal_list)
+            return self._enqueue(feat, feat_is_nhwc, cams, rois, roi_start, counts, N, img_metas)
+        assert not feat_is_nhwc
+        counts = [int(p.shape[0]) for p in proposal_list]
+        N = max(sum(counts), 1)
+        mkey = self._masks(img_metas, feat.shape[2], feat.shape[3])[0]
+        key = (N, tuple(feat.shape), mkey, self._vel_dt(img_metas))
+        ent = self._graphs.get(key)
+        if ent is None:
+            # warm-up (eager) run: sizes every buffer and sets kernel attributes, then capture
+            static_feat = torch.empty(tuple(feat.shape), dtype=torch.float32, device=self.device)
+            static_feat.copy_(feat, non_blocking=True)
+            cams = self._upload_cams(img_metas)
+            rois, roi_start, counts, N = self._upload_rois(proposal_list)
+            self._enqueue(static_feat, False, cams, rois, roi_start, counts, N, img_metas)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            launches0 = self.launch_count()
+            with torch.cuda.graph(graph):
+                out = self._enqueue(static_feat, False, cams, rois, roi_start, counts, N, img_metas)
+            ent = dict(graph=graph, out=out, feat=static_feat, launches=self.launch_count() - launches0,
+                       keep=dict(self._buf))     # the graph bakes these buffer addresses in
+            self._graphs[key] = ent
+        ent['feat'].copy_(feat, non_blocking=True)
+        self._upload_cams(img_metas)
+        _, _, counts, _ = self._upload_rois(proposal_list)
+        ent['graph'].replay()
+        self.graph_launches += ent['launches']
+        out = dict(ent['out'])
+        out['num_per_view'] = counts
         return out
 
     @torch.no_grad()

@@ -170,7 +170,8 @@ def test_tcgen05_gemm_3xtf32_and_im2col(state_dicts):
         Cc = torch.full((M, N), float('nan'), device='cuda')
         lib.check(h.mv2d_gemm_3xtf32(ah.data_ptr(), al.data_ptr(), K, wh.data_ptr(), wl.data_ptr(), K, b.data_ptr(),
                                      Cc.data_ptr(), N, M, N, K, 0, lib.stream_ptr()), 'gemm_3xtf32')
-        assert_close(Cc, A.double() @ W.double().T + b.double(), 2e-5, 2e-5, f'3xtf32 {M}x{N}x{K}')
+        # fp32 accumulation inside the tensor core (K up to 2304, three products per step)
+        assert_close(Cc, A.double() @ W.double().T + b.double(), 1e-4, 1e-4, f'3xtf32 {M}x{N}x{K}')
     for n_rois in (1, 2, 7, 300):
         x = torch.randn(n_rois, 256, 7, 7, generator=g).cuda()
         w = (torch.randn(256, 256, 3, 3, generator=g) / 48).cuda()
@@ -183,7 +184,7 @@ def test_tcgen05_gemm_3xtf32_and_im2col(state_dicts):
                                      b.data_ptr(), out.data_ptr(), 256, n_rois * 49, 256, 2304, 1 | 128,
                                      lib.stream_ptr()), 'gemm_3xtf32(im2col)')
         ref = F.conv2d(x.double(), w.double(), b.double(), padding=1).relu().permute(0, 2, 3, 1).reshape(-1, 256)
-        assert_close(out, ref, 3e-5, 3e-5, f'im2col conv n={n_rois}')
+        assert_close(out, ref, 1e-4, 1e-4, f'im2col conv n={n_rois}')
 
 
 def test_full_size_properties(state_dicts):
@@ -204,5 +205,9 @@ def test_full_size_properties(state_dicts):
     gperm = torch.cat([p + int(s) for p, s in zip(perms, starts[:-1])]).cuda()
     assert_close(o3['cls_scores'], c1[:, gperm], 2e-4, 2e-4, 'permuted cls')
     assert_close(o3['bbox_preds'], b1[:, gperm], 2e-4, 2e-4, 'permuted box')
+    # CUDA-graph replay of the whole path is bitwise identical to the eager launches
+    o4 = eng.forward(featc, boxes, metas, use_graph=True)
+    o4 = eng.forward(featc, boxes, metas, use_graph=True)
+    assert torch.equal(c1, o4['cls_scores']) and torch.equal(b1, o4['bbox_preds']), 'graph replay differs'
     # every query attends at least to its own RoI
     assert int(o1['match_cnt'].min()) >= 1 and bool((o1['match'][:, 0].cpu() == torch.arange(300)).all())

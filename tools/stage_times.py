@@ -39,6 +39,19 @@ for _ in range(reps):
     torch.cuda.synchronize()
     for i, n in enumerate(names):
         acc[n] = acc.get(n, 0.0) + evs[i].elapsed_time(evs[i + 1])
+# whole path, eager vs CUDA graph
+def timed(fn, reps=30):
+    for _ in range(3): fn()
+    torch.cuda.synchronize()
+    a, b = ev(), ev()
+    a.record()
+    for _ in range(reps): fn()
+    b.record(); torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps * 1e3
+t_eager = timed(lambda: eng.forward(featc, boxes, metas))
+t_graph = timed(lambda: eng.forward(featc, boxes, metas, use_graph=True))
+og = eng.forward(featc, boxes, metas, use_graph=True); oe_cls = eng.forward(featc, boxes, metas)['cls_scores'].clone()
+print(f'whole path: eager {t_eager:.1f} us   graph {t_graph:.1f} us   graph==eager: {torch.equal(og["cls_scores"], oe_cls)}')
 tot = sum(acc.values())
 for n, t in acc.items():
     print(f'{n:16s} {t / reps * 1e3:9.1f} us  {100 * t / tot:5.1f} %')
