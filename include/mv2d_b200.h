@@ -97,7 +97,7 @@ typedef struct Mv2dQgParams {
     const float *w_conv, *b_conv;     /* shared_convs.0.conv repacked [256, 9*256] (tap-major K), TF32 "hi" part */
     const float *w_conv_lo;           /* TF32 "lo" part: w = hi + lo (3xTF32 error-compensated tcgen05 GEMM) */
     const float *w_fc, *b_fc;         /* shared_fcs.0 [1024,256] */
-    const float *w_enc0, *b_enc0;     /* extra_enc.0 [512,1040] */
+    const float *w_enc0, *b_enc0;     /* extra_enc.0 [512,1040] zero-padded along K to [512,1056] */
     const float *w_enc2, *b_enc2;     /* extra_enc.2 [256,512] */
     const float *w_center, *b_center; /* fc_center [3,256] */
     const float *w_qe0, *b_qe0;       /* query_embedding.0 [256,384] */
@@ -141,10 +141,11 @@ MV2D_API int mv2d_box_corr(const Mv2dCorrParams* p, void* stream);
 typedef struct Mv2dLayerWeights {
     const float *sa_in_w, *sa_in_b;     /* attentions.0.attn.in_proj [768,256] */
     const float *sa_out_w, *sa_out_b;   /* attentions.0.attn.out_proj [256,256] */
-    const float *ca_q_w, *ca_q_b;       /* absorbed  scale*Wk_h^T Wq_h : [2048,256], [2048] */
-    const float *ca_o_w, *ca_o_b;       /* absorbed  Wo[:,h] Wv_h      : [256,2048], [256]  */
-    const float *ffn_w1, *ffn_b1;       /* ffns.0.layers.0.0 [2048,256] */
-    const float *ffn_w2, *ffn_b2;       /* ffns.0.layers.1   [256,2048] */
+    /* the four wide matrices run as 3xTF32 tcgen05 GEMMs: w = hi + lo, both TF32-representable */
+    const float *ca_q_w, *ca_q_w_lo, *ca_q_b;   /* absorbed  scale*Wk_h^T Wq_h : [2048,256], [2048] */
+    const float *ca_o_w, *ca_o_w_lo, *ca_o_b;   /* absorbed  Wo[:,h] Wv_h      : [256,2048], [256]  */
+    const float *ffn_w1, *ffn_w1_lo, *ffn_b1;   /* ffns.0.layers.0.0 [2048,256] */
+    const float *ffn_w2, *ffn_w2_lo, *ffn_b2;   /* ffns.0.layers.1   [256,2048] */
     const float *ln_g[3], *ln_b[3];     /* norms.{0,1,2} */
 } Mv2dLayerWeights;
 

@@ -11,6 +11,7 @@
 // and the work per layer is bound by the bytes of the key rows it reads (HBM/L2), not flops.
 #include "common.cuh"
 #include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
 #include "mv2d_internal.h"
 
 namespace mv2d {
@@ -27,6 +28,8 @@ struct LnArgs {
     const float* qpos;   // nullable
     const float* gamma2; const float* beta2;  // nullable: post_norm
     float* out; float* out_q; float* out2;
+    float* out_hi; float* out_lo;      // nullable: TF32 split of `out`   (A operand of a 3xTF32 GEMM)
+    float* outq_hi; float* outq_lo;    // nullable: TF32 split of `out_q`
     int rows;
 };
 
@@ -84,10 +87,24 @@ __global__ void __launch_bounds__(256) ln_kernel(LnArgs a) {
     for (int i = 0; i < 2; ++i) {
         const int c = i * 128 + lane * 4;
         *reinterpret_cast<float4*>(a.out + o + c) = make_float4(y[i * 4], y[i * 4 + 1], y[i * 4 + 2], y[i * 4 + 3]);
+        if (a.out_hi) {
+            float hi[4], lo[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { hi[k] = round_tf32(y[i * 4 + k]); lo[k] = round_tf32(y[i * 4 + k] - hi[k]); }
+            *reinterpret_cast<float4*>(a.out_hi + o + c) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<float4*>(a.out_lo + o + c) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+        }
         if (a.out_q) {
             float4 qp = *reinterpret_cast<const float4*>(a.qpos + o + c);
-            *reinterpret_cast<float4*>(a.out_q + o + c) =
-                make_float4(y[i * 4] + qp.x, y[i * 4 + 1] + qp.y, y[i * 4 + 2] + qp.z, y[i * 4 + 3] + qp.w);
+            const float z[4] = {y[i * 4] + qp.x, y[i * 4 + 1] + qp.y, y[i * 4 + 2] + qp.z, y[i * 4 + 3] + qp.w};
+            *reinterpret_cast<float4*>(a.out_q + o + c) = make_float4(z[0], z[1], z[2], z[3]);
+            if (a.outq_hi) {
+                float hi[4], lo[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { hi[k] = round_tf32(z[k]); lo[k] = round_tf32(z[k] - hi[k]); }
+                *reinterpret_cast<float4*>(a.outq_hi + o + c) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<float4*>(a.outq_lo + o + c) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+            }
         }
     }
     if (a.out2) {
@@ -105,65 +122,98 @@ __global__ void __launch_bounds__(256) ln_kernel(LnArgs a) {
 // ------------------------------------------------------------------------------------------
 // FlattenMHSelfAttention core (petr_transformer.py:314-370): all N queries form ONE sequence.
 // qkv [N,768] (q | k | v, head h = channels 32h..32h+31), q already includes the bias; the
-// 1/sqrt(32) scale is applied here.  grid (ceil(N/8), 8 heads), 256 threads: one query per warp;
-// lanes = keys for QK^T (two independent 32-key groups in flight), lanes = channels for PV;
-// K/V tiles of 128 keys staged in padded shared memory; online softmax across tiles.
+// 1/sqrt(32) scale is applied here.  grid (ceil(N/8), 8 heads), 256 threads, one query per warp.
+// K/V tiles of 128 keys live in shared memory with a 36-float row stride (16-byte aligned,
+// conflict-free LDS.128).  QK^T: lane = key (4 keys per lane per tile), q in registers.
+// PV: probabilities go through shared memory; lane = (key phase, channel quad) so each step is
+// one LDS + one LDS.128 + 4 FMA; the 4 key phases are folded with two shuffles at the end.
 #define SA_KT 128
+#define SA_LD 36
 __global__ void __launch_bounds__(256)
 self_attn_kernel(const float* __restrict__ qkv, const uint8_t* __restrict__ mask, int N, float* __restrict__ out) {
-    __shared__ float Ks[SA_KT][33];
-    __shared__ float Vs[SA_KT][33];
-    __shared__ float Qs[8][32];
+    __shared__ __align__(16) float Ks[SA_KT][SA_LD];
+    __shared__ __align__(16) float Vs[SA_KT][SA_LD];
+    __shared__ float Ps[8][SA_KT];
     const int hd = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qi = blockIdx.x * 8 + warp;
     const bool qok = qi < N;
-    Qs[warp][lane] = qok ? __ldg(qkv + (long long)qi * 768 + hd * 32 + lane) * 0.17677669529663687f : 0.f;
-    float m = -INFINITY, l = 0.f, acc = 0.f;
+    float q[32];
+#pragma unroll
+    for (int d4 = 0; d4 < 8; ++d4) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (qok) v = __ldg(reinterpret_cast<const float4*>(qkv + (long long)qi * 768 + hd * 32) + d4);
+        q[d4 * 4 + 0] = v.x * 0.17677669529663687f; q[d4 * 4 + 1] = v.y * 0.17677669529663687f;
+        q[d4 * 4 + 2] = v.z * 0.17677669529663687f; q[d4 * 4 + 3] = v.w * 0.17677669529663687f;
+    }
+    const int kq = lane >> 3, cq = lane & 7;
+    float m = -INFINITY, l = 0.f;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int k0 = 0; k0 < N; k0 += SA_KT) {
         __syncthreads();
-        for (int i = threadIdx.x; i < SA_KT * 32; i += 256) {
-            const int r = i >> 5, c = i & 31, k = k0 + r;
-            Ks[r][c] = (k < N) ? __ldg(qkv + (long long)k * 768 + 256 + hd * 32 + c) : 0.f;
-            Vs[r][c] = (k < N) ? __ldg(qkv + (long long)k * 768 + 512 + hd * 32 + c) : 0.f;
+        for (int i = threadIdx.x; i < SA_KT * 8; i += 256) {
+            const int r = i >> 3, c4 = i & 7, k = k0 + r;
+            float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
+            if (k < N) {
+                kv = __ldg(reinterpret_cast<const float4*>(qkv + (long long)k * 768 + 256 + hd * 32) + c4);
+                vv = __ldg(reinterpret_cast<const float4*>(qkv + (long long)k * 768 + 512 + hd * 32) + c4);
+            }
+            *reinterpret_cast<float4*>(&Ks[r][c4 * 4]) = kv;
+            *reinterpret_cast<float4*>(&Vs[r][c4 * 4]) = vv;
         }
         __syncthreads();
         if (!qok) continue;
         const int ng = min(SA_KT, N - k0);
         float s[SA_KT / 32];
-#pragma unroll
-        for (int g = 0; g < SA_KT / 32; ++g) s[g] = 0.f;
-#pragma unroll
-        for (int d = 0; d < 32; ++d) {
-            const float qd = Qs[warp][d];
-#pragma unroll
-            for (int g = 0; g < SA_KT / 32; ++g) s[g] = fmaf(qd, Ks[g * 32 + lane][d], s[g]);
-        }
         float mx = -INFINITY;
 #pragma unroll
         for (int g = 0; g < SA_KT / 32; ++g) {
             const int kk = g * 32 + lane;
-            if (kk >= ng || (mask && mask[(long long)qi * N + k0 + kk])) s[g] = -INFINITY;
-            mx = fmaxf(mx, s[g]);
+            float x = 0.f;
+#pragma unroll
+            for (int d4 = 0; d4 < 8; ++d4) {
+                const float4 kv = *reinterpret_cast<const float4*>(&Ks[kk][d4 * 4]);
+                x = fmaf(q[d4 * 4 + 0], kv.x, x); x = fmaf(q[d4 * 4 + 1], kv.y, x);
+                x = fmaf(q[d4 * 4 + 2], kv.z, x); x = fmaf(q[d4 * 4 + 3], kv.w, x);
+            }
+            if (kk >= ng || (mask && mask[(long long)qi * N + k0 + kk])) x = -INFINITY;
+            s[g] = x;
+            mx = fmaxf(mx, x);
         }
         const float mn = fmaxf(m, warp_max(mx));
         if (mn == -INFINITY) continue;
         const float alpha = __expf(m - mn);      // exp(-inf) = 0 on the first tile
         float psum = 0.f;
 #pragma unroll
-        for (int g = 0; g < SA_KT / 32; ++g) { s[g] = __expf(s[g] - mn); psum += s[g]; }
-        l = l * alpha + warp_sum(psum);
-        float a0 = acc * alpha, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            a0 = fmaf(__shfl_sync(0xffffffffu, s[0], j), Vs[j][lane], a0);
-            a1 = fmaf(__shfl_sync(0xffffffffu, s[1], j), Vs[32 + j][lane], a1);
-            a2 = fmaf(__shfl_sync(0xffffffffu, s[2], j), Vs[64 + j][lane], a2);
-            a3 = fmaf(__shfl_sync(0xffffffffu, s[3], j), Vs[96 + j][lane], a3);
+        for (int g = 0; g < SA_KT / 32; ++g) {
+            const float pv = __expf(s[g] - mn);
+            Ps[warp][g * 32 + lane] = pv;
+            psum += pv;
         }
-        acc = (a0 + a1) + (a2 + a3);
+        l = l * alpha + warp_sum(psum);
+        acc.x *= alpha; acc.y *= alpha; acc.z *= alpha; acc.w *= alpha;
+        __syncwarp();
+#pragma unroll 8
+        for (int t = 0; t < SA_KT / 4; ++t) {
+            const int j = t * 4 + kq;
+            const float pj = Ps[warp][j];
+            const float4 vv = *reinterpret_cast<const float4*>(&Vs[j][cq * 4]);
+            acc.x = fmaf(pj, vv.x, acc.x); acc.y = fmaf(pj, vv.y, acc.y);
+            acc.z = fmaf(pj, vv.z, acc.z); acc.w = fmaf(pj, vv.w, acc.w);
+        }
+        __syncwarp();
         m = mn;
     }
-    if (qok) out[(long long)qi * MV2D_C + hd * 32 + lane] = l > 0.f ? acc / l : 0.f;
+    // fold the 4 key phases (lanes differing in bits 3,4)
+#pragma unroll
+    for (int o = 8; o <= 16; o <<= 1) {
+        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+        acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o); acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+    }
+    if (qok && kq == 0) {
+        const float inv = l > 0.f ? 1.f / l : 0.f;
+        *reinterpret_cast<float4*>(out + (long long)qi * MV2D_C + hd * 32 + cq * 4) =
+            make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -177,7 +227,8 @@ self_attn_kernel(const float* __restrict__ qkv, const uint8_t* __restrict__ mask
 // chunk loads while this one is consumed).  Per chunk: logits (warp per key, lanes along the
 // 256 channels, warp-shuffle transpose-reduce over 8 heads), online softmax (warp per head,
 // lane per key), probability-weighted sum of the memory rows.  Per-lane state: 8 heads x 8 ch.
-#define XA_CH 32
+#define XA_CH 16
+#define XA_THREADS 128
 __device__ __forceinline__ void xa_cp16(void* smem, const void* gmem) {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
@@ -210,44 +261,43 @@ struct XaArgs {
     const int* match; const int* match_cnt; int max_match;
     const uint32_t* keymask; int mask_words;
     int mode; int N; int klist_cap;
-    float* ctx;
+    float* ctx; float* ctx_lo;    // ctx_lo != nullptr: write the TF32 hi/lo split (operands of the 3xTF32 output GEMM)
 };
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(XA_THREADS)
 cross_attn_kernel(XaArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* kbuf = reinterpret_cast<float*>(smem_raw);               // [2][XA_CH][256] key-input rows
     float* vbuf = kbuf + 2 * XA_CH * MV2D_C;                        // [2][XA_CH][256] memory rows
     float* sc = vbuf + 2 * XA_CH * MV2D_C;                          // [XA_CH][8] logits -> probs
-    float* red = sc + XA_CH * 8;                                    // [2048] cross-warp sum
-    float* stat = red + 2048;                                       // m[8], l[8], alpha[8]
+    float* stat = sc + XA_CH * 8;                                   // m[8], l[8], alpha[8]
     uint16_t* klist = reinterpret_cast<uint16_t*>(stat + 24);       // [klist_cap]
     __shared__ int nkeys_s;
     __shared__ int grp_cnt[128];
+    constexpr int NW = XA_THREADS / 32;
     const int n = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, t = threadIdx.x;
 
     // ---- key list
     if (t == 0) nkeys_s = 0;
-    for (int i = t; i < 2048; i += 256) red[i] = 0.f;
     if (t < 8) { stat[t] = -INFINITY; stat[8 + t] = 0.f; stat[16 + t] = 1.f; }
     __syncthreads();
     if (a.mode == 0) {
         const int cnt = a.match_cnt[n];
-        for (int i = t; i < cnt * MV2D_TOK; i += 256)
+        for (int i = t; i < cnt * MV2D_TOK; i += XA_THREADS)
             klist[i] = (uint16_t)(a.match[(long long)n * a.max_match + i / MV2D_TOK] * MV2D_TOK + i % MV2D_TOK);
         if (t == 0) nkeys_s = cnt * MV2D_TOK;
     } else {
         // deterministic compaction of the set bits: per-32-word group counts, then a prefix
         const uint32_t* km = a.keymask + (long long)n * a.mask_words;
         const int ngroups = (a.mask_words + 31) / 32;           // host guarantees <= 128
-        for (int g = warp; g < ngroups; g += 8) {
+        for (int g = warp; g < ngroups; g += NW) {
             const int w = g * 32 + lane;
             const int c = __popc((w < a.mask_words) ? km[w] : 0u);
             const int tot = __reduce_add_sync(0xffffffffu, c);
             if (lane == 0) grp_cnt[g] = tot;
         }
         __syncthreads();
-        for (int g = warp; g < ngroups; g += 8) {
+        for (int g = warp; g < ngroups; g += NW) {
             int base = 0;
             for (int i = 0; i < g; ++i) base += grp_cnt[i];
             const int w = g * 32 + lane;
@@ -266,10 +316,10 @@ cross_attn_kernel(XaArgs a) {
     const int nkeys = nkeys_s;
     const int nchunks = (nkeys + XA_CH - 1) / XA_CH;
 
-    // stage chunk c into buffer c&1: 32 keys x (1 KB + 1 KB) = 4096 16-byte copies, 16 per thread
+    // stage chunk c into buffer c&1: 16 keys x (1 KB + 1 KB) = 2048 16-byte copies, 16 per thread
     auto stage = [&](int c) {
         const int base = c * XA_CH, cn = min(XA_CH, nkeys - base), buf = c & 1;
-        for (int i = t; i < cn * 64; i += 256) {
+        for (int i = t; i < cn * 64; i += XA_THREADS) {
             const int j = i >> 6, q4 = i & 63;
             const long long row = (long long)klist[base + j] * MV2D_C + q4 * 4;
             xa_cp16(kbuf + (buf * XA_CH + j) * MV2D_C + q4 * 4, a.kin_rows + row);
@@ -299,33 +349,39 @@ cross_attn_kernel(XaArgs a) {
         if (c + 1 < nchunks) { stage(c + 1); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
         else asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
-        // pass 1: logits of 4 keys per warp
-        for (int j = warp; j < cn; j += 8) {
+        // pass 1: logits, 4 keys per warp
+        for (int j = warp; j < cn; j += NW) {
             const float* row = kbuf + (buf * XA_CH + j) * MV2D_C;
             const float4 k0 = *reinterpret_cast<const float4*>(row + lane * 4);
             const float4 k1 = *reinterpret_cast<const float4*>(row + 128 + lane * 4);
-            float s[8];
+            float sv[8];
 #pragma unroll
             for (int h = 0; h < 8; ++h) {
                 float x = qv[h][0] * k0.x;
                 x = fmaf(qv[h][1], k0.y, x); x = fmaf(qv[h][2], k0.z, x); x = fmaf(qv[h][3], k0.w, x);
                 x = fmaf(qv[h][4], k1.x, x); x = fmaf(qv[h][5], k1.y, x); x = fmaf(qv[h][6], k1.z, x);
                 x = fmaf(qv[h][7], k1.w, x);
-                s[h] = x;
+                sv[h] = x;
             }
-            reduce8(s, lane);
-            if ((lane & 3) == 0) sc[j * 8 + (lane >> 2)] = s[0];
+            reduce8(sv, lane);
+            if ((lane & 3) == 0) sc[j * 8 + (lane >> 2)] = sv[0];
         }
         __syncthreads();
-        // online softmax: warp = head, lane = key
+        // online softmax: each warp owns two heads (one per 16-lane half), lane & 15 = key
         {
-            const int h = warp;
-            const float sv = lane < cn ? sc[lane * 8 + h] : -INFINITY;
-            const float m_old = stat[h], m_new = fmaxf(m_old, warp_max(sv));
-            const float p = lane < cn ? __expf(sv - m_new) : 0.f;
-            if (lane < cn) sc[lane * 8 + h] = p;
-            const float sum = warp_sum(p);
-            if (lane == 0) {
+            const int h = warp + ((lane >> 4) << 2), key = lane & 15;
+            const float sv = key < cn ? sc[key * 8 + h] : -INFINITY;
+            float mx = sv;
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            const float m_old = stat[h], m_new = fmaxf(m_old, mx);
+            const float p = key < cn ? __expf(sv - m_new) : 0.f;
+            float sum = p;
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            __syncwarp();
+            if (key < cn) sc[key * 8 + h] = p;
+            if (key == 0) {
                 const float alpha = (m_old == -INFINITY) ? 0.f : __expf(m_old - m_new);
                 stat[16 + h] = alpha;
                 stat[8 + h] = stat[8 + h] * alpha + sum;
@@ -340,7 +396,7 @@ cross_attn_kernel(XaArgs a) {
 #pragma unroll
             for (int cc = 0; cc < 8; ++cc) acc[h][cc] *= al;
         }
-        for (int j = warp; j < cn; j += 8) {
+        for (int j = warp; j < cn; j += NW) {
             const float* row = vbuf + (buf * XA_CH + j) * MV2D_C;
             const float4 v0 = *reinterpret_cast<const float4*>(row + lane * 4);
             const float4 v1 = *reinterpret_cast<const float4*>(row + 128 + lane * 4);
@@ -357,20 +413,52 @@ cross_attn_kernel(XaArgs a) {
         }
         __syncthreads();   // everyone done with buffer `buf` and `sc` before they are refilled
     }
-    // ---- cross-warp sum (fixed warp order => bitwise reproducible), normalise, store
-    for (int wv = 0; wv < 8; ++wv) {
-        if (warp == wv) {
+    // ---- cross-warp tree sum through shared memory (fixed order => bitwise reproducible):
+    // warps 2,3 -> warps 0,1 ; warp 1 -> warp 0 ; warp 0 normalises and stores.
+    float4* T = reinterpret_cast<float4*>(kbuf);   // [2][512] float4, the staging buffers are free now
+    auto put = [&](int slot) {
 #pragma unroll
-            for (int h = 0; h < 8; ++h)
-#pragma unroll
-                for (int c = 0; c < 8; ++c)
-                    red[h * 256 + (c >> 2) * 128 + lane * 4 + (c & 3)] += acc[h][c];
+        for (int h = 0; h < 8; ++h) {
+            T[slot * 512 + h * 64 + lane] = make_float4(acc[h][0], acc[h][1], acc[h][2], acc[h][3]);
+            T[slot * 512 + h * 64 + 32 + lane] = make_float4(acc[h][4], acc[h][5], acc[h][6], acc[h][7]);
         }
-        __syncthreads();
-    }
-    for (int i = t; i < 2048; i += 256) {
-        const float l = stat[8 + (i >> 8)];
-        a.ctx[(long long)n * 2048 + i] = l > 0.f ? red[i] / l : 0.f;
+    };
+    auto add = [&](int slot) {
+#pragma unroll
+        for (int h = 0; h < 8; ++h) {
+            const float4 x0 = T[slot * 512 + h * 64 + lane], x1 = T[slot * 512 + h * 64 + 32 + lane];
+            acc[h][0] += x0.x; acc[h][1] += x0.y; acc[h][2] += x0.z; acc[h][3] += x0.w;
+            acc[h][4] += x1.x; acc[h][5] += x1.y; acc[h][6] += x1.z; acc[h][7] += x1.w;
+        }
+    };
+    if (warp >= 2) put(warp - 2);
+    __syncthreads();
+    if (warp < 2) add(warp);
+    __syncthreads();
+    if (warp == 1) put(0);
+    __syncthreads();
+    if (warp == 0) {
+        add(0);
+#pragma unroll
+        for (int h = 0; h < 8; ++h) {
+            const float l = stat[8 + h], inv = l > 0.f ? 1.f / l : 0.f;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                float v[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) v[k] = acc[h][half * 4 + k] * inv;
+                const long long o = (long long)n * 2048 + h * 256 + half * 128 + lane * 4;
+                if (a.ctx_lo) {
+                    float hi[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) { hi[k] = round_tf32(v[k]); v[k] = round_tf32(v[k] - hi[k]); }
+                    *reinterpret_cast<float4*>(a.ctx + o) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<float4*>(a.ctx_lo + o) = make_float4(v[0], v[1], v[2], v[3]);
+                } else {
+                    *reinterpret_cast<float4*>(a.ctx + o) = make_float4(v[0], v[1], v[2], v[3]);
+                }
+            }
+        }
     }
 }
 
@@ -424,6 +512,17 @@ static int gemm(const float* A, int lda, const float* W, int ldw, const float* b
     return launch_gemm_simt(g, A_PLAIN, st);
 }
 
+// 3xTF32 tcgen05 GEMM on pre-split operands (the four wide products of a decoder layer)
+static int tc3(const float* A_hi, const float* A_lo, int lda, const float* W_hi, const float* W_lo, int ldw,
+               const float* bias, float* Cc, float* C_lo, int ldc, int M, int N, int K, int flags, int nsplit,
+               long long split_stride, cudaStream_t st) {
+    TcGemm t{};
+    t.A = A_hi; t.A_lo = A_lo; t.lda = lda; t.W = W_hi; t.W_lo = W_lo; t.ldw = ldw; t.bias = bias;
+    t.C = Cc; t.C_lo = C_lo; t.ldc = ldc; t.M = M; t.N = N; t.K = K; t.passes = 3; t.im2col = 0; t.flags = flags;
+    t.nsplit = nsplit; t.split_stride = split_stride;
+    return launch_gemm_tc(t, st);
+}
+
 static int ln(const LnArgs& a, cudaStream_t st) {
     if (a.rows == 0) return 0;
     ln_kernel<<<cdiv(a.rows, 8), 256, 0, st>>>(a);
@@ -431,12 +530,12 @@ static int ln(const LnArgs& a, cudaStream_t st) {
     return 0;
 }
 
-#define DEC_SPLIT 4
+#define DEC_SPLIT 8
 
 size_t decoder_workspace_bytes(int N, int L) {
     size_t n = (size_t)(N > 0 ? N : 1), l = (size_t)(L > 0 ? L : 1);
-    // x, xq, x1, x1q, x2 (5*256) + qkv 768 + sa 256 + qt 2048 + ctx 2048 + hdn 2048 + partial 4*256
-    size_t per = 5 * MV2D_C + 768 + MV2D_C + 2048 + 2048 + 2048 + DEC_SPLIT * MV2D_C;
+    // x, xq, x1, x1q, x2 + 4 hi/lo copies (9*256) + qkv 768 + sa 256 + qt 2048 + ctx hi/lo + hdn hi/lo + partials
+    size_t per = 9 * MV2D_C + 768 + MV2D_C + 2048 + 2 * 2048 + 2 * 2048 + DEC_SPLIT * MV2D_C;
     // branches: 4 x [L,N,256]
     return (n * per + 4 * l * n * MV2D_C) * sizeof(float);
 }
@@ -455,11 +554,17 @@ int run_decoder(const Mv2dDecoderParams& p, cudaStream_t st) {
     float* x1 = ws;   ws += (size_t)N * C;
     float* x1q = ws;  ws += (size_t)N * C;
     float* x2 = ws;   ws += (size_t)N * C;
+    float* x1q_hi = ws; ws += (size_t)N * C;
+    float* x1q_lo = ws; ws += (size_t)N * C;
+    float* x2_hi = ws;  ws += (size_t)N * C;
+    float* x2_lo = ws;  ws += (size_t)N * C;
     float* qkv = ws;  ws += (size_t)N * 768;
     float* sa = ws;   ws += (size_t)N * C;
     float* qt = ws;   ws += (size_t)N * 2048;
     float* ctx = ws;  ws += (size_t)N * 2048;
+    float* ctx_lo = ws; ws += (size_t)N * 2048;
     float* hdn = ws;  ws += (size_t)N * 2048;
+    float* hdn_lo = ws; ws += (size_t)N * 2048;
     float* part = ws; ws += (size_t)DEC_SPLIT * N * C;
     float* b0 = ws;   ws += (size_t)L * N * C;
     float* b1 = ws;   ws += (size_t)L * N * C;
@@ -475,7 +580,7 @@ int run_decoder(const Mv2dDecoderParams& p, cudaStream_t st) {
         return (int)e;
     }
     const int klist_cap = p.mode == 0 ? p.max_match * MV2D_TOK : p.mask_words * 32;
-    const size_t xa_smem = (size_t)(4 * XA_CH * MV2D_C + XA_CH * 8 + 2048 + 24) * sizeof(float) + (size_t)klist_cap * sizeof(uint16_t);
+    const size_t xa_smem = (size_t)(4 * XA_CH * MV2D_C + XA_CH * 8 + 24) * sizeof(float) + (size_t)klist_cap * sizeof(uint16_t);
     MV2D_CHECK_ARG(xa_smem <= 227 * 1024, "decoder: key list does not fit shared memory");
     MV2D_CHECK_ARG(p.mode == 0 || p.mask_words <= 4096, "decoder: mask_words=%d > 4096", p.mask_words);
     if ((e = cudaFuncSetAttribute(cross_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xa_smem)) != cudaSuccess) {
@@ -500,26 +605,28 @@ int run_decoder(const Mv2dDecoderParams& p, cudaStream_t st) {
         {
             LnArgs a{}; a.partial = part; a.nsplit = 1; a.bias = w.sa_out_b; a.residual = x;
             a.gamma = w.ln_g[0]; a.beta = w.ln_b[0]; a.qpos = p.query_pos; a.out = x1; a.out_q = x1q; a.rows = N;
+            a.outq_hi = x1q_hi; a.outq_lo = x1q_lo;
             if ((rc = ln(a, st))) return rc;
         }
         // --- sparse cross attention (absorbed)
-        if ((rc = gemm(x1q, C, w.ca_q_w, C, w.ca_q_b, qt, 2048, N, 2048, C, 0, st))) return rc;
+        if ((rc = tc3(x1q_hi, x1q_lo, C, w.ca_q_w, w.ca_q_w_lo, C, w.ca_q_b, qt, nullptr, 2048, N, 2048, C, 0, 1, 0, st))) return rc;
         {
             XaArgs a{}; a.qt = qt; a.kin_rows = p.kin_rows; a.mem_rows = p.mem_rows; a.match = p.match;
             a.match_cnt = p.match_cnt; a.max_match = p.max_match; a.keymask = p.keymask; a.mask_words = p.mask_words;
-            a.mode = p.mode; a.N = N; a.klist_cap = klist_cap; a.ctx = ctx;
-            cross_attn_kernel<<<N, 256, xa_smem, st>>>(a);
+            a.mode = p.mode; a.N = N; a.klist_cap = klist_cap; a.ctx = ctx; a.ctx_lo = ctx_lo;
+            cross_attn_kernel<<<N, XA_THREADS, xa_smem, st>>>(a);
             MV2D_CHECK_LAUNCH("cross_attn");
         }
-        if ((rc = gemm(ctx, 2048, w.ca_o_w, 2048, nullptr, part, C, N, C, 2048, 0, st, DEC_SPLIT, NC))) return rc;
+        if ((rc = tc3(ctx, ctx_lo, 2048, w.ca_o_w, w.ca_o_w_lo, 2048, nullptr, part, nullptr, C, N, C, 2048, 0, DEC_SPLIT, NC, st))) return rc;
         {
             LnArgs a{}; a.partial = part; a.nsplit = DEC_SPLIT; a.split_stride = NC; a.bias = w.ca_o_b; a.residual = x1;
-            a.gamma = w.ln_g[1]; a.beta = w.ln_b[1]; a.out = x2; a.rows = N;
+            a.gamma = w.ln_g[1]; a.beta = w.ln_b[1]; a.out = x2; a.rows = N; a.out_hi = x2_hi; a.out_lo = x2_lo;
             if ((rc = ln(a, st))) return rc;
         }
         // --- FFN
-        if ((rc = gemm(x2, C, w.ffn_w1, C, w.ffn_b1, hdn, 2048, N, 2048, C, GEMM_RELU, st))) return rc;
-        if ((rc = gemm(hdn, 2048, w.ffn_w2, 2048, nullptr, part, C, N, C, 2048, 0, st, DEC_SPLIT, NC))) return rc;
+        if ((rc = tc3(x2_hi, x2_lo, C, w.ffn_w1, w.ffn_w1_lo, C, w.ffn_b1, hdn, hdn_lo, 2048, N, 2048, C,
+                      GEMM_RELU | GEMM_SPLIT_OUT, 1, 0, st))) return rc;
+        if ((rc = tc3(hdn, hdn_lo, 2048, w.ffn_w2, w.ffn_w2_lo, 2048, nullptr, part, nullptr, C, N, C, 2048, 0, DEC_SPLIT, NC, st))) return rc;
         {
             LnArgs a{}; a.partial = part; a.nsplit = DEC_SPLIT; a.split_stride = NC; a.bias = w.ffn_b2; a.residual = x2;
             a.gamma = w.ln_g[2]; a.beta = w.ln_b[2]; a.qpos = p.query_pos; a.out = x; a.out_q = xq;

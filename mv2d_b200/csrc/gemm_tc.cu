@@ -15,6 +15,9 @@
 // epilogue (TMEM lane quadrant = warp_idx % 4).  One output tile per CTA; several CTAs per SM
 // overlap each other's prologue/epilogue.
 #include <cuda.h>
+#include <cstring>
+#include <mutex>
+#include <unordered_map>
 #include "common.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
@@ -91,7 +94,8 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 
 struct TcArgs {
-    float* C; int ldc;
+    float* C; float* C_lo; int ldc;
+    int nkb_per_split; long long split_stride;
     const float* bias;
     int M, N, K;
     int flags;
@@ -117,7 +121,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m_tile = blockIdx.y, n0 = blockIdx.x * BN;
-    const int nkb = g.K / TC_BK;
+    const int nkb = g.nkb_per_split, kb0 = blockIdx.z * g.nkb_per_split;   // this CTA's K range (split-K)
 
     if (warp == 0 && lane == 0) {
         tmap_prefetch(&tmA); tmap_prefetch(&tmW);
@@ -146,7 +150,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 constexpr int A_TX = IM2COL ? 2 * MV2D_TOK * TC_BK * 4 : A_BYTES;
                 mbar_expect_tx(&full_bar[s], NOP * (A_TX + W_BYTES));
                 if (IM2COL) {
-                    const int tap = kb / (MV2D_C / TC_BK), c0 = (kb % (MV2D_C / TC_BK)) * TC_BK;
+                    const int kg = kb0 + kb;
+                    const int tap = kg / (MV2D_C / TC_BK), c0 = (kg % (MV2D_C / TC_BK)) * TC_BK;
                     const int dx = tap % 3 - 1, dy = tap / 3 - 1;
 #pragma unroll
                     for (int r = 0; r < 2; ++r) {   // two RoIs per 128-row tile, 64 rows apart
@@ -155,11 +160,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             tma_load_4d(&tmAlo, &full_bar[s], st + A_BYTES + r * (A_BYTES / 2), c0, dx, dy, m_tile * 2 + r);
                     }
                 } else {
-                    tma_load_2d(&tmA, &full_bar[s], st, kb * TC_BK, m_tile * TC_BM);
-                    if (PASSES == 3) tma_load_2d(&tmAlo, &full_bar[s], st + A_BYTES, kb * TC_BK, m_tile * TC_BM);
+                    tma_load_2d(&tmA, &full_bar[s], st, (kb0 + kb) * TC_BK, m_tile * TC_BM);
+                    if (PASSES == 3) tma_load_2d(&tmAlo, &full_bar[s], st + A_BYTES, (kb0 + kb) * TC_BK, m_tile * TC_BM);
                 }
-                tma_load_2d(&tmW, &full_bar[s], st + NOP * A_BYTES, kb * TC_BK, n0);
-                if (PASSES == 3) tma_load_2d(&tmWlo, &full_bar[s], st + NOP * A_BYTES + W_BYTES, kb * TC_BK, n0);
+                tma_load_2d(&tmW, &full_bar[s], st + NOP * A_BYTES, (kb0 + kb) * TC_BK, n0);
+                if (PASSES == 3) tma_load_2d(&tmWlo, &full_bar[s], st + NOP * A_BYTES + W_BYTES, (kb0 + kb) * TC_BK, n0);
             }
         }
     } else if (warp == 1) {
@@ -210,6 +215,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (!row_ok) continue;
             const int n = n0 + c * 32;
             const long long o = orow * g.ldc + n;
+            if (gridDim.z > 1) {   // split-K: raw partial sums, finished by the LN/reduce kernel
+                float* dst = g.C + blockIdx.z * g.split_stride + o;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                                      __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                continue;
+            }
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
                 float x[4];
@@ -218,6 +231,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     x[i] = __uint_as_float(v[j + i]);
                     if (g.bias) x[i] += __ldg(g.bias + n + j + i);
                     if (g.flags & GEMM_RELU) x[i] = fmaxf(x[i], 0.f);
+                }
+                if (g.flags & GEMM_SPLIT_OUT) {
+                    float hi[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) { hi[i] = round_tf32(x[i]); x[i] = round_tf32(x[i] - hi[i]); }
+                    *reinterpret_cast<float4*>(g.C + o + j) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<float4*>(g.C_lo + o + j) = make_float4(x[0], x[1], x[2], x[3]);
+                    continue;
                 }
                 if (g.flags & GEMM_GATE) {
                     const float4 xx = __ldg(reinterpret_cast<const float4*>(g.gx + o + j));
@@ -264,8 +285,39 @@ static EncodeTiledFn get_encode() {
     return fn;
 }
 
-// 2-D K-contiguous operand [rows, K] with leading dimension ld (floats); box = [32 floats, box_rows]
+// Encoding a tensor map is a pure host computation (~1 us); the decoder issues ~100 GEMMs per sample on
+// a handful of stable buffers, so the encoded maps are cached by (base, rows, K, ld, box_rows).
+struct MapKey {
+    const void* base; int rows, K, ld, box;
+    bool operator==(const MapKey& o) const { return base == o.base && rows == o.rows && K == o.K && ld == o.ld && box == o.box; }
+};
+struct MapKeyHash {
+    size_t operator()(const MapKey& k) const {
+        size_t h = (size_t)k.base;
+        h = h * 1000003u ^ (size_t)k.rows; h = h * 1000003u ^ (size_t)k.K;
+        h = h * 1000003u ^ (size_t)k.ld; h = h * 1000003u ^ (size_t)k.box;
+        return h;
+    }
+};
+static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_map_cache;
+static std::mutex g_map_mutex;
+
+static int make_map_2d_uncached(CUtensorMap* m, const float* base, int rows, int K, int ld, int box_rows);
 static int make_map_2d(CUtensorMap* m, const float* base, int rows, int K, int ld, int box_rows) {
+    MapKey key{base, rows, K, ld, box_rows};
+    std::lock_guard<std::mutex> lock(g_map_mutex);
+    auto it = g_map_cache.find(key);
+    if (it != g_map_cache.end()) { *m = it->second; return 0; }
+    int rc = make_map_2d_uncached(m, base, rows, K, ld, box_rows);
+    if (rc == 0) {
+        if (g_map_cache.size() > 4096) g_map_cache.clear();
+        g_map_cache.emplace(key, *m);
+    }
+    return rc;
+}
+
+// 2-D K-contiguous operand [rows, K] with leading dimension ld (floats); box = [32 floats, box_rows]
+static int make_map_2d_uncached(CUtensorMap* m, const float* base, int rows, int K, int ld, int box_rows) {
     EncodeTiledFn enc = get_encode();
     MV2D_CHECK_ARG(enc != nullptr, "gemm_tc: cuTensorMapEncodeTiled not available");
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
@@ -296,7 +348,7 @@ static int make_map_tokens(CUtensorMap* m, const float* base, int n_rois) {
 
 template <int BN, int PASSES, bool IM2COL, int STAGES>
 static int launch_tc(const CUtensorMap& a, const CUtensorMap& alo, const CUtensorMap& w, const CUtensorMap& wlo,
-                     const TcArgs& g, int m_tiles, cudaStream_t st) {
+                     const TcArgs& g, int m_tiles, int nsplit, cudaStream_t st) {
     constexpr int NOP = PASSES == 3 ? 2 : 1;
     constexpr size_t smem = (size_t)STAGES * NOP * (TC_BM * TC_BK * 4 + BN * TC_BK * 4) + 1024 + 256;
     auto kern = gemm_tc_kernel<BN, PASSES, IM2COL, STAGES>;
@@ -306,7 +358,7 @@ static int launch_tc(const CUtensorMap& a, const CUtensorMap& alo, const CUtenso
         if (e != cudaSuccess) { set_error("gemm_tc: smem attr: %s", cudaGetErrorString(e)); return (int)e; }
         attr_set = true;
     }
-    dim3 grid(g.N / BN, m_tiles, 1);
+    dim3 grid(g.N / BN, m_tiles, nsplit);
     kern<<<grid, TC_THREADS, smem, st>>>(a, alo, w, wlo, g);
     MV2D_CHECK_LAUNCH("gemm_tc");
     return 0;
@@ -319,7 +371,11 @@ int launch_gemm_tc(const TcGemm& t, cudaStream_t st) {
     CUtensorMap a, alo, w, wlo;
     int rc;
     TcArgs g{};
-    g.C = t.C; g.ldc = t.ldc; g.bias = t.bias; g.M = t.M; g.N = t.N; g.K = t.K; g.flags = t.flags;
+    const int nsplit = t.nsplit > 1 ? t.nsplit : 1;
+    MV2D_CHECK_ARG((t.K / TC_BK) % nsplit == 0, "gemm_tc: K=%d does not split %d ways into 32-wide blocks", t.K, nsplit);
+    MV2D_CHECK_ARG(!(t.flags & GEMM_SPLIT_OUT) || t.C_lo, "gemm_tc: split output needs C_lo");
+    g.C = t.C; g.C_lo = t.C_lo; g.ldc = t.ldc; g.bias = t.bias; g.M = t.M; g.N = t.N; g.K = t.K; g.flags = t.flags;
+    g.nkb_per_split = t.K / TC_BK / nsplit; g.split_stride = t.split_stride;
     g.gx = t.gx; g.gs = t.gs; g.gfeat = t.gfeat; g.kin = t.kin;
     int m_tiles;
     if (t.im2col) {
@@ -335,9 +391,9 @@ int launch_gemm_tc(const TcGemm& t, cudaStream_t st) {
     }
     if ((rc = make_map_2d(&w, t.W, t.N, t.K, t.ldw, 128))) return rc;
     if ((rc = make_map_2d(&wlo, t.passes == 3 ? t.W_lo : t.W, t.N, t.K, t.ldw, 128))) return rc;
-    if (t.im2col) return launch_tc<128, 3, true, 3>(a, alo, w, wlo, g, m_tiles, st);
-    if (t.passes == 3) return launch_tc<128, 3, false, 3>(a, alo, w, wlo, g, m_tiles, st);
-    return launch_tc<128, 1, false, 3>(a, alo, w, wlo, g, m_tiles, st);
+    if (t.im2col) return launch_tc<128, 3, true, 3>(a, alo, w, wlo, g, m_tiles, nsplit, st);
+    if (t.passes == 3) return launch_tc<128, 3, false, 3>(a, alo, w, wlo, g, m_tiles, nsplit, st);
+    return launch_tc<128, 1, false, 3>(a, alo, w, wlo, g, m_tiles, nsplit, st);
 }
 
 __global__ void split_tf32_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo, long long n) {
@@ -364,6 +420,7 @@ int launch_gemm_tc_or_simt(const GemmArgs& g, cudaStream_t stream) {
         t.A = g.A; t.lda = g.lda; t.W = g.W; t.ldw = g.ldw; t.C = g.C; t.ldc = g.ldc; t.bias = g.bias;
         t.M = g.M; t.N = g.N; t.K = g.K; t.passes = 1; t.im2col = 0;
         t.flags = g.flags & (GEMM_RELU | GEMM_GATE | GEMM_ROUND_TF32);
+        t.nsplit = 1;
         t.gx = g.gx; t.gs = g.gs; t.gfeat = g.gfeat; t.kin = g.kin;
         return launch_gemm_tc(t, stream);
     }

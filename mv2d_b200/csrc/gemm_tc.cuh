@@ -7,6 +7,7 @@ namespace mv2d {
 enum GemmTcFlags : int {
     GEMM_FORCE_TC = 16,       // mv2d_gemm: run the single-pass tcgen05 kernel whatever the shape heuristics say
     GEMM_ROUND_TF32 = 64,     // epilogue rounds the result to TF32 (it feeds a single-pass TF32 GEMM)
+    GEMM_SPLIT_OUT = 256,     // epilogue writes the TF32 hi part to C and the lo part to C_lo (feeds a 3xTF32 GEMM)
 };
 
 // round-to-nearest (ties away) fp32 -> tf32, kept in an fp32 container
@@ -19,9 +20,10 @@ __device__ __forceinline__ float round_tf32(float x) {
 struct TcGemm {
     const float* A; const float* A_lo; int lda;     // A_lo only for passes == 3
     const float* W; const float* W_lo; int ldw;
-    float* C; int ldc;
+    float* C; float* C_lo; int ldc;
     const float* bias;
     int M, N, K;
+    int nsplit; long long split_stride;   // split-K: raw partial sums of split z go to C + z * split_stride
     int passes;        // 1 = single-pass TF32 (operands already TF32-representable), 3 = 3xTF32
     int im2col;        // A = [n_rois,7,7,256] tokens, M = 49*n_rois, K = 2304 ordered (tap, c_in)
     int flags;         // GEMM_RELU | GEMM_GATE | GEMM_ROUND_TF32

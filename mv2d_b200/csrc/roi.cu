@@ -80,7 +80,7 @@ roi_align_tokens_kernel(const float* __restrict__ rois, const float* __restrict_
 // K' = RoI-frame intrinsics (fp64), feature = clamp(float(K')*scale), M = float(inv(K' E^T)).
 __global__ void box_params_kernel(const float* __restrict__ rois, const double* __restrict__ intrinsics,
                                   const double* __restrict__ extrinsics, int N, float feat_scale,
-                                  float* __restrict__ cat /*[N,1040]*/, float* __restrict__ m_roi /*[N,16]*/,
+                                  float* __restrict__ cat /*[N,MV2D_CAT_LD]*/, float* __restrict__ m_roi /*[N,16]*/,
                                   double* __restrict__ k_out /*nullable [N,16]*/) {
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N) return;
@@ -96,7 +96,8 @@ __global__ void box_params_kernel(const float* __restrict__ rois, const double* 
     const bool invalid = (wx < 4.f) || (wy < 4.f);
     for (int i = 0; i < 16; ++i) {
         float f = invalid ? 0.f : (float)K[i] * feat_scale;
-        cat[(long long)n * 1040 + 1024 + i] = fminf(fmaxf(f, -5e3f), 5e3f);
+        cat[(long long)n * MV2D_CAT_LD + 1024 + i] = fminf(fmaxf(f, -5e3f), 5e3f);
+        cat[(long long)n * MV2D_CAT_LD + 1040 + i] = 0.f;   // zero K-padding (weights are zero-padded too)
         if (k_out) k_out[n * 16 + i] = K[i];
     }
     for (int i = 0; i < 4; ++i)
@@ -168,7 +169,7 @@ static int gemm(const float* A, int lda, const float* W, int ldw, const float* b
 
 size_t roi_align_qg_workspace_bytes(int N) {
     size_t n = (size_t)(N > 0 ? N : 1);
-    return n * ((size_t)3 * MV2D_TOK * MV2D_C + MV2D_C + 1040 + 512 + MV2D_C + 16 + 384 + MV2D_C) * sizeof(float);
+    return n * ((size_t)3 * MV2D_TOK * MV2D_C + MV2D_C + MV2D_CAT_LD + 512 + MV2D_C + 16 + 384 + MV2D_C) * sizeof(float);
 }
 
 int run_roi_align_qg(const Mv2dQgParams& p, cudaStream_t st) {
@@ -181,7 +182,7 @@ int run_roi_align_qg(const Mv2dQgParams& p, cudaStream_t st) {
     float* thi = ws;    ws += (size_t)N * MV2D_TOK * C;
     float* tlo = ws;    ws += (size_t)N * MV2D_TOK * C;
     float* pool = ws;   ws += (size_t)N * C;
-    float* cat = ws;    ws += (size_t)N * 1040;
+    float* cat = ws;    ws += (size_t)N * MV2D_CAT_LD;
     float* e0 = ws;     ws += (size_t)N * 512;
     float* enc = ws;    ws += (size_t)N * C;
     float* mroi = ws;   ws += (size_t)N * 16;
@@ -204,8 +205,8 @@ int run_roi_align_qg(const Mv2dQgParams& p, cudaStream_t st) {
     }
     avgpool49_kernel<<<cdiv(N * C, 256), 256, 0, st>>>(conv, pool, N);
     MV2D_CHECK_LAUNCH("avgpool49");
-    if ((rc = gemm(pool, C, p.w_fc, C, p.b_fc, cat, 1040, N, 1024, C, GEMM_RELU | GEMM_CLAMP5E3, A_PLAIN, st))) return rc;
-    if ((rc = gemm(cat, 1040, p.w_enc0, 1040, p.b_enc0, e0, 512, N, 512, 1040, GEMM_RELU, A_PLAIN, st))) return rc;
+    if ((rc = gemm(pool, C, p.w_fc, C, p.b_fc, cat, MV2D_CAT_LD, N, 1024, C, GEMM_RELU | GEMM_CLAMP5E3, A_PLAIN, st))) return rc;
+    if ((rc = gemm(cat, MV2D_CAT_LD, p.w_enc0, MV2D_CAT_LD, p.b_enc0, e0, 512, N, 512, MV2D_CAT_LD, GEMM_RELU, A_PLAIN, st))) return rc;
     if ((rc = gemm(e0, 512, p.w_enc2, 512, p.b_enc2, enc, C, N, C, 512, GEMM_RELU, A_PLAIN, st))) return rc;
     qg_tail_kernel<<<cdiv(N, 4), 128, 0, st>>>(enc, p.w_center, p.b_center, mroi, p.dim_t, N, p.pc_range[0],
                                                p.pc_range[1], p.pc_range[2], p.pc_range[3], p.pc_range[4],

@@ -97,7 +97,8 @@ class PackedWeights:
         put('w_conv_lo', wc_lo)
         put('b_conv', sd[qg + 'shared_convs.0.conv.bias'])
         put('w_fc', sd[qg + 'shared_fcs.0.weight']); put('b_fc', sd[qg + 'shared_fcs.0.bias'])
-        put('w_enc0', sd[qg + 'extra_enc.0.weight']); put('b_enc0', sd[qg + 'extra_enc.0.bias'])
+        put('w_enc0', torch.nn.functional.pad(sd[qg + 'extra_enc.0.weight'].float(), (0, 16)))   # K 1040 -> 1056
+        put('b_enc0', sd[qg + 'extra_enc.0.bias'])
         put('w_enc2', sd[qg + 'extra_enc.2.weight']); put('b_enc2', sd[qg + 'extra_enc.2.bias'])
         put('w_center', sd[qg + 'fc_center.weight']); put('b_center', sd[qg + 'fc_center.bias'])
         bh = 'bbox_head.'
@@ -115,13 +116,14 @@ class PackedWeights:
             qw, qb, ow, ob = absorb_cross_attention(
                 sd[p + 'attentions.1.attn.in_proj_weight'], sd[p + 'attentions.1.attn.in_proj_bias'],
                 sd[p + 'attentions.1.attn.out_proj.weight'], sd[p + 'attentions.1.attn.out_proj.bias'])
-            lw.ca_q_w = put(f'l{l}.ca_q_w', qw).data_ptr()
+            for field, mat in (('ca_q_w', qw), ('ca_o_w', ow), ('ffn_w1', sd[p + 'ffns.0.layers.0.0.weight']),
+                               ('ffn_w2', sd[p + 'ffns.0.layers.1.weight'])):
+                hi, lo = split_tf32(mat)     # 3xTF32 tcgen05 operands
+                setattr(lw, field, put(f'l{l}.{field}', hi).data_ptr())
+                setattr(lw, field + '_lo', put(f'l{l}.{field}_lo', lo).data_ptr())
             lw.ca_q_b = put(f'l{l}.ca_q_b', qb).data_ptr()
-            lw.ca_o_w = put(f'l{l}.ca_o_w', ow).data_ptr()
             lw.ca_o_b = put(f'l{l}.ca_o_b', ob).data_ptr()
-            lw.ffn_w1 = put(f'l{l}.ffn_w1', sd[p + 'ffns.0.layers.0.0.weight']).data_ptr()
             lw.ffn_b1 = put(f'l{l}.ffn_b1', sd[p + 'ffns.0.layers.0.0.bias']).data_ptr()
-            lw.ffn_w2 = put(f'l{l}.ffn_w2', sd[p + 'ffns.0.layers.1.weight']).data_ptr()
             lw.ffn_b2 = put(f'l{l}.ffn_b2', sd[p + 'ffns.0.layers.1.bias']).data_ptr()
             for n in range(3):
                 lw.ln_g[n] = put(f'l{l}.ln_g{n}', sd[p + f'norms.{n}.weight']).data_ptr()

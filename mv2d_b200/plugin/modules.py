@@ -1,0 +1,439 @@
+"""Parameter-holding modules with the reference's names/kwargs; forwards call libmv2d_b200.
+
+Every class cites the reference class it stands in for.  Training-only paths (losses, DN query
+preparation, assigners) are out of scope this round and raise.
+"""
+import copy
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from ..engine import HotPath
+from ..registry import (ATTENTION, BBOX_CODERS, DETECTORS, HEADS, LOSSES, NECKS, POSITIONAL_ENCODING,
+                        ROI_EXTRACTORS, TRANSFORMER, TRANSFORMER_LAYER, TRANSFORMER_LAYER_SEQUENCE,
+                        build_from_cfg)
+
+
+# ------------------------------------------------------------------ small config holders
+class _LossCfg(nn.Module):
+    """Loss configs are carried (``use_sigmoid`` is read by QueryGenerator, query_generator.py:90);
+    the losses themselves belong to the training rows that are out of scope."""
+
+    def __init__(self, use_sigmoid=False, **kwargs):
+        super().__init__()
+        self.use_sigmoid = use_sigmoid
+        self.cfg = dict(kwargs)
+
+
+for _n in ('FocalLoss', 'L1Loss', 'CrossEntropyLoss', 'SmoothL1Loss'):
+    LOSSES.register_module(name=_n, module=_LossCfg)
+
+
+@ROI_EXTRACTORS.register_module()
+class SingleRoIExtractor(nn.Module):
+    """mmdet SingleRoIExtractor with one RoIAlign level (exp/...single_frame...:46-50).  Holds the
+    configuration; the pooling itself is ``roi_align_tokens_kernel`` inside ``mv2d_roi_align_qg``."""
+
+    def __init__(self, roi_layer, out_channels, featmap_strides, **kwargs):
+        super().__init__()
+        assert roi_layer['type'] == 'RoIAlign' and len(featmap_strides) == 1
+        assert roi_layer.get('output_size', 7) == 7, 'libmv2d_b200 is specialised for 7x7 RoI tokens'
+        assert roi_layer.get('sampling_ratio', -1) <= 0, 'adaptive sampling grid only (sampling_ratio=-1)'
+        self.roi_layer = dict(roi_layer)
+        self.out_channels = out_channels
+        self.featmap_strides = list(featmap_strides)
+
+    @property
+    def num_inputs(self):
+        return len(self.featmap_strides)
+
+
+@BBOX_CODERS.register_module()
+class NMSFreeCoder:
+    """core/bbox/coders/nms_free_coder.py:18-123; decode runs ``mv2d_nms_free_decode``."""
+
+    def __init__(self, pc_range, post_center_range=None, max_num=100, score_threshold=None, num_classes=10):
+        assert score_threshold is None, 'score_threshold is not used by the MV2D configs'
+        self.pc_range = pc_range
+        self.post_center_range = post_center_range
+        self.max_num = max_num
+        self.num_classes = num_classes
+
+
+@POSITIONAL_ENCODING.register_module()
+class SinePositionalEncoding3D(nn.Module):
+    """models/utils/positional_encoding.py:14-106 (normalize=True path is what PE uses)."""
+
+    def __init__(self, num_feats, temperature=10000, normalize=False, scale=2 * np.pi, eps=1e-6, offset=0.,
+                 init_cfg=None):
+        super().__init__()
+        assert num_feats == 128 and normalize and temperature == 10000 and offset == 0.
+        self.num_feats, self.temperature, self.normalize = num_feats, temperature, normalize
+        self.scale, self.eps, self.offset = scale, eps, offset
+
+
+class SELayer(nn.Module):
+    """models/utils/pe.py:36-48 (parameters only)."""
+
+    def __init__(self, channels):
+        super().__init__()
+        self.conv_reduce = nn.Conv2d(channels, channels, 1, bias=True)
+        self.conv_expand = nn.Conv2d(channels, channels, 1, bias=True)
+
+
+class PE(nn.Module):
+    """models/utils/pe.py:51-169.  ``forward(mlvl_feats, img_metas)`` runs ``mv2d_pe3d``."""
+
+    def __init__(self, positional_encoding, strides, position_range, depth_num, depth_start=1, LID=True,
+                 embed_dims=256, with_fpe=False, adapt_pos3d=True, no_sin_enc=False):
+        super().__init__()
+        assert LID and with_fpe and adapt_pos3d and not no_sin_enc and embed_dims == 256 and len(strides) == 1, \
+            'libmv2d_b200 implements the configuration the MV2D configs use (LID, with_fpe, adapt_pos3d)'
+        self.strides, self.position_range = strides, position_range
+        self.depth_num, self.depth_start, self.embed_dims = depth_num, depth_start, embed_dims
+        self.position_encoder = nn.Sequential(nn.Conv2d(3 * depth_num, embed_dims * 4, 1), nn.ReLU(),
+                                              nn.Conv2d(embed_dims * 4, embed_dims, 1))
+        self.adapt_pos3d = nn.Sequential(nn.Conv2d(embed_dims * 3 // 2, embed_dims * 4, 1), nn.ReLU(),
+                                         nn.Conv2d(embed_dims * 4, embed_dims, 1))
+        self.positional_encoding = build_from_cfg(positional_encoding, POSITIONAL_ENCODING)
+        self.fpe = SELayer(embed_dims)
+        self._owner = None   # the head that owns the engine
+
+    def forward(self, mlvl_feats, img_metas):
+        assert self._owner is not None, 'PE must be owned by an MV2D head'
+        eng = self._owner.engine()
+        out = []
+        for x in mlvl_feats:
+            feat, feat_tf32 = eng.to_nhwc(x.float().contiguous())
+            i2l, _ = eng.geom_prep(eng._upload_cams(img_metas))
+            pe, _ = eng.pe3d(feat, i2l, img_metas, feat_tf32)
+            out.append(pe.permute(0, 3, 1, 2))   # NCHW view, as the reference returns
+        return out
+
+
+class QueryGenerator(nn.Module):
+    """roi_heads/utils/query_generator.py:19-405, the configuration the MV2D configs use:
+    conv3x3 -> avg-pool -> FC(1024) -> cat intrinsics(16) -> MLP(512,256) -> fc_center(3)."""
+
+    def __init__(self, return_cfg=dict(), wich_cp=False, with_avg_pool=True, with_center=True, roi_feat_size=7,
+                 in_channels=256, num_classes=10, extra_encoding=None, num_shared_convs=1, num_shared_fcs=1,
+                 conv_out_channels=256, fc_out_channels=1024, loss_cls=None, **kwargs):
+        super().__init__()
+        extra_encoding = extra_encoding or dict(num_layers=2, feat_channels=[512, 256],
+                                                features=[dict(type='intrinsic', in_channels=16)])
+        assert with_avg_pool and with_center and num_shared_convs == 1 and num_shared_fcs == 1
+        assert roi_feat_size == 7 and in_channels == 256 and conv_out_channels == 256 and fc_out_channels == 1024
+        assert list(extra_encoding['feat_channels']) == [512, 256]
+        assert [f['type'] for f in extra_encoding['features']] == ['intrinsic']
+        conv = nn.Module()
+        conv.conv = nn.Conv2d(in_channels, conv_out_channels, 3, padding=1)
+        self.shared_convs = nn.ModuleList([conv])
+        self.shared_fcs = nn.ModuleList([nn.Linear(conv_out_channels, fc_out_channels)])
+        self.extra_enc = nn.Sequential(nn.Linear(fc_out_channels + 16, 512), nn.ReLU(inplace=True),
+                                       nn.Linear(512, 256), nn.ReLU(inplace=True))
+        self.fc_center = nn.Linear(256, 3)
+        self.loss_cls = loss_cls
+
+
+class BoxCorrelation(nn.Module):
+    """roi_heads/utils/box_correlation.py:11-398 (``topk_matched`` mode).  The gen_* methods run
+    ``mv2d_box_corr`` and return the reference's tensors."""
+
+    def __init__(self, sample_size=4, num_depth=8, depth_start=0.5, depth_end=70, correlation_mode=None,
+                 LID=True, expand_stride=0, force_cpu=False):
+        super().__init__()
+        assert LID and correlation_mode and correlation_mode.startswith('topk_matched'), correlation_mode
+        info = correlation_mode.split(':')
+        self.topk, self.iou_thr, self.ratio = int(info[1]), float(info[2]), float(info[3])
+        self.sample_size, self.num_depth = sample_size, num_depth
+        self.depth_start, self.depth_end, self.expand_stride = depth_start, depth_end, expand_stride
+        self.correlation_mode = correlation_mode
+        self._owner = None
+
+    def engine_cfg(self):
+        return dict(sample_size=self.sample_size, corr_num_depth=self.num_depth, corr_depth_start=self.depth_start,
+                    corr_depth_end=float(self.depth_end), topk=self.topk, iou_thr=self.iou_thr, ratio=self.ratio,
+                    expand_stride=self.expand_stride)
+
+    def _run(self, rois, num_proposals_per_img, img_metas, h, w):
+        eng = self._owner.engine()
+        V = len(img_metas)
+        starts = np.concatenate([[0], np.cumsum(num_proposals_per_img)]).astype(np.int32)
+        roi_start = torch.from_numpy(starts).to(eng.device)
+        _, trans = eng.geom_prep(eng._upload_cams(img_metas))
+        return eng.box_corr(rois.float().contiguous(), roi_start, trans, rois.shape[0], V, img_metas, h, w)
+
+    @torch.no_grad()
+    def gen_box_roi_correlation(self, rois, num_proposals_per_img, img_metas):
+        """-> (corr int64 [N,M] padded with 0, mask bool [N,M]) as box_correlation.py:165-193."""
+        if rois.numel() == 0:
+            return rois.new_zeros((0, 0), dtype=torch.int64), rois.new_zeros((0, 0), dtype=torch.bool)
+        out = self._run(rois, num_proposals_per_img, img_metas, 1, 1)
+        cnt = out['match_cnt'].long()
+        M = int(cnt.max())
+        mask = torch.arange(M, device=rois.device)[None] < cnt[:, None]
+        corr = out['match'][:, :M].long() * mask
+        return corr, mask
+
+    @torch.no_grad()
+    def gen_box_correlation(self, rois, num_proposals_per_img, img_metas, feat, stride):
+        """-> bool [N,V,h,w] as box_correlation.py:95-162 (padding mask already removed)."""
+        _, _, h, w = feat.shape
+        out = self._run(rois, num_proposals_per_img, img_metas, h, w)
+        V, N = len(img_metas), rois.shape[0]
+        words = out['keymask']
+        bits = (words[:, :, None] >> torch.arange(32, device=words.device, dtype=torch.int32)) & 1
+        return bits.view(N, -1)[:, :V * h * w].bool().view(N, V, h, w)
+
+
+@ATTENTION.register_module()
+class FlattenMHSelfAttention(nn.Module):
+    """models/utils/petr_transformer.py:314-370 (over mmcv MultiheadAttention): parameters
+    ``attn.in_proj_weight/bias``, ``attn.out_proj``."""
+
+    def __init__(self, embed_dims, num_heads, attn_drop=0., proj_drop=0., dropout_layer=None, init_cfg=None,
+                 batch_first=False, **kwargs):
+        super().__init__()
+        assert embed_dims == 256 and num_heads == 8
+        self.embed_dims, self.num_heads, self.batch_first = embed_dims, num_heads, batch_first
+        self.attn = nn.MultiheadAttention(embed_dims, num_heads, kwargs.get('dropout', attn_drop))
+
+
+@ATTENTION.register_module()
+class PETRMultiheadAttention(FlattenMHSelfAttention):
+    """models/utils/petr_transformer.py:373-513."""
+
+
+class _FFN(nn.Module):
+    """mmcv FFN parameter layout: layers.0.0 = Linear(256,2048), layers.1 = Linear(2048,256)."""
+
+    def __init__(self, embed_dims, feedforward_channels, ffn_drop=0.):
+        super().__init__()
+        self.layers = nn.Sequential(
+            nn.Sequential(nn.Linear(embed_dims, feedforward_channels), nn.ReLU(inplace=True), nn.Dropout(ffn_drop)),
+            nn.Linear(feedforward_channels, embed_dims), nn.Dropout(ffn_drop))
+
+
+@TRANSFORMER_LAYER.register_module()
+class PETRTransformerDecoderLayer(nn.Module):
+    """models/utils/petr_transformer.py:194-311 over mmcv BaseTransformerLayer."""
+
+    def __init__(self, attn_cfgs, feedforward_channels, ffn_dropout=0.0, operation_order=None, act_cfg=None,
+                 norm_cfg=None, ffn_num_fcs=2, with_cp=True, **kwargs):
+        super().__init__()
+        assert tuple(operation_order) == ('self_attn', 'norm', 'cross_attn', 'norm', 'ffn', 'norm'), \
+            'libmv2d_b200 implements the operation order of the MV2D configs'
+        assert feedforward_channels == 2048 and ffn_num_fcs == 2
+        self.operation_order = tuple(operation_order)
+        self.attentions = nn.ModuleList([build_from_cfg(c, ATTENTION) for c in attn_cfgs])
+        self.embed_dims = self.attentions[0].embed_dims
+        self.ffns = nn.ModuleList([_FFN(self.embed_dims, feedforward_channels, ffn_dropout)])
+        self.norms = nn.ModuleList([nn.LayerNorm(self.embed_dims) for _ in range(3)])
+        self.use_checkpoint = with_cp
+        self.pre_norm = False
+
+
+@TRANSFORMER_LAYER_SEQUENCE.register_module()
+class PETRTransformerDecoder(nn.Module):
+    """models/utils/petr_transformer.py:546-593."""
+
+    def __init__(self, transformerlayers=None, num_layers=None, post_norm_cfg=dict(type='LN'),
+                 return_intermediate=False, init_cfg=None):
+        super().__init__()
+        assert return_intermediate and post_norm_cfg is not None
+        self.num_layers = num_layers
+        self.layers = nn.ModuleList([build_from_cfg(copy.deepcopy(transformerlayers), TRANSFORMER_LAYER)
+                                     for _ in range(num_layers)])
+        self.embed_dims = self.layers[0].embed_dims
+        self.post_norm = nn.LayerNorm(self.embed_dims)
+        self.return_intermediate = return_intermediate
+
+
+@TRANSFORMER.register_module()
+class MV2DTransformer(nn.Module):
+    """roi_heads/bbox_heads/cross_attention_head.py:22-49."""
+
+    def __init__(self, encoder=None, decoder=None, init_cfg=None, cross=False):
+        super().__init__()
+        assert encoder is None
+        self.decoder = build_from_cfg(decoder, TRANSFORMER_LAYER_SEQUENCE)
+        self.embed_dims = self.decoder.embed_dims
+
+
+@HEADS.register_module()
+class CrossAttentionBoxHead(nn.Module):
+    """roi_heads/bbox_heads/cross_attention_head.py:87-242 (forward + get_bboxes)."""
+
+    def __init__(self, num_classes, transformer, pc_range, embed_dims=256, num_reg_fcs=2,
+                 group_reg_dims=(2, 2, 1, 1, 2, 2), use_reg_layer=False, pre_embed=False, loss_cls=None,
+                 loss_bbox=None, bbox_coder=None, sync_cls_avg_factor=False, train_cfg=None, test_cfg=None,
+                 **kwargs):
+        super().__init__()
+        assert num_classes == 10 and embed_dims == 256 and num_reg_fcs == 2 and not use_reg_layer and not pre_embed
+        assert sum(group_reg_dims) == 10
+        self.loss_cls = build_from_cfg(loss_cls, LOSSES) if loss_cls else _LossCfg()
+        self.loss_bbox = build_from_cfg(loss_bbox, LOSSES) if loss_bbox else _LossCfg()
+        self.transformer = build_from_cfg(transformer, TRANSFORMER)
+        self.pc_range, self.embed_dims, self.num_classes = pc_range, embed_dims, num_classes
+        self.num_pred = transformer['decoder']['num_layers']
+        self.query_embedding = nn.Sequential(nn.Linear(embed_dims * 3 // 2, embed_dims), nn.ReLU(),
+                                             nn.Linear(embed_dims, embed_dims))
+        cls_branch = []
+        for _ in range(num_reg_fcs):
+            cls_branch += [nn.Linear(embed_dims, embed_dims), nn.LayerNorm(embed_dims), nn.ReLU(inplace=True)]
+        cls_branch.append(nn.Linear(embed_dims, num_classes))
+        reg_branch = []
+        for _ in range(num_reg_fcs):
+            reg_branch += [nn.Linear(embed_dims, embed_dims), nn.ReLU()]
+        reg_branch.append(nn.Linear(embed_dims, sum(group_reg_dims)))
+        self.cls_branches = nn.ModuleList([copy.deepcopy(nn.Sequential(*cls_branch)) for _ in range(self.num_pred)])
+        self.reg_branches = nn.ModuleList([copy.deepcopy(nn.Sequential(*reg_branch)) for _ in range(self.num_pred)])
+        self.bbox_coder = build_from_cfg(bbox_coder, BBOX_CODERS) if bbox_coder else None
+        code_weights = kwargs.get('code_weights', [1.0] * 8 + [0.2, 0.2])[:kwargs.get('code_size', 10)]
+        self.code_weights = nn.Parameter(torch.tensor(code_weights), requires_grad=False)
+        self.train_cfg, self.test_cfg = train_cfg, test_cfg
+        self._owner = None
+
+    def get_bboxes(self, preds_dicts, img_metas, rescale=False):
+        """cross_attention_head.py:356-377: NMS-free decode (top-k, denormalise, range filter) + z-shift."""
+        eng = self._owner.engine()
+        ret = []
+        for i, (cls, box) in enumerate(zip(preds_dicts['cls_scores'], preds_dicts['bbox_preds'])):
+            boxes, scores, labels = eng.decode(cls, box, self.bbox_coder.max_num)
+            bt = img_metas[i].get('box_type_3d') if i < len(img_metas) else None
+            ret.append([bt(boxes, boxes.size(-1)) if bt is not None else boxes, scores, labels])
+        return ret
+
+    def loss(self, *args, **kwargs):
+        raise NotImplementedError('training rows (losses/assignment) are out of scope this round: DESIGN.md section 7')
+
+
+# ------------------------------------------------------------------ RoI heads
+@HEADS.register_module()
+class MV2DHead(nn.Module):
+    """roi_heads/mv2d_head.py:19-267.  ``simple_test`` / ``_bbox_forward`` run the five C-ABI stages
+    (the dense-feature-map decoder of the base class is what MV2DTHead uses)."""
+    MODE = 'T'
+
+    def __init__(self, bbox_roi_extractor, bbox_head, query_generator, pe, box_correlation, pc_range,
+                 intrins_feat_scale=0.1, feat_lvl=0, force_fp32=False, train_cfg=None, test_cfg=None, **kwargs):
+        super().__init__()
+        self.train_cfg, self.test_cfg = train_cfg, test_cfg
+        self.bbox_roi_extractor = build_from_cfg(bbox_roi_extractor, ROI_EXTRACTORS)
+        bbox_head = dict(bbox_head, train_cfg=train_cfg, test_cfg=test_cfg)
+        self.bbox_head = build_from_cfg(bbox_head, HEADS)
+        self.query_generator = QueryGenerator(**dict(query_generator, loss_cls=self.bbox_head.loss_cls))
+        self.position_encoding = PE(**pe)
+        self.box_corr_module = BoxCorrelation(**box_correlation)
+        self.pc_range, self.intrins_feat_scale, self.feat_lvl, self.force_fp32 = pc_range, intrins_feat_scale, feat_lvl, force_fp32
+        self.roi_size = [7, 7]
+        self.stage_loss_weights = train_cfg.get('stage_loss_weights') if train_cfg else None
+        for m in (self.position_encoding, self.box_corr_module, self.bbox_head):
+            object.__setattr__(m, '_owner', self)
+        self._engine = None
+        self.register_load_state_dict_post_hook(lambda module, incompatible: setattr(module, '_engine', None))
+
+    @property
+    def strides(self):
+        return self.position_encoding.strides
+
+    @property
+    def num_classes(self):
+        return self.bbox_head.num_classes
+
+    @property
+    def with_bbox(self):
+        return True
+
+    def engine(self):
+        """The packed-weight engine, rebuilt after load_state_dict()."""
+        if self._engine is None:
+            pe = self.position_encoding
+            cfg = dict(pc_range=list(self.pc_range), position_range=list(pe.position_range), depth_num=pe.depth_num,
+                       depth_start=float(pe.depth_start), stride=pe.strides[0],
+                       intrins_feat_scale=self.intrins_feat_scale,
+                       num_views_per_frame=getattr(self, 'num_views', 6))
+            cfg.update(self.box_corr_module.engine_cfg())
+            dev = next(self.parameters()).device
+            self._engine = HotPath(self.state_dict(), mode=self.MODE, device=dev, **cfg)
+        return self._engine
+
+    def _results(self, out):
+        L = out['cls_scores'].shape[0]
+        N = out['N']
+        return dict(cls_scores=[out['cls_scores'][l] for l in range(L)],
+                    bbox_preds=[out['bbox_preds'][l] for l in range(L)],
+                    bbox_feats=out['tok_feat'].view(N, 7, 7, 256).permute(0, 3, 1, 2), return_feats=dict(),
+                    intrinsics=out['roi_intrinsics'].view(N, 4, 4), extrinsics=None, rois=out['rois'],
+                    dn_mask_dict=None)
+
+    @torch.no_grad()
+    def _bbox_forward(self, x, proposal_list, img_metas):
+        """x: list with the P4 feature [V,256,h,w] (the PE is computed inside the fused path; a
+        reference-style [V,512,h,w] feat||pe tensor is accepted and its first half is used)."""
+        feat = x[self.feat_lvl]
+        if feat.shape[1] == 2 * self.position_encoding.embed_dims:
+            feat = feat[:, :self.position_encoding.embed_dims]
+        out = self.engine().forward(feat, proposal_list, img_metas)
+        return self._results(out)
+
+    @torch.no_grad()
+    def simple_test(self, x, proposal_list, img_metas, rescale=False):
+        assert len(img_metas) // img_metas[0]['num_views'] == 1   # mv2d_head.py:251
+        res = self._bbox_forward(x, proposal_list, img_metas)
+        return self.bbox_head.get_bboxes({'cls_scores': [res['cls_scores'][-1]], 'bbox_preds': [res['bbox_preds'][-1]]},
+                                         img_metas)
+
+    def forward_train(self, *args, **kwargs):
+        raise NotImplementedError('training rows are out of scope this round: DESIGN.md section 7')
+
+
+@HEADS.register_module()
+class MV2DSHead(MV2DHead):
+    """roi_heads/mv2d_s_head.py:19-305 (eval forward: RoI-token keys of self + epipolar matches)."""
+    MODE = 'S'
+
+    def __init__(self, use_denoise=False, neg_bbox_loss=False, denoise_scalar=10, denoise_noise_scale=1.0,
+                 denoise_noise_trans=0.0, denoise_weight=1.0, denoise_split=0.75, **kwargs):
+        super().__init__(**kwargs)
+        self.use_denoise = use_denoise
+
+
+@HEADS.register_module()
+class MV2DTHead(MV2DSHead):
+    """roi_heads/mv2d_t_head.py:19-142 (two frames: dense feature-map keys + per-query mask, velocity / dt)."""
+    MODE = 'T'
+
+    def __init__(self, num_views=6, **kwargs):
+        self.num_views = num_views
+        super().__init__(**kwargs)
+
+
+# ------------------------------------------------------------------ detector shells
+@DETECTORS.register_module()
+class MV2D(nn.Module):
+    """detectors/mv2d.py:18-293, thin shell: the 2D detector + FPN stay torch (north star) and are
+    injected as ``base_detector`` (any callable ``(img[V,3,H,W], img_metas) -> (feat[V,256,h,w], detections)``);
+    ``simple_test`` hands their outputs to the roi_head exactly as mv2d.py:251-261 does."""
+
+    def __init__(self, base_detector=None, neck=None, roi_head=None, train_cfg=None, test_cfg=None,
+                 use_grid_mask=None, **kwargs):
+        super().__init__()
+        roi_head = dict(roi_head, train_cfg=(train_cfg or {}).get('rcnn') if train_cfg else None,
+                        test_cfg=(test_cfg or {}).get('rcnn') if test_cfg else None)
+        self.roi_head = build_from_cfg(roi_head, HEADS)
+        self.base_detector = base_detector if callable(base_detector) else None
+        self.neck_cfg, self.train_cfg, self.test_cfg = neck, train_cfg, test_cfg
+
+    @torch.no_grad()
+    def simple_test(self, img, img_metas, detections=None, feat=None):
+        if feat is None or detections is None:
+            assert self.base_detector is not None, 'inject a torch 2D detector or pass feat/detections'
+            feat, detections = self.base_detector(img, img_metas)
+        return self.roi_head.simple_test([feat], detections, img_metas)
+
+
+@DETECTORS.register_module()
+class MV2DT(MV2D):
+    """detectors/mv2d_t.py:17-136 (same shell; the T head consumes 12 views)."""

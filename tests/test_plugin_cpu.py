@@ -1,0 +1,32 @@
+"""CPU: the registry surface builds from our configs and -- unchanged -- from the reference's
+experiment configs, with exactly the reference's state_dict names and shapes."""
+import os
+
+import pytest
+
+from conftest import ROOT
+from mv2d_b200.plugin.build import build_roi_head
+
+OURS = [os.path.join(ROOT, 'configs', 'mv2d_b200', n) for n in ('mv2d_s_r50_1408x512.py', 'mv2d_t_r50_1408x512.py')]
+REF_DIR = '/root/reference/configs/mv2d/exp'
+REF = [os.path.join(REF_DIR, n) for n in sorted(os.listdir(REF_DIR))] if os.path.isdir(REF_DIR) else []
+
+
+@pytest.mark.parametrize('path', OURS + REF)
+def test_roi_head_builds_with_reference_state_dict(path, state_dicts):
+    head = build_roi_head(path, device=None)
+    sd, ref = head.state_dict(), state_dicts(6)
+    assert set(sd) == set(ref), (set(sd) ^ set(ref))
+    for k, v in ref.items():
+        assert tuple(sd[k].shape) == tuple(v.shape), k
+    head.load_state_dict(ref, strict=True)
+    assert type(head).__name__ == ('MV2DTHead' if 'two_frames' in path or '_t_' in path else 'MV2DSHead')
+    assert head.box_corr_module.topk == (20 if head.MODE == 'T' else 1)
+
+
+def test_config_delete_and_base_semantics(tmp_path):
+    from mv2d_b200.config import Config
+    (tmp_path / 'base.py').write_text("a = dict(x=1, y=dict(p=1, q=2))\nb = 3\n")
+    (tmp_path / 'child.py').write_text("_base_ = ['./base.py']\na = dict(y=dict(_delete_=True, r=5), z=7)\n")
+    cfg = Config.fromfile(str(tmp_path / 'child.py'))
+    assert cfg.a.x == 1 and cfg.a.z == 7 and dict(cfg.a.y) == {'r': 5} and cfg.b == 3
