@@ -205,6 +205,9 @@ MV2D_API int mv2d_nms_free_decode(const float* cls /*[N,10]*/, const float* box 
                          float* out_scores /*[max_num]*/, int* out_labels /*[max_num]*/,
                          uint8_t* out_valid /*[max_num]*/, void* stream);
 
+/* debug: spin `cycles` SM clocks in a 1-warp kernel; out[0] = elapsed ns (globaltimer), out[1] = cycles */
+MV2D_API int mv2d_debug_clock_probe(long long cycles, long long* out /*device [2]*/, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

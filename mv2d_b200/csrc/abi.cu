@@ -2,6 +2,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include "common.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
@@ -14,6 +15,10 @@ void set_error(const char* fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+}
+bool pdl_enabled() {
+    static const bool on = []() { const char* e = getenv("MV2D_NO_PDL"); return !(e && e[0] == '1'); }();
+    return on;
 }
 static std::atomic<unsigned long long> g_launches{0};
 void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
@@ -114,6 +119,11 @@ int mv2d_nms_free_decode(const float* cls, const float* box, int N, int max_num,
                    "nms_free_decode: null pointer");
     return run_nms_free_decode(cls, box, N, max_num, post_range, out_boxes, out_scores, out_labels, out_valid,
                                (cudaStream_t)stream);
+}
+
+int mv2d_debug_clock_probe(long long cycles, long long* out, void* stream) {
+    MV2D_CHECK_ARG(out != nullptr && cycles > 0, "clock_probe: bad arguments");
+    return run_clock_probe(cycles, out, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -38,6 +38,27 @@ void note_launch();   // counts kernel launches enqueued by this library (mv2d_l
 
 __host__ __device__ inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
+// ---- Programmatic dependent launch (PDL).  Every kernel of the library starts with pdl_wait()
+// (griddepcontrol.wait: blocks until the preceding kernel in the stream has completed and its writes are
+// visible) and then lets ITS successor begin launching (griddepcontrol.launch_dependents), so launch
+// latency, CTA scheduling and kernel prologues overlap with the predecessor's tail.  The path is a chain
+// of ~90 short dependent kernels per sample, so this matters more than any single kernel's speed.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+bool pdl_enabled();   // abi.cu: false when MV2D_NO_PDL=1
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---- fp64 4x4 inverse, Gauss-Jordan with partial pivoting (what LAPACK getrf/getri amount to
 // for a 4x4; replaces np.linalg.inv pe.py:111 and torch.inverse box_correlation.py:120,176,
 // query_generator.py:339).  m and out are row-major.

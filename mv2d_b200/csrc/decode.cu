@@ -13,6 +13,8 @@ nms_free_decode_kernel(const float* __restrict__ cls, const float* __restrict__ 
                        int max_num, float r0, float r1, float r2, float r3, float r4, float r5,
                        float* __restrict__ out_boxes, float* __restrict__ out_scores, int* __restrict__ out_labels,
                        uint8_t* __restrict__ out_valid) {
+    pdl_wait();
+    pdl_trigger();
     extern __shared__ unsigned char raw[];
     float* key = reinterpret_cast<float*>(raw);
     int* idx = reinterpret_cast<int*>(key + npow2);
@@ -62,10 +64,27 @@ int run_nms_free_decode(const float* cls, const float* box, int N, int max_num, 
     MV2D_CHECK_ARG(smem <= 200 * 1024, "nms_free_decode: N=%d too large for the single-CTA sort", N);
     cudaError_t e = cudaFuncSetAttribute(nms_free_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("nms_free_decode: %s", cudaGetErrorString(e)); return (int)e; }
-    nms_free_decode_kernel<<<1, 1024, smem, st>>>(cls, box, total, npow2, max_num, post_range[0], post_range[1],
+    launch_k(nms_free_decode_kernel, dim3(1), dim3(1024), smem, st, cls, box, total, npow2, max_num, post_range[0], post_range[1],
                                                  post_range[2], post_range[3], post_range[4], post_range[5],
                                                  out_boxes, out_scores, out_labels, out_valid);
     MV2D_CHECK_LAUNCH("nms_free_decode");
+    return 0;
+}
+
+// debug: SM clock rate as seen by a running kernel: spin `cycles` SM clocks, report elapsed globaltimer ns
+__global__ void clock_probe_kernel(long long cycles, long long* out) {
+    pdl_wait();
+    pdl_trigger();
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    const long long c0 = clock64();
+    while (clock64() - c0 < cycles) {}
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    if (threadIdx.x == 0 && blockIdx.x == 0) { out[0] = (long long)(t1 - t0); out[1] = cycles; }
+}
+int run_clock_probe(long long cycles, long long* out, cudaStream_t st) {
+    launch_k(clock_probe_kernel, dim3(1), dim3(32), 0, st, cycles, out);
+    MV2D_CHECK_LAUNCH("clock_probe");
     return 0;
 }
 

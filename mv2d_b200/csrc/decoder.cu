@@ -34,6 +34,8 @@ struct LnArgs {
 };
 
 __global__ void __launch_bounds__(256) ln_kernel(LnArgs a) {
+    pdl_wait();
+    pdl_trigger();
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= a.rows) return;
     const int grp = a.rows_per_group > 0 ? row / a.rows_per_group : 0;
@@ -131,6 +133,8 @@ __global__ void __launch_bounds__(256) ln_kernel(LnArgs a) {
 #define SA_LD 36
 __global__ void __launch_bounds__(256)
 self_attn_kernel(const float* __restrict__ qkv, const uint8_t* __restrict__ mask, int N, float* __restrict__ out) {
+    pdl_wait();
+    pdl_trigger();
     __shared__ __align__(16) float Ks[SA_KT][SA_LD];
     __shared__ __align__(16) float Vs[SA_KT][SA_LD];
     __shared__ float Ps[8][SA_KT];
@@ -227,8 +231,7 @@ self_attn_kernel(const float* __restrict__ qkv, const uint8_t* __restrict__ mask
 // chunk loads while this one is consumed).  Per chunk: logits (warp per key, lanes along the
 // 256 channels, warp-shuffle transpose-reduce over 8 heads), online softmax (warp per head,
 // lane per key), probability-weighted sum of the memory rows.  Per-lane state: 8 heads x 8 ch.
-#define XA_CH 16
-#define XA_THREADS 128
+// S head (~64 keys / query): 4 warps, 16-key chunks, 3 CTAs / SM.  T head (~2000 keys / query): 8 warps, 32-key chunks.
 __device__ __forceinline__ void xa_cp16(void* smem, const void* gmem) {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
@@ -264,8 +267,12 @@ struct XaArgs {
     float* ctx; float* ctx_lo;    // ctx_lo != nullptr: write the TF32 hi/lo split (operands of the 3xTF32 output GEMM)
 };
 
+template <int XA_CH, int XA_THREADS>
 __global__ void __launch_bounds__(XA_THREADS)
 cross_attn_kernel(XaArgs a) {
+    static_assert(XA_CH == XA_THREADS / 8, "one softmax lane per key: CH = 4 * warps");
+    pdl_wait();
+    pdl_trigger();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* kbuf = reinterpret_cast<float*>(smem_raw);               // [2][XA_CH][256] key-input rows
     float* vbuf = kbuf + 2 * XA_CH * MV2D_C;                        // [2][XA_CH][256] memory rows
@@ -367,18 +374,18 @@ cross_attn_kernel(XaArgs a) {
             if ((lane & 3) == 0) sc[j * 8 + (lane >> 2)] = sv[0];
         }
         __syncthreads();
-        // online softmax: each warp owns two heads (one per 16-lane half), lane & 15 = key
+        // online softmax: a warp owns 8/NW heads, XA_CH lanes each (lane % XA_CH = key)
         {
-            const int h = warp + ((lane >> 4) << 2), key = lane & 15;
+            const int h = warp + (lane / XA_CH) * NW, key = lane % XA_CH;
             const float sv = key < cn ? sc[key * 8 + h] : -INFINITY;
             float mx = sv;
 #pragma unroll
-            for (int o = 8; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            for (int o = XA_CH / 2; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
             const float m_old = stat[h], m_new = fmaxf(m_old, mx);
             const float p = key < cn ? __expf(sv - m_new) : 0.f;
             float sum = p;
 #pragma unroll
-            for (int o = 8; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            for (int o = XA_CH / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
             __syncwarp();
             if (key < cn) sc[key * 8 + h] = p;
             if (key == 0) {
@@ -414,8 +421,8 @@ cross_attn_kernel(XaArgs a) {
         __syncthreads();   // everyone done with buffer `buf` and `sc` before they are refilled
     }
     // ---- cross-warp tree sum through shared memory (fixed order => bitwise reproducible):
-    // warps 2,3 -> warps 0,1 ; warp 1 -> warp 0 ; warp 0 normalises and stores.
-    float4* T = reinterpret_cast<float4*>(kbuf);   // [2][512] float4, the staging buffers are free now
+    // upper half of the warps -> lower half, repeatedly; warp 0 normalises and stores.
+    float4* T = reinterpret_cast<float4*>(kbuf);   // [NW/2][512] float4, the staging buffers are free now
     auto put = [&](int slot) {
 #pragma unroll
         for (int h = 0; h < 8; ++h) {
@@ -431,14 +438,14 @@ cross_attn_kernel(XaArgs a) {
             acc[h][4] += x1.x; acc[h][5] += x1.y; acc[h][6] += x1.z; acc[h][7] += x1.w;
         }
     };
-    if (warp >= 2) put(warp - 2);
-    __syncthreads();
-    if (warp < 2) add(warp);
-    __syncthreads();
-    if (warp == 1) put(0);
-    __syncthreads();
+#pragma unroll
+    for (int stride = NW / 2; stride >= 1; stride >>= 1) {
+        if (warp >= stride && warp < 2 * stride) put(warp - stride);
+        __syncthreads();
+        if (warp < stride) add(warp);
+        __syncthreads();
+    }
     if (warp == 0) {
-        add(0);
 #pragma unroll
         for (int h = 0; h < 8; ++h) {
             const float l = stat[8 + h], inv = l > 0.f ? 1.f / l : 0.f;
@@ -470,6 +477,8 @@ head10_kernel(const float* __restrict__ xc, const float* __restrict__ xr, const 
               const float* __restrict__ bc, const float* __restrict__ wr, const float* __restrict__ br,
               const float* __restrict__ ref, int L, int N, float pc0, float pc1, float pc2, float pc3,
               float pc4, float pc5, float vel_dt, float* __restrict__ cls, float* __restrict__ box) {
+    pdl_wait();
+    pdl_trigger();
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= L * N) return;
     const int l = row / N, n = row % N;
@@ -525,7 +534,7 @@ static int tc3(const float* A_hi, const float* A_lo, int lda, const float* W_hi,
 
 static int ln(const LnArgs& a, cudaStream_t st) {
     if (a.rows == 0) return 0;
-    ln_kernel<<<cdiv(a.rows, 8), 256, 0, st>>>(a);
+    launch_k(ln_kernel, dim3(cdiv(a.rows, 8)), dim3(256), 0, st, a);
     MV2D_CHECK_LAUNCH("ln");
     return 0;
 }
@@ -580,10 +589,12 @@ int run_decoder(const Mv2dDecoderParams& p, cudaStream_t st) {
         return (int)e;
     }
     const int klist_cap = p.mode == 0 ? p.max_match * MV2D_TOK : p.mask_words * 32;
-    const size_t xa_smem = (size_t)(4 * XA_CH * MV2D_C + XA_CH * 8 + 24) * sizeof(float) + (size_t)klist_cap * sizeof(uint16_t);
+    const int xa_ch = p.mode == 0 ? 16 : 32;
+    const size_t xa_smem = (size_t)(4 * xa_ch * MV2D_C + xa_ch * 8 + 24) * sizeof(float) + (size_t)klist_cap * sizeof(uint16_t);
     MV2D_CHECK_ARG(xa_smem <= 227 * 1024, "decoder: key list does not fit shared memory");
+    auto xa_kernel = p.mode == 0 ? cross_attn_kernel<16, 128> : cross_attn_kernel<32, 256>;
     MV2D_CHECK_ARG(p.mode == 0 || p.mask_words <= 4096, "decoder: mask_words=%d > 4096", p.mask_words);
-    if ((e = cudaFuncSetAttribute(cross_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xa_smem)) != cudaSuccess) {
+    if ((e = cudaFuncSetAttribute(xa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xa_smem)) != cudaSuccess) {
         set_error("decoder: smem attr %s", cudaGetErrorString(e));
         return (int)e;
     }
@@ -599,7 +610,7 @@ int run_decoder(const Mv2dDecoderParams& p, cudaStream_t st) {
             g.M = N; g.N = 768; g.K = C; g.batch = 1; g.nsplit = 1;
             if ((rc = launch_gemm_small(g, x, 512, st))) return rc;
         }
-        self_attn_kernel<<<dim3(cdiv(N, 8), MV2D_HEADS), 256, 0, st>>>(qkv, p.self_attn_mask, N, sa);
+        launch_k(self_attn_kernel, dim3(cdiv(N, 8), MV2D_HEADS), dim3(256), 0, st, (const float*)qkv, p.self_attn_mask, N, sa);
         MV2D_CHECK_LAUNCH("self_attn");
         if ((rc = gemm(sa, C, w.sa_out_w, C, nullptr, part, C, N, C, C, 0, st))) return rc;
         {
@@ -614,7 +625,7 @@ int run_decoder(const Mv2dDecoderParams& p, cudaStream_t st) {
             XaArgs a{}; a.qt = qt; a.kin_rows = p.kin_rows; a.mem_rows = p.mem_rows; a.match = p.match;
             a.match_cnt = p.match_cnt; a.max_match = p.max_match; a.keymask = p.keymask; a.mask_words = p.mask_words;
             a.mode = p.mode; a.N = N; a.klist_cap = klist_cap; a.ctx = ctx; a.ctx_lo = ctx_lo;
-            cross_attn_kernel<<<N, XA_THREADS, xa_smem, st>>>(a);
+            launch_k(xa_kernel, dim3(N), dim3(p.mode == 0 ? 128 : 256), xa_smem, st, a);
             MV2D_CHECK_LAUNCH("cross_attn");
         }
         if ((rc = tc3(ctx, ctx_lo, 2048, w.ca_o_w, w.ca_o_w_lo, 2048, nullptr, part, nullptr, C, N, C, 2048, 0, DEC_SPLIT, NC, st))) return rc;
@@ -650,7 +661,7 @@ int run_decoder(const Mv2dDecoderParams& p, cudaStream_t st) {
     }
     if ((rc = gemm(p.outs_dec, C, B.reg_w0, C, B.reg_b0, b2, C, N, C, C, GEMM_RELU, st, 1, 0, L, NC, CC, NC, C))) return rc;
     if ((rc = gemm(b2, C, B.reg_w1, C, B.reg_b1, b3, C, N, C, C, GEMM_RELU, st, 1, 0, L, NC, CC, NC, C))) return rc;
-    head10_kernel<<<cdiv(L * N, 8), 256, 0, st>>>(b1, b3, B.cls_w2, B.cls_b2, B.reg_w2, B.reg_b2, p.ref, L, N,
+    launch_k(head10_kernel, dim3(cdiv(L * N, 8)), dim3(256), 0, st, (const float*)b1, (const float*)b3, B.cls_w2, B.cls_b2, B.reg_w2, B.reg_b2, p.ref, L, N,
                                                  p.pc_range[0], p.pc_range[1], p.pc_range[2], p.pc_range[3],
                                                  p.pc_range[4], p.pc_range[5], p.vel_dt, p.cls_scores, p.bbox_preds);
     MV2D_CHECK_LAUNCH("head10");

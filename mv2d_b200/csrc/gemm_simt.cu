@@ -17,6 +17,8 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 
 __global__ void __launch_bounds__(64)
 gemm_small_kernel(GemmSmallArgs a) {
+    pdl_wait();
+    pdl_trigger();
     const GemmArgs& g = a.g;
     __shared__ __align__(16) float As[GS_STAGES][GS_BM][GS_BK];
     __shared__ __align__(16) float Ws[GS_STAGES][GS_BN][GS_BK];
@@ -116,9 +118,9 @@ static int launch_cfg(const GemmArgs& g, int amode, cudaStream_t stream) {
     constexpr int NT = (BM / (4 * RM)) * (BN / (4 * RN));
     dim3 grid(cdiv(g.N, BN), cdiv(g.M, BM), g.batch * g.nsplit);
     if (amode == A_PLAIN)
-        gemm_simt_kernel<BM, BN, BK, RM, RN, A_PLAIN><<<grid, NT, 0, stream>>>(g);
+        launch_k(gemm_simt_kernel<BM, BN, BK, RM, RN, A_PLAIN>, grid, dim3(NT), 0, stream, g);
     else
-        gemm_simt_kernel<BM, BN, BK, RM, RN, A_IM2COL3X3><<<grid, NT, 0, stream>>>(g);
+        launch_k(gemm_simt_kernel<BM, BN, BK, RM, RN, A_IM2COL3X3>, grid, dim3(NT), 0, stream, g);
     MV2D_CHECK_LAUNCH("gemm_simt");
     return 0;
 }
@@ -153,7 +155,7 @@ int launch_gemm_small(const GemmArgs& g, const float* A2, int n_switch, cudaStre
     GemmSmallArgs a{};
     a.g = g; a.A2 = A2; a.n_switch = n_switch;
     dim3 grid(cdiv(g.N, GS_BN), cdiv(g.M, GS_BM), g.batch * g.nsplit);
-    gemm_small_kernel<<<grid, 64, 0, stream>>>(a);
+    launch_k(gemm_small_kernel, grid, dim3(64), 0, stream, a);
     MV2D_CHECK_LAUNCH("gemm_small");
     return 0;
 }

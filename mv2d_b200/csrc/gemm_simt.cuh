@@ -33,6 +33,8 @@ struct GemmArgs {
 template <int BM, int BN, int BK, int RM, int RN, int AMODE>
 __global__ void __launch_bounds__((BM / (4 * RM)) * (BN / (4 * RN)))
 gemm_simt_kernel(GemmArgs g) {
+    pdl_wait();
+    pdl_trigger();
     constexpr int TY = BM / (4 * RM), TX = BN / (4 * RN), NT = TY * TX;
     constexpr int KQ = BK / 4;
     constexpr int A_F4 = BM * KQ, W_F4 = BN * KQ;

@@ -138,6 +138,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+    // everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the previous kernel
+    pdl_wait();
+    pdl_trigger();
 
     if (warp == 0) {
         // ================= TMA producer =================
@@ -359,7 +362,7 @@ static int launch_tc(const CUtensorMap& a, const CUtensorMap& alo, const CUtenso
         attr_set = true;
     }
     dim3 grid(g.N / BN, m_tiles, nsplit);
-    kern<<<grid, TC_THREADS, smem, st>>>(a, alo, w, wlo, g);
+    launch_k(kern, grid, dim3(TC_THREADS), smem, st, a, alo, w, wlo, g);
     MV2D_CHECK_LAUNCH("gemm_tc");
     return 0;
 }
@@ -397,6 +400,8 @@ int launch_gemm_tc(const TcGemm& t, cudaStream_t st) {
 }
 
 __global__ void split_tf32_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo, long long n) {
+    pdl_wait();
+    pdl_trigger();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float v = x[i], h = round_tf32(v);
@@ -406,7 +411,7 @@ __global__ void split_tf32_kernel(const float* __restrict__ x, float* __restrict
 
 int launch_split_tf32(const float* x, float* hi, float* lo, long long n, cudaStream_t st) {
     if (n <= 0) return 0;
-    split_tf32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, hi, lo, n);
+    launch_k(split_tf32_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, x, hi, lo, n);
     MV2D_CHECK_LAUNCH("split_tf32");
     return 0;
 }

@@ -12,6 +12,8 @@ namespace mv2d {
 // (pe.py:111; box_correlation.py:118-122).  One block, V*V threads.
 __global__ void geom_prep_kernel(const double* __restrict__ lidar2img, int V,
                                  double* __restrict__ img2lidar, double* __restrict__ trans) {
+    pdl_wait();
+    pdl_trigger();
     __shared__ double inv_s[MV2D_MAXV][16];
     int t = threadIdx.x;
     if (t < V) {
@@ -30,6 +32,8 @@ __global__ void geom_prep_kernel(const double* __restrict__ lidar2img, int V,
 
 // ---- NCHW -> NHWC (the FPN hands us NCHW; every kernel below wants C contiguous)
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, float* __restrict__ out, float* __restrict__ out_tf32, int C, int HW) {
+    pdl_wait();
+    pdl_trigger();
     __shared__ float tile[32][33];
     const int v = blockIdx.z;
     const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -56,6 +60,8 @@ __global__ void pe_coords_kernel(const double* __restrict__ img2lidar, float* __
                                  int V, int h, int w, int D, double pad_h, double pad_w,
                                  double depth_start, double pr0, double pr1, double pr2,
                                  double pr3, double pr4, double pr5) {
+    pdl_wait();
+    pdl_trigger();
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long total = (long long)V * h * w * D;
     if (gid >= total) return;
@@ -86,6 +92,8 @@ __global__ void pe_coords_kernel(const double* __restrict__ img2lidar, float* __
 // Step 1: per pixel the three normalised embeds (view, y, x) from the not-mask cumsums.
 __global__ void sine_prep_kernel(const uint8_t* __restrict__ not_mask, float* __restrict__ emb,
                                  int V, int h, int w, float stride, float scale, float eps) {
+    pdl_wait();
+    pdl_trigger();
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= V * h * w) return;
     const int x = p % w, y = (p / w) % h, v = p / (w * h);
@@ -117,6 +125,8 @@ __global__ void sine_prep_kernel(const uint8_t* __restrict__ not_mask, float* __
 // Step 2: [P, 384] = per embed (n, y, x): 64 sines of even dim_t then 64 cosines of odd dim_t.
 __global__ void sine_embed_kernel(const float* __restrict__ emb, const float* __restrict__ dim_t,
                                   float* __restrict__ out, int P) {
+    pdl_wait();
+    pdl_trigger();
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (long long)P * 384) return;
     const int c = (int)(gid % 384);
@@ -141,14 +151,14 @@ static int gemm(const float* A, int lda, const float* W, int ldw, const float* b
 
 int run_geom_prep(const double* lidar2img, int V, double* img2lidar, double* trans, cudaStream_t st) {
     MV2D_CHECK_ARG(V >= 1 && V <= MV2D_MAXV, "geom_prep: V=%d out of range", V);
-    geom_prep_kernel<<<1, V * V, 0, st>>>(lidar2img, V, img2lidar, trans);
+    launch_k(geom_prep_kernel, dim3(1), dim3(V * V), 0, st, lidar2img, V, img2lidar, trans);
     MV2D_CHECK_LAUNCH("geom_prep");
     return 0;
 }
 
 int run_nchw_to_nhwc(const float* in, float* out, float* out_tf32, int V, int C, int HW, cudaStream_t st) {
     dim3 grid(cdiv(HW, 32), cdiv(C, 32), V), block(32, 8);
-    nchw_to_nhwc_kernel<<<grid, block, 0, st>>>(in, out, out_tf32, C, HW);
+    launch_k(nchw_to_nhwc_kernel, grid, block, 0, st, in, out, out_tf32, C, HW);
     MV2D_CHECK_LAUNCH("nchw_to_nhwc");
     return 0;
 }
@@ -171,7 +181,7 @@ int run_pe3d(const Mv2dPeParams& p, cudaStream_t st) {
     int rc;
     {
         long long total = (long long)P * D;
-        pe_coords_kernel<<<(unsigned)cdiv((int)total, 256), 256, 0, st>>>(
+        launch_k(pe_coords_kernel, dim3((unsigned)cdiv((int)total, 256)), dim3(256), 0, st, 
             p.img2lidar, A1, p.V, p.h, p.w, D, (double)p.pad_h, (double)p.pad_w, p.depth_start,
             p.position_range[0], p.position_range[1], p.position_range[2], p.position_range[3],
             p.position_range[4], p.position_range[5]);
@@ -182,10 +192,10 @@ int run_pe3d(const Mv2dPeParams& p, cudaStream_t st) {
     if ((rc = gemm(Hd, 4 * C, p.w_pos2, 4 * C, p.b_pos2, X, C, P, C, 4 * C, GEMM_TF32_OK, st))) return rc;
     // sine branch: 384 -> 1024 -> 256  (input-independent given masks + weights; recomputed here)
     if (!p.sine_branch_cached) {
-        sine_prep_kernel<<<cdiv(P, 128), 128, 0, st>>>(p.not_mask, EM, p.V, p.h, p.w, (float)p.stride,
+        launch_k(sine_prep_kernel, dim3(cdiv(P, 128)), dim3(128), 0, st, p.not_mask, EM, p.V, p.h, p.w, (float)p.stride,
                                                       6.283185307179586f, 1e-6f);
         MV2D_CHECK_LAUNCH("sine_prep");
-        sine_embed_kernel<<<(unsigned)(((long long)P * 384 + 255) / 256), 256, 0, st>>>(EM, p.dim_t, S, P);
+        launch_k(sine_embed_kernel, dim3((unsigned)(((long long)P * 384 + 255) / 256)), dim3(256), 0, st, (const float*)EM, p.dim_t, S, P);
         MV2D_CHECK_LAUNCH("sine_embed");
         if ((rc = gemm(S, 384, p.w_adapt0, 384, p.b_adapt0, Hd, 4 * C, P, 4 * C, 384, GEMM_RELU | GEMM_TF32_OK | GEMM_ROUND_TF32, st))) return rc;
         if ((rc = gemm(Hd, 4 * C, p.w_adapt2, 4 * C, p.b_adapt2, SB, C, P, C, 4 * C, GEMM_TF32_OK, st))) return rc;

@@ -20,6 +20,8 @@ roi_align_tokens_kernel(const float* __restrict__ rois, const float* __restrict_
                         const float* __restrict__ pe, int h, int w, float spatial_scale,
                         float* __restrict__ tok_feat, float* __restrict__ tok_kin,
                         float* __restrict__ tok_hi, float* __restrict__ tok_lo) {
+    pdl_wait();
+    pdl_trigger();
     const int n = blockIdx.y, bin = blockIdx.x;
     const int ph = bin / MV2D_ROI, pw = bin % MV2D_ROI;
     const float* r = rois + n * 5;
@@ -82,6 +84,8 @@ __global__ void box_params_kernel(const float* __restrict__ rois, const double* 
                                   const double* __restrict__ extrinsics, int N, float feat_scale,
                                   float* __restrict__ cat /*[N,MV2D_CAT_LD]*/, float* __restrict__ m_roi /*[N,16]*/,
                                   double* __restrict__ k_out /*nullable [N,16]*/) {
+    pdl_wait();
+    pdl_trigger();
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N) return;
     const float* r = rois + n * 5;
@@ -112,6 +116,8 @@ __global__ void box_params_kernel(const float* __restrict__ rois, const double* 
 
 // AvgPool2d(7) over the ReLU'd conv output: [N,49,256] -> [N,256]
 __global__ void avgpool49_kernel(const float* __restrict__ x, float* __restrict__ out, int N) {
+    pdl_wait();
+    pdl_trigger();
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= N * MV2D_C) return;
     const int n = gid / MV2D_C, c = gid % MV2D_C;
@@ -127,6 +133,8 @@ __global__ void qg_tail_kernel(const float* __restrict__ enc, const float* __res
                                const float* __restrict__ dim_t, int N, float pc0, float pc1, float pc2,
                                float pc3, float pc4, float pc5, float* __restrict__ ref,
                                float* __restrict__ center_lidar, float* __restrict__ posemb) {
+    pdl_wait();
+    pdl_trigger();
     const int n = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
     const int lane = threadIdx.x & 31;
     if (n >= N) return;
@@ -190,10 +198,10 @@ int run_roi_align_qg(const Mv2dQgParams& p, cudaStream_t st) {
     float* qh = ws;     ws += (size_t)N * C;
     MV2D_CHECK_ARG((size_t)(ws - p.workspace) * sizeof(float) <= p.workspace_bytes, "roi_align_qg: workspace too small");
     int rc;
-    roi_align_tokens_kernel<<<dim3(MV2D_TOK, N), 64, 0, st>>>(p.rois, p.feat, p.tok_kin ? p.pe : nullptr, p.h, p.w,
+    launch_k(roi_align_tokens_kernel, dim3(MV2D_TOK, N), dim3(64), 0, st, p.rois, p.feat, p.tok_kin ? p.pe : nullptr, p.h, p.w,
                                                             1.0f / (float)p.stride, p.tok_feat, p.tok_kin, thi, tlo);
     MV2D_CHECK_LAUNCH("roi_align_tokens");
-    box_params_kernel<<<cdiv(N, 64), 64, 0, st>>>(p.rois, p.intrinsics, p.extrinsics, N, p.intrins_feat_scale, cat,
+    launch_k(box_params_kernel, dim3(cdiv(N, 64)), dim3(64), 0, st, p.rois, p.intrinsics, p.extrinsics, N, p.intrins_feat_scale, cat,
                                                   mroi, p.roi_intrinsics);
     MV2D_CHECK_LAUNCH("box_params");
     // shared conv 3x3 (+ReLU) as implicit GEMM over the tokens, avg-pool, FC chain
@@ -203,12 +211,12 @@ int run_roi_align_qg(const Mv2dQgParams& p, cudaStream_t st) {
         t.C = conv; t.ldc = C; t.M = N * MV2D_TOK; t.N = C; t.K = 9 * C; t.passes = 3; t.im2col = 1; t.flags = GEMM_RELU;
         if ((rc = launch_gemm_tc(t, st))) return rc;
     }
-    avgpool49_kernel<<<cdiv(N * C, 256), 256, 0, st>>>(conv, pool, N);
+    launch_k(avgpool49_kernel, dim3(cdiv(N * C, 256)), dim3(256), 0, st, (const float*)conv, pool, N);
     MV2D_CHECK_LAUNCH("avgpool49");
     if ((rc = gemm(pool, C, p.w_fc, C, p.b_fc, cat, MV2D_CAT_LD, N, 1024, C, GEMM_RELU | GEMM_CLAMP5E3, A_PLAIN, st))) return rc;
     if ((rc = gemm(cat, MV2D_CAT_LD, p.w_enc0, MV2D_CAT_LD, p.b_enc0, e0, 512, N, 512, MV2D_CAT_LD, GEMM_RELU, A_PLAIN, st))) return rc;
     if ((rc = gemm(e0, 512, p.w_enc2, 512, p.b_enc2, enc, C, N, C, 512, GEMM_RELU, A_PLAIN, st))) return rc;
-    qg_tail_kernel<<<cdiv(N, 4), 128, 0, st>>>(enc, p.w_center, p.b_center, mroi, p.dim_t, N, p.pc_range[0],
+    launch_k(qg_tail_kernel, dim3(cdiv(N, 4)), dim3(128), 0, st, (const float*)enc, p.w_center, p.b_center, mroi, p.dim_t, N, p.pc_range[0],
                                                p.pc_range[1], p.pc_range[2], p.pc_range[3], p.pc_range[4],
                                                p.pc_range[5], p.ref, p.center_lidar, pemb);
     MV2D_CHECK_LAUNCH("qg_tail");
@@ -237,6 +245,8 @@ __device__ inline float block_min128(float v, float* red) {
 
 __global__ void __launch_bounds__(128)
 box_corr_kernel(Mv2dCorrParams p) {
+    pdl_wait();
+    pdl_trigger();
     __shared__ float red[4];
     __shared__ float iou_s[CORR_MAXR];
     __shared__ int cnt_s, kept_s;
@@ -320,6 +330,8 @@ box_corr_kernel(Mv2dCorrParams p) {
 // RoIs, minus padded-out cells (box_correlation.py:102-115,147-157; mv2d_t_head.py:67-88).
 __global__ void __launch_bounds__(256)
 key_mask_kernel(Mv2dCorrParams p, int words) {
+    pdl_wait();
+    pdl_trigger();
     extern __shared__ uint32_t bits[];
     __shared__ int total;
     const int n = blockIdx.x, t = threadIdx.x;
@@ -370,11 +382,11 @@ int run_box_corr(const Mv2dCorrParams& p, cudaStream_t st) {
                    "box_corr: sample_size^2*num_depth must be 128 (got %d)", p.sample_size * p.sample_size * p.num_depth);
     MV2D_CHECK_ARG(p.max_match >= 1 && p.topk >= 1, "box_corr: bad max_match/topk");
     if (p.N == 0) return 0;
-    box_corr_kernel<<<p.N, 128, 0, st>>>(p);
+    launch_k(box_corr_kernel, dim3(p.N), dim3(128), 0, st, p);
     MV2D_CHECK_LAUNCH("box_corr");
     if (p.keymask) {
         const int words = cdiv(p.V * p.h * p.w, 32);
-        key_mask_kernel<<<p.N, 256, words * sizeof(uint32_t), st>>>(p, words);
+        launch_k(key_mask_kernel, dim3(p.N), dim3(256), words * sizeof(uint32_t), st, p, words);
         MV2D_CHECK_LAUNCH("key_mask");
     }
     return 0;

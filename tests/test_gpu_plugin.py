@@ -37,7 +37,7 @@ def close(a, b, atol=1e-3, rtol=1e-3):
     assert (np.abs(a - b) <= atol + rtol * np.abs(b)).all(), f'max |d| = {np.abs(a - b).max():.3e}'
 
 
-@pytest.mark.parametrize('name', ['s_small', 's_empty', 't_small'])
+@pytest.mark.parametrize('name', ['s_small', 's_cfg2', 't_small'])
 def test_head_bbox_forward_and_simple_test(name, state_dicts):
     spec, g = golden(name)
     h = head(spec['mode'], state_dicts)

@@ -52,6 +52,13 @@ t_eager = timed(lambda: eng.forward(featc, boxes, metas))
 t_graph = timed(lambda: eng.forward(featc, boxes, metas, use_graph=True))
 og = eng.forward(featc, boxes, metas, use_graph=True); oe_cls = eng.forward(featc, boxes, metas)['cls_scores'].clone()
 print(f'whole path: eager {t_eager:.1f} us   graph {t_graph:.1f} us   graph==eager: {torch.equal(og["cls_scores"], oe_cls)}')
+# SM clock seen by kernels right after a burst of path replays
+from mv2d_b200 import lib as L
+probe = torch.zeros(2, dtype=torch.int64, device='cuda')
+for _ in range(20): eng.forward(featc, boxes, metas, use_graph=True)
+L.check(eng.lib.mv2d_debug_clock_probe(2_000_000, probe.data_ptr(), L.stream_ptr()), 'probe')
+torch.cuda.synchronize()
+print(f'SM clock under this load: {probe[1].item() / probe[0].item() * 1e3:.0f} MHz')
 tot = sum(acc.values())
 for n, t in acc.items():
     print(f'{n:16s} {t / reps * 1e3:9.1f} us  {100 * t / tot:5.1f} %')
