@@ -158,14 +158,13 @@ def main():
         return
     import torch
     import torch.distributed as dist
+    from mv2d_b200 import dist as D
     from mv2d_b200 import synth
     from mv2d_b200.engine import HotPath
     assert torch.cuda.is_available(), 'bench.py needs a GPU (mv2d_b200 has no CPU fallback)'
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
-    if world > 1:
-        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        dist.init_process_group('nccl', device_id=dev)
+    D.init('nccl', dev)
     assert world == args.gpus, f'--gpus {args.gpus} but WORLD_SIZE={world}'
     peaks = measured_peaks()
 
@@ -174,7 +173,7 @@ def main():
     eng = HotPath(sd, mode=mode, device=dev)
     # a few distinct samples per rank (different seeds per rank: replicas work on different data)
     n_var = 4
-    samples = [make_inputs(mode, seed=100 * rank + i) for i in range(n_var)]
+    samples = [make_inputs(mode, seed=i) for i in D.shard_samples(n_var * world, rank, world)]
     feats_dev = [s[0].to(dev) for s in samples]
     feats_pin = [s[0].pin_memory() for s in samples]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
@@ -228,13 +227,10 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
 
     # max over ranks of the summed device time
-    t = torch.tensor([total_ms, e2e_total_ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, e2e_total_ms = t.tolist()
+    total_ms, e2e_total_ms = D.max_over_ranks([total_ms, e2e_total_ms], device=dev)
     ms_per_step = total_ms / args.steps
-    value = world * 1e3 / ms_per_step
-    e2e_value = world * 1e3 / (e2e_total_ms / args.steps)
+    value = D.aggregate_throughput(world, args.steps, 1, total_ms)
+    e2e_value = D.aggregate_throughput(world, args.steps, 1, e2e_total_ms)
 
     if rank != 0:
         if world > 1:

@@ -154,15 +154,23 @@ self_attn_kernel(const float* __restrict__ qkv, const uint8_t* __restrict__ mask
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int k0 = 0; k0 < N; k0 += SA_KT) {
         __syncthreads();
-        for (int i = threadIdx.x; i < SA_KT * 8; i += 256) {
-            const int r = i >> 3, c4 = i & 7, k = k0 + r;
-            float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
-            if (k < N) {
-                kv = __ldg(reinterpret_cast<const float4*>(qkv + (long long)k * 768 + 256 + hd * 32) + c4);
-                vv = __ldg(reinterpret_cast<const float4*>(qkv + (long long)k * 768 + 512 + hd * 32) + c4);
+        {   // all 8 loads of a thread are issued before the first store (one memory latency per tile)
+            float4 kv[4], vv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = threadIdx.x + u * 256, r = i >> 3, c4 = i & 7, k = k0 + r;
+                kv[u] = make_float4(0.f, 0.f, 0.f, 0.f); vv[u] = kv[u];
+                if (k < N) {
+                    kv[u] = __ldg(reinterpret_cast<const float4*>(qkv + (long long)k * 768 + 256 + hd * 32) + c4);
+                    vv[u] = __ldg(reinterpret_cast<const float4*>(qkv + (long long)k * 768 + 512 + hd * 32) + c4);
+                }
             }
-            *reinterpret_cast<float4*>(&Ks[r][c4 * 4]) = kv;
-            *reinterpret_cast<float4*>(&Vs[r][c4 * 4]) = vv;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = threadIdx.x + u * 256, r = i >> 3, c4 = i & 7;
+                *reinterpret_cast<float4*>(&Ks[r][c4 * 4]) = kv[u];
+                *reinterpret_cast<float4*>(&Vs[r][c4 * 4]) = vv[u];
+            }
         }
         __syncthreads();
         if (!qok) continue;

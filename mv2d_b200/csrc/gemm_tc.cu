@@ -104,7 +104,7 @@ struct TcArgs {
 };
 
 template <int BN, int PASSES, bool IM2COL, int STAGES>
-__global__ void __launch_bounds__(TC_THREADS)
+__global__ void __launch_bounds__(TC_THREADS, (PASSES == 1 ? 2 : 1))
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
                const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmWlo, TcArgs g) {
     constexpr int A_BYTES = TC_BM * TC_BK * 4;      // 16 KB
@@ -196,69 +196,104 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             umma_commit(tmem_full_bar);                   // accumulator complete
         }
     } else {
-        // ================= epilogue: TMEM -> registers -> global =================
+        // ================= epilogue: TMEM -> registers -> (smem transpose) -> global =================
+        // tcgen05.ld hands each thread one ROW of the tile (32 consecutive columns per chunk).  Storing that
+        // directly would write 16-byte pieces 4 KB apart; instead every warp transposes its 32x32 chunk through
+        // a private, XOR-swizzled 4 KB staging tile (the pipeline stages are free by now) so that each store /
+        // load instruction of the warp touches 4 rows x 128 contiguous bytes.
         mbar_wait(tmem_full_bar, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int q = warp & 3;                           // TMEM lane quadrant this warp may access
-        const int r = q * 32 + lane;                      // row inside the tile
-        long long orow;
-        bool row_ok;
-        if (IM2COL) {
-            const int roi = m_tile * 2 + (r >> 6), tok = r & 63;
-            row_ok = tok < MV2D_TOK && roi < g.n_rois;
-            orow = (long long)roi * MV2D_TOK + tok;
-        } else {
+        float* stg = reinterpret_cast<float*>(smem) + q * 1024;
+        auto out_row = [&](int r, long long& orow) -> bool {   // tile row -> output row
+            if (IM2COL) {
+                const int roi = m_tile * 2 + (r >> 6), tok = r & 63;
+                orow = (long long)roi * MV2D_TOK + tok;
+                return tok < MV2D_TOK && roi < g.n_rois;
+            }
             orow = (long long)m_tile * TC_BM + r;
-            row_ok = orow < g.M;
-        }
+            return orow < g.M;
+        };
+        // registers (my row, 32 cols) -> global [4 rows x 128 B per instruction]
+        auto store_t = [&](float* __restrict__ dst, const float (&x)[32], int n) {
+            __syncwarp();
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4)
+                *reinterpret_cast<float4*>(stg + lane * 32 + ((j4 ^ (lane & 7)) << 2)) =
+                    make_float4(x[j4 * 4], x[j4 * 4 + 1], x[j4 * 4 + 2], x[j4 * 4 + 3]);
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int rr = i * 4 + (lane >> 3), cc = lane & 7;
+                const float4 v4 = *reinterpret_cast<const float4*>(stg + rr * 32 + ((cc ^ (rr & 7)) << 2));
+                long long orow;
+                if (out_row(q * 32 + rr, orow)) *reinterpret_cast<float4*>(dst + orow * g.ldc + n + cc * 4) = v4;
+            }
+        };
+        // global -> registers (my row, 32 cols), same access pattern in reverse
+        auto load_t = [&](const float* __restrict__ src, float (&x)[32], int n) {
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int rr = i * 4 + (lane >> 3), cc = lane & 7;
+                long long orow;
+                float4 v4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (out_row(q * 32 + rr, orow)) v4 = __ldg(reinterpret_cast<const float4*>(src + orow * g.ldc + n + cc * 4));
+                *reinterpret_cast<float4*>(stg + rr * 32 + ((cc ^ (rr & 7)) << 2)) = v4;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+                const float4 v4 = *reinterpret_cast<const float4*>(stg + lane * 32 + ((j4 ^ (lane & 7)) << 2));
+                x[j4 * 4] = v4.x; x[j4 * 4 + 1] = v4.y; x[j4 * 4 + 2] = v4.z; x[j4 * 4 + 3] = v4.w;
+            }
+        };
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
             uint32_t v[32];
             tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
-            if (!row_ok) continue;
             const int n = n0 + c * 32;
-            const long long o = orow * g.ldc + n;
-            if (gridDim.z > 1) {   // split-K: raw partial sums, finished by the LN/reduce kernel
-                float* dst = g.C + blockIdx.z * g.split_stride + o;
+            float x[32];
 #pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                    *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
-                                                                      __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+            for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
+            if (gridDim.z > 1) {   // split-K: raw partial sums, finished by the LN/reduce kernel
+                store_t(g.C + blockIdx.z * g.split_stride, x, n);
                 continue;
             }
+            if (g.bias) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-                float x[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    x[i] = __uint_as_float(v[j + i]);
-                    if (g.bias) x[i] += __ldg(g.bias + n + j + i);
-                    if (g.flags & GEMM_RELU) x[i] = fmaxf(x[i], 0.f);
-                }
-                if (g.flags & GEMM_SPLIT_OUT) {
-                    float hi[4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) { hi[i] = round_tf32(x[i]); x[i] = round_tf32(x[i] - hi[i]); }
-                    *reinterpret_cast<float4*>(g.C + o + j) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-                    *reinterpret_cast<float4*>(g.C_lo + o + j) = make_float4(x[0], x[1], x[2], x[3]);
-                    continue;
-                }
-                if (g.flags & GEMM_GATE) {
-                    const float4 xx = __ldg(reinterpret_cast<const float4*>(g.gx + o + j));
-                    const float4 ss = __ldg(reinterpret_cast<const float4*>(g.gs + o + j));
-                    x[0] = xx.x * sigmoid_f(x[0]) + ss.x; x[1] = xx.y * sigmoid_f(x[1]) + ss.y;
-                    x[2] = xx.z * sigmoid_f(x[2]) + ss.z; x[3] = xx.w * sigmoid_f(x[3]) + ss.w;
-                    if (g.kin) {
-                        const float4 ff = __ldg(reinterpret_cast<const float4*>(g.gfeat + o + j));
-                        *reinterpret_cast<float4*>(g.kin + o + j) = make_float4(x[0] + ff.x, x[1] + ff.y, x[2] + ff.z, x[3] + ff.w);
-                    }
-                }
-                if (g.flags & GEMM_ROUND_TF32) {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) x[i] = round_tf32(x[i]);
-                }
-                *reinterpret_cast<float4*>(g.C + o + j) = make_float4(x[0], x[1], x[2], x[3]);
+                for (int j = 0; j < 32; ++j) x[j] += __ldg(g.bias + n + j);
             }
+            if (g.flags & GEMM_RELU) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
+            }
+            if (g.flags & GEMM_GATE) {   // pe = gx * sigmoid(acc) + gs ; kin = pe + gfeat   (pe.py:44-48,166)
+                float t[32];
+                load_t(g.gx, t, n);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) x[j] = t[j] * sigmoid_f(x[j]);
+                load_t(g.gs, t, n);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) x[j] += t[j];
+                if (g.kin) {
+                    load_t(g.gfeat, t, n);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) t[j] += x[j];
+                    store_t(g.kin, t, n);
+                }
+            }
+            if (g.flags & GEMM_ROUND_TF32) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) x[j] = round_tf32(x[j]);
+            }
+            if (g.flags & GEMM_SPLIT_OUT) {
+                float lo[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) { const float hi = round_tf32(x[j]); lo[j] = round_tf32(x[j] - hi); x[j] = hi; }
+                store_t(g.C_lo, lo, n);
+            }
+            store_t(g.C, x, n);
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -368,7 +403,9 @@ static int launch_tc(const CUtensorMap& a, const CUtensorMap& alo, const CUtenso
 }
 
 int launch_gemm_tc(const TcGemm& t, cudaStream_t st) {
-    MV2D_CHECK_ARG(t.M > 0 && t.N % 128 == 0 && t.K % TC_BK == 0, "gemm_tc: need N%%128==0 and K%%32==0 (N=%d K=%d)", t.N, t.K);
+    // small-M problems (the decoder, M ~ 300) are latency bound: 64-wide N tiles double the CTA count
+    const int bn = (t.M <= 512 && !t.im2col && t.passes == 3) ? 64 : 128;
+    MV2D_CHECK_ARG(t.M > 0 && t.N % bn == 0 && t.K % TC_BK == 0, "gemm_tc: need N%%%d==0 and K%%32==0 (N=%d K=%d)", bn, t.N, t.K);
     MV2D_CHECK_ARG((t.ldc & 3) == 0 && ((uintptr_t)t.C & 15) == 0, "gemm_tc: C must be 16-byte aligned");
     MV2D_CHECK_ARG(t.passes == 1 || (t.A_lo && t.W_lo), "gemm_tc: 3xTF32 needs the lo operands");
     CUtensorMap a, alo, w, wlo;
@@ -392,9 +429,10 @@ int launch_gemm_tc(const TcGemm& t, cudaStream_t st) {
         if ((rc = make_map_2d(&a, t.A, t.M, t.K, t.lda, TC_BM))) return rc;
         if ((rc = make_map_2d(&alo, t.passes == 3 ? t.A_lo : t.A, t.M, t.K, t.lda, TC_BM))) return rc;
     }
-    if ((rc = make_map_2d(&w, t.W, t.N, t.K, t.ldw, 128))) return rc;
-    if ((rc = make_map_2d(&wlo, t.passes == 3 ? t.W_lo : t.W, t.N, t.K, t.ldw, 128))) return rc;
+    if ((rc = make_map_2d(&w, t.W, t.N, t.K, t.ldw, bn))) return rc;
+    if ((rc = make_map_2d(&wlo, t.passes == 3 ? t.W_lo : t.W, t.N, t.K, t.ldw, bn))) return rc;
     if (t.im2col) return launch_tc<128, 3, true, 3>(a, alo, w, wlo, g, m_tiles, nsplit, st);
+    if (t.passes == 3 && bn == 64) return launch_tc<64, 3, false, 4>(a, alo, w, wlo, g, m_tiles, nsplit, st);
     if (t.passes == 3) return launch_tc<128, 3, false, 3>(a, alo, w, wlo, g, m_tiles, nsplit, st);
     return launch_tc<128, 1, false, 3>(a, alo, w, wlo, g, m_tiles, nsplit, st);
 }
