@@ -340,8 +340,7 @@ def roofline_section(eng, out, mode, N, flush, peaks):
     # --- per-stage device time (eager launches, L2 flushed before each stage)
     feat_nchw, boxes, metas = out['_inputs']
     V, _, hh, ww = feat_nchw.shape
-    cams = eng._upload_cams(metas)
-    rois, roi_start, counts, _ = eng._upload_rois(boxes)
+    cams, rois, roi_start, counts, _ = eng._upload_meta(boxes, metas)
     st = {}
     st['nchw_to_nhwc'] = time_fn(lambda: eng.to_nhwc(feat_nchw))
     f, f32r = eng.to_nhwc(feat_nchw)

@@ -404,7 +404,7 @@ static int launch_tc(const CUtensorMap& a, const CUtensorMap& alo, const CUtenso
 
 int launch_gemm_tc(const TcGemm& t, cudaStream_t st) {
     // small-M problems (the decoder, M ~ 300) are latency bound: 64-wide N tiles double the CTA count
-    const int bn = (t.M <= 512 && !t.im2col && t.passes == 3) ? 64 : 128;
+    const int bn = (t.M <= 512 && !t.im2col && t.passes == 3) ? 64 : 128;   // (a 256-wide, 2-stage im2col variant measured slower than 128-wide / 3 stages)
     MV2D_CHECK_ARG(t.M > 0 && t.N % bn == 0 && t.K % TC_BK == 0, "gemm_tc: need N%%%d==0 and K%%32==0 (N=%d K=%d)", bn, t.N, t.K);
     MV2D_CHECK_ARG((t.ldc & 3) == 0 && ((uintptr_t)t.C & 15) == 0, "gemm_tc: C must be 16-byte aligned");
     MV2D_CHECK_ARG(t.passes == 1 || (t.A_lo && t.W_lo), "gemm_tc: 3xTF32 needs the lo operands");
@@ -431,6 +431,7 @@ int launch_gemm_tc(const TcGemm& t, cudaStream_t st) {
     }
     if ((rc = make_map_2d(&w, t.W, t.N, t.K, t.ldw, bn))) return rc;
     if ((rc = make_map_2d(&wlo, t.passes == 3 ? t.W_lo : t.W, t.N, t.K, t.ldw, bn))) return rc;
+    if (t.im2col && bn == 256) return launch_tc<256, 3, true, 2>(a, alo, w, wlo, g, m_tiles, nsplit, st);
     if (t.im2col) return launch_tc<128, 3, true, 3>(a, alo, w, wlo, g, m_tiles, nsplit, st);
     if (t.passes == 3 && bn == 64) return launch_tc<64, 3, false, 4>(a, alo, w, wlo, g, m_tiles, nsplit, st);
     if (t.passes == 3) return launch_tc<128, 3, false, 3>(a, alo, w, wlo, g, m_tiles, nsplit, st);

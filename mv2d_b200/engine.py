@@ -98,54 +98,68 @@ class HotPath:
         return ent
 
     # ------------------------------------------------------------------ stages
-    def _pinned(self, name, shape, dtype):
-        n = int(np.prod(shape))
-        t = self._pin.get(name)
-        if t is None or t.numel() < n or t.dtype != dtype:
-            t = torch.empty(max(n, 1), dtype=dtype).pin_memory()
-            self._pin[name] = t
-        return t[:n].view(*shape)
-
-    def _upload_cams(self, img_metas):
+    def _upload_meta(self, proposal_list, img_metas):
+        """Per-sample metadata in ONE pinned staging buffer and ONE H2D copy:
+        [lidar2img | intrinsics | extrinsics] (3*V*16 f64), rois (N*5 f32), roi_start ((V+1) i32).
+        rois follow mmdet bbox2roi: (view, x1, y1, x2, y2); an empty detection set becomes the
+        reference's dummy box (mv2d_s_head.py:124-127)."""
         V = len(img_metas)
-        cams_t = self._pinned('cams', (3, V, 16), torch.float64)
-        cams = cams_t.numpy()
-        for v, m in enumerate(img_metas):
-            cams[0, v] = np.asarray(m['lidar2img'], dtype=np.float64).reshape(16)
-            cams[1, v] = np.asarray(m['intrinsics'], dtype=np.float64).reshape(16)
-            cams[2, v] = np.asarray(m['extrinsics'], dtype=np.float64).reshape(16)
-        d = self._get('cams', (3, V, 16), torch.float64)
-        d.copy_(cams_t, non_blocking=True)
-        return d
-
-    def _upload_rois(self, proposal_list):
-        if sum(len(p) for p in proposal_list) == 0:   # mv2d_s_head.py:124-127
+        if sum(len(p) for p in proposal_list) == 0:
             p0 = torch.tensor([[0, 50, 50, 100, 100, 0]], dtype=torch.float32, device=proposal_list[0].device)
             proposal_list = [p0] + list(proposal_list[1:])
         counts = [int(p.shape[0]) for p in proposal_list]
         N = sum(counts)
-        starts = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
-        rois = self._get('rois', (N, 5))
-        if proposal_list[0].is_cuda:   # bbox2roi on the device the detections live on
-            view = torch.repeat_interleave(torch.arange(len(counts), device=self.device, dtype=torch.float32),
-                                           torch.tensor(counts, device=self.device))
-            rois[:, 0] = view
-            rois[:, 1:] = torch.cat([p[:, :4].float() for p in proposal_list], 0)
-        else:
-            host_t = self._pinned('rois', (N, 5), torch.float32)
-            host = host_t.numpy()
+        on_device = proposal_list[0].is_cuda
+        cam_b, roi_b, st_b = 3 * V * 16 * 8, N * 5 * 4, (V + 1) * 4
+        roi_off = cam_b
+        st_off = (roi_off + roi_b + 7) // 8 * 8
+        total = st_off + st_b
+        pin = self._pin.get('meta')
+        if pin is None:   # fixed capacity: captured graphs bake the device address in, it must never move
+            pin = torch.empty(128 * 1024, dtype=torch.uint8).pin_memory()
+            self._pin['meta'] = pin
+        assert total <= pin.numel(), f'too many RoIs/views for the metadata buffer ({total} B)'
+        dev = self._get('meta', (pin.numel(),), torch.uint8)
+        host = pin.numpy()
+        cams = host[:cam_b].view(np.float64).reshape(3, V, 16)
+        for v, m in enumerate(img_metas):
+            cams[0, v] = np.asarray(m['lidar2img'], dtype=np.float64).reshape(16)
+            cams[1, v] = np.asarray(m['intrinsics'], dtype=np.float64).reshape(16)
+            cams[2, v] = np.asarray(m['extrinsics'], dtype=np.float64).reshape(16)
+        if not on_device:
+            rh = host[roi_off:roi_off + roi_b].view(np.float32).reshape(N, 5)
             o = 0
             for v, p in enumerate(proposal_list):
                 n = counts[v]
-                host[o:o + n, 0] = v
-                host[o:o + n, 1:] = p[:, :4].float().numpy()
+                rh[o:o + n, 0] = v
+                rh[o:o + n, 1:] = p[:, :4].float().numpy()
                 o += n
-            rois.copy_(host_t, non_blocking=True)
-        roi_start = self._get('roi_start', (len(counts) + 1,), torch.int32)
-        starts_t = self._pinned('roi_start', (len(counts) + 1,), torch.int32)
-        starts_t.copy_(torch.from_numpy(starts))
-        roi_start.copy_(starts_t, non_blocking=True)
-        return rois, roi_start, counts, N
+        host[st_off:st_off + st_b].view(np.int32)[:] = np.concatenate([[0], np.cumsum(counts)])
+        dev[:total].copy_(pin[:total], non_blocking=True)
+        d_cams = dev[:cam_b].view(torch.float64).view(3, V, 16)
+        d_rois = dev[roi_off:roi_off + roi_b].view(torch.float32).view(N, 5)
+        d_start = dev[st_off:st_off + st_b].view(torch.int32)
+        if on_device:   # detections already live on the GPU: bbox2roi there
+            view = torch.repeat_interleave(torch.arange(V, device=self.device, dtype=torch.float32),
+                                           torch.tensor(counts, device=self.device))
+            d_rois[:, 0] = view
+            d_rois[:, 1:] = torch.cat([p[:, :4].float() for p in proposal_list], 0)
+        return d_cams, d_rois, d_start, counts, N
+
+    def _upload_cams(self, img_metas):
+        """Camera matrices only (stage-level entry points of the plugin modules)."""
+        V = len(img_metas)
+        cams = np.empty((3, V, 16), dtype=np.float64)
+        for v, m in enumerate(img_metas):
+            cams[0, v] = np.asarray(m['lidar2img'], dtype=np.float64).reshape(16)
+            cams[1, v] = np.asarray(m['intrinsics'], dtype=np.float64).reshape(16)
+            cams[2, v] = np.asarray(m['extrinsics'], dtype=np.float64).reshape(16)
+        d = self._get('cams_only', (3, V, 16), torch.float64)
+        d.copy_(torch.from_numpy(cams), non_blocking=True)
+        return d
+
+    def _upload_rois(self, proposal_list):
+        raise RuntimeError('use _upload_meta')
 
     def geom_prep(self, cams):
         V = cams.shape[1]
@@ -321,8 +335,7 @@ class HotPath:
         masks) signature: inputs are copied into the graph's static buffers, then one launch."""
         if not use_graph:
             feat = feat.to(self.device, torch.float32, non_blocking=True).contiguous()
-            cams = self._upload_cams(img_metas)
-            rois, roi_start, counts, N = self._upload_rois(proposal_list)
+            cams, rois, roi_start, counts, N = self._upload_meta(proposal_list, img_metas)
             return self._enqueue(feat, feat_is_nhwc, cams, rois, roi_start, counts, N, img_metas)
         assert not feat_is_nhwc
         counts = [int(p.shape[0]) for p in proposal_list]
@@ -334,8 +347,7 @@ class HotPath:
             # warm-up (eager) run: sizes every buffer and sets kernel attributes, then capture
             static_feat = torch.empty(tuple(feat.shape), dtype=torch.float32, device=self.device)
             static_feat.copy_(feat, non_blocking=True)
-            cams = self._upload_cams(img_metas)
-            rois, roi_start, counts, N = self._upload_rois(proposal_list)
+            cams, rois, roi_start, counts, N = self._upload_meta(proposal_list, img_metas)
             self._enqueue(static_feat, False, cams, rois, roi_start, counts, N, img_metas)
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
@@ -346,8 +358,7 @@ class HotPath:
                        keep=dict(self._buf))     # the graph bakes these buffer addresses in
             self._graphs[key] = ent
         ent['feat'].copy_(feat, non_blocking=True)
-        self._upload_cams(img_metas)
-        _, _, counts, _ = self._upload_rois(proposal_list)
+        _, _, _, counts, _ = self._upload_meta(proposal_list, img_metas)
         ent['graph'].replay()
         self.graph_launches += ent['launches']
         out = dict(ent['out'])

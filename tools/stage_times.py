@@ -26,7 +26,7 @@ acc = {}
 for _ in range(reps):
     names.clear(); evs[:] = [ev()]; evs[0].record()
     f, f32r = eng.to_nhwc(featc); mark('nchw_to_nhwc')
-    cams = eng._upload_cams(metas); rois, roi_start, counts, N = eng._upload_rois(boxes); mark('uploads')
+    cams, rois, roi_start, counts, N = eng._upload_meta(boxes, metas); mark('uploads')
     i2l, trans = eng.geom_prep(cams); mark('geom_prep')
     pe, kin = eng.pe3d(f, i2l, metas, f32r); mark('pe3d')
     qg = eng.roi_align_qg(rois, cams, f, pe, N); mark('roi_align_qg')
