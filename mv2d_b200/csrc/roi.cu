@@ -20,6 +20,7 @@ roi_align_tokens_kernel(const float* __restrict__ rois, const float* __restrict_
                         const float* __restrict__ pe, int h, int w, float spatial_scale,
                         float* __restrict__ tok_feat, float* __restrict__ tok_kin,
                         float* __restrict__ tok_hi, float* __restrict__ tok_lo) {
+    // feat == nullptr: second phase -- pool only pe and add the already pooled tok_feat (tok_kin = tok_feat + pool(pe))
     pdl_wait();
     pdl_trigger();
     const int n = blockIdx.y, bin = blockIdx.x;
@@ -32,7 +33,7 @@ roi_align_tokens_kernel(const float* __restrict__ rois, const float* __restrict_
     const float bw = rw / (float)MV2D_ROI, bh = rh / (float)MV2D_ROI;
     const int gh = (int)ceilf(rh / (float)MV2D_ROI), gw = (int)ceilf(rw / (float)MV2D_ROI);
     const float count = (float)max(gh * gw, 1);
-    const float4* f4 = reinterpret_cast<const float4*>(feat) + (long long)v * h * w * 64 + threadIdx.x;
+    const float4* f4 = feat ? reinterpret_cast<const float4*>(feat) + (long long)v * h * w * 64 + threadIdx.x : nullptr;
     const float4* p4 = pe ? reinterpret_cast<const float4*>(pe) + (long long)v * h * w * 64 + threadIdx.x : nullptr;
     float4 af = make_float4(0.f, 0.f, 0.f, 0.f), ap = af;
     for (int iy = 0; iy < gh; ++iy) {
@@ -48,11 +49,14 @@ roi_align_tokens_kernel(const float* __restrict__ rois, const float* __restrict_
             const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
             const int o1 = (yl * w + xl) * 64, o2 = (yl * w + xh) * 64, o3 = (yh * w + xl) * 64,
                       o4 = (yh * w + xh) * 64;
-            float4 a = __ldg(f4 + o1), b = __ldg(f4 + o2), c = __ldg(f4 + o3), d = __ldg(f4 + o4);
-            af.x += w1 * a.x + w2 * b.x + w3 * c.x + w4 * d.x;
-            af.y += w1 * a.y + w2 * b.y + w3 * c.y + w4 * d.y;
-            af.z += w1 * a.z + w2 * b.z + w3 * c.z + w4 * d.z;
-            af.w += w1 * a.w + w2 * b.w + w3 * c.w + w4 * d.w;
+            float4 a, b, c, d;
+            if (f4) {
+                a = __ldg(f4 + o1); b = __ldg(f4 + o2); c = __ldg(f4 + o3); d = __ldg(f4 + o4);
+                af.x += w1 * a.x + w2 * b.x + w3 * c.x + w4 * d.x;
+                af.y += w1 * a.y + w2 * b.y + w3 * c.y + w4 * d.y;
+                af.z += w1 * a.z + w2 * b.z + w3 * c.z + w4 * d.z;
+                af.w += w1 * a.w + w2 * b.w + w3 * c.w + w4 * d.w;
+            }
             if (p4) {
                 a = __ldg(p4 + o1); b = __ldg(p4 + o2); c = __ldg(p4 + o3); d = __ldg(p4 + o4);
                 ap.x += w1 * a.x + w2 * b.x + w3 * c.x + w4 * d.x;
@@ -62,10 +66,11 @@ roi_align_tokens_kernel(const float* __restrict__ rois, const float* __restrict_
             }
         }
     }
-    af.x /= count; af.y /= count; af.z /= count; af.w /= count;
     const long long o = ((long long)n * MV2D_TOK + bin) * 64 + threadIdx.x;
-    reinterpret_cast<float4*>(tok_feat)[o] = af;
-    {   // TF32 hi/lo split of the pooled feature: operands of the 3xTF32 conv GEMM
+    if (!f4) af = reinterpret_cast<const float4*>(tok_feat)[o];   // phase 2: pooled feature from phase 1
+    else { af.x /= count; af.y /= count; af.z /= count; af.w /= count; }
+    if (f4) reinterpret_cast<float4*>(tok_feat)[o] = af;
+    if (f4) {   // TF32 hi/lo split of the pooled feature: operands of the 3xTF32 conv GEMM
         float4 hi = make_float4(round_tf32(af.x), round_tf32(af.y), round_tf32(af.z), round_tf32(af.w));
         reinterpret_cast<float4*>(tok_hi)[o] = hi;
         reinterpret_cast<float4*>(tok_lo)[o] = make_float4(round_tf32(af.x - hi.x), round_tf32(af.y - hi.y),
@@ -184,7 +189,16 @@ int run_roi_align_qg(const Mv2dQgParams& p, cudaStream_t st) {
     const int N = p.N, C = MV2D_C;
     MV2D_CHECK_ARG(N >= 0 && p.V >= 1 && p.V <= MV2D_MAXV, "roi_align_qg: bad N/V");
     if (N == 0) return 0;
-    MV2D_CHECK_ARG(p.tok_kin == nullptr || p.pe != nullptr, "roi_align_qg: tok_kin needs pe");
+    MV2D_CHECK_ARG(p.phase >= 0 && p.phase <= 2, "roi_align_qg: phase must be 0, 1 or 2");
+    MV2D_CHECK_ARG(p.phase == 1 || p.tok_kin == nullptr || p.pe != nullptr, "roi_align_qg: tok_kin needs pe");
+    if (p.phase == 2) {   // only the position-embedding tokens: tok_kin = tok_feat + RoIAlign(pe)
+        if (p.tok_kin == nullptr) return 0;
+        launch_k(roi_align_tokens_kernel, dim3(MV2D_TOK, N), dim3(64), 0, st, p.rois, (const float*)nullptr, p.pe, p.h, p.w,
+                 1.0f / (float)p.stride, p.tok_feat, p.tok_kin, (float*)nullptr, (float*)nullptr);
+        MV2D_CHECK_LAUNCH("roi_align_tokens(pe)");
+        return 0;
+    }
+    const bool with_pe = p.phase == 0 && p.tok_kin != nullptr;
     float* ws = p.workspace;
     float* conv = ws;   ws += (size_t)N * MV2D_TOK * C;
     float* thi = ws;    ws += (size_t)N * MV2D_TOK * C;
@@ -198,8 +212,8 @@ int run_roi_align_qg(const Mv2dQgParams& p, cudaStream_t st) {
     float* qh = ws;     ws += (size_t)N * C;
     MV2D_CHECK_ARG((size_t)(ws - p.workspace) * sizeof(float) <= p.workspace_bytes, "roi_align_qg: workspace too small");
     int rc;
-    launch_k(roi_align_tokens_kernel, dim3(MV2D_TOK, N), dim3(64), 0, st, p.rois, p.feat, p.tok_kin ? p.pe : nullptr, p.h, p.w,
-                                                            1.0f / (float)p.stride, p.tok_feat, p.tok_kin, thi, tlo);
+    launch_k(roi_align_tokens_kernel, dim3(MV2D_TOK, N), dim3(64), 0, st, p.rois, p.feat, with_pe ? p.pe : (const float*)nullptr, p.h, p.w,
+             1.0f / (float)p.stride, p.tok_feat, with_pe ? p.tok_kin : (float*)nullptr, thi, tlo);
     MV2D_CHECK_LAUNCH("roi_align_tokens");
     launch_k(box_params_kernel, dim3(cdiv(N, 64)), dim3(64), 0, st, p.rois, p.intrinsics, p.extrinsics, N, p.intrins_feat_scale, cat,
                                                   mroi, p.roi_intrinsics);

@@ -46,7 +46,7 @@ def feat_pad_mask(img_metas, h, w):
 class HotPath:
     """MV2D-S ('S') / MV2D-T ('T') decoder hot path on one GPU."""
 
-    def __init__(self, state_dict, mode='S', device='cuda', cache_sine_branch=False, **cfg):
+    def __init__(self, state_dict, mode='S', device='cuda', cache_sine_branch=False, overlap=True, **cfg):
         if not torch.cuda.is_available():
             raise RuntimeError('mv2d_b200.HotPath needs a CUDA device (there is no CPU fallback)')
         self.lib = lib.load()
@@ -64,6 +64,9 @@ class HotPath:
         self._buf = {}
         self._pin = {}
         self._graphs = {}
+        self.overlap = overlap
+        self._side = torch.cuda.Stream(device=self.device)
+        self._ev_fork, self._ev_join = torch.cuda.Event(), torch.cuda.Event()
         self.graph_launches = 0
         c = self.cfg
         S, Dn = c['sample_size'], c['corr_num_depth']
@@ -209,7 +212,7 @@ class HotPath:
         lib.check(self.lib.mv2d_pe3d(C.byref(p), lib.stream_ptr()), 'mv2d_pe3d')
         return pe, kin
 
-    def roi_align_qg(self, rois, cams, feat_nhwc, pe_nhwc, N):
+    def roi_align_qg(self, rois, cams, feat_nhwc, pe_nhwc, N, phase=0):
         V, h, w, _ = feat_nhwc.shape
         c, W = self.cfg, self.w
         tok_feat = self._get('tok_feat', (N, 49, 256))
@@ -221,12 +224,12 @@ class HotPath:
         ws_bytes = self.lib.mv2d_roi_align_qg_workspace_bytes(N)
         ws = self._get('qg_ws', (ws_bytes // 4,))
         p = lib.QgParams()
-        p.N, p.V, p.h, p.w, p.stride = N, V, h, w, c['stride']
+        p.N, p.V, p.h, p.w, p.stride, p.phase = N, V, h, w, c['stride'], phase
         p.pc_range = (C.c_float * 6)(*c['pc_range'])
         p.intrins_feat_scale = c['intrins_feat_scale']
         p.rois, p.intrinsics, p.extrinsics = rois.data_ptr(), cams[1].data_ptr(), cams[2].data_ptr()
         p.feat = feat_nhwc.data_ptr()
-        p.pe = pe_nhwc.data_ptr() if tok_kin is not None else None
+        p.pe = pe_nhwc.data_ptr() if (tok_kin is not None and pe_nhwc is not None) else None
         p.dim_t = W.p('dim_t')
         for f in ('w_conv', 'b_conv', 'w_conv_lo', 'w_fc', 'b_fc', 'w_enc0', 'b_enc0', 'w_enc2', 'b_enc2', 'w_center',
                   'b_center', 'w_qe0', 'b_qe0', 'w_qe2', 'b_qe2'):
@@ -311,9 +314,25 @@ class HotPath:
             _, _, h, w = feat_in.shape
             feat, feat_tf32 = self.to_nhwc(feat_in)
         i2l, trans = self.geom_prep(cams)
-        pe, kin = self.pe3d(feat, i2l, img_metas, feat_tf32)
-        qg = self.roi_align_qg(rois, cams, feat, pe, N)
-        corr = self.box_corr(rois, roi_start, trans, N, V, img_metas, h, w)
+        if self.overlap:
+            # fork: everything of the query generator that does not need the position embedding (RoIAlign
+            # of the image feature, 3x3 conv, FC chain, reference points, query embedding) and the box
+            # correlation run on a side stream, concurrently with the PE MLPs on the main stream
+            main = torch.cuda.current_stream()
+            self._ev_fork.record(main)
+            with torch.cuda.stream(self._side):
+                self._side.wait_event(self._ev_fork)
+                qg = self.roi_align_qg(rois, cams, feat, None, N, phase=1)
+                corr = self.box_corr(rois, roi_start, trans, N, V, img_metas, h, w)
+                self._ev_join.record(self._side)
+            pe, kin = self.pe3d(feat, i2l, img_metas, feat_tf32)
+            main.wait_event(self._ev_join)
+            if self.mode == 'S':
+                self.roi_align_qg(rois, cams, feat, pe, N, phase=2)      # tok_kin = tok_feat + RoIAlign(pe)
+        else:
+            pe, kin = self.pe3d(feat, i2l, img_metas, feat_tf32)
+            qg = self.roi_align_qg(rois, cams, feat, pe, N)
+            corr = self.box_corr(rois, roi_start, trans, N, V, img_metas, h, w)
         if self.mode == 'S':
             cls, box, outs = self.decoder(qg, corr, qg['tok_kin'].view(-1, 256), qg['tok_feat'].view(-1, 256), N)
         else:

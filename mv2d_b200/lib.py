@@ -32,7 +32,7 @@ class PeParams(C.Structure):
 class QgParams(C.Structure):
     _fields_ = [
         ('N', C.c_int), ('V', C.c_int), ('h', C.c_int), ('w', C.c_int), ('stride', C.c_int),
-        ('reserved0', C.c_int),
+        ('phase', C.c_int),
         ('pc_range', C.c_float * 6), ('intrins_feat_scale', C.c_float), ('reserved1', C.c_float),
         ('rois', c_f), ('intrinsics', c_f), ('extrinsics', c_f), ('feat', c_f), ('pe', c_f),
         ('dim_t', c_f),
