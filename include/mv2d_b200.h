@@ -162,7 +162,10 @@ typedef struct Mv2dBranchWeights {      /* stacked over layers: leading dim L */
 
 typedef struct Mv2dDecoderParams {
     int N, L, mode /*0 = RoI-token keys (S), 1 = feature-map keys (T)*/, num_rows;
-    int max_match, mask_words, reserved0, reserved1;
+    int max_match, mask_words;
+    int persistent;             /* 1 = all layers + branches in ONE cooperative launch (one CTA per SM, device-wide
+                                 *     barriers between stages); 0 = one launch per stage (~75 launches) */
+    int reserved1;
     float pc_range[6];
     float vel_dt;               /* T head: bbox_preds[..., 8:10] /= vel_dt ; 0 = off (mv2d_t_head.py:130-142) */
     float reserved2;

@@ -33,10 +33,8 @@ struct LnArgs {
     int rows;
 };
 
-__global__ void __launch_bounds__(256) ln_kernel(LnArgs a) {
-    pdl_wait();
-    pdl_trigger();
-    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+__device__ __forceinline__ void ln_body(const LnArgs& a, int vb) {
+    const int row = vb * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= a.rows) return;
     const int grp = a.rows_per_group > 0 ? row / a.rows_per_group : 0;
     const long long o = (long long)row * MV2D_C;
@@ -121,6 +119,12 @@ __global__ void __launch_bounds__(256) ln_kernel(LnArgs a) {
     }
 }
 
+__global__ void __launch_bounds__(256) ln_kernel(LnArgs a) {
+    pdl_wait();
+    pdl_trigger();
+    ln_body(a, blockIdx.x);
+}
+
 // ------------------------------------------------------------------------------------------
 // FlattenMHSelfAttention core (petr_transformer.py:314-370): all N queries form ONE sequence.
 // qkv [N,768] (q | k | v, head h = channels 32h..32h+31), q already includes the bias; the
@@ -131,15 +135,15 @@ __global__ void __launch_bounds__(256) ln_kernel(LnArgs a) {
 // one LDS + one LDS.128 + 4 FMA; the 4 key phases are folded with two shuffles at the end.
 #define SA_KT 128
 #define SA_LD 36
-__global__ void __launch_bounds__(256)
-self_attn_kernel(const float* __restrict__ qkv, const uint8_t* __restrict__ mask, int N, float* __restrict__ out) {
-    pdl_wait();
-    pdl_trigger();
-    __shared__ __align__(16) float Ks[SA_KT][SA_LD];
-    __shared__ __align__(16) float Vs[SA_KT][SA_LD];
-    __shared__ float Ps[8][SA_KT];
-    const int hd = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int qi = blockIdx.x * 8 + warp;
+#define SA_SMEM_BYTES ((2 * SA_KT * SA_LD + 8 * SA_KT) * 4)
+__device__ __forceinline__ void
+self_attn_body(const float* __restrict__ qkv, const uint8_t* __restrict__ mask, int N, float* __restrict__ out,
+               int vbx, int hd, float* smem_f) {
+    float (*Ks)[SA_LD] = reinterpret_cast<float (*)[SA_LD]>(smem_f);
+    float (*Vs)[SA_LD] = reinterpret_cast<float (*)[SA_LD]>(smem_f + SA_KT * SA_LD);
+    float (*Ps)[SA_KT] = reinterpret_cast<float (*)[SA_KT]>(smem_f + 2 * SA_KT * SA_LD);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qi = vbx * 8 + warp;
     const bool qok = qi < N;
     float q[32];
 #pragma unroll
@@ -228,6 +232,14 @@ self_attn_kernel(const float* __restrict__ qkv, const uint8_t* __restrict__ mask
     }
 }
 
+__global__ void __launch_bounds__(256)
+self_attn_kernel(const float* __restrict__ qkv, const uint8_t* __restrict__ mask, int N, float* __restrict__ out) {
+    pdl_wait();
+    pdl_trigger();
+    extern __shared__ __align__(16) float sa_smem[];
+    self_attn_body(qkv, mask, N, out, blockIdx.x, blockIdx.y, sa_smem);
+}
+
 // ------------------------------------------------------------------------------------------
 // Sparse multi-view cross-attention core, absorbed form.  One CTA (8 warps) per query.
 //   qt   [N, 8*256]   q~ per head (scale folded in)
@@ -276,12 +288,8 @@ struct XaArgs {
 };
 
 template <int XA_CH, int XA_THREADS>
-__global__ void __launch_bounds__(XA_THREADS)
-cross_attn_kernel(XaArgs a) {
+__device__ __forceinline__ void cross_attn_body(const XaArgs& a, int n, unsigned char* smem_raw) {
     static_assert(XA_CH == XA_THREADS / 8, "one softmax lane per key: CH = 4 * warps");
-    pdl_wait();
-    pdl_trigger();
-    extern __shared__ __align__(16) unsigned char smem_raw[];
     float* kbuf = reinterpret_cast<float*>(smem_raw);               // [2][XA_CH][256] key-input rows
     float* vbuf = kbuf + 2 * XA_CH * MV2D_C;                        // [2][XA_CH][256] memory rows
     float* sc = vbuf + 2 * XA_CH * MV2D_C;                          // [XA_CH][8] logits -> probs
@@ -290,7 +298,7 @@ cross_attn_kernel(XaArgs a) {
     __shared__ int nkeys_s;
     __shared__ int grp_cnt[128];
     constexpr int NW = XA_THREADS / 32;
-    const int n = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, t = threadIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, t = threadIdx.x;
 
     // ---- key list
     if (t == 0) nkeys_s = 0;
@@ -477,17 +485,24 @@ cross_attn_kernel(XaArgs a) {
     }
 }
 
+template <int XA_CH, int XA_THREADS>
+__global__ void __launch_bounds__(XA_THREADS)
+cross_attn_kernel(XaArgs a) {
+    pdl_wait();
+    pdl_trigger();
+    extern __shared__ __align__(16) unsigned char xa_smem_raw[];
+    cross_attn_body<XA_CH, XA_THREADS>(a, blockIdx.x, xa_smem_raw);
+}
+
 // ------------------------------------------------------------------------------------------
 // Final 256 -> 10 heads of both branches + reference-point refinement
 // (cross_attention_head.py:221-238).  One warp per (layer, query).
-__global__ void __launch_bounds__(256)
-head10_kernel(const float* __restrict__ xc, const float* __restrict__ xr, const float* __restrict__ wc,
-              const float* __restrict__ bc, const float* __restrict__ wr, const float* __restrict__ br,
-              const float* __restrict__ ref, int L, int N, float pc0, float pc1, float pc2, float pc3,
-              float pc4, float pc5, float vel_dt, float* __restrict__ cls, float* __restrict__ box) {
-    pdl_wait();
-    pdl_trigger();
-    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+__device__ __forceinline__ void
+head10_body(const float* __restrict__ xc, const float* __restrict__ xr, const float* __restrict__ wc,
+            const float* __restrict__ bc, const float* __restrict__ wr, const float* __restrict__ br,
+            const float* __restrict__ ref, int L, int N, float pc0, float pc1, float pc2, float pc3,
+            float pc4, float pc5, float vel_dt, float* __restrict__ cls, float* __restrict__ box, int vb) {
+    const int row = vb * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= L * N) return;
     const int l = row / N, n = row % N;
     float a[8], b[8];
@@ -517,6 +532,20 @@ head10_kernel(const float* __restrict__ xc, const float* __restrict__ xr, const 
         }
     }
 }
+
+__global__ void __launch_bounds__(256)
+head10_kernel(const float* __restrict__ xc, const float* __restrict__ xr, const float* __restrict__ wc,
+              const float* __restrict__ bc, const float* __restrict__ wr, const float* __restrict__ br,
+              const float* __restrict__ ref, int L, int N, float pc0, float pc1, float pc2, float pc3,
+              float pc4, float pc5, float vel_dt, float* __restrict__ cls, float* __restrict__ box) {
+    pdl_wait();
+    pdl_trigger();
+    head10_body(xc, xr, wc, bc, wr, br, ref, L, N, pc0, pc1, pc2, pc3, pc4, pc5, vel_dt, cls, box, blockIdx.x);
+}
+
+}  // namespace mv2d
+#include "decoder_mega.cuh"
+namespace mv2d {
 
 // ------------------------------------------------------------------------------------------
 static int gemm(const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc, int M, int N,
@@ -548,13 +577,17 @@ static int ln(const LnArgs& a, cudaStream_t st) {
 }
 
 #define DEC_SPLIT 8
+static size_t xa_smem_mega(int mode, int klist_cap) {
+    (void)mode;
+    return (size_t)(4 * 32 * MV2D_C + 32 * 8 + 24) * sizeof(float) + (size_t)klist_cap * sizeof(uint16_t);
+}
 
 size_t decoder_workspace_bytes(int N, int L) {
     size_t n = (size_t)(N > 0 ? N : 1), l = (size_t)(L > 0 ? L : 1);
     // x, xq, x1, x1q, x2 + 4 hi/lo copies (9*256) + qkv 768 + sa 256 + qt 2048 + ctx hi/lo + hdn hi/lo + partials
     size_t per = 9 * MV2D_C + 768 + MV2D_C + 2048 + 2 * 2048 + 2 * 2048 + DEC_SPLIT * MV2D_C;
     // branches: 4 x [L,N,256]
-    return (n * per + 4 * l * n * MV2D_C) * sizeof(float);
+    return (n * per + 4 * l * n * MV2D_C) * sizeof(float) + 4096;   // + the device-wide barrier word and phase timestamps of the persistent kernel
 }
 
 int run_decoder(const Mv2dDecoderParams& p, cudaStream_t st) {
@@ -587,6 +620,7 @@ int run_decoder(const Mv2dDecoderParams& p, cudaStream_t st) {
     float* b1 = ws;   ws += (size_t)L * N * C;
     float* b2 = ws;   ws += (size_t)L * N * C;
     float* b3 = ws;   ws += (size_t)L * N * C;
+    unsigned* barrier = reinterpret_cast<unsigned*>(reinterpret_cast<uintptr_t>(ws + 63) & ~(uintptr_t)63); ws += 1024;
     MV2D_CHECK_ARG((size_t)(ws - p.workspace) * sizeof(float) <= p.workspace_bytes, "decoder: workspace too small");
     const long long NC = (long long)N * C;
     cudaError_t e;
@@ -608,6 +642,66 @@ int run_decoder(const Mv2dDecoderParams& p, cudaStream_t st) {
     }
     int rc;
     const Mv2dBranchWeights& B = *p.branches;
+    if (p.persistent) {
+        // ---- one cooperative launch for all layers + branches (decoder_mega.cuh)
+        static int num_sms = 0;
+        if (num_sms == 0) {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+        }
+        MegaParams* mp = new MegaParams();           // ~20 KB: keep it off the stack
+        MegaParams& m = *mp;
+        m.N = N; m.L = L; m.mode = p.mode; m.max_match = p.max_match; m.mask_words = p.mask_words; m.klist_cap = klist_cap;
+        for (int i = 0; i < 6; ++i) m.pc_range[i] = p.pc_range[i];
+        m.vel_dt = p.vel_dt;
+        m.query_pos = p.query_pos; m.ref = p.ref; m.kin_rows = p.kin_rows; m.mem_rows = p.mem_rows;
+        m.match = p.match; m.match_cnt = p.match_cnt; m.keymask = p.keymask; m.self_attn_mask = p.self_attn_mask;
+        m.x = x; m.xq = xq; m.x1 = x1; m.x1q = x1q; m.x2 = x2; m.x1q_hi = x1q_hi; m.x1q_lo = x1q_lo; m.x2_hi = x2_hi; m.x2_lo = x2_lo;
+        m.qkv = qkv; m.sa = sa; m.qt = qt; m.ctx = ctx; m.ctx_lo = ctx_lo; m.hdn = hdn; m.hdn_lo = hdn_lo; m.part = part;
+        m.b0 = b0; m.b1 = b1; m.b2 = b2; m.b3 = b3; m.cls = p.cls_scores; m.box = p.bbox_preds; m.outs_dec = p.outs_dec;
+        m.br = B; m.barrier = barrier;
+        rc = 0;
+        for (int l = 0; l < L && rc == 0; ++l) {
+            const Mv2dLayerWeights& w = p.layers[l];
+            MegaLayer& y = m.layer[l];
+            y.sa_in_w = w.sa_in_w; y.sa_in_b = w.sa_in_b; y.sa_out_w = w.sa_out_w; y.sa_out_b = w.sa_out_b;
+            y.ca_q_b = w.ca_q_b; y.ca_o_b = w.ca_o_b; y.ffn_b1 = w.ffn_b1; y.ffn_b2 = w.ffn_b2;
+            for (int i = 0; i < 3; ++i) { y.ln_g[i] = w.ln_g[i]; y.ln_b[i] = w.ln_b[i]; }
+            struct { const float *ah, *al; int lda; const float *wh, *wl; int ldw, n, k; } gm[4] = {
+                {x1q_hi, x1q_lo, C, w.ca_q_w, w.ca_q_w_lo, C, 2048, C},
+                {ctx, ctx_lo, 2048, w.ca_o_w, w.ca_o_w_lo, 2048, C, 2048},
+                {x2_hi, x2_lo, C, w.ffn_w1, w.ffn_w1_lo, C, 2048, C},
+                {hdn, hdn_lo, 2048, w.ffn_w2, w.ffn_w2_lo, 2048, C, 2048}};
+            for (int g = 0; g < 4 && rc == 0; ++g) {
+                if ((rc = tc_make_map_2d(&y.maps[g][0], gm[g].ah, N, gm[g].k, gm[g].lda, 128))) break;
+                if ((rc = tc_make_map_2d(&y.maps[g][1], gm[g].al, N, gm[g].k, gm[g].lda, 128))) break;
+                if ((rc = tc_make_map_2d(&y.maps[g][2], gm[g].wh, gm[g].n, gm[g].k, gm[g].ldw, mega_tc::BN))) break;
+                if ((rc = tc_make_map_2d(&y.maps[g][3], gm[g].wl, gm[g].n, gm[g].k, gm[g].ldw, mega_tc::BN))) break;
+            }
+        }
+        if (rc) { delete mp; return rc; }
+        size_t smem = (size_t)mega_tc::SMEM_BYTES;
+        if (xa_smem_mega(p.mode, klist_cap) > smem) smem = xa_smem_mega(p.mode, klist_cap);
+        smem += 1024;
+        if ((e = cudaFuncSetAttribute(decoder_mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess ||
+            (e = cudaMemsetAsync(barrier, 0, sizeof(unsigned), st)) != cudaSuccess) {
+            set_error("decoder(persistent): setup %s", cudaGetErrorString(e));
+            delete mp;
+            return (int)e;
+        }
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(num_sms); cfg.blockDim = dim3(MEGA_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeCooperative;
+        attr[0].val.cooperative = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        e = cudaLaunchKernelEx(&cfg, decoder_mega_kernel, m);
+        delete mp;
+        note_launch();
+        if (e != cudaSuccess) { set_error("decoder(persistent): launch %s", cudaGetErrorString(e)); return (int)e; }
+        return 0;
+    }
     for (int l = 0; l < L; ++l) {
         const Mv2dLayerWeights& w = p.layers[l];
         float* inter = p.outs_dec + (long long)l * NC;
@@ -618,7 +712,7 @@ int run_decoder(const Mv2dDecoderParams& p, cudaStream_t st) {
             g.M = N; g.N = 768; g.K = C; g.batch = 1; g.nsplit = 1;
             if ((rc = launch_gemm_small(g, x, 512, st))) return rc;
         }
-        launch_k(self_attn_kernel, dim3(cdiv(N, 8), MV2D_HEADS), dim3(256), 0, st, (const float*)qkv, p.self_attn_mask, N, sa);
+        launch_k(self_attn_kernel, dim3(cdiv(N, 8), MV2D_HEADS), dim3(256), SA_SMEM_BYTES, st, (const float*)qkv, p.self_attn_mask, N, sa);
         MV2D_CHECK_LAUNCH("self_attn");
         if ((rc = gemm(sa, C, w.sa_out_w, C, nullptr, part, C, N, C, C, 0, st))) return rc;
         {

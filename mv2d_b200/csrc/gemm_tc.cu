@@ -122,6 +122,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m_tile = blockIdx.y, n0 = blockIdx.x * BN;
     const int nkb = g.nkb_per_split, kb0 = blockIdx.z * g.nkb_per_split;   // this CTA's K range (split-K)
+    // CTAs that share an operand tile walk K in rotated order, so they do not all hit the same L2 lines at once
+    const int rot = IM2COL ? 0 : (int)((blockIdx.x + 3 * blockIdx.y) % nkb);
 
     if (warp == 0 && lane == 0) {
         tmap_prefetch(&tmA); tmap_prefetch(&tmW);
@@ -163,11 +165,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             tma_load_4d(&tmAlo, &full_bar[s], st + A_BYTES + r * (A_BYTES / 2), c0, dx, dy, m_tile * 2 + r);
                     }
                 } else {
-                    tma_load_2d(&tmA, &full_bar[s], st, (kb0 + kb) * TC_BK, m_tile * TC_BM);
-                    if (PASSES == 3) tma_load_2d(&tmAlo, &full_bar[s], st + A_BYTES, (kb0 + kb) * TC_BK, m_tile * TC_BM);
+                    tma_load_2d(&tmA, &full_bar[s], st, (kb0 + (kb + rot) % nkb) * TC_BK, m_tile * TC_BM);
+                    if (PASSES == 3) tma_load_2d(&tmAlo, &full_bar[s], st + A_BYTES, (kb0 + (kb + rot) % nkb) * TC_BK, m_tile * TC_BM);
                 }
-                tma_load_2d(&tmW, &full_bar[s], st + NOP * A_BYTES, (kb0 + kb) * TC_BK, n0);
-                if (PASSES == 3) tma_load_2d(&tmWlo, &full_bar[s], st + NOP * A_BYTES + W_BYTES, (kb0 + kb) * TC_BK, n0);
+                tma_load_2d(&tmW, &full_bar[s], st + NOP * A_BYTES, (kb0 + (kb + rot) % nkb) * TC_BK, n0);
+                if (PASSES == 3) tma_load_2d(&tmWlo, &full_bar[s], st + NOP * A_BYTES + W_BYTES, (kb0 + (kb + rot) % nkb) * TC_BK, n0);
             }
         }
     } else if (warp == 1) {
@@ -367,6 +369,10 @@ static int make_map_2d_uncached(CUtensorMap* m, const float* base, int rows, int
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     MV2D_CHECK_ARG(r == CUDA_SUCCESS, "gemm_tc: cuTensorMapEncodeTiled(2d) failed with %d", (int)r);
     return 0;
+}
+
+int tc_make_map_2d(void* map, const float* base, int rows, int K, int ld, int box_rows) {
+    return make_map_2d(reinterpret_cast<CUtensorMap*>(map), base, rows, K, ld, box_rows);
 }
 
 // 4-D RoI tokens [n_rois, 7, 7, 256]; box = [32 ch, 7, 7, 1]

@@ -32,6 +32,9 @@ struct TcGemm {
 
 int launch_gemm_tc(const TcGemm& t, cudaStream_t st);
 
+// encode a 2-D, K-contiguous, 128B-swizzled tensor map [rows, K] (box = 32 floats x box_rows); `map` points at a CUtensorMap
+int tc_make_map_2d(void* map, const float* base, int rows, int K, int ld, int box_rows);
+
 // x -> hi = rna_tf32(x), lo = rna_tf32(x - hi)   (both exactly TF32-representable)
 int launch_split_tf32(const float* x, float* hi, float* lo, long long n, cudaStream_t st);
 

@@ -8,6 +8,7 @@ Mirrors ``MV2DHead.simple_test`` minus decode
 """
 import ctypes as C
 import math
+import os
 
 import numpy as np
 import torch
@@ -46,7 +47,8 @@ def feat_pad_mask(img_metas, h, w):
 class HotPath:
     """MV2D-S ('S') / MV2D-T ('T') decoder hot path on one GPU."""
 
-    def __init__(self, state_dict, mode='S', device='cuda', cache_sine_branch=False, overlap=True, **cfg):
+    def __init__(self, state_dict, mode='S', device='cuda', cache_sine_branch=False, overlap=True,
+                 persistent_decoder=None, **cfg):
         if not torch.cuda.is_available():
             raise RuntimeError('mv2d_b200.HotPath needs a CUDA device (there is no CPU fallback)')
         self.lib = lib.load()
@@ -65,6 +67,11 @@ class HotPath:
         self._pin = {}
         self._graphs = {}
         self.overlap = overlap
+        if persistent_decoder is None:
+            # measured on B200 (profiles/r01_persistent_decoder.md): the single-launch persistent decoder is
+            # correct but ~30 % slower than one launch per stage at N = 300, so it is opt-in
+            persistent_decoder = os.environ.get('MV2D_DECODER', 'staged') == 'persistent'
+        self.persistent_decoder = persistent_decoder
         self._side = torch.cuda.Stream(device=self.device)
         self._ev_fork, self._ev_join = torch.cuda.Event(), torch.cuda.Event()
         self.graph_launches = 0
@@ -278,6 +285,7 @@ class HotPath:
         ws = self._get('dec_ws', (ws_bytes // 4,))
         p = lib.DecoderParams()
         p.N, p.L = N, L
+        p.persistent = 1 if self.persistent_decoder else 0
         p.mode = 0 if self.mode == 'S' else 1
         p.num_rows = kin_rows.shape[0]
         p.pc_range = (C.c_float * 6)(*c['pc_range'])

@@ -81,7 +81,7 @@ class BranchWeights(C.Structure):
 class DecoderParams(C.Structure):
     _fields_ = [
         ('N', C.c_int), ('L', C.c_int), ('mode', C.c_int), ('num_rows', C.c_int),
-        ('max_match', C.c_int), ('mask_words', C.c_int), ('reserved0', C.c_int),
+        ('max_match', C.c_int), ('mask_words', C.c_int), ('persistent', C.c_int),
         ('reserved1', C.c_int),
         ('pc_range', C.c_float * 6), ('vel_dt', C.c_float), ('reserved2', C.c_float),
         ('query_pos', c_f), ('ref', c_f), ('kin_rows', c_f), ('mem_rows', c_f),

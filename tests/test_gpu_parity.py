@@ -108,6 +108,37 @@ def test_cuda_path_matches_oracle_on_fresh_inputs(mode, V, n, seed, state_dicts)
     assert_close(out['bbox_preds'], box, what='bbox_preds')
 
 
+@pytest.mark.parametrize('name', ['s_small', 't_small'])
+def test_persistent_decoder_matches_reference_golden(name, state_dicts):
+    """The single-launch (cooperative, device-wide barriers) decoder against the same goldens."""
+    from mv2d_b200.engine import HotPath
+    spec, g = load_golden(name)
+    eng = HotPath(state_dicts(spec['num_layers']), mode=spec['mode'], persistent_decoder=True)
+    feat, boxes, metas = synth.case_inputs(spec)
+    before = eng.launch_count()
+    out = eng.forward(feat.cuda(), boxes, metas)
+    torch.cuda.synchronize()
+    assert_close(out['cls_scores'], g['cls_scores'], what='cls_scores')
+    assert_close(out['bbox_preds'], g['bbox_preds'], what='bbox_preds')
+    assert eng.launch_count() - before < 40   # PE + query generator + ONE decoder launch
+
+
+@pytest.mark.parametrize('mode,V,per_view', [('S', 6, 75), ('T', 12, 75)])
+def test_maximum_sizes_match_oracle(mode, V, per_view, state_dicts):
+    """The 2D detector's cap is 75 boxes per view (exp configs, max_per_img=75): 450 / 900 queries."""
+    from oracle import mv2d_oracle as O
+    eng = engine(mode, 6, state_dicts)
+    feat, boxes, metas = synth.make_sample(41, V, per_view)
+    out = eng.forward(feat.cuda(), boxes, metas)
+    torch.cuda.synchronize()
+    assert out['N'] == V * per_view
+    fn = O.mv2d_s_forward if mode == 'S' else O.mv2d_t_forward
+    with torch.no_grad():
+        cls, box = fn(state_dicts(6), feat, boxes, metas, O.make_cfg(mode))
+    assert_close(out['cls_scores'], cls, what='cls_scores')
+    assert_close(out['bbox_preds'], box, what='bbox_preds')
+
+
 def test_gemm_kernel_vs_torch_fp32():
     """The FFMA GEMM against torch fp32 (fp64-accumulated reference for the bound)."""
     import ctypes as C
