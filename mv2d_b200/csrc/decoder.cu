@@ -136,6 +136,7 @@ __global__ void __launch_bounds__(256) ln_kernel(LnArgs a) {
 #define SA_KT 128
 #define SA_LD 36
 #define SA_SMEM_BYTES ((2 * SA_KT * SA_LD + 8 * SA_KT) * 4)
+#define SA_QPW 2     // queries per warp: every K/V tile staged in shared memory serves 16 queries
 __device__ __forceinline__ void
 self_attn_body(const float* __restrict__ qkv, const uint8_t* __restrict__ mask, int N, float* __restrict__ out,
                int vbx, int hd, float* smem_f) {
@@ -143,19 +144,22 @@ self_attn_body(const float* __restrict__ qkv, const uint8_t* __restrict__ mask, 
     float (*Vs)[SA_LD] = reinterpret_cast<float (*)[SA_LD]>(smem_f + SA_KT * SA_LD);
     float (*Ps)[SA_KT] = reinterpret_cast<float (*)[SA_KT]>(smem_f + 2 * SA_KT * SA_LD);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int qi = vbx * 8 + warp;
-    const bool qok = qi < N;
-    float q[32];
-#pragma unroll
-    for (int d4 = 0; d4 < 8; ++d4) {
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (qok) v = __ldg(reinterpret_cast<const float4*>(qkv + (long long)qi * 768 + hd * 32) + d4);
-        q[d4 * 4 + 0] = v.x * 0.17677669529663687f; q[d4 * 4 + 1] = v.y * 0.17677669529663687f;
-        q[d4 * 4 + 2] = v.z * 0.17677669529663687f; q[d4 * 4 + 3] = v.w * 0.17677669529663687f;
-    }
     const int kq = lane >> 3, cq = lane & 7;
-    float m = -INFINITY, l = 0.f;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int qi[SA_QPW];
+    float q[SA_QPW][32], m[SA_QPW], l[SA_QPW];
+    float4 acc[SA_QPW];
+#pragma unroll
+    for (int u = 0; u < SA_QPW; ++u) {
+        qi[u] = (vbx * 8 + warp) * SA_QPW + u;
+        m[u] = -INFINITY; l[u] = 0.f; acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int d4 = 0; d4 < 8; ++d4) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (qi[u] < N) v = __ldg(reinterpret_cast<const float4*>(qkv + (long long)qi[u] * 768 + hd * 32) + d4);
+            q[u][d4 * 4 + 0] = v.x * 0.17677669529663687f; q[u][d4 * 4 + 1] = v.y * 0.17677669529663687f;
+            q[u][d4 * 4 + 2] = v.z * 0.17677669529663687f; q[u][d4 * 4 + 3] = v.w * 0.17677669529663687f;
+        }
+    }
     for (int k0 = 0; k0 < N; k0 += SA_KT) {
         __syncthreads();
         {   // all 8 loads of a thread are issued before the first store (one memory latency per tile)
@@ -177,58 +181,64 @@ self_attn_body(const float* __restrict__ qkv, const uint8_t* __restrict__ mask, 
             }
         }
         __syncthreads();
-        if (!qok) continue;
         const int ng = min(SA_KT, N - k0);
-        float s[SA_KT / 32];
-        float mx = -INFINITY;
 #pragma unroll
-        for (int g = 0; g < SA_KT / 32; ++g) {
-            const int kk = g * 32 + lane;
-            float x = 0.f;
+        for (int u = 0; u < SA_QPW; ++u) {
+            if (qi[u] >= N) continue;                    // warp-uniform
+            float s[SA_KT / 32];
+            float mx = -INFINITY;
 #pragma unroll
-            for (int d4 = 0; d4 < 8; ++d4) {
-                const float4 kv = *reinterpret_cast<const float4*>(&Ks[kk][d4 * 4]);
-                x = fmaf(q[d4 * 4 + 0], kv.x, x); x = fmaf(q[d4 * 4 + 1], kv.y, x);
-                x = fmaf(q[d4 * 4 + 2], kv.z, x); x = fmaf(q[d4 * 4 + 3], kv.w, x);
+            for (int g = 0; g < SA_KT / 32; ++g) {
+                const int kk = g * 32 + lane;
+                float x = 0.f;
+#pragma unroll
+                for (int d4 = 0; d4 < 8; ++d4) {
+                    const float4 kv = *reinterpret_cast<const float4*>(&Ks[kk][d4 * 4]);
+                    x = fmaf(q[u][d4 * 4 + 0], kv.x, x); x = fmaf(q[u][d4 * 4 + 1], kv.y, x);
+                    x = fmaf(q[u][d4 * 4 + 2], kv.z, x); x = fmaf(q[u][d4 * 4 + 3], kv.w, x);
+                }
+                if (kk >= ng || (mask && mask[(long long)qi[u] * N + k0 + kk])) x = -INFINITY;
+                s[g] = x;
+                mx = fmaxf(mx, x);
             }
-            if (kk >= ng || (mask && mask[(long long)qi * N + k0 + kk])) x = -INFINITY;
-            s[g] = x;
-            mx = fmaxf(mx, x);
-        }
-        const float mn = fmaxf(m, warp_max(mx));
-        if (mn == -INFINITY) continue;
-        const float alpha = __expf(m - mn);      // exp(-inf) = 0 on the first tile
-        float psum = 0.f;
+            const float mn = fmaxf(m[u], warp_max(mx));
+            if (mn == -INFINITY) continue;
+            const float alpha = __expf(m[u] - mn);       // exp(-inf) = 0 on the first tile
+            float psum = 0.f;
+            __syncwarp();
 #pragma unroll
-        for (int g = 0; g < SA_KT / 32; ++g) {
-            const float pv = __expf(s[g] - mn);
-            Ps[warp][g * 32 + lane] = pv;
-            psum += pv;
-        }
-        l = l * alpha + warp_sum(psum);
-        acc.x *= alpha; acc.y *= alpha; acc.z *= alpha; acc.w *= alpha;
-        __syncwarp();
+            for (int g = 0; g < SA_KT / 32; ++g) {
+                const float pv = __expf(s[g] - mn);
+                Ps[warp][g * 32 + lane] = pv;
+                psum += pv;
+            }
+            l[u] = l[u] * alpha + warp_sum(psum);
+            acc[u].x *= alpha; acc[u].y *= alpha; acc[u].z *= alpha; acc[u].w *= alpha;
+            __syncwarp();
 #pragma unroll 8
-        for (int t = 0; t < SA_KT / 4; ++t) {
-            const int j = t * 4 + kq;
-            const float pj = Ps[warp][j];
-            const float4 vv = *reinterpret_cast<const float4*>(&Vs[j][cq * 4]);
-            acc.x = fmaf(pj, vv.x, acc.x); acc.y = fmaf(pj, vv.y, acc.y);
-            acc.z = fmaf(pj, vv.z, acc.z); acc.w = fmaf(pj, vv.w, acc.w);
+            for (int t = 0; t < SA_KT / 4; ++t) {
+                const int j = t * 4 + kq;
+                const float pj = Ps[warp][j];
+                const float4 vv = *reinterpret_cast<const float4*>(&Vs[j][cq * 4]);
+                acc[u].x = fmaf(pj, vv.x, acc[u].x); acc[u].y = fmaf(pj, vv.y, acc[u].y);
+                acc[u].z = fmaf(pj, vv.z, acc[u].z); acc[u].w = fmaf(pj, vv.w, acc[u].w);
+            }
+            m[u] = mn;
         }
-        __syncwarp();
-        m = mn;
     }
-    // fold the 4 key phases (lanes differing in bits 3,4)
 #pragma unroll
-    for (int o = 8; o <= 16; o <<= 1) {
-        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
-        acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o); acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
-    }
-    if (qok && kq == 0) {
-        const float inv = l > 0.f ? 1.f / l : 0.f;
-        *reinterpret_cast<float4*>(out + (long long)qi * MV2D_C + hd * 32 + cq * 4) =
-            make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
+    for (int u = 0; u < SA_QPW; ++u) {
+        // fold the 4 key phases (lanes differing in bits 3,4)
+#pragma unroll
+        for (int o = 8; o <= 16; o <<= 1) {
+            acc[u].x += __shfl_xor_sync(0xffffffffu, acc[u].x, o); acc[u].y += __shfl_xor_sync(0xffffffffu, acc[u].y, o);
+            acc[u].z += __shfl_xor_sync(0xffffffffu, acc[u].z, o); acc[u].w += __shfl_xor_sync(0xffffffffu, acc[u].w, o);
+        }
+        if (qi[u] < N && kq == 0) {
+            const float inv = l[u] > 0.f ? 1.f / l[u] : 0.f;
+            *reinterpret_cast<float4*>(out + (long long)qi[u] * MV2D_C + hd * 32 + cq * 4) =
+                make_float4(acc[u].x * inv, acc[u].y * inv, acc[u].z * inv, acc[u].w * inv);
+        }
     }
 }
 
@@ -712,7 +722,7 @@ int run_decoder(const Mv2dDecoderParams& p, cudaStream_t st) {
             g.M = N; g.N = 768; g.K = C; g.batch = 1; g.nsplit = 1;
             if ((rc = launch_gemm_small(g, x, 512, st))) return rc;
         }
-        launch_k(self_attn_kernel, dim3(cdiv(N, 8), MV2D_HEADS), dim3(256), SA_SMEM_BYTES, st, (const float*)qkv, p.self_attn_mask, N, sa);
+        launch_k(self_attn_kernel, dim3(cdiv(N, 8 * SA_QPW), MV2D_HEADS), dim3(256), SA_SMEM_BYTES, st, (const float*)qkv, p.self_attn_mask, N, sa);
         MV2D_CHECK_LAUNCH("self_attn");
         if ((rc = gemm(sa, C, w.sa_out_w, C, nullptr, part, C, N, C, C, 0, st))) return rc;
         {

@@ -79,10 +79,13 @@ __global__ void pe_coords_kernel(const double* __restrict__ img2lidar, float* __
     float r[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
+        // the frustum point and its normalisation in fp64 as the reference; the logit itself in fp32: the value is
+        // rounded to TF32 (2^-11) right below because it feeds a TF32 tensor-core GEMM, fp32 log error (2^-23) is noise
         double c = m[i * 4 + 0] * c0 + m[i * 4 + 1] * c1 + m[i * 4 + 2] * cd + m[i * 4 + 3];
         c = (c - lo[i]) / (hi[i] - lo[i]);
-        c = fmin(fmax(c, 0.0), 1.0);                       // inverse_sigmoid, fp64 then .float()
-        r[i] = round_tf32((float)log(fmax(c, 1e-5) / fmax(1.0 - c, 1e-5)));   // operand of a TF32 GEMM
+        const float cf = (float)fmin(fmax(c, 0.0), 1.0);
+        const float num = fmaxf(cf, 1e-5f), den = fmaxf((float)(1.0 - fmin(fmax(c, 0.0), 1.0)), 1e-5f);
+        r[i] = round_tf32(logf(num / den));                // inverse_sigmoid -> operand of a TF32 GEMM
     }
     float* o = out + p * (3 * D) + d * 3;
     o[0] = r[0]; o[1] = r[1]; o[2] = r[2];
@@ -133,9 +136,10 @@ __global__ void sine_embed_kernel(const float* __restrict__ emb, const float* __
     const long long p = gid / 384;
     const int e = c >> 7, i = c & 127;
     const float val = emb[p * 3 + e];
+    // arguments lie in [0, 2*pi]; the SFU sine/cosine (abs. error ~1e-6 there) is far inside the TF32 rounding below
     float r;
-    if (i < 64) r = sinf(val / __ldg(dim_t + 2 * i));
-    else        r = cosf(val / __ldg(dim_t + 2 * (i - 64) + 1));
+    if (i < 64) r = __sinf(val / __ldg(dim_t + 2 * i));
+    else        r = __cosf(val / __ldg(dim_t + 2 * (i - 64) + 1));
     out[gid] = round_tf32(r);   // operand of a TF32 GEMM
 }
 

@@ -426,6 +426,26 @@ class MV2D(nn.Module):
         self.base_detector = base_detector if callable(base_detector) else None
         self.neck_cfg, self.train_cfg, self.test_cfg = neck, train_cfg, test_cfg
 
+    def process_2d_detections(self, results, device):
+        """detectors/mv2d.py:60-86 (next row f2): per view, the 2D detector's per-class box arrays
+        [n_c, 5] -> one [n, 6] tensor (x1, y1, x2, y2, score, label), boxes smaller than
+        ``detection_proposal.min_bbox_size`` dropped.  Accepts numpy arrays (the reference's bbox2result
+        format) or tensors that already live on the device (no host round trip in that case)."""
+        cfg = self.train_cfg if self.train_cfg is not None else (self.test_cfg or {})
+        min_size = (cfg.get('detection_proposal') or {}).get('min_bbox_size', 0)
+        out = []
+        for res in results:
+            per_cls = []
+            for label_id, boxes in enumerate(res):
+                b = torch.as_tensor(boxes, dtype=torch.float32).reshape(-1, 5).to(device)
+                per_cls.append(torch.cat([b, b.new_full((b.shape[0], 1), float(label_id))], dim=1))
+            det = torch.cat(per_cls, dim=0) if per_cls else torch.zeros((0, 6), device=device)
+            if min_size > 0:
+                wh = det[:, 2:4] - det[:, 0:2]
+                det = det[(wh >= min_size).all(dim=1)]
+            out.append(det)
+        return out
+
     @torch.no_grad()
     def simple_test(self, img, img_metas, detections=None, feat=None):
         if feat is None or detections is None:

@@ -214,7 +214,10 @@ def test_tcgen05_gemm_3xtf32_and_im2col(state_dicts):
         lib.check(h.mv2d_gemm_3xtf32(th.data_ptr(), tl.data_ptr(), 256, wh.data_ptr(), wl.data_ptr(), 2304,
                                      b.data_ptr(), out.data_ptr(), 256, n_rois * 49, 256, 2304, 1 | 128,
                                      lib.stream_ptr()), 'gemm_3xtf32(im2col)')
-        ref = F.conv2d(x.double(), w.double(), b.double(), padding=1).relu().permute(0, 2, 3, 1).reshape(-1, 256)
+        # fp64 reference as an explicit im2col matmul (no cuDNN involved)
+        xp = F.pad(x.double(), (1, 1, 1, 1)).permute(0, 2, 3, 1)                      # [n, 9, 9, c]
+        cols = torch.stack([xp[:, ky:ky + 7, kx:kx + 7] for ky in range(3) for kx in range(3)], 3)
+        ref = (cols.reshape(-1, 9 * 256) @ wk.double().T + b.double()).relu()
         assert_close(out, ref, 1e-4, 1e-4, f'im2col conv n={n_rois}')
 
 

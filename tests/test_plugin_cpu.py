@@ -30,3 +30,29 @@ def test_config_delete_and_base_semantics(tmp_path):
     (tmp_path / 'child.py').write_text("_base_ = ['./base.py']\na = dict(y=dict(_delete_=True, r=5), z=7)\n")
     cfg = Config.fromfile(str(tmp_path / 'child.py'))
     assert cfg.a.x == 1 and cfg.a.z == 7 and dict(cfg.a.y) == {'r': 5} and cfg.b == 3
+
+
+def test_process_2d_detections_matches_reference_semantics():
+    """detectors/mv2d.py:60-86: per-class arrays -> [n,6] with label column, min-size filter (8 px)."""
+    import numpy as np
+    import torch
+    from mv2d_b200.plugin.modules import MV2D
+    shell = MV2D.__new__(MV2D)
+    torch.nn.Module.__init__(shell)
+    shell.train_cfg = None
+    shell.test_cfg = dict(detection_proposal=dict(min_bbox_size=8))
+    rng = np.random.default_rng(0)
+    res = []
+    for _ in range(3):
+        per_cls = []
+        for c in range(10):
+            n = int(rng.integers(0, 4))
+            xy = rng.uniform(0, 500, size=(n, 2))
+            wh = rng.uniform(2, 40, size=(n, 2))
+            per_cls.append(np.concatenate([xy, xy + wh, rng.uniform(0, 1, size=(n, 1))], 1).astype(np.float32))
+        res.append(per_cls)
+    out = shell.process_2d_detections(res, 'cpu')
+    for view, det in zip(res, out):
+        ref = np.concatenate([np.concatenate([b, np.full((len(b), 1), c, np.float32)], 1) for c, b in enumerate(view)], 0)
+        ref = ref[((ref[:, 2:4] - ref[:, 0:2]) >= 8).all(1)]
+        assert det.shape[1] == 6 and np.array_equal(det.numpy(), ref)
