@@ -54,7 +54,9 @@ MV2D_API int mv2d_nchw_to_nhwc(const float* in, float* out, float* out_tf32, int
 /* ---- K1  PE.forward  (utils/pe.py:137-169 incl. position_encoding :84-135, SELayer :44-48,
  * SinePositionalEncoding3D positional_encoding.py:58-96 + adapt_pos3d) */
 typedef struct Mv2dPeParams {
-    int V, h, w, depth_num, pad_h, pad_w, stride, reserved0;
+    /* phase: 0 = everything; 1 = the part that does not read `feat` (frustum coordinates, position MLP, sine
+     *        branch: can overlap the host-to-device copy of the feature map); 2 = SE gate + combine (after 1) */
+    int V, h, w, depth_num, pad_h, pad_w, stride, phase;
     double depth_start;
     double position_range[6];
     const float* feat;         /* [V,h,w,256] */

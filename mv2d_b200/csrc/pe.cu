@@ -183,7 +183,9 @@ int run_pe3d(const Mv2dPeParams& p, cudaStream_t st) {
     MV2D_CHECK_ARG((size_t)(ws - p.workspace) * sizeof(float) <= p.workspace_bytes,
                    "pe3d: workspace too small (%zu needed)", (size_t)(ws - p.workspace) * sizeof(float));
     int rc;
-    {
+    MV2D_CHECK_ARG(p.phase >= 0 && p.phase <= 2, "pe3d: phase must be 0, 1 or 2");
+    MV2D_CHECK_ARG(p.phase == 0 || !p.sine_branch_cached, "pe3d: phases cannot be combined with a cached sine branch");
+    if (p.phase != 2) {
         long long total = (long long)P * D;
         launch_k(pe_coords_kernel, dim3((unsigned)cdiv((int)total, 256)), dim3(256), 0, st, 
             p.img2lidar, A1, p.V, p.h, p.w, D, (double)p.pad_h, (double)p.pad_w, p.depth_start,
@@ -192,10 +194,14 @@ int run_pe3d(const Mv2dPeParams& p, cudaStream_t st) {
         MV2D_CHECK_LAUNCH("pe_coords");
     }
     // position_encoder: 192 -> 1024 -> 256
+    if (p.phase != 2) {
     if ((rc = gemm(A1, 3 * D, p.w_pos0, 3 * D, p.b_pos0, Hd, 4 * C, P, 4 * C, 3 * D, GEMM_RELU | GEMM_TF32_OK | GEMM_ROUND_TF32, st))) return rc;
     if ((rc = gemm(Hd, 4 * C, p.w_pos2, 4 * C, p.b_pos2, X, C, P, C, 4 * C, GEMM_TF32_OK, st))) return rc;
+    }
     // sine branch: 384 -> 1024 -> 256  (input-independent given masks + weights; recomputed here)
-    if (!p.sine_branch_cached) {
+    if (p.phase == 2) {
+        // X and SB were left in the workspace by phase 1
+    } else if (!p.sine_branch_cached) {
         launch_k(sine_prep_kernel, dim3(cdiv(P, 128)), dim3(128), 0, st, p.not_mask, EM, p.V, p.h, p.w, (float)p.stride,
                                                       6.283185307179586f, 1e-6f);
         MV2D_CHECK_LAUNCH("sine_prep");
@@ -206,6 +212,7 @@ int run_pe3d(const Mv2dPeParams& p, cudaStream_t st) {
     } else {
         SB = const_cast<float*>(p.sine_branch_cached);
     }
+    if (p.phase == 1) return 0;   // everything that does not read the image feature is done
     // SE gate on the image feature, fused combine: pe = X * sigmoid(gate) + SB ; kin = pe + feat
     if ((rc = gemm(p.feat_tf32 ? p.feat_tf32 : p.feat, C, p.w_se_reduce, C, p.b_se_reduce, G1, C, P, C, C,
                    GEMM_RELU | GEMM_TF32_OK | GEMM_ROUND_TF32, st))) return rc;

@@ -73,6 +73,7 @@ class HotPath:
             persistent_decoder = os.environ.get('MV2D_DECODER', 'staged') == 'persistent'
         self.persistent_decoder = persistent_decoder
         self._side = torch.cuda.Stream(device=self.device)
+        self._copy = torch.cuda.Stream(device=self.device)
         self._ev_fork, self._ev_join = torch.cuda.Event(), torch.cuda.Event()
         self.graph_launches = 0
         c = self.cfg
@@ -187,9 +188,10 @@ class HotPath:
                                              lib.stream_ptr()), 'mv2d_nchw_to_nhwc')
         return out, out_tf32
 
-    def pe3d(self, feat_nhwc, img2lidar, img_metas, feat_tf32=None):
-        """PE.forward (utils/pe.py:137-169) -> (pe [V,h,w,256], kin = feat + pe or None)."""
-        V, h, w, _ = feat_nhwc.shape
+    def pe3d(self, feat_nhwc, img2lidar, img_metas, feat_tf32=None, phase=0, dims=None):
+        """PE.forward (utils/pe.py:137-169) -> (pe [V,h,w,256], kin = feat + pe or None).
+        phase 1 = the feature-independent part only (feat_nhwc may still be in flight), 2 = the rest."""
+        V, h, w = dims if dims is not None else feat_nhwc.shape[:3]
         c, W = self.cfg, self.w
         key, pad_mask, not_mask, _ = self._masks(img_metas, h, w)
         pe = self._get('pe', (V, h, w, 256))
@@ -198,6 +200,7 @@ class HotPath:
         ws = self._get('pe_ws', (ws_bytes // 4,))
         p = lib.PeParams()
         p.V, p.h, p.w, p.depth_num = V, h, w, c['depth_num']
+        p.phase = phase
         p.pad_h, p.pad_w = int(img_metas[0]['pad_shape'][0]), int(img_metas[0]['pad_shape'][1])
         p.stride = c['stride']
         p.depth_start = c['depth_start']
@@ -207,10 +210,10 @@ class HotPath:
         for f in ('w_pos0', 'b_pos0', 'w_pos2', 'b_pos2', 'w_adapt0', 'b_adapt0', 'w_adapt2', 'b_adapt2',
                   'w_se_reduce', 'b_se_reduce', 'w_se_expand', 'b_se_expand'):
             setattr(p, f, W.p(f))
-        cached = self._sine_cache.get(key) if self.cache_sine_branch else None
+        cached = self._sine_cache.get(key) if (self.cache_sine_branch and phase == 0) else None
         if cached is not None:
             p.sine_branch_cached = cached.data_ptr()
-        elif self.cache_sine_branch:
+        elif self.cache_sine_branch and phase == 0:
             self._sine_cache[key] = torch.empty((V * h * w, 256), device=self.device)
             p.sine_branch_out = self._sine_cache[key].data_ptr()
         p.pe = pe.data_ptr()
@@ -311,8 +314,15 @@ class HotPath:
         ts = np.array([m['timestamp'] for m in img_metas], dtype=np.float64)   # mv2d_t_head.py:131-132
         return float(ts[nvf:].mean() - ts[:nvf].mean())
 
-    def _enqueue(self, feat_in, feat_is_nhwc, cams, rois, roi_start, counts, N, img_metas):
-        """Enqueue every stage of the path on the current stream (capturable: no host sync)."""
+    def _enqueue_pre(self, cams, img_metas, dims):
+        """Everything that does not read the feature map: camera geometry, frustum coordinates, position MLP
+        and sine branch.  With host-resident inputs this overlaps the H2D copy of the feature map."""
+        i2l, trans = self.geom_prep(cams)
+        feat_buf = self._get('feat_nhwc', (dims[0], dims[1], dims[2], 256))
+        self.pe3d(feat_buf, i2l, img_metas, None, phase=1, dims=dims)
+        return i2l, trans
+
+    def _enqueue_post(self, feat_in, feat_is_nhwc, cams, rois, roi_start, counts, N, img_metas, i2l, trans, pe_phase=2):
         V = len(img_metas)
         feat_tf32 = None
         if feat_is_nhwc:
@@ -321,11 +331,10 @@ class HotPath:
         else:
             _, _, h, w = feat_in.shape
             feat, feat_tf32 = self.to_nhwc(feat_in)
-        i2l, trans = self.geom_prep(cams)
         if self.overlap:
             # fork: everything of the query generator that does not need the position embedding (RoIAlign
             # of the image feature, 3x3 conv, FC chain, reference points, query embedding) and the box
-            # correlation run on a side stream, concurrently with the PE MLPs on the main stream
+            # correlation run on a side stream, concurrently with the SE gate / PE combine on the main stream
             main = torch.cuda.current_stream()
             self._ev_fork.record(main)
             with torch.cuda.stream(self._side):
@@ -333,12 +342,12 @@ class HotPath:
                 qg = self.roi_align_qg(rois, cams, feat, None, N, phase=1)
                 corr = self.box_corr(rois, roi_start, trans, N, V, img_metas, h, w)
                 self._ev_join.record(self._side)
-            pe, kin = self.pe3d(feat, i2l, img_metas, feat_tf32)
+            pe, kin = self.pe3d(feat, i2l, img_metas, feat_tf32, phase=pe_phase)
             main.wait_event(self._ev_join)
             if self.mode == 'S':
                 self.roi_align_qg(rois, cams, feat, pe, N, phase=2)      # tok_kin = tok_feat + RoIAlign(pe)
         else:
-            pe, kin = self.pe3d(feat, i2l, img_metas, feat_tf32)
+            pe, kin = self.pe3d(feat, i2l, img_metas, feat_tf32, phase=pe_phase)
             qg = self.roi_align_qg(rois, cams, feat, pe, N)
             corr = self.box_corr(rois, roi_start, trans, N, V, img_metas, h, w)
         if self.mode == 'S':
@@ -351,6 +360,16 @@ class HotPath:
         out.update(qg)
         out.update(corr)
         return out
+
+    def _enqueue(self, feat_in, feat_is_nhwc, cams, rois, roi_start, counts, N, img_metas):
+        """Enqueue every stage of the path on the current stream (capturable: no host sync)."""
+        dims = (feat_in.shape[0], feat_in.shape[1], feat_in.shape[2]) if feat_is_nhwc else \
+               (feat_in.shape[0], feat_in.shape[2], feat_in.shape[3])
+        del dims
+        # device-resident input: the whole PE runs on the main stream beside the query generator (side stream)
+        i2l, trans = self.geom_prep(cams)
+        return self._enqueue_post(feat_in, feat_is_nhwc, cams, rois, roi_start, counts, N, img_metas, i2l, trans,
+                                  pe_phase=0)
 
     @torch.no_grad()
     def forward(self, feat, proposal_list, img_metas, feat_is_nhwc=False, use_graph=False):
@@ -368,7 +387,8 @@ class HotPath:
         counts = [int(p.shape[0]) for p in proposal_list]
         N = max(sum(counts), 1)
         mkey = self._masks(img_metas, feat.shape[2], feat.shape[3])[0]
-        key = (N, tuple(feat.shape), mkey, self._vel_dt(img_metas))
+        host_input = not feat.is_cuda
+        key = (N, tuple(feat.shape), mkey, self._vel_dt(img_metas), host_input)
         ent = self._graphs.get(key)
         if ent is None:
             # warm-up (eager) run: sizes every buffer and sets kernel attributes, then capture
@@ -377,16 +397,42 @@ class HotPath:
             cams, rois, roi_start, counts, N = self._upload_meta(proposal_list, img_metas)
             self._enqueue(static_feat, False, cams, rois, roi_start, counts, N, img_metas)
             torch.cuda.synchronize()
-            graph = torch.cuda.CUDAGraph()
+            dims = (feat.shape[0], feat.shape[2], feat.shape[3])
             launches0 = self.launch_count()
-            with torch.cuda.graph(graph):
-                out = self._enqueue(static_feat, False, cams, rois, roi_start, counts, N, img_metas)
-            ent = dict(graph=graph, out=out, feat=static_feat, launches=self.launch_count() - launches0,
-                       keep=dict(self._buf))     # the graph bakes these buffer addresses in
+            if host_input:
+                # two graphs: `pre` does not touch the feature map and runs while it is still being copied in
+                g_pre, g_post = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g_pre):
+                    i2l, trans = self._enqueue_pre(cams, img_metas, dims)
+                with torch.cuda.graph(g_post, pool=g_pre.pool()):
+                    out = self._enqueue_post(static_feat, False, cams, rois, roi_start, counts, N, img_metas, i2l, trans)
+                graphs = (g_pre, g_post)
+            else:
+                g_all = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g_all):
+                    out = self._enqueue(static_feat, False, cams, rois, roi_start, counts, N, img_metas)
+                graphs = (g_all,)
+            ent = dict(graphs=graphs, out=out, feat=static_feat, launches=self.launch_count() - launches0,
+                       keep=dict(self._buf), ev_in=torch.cuda.Event(), ev_done=torch.cuda.Event())
             self._graphs[key] = ent
-        ent['feat'].copy_(feat, non_blocking=True)
-        _, _, _, counts, _ = self._upload_meta(proposal_list, img_metas)
-        ent['graph'].replay()
+        main = torch.cuda.current_stream()
+        if host_input:
+            # H2D of the feature map on the copy stream, overlapped with the feature-independent graph
+            # (the small metadata copy goes first: both copies share the H2D engine, and graph `pre` needs it)
+            _, _, _, counts, _ = self._upload_meta(proposal_list, img_metas)
+            self._copy.wait_event(ent['ev_done'])            # the previous step may still be reading the buffer
+            self._copy.wait_stream(main)
+            with torch.cuda.stream(self._copy):
+                ent['feat'].copy_(feat, non_blocking=True)
+                ent['ev_in'].record(self._copy)
+            ent['graphs'][0].replay()
+            main.wait_event(ent['ev_in'])
+            ent['graphs'][1].replay()
+            ent['ev_done'].record(main)
+        else:
+            ent['feat'].copy_(feat, non_blocking=True)
+            _, _, _, counts, _ = self._upload_meta(proposal_list, img_metas)
+            ent['graphs'][0].replay()
         self.graph_launches += ent['launches']
         out = dict(ent['out'])
         out['num_per_view'] = counts

@@ -18,7 +18,7 @@ c_f = C.c_void_p  # device pointers travel as integers (tensor.data_ptr())
 class PeParams(C.Structure):
     _fields_ = [
         ('V', C.c_int), ('h', C.c_int), ('w', C.c_int), ('depth_num', C.c_int),
-        ('pad_h', C.c_int), ('pad_w', C.c_int), ('stride', C.c_int), ('reserved0', C.c_int),
+        ('pad_h', C.c_int), ('pad_w', C.c_int), ('stride', C.c_int), ('phase', C.c_int),
         ('depth_start', C.c_double), ('position_range', C.c_double * 6),
         ('feat', c_f), ('feat_tf32', c_f), ('img2lidar', c_f), ('not_mask', c_f), ('dim_t', c_f),
         ('w_pos0', c_f), ('b_pos0', c_f), ('w_pos2', c_f), ('b_pos2', c_f),
