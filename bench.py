@@ -10,10 +10,11 @@ path -- (FPN P4 feature [6,256,32,88], per-view 2D boxes, img_metas) -> (cls_sco
 bbox_preds) of all 6 layers -- over one sample.  Metric: samples/sec, whole job.
 
   value  : inputs already resident in HBM; each step = one CUDA-graph replay of the whole path
-           (65 kernels); L2 is flushed (256 MB memset) before every timed step, and each step is
+           (97 kernels); L2 is flushed (256 MB memset) before every timed step, and each step is
            timed with its own pair of CUDA events on the launching stream.
   e2e    : the public API call with HOST (pinned) buffers: H2D of the feature map, boxes and
-           camera matrices, the path, D2H of cls_scores/bbox_preds -- all inside the timed region.
+           camera matrices, the path, D2H of cls_scores/bbox_preds -- all inside the timed region
+           (the feature-map copy overlaps the part of the PE that does not read it).
   N > 1  : one process per GPU, independent replicas on different samples (the decoder is
            per-sample: no data-path collective); NCCL only for the barrier and the max-over-ranks.
   --impl reference : the CPU restatement of the reference (oracle/, kind "port": the reference's
@@ -254,7 +255,7 @@ def main():
         ms_per_step=ms_per_step, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32',
         data='synthetic',
         config=dict(workload=f'MV2D-{mode} R50 1408x512 V={len(metas)} N={N} L={eng.L} bs=1 per GPU (BASELINE configs[{1 if mode == "S" else 2}])',
-                    precision='fp32 storage; TF32 tcgen05 in the PE MLPs, 3xTF32 tcgen05 in the QG conv, FFMA elsewhere',
+                    precision='fp32 storage; single-pass TF32 tcgen05 in the PE MLPs, 3xTF32 tcgen05 in the QG conv and the four wide decoder GEMMs, fp32 FFMA elsewhere, fp64 geometry',
                     l2='flushed (256 MB memset) before every timed step',
                     timing='per-step CUDA events on the launching stream, max over ranks',
                     launch='one CUDA-graph replay of the whole path per step',
@@ -319,7 +320,7 @@ def roofline_section(eng, out, mode, N, flush, peaks):
         bytes_layer = algorithmic_bytes_attention(N, mc, 'S')
         extra = dict(matches_per_query=mc)
     else:
-        corr = dict(keymask=out['keymask'], mask_words=out['mask_words'])
+        corr = dict(keymask=out['keymask'], mask_words=out['mask_words'], key_list=out['key_list'], key_cnt=out['key_cnt'])
         mem_rows = out['feat_nhwc'].view(-1, 256)
         kin_rows = eng._buf['kin'][:mem_rows.numel()].view(-1, 256)
         km = out['keymask'].cpu().numpy().view(np.uint32)

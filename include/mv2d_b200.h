@@ -137,6 +137,8 @@ typedef struct Mv2dCorrParams {
     const uint8_t* pad_mask;  /* nullable [V,h,w] 1 = padded-out cell (key_padding_mask) */
     uint32_t* keymask;        /* out, nullable [N, ceil(V*h*w/32)] */
     int* key_cnt;             /* out, nullable [N] */
+    uint16_t* key_list;       /* out, nullable [N, V*h*w]: the set bits of keymask in ascending order (compacted once
+                               * here instead of once per decoder layer); needs key_cnt */
 } Mv2dCorrParams;
 MV2D_API int mv2d_box_corr(const Mv2dCorrParams* p, void* stream);
 
@@ -178,6 +180,8 @@ typedef struct Mv2dDecoderParams {
     const int* match;           /* mode 0: [N,max_match] RoI ids */
     const int* match_cnt;       /* mode 0: [N] */
     const uint32_t* keymask;    /* mode 1: [N,mask_words] */
+    const uint16_t* key_list;   /* mode 1, nullable: [N, mask_words*32] compacted key ids from mv2d_box_corr */
+    const int* key_cnt;         /* mode 1, with key_list: [N] */
     const uint8_t* self_attn_mask; /* nullable [N,N] 1 = masked (DN training) */
     const Mv2dLayerWeights* layers;   /* HOST array [L] */
     const Mv2dBranchWeights* branches;/* HOST pointer */

@@ -293,6 +293,7 @@ struct XaArgs {
     const float* qt; const float* kin_rows; const float* mem_rows;
     const int* match; const int* match_cnt; int max_match;
     const uint32_t* keymask; int mask_words;
+    const uint16_t* key_list; const int* key_cnt;    // mode 1: compacted key ids from box_corr (nullptr: compact here)
     int mode; int N; int klist_cap;
     float* ctx; float* ctx_lo;    // ctx_lo != nullptr: write the TF32 hi/lo split (operands of the 3xTF32 output GEMM)
 };
@@ -304,7 +305,8 @@ __device__ __forceinline__ void cross_attn_body(const XaArgs& a, int n, unsigned
     float* vbuf = kbuf + 2 * XA_CH * MV2D_C;                        // [2][XA_CH][256] memory rows
     float* sc = vbuf + 2 * XA_CH * MV2D_C;                          // [XA_CH][8] logits -> probs
     float* stat = sc + XA_CH * 8;                                   // m[8], l[8], alpha[8]
-    uint16_t* klist = reinterpret_cast<uint16_t*>(stat + 24);       // [klist_cap]
+    const uint16_t* klist = reinterpret_cast<uint16_t*>(stat + 24); // [klist_cap] (or the global list of box_corr)
+    uint16_t* klist_s = reinterpret_cast<uint16_t*>(stat + 24);
     __shared__ int nkeys_s;
     __shared__ int grp_cnt[128];
     constexpr int NW = XA_THREADS / 32;
@@ -317,8 +319,11 @@ __device__ __forceinline__ void cross_attn_body(const XaArgs& a, int n, unsigned
     if (a.mode == 0) {
         const int cnt = a.match_cnt[n];
         for (int i = t; i < cnt * MV2D_TOK; i += XA_THREADS)
-            klist[i] = (uint16_t)(a.match[(long long)n * a.max_match + i / MV2D_TOK] * MV2D_TOK + i % MV2D_TOK);
+            klist_s[i] = (uint16_t)(a.match[(long long)n * a.max_match + i / MV2D_TOK] * MV2D_TOK + i % MV2D_TOK);
         if (t == 0) nkeys_s = cnt * MV2D_TOK;
+    } else if (a.key_list) {
+        klist = a.key_list + (long long)n * a.mask_words * 32;
+        if (t == 0) nkeys_s = a.key_cnt[n];
     } else {
         // deterministic compaction of the set bits: per-32-word group counts, then a prefix
         const uint32_t* km = a.keymask + (long long)n * a.mask_words;
@@ -341,7 +346,7 @@ __device__ __forceinline__ void cross_attn_body(const XaArgs& a, int n, unsigned
             for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
             int pos = base + incl - c;
             uint32_t b = bits;
-            while (b) { const int bit = __ffs(b) - 1; b &= b - 1; klist[pos++] = (uint16_t)(w * 32 + bit); }
+            while (b) { const int bit = __ffs(b) - 1; b &= b - 1; klist_s[pos++] = (uint16_t)(w * 32 + bit); }
             if (g == ngroups - 1 && lane == 31) nkeys_s = base + incl;
         }
     }
@@ -640,11 +645,14 @@ int run_decoder(const Mv2dDecoderParams& p, cudaStream_t st) {
         set_error("decoder: init %s", cudaGetErrorString(e));
         return (int)e;
     }
-    const int klist_cap = p.mode == 0 ? p.max_match * MV2D_TOK : p.mask_words * 32;
+    const bool global_list = p.mode == 1 && p.key_list != nullptr;
+    const int klist_cap = p.mode == 0 ? p.max_match * MV2D_TOK : (global_list ? 0 : p.mask_words * 32);
+    // S head (~64 keys / query): 4 warps, 16-key chunks, 3 CTAs per SM.  T head (~2000 keys / query): 8 warps and
+    // 32-key chunks measured faster than the small variant even when that runs 3 CTAs per SM (fewer barriers per key)
     const int xa_ch = p.mode == 0 ? 16 : 32;
     const size_t xa_smem = (size_t)(4 * xa_ch * MV2D_C + xa_ch * 8 + 24) * sizeof(float) + (size_t)klist_cap * sizeof(uint16_t);
     MV2D_CHECK_ARG(xa_smem <= 227 * 1024, "decoder: key list does not fit shared memory");
-    auto xa_kernel = p.mode == 0 ? cross_attn_kernel<16, 128> : cross_attn_kernel<32, 256>;
+    auto xa_kernel = xa_ch == 16 ? cross_attn_kernel<16, 128> : cross_attn_kernel<32, 256>;
     MV2D_CHECK_ARG(p.mode == 0 || p.mask_words <= 4096, "decoder: mask_words=%d > 4096", p.mask_words);
     if ((e = cudaFuncSetAttribute(xa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xa_smem)) != cudaSuccess) {
         set_error("decoder: smem attr %s", cudaGetErrorString(e));
@@ -667,6 +675,7 @@ int run_decoder(const Mv2dDecoderParams& p, cudaStream_t st) {
         m.vel_dt = p.vel_dt;
         m.query_pos = p.query_pos; m.ref = p.ref; m.kin_rows = p.kin_rows; m.mem_rows = p.mem_rows;
         m.match = p.match; m.match_cnt = p.match_cnt; m.keymask = p.keymask; m.self_attn_mask = p.self_attn_mask;
+        m.key_list = p.key_list; m.key_cnt = p.key_cnt;
         m.x = x; m.xq = xq; m.x1 = x1; m.x1q = x1q; m.x2 = x2; m.x1q_hi = x1q_hi; m.x1q_lo = x1q_lo; m.x2_hi = x2_hi; m.x2_lo = x2_lo;
         m.qkv = qkv; m.sa = sa; m.qt = qt; m.ctx = ctx; m.ctx_lo = ctx_lo; m.hdn = hdn; m.hdn_lo = hdn_lo; m.part = part;
         m.b0 = b0; m.b1 = b1; m.b2 = b2; m.b3 = b3; m.cls = p.cls_scores; m.box = p.bbox_preds; m.outs_dec = p.outs_dec;
@@ -736,8 +745,9 @@ int run_decoder(const Mv2dDecoderParams& p, cudaStream_t st) {
         {
             XaArgs a{}; a.qt = qt; a.kin_rows = p.kin_rows; a.mem_rows = p.mem_rows; a.match = p.match;
             a.match_cnt = p.match_cnt; a.max_match = p.max_match; a.keymask = p.keymask; a.mask_words = p.mask_words;
+            a.key_list = p.key_list; a.key_cnt = p.key_cnt;
             a.mode = p.mode; a.N = N; a.klist_cap = klist_cap; a.ctx = ctx; a.ctx_lo = ctx_lo;
-            launch_k(xa_kernel, dim3(N), dim3(p.mode == 0 ? 128 : 256), xa_smem, st, a);
+            launch_k(xa_kernel, dim3(N), dim3(xa_ch == 16 ? 128 : 256), xa_smem, st, a);
             MV2D_CHECK_LAUNCH("cross_attn");
         }
         if ((rc = tc3(ctx, ctx_lo, 2048, w.ca_o_w, w.ca_o_w_lo, 2048, nullptr, part, nullptr, C, N, C, 2048, 0, DEC_SPLIT, NC, st))) return rc;

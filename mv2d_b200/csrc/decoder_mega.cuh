@@ -293,6 +293,7 @@ struct MegaParams {
     float pc_range[6]; float vel_dt;
     const float *query_pos, *ref, *kin_rows, *mem_rows;
     const int *match, *match_cnt; const uint32_t* keymask; const uint8_t* self_attn_mask;
+    const uint16_t* key_list; const int* key_cnt;
     float *x, *xq, *x1, *x1q, *x2, *x1q_hi, *x1q_lo, *x2_hi, *x2_lo, *qkv, *sa, *qt, *ctx, *ctx_lo, *hdn, *hdn_lo, *part;
     float *b0, *b1, *b2, *b3;
     float *cls, *box, *outs_dec;
@@ -383,6 +384,7 @@ decoder_mega_kernel(const __grid_constant__ MegaParams p) {
         {
             XaArgs a{}; a.qt = p.qt; a.kin_rows = p.kin_rows; a.mem_rows = p.mem_rows; a.match = p.match;
             a.match_cnt = p.match_cnt; a.max_match = p.max_match; a.keymask = p.keymask; a.mask_words = p.mask_words;
+            a.key_list = p.key_list; a.key_cnt = p.key_cnt;
             a.mode = p.mode; a.N = N; a.klist_cap = p.klist_cap; a.ctx = p.ctx; a.ctx_lo = p.ctx_lo;
             for (int n = cta; n < N; n += ncta) {
                 cross_attn_body<32, 256>(a, n, smem);

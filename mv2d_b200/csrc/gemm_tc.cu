@@ -15,6 +15,7 @@
 // epilogue (TMEM lane quadrant = warp_idx % 4).  One output tile per CTA; several CTAs per SM
 // overlap each other's prologue/epilogue.
 #include <cuda.h>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <unordered_map>
@@ -306,6 +307,157 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
 }
 
+// ---------------------------------------------------------------------------- cluster-multicast variant
+// The decoder's wide GEMMs (M ~ 300, 3xTF32, 128x64 tiles) are bound by L2->SM traffic: every N-tile CTA
+// re-reads the same A tile (hi and lo).  Here the four CTAs of a thread-block cluster that share an M-tile
+// each load one quarter of the A rows and TMA-multicast it into all four shared memories, so A crosses the
+// L2->SM fabric once per cluster instead of four times.  A smem slot is refilled by the PEERS as well, so
+// its "empty" barrier collects one tcgen05.commit arrival from each of the 4 CTAs (multicast commit).
+#define TC_MC 4
+__device__ __forceinline__ void tma_load_2d_mc(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <int STAGES>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_mc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
+                  const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmWlo, TcArgs g) {
+    constexpr int BN = 64, PASSES = 3;
+    constexpr int A_BYTES = TC_BM * TC_BK * 4, W_BYTES = BN * TC_BK * 4;
+    constexpr int STAGE_BYTES = 2 * (A_BYTES + W_BYTES);
+    constexpr int A_QUARTER = A_BYTES / TC_MC;                 // 32 rows x 128 B
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tmem_full_bar = empty_bar + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m_tile = blockIdx.y, n0 = blockIdx.x * BN;
+    const int nkb = g.nkb_per_split, kb0 = blockIdx.z * g.nkb_per_split;
+    uint32_t rank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    constexpr uint16_t mask = (1u << TC_MC) - 1;
+
+    if (warp == 0 && lane == 0) {
+        tmap_prefetch(&tmA); tmap_prefetch(&tmW); tmap_prefetch(&tmAlo); tmap_prefetch(&tmWlo);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], TC_MC); }
+        mbar_init(tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(BN));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();                        // every CTA's barriers exist before any peer signals them
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();
+    pdl_trigger();
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % STAGES, ph = (kb / STAGES) & 1;
+                mbar_wait(&empty_bar[s], ph ^ 1);                       // all 4 CTAs released slot s
+                uint8_t* st = smem + s * STAGE_BYTES;
+                mbar_expect_tx(&full_bar[s], STAGE_BYTES);              // own W tiles + 4 multicast quarters of A hi/lo
+                const int k = (kb0 + kb) * TC_BK;
+                tma_load_2d_mc(&tmA, &full_bar[s], st + rank * A_QUARTER, k, m_tile * TC_BM + rank * 32, mask);
+                tma_load_2d_mc(&tmAlo, &full_bar[s], st + A_BYTES + rank * A_QUARTER, k, m_tile * TC_BM + rank * 32, mask);
+                tma_load_2d(&tmW, &full_bar[s], st + 2 * A_BYTES, k, n0);
+                tma_load_2d(&tmWlo, &full_bar[s], st + 2 * A_BYTES + W_BYTES, k, n0);
+            }
+        }
+    } else if (warp == 1) {
+        constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+        if (lane == 0) {
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % STAGES, ph = (kb / STAGES) & 1;
+                mbar_wait(&full_bar[s], ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+                const uint64_t a_hi = make_desc(sa), a_lo = make_desc(sa + A_BYTES);
+                const uint64_t w_hi = make_desc(sa + 2 * A_BYTES), w_lo = make_desc(sa + 2 * A_BYTES + W_BYTES);
+#pragma unroll
+                for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
+                    const uint64_t adv = (uint64_t)((k * TC_UMMA_K * 4) >> 4);
+                    umma_tf32(tmem_base, a_hi + adv, w_hi + adv, idesc, (kb | k) != 0);
+                    umma_tf32(tmem_base, a_hi + adv, w_lo + adv, idesc, 1);
+                    umma_tf32(tmem_base, a_lo + adv, w_hi + adv, idesc, 1);
+                }
+                umma_commit_mc(&empty_bar[s], mask);      // slot s is free in THIS CTA: tell all 4 producers
+            }
+            umma_commit(tmem_full_bar);
+        }
+    } else {
+        mbar_wait(tmem_full_bar, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int q = warp & 3;
+        // the peers may still be multicasting into the pipeline stages: stage through a private area behind them
+        float* stg = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256) + q * 1024;
+        auto store_t = [&](float* __restrict__ dst, const float (&x)[32], int n) {
+            __syncwarp();
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4)
+                *reinterpret_cast<float4*>(stg + lane * 32 + ((j4 ^ (lane & 7)) << 2)) =
+                    make_float4(x[j4 * 4], x[j4 * 4 + 1], x[j4 * 4 + 2], x[j4 * 4 + 3]);
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int rr = i * 4 + (lane >> 3), cc = lane & 7;
+                const float4 v4 = *reinterpret_cast<const float4*>(stg + rr * 32 + ((cc ^ (rr & 7)) << 2));
+                const long long orow = (long long)m_tile * TC_BM + q * 32 + rr;
+                if (orow < g.M) *reinterpret_cast<float4*>(dst + orow * g.ldc + n + cc * 4) = v4;
+            }
+        };
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+            uint32_t v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+            const int n = n0 + c * 32;
+            float x[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
+            if (gridDim.z > 1) { store_t(g.C + blockIdx.z * g.split_stride, x, n); continue; }
+            if (g.bias) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) x[j] += __ldg(g.bias + n + j);
+            }
+            if (g.flags & GEMM_RELU) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
+            }
+            if (g.flags & GEMM_SPLIT_OUT) {
+                float lo[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) { const float hi = round_tf32(x[j]); lo[j] = round_tf32(x[j] - hi); x[j] = hi; }
+                store_t(g.C_lo, lo, n);
+            }
+            store_t(g.C, x, n);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();                        // nobody leaves while a peer can still write its smem / barriers
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN));
+    }
+}
+
 // ---------------------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -408,6 +560,38 @@ static int launch_tc(const CUtensorMap& a, const CUtensorMap& alo, const CUtenso
     return 0;
 }
 
+static bool mc_enabled() {
+    static const bool on = []() { const char* e = getenv("MV2D_TC_MULTICAST"); return !(e && e[0] == '0'); }();
+    return on;
+}
+
+static int launch_tc_mc(const CUtensorMap& a, const CUtensorMap& alo, const CUtensorMap& w, const CUtensorMap& wlo,
+                        const TcArgs& g, int m_tiles, int nsplit, cudaStream_t st) {
+    constexpr int STAGES = 4;
+    constexpr size_t smem = (size_t)STAGES * 2 * (TC_BM * TC_BK * 4 + 64 * TC_BK * 4) + 256 + 4 * 4096 + 1024;
+    auto kern = gemm_tc_mc_kernel<STAGES>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_error("gemm_tc_mc: smem attr: %s", cudaGetErrorString(e)); return (int)e; }
+        attr_set = true;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(g.N / 64, m_tiles, nsplit); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = TC_MC; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cap);
+    cfg.attrs = attr; cfg.numAttrs = (pdl_enabled() && cap == cudaStreamCaptureStatusNone) ? 2 : 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a, alo, w, wlo, g);
+    note_launch();
+    if (e != cudaSuccess) { set_error("gemm_tc_mc: %s", cudaGetErrorString(e)); return (int)e; }
+    return 0;
+}
+
 int launch_gemm_tc(const TcGemm& t, cudaStream_t st) {
     // small-M problems (the decoder, M ~ 300) are latency bound: 64-wide N tiles double the CTA count
     const int bn = (t.M <= 512 && !t.im2col && t.passes == 3) ? 64 : 128;   // (a 256-wide, 2-stage im2col variant measured slower than 128-wide / 3 stages)
@@ -439,6 +623,12 @@ int launch_gemm_tc(const TcGemm& t, cudaStream_t st) {
     if ((rc = make_map_2d(&wlo, t.passes == 3 ? t.W_lo : t.W, t.N, t.K, t.ldw, bn))) return rc;
     if (t.im2col && bn == 256) return launch_tc<256, 3, true, 2>(a, alo, w, wlo, g, m_tiles, nsplit, st);
     if (t.im2col) return launch_tc<128, 3, true, 3>(a, alo, w, wlo, g, m_tiles, nsplit, st);
+    if (t.passes == 3 && bn == 64 && mc_enabled() && (t.N / 64) % TC_MC == 0) {
+        // A is loaded in 32-row quarters and multicast across the 4-CTA cluster that shares the M-tile
+        if ((rc = make_map_2d(&a, t.A, t.M, t.K, t.lda, 32))) return rc;
+        if ((rc = make_map_2d(&alo, t.A_lo, t.M, t.K, t.lda, 32))) return rc;
+        return launch_tc_mc(a, alo, w, wlo, g, m_tiles, nsplit, st);
+    }
     if (t.passes == 3 && bn == 64) return launch_tc<64, 3, false, 4>(a, alo, w, wlo, g, m_tiles, nsplit, st);
     if (t.passes == 3) return launch_tc<128, 3, false, 3>(a, alo, w, wlo, g, m_tiles, nsplit, st);
     return launch_tc<128, 1, false, 3>(a, alo, w, wlo, g, m_tiles, nsplit, st);

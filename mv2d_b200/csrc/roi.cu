@@ -388,6 +388,32 @@ key_mask_kernel(Mv2dCorrParams p, int words) {
         __syncthreads();
         if (t == 0) p.key_cnt[n] = total;
     }
+    if (p.key_list) {
+        // ordered compaction of the set bits (done once here; every decoder layer streams this list)
+        __shared__ int grp_cnt[128];
+        const int warp = t >> 5, lane = t & 31, nw = blockDim.x >> 5;
+        const int ngroups = (words + 31) / 32;                  // host guarantees <= 128
+        for (int g = warp; g < ngroups; g += nw) {
+            const int w = g * 32 + lane;
+            const int c = __popc((w < words) ? bits[w] : 0u);
+            const int tot = __reduce_add_sync(0xffffffffu, c);
+            if (lane == 0) grp_cnt[g] = tot;
+        }
+        __syncthreads();
+        uint16_t* kl = p.key_list + (long long)n * words * 32;
+        for (int g = warp; g < ngroups; g += nw) {
+            int base = 0;
+            for (int i = 0; i < g; ++i) base += grp_cnt[i];
+            const int w = g * 32 + lane;
+            uint32_t b = (w < words) ? bits[w] : 0u;
+            const int c = __popc(b);
+            int incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+            int pos = base + incl - c;
+            while (b) { const int bit = __ffs(b) - 1; b &= b - 1; kl[pos++] = (uint16_t)(w * 32 + bit); }
+        }
+    }
 }
 
 int run_box_corr(const Mv2dCorrParams& p, cudaStream_t st) {
@@ -400,6 +426,8 @@ int run_box_corr(const Mv2dCorrParams& p, cudaStream_t st) {
     MV2D_CHECK_LAUNCH("box_corr");
     if (p.keymask) {
         const int words = cdiv(p.V * p.h * p.w, 32);
+        MV2D_CHECK_ARG(words <= 4096, "box_corr: V*h*w too large for the key list (words=%d)", words);
+        MV2D_CHECK_ARG(!p.key_list || p.key_cnt, "box_corr: key_list needs key_cnt");
         launch_k(key_mask_kernel, dim3(p.N), dim3(256), words * sizeof(uint32_t), st, p, words);
         MV2D_CHECK_LAUNCH("key_mask");
     }

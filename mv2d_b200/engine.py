@@ -274,8 +274,9 @@ class HotPath:
             _, pad_mask, _, has_pad = self._masks(img_metas, h, w)
             p.h, p.w, p.stride, p.expand_stride = h, w, c['stride'], c['expand_stride']
             p.pad_mask = pad_mask.data_ptr() if has_pad else None
-            p.keymask, p.key_cnt = keymask.data_ptr(), key_cnt.data_ptr()
-            out.update(keymask=keymask, key_cnt=key_cnt, mask_words=words)
+            key_list = self._get('key_list', (N, words * 32), torch.int16)
+            p.keymask, p.key_cnt, p.key_list = keymask.data_ptr(), key_cnt.data_ptr(), key_list.data_ptr()
+            out.update(keymask=keymask, key_cnt=key_cnt, key_list=key_list, mask_words=words)
         lib.check(self.lib.mv2d_box_corr(C.byref(p), lib.stream_ptr()), 'mv2d_box_corr')
         return out
 
@@ -299,6 +300,8 @@ class HotPath:
             p.match, p.match_cnt, p.max_match = corr['match'].data_ptr(), corr['match_cnt'].data_ptr(), corr['max_match']
         else:
             p.keymask, p.mask_words = corr['keymask'].data_ptr(), corr['mask_words']
+            if corr.get('key_list') is not None:
+                p.key_list, p.key_cnt = corr['key_list'].data_ptr(), corr['key_cnt'].data_ptr()
         p.self_attn_mask = self_attn_mask.data_ptr() if self_attn_mask is not None else None
         p.layers, p.branches = W.layers_ptr(), W.branches_ptr()
         p.cls_scores, p.bbox_preds, p.outs_dec = cls.data_ptr(), box.data_ptr(), outs.data_ptr()

@@ -54,7 +54,7 @@ class CorrParams(C.Structure):
         ('rois', c_f), ('roi_start', c_f), ('trans', c_f), ('lin', c_f), ('depths', c_f),
         ('match', c_f), ('match_cnt', c_f),
         ('h', C.c_int), ('w', C.c_int), ('stride', C.c_int), ('expand_stride', C.c_int),
-        ('pad_mask', c_f), ('keymask', c_f), ('key_cnt', c_f),
+        ('pad_mask', c_f), ('keymask', c_f), ('key_cnt', c_f), ('key_list', c_f),
     ]
 
 
@@ -85,7 +85,8 @@ class DecoderParams(C.Structure):
         ('reserved1', C.c_int),
         ('pc_range', C.c_float * 6), ('vel_dt', C.c_float), ('reserved2', C.c_float),
         ('query_pos', c_f), ('ref', c_f), ('kin_rows', c_f), ('mem_rows', c_f),
-        ('match', c_f), ('match_cnt', c_f), ('keymask', c_f), ('self_attn_mask', c_f),
+        ('match', c_f), ('match_cnt', c_f), ('keymask', c_f), ('key_list', c_f), ('key_cnt', c_f),
+        ('self_attn_mask', c_f),
         ('layers', C.POINTER(LayerWeights)), ('branches', C.POINTER(BranchWeights)),
         ('cls_scores', c_f), ('bbox_preds', c_f), ('outs_dec', c_f),
         ('workspace', c_f), ('workspace_bytes', C.c_size_t),

@@ -44,7 +44,7 @@ for mode, V in (('S', 6), ('T', 12)):
             mc = float(out['match_cnt'].float().mean())
             n_k, mask_b, gathered = 49 * n, n * mc * 49, n * mc * 49
         else:
-            corr = dict(keymask=out['keymask'], mask_words=out['mask_words'])
+            corr = dict(keymask=out['keymask'], mask_words=out['mask_words'], key_list=out['key_list'], key_cnt=out['key_cnt'])
             mem_rows = out['feat_nhwc'].view(-1, 256)
             kin_rows = eng._buf['kin'][:mem_rows.numel()].view(-1, 256)
             km = out['keymask'].cpu().numpy().view(np.uint32)
