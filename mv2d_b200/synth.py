@@ -203,7 +203,22 @@ CASES = {
                   img_shape=(480, 1376, 3), pad_shape=(512, 1408, 3)),
     # config 3 of BASELINE.json (one of its two samples): 12 views, 300 queries
     't_cfg3': dict(mode='T', seed=7, num_views=12, boxes_per_view=25, num_layers=6),
+    # row a20: training-mode forward with denoising queries (7 GT boxes x 10 noised copies prepended)
+    't_dn': dict(mode='T', seed=8, num_views=12, boxes_per_view=[3, 2, 4, 3, 2, 3, 3, 2, 4, 3, 2, 3], num_layers=2,
+                 dn=dict(num_gt=7, seed=80)),
 }
+
+
+def make_dn_inputs(dn_spec, scalar=10):
+    """Synthetic GT for the denoising branch: boxes [G,9] = (gravity centre xyz, w, l, h, yaw, vx, vy),
+    labels [G], and the uniform noise prepare_for_dn draws with torch.rand_like ([scalar*G, 3] in [0,1))."""
+    rng = np.random.Generator(np.random.PCG64(dn_spec['seed']))
+    G = dn_spec['num_gt']
+    boxes = np.concatenate([rng.uniform(-40, 40, (G, 2)), rng.uniform(-3, 1, (G, 1)), rng.uniform(0.5, 5, (G, 3)),
+                            rng.uniform(-3.1, 3.1, (G, 1)), rng.uniform(-2, 2, (G, 2))], 1).astype(np.float32)
+    labels = rng.integers(0, 10, G).astype(np.int64)
+    rand = rng.uniform(0, 1, (scalar * G, 3)).astype(np.float32)
+    return torch.from_numpy(boxes), torch.from_numpy(labels), torch.from_numpy(rand)
 
 
 def case_inputs(spec):

@@ -62,11 +62,28 @@ def run_reference(spec, weight_seed=0):
 
     head.box_corr_module.gen_box_roi_correlation = wrap_s
     head.box_corr_module.gen_box_correlation = wrap_t
+    dn_patch = None
+    if 'dn' in spec:
+        # training-mode forward with denoising queries (row a20).  Only the HEAD's `training` flag is raised
+        # (children stay in eval: dropout off); .cuda() is a no-op here and the noise is injected.
+        gt_boxes, gt_labels, rand = synth.make_dn_inputs(spec['dn'])
+
+        class _Boxes:   # the two attributes prepare_for_dn reads from LiDARInstance3DBoxes (mv2d_s_head.py:42)
+            gravity_center = gt_boxes[:, :3]
+            tensor = torch.cat([gt_boxes[:, :3], gt_boxes[:, 3:]], 1)
+        metas[0] = dict(metas[0], gt_bboxes_3d=_Boxes(), gt_labels_3d=gt_labels)
+        head.training = True
+        dn_patch = (torch.Tensor.cuda, torch.rand_like)
+        torch.Tensor.cuda = lambda self, *a, **k: self
+        torch.rand_like = lambda t, *a, **k: rand.clone()
     with torch.no_grad(), warnings.catch_warnings():
         warnings.simplefilter('ignore')
         pe = head.position_encoding([feat], metas)[0]
         x = [torch.cat([feat, pe], dim=1)]
         out = head._bbox_forward(x, [b.clone() for b in boxes], metas)
+        if dn_patch is not None:
+            torch.Tensor.cuda, torch.rand_like = dn_patch
+            head.training = False
         L = spec['num_layers']
         N = out['rois'].shape[0]
         # MV2DHead.simple_test tail (mv2d_head.py:262-265): get_bboxes = NMSFreeCoder.decode +
@@ -83,8 +100,8 @@ def run_reference(spec, weight_seed=0):
         rois=out['rois'].numpy(),
         intrinsics=out['intrinsics'].numpy(), extrinsics=out['extrinsics'].numpy(),
         center_lidar=cap['center_lidar'].numpy(),
-        query_pos=cap['query_pos'].reshape(N, -1).numpy(),
-        outs_dec=cap['outs_dec'].reshape(L, N, -1).numpy(),
+        query_pos=cap['query_pos'].reshape(-1, 256)[-N:].numpy(),
+        outs_dec=cap['outs_dec'].reshape(L, -1, 256)[:, -N:].numpy(),
         pe_sub=pe.flatten()[::PE_SUBSAMPLE].numpy().copy(),
         roi_feat_sub=out['bbox_feats'].flatten()[::PE_SUBSAMPLE].numpy().copy(),
         dec_boxes=decoded['bboxes'].numpy(), dec_scores=decoded['scores'].numpy(),
@@ -95,6 +112,13 @@ def run_reference(spec, weight_seed=0):
         g['corr_mask'] = cap['corr_mask'].numpy()
     if 'key_mask' in cap:
         g['key_mask_packed'] = np.packbits(cap['key_mask'].numpy().reshape(N, -1), axis=1)
+    if out.get('dn_mask_dict'):
+        md = out['dn_mask_dict']
+        kc, kb = md['output_known_lbs_bboxes']
+        g['dn_cls'] = kc[:, 0].numpy()          # [L, pad, 10]
+        g['dn_box'] = kb[:, 0].numpy()
+        g['dn_labels'] = md['known_lbs_bboxes'][0].numpy()
+        g['dn_pad'] = np.int64(md['pad_size'])
     return g
 
 

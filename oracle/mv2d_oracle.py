@@ -561,7 +561,36 @@ def mv2d_s_forward(sd, feat, proposal_list, img_metas, cfg=None, return_stages=F
     return cls, box
 
 
-def mv2d_t_forward(sd, feat, proposal_list, img_metas, cfg=None, return_stages=False):
+def prepare_for_dn(ref, gt_boxes, gt_labels, rand, cfg, scalar=10, noise_scale=1.25, noise_trans=0.0, split=0.6,
+                   num_classes=10, eps=1e-4):
+    """MV2DSHead.prepare_for_dn, training branch, batch_size 1 (roi_heads/mv2d_s_head.py:39-120), with the
+    uniform noise `rand` ([scalar*G,3] in [0,1), what torch.rand_like returns there) passed in.
+    Returns (padded reference points [pad+N,3], self-attention mask [T,T] bool, known_labels, pad_size)."""
+    pc = cfg['pc_range']
+    G = gt_boxes.shape[0]
+    centers = gt_boxes[:, :3].repeat(scalar, 1).clone()
+    scale = gt_boxes[:, 3:6].repeat(scalar, 1)
+    labels = gt_labels.repeat(scalar).clone()
+    rand_prob = rand * 2 - 1.0
+    centers = centers + rand_prob * (scale / 2 + noise_trans) * noise_scale
+    for i in range(3):
+        centers[:, i] = (centers[:, i] - pc[i]) / (pc[i + 3] - pc[i])
+    centers = centers.clamp(min=eps, max=1.0 - eps)
+    labels[torch.norm(rand_prob, 2, 1) > split] = num_classes
+    pad = G * scalar
+    padded = torch.cat([torch.zeros(pad, 3), ref], 0)
+    idx = torch.cat([torch.arange(G) + G * i for i in range(scalar)])
+    padded[idx] = centers
+    T = pad + ref.shape[0]
+    mask = torch.zeros(T, T, dtype=torch.bool)
+    mask[pad:, :pad] = True                        # matching queries cannot see the denoising ones
+    for i in range(scalar):                        # denoising groups cannot see each other
+        mask[G * i:G * (i + 1), G * (i + 1):pad] = True
+        mask[G * i:G * (i + 1), :G * i] = True
+    return padded, mask, labels, pad
+
+
+def mv2d_t_forward(sd, feat, proposal_list, img_metas, cfg=None, return_stages=False, dn=None):
     """MV2DTHead eval forward (roi_heads/mv2d_t_head.py:26-142): dense feature-map keys
     compacted to the union of per-query masks, per-query bool cross mask, velocity / dt."""
     cfg = cfg or make_cfg('T')
@@ -573,17 +602,28 @@ def mv2d_t_forward(sd, feat, proposal_list, img_metas, cfg=None, return_stages=F
     key_mask = box_correlation_mask(rois, num_per_view, img_metas, h, w, cfg)  # [N,V,h,w]
     pad_mask = feat_masks(img_metas, h, w)[0]  # [V,h,w]
     cross = ~key_mask
-    roi_mask = key_mask.any(0)  # [V,h,w]
+    if dn is not None:   # training: a query without any key gets key (0,0,0) un-masked (mv2d_t_head.py:80-82)
+        invalid = cross.view(cross.shape[0], -1).all(1)
+        cross[invalid, 0, 0, 0] = False
+    roi_mask = (~cross).any(0)  # [V,h,w]
     mem = feat.permute(0, 2, 3, 1)[roi_mask]  # [Nk,C]
     pos = pe.permute(0, 2, 3, 1)[roi_mask]
     kpm = pad_mask[roi_mask][None]  # [1,Nk]
     cross = cross[:, roi_mask]  # [N,Nk]
-    qpos = query_embed(sd, ref[None])  # [1,N,C]
-    outs = decoder(sd, qpos.permute(1, 0, 2), mem[:, None], pos[:, None], cfg, cross_mask=cross,
-                   key_padding_mask=kpm)  # [L,N,1,C]
-    outs = outs.transpose(1, 2)  # [L,1,N,C]
-    cls, box = branches(sd, outs, ref[None], cfg)
+    self_mask, pad, ref_all = None, 0, ref
+    if dn is not None:   # denoising queries are prepended; they see every compacted key (mv2d_t_head.py:91-98)
+        ref_all, self_mask, dn_labels, pad = prepare_for_dn(ref, dn['gt_boxes'], dn['gt_labels'], dn['rand'], cfg)
+        cross = torch.cat([cross.all(dim=0)[None].repeat(pad, 1), cross], 0)
+    qpos = query_embed(sd, ref_all[None])  # [1,T,C]
+    outs = decoder(sd, qpos.permute(1, 0, 2), mem[:, None], pos[:, None], cfg, self_mask=self_mask,
+                   cross_mask=cross, key_padding_mask=kpm)  # [L,T,1,C]
+    outs = outs.transpose(1, 2)  # [L,1,T,C]
+    cls, box = branches(sd, outs, ref_all[None], cfg)
     cls, box = cls.flatten(1, 2), box.flatten(1, 2)
+    dn_out = None
+    if dn is not None:
+        dn_out = dict(cls=cls[:, :pad], box=box[:, :pad], ref=ref_all[:pad], attn_mask=self_mask, labels=dn_labels)
+        cls, box, outs = cls[:, pad:], box[:, pad:], outs[:, :, pad:]
     nvf = cfg['num_views_per_frame']
     if len(img_metas) > nvf:
         ts = np.array([m['timestamp'] for m in img_metas])
@@ -592,7 +632,7 @@ def mv2d_t_forward(sd, feat, proposal_list, img_metas, cfg=None, return_stages=F
     if return_stages:
         return cls, box, dict(pe=pe, rois=rois, intrinsics=K, extrinsics=E, roi_feat=roi_feat,
                               intrins_feat=ifeat, ref=ref, key_mask=key_mask,
-                              query_pos=qpos[0], outs_dec=outs[:, 0], **qg)
+                              query_pos=qpos[0, pad:], outs_dec=outs[:, 0], dn=dn_out, **qg)
     return cls, box
 
 

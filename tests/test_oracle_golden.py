@@ -41,8 +41,17 @@ def test_oracle_matches_reference_golden(name, state_dicts):
     feat, boxes, metas = synth.case_inputs(spec)
     cfg = O.make_cfg(spec['mode'], num_layers=spec['num_layers'])
     fn = O.mv2d_s_forward if spec['mode'] == 'S' else O.mv2d_t_forward
+    kw = {}
+    if 'dn' in spec:   # row a20: training-mode forward with denoising queries
+        gt_boxes, gt_labels, rand = synth.make_dn_inputs(spec['dn'])
+        kw['dn'] = dict(gt_boxes=gt_boxes, gt_labels=gt_labels, rand=rand)
     with torch.no_grad():
-        cls, box, st = fn(sd, feat, boxes, metas, cfg, return_stages=True)
+        cls, box, st = fn(sd, feat, boxes, metas, cfg, return_stages=True, **kw)
+    if 'dn' in spec:
+        assert st['dn']['cls'].shape[1] == int(g['dn_pad']) == 10 * spec['dn']['num_gt']
+        close(st['dn']['cls'], g['dn_cls'], 1e-4, 1e-4)
+        close(st['dn']['box'], g['dn_box'], 1e-4, 1e-4)
+        assert np.array_equal(st['dn']['labels'].numpy(), g['dn_labels'])
     # stage level
     close(st['rois'], g['rois'], 0)
     close(st['pe'].flatten()[::PE_SUB], g['pe_sub'], 1e-4)
