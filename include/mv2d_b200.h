@@ -32,7 +32,7 @@ extern "C" {
 #define MV2D_API
 #endif
 
-#define MV2D_ABI_VERSION 1
+#define MV2D_ABI_VERSION 2
 #define MV2D_MAX_LAYERS 8
 
 MV2D_API int mv2d_abi_version(void);
@@ -40,7 +40,7 @@ MV2D_API const char* mv2d_last_error(void);
 /* number of kernel launches this library has enqueued so far in this process */
 MV2D_API unsigned long long mv2d_launch_count(void);
 /* sizeof() of the parameter structs, so a binding can verify its mirror of this header */
-MV2D_API size_t mv2d_sizeof(int which); /* 0 Pe, 1 Qg, 2 Corr, 3 Decoder, 4 LayerWeights, 5 BranchWeights */
+MV2D_API size_t mv2d_sizeof(int which); /* 0 Pe, 1 Qg, 2 Corr, 3 Decoder, 4 LayerWeights, 5 BranchWeights, 6 Dn */
 
 /* ---- geometry (utils/pe.py:111; roi_heads/utils/box_correlation.py:118-122,174-178)
  * img2lidar[v] = inv(lidar2img[v]);  trans[src][dst] = lidar2img[dst] @ img2lidar[src]  (fp64) */
@@ -169,7 +169,8 @@ typedef struct Mv2dDecoderParams {
     int max_match, mask_words;
     int persistent;             /* 1 = all layers + branches in ONE cooperative launch (one CTA per SM, device-wide
                                  *     barriers between stages); 0 = one launch per stage (~75 launches) */
-    int reserved1;
+    int vel_row_start;          /* vel_dt applies to query rows >= this (denoising rows are prepended and are not
+                                 *     rescaled, mv2d_t_head.py:112-118 vs :136-140); 0 = all rows */
     float pc_range[6];
     float vel_dt;               /* T head: bbox_preds[..., 8:10] /= vel_dt ; 0 = off (mv2d_t_head.py:130-142) */
     float reserved2;
@@ -193,6 +194,55 @@ typedef struct Mv2dDecoderParams {
 } Mv2dDecoderParams;
 MV2D_API size_t mv2d_decoder_workspace_bytes(int N, int L);
 MV2D_API int mv2d_decoder(const Mv2dDecoderParams* p, void* stream);
+
+/* ---- row a20: denoising queries of the training-mode forward -----------------------------------------------
+ * Replaces MV2DSHead.prepare_for_dn (mv2d_s_head.py:39-120, training branch, batch_size 1) plus the way both
+ * heads extend the cross-attention mask for the prepended queries (mv2d_s_head.py:159-172,
+ * mv2d_t_head.py:79-98) and the query embedding of the padded reference points
+ * (cross_attention_head.py:199-206).  T = scalar*G + N query rows come out, denoising rows first:
+ *   ref_all[i]   i < pad: clamp(normalise(centre_g + (2*rand-1) * (size_g/2 + noise_trans) * noise_scale), eps, 1-eps)
+ *                         with g = i % G ; i >= pad: ref[i-pad]
+ *   dn_labels[i] = |2*rand-1|_2 > split ? num_classes : gt_labels[g]
+ *   attn_mask    [T,T] u8, 1 = masked: matching rows do not see denoising rows, denoising groups do not see
+ *                each other
+ *   keys         S: match_all[i] = every RoI for i < pad, the RoI's own match list otherwise
+ *                T: keymask_all[i] = OR of all rows for i < pad, the own row otherwise; with train_unmask a
+ *                   matching row without any key gets key 0 (mv2d_t_head.py:80-82)
+ *   query_pos_all = query_embedding(pos2posemb3d(ref_all))
+ * The uniform noise is an INPUT (the caller draws it, as torch.rand_like does in the reference). */
+typedef struct Mv2dDnParams {
+    int N, G, scalar, num_classes;
+    int mode;                   /* 0 = S (match lists), 1 = T (key masks) */
+    int max_match;              /* S: row stride of `match` */
+    int max_match_all;          /* S: row stride of `match_all`, >= max(N, max_match) */
+    int mask_words;             /* T */
+    int train_unmask;           /* T */
+    int reserved0;
+    float noise_scale, noise_trans, split, eps;
+    float pc_range[6];
+    const float* gt_boxes;      /* [G,9] gravity centre xyz, w, l, h, yaw, vx, vy */
+    const int* gt_labels;       /* [G] */
+    const float* rand;          /* [scalar*G,3] uniform [0,1) */
+    const float* ref;           /* [N,3] from mv2d_roi_align_qg */
+    const int* match;           /* S: [N,max_match] from mv2d_box_corr */
+    const int* match_cnt;       /* S: [N] */
+    const uint32_t* keymask;    /* T: [N,mask_words] from mv2d_box_corr */
+    const int* key_cnt;         /* T: [N] */
+    const float *w_qe0, *b_qe0, *w_qe2, *b_qe2, *dim_t;   /* query_embedding weights, as in Mv2dQgParams */
+    float* ref_all;             /* out [T,3] */
+    int* dn_labels;             /* out [scalar*G] */
+    uint8_t* attn_mask;         /* out [T,T] */
+    float* query_pos_all;       /* out [T,256] */
+    int* match_all;             /* S out [T,max_match_all] */
+    int* match_cnt_all;         /* S out [T] */
+    uint32_t* keymask_all;      /* T out [T,mask_words] */
+    uint16_t* key_list_all;     /* T out [T,mask_words*32] */
+    int* key_cnt_all;           /* T out [T] */
+    float* workspace;
+    size_t workspace_bytes;
+} Mv2dDnParams;
+MV2D_API size_t mv2d_dn_workspace_bytes(int T, int mask_words);
+MV2D_API int mv2d_dn_prepare(const Mv2dDnParams* p, void* stream);
 
 /* ---- low-level GEMM, exposed for tests and microbenchmarks:
  * C[M,N] = act(A[M,K] . W[N,K]^T + bias); flags: 1 relu, 8 allow TF32 tensor cores,

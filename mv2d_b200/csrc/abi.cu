@@ -40,6 +40,7 @@ size_t mv2d_sizeof(int which) {
         case 3: return sizeof(Mv2dDecoderParams);
         case 4: return sizeof(Mv2dLayerWeights);
         case 5: return sizeof(Mv2dBranchWeights);
+        case 6: return sizeof(Mv2dDnParams);
         default: return 0;
     }
 }
@@ -93,6 +94,13 @@ int mv2d_box_corr(const Mv2dCorrParams* p, void* stream) {
     MV2D_CHECK_ARG(p->N == 0 || (p->rois && p->roi_start && p->trans && p->lin && p->depths && p->match && p->match_cnt),
                    "box_corr: null pointer");
     return run_box_corr(*p, (cudaStream_t)stream);
+}
+
+size_t mv2d_dn_workspace_bytes(int T, int mask_words) { return dn_workspace_bytes(T, mask_words); }
+int mv2d_dn_prepare(const Mv2dDnParams* p, void* stream) {
+    NONNULL(p, "dn_prepare");
+    MV2D_CHECK_ARG(p->workspace && p->w_qe0 && p->b_qe0 && p->w_qe2 && p->b_qe2 && p->dim_t, "dn_prepare: null pointer");
+    return run_dn_prepare(*p, (cudaStream_t)stream);
 }
 
 size_t mv2d_decoder_workspace_bytes(int N, int L) { return decoder_workspace_bytes(N, L); }

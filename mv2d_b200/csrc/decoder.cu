@@ -516,7 +516,7 @@ __device__ __forceinline__ void
 head10_body(const float* __restrict__ xc, const float* __restrict__ xr, const float* __restrict__ wc,
             const float* __restrict__ bc, const float* __restrict__ wr, const float* __restrict__ br,
             const float* __restrict__ ref, int L, int N, float pc0, float pc1, float pc2, float pc3,
-            float pc4, float pc5, float vel_dt, float* __restrict__ cls, float* __restrict__ box, int vb) {
+            float pc4, float pc5, float vel_dt, int vel_row_start, float* __restrict__ cls, float* __restrict__ box, int vb) {
     const int row = vb * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= L * N) return;
     const int l = row / N, n = row % N;
@@ -542,7 +542,7 @@ head10_body(const float* __restrict__ xc, const float* __restrict__ xr, const fl
             if (o == 0) s2 = sigmoid_f(s2 + inverse_sigmoid_f(ref[n * 3 + 0])) * (pc3 - pc0) + pc0;
             else if (o == 1) s2 = sigmoid_f(s2 + inverse_sigmoid_f(ref[n * 3 + 1])) * (pc4 - pc1) + pc1;
             else if (o == 4) s2 = sigmoid_f(s2 + inverse_sigmoid_f(ref[n * 3 + 2])) * (pc5 - pc2) + pc2;
-            else if (o >= 8 && vel_dt != 0.f) s2 = s2 / vel_dt;
+            else if (o >= 8 && vel_dt != 0.f && n >= vel_row_start) s2 = s2 / vel_dt;
             box[(long long)row * 10 + o] = s2;
         }
     }
@@ -552,10 +552,10 @@ __global__ void __launch_bounds__(256)
 head10_kernel(const float* __restrict__ xc, const float* __restrict__ xr, const float* __restrict__ wc,
               const float* __restrict__ bc, const float* __restrict__ wr, const float* __restrict__ br,
               const float* __restrict__ ref, int L, int N, float pc0, float pc1, float pc2, float pc3,
-              float pc4, float pc5, float vel_dt, float* __restrict__ cls, float* __restrict__ box) {
+              float pc4, float pc5, float vel_dt, int vel_row_start, float* __restrict__ cls, float* __restrict__ box) {
     pdl_wait();
     pdl_trigger();
-    head10_body(xc, xr, wc, bc, wr, br, ref, L, N, pc0, pc1, pc2, pc3, pc4, pc5, vel_dt, cls, box, blockIdx.x);
+    head10_body(xc, xr, wc, bc, wr, br, ref, L, N, pc0, pc1, pc2, pc3, pc4, pc5, vel_dt, vel_row_start, cls, box, blockIdx.x);
 }
 
 }  // namespace mv2d
@@ -672,7 +672,7 @@ int run_decoder(const Mv2dDecoderParams& p, cudaStream_t st) {
         MegaParams& m = *mp;
         m.N = N; m.L = L; m.mode = p.mode; m.max_match = p.max_match; m.mask_words = p.mask_words; m.klist_cap = klist_cap;
         for (int i = 0; i < 6; ++i) m.pc_range[i] = p.pc_range[i];
-        m.vel_dt = p.vel_dt;
+        m.vel_dt = p.vel_dt; m.vel_row_start = p.vel_row_start;
         m.query_pos = p.query_pos; m.ref = p.ref; m.kin_rows = p.kin_rows; m.mem_rows = p.mem_rows;
         m.match = p.match; m.match_cnt = p.match_cnt; m.keymask = p.keymask; m.self_attn_mask = p.self_attn_mask;
         m.key_list = p.key_list; m.key_cnt = p.key_cnt;
@@ -785,7 +785,7 @@ int run_decoder(const Mv2dDecoderParams& p, cudaStream_t st) {
     if ((rc = gemm(b2, C, B.reg_w1, C, B.reg_b1, b3, C, N, C, C, GEMM_RELU, st, 1, 0, L, NC, CC, NC, C))) return rc;
     launch_k(head10_kernel, dim3(cdiv(L * N, 8)), dim3(256), 0, st, (const float*)b1, (const float*)b3, B.cls_w2, B.cls_b2, B.reg_w2, B.reg_b2, p.ref, L, N,
                                                  p.pc_range[0], p.pc_range[1], p.pc_range[2], p.pc_range[3],
-                                                 p.pc_range[4], p.pc_range[5], p.vel_dt, p.cls_scores, p.bbox_preds);
+                                                 p.pc_range[4], p.pc_range[5], p.vel_dt, p.vel_row_start, p.cls_scores, p.bbox_preds);
     MV2D_CHECK_LAUNCH("head10");
     return 0;
 }

@@ -290,7 +290,7 @@ struct MegaLayer {
 
 struct MegaParams {
     int N, L, mode, max_match, mask_words, klist_cap;
-    float pc_range[6]; float vel_dt;
+    float pc_range[6]; float vel_dt; int vel_row_start;
     const float *query_pos, *ref, *kin_rows, *mem_rows;
     const int *match, *match_cnt; const uint32_t* keymask; const uint8_t* self_attn_mask;
     const uint16_t* key_list; const int* key_cnt;
@@ -449,7 +449,7 @@ decoder_mega_kernel(const __grid_constant__ MegaParams p) {
     grid_sync(p.barrier, gen);
     for (int vb = cta; vb < cdiv(p.L * N, 8); vb += ncta)
         head10_body(p.b1, p.b3, p.br.cls_w2, p.br.cls_b2, p.br.reg_w2, p.br.reg_b2, p.ref, p.L, N, p.pc_range[0], p.pc_range[1],
-                    p.pc_range[2], p.pc_range[3], p.pc_range[4], p.pc_range[5], p.vel_dt, p.cls, p.box, vb);
+                    p.pc_range[2], p.pc_range[3], p.pc_range[4], p.pc_range[5], p.vel_dt, p.vel_row_start, p.cls, p.box, vb);
 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();

@@ -560,8 +560,10 @@ static int launch_tc(const CUtensorMap& a, const CUtensorMap& alo, const CUtenso
     return 0;
 }
 
+// Cluster-multicast variant of the BN=64 3xTF32 GEMM.  Measured on B200 (profiles/README.md): no gain over the
+// plain kernel at the decoder's sizes (the A tile is L2-resident either way), so it is opt-in: MV2D_TC_MULTICAST=1.
 static bool mc_enabled() {
-    static const bool on = []() { const char* e = getenv("MV2D_TC_MULTICAST"); return !(e && e[0] == '0'); }();
+    static const bool on = []() { const char* e = getenv("MV2D_TC_MULTICAST"); return e && e[0] == '1'; }();
     return on;
 }
 

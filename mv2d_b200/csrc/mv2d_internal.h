@@ -14,6 +14,8 @@ size_t roi_align_qg_workspace_bytes(int N);
 int run_box_corr(const Mv2dCorrParams& p, cudaStream_t st);
 int run_decoder(const Mv2dDecoderParams& p, cudaStream_t st);
 size_t decoder_workspace_bytes(int N, int L);
+int run_dn_prepare(const Mv2dDnParams& p, cudaStream_t st);
+size_t dn_workspace_bytes(int T, int mask_words);
 int run_nms_free_decode(const float* cls, const float* box, int N, int max_num, const float* post_range,
                         float* out_boxes, float* out_scores, int* out_labels, uint8_t* out_valid,
                         cudaStream_t st);

@@ -4,6 +4,7 @@
 //   reference: roi_heads/mv2d_head.py:51-72,95-101; roi_heads/utils/query_generator.py:333-405;
 //              roi_heads/utils/box_correlation.py:95-398; mmcv RoIAlign
 #include "common.cuh"
+#include "keylist.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
 #include "mv2d_internal.h"
@@ -391,28 +392,7 @@ key_mask_kernel(Mv2dCorrParams p, int words) {
     if (p.key_list) {
         // ordered compaction of the set bits (done once here; every decoder layer streams this list)
         __shared__ int grp_cnt[128];
-        const int warp = t >> 5, lane = t & 31, nw = blockDim.x >> 5;
-        const int ngroups = (words + 31) / 32;                  // host guarantees <= 128
-        for (int g = warp; g < ngroups; g += nw) {
-            const int w = g * 32 + lane;
-            const int c = __popc((w < words) ? bits[w] : 0u);
-            const int tot = __reduce_add_sync(0xffffffffu, c);
-            if (lane == 0) grp_cnt[g] = tot;
-        }
-        __syncthreads();
-        uint16_t* kl = p.key_list + (long long)n * words * 32;
-        for (int g = warp; g < ngroups; g += nw) {
-            int base = 0;
-            for (int i = 0; i < g; ++i) base += grp_cnt[i];
-            const int w = g * 32 + lane;
-            uint32_t b = (w < words) ? bits[w] : 0u;
-            const int c = __popc(b);
-            int incl = c;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
-            int pos = base + incl - c;
-            while (b) { const int bit = __ffs(b) - 1; b &= b - 1; kl[pos++] = (uint16_t)(w * 32 + bit); }
-        }
+        compact_key_bits(bits, words, grp_cnt, p.key_list + (long long)n * words * 32);
     }
 }
 

@@ -23,6 +23,8 @@ DEFAULTS = dict(
     depth_num=64, depth_start=1.0, stride=16, intrins_feat_scale=0.1,
     sample_size=4, corr_num_depth=8, corr_depth_start=0.5, corr_depth_end=70.0,
     topk=1, iou_thr=0.0, ratio=0.0, expand_stride=0, num_views_per_frame=6,
+    # denoising queries of the training-mode forward: MV2DSHead constructor defaults (mv2d_s_head.py:20-27)
+    denoise_scalar=10, denoise_noise_scale=1.0, denoise_noise_trans=0.0, denoise_split=0.75, num_classes=10,
 )
 
 
@@ -56,7 +58,8 @@ class HotPath:
         self.device = torch.device(device)
         self.cfg = dict(DEFAULTS)
         if mode == 'T':
-            self.cfg.update(topk=20, expand_stride=2)
+            # exp/mv2d_r50_frcnn_two_frames_1408x512_ep72.py:44-47, 121-124
+            self.cfg.update(topk=20, expand_stride=2, denoise_noise_scale=1.25, denoise_split=0.6)
         self.cfg.update(cfg)
         self.w = PackedWeights(state_dict, self.device)
         self.L = self.w.num_layers
@@ -280,7 +283,62 @@ class HotPath:
         lib.check(self.lib.mv2d_box_corr(C.byref(p), lib.stream_ptr()), 'mv2d_box_corr')
         return out
 
-    def decoder(self, qg, corr, kin_rows, mem_rows, N, vel_dt=0.0, self_attn_mask=None):
+    def dn_prepare(self, qg, corr, N, dn):
+        """Row a20 (training-mode forward): prepend scalar*G denoising queries built from the GT boxes.
+        dn = dict(gt_boxes [G,9] = (gravity centre, w, l, h, yaw, vx, vy), gt_labels [G], rand [scalar*G,3] or
+        None -> torch.rand).  Returns (qg', corr', T, pad, extras) for ``decoder``
+        (mv2d_s_head.py:39-120,158-180; mv2d_t_head.py:79-98)."""
+        c, W = self.cfg, self.w
+        dev = self.device
+        gt = dn['gt_boxes'].to(dev, torch.float32).contiguous().view(-1, 9)
+        G, scalar = gt.shape[0], c['denoise_scalar']
+        labels = dn['gt_labels'].to(dev).to(torch.int32).contiguous()
+        pad = G * scalar
+        rand = dn.get('rand')
+        rand = torch.rand(pad, 3, device=dev) if rand is None else rand.to(dev, torch.float32).contiguous()
+        assert tuple(rand.shape) == (pad, 3) and labels.numel() == G
+        T = pad + N
+        p = lib.DnParams()
+        p.N, p.G, p.scalar, p.num_classes = N, G, scalar, c['num_classes']
+        p.mode = 0 if self.mode == 'S' else 1
+        p.noise_scale, p.noise_trans = c['denoise_noise_scale'], c['denoise_noise_trans']
+        p.split, p.eps = c['denoise_split'], 1e-4
+        p.pc_range = (C.c_float * 6)(*c['pc_range'])
+        p.gt_boxes, p.gt_labels, p.rand, p.ref = gt.data_ptr(), labels.data_ptr(), rand.data_ptr(), qg['ref'].data_ptr()
+        for k in ('w_qe0', 'b_qe0', 'w_qe2', 'b_qe2', 'dim_t'):
+            setattr(p, k, W.p(k))
+        ref_all = self._get('dn_ref', (T, 3))
+        dn_labels = self._get('dn_labels', (pad,), torch.int32)
+        attn_mask = self._get('dn_attn_mask', (T, T), torch.uint8)
+        qpos_all = self._get('dn_query_pos', (T, 256))
+        p.ref_all, p.dn_labels, p.attn_mask, p.query_pos_all = (ref_all.data_ptr(), dn_labels.data_ptr(),
+                                                                attn_mask.data_ptr(), qpos_all.data_ptr())
+        corr2 = dict(corr)
+        words = 0
+        if self.mode == 'S':
+            mm = max(N, corr['max_match'])
+            match_all = self._get('dn_match', (T, mm), torch.int32)
+            cnt_all = self._get('dn_match_cnt', (T,), torch.int32)
+            p.match, p.match_cnt, p.max_match, p.max_match_all = (corr['match'].data_ptr(), corr['match_cnt'].data_ptr(),
+                                                                  corr['max_match'], mm)
+            p.match_all, p.match_cnt_all = match_all.data_ptr(), cnt_all.data_ptr()
+            corr2.update(match=match_all, match_cnt=cnt_all, max_match=mm)
+        else:
+            words = corr['mask_words']
+            km_all = self._get('dn_keymask', (T, words), torch.int32)
+            kl_all = self._get('dn_key_list', (T, words * 32), torch.int16)
+            kc_all = self._get('dn_key_cnt', (T,), torch.int32)
+            p.keymask, p.key_cnt, p.mask_words, p.train_unmask = corr['keymask'].data_ptr(), corr['key_cnt'].data_ptr(), words, 1
+            p.keymask_all, p.key_list_all, p.key_cnt_all = km_all.data_ptr(), kl_all.data_ptr(), kc_all.data_ptr()
+            corr2.update(keymask=km_all, key_list=kl_all, key_cnt=kc_all)
+        ws_bytes = self.lib.mv2d_dn_workspace_bytes(T, words)
+        ws = self._get('dn_ws', (ws_bytes // 4 + 1,))
+        p.workspace, p.workspace_bytes = ws.data_ptr(), ws_bytes
+        lib.check(self.lib.mv2d_dn_prepare(C.byref(p), lib.stream_ptr()), 'mv2d_dn_prepare')
+        qg2 = dict(qg, query_pos=qpos_all, ref=ref_all)
+        return qg2, corr2, T, pad, dict(dn_labels=dn_labels, dn_attn_mask=attn_mask, dn_ref=ref_all[:pad])
+
+    def decoder(self, qg, corr, kin_rows, mem_rows, N, vel_dt=0.0, self_attn_mask=None, vel_row_start=0):
         c, W, L = self.cfg, self.w, self.L
         cls = self._get('cls_scores', (L, N, 10))
         box = self._get('bbox_preds', (L, N, 10))
@@ -293,7 +351,7 @@ class HotPath:
         p.mode = 0 if self.mode == 'S' else 1
         p.num_rows = kin_rows.shape[0]
         p.pc_range = (C.c_float * 6)(*c['pc_range'])
-        p.vel_dt = vel_dt
+        p.vel_dt, p.vel_row_start = vel_dt, vel_row_start
         p.query_pos, p.ref = qg['query_pos'].data_ptr(), qg['ref'].data_ptr()
         p.kin_rows, p.mem_rows = kin_rows.data_ptr(), mem_rows.data_ptr()
         if self.mode == 'S':
@@ -325,7 +383,8 @@ class HotPath:
         self.pe3d(feat_buf, i2l, img_metas, None, phase=1, dims=dims)
         return i2l, trans
 
-    def _enqueue_post(self, feat_in, feat_is_nhwc, cams, rois, roi_start, counts, N, img_metas, i2l, trans, pe_phase=2):
+    def _enqueue_post(self, feat_in, feat_is_nhwc, cams, rois, roi_start, counts, N, img_metas, i2l, trans, pe_phase=2,
+                      dn=None):
         V = len(img_metas)
         feat_tf32 = None
         if feat_is_nhwc:
@@ -353,18 +412,26 @@ class HotPath:
             pe, kin = self.pe3d(feat, i2l, img_metas, feat_tf32, phase=pe_phase)
             qg = self.roi_align_qg(rois, cams, feat, pe, N)
             corr = self.box_corr(rois, roi_start, trans, N, V, img_metas, h, w)
+        qg_d, corr_d, T, pad, extra, sa_mask = qg, corr, N, 0, {}, None
+        if dn is not None:      # training-mode forward: denoising queries are prepended (row a20)
+            qg_d, corr_d, T, pad, extra = self.dn_prepare(qg, corr, N, dn)
+            sa_mask = extra['dn_attn_mask']
         if self.mode == 'S':
-            cls, box, outs = self.decoder(qg, corr, qg['tok_kin'].view(-1, 256), qg['tok_feat'].view(-1, 256), N)
+            cls, box, outs = self.decoder(qg_d, corr_d, qg['tok_kin'].view(-1, 256), qg['tok_feat'].view(-1, 256), T,
+                                          self_attn_mask=sa_mask)
         else:
-            cls, box, outs = self.decoder(qg, corr, kin.view(-1, 256), feat.view(-1, 256), N,
-                                          vel_dt=self._vel_dt(img_metas))
-        out = dict(cls_scores=cls, bbox_preds=box, outs_dec=outs, rois=rois, pe=pe, feat_nhwc=feat, N=N,
-                   num_per_view=counts)
+            cls, box, outs = self.decoder(qg_d, corr_d, kin.view(-1, 256), feat.view(-1, 256), T,
+                                          vel_dt=self._vel_dt(img_metas), self_attn_mask=sa_mask, vel_row_start=pad)
+        out = dict(cls_scores=cls[:, pad:], bbox_preds=box[:, pad:], outs_dec=outs[:, pad:], rois=rois, pe=pe,
+                   feat_nhwc=feat, N=N, num_per_view=counts)
         out.update(qg)
         out.update(corr)
+        if dn is not None:
+            out.update(extra, dn_cls_scores=cls[:, :pad], dn_bbox_preds=box[:, :pad], dn_pad=pad,
+                       query_pos=qg_d['query_pos'][pad:])
         return out
 
-    def _enqueue(self, feat_in, feat_is_nhwc, cams, rois, roi_start, counts, N, img_metas):
+    def _enqueue(self, feat_in, feat_is_nhwc, cams, rois, roi_start, counts, N, img_metas, dn=None):
         """Enqueue every stage of the path on the current stream (capturable: no host sync)."""
         dims = (feat_in.shape[0], feat_in.shape[1], feat_in.shape[2]) if feat_is_nhwc else \
                (feat_in.shape[0], feat_in.shape[2], feat_in.shape[3])
@@ -372,20 +439,25 @@ class HotPath:
         # device-resident input: the whole PE runs on the main stream beside the query generator (side stream)
         i2l, trans = self.geom_prep(cams)
         return self._enqueue_post(feat_in, feat_is_nhwc, cams, rois, roi_start, counts, N, img_metas, i2l, trans,
-                                  pe_phase=0)
+                                  pe_phase=0, dn=dn)
 
     @torch.no_grad()
-    def forward(self, feat, proposal_list, img_metas, feat_is_nhwc=False, use_graph=False):
+    def forward(self, feat, proposal_list, img_metas, feat_is_nhwc=False, use_graph=False, dn=None):
         """feat [V,256,h,w] fp32 (NCHW as the FPN emits it; device, or pinned host memory),
         proposal_list: V tensors [n_v, >=4] (device or host), img_metas: V dicts.  Returns a dict
         with cls_scores / bbox_preds [L,N,10] and the stage tensors (views of reused buffers).
 
         use_graph=True replays a CUDA graph of the whole path captured for this (N, V, h, w,
-        masks) signature: inputs are copied into the graph's static buffers, then one launch."""
+        masks) signature: inputs are copied into the graph's static buffers, then one launch.
+
+        dn = dict(gt_boxes, gt_labels[, rand]) runs the training-mode forward with denoising queries
+        (``dn_prepare``; eager only): the result additionally holds dn_cls_scores / dn_bbox_preds
+        [L,pad,10], dn_labels, dn_attn_mask, dn_pad."""
         if not use_graph:
             feat = feat.to(self.device, torch.float32, non_blocking=True).contiguous()
             cams, rois, roi_start, counts, N = self._upload_meta(proposal_list, img_metas)
-            return self._enqueue(feat, feat_is_nhwc, cams, rois, roi_start, counts, N, img_metas)
+            return self._enqueue(feat, feat_is_nhwc, cams, rois, roi_start, counts, N, img_metas, dn=dn)
+        assert dn is None, 'the denoising (training-mode) forward is eager only'
         assert not feat_is_nhwc
         counts = [int(p.shape[0]) for p in proposal_list]
         N = max(sum(counts), 1)

@@ -9,7 +9,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'lib', 'libmv2d_b200.so')
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_LAYERS = 8
 
 c_f = C.c_void_p  # device pointers travel as integers (tensor.data_ptr())
@@ -82,7 +82,7 @@ class DecoderParams(C.Structure):
     _fields_ = [
         ('N', C.c_int), ('L', C.c_int), ('mode', C.c_int), ('num_rows', C.c_int),
         ('max_match', C.c_int), ('mask_words', C.c_int), ('persistent', C.c_int),
-        ('reserved1', C.c_int),
+        ('vel_row_start', C.c_int),
         ('pc_range', C.c_float * 6), ('vel_dt', C.c_float), ('reserved2', C.c_float),
         ('query_pos', c_f), ('ref', c_f), ('kin_rows', c_f), ('mem_rows', c_f),
         ('match', c_f), ('match_cnt', c_f), ('keymask', c_f), ('key_list', c_f), ('key_cnt', c_f),
@@ -93,7 +93,24 @@ class DecoderParams(C.Structure):
     ]
 
 
-_STRUCTS = [PeParams, QgParams, CorrParams, DecoderParams, LayerWeights, BranchWeights]
+class DnParams(C.Structure):
+    _fields_ = [
+        ('N', C.c_int), ('G', C.c_int), ('scalar', C.c_int), ('num_classes', C.c_int),
+        ('mode', C.c_int), ('max_match', C.c_int), ('max_match_all', C.c_int), ('mask_words', C.c_int),
+        ('train_unmask', C.c_int), ('reserved0', C.c_int),
+        ('noise_scale', C.c_float), ('noise_trans', C.c_float), ('split', C.c_float), ('eps', C.c_float),
+        ('pc_range', C.c_float * 6),
+        ('gt_boxes', c_f), ('gt_labels', c_f), ('rand', c_f), ('ref', c_f),
+        ('match', c_f), ('match_cnt', c_f), ('keymask', c_f), ('key_cnt', c_f),
+        ('w_qe0', c_f), ('b_qe0', c_f), ('w_qe2', c_f), ('b_qe2', c_f), ('dim_t', c_f),
+        ('ref_all', c_f), ('dn_labels', c_f), ('attn_mask', c_f), ('query_pos_all', c_f),
+        ('match_all', c_f), ('match_cnt_all', c_f),
+        ('keymask_all', c_f), ('key_list_all', c_f), ('key_cnt_all', c_f),
+        ('workspace', c_f), ('workspace_bytes', C.c_size_t),
+    ]
+
+
+_STRUCTS = [PeParams, QgParams, CorrParams, DecoderParams, LayerWeights, BranchWeights, DnParams]
 
 # every symbol include/mv2d_b200.h declares: (name, restype, argtypes)
 SYMBOLS = [
@@ -111,6 +128,8 @@ SYMBOLS = [
     ('mv2d_roi_align_qg_workspace_bytes', C.c_size_t, [C.c_int]),
     ('mv2d_roi_align_qg', C.c_int, [C.POINTER(QgParams), c_f]),
     ('mv2d_box_corr', C.c_int, [C.POINTER(CorrParams), c_f]),
+    ('mv2d_dn_workspace_bytes', C.c_size_t, [C.c_int, C.c_int]),
+    ('mv2d_dn_prepare', C.c_int, [C.POINTER(DnParams), c_f]),
     ('mv2d_decoder_workspace_bytes', C.c_size_t, [C.c_int, C.c_int]),
     ('mv2d_decoder', C.c_int, [C.POINTER(DecoderParams), c_f]),
     ('mv2d_gemm', C.c_int, [c_f, C.c_int, c_f, C.c_int, c_f, c_f, C.c_int, C.c_int, C.c_int, C.c_int,

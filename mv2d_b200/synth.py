@@ -203,6 +203,8 @@ CASES = {
                   img_shape=(480, 1376, 3), pad_shape=(512, 1408, 3)),
     # config 3 of BASELINE.json (one of its two samples): 12 views, 300 queries
     't_cfg3': dict(mode='T', seed=7, num_views=12, boxes_per_view=25, num_layers=6),
+    's_dn': dict(mode='S', seed=9, num_views=6, boxes_per_view=[4, 3, 5, 2, 4, 3], num_layers=2,
+                 dn=dict(num_gt=5, seed=81)),
     # row a20: training-mode forward with denoising queries (7 GT boxes x 10 noised copies prepended)
     't_dn': dict(mode='T', seed=8, num_views=12, boxes_per_view=[3, 2, 4, 3, 2, 3, 3, 2, 4, 3, 2, 3], num_layers=2,
                  dn=dict(num_gt=7, seed=80)),

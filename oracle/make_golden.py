@@ -33,6 +33,8 @@ def run_reference(spec, weight_seed=0):
     cfg = ref_shim.load_reference_config(CFG[spec['mode']])
     roi_head = copy.deepcopy(cfg['model']['roi_head'])
     roi_head['bbox_head']['transformer']['decoder']['num_layers'] = spec['num_layers']
+    if 'dn' in spec:
+        roi_head['use_denoise'] = True     # the single-frame exp configs ship with it off; the code path exists
     roi_head.update(train_cfg=None, test_cfg=ref_shim.ConfigDict(cfg['model']['test_cfg']['rcnn']))
     with warnings.catch_warnings():
         warnings.simplefilter('ignore')

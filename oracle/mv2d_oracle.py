@@ -37,7 +37,7 @@ DEFAULT_CFG = dict(
 def make_cfg(mode='S', **over):
     cfg = dict(DEFAULT_CFG)
     if mode == 'T':  # exp/mv2d_r50_frcnn_two_frames_1408x512_ep72.py:121-124
-        cfg.update(topk=20, expand_stride=2)
+        cfg.update(topk=20, expand_stride=2, denoise_noise_scale=1.25, denoise_split=0.6)   # :44-47
     cfg['mode'] = mode
     cfg.update(over)
     return cfg
@@ -532,41 +532,15 @@ def _prologue(sd, feat, pe, proposal_list, img_metas, cfg):
     return proposal_list, rois, K, E, roi_feat, ifeat, ref, qg
 
 
-def mv2d_s_forward(sd, feat, proposal_list, img_metas, cfg=None, return_stages=False):
-    """MV2DHead.simple_test minus decode for MV2DSHead, eval mode
-    (roi_heads/mv2d_head.py:249-261 -> mv2d_s_head.py:122-211).
-    Returns (cls_scores [L,N,10], bbox_preds [L,N,10])."""
-    cfg = cfg or make_cfg('S')
-    pe = pe_forward(sd, feat, img_metas, cfg)
-    proposal_list, rois, K, E, roi_feat, ifeat, ref, qg = _prologue(sd, feat, pe, proposal_list,
-                                                                    img_metas, cfg)
-    roi_pe = roi_align(pe, rois, cfg['roi_size'], 1.0 / cfg['stride'])
-    num_per_view = [len(p) for p in proposal_list]
-    corr, mask = box_roi_correlation(rois, num_per_view, img_metas, cfg)
-    N, M = corr.shape
-    C = feat.shape[1]
-    # corr_feats [N,M,C,7,7] -> memory [M*49, N, C]  (cross_attention_head.py:26-31)
-    mem = roi_feat[corr].permute(1, 3, 4, 0, 2).reshape(M * 49, N, C)
-    pos = roi_pe[corr].permute(1, 3, 4, 0, 2).reshape(M * 49, N, C)
-    kpm = (~mask)[:, :, None].expand(N, M, 49).reshape(N, M * 49)
-    qpos = query_embed(sd, ref[:, None])  # [N,1,C] (bs=N, nq=1)
-    outs = decoder(sd, qpos.permute(1, 0, 2), mem, pos, cfg, key_padding_mask=kpm)  # [L,1,N,C]
-    outs = outs.transpose(1, 2)  # [L,N,1,C]
-    cls, box = branches(sd, outs, ref[:, None], cfg)
-    cls, box = cls.flatten(1, 2), box.flatten(1, 2)
-    if return_stages:
-        return cls, box, dict(pe=pe, rois=rois, intrinsics=K, extrinsics=E, roi_feat=roi_feat,
-                              roi_pe=roi_pe, intrins_feat=ifeat, ref=ref, corr=corr,
-                              corr_mask=mask, query_pos=qpos[:, 0], outs_dec=outs[:, :, 0], **qg)
-    return cls, box
-
-
-def prepare_for_dn(ref, gt_boxes, gt_labels, rand, cfg, scalar=10, noise_scale=1.25, noise_trans=0.0, split=0.6,
+def prepare_for_dn(ref, gt_boxes, gt_labels, rand, cfg, scalar=10, noise_scale=None, noise_trans=0.0, split=None,
                    num_classes=10, eps=1e-4):
     """MV2DSHead.prepare_for_dn, training branch, batch_size 1 (roi_heads/mv2d_s_head.py:39-120), with the
     uniform noise `rand` ([scalar*G,3] in [0,1), what torch.rand_like returns there) passed in.
     Returns (padded reference points [pad+N,3], self-attention mask [T,T] bool, known_labels, pad_size)."""
     pc = cfg['pc_range']
+    # config values: two_frames exp config (1.25, 0.6); MV2DSHead constructor defaults otherwise (1.0, 0.75)
+    noise_scale = cfg.get('denoise_noise_scale', 1.0) if noise_scale is None else noise_scale
+    split = cfg.get('denoise_split', 0.75) if split is None else split
     G = gt_boxes.shape[0]
     centers = gt_boxes[:, :3].repeat(scalar, 1).clone()
     scale = gt_boxes[:, 3:6].repeat(scalar, 1)
@@ -588,6 +562,55 @@ def prepare_for_dn(ref, gt_boxes, gt_labels, rand, cfg, scalar=10, noise_scale=1
         mask[G * i:G * (i + 1), G * (i + 1):pad] = True
         mask[G * i:G * (i + 1), :G * i] = True
     return padded, mask, labels, pad
+
+
+def mv2d_s_forward(sd, feat, proposal_list, img_metas, cfg=None, return_stages=False, dn=None):
+    """MV2DHead.simple_test minus decode for MV2DSHead, eval mode
+    (roi_heads/mv2d_head.py:249-261 -> mv2d_s_head.py:122-211).
+    Returns (cls_scores [L,N,10], bbox_preds [L,N,10])."""
+    cfg = cfg or make_cfg('S')
+    pe = pe_forward(sd, feat, img_metas, cfg)
+    proposal_list, rois, K, E, roi_feat, ifeat, ref, qg = _prologue(sd, feat, pe, proposal_list,
+                                                                    img_metas, cfg)
+    roi_pe = roi_align(pe, rois, cfg['roi_size'], 1.0 / cfg['stride'])
+    num_per_view = [len(p) for p in proposal_list]
+    corr, mask = box_roi_correlation(rois, num_per_view, img_metas, cfg)
+    N, M = corr.shape
+    C = feat.shape[1]
+    # corr_feats [N,M,C,7,7] -> memory [M*49, N, C]  (cross_attention_head.py:26-31)
+    mem = roi_feat[corr].permute(1, 3, 4, 0, 2).reshape(M * 49, N, C)
+    pos = roi_pe[corr].permute(1, 3, 4, 0, 2).reshape(M * 49, N, C)
+    kpm = (~mask)[:, :, None].expand(N, M, 49).reshape(N, M * 49)
+    dn_out = None
+    if dn is None:
+        qpos = query_embed(sd, ref[:, None])  # [N,1,C] (bs=N, nq=1)
+        outs = decoder(sd, qpos.permute(1, 0, 2), mem, pos, cfg, key_padding_mask=kpm)  # [L,1,N,C]
+        outs = outs.transpose(1, 2)  # [L,N,1,C]
+        cls, box = branches(sd, outs, ref[:, None], cfg)
+        cls, box = cls.flatten(1, 2), box.flatten(1, 2)
+    else:
+        # training with denoising queries (mv2d_s_head.py:158-180): ONE batch entry, every RoI's tokens as
+        # memory, a [T, N*49] cross mask (denoising rows see everything) and the group self-attention mask
+        vis = torch.zeros(N, N + 1, dtype=torch.bool)
+        vis.scatter_(1, torch.where(mask, corr, torch.full_like(corr, N)), True)
+        cross = ~vis[:, :N, None].expand(N, N, 49).reshape(N, N * 49)
+        ref_all, self_mask, dn_labels, pad = prepare_for_dn(ref, dn['gt_boxes'], dn['gt_labels'], dn['rand'], cfg)
+        cross = torch.cat([torch.zeros(pad, N * 49, dtype=torch.bool), cross], 0)
+        mem1 = roi_feat.permute(0, 2, 3, 1).reshape(N * 49, 1, C)
+        pos1 = roi_pe.permute(0, 2, 3, 1).reshape(N * 49, 1, C)
+        qall = query_embed(sd, ref_all[None])  # [1,T,C]
+        outs = decoder(sd, qall.permute(1, 0, 2), mem1, pos1, cfg, self_mask=self_mask, cross_mask=cross)  # [L,T,1,C]
+        cls, box = branches(sd, outs.transpose(1, 2), ref_all[None], cfg)   # [L,1,T,10]
+        cls, box = cls.flatten(1, 2), box.flatten(1, 2)
+        dn_out = dict(cls=cls[:, :pad], box=box[:, :pad], ref=ref_all[:pad], attn_mask=self_mask, labels=dn_labels)
+        cls, box = cls[:, pad:], box[:, pad:]
+        outs = outs[:, pad:]                    # [L,N,1,C]
+        qpos = qall[0, pad:, None]
+    if return_stages:
+        return cls, box, dict(pe=pe, rois=rois, intrinsics=K, extrinsics=E, roi_feat=roi_feat,
+                              roi_pe=roi_pe, intrins_feat=ifeat, ref=ref, corr=corr,
+                              corr_mask=mask, query_pos=qpos[:, 0], outs_dec=outs[:, :, 0], dn=dn_out, **qg)
+    return cls, box
 
 
 def mv2d_t_forward(sd, feat, proposal_list, img_metas, cfg=None, return_stages=False, dn=None):

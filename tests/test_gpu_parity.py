@@ -55,10 +55,25 @@ def test_cuda_path_matches_reference_golden(name, state_dicts):
     spec, g = load_golden(name)
     eng = engine(spec['mode'], spec['num_layers'], state_dicts)
     feat, boxes, metas = synth.case_inputs(spec)
-    out = eng.forward(feat.cuda(), [b.cuda() for b in boxes], metas)
+    dn = None
+    if 'dn' in spec:     # row a20: training-mode forward, denoising queries prepended
+        gt_boxes, gt_labels, rand = synth.make_dn_inputs(spec['dn'])
+        dn = dict(gt_boxes=gt_boxes, gt_labels=gt_labels, rand=rand)
+    out = eng.forward(feat.cuda(), [b.cuda() for b in boxes], metas, dn=dn)
     torch.cuda.synchronize()
     N = out['N']
     assert N == g['rois'].shape[0]
+    if dn is not None:
+        from oracle import mv2d_oracle as O
+        pad = int(g['dn_pad'])
+        assert out['dn_pad'] == pad
+        assert np.array_equal(out['dn_labels'].cpu().numpy(), g['dn_labels'])
+        ref_all, sa_mask, _, _ = O.prepare_for_dn(out['ref'].cpu(), gt_boxes, gt_labels, rand,
+                                                  O.make_cfg(spec['mode']))
+        assert np.array_equal(out['dn_attn_mask'].cpu().numpy().astype(bool), sa_mask.numpy())
+        assert_close(out['dn_ref'], ref_all[:pad], 1e-6, 0, 'dn reference points')
+        assert_close(out['dn_cls_scores'], g['dn_cls'], what='dn cls_scores')
+        assert_close(out['dn_bbox_preds'], g['dn_box'], what='dn bbox_preds')
     assert np.array_equal(out['rois'].cpu().numpy(), g['rois'])
     # ---- stage level
     pe = out['pe'].permute(0, 3, 1, 2).contiguous()          # back to NCHW for the comparison
@@ -178,6 +193,30 @@ def test_tcgen05_gemm_single_pass_tf32():
         if flags & 1:
             ref = ref.relu()
         assert_close(Cc, ref, 2e-5, 2e-5, f'gemm_tc {M}x{N}x{K}')
+
+
+def test_cluster_multicast_gemm_variant():
+    """MV2D_TC_MULTICAST=1 (read once per process, hence the subprocess) routes the decoder's BN=64 3xTF32 GEMMs
+    through the 4-CTA-cluster kernel whose A tile is TMA-multicast; same goldens, same gate."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import json, numpy as np, torch\n"
+        "from mv2d_b200 import synth\n"
+        "from mv2d_b200.engine import HotPath\n"
+        "g = dict(np.load('tests/golden/s_cfg2.npz')); spec = json.loads(bytes(g.pop('spec')).decode())\n"
+        "eng = HotPath(synth.make_state_dict(0, num_layers=spec['num_layers']), mode='S')\n"
+        "feat, boxes, metas = synth.case_inputs(spec)\n"
+        "out = eng.forward(feat.cuda(), boxes, metas); torch.cuda.synchronize()\n"
+        "for k in ('cls_scores', 'bbox_preds'):\n"
+        "    a, b = out[k].cpu().numpy().astype(np.float64), g[k].astype(np.float64)\n"
+        "    assert np.isfinite(a).all() and (np.abs(a - b) <= 1e-3 + 1e-3 * np.abs(b)).all(), k\n"
+        "print('MC_OK')\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, '-c', code], cwd=root, env=dict(os.environ, MV2D_TC_MULTICAST='1'),
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and 'MC_OK' in r.stdout, r.stderr[-2000:]
 
 
 def test_tcgen05_gemm_3xtf32_and_im2col(state_dicts):
