@@ -153,6 +153,11 @@ typedef struct Mv2dLayerWeights {
     const float *ffn_w1, *ffn_w1_lo, *ffn_b1;   /* ffns.0.layers.0.0 [2048,256] */
     const float *ffn_w2, *ffn_w2_lo, *ffn_b2;   /* ffns.0.layers.1   [256,2048] */
     const float *ln_g[3], *ln_b[3];     /* norms.{0,1,2} */
+    const float *sa_const;              /* nullable, read for layers[0] only: [256] = out_proj(bv) + bo.  The decoder's
+                                         * target starts at zero (cross_attention_head.py:32), so in the first layer
+                                         * every self-attention VALUE row is the bias bv and the attention output is
+                                         * this constant for every query, whatever q, k and the mask are.  With it the
+                                         * staged decoder skips layer 0's in_proj / attention / out_proj launches. */
 } Mv2dLayerWeights;
 
 typedef struct Mv2dBranchWeights {      /* stacked over layers: leading dim L */

@@ -31,6 +31,7 @@ struct LnArgs {
     float* out_hi; float* out_lo;      // nullable: TF32 split of `out`   (A operand of a 3xTF32 GEMM)
     float* outq_hi; float* outq_lo;    // nullable: TF32 split of `out_q`
     int rows;
+    int bcast_in;     // 1: `partial` is ONE [256] row shared by every output row
 };
 
 __device__ __forceinline__ void ln_body(const LnArgs& a, int vb) {
@@ -38,13 +39,14 @@ __device__ __forceinline__ void ln_body(const LnArgs& a, int vb) {
     if (row >= a.rows) return;
     const int grp = a.rows_per_group > 0 ? row / a.rows_per_group : 0;
     const long long o = (long long)row * MV2D_C;
+    const long long oi = a.bcast_in ? 0 : o;
     float v[8];
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
         const int c = i * 128 + lane * 4;
-        float4 s = *reinterpret_cast<const float4*>(a.partial + o + c);
+        float4 s = *reinterpret_cast<const float4*>(a.partial + oi + c);
         for (int k = 1; k < a.nsplit; ++k) {
-            float4 t = *reinterpret_cast<const float4*>(a.partial + k * a.split_stride + o + c);
+            float4 t = *reinterpret_cast<const float4*>(a.partial + k * a.split_stride + oi + c);
             s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
         }
         if (a.bias) {
@@ -640,8 +642,13 @@ int run_decoder(const Mv2dDecoderParams& p, cudaStream_t st) {
     const long long NC = (long long)N * C;
     cudaError_t e;
     // target = 0 ; query + query_pos = query_pos   (cross_attention_head.py:32)
-    if ((e = cudaMemsetAsync(x, 0, NC * sizeof(float), st)) != cudaSuccess ||
-        (e = cudaMemcpyAsync(xq, p.query_pos, NC * sizeof(float), cudaMemcpyDeviceToDevice, st)) != cudaSuccess) {
+    // The first layer's self-attention sees value = target = 0, so every value row is the bias bv and the attention
+    // output is out_proj(bv) + bo for EVERY query whatever the weights/mask: a [256] constant packed once
+    // (Mv2dLayerWeights.sa_const).  With it, layer 0 starts at LayerNorm 1 and x / xq are first written by its LN 3.
+    const bool fold0 = !p.persistent && p.layers[0].sa_const != nullptr;
+    if (!fold0 &&
+        ((e = cudaMemsetAsync(x, 0, NC * sizeof(float), st)) != cudaSuccess ||
+         (e = cudaMemcpyAsync(xq, p.query_pos, NC * sizeof(float), cudaMemcpyDeviceToDevice, st)) != cudaSuccess)) {
         set_error("decoder: init %s", cudaGetErrorString(e));
         return (int)e;
     }
@@ -724,21 +731,28 @@ int run_decoder(const Mv2dDecoderParams& p, cudaStream_t st) {
     for (int l = 0; l < L; ++l) {
         const Mv2dLayerWeights& w = p.layers[l];
         float* inter = p.outs_dec + (long long)l * NC;
-        // --- self attention: q,k from (x + qpos), v from x
-        {
-            GemmArgs g{};
-            g.A = xq; g.lda = C; g.W = w.sa_in_w; g.ldw = C; g.C = qkv; g.ldc = 768; g.bias = w.sa_in_b;
-            g.M = N; g.N = 768; g.K = C; g.batch = 1; g.nsplit = 1;
-            if ((rc = launch_gemm_small(g, x, 512, st))) return rc;
-        }
-        launch_k(self_attn_kernel, dim3(cdiv(N, 8 * SA_QPW), MV2D_HEADS), dim3(256), SA_SMEM_BYTES, st, (const float*)qkv, p.self_attn_mask, N, sa);
-        MV2D_CHECK_LAUNCH("self_attn");
-        if ((rc = gemm(sa, C, w.sa_out_w, C, nullptr, part, C, N, C, C, 0, st))) return rc;
-        {
-            LnArgs a{}; a.partial = part; a.nsplit = 1; a.bias = w.sa_out_b; a.residual = x;
+        if (l == 0 && fold0) {
+            LnArgs a{}; a.partial = w.sa_const; a.bcast_in = 1; a.nsplit = 1;
             a.gamma = w.ln_g[0]; a.beta = w.ln_b[0]; a.qpos = p.query_pos; a.out = x1; a.out_q = x1q; a.rows = N;
             a.outq_hi = x1q_hi; a.outq_lo = x1q_lo;
             if ((rc = ln(a, st))) return rc;
+        } else {
+            // --- self attention: q,k from (x + qpos), v from x
+            {
+                GemmArgs g{};
+                g.A = xq; g.lda = C; g.W = w.sa_in_w; g.ldw = C; g.C = qkv; g.ldc = 768; g.bias = w.sa_in_b;
+                g.M = N; g.N = 768; g.K = C; g.batch = 1; g.nsplit = 1;
+                if ((rc = launch_gemm_small(g, x, 512, st))) return rc;
+            }
+            launch_k(self_attn_kernel, dim3(cdiv(N, 8 * SA_QPW), MV2D_HEADS), dim3(256), SA_SMEM_BYTES, st, (const float*)qkv, p.self_attn_mask, N, sa);
+            MV2D_CHECK_LAUNCH("self_attn");
+            if ((rc = gemm(sa, C, w.sa_out_w, C, nullptr, part, C, N, C, C, 0, st))) return rc;
+            {
+                LnArgs a{}; a.partial = part; a.nsplit = 1; a.bias = w.sa_out_b; a.residual = x;
+                a.gamma = w.ln_g[0]; a.beta = w.ln_b[0]; a.qpos = p.query_pos; a.out = x1; a.out_q = x1q; a.rows = N;
+                a.outq_hi = x1q_hi; a.outq_lo = x1q_lo;
+                if ((rc = ln(a, st))) return rc;
+            }
         }
         // --- sparse cross attention (absorbed)
         if ((rc = tc3(x1q_hi, x1q_lo, C, w.ca_q_w, w.ca_q_w_lo, C, w.ca_q_b, qt, nullptr, 2048, N, 2048, C, 0, 1, 0, st))) return rc;

@@ -50,7 +50,7 @@ class HotPath:
     """MV2D-S ('S') / MV2D-T ('T') decoder hot path on one GPU."""
 
     def __init__(self, state_dict, mode='S', device='cuda', cache_sine_branch=False, overlap=True,
-                 persistent_decoder=None, **cfg):
+                 persistent_decoder=None, fold_first_self_attn=True, **cfg):
         if not torch.cuda.is_available():
             raise RuntimeError('mv2d_b200.HotPath needs a CUDA device (there is no CPU fallback)')
         self.lib = lib.load()
@@ -61,7 +61,8 @@ class HotPath:
             # exp/mv2d_r50_frcnn_two_frames_1408x512_ep72.py:44-47, 121-124
             self.cfg.update(topk=20, expand_stride=2, denoise_noise_scale=1.25, denoise_split=0.6)
         self.cfg.update(cfg)
-        self.w = PackedWeights(state_dict, self.device)
+        # fold_first_self_attn: layer 0's self-attention output is a packed constant (pack.first_layer_self_attn_const)
+        self.w = PackedWeights(state_dict, self.device, fold_first_self_attn=fold_first_self_attn)
         self.L = self.w.num_layers
         self.cache_sine_branch = cache_sine_branch
         self._sine_cache = {}
@@ -76,8 +77,9 @@ class HotPath:
             persistent_decoder = os.environ.get('MV2D_DECODER', 'staged') == 'persistent'
         self.persistent_decoder = persistent_decoder
         self._side = torch.cuda.Stream(device=self.device)
+        self._side2 = torch.cuda.Stream(device=self.device)
         self._copy = torch.cuda.Stream(device=self.device)
-        self._ev_fork, self._ev_join = torch.cuda.Event(), torch.cuda.Event()
+        self._ev_fork, self._ev_join, self._ev_join2 = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
         self.graph_launches = 0
         c = self.cfg
         S, Dn = c['sample_size'], c['corr_num_depth']
@@ -395,17 +397,22 @@ class HotPath:
             feat, feat_tf32 = self.to_nhwc(feat_in)
         if self.overlap:
             # fork: everything of the query generator that does not need the position embedding (RoIAlign
-            # of the image feature, 3x3 conv, FC chain, reference points, query embedding) and the box
-            # correlation run on a side stream, concurrently with the SE gate / PE combine on the main stream
+            # of the image feature, 3x3 conv, FC chain, reference points, query embedding) runs on a side
+            # stream and the box correlation on a second one, concurrently with the position MLPs / SE gate /
+            # PE combine on the main stream
             main = torch.cuda.current_stream()
             self._ev_fork.record(main)
             with torch.cuda.stream(self._side):
                 self._side.wait_event(self._ev_fork)
                 qg = self.roi_align_qg(rois, cams, feat, None, N, phase=1)
-                corr = self.box_corr(rois, roi_start, trans, N, V, img_metas, h, w)
                 self._ev_join.record(self._side)
+            with torch.cuda.stream(self._side2):
+                self._side2.wait_event(self._ev_fork)
+                corr = self.box_corr(rois, roi_start, trans, N, V, img_metas, h, w)
+                self._ev_join2.record(self._side2)
             pe, kin = self.pe3d(feat, i2l, img_metas, feat_tf32, phase=pe_phase)
             main.wait_event(self._ev_join)
+            main.wait_event(self._ev_join2)
             if self.mode == 'S':
                 self.roi_align_qg(rois, cams, feat, pe, N, phase=2)      # tok_kin = tok_feat + RoIAlign(pe)
         else:

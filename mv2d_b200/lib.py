@@ -63,7 +63,7 @@ class LayerWeights(C.Structure):
         ('sa_in_w', c_f), ('sa_in_b', c_f), ('sa_out_w', c_f), ('sa_out_b', c_f),
         ('ca_q_w', c_f), ('ca_q_w_lo', c_f), ('ca_q_b', c_f), ('ca_o_w', c_f), ('ca_o_w_lo', c_f), ('ca_o_b', c_f),
         ('ffn_w1', c_f), ('ffn_w1_lo', c_f), ('ffn_b1', c_f), ('ffn_w2', c_f), ('ffn_w2_lo', c_f), ('ffn_b2', c_f),
-        ('ln_g', c_f * 3), ('ln_b', c_f * 3),
+        ('ln_g', c_f * 3), ('ln_b', c_f * 3), ('sa_const', c_f),
     ]
 
 

@@ -50,6 +50,16 @@ def absorb_cross_attention(in_w, in_b, out_w, out_b):
     return ca_q_w.float(), ca_q_b.float(), ca_o_w.float(), ca_o_b.float()
 
 
+def first_layer_self_attn_const(in_proj_bias, out_w, out_b):
+    """Self-attention output of decoder layer 0.  The target starts at zero (cross_attention_head.py:32,
+    ``target = torch.zeros_like(query_embed)``), value = target, so every value row equals the value bias bv;
+    a softmax-weighted mean of identical rows is that row, hence attn_out = out_proj(bv) + bo for every query
+    regardless of q, k and masks (petr_transformer.py:314-370).  fp64, rounded once."""
+    E = out_w.shape[0]
+    bv = in_proj_bias.double()[2 * E:]
+    return (out_w.double() @ bv + out_b.double()).float()
+
+
 def round_tf32(t):
     """Round-to-nearest (ties away from zero) fp32 -> TF32, kept in fp32: what cvt.rna.tf32.f32 does."""
     bits = t.detach().float().contiguous().view(torch.int32)
@@ -66,7 +76,7 @@ def split_tf32(t):
 class PackedWeights:
     """Device-resident weights + the host-side ctypes structs that point at them."""
 
-    def __init__(self, state_dict, device, num_layers=None):
+    def __init__(self, state_dict, device, num_layers=None, fold_first_self_attn=True):
         sd = _strip(state_dict)
         if num_layers is None:
             num_layers = 1 + max(int(k.split('.')[4]) for k in sd
@@ -128,6 +138,10 @@ class PackedWeights:
             for n in range(3):
                 lw.ln_g[n] = put(f'l{l}.ln_g{n}', sd[p + f'norms.{n}.weight']).data_ptr()
                 lw.ln_b[n] = put(f'l{l}.ln_b{n}', sd[p + f'norms.{n}.bias']).data_ptr()
+            if l == 0 and fold_first_self_attn:
+                lw.sa_const = put('l0.sa_const', first_layer_self_attn_const(
+                    sd[p + 'attentions.0.attn.in_proj_bias'], sd[p + 'attentions.0.attn.out_proj.weight'],
+                    sd[p + 'attentions.0.attn.out_proj.bias'])).data_ptr()
 
         def stack(fmt):
             return torch.stack([sd[fmt.format(l)] for l in range(num_layers)], 0)

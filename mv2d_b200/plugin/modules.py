@@ -355,28 +355,52 @@ class MV2DHead(nn.Module):
                        intrins_feat_scale=self.intrins_feat_scale,
                        num_views_per_frame=getattr(self, 'num_views', 6))
             cfg.update(self.box_corr_module.engine_cfg())
+            cfg.update(self._denoise_cfg())
             dev = next(self.parameters()).device
             self._engine = HotPath(self.state_dict(), mode=self.MODE, device=dev, **cfg)
         return self._engine
 
-    def _results(self, out):
+    def _denoise_cfg(self):
+        return {}
+
+    def _dn_inputs(self, img_metas):
+        """Denoising-query inputs of the training-mode forward, or None (eval / use_denoise off)."""
+        return None
+
+    def _results(self, out, dn=None):
         L = out['cls_scores'].shape[0]
         N = out['N']
+        mask_dict = None
+        if dn is not None:
+            # the dict MV2DSHead.prepare_for_dn returns (mv2d_s_head.py:106-113) + output_known_lbs_bboxes (:193-196)
+            G, pad, scalar = dn['gt_labels'].numel(), out['dn_pad'], self.denoise_scalar
+            dev = out['cls_scores'].device
+            idx = torch.arange(G, device=dev)
+            mask_dict = dict(
+                known_indice=idx.repeat(scalar), batch_idx=torch.zeros(G, dtype=torch.long, device=dev),
+                map_known_indice=torch.cat([idx + G * i for i in range(scalar)]) if scalar else idx[:0],
+                known_lbs_bboxes=(out['dn_labels'].long(), dn['gt_boxes'].to(dev).repeat(scalar, 1)),
+                know_idx=[torch.ones_like(dn['gt_labels']).to(dev)], pad_size=pad)
+            if pad > 0:
+                mask_dict['output_known_lbs_bboxes'] = (out['dn_cls_scores'][:, None], out['dn_bbox_preds'][:, None])
         return dict(cls_scores=[out['cls_scores'][l] for l in range(L)],
                     bbox_preds=[out['bbox_preds'][l] for l in range(L)],
                     bbox_feats=out['tok_feat'].view(N, 7, 7, 256).permute(0, 3, 1, 2), return_feats=dict(),
                     intrinsics=out['roi_intrinsics'].view(N, 4, 4), extrinsics=None, rois=out['rois'],
-                    dn_mask_dict=None)
+                    dn_mask_dict=mask_dict)
 
     @torch.no_grad()
     def _bbox_forward(self, x, proposal_list, img_metas):
         """x: list with the P4 feature [V,256,h,w] (the PE is computed inside the fused path; a
-        reference-style [V,512,h,w] feat||pe tensor is accepted and its first half is used)."""
+        reference-style [V,512,h,w] feat||pe tensor is accepted and its first half is used).
+        In training mode with ``use_denoise`` the GT boxes of ``img_metas[0]`` spawn the denoising queries
+        (mv2d_s_head.py:158-180, mv2d_t_head.py:91-98); forward only -- no autograd through the kernels."""
         feat = x[self.feat_lvl]
         if feat.shape[1] == 2 * self.position_encoding.embed_dims:
             feat = feat[:, :self.position_encoding.embed_dims]
-        out = self.engine().forward(feat, proposal_list, img_metas)
-        return self._results(out)
+        dn = self._dn_inputs(img_metas)
+        out = self.engine().forward(feat, proposal_list, img_metas, dn=dn)
+        return self._results(out, dn)
 
     @torch.no_grad()
     def simple_test(self, x, proposal_list, img_metas, rescale=False):
@@ -386,7 +410,8 @@ class MV2DHead(nn.Module):
                                          img_metas)
 
     def forward_train(self, *args, **kwargs):
-        raise NotImplementedError('training rows are out of scope this round: DESIGN.md section 7')
+        raise NotImplementedError('losses / assignment / backward are out of scope (DESIGN.md section 7); the '
+                                  'training-mode FORWARD incl. denoising queries is _bbox_forward under .train()')
 
 
 @HEADS.register_module()
@@ -397,7 +422,21 @@ class MV2DSHead(MV2DHead):
     def __init__(self, use_denoise=False, neg_bbox_loss=False, denoise_scalar=10, denoise_noise_scale=1.0,
                  denoise_noise_trans=0.0, denoise_weight=1.0, denoise_split=0.75, **kwargs):
         super().__init__(**kwargs)
-        self.use_denoise = use_denoise
+        self.use_denoise, self.neg_bbox_loss = use_denoise, neg_bbox_loss
+        self.denoise_scalar, self.denoise_noise_scale, self.denoise_noise_trans = denoise_scalar, denoise_noise_scale, denoise_noise_trans
+        self.denoise_weight, self.denoise_split = denoise_weight, denoise_split
+
+    def _denoise_cfg(self):
+        return dict(denoise_scalar=self.denoise_scalar, denoise_noise_scale=self.denoise_noise_scale,
+                    denoise_noise_trans=self.denoise_noise_trans, denoise_split=self.denoise_split,
+                    num_classes=self.num_classes)
+
+    def _dn_inputs(self, img_metas, rand=None):
+        if not (self.training and self.use_denoise):
+            return None
+        gt = img_metas[0]['gt_bboxes_3d']       # mv2d_s_head.py:41-44: gravity centre + tensor[:, 3:]
+        boxes = torch.cat((gt.gravity_center, gt.tensor[:, 3:]), dim=1)
+        return dict(gt_boxes=boxes, gt_labels=img_metas[0]['gt_labels_3d'], rand=rand)
 
 
 @HEADS.register_module()

@@ -195,6 +195,28 @@ def test_tcgen05_gemm_single_pass_tf32():
         assert_close(Cc, ref, 2e-5, 2e-5, f'gemm_tc {M}x{N}x{K}')
 
 
+def test_first_layer_fold_equals_unfolded(state_dicts):
+    """Layer 0's self-attention as a packed constant (default) against the decoder that runs it."""
+    from mv2d_b200.engine import HotPath
+    for name in ('s_small', 't_dn'):
+        spec = synth.CASES[name]
+        feat, boxes, metas = synth.case_inputs(spec)
+        dn = None
+        if 'dn' in spec:
+            gt_boxes, gt_labels, rand = synth.make_dn_inputs(spec['dn'])
+            dn = dict(gt_boxes=gt_boxes, gt_labels=gt_labels, rand=rand)
+        outs = []
+        for fold in (True, False):
+            eng = HotPath(state_dicts(spec['num_layers']), mode=spec['mode'], fold_first_self_attn=fold)
+            n0 = eng.launch_count()
+            o = eng.forward(feat.cuda(), boxes, metas, dn=dn)
+            torch.cuda.synchronize()
+            outs.append((o['cls_scores'].clone(), o['bbox_preds'].clone(), eng.launch_count() - n0))
+        assert outs[1][2] - outs[0][2] == 3          # in_proj, attention, out_proj launches dropped
+        assert_close(outs[0][0], outs[1][0], 2e-5, 1e-5, 'cls fold/unfold')
+        assert_close(outs[0][1], outs[1][1], 2e-5, 1e-5, 'box fold/unfold')
+
+
 def test_cluster_multicast_gemm_variant():
     """MV2D_TC_MULTICAST=1 (read once per process, hence the subprocess) routes the decoder's BN=64 3xTF32 GEMMs
     through the 4-CTA-cluster kernel whose A tile is TMA-multicast; same goldens, same gate."""

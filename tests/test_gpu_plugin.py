@@ -52,6 +52,42 @@ def test_head_bbox_forward_and_simple_test(name, state_dicts):
     close(s, g['dec_scores'], 1e-3, 1e-3)
 
 
+def test_training_mode_forward_with_denoising_queries(state_dicts, monkeypatch):
+    """head.train() + use_denoise: _bbox_forward prepends the denoising queries built from img_metas[0]'s GT
+    (mv2d_t_head.py:91-118) and returns the reference's dn_mask_dict; checked against the oracle with the
+    same noise."""
+    from oracle import mv2d_oracle as O
+    spec = dict(synth.CASES['t_dn'], num_layers=6)
+    h = head('T', state_dicts)
+    feat, boxes, metas = synth.case_inputs(spec)
+    gt_boxes, gt_labels, rand = synth.make_dn_inputs(spec['dn'])
+
+    class Boxes:      # the two attributes read from LiDARInstance3DBoxes
+        gravity_center = gt_boxes[:, :3].cuda()
+        tensor = gt_boxes.cuda()
+    metas = [dict(metas[0], gt_bboxes_3d=Boxes(), gt_labels_3d=gt_labels.cuda())] + list(metas[1:])
+    monkeypatch.setattr(torch, 'rand', lambda *a, **k: rand.clone().to(k.get('device', 'cpu')))
+    h.train()
+    try:
+        res = h._bbox_forward([feat.cuda()], [b.cuda() for b in boxes], metas)
+    finally:
+        h.eval()
+    monkeypatch.undo()
+    with torch.no_grad():
+        cls, box, st = O.mv2d_t_forward(state_dicts(6), feat, boxes, metas, O.make_cfg('T'), return_stages=True,
+                                        dn=dict(gt_boxes=gt_boxes, gt_labels=gt_labels, rand=rand))
+    md = res['dn_mask_dict']
+    assert md['pad_size'] == 70 and md['known_lbs_bboxes'][1].shape == (70, 9)
+    assert torch.equal(md['known_lbs_bboxes'][0].cpu(), st['dn']['labels'])
+    assert torch.equal(md['map_known_indice'].cpu(), torch.arange(70))
+    close(torch.stack(res['cls_scores']), cls)
+    close(torch.stack(res['bbox_preds']), box)
+    close(md['output_known_lbs_bboxes'][0][:, 0], st['dn']['cls'])
+    close(md['output_known_lbs_bboxes'][1][:, 0], st['dn']['box'])
+    # eval mode: no denoising queries
+    assert h._bbox_forward([feat.cuda()], [b.cuda() for b in boxes], metas)['dn_mask_dict'] is None
+
+
 def test_submodule_interfaces(state_dicts):
     """PE.forward and BoxCorrelation.gen_* through the reference's call signatures."""
     spec, g = golden('s_small')

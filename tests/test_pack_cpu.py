@@ -4,7 +4,7 @@ against the oracle's MHA call on random inputs with a per-query key mask."""
 import torch
 import torch.nn.functional as F
 
-from mv2d_b200.pack import PackedWeights, absorb_cross_attention
+from mv2d_b200.pack import PackedWeights, absorb_cross_attention, first_layer_self_attn_const
 from oracle import mv2d_oracle as O
 
 
@@ -39,3 +39,18 @@ def test_conv_repack_matches_conv2d(state_dicts):
     out = cols.reshape(3, 49, 9 * 256) @ (w.t['w_conv'] + w.t['w_conv_lo']).T + w.t['b_conv']   # hi + lo = w
     assert (out.view(3, 7, 7, 256).permute(0, 3, 1, 2) - ref).abs().max() < 2e-4
     assert w.num_layers == 1 and w.t['br.cls_w2'].shape == (1, 10, 256)
+
+
+def test_first_layer_self_attention_is_a_constant(state_dicts):
+    """The folding the staged decoder uses for layer 0: with target = 0 the FlattenMHSelfAttention output is
+    out_proj(bv) + bo for every query, for any query_pos and any (non-degenerate) attention mask."""
+    sd = state_dicts(2)
+    p = 'bbox_head.transformer.decoder.layers.0.attentions.0.attn.'
+    const = first_layer_self_attn_const(sd[p + 'in_proj_bias'], sd[p + 'out_proj.weight'], sd[p + 'out_proj.bias'])
+    g = torch.Generator().manual_seed(5)
+    qpos = torch.randn(37, 1, 256, generator=g) * 3
+    mask = torch.rand(37, 37, generator=g) < 0.5
+    mask[torch.arange(37), torch.arange(37)] = False        # at least one visible key per row
+    for m in (None, mask):
+        sa = O._mha(sd, p, qpos, qpos, torch.zeros_like(qpos), 8, attn_mask=m)
+        assert (sa[:, 0] - const[None]).abs().max() < 1e-6
