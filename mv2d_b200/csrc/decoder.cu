@@ -9,6 +9,7 @@
 // cancels), and the head output is  Wv_h (sum_k p_hk memory_k) + bv_h.  So the kernel streams
 // the RAW key rows once per query -- no K/V projection of 49*N (or ~25k) keys per layer --
 // and the work per layer is bound by the bytes of the key rows it reads (HBM/L2), not flops.
+#include <stdlib.h>
 #include "common.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
@@ -131,14 +132,19 @@ __global__ void __launch_bounds__(256) ln_kernel(LnArgs a) {
 // FlattenMHSelfAttention core (petr_transformer.py:314-370): all N queries form ONE sequence.
 // qkv [N,768] (q | k | v, head h = channels 32h..32h+31), q already includes the bias; the
 // 1/sqrt(32) scale is applied here.  grid (ceil(N/8), 8 heads), 256 threads, one query per warp.
-// K/V tiles of 128 keys live in shared memory with a 36-float row stride (16-byte aligned,
-// conflict-free LDS.128).  QK^T: lane = key (4 keys per lane per tile), q in registers.
+// K/V tiles of up to 320 keys (one tile at N = 300) are copied with cp.async into shared memory with a 36-float
+// row stride (16-byte aligned, conflict-free LDS.128).  QK^T: lane = key (up to 10 keys per lane), q in registers.
 // PV: probabilities go through shared memory; lane = (key phase, channel quad) so each step is
 // one LDS + one LDS.128 + 4 FMA; the 4 key phases are folded with two shuffles at the end.
-#define SA_KT 128
+#define SA_KT 320
 #define SA_LD 36
 #define SA_SMEM_BYTES ((2 * SA_KT * SA_LD + 8 * SA_KT) * 4)
-#define SA_QPW 2     // queries per warp: every K/V tile staged in shared memory serves 16 queries
+#define SA_QPW 1     // queries per warp
+__device__ __forceinline__ void sa_cp16(void* smem, const void* gmem) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
+
 __device__ __forceinline__ void
 self_attn_body(const float* __restrict__ qkv, const uint8_t* __restrict__ mask, int N, float* __restrict__ out,
                int vbx, int hd, float* smem_f) {
@@ -147,12 +153,118 @@ self_attn_body(const float* __restrict__ qkv, const uint8_t* __restrict__ mask, 
     float (*Ps)[SA_KT] = reinterpret_cast<float (*)[SA_KT]>(smem_f + 2 * SA_KT * SA_LD);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kq = lane >> 3, cq = lane & 7;
-    int qi[SA_QPW];
-    float q[SA_QPW][32], m[SA_QPW], l[SA_QPW];
-    float4 acc[SA_QPW];
+    const int qi = vbx * 8 + warp;
+    float q[32], m = -INFINITY, l = 0.f;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k0 = 0; k0 < N; k0 += SA_KT) {
+        const int ng = min(SA_KT, N - k0);
+        __syncthreads();
+        // the head's K and V rows of this tile (128 B each) go straight to shared memory, all copies in flight at once
+        for (int i = threadIdx.x; i < ng * 8; i += 256) {
+            const int r = i >> 3, c4 = i & 7;
+            const float* src = qkv + (long long)(k0 + r) * 768 + 256 + hd * 32 + c4 * 4;
+            sa_cp16(&Ks[r][c4 * 4], src);
+            sa_cp16(&Vs[r][c4 * 4], src + 256);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        if (k0 == 0) {
 #pragma unroll
-    for (int u = 0; u < SA_QPW; ++u) {
-        qi[u] = (vbx * 8 + warp) * SA_QPW + u;
+            for (int d4 = 0; d4 < 8; ++d4) {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                // ld.global.cg: inside the persistent kernel qkv was written by other CTAs a phase ago (no .nc path)
+                if (qi < N) v = __ldcg(reinterpret_cast<const float4*>(qkv + (long long)qi * 768 + hd * 32) + d4);
+                q[d4 * 4 + 0] = v.x * 0.17677669529663687f; q[d4 * 4 + 1] = v.y * 0.17677669529663687f;
+                q[d4 * 4 + 2] = v.z * 0.17677669529663687f; q[d4 * 4 + 3] = v.w * 0.17677669529663687f;
+            }
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        if (qi >= N) continue;                    // warp-uniform
+        const int ngrp = (ng + 31) >> 5;
+        float s[SA_KT / 32];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int g = 0; g < SA_KT / 32; ++g) {
+            s[g] = -INFINITY;
+            if (g < ngrp) {
+                const int kk = g * 32 + lane;
+                float x = 0.f;
+                if (kk < ng) {
+#pragma unroll
+                    for (int d4 = 0; d4 < 8; ++d4) {
+                        const float4 kv = *reinterpret_cast<const float4*>(&Ks[kk][d4 * 4]);
+                        x = fmaf(q[d4 * 4 + 0], kv.x, x); x = fmaf(q[d4 * 4 + 1], kv.y, x);
+                        x = fmaf(q[d4 * 4 + 2], kv.z, x); x = fmaf(q[d4 * 4 + 3], kv.w, x);
+                    }
+                }
+                if (kk >= ng || (mask && mask[(long long)qi * N + k0 + kk])) x = -INFINITY;
+                s[g] = x;
+                mx = fmaxf(mx, x);
+            }
+        }
+        const float mn = fmaxf(m, warp_max(mx));
+        if (mn == -INFINITY) continue;
+        const float alpha = __expf(m - mn);       // exp(-inf) = 0 on the first tile
+        float psum = 0.f;
+        __syncwarp();
+#pragma unroll
+        for (int g = 0; g < SA_KT / 32; ++g) {
+            if (g < ngrp) {
+                const float pv = __expf(s[g] - mn);
+                Ps[warp][g * 32 + lane] = pv;
+                psum += pv;
+            }
+        }
+        l = l * alpha + warp_sum(psum);
+        acc.x *= alpha; acc.y *= alpha; acc.z *= alpha; acc.w *= alpha;
+        __syncwarp();
+        const int nt = (ng + 3) >> 2;             // keys beyond ng inside the last group carry p = 0 and finite (stale) V
+#pragma unroll 5
+        for (int t = 0; t < nt; ++t) {
+            const int j = t * 4 + kq;
+            const float pj = j < ng ? Ps[warp][j] : 0.f;
+            const float4 vv = *reinterpret_cast<const float4*>(&Vs[j < ng ? j : 0][cq * 4]);
+            acc.x = fmaf(pj, vv.x, acc.x); acc.y = fmaf(pj, vv.y, acc.y);
+            acc.z = fmaf(pj, vv.z, acc.z); acc.w = fmaf(pj, vv.w, acc.w);
+        }
+        m = mn;
+    }
+    // fold the 4 key phases (lanes differing in bits 3,4)
+#pragma unroll
+    for (int o = 8; o <= 16; o <<= 1) {
+        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+        acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o); acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+    }
+    if (qi < N && kq == 0) {
+        const float inv = l > 0.f ? 1.f / l : 0.f;
+        *reinterpret_cast<float4*>(out + (long long)qi * MV2D_C + hd * 32 + cq * 4) =
+            make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
+    }
+}
+
+// Previous formulation (128-key tiles, two queries per warp, register-staged loads): kept for the persistent
+// decoder (decoder_mega.cuh).  Measured on B200: with the 100 KB single-tile variant above inlined, the persistent
+// kernel's later tcgen05 split-K phase returned wrong sums (self-attention output itself was right; the TMA
+// stage buffers alias the region the variant dirties -- suspected generic/async proxy ordering, not root-caused).
+// The staged decoder (one kernel per stage, no aliasing) is unaffected and uses the variant above.
+#define SA1_KT 128
+#define SA1_LD 36
+#define SA1_SMEM_BYTES ((2 * SA1_KT * SA1_LD + 8 * SA1_KT) * 4)
+#define SA1_QPW 2     // queries per warp: every K/V tile staged in shared memory serves 16 queries
+__device__ __forceinline__ void
+self_attn_body_v1(const float* __restrict__ qkv, const uint8_t* __restrict__ mask, int N, float* __restrict__ out,
+               int vbx, int hd, float* smem_f) {
+    float (*Ks)[SA1_LD] = reinterpret_cast<float (*)[SA1_LD]>(smem_f);
+    float (*Vs)[SA1_LD] = reinterpret_cast<float (*)[SA1_LD]>(smem_f + SA1_KT * SA1_LD);
+    float (*Ps)[SA1_KT] = reinterpret_cast<float (*)[SA1_KT]>(smem_f + 2 * SA1_KT * SA1_LD);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kq = lane >> 3, cq = lane & 7;
+    int qi[SA1_QPW];
+    float q[SA1_QPW][32], m[SA1_QPW], l[SA1_QPW];
+    float4 acc[SA1_QPW];
+#pragma unroll
+    for (int u = 0; u < SA1_QPW; ++u) {
+        qi[u] = (vbx * 8 + warp) * SA1_QPW + u;
         m[u] = -INFINITY; l[u] = 0.f; acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int d4 = 0; d4 < 8; ++d4) {
@@ -162,7 +274,7 @@ self_attn_body(const float* __restrict__ qkv, const uint8_t* __restrict__ mask, 
             q[u][d4 * 4 + 2] = v.z * 0.17677669529663687f; q[u][d4 * 4 + 3] = v.w * 0.17677669529663687f;
         }
     }
-    for (int k0 = 0; k0 < N; k0 += SA_KT) {
+    for (int k0 = 0; k0 < N; k0 += SA1_KT) {
         __syncthreads();
         {   // all 8 loads of a thread are issued before the first store (one memory latency per tile)
             float4 kv[4], vv[4];
@@ -183,14 +295,14 @@ self_attn_body(const float* __restrict__ qkv, const uint8_t* __restrict__ mask, 
             }
         }
         __syncthreads();
-        const int ng = min(SA_KT, N - k0);
+        const int ng = min(SA1_KT, N - k0);
 #pragma unroll
-        for (int u = 0; u < SA_QPW; ++u) {
+        for (int u = 0; u < SA1_QPW; ++u) {
             if (qi[u] >= N) continue;                    // warp-uniform
-            float s[SA_KT / 32];
+            float s[SA1_KT / 32];
             float mx = -INFINITY;
 #pragma unroll
-            for (int g = 0; g < SA_KT / 32; ++g) {
+            for (int g = 0; g < SA1_KT / 32; ++g) {
                 const int kk = g * 32 + lane;
                 float x = 0.f;
 #pragma unroll
@@ -209,7 +321,7 @@ self_attn_body(const float* __restrict__ qkv, const uint8_t* __restrict__ mask, 
             float psum = 0.f;
             __syncwarp();
 #pragma unroll
-            for (int g = 0; g < SA_KT / 32; ++g) {
+            for (int g = 0; g < SA1_KT / 32; ++g) {
                 const float pv = __expf(s[g] - mn);
                 Ps[warp][g * 32 + lane] = pv;
                 psum += pv;
@@ -218,7 +330,7 @@ self_attn_body(const float* __restrict__ qkv, const uint8_t* __restrict__ mask, 
             acc[u].x *= alpha; acc[u].y *= alpha; acc[u].z *= alpha; acc[u].w *= alpha;
             __syncwarp();
 #pragma unroll 8
-            for (int t = 0; t < SA_KT / 4; ++t) {
+            for (int t = 0; t < SA1_KT / 4; ++t) {
                 const int j = t * 4 + kq;
                 const float pj = Ps[warp][j];
                 const float4 vv = *reinterpret_cast<const float4*>(&Vs[j][cq * 4]);
@@ -229,7 +341,7 @@ self_attn_body(const float* __restrict__ qkv, const uint8_t* __restrict__ mask, 
         }
     }
 #pragma unroll
-    for (int u = 0; u < SA_QPW; ++u) {
+    for (int u = 0; u < SA1_QPW; ++u) {
         // fold the 4 key phases (lanes differing in bits 3,4)
 #pragma unroll
         for (int o = 8; o <= 16; o <<= 1) {
@@ -512,6 +624,214 @@ cross_attn_kernel(XaArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------
+// S head cross-attention, one CTA per (query, matched RoI).  The 49 tokens of a RoI are CONTIGUOUS in
+// tok_kin / tok_feat, so one elected thread fetches each 50 176-byte block with a single bulk copy
+// (cp.async.bulk + mbarrier); every unit of work is the same size, which removes the tail the per-query kernel
+// has (a query with 6 matches streams 6x the keys of the median query and set the kernel time).
+// A query with one match (~3 of 4) is finished by its CTA.  Otherwise each CTA leaves its un-normalised
+// (acc, m, l) record in global memory and the LAST one to arrive (atomic ticket) merges the records in slot
+// order -- fixed order => bitwise reproducible whichever CTA does the merge -- and re-arms the ticket.
+#define XR_THREADS 256
+#define XR_BLK_BYTES (MV2D_TOK * MV2D_C * 4)
+#define XR_REC (2048 + 16)        // floats per partial record: acc[8][256], m[8], l[8]
+#define XR_MAXM 8                 // match slots the partial-record scratch is sized for
+#define XR_SMEM_BYTES (2 * XR_BLK_BYTES + 64 * 8 * 4 + 32 * 4 + 16)
+
+struct XrArgs {
+    const float* qt; const float* kin_rows; const float* mem_rows;
+    const int* match; const int* match_cnt; int max_match;
+    float* ctx; float* ctx_lo; float* part; int* ticket;
+};
+
+__device__ __forceinline__ uint32_t xr_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__global__ void __launch_bounds__(XR_THREADS, 2)
+xa_roi_kernel(XrArgs a) {
+    pdl_wait();
+    pdl_trigger();
+    const int n = blockIdx.x, slot = blockIdx.y;
+    const int cnt = min(a.match_cnt[n], XR_MAXM);
+    if (slot >= cnt) return;
+    extern __shared__ __align__(128) unsigned char xr_smem[];
+    float* Ks = reinterpret_cast<float*>(xr_smem);
+    float* Vs = Ks + MV2D_TOK * MV2D_C;
+    float* sc = Vs + MV2D_TOK * MV2D_C;          // [64][8] logits -> probabilities
+    float* stat = sc + 64 * 8;                   // m[8], l[8]
+    uint64_t* bar = reinterpret_cast<uint64_t*>(stat + 32);
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    constexpr int NW = XR_THREADS / 32;
+    const long long blk = (long long)a.match[(long long)n * a.max_match + slot] * MV2D_TOK * MV2D_C;
+    if (t == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(xr_smem_u32(bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(xr_smem_u32(bar)), "r"(2 * XR_BLK_BYTES) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(xr_smem_u32(Ks)), "l"(a.kin_rows + blk), "r"(XR_BLK_BYTES), "r"(xr_smem_u32(bar)) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(xr_smem_u32(Vs)), "l"(a.mem_rows + blk), "r"(XR_BLK_BYTES), "r"(xr_smem_u32(bar)) : "memory");
+    }
+    {
+        // ---- logits.  q~ slice of this lane: 8 heads x channels {lane*4..+3, 128+lane*4..+3}
+        float qv[8][8];
+#pragma unroll
+        for (int h = 0; h < 8; ++h) {
+            const float4 x0 = *reinterpret_cast<const float4*>(a.qt + (long long)n * 2048 + h * 256 + lane * 4);
+            const float4 x1 = *reinterpret_cast<const float4*>(a.qt + (long long)n * 2048 + h * 256 + 128 + lane * 4);
+            qv[h][0] = x0.x; qv[h][1] = x0.y; qv[h][2] = x0.z; qv[h][3] = x0.w;
+            qv[h][4] = x1.x; qv[h][5] = x1.y; qv[h][6] = x1.z; qv[h][7] = x1.w;
+        }
+        __syncthreads();            // barrier initialised before anyone polls it
+        {
+            uint32_t done = 0;
+            while (!done)
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                             : "=r"(done) : "r"(xr_smem_u32(bar)) : "memory");
+        }
+        for (int j = warp; j < MV2D_TOK; j += NW) {
+            const float* row = Ks + j * MV2D_C;
+            const float4 k0 = *reinterpret_cast<const float4*>(row + lane * 4);
+            const float4 k1 = *reinterpret_cast<const float4*>(row + 128 + lane * 4);
+            float sv[8];
+#pragma unroll
+            for (int h = 0; h < 8; ++h) {
+                float x = qv[h][0] * k0.x;
+                x = fmaf(qv[h][1], k0.y, x); x = fmaf(qv[h][2], k0.z, x); x = fmaf(qv[h][3], k0.w, x);
+                x = fmaf(qv[h][4], k1.x, x); x = fmaf(qv[h][5], k1.y, x); x = fmaf(qv[h][6], k1.z, x);
+                x = fmaf(qv[h][7], k1.w, x);
+                sv[h] = x;
+            }
+            reduce8(sv, lane);
+            if ((lane & 3) == 0) sc[j * 8 + (lane >> 2)] = sv[0];
+        }
+    }
+    __syncthreads();
+    {   // ---- softmax statistics of this block: warp = head, lanes = keys {lane, lane + 32}
+        const int h = warp;
+        const float s0 = sc[lane * 8 + h];
+        const float s1 = lane + 32 < MV2D_TOK ? sc[(lane + 32) * 8 + h] : -INFINITY;
+        const float mx = warp_max(fmaxf(s0, s1));
+        const float p0 = __expf(s0 - mx), p1 = lane + 32 < MV2D_TOK ? __expf(s1 - mx) : 0.f;
+        const float sum = warp_sum(p0 + p1);
+        sc[lane * 8 + h] = p0;
+        if (lane + 32 < MV2D_TOK) sc[(lane + 32) * 8 + h] = p1;
+        if (lane == 0) { stat[h] = mx; stat[8 + h] = sum; }
+    }
+    __syncthreads();
+    // ---- acc = sum_k p_k * mem_k
+    float acc[8][8];
+#pragma unroll
+    for (int h = 0; h < 8; ++h)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[h][c] = 0.f;
+    for (int j = warp; j < MV2D_TOK; j += NW) {
+        const float* row = Vs + j * MV2D_C;
+        const float4 v0 = *reinterpret_cast<const float4*>(row + lane * 4);
+        const float4 v1 = *reinterpret_cast<const float4*>(row + 128 + lane * 4);
+        const float4 p0 = *reinterpret_cast<const float4*>(sc + j * 8);
+        const float4 p1 = *reinterpret_cast<const float4*>(sc + j * 8 + 4);
+        const float pp[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+#pragma unroll
+        for (int h = 0; h < 8; ++h) {
+            acc[h][0] = fmaf(pp[h], v0.x, acc[h][0]); acc[h][1] = fmaf(pp[h], v0.y, acc[h][1]);
+            acc[h][2] = fmaf(pp[h], v0.z, acc[h][2]); acc[h][3] = fmaf(pp[h], v0.w, acc[h][3]);
+            acc[h][4] = fmaf(pp[h], v1.x, acc[h][4]); acc[h][5] = fmaf(pp[h], v1.y, acc[h][5]);
+            acc[h][6] = fmaf(pp[h], v1.z, acc[h][6]); acc[h][7] = fmaf(pp[h], v1.w, acc[h][7]);
+        }
+    }
+    // ---- cross-warp tree sum through the (now free) key block, fixed order
+    float4* T = reinterpret_cast<float4*>(Ks);   // [NW/2][512] float4
+#pragma unroll
+    for (int stride = NW / 2; stride >= 1; stride >>= 1) {
+        if (warp >= stride && warp < 2 * stride) {
+#pragma unroll
+            for (int h = 0; h < 8; ++h) {
+                T[(warp - stride) * 512 + h * 64 + lane] = make_float4(acc[h][0], acc[h][1], acc[h][2], acc[h][3]);
+                T[(warp - stride) * 512 + h * 64 + 32 + lane] = make_float4(acc[h][4], acc[h][5], acc[h][6], acc[h][7]);
+            }
+        }
+        __syncthreads();
+        if (warp < stride) {
+#pragma unroll
+            for (int h = 0; h < 8; ++h) {
+                const float4 x0 = T[warp * 512 + h * 64 + lane], x1 = T[warp * 512 + h * 64 + 32 + lane];
+                acc[h][0] += x0.x; acc[h][1] += x0.y; acc[h][2] += x0.z; acc[h][3] += x0.w;
+                acc[h][4] += x1.x; acc[h][5] += x1.y; acc[h][6] += x1.z; acc[h][7] += x1.w;
+            }
+        }
+        __syncthreads();
+    }
+    if (warp != 0) return;
+    float inv[8];
+    if (cnt == 1) {
+#pragma unroll
+        for (int h = 0; h < 8; ++h) inv[h] = 1.f / stat[8 + h];
+    } else {
+        // leave the un-normalised record; the last CTA of this query merges all of them in slot order
+        float* rec = a.part + ((long long)n * XR_MAXM + slot) * XR_REC;
+#pragma unroll
+        for (int h = 0; h < 8; ++h) {
+            *reinterpret_cast<float4*>(rec + h * 256 + lane * 4) = make_float4(acc[h][0], acc[h][1], acc[h][2], acc[h][3]);
+            *reinterpret_cast<float4*>(rec + h * 256 + 128 + lane * 4) = make_float4(acc[h][4], acc[h][5], acc[h][6], acc[h][7]);
+        }
+        if (lane < 16) rec[2048 + lane] = stat[lane];
+        __threadfence();
+        __syncwarp();
+        int tk = 0;
+        if (lane == 0) tk = atomicAdd(a.ticket + n, 1);
+        tk = __shfl_sync(0xffffffffu, tk, 0);
+        if (tk != cnt - 1) return;
+        __threadfence();
+        const float* base = a.part + (long long)n * XR_MAXM * XR_REC;
+        float M[8], Lsum[8];
+#pragma unroll
+        for (int h = 0; h < 8; ++h) { M[h] = -INFINITY; Lsum[h] = 0.f; }
+        for (int s2 = 0; s2 < cnt; ++s2)
+#pragma unroll
+            for (int h = 0; h < 8; ++h) M[h] = fmaxf(M[h], __ldcg(base + s2 * XR_REC + 2048 + h));
+#pragma unroll
+        for (int h = 0; h < 8; ++h)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) acc[h][c] = 0.f;
+        for (int s2 = 0; s2 < cnt; ++s2) {
+            const float* r2 = base + s2 * XR_REC;
+#pragma unroll
+            for (int h = 0; h < 8; ++h) {
+                const float w = __expf(__ldcg(r2 + 2048 + h) - M[h]);
+                Lsum[h] = fmaf(__ldcg(r2 + 2056 + h), w, Lsum[h]);
+                const float4 x0 = __ldcg(reinterpret_cast<const float4*>(r2 + h * 256 + lane * 4));
+                const float4 x1 = __ldcg(reinterpret_cast<const float4*>(r2 + h * 256 + 128 + lane * 4));
+                acc[h][0] = fmaf(x0.x, w, acc[h][0]); acc[h][1] = fmaf(x0.y, w, acc[h][1]);
+                acc[h][2] = fmaf(x0.z, w, acc[h][2]); acc[h][3] = fmaf(x0.w, w, acc[h][3]);
+                acc[h][4] = fmaf(x1.x, w, acc[h][4]); acc[h][5] = fmaf(x1.y, w, acc[h][5]);
+                acc[h][6] = fmaf(x1.z, w, acc[h][6]); acc[h][7] = fmaf(x1.w, w, acc[h][7]);
+            }
+        }
+#pragma unroll
+        for (int h = 0; h < 8; ++h) inv[h] = 1.f / Lsum[h];
+        if (lane == 0) a.ticket[n] = 0;          // re-armed for the next layer (stream order)
+    }
+#pragma unroll
+    for (int h = 0; h < 8; ++h) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            float v[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[k] = acc[h][half * 4 + k] * inv[h];
+            const long long o = (long long)n * 2048 + h * 256 + half * 128 + lane * 4;
+            if (a.ctx_lo) {
+                float hi[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { hi[k] = round_tf32(v[k]); v[k] = round_tf32(v[k] - hi[k]); }
+                *reinterpret_cast<float4*>(a.ctx + o) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<float4*>(a.ctx_lo + o) = make_float4(v[0], v[1], v[2], v[3]);
+            } else {
+                *reinterpret_cast<float4*>(a.ctx + o) = make_float4(v[0], v[1], v[2], v[3]);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // Final 256 -> 10 heads of both branches + reference-point refinement
 // (cross_attention_head.py:221-238).  One warp per (layer, query).
 __device__ __forceinline__ void
@@ -602,7 +922,7 @@ static size_t xa_smem_mega(int mode, int klist_cap) {
 size_t decoder_workspace_bytes(int N, int L) {
     size_t n = (size_t)(N > 0 ? N : 1), l = (size_t)(L > 0 ? L : 1);
     // x, xq, x1, x1q, x2 + 4 hi/lo copies (9*256) + qkv 768 + sa 256 + qt 2048 + ctx hi/lo + hdn hi/lo + partials
-    size_t per = 9 * MV2D_C + 768 + MV2D_C + 2048 + 2 * 2048 + 2 * 2048 + DEC_SPLIT * MV2D_C;
+    size_t per = 9 * MV2D_C + 768 + MV2D_C + 2048 + 2 * 2048 + 2 * 2048 + DEC_SPLIT * MV2D_C + XR_MAXM * XR_REC + 1;
     // branches: 4 x [L,N,256]
     return (n * per + 4 * l * n * MV2D_C) * sizeof(float) + 4096;   // + the device-wide barrier word and phase timestamps of the persistent kernel
 }
@@ -637,6 +957,8 @@ int run_decoder(const Mv2dDecoderParams& p, cudaStream_t st) {
     float* b1 = ws;   ws += (size_t)L * N * C;
     float* b2 = ws;   ws += (size_t)L * N * C;
     float* b3 = ws;   ws += (size_t)L * N * C;
+    float* xr_part = ws; ws += (size_t)N * XR_MAXM * XR_REC;
+    int* xr_ticket = reinterpret_cast<int*>(ws); ws += N;
     unsigned* barrier = reinterpret_cast<unsigned*>(reinterpret_cast<uintptr_t>(ws + 63) & ~(uintptr_t)63); ws += 1024;
     MV2D_CHECK_ARG((size_t)(ws - p.workspace) * sizeof(float) <= p.workspace_bytes, "decoder: workspace too small");
     const long long NC = (long long)N * C;
@@ -664,6 +986,20 @@ int run_decoder(const Mv2dDecoderParams& p, cudaStream_t st) {
     if ((e = cudaFuncSetAttribute(xa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xa_smem)) != cudaSuccess) {
         set_error("decoder: smem attr %s", cudaGetErrorString(e));
         return (int)e;
+    }
+    // S head: one CTA per (query, matched RoI) with bulk copies (xa_roi_kernel); MV2D_XA_ROI=0 keeps the per-query kernel
+    static const bool xr_on = []() { const char* v = getenv("MV2D_XA_ROI"); return !(v && v[0] == '0'); }();
+    const bool use_xr = xr_on && p.mode == 0 && !p.persistent && p.max_match <= XR_MAXM;
+    if ((e = cudaFuncSetAttribute(self_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SA_SMEM_BYTES)) != cudaSuccess) {
+        set_error("decoder: self_attn smem attr %s", cudaGetErrorString(e));
+        return (int)e;
+    }
+    if (use_xr) {
+        if ((e = cudaFuncSetAttribute(xa_roi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XR_SMEM_BYTES)) != cudaSuccess ||
+            (e = cudaMemsetAsync(xr_ticket, 0, (size_t)N * sizeof(int), st)) != cudaSuccess) {
+            set_error("decoder: xa_roi setup %s", cudaGetErrorString(e));
+            return (int)e;
+        }
     }
     int rc;
     const Mv2dBranchWeights& B = *p.branches;
@@ -709,6 +1045,7 @@ int run_decoder(const Mv2dDecoderParams& p, cudaStream_t st) {
         if (rc) { delete mp; return rc; }
         size_t smem = (size_t)mega_tc::SMEM_BYTES;
         if (xa_smem_mega(p.mode, klist_cap) > smem) smem = xa_smem_mega(p.mode, klist_cap);
+        if ((size_t)SA_SMEM_BYTES > smem) smem = SA_SMEM_BYTES;
         smem += 1024;
         if ((e = cudaFuncSetAttribute(decoder_mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess ||
             (e = cudaMemsetAsync(barrier, 0, sizeof(unsigned), st)) != cudaSuccess) {
@@ -756,7 +1093,13 @@ int run_decoder(const Mv2dDecoderParams& p, cudaStream_t st) {
         }
         // --- sparse cross attention (absorbed)
         if ((rc = tc3(x1q_hi, x1q_lo, C, w.ca_q_w, w.ca_q_w_lo, C, w.ca_q_b, qt, nullptr, 2048, N, 2048, C, 0, 1, 0, st))) return rc;
-        {
+        if (use_xr) {
+            XrArgs a{}; a.qt = qt; a.kin_rows = p.kin_rows; a.mem_rows = p.mem_rows; a.match = p.match;
+            a.match_cnt = p.match_cnt; a.max_match = p.max_match; a.ctx = ctx; a.ctx_lo = ctx_lo;
+            a.part = xr_part; a.ticket = xr_ticket;
+            launch_k(xa_roi_kernel, dim3(N, p.max_match), dim3(XR_THREADS), (size_t)XR_SMEM_BYTES, st, a);
+            MV2D_CHECK_LAUNCH("xa_roi");
+        } else {
             XaArgs a{}; a.qt = qt; a.kin_rows = p.kin_rows; a.mem_rows = p.mem_rows; a.match = p.match;
             a.match_cnt = p.match_cnt; a.max_match = p.max_match; a.keymask = p.keymask; a.mask_words = p.mask_words;
             a.key_list = p.key_list; a.key_cnt = p.key_cnt;

@@ -358,9 +358,9 @@ decoder_mega_kernel(const __grid_constant__ MegaParams p) {
         grid_sync(p.barrier, gen);
         // ---- 2. self-attention core
         {
-            const int qb = cdiv(N, 8 * SA_QPW);
+            const int qb = cdiv(N, 8 * SA1_QPW);
             for (int t = cta; t < qb * MV2D_HEADS; t += ncta)
-                self_attn_body(p.qkv, p.self_attn_mask, N, p.sa, t % qb, t / qb, smem_f);
+                self_attn_body_v1(p.qkv, p.self_attn_mask, N, p.sa, t % qb, t / qb, smem_f);
         }
         grid_sync(p.barrier, gen);
         // ---- 3. out-projection (raw; bias + residual + LN in the next phase)
