@@ -32,7 +32,7 @@ extern "C" {
 #define MV2D_API
 #endif
 
-#define MV2D_ABI_VERSION 2
+#define MV2D_ABI_VERSION 3
 #define MV2D_MAX_LAYERS 8
 
 MV2D_API int mv2d_abi_version(void);
@@ -40,7 +40,7 @@ MV2D_API const char* mv2d_last_error(void);
 /* number of kernel launches this library has enqueued so far in this process */
 MV2D_API unsigned long long mv2d_launch_count(void);
 /* sizeof() of the parameter structs, so a binding can verify its mirror of this header */
-MV2D_API size_t mv2d_sizeof(int which); /* 0 Pe, 1 Qg, 2 Corr, 3 Decoder, 4 LayerWeights, 5 BranchWeights, 6 Dn */
+MV2D_API size_t mv2d_sizeof(int which); /* 0 Pe, 1 Qg, 2 Corr, 3 Decoder, 4 LayerWeights, 5 BranchWeights, 6 Dn, 7 Kv */
 
 /* ---- geometry (utils/pe.py:111; roi_heads/utils/box_correlation.py:118-122,174-178)
  * img2lidar[v] = inv(lidar2img[v]);  trans[src][dst] = lidar2img[dst] @ img2lidar[src]  (fp64) */
@@ -158,6 +158,13 @@ typedef struct Mv2dLayerWeights {
                                          * every self-attention VALUE row is the bias bv and the attention output is
                                          * this constant for every query, whatever q, k and the mask are.  With it the
                                          * staged decoder skips layer 0's in_proj / attention / out_proj launches. */
+    /* plain (not absorbed) cross-attention projections, used by the key-stationary form of the two-frame head
+     * (xa_form 1): attentions.1.attn.in_proj / out_proj split per role */
+    const float *xa_q_w, *xa_q_b;       /* Wq / sqrt(32), bq / sqrt(32) : [256,256], [256] */
+    const float *xa_k_w, *xa_k_w_lo;    /* Wk as TF32 hi + lo : [256,256] (bk only shifts the logits of a query by a
+                                         * constant, softmax cancels it) */
+    const float *xa_v_w, *xa_v_w_lo;    /* Wv as TF32 hi + lo : [256,256] */
+    const float *xa_o_w, *xa_o_b;       /* Wo [256,256], Wo bv + bo [256] (probabilities sum to one) */
 } Mv2dLayerWeights;
 
 typedef struct Mv2dBranchWeights {      /* stacked over layers: leading dim L */
@@ -196,9 +203,36 @@ typedef struct Mv2dDecoderParams {
     float* outs_dec;            /* out [L,N,256] post-normed intermediates */
     float* workspace;
     size_t workspace_bytes;
+    /* ---- ABI 3 */
+    int layer_begin, layer_end; /* run decoder layers [layer_begin, layer_end) (layer_end 0 = L); the branches run when
+                                 * layer_end reaches L.  The state between calls lives in `workspace`, so a caller can
+                                 * interleave the layers with mv2d_kv_project on another stream. */
+    int xa_form;                /* mode 1 only: 0 = query-stationary absorbed form (streams each query's raw key rows),
+                                 *              1 = key-stationary form over 8x8 cell tiles of projected K / V */
+    int grid_h, grid_w;         /* xa_form 1: the feature grid; num_rows = V * grid_h * grid_w */
+    int reserved3;
+    const float* kp;            /* xa_form 1: [L,num_rows,256] projected keys   from mv2d_kv_project */
+    const float* vp;            /* xa_form 1: [L,num_rows,256] projected values from mv2d_kv_project */
+    void* xa_workspace;         /* xa_form 1: mv2d_xa_tile_workspace_bytes(N, V, grid_h, grid_w) */
+    size_t xa_workspace_bytes;
 } Mv2dDecoderParams;
 MV2D_API size_t mv2d_decoder_workspace_bytes(int N, int L);
+MV2D_API size_t mv2d_xa_tile_workspace_bytes(int N, int V, int grid_h, int grid_w);
 MV2D_API int mv2d_decoder(const Mv2dDecoderParams* p, void* stream);
+
+/* ---- K/V projection of the two-frame head's keys (SURVEY.md 8b "kv_proj"; utils/petr_transformer.py:503-508 ->
+ * torch.nn.MultiheadAttention in_proj on key = memory + pos and value = memory).  For every layer l in
+ * [layer_begin, layer_end):  kp[l] = (kin_hi + kin_lo) (Wk_l)^T,  vp[l] = (mem_hi + mem_lo) (Wv_l)^T  as
+ * error-compensated 3xTF32 tcgen05 GEMMs (fp32-grade).  The operands are the TF32 splits mv2d_split_tf32 makes. */
+typedef struct Mv2dKvParams {
+    int num_rows, L, layer_begin, layer_end;
+    const float *kin_hi, *kin_lo;      /* [num_rows,256] */
+    const float *mem_hi, *mem_lo;      /* [num_rows,256] */
+    const Mv2dLayerWeights* layers;    /* HOST array [L] */
+    float* kp;                         /* out [L,num_rows,256] */
+    float* vp;                         /* out [L,num_rows,256] */
+} Mv2dKvParams;
+MV2D_API int mv2d_kv_project(const Mv2dKvParams* p, void* stream);
 
 /* ---- row a20: denoising queries of the training-mode forward -----------------------------------------------
  * Replaces MV2DSHead.prepare_for_dn (mv2d_s_head.py:39-120, training branch, batch_size 1) plus the way both

@@ -41,6 +41,7 @@ size_t mv2d_sizeof(int which) {
         case 4: return sizeof(Mv2dLayerWeights);
         case 5: return sizeof(Mv2dBranchWeights);
         case 6: return sizeof(Mv2dDnParams);
+        case 7: return sizeof(Mv2dKvParams);
         default: return 0;
     }
 }
@@ -104,6 +105,12 @@ int mv2d_dn_prepare(const Mv2dDnParams* p, void* stream) {
 }
 
 size_t mv2d_decoder_workspace_bytes(int N, int L) { return decoder_workspace_bytes(N, L); }
+size_t mv2d_xa_tile_workspace_bytes(int N, int V, int grid_h, int grid_w) { return xa_tile_workspace_bytes(N, V, grid_h, grid_w); }
+int mv2d_kv_project(const Mv2dKvParams* p, void* stream) {
+    NONNULL(p, "kv_project");
+    MV2D_CHECK_ARG(p->kin_hi && p->kin_lo && p->mem_hi && p->mem_lo && p->layers && p->kp && p->vp, "kv_project: null pointer");
+    return run_kv_project(*p, (cudaStream_t)stream);
+}
 int mv2d_decoder(const Mv2dDecoderParams* p, void* stream) {
     NONNULL(p, "decoder");
     MV2D_CHECK_ARG(p->N == 0 || (p->query_pos && p->ref && p->kin_rows && p->mem_rows && p->cls_scores &&

@@ -882,6 +882,7 @@ head10_kernel(const float* __restrict__ xc, const float* __restrict__ xr, const 
 
 }  // namespace mv2d
 #include "decoder_mega.cuh"
+#include "xa_tile.cuh"
 namespace mv2d {
 
 // ------------------------------------------------------------------------------------------
@@ -927,6 +928,49 @@ size_t decoder_workspace_bytes(int N, int L) {
     return (n * per + 4 * l * n * MV2D_C) * sizeof(float) + 4096;   // + the device-wide barrier word and phase timestamps of the persistent kernel
 }
 
+// ---- key-stationary cross-attention of the two-frame head (xa_tile.cuh): caller-owned scratch
+struct XtWs {
+    int* tile_cnt; uint16_t* tile_q; unsigned long long* tile_mask; short* slot_of; float* qp; float* ctx; float* rec;
+    size_t bytes;
+};
+static XtWs xt_carve(void* base, int N, int ntiles) {
+    XtWs w{};
+    size_t off = 0;
+    auto take = [&](size_t bytes) { void* r = base ? (char*)base + off : nullptr; off += (bytes + 255) & ~(size_t)255; return r; };
+    const size_t n = (size_t)(N > 0 ? N : 1), t = (size_t)(ntiles > 0 ? ntiles : 1);
+    w.tile_cnt = (int*)take(t * sizeof(int));
+    w.tile_q = (uint16_t*)take(t * n * sizeof(uint16_t));
+    w.tile_mask = (unsigned long long*)take(t * n * sizeof(unsigned long long));
+    w.slot_of = (short*)take(t * n * sizeof(short));
+    w.qp = (float*)take(n * MV2D_C * sizeof(float));
+    w.ctx = (float*)take(n * MV2D_C * sizeof(float));
+    w.rec = (float*)take(t * n * XT_REC * sizeof(float));
+    w.bytes = off;
+    return w;
+}
+static int xt_ntiles(int V, int h, int w) { return V * cdiv(h, XT_TS) * cdiv(w, XT_TS); }
+
+size_t xa_tile_workspace_bytes(int N, int V, int h, int w) { return xt_carve(nullptr, N, xt_ntiles(V, h, w)).bytes; }
+
+int run_kv_project(const Mv2dKvParams& p, cudaStream_t st) {
+    const int le = p.layer_end > 0 ? p.layer_end : p.L;
+    MV2D_CHECK_ARG(p.num_rows > 0 && p.L >= 1 && p.L <= MV2D_MAX_LAYERS && p.layer_begin >= 0 && p.layer_begin < le && le <= p.L,
+                   "kv_project: bad num_rows=%d / layers [%d,%d) of %d", p.num_rows, p.layer_begin, le, p.L);
+    const long long RC = (long long)p.num_rows * MV2D_C;
+    for (int l = p.layer_begin; l < le; ++l) {
+        const Mv2dLayerWeights& w = p.layers[l];
+        MV2D_CHECK_ARG(w.xa_k_w && w.xa_k_w_lo && w.xa_v_w && w.xa_v_w_lo, "kv_project: layer %d has no xa_k / xa_v weights", l);
+        int rc;
+        TcGemm t{};
+        t.lda = MV2D_C; t.ldw = MV2D_C; t.ldc = MV2D_C; t.M = p.num_rows; t.N = MV2D_C; t.K = MV2D_C; t.passes = 3; t.nsplit = 1;
+        t.A = p.kin_hi; t.A_lo = p.kin_lo; t.W = w.xa_k_w; t.W_lo = w.xa_k_w_lo; t.C = p.kp + l * RC;
+        if ((rc = launch_gemm_tc(t, st))) return rc;
+        t.A = p.mem_hi; t.A_lo = p.mem_lo; t.W = w.xa_v_w; t.W_lo = w.xa_v_w_lo; t.C = p.vp + l * RC;
+        if ((rc = launch_gemm_tc(t, st))) return rc;
+    }
+    return 0;
+}
+
 int run_decoder(const Mv2dDecoderParams& p, cudaStream_t st) {
     const int N = p.N, L = p.L, C = MV2D_C;
     MV2D_CHECK_ARG(N >= 0 && L >= 1 && L <= MV2D_MAX_LAYERS, "decoder: bad N=%d / L=%d", N, L);
@@ -963,12 +1007,41 @@ int run_decoder(const Mv2dDecoderParams& p, cudaStream_t st) {
     MV2D_CHECK_ARG((size_t)(ws - p.workspace) * sizeof(float) <= p.workspace_bytes, "decoder: workspace too small");
     const long long NC = (long long)N * C;
     cudaError_t e;
+    const int lb = p.layer_begin, le = p.layer_end > 0 ? p.layer_end : L;
+    MV2D_CHECK_ARG(lb >= 0 && lb < le && le <= L, "decoder: bad layer range [%d,%d) of %d", lb, le, L);
+    MV2D_CHECK_ARG(!p.persistent || (lb == 0 && le == L), "decoder: the persistent kernel runs all layers");
+    const bool first = lb == 0, last = le == L;
+    // two-frame head, key-stationary form over 8x8 tiles of projected keys / values (xa_tile.cuh)
+    const bool xt = p.mode == 1 && p.xa_form == 1 && !p.persistent;
+    XtGeom xg{};
+    XtWs xw{};
+    if (xt) {
+        MV2D_CHECK_ARG(p.grid_h > 0 && p.grid_w > 0 && p.num_rows % (p.grid_h * p.grid_w) == 0,
+                       "decoder: xa_form 1 needs the feature grid (num_rows=%d, grid %dx%d)", p.num_rows, p.grid_h, p.grid_w);
+        xg.N = N; xg.h = p.grid_h; xg.w = p.grid_w; xg.V = p.num_rows / (p.grid_h * p.grid_w);
+        xg.tiles_x = cdiv(xg.w, XT_TS); xg.tiles_y = cdiv(xg.h, XT_TS); xg.ntiles = xg.V * xg.tiles_x * xg.tiles_y;
+        MV2D_CHECK_ARG(xg.ntiles <= XT_MERGE_MAXT && N <= 32767, "decoder: xa_form 1 supports <= %d tiles and <= 32767 queries", XT_MERGE_MAXT);
+        MV2D_CHECK_ARG(p.kp && p.vp && p.xa_workspace, "decoder: xa_form 1 needs kp / vp (mv2d_kv_project) and xa_workspace");
+        MV2D_CHECK_ARG(p.mask_words * 32 >= p.num_rows, "decoder: keymask has %d words for %d cells", p.mask_words, p.num_rows);
+        xw = xt_carve(p.xa_workspace, N, xg.ntiles);
+        MV2D_CHECK_ARG(xw.bytes <= p.xa_workspace_bytes, "decoder: xa_workspace too small (%zu < %zu)", p.xa_workspace_bytes, xw.bytes);
+        if ((e = cudaFuncSetAttribute(xt_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XT_SMEM_BYTES)) != cudaSuccess) {
+            set_error("decoder: xt_attn smem attr %s", cudaGetErrorString(e));
+            return (int)e;
+        }
+        if (first) {
+            XtPrepArgs a{}; a.g = xg; a.keymask = p.keymask; a.mask_words = p.mask_words;
+            a.tile_cnt = xw.tile_cnt; a.tile_q = xw.tile_q; a.tile_mask = xw.tile_mask; a.slot_of = xw.slot_of;
+            launch_k(xt_prep_kernel, dim3(xg.ntiles), dim3(256), 0, st, a);
+            MV2D_CHECK_LAUNCH("xt_prep");
+        }
+    }
     // target = 0 ; query + query_pos = query_pos   (cross_attention_head.py:32)
     // The first layer's self-attention sees value = target = 0, so every value row is the bias bv and the attention
     // output is out_proj(bv) + bo for EVERY query whatever the weights/mask: a [256] constant packed once
     // (Mv2dLayerWeights.sa_const).  With it, layer 0 starts at LayerNorm 1 and x / xq are first written by its LN 3.
     const bool fold0 = !p.persistent && p.layers[0].sa_const != nullptr;
-    if (!fold0 &&
+    if (first && !fold0 &&
         ((e = cudaMemsetAsync(x, 0, NC * sizeof(float), st)) != cudaSuccess ||
          (e = cudaMemcpyAsync(xq, p.query_pos, NC * sizeof(float), cudaMemcpyDeviceToDevice, st)) != cudaSuccess)) {
         set_error("decoder: init %s", cudaGetErrorString(e));
@@ -996,7 +1069,7 @@ int run_decoder(const Mv2dDecoderParams& p, cudaStream_t st) {
     }
     if (use_xr) {
         if ((e = cudaFuncSetAttribute(xa_roi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XR_SMEM_BYTES)) != cudaSuccess ||
-            (e = cudaMemsetAsync(xr_ticket, 0, (size_t)N * sizeof(int), st)) != cudaSuccess) {
+            (first && (e = cudaMemsetAsync(xr_ticket, 0, (size_t)N * sizeof(int), st)) != cudaSuccess)) {
             set_error("decoder: xa_roi setup %s", cudaGetErrorString(e));
             return (int)e;
         }
@@ -1065,7 +1138,7 @@ int run_decoder(const Mv2dDecoderParams& p, cudaStream_t st) {
         if (e != cudaSuccess) { set_error("decoder(persistent): launch %s", cudaGetErrorString(e)); return (int)e; }
         return 0;
     }
-    for (int l = 0; l < L; ++l) {
+    for (int l = lb; l < le; ++l) {
         const Mv2dLayerWeights& w = p.layers[l];
         float* inter = p.outs_dec + (long long)l * NC;
         if (l == 0 && fold0) {
@@ -1091,6 +1164,28 @@ int run_decoder(const Mv2dDecoderParams& p, cudaStream_t st) {
                 if ((rc = ln(a, st))) return rc;
             }
         }
+        if (xt) {
+            // --- sparse cross attention, key-stationary: q projection, per-tile partial attention, merge, output projection
+            MV2D_CHECK_ARG(w.xa_q_w && w.xa_q_b && w.xa_o_w && w.xa_o_b, "decoder: layer %d has no xa_q / xa_o weights", l);
+            if ((rc = gemm(x1q, C, w.xa_q_w, C, w.xa_q_b, xw.qp, C, N, C, C, 0, st))) return rc;
+            {
+                XtAttnArgs a{}; a.g = xg; a.q = xw.qp; a.kp = p.kp + (long long)l * p.num_rows * C; a.vp = p.vp + (long long)l * p.num_rows * C;
+                a.tile_cnt = xw.tile_cnt; a.tile_q = xw.tile_q; a.tile_mask = xw.tile_mask; a.rec = xw.rec;
+                static const int qs_env = []() { const char* v = getenv("MV2D_XT_QSPLIT"); return v ? atoi(v) : 0; }();
+                a.qsplit = qs_env > 0 ? qs_env : 2;
+                launch_k(xt_attn_kernel, dim3(xg.ntiles, a.qsplit), dim3(XT_THREADS), (size_t)XT_SMEM_BYTES, st, a);
+                MV2D_CHECK_LAUNCH("xt_attn");
+            }
+            {
+                XtMergeArgs a{}; a.g = xg; a.slot_of = xw.slot_of; a.rec = xw.rec; a.ctx = xw.ctx;
+                launch_k(xt_merge_kernel, dim3(N), dim3(XT_MERGE_THREADS), 0, st, a);
+                MV2D_CHECK_LAUNCH("xt_merge");
+            }
+            if ((rc = gemm(xw.ctx, C, w.xa_o_w, C, nullptr, part, C, N, C, C, 0, st))) return rc;
+            LnArgs a{}; a.partial = part; a.nsplit = 1; a.bias = w.xa_o_b; a.residual = x1;
+            a.gamma = w.ln_g[1]; a.beta = w.ln_b[1]; a.out = x2; a.rows = N; a.out_hi = x2_hi; a.out_lo = x2_lo;
+            if ((rc = ln(a, st))) return rc;
+        } else {
         // --- sparse cross attention (absorbed)
         if ((rc = tc3(x1q_hi, x1q_lo, C, w.ca_q_w, w.ca_q_w_lo, C, w.ca_q_b, qt, nullptr, 2048, N, 2048, C, 0, 1, 0, st))) return rc;
         if (use_xr) {
@@ -1113,6 +1208,7 @@ int run_decoder(const Mv2dDecoderParams& p, cudaStream_t st) {
             a.gamma = w.ln_g[1]; a.beta = w.ln_b[1]; a.out = x2; a.rows = N; a.out_hi = x2_hi; a.out_lo = x2_lo;
             if ((rc = ln(a, st))) return rc;
         }
+        }
         // --- FFN
         if ((rc = tc3(x2_hi, x2_lo, C, w.ffn_w1, w.ffn_w1_lo, C, w.ffn_b1, hdn, hdn_lo, 2048, N, 2048, C,
                       GEMM_RELU | GEMM_SPLIT_OUT, 1, 0, st))) return rc;
@@ -1124,6 +1220,7 @@ int run_decoder(const Mv2dDecoderParams& p, cudaStream_t st) {
             if ((rc = ln(a, st))) return rc;
         }
     }
+    if (!last) return 0;
     // --- branches, batched over layers (cross_attention_head.py:216-231)
     const long long CC = (long long)C * C;
     if ((rc = gemm(p.outs_dec, C, B.cls_w0, C, nullptr, b0, C, N, C, C, 0, st, 1, 0, L, NC, CC, NC, 0))) return rc;

@@ -50,7 +50,7 @@ class HotPath:
     """MV2D-S ('S') / MV2D-T ('T') decoder hot path on one GPU."""
 
     def __init__(self, state_dict, mode='S', device='cuda', cache_sine_branch=False, overlap=True,
-                 persistent_decoder=None, fold_first_self_attn=True, **cfg):
+                 persistent_decoder=None, fold_first_self_attn=True, xa_form=None, **cfg):
         if not torch.cuda.is_available():
             raise RuntimeError('mv2d_b200.HotPath needs a CUDA device (there is no CPU fallback)')
         self.lib = lib.load()
@@ -76,6 +76,14 @@ class HotPath:
             # correct but ~30 % slower than one launch per stage at N = 300, so it is opt-in
             persistent_decoder = os.environ.get('MV2D_DECODER', 'staged') == 'persistent'
         self.persistent_decoder = persistent_decoder
+        if xa_form is None:
+            # two-frame head: 1 = key-stationary cross-attention over projected K/V tiles (csrc/xa_tile.cuh),
+            #                 0 = query-stationary absorbed form (the S head's formulation applied to ~2000 keys/query)
+            xa_form = int(os.environ.get('MV2D_XA_FORM', '1'))
+        self.xa_form = xa_form if (mode == 'T' and not persistent_decoder) else 0
+        self._kv = torch.cuda.Stream(device=self.device)
+        self._ev_pe = torch.cuda.Event()
+        self._ev_kv = [torch.cuda.Event() for _ in range(self.L)]
         self._side = torch.cuda.Stream(device=self.device)
         self._side2 = torch.cuda.Stream(device=self.device)
         self._copy = torch.cuda.Stream(device=self.device)
@@ -197,6 +205,7 @@ class HotPath:
         """PE.forward (utils/pe.py:137-169) -> (pe [V,h,w,256], kin = feat + pe or None).
         phase 1 = the feature-independent part only (feat_nhwc may still be in flight), 2 = the rest."""
         V, h, w = dims if dims is not None else feat_nhwc.shape[:3]
+        self._last_grid = (h, w)
         c, W = self.cfg, self.w
         key, pad_mask, not_mask, _ = self._masks(img_metas, h, w)
         pe = self._get('pe', (V, h, w, 256))
@@ -340,8 +349,37 @@ class HotPath:
         qg2 = dict(qg, query_pos=qpos_all, ref=ref_all)
         return qg2, corr2, T, pad, dict(dn_labels=dn_labels, dn_attn_mask=attn_mask, dn_ref=ref_all[:pad])
 
-    def decoder(self, qg, corr, kin_rows, mem_rows, N, vel_dt=0.0, self_attn_mask=None, vel_row_start=0):
+    def kv_project(self, kin_rows, mem_rows, record_events=False):
+        """Two-frame head, xa_form 1: K_l = (mem + pos) Wk_l^T and V_l = mem Wv_l^T for every decoder layer
+        (3xTF32 tcgen05 GEMMs over all V*h*w cells), on the current stream.  With record_events the per-layer
+        events ``_ev_kv[l]`` are recorded so the decoder layers on another stream can start as soon as their
+        projection is done."""
+        L, R = self.L, kin_rows.shape[0]
+        n = R * 256
+        kin_hi, kin_lo = self._get('kin_hi', (R, 256)), self._get('kin_lo', (R, 256))
+        mem_hi, mem_lo = self._get('mem_hi', (R, 256)), self._get('mem_lo', (R, 256))
+        kp, vp = self._get('kp', (L, R, 256)), self._get('vp', (L, R, 256))
+        st = lib.stream_ptr()
+        lib.check(self.lib.mv2d_split_tf32(kin_rows.data_ptr(), kin_hi.data_ptr(), kin_lo.data_ptr(), n, st), 'mv2d_split_tf32')
+        lib.check(self.lib.mv2d_split_tf32(mem_rows.data_ptr(), mem_hi.data_ptr(), mem_lo.data_ptr(), n, st), 'mv2d_split_tf32')
+        p = lib.KvParams()
+        p.num_rows, p.L = R, L
+        p.kin_hi, p.kin_lo, p.mem_hi, p.mem_lo = kin_hi.data_ptr(), kin_lo.data_ptr(), mem_hi.data_ptr(), mem_lo.data_ptr()
+        p.layers = self.w.layers_ptr()
+        p.kp, p.vp = kp.data_ptr(), vp.data_ptr()
+        for l in range(L):
+            p.layer_begin, p.layer_end = l, l + 1
+            lib.check(self.lib.mv2d_kv_project(C.byref(p), st), 'mv2d_kv_project')
+            if record_events:
+                self._ev_kv[l].record(torch.cuda.current_stream())
+        return kp, vp
+
+    def decoder(self, qg, corr, kin_rows, mem_rows, N, vel_dt=0.0, self_attn_mask=None, vel_row_start=0,
+                kv=None, grid=None, wait_kv_events=False):
         c, W, L = self.cfg, self.w, self.L
+        if self.xa_form == 1 and kv is None:    # stage-level call: project on this stream, then decode
+            grid = grid or self._last_grid
+            kv = self.kv_project(kin_rows, mem_rows)
         cls = self._get('cls_scores', (L, N, 10))
         box = self._get('bbox_preds', (L, N, 10))
         outs = self._get('outs_dec', (L, N, 256))
@@ -366,7 +404,21 @@ class HotPath:
         p.layers, p.branches = W.layers_ptr(), W.branches_ptr()
         p.cls_scores, p.bbox_preds, p.outs_dec = cls.data_ptr(), box.data_ptr(), outs.data_ptr()
         p.workspace, p.workspace_bytes = ws.data_ptr(), ws_bytes
-        lib.check(self.lib.mv2d_decoder(C.byref(p), lib.stream_ptr()), 'mv2d_decoder')
+        if kv is not None:      # two-frame head, key-stationary cross-attention over the projected K/V
+            V = kin_rows.shape[0] // (grid[0] * grid[1])
+            xa_bytes = self.lib.mv2d_xa_tile_workspace_bytes(N, V, grid[0], grid[1])
+            xa_ws = self._get('xa_ws', (xa_bytes,), torch.uint8)
+            p.xa_form, p.grid_h, p.grid_w = 1, grid[0], grid[1]
+            p.kp, p.vp = kv[0].data_ptr(), kv[1].data_ptr()
+            p.xa_workspace, p.xa_workspace_bytes = xa_ws.data_ptr(), xa_bytes
+        if kv is not None and wait_kv_events:
+            main = torch.cuda.current_stream()
+            for l in range(L):          # layer l starts when its projection (on the kv stream) is done
+                main.wait_event(self._ev_kv[l])
+                p.layer_begin, p.layer_end = l, l + 1
+                lib.check(self.lib.mv2d_decoder(C.byref(p), lib.stream_ptr()), 'mv2d_decoder')
+        else:
+            lib.check(self.lib.mv2d_decoder(C.byref(p), lib.stream_ptr()), 'mv2d_decoder')
         return cls, box, outs
 
     # ------------------------------------------------------------------ whole path
@@ -411,6 +463,12 @@ class HotPath:
                 corr = self.box_corr(rois, roi_start, trans, N, V, img_metas, h, w)
                 self._ev_join2.record(self._side2)
             pe, kin = self.pe3d(feat, i2l, img_metas, feat_tf32, phase=pe_phase)
+            if self.xa_form == 1:
+                # K/V projections of all layers on their own stream; decoder layer l waits for projection l only
+                self._ev_pe.record(main)
+                with torch.cuda.stream(self._kv):
+                    self._kv.wait_event(self._ev_pe)
+                    kv = self.kv_project(kin.view(-1, 256), feat.view(-1, 256), record_events=True)
             main.wait_event(self._ev_join)
             main.wait_event(self._ev_join2)
             if self.mode == 'S':
@@ -419,6 +477,8 @@ class HotPath:
             pe, kin = self.pe3d(feat, i2l, img_metas, feat_tf32, phase=pe_phase)
             qg = self.roi_align_qg(rois, cams, feat, pe, N)
             corr = self.box_corr(rois, roi_start, trans, N, V, img_metas, h, w)
+            if self.xa_form == 1:
+                kv = self.kv_project(kin.view(-1, 256), feat.view(-1, 256))
         qg_d, corr_d, T, pad, extra, sa_mask = qg, corr, N, 0, {}, None
         if dn is not None:      # training-mode forward: denoising queries are prepended (row a20)
             qg_d, corr_d, T, pad, extra = self.dn_prepare(qg, corr, N, dn)
@@ -428,7 +488,9 @@ class HotPath:
                                           self_attn_mask=sa_mask)
         else:
             cls, box, outs = self.decoder(qg_d, corr_d, kin.view(-1, 256), feat.view(-1, 256), T,
-                                          vel_dt=self._vel_dt(img_metas), self_attn_mask=sa_mask, vel_row_start=pad)
+                                          vel_dt=self._vel_dt(img_metas), self_attn_mask=sa_mask, vel_row_start=pad,
+                                          kv=kv if self.xa_form == 1 else None, grid=(h, w),
+                                          wait_kv_events=self.xa_form == 1 and self.overlap)
         out = dict(cls_scores=cls[:, pad:], bbox_preds=box[:, pad:], outs_dec=outs[:, pad:], rois=rois, pe=pe,
                    feat_nhwc=feat, N=N, num_per_view=counts)
         out.update(qg)

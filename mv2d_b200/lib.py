@@ -9,7 +9,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'lib', 'libmv2d_b200.so')
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_LAYERS = 8
 
 c_f = C.c_void_p  # device pointers travel as integers (tensor.data_ptr())
@@ -64,6 +64,8 @@ class LayerWeights(C.Structure):
         ('ca_q_w', c_f), ('ca_q_w_lo', c_f), ('ca_q_b', c_f), ('ca_o_w', c_f), ('ca_o_w_lo', c_f), ('ca_o_b', c_f),
         ('ffn_w1', c_f), ('ffn_w1_lo', c_f), ('ffn_b1', c_f), ('ffn_w2', c_f), ('ffn_w2_lo', c_f), ('ffn_b2', c_f),
         ('ln_g', c_f * 3), ('ln_b', c_f * 3), ('sa_const', c_f),
+        ('xa_q_w', c_f), ('xa_q_b', c_f), ('xa_k_w', c_f), ('xa_k_w_lo', c_f), ('xa_v_w', c_f), ('xa_v_w_lo', c_f),
+        ('xa_o_w', c_f), ('xa_o_b', c_f),
     ]
 
 
@@ -90,6 +92,17 @@ class DecoderParams(C.Structure):
         ('layers', C.POINTER(LayerWeights)), ('branches', C.POINTER(BranchWeights)),
         ('cls_scores', c_f), ('bbox_preds', c_f), ('outs_dec', c_f),
         ('workspace', c_f), ('workspace_bytes', C.c_size_t),
+        ('layer_begin', C.c_int), ('layer_end', C.c_int), ('xa_form', C.c_int), ('grid_h', C.c_int),
+        ('grid_w', C.c_int), ('reserved3', C.c_int),
+        ('kp', c_f), ('vp', c_f), ('xa_workspace', c_f), ('xa_workspace_bytes', C.c_size_t),
+    ]
+
+
+class KvParams(C.Structure):
+    _fields_ = [
+        ('num_rows', C.c_int), ('L', C.c_int), ('layer_begin', C.c_int), ('layer_end', C.c_int),
+        ('kin_hi', c_f), ('kin_lo', c_f), ('mem_hi', c_f), ('mem_lo', c_f),
+        ('layers', C.POINTER(LayerWeights)), ('kp', c_f), ('vp', c_f),
     ]
 
 
@@ -110,7 +123,7 @@ class DnParams(C.Structure):
     ]
 
 
-_STRUCTS = [PeParams, QgParams, CorrParams, DecoderParams, LayerWeights, BranchWeights, DnParams]
+_STRUCTS = [PeParams, QgParams, CorrParams, DecoderParams, LayerWeights, BranchWeights, DnParams, KvParams]
 
 # every symbol include/mv2d_b200.h declares: (name, restype, argtypes)
 SYMBOLS = [
@@ -132,6 +145,8 @@ SYMBOLS = [
     ('mv2d_dn_prepare', C.c_int, [C.POINTER(DnParams), c_f]),
     ('mv2d_decoder_workspace_bytes', C.c_size_t, [C.c_int, C.c_int]),
     ('mv2d_decoder', C.c_int, [C.POINTER(DecoderParams), c_f]),
+    ('mv2d_xa_tile_workspace_bytes', C.c_size_t, [C.c_int] * 4),
+    ('mv2d_kv_project', C.c_int, [C.POINTER(KvParams), c_f]),
     ('mv2d_gemm', C.c_int, [c_f, C.c_int, c_f, C.c_int, c_f, c_f, C.c_int, C.c_int, C.c_int, C.c_int,
                             C.c_int, c_f]),
     ('mv2d_debug_clock_probe', C.c_int, [C.c_longlong, c_f, c_f]),

@@ -50,6 +50,18 @@ def absorb_cross_attention(in_w, in_b, out_w, out_b):
     return ca_q_w.float(), ca_q_b.float(), ca_o_w.float(), ca_o_b.float()
 
 
+def plain_cross_attention(in_w, in_b, out_w, out_b):
+    """Per-role cross-attention projections for the key-stationary kernel: the 1/sqrt(head_dim) scale is
+    folded into the query side, the key bias is dropped (it shifts all logits of a (query, head) by the same
+    amount) and the value bias moves behind the softmax: out = Wo ctx + (Wo bv + bo).  fp64, rounded once."""
+    in_w, in_b, out_w, out_b = [t.detach().double().cpu() for t in (in_w, in_b, out_w, out_b)]
+    scale = 1.0 / math.sqrt(HD)
+    wq, wk, wv = in_w[:EMBED], in_w[EMBED:2 * EMBED], in_w[2 * EMBED:]
+    bq, bv = in_b[:EMBED], in_b[2 * EMBED:]
+    return ((scale * wq).float(), (scale * bq).float(), wk.float(), wv.float(), out_w.float(),
+            (out_w @ bv + out_b).float())
+
+
 def first_layer_self_attn_const(in_proj_bias, out_w, out_b):
     """Self-attention output of decoder layer 0.  The target starts at zero (cross_attention_head.py:32,
     ``target = torch.zeros_like(query_embed)``), value = target, so every value row equals the value bias bv;
@@ -131,6 +143,18 @@ class PackedWeights:
                 hi, lo = split_tf32(mat)     # 3xTF32 tcgen05 operands
                 setattr(lw, field, put(f'l{l}.{field}', hi).data_ptr())
                 setattr(lw, field + '_lo', put(f'l{l}.{field}_lo', lo).data_ptr())
+            # plain projections for the key-stationary form of the two-frame head (xa_tile.cuh)
+            xq_w, xq_b, xk_w, xv_w, xo_w, xo_b = plain_cross_attention(
+                sd[p + 'attentions.1.attn.in_proj_weight'], sd[p + 'attentions.1.attn.in_proj_bias'],
+                sd[p + 'attentions.1.attn.out_proj.weight'], sd[p + 'attentions.1.attn.out_proj.bias'])
+            lw.xa_q_w = put(f'l{l}.xa_q_w', xq_w).data_ptr()
+            lw.xa_q_b = put(f'l{l}.xa_q_b', xq_b).data_ptr()
+            for field, mat in (('xa_k_w', xk_w), ('xa_v_w', xv_w)):
+                hi, lo = split_tf32(mat)
+                setattr(lw, field, put(f'l{l}.{field}', hi).data_ptr())
+                setattr(lw, field + '_lo', put(f'l{l}.{field}_lo', lo).data_ptr())
+            lw.xa_o_w = put(f'l{l}.xa_o_w', xo_w).data_ptr()
+            lw.xa_o_b = put(f'l{l}.xa_o_b', xo_b).data_ptr()
             lw.ca_q_b = put(f'l{l}.ca_q_b', qb).data_ptr()
             lw.ca_o_b = put(f'l{l}.ca_o_b', ob).data_ptr()
             lw.ffn_b1 = put(f'l{l}.ffn_b1', sd[p + 'ffns.0.layers.0.0.bias']).data_ptr()

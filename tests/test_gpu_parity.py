@@ -306,3 +306,23 @@ def test_full_size_properties(state_dicts):
     assert torch.equal(c1, o4['cls_scores']) and torch.equal(b1, o4['bbox_preds']), 'graph replay differs'
     # every query attends at least to its own RoI
     assert int(o1['match_cnt'].min()) >= 1 and bool((o1['match'][:, 0].cpu() == torch.arange(300)).all())
+
+
+@pytest.mark.parametrize('name', ['t_small', 't_cfg3', 't_pad'])
+def test_two_frame_query_stationary_form_matches_golden(name, state_dicts):
+    """xa_form 0 (every query streams its own raw key rows, absorbed projections) stays available beside the
+    default key-stationary form (xa_form 1, projected K/V tiles); both must meet the gate, and agree closely."""
+    from mv2d_b200.engine import HotPath
+    spec, g = load_golden(name)
+    feat, boxes, metas = synth.case_inputs(spec)
+    outs = {}
+    for form in (0, 1):
+        eng = HotPath(state_dicts(spec['num_layers']), mode='T', xa_form=form)
+        assert eng.xa_form == form
+        out = eng.forward(feat.cuda(), [b.cuda() for b in boxes], metas)
+        torch.cuda.synchronize()
+        assert_close(out['cls_scores'], g['cls_scores'], what=f'cls_scores (xa_form {form})')
+        assert_close(out['bbox_preds'], g['bbox_preds'], what=f'bbox_preds (xa_form {form})')
+        outs[form] = (out['cls_scores'].clone(), out['bbox_preds'].clone())
+    assert_close(outs[1][0], outs[0][0], 2e-4, 2e-4, 'cls_scores form 1 vs form 0')
+    assert_close(outs[1][1], outs[0][1], 2e-4, 2e-4, 'bbox_preds form 1 vs form 0')
