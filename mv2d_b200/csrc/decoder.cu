@@ -42,13 +42,21 @@ __device__ __forceinline__ void ln_body(const LnArgs& a, int vb) {
     const long long o = (long long)row * MV2D_C;
     const long long oi = a.bcast_in ? 0 : o;
     float v[8];
+    // all loads of the row (up to 8 split-K partials x 2 halves) are issued before the first add: one memory
+    // latency per row instead of one per partial
+    float4 pt[2][8];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (k < a.nsplit) pt[i][k] = *reinterpret_cast<const float4*>(a.partial + k * a.split_stride + oi + i * 128 + lane * 4);
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
         const int c = i * 128 + lane * 4;
-        float4 s = *reinterpret_cast<const float4*>(a.partial + oi + c);
-        for (int k = 1; k < a.nsplit; ++k) {
-            float4 t = *reinterpret_cast<const float4*>(a.partial + k * a.split_stride + oi + c);
-            s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+        float4 s = pt[i][0];
+#pragma unroll
+        for (int k = 1; k < 8; ++k) {
+            if (k < a.nsplit) { s.x += pt[i][k].x; s.y += pt[i][k].y; s.z += pt[i][k].z; s.w += pt[i][k].w; }
         }
         if (a.bias) {
             float4 t = __ldg(reinterpret_cast<const float4*>(a.bias + grp * a.group_stride + c));
@@ -909,6 +917,7 @@ static int tc3(const float* A_hi, const float* A_lo, int lda, const float* W_hi,
 
 static int ln(const LnArgs& a, cudaStream_t st) {
     if (a.rows == 0) return 0;
+    MV2D_CHECK_ARG(a.nsplit >= 1 && a.nsplit <= 8, "ln: nsplit=%d must be in [1,8]", a.nsplit);
     launch_k(ln_kernel, dim3(cdiv(a.rows, 8)), dim3(256), 0, st, a);
     MV2D_CHECK_LAUNCH("ln");
     return 0;
@@ -930,7 +939,8 @@ size_t decoder_workspace_bytes(int N, int L) {
 
 // ---- key-stationary cross-attention of the two-frame head (xa_tile.cuh): caller-owned scratch
 struct XtWs {
-    int* tile_cnt; uint16_t* tile_q; unsigned long long* tile_mask; short* slot_of; float* qp; float* ctx; float* rec;
+    int* tile_cnt; int* tile_work; int* order; uint16_t* tile_q; unsigned long long* tile_mask; short* slot_of;
+    int* qlist; int* qcnt; float* qp; float* ctx; float* rec;
     size_t bytes;
 };
 static XtWs xt_carve(void* base, int N, int ntiles) {
@@ -939,6 +949,10 @@ static XtWs xt_carve(void* base, int N, int ntiles) {
     auto take = [&](size_t bytes) { void* r = base ? (char*)base + off : nullptr; off += (bytes + 255) & ~(size_t)255; return r; };
     const size_t n = (size_t)(N > 0 ? N : 1), t = (size_t)(ntiles > 0 ? ntiles : 1);
     w.tile_cnt = (int*)take(t * sizeof(int));
+    w.tile_work = (int*)take(t * sizeof(int));
+    w.order = (int*)take(t * sizeof(int));
+    w.qlist = (int*)take(t * n * sizeof(int));
+    w.qcnt = (int*)take(n * sizeof(int));
     w.tile_q = (uint16_t*)take(t * n * sizeof(uint16_t));
     w.tile_mask = (unsigned long long*)take(t * n * sizeof(unsigned long long));
     w.slot_of = (short*)take(t * n * sizeof(short));
@@ -1025,15 +1039,21 @@ int run_decoder(const Mv2dDecoderParams& p, cudaStream_t st) {
         MV2D_CHECK_ARG(p.mask_words * 32 >= p.num_rows, "decoder: keymask has %d words for %d cells", p.mask_words, p.num_rows);
         xw = xt_carve(p.xa_workspace, N, xg.ntiles);
         MV2D_CHECK_ARG(xw.bytes <= p.xa_workspace_bytes, "decoder: xa_workspace too small (%zu < %zu)", p.xa_workspace_bytes, xw.bytes);
-        if ((e = cudaFuncSetAttribute(xt_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XT_SMEM_BYTES)) != cudaSuccess) {
+        if ((e = cudaFuncSetAttribute(xt_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XT_SMEM_BYTES)) != cudaSuccess ||
+            (e = cudaFuncSetAttribute(xt_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, XT_MERGE_MAXT * 36)) != cudaSuccess) {
             set_error("decoder: xt_attn smem attr %s", cudaGetErrorString(e));
             return (int)e;
         }
         if (first) {
             XtPrepArgs a{}; a.g = xg; a.keymask = p.keymask; a.mask_words = p.mask_words;
             a.tile_cnt = xw.tile_cnt; a.tile_q = xw.tile_q; a.tile_mask = xw.tile_mask; a.slot_of = xw.slot_of;
+            a.tile_work = xw.tile_work;
             launch_k(xt_prep_kernel, dim3(xg.ntiles), dim3(256), 0, st, a);
             MV2D_CHECK_LAUNCH("xt_prep");
+            XtListArgs b{}; b.g = xg; b.slot_of = xw.slot_of; b.tile_work = xw.tile_work; b.qlist = xw.qlist; b.qcnt = xw.qcnt;
+            b.order = xw.order;
+            launch_k(xt_list_kernel, dim3(N + 1), dim3(256), 0, st, b);
+            MV2D_CHECK_LAUNCH("xt_list");
         }
     }
     // target = 0 ; query + query_pos = query_pos   (cross_attention_head.py:32)
@@ -1170,15 +1190,15 @@ int run_decoder(const Mv2dDecoderParams& p, cudaStream_t st) {
             if ((rc = gemm(x1q, C, w.xa_q_w, C, w.xa_q_b, xw.qp, C, N, C, C, 0, st))) return rc;
             {
                 XtAttnArgs a{}; a.g = xg; a.q = xw.qp; a.kp = p.kp + (long long)l * p.num_rows * C; a.vp = p.vp + (long long)l * p.num_rows * C;
-                a.tile_cnt = xw.tile_cnt; a.tile_q = xw.tile_q; a.tile_mask = xw.tile_mask; a.rec = xw.rec;
+                a.tile_cnt = xw.tile_cnt; a.tile_q = xw.tile_q; a.tile_mask = xw.tile_mask; a.rec = xw.rec; a.order = xw.order;
                 static const int qs_env = []() { const char* v = getenv("MV2D_XT_QSPLIT"); return v ? atoi(v) : 0; }();
-                a.qsplit = qs_env > 0 ? qs_env : 2;
+                a.qsplit = qs_env > 0 ? qs_env : 1;
                 launch_k(xt_attn_kernel, dim3(xg.ntiles, a.qsplit), dim3(XT_THREADS), (size_t)XT_SMEM_BYTES, st, a);
                 MV2D_CHECK_LAUNCH("xt_attn");
             }
             {
-                XtMergeArgs a{}; a.g = xg; a.slot_of = xw.slot_of; a.rec = xw.rec; a.ctx = xw.ctx;
-                launch_k(xt_merge_kernel, dim3(N), dim3(XT_MERGE_THREADS), 0, st, a);
+                XtMergeArgs a{}; a.g = xg; a.qlist = xw.qlist; a.qcnt = xw.qcnt; a.rec = xw.rec; a.ctx = xw.ctx;
+                launch_k(xt_merge_kernel, dim3(N), dim3(XT_MERGE_THREADS), (size_t)xg.ntiles * 36, st, a);
                 MV2D_CHECK_LAUNCH("xt_merge");
             }
             if ((rc = gemm(xw.ctx, C, w.xa_o_w, C, nullptr, part, C, N, C, C, 0, st))) return rc;

@@ -23,8 +23,8 @@ namespace mv2d {
 #define XT_TS 8                        // tile side, cells
 #define XT_KEYS (XT_TS * XT_TS)
 #define XT_REC 272                     // floats per record: acc[256], m[8], l[8]
-#define XT_THREADS 256
-#define XT_SMEM_BYTES (2 * XT_KEYS * MV2D_C * 4 + (XT_THREADS / 32) * XT_KEYS * 8 * 4 + 64)
+#define XT_THREADS 512
+#define XT_SMEM_BYTES (2 * XT_KEYS * MV2D_C * 4 + (XT_THREADS / 32) * XT_KEYS * 8 * 4 + (XT_THREADS / 32) * 80 + 64)
 
 struct XtGeom {
     int N, V, h, w, tiles_x, tiles_y, ntiles;
@@ -37,6 +37,7 @@ struct XtPrepArgs {
     uint16_t* tile_q;                  // [ntiles, N] queries with a key in the tile, ascending
     unsigned long long* tile_mask;     // [ntiles, N] their 64-bit key masks (bit r*8+c = cell (ty*8+r, tx*8+c))
     short* slot_of;                    // [N, ntiles] position of the query in the tile's list, -1 = none
+    int* tile_work;                    // [ntiles] sum over the tile's queries of their key counts
 };
 
 // grid = ntiles, 256 threads
@@ -47,7 +48,9 @@ __global__ void __launch_bounds__(256) xt_prep_kernel(XtPrepArgs a) {
     const int tx = t % a.g.tiles_x, ty = (t / a.g.tiles_x) % a.g.tiles_y, v = t / (a.g.tiles_x * a.g.tiles_y);
     const int ncols = min(XT_TS, a.g.w - tx * XT_TS);
     __shared__ int wsum[8];
-    int running = 0;
+    __shared__ int work_s;
+    if (tid == 0) work_s = 0;
+    int running = 0, work = 0;
     for (int base = 0; base < a.g.N; base += 256) {
         const int n = base + tid;
         unsigned long long m64 = 0ull;
@@ -67,6 +70,7 @@ __global__ void __launch_bounds__(256) xt_prep_kernel(XtPrepArgs a) {
             }
         }
         const bool active = m64 != 0ull;
+        work += __popcll(m64);
         const unsigned bal = __ballot_sync(0xffffffffu, active);
         if (lane == 0) wsum[warp] = __popc(bal);
         __syncthreads();
@@ -84,7 +88,72 @@ __global__ void __launch_bounds__(256) xt_prep_kernel(XtPrepArgs a) {
         running += total;
         __syncthreads();
     }
-    if (tid == 0) a.tile_cnt[t] = running;
+    work = __reduce_add_sync(0xffffffffu, work);
+    if (lane == 0) atomicAdd(&work_s, work);
+    __syncthreads();
+    if (tid == 0) { a.tile_cnt[t] = running; a.tile_work[t] = work_s; }
+}
+
+// ---- per-query record lists and a heaviest-first tile order, built once per sample
+struct XtListArgs {
+    XtGeom g;
+    const short* slot_of;              // [N, ntiles]
+    const int* tile_work;              // [ntiles] keys x queries of the tile
+    int* qlist;                        // [N, ntiles] record ids (tile * N + slot) of the query, ascending tile order
+    int* qcnt;                         // [N]
+    int* order;                        // [ntiles] tiles sorted by work, heaviest first (ties: lower id first)
+};
+
+// grid = N + 1, 256 threads.  Blocks 0..N-1: ordered compaction of slot_of[n, :]; block N: the tile order.
+__global__ void __launch_bounds__(256) xt_list_kernel(XtListArgs a) {
+    pdl_wait();
+    pdl_trigger();
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nt = a.g.ntiles;
+    if ((int)blockIdx.x == a.g.N) {
+        // rank by counting: ntiles <= 2048, so this is at most 4M comparisons for one CTA, once per sample
+        for (int t = tid; t < nt; t += 256) {
+            const int w = a.tile_work[t];
+            int rank = 0;
+            for (int u = 0; u < nt; ++u) {
+                const int x = __ldg(a.tile_work + u);
+                rank += (x > w) || (x == w && u < t);
+            }
+            a.order[rank] = t;
+        }
+        return;
+    }
+    const int n = blockIdx.x;
+    __shared__ int chunk_cnt[64];      // ntiles <= 2048 => <= 64 chunks of 32
+    const int nchunks = (nt + 31) >> 5;
+    int sv[8];
+    unsigned bal[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const int c = warp + u * 8;
+        sv[u] = -1; bal[u] = 0u;
+        if (c < nchunks) {
+            const int t = c * 32 + lane;
+            sv[u] = t < nt ? (int)a.slot_of[(long long)n * nt + t] : -1;
+            bal[u] = __ballot_sync(0xffffffffu, sv[u] >= 0);
+            if (lane == 0) chunk_cnt[c] = __popc(bal[u]);
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const int c = warp + u * 8;
+        if (c < nchunks) {
+            int base = 0;
+            for (int i = 0; i < c; ++i) base += chunk_cnt[i];
+            if (sv[u] >= 0) a.qlist[(long long)n * nt + base + __popc(bal[u] & ((1u << lane) - 1u))] = (c * 32 + lane) * a.g.N + sv[u];
+        }
+    }
+    if (tid == 0) {
+        int tot = 0;
+        for (int i = 0; i < nchunks; ++i) tot += chunk_cnt[i];
+        a.qcnt[n] = tot;
+    }
 }
 
 struct XtAttnArgs {
@@ -92,19 +161,15 @@ struct XtAttnArgs {
     const float* q;                    // [N,256] projected queries, 1/sqrt(32) folded in
     const float* kp; const float* vp;  // [V*h*w,256] projected keys / values of this layer
     const int* tile_cnt; const uint16_t* tile_q; const unsigned long long* tile_mask;
+    const int* order;                  // [ntiles] heaviest tile first
     float* rec;                        // [ntiles*N, XT_REC]
     int qsplit;                        // gridDim.y: the tile's query list is dealt round-robin to this many CTAs
 };
 
-// transpose-reduce 8 per-lane partials over the 8 lanes of a head group: 7 shuffles instead of 24.
-// result: lane holds in v[0] the full sum of index (lane & 7).
-__device__ __forceinline__ void reduce8_in8(float (&v)[8], int lane) {
-    const bool up4 = lane & 4, up2 = lane & 2, up1 = lane & 1;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const float send = up4 ? v[i] : v[i + 4], keep = up4 ? v[i + 4] : v[i];
-        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-    }
+// transpose-reduce 4 per-lane partials over the 4 lanes of a head: 3 shuffles instead of 8.
+// result: lane holds in v[0] the full sum of index (lane & 3).
+__device__ __forceinline__ void reduce4_in4(float (&v)[4], int lane) {
+    const bool up2 = lane & 2, up1 = lane & 1;
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
         const float send = up2 ? v[i] : v[i + 2], keep = up2 ? v[i + 2] : v[i];
@@ -116,19 +181,31 @@ __device__ __forceinline__ void reduce8_in8(float (&v)[8], int lane) {
 
 __device__ __forceinline__ uint32_t xt_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-// grid = (ntiles, qsplit), 256 threads, XT_SMEM_BYTES dynamic shared memory
+__device__ __forceinline__ void xt_wait(uint64_t* bar) {
+    uint32_t done = 0;
+    while (!done)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(xt_smem_u32(bar)) : "memory");
+}
+
+// grid = (ntiles, qsplit), XT_THREADS threads, XT_SMEM_BYTES dynamic shared memory.
+// Lane layout: lane = 4*head + part; the lane owns two 4-channel chunks of its head's 32 channels of q, of every K / V
+// row and of the accumulator (two conflict-free LDS.128 per row).  A logit is the sum of 4 lanes' partial dots; four keys are reduced
+// together with a 3-shuffle transpose, which leaves the logit of (head, key 4*grp + part) in lane 4*head + part -- the
+// softmax statistics of a head therefore live in the registers of its 4 lanes.
 __global__ void __launch_bounds__(XT_THREADS, 1) xt_attn_kernel(XtAttnArgs a) {
     pdl_wait();
     pdl_trigger();
-    const int t = blockIdx.x;
+    const int t = a.order[blockIdx.x];
     const int cnt = a.tile_cnt[t];
     constexpr int NW = XT_THREADS / 32;
     if ((int)blockIdx.y * NW >= cnt) return;
     extern __shared__ __align__(128) unsigned char xt_smem[];
     float* Ks = reinterpret_cast<float*>(xt_smem);
     float* Vs = Ks + XT_KEYS * MV2D_C;
-    float* scb = Vs + XT_KEYS * MV2D_C;                          // [NW][64 slots][8 heads]
-    uint64_t* bar = reinterpret_cast<uint64_t*>(scb + NW * XT_KEYS * 8);
+    float* scb = Vs + XT_KEYS * MV2D_C;                          // [NW][64 slots][8 heads] probabilities
+    unsigned char* klb = reinterpret_cast<unsigned char*>(scb + NW * XT_KEYS * 8);   // [NW][80] key ids of the query
+    uint64_t* bar = reinterpret_cast<uint64_t*>(klb + NW * 80);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int tx = t % a.g.tiles_x, ty = (t / a.g.tiles_x) % a.g.tiles_y, v = t / (a.g.tiles_x * a.g.tiles_y);
     const int ncols = min(XT_TS, a.g.w - tx * XT_TS), nrows = min(XT_TS, a.g.h - ty * XT_TS);
@@ -147,180 +224,200 @@ __global__ void __launch_bounds__(XT_THREADS, 1) xt_attn_kernel(XtAttnArgs a) {
     }
     __syncthreads();            // barrier initialised before anyone polls it
     float* sc = scb + warp * XT_KEYS * 8;
+    unsigned char* kl = klb + warp * 80;
+    const uint32_t* kl4 = reinterpret_cast<const uint32_t*>(kl);
     bool waited = false;
+    // the lane's two 16-byte chunks of its head's 128-byte slice: chunks (part, part+4), swapped for odd heads so that
+    // the 8 lanes of a quarter warp cover all 32 banks in each of the two LDS.128
+    const int hd = lane >> 2, part = lane & 3;
+    const int offA = hd * 32 + ((part + 4 * (hd & 1)) & 7) * 4, offB = hd * 32 + (((part + 4 * (hd & 1)) & 7) ^ 4) * 4;
     const int step = a.qsplit * NW;
     int i = blockIdx.y * NW + warp;
     // software pipeline: the next query's list entry and q slice are in flight while this one is processed
-    int n_nx = 0; unsigned long long m_nx = 0ull; float4 q0_nx = make_float4(0.f, 0.f, 0.f, 0.f), q1_nx = q0_nx;
+    int n_nx = 0; unsigned long long m_nx = 0ull; float4 qa_nx = make_float4(0.f, 0.f, 0.f, 0.f), qb_nx = qa_nx;
     auto fetch = [&](int ii) {
         n_nx = a.tile_q[(long long)t * a.g.N + ii];
         m_nx = a.tile_mask[(long long)t * a.g.N + ii];
-        q0_nx = __ldg(reinterpret_cast<const float4*>(a.q + (long long)n_nx * MV2D_C + lane * 4));
-        q1_nx = __ldg(reinterpret_cast<const float4*>(a.q + (long long)n_nx * MV2D_C + 128 + lane * 4));
+        qa_nx = __ldg(reinterpret_cast<const float4*>(a.q + (long long)n_nx * MV2D_C + offA));
+        qb_nx = __ldg(reinterpret_cast<const float4*>(a.q + (long long)n_nx * MV2D_C + offB));
     };
     if (i < cnt) fetch(i);
     for (; i < cnt; i += step) {
-        // this lane's slice of q: channels 4*lane..+3 (head lane>>3) and 128+4*lane..+3 (head 4+(lane>>3))
         const unsigned long long m64 = m_nx;
-        const float4 q0 = q0_nx, q1 = q1_nx;
-        const int nk = __popcll(m64);
+        const float4 qa = qa_nx, qb = qb_nx;
+        const unsigned mlo = (unsigned)m64, mhi = (unsigned)(m64 >> 32);
+        const int nlo = __popc(mlo), nk = nlo + __popc(mhi);
         if (i + step < cnt) fetch(i + step);
-        if (!waited) {
-            uint32_t done = 0;
-            while (!done)
-                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                             : "=r"(done) : "r"(xt_smem_u32(bar)) : "memory");
-            waited = true;
+        // ---- key ids of the query, ascending, padded with the first key up to the next multiple of 8
+        __syncwarp();           // the previous query's loops are done with kl / sc
+        {
+            const unsigned lt = (1u << lane) - 1u;
+            if ((mlo >> lane) & 1u) kl[__popc(mlo & lt)] = (unsigned char)lane;
+            if ((mhi >> lane) & 1u) kl[nlo + __popc(mhi & lt)] = (unsigned char)(32 + lane);
+            if (lane < 8) kl[nk + lane] = (unsigned char)(mlo ? __ffs(mlo) - 1 : 31 + __ffs(mhi));
         }
-        // ---- logits of the query's keys in this tile, 8 keys per step
-        unsigned long long mm = m64;
-        for (int s0 = 0; s0 < nk; s0 += 8) {
-            float p0[8], p1[8];
+        __syncwarp();
+        if (!waited) { xt_wait(bar); waited = true; }
+        // ---- logits, 4 keys per step
+        float sv[16];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                p0[j] = 0.f; p1[j] = 0.f;
-                if (mm) {                                   // warp-uniform
-                    const int k = __ffsll((long long)mm) - 1;
-                    mm &= mm - 1;
-                    const float* row = Ks + k * MV2D_C;
-                    const float4 k0 = *reinterpret_cast<const float4*>(row + lane * 4);
-                    const float4 k1 = *reinterpret_cast<const float4*>(row + 128 + lane * 4);
-                    p0[j] = fmaf(q0.w, k0.w, fmaf(q0.z, k0.z, fmaf(q0.y, k0.y, q0.x * k0.x)));
-                    p1[j] = fmaf(q1.w, k1.w, fmaf(q1.z, k1.z, fmaf(q1.y, k1.y, q1.x * k1.x)));
+        for (int grp = 0; grp < 16; ++grp) {
+            sv[grp] = -INFINITY;
+            if (grp * 4 < nk) {                             // warp-uniform
+                const uint32_t kw = kl4[grp];
+                float p[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float* row = Ks + ((kw >> (8 * j)) & 0xffu) * MV2D_C;
+                    const float4 ka = *reinterpret_cast<const float4*>(row + offA);
+                    const float4 kb = *reinterpret_cast<const float4*>(row + offB);
+                    float x = qa.x * ka.x;
+                    x = fmaf(qa.y, ka.y, x); x = fmaf(qa.z, ka.z, x); x = fmaf(qa.w, ka.w, x);
+                    x = fmaf(qb.x, kb.x, x); x = fmaf(qb.y, kb.y, x); x = fmaf(qb.z, kb.z, x); x = fmaf(qb.w, kb.w, x);
+                    p[j] = x;
                 }
-            }
-            reduce8_in8(p0, lane);
-            reduce8_in8(p1, lane);
-            const int slot = s0 + (lane & 7);
-            if (slot < nk) {
-                sc[slot * 8 + (lane >> 3)] = p0[0];
-                sc[slot * 8 + 4 + (lane >> 3)] = p1[0];
+                reduce4_in4(p, lane);
+                if (grp * 4 + part < nk) sv[grp] = p[0];
             }
         }
-        __syncwarp();
-        // ---- softmax statistics: lane = (head = lane & 7, phase = lane >> 3), slots phase, phase+4, ...
-        float mx = -INFINITY;
-        {
-            const int h = lane & 7;
-            for (int s = lane >> 3; s < nk; s += 4) mx = fmaxf(mx, sc[s * 8 + h]);
-            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
-            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
-            float sum = 0.f;
-            for (int s = lane >> 3; s < nk; s += 4) {
-                const float p = __expf(sc[s * 8 + h] - mx);
-                sc[s * 8 + h] = p;
-                sum += p;
+        // ---- softmax statistics in registers: over the lane's 16 values, then over the head's 4 lanes
+        float mx = sv[0];
+#pragma unroll
+        for (int grp = 1; grp < 16; ++grp) mx = fmaxf(mx, sv[grp]);
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+        float l = 0.f;
+#pragma unroll
+        for (int grp = 0; grp < 16; ++grp) {
+            if (grp * 4 < nk) {
+                const float e = __expf(sv[grp] - mx);       // exp(-inf) = 0 for the padding slots
+                l += e;
+                sc[(grp * 4 + part) * 8 + hd] = e;
             }
-            sum += __shfl_xor_sync(0xffffffffu, sum, 8);
-            sum += __shfl_xor_sync(0xffffffffu, sum, 16);
-            float* r = a.rec + ((long long)t * a.g.N + i) * XT_REC;
-            if (lane < 8) { r[256 + lane] = mx; r[264 + lane] = sum; }
         }
+        l += __shfl_xor_sync(0xffffffffu, l, 1);
+        l += __shfl_xor_sync(0xffffffffu, l, 2);
+        float* r = a.rec + ((long long)t * a.g.N + i) * XT_REC;
+        if (part == 0) { r[256 + hd] = mx; r[264 + hd] = l; }
         __syncwarp();
-        // ---- acc = sum_k p_k * V_k over the query's keys
+        // ---- acc = sum_k p_k * V_k over the query's keys, 4 keys per step (padding slots carry p = 0)
         float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
-        mm = m64;
-        for (int s = 0; s < nk; ++s) {
-            const int k = __ffsll((long long)mm) - 1;
-            mm &= mm - 1;
-            const float* row = Vs + k * MV2D_C;
-            const float4 v0 = *reinterpret_cast<const float4*>(row + lane * 4);
-            const float4 v1 = *reinterpret_cast<const float4*>(row + 128 + lane * 4);
-            const float w0 = sc[s * 8 + (lane >> 3)], w1 = sc[s * 8 + 4 + (lane >> 3)];
-            a0.x = fmaf(w0, v0.x, a0.x); a0.y = fmaf(w0, v0.y, a0.y); a0.z = fmaf(w0, v0.z, a0.z); a0.w = fmaf(w0, v0.w, a0.w);
-            a1.x = fmaf(w1, v1.x, a1.x); a1.y = fmaf(w1, v1.y, a1.y); a1.z = fmaf(w1, v1.z, a1.z); a1.w = fmaf(w1, v1.w, a1.w);
+        for (int s = 0; s < nk; s += 4) {
+            const uint32_t kw = kl4[s >> 2];
+            float4 va[4], vb[4];
+            float w[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float* row = Vs + ((kw >> (8 * j)) & 0xffu) * MV2D_C;
+                va[j] = *reinterpret_cast<const float4*>(row + offA);
+                vb[j] = *reinterpret_cast<const float4*>(row + offB);
+                w[j] = sc[(s + j) * 8 + hd];
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                a0.x = fmaf(w[j], va[j].x, a0.x); a0.y = fmaf(w[j], va[j].y, a0.y);
+                a0.z = fmaf(w[j], va[j].z, a0.z); a0.w = fmaf(w[j], va[j].w, a0.w);
+                a1.x = fmaf(w[j], vb[j].x, a1.x); a1.y = fmaf(w[j], vb[j].y, a1.y);
+                a1.z = fmaf(w[j], vb[j].z, a1.z); a1.w = fmaf(w[j], vb[j].w, a1.w);
+            }
         }
-        {
-            float* r = a.rec + ((long long)t * a.g.N + i) * XT_REC;
-            *reinterpret_cast<float4*>(r + lane * 4) = a0;
-            *reinterpret_cast<float4*>(r + 128 + lane * 4) = a1;
-        }
-        __syncwarp();           // sc is rewritten by the next query of this warp
+        *reinterpret_cast<float4*>(r + offA) = a0;
+        *reinterpret_cast<float4*>(r + offB) = a1;
     }
     // a CTA must not exit while its bulk copies are in flight
-    if (!waited) {
-        uint32_t done = 0;
-        while (!done)
-            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                         : "=r"(done) : "r"(xt_smem_u32(bar)) : "memory");
-    }
+    if (!waited) xt_wait(bar);
 }
 
 struct XtMergeArgs {
     XtGeom g;
-    const short* slot_of;              // [N, ntiles]
+    const int* qlist;                  // [N, ntiles] record ids of the query (xt_list_kernel)
+    const int* qcnt;                   // [N]
     const float* rec;
     float* ctx;                        // [N,256] softmax-weighted mean of the projected values (heads concatenated)
 };
 
-#define XT_MERGE_THREADS 128
+#define XT_MERGE_THREADS 256
 #define XT_MERGE_MAXT 2048             // tiles a query's list is sized for (V*ceil(h/8)*ceil(w/8) <= 2048)
 
-// grid = N, 128 threads
+// grid = N, 256 threads, dynamic shared memory = cnt-independent: ntiles * (4 + 32) bytes.
+// The query's record ids are staged in shared memory, the per-head maxima are found first, then the weight
+// exp(m_r - M) of every (record, head) is computed once; the accumulation is nothing but independent, coalesced
+// 16-byte loads: thread = (record phase 0..3, float4 of the 256 channels), records phase, phase+4, ... in ascending
+// order, the four phases folded in a fixed order => bitwise reproducible.
 __global__ void __launch_bounds__(XT_MERGE_THREADS) xt_merge_kernel(XtMergeArgs a) {
     pdl_wait();
     pdl_trigger();
     const int n = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    __shared__ int list[XT_MERGE_MAXT];
-    __shared__ int cnt_s;
-    __shared__ float Ms[4][8], Mg[8], Ls[4][8];
-    __shared__ float4 accs[3][64];
-    if (warp == 0) {
-        int running = 0;
-        for (int base = 0; base < a.g.ntiles; base += 32) {
-            const int t = base + lane;
-            const int s = t < a.g.ntiles ? (int)a.slot_of[(long long)n * a.g.ntiles + t] : -1;
-            const unsigned bal = __ballot_sync(0xffffffffu, s >= 0);
-            if (s >= 0) list[running + __popc(bal & ((1u << lane) - 1u))] = t * a.g.N + s;
-            running += __popc(bal);
-        }
-        if (lane == 0) cnt_s = running;
-    }
+    extern __shared__ __align__(16) unsigned char xm_smem[];
+    int* list = reinterpret_cast<int*>(xm_smem);                                  // [ntiles]
+    float* wgt = reinterpret_cast<float*>(xm_smem) + a.g.ntiles;                   // [ntiles][8]
+    __shared__ float Ms[8][8], Mg[8], Lw[8][8];
+    __shared__ float4 fold[3][64];
+    const int cnt = a.qcnt[n];
+    for (int r = tid; r < cnt; r += XT_MERGE_THREADS) list[r] = a.qlist[(long long)n * a.g.ntiles + r];
     __syncthreads();
-    const int cnt = cnt_s;
-    // ---- global max per head
+    const int h = tid & 7, rsub = tid >> 3;             // (record phase 0..31, head)
+    // ---- global max per head (the raw maxima are parked in wgt)
     {
-        const int h = lane & 7;
         float mx = -INFINITY;
-        for (int r = warp * 4 + (lane >> 3); r < cnt; r += 16) mx = fmaxf(mx, __ldcg(a.rec + (long long)list[r] * XT_REC + 256 + h));
+        for (int r = rsub; r < cnt; r += 32) {
+            const float m = __ldcg(a.rec + (long long)list[r] * XT_REC + 256 + h);
+            wgt[r * 8 + h] = m;
+            mx = fmaxf(mx, m);
+        }
         mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
         mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
         if (lane < 8) Ms[warp][lane] = mx;
     }
     __syncthreads();
-    if (tid < 8) Mg[tid] = fmaxf(fmaxf(Ms[0][tid], Ms[1][tid]), fmaxf(Ms[2][tid], Ms[3][tid]));
-    __syncthreads();
-    // ---- weighted sums: warp w takes records w, w+4, ... in ascending order
-    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
-    float lsum = 0.f;
-    const float M0 = Mg[lane >> 3], M1 = Mg[4 + (lane >> 3)], Ml = Mg[lane & 7];
-    for (int r = warp; r < cnt; r += 4) {
-        const float* rp = a.rec + (long long)list[r] * XT_REC;
-        const float4 x0 = __ldcg(reinterpret_cast<const float4*>(rp + lane * 4));
-        const float4 x1 = __ldcg(reinterpret_cast<const float4*>(rp + 128 + lane * 4));
-        const float w0 = __expf(__ldcg(rp + 256 + (lane >> 3)) - M0);
-        const float w1 = __expf(__ldcg(rp + 260 + (lane >> 3)) - M1);
-        a0.x = fmaf(x0.x, w0, a0.x); a0.y = fmaf(x0.y, w0, a0.y); a0.z = fmaf(x0.z, w0, a0.z); a0.w = fmaf(x0.w, w0, a0.w);
-        a1.x = fmaf(x1.x, w1, a1.x); a1.y = fmaf(x1.y, w1, a1.y); a1.z = fmaf(x1.z, w1, a1.z); a1.w = fmaf(x1.w, w1, a1.w);
-        if (lane < 8) lsum = fmaf(__ldcg(rp + 264 + lane), __expf(__ldcg(rp + 256 + lane) - Ml), lsum);
-    }
-    if (lane < 8) Ls[warp][lane] = lsum;
-    if (warp > 0) { accs[warp - 1][lane] = a0; accs[warp - 1][32 + lane] = a1; }
-    __syncthreads();
-    if (warp == 0) {
+    if (tid < 8) {
+        float mx = Ms[0][tid];
 #pragma unroll
-        for (int w = 0; w < 3; ++w) {
-            const float4 y0 = accs[w][lane], y1 = accs[w][32 + lane];
-            a0.x += y0.x; a0.y += y0.y; a0.z += y0.z; a0.w += y0.w;
-            a1.x += y1.x; a1.y += y1.y; a1.z += y1.z; a1.w += y1.w;
+        for (int w = 1; w < 8; ++w) mx = fmaxf(mx, Ms[w][tid]);
+        Mg[tid] = mx;
+    }
+    __syncthreads();
+    {   // ---- weights, and l = sum_r l_r * w_r (thread (rsub, h) owns records rsub, rsub+32, ...: fixed order)
+        const float Mh = Mg[h];
+        float lsum = 0.f;
+        for (int r = rsub; r < cnt; r += 32) {
+            const float w = __expf(wgt[r * 8 + h] - Mh);
+            wgt[r * 8 + h] = w;
+            lsum = fmaf(__ldcg(a.rec + (long long)list[r] * XT_REC + 264 + h), w, lsum);
         }
-        const int h0 = lane >> 3;
-        const float l0 = Ls[0][h0] + Ls[1][h0] + Ls[2][h0] + Ls[3][h0];
-        const float l1 = Ls[0][4 + h0] + Ls[1][4 + h0] + Ls[2][4 + h0] + Ls[3][4 + h0];
-        const float i0 = l0 > 0.f ? 1.f / l0 : 0.f, i1 = l1 > 0.f ? 1.f / l1 : 0.f;
-        float* o = a.ctx + (long long)n * MV2D_C;
-        *reinterpret_cast<float4*>(o + lane * 4) = make_float4(a0.x * i0, a0.y * i0, a0.z * i0, a0.w * i0);
-        *reinterpret_cast<float4*>(o + 128 + lane * 4) = make_float4(a1.x * i1, a1.y * i1, a1.z * i1, a1.w * i1);
+        lsum += __shfl_xor_sync(0xffffffffu, lsum, 8);
+        lsum += __shfl_xor_sync(0xffffffffu, lsum, 16);
+        if (lane < 8) Lw[warp][lane] = lsum;
+    }
+    __syncthreads();
+    const int ph = tid >> 6, c4 = tid & 63, hc = c4 >> 3;       // record phase, float4 index, its head
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int r = ph;
+    for (; r + 12 < cnt; r += 16) {
+        float4 x[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) x[j] = __ldcg(reinterpret_cast<const float4*>(a.rec + (long long)list[r + 4 * j] * XT_REC) + c4);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float w = wgt[(r + 4 * j) * 8 + hc];
+            acc.x = fmaf(x[j].x, w, acc.x); acc.y = fmaf(x[j].y, w, acc.y); acc.z = fmaf(x[j].z, w, acc.z); acc.w = fmaf(x[j].w, w, acc.w);
+        }
+    }
+    for (; r < cnt; r += 4) {
+        const float4 x = __ldcg(reinterpret_cast<const float4*>(a.rec + (long long)list[r] * XT_REC) + c4);
+        const float w = wgt[r * 8 + hc];
+        acc.x = fmaf(x.x, w, acc.x); acc.y = fmaf(x.y, w, acc.y); acc.z = fmaf(x.z, w, acc.z); acc.w = fmaf(x.w, w, acc.w);
+    }
+    if (ph > 0) fold[ph - 1][c4] = acc;
+    __syncthreads();
+    if (ph == 0) {
+#pragma unroll
+        for (int w = 0; w < 3; ++w) { const float4 y = fold[w][c4]; acc.x += y.x; acc.y += y.y; acc.z += y.z; acc.w += y.w; }
+        float l = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) l += Lw[w][hc];
+        const float inv = l > 0.f ? 1.f / l : 0.f;
+        reinterpret_cast<float4*>(a.ctx + (long long)n * MV2D_C)[c4] = make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
     }
 }
 
