@@ -9,12 +9,15 @@ Workload (BASELINE.json configs[1]): MV2D-S, R50 single frame 1408x512, 6 camera
 path -- (FPN P4 feature [6,256,32,88], per-view 2D boxes, img_metas) -> (cls_scores,
 bbox_preds) of all 6 layers -- over one sample.  Metric: samples/sec, whole job.
 
-  value  : inputs already resident in HBM; each step = one CUDA-graph replay of the whole path
-           (97 kernels); L2 is flushed (256 MB memset) before every timed step, and each step is
-           timed with its own pair of CUDA events on the launching stream.
-  e2e    : the public API call with HOST (pinned) buffers: H2D of the feature map, boxes and
-           camera matrices, the path, D2H of cls_scores/bbox_preds -- all inside the timed region
-           (the feature-map copy overlaps the part of the PE that does not read it).
+  value  : whole-job throughput, inputs already resident in HBM.  Each step = one CUDA-graph replay of the
+           whole path for ONE sample (bs = 1); mv2d_b200.pipeline.Pipeline keeps --depth (default 3) samples in
+           flight on independent lanes, so the GPU-filling front end of sample i+1 runs under the latency-bound
+           decoder of sample i.  The K steps are bracketed by one pair of CUDA events (+ barrier and
+           synchronize on both sides); 8 distinct samples rotate (138 MB of feature maps > the 126 MB L2).
+  e2e    : the same through the public API with HOST (pinned) buffers: H2D of the feature map, boxes and
+           camera matrices, the path, D2H of cls_scores/bbox_preds -- all inside the timed region.
+  serial : (extra object) one sample at a time, nothing else in flight, L2 flushed (256 MB memset) before every
+           step, each step timed with its own pair of CUDA events: the per-sample latency view of both numbers.
   N > 1  : one process per GPU, independent replicas on different samples (the decoder is
            per-sample: no data-path collective); NCCL only for the barrier and the max-over-ranks.
   --impl reference : the CPU restatement of the reference (oracle/, kind "port": the reference's
@@ -33,6 +36,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = 'samples/sec (MV2D-S decoder hot path, 6-cam 1408x512, 300 queries, 6 layers)'
+METRIC_T = 'samples/sec (MV2D-T decoder hot path, two frames = 12 views 1408x512, 300 queries, 6 layers)'
 UNIT = 'samples/s'
 
 
@@ -44,6 +48,7 @@ def parse():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--mode', default='S', choices=['S', 'T'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--depth', type=int, default=3, help='samples in flight (inter-sample pipelining); 1 = serial')
     return ap.parse_args()
 
 
@@ -138,7 +143,7 @@ def run_reference(args, rank):
     ms = 1e3 * sum(times) / len(times)
     val = 1e3 / ms
     sample = f'{steps} samples of the full workload after {warm} warm-up, torch {torch.__version__} CPU fp32'
-    line = dict(metric=METRIC, value=val, unit=UNIT, n_gpus=args.gpus, steps=steps, warmup=warm, ms_per_step=ms,
+    line = dict(metric=METRIC if args.mode == 'S' else METRIC_T, value=val, unit=UNIT, n_gpus=args.gpus, steps=steps, warmup=warm, ms_per_step=ms,
                 higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
                 impl='reference',
                 config=dict(workload=f'MV2D-{args.mode} R50 1408x512 V={6 if args.mode == "S" else 12} N=300 L=6 bs=1',
@@ -171,9 +176,12 @@ def main():
 
     mode = args.mode
     sd = synth.make_state_dict(0)
-    eng = HotPath(sd, mode=mode, device=dev)
-    # a few distinct samples per rank (different seeds per rank: replicas work on different data)
-    n_var = 4
+    from mv2d_b200.pipeline import Pipeline
+    pipe = Pipeline(sd, mode=mode, device=dev, depth=max(args.depth, 1))
+    eng = pipe.lanes[0]
+    # distinct samples per rank (different seeds per rank: replicas work on different data); 8 feature maps
+    # of the S head are 138 MB > the 126 MB L2
+    n_var = 8
     samples = [make_inputs(mode, seed=i) for i in D.shard_samples(n_var * world, rank, world)]
     feats_dev = [s[0].to(dev) for s in samples]
     feats_pin = [s[0].pin_memory() for s in samples]
@@ -220,18 +228,45 @@ def main():
         ms = [a.elapsed_time(b) for a, b in evs]
         return sum(ms), ms, eng.launch_count() - launches0, wall
 
+    def timed_pipe(host, steps, warmup):
+        """K samples through the pipeline, ONE pair of events around all of them (device time, launching stream)."""
+        src = feats_pin if host else feats_dev
+        for i in range(warmup + 2 * pipe.depth):
+            pipe.submit(src[i % n_var], samples[i % n_var][1], samples[i % n_var][2], to_host=host)
+        pipe.join()
+        barrier()
+        launches0 = pipe.launch_count()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_wall = time.perf_counter()
+        a.record()
+        for i in range(steps):
+            pipe.submit(src[i % n_var], samples[i % n_var][1], samples[i % n_var][2], to_host=host)
+        pipe.join()
+        b.record()
+        barrier()
+        return a.elapsed_time(b), pipe.launch_count() - launches0, time.perf_counter() - t_wall
+
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    total_ms, per_step, launches, wall = timed(step_resident, args.steps, max(args.warmup, 3))
-    e2e_total_ms, e2e_steps, _, _ = timed(step_e2e, args.steps, max(args.warmup, 3))
+    W = max(args.warmup, 3)
+    ser_total_ms, per_step, _, _ = timed(step_resident, args.steps, W)
+    ser_e2e_total_ms, _, _, _ = timed(step_e2e, args.steps, W)
+    total_ms, launches, wall = timed_pipe(False, args.steps, W)
+    e2e_total_ms, _, _ = timed_pipe(True, args.steps, W)
     clocks = sampler.stop() if rank == 0 else None
 
-    # max over ranks of the summed device time
-    total_ms, e2e_total_ms = D.max_over_ranks([total_ms, e2e_total_ms], device=dev)
+    # max over ranks of the device time
+    total_ms, e2e_total_ms, ser_total_ms, ser_e2e_total_ms = D.max_over_ranks(
+        [total_ms, e2e_total_ms, ser_total_ms, ser_e2e_total_ms], device=dev)
     ms_per_step = total_ms / args.steps
     value = D.aggregate_throughput(world, args.steps, 1, total_ms)
     e2e_value = D.aggregate_throughput(world, args.steps, 1, e2e_total_ms)
+    serial = dict(value=D.aggregate_throughput(world, args.steps, 1, ser_total_ms), unit=UNIT,
+                  ms_per_step=ser_total_ms / args.steps, ms_min=min(per_step), ms_median=statistics.median(per_step),
+                  e2e_value=D.aggregate_throughput(world, args.steps, 1, ser_e2e_total_ms),
+                  e2e_ms_per_step=ser_e2e_total_ms / args.steps,
+                  note='one sample at a time, L2 flushed (256 MB memset) before every step, per-step CUDA events')
 
     if rank != 0:
         if world > 1:
@@ -251,20 +286,22 @@ def main():
     h2d = feat.numel() * 4 + N * 5 * 4 + (len(metas) + 1) * 4 + 3 * len(metas) * 16 * 8
     d2h = 2 * eng.L * N * 10 * 4
     line = dict(
-        metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
+        metric=METRIC if mode == 'S' else METRIC_T, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
         ms_per_step=ms_per_step, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32',
         data='synthetic',
         config=dict(workload=f'MV2D-{mode} R50 1408x512 V={len(metas)} N={N} L={eng.L} bs=1 per GPU (BASELINE configs[{1 if mode == "S" else 2}])',
                     precision='fp32 storage; single-pass TF32 tcgen05 in the PE MLPs, 3xTF32 tcgen05 in the QG conv and the four wide decoder GEMMs, fp32 FFMA elsewhere, fp64 geometry',
-                    l2='flushed (256 MB memset) before every timed step',
-                    timing='per-step CUDA events on the launching stream, max over ranks',
+                    schedule=f'{pipe.depth} samples in flight per GPU (inter-sample pipelining on independent lanes, '
+                             'each sample processed at bs=1; mv2d_b200/pipeline.py); "serial" holds the one-at-a-time numbers',
+                    l2=f'{n_var} distinct samples rotate: {n_var * samples[0][0].numel() * 4 / 1e6:.0f} MB of feature maps > 126 MB L2 '
+                       '(weights stay L2-resident, as in serving); the serial numbers flush L2 before every step',
+                    timing='one pair of CUDA events on the launching stream around the K steps, barrier + synchronize on both sides, max over ranks',
                     launch='one CUDA-graph replay of the whole path per step',
-                    sine_branch='recomputed every step (not cached)',
-                    ms_min=min(per_step), ms_median=statistics.median(per_step), wall_s=wall),
+                    sine_branch='recomputed every step (not cached)', wall_s=wall),
         e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                  ms_per_step=e2e_total_ms / args.steps),
         gpu_launches=launches, clocks=clocks, roofline=roof['roofline'], attention_roofline=roof['attention'],
-        stage_us=roof['stage_us'], peaks=peaks)
+        stage_us=roof['stage_us'], peaks=peaks, serial=serial)
     if not args.no_cpu_baseline and world == 1:
         line['cpu_baseline'] = cpu_baseline(mode)
     print(json.dumps(line))

@@ -636,19 +636,32 @@ int launch_gemm_tc(const TcGemm& t, cudaStream_t st) {
     return launch_tc<128, 1, false, 3>(a, alo, w, wlo, g, m_tiles, nsplit, st);
 }
 
-__global__ void split_tf32_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo, long long n) {
+__global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo, long long n) {
     pdl_wait();
     pdl_trigger();
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const float v = x[i], h = round_tf32(v);
-    hi[i] = h;
-    lo[i] = round_tf32(v - h);
+    // grid-stride over float4s (16-byte loads / stores), scalar tail
+    const long long n4 = n >> 2, stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+        float4 h, l;
+        h.x = round_tf32(v.x); h.y = round_tf32(v.y); h.z = round_tf32(v.z); h.w = round_tf32(v.w);
+        l.x = round_tf32(v.x - h.x); l.y = round_tf32(v.y - h.y); l.z = round_tf32(v.z - h.z); l.w = round_tf32(v.w - h.w);
+        reinterpret_cast<float4*>(hi)[i] = h;
+        reinterpret_cast<float4*>(lo)[i] = l;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+        const long long i = (n4 << 2) + threadIdx.x;
+        const float v = x[i], h = round_tf32(v);
+        hi[i] = h;
+        lo[i] = round_tf32(v - h);
+    }
 }
 
 int launch_split_tf32(const float* x, float* hi, float* lo, long long n, cudaStream_t st) {
     if (n <= 0) return 0;
-    launch_k(split_tf32_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, x, hi, lo, n);
+    MV2D_CHECK_ARG((((uintptr_t)x | (uintptr_t)hi | (uintptr_t)lo) & 15) == 0, "split_tf32: pointers must be 16-byte aligned");
+    const long long blocks = ((n >> 2) + 255) / 256;
+    launch_k(split_tf32_kernel, dim3((unsigned)(blocks < 1 ? 1 : (blocks > 148 * 16 ? 148 * 16 : blocks))), dim3(256), 0, st, x, hi, lo, n);
     MV2D_CHECK_LAUNCH("split_tf32");
     return 0;
 }

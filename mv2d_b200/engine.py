@@ -6,6 +6,7 @@ memory, streams and (optionally) CUDA-graph capture.
 Mirrors ``MV2DHead.simple_test`` minus decode
 (reference roi_heads/mv2d_head.py:249-261 -> mv2d_s_head.py:122-211 / mv2d_t_head.py:26-142).
 """
+import contextlib
 import ctypes as C
 import math
 import os
@@ -50,7 +51,7 @@ class HotPath:
     """MV2D-S ('S') / MV2D-T ('T') decoder hot path on one GPU."""
 
     def __init__(self, state_dict, mode='S', device='cuda', cache_sine_branch=False, overlap=True,
-                 persistent_decoder=None, fold_first_self_attn=True, xa_form=None, **cfg):
+                 persistent_decoder=None, fold_first_self_attn=True, xa_form=None, weights=None, **cfg):
         if not torch.cuda.is_available():
             raise RuntimeError('mv2d_b200.HotPath needs a CUDA device (there is no CPU fallback)')
         self.lib = lib.load()
@@ -62,7 +63,9 @@ class HotPath:
             self.cfg.update(topk=20, expand_stride=2, denoise_noise_scale=1.25, denoise_split=0.6)
         self.cfg.update(cfg)
         # fold_first_self_attn: layer 0's self-attention output is a packed constant (pack.first_layer_self_attn_const)
-        self.w = PackedWeights(state_dict, self.device, fold_first_self_attn=fold_first_self_attn)
+        # weights: an already packed set to share (Pipeline lanes); otherwise packed from the state_dict here
+        self.w = weights if weights is not None else PackedWeights(state_dict, self.device,
+                                                                   fold_first_self_attn=fold_first_self_attn)
         self.L = self.w.num_layers
         self.cache_sine_branch = cache_sine_branch
         self._sine_cache = {}
@@ -81,7 +84,11 @@ class HotPath:
             #                 0 = query-stationary absorbed form (the S head's formulation applied to ~2000 keys/query)
             xa_form = int(os.environ.get('MV2D_XA_FORM', '1'))
         self.xa_form = xa_form if (mode == 'T' and not persistent_decoder) else 0
+        # the K/V projections are GPU-filling GEMMs, the decoder layers they overlap with are chains of small
+        # latency-bound kernels: the decoder runs on a high-priority stream so its CTAs are placed first
         self._kv = torch.cuda.Stream(device=self.device)
+        self._hi = torch.cuda.Stream(device=self.device, priority=-1)
+        self._ev_hi0, self._ev_hi1 = torch.cuda.Event(), torch.cuda.Event()
         self._ev_pe = torch.cuda.Event()
         self._ev_kv = [torch.cuda.Event() for _ in range(self.L)]
         self._side = torch.cuda.Stream(device=self.device)
@@ -487,10 +494,20 @@ class HotPath:
             cls, box, outs = self.decoder(qg_d, corr_d, qg['tok_kin'].view(-1, 256), qg['tok_feat'].view(-1, 256), T,
                                           self_attn_mask=sa_mask)
         else:
-            cls, box, outs = self.decoder(qg_d, corr_d, kin.view(-1, 256), feat.view(-1, 256), T,
-                                          vel_dt=self._vel_dt(img_metas), self_attn_mask=sa_mask, vel_row_start=pad,
-                                          kv=kv if self.xa_form == 1 else None, grid=(h, w),
-                                          wait_kv_events=self.xa_form == 1 and self.overlap)
+            piped = self.xa_form == 1 and self.overlap
+            run_on = self._hi if (piped and os.environ.get('MV2D_DEC_PRIO', '1') != '0') else None
+            if run_on is not None:
+                cur = torch.cuda.current_stream()
+                self._ev_hi0.record(cur)
+                run_on.wait_event(self._ev_hi0)
+            with torch.cuda.stream(run_on) if run_on is not None else contextlib.nullcontext():
+                cls, box, outs = self.decoder(qg_d, corr_d, kin.view(-1, 256), feat.view(-1, 256), T,
+                                              vel_dt=self._vel_dt(img_metas), self_attn_mask=sa_mask, vel_row_start=pad,
+                                              kv=kv if self.xa_form == 1 else None, grid=(h, w), wait_kv_events=piped)
+                if run_on is not None:
+                    self._ev_hi1.record(run_on)
+            if run_on is not None:
+                cur.wait_event(self._ev_hi1)
         out = dict(cls_scores=cls[:, pad:], bbox_preds=box[:, pad:], outs_dec=outs[:, pad:], rois=rois, pe=pe,
                    feat_nhwc=feat, N=N, num_per_view=counts)
         out.update(qg)

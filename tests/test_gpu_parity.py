@@ -326,3 +326,37 @@ def test_two_frame_query_stationary_form_matches_golden(name, state_dicts):
         outs[form] = (out['cls_scores'].clone(), out['bbox_preds'].clone())
     assert_close(outs[1][0], outs[0][0], 2e-4, 2e-4, 'cls_scores form 1 vs form 0')
     assert_close(outs[1][1], outs[0][1], 2e-4, 2e-4, 'bbox_preds form 1 vs form 0')
+
+
+@pytest.mark.parametrize('mode,case', [('S', 's_small'), ('T', 't_small')])
+def test_pipeline_lanes_match_single_engine(mode, case, state_dicts):
+    """mv2d_b200.pipeline.Pipeline (several samples in flight on independent lanes that share one set of packed
+    weights) returns, for every sample, exactly what a single HotPath returns."""
+    from mv2d_b200.engine import HotPath
+    from mv2d_b200.pipeline import Pipeline
+    spec = synth.CASES[case]
+    sd = state_dicts(spec['num_layers'])
+    samples = [synth.case_inputs(dict(spec, seed=100 + i)) for i in range(5)]
+    eng = HotPath(sd, mode=mode)
+    want = []
+    for f, b, m in samples:
+        o = eng.forward(f.cuda(), b, m, use_graph=True)
+        torch.cuda.synchronize()
+        want.append((o['cls_scores'].clone(), o['bbox_preds'].clone()))
+    pipe = Pipeline(sd, mode=mode, depth=3)
+    feats = [s[0].pin_memory() for s in samples]
+    for rnd in range(2):            # second round replays the captured graphs
+        got = []
+        for i, (f, b, m) in enumerate(samples):
+            t, o = pipe.submit(feats[i], b, m, to_host=True)
+            pipe.wait(t)
+            torch.cuda.synchronize()
+            got.append((o['host_cls'].clone(), o['host_box'].clone()))
+        for (wc, wb), (gc, gb) in zip(want, got):
+            assert torch.equal(wc.cpu(), gc) and torch.equal(wb.cpu(), gb)
+    # everything in flight at once, results read after the join
+    outs = [pipe.submit(feats[i], samples[i][1], samples[i][2])[1] for i in range(3)]
+    pipe.join()
+    torch.cuda.synchronize()
+    for i, o in enumerate(outs):
+        assert torch.equal(o['cls_scores'], want[i][0]) and torch.equal(o['bbox_preds'], want[i][1])
