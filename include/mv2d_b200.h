@@ -210,7 +210,7 @@ typedef struct Mv2dDecoderParams {
     int xa_form;                /* mode 1 only: 0 = query-stationary absorbed form (streams each query's raw key rows),
                                  *              1 = key-stationary form over 8x8 cell tiles of projected K / V */
     int grid_h, grid_w;         /* xa_form 1: the feature grid; num_rows = V * grid_h * grid_w */
-    int reserved3;
+    int xa_prepared;            /* xa_form 1: 1 = mv2d_xa_tile_prepare already ran on xa_workspace for this sample */
     const float* kp;            /* xa_form 1: [L,num_rows,256] projected keys   from mv2d_kv_project */
     const float* vp;            /* xa_form 1: [L,num_rows,256] projected values from mv2d_kv_project */
     void* xa_workspace;         /* xa_form 1: mv2d_xa_tile_workspace_bytes(N, V, grid_h, grid_w) */
@@ -218,6 +218,11 @@ typedef struct Mv2dDecoderParams {
 } Mv2dDecoderParams;
 MV2D_API size_t mv2d_decoder_workspace_bytes(int N, int L);
 MV2D_API size_t mv2d_xa_tile_workspace_bytes(int N, int V, int grid_h, int grid_w);
+/* xa_form 1: per-tile query lists, per-query record lists and the tile order, built from the key masks alone
+ * (so it can run right after mv2d_box_corr, beside the position embedding).  Reads N, num_rows, grid_h, grid_w,
+ * keymask, mask_words, xa_workspace(_bytes) of the decoder parameters.  A decoder call with xa_prepared = 1 then
+ * skips this step. */
+MV2D_API int mv2d_xa_tile_prepare(const Mv2dDecoderParams* p, void* stream);
 MV2D_API int mv2d_decoder(const Mv2dDecoderParams* p, void* stream);
 
 /* ---- K/V projection of the two-frame head's keys (SURVEY.md 8b "kv_proj"; utils/petr_transformer.py:503-508 ->

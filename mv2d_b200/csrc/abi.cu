@@ -106,6 +106,11 @@ int mv2d_dn_prepare(const Mv2dDnParams* p, void* stream) {
 
 size_t mv2d_decoder_workspace_bytes(int N, int L) { return decoder_workspace_bytes(N, L); }
 size_t mv2d_xa_tile_workspace_bytes(int N, int V, int grid_h, int grid_w) { return xa_tile_workspace_bytes(N, V, grid_h, grid_w); }
+int mv2d_xa_tile_prepare(const Mv2dDecoderParams* p, void* stream) {
+    NONNULL(p, "xa_tile_prepare");
+    MV2D_CHECK_ARG(p->N == 0 || (p->keymask && p->xa_workspace), "xa_tile_prepare: null pointer");
+    return run_xa_tile_prepare(*p, (cudaStream_t)stream);
+}
 int mv2d_kv_project(const Mv2dKvParams* p, void* stream) {
     NONNULL(p, "kv_project");
     MV2D_CHECK_ARG(p->kin_hi && p->kin_lo && p->mem_hi && p->mem_lo && p->layers && p->kp && p->vp, "kv_project: null pointer");

@@ -985,6 +985,42 @@ int run_kv_project(const Mv2dKvParams& p, cudaStream_t st) {
     return 0;
 }
 
+static int xt_setup(const Mv2dDecoderParams& p, XtGeom& xg, XtWs& xw) {
+    const int N = p.N;
+    MV2D_CHECK_ARG(p.grid_h > 0 && p.grid_w > 0 && p.num_rows > 0 && p.num_rows % (p.grid_h * p.grid_w) == 0,
+                   "decoder: xa_form 1 needs the feature grid (num_rows=%d, grid %dx%d)", p.num_rows, p.grid_h, p.grid_w);
+    xg.N = N; xg.h = p.grid_h; xg.w = p.grid_w; xg.V = p.num_rows / (p.grid_h * p.grid_w);
+    xg.tiles_x = cdiv(xg.w, XT_TS); xg.tiles_y = cdiv(xg.h, XT_TS); xg.ntiles = xg.V * xg.tiles_x * xg.tiles_y;
+    MV2D_CHECK_ARG(xg.ntiles <= XT_MERGE_MAXT && N <= 32767, "decoder: xa_form 1 supports <= %d tiles and <= 32767 queries", XT_MERGE_MAXT);
+    MV2D_CHECK_ARG(p.keymask && p.xa_workspace, "decoder: xa_form 1 needs the key masks and xa_workspace");
+    MV2D_CHECK_ARG(p.mask_words * 32 >= p.num_rows, "decoder: keymask has %d words for %d cells", p.mask_words, p.num_rows);
+    xw = xt_carve(p.xa_workspace, N, xg.ntiles);
+    MV2D_CHECK_ARG(xw.bytes <= p.xa_workspace_bytes, "decoder: xa_workspace too small (%zu < %zu)", p.xa_workspace_bytes, xw.bytes);
+    return 0;
+}
+
+static int xt_prepare(const Mv2dDecoderParams& p, const XtGeom& xg, const XtWs& xw, cudaStream_t st) {
+    XtPrepArgs a{}; a.g = xg; a.keymask = p.keymask; a.mask_words = p.mask_words;
+    a.tile_cnt = xw.tile_cnt; a.tile_q = xw.tile_q; a.tile_mask = xw.tile_mask; a.slot_of = xw.slot_of;
+    a.tile_work = xw.tile_work;
+    launch_k(xt_prep_kernel, dim3(xg.ntiles), dim3(256), 0, st, a);
+    MV2D_CHECK_LAUNCH("xt_prep");
+    XtListArgs b{}; b.g = xg; b.slot_of = xw.slot_of; b.tile_work = xw.tile_work; b.qlist = xw.qlist; b.qcnt = xw.qcnt;
+    b.order = xw.order;
+    launch_k(xt_list_kernel, dim3(xg.N + 1), dim3(256), 0, st, b);
+    MV2D_CHECK_LAUNCH("xt_list");
+    return 0;
+}
+
+int run_xa_tile_prepare(const Mv2dDecoderParams& p, cudaStream_t st) {
+    if (p.N == 0) return 0;
+    XtGeom xg{};
+    XtWs xw{};
+    int rc;
+    if ((rc = xt_setup(p, xg, xw))) return rc;
+    return xt_prepare(p, xg, xw, st);
+}
+
 int run_decoder(const Mv2dDecoderParams& p, cudaStream_t st) {
     const int N = p.N, L = p.L, C = MV2D_C;
     MV2D_CHECK_ARG(N >= 0 && L >= 1 && L <= MV2D_MAX_LAYERS, "decoder: bad N=%d / L=%d", N, L);
@@ -1030,31 +1066,15 @@ int run_decoder(const Mv2dDecoderParams& p, cudaStream_t st) {
     XtGeom xg{};
     XtWs xw{};
     if (xt) {
-        MV2D_CHECK_ARG(p.grid_h > 0 && p.grid_w > 0 && p.num_rows % (p.grid_h * p.grid_w) == 0,
-                       "decoder: xa_form 1 needs the feature grid (num_rows=%d, grid %dx%d)", p.num_rows, p.grid_h, p.grid_w);
-        xg.N = N; xg.h = p.grid_h; xg.w = p.grid_w; xg.V = p.num_rows / (p.grid_h * p.grid_w);
-        xg.tiles_x = cdiv(xg.w, XT_TS); xg.tiles_y = cdiv(xg.h, XT_TS); xg.ntiles = xg.V * xg.tiles_x * xg.tiles_y;
-        MV2D_CHECK_ARG(xg.ntiles <= XT_MERGE_MAXT && N <= 32767, "decoder: xa_form 1 supports <= %d tiles and <= 32767 queries", XT_MERGE_MAXT);
-        MV2D_CHECK_ARG(p.kp && p.vp && p.xa_workspace, "decoder: xa_form 1 needs kp / vp (mv2d_kv_project) and xa_workspace");
-        MV2D_CHECK_ARG(p.mask_words * 32 >= p.num_rows, "decoder: keymask has %d words for %d cells", p.mask_words, p.num_rows);
-        xw = xt_carve(p.xa_workspace, N, xg.ntiles);
-        MV2D_CHECK_ARG(xw.bytes <= p.xa_workspace_bytes, "decoder: xa_workspace too small (%zu < %zu)", p.xa_workspace_bytes, xw.bytes);
+        int rc0;
+        if ((rc0 = xt_setup(p, xg, xw))) return rc0;
+        MV2D_CHECK_ARG(p.kp && p.vp, "decoder: xa_form 1 needs kp / vp (mv2d_kv_project)");
         if ((e = cudaFuncSetAttribute(xt_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XT_SMEM_BYTES)) != cudaSuccess ||
             (e = cudaFuncSetAttribute(xt_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, XT_MERGE_MAXT * 36)) != cudaSuccess) {
-            set_error("decoder: xt_attn smem attr %s", cudaGetErrorString(e));
+            set_error("decoder: xt smem attr %s", cudaGetErrorString(e));
             return (int)e;
         }
-        if (first) {
-            XtPrepArgs a{}; a.g = xg; a.keymask = p.keymask; a.mask_words = p.mask_words;
-            a.tile_cnt = xw.tile_cnt; a.tile_q = xw.tile_q; a.tile_mask = xw.tile_mask; a.slot_of = xw.slot_of;
-            a.tile_work = xw.tile_work;
-            launch_k(xt_prep_kernel, dim3(xg.ntiles), dim3(256), 0, st, a);
-            MV2D_CHECK_LAUNCH("xt_prep");
-            XtListArgs b{}; b.g = xg; b.slot_of = xw.slot_of; b.tile_work = xw.tile_work; b.qlist = xw.qlist; b.qcnt = xw.qcnt;
-            b.order = xw.order;
-            launch_k(xt_list_kernel, dim3(N + 1), dim3(256), 0, st, b);
-            MV2D_CHECK_LAUNCH("xt_list");
-        }
+        if (first && !p.xa_prepared && (rc0 = xt_prepare(p, xg, xw, st))) return rc0;
     }
     // target = 0 ; query + query_pos = query_pos   (cross_attention_head.py:32)
     // The first layer's self-attention sees value = target = 0, so every value row is the bias bv and the attention

@@ -16,6 +16,7 @@ int run_decoder(const Mv2dDecoderParams& p, cudaStream_t st);
 size_t decoder_workspace_bytes(int N, int L);
 size_t xa_tile_workspace_bytes(int N, int V, int h, int w);
 int run_kv_project(const Mv2dKvParams& p, cudaStream_t st);
+int run_xa_tile_prepare(const Mv2dDecoderParams& p, cudaStream_t st);
 int run_dn_prepare(const Mv2dDnParams& p, cudaStream_t st);
 size_t dn_workspace_bytes(int T, int mask_words);
 int run_nms_free_decode(const float* cls, const float* box, int N, int max_num, const float* post_range,

@@ -24,6 +24,7 @@ namespace mv2d {
 #define XT_KEYS (XT_TS * XT_TS)
 #define XT_REC 272                     // floats per record: acc[256], m[8], l[8]
 #define XT_THREADS 512
+#define XT_MERGE_MAXT 2048             // tiles per sample the lists are sized for (V*ceil(h/8)*ceil(w/8) <= 2048)
 #define XT_SMEM_BYTES (2 * XT_KEYS * MV2D_C * 4 + (XT_THREADS / 32) * XT_KEYS * 8 * 4 + (XT_THREADS / 32) * 80 + 64)
 
 struct XtGeom {
@@ -111,12 +112,16 @@ __global__ void __launch_bounds__(256) xt_list_kernel(XtListArgs a) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nt = a.g.ntiles;
     if ((int)blockIdx.x == a.g.N) {
-        // rank by counting: ntiles <= 2048, so this is at most 4M comparisons for one CTA, once per sample
+        // rank by counting out of shared memory: ntiles <= 2048, once per sample
+        __shared__ int work_s[XT_MERGE_MAXT];
+        for (int t = tid; t < nt; t += 256) work_s[t] = a.tile_work[t];
+        __syncthreads();
         for (int t = tid; t < nt; t += 256) {
-            const int w = a.tile_work[t];
+            const int w = work_s[t];
             int rank = 0;
+#pragma unroll 8
             for (int u = 0; u < nt; ++u) {
-                const int x = __ldg(a.tile_work + u);
+                const int x = work_s[u];
                 rank += (x > w) || (x == w && u < t);
             }
             a.order[rank] = t;
@@ -337,7 +342,6 @@ struct XtMergeArgs {
 };
 
 #define XT_MERGE_THREADS 256
-#define XT_MERGE_MAXT 2048             // tiles a query's list is sized for (V*ceil(h/8)*ceil(w/8) <= 2048)
 
 // grid = N, 256 threads, dynamic shared memory = cnt-independent: ntiles * (4 + 32) bytes.
 // The query's record ids are staged in shared memory, the per-head maxima are found first, then the weight

@@ -299,6 +299,17 @@ class HotPath:
             p.keymask, p.key_cnt, p.key_list = keymask.data_ptr(), key_cnt.data_ptr(), key_list.data_ptr()
             out.update(keymask=keymask, key_cnt=key_cnt, key_list=key_list, mask_words=words)
         lib.check(self.lib.mv2d_box_corr(C.byref(p), lib.stream_ptr()), 'mv2d_box_corr')
+        if self.mode == 'T' and self.xa_form == 1 and N > 0:
+            # tile / record lists of the key-stationary cross-attention depend on the masks only: build them here,
+            # beside the position embedding, instead of at the head of the decoder
+            d = lib.DecoderParams()
+            d.N, d.num_rows, d.grid_h, d.grid_w = N, V * h * w, h, w
+            d.keymask, d.mask_words = out['keymask'].data_ptr(), out['mask_words']
+            xa_bytes = self.lib.mv2d_xa_tile_workspace_bytes(N, V, h, w)
+            xa_ws = self._get('xa_ws', (xa_bytes,), torch.uint8)
+            d.xa_workspace, d.xa_workspace_bytes = xa_ws.data_ptr(), xa_bytes
+            lib.check(self.lib.mv2d_xa_tile_prepare(C.byref(d), lib.stream_ptr()), 'mv2d_xa_tile_prepare')
+            out['xa_prepared_for'] = (out['keymask'].data_ptr(), N, xa_ws.data_ptr())
         return out
 
     def dn_prepare(self, qg, corr, N, dn):
@@ -418,6 +429,7 @@ class HotPath:
             p.xa_form, p.grid_h, p.grid_w = 1, grid[0], grid[1]
             p.kp, p.vp = kv[0].data_ptr(), kv[1].data_ptr()
             p.xa_workspace, p.xa_workspace_bytes = xa_ws.data_ptr(), xa_bytes
+            p.xa_prepared = int(corr.get('xa_prepared_for') == (corr['keymask'].data_ptr(), N, xa_ws.data_ptr()))
         if kv is not None and wait_kv_events:
             main = torch.cuda.current_stream()
             for l in range(L):          # layer l starts when its projection (on the kv stream) is done

@@ -93,7 +93,7 @@ class DecoderParams(C.Structure):
         ('cls_scores', c_f), ('bbox_preds', c_f), ('outs_dec', c_f),
         ('workspace', c_f), ('workspace_bytes', C.c_size_t),
         ('layer_begin', C.c_int), ('layer_end', C.c_int), ('xa_form', C.c_int), ('grid_h', C.c_int),
-        ('grid_w', C.c_int), ('reserved3', C.c_int),
+        ('grid_w', C.c_int), ('xa_prepared', C.c_int),
         ('kp', c_f), ('vp', c_f), ('xa_workspace', c_f), ('xa_workspace_bytes', C.c_size_t),
     ]
 
@@ -147,6 +147,7 @@ SYMBOLS = [
     ('mv2d_decoder', C.c_int, [C.POINTER(DecoderParams), c_f]),
     ('mv2d_xa_tile_workspace_bytes', C.c_size_t, [C.c_int] * 4),
     ('mv2d_kv_project', C.c_int, [C.POINTER(KvParams), c_f]),
+    ('mv2d_xa_tile_prepare', C.c_int, [C.POINTER(DecoderParams), c_f]),
     ('mv2d_gemm', C.c_int, [c_f, C.c_int, c_f, C.c_int, c_f, c_f, C.c_int, C.c_int, C.c_int, C.c_int,
                             C.c_int, c_f]),
     ('mv2d_debug_clock_probe', C.c_int, [C.c_longlong, c_f, c_f]),

@@ -360,3 +360,21 @@ def test_pipeline_lanes_match_single_engine(mode, case, state_dicts):
     torch.cuda.synchronize()
     for i, o in enumerate(outs):
         assert torch.equal(o['cls_scores'], want[i][0]) and torch.equal(o['bbox_preds'], want[i][1])
+
+
+@pytest.mark.parametrize('mode,V,n,seed', [('T', 12, 3, 41), ('S', 6, 5, 42)])
+def test_odd_feature_grid_matches_oracle(mode, V, n, seed, state_dicts):
+    """480x1360 images -> a 30x85 feature grid: the cell count is no multiple of 128 (GEMM row tiles), of 32 (mask
+    words) or of 8 (the 8x8 key tiles of the two-frame head have ragged right / bottom edges)."""
+    from oracle import mv2d_oracle as O
+    eng = engine(mode, 6, state_dicts)
+    shape = (480, 1360, 3)
+    feat, boxes, metas = synth.make_sample(seed, V, n, img_shape=shape, pad_shape=shape, cam_jitter_deg=2.0)
+    assert tuple(feat.shape[-2:]) == (30, 85)
+    fn = O.mv2d_s_forward if mode == 'S' else O.mv2d_t_forward
+    with torch.no_grad():
+        cls, box = fn(state_dicts(6), feat, boxes, metas, O.make_cfg(mode))
+    out = eng.forward(feat.cuda(), boxes, metas)
+    torch.cuda.synchronize()
+    assert_close(out['cls_scores'], cls, what='cls_scores')
+    assert_close(out['bbox_preds'], box, what='bbox_preds')
