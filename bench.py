@@ -170,6 +170,8 @@ def main():
     assert torch.cuda.is_available(), 'bench.py needs a GPU (mv2d_b200 has no CPU fallback)'
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
+    if os.environ.get('NCCL_DEBUG', '').upper() == 'VERSION':
+        os.environ['NCCL_DEBUG'] = 'WARN'       # keep stdout to the one JSON line (NCCL prints its version there)
     D.init('nccl', dev)
     assert world == args.gpus, f'--gpus {args.gpus} but WORLD_SIZE={world}'
     peaks = measured_peaks()

@@ -165,6 +165,7 @@ typedef struct Mv2dLayerWeights {
                                          * constant, softmax cancels it) */
     const float *xa_v_w, *xa_v_w_lo;    /* Wv as TF32 hi + lo : [256,256] */
     const float *xa_o_w, *xa_o_b;       /* Wo [256,256], Wo bv + bo [256] (probabilities sum to one) */
+    const float *xa_k_raw, *xa_v_raw;   /* Wk, Wv as plain fp32 (= hi + lo): operands of the in-kernel-split GEMM */
 } Mv2dLayerWeights;
 
 typedef struct Mv2dBranchWeights {      /* stacked over layers: leading dim L */
@@ -231,8 +232,8 @@ MV2D_API int mv2d_decoder(const Mv2dDecoderParams* p, void* stream);
  * error-compensated 3xTF32 tcgen05 GEMMs (fp32-grade).  The operands are the TF32 splits mv2d_split_tf32 makes. */
 typedef struct Mv2dKvParams {
     int num_rows, L, layer_begin, layer_end;
-    const float *kin_hi, *kin_lo;      /* [num_rows,256] */
-    const float *mem_hi, *mem_lo;      /* [num_rows,256] */
+    const float *kin_hi, *kin_lo;      /* [num_rows,256]; kin_lo == mem_lo == NULL: kin_hi / mem_hi are the plain fp32 */
+    const float *mem_hi, *mem_lo;      /* [num_rows,256]  rows and the GEMM splits operands and weights in-kernel    */
     const Mv2dLayerWeights* layers;    /* HOST array [L] */
     float* kp;                         /* out [L,num_rows,256] */
     float* vp;                         /* out [L,num_rows,256] */
@@ -297,7 +298,9 @@ MV2D_API int mv2d_gemm(const float* A, int lda, const float* W, int ldw, const f
 /* x -> hi = tf32(x), lo = tf32(x - hi): the operand split of the 3xTF32 GEMM */
 MV2D_API int mv2d_split_tf32(const float* x, float* hi, float* lo, long long n, void* stream);
 /* error-compensated 3xTF32 tcgen05 GEMM: C = act((A_hi+A_lo) . (W_hi+W_lo)^T + bias), fp32-grade.
- * flags: 1 relu, 128 A is the implicit 3x3 im2col of [M/49,7,7,256] RoI tokens (K = 2304) */
+ * With A_lo == W_lo == NULL the operands are plain fp32 and the kernel splits them in shared memory itself (one
+ * copy of each operand crosses L2 instead of two); the result is bit-identical to the pre-split call.
+ * flags: 1 relu, 128 A is the implicit 3x3 im2col of [M/49,7,7,256] RoI tokens (K = 2304; pre-split operands only) */
 MV2D_API int mv2d_gemm_3xtf32(const float* A_hi, const float* A_lo, int lda, const float* W_hi, const float* W_lo,
                               int ldw, const float* bias, float* C, int ldc, int M, int N, int K, int flags,
                               void* stream);

@@ -65,7 +65,7 @@ int mv2d_split_tf32(const float* x, float* hi, float* lo, long long n, void* str
 
 int mv2d_gemm_3xtf32(const float* A_hi, const float* A_lo, int lda, const float* W_hi, const float* W_lo, int ldw,
                      const float* bias, float* C, int ldc, int M, int N, int K, int flags, void* stream) {
-    MV2D_CHECK_ARG(A_hi && A_lo && W_hi && W_lo && C, "gemm_3xtf32: null pointer");
+    MV2D_CHECK_ARG(A_hi && W_hi && C && ((A_lo && W_lo) || (!A_lo && !W_lo)), "gemm_3xtf32: null pointer");
     TcGemm t{};
     t.A = A_hi; t.A_lo = A_lo; t.lda = lda; t.W = W_hi; t.W_lo = W_lo; t.ldw = ldw; t.bias = bias;
     t.C = C; t.ldc = ldc; t.M = M; t.N = N; t.K = K; t.passes = 3; t.im2col = (flags & 128) ? 1 : 0;
@@ -113,7 +113,8 @@ int mv2d_xa_tile_prepare(const Mv2dDecoderParams* p, void* stream) {
 }
 int mv2d_kv_project(const Mv2dKvParams* p, void* stream) {
     NONNULL(p, "kv_project");
-    MV2D_CHECK_ARG(p->kin_hi && p->kin_lo && p->mem_hi && p->mem_lo && p->layers && p->kp && p->vp, "kv_project: null pointer");
+    MV2D_CHECK_ARG(p->kin_hi && p->mem_hi && p->layers && p->kp && p->vp && ((p->kin_lo && p->mem_lo) || (!p->kin_lo && !p->mem_lo)),
+                   "kv_project: null pointer");
     return run_kv_project(*p, (cudaStream_t)stream);
 }
 int mv2d_decoder(const Mv2dDecoderParams* p, void* stream) {

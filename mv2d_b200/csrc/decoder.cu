@@ -973,13 +973,15 @@ int run_kv_project(const Mv2dKvParams& p, cudaStream_t st) {
     const long long RC = (long long)p.num_rows * MV2D_C;
     for (int l = p.layer_begin; l < le; ++l) {
         const Mv2dLayerWeights& w = p.layers[l];
-        MV2D_CHECK_ARG(w.xa_k_w && w.xa_k_w_lo && w.xa_v_w && w.xa_v_w_lo, "kv_project: layer %d has no xa_k / xa_v weights", l);
+        const bool raw = p.kin_lo == nullptr;      // plain fp32 rows: the GEMM splits rows and weights in shared memory
+        MV2D_CHECK_ARG(w.xa_k_w && w.xa_v_w && (raw ? (w.xa_k_raw && w.xa_v_raw) : (w.xa_k_w_lo && w.xa_v_w_lo)),
+                       "kv_project: layer %d has no xa_k / xa_v weights", l);
         int rc;
         TcGemm t{};
         t.lda = MV2D_C; t.ldw = MV2D_C; t.ldc = MV2D_C; t.M = p.num_rows; t.N = MV2D_C; t.K = MV2D_C; t.passes = 3; t.nsplit = 1;
-        t.A = p.kin_hi; t.A_lo = p.kin_lo; t.W = w.xa_k_w; t.W_lo = w.xa_k_w_lo; t.C = p.kp + l * RC;
+        t.A = p.kin_hi; t.A_lo = p.kin_lo; t.W = raw ? w.xa_k_raw : w.xa_k_w; t.W_lo = raw ? nullptr : w.xa_k_w_lo; t.C = p.kp + l * RC;
         if ((rc = launch_gemm_tc(t, st))) return rc;
-        t.A = p.mem_hi; t.A_lo = p.mem_lo; t.W = w.xa_v_w; t.W_lo = w.xa_v_w_lo; t.C = p.vp + l * RC;
+        t.A = p.mem_hi; t.A_lo = p.mem_lo; t.W = raw ? w.xa_v_raw : w.xa_v_w; t.W_lo = raw ? nullptr : w.xa_v_w_lo; t.C = p.vp + l * RC;
         if ((rc = launch_gemm_tc(t, st))) return rc;
     }
     return 0;

@@ -104,10 +104,15 @@ struct TcArgs {
     const float* gx; const float* gs; const float* gfeat; float* kin;  // GEMM_GATE extras
 };
 
-template <int BN, int PASSES, bool IM2COL, int STAGES>
+// RAW (PASSES == 3 only): the operands arrive as plain fp32 -- ONE copy of each tile crosses the L2->SM fabric instead
+// of a pre-split hi and lo copy -- and the four epilogue warps, idle during the main loop, split every stage in
+// shared memory (hi in place, lo beside it; element-wise, so the 128B swizzle TMA wrote is preserved) before the
+// MMA warp consumes it: full_bar (TMA landed) -> split -> fence.proxy.async -> conv_bar -> tcgen05.mma.
+template <int BN, int PASSES, bool IM2COL, int STAGES, bool RAW = false>
 __global__ void __launch_bounds__(TC_THREADS, (PASSES == 1 ? 2 : 1))
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
                const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmWlo, TcArgs g) {
+    static_assert(!RAW || (PASSES == 3 && !IM2COL), "RAW is the in-kernel split of the plain 3xTF32 GEMM");
     constexpr int A_BYTES = TC_BM * TC_BK * 4;      // 16 KB
     constexpr int W_BYTES = BN * TC_BK * 4;
     constexpr int NOP = PASSES == 3 ? 2 : 1;        // hi (+ lo) copies of each operand
@@ -118,7 +123,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tmem_full_bar = empty_bar + STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+    uint64_t* conv_bar = tmem_full_bar + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(conv_bar + STAGES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m_tile = blockIdx.y, n0 = blockIdx.x * BN;
@@ -129,7 +135,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 0 && lane == 0) {
         tmap_prefetch(&tmA); tmap_prefetch(&tmW);
         if (PASSES == 3) { tmap_prefetch(&tmAlo); tmap_prefetch(&tmWlo); }
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); mbar_init(&conv_bar[s], 128); }
         mbar_init(tmem_full_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -154,7 +160,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 uint8_t* st = smem + s * STAGE_BYTES;
                 // bytes TMA will deliver: an im2col box is 49 rows x 128 B per RoI, not a full 64-row half tile
                 constexpr int A_TX = IM2COL ? 2 * MV2D_TOK * TC_BK * 4 : A_BYTES;
-                mbar_expect_tx(&full_bar[s], NOP * (A_TX + W_BYTES));
+                mbar_expect_tx(&full_bar[s], (RAW ? 1 : NOP) * (A_TX + W_BYTES));
                 if (IM2COL) {
                     const int kg = kb0 + kb;
                     const int tap = kg / (MV2D_C / TC_BK), c0 = (kg % (MV2D_C / TC_BK)) * TC_BK;
@@ -167,10 +173,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                 } else {
                     tma_load_2d(&tmA, &full_bar[s], st, (kb0 + (kb + rot) % nkb) * TC_BK, m_tile * TC_BM);
-                    if (PASSES == 3) tma_load_2d(&tmAlo, &full_bar[s], st + A_BYTES, (kb0 + (kb + rot) % nkb) * TC_BK, m_tile * TC_BM);
+                    if (PASSES == 3 && !RAW) tma_load_2d(&tmAlo, &full_bar[s], st + A_BYTES, (kb0 + (kb + rot) % nkb) * TC_BK, m_tile * TC_BM);
                 }
                 tma_load_2d(&tmW, &full_bar[s], st + NOP * A_BYTES, (kb0 + (kb + rot) % nkb) * TC_BK, n0);
-                if (PASSES == 3) tma_load_2d(&tmWlo, &full_bar[s], st + NOP * A_BYTES + W_BYTES, (kb0 + (kb + rot) % nkb) * TC_BK, n0);
+                if (PASSES == 3 && !RAW) tma_load_2d(&tmWlo, &full_bar[s], st + NOP * A_BYTES + W_BYTES, (kb0 + (kb + rot) % nkb) * TC_BK, n0);
             }
         }
     } else if (warp == 1) {
@@ -180,7 +186,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == 0) {
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % STAGES, ph = (kb / STAGES) & 1;
-                mbar_wait(&full_bar[s], ph);
+                mbar_wait(RAW ? &conv_bar[s] : &full_bar[s], ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
                 const uint64_t a_hi = make_desc(sa), a_lo = make_desc(sa + A_BYTES);
@@ -204,6 +210,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // directly would write 16-byte pieces 4 KB apart; instead every warp transposes its 32x32 chunk through
         // a private, XOR-swizzled 4 KB staging tile (the pipeline stages are free by now) so that each store /
         // load instruction of the warp touches 4 rows x 128 contiguous bytes.
+        if (RAW) {
+            // ---- operand split, stage by stage, while the MMA warp works on the previous ones
+            const int te = threadIdx.x - 64;              // 0..127
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % STAGES, ph = (kb / STAGES) & 1;
+                mbar_wait(&full_bar[s], ph);
+                float4* a4 = reinterpret_cast<float4*>(smem + s * STAGE_BYTES);
+                float4* w4 = reinterpret_cast<float4*>(smem + s * STAGE_BYTES + NOP * A_BYTES);
+                // all loads first (independent LDS.128, one shared-memory latency), then split and store
+                constexpr int NA = A_BYTES / 16 / 128, NWV = W_BYTES / 16 / 128;
+                float4 va[NA], vw[NWV];
+#pragma unroll
+                for (int i = 0; i < NA; ++i) va[i] = a4[te + i * 128];
+#pragma unroll
+                for (int i = 0; i < NWV; ++i) vw[i] = w4[te + i * 128];
+                auto split4 = [](const float4 v, float4* hi, float4* lo) {
+                    float4 h, l;
+                    h.x = round_tf32(v.x); h.y = round_tf32(v.y); h.z = round_tf32(v.z); h.w = round_tf32(v.w);
+                    l.x = round_tf32(v.x - h.x); l.y = round_tf32(v.y - h.y); l.z = round_tf32(v.z - h.z); l.w = round_tf32(v.w - h.w);
+                    *hi = h; *lo = l;
+                };
+#pragma unroll
+                for (int i = 0; i < NA; ++i) split4(va[i], a4 + te + i * 128, a4 + A_BYTES / 16 + te + i * 128);
+#pragma unroll
+                for (int i = 0; i < NWV; ++i) split4(vw[i], w4 + te + i * 128, w4 + W_BYTES / 16 + te + i * 128);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA's async-proxy reads
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&conv_bar[s])) : "memory");
+            }
+        }
         mbar_wait(tmem_full_bar, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int q = warp & 3;                           // TMEM lane quadrant this warp may access
@@ -542,12 +577,12 @@ static int make_map_tokens(CUtensorMap* m, const float* base, int n_rois) {
     return 0;
 }
 
-template <int BN, int PASSES, bool IM2COL, int STAGES>
+template <int BN, int PASSES, bool IM2COL, int STAGES, bool RAW = false>
 static int launch_tc(const CUtensorMap& a, const CUtensorMap& alo, const CUtensorMap& w, const CUtensorMap& wlo,
                      const TcArgs& g, int m_tiles, int nsplit, cudaStream_t st) {
     constexpr int NOP = PASSES == 3 ? 2 : 1;
     constexpr size_t smem = (size_t)STAGES * NOP * (TC_BM * TC_BK * 4 + BN * TC_BK * 4) + 1024 + 256;
-    auto kern = gemm_tc_kernel<BN, PASSES, IM2COL, STAGES>;
+    auto kern = gemm_tc_kernel<BN, PASSES, IM2COL, STAGES, RAW>;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -599,7 +634,9 @@ int launch_gemm_tc(const TcGemm& t, cudaStream_t st) {
     const int bn = (t.M <= 512 && !t.im2col && t.passes == 3) ? 64 : 128;   // (a 256-wide, 2-stage im2col variant measured slower than 128-wide / 3 stages)
     MV2D_CHECK_ARG(t.M > 0 && t.N % bn == 0 && t.K % TC_BK == 0, "gemm_tc: need N%%%d==0 and K%%32==0 (N=%d K=%d)", bn, t.N, t.K);
     MV2D_CHECK_ARG((t.ldc & 3) == 0 && ((uintptr_t)t.C & 15) == 0, "gemm_tc: C must be 16-byte aligned");
-    MV2D_CHECK_ARG(t.passes == 1 || (t.A_lo && t.W_lo), "gemm_tc: 3xTF32 needs the lo operands");
+    // 3xTF32 with both lo operands null: plain fp32 operands, split inside the kernel (RAW)
+    const bool raw = t.passes == 3 && !t.A_lo && !t.W_lo && !t.im2col;
+    MV2D_CHECK_ARG(t.passes == 1 || raw || (t.A_lo && t.W_lo), "gemm_tc: 3xTF32 needs both lo operands (or neither: in-kernel split)");
     CUtensorMap a, alo, w, wlo;
     int rc;
     TcArgs g{};
@@ -619,10 +656,12 @@ int launch_gemm_tc(const TcGemm& t, cudaStream_t st) {
     } else {
         m_tiles = cdiv(t.M, TC_BM);
         if ((rc = make_map_2d(&a, t.A, t.M, t.K, t.lda, TC_BM))) return rc;
-        if ((rc = make_map_2d(&alo, t.passes == 3 ? t.A_lo : t.A, t.M, t.K, t.lda, TC_BM))) return rc;
+        if ((rc = make_map_2d(&alo, (t.passes == 3 && !raw) ? t.A_lo : t.A, t.M, t.K, t.lda, TC_BM))) return rc;
     }
     if ((rc = make_map_2d(&w, t.W, t.N, t.K, t.ldw, bn))) return rc;
-    if ((rc = make_map_2d(&wlo, t.passes == 3 ? t.W_lo : t.W, t.N, t.K, t.ldw, bn))) return rc;
+    if ((rc = make_map_2d(&wlo, (t.passes == 3 && !raw) ? t.W_lo : t.W, t.N, t.K, t.ldw, bn))) return rc;
+    if (raw && bn == 64) return launch_tc<64, 3, false, 4, true>(a, alo, w, wlo, g, m_tiles, nsplit, st);
+    if (raw) return launch_tc<128, 3, false, 3, true>(a, alo, w, wlo, g, m_tiles, nsplit, st);
     if (t.im2col && bn == 256) return launch_tc<256, 3, true, 2>(a, alo, w, wlo, g, m_tiles, nsplit, st);
     if (t.im2col) return launch_tc<128, 3, true, 3>(a, alo, w, wlo, g, m_tiles, nsplit, st);
     if (t.passes == 3 && bn == 64 && mc_enabled() && (t.N / 64) % TC_MC == 0) {

@@ -374,15 +374,21 @@ class HotPath:
         projection is done."""
         L, R = self.L, kin_rows.shape[0]
         n = R * 256
-        kin_hi, kin_lo = self._get('kin_hi', (R, 256)), self._get('kin_lo', (R, 256))
-        mem_hi, mem_lo = self._get('mem_hi', (R, 256)), self._get('mem_lo', (R, 256))
         kp, vp = self._get('kp', (L, R, 256)), self._get('vp', (L, R, 256))
         st = lib.stream_ptr()
-        lib.check(self.lib.mv2d_split_tf32(kin_rows.data_ptr(), kin_hi.data_ptr(), kin_lo.data_ptr(), n, st), 'mv2d_split_tf32')
-        lib.check(self.lib.mv2d_split_tf32(mem_rows.data_ptr(), mem_hi.data_ptr(), mem_lo.data_ptr(), n, st), 'mv2d_split_tf32')
         p = lib.KvParams()
         p.num_rows, p.L = R, L
-        p.kin_hi, p.kin_lo, p.mem_hi, p.mem_lo = kin_hi.data_ptr(), kin_lo.data_ptr(), mem_hi.data_ptr(), mem_lo.data_ptr()
+        if os.environ.get('MV2D_KV_RAW', '0') == '1':
+            # plain fp32 rows: the GEMM splits rows and weights into TF32 hi/lo in shared memory.  Bit-identical to
+            # the pre-split call and half the L2->SM bytes, but measured SLOWER on B200 (672 vs 528 us for the 12
+            # projections): with 3 x 64 KB stages the split sits on the TMA -> MMA latency chain.  Opt-in.
+            p.kin_hi, p.mem_hi = kin_rows.data_ptr(), mem_rows.data_ptr()
+        else:
+            kin_hi, kin_lo = self._get('kin_hi', (R, 256)), self._get('kin_lo', (R, 256))
+            mem_hi, mem_lo = self._get('mem_hi', (R, 256)), self._get('mem_lo', (R, 256))
+            lib.check(self.lib.mv2d_split_tf32(kin_rows.data_ptr(), kin_hi.data_ptr(), kin_lo.data_ptr(), n, st), 'mv2d_split_tf32')
+            lib.check(self.lib.mv2d_split_tf32(mem_rows.data_ptr(), mem_hi.data_ptr(), mem_lo.data_ptr(), n, st), 'mv2d_split_tf32')
+            p.kin_hi, p.kin_lo, p.mem_hi, p.mem_lo = kin_hi.data_ptr(), kin_lo.data_ptr(), mem_hi.data_ptr(), mem_lo.data_ptr()
         p.layers = self.w.layers_ptr()
         p.kp, p.vp = kp.data_ptr(), vp.data_ptr()
         for l in range(L):

@@ -65,7 +65,7 @@ class LayerWeights(C.Structure):
         ('ffn_w1', c_f), ('ffn_w1_lo', c_f), ('ffn_b1', c_f), ('ffn_w2', c_f), ('ffn_w2_lo', c_f), ('ffn_b2', c_f),
         ('ln_g', c_f * 3), ('ln_b', c_f * 3), ('sa_const', c_f),
         ('xa_q_w', c_f), ('xa_q_b', c_f), ('xa_k_w', c_f), ('xa_k_w_lo', c_f), ('xa_v_w', c_f), ('xa_v_w_lo', c_f),
-        ('xa_o_w', c_f), ('xa_o_b', c_f),
+        ('xa_o_w', c_f), ('xa_o_b', c_f), ('xa_k_raw', c_f), ('xa_v_raw', c_f),
     ]
 
 

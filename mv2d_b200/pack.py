@@ -153,6 +153,8 @@ class PackedWeights:
                 hi, lo = split_tf32(mat)
                 setattr(lw, field, put(f'l{l}.{field}', hi).data_ptr())
                 setattr(lw, field + '_lo', put(f'l{l}.{field}_lo', lo).data_ptr())
+            lw.xa_k_raw = put(f'l{l}.xa_k_raw', xk_w).data_ptr()
+            lw.xa_v_raw = put(f'l{l}.xa_v_raw', xv_w).data_ptr()
             lw.xa_o_w = put(f'l{l}.xa_o_w', xo_w).data_ptr()
             lw.xa_o_b = put(f'l{l}.xa_o_b', xo_b).data_ptr()
             lw.ca_q_b = put(f'l{l}.ca_q_b', qb).data_ptr()

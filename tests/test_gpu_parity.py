@@ -264,6 +264,12 @@ def test_tcgen05_gemm_3xtf32_and_im2col(state_dicts):
                                      Cc.data_ptr(), N, M, N, K, 0, lib.stream_ptr()), 'gemm_3xtf32')
         # fp32 accumulation inside the tensor core (K up to 2304, three products per step)
         assert_close(Cc, A.double() @ W.double().T + b.double(), 1e-4, 1e-4, f'3xtf32 {M}x{N}x{K}')
+        # plain fp32 operands, split into hi/lo inside the kernel (lo pointers NULL): same arithmetic, same bits
+        Cr = torch.full((M, N), float('nan'), device='cuda')
+        lib.check(h.mv2d_gemm_3xtf32(A.data_ptr(), None, K, W.data_ptr(), None, K, b.data_ptr(),
+                                     Cr.data_ptr(), N, M, N, K, 0, lib.stream_ptr()), 'gemm_3xtf32(raw)')
+        torch.cuda.synchronize()
+        assert torch.equal(Cr, Cc), f'in-kernel split differs from pre-split operands, max |d| = {(Cr - Cc).abs().max().item():.3e}'
     for n_rois in (1, 2, 7, 300):
         x = torch.randn(n_rois, 256, 7, 7, generator=g).cuda()
         w = (torch.randn(256, 256, 3, 3, generator=g) / 48).cuda()
