@@ -10,7 +10,7 @@ path -- (FPN P4 feature [6,256,32,88], per-view 2D boxes, img_metas) -> (cls_sco
 bbox_preds) of all 6 layers -- over one sample.  Metric: samples/sec, whole job.
 
   value  : whole-job throughput, inputs already resident in HBM.  Each step = one CUDA-graph replay of the
-           whole path for ONE sample (bs = 1); mv2d_b200.pipeline.Pipeline keeps --depth (default 3) samples in
+           whole path for ONE sample (bs = 1); mv2d_b200.pipeline.Pipeline keeps --depth (default 4) samples in
            flight on independent lanes, so the GPU-filling front end of sample i+1 runs under the latency-bound
            decoder of sample i.  The K steps are bracketed by one pair of CUDA events (+ barrier and
            synchronize on both sides); 8 distinct samples rotate (138 MB of feature maps > the 126 MB L2).
@@ -48,7 +48,7 @@ def parse():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--mode', default='S', choices=['S', 'T'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--depth', type=int, default=3, help='samples in flight (inter-sample pipelining); 1 = serial')
+    ap.add_argument('--depth', type=int, default=4, help='samples in flight (inter-sample pipelining); 1 = serial')
     return ap.parse_args()
 
 

@@ -7,7 +7,8 @@ import sys
 
 
 def short(name):
-    name = re.sub(r'^mv2d::', '', name)
+    name = re.sub(r'^void ', '', name)
+    name = re.sub(r'mv2d::', '', name)
     m = re.match(r'([\w:]+(<[^(]*>)?)', name)
     return m.group(1) if m else name[:60]
 

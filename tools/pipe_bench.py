@@ -13,7 +13,7 @@ samples = [synth.case_inputs(dict(case, seed=i)) for i in range(8)]
 feats = [s[0].cuda() for s in samples]
 pins = [s[0].pin_memory() for s in samples]
 steps = 64
-for depth in (1, 2, 3):
+for depth in [int(x) for x in (sys.argv[2].split(',') if len(sys.argv) > 2 else '1,2,3'.split(','))]:
     pipe = Pipeline(sd, mode=mode, depth=depth)
     for host in (False, True):
         src = pins if host else feats
