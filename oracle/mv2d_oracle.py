@@ -676,3 +676,96 @@ def nms_free_decode(cls_scores, bbox_preds, cfg, max_num=300):
     boxes = boxes.clone()
     boxes[:, 2] = boxes[:, 2] - boxes[:, 5] * 0.5
     return boxes, scores, labels
+
+
+# ============================================================================= training targets and losses
+# SURVEY.md 8f rank 3 ("next" row f3): Hungarian targets + focal / L1 losses of one decoder layer, and the
+# denoising loss.  Forward values only (no autograd here: the restatement is the checker of the CUDA kernels).
+LOSS_CFG = dict(   # configs/mv2d/exp/mv2d_r50_frcnn_single_frame_roi_1408x512_ep72.py:87-95,132-137
+    code_weights=[1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.5, 1.5, 2.0, 2.0],
+    cls_loss_weight=2.0, focal_gamma=2.0, focal_alpha=0.25, bbox_loss_weight=0.25,
+    cls_cost_weight=2.0, reg_cost_weight=0.25, num_classes=10, bg_cls_weight=0.0,
+)
+
+
+def normalize_bbox(b):
+    """core/bbox/util.py:38-58: (cx, cy, cz, w, l, h, rot, vx, vy) -> (cx, cy, log w, log l, cz, log h, sin, cos, vx, vy)."""
+    return torch.cat([b[..., 0:1], b[..., 1:2], b[..., 3:4].log(), b[..., 4:5].log(), b[..., 2:3], b[..., 5:6].log(),
+                      b[..., 6:7].sin(), b[..., 6:7].cos(), b[..., 7:8], b[..., 8:9]], dim=-1)
+
+
+def match_cost(cls_pred, bbox_pred, gt_boxes, gt_labels, lc=LOSS_CFG):
+    """hungarian_assigner_3d.py:119-131: FocalLossCost (mmdet 2.25.1) + BBox3DL1Cost (match_cost.py:24-26) on the
+    first 8 normalised box codes, then nan_to_num(100, 100, -100)."""
+    a, g, eps = lc['focal_alpha'], lc['focal_gamma'], 1e-12
+    p = cls_pred.sigmoid()
+    neg = -(1 - p + eps).log() * (1 - a) * p.pow(g)
+    pos = -(p + eps).log() * a * (1 - p).pow(g)
+    cls_cost = (pos[:, gt_labels] - neg[:, gt_labels]) * lc['cls_cost_weight']
+    reg_cost = torch.cdist(bbox_pred[:, :8], normalize_bbox(gt_boxes)[:, :8], p=1) * lc['reg_cost_weight']
+    return torch.nan_to_num(cls_cost + reg_cost, nan=100.0, posinf=100.0, neginf=-100.0)
+
+
+def hungarian_assign(cls_pred, bbox_pred, gt_boxes, gt_labels, lc=LOSS_CFG):
+    """hungarian_assigner_3d.py:66-150 -> assigned gt index per query, -1 = background."""
+    from scipy.optimize import linear_sum_assignment
+    N, G = bbox_pred.shape[0], gt_boxes.shape[0]
+    out = torch.full((N,), -1, dtype=torch.long)
+    if N == 0 or G == 0:
+        return out
+    rows, cols = linear_sum_assignment(match_cost(cls_pred, bbox_pred, gt_boxes, gt_labels, lc))
+    out[torch.from_numpy(rows)] = torch.from_numpy(cols)
+    return out
+
+
+def _focal_loss_sum(pred, labels, lc):
+    """mmdet FocalLoss (sigmoid) element sum; labels == num_classes is background."""
+    C = pred.shape[1]
+    t = F.one_hot(labels, num_classes=C + 1)[:, :C].type_as(pred)
+    p = pred.sigmoid()
+    pt = (1 - p) * t + p * (1 - t)
+    fw = (lc['focal_alpha'] * t + (1 - lc['focal_alpha']) * (1 - t)) * pt.pow(lc['focal_gamma'])
+    return (F.binary_cross_entropy_with_logits(pred, t, reduction='none') * fw).sum()
+
+
+def loss_single(cls_scores, bbox_preds, gt_boxes, gt_labels, lc=LOSS_CFG):
+    """cross_attention_head.py:379-434 for one sample and one decoder layer (as mv2d_s_head.py:281-286 calls it).
+    gt_boxes [G,9] = (gravity centre, w, l, h, yaw, vx, vy).  Returns (loss_cls, loss_bbox, assigned [N])."""
+    N = cls_scores.shape[0]
+    eps = torch.finfo(torch.float32).eps
+    assigned = hungarian_assign(cls_scores, bbox_preds, gt_boxes, gt_labels, lc)
+    pos = assigned >= 0
+    num_pos, num_neg = int(pos.sum()), int((~pos).sum())
+    labels = torch.full((N,), lc['num_classes'], dtype=torch.long)
+    labels[pos] = gt_labels[assigned[pos]]
+    cls_avg = max(num_pos * 1.0 + num_neg * lc['bg_cls_weight'], 1)
+    loss_cls = lc['cls_loss_weight'] * _focal_loss_sum(cls_scores, labels, lc) / (cls_avg + eps)
+    targets = torch.zeros(N, gt_boxes.shape[1] if gt_boxes.numel() else 9)
+    targets[pos] = gt_boxes[assigned[pos]]
+    nt = normalize_bbox(targets)
+    ok = torch.isfinite(nt).all(dim=-1)
+    w = pos.float()[:, None] * torch.tensor(lc['code_weights'])
+    if int(ok.sum()) == 0:
+        loss_bbox = torch.zeros(())
+    else:
+        loss_bbox = lc['bbox_loss_weight'] * ((bbox_preds[ok, :10] - nt[ok, :10]).abs() * w[ok]).sum() / (max(num_pos, 1) + eps)
+    return torch.nan_to_num(loss_cls), torch.nan_to_num(loss_bbox), assigned
+
+
+def dn_loss_single(cls_scores, bbox_preds, known_boxes, known_labels, num_tgt, split, lc=LOSS_CFG):
+    """cross_attention_head.py:475-538 (neg_bbox_loss False): cls_scores/bbox_preds [pad,10] of the denoising
+    queries, known_boxes [pad,9] = the GT box each one was noised from, known_labels [pad] (num_classes = negative)."""
+    eps = torch.finfo(torch.float32).eps
+    cls_avg = max(num_tgt * 3.14159 / 6 * split * split * split, 1)
+    loss_cls = lc['cls_loss_weight'] * _focal_loss_sum(cls_scores, known_labels.long(), lc) / (cls_avg + eps)
+    kb = known_boxes.clone()
+    kb[known_labels == lc['num_classes']] = 0
+    nt = normalize_bbox(kb)
+    ok = torch.isfinite(nt).all(dim=-1)
+    w = torch.tensor(lc['code_weights']).repeat(kb.shape[0], 1)
+    w[:, 6:8] = 0
+    if int(ok.sum()) == 0:
+        loss_bbox = torch.zeros(())
+    else:
+        loss_bbox = lc['bbox_loss_weight'] * ((bbox_preds[ok, :10] - nt[ok, :10]).abs() * w[ok]).sum() / (max(num_tgt, 1) + eps)
+    return torch.nan_to_num(loss_cls), torch.nan_to_num(loss_bbox)

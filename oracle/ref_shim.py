@@ -19,6 +19,7 @@ import warnings
 
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 REFERENCE_ROOT = '/root/reference'
 
@@ -628,3 +629,146 @@ def build_reference_head(cfg_path):
         warnings.simplefilter('ignore')
         head = build_from_cfg(roi_head, HEADS)
     return head.eval(), cfg
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Training targets / losses.  The reference's own code for this row --
+# HungarianAssigner3D.assign (core/bbox/assigners/hungarian_assigner_3d.py:66-150), BBox3DL1Cost
+# (core/bbox/match_costs/match_cost.py:6-26), normalize_bbox (core/bbox/util.py:38-58) and
+# CrossAttentionBoxHead.loss_single / get_targets / dn_loss_single (cross_attention_head.py:244-343,379-538) --
+# runs unmodified; what it imports from mmdet 2.25.1 is restated below from that version's published behaviour
+# (unpinned by any reference test, like the rest of this shim).
+MATCH_COST = Registry('match_cost')
+
+
+@MATCH_COST.register_module()
+class FocalLossCost:
+    """mmdet/core/bbox/match_costs/match_cost.py FocalLossCost._focal_loss_cost (2.25.1)."""
+
+    def __init__(self, weight=1., alpha=0.25, gamma=2, eps=1e-12, binary_input=False):
+        self.weight, self.alpha, self.gamma, self.eps = weight, alpha, gamma, eps
+
+    def __call__(self, cls_pred, gt_labels):
+        cls_pred = cls_pred.sigmoid()
+        neg_cost = -(1 - cls_pred + self.eps).log() * (1 - self.alpha) * cls_pred.pow(self.gamma)
+        pos_cost = -(cls_pred + self.eps).log() * self.alpha * (1 - cls_pred).pow(self.gamma)
+        cls_cost = pos_cost[:, gt_labels] - neg_cost[:, gt_labels]
+        return cls_cost * self.weight
+
+
+@MATCH_COST.register_module()
+class IoUCost:
+    def __init__(self, iou_mode='giou', weight=1.):
+        self.weight = weight
+
+    def __call__(self, *a, **k):
+        raise NotImplementedError('IoUCost weight is 0 in the reference configs and never called (hungarian_assigner_3d.py:119-127)')
+
+
+def build_match_cost(cfg):
+    return build_from_cfg(cfg, MATCH_COST)
+
+
+class AssignResult:
+    """mmdet/core/bbox/assigners/assign_result.py (fields only)."""
+
+    def __init__(self, num_gts, gt_inds, max_overlaps, labels=None):
+        self.num_gts, self.gt_inds, self.max_overlaps, self.labels = num_gts, gt_inds, max_overlaps, labels
+
+
+class BaseAssigner:
+    pass
+
+
+class SamplingResult:
+    """mmdet/core/bbox/samplers/sampling_result.py."""
+
+    def __init__(self, pos_inds, neg_inds, bboxes, gt_bboxes, assign_result, gt_flags):
+        self.pos_inds, self.neg_inds = pos_inds, neg_inds
+        self.pos_bboxes, self.neg_bboxes = bboxes[pos_inds], bboxes[neg_inds]
+        self.num_gts = gt_bboxes.shape[0]
+        self.pos_assigned_gt_inds = assign_result.gt_inds[pos_inds] - 1
+        if gt_bboxes.numel() == 0:
+            self.pos_gt_bboxes = torch.empty_like(gt_bboxes).view(-1, 4)
+        else:
+            self.pos_gt_bboxes = gt_bboxes[self.pos_assigned_gt_inds.long(), :]
+
+
+class PseudoSampler:
+    """mmdet/core/bbox/samplers/pseudo_sampler.py."""
+
+    def __init__(self, **kwargs):
+        pass
+
+    def sample(self, assign_result, bboxes, gt_bboxes, *args, **kwargs):
+        pos_inds = torch.nonzero(assign_result.gt_inds > 0, as_tuple=False).squeeze(-1).unique()
+        neg_inds = torch.nonzero(assign_result.gt_inds == 0, as_tuple=False).squeeze(-1).unique()
+        gt_flags = bboxes.new_zeros(bboxes.shape[0], dtype=torch.uint8)
+        return SamplingResult(pos_inds, neg_inds, bboxes, gt_bboxes, assign_result, gt_flags)
+
+
+def _weight_reduce_loss(loss, weight=None, reduction='mean', avg_factor=None):
+    """mmdet/models/losses/utils.py weight_reduce_loss."""
+    if weight is not None:
+        loss = loss * weight
+    if avg_factor is None:
+        return loss.mean() if reduction == 'mean' else (loss.sum() if reduction == 'sum' else loss)
+    if reduction == 'mean':
+        eps = torch.finfo(torch.float32).eps
+        return loss.sum() / (avg_factor + eps)
+    assert reduction == 'none'
+    return loss
+
+
+class FocalLoss(nn.Module):
+    """mmdet/models/losses/focal_loss.py, use_sigmoid=True, the py_sigmoid_focal_loss path (the mmcv CUDA op
+    computes the same -alpha_t (1 - p_t)^gamma log p_t)."""
+
+    def __init__(self, use_sigmoid=True, gamma=2.0, alpha=0.25, reduction='mean', loss_weight=1.0, activated=False):
+        super().__init__()
+        assert use_sigmoid and not activated
+        self.use_sigmoid, self.gamma, self.alpha, self.reduction, self.loss_weight = use_sigmoid, gamma, alpha, reduction, loss_weight
+
+    def forward(self, pred, target, weight=None, avg_factor=None, reduction_override=None):
+        num_classes = pred.size(1)
+        target = F.one_hot(target, num_classes=num_classes + 1)[:, :num_classes].type_as(pred)
+        p = pred.sigmoid()
+        pt = (1 - p) * target + p * (1 - target)
+        focal_weight = (self.alpha * target + (1 - self.alpha) * (1 - target)) * pt.pow(self.gamma)
+        loss = F.binary_cross_entropy_with_logits(pred, target, reduction='none') * focal_weight
+        if weight is not None and weight.shape != loss.shape:
+            weight = weight.view(-1, 1) if weight.size(0) == loss.size(0) else weight.view(loss.size(0), -1)
+        return self.loss_weight * _weight_reduce_loss(loss, weight, self.reduction, avg_factor)
+
+
+class L1Loss(nn.Module):
+    """mmdet/models/losses/smooth_l1_loss.py L1Loss."""
+
+    def __init__(self, reduction='mean', loss_weight=1.0):
+        super().__init__()
+        self.reduction, self.loss_weight = reduction, loss_weight
+
+    def forward(self, pred, target, weight=None, avg_factor=None, reduction_override=None):
+        if target.numel() == 0:
+            return self.loss_weight * pred.sum() * 0
+        return self.loss_weight * _weight_reduce_loss(torch.abs(pred - target), weight, self.reduction, avg_factor)
+
+
+def install_loss_support():
+    """Stand-ins the reference's assigner / match-cost modules import, then the reference modules themselves."""
+    install()
+    import os
+    _mod('mmdet.core.bbox.assigners', AssignResult=AssignResult, BaseAssigner=BaseAssigner)
+    _mod('mmdet.core.bbox.match_costs', build_match_cost=build_match_cost)
+    _mod('mmdet.core.bbox.match_costs.builder', MATCH_COST=MATCH_COST)
+    _mod('mmdet.core.bbox.iou_calculators', bbox_overlaps=None)
+    sys.modules['mmdet.core.bbox.builder'].BBOX_ASSIGNERS = BBOX_ASSIGNERS
+    for pkg in ('mmdet3d_plugin.core.bbox.assigners', 'mmdet3d_plugin.core.bbox.match_costs'):
+        if pkg not in sys.modules:
+            m = types.ModuleType(pkg)
+            m.__path__ = [os.path.join(REFERENCE_ROOT, *pkg.split('.'))]
+            sys.modules[pkg] = m
+    import importlib
+    mc = importlib.import_module('mmdet3d_plugin.core.bbox.match_costs.match_cost')      # registers BBox3DL1Cost
+    asg = importlib.import_module('mmdet3d_plugin.core.bbox.assigners.hungarian_assigner_3d')
+    return asg.HungarianAssigner3D, mc.BBox3DL1Cost
