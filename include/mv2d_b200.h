@@ -40,7 +40,7 @@ MV2D_API const char* mv2d_last_error(void);
 /* number of kernel launches this library has enqueued so far in this process */
 MV2D_API unsigned long long mv2d_launch_count(void);
 /* sizeof() of the parameter structs, so a binding can verify its mirror of this header */
-MV2D_API size_t mv2d_sizeof(int which); /* 0 Pe, 1 Qg, 2 Corr, 3 Decoder, 4 LayerWeights, 5 BranchWeights, 6 Dn, 7 Kv */
+MV2D_API size_t mv2d_sizeof(int which); /* 0 Pe, 1 Qg, 2 Corr, 3 Decoder, 4 LayerWeights, 5 BranchWeights, 6 Dn, 7 Kv, 8 Loss */
 
 /* ---- geometry (utils/pe.py:111; roi_heads/utils/box_correlation.py:118-122,174-178)
  * img2lidar[v] = inv(lidar2img[v]);  trans[src][dst] = lidar2img[dst] @ img2lidar[src]  (fp64) */
@@ -288,6 +288,42 @@ typedef struct Mv2dDnParams {
 } Mv2dDnParams;
 MV2D_API size_t mv2d_dn_workspace_bytes(int T, int mask_words);
 MV2D_API int mv2d_dn_prepare(const Mv2dDnParams* p, void* stream);
+
+/* ---- f3 (next row): training targets and losses of one sample, all decoder layers in one call
+ * (core/bbox/assigners/hungarian_assigner_3d.py:66-150; core/bbox/match_costs/match_cost.py:6-26;
+ *  core/bbox/util.py:38-58; bbox_heads/cross_attention_head.py:244-343,379-434 loss_single, :475-538 dn_loss_single,
+ *  as roi_heads/mv2d_s_head.py:278-299 calls them: per layer, one sample).  For every layer l:
+ *   cost[n,g]   = cls_cost_weight * FocalLossCost(cls[l,n], label_g) + reg_cost_weight * |box[l,n,:8] - norm(gt_g)[:8]|_1
+ *   assigned[l] = linear sum assignment of cost (the reference: scipy on the host after a .cpu() sync), -1 = background
+ *   losses[l]   = { cls_loss_weight * focal(cls, targets) / max(num_pos, 1),
+ *                   bbox_loss_weight * sum_pos |box - norm(gt)| * code_weights / max(num_pos, 1),
+ *                   the same two for the denoising queries (avg factors pad*pi/6*split^3 and pad; codes 6:8 unweighted) }
+ * Ties between equal costs are broken in favour of unassigned columns, then the lower index (scipy's scan order can
+ * differ there; exact ties do not occur with real-valued predictions). */
+typedef struct Mv2dLossParams {
+    int N, G, L, num_classes;
+    int pad;                    /* number of denoising queries, 0 = none */
+    int neg_bbox_loss;          /* 1: negative denoising queries keep their box target (exp two_frames config :45,
+                                 *    cross_attention_head.py:521-523); 0: only positives enter the denoising box loss */
+    long long layer_stride;     /* elements between layers of cls_scores / bbox_preds (rows are [*,10] contiguous) */
+    long long dn_layer_stride;  /* same for dn_cls / dn_box */
+    float cls_cost_weight, reg_cost_weight, cls_loss_weight, bbox_loss_weight;
+    float focal_alpha, focal_gamma, dn_split, reserved1;
+    float code_weights[10];
+    const float* cls_scores;    /* [L,N,num_classes] */
+    const float* bbox_preds;    /* [L,N,10] */
+    const float* gt_boxes;      /* [G,9] gravity centre xyz, w, l, h, yaw, vx, vy */
+    const int* gt_labels;       /* [G] */
+    const float* dn_cls;        /* nullable [L,pad,num_classes] */
+    const float* dn_box;        /* nullable [L,pad,10] */
+    const int* dn_labels;       /* nullable [pad]: label, num_classes = negative; query i was noised from box i % G */
+    int* assigned;              /* out [L,N] */
+    float* losses;              /* out [L,4]: loss_cls, loss_bbox, dn_loss_cls, dn_loss_bbox */
+    float* workspace;
+    size_t workspace_bytes;
+} Mv2dLossParams;
+MV2D_API size_t mv2d_loss_workspace_bytes(int N, int G, int L);
+MV2D_API int mv2d_loss(const Mv2dLossParams* p, void* stream);
 
 /* ---- low-level GEMM, exposed for tests and microbenchmarks:
  * C[M,N] = act(A[M,K] . W[N,K]^T + bias); flags: 1 relu, 8 allow TF32 tensor cores,

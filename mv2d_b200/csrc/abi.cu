@@ -42,6 +42,7 @@ size_t mv2d_sizeof(int which) {
         case 5: return sizeof(Mv2dBranchWeights);
         case 6: return sizeof(Mv2dDnParams);
         case 7: return sizeof(Mv2dKvParams);
+        case 8: return sizeof(Mv2dLossParams);
         default: return 0;
     }
 }
@@ -123,6 +124,12 @@ int mv2d_decoder(const Mv2dDecoderParams* p, void* stream) {
                                  p->bbox_preds && p->outs_dec && p->workspace),
                    "decoder: null pointer");
     return run_decoder(*p, (cudaStream_t)stream);
+}
+
+size_t mv2d_loss_workspace_bytes(int N, int G, int L) { return loss_workspace_bytes(N, G, L); }
+int mv2d_loss(const Mv2dLossParams* p, void* stream) {
+    NONNULL(p, "loss");
+    return run_loss(*p, (cudaStream_t)stream);
 }
 
 int mv2d_gemm(const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc, int M, int N,

@@ -23,6 +23,9 @@ int run_nms_free_decode(const float* cls, const float* box, int N, int max_num, 
                         float* out_boxes, float* out_scores, int* out_labels, uint8_t* out_valid,
                         cudaStream_t st);
 
+int run_loss(const Mv2dLossParams& p, cudaStream_t st);
+size_t loss_workspace_bytes(int N, int G, int L);
+
 int run_clock_probe(long long cycles, long long* out, cudaStream_t st);
 
 }  // namespace mv2d

@@ -617,6 +617,90 @@ class HotPath:
         out['num_per_view'] = counts
         return out
 
+    LOSS_DEFAULTS = dict(   # configs/mv2d/exp/mv2d_r50_frcnn_single_frame_roi_1408x512_ep72.py:87-95,132-137
+        code_weights=[1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.5, 1.5, 2.0, 2.0],
+        cls_loss_weight=2.0, focal_gamma=2.0, focal_alpha=0.25, bbox_loss_weight=0.25,
+        cls_cost_weight=2.0, reg_cost_weight=0.25)
+
+    @torch.no_grad()
+    def loss(self, cls_scores, bbox_preds, gt_boxes, gt_labels, dn_cls=None, dn_box=None, dn_labels=None,
+             neg_bbox_loss=None, **over):
+        """Next row f3: Hungarian targets + focal / L1 losses of every decoder layer (and the denoising losses) in
+        one device call, no host round trip (mv2d_s_head.py:278-299 -> bbox_head.loss / dn_loss_single).
+        cls_scores / bbox_preds [L,N,10] (views with a layer stride are fine), gt_boxes [G,9] = (gravity centre,
+        w, l, h, yaw, vx, vy), gt_labels [G].  Returns dict(loss_cls [L], loss_bbox [L], dn_loss_cls [L],
+        dn_loss_bbox [L], assigned [L,N] int32 with -1 = background).  Forward values only."""
+        c = dict(self.LOSS_DEFAULTS, **over)
+        dev = self.device
+        L, N = cls_scores.shape[0], cls_scores.shape[1]
+
+        def rows(t):        # [L, M, 10] with contiguous rows; the layer stride may be larger than M*10
+            assert t.dim() == 3 and t.shape[2] == 10 and t.dtype == torch.float32 and t.is_cuda
+            if t.shape[1] > 0 and (t.stride(2) != 1 or t.stride(1) != 10):
+                t = t.contiguous()
+            return t, (t.stride(0) if t.shape[0] > 1 else t.shape[1] * 10)
+        cls_scores, ls = rows(cls_scores)
+        bbox_preds, ls2 = rows(bbox_preds)
+        if ls != ls2:       # one layer stride for both: fall back to packed copies
+            (cls_scores, ls), (bbox_preds, ls2) = rows(cls_scores.contiguous()), rows(bbox_preds.contiguous())
+        gt = gt_boxes.to(dev, torch.float32).contiguous().view(-1, 9)
+        lab = gt_labels.to(dev).to(torch.int32).contiguous()
+        G = gt.shape[0]
+        p = lib.LossParams()
+        p.N, p.G, p.L, p.num_classes = N, G, L, self.cfg['num_classes']
+        p.layer_stride = ls
+        for k in ('cls_cost_weight', 'reg_cost_weight', 'cls_loss_weight', 'bbox_loss_weight', 'focal_alpha', 'focal_gamma'):
+            setattr(p, k, c[k])
+        p.dn_split = self.cfg['denoise_split']
+        # exp/mv2d_r50_frcnn_two_frames_1408x512_ep72.py:45 turns neg_bbox_loss on, the S head default is off
+        p.neg_bbox_loss = int((self.mode == 'T') if neg_bbox_loss is None else neg_bbox_loss)
+        p.code_weights = (C.c_float * 10)(*c['code_weights'])
+        p.cls_scores, p.bbox_preds = cls_scores.data_ptr(), bbox_preds.data_ptr()
+        p.gt_boxes, p.gt_labels = gt.data_ptr(), lab.data_ptr()
+        keep = [gt, lab, cls_scores, bbox_preds]
+        if dn_cls is not None and dn_cls.shape[1] > 0:
+            dn_cls, ds = rows(dn_cls)
+            dn_box, ds2 = rows(dn_box)
+            if ds != ds2:
+                (dn_cls, ds), (dn_box, ds2) = rows(dn_cls.contiguous()), rows(dn_box.contiguous())
+            dl = dn_labels.to(dev).to(torch.int32).contiguous()
+            p.pad, p.dn_layer_stride = dn_cls.shape[1], ds
+            p.dn_cls, p.dn_box, p.dn_labels = dn_cls.data_ptr(), dn_box.data_ptr(), dl.data_ptr()
+            keep += [dn_cls, dn_box, dl]
+        assigned = torch.empty((L, N), dtype=torch.int32, device=dev)
+        losses = torch.empty((L, 4), dtype=torch.float32, device=dev)
+        ws_bytes = self.lib.mv2d_loss_workspace_bytes(N, G, L)
+        ws = self._get('loss_ws', (ws_bytes // 4 + 1,))
+        p.assigned, p.losses, p.workspace, p.workspace_bytes = assigned.data_ptr(), losses.data_ptr(), ws.data_ptr(), ws_bytes
+        lib.check(self.lib.mv2d_loss(C.byref(p), lib.stream_ptr()), 'mv2d_loss')
+        return dict(loss_cls=losses[:, 0], loss_bbox=losses[:, 1], dn_loss_cls=losses[:, 2], dn_loss_bbox=losses[:, 3],
+                    assigned=assigned)
+
+    @torch.no_grad()
+    def forward_losses(self, feat, proposal_list, img_metas, gt_boxes, gt_labels, rand=None, use_denoise=None,
+                       stage_loss_weights=None, denoise_weight=1.0):
+        """Training-mode forward + the loss dict of MV2DSHead.forward_train (mv2d_s_head.py:262-307), forward values
+        only (there are no backward kernels yet): the hot path with denoising queries when ``use_denoise`` (default:
+        the two-frame head, as in the exp configs), then ``loss``.  Keys follow the reference: ``l{i}.loss_cls``,
+        ``l{i}.loss_bbox``, ``l{i}.dn_loss_cls``, ``l{i}.dn_loss_bbox``, each times stage_loss_weights[i]
+        (default 0.1 per layer, exp/...:131)."""
+        use_denoise = (self.mode == 'T') if use_denoise is None else use_denoise
+        dn = dict(gt_boxes=gt_boxes, gt_labels=gt_labels, rand=rand) if (use_denoise and gt_boxes.shape[0] > 0) else None
+        out = self.forward(feat, proposal_list, img_metas, dn=dn)
+        kw = {}
+        if dn is not None:
+            kw = dict(dn_cls=out['dn_cls_scores'], dn_box=out['dn_bbox_preds'], dn_labels=out['dn_labels'])
+        l = self.loss(out['cls_scores'], out['bbox_preds'], gt_boxes, gt_labels, **kw)
+        w = stage_loss_weights or [0.1] * self.L
+        losses = {}
+        for i in range(self.L):
+            if dn is not None:
+                losses[f'l{i}.dn_loss_cls'] = l['dn_loss_cls'][i] * denoise_weight * w[i]
+                losses[f'l{i}.dn_loss_bbox'] = l['dn_loss_bbox'][i] * denoise_weight * w[i]
+            losses[f'l{i}.loss_cls'] = l['loss_cls'][i] * w[i]
+            losses[f'l{i}.loss_bbox'] = l['loss_bbox'][i] * w[i]
+        return losses, out, l
+
     @torch.no_grad()
     def decode(self, cls_scores, bbox_preds, max_num=300):
         """NMSFreeCoder.decode_single + z-shift on the device (next row f1)."""

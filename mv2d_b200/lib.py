@@ -123,7 +123,22 @@ class DnParams(C.Structure):
     ]
 
 
-_STRUCTS = [PeParams, QgParams, CorrParams, DecoderParams, LayerWeights, BranchWeights, DnParams, KvParams]
+class LossParams(C.Structure):
+    _fields_ = [
+        ('N', C.c_int), ('G', C.c_int), ('L', C.c_int), ('num_classes', C.c_int),
+        ('pad', C.c_int), ('neg_bbox_loss', C.c_int),
+        ('layer_stride', C.c_longlong), ('dn_layer_stride', C.c_longlong),
+        ('cls_cost_weight', C.c_float), ('reg_cost_weight', C.c_float), ('cls_loss_weight', C.c_float),
+        ('bbox_loss_weight', C.c_float),
+        ('focal_alpha', C.c_float), ('focal_gamma', C.c_float), ('dn_split', C.c_float), ('reserved1', C.c_float),
+        ('code_weights', C.c_float * 10),
+        ('cls_scores', c_f), ('bbox_preds', c_f), ('gt_boxes', c_f), ('gt_labels', c_f),
+        ('dn_cls', c_f), ('dn_box', c_f), ('dn_labels', c_f),
+        ('assigned', c_f), ('losses', c_f), ('workspace', c_f), ('workspace_bytes', C.c_size_t),
+    ]
+
+
+_STRUCTS = [PeParams, QgParams, CorrParams, DecoderParams, LayerWeights, BranchWeights, DnParams, KvParams, LossParams]
 
 # every symbol include/mv2d_b200.h declares: (name, restype, argtypes)
 SYMBOLS = [
@@ -147,6 +162,8 @@ SYMBOLS = [
     ('mv2d_decoder', C.c_int, [C.POINTER(DecoderParams), c_f]),
     ('mv2d_xa_tile_workspace_bytes', C.c_size_t, [C.c_int] * 4),
     ('mv2d_kv_project', C.c_int, [C.POINTER(KvParams), c_f]),
+    ('mv2d_loss_workspace_bytes', C.c_size_t, [C.c_int] * 3),
+    ('mv2d_loss', C.c_int, [C.POINTER(LossParams), c_f]),
     ('mv2d_xa_tile_prepare', C.c_int, [C.POINTER(DecoderParams), c_f]),
     ('mv2d_gemm', C.c_int, [c_f, C.c_int, c_f, C.c_int, c_f, c_f, C.c_int, C.c_int, C.c_int, C.c_int,
                             C.c_int, c_f]),

@@ -79,9 +79,11 @@ def main():
                 for l in range(L):
                     a, b = head.dn_loss_single(torch.from_numpy(g['dn_cls'][l]).clone(), torch.from_numpy(g['dn_box'][l]).clone(),
                                                known_boxes.clone(), known_labels.clone(), pad,
-                                               cfg['model']['roi_head'].get('pc_range', None), mode_split, neg_bbox_loss=False)
+                                               cfg['model']['roi_head'].get('pc_range', None), mode_split,
+                                               neg_bbox_loss=spec['mode'] == 'T')     # exp two_frames config :45
                     dc.append(float(a)); db.append(float(b))
-                out.update(dn_loss_cls=np.array(dc, np.float64), dn_loss_bbox=np.array(db, np.float64), dn_split=np.float64(mode_split))
+                out.update(dn_loss_cls=np.array(dc, np.float64), dn_loss_bbox=np.array(db, np.float64), dn_split=np.float64(mode_split),
+                           dn_neg_bbox_loss=np.int64(spec['mode'] == 'T'))
         path = os.path.join(ROOT, 'tests', 'golden', f'{name}.npz')
         np.savez_compressed(path, **out)
         print(name, 'L', L, 'N', N, 'G', gt_boxes.shape[0], 'loss_cls', lcs[-1], 'loss_bbox', lbs[-1],

@@ -752,14 +752,15 @@ def loss_single(cls_scores, bbox_preds, gt_boxes, gt_labels, lc=LOSS_CFG):
     return torch.nan_to_num(loss_cls), torch.nan_to_num(loss_bbox), assigned
 
 
-def dn_loss_single(cls_scores, bbox_preds, known_boxes, known_labels, num_tgt, split, lc=LOSS_CFG):
+def dn_loss_single(cls_scores, bbox_preds, known_boxes, known_labels, num_tgt, split, lc=LOSS_CFG, neg_bbox_loss=False):
     """cross_attention_head.py:475-538 (neg_bbox_loss False): cls_scores/bbox_preds [pad,10] of the denoising
     queries, known_boxes [pad,9] = the GT box each one was noised from, known_labels [pad] (num_classes = negative)."""
     eps = torch.finfo(torch.float32).eps
     cls_avg = max(num_tgt * 3.14159 / 6 * split * split * split, 1)
     loss_cls = lc['cls_loss_weight'] * _focal_loss_sum(cls_scores, known_labels.long(), lc) / (cls_avg + eps)
     kb = known_boxes.clone()
-    kb[known_labels == lc['num_classes']] = 0
+    if not neg_bbox_loss:       # cross_attention_head.py:521-523
+        kb[known_labels == lc['num_classes']] = 0
     nt = normalize_bbox(kb)
     ok = torch.isfinite(nt).all(dim=-1)
     w = torch.tensor(lc['code_weights']).repeat(kb.shape[0], 1)

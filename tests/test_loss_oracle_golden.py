@@ -37,7 +37,7 @@ def test_loss_restatement_matches_reference(name):
         labels = torch.from_numpy(s['dn_labels'])
         for l in range(cls.shape[0]):
             a, b = O.dn_loss_single(torch.from_numpy(s['dn_cls'][l]), torch.from_numpy(s['dn_box'][l]), known, labels, pad,
-                                    float(g['dn_split']))
+                                    float(g['dn_split']), neg_bbox_loss=bool(g['dn_neg_bbox_loss']))
             assert abs(float(a) - g['dn_loss_cls'][l]) <= 1e-5 * abs(g['dn_loss_cls'][l]) + 1e-7
             assert abs(float(b) - g['dn_loss_bbox'][l]) <= 1e-5 * abs(g['dn_loss_bbox'][l]) + 1e-7
 
