@@ -38,3 +38,18 @@ roi_head = dict(
             strides=roi_strides, position_range=post_range, depth_num=64, with_fpe=True),
 )
 test_rcnn = dict(score_thr=0.0, nms=dict(nms_thr=1.0, use_rotate_nms=True), max_per_scene=300)
+
+# training-side settings of the roi_head (reference: configs/mv2d/exp/mv2d_r50_frcnn_single_frame_roi_1408x512_ep72.py:130-141):
+# consumed by the loss row (mv2d_loss: Hungarian cost weights, per-layer loss weights)
+model = dict(
+    train_cfg=dict(
+        rcnn=dict(
+            stage_loss_weights=[0.1, 0.1, 0.1, 0.1, 0.1, 0.1],
+            assigner=dict(type='HungarianAssigner3D',
+                          cls_cost=dict(type='FocalLossCost', weight=2.0),
+                          reg_cost=dict(type='BBox3DL1Cost', weight=0.25),
+                          iou_cost=dict(type='IoUCost', weight=0.0),
+                          pc_range=point_cloud_range),
+            sampler_cfg=dict(type='PseudoSampler'),
+            pos_weight=-1,
+            debug=False)))

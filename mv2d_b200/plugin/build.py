@@ -18,12 +18,14 @@ def roi_head_cfg(cfg):
     return rh
 
 
-def build_roi_head(cfg_path, device='cuda'):
-    """HEADS.build(cfg.model.roi_head) with train_cfg=None, test_cfg=cfg.model.test_cfg.rcnn --
+def build_roi_head(cfg_path, device='cuda', train=False):
+    """HEADS.build(cfg.model.roi_head) with test_cfg=cfg.model.test_cfg.rcnn and train_cfg=None (evaluation) or
+    cfg.model.train_cfg.rcnn (train=True: assigner / stage loss weights for the loss row) --
     what MV2D.__init__ does (reference detectors/mv2d.py:34-38)."""
     cfg = Config.fromfile(cfg_path)
     rh = roi_head_cfg(cfg)
     test = dict(cfg['model'].get('test_cfg', {}) or {}).get('rcnn')
-    rh.update(train_cfg=None, test_cfg=test)
+    tr = dict(cfg['model'].get('train_cfg', {}) or {}).get('rcnn') if train else None
+    rh.update(train_cfg=tr, test_cfg=test)
     head = build_from_cfg(rh, HEADS).eval()
     return head.to(device) if device is not None else head

@@ -10,7 +10,7 @@ import torch
 import torch.nn as nn
 
 from ..engine import HotPath
-from ..registry import (ATTENTION, BBOX_CODERS, DETECTORS, HEADS, LOSSES, NECKS, POSITIONAL_ENCODING,
+from ..registry import (ATTENTION, BBOX_ASSIGNERS, BBOX_CODERS, BBOX_SAMPLERS, MATCH_COST, DETECTORS, HEADS, LOSSES, NECKS, POSITIONAL_ENCODING,
                         ROI_EXTRACTORS, TRANSFORMER, TRANSFORMER_LAYER, TRANSFORMER_LAYER_SEQUENCE,
                         build_from_cfg)
 
@@ -261,6 +261,31 @@ class MV2DTransformer(nn.Module):
         self.embed_dims = self.decoder.embed_dims
 
 
+class _Cfg:
+    """Plain holder of constructor kwargs (assigner / match costs / sampler: their arithmetic runs inside
+    mv2d_loss, csrc/loss.cu)."""
+
+    def __init__(self, **kwargs):
+        self.cfg = dict(kwargs)
+        self.weight = kwargs.get('weight', 1.0)
+
+
+@BBOX_ASSIGNERS.register_module()
+class HungarianAssigner3D(_Cfg):
+    """core/bbox/assigners/hungarian_assigner_3d.py:29-64: cls_cost / reg_cost / iou_cost configs, pc_range."""
+
+    def __init__(self, cls_cost=None, reg_cost=None, iou_cost=None, pc_range=None):
+        super().__init__(pc_range=pc_range)
+        self.cls_cost = build_from_cfg(cls_cost or dict(type='FocalLossCost', weight=1.0), MATCH_COST)
+        self.reg_cost = build_from_cfg(reg_cost or dict(type='BBox3DL1Cost', weight=1.0), MATCH_COST)
+        self.iou_cost = build_from_cfg(iou_cost or dict(type='IoUCost', weight=0.0), MATCH_COST)
+
+
+for _n in ('FocalLossCost', 'BBox3DL1Cost', 'IoUCost', 'ClassificationCost', 'BBoxL1Cost'):
+    MATCH_COST.register_module(name=_n, module=type(_n, (_Cfg,), {}))
+BBOX_SAMPLERS.register_module(name='PseudoSampler', module=type('PseudoSampler', (_Cfg,), {}))
+
+
 @HEADS.register_module()
 class CrossAttentionBoxHead(nn.Module):
     """roi_heads/bbox_heads/cross_attention_head.py:87-242 (forward + get_bboxes)."""
@@ -293,6 +318,7 @@ class CrossAttentionBoxHead(nn.Module):
         code_weights = kwargs.get('code_weights', [1.0] * 8 + [0.2, 0.2])[:kwargs.get('code_size', 10)]
         self.code_weights = nn.Parameter(torch.tensor(code_weights), requires_grad=False)
         self.train_cfg, self.test_cfg = train_cfg, test_cfg
+        self.assigner = build_from_cfg(train_cfg['assigner'], BBOX_ASSIGNERS) if (train_cfg and train_cfg.get('assigner')) else None
         self._owner = None
 
     def get_bboxes(self, preds_dicts, img_metas, rescale=False):
@@ -305,8 +331,50 @@ class CrossAttentionBoxHead(nn.Module):
             ret.append([bt(boxes, boxes.size(-1)) if bt is not None else boxes, scores, labels])
         return ret
 
-    def loss(self, *args, **kwargs):
-        raise NotImplementedError('training rows (losses/assignment) are out of scope this round: DESIGN.md section 7')
+    # ---- next row f3: targets + losses, forward values (no backward kernels yet) -- csrc/loss.cu
+    def _loss_kwargs(self):
+        kw = dict(code_weights=[float(x) for x in self.code_weights.tolist()])
+        lc, lb = self.loss_cls.cfg, self.loss_bbox.cfg
+        kw.update(cls_loss_weight=lc.get('loss_weight', 1.0), focal_gamma=lc.get('gamma', 2.0), focal_alpha=lc.get('alpha', 0.25),
+                  bbox_loss_weight=lb.get('loss_weight', 1.0))
+        if self.assigner is not None:
+            kw.update(cls_cost_weight=self.assigner.cls_cost.weight, reg_cost_weight=self.assigner.reg_cost.weight)
+        return kw
+
+    @staticmethod
+    def _gt_tensor(gt):
+        """LiDARInstance3DBoxes-like (gravity_center, tensor) or a plain [G,9] tensor (cross_attention_head.py:450-452)."""
+        if hasattr(gt, 'gravity_center'):
+            return torch.cat((gt.gravity_center, gt.tensor[:, 3:]), dim=1)
+        return gt
+
+    @torch.no_grad()
+    def loss(self, gt_bboxes_3d_list, gt_labels_3d_list, preds_dicts, cls_reg_targets=None, gt_bboxes_ignore=None):
+        """cross_attention_head.py:436-462 for one sample: {'loss_cls', 'loss_bbox'} of the given layer's predictions."""
+        assert gt_bboxes_ignore is None and len(gt_bboxes_3d_list) == 1
+        cls, box = preds_dicts['cls_scores'][0], preds_dicts['bbox_preds'][0]
+        out = self._owner.engine().loss(cls.view(1, -1, 10), box.view(1, -1, 10), self._gt_tensor(gt_bboxes_3d_list[0]),
+                                        gt_labels_3d_list[0], **self._loss_kwargs())
+        return dict(loss_cls=out['loss_cls'][0], loss_bbox=out['loss_bbox'][0])
+
+    @torch.no_grad()
+    def dn_loss_single(self, cls_scores, bbox_preds, known_bboxs, known_labels, num_total_pos, pc_range, split,
+                       neg_bbox_loss=False):
+        """cross_attention_head.py:475-538.  known_bboxs [pad,9] repeats the G ground-truth boxes (query i <- box i % G)."""
+        eng = self._owner.engine()
+        pad = known_labels.numel()
+        G = max(pad // max(eng.cfg['denoise_scalar'], 1), 1)
+        assert pad % G == 0 and torch.equal(known_bboxs[:G].repeat(pad // G, 1), known_bboxs), 'known_bboxs must tile the GT boxes'
+        dummy = torch.zeros((1, 0, 10), device=cls_scores.device)
+        saved = eng.cfg['denoise_split']
+        eng.cfg['denoise_split'] = split
+        try:
+            out = eng.loss(dummy, dummy, known_bboxs[:G], torch.zeros(G, dtype=torch.int32), dn_cls=cls_scores.view(1, -1, 10),
+                           dn_box=bbox_preds.view(1, -1, 10), dn_labels=known_labels, neg_bbox_loss=neg_bbox_loss,
+                           **self._loss_kwargs())
+        finally:
+            eng.cfg['denoise_split'] = saved
+        return out['dn_loss_cls'][0], out['dn_loss_bbox'][0]
 
 
 # ------------------------------------------------------------------ RoI heads
@@ -410,8 +478,10 @@ class MV2DHead(nn.Module):
                                          img_metas)
 
     def forward_train(self, *args, **kwargs):
-        raise NotImplementedError('losses / assignment / backward are out of scope (DESIGN.md section 7); the '
-                                  'training-mode FORWARD incl. denoising queries is _bbox_forward under .train()')
+        raise NotImplementedError('there are no backward kernels yet (DESIGN.md section 7).  The training-mode FORWARD incl. '
+                                  'denoising queries is _bbox_forward under .train(); the loss VALUES of that forward '
+                                  '(Hungarian targets, focal / L1, denoising) come from bbox_head.loss / dn_loss_single '
+                                  'or HotPath.forward_losses')
 
 
 @HEADS.register_module()

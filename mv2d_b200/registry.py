@@ -55,3 +55,6 @@ POSITIONAL_ENCODING = Registry('position encoding')
 BBOX_CODERS = Registry('bbox_coder')
 ROI_EXTRACTORS = Registry('roi_extractor')
 LOSSES = Registry('loss')
+BBOX_ASSIGNERS = Registry('bbox_assigner')
+BBOX_SAMPLERS = Registry('bbox_sampler')
+MATCH_COST = Registry('match_cost')

@@ -118,3 +118,30 @@ def test_missing_library_fails_loudly(monkeypatch):
     monkeypatch.setattr(lib, 'LIB_PATH', '/nonexistent/libmv2d_b200.so')
     with pytest.raises(RuntimeError, match='no CPU fallback'):
         lib.load()
+
+
+def test_bbox_head_loss_interface_matches_reference_golden(state_dicts):
+    """Row f3 through the reference-facing interface: bbox_head.loss(gt_boxes, gt_labels, {'cls_scores': [..],
+    'bbox_preds': [..]}) per layer, as mv2d_s_head.py:281-286 calls it, and bbox_head.dn_loss_single, with the
+    cost / loss weights read from the config (train_cfg.assigner, loss_cls, loss_bbox, code_weights)."""
+    from test_loss_oracle_golden import load_loss_case
+    from mv2d_b200.plugin.build import build_roi_head
+    h = build_roi_head(CFG['S'], device='cuda', train=True)
+    h.load_state_dict(state_dicts(6), strict=True)
+    assert type(h.bbox_head.assigner).__name__ == 'HungarianAssigner3D' and h.stage_loss_weights == [0.1] * 6
+    g, s, gt_boxes, gt_labels = load_loss_case('loss_s_dn')
+    cls, box = torch.from_numpy(s['cls_scores']).cuda(), torch.from_numpy(s['bbox_preds']).cuda()
+
+    class Boxes:        # LiDARInstance3DBoxes look-alike, as the reference passes it
+        gravity_center = gt_boxes[:, :3].cuda()
+        tensor = torch.cat([gt_boxes[:, :3], gt_boxes[:, 3:]], 1).cuda()
+    for l in range(cls.shape[0]):
+        d = h.bbox_head.loss([Boxes()], [gt_labels.cuda()], {'cls_scores': [cls[l]], 'bbox_preds': [box[l]]})
+        close(d['loss_cls'], g['loss_cls'][l], 1e-6, 2e-5)
+        close(d['loss_bbox'], g['loss_bbox'][l], 1e-6, 2e-5)
+        pad = int(s['dn_pad'])
+        known = gt_boxes.repeat(pad // gt_boxes.shape[0], 1).cuda()
+        a, b = h.bbox_head.dn_loss_single(torch.from_numpy(s['dn_cls'][l]).cuda(), torch.from_numpy(s['dn_box'][l]).cuda(), known,
+                                          torch.from_numpy(s['dn_labels']).cuda(), pad, None, float(g['dn_split']), neg_bbox_loss=False)
+        close(a, g['dn_loss_cls'][l], 1e-6, 2e-5)
+        close(b, g['dn_loss_bbox'][l], 1e-6, 2e-5)
