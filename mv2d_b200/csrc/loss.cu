@@ -259,7 +259,7 @@ size_t loss_workspace_bytes(int N, int G, int L) {
 int run_loss(const Mv2dLossParams& p, cudaStream_t st) {
     MV2D_CHECK_ARG(p.N >= 0 && p.G >= 0 && p.L >= 1 && p.L <= MV2D_MAX_LAYERS && p.num_classes >= 1 && p.num_classes <= 64,
                    "loss: bad N=%d G=%d L=%d classes=%d", p.N, p.G, p.L, p.num_classes);
-    MV2D_CHECK_ARG(p.losses && p.assigned, "loss: null output");
+    MV2D_CHECK_ARG(p.losses && (p.N == 0 || p.assigned), "loss: null output");
     MV2D_CHECK_ARG(p.N == 0 || (p.cls_scores && p.bbox_preds), "loss: null predictions");
     MV2D_CHECK_ARG(p.G == 0 || (p.gt_boxes && p.gt_labels), "loss: null ground truth");
     MV2D_CHECK_ARG(p.pad == 0 || p.G > 0, "loss: denoising queries need ground truth");
