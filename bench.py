@@ -344,7 +344,11 @@ def roofline_section(eng, out, mode, N, flush, peaks):
     achieved = flops / (t_conv * 1e-6) / 1e12
     roofline = dict(kernel='gemm_tc_kernel<128,3,im2col,3> (query-generator 3x3 conv, 3xTF32 tcgen05 + 4-D TMA)',
                     bound='tensor', achieved=achieved, peak=peaks['bf16_tflops'], unit='TFLOP/s',
-                    frac=achieved / peaks['bf16_tflops'], traffic=None, us_per_launch=t_conv,
+                    frac=achieved / peaks['bf16_tflops'],
+                    # dram__bytes_read.sum + dram__bytes_write.sum of this launch at N = 300 from the committed
+                    # `ncu --set full` capture (profiles/r01_ncu_full_tc_kernels.csv: 34.88 MB + 0.07 MB); the
+                    # algorithmic bytes are 2 x 15.05 MB of hi/lo tokens + 4.7 MB of weights + 15.05 MB out (L2-resident)
+                    traffic=(34.882816e6 + 0.07168e6) if N == 300 else None, us_per_launch=t_conv,
                     algorithmic_flops=flops, tf32_flops_issued=3 * flops * 128.0 / 98.0,
                     note='achieved counts the conv flops once (17.3 GFLOP at N=300); the kernel issues 3 TF32 MMAs '
                          'per product (error compensation) on 128-row tiles that hold 98 real rows; peak = measured '
