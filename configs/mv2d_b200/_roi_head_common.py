@@ -42,6 +42,8 @@ test_rcnn = dict(score_thr=0.0, nms=dict(nms_thr=1.0, use_rotate_nms=True), max_
 # training-side settings of the roi_head (reference: configs/mv2d/exp/mv2d_r50_frcnn_single_frame_roi_1408x512_ep72.py:130-141):
 # consumed by the loss row (mv2d_loss: Hungarian cost weights, per-layer loss weights)
 model = dict(
+    # the MV2D neck: a one-level FPN on the 2D detector's P4 (reference configs/mv2d/exp/*.py:32-39)
+    neck=dict(type='FPN', in_channels=[256, 256, 256, 256, 256], out_channels=256, start_level=2, end_level=2, num_outs=1),
     train_cfg=dict(
         rcnn=dict(
             stage_loss_weights=[0.1, 0.1, 0.1, 0.1, 0.1, 0.1],

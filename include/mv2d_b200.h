@@ -40,7 +40,7 @@ MV2D_API const char* mv2d_last_error(void);
 /* number of kernel launches this library has enqueued so far in this process */
 MV2D_API unsigned long long mv2d_launch_count(void);
 /* sizeof() of the parameter structs, so a binding can verify its mirror of this header */
-MV2D_API size_t mv2d_sizeof(int which); /* 0 Pe, 1 Qg, 2 Corr, 3 Decoder, 4 LayerWeights, 5 BranchWeights, 6 Dn, 7 Kv, 8 Loss */
+MV2D_API size_t mv2d_sizeof(int which); /* 0 Pe, 1 Qg, 2 Corr, 3 Decoder, 4 LayerWeights, 5 BranchWeights, 6 Dn, 7 Kv, 8 Loss, 9 Neck */
 
 /* ---- geometry (utils/pe.py:111; roi_heads/utils/box_correlation.py:118-122,174-178)
  * img2lidar[v] = inv(lidar2img[v]);  trans[src][dst] = lidar2img[dst] @ img2lidar[src]  (fp64) */
@@ -324,6 +324,22 @@ typedef struct Mv2dLossParams {
 } Mv2dLossParams;
 MV2D_API size_t mv2d_loss_workspace_bytes(int N, int G, int L);
 MV2D_API int mv2d_loss(const Mv2dLossParams* p, void* stream);
+
+/* ---- f4 (next row): the MV2D neck = one-level mmdet FPN on the 2D detector's P4 (configs/mv2d/exp/*.py:32-39,
+ * detectors/mv2d.py:122-127):  feat = conv3x3(conv1x1(x) + lat_b, padding 1) + fpn_b,  emitted channels-last
+ * (the layout the rest of this library consumes), both convolutions as 3xTF32 tcgen05 GEMMs (fp32-grade). */
+typedef struct Mv2dNeckParams {
+    int V, h, w, in_is_nhwc;
+    const float* x;                          /* detector P4: [V,256,h,w], or [V,h,w,256] when in_is_nhwc */
+    const float *lat_w, *lat_w_lo, *lat_b;   /* neck.lateral_convs.0.conv: [256,256] as TF32 hi + lo, bias [256] */
+    const float *fpn_w, *fpn_w_lo, *fpn_b;   /* neck.fpn_convs.0.conv: [256, 9*256], K ordered (ky, kx, c_in), hi + lo, bias */
+    float* feat;                             /* out [V,h,w,256] */
+    float* feat_tf32;                        /* out, nullable: feat rounded to TF32 (as mv2d_nchw_to_nhwc emits it) */
+    float* workspace;
+    size_t workspace_bytes;
+} Mv2dNeckParams;
+MV2D_API size_t mv2d_fpn_neck_workspace_bytes(int V, int h, int w);
+MV2D_API int mv2d_fpn_neck(const Mv2dNeckParams* p, void* stream);
 
 /* ---- low-level GEMM, exposed for tests and microbenchmarks:
  * C[M,N] = act(A[M,K] . W[N,K]^T + bias); flags: 1 relu, 8 allow TF32 tensor cores,

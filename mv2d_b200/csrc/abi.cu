@@ -43,6 +43,7 @@ size_t mv2d_sizeof(int which) {
         case 6: return sizeof(Mv2dDnParams);
         case 7: return sizeof(Mv2dKvParams);
         case 8: return sizeof(Mv2dLossParams);
+        case 9: return sizeof(Mv2dNeckParams);
         default: return 0;
     }
 }
@@ -130,6 +131,13 @@ size_t mv2d_loss_workspace_bytes(int N, int G, int L) { return loss_workspace_by
 int mv2d_loss(const Mv2dLossParams* p, void* stream) {
     NONNULL(p, "loss");
     return run_loss(*p, (cudaStream_t)stream);
+}
+
+size_t mv2d_fpn_neck_workspace_bytes(int V, int h, int w) { return fpn_neck_workspace_bytes(V, h, w); }
+int mv2d_fpn_neck(const Mv2dNeckParams* p, void* stream) {
+    NONNULL(p, "fpn_neck");
+    MV2D_CHECK_ARG(p->x && p->lat_w && p->lat_w_lo && p->lat_b && p->fpn_w && p->fpn_w_lo && p->fpn_b && p->feat, "fpn_neck: null pointer");
+    return run_fpn_neck(*p, (cudaStream_t)stream);
 }
 
 int mv2d_gemm(const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc, int M, int N,

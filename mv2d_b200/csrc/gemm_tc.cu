@@ -11,6 +11,8 @@
 //   * IM2COL: the A operand is the implicit im2col of the [N,7,7,256] RoI tokens: a 4-D tensor
 //     map with box (32 ch, 7, 7, 1) loaded at (c0, dx-1, dy-1, roi); TMA zero-fills the halo.
 //     Two RoIs share one 128-row tile (rows 0..48 and 64..112).
+//   * IM2COL = 2: the same trick on a whole feature map [V,h,w,256] (3x3 conv, padding 1, of the FPN neck): a
+//     tile is 16 rows x 8 columns of pixels, the box (32 ch, 8, 16, 1) is loaded at (c0, x0+dx-1, y0+dy-1, v).
 // Warp roles (192 threads): warp 0 TMA producer, warp 1 TMEM alloc + MMA issue, warps 2..5
 // epilogue (TMEM lane quadrant = warp_idx % 4).  One output tile per CTA; several CTAs per SM
 // overlap each other's prologue/epilogue.
@@ -100,7 +102,8 @@ struct TcArgs {
     const float* bias;
     int M, N, K;
     int flags;
-    int n_rois;                                                        // IM2COL: number of RoIs
+    int n_rois;                                                        // IM2COL 1: number of RoIs
+    int fm_h, fm_w;                                                    // IM2COL 2: feature grid (tiles of 16 x 8 pixels)
     const float* gx; const float* gs; const float* gfeat; float* kin;  // GEMM_GATE extras
 };
 
@@ -108,7 +111,7 @@ struct TcArgs {
 // of a pre-split hi and lo copy -- and the four epilogue warps, idle during the main loop, split every stage in
 // shared memory (hi in place, lo beside it; element-wise, so the 128B swizzle TMA wrote is preserved) before the
 // MMA warp consumes it: full_bar (TMA landed) -> split -> fence.proxy.async -> conv_bar -> tcgen05.mma.
-template <int BN, int PASSES, bool IM2COL, int STAGES, bool RAW = false>
+template <int BN, int PASSES, int IM2COL, int STAGES, bool RAW = false>
 __global__ void __launch_bounds__(TC_THREADS, (PASSES == 1 ? 2 : 1))
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
                const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmWlo, TcArgs g) {
@@ -159,9 +162,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 mbar_wait(&empty_bar[s], ph ^ 1);
                 uint8_t* st = smem + s * STAGE_BYTES;
                 // bytes TMA will deliver: an im2col box is 49 rows x 128 B per RoI, not a full 64-row half tile
-                constexpr int A_TX = IM2COL ? 2 * MV2D_TOK * TC_BK * 4 : A_BYTES;
+                constexpr int A_TX = IM2COL == 1 ? 2 * MV2D_TOK * TC_BK * 4 : A_BYTES;
                 mbar_expect_tx(&full_bar[s], (RAW ? 1 : NOP) * (A_TX + W_BYTES));
-                if (IM2COL) {
+                if (IM2COL == 2) {
+                    const int kg = kb0 + kb;
+                    const int tap = kg / (MV2D_C / TC_BK), c0 = (kg % (MV2D_C / TC_BK)) * TC_BK;
+                    const int tiles_x = (g.fm_w + 7) >> 3, tiles_y = (g.fm_h + 15) >> 4;
+                    const int tx = m_tile % tiles_x, ty = (m_tile / tiles_x) % tiles_y, v = m_tile / (tiles_x * tiles_y);
+                    const int x0 = tx * 8 + tap % 3 - 1, y0 = ty * 16 + tap / 3 - 1;
+                    tma_load_4d(&tmA, &full_bar[s], st, c0, x0, y0, v);
+                    if (PASSES == 3) tma_load_4d(&tmAlo, &full_bar[s], st + A_BYTES, c0, x0, y0, v);
+                } else if (IM2COL == 1) {
                     const int kg = kb0 + kb;
                     const int tap = kg / (MV2D_C / TC_BK), c0 = (kg % (MV2D_C / TC_BK)) * TC_BK;
                     const int dx = tap % 3 - 1, dy = tap / 3 - 1;
@@ -244,10 +255,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int q = warp & 3;                           // TMEM lane quadrant this warp may access
         float* stg = reinterpret_cast<float*>(smem) + q * 1024;
         auto out_row = [&](int r, long long& orow) -> bool {   // tile row -> output row
-            if (IM2COL) {
+            if (IM2COL == 1) {
                 const int roi = m_tile * 2 + (r >> 6), tok = r & 63;
                 orow = (long long)roi * MV2D_TOK + tok;
                 return tok < MV2D_TOK && roi < g.n_rois;
+            }
+            if (IM2COL == 2) {
+                const int tiles_x = (g.fm_w + 7) >> 3, tiles_y = (g.fm_h + 15) >> 4;
+                const int tx = m_tile % tiles_x, ty = (m_tile / tiles_x) % tiles_y, v = m_tile / (tiles_x * tiles_y);
+                const int y = ty * 16 + (r >> 3), x = tx * 8 + (r & 7);
+                orow = ((long long)v * g.fm_h + y) * g.fm_w + x;
+                return y < g.fm_h && x < g.fm_w;
             }
             orow = (long long)m_tile * TC_BM + r;
             return orow < g.M;
@@ -577,7 +595,22 @@ static int make_map_tokens(CUtensorMap* m, const float* base, int n_rois) {
     return 0;
 }
 
-template <int BN, int PASSES, bool IM2COL, int STAGES, bool RAW = false>
+// 4-D feature map [V, h, w, 256]; box = [32 ch, 8 x, 16 y, 1]
+static int make_map_fmap(CUtensorMap* m, const float* base, int V, int h, int w) {
+    EncodeTiledFn enc = get_encode();
+    MV2D_CHECK_ARG(enc != nullptr, "gemm_tc: cuTensorMapEncodeTiled not available");
+    cuuint64_t dims[4] = {MV2D_C, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)V};
+    cuuint64_t strides[3] = {MV2D_C * 4, (cuuint64_t)w * MV2D_C * 4, (cuuint64_t)h * w * MV2D_C * 4};
+    cuuint32_t box[4] = {TC_BK, 8, 16, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)base, dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MV2D_CHECK_ARG(r == CUDA_SUCCESS, "gemm_tc: cuTensorMapEncodeTiled(fmap) failed with %d", (int)r);
+    return 0;
+}
+
+template <int BN, int PASSES, int IM2COL, int STAGES, bool RAW = false>
 static int launch_tc(const CUtensorMap& a, const CUtensorMap& alo, const CUtensorMap& w, const CUtensorMap& wlo,
                      const TcArgs& g, int m_tiles, int nsplit, cudaStream_t st) {
     constexpr int NOP = PASSES == 3 ? 2 : 1;
@@ -647,7 +680,14 @@ int launch_gemm_tc(const TcGemm& t, cudaStream_t st) {
     g.nkb_per_split = t.K / TC_BK / nsplit; g.split_stride = t.split_stride;
     g.gx = t.gx; g.gs = t.gs; g.gfeat = t.gfeat; g.kin = t.kin;
     int m_tiles;
-    if (t.im2col) {
+    if (t.im2col == 2) {
+        MV2D_CHECK_ARG(t.K == 9 * MV2D_C && t.passes == 3 && t.fm_v > 0 && t.fm_h > 0 && t.fm_w > 0 && t.M == t.fm_v * t.fm_h * t.fm_w,
+                       "gemm_tc: feature-map im2col expects K=2304, 3 passes, M = V*h*w");
+        g.fm_h = t.fm_h; g.fm_w = t.fm_w;
+        m_tiles = t.fm_v * cdiv(t.fm_h, 16) * cdiv(t.fm_w, 8);
+        if ((rc = make_map_fmap(&a, t.A, t.fm_v, t.fm_h, t.fm_w))) return rc;
+        if ((rc = make_map_fmap(&alo, t.A_lo, t.fm_v, t.fm_h, t.fm_w))) return rc;
+    } else if (t.im2col) {
         MV2D_CHECK_ARG(t.K == 9 * MV2D_C && t.passes == 3, "gemm_tc: im2col expects K=2304, 3 passes");
         g.n_rois = t.M / MV2D_TOK;
         m_tiles = cdiv(g.n_rois, 2);
@@ -662,8 +702,9 @@ int launch_gemm_tc(const TcGemm& t, cudaStream_t st) {
     if ((rc = make_map_2d(&wlo, (t.passes == 3 && !raw) ? t.W_lo : t.W, t.N, t.K, t.ldw, bn))) return rc;
     if (raw && bn == 64) return launch_tc<64, 3, false, 4, true>(a, alo, w, wlo, g, m_tiles, nsplit, st);
     if (raw) return launch_tc<128, 3, false, 3, true>(a, alo, w, wlo, g, m_tiles, nsplit, st);
-    if (t.im2col && bn == 256) return launch_tc<256, 3, true, 2>(a, alo, w, wlo, g, m_tiles, nsplit, st);
-    if (t.im2col) return launch_tc<128, 3, true, 3>(a, alo, w, wlo, g, m_tiles, nsplit, st);
+    if (t.im2col == 2) return launch_tc<128, 3, 2, 3>(a, alo, w, wlo, g, m_tiles, nsplit, st);
+    if (t.im2col && bn == 256) return launch_tc<256, 3, 1, 2>(a, alo, w, wlo, g, m_tiles, nsplit, st);
+    if (t.im2col) return launch_tc<128, 3, 1, 3>(a, alo, w, wlo, g, m_tiles, nsplit, st);
     if (t.passes == 3 && bn == 64 && mc_enabled() && (t.N / 64) % TC_MC == 0) {
         // A is loaded in 32-row quarters and multicast across the 4-CTA cluster that shares the M-tile
         if ((rc = make_map_2d(&a, t.A, t.M, t.K, t.lda, 32))) return rc;

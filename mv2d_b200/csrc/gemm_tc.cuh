@@ -25,7 +25,9 @@ struct TcGemm {
     int M, N, K;
     int nsplit; long long split_stride;   // split-K: raw partial sums of split z go to C + z * split_stride
     int passes;        // 1 = single-pass TF32 (operands already TF32-representable), 3 = 3xTF32
-    int im2col;        // A = [n_rois,7,7,256] tokens, M = 49*n_rois, K = 2304 ordered (tap, c_in)
+    int im2col;        // 1: A = [n_rois,7,7,256] tokens, M = 49*n_rois, K = 2304 ordered (tap, c_in)
+                       // 2: A = [fm_v,fm_h,fm_w,256] feature map, M = fm_v*fm_h*fm_w, same K order (3x3, padding 1)
+    int fm_v, fm_h, fm_w;
     int flags;         // GEMM_RELU | GEMM_GATE | GEMM_ROUND_TF32
     const float* gx; const float* gs; const float* gfeat; float* kin;
 };

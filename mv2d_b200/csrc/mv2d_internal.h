@@ -26,6 +26,9 @@ int run_nms_free_decode(const float* cls, const float* box, int N, int max_num, 
 int run_loss(const Mv2dLossParams& p, cudaStream_t st);
 size_t loss_workspace_bytes(int N, int G, int L);
 
+int run_fpn_neck(const Mv2dNeckParams& p, cudaStream_t st);
+size_t fpn_neck_workspace_bytes(int V, int h, int w);
+
 int run_clock_probe(long long cycles, long long* out, cudaStream_t st);
 
 }  // namespace mv2d

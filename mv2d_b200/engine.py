@@ -16,7 +16,7 @@ import torch
 import torch.nn.functional as F
 
 from . import lib
-from .pack import PackedWeights
+from .pack import PackedNeck, PackedWeights
 
 DEFAULTS = dict(
     pc_range=[-51.2, -51.2, -5.0, 51.2, 51.2, 3.0],
@@ -206,6 +206,31 @@ class HotPath:
         out_tf32 = self._get('feat_tf32', (V, h, w, Cc))
         lib.check(self.lib.mv2d_nchw_to_nhwc(lib.ptr(feat_nchw), out.data_ptr(), out_tf32.data_ptr(), V, Cc, h * w,
                                              lib.stream_ptr()), 'mv2d_nchw_to_nhwc')
+        return out, out_tf32
+
+    def neck(self, x, neck_weights, in_is_nhwc=False):
+        """Next row f4: the MV2D neck (one-level FPN: 1x1 lateral + 3x3 output conv, detectors/mv2d.py:122-127) on the
+        2D detector's P4 ``x`` [V,256,h,w] -> channels-last feature map [V,h,w,256] (+ TF32 copy): feed it to
+        ``forward(..., feat_is_nhwc=True)``.  ``neck_weights``: a ``PackedNeck`` or a ``neck.*`` state_dict."""
+        if not isinstance(neck_weights, PackedNeck):
+            key = id(neck_weights)
+            if getattr(self, '_neck_cache', (None, None))[0] != key:
+                self._neck_cache = (key, PackedNeck(neck_weights, self.device))
+            neck_weights = self._neck_cache[1]
+        x = x.to(self.device, torch.float32).contiguous()
+        V, h, w = (x.shape[0], x.shape[1], x.shape[2]) if in_is_nhwc else (x.shape[0], x.shape[2], x.shape[3])
+        out = self._get('feat_nhwc', (V, h, w, 256))
+        out_tf32 = self._get('feat_tf32', (V, h, w, 256))
+        ws_bytes = self.lib.mv2d_fpn_neck_workspace_bytes(V, h, w)
+        ws = self._get('neck_ws', (ws_bytes // 4 + 1,))
+        p = lib.NeckParams()
+        p.V, p.h, p.w, p.in_is_nhwc = V, h, w, int(in_is_nhwc)
+        p.x = x.data_ptr()
+        for k in ('lat_w', 'lat_w_lo', 'lat_b', 'fpn_w', 'fpn_w_lo', 'fpn_b'):
+            setattr(p, k, neck_weights.p(k))
+        p.feat, p.feat_tf32 = out.data_ptr(), out_tf32.data_ptr()
+        p.workspace, p.workspace_bytes = ws.data_ptr(), ws_bytes
+        lib.check(self.lib.mv2d_fpn_neck(C.byref(p), lib.stream_ptr()), 'mv2d_fpn_neck')
         return out, out_tf32
 
     def pe3d(self, feat_nhwc, img2lidar, img_metas, feat_tf32=None, phase=0, dims=None):
@@ -469,6 +494,9 @@ class HotPath:
         if feat_is_nhwc:
             feat = feat_in
             _, h, w, _ = feat.shape
+            own = self._buf.get('feat_nhwc')
+            if own is not None and 'feat_tf32' in self._buf and feat.data_ptr() == own.data_ptr():
+                feat_tf32 = self._get('feat_tf32', tuple(feat.shape))    # written beside it by ``neck``
         else:
             _, _, h, w = feat_in.shape
             feat, feat_tf32 = self.to_nhwc(feat_in)

@@ -138,7 +138,16 @@ class LossParams(C.Structure):
     ]
 
 
-_STRUCTS = [PeParams, QgParams, CorrParams, DecoderParams, LayerWeights, BranchWeights, DnParams, KvParams, LossParams]
+class NeckParams(C.Structure):
+    _fields_ = [
+        ('V', C.c_int), ('h', C.c_int), ('w', C.c_int), ('in_is_nhwc', C.c_int),
+        ('x', c_f), ('lat_w', c_f), ('lat_w_lo', c_f), ('lat_b', c_f),
+        ('fpn_w', c_f), ('fpn_w_lo', c_f), ('fpn_b', c_f),
+        ('feat', c_f), ('feat_tf32', c_f), ('workspace', c_f), ('workspace_bytes', C.c_size_t),
+    ]
+
+
+_STRUCTS = [PeParams, QgParams, CorrParams, DecoderParams, LayerWeights, BranchWeights, DnParams, KvParams, LossParams, NeckParams]
 
 # every symbol include/mv2d_b200.h declares: (name, restype, argtypes)
 SYMBOLS = [
@@ -164,6 +173,8 @@ SYMBOLS = [
     ('mv2d_kv_project', C.c_int, [C.POINTER(KvParams), c_f]),
     ('mv2d_loss_workspace_bytes', C.c_size_t, [C.c_int] * 3),
     ('mv2d_loss', C.c_int, [C.POINTER(LossParams), c_f]),
+    ('mv2d_fpn_neck_workspace_bytes', C.c_size_t, [C.c_int] * 3),
+    ('mv2d_fpn_neck', C.c_int, [C.POINTER(NeckParams), c_f]),
     ('mv2d_xa_tile_prepare', C.c_int, [C.POINTER(DecoderParams), c_f]),
     ('mv2d_gemm', C.c_int, [c_f, C.c_int, c_f, C.c_int, c_f, c_f, C.c_int, C.c_int, C.c_int, C.c_int,
                             C.c_int, c_f]),

@@ -85,6 +85,29 @@ def split_tf32(t):
     return hi, round_tf32(t - hi)
 
 
+class PackedNeck:
+    """``neck.*`` (one-level FPN) as the operands of mv2d_fpn_neck: TF32 hi / lo splits, the 3x3 kernel K-major with K
+    ordered (ky, kx, c_in).  Accepts keys with or without the ``neck.`` prefix."""
+
+    def __init__(self, state_dict, device):
+        sd = {(k[len('neck.'):] if k.startswith('neck.') else k): v for k, v in state_dict.items()}
+        lat, fpn = sd['lateral_convs.0.conv.weight'], sd['fpn_convs.0.conv.weight']
+        assert tuple(lat.shape) == (EMBED, EMBED, 1, 1) and tuple(fpn.shape) == (EMBED, EMBED, 3, 3), \
+            'the MV2D neck is a one-level FPN, 256 -> 256 (configs/mv2d/exp/*.py:32-39)'
+        self.t = {}
+
+        def put(name, t):
+            self.t[name] = t.detach().float().contiguous().to(device)
+
+        hi, lo = split_tf32(lat.reshape(EMBED, EMBED))
+        put('lat_w', hi); put('lat_w_lo', lo); put('lat_b', sd['lateral_convs.0.conv.bias'])
+        hi, lo = split_tf32(fpn.permute(0, 2, 3, 1).reshape(EMBED, -1))
+        put('fpn_w', hi); put('fpn_w_lo', lo); put('fpn_b', sd['fpn_convs.0.conv.bias'])
+
+    def p(self, name):
+        return self.t[name].data_ptr()
+
+
 class PackedWeights:
     """Device-resident weights + the host-side ctypes structs that point at them."""
 

@@ -7,7 +7,7 @@ reference ``state_dict`` loads with ``strict=True`` -- whose forward runs the sm
 through the C ABI.  The modules only HOLD parameters; arithmetic happens in
 ``mv2d_b200/csrc``.
 """
-from .modules import (PE, BoxCorrelation, CrossAttentionBoxHead, FlattenMHSelfAttention,  # noqa: F401
+from .modules import (FPN, HungarianAssigner3D, PE, BoxCorrelation, CrossAttentionBoxHead, FlattenMHSelfAttention,  # noqa: F401
                       MV2D, MV2DT, MV2DHead, MV2DSHead, MV2DTHead, MV2DTransformer, NMSFreeCoder,
                       PETRMultiheadAttention, PETRTransformerDecoder, PETRTransformerDecoderLayer,
                       QueryGenerator, SinePositionalEncoding3D, SingleRoIExtractor)

@@ -467,7 +467,13 @@ class MV2DHead(nn.Module):
         if feat.shape[1] == 2 * self.position_encoding.embed_dims:
             feat = feat[:, :self.position_encoding.embed_dims]
         dn = self._dn_inputs(img_metas)
-        out = self.engine().forward(feat, proposal_list, img_metas, dn=dn)
+        # a channels-last map presented in the reference's [V,C,h,w] shape (what the FPN neck module returns after
+        # .permute(0, 3, 1, 2)) is consumed in place: no transpose back and forth
+        cl = feat.is_cuda and feat.dim() == 4 and feat.stride(1) == 1 and feat.permute(0, 2, 3, 1).is_contiguous()
+        if cl:
+            out = self.engine().forward(feat.permute(0, 2, 3, 1), proposal_list, img_metas, feat_is_nhwc=True, dn=dn)
+        else:
+            out = self.engine().forward(feat, proposal_list, img_metas, dn=dn)
         return self._results(out, dn)
 
     @torch.no_grad()
@@ -520,6 +526,39 @@ class MV2DTHead(MV2DSHead):
 
 
 # ------------------------------------------------------------------ detector shells
+class _ConvHolder(nn.Module):
+    """mmcv ConvModule without norm / activation: parameter names ``conv.weight`` / ``conv.bias``."""
+
+    def __init__(self, cin, cout, k):
+        super().__init__()
+        self.conv = nn.Conv2d(cin, cout, k, padding=k // 2)
+
+
+@NECKS.register_module()
+class FPN(nn.Module):
+    """The MV2D neck (next row f4): mmdet FPN restricted to what configs/mv2d/exp/*.py:32-39 build -- ONE level
+    (start_level = end_level, num_outs = 1), 256 -> 256: ``lateral_convs.0.conv`` (1x1) and ``fpn_convs.0.conv`` (3x3).
+    Holds the parameters under mmdet's names; ``forward`` runs mv2d_fpn_neck and returns the channels-last map the
+    roi_head consumes (``.permute(0, 3, 1, 2)`` is the reference layout as a view)."""
+
+    def __init__(self, in_channels, out_channels, num_outs, start_level=0, end_level=-1, **kwargs):
+        super().__init__()
+        end = len(in_channels) - 1 if end_level == -1 else end_level
+        assert num_outs == 1 and end == start_level and in_channels[start_level] == 256 and out_channels == 256, \
+            'libmv2d_b200 implements the one-level 256 -> 256 neck of the MV2D configs'
+        self.start_level = start_level
+        self.lateral_convs = nn.ModuleList([_ConvHolder(256, 256, 1)])
+        self.fpn_convs = nn.ModuleList([_ConvHolder(256, 256, 3)])
+        self._packed = None
+
+    def forward(self, inputs, engine):
+        from ..pack import PackedNeck
+        x = inputs[self.start_level] if isinstance(inputs, (list, tuple)) else inputs
+        if self._packed is None or self._packed[0] != x.device:
+            self._packed = (x.device, PackedNeck(self.state_dict(), x.device))
+        return engine.neck(x, self._packed[1])
+
+
 @DETECTORS.register_module()
 class MV2D(nn.Module):
     """detectors/mv2d.py:18-293, thin shell: the 2D detector + FPN stay torch (north star) and are
@@ -534,6 +573,21 @@ class MV2D(nn.Module):
         self.roi_head = build_from_cfg(roi_head, HEADS)
         self.base_detector = base_detector if callable(base_detector) else None
         self.neck_cfg, self.train_cfg, self.test_cfg = neck, train_cfg, test_cfg
+        self.neck = build_from_cfg(neck, NECKS) if isinstance(neck, dict) and neck.get('type') in NECKS else None
+
+    @property
+    def with_neck(self):
+        return self.neck is not None
+
+    @torch.no_grad()
+    def process_detector_feat(self, detector_feat):
+        """detectors/mv2d.py:122-127.  Returns (feat, is_channels_last): with the neck the feature map comes out of
+        mv2d_fpn_neck channels-last, which is what the roi_head's kernels read."""
+        if self.with_neck:
+            feat, _ = self.neck(detector_feat, self.roi_head.engine())
+            return feat, True
+        x = detector_feat[0] if isinstance(detector_feat, (list, tuple)) else detector_feat
+        return x, False
 
     def process_2d_detections(self, results, device):
         """detectors/mv2d.py:60-86 (next row f2): per view, the 2D detector's per-class box arrays
@@ -560,6 +614,9 @@ class MV2D(nn.Module):
         if feat is None or detections is None:
             assert self.base_detector is not None, 'inject a torch 2D detector or pass feat/detections'
             feat, detections = self.base_detector(img, img_metas)
+            if self.with_neck:      # mv2d.py:122-127: the detector hands over its FPN outputs, the neck makes P4'
+                cl, _ = self.process_detector_feat(feat)
+                feat = cl.permute(0, 3, 1, 2)
         return self.roi_head.simple_test([feat], detections, img_metas)
 
 

@@ -104,6 +104,14 @@ def _bias(rng, n, lo=-0.1, hi=0.1):
     return torch.from_numpy(rng.uniform(lo, hi, size=(n,)).astype(np.float32))
 
 
+def make_neck_state_dict(seed=0, embed=EMBED):
+    """``neck.*`` of the reference model: a one-level mmdet FPN (configs/mv2d/exp/*.py:32-39) = a 1x1 lateral conv and
+    a 3x3 output conv, both 256 -> 256 with bias."""
+    rng = np.random.Generator(np.random.PCG64(7000 + seed))
+    return {'lateral_convs.0.conv.weight': _xavier(rng, (embed, embed, 1, 1)), 'lateral_convs.0.conv.bias': _bias(rng, embed),
+            'fpn_convs.0.conv.weight': _xavier(rng, (embed, embed, 3, 3)), 'fpn_convs.0.conv.bias': _bias(rng, embed)}
+
+
 def make_state_dict(seed=0, num_layers=6, embed=EMBED, ffn=2048, num_classes=10, code_size=10,
                     depth_num=64):
     """Hot-path ``state_dict`` with the reference's key names and shapes."""

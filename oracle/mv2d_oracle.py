@@ -770,3 +770,14 @@ def dn_loss_single(cls_scores, bbox_preds, known_boxes, known_labels, num_tgt, s
     else:
         loss_bbox = lc['bbox_loss_weight'] * ((bbox_preds[ok, :10] - nt[ok, :10]).abs() * w[ok]).sum() / (max(num_tgt, 1) + eps)
     return torch.nan_to_num(loss_cls), torch.nan_to_num(loss_bbox)
+
+
+# ============================================================================= neck
+def fpn_neck(neck_sd, x):
+    """The MV2D neck: mmdet 2.25.1 FPN with in_channels [256]*5, start_level = end_level = 2, num_outs = 1
+    (configs/mv2d/exp/mv2d_r50_frcnn_single_frame_roi_1408x512_ep72.py:32-39; called in detectors/mv2d.py:122-127).
+    One level => no top-down path: out = fpn_convs[0](lateral_convs[0](x)), ConvModules without norm / activation.
+    mmdet is third-party and absent from /root/reference: restated from its published FPN.forward (unpinned)."""
+    sd = {(k[len('neck.'):] if k.startswith('neck.') else k): v for k, v in neck_sd.items()}
+    lat = F.conv2d(x, sd['lateral_convs.0.conv.weight'], sd['lateral_convs.0.conv.bias'])
+    return F.conv2d(lat, sd['fpn_convs.0.conv.weight'], sd['fpn_convs.0.conv.bias'], padding=1)

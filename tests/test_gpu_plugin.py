@@ -145,3 +145,35 @@ def test_bbox_head_loss_interface_matches_reference_golden(state_dicts):
                                           torch.from_numpy(s['dn_labels']).cuda(), pad, None, float(g['dn_split']), neg_bbox_loss=False)
         close(a, g['dn_loss_cls'][l], 1e-6, 2e-5)
         close(b, g['dn_loss_bbox'][l], 1e-6, 2e-5)
+
+
+def test_detector_shell_with_neck_matches_oracle(state_dicts):
+    """DETECTORS.build(cfg.model) with the config's one-level FPN neck: a stub 2D detector hands over its five FPN
+    levels + detections, MV2D.simple_test runs neck -> roi_head (detectors/mv2d.py:251-261, :122-127); compared with
+    the oracle's neck + S forward + decode."""
+    from mv2d_b200.config import Config
+    from mv2d_b200.plugin.build import roi_head_cfg
+    from mv2d_b200.registry import DETECTORS, build_from_cfg
+    from oracle import mv2d_oracle as O
+    cfg = Config.fromfile(CFG['S'])
+    model = dict(cfg['model'])
+    model['roi_head'] = roi_head_cfg(cfg)
+    p4, boxes, metas = synth.make_sample(77, 6, 5)
+    levels = [torch.zeros(6, 256, 8, 8), torch.zeros(6, 256, 8, 8), p4, torch.zeros(6, 256, 8, 8), torch.zeros(6, 256, 8, 8)]
+    model['base_detector'] = lambda img, img_metas: ([l.cuda() for l in levels], [b.cuda() for b in boxes])
+    det = build_from_cfg(model, DETECTORS).cuda()
+    assert det.with_neck and type(det.neck).__name__ == 'FPN'
+    sd, nsd = state_dicts(6), synth.make_neck_state_dict(9)
+    det.roi_head.load_state_dict(sd, strict=True)
+    det.neck.load_state_dict(nsd, strict=True)
+    (b, s, l), = det.simple_test(None, metas)
+    with torch.no_grad():
+        cls, box = O.mv2d_s_forward(sd, O.fpn_neck(nsd, p4), boxes, metas, O.make_cfg('S'))
+        rb, rs, rl = O.nms_free_decode(cls[-1], box[-1], O.make_cfg('S')) if hasattr(O, 'nms_free_decode') else (None, None, None)
+    if rs is not None:
+        assert s.shape == rs.shape
+        close(s, rs.numpy(), 1e-3, 1e-3)
+    res = det.roi_head._bbox_forward([det.process_detector_feat([l.cuda() for l in levels])[0].permute(0, 3, 1, 2)],
+                                     [x.cuda() for x in boxes], metas)
+    close(torch.stack(res['cls_scores']), cls.numpy())
+    close(torch.stack(res['bbox_preds']), box.numpy())
