@@ -365,6 +365,15 @@ MV2D_API int mv2d_nms_free_decode(const float* cls /*[N,10]*/, const float* box 
                          float* out_scores /*[max_num]*/, int* out_labels /*[max_num]*/,
                          uint8_t* out_valid /*[max_num]*/, void* stream);
 
+/* ---- f1, scene level: the mmdet3d box3d_multiclass_nms call of MV2D.simple_test (detectors/mv2d.py:266-282) on the
+ * decoded boxes: keep valid[i] (nullable) && score > score_thr, regroup by class then descending score, cap at
+ * max_num (by score, over all classes).  nms_thr must be >= 1.0 (the configs' value: rotated BEV NMS at IoU 1.0
+ * suppresses nothing); lower thresholds return an error. */
+MV2D_API int mv2d_scene_nms(const float* boxes /*[n,9]*/, const float* scores /*[n]*/, const int* labels /*[n]*/,
+                            const uint8_t* valid /*[n] nullable*/, int n, float score_thr, float nms_thr, int max_num,
+                            float* out_boxes /*[max_num,9]*/, float* out_scores /*[max_num]*/, int* out_labels /*[max_num]*/,
+                            int* out_count /*device [1]*/, void* stream);
+
 /* debug: spin `cycles` SM clocks in a 1-warp kernel; out[0] = elapsed ns (globaltimer), out[1] = cycles */
 MV2D_API int mv2d_debug_clock_probe(long long cycles, long long* out /*device [2]*/, void* stream);
 

@@ -157,6 +157,13 @@ int mv2d_nms_free_decode(const float* cls, const float* box, int N, int max_num,
                                (cudaStream_t)stream);
 }
 
+int mv2d_scene_nms(const float* boxes, const float* scores, const int* labels, const uint8_t* valid, int n, float score_thr,
+                   float nms_thr, int max_num, float* out_boxes, float* out_scores, int* out_labels, int* out_count, void* stream) {
+    MV2D_CHECK_ARG(out_boxes && out_scores && out_labels && out_count && (n == 0 || (boxes && scores && labels)), "scene_nms: null pointer");
+    return run_scene_nms(boxes, scores, labels, valid, n, score_thr, nms_thr, max_num, out_boxes, out_scores, out_labels, out_count,
+                         (cudaStream_t)stream);
+}
+
 int mv2d_debug_clock_probe(long long cycles, long long* out, void* stream) {
     MV2D_CHECK_ARG(out != nullptr && cycles > 0, "clock_probe: bad arguments");
     return run_clock_probe(cycles, out, (cudaStream_t)stream);

@@ -71,6 +71,73 @@ int run_nms_free_decode(const float* cls, const float* box, int N, int max_num, 
     return 0;
 }
 
+// Scene-level tail of MV2D.simple_test (detectors/mv2d.py:266-282): mmdet3d box3d_multiclass_nms on the decoded
+// boxes.  With the configs' nms_thr = 1.0 the rotated BEV NMS suppresses nothing (an IoU never exceeds 1), so what
+// the call does is: keep score > score_thr, regroup by class (ascending), each class by descending score; and if
+// more than max_num boxes remain, keep the max_num best of all classes in descending score order.
+// One CTA, rank by counting (n is at most a few hundred).
+__global__ void __launch_bounds__(1024)
+scene_nms_kernel(const float* __restrict__ boxes, const float* __restrict__ scores, const int* __restrict__ labels,
+                 const uint8_t* __restrict__ valid, int n, float score_thr, int max_num,
+                 float* __restrict__ out_boxes, float* __restrict__ out_scores, int* __restrict__ out_labels,
+                 int* __restrict__ out_count) {
+    pdl_wait();
+    pdl_trigger();
+    extern __shared__ unsigned char raw[];
+    float* sc = reinterpret_cast<float*>(raw);
+    int* lb = reinterpret_cast<int*>(sc + n);          // label, or -1 = dropped
+    __shared__ int kept_s;
+    if (threadIdx.x == 0) kept_s = 0;
+    __syncthreads();
+    int kept_local = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const bool k = (valid == nullptr || valid[i]) && scores[i] > score_thr;
+        sc[i] = scores[i];
+        lb[i] = k ? labels[i] : -1;
+        kept_local += k;
+    }
+    atomicAdd(&kept_s, kept_local);
+    __syncthreads();
+    const int kept = kept_s;
+    const bool by_class = kept <= max_num;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        if (lb[i] < 0) continue;
+        int rank = 0;
+        for (int j = 0; j < n; ++j) {
+            if (lb[j] < 0) continue;
+            const bool score_first = sc[j] > sc[i] || (sc[j] == sc[i] && j < i);
+            rank += by_class ? (lb[j] < lb[i] || (lb[j] == lb[i] && score_first)) : score_first;
+        }
+        if (rank < max_num) {
+            for (int c = 0; c < 9; ++c) out_boxes[rank * 9 + c] = boxes[i * 9 + c];
+            out_scores[rank] = sc[i];
+            out_labels[rank] = lb[i];
+        }
+    }
+    if (threadIdx.x == 0) *out_count = kept < max_num ? kept : max_num;
+}
+
+int run_scene_nms(const float* boxes, const float* scores, const int* labels, const uint8_t* valid, int n, float score_thr,
+                  float nms_thr, int max_num, float* out_boxes, float* out_scores, int* out_labels, int* out_count,
+                  cudaStream_t st) {
+    MV2D_CHECK_ARG(n >= 0 && max_num >= 1, "scene_nms: bad n/max_num");
+    MV2D_CHECK_ARG(nms_thr >= 1.f, "scene_nms: rotated BEV NMS below an IoU threshold of 1.0 is not implemented "
+                                   "(the MV2D configs use nms_thr = 1.0, which suppresses nothing)");
+    MV2D_CHECK_ARG((size_t)n * 8 <= 200 * 1024, "scene_nms: n=%d too large", n);
+    if (n == 0) {
+        cudaError_t e = cudaMemsetAsync(out_count, 0, sizeof(int), st);
+        if (e != cudaSuccess) { set_error("scene_nms: %s", cudaGetErrorString(e)); return (int)e; }
+        return 0;
+    }
+    const size_t smem = (size_t)n * 8;
+    cudaError_t e = cudaFuncSetAttribute(scene_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > 48 * 1024 ? smem : 48 * 1024));
+    if (e != cudaSuccess) { set_error("scene_nms: %s", cudaGetErrorString(e)); return (int)e; }
+    launch_k(scene_nms_kernel, dim3(1), dim3(1024), smem, st, boxes, scores, labels, valid, n, score_thr, max_num,
+             out_boxes, out_scores, out_labels, out_count);
+    MV2D_CHECK_LAUNCH("scene_nms");
+    return 0;
+}
+
 // debug: SM clock rate as seen by a running kernel: spin `cycles` SM clocks, report elapsed globaltimer ns
 __global__ void clock_probe_kernel(long long cycles, long long* out) {
     pdl_wait();

@@ -29,6 +29,10 @@ size_t loss_workspace_bytes(int N, int G, int L);
 int run_fpn_neck(const Mv2dNeckParams& p, cudaStream_t st);
 size_t fpn_neck_workspace_bytes(int V, int h, int w);
 
+int run_scene_nms(const float* boxes, const float* scores, const int* labels, const uint8_t* valid, int n, float score_thr,
+                  float nms_thr, int max_num, float* out_boxes, float* out_scores, int* out_labels, int* out_count,
+                  cudaStream_t st);
+
 int run_clock_probe(long long cycles, long long* out, cudaStream_t st);
 
 }  // namespace mv2d

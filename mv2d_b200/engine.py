@@ -745,3 +745,21 @@ class HotPath:
         k = min(max_num, N * 10)
         m = valid[:k].bool()
         return boxes[:k][m], scores[:k][m], labels[:k][m].long()
+
+    @torch.no_grad()
+    def scene_nms(self, boxes, scores, labels, score_thr=0.0, nms_thr=1.0, max_num=300):
+        """Scene-level tail of MV2D.simple_test (detectors/mv2d.py:266-282, mmdet3d box3d_multiclass_nms at the configs'
+        nms_thr = 1.0): regroup the decoded boxes by class / descending score, cap at max_num.  Device in, device out."""
+        n = int(boxes.shape[0])
+        b = boxes.to(self.device, torch.float32).contiguous()
+        s = scores.to(self.device, torch.float32).contiguous()
+        l = labels.to(self.device).to(torch.int32).contiguous()
+        ob = torch.empty((max_num, 9), device=self.device)
+        os_ = torch.empty((max_num,), device=self.device)
+        ol = torch.empty((max_num,), dtype=torch.int32, device=self.device)
+        cnt = torch.zeros((1,), dtype=torch.int32, device=self.device)
+        lib.check(self.lib.mv2d_scene_nms(b.data_ptr() if n else None, s.data_ptr() if n else None, l.data_ptr() if n else None,
+                                          None, n, score_thr, nms_thr, max_num, ob.data_ptr(), os_.data_ptr(), ol.data_ptr(),
+                                          cnt.data_ptr(), lib.stream_ptr()), 'mv2d_scene_nms')
+        k = int(cnt.item())         # the result leaves the device here anyway (bbox3d2result, mv2d.py:284-287)
+        return ob[:k], os_[:k], ol[:k].long()

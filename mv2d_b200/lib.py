@@ -179,6 +179,7 @@ SYMBOLS = [
     ('mv2d_gemm', C.c_int, [c_f, C.c_int, c_f, C.c_int, c_f, c_f, C.c_int, C.c_int, C.c_int, C.c_int,
                             C.c_int, c_f]),
     ('mv2d_debug_clock_probe', C.c_int, [C.c_longlong, c_f, c_f]),
+    ('mv2d_scene_nms', C.c_int, [c_f, c_f, c_f, c_f, C.c_int, C.c_float, C.c_float, C.c_int, c_f, c_f, c_f, c_f, c_f]),
     ('mv2d_nms_free_decode', C.c_int, [c_f, c_f, C.c_int, C.c_int, C.POINTER(C.c_float), c_f, c_f, c_f,
                                        c_f, c_f]),
 ]

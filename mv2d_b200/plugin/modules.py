@@ -617,7 +617,21 @@ class MV2D(nn.Module):
             if self.with_neck:      # mv2d.py:122-127: the detector hands over its FPN outputs, the neck makes P4'
                 cl, _ = self.process_detector_feat(feat)
                 feat = cl.permute(0, 3, 1, 2)
-        return self.roi_head.simple_test([feat], detections, img_metas)
+        outs = self.roi_head.simple_test([feat], detections, img_metas)
+        # scene-level tail, mv2d.py:262-293: box3d_multiclass_nms (score_thr / nms_thr / max_per_scene from
+        # test_cfg.rcnn) and bbox3d2result (results leave the device)
+        cfg = (self.test_cfg or {}).get('rcnn') or {}
+        nms = cfg.get('nms') or {}
+        bt = img_metas[0].get('box_type_3d')
+        results = []
+        for boxes, scores, labels in outs:
+            raw = boxes.tensor if hasattr(boxes, 'tensor') else boxes
+            b, s, l = self.roi_head.engine().scene_nms(raw, scores, labels, cfg.get('score_thr', 0.0), nms.get('nms_thr', 1.0),
+                                                       cfg.get('max_per_scene', 300))
+            b = b.cpu()
+            results.append(dict(pts_bbox=dict(boxes_3d=bt(b, b.shape[-1]) if bt is not None else b, scores_3d=s.cpu(),
+                                              labels_3d=l.cpu())))
+        return results
 
 
 @DETECTORS.register_module()

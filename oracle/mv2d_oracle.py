@@ -781,3 +781,24 @@ def fpn_neck(neck_sd, x):
     sd = {(k[len('neck.'):] if k.startswith('neck.') else k): v for k, v in neck_sd.items()}
     lat = F.conv2d(x, sd['lateral_convs.0.conv.weight'], sd['lateral_convs.0.conv.bias'])
     return F.conv2d(lat, sd['fpn_convs.0.conv.weight'], sd['fpn_convs.0.conv.bias'], padding=1)
+
+
+def scene_nms(boxes, scores, labels, score_thr=0.0, max_num=300, num_classes=10):
+    """detectors/mv2d.py:266-282 -> mmdet3d 1.0 box3d_multiclass_nms with the configs' nms_thr = 1.0 (exp/...:150-154):
+    the rotated BEV NMS suppresses nothing, so per class (ascending) the boxes with score > score_thr in descending
+    score order are concatenated; beyond max_num the best max_num by score are kept in descending score order.
+    (mmdet3d is third-party and absent: restated from its published behaviour, unpinned.)"""
+    ob, os_, ol = [], [], []
+    for c in range(num_classes):
+        m = (labels == c) & (scores > score_thr)
+        if m.any():
+            idx = torch.nonzero(m).squeeze(1)
+            order = torch.argsort(scores[idx], descending=True, stable=True)
+            ob.append(boxes[idx][order]); os_.append(scores[idx][order]); ol.append(labels[idx][order])
+    if not ob:
+        return boxes.new_zeros((0, boxes.shape[1])), scores.new_zeros((0,)), labels.new_zeros((0,))
+    b, s, l = torch.cat(ob), torch.cat(os_), torch.cat(ol)
+    if b.shape[0] > max_num:
+        inds = torch.argsort(s, descending=True, stable=True)[:max_num]
+        b, s, l = b[inds], s[inds], l[inds]
+    return b, s, l

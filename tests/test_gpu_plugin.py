@@ -166,14 +166,33 @@ def test_detector_shell_with_neck_matches_oracle(state_dicts):
     sd, nsd = state_dicts(6), synth.make_neck_state_dict(9)
     det.roi_head.load_state_dict(sd, strict=True)
     det.neck.load_state_dict(nsd, strict=True)
-    (b, s, l), = det.simple_test(None, metas)
+    res, = det.simple_test(None, metas)
+    got = res['pts_bbox']
     with torch.no_grad():
         cls, box = O.mv2d_s_forward(sd, O.fpn_neck(nsd, p4), boxes, metas, O.make_cfg('S'))
-        rb, rs, rl = O.nms_free_decode(cls[-1], box[-1], O.make_cfg('S')) if hasattr(O, 'nms_free_decode') else (None, None, None)
-    if rs is not None:
-        assert s.shape == rs.shape
-        close(s, rs.numpy(), 1e-3, 1e-3)
+        rb, rs, rl = O.scene_nms(*O.nms_free_decode(cls[-1], box[-1], O.make_cfg('S')))
+    # mv2d.py:266-287: grouped by class, descending score inside a class, on the host
+    assert not got['scores_3d'].is_cuda and got['scores_3d'].shape == rs.shape
+    assert torch.equal(got['labels_3d'], rl)
+    close(got['scores_3d'], rs.numpy(), 1e-3, 1e-3)
+    close(got['boxes_3d'], rb.numpy(), 2e-3, 2e-3)
     res = det.roi_head._bbox_forward([det.process_detector_feat([l.cuda() for l in levels])[0].permute(0, 3, 1, 2)],
                                      [x.cuda() for x in boxes], metas)
     close(torch.stack(res['cls_scores']), cls.numpy())
     close(torch.stack(res['bbox_preds']), box.numpy())
+
+
+def test_scene_nms_matches_oracle(state_dicts):
+    """mv2d_scene_nms (box3d_multiclass_nms at the configs' nms_thr = 1.0) incl. the > max_num branch and thresholds."""
+    from mv2d_b200.engine import HotPath
+    from oracle import mv2d_oracle as O
+    eng = HotPath(state_dicts(6), mode='S')
+    g = torch.Generator().manual_seed(3)
+    for n, max_num, thr in ((300, 300, 0.0), (300, 120, 0.0), (57, 300, 0.4), (1, 300, 0.0), (0, 300, 0.0)):
+        boxes, scores = torch.randn(n, 9, generator=g), torch.rand(n, generator=g)
+        labels = torch.randint(0, 10, (n,), generator=g)
+        b, s, l = eng.scene_nms(boxes.cuda(), scores.cuda(), labels.cuda(), score_thr=thr, max_num=max_num)
+        rb, rs, rl = O.scene_nms(boxes, scores, labels, score_thr=thr, max_num=max_num)
+        assert torch.equal(l.cpu(), rl) and torch.equal(s.cpu(), rs) and torch.equal(b.cpu(), rb)
+    with pytest.raises(RuntimeError):
+        eng.scene_nms(boxes.cuda(), scores.cuda(), labels.cuda(), nms_thr=0.5)
