@@ -216,6 +216,8 @@ typedef struct Mv2dDecoderParams {
     const float* vp;            /* xa_form 1: [L,num_rows,256] projected values from mv2d_kv_project */
     void* xa_workspace;         /* xa_form 1: mv2d_xa_tile_workspace_bytes(N, V, grid_h, grid_w) */
     size_t xa_workspace_bytes;
+    uint8_t* row_tile_live;     /* mv2d_xa_tile_prepare only, nullable out [ceil(num_rows/128)]: 1 = some query has a key
+                                 * among rows 128 t .. 128 t + 127 (input of mv2d_kv_project) */
 } Mv2dDecoderParams;
 MV2D_API size_t mv2d_decoder_workspace_bytes(int N, int L);
 MV2D_API size_t mv2d_xa_tile_workspace_bytes(int N, int V, int grid_h, int grid_w);
@@ -237,6 +239,9 @@ typedef struct Mv2dKvParams {
     const Mv2dLayerWeights* layers;    /* HOST array [L] */
     float* kp;                         /* out [L,num_rows,256] */
     float* vp;                         /* out [L,num_rows,256] */
+    const uint8_t* row_tile_live;      /* nullable, device [ceil(num_rows/128)] from mv2d_xa_tile_prepare: 128-row tiles no
+                                        * query has a key in are not projected (their kp / vp rows stay untouched and
+                                        * are never read by the attention) */
 } Mv2dKvParams;
 MV2D_API int mv2d_kv_project(const Mv2dKvParams* p, void* stream);
 

@@ -979,6 +979,7 @@ int run_kv_project(const Mv2dKvParams& p, cudaStream_t st) {
         int rc;
         TcGemm t{};
         t.lda = MV2D_C; t.ldw = MV2D_C; t.ldc = MV2D_C; t.M = p.num_rows; t.N = MV2D_C; t.K = MV2D_C; t.passes = 3; t.nsplit = 1;
+        t.m_tile_live = p.row_tile_live;
         t.A = p.kin_hi; t.A_lo = p.kin_lo; t.W = raw ? w.xa_k_raw : w.xa_k_w; t.W_lo = raw ? nullptr : w.xa_k_w_lo; t.C = p.kp + l * RC;
         if ((rc = launch_gemm_tc(t, st))) return rc;
         t.A = p.mem_hi; t.A_lo = p.mem_lo; t.W = raw ? w.xa_v_raw : w.xa_v_w; t.W_lo = raw ? nullptr : w.xa_v_w_lo; t.C = p.vp + l * RC;
@@ -1011,6 +1012,10 @@ static int xt_prepare(const Mv2dDecoderParams& p, const XtGeom& xg, const XtWs& 
     b.order = xw.order;
     launch_k(xt_list_kernel, dim3(xg.N + 1), dim3(256), 0, st, b);
     MV2D_CHECK_LAUNCH("xt_list");
+    if (p.row_tile_live) {
+        launch_k(xt_rowlive_kernel, dim3(cdiv(p.num_rows, 128)), dim3(128), 0, st, p.keymask, p.mask_words, xg.N, p.num_rows, p.row_tile_live);
+        MV2D_CHECK_LAUNCH("xt_rowlive");
+    }
     return 0;
 }
 

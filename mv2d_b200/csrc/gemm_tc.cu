@@ -104,6 +104,7 @@ struct TcArgs {
     int flags;
     int n_rois;                                                        // IM2COL 1: number of RoIs
     int fm_h, fm_w;                                                    // IM2COL 2: feature grid (tiles of 16 x 8 pixels)
+    const uint8_t* m_tile_live;                                        // nullable [m_tiles]: 0 = nobody reads this row tile, skip it
     const float* gx; const float* gs; const float* gfeat; float* kin;  // GEMM_GATE extras
 };
 
@@ -131,6 +132,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m_tile = blockIdx.y, n0 = blockIdx.x * BN;
+    if (g.m_tile_live != nullptr) {             // CTA-uniform: before any barrier / TMEM allocation
+        pdl_wait();
+        if (g.m_tile_live[m_tile] == 0) return;
+    }
     const int nkb = g.nkb_per_split, kb0 = blockIdx.z * g.nkb_per_split;   // this CTA's K range (split-K)
     // CTAs that share an operand tile walk K in rotated order, so they do not all hit the same L2 lines at once
     const int rot = IM2COL ? 0 : (int)((blockIdx.x + 3 * blockIdx.y) % nkb);
@@ -679,6 +684,7 @@ int launch_gemm_tc(const TcGemm& t, cudaStream_t st) {
     g.C = t.C; g.C_lo = t.C_lo; g.ldc = t.ldc; g.bias = t.bias; g.M = t.M; g.N = t.N; g.K = t.K; g.flags = t.flags;
     g.nkb_per_split = t.K / TC_BK / nsplit; g.split_stride = t.split_stride;
     g.gx = t.gx; g.gs = t.gs; g.gfeat = t.gfeat; g.kin = t.kin;
+    g.m_tile_live = t.m_tile_live;
     int m_tiles;
     if (t.im2col == 2) {
         MV2D_CHECK_ARG(t.K == 9 * MV2D_C && t.passes == 3 && t.fm_v > 0 && t.fm_h > 0 && t.fm_w > 0 && t.M == t.fm_v * t.fm_h * t.fm_w,

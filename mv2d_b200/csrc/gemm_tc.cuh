@@ -28,6 +28,7 @@ struct TcGemm {
     int im2col;        // 1: A = [n_rois,7,7,256] tokens, M = 49*n_rois, K = 2304 ordered (tap, c_in)
                        // 2: A = [fm_v,fm_h,fm_w,256] feature map, M = fm_v*fm_h*fm_w, same K order (3x3, padding 1)
     int fm_v, fm_h, fm_w;
+    const uint8_t* m_tile_live;   // nullable, device [ceil(M/128)]: row tiles with 0 are skipped (their C rows stay untouched)
     int flags;         // GEMM_RELU | GEMM_GATE | GEMM_ROUND_TF32
     const float* gx; const float* gs; const float* gfeat; float* kin;
 };

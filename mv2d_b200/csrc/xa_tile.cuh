@@ -161,6 +161,23 @@ __global__ void __launch_bounds__(256) xt_list_kernel(XtListArgs a) {
     }
 }
 
+// 128-row tiles of the K/V projection GEMM that hold at least one key of some query: grid = tiles, 128 threads
+__global__ void __launch_bounds__(128) xt_rowlive_kernel(const uint32_t* __restrict__ keymask, int mask_words, int N, int num_rows,
+                                                         uint8_t* __restrict__ live) {
+    pdl_wait();
+    pdl_trigger();
+    const int t = blockIdx.x, w0 = t * 4;
+    int any = 0;
+    for (int n = threadIdx.x; n < N; n += 128) {
+        const uint32_t* km = keymask + (long long)n * mask_words;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (w0 + j < mask_words) any |= km[w0 + j] != 0u;
+    }
+    any = __syncthreads_or(any);
+    if (threadIdx.x == 0) live[t] = any ? 1 : 0;
+}
+
 struct XtAttnArgs {
     XtGeom g;
     const float* q;                    // [N,256] projected queries, 1/sqrt(32) folded in

@@ -333,8 +333,11 @@ class HotPath:
             xa_bytes = self.lib.mv2d_xa_tile_workspace_bytes(N, V, h, w)
             xa_ws = self._get('xa_ws', (xa_bytes,), torch.uint8)
             d.xa_workspace, d.xa_workspace_bytes = xa_ws.data_ptr(), xa_bytes
+            row_live = self._get('kv_row_live', ((V * h * w + 127) // 128,), torch.uint8)
+            d.row_tile_live = row_live.data_ptr()
             lib.check(self.lib.mv2d_xa_tile_prepare(C.byref(d), lib.stream_ptr()), 'mv2d_xa_tile_prepare')
             out['xa_prepared_for'] = (out['keymask'].data_ptr(), N, xa_ws.data_ptr())
+            out['row_tile_live'] = row_live     # 128-row tiles of the K/V projection some query has a key in
         return out
 
     def dn_prepare(self, qg, corr, N, dn):
@@ -392,7 +395,7 @@ class HotPath:
         qg2 = dict(qg, query_pos=qpos_all, ref=ref_all)
         return qg2, corr2, T, pad, dict(dn_labels=dn_labels, dn_attn_mask=attn_mask, dn_ref=ref_all[:pad])
 
-    def kv_project(self, kin_rows, mem_rows, record_events=False):
+    def kv_project(self, kin_rows, mem_rows, record_events=False, row_live=None):
         """Two-frame head, xa_form 1: K_l = (mem + pos) Wk_l^T and V_l = mem Wv_l^T for every decoder layer
         (3xTF32 tcgen05 GEMMs over all V*h*w cells), on the current stream.  With record_events the per-layer
         events ``_ev_kv[l]`` are recorded so the decoder layers on another stream can start as soon as their
@@ -416,6 +419,8 @@ class HotPath:
             p.kin_hi, p.kin_lo, p.mem_hi, p.mem_lo = kin_hi.data_ptr(), kin_lo.data_ptr(), mem_hi.data_ptr(), mem_lo.data_ptr()
         p.layers = self.w.layers_ptr()
         p.kp, p.vp = kp.data_ptr(), vp.data_ptr()
+        if row_live is not None and os.environ.get('MV2D_KV_SKIP', '1') != '0':
+            p.row_tile_live = row_live.data_ptr()
         for l in range(L):
             p.layer_begin, p.layer_end = l, l + 1
             lib.check(self.lib.mv2d_kv_project(C.byref(p), st), 'mv2d_kv_project')
@@ -521,7 +526,10 @@ class HotPath:
                 self._ev_pe.record(main)
                 with torch.cuda.stream(self._kv):
                     self._kv.wait_event(self._ev_pe)
-                    kv = self.kv_project(kin.view(-1, 256), feat.view(-1, 256), record_events=True)
+                    self._kv.wait_event(self._ev_join2)        # the live-tile flags come from the box correlation stream
+                    # denoising queries may add keys (train_unmask gives key 0 to a query without any): project everything
+                    kv = self.kv_project(kin.view(-1, 256), feat.view(-1, 256), record_events=True,
+                                         row_live=corr.get('row_tile_live') if dn is None else None)
             main.wait_event(self._ev_join)
             main.wait_event(self._ev_join2)
             if self.mode == 'S':

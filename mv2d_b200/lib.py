@@ -95,6 +95,7 @@ class DecoderParams(C.Structure):
         ('layer_begin', C.c_int), ('layer_end', C.c_int), ('xa_form', C.c_int), ('grid_h', C.c_int),
         ('grid_w', C.c_int), ('xa_prepared', C.c_int),
         ('kp', c_f), ('vp', c_f), ('xa_workspace', c_f), ('xa_workspace_bytes', C.c_size_t),
+        ('row_tile_live', c_f),
     ]
 
 
@@ -102,7 +103,7 @@ class KvParams(C.Structure):
     _fields_ = [
         ('num_rows', C.c_int), ('L', C.c_int), ('layer_begin', C.c_int), ('layer_end', C.c_int),
         ('kin_hi', c_f), ('kin_lo', c_f), ('mem_hi', c_f), ('mem_lo', c_f),
-        ('layers', C.POINTER(LayerWeights)), ('kp', c_f), ('vp', c_f),
+        ('layers', C.POINTER(LayerWeights)), ('kp', c_f), ('vp', c_f), ('row_tile_live', c_f),
     ]
 
 
