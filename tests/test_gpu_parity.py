@@ -384,3 +384,29 @@ def test_odd_feature_grid_matches_oracle(mode, V, n, seed, state_dicts):
     torch.cuda.synchronize()
     assert_close(out['cls_scores'], cls, what='cls_scores')
     assert_close(out['bbox_preds'], box, what='bbox_preds')
+
+
+def test_two_frame_kv_projection_skips_unused_row_tiles(state_dicts):
+    """The K/V projection leaves 128-row tiles without any key untouched.  Poisoning the K/V buffers with NaN before
+    the run shows that those rows are never read by the attention, and that some tiles really are skipped."""
+    from mv2d_b200.engine import HotPath
+    spec, g = load_golden('t_small')
+    feat, boxes, metas = synth.case_inputs(spec)
+    eng = HotPath(state_dicts(spec['num_layers']), mode='T')
+    out = eng.forward(feat.cuda(), [b.cuda() for b in boxes], metas)
+    torch.cuda.synchronize()
+    want = (out['cls_scores'].clone(), out['bbox_preds'].clone())
+    live = out['row_tile_live'].cpu().numpy()
+    assert 0 < live.sum() < live.size, 'this case has both used and unused row tiles'
+    eng._buf['kp'].fill_(float('nan'))
+    eng._buf['vp'].fill_(float('nan'))
+    out = eng.forward(feat.cuda(), [b.cuda() for b in boxes], metas)
+    torch.cuda.synchronize()
+    assert torch.equal(out['cls_scores'], want[0]) and torch.equal(out['bbox_preds'], want[1])
+    R = eng._buf['kp'].numel() // (eng.L * 256)
+    kp = eng._buf['kp'][:eng.L * R * 256].view(eng.L, R, 256)
+    rows_nan = torch.isnan(kp[0]).any(dim=1).view(-1).cpu().numpy()
+    for t in range(live.size):
+        seg = rows_nan[t * 128:(t + 1) * 128]
+        assert seg.all() if live[t] == 0 else not seg.any()
+    assert_close(out['cls_scores'], g['cls_scores'], what='cls_scores')
