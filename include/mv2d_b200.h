@@ -78,6 +78,10 @@ typedef struct Mv2dPeParams {
     float* kin;                /* out, nullable: feat + pe (keys of the two-frame head) */
     float* workspace;
     size_t workspace_bytes;
+    int sine_separable;        /* 1 = the caller guarantees not_mask is all ones (no padded cells): the first layer of
+                                * the sine branch is evaluated as W1.s(v,y,x) = Tv[v] + Ty[y] + Tx[x] from three
+                                * (V + h + w)-row tables instead of a GEMM over all V*h*w cells; 0 = general masks */
+    int reserved0;
 } Mv2dPeParams;
 MV2D_API size_t mv2d_pe3d_workspace_bytes(int V, int h, int w, int depth_num);
 MV2D_API int mv2d_pe3d(const Mv2dPeParams* p, void* stream);

@@ -143,6 +143,56 @@ __global__ void sine_embed_kernel(const float* __restrict__ emb, const float* __
     out[gid] = round_tf32(r);   // operand of a TF32 GEMM
 }
 
+// ---- separable form of the sine branch's first layer (no padded cells: not_mask is all ones).
+// The 384 sine features of a cell are [f(e_view) | f(e_y) | f(e_x)], and each normalised embed depends on ONE
+// coordinate only, so  W1 . s(v,y,x) = Tv[v] + Ty[y] + Tx[x]  with three tiny tables (V + h + w rows instead of
+// V*h*w): the 384 -> 1024 GEMM over all cells (13 GFLOP at V = 6) becomes a 126-row GEMM plus an element-wise
+// gather-add.  Exact in real arithmetic; the tables are accumulated in fp32 FFMA (the full-size GEMM was TF32).
+// Step A: rows r < V: view v = r; r < V + h: y = r - V; else x = r - V - h.  F[r] holds the row's 128 features in its
+// own 128-column slot of a zero-padded [rows, 384] matrix, so ONE GEMM against W1 [1024, 384] yields all three tables.
+__global__ void __launch_bounds__(128) sine_axis_kernel(const float* __restrict__ dim_t, float* __restrict__ F,
+                                                        int V, int h, int w, float stride, float scale, float eps) {
+    pdl_wait();
+    pdl_trigger();
+    const int r = blockIdx.x, i = threadIdx.x;
+    int axis, idx, len;
+    if (r < V) { axis = 0; idx = r; len = V; }
+    else if (r < V + h) { axis = 1; idx = r - V; len = h; }
+    else { axis = 2; idx = r - V - h; len = w; }
+    // same fp32 operations as sine_prep_kernel with an all-ones mask: cumsum = idx + 1, last = len
+    float e = (float)(idx + 1), l = (float)len;
+    if (axis > 0 && stride > 0.f) { e = (e - 0.5f) * stride; l = (l - 0.5f) * stride; }
+    const float val = e / (l + eps) * scale;
+    float f;
+    if (i < 64) f = __sinf(val / __ldg(dim_t + 2 * i));
+    else        f = __cosf(val / __ldg(dim_t + 2 * (i - 64) + 1));
+    float* row = F + (long long)r * 384;
+    row[i] = axis == 0 ? f : 0.f;
+    row[128 + i] = axis == 1 ? f : 0.f;
+    row[256 + i] = axis == 2 ? f : 0.f;
+}
+
+// Step C: hidden[p, :] = tf32(relu(Tv[v] + Ty[y] + Tx[x] + b)), the A operand of the 1024 -> 256 TF32 GEMM.
+__global__ void __launch_bounds__(256) sine_hidden_kernel(const float* __restrict__ T, const float* __restrict__ bias,
+                                                          float* __restrict__ Hd, int V, int h, int w) {
+    pdl_wait();
+    pdl_trigger();
+    const long long gid = (long long)blockIdx.x * 256 + threadIdx.x;      // one float4 of a 1024-wide row
+    const long long total = (long long)V * h * w * 256;
+    if (gid >= total) return;
+    const int j4 = (int)(gid & 255);
+    const long long p = gid >> 8;
+    const int x = (int)(p % w), y = (int)((p / w) % h), v = (int)(p / ((long long)w * h));
+    const float4 a = __ldg(reinterpret_cast<const float4*>(T + (long long)v * 1024) + j4);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(T + (long long)(V + y) * 1024) + j4);
+    const float4 c = __ldg(reinterpret_cast<const float4*>(T + (long long)(V + h + x) * 1024) + j4);
+    const float4 d = __ldg(reinterpret_cast<const float4*>(bias) + j4);
+    float4 o;
+    o.x = round_tf32(fmaxf(((a.x + b.x) + c.x) + d.x, 0.f)); o.y = round_tf32(fmaxf(((a.y + b.y) + c.y) + d.y, 0.f));
+    o.z = round_tf32(fmaxf(((a.z + b.z) + c.z) + d.z, 0.f)); o.w = round_tf32(fmaxf(((a.w + b.w) + c.w) + d.w, 0.f));
+    reinterpret_cast<float4*>(Hd)[gid] = o;
+}
+
 static int gemm(const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc,
                 int M, int N, int K, int flags, cudaStream_t st, const float* gx = nullptr,
                 const float* gs = nullptr, const float* gfeat = nullptr, float* kin = nullptr) {
@@ -201,6 +251,18 @@ int run_pe3d(const Mv2dPeParams& p, cudaStream_t st) {
     // sine branch: 384 -> 1024 -> 256  (input-independent given masks + weights; recomputed here)
     if (p.phase == 2) {
         // X and SB were left in the workspace by phase 1
+    } else if (!p.sine_branch_cached && p.sine_separable) {
+        // no padded cells: per-axis tables instead of the 384 -> 1024 GEMM over every cell
+        const int rows = p.V + p.h + p.w;
+        float* Fm = S;                              // [rows, 384]
+        float* Tm = S + (size_t)rows * 384;         // [rows, 1024]
+        MV2D_CHECK_ARG((size_t)rows * (384 + 1024) <= (size_t)P * 384, "pe3d: separable sine tables do not fit the workspace");
+        launch_k(sine_axis_kernel, dim3(rows), dim3(128), 0, st, p.dim_t, Fm, p.V, p.h, p.w, (float)p.stride, 6.283185307179586f, 1e-6f);
+        MV2D_CHECK_LAUNCH("sine_axis");
+        if ((rc = gemm(Fm, 384, p.w_adapt0, 384, nullptr, Tm, 4 * C, rows, 4 * C, 384, 0, st))) return rc;     // fp32 FFMA
+        launch_k(sine_hidden_kernel, dim3((unsigned)(((long long)P * 256 + 255) / 256)), dim3(256), 0, st, (const float*)Tm, p.b_adapt0, Hd, p.V, p.h, p.w);
+        MV2D_CHECK_LAUNCH("sine_hidden");
+        if ((rc = gemm(Hd, 4 * C, p.w_adapt2, 4 * C, p.b_adapt2, SB, C, P, C, 4 * C, GEMM_TF32_OK, st))) return rc;
     } else if (!p.sine_branch_cached) {
         launch_k(sine_prep_kernel, dim3(cdiv(P, 128)), dim3(128), 0, st, p.not_mask, EM, p.V, p.h, p.w, (float)p.stride,
                                                       6.283185307179586f, 1e-6f);

@@ -239,7 +239,7 @@ class HotPath:
         V, h, w = dims if dims is not None else feat_nhwc.shape[:3]
         self._last_grid = (h, w)
         c, W = self.cfg, self.w
-        key, pad_mask, not_mask, _ = self._masks(img_metas, h, w)
+        key, pad_mask, not_mask, has_pad = self._masks(img_metas, h, w)
         pe = self._get('pe', (V, h, w, 256))
         kin = self._get('kin', (V, h, w, 256)) if self.mode == 'T' else None
         ws_bytes = self.lib.mv2d_pe3d_workspace_bytes(V, h, w, c['depth_num'])
@@ -247,6 +247,8 @@ class HotPath:
         p = lib.PeParams()
         p.V, p.h, p.w, p.depth_num = V, h, w, c['depth_num']
         p.phase = phase
+        # no padded cells (img_shape == pad_shape in every view): the sine branch's first layer is separable
+        p.sine_separable = int((not has_pad) and os.environ.get('MV2D_SINE_SEPARABLE', '1') != '0')
         p.pad_h, p.pad_w = int(img_metas[0]['pad_shape'][0]), int(img_metas[0]['pad_shape'][1])
         p.stride = c['stride']
         p.depth_start = c['depth_start']
