@@ -56,3 +56,23 @@ def test_process_2d_detections_matches_reference_semantics():
         ref = np.concatenate([np.concatenate([b, np.full((len(b), 1), c, np.float32)], 1) for c, b in enumerate(view)], 0)
         ref = ref[((ref[:, 2:4] - ref[:, 0:2]) >= 8).all(1)]
         assert det.shape[1] == 6 and np.array_equal(det.numpy(), ref)
+
+
+@pytest.mark.parametrize('path', OURS + REF)
+def test_neck_and_training_side_build_from_the_registry(path):
+    """The configs' neck (one-level FPN) and train_cfg.rcnn (HungarianAssigner3D with its match costs, stage loss
+    weights) build through the registries under the reference's type names; the neck carries mmdet's parameter names."""
+    from mv2d_b200.config import Config
+    from mv2d_b200.plugin import modules  # noqa: F401
+    from mv2d_b200.registry import NECKS, build_from_cfg
+    cfg = Config.fromfile(path)
+    neck = build_from_cfg(dict(cfg['model']['neck']), NECKS)
+    assert set(neck.state_dict()) == {'lateral_convs.0.conv.weight', 'lateral_convs.0.conv.bias',
+                                      'fpn_convs.0.conv.weight', 'fpn_convs.0.conv.bias'}
+    assert tuple(neck.state_dict()['fpn_convs.0.conv.weight'].shape) == (256, 256, 3, 3) and neck.start_level == 2
+    head = build_roi_head(path, device=None, train=True)
+    a = head.bbox_head.assigner
+    assert type(a).__name__ == 'HungarianAssigner3D' and a.cls_cost.weight == 2.0 and a.reg_cost.weight == 0.25
+    assert head.stage_loss_weights == [0.1] * 6
+    kw = head.bbox_head._loss_kwargs()
+    assert kw['code_weights'] == [1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.5, 1.5, 2.0, 2.0] and kw['cls_loss_weight'] == 2.0 and kw['bbox_loss_weight'] == 0.25
