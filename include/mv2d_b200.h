@@ -32,7 +32,7 @@ extern "C" {
 #define MV2D_API
 #endif
 
-#define MV2D_ABI_VERSION 3
+#define MV2D_ABI_VERSION 4
 #define MV2D_MAX_LAYERS 8
 
 MV2D_API int mv2d_abi_version(void);
@@ -40,7 +40,7 @@ MV2D_API const char* mv2d_last_error(void);
 /* number of kernel launches this library has enqueued so far in this process */
 MV2D_API unsigned long long mv2d_launch_count(void);
 /* sizeof() of the parameter structs, so a binding can verify its mirror of this header */
-MV2D_API size_t mv2d_sizeof(int which); /* 0 Pe, 1 Qg, 2 Corr, 3 Decoder, 4 LayerWeights, 5 BranchWeights, 6 Dn, 7 Kv, 8 Loss, 9 Neck */
+MV2D_API size_t mv2d_sizeof(int which); /* 0 Pe, 1 Qg, 2 Corr, 3 Decoder, 4 LayerWeights, 5 BranchWeights, 6 Dn, 7 Kv, 8 Loss, 9 Neck, 10 Train */
 
 /* ---- geometry (utils/pe.py:111; roi_heads/utils/box_correlation.py:118-122,174-178)
  * img2lidar[v] = inv(lidar2img[v]);  trans[src][dst] = lidar2img[dst] @ img2lidar[src]  (fp64) */
@@ -349,6 +349,74 @@ typedef struct Mv2dNeckParams {
 } Mv2dNeckParams;
 MV2D_API size_t mv2d_fpn_neck_workspace_bytes(int V, int h, int w);
 MV2D_API int mv2d_fpn_neck(const Mv2dNeckParams* p, void* stream);
+
+/* ---- row e / BASELINE configs[3]: the training step of the MV2D-S decoder slice (ABI 4) ---------------------------
+ * Forward with saved activations + Hungarian targets + losses, then the BACKWARD (torch autograd in the reference)
+ * of: CrossAttentionBoxHead.forward (bbox_heads/cross_attention_head.py:199-242: query embedding, MV2DTransformer /
+ * PETRTransformerDecoder utils/petr_transformer.py:194-593, post_norm, cls / reg branches, reference-point
+ * refinement) and loss_single (:379-434), summed over layers with stage_loss_weights as MV2DSHead.forward_train does
+ * (roi_heads/mv2d_s_head.py:262-307).  The single-frame configs train WITHOUT denoising queries
+ * (configs/mv2d/exp/mv2d_r50_frcnn_single_frame_roi_1408x512_ep*.py:44), so query i attends to the 49 tokens of
+ * every RoI in match[i][0 .. match_cnt[i]) and self-attention is unmasked.
+ *
+ * Parameters and gradients live in ONE flat fp32 buffer each (so the data-parallel exchange is a single NCCL
+ * all-reduce and the optimizer a single fused pass).  Tensor ids, in buffer order (every tensor starts at a
+ * multiple of 16 floats; names relative to `bbox_head.`):
+ *   0 query_embedding.0.weight [256,384]   1 query_embedding.0.bias   2 query_embedding.2.weight [256,256]
+ *   3 query_embedding.2.bias   4 transformer.decoder.post_norm.weight   5 .bias
+ *   then for every layer l, 6 + 34 l + k with k =
+ *    0 attentions.0.attn.in_proj_weight [768,256]  1 in_proj_bias  2 out_proj.weight [256,256]  3 out_proj.bias
+ *    4 attentions.1.attn.in_proj_weight [768,256]  5 in_proj_bias  6 out_proj.weight            7 out_proj.bias
+ *    8 ffns.0.layers.0.0.weight [2048,256]  9 .bias  10 ffns.0.layers.1.weight [256,2048]  11 .bias
+ *    12..17 norms.{0,1,2}.{weight,bias}
+ *    18 cls_branches.l.0.weight  19 .0.bias  20 .1.weight (LN)  21 .1.bias  22 .3.weight  23 .3.bias  24 .4.weight (LN)
+ *    25 .4.bias  26 .6.weight [10,256]  27 .6.bias [10]
+ *    28 reg_branches.l.0.weight  29 .0.bias  30 .2.weight  31 .2.bias  32 .4.weight [10,256]  33 .4.bias [10]      */
+#define MV2D_TRAIN_GLOBAL_TENSORS 6
+#define MV2D_TRAIN_LAYER_TENSORS 34
+MV2D_API long long mv2d_train_param_total(int L);                      /* floats in the flat buffer */
+MV2D_API int mv2d_train_param_info(int L, int tensor_id, long long* offset, long long* numel);
+
+typedef struct Mv2dTrainParams {
+    int N, L, max_match, G;
+    int num_classes, reserved0;
+    float pc_range[6];
+    float cls_cost_weight, reg_cost_weight, cls_loss_weight, bbox_loss_weight, focal_alpha, focal_gamma;
+    float code_weights[10];
+    float stage_loss_weights[MV2D_MAX_LAYERS];   /* roi_head.stage_loss_weights (exp configs: 0.1 per layer ... 1.0 last) */
+    const float* params;        /* flat parameters */
+    float* grads;               /* flat gradients; the backward ACCUMULATES into it (the caller zeroes it per step) */
+    const float* dim_t;         /* [128] temperature ** (2*(i//2)/128) */
+    const float* ref;           /* [N,3] normalised reference points (mv2d_roi_align_qg) */
+    const float* tok_kin;       /* [N,49,256] RoI-pooled (feat + pe): key input */
+    const float* tok_mem;       /* [N,49,256] RoI-pooled feat: value input */
+    const int* match;           /* [N,max_match] from mv2d_box_corr */
+    const int* match_cnt;       /* [N] */
+    const float* gt_boxes;      /* [G,9] gravity centre xyz, w, l, h, yaw, vx, vy */
+    const int* gt_labels;       /* [G] */
+    float* cls_scores;          /* out of the forward, in of the backward [L,N,10] */
+    float* bbox_preds;          /* out / in [L,N,10] */
+    int* assigned;              /* out / in [L,N] */
+    float* losses;              /* out [L,4] as mv2d_loss (unweighted by stage_loss_weights) */
+    float* d_ref;               /* backward out [N,3] */
+    float* d_tok_kin;           /* backward out [N,49,256] */
+    float* d_tok_mem;           /* backward out [N,49,256] */
+    float* workspace;           /* saved activations of the forward + scratch of the backward; must survive between the
+                                 * two calls */
+    size_t workspace_bytes;
+} Mv2dTrainParams;
+MV2D_API size_t mv2d_decoder_train_workspace_bytes(int N, int L, int max_match, int G);
+MV2D_API int mv2d_decoder_train_forward(const Mv2dTrainParams* p, void* stream);
+/* tests: float offset of a saved activation in `workspace` after the forward.  which = 0 query_pos [N,256];
+ * per layer: 1 x after norms.0, 2 after norms.1, 3 layer output, 4 post-normed intermediate, 5 cross-attention
+ * context, 6 self-attention context (all [N,256]).  -1 = unknown */
+MV2D_API long long mv2d_train_debug_offset(int N, int L, int max_match, int G, int layer, int which);
+MV2D_API int mv2d_decoder_train_backward(const Mv2dTrainParams* p, void* stream);
+
+/* fused AdamW step over flat buffers (torch.optim.AdamW semantics; configs/mv2d/exp/*.py optimizer):
+ * g is multiplied by grad_scale first (1 / world_size after a sum all-reduce); step counts from 1 */
+MV2D_API int mv2d_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr,
+                             float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream);
 
 /* ---- low-level GEMM, exposed for tests and microbenchmarks:
  * C[M,N] = act(A[M,K] . W[N,K]^T + bias); flags: 1 relu, 8 allow TF32 tensor cores,

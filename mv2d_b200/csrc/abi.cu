@@ -44,6 +44,7 @@ size_t mv2d_sizeof(int which) {
         case 7: return sizeof(Mv2dKvParams);
         case 8: return sizeof(Mv2dLossParams);
         case 9: return sizeof(Mv2dNeckParams);
+        case 10: return sizeof(Mv2dTrainParams);
         default: return 0;
     }
 }
@@ -138,6 +139,28 @@ int mv2d_fpn_neck(const Mv2dNeckParams* p, void* stream) {
     NONNULL(p, "fpn_neck");
     MV2D_CHECK_ARG(p->x && p->lat_w && p->lat_w_lo && p->lat_b && p->fpn_w && p->fpn_w_lo && p->fpn_b && p->feat, "fpn_neck: null pointer");
     return run_fpn_neck(*p, (cudaStream_t)stream);
+}
+
+long long mv2d_train_param_total(int L) { return train_param_total(L); }
+int mv2d_train_param_info(int L, int tensor_id, long long* offset, long long* numel) {
+    return train_param_info(L, tensor_id, offset, numel);
+}
+size_t mv2d_decoder_train_workspace_bytes(int N, int L, int max_match, int G) { return train_workspace_bytes(N, L, max_match, G); }
+long long mv2d_train_debug_offset(int N, int L, int max_match, int G, int layer, int which) {
+    return train_debug_offset(N, L, max_match, G, layer, which);
+}
+int mv2d_decoder_train_forward(const Mv2dTrainParams* p, void* stream) {
+    NONNULL(p, "decoder_train_forward");
+    return run_train_forward(*p, (cudaStream_t)stream);
+}
+int mv2d_decoder_train_backward(const Mv2dTrainParams* p, void* stream) {
+    NONNULL(p, "decoder_train_backward");
+    return run_train_backward(*p, (cudaStream_t)stream);
+}
+int mv2d_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
+                    float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream) {
+    return run_adamw(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale,
+                     (cudaStream_t)stream);
 }
 
 int mv2d_gemm(const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc, int M, int N,

@@ -35,4 +35,14 @@ int run_scene_nms(const float* boxes, const float* scores, const int* labels, co
 
 int run_clock_probe(long long cycles, long long* out, cudaStream_t st);
 
+// train.cu
+long long train_param_total(int L);
+int train_param_info(int L, int tensor_id, long long* offset, long long* numel);
+size_t train_workspace_bytes(int N, int L, int max_match, int G);
+long long train_debug_offset(int N, int L, int max_match, int G, int layer, int which);
+int run_train_forward(const Mv2dTrainParams& p, cudaStream_t st);
+int run_train_backward(const Mv2dTrainParams& p, cudaStream_t st);
+int run_adamw(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps, float wd,
+              int step, float grad_scale, cudaStream_t st);
+
 }  // namespace mv2d

@@ -1,0 +1,1171 @@
+// Training step of the MV2D-S decoder slice (SURVEY.md 8e / BASELINE configs[3]): forward WITH saved activations,
+// Hungarian targets + losses, and the BACKWARD of rows a12-a18 + f3 -- query embedding, six decoder layers
+// (flattened self-attention, sparse per-RoI cross-attention, FFN, LayerNorms), post-norm, cls / reg branches with
+// the reference-point refinement, focal + L1 losses -- down to the gradients of every parameter of that slice and of
+// its inputs (reference points, RoI key tokens, RoI value tokens).
+//   reference: roi_heads/bbox_heads/cross_attention_head.py:199-242 (forward), :379-434 (loss_single);
+//              utils/petr_transformer.py:194-370,373-513,569-593; utils/pe.py:21-33;
+//              roi_heads/mv2d_s_head.py:262-307 (forward_train: sum over layers of stage_loss_weight * loss);
+//              the backward itself is torch autograd in the reference.
+// The reference trains MV2D-S without denoising queries (configs/mv2d/exp/*single_frame*:44 use_denoise=False), so
+// every query attends to the 49 tokens of each RoI in its own match list and self-attention is unmasked.
+//
+// Layout: parameters and gradients are ONE flat fp32 buffer each (mv2d_train_param_info), so the data-parallel
+// gradient exchange is a single NCCL all-reduce and the optimizer a single fused pass.  The inference path keeps the
+// absorbed cross-attention weights; training uses the plain in_proj / out_proj form because those are the leaves
+// the optimizer updates.
+//
+// First correct version: every contraction runs through one bounds-checked fp32 FFMA GEMM (sgemm_kernel) that
+// takes its operands by strides (A W^T, dC W and dC^T A without materialised transposes; weight gradients use
+// split-K with atomic accumulation into the flat gradient buffer); the attention kernels keep the probabilities
+// of the forward and run one warp per (query, head) / (key, head).  Moving the wide GEMMs onto the tcgen05 path
+// of gemm_tc.cu is the next step for this row.
+#include <algorithm>
+#include "common.cuh"
+#include "mv2d_internal.h"
+
+namespace mv2d {
+
+namespace {
+
+constexpr int TC_ = MV2D_C;        // 256
+constexpr int TH = MV2D_HEADS;     // 8
+constexpr int THD = MV2D_HD;       // 32
+constexpr int TTOK = MV2D_TOK;     // 49
+constexpr int TFF = 2048;
+constexpr int TPE = 384;           // 3 x 128 sin/cos features of the query embedding
+constexpr int TCODE = 10;
+
+// ------------------------------------------------------------------------------------------------ parameter layout
+enum TrainGlobal { TG_QE0_W, TG_QE0_B, TG_QE2_W, TG_QE2_B, TG_POST_G, TG_POST_B, TG_COUNT };
+enum TrainLayer {
+    TL_SA_IN_W, TL_SA_IN_B, TL_SA_OUT_W, TL_SA_OUT_B, TL_CA_IN_W, TL_CA_IN_B, TL_CA_OUT_W, TL_CA_OUT_B,
+    TL_FFN_W1, TL_FFN_B1, TL_FFN_W2, TL_FFN_B2, TL_LN0_G, TL_LN0_B, TL_LN1_G, TL_LN1_B, TL_LN2_G, TL_LN2_B,
+    TL_CLS_W0, TL_CLS_B0, TL_CLS_G0, TL_CLS_BE0, TL_CLS_W1, TL_CLS_B1, TL_CLS_G1, TL_CLS_BE1, TL_CLS_W2, TL_CLS_B2,
+    TL_REG_W0, TL_REG_B0, TL_REG_W1, TL_REG_B1, TL_REG_W2, TL_REG_B2, TL_COUNT
+};
+const long long kGlobalNumel[TG_COUNT] = {256 * 384, 256, 256 * 256, 256, 256, 256};
+const long long kLayerNumel[TL_COUNT] = {
+    768 * 256, 768, 256 * 256, 256, 768 * 256, 768, 256 * 256, 256,
+    2048 * 256, 2048, 256 * 2048, 256, 256, 256, 256, 256, 256, 256,
+    256 * 256, 256, 256, 256, 256 * 256, 256, 256, 256, 10 * 256, 10,
+    256 * 256, 256, 256 * 256, 256, 10 * 256, 10};
+
+inline long long pad16(long long n) { return (n + 15) / 16 * 16; }
+
+long long layer_block_floats() {
+    long long s = 0;
+    for (int t = 0; t < TL_COUNT; ++t) s += pad16(kLayerNumel[t]);
+    return s;
+}
+long long global_block_floats() {
+    long long s = 0;
+    for (int t = 0; t < TG_COUNT; ++t) s += pad16(kGlobalNumel[t]);
+    return s;
+}
+long long global_off(int t) {
+    long long s = 0;
+    for (int i = 0; i < t; ++i) s += pad16(kGlobalNumel[i]);
+    return s;
+}
+long long layer_off(int l, int t) {
+    long long s = global_block_floats() + (long long)l * layer_block_floats();
+    for (int i = 0; i < t; ++i) s += pad16(kLayerNumel[i]);
+    return s;
+}
+
+// ------------------------------------------------------------------------------------------------ generic fp32 GEMM
+// C[M,N] (op)= sum_k A(m,k) B(k,n) (+ bias[n]),  A(m,k) = A[m*sam + k*sak],  B(k,n) = B[k*sbk + n*sbn].
+enum SgFlags { SG_RELU = 1, SG_ACC = 2, SG_ATOMIC = 4 };
+struct Sg {
+    const float* A; const float* B; float* C; const float* bias; const float* mask;
+    long long sam, sak, sbk, sbn;
+    int ldc, ldmask, M, N, K, klen, flags;
+};
+
+template <bool AK1, bool BN1>
+__global__ void __launch_bounds__(256) sgemm_kernel(Sg g) {
+    pdl_wait();
+    pdl_trigger();
+    __shared__ __align__(16) float As[16][68];
+    __shared__ __align__(16) float Bs[16][68];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+    const int kbeg = blockIdx.z * g.klen;
+    const int kend = min(g.K, kbeg + g.klen);
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int k0 = kbeg; k0 < kend; k0 += 16) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int idx = tid + i * 256;
+            int m, k;
+            if (AK1) { k = idx & 15; m = idx >> 4; } else { m = idx & 63; k = idx >> 6; }
+            float v = 0.f;
+            if (m0 + m < g.M && k0 + k < kend) v = __ldg(g.A + (long long)(m0 + m) * g.sam + (long long)(k0 + k) * g.sak);
+            As[k][m] = v;
+            int n, kb;
+            if (BN1) { n = idx & 63; kb = idx >> 6; } else { kb = idx & 15; n = idx >> 4; }
+            float w = 0.f;
+            if (n0 + n < g.N && k0 + kb < kend) w = __ldg(g.B + (long long)(k0 + kb) * g.sbk + (long long)(n0 + n) * g.sbn);
+            Bs[kb][n] = w;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+            const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + ty * 4 + i;
+        if (m >= g.M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx * 4 + j;
+            if (n >= g.N) continue;
+            float v = acc[i][j];
+            if (g.bias && blockIdx.z == 0) v += __ldg(g.bias + n);
+            float* c = g.C + (long long)m * g.ldc + n;
+            if (g.flags & SG_ATOMIC) { atomicAdd(c, v); continue; }
+            if (g.flags & SG_RELU) v = fmaxf(v, 0.f);
+            if (g.mask && !(g.mask[(long long)m * g.ldmask + n] > 0.f)) v = 0.f;
+            if (g.flags & SG_ACC) v += *c;
+            *c = v;
+        }
+    }
+}
+
+int launch_sgemm(const Sg& g, int splits, cudaStream_t st) {
+    if (g.M <= 0 || g.N <= 0 || g.K <= 0) return 0;
+    dim3 grid(cdiv(g.N, 64), cdiv(g.M, 64), splits);
+    const bool ak1 = g.sak == 1, bn1 = g.sbn == 1;
+    if (ak1 && bn1) launch_k(sgemm_kernel<true, true>, grid, dim3(256), 0, st, g);
+    else if (ak1) launch_k(sgemm_kernel<true, false>, grid, dim3(256), 0, st, g);
+    else if (bn1) launch_k(sgemm_kernel<false, true>, grid, dim3(256), 0, st, g);
+    else launch_k(sgemm_kernel<false, false>, grid, dim3(256), 0, st, g);
+    MV2D_CHECK_LAUNCH("train sgemm");
+    return 0;
+}
+
+// Y[M,Nout] = act(X[M,K] W[Nout,K]^T + b)
+int linear_fwd(const float* X, int ldx, const float* W, int ldw, const float* b, float* Y, int ldy, int M, int Nout, int K,
+               bool relu, cudaStream_t st) {
+    Sg g{};
+    g.A = X; g.sam = ldx; g.sak = 1; g.B = W; g.sbk = 1; g.sbn = ldw; g.C = Y; g.ldc = ldy; g.bias = b;
+    g.M = M; g.N = Nout; g.K = K; g.klen = K; g.flags = relu ? SG_RELU : 0;
+    return launch_sgemm(g, 1, st);
+}
+// dX[M,K] (+)= (dY[M,Nout] W[Nout,K]) . [mask > 0]
+int linear_dgrad(const float* dY, int ldy, const float* W, int ldw, float* dX, int ldx, int M, int Nout, int K,
+                 const float* mask, int ldmask, bool accumulate, cudaStream_t st) {
+    Sg g{};
+    g.A = dY; g.sam = ldy; g.sak = 1; g.B = W; g.sbk = ldw; g.sbn = 1; g.C = dX; g.ldc = ldx; g.mask = mask; g.ldmask = ldmask;
+    g.M = M; g.N = K; g.K = Nout; g.klen = Nout; g.flags = accumulate ? SG_ACC : 0;
+    return launch_sgemm(g, 1, st);
+}
+// dW[Nout,K] += dY[M,Nout]^T X[M,K]   (split over the M rows, atomic accumulation)
+int linear_wgrad(const float* dY, int ldy, const float* X, int ldx, float* dW, int ldw, int M, int Nout, int K, cudaStream_t st) {
+    Sg g{};
+    g.A = dY; g.sam = 1; g.sak = ldy; g.B = X; g.sbk = ldx; g.sbn = 1; g.C = dW; g.ldc = ldw;
+    g.M = Nout; g.N = K; g.K = M; g.flags = SG_ATOMIC;
+    const int tiles = cdiv(Nout, 64) * cdiv(K, 64);
+    int splits = cdiv(296, tiles);
+    splits = std::max(1, std::min(splits, cdiv(M, 64)));
+    g.klen = cdiv(cdiv(M, splits), 16) * 16;
+    splits = cdiv(M, g.klen);
+    return launch_sgemm(g, splits, st);
+}
+
+// out[n] += sum_m X[m*ld + n]   (bias gradients)
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ X, int ld, int M, int N, int rows_per_block,
+                                                     float* __restrict__ out) {
+    pdl_wait();
+    pdl_trigger();
+    __shared__ float s[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int n = blockIdx.x * 32 + tx;
+    const int r0 = blockIdx.y * rows_per_block, r1 = min(M, r0 + rows_per_block);
+    float a = 0.f;
+    if (n < N)
+        for (int r = r0 + ty; r < r1; r += 8) a += X[(long long)r * ld + n];
+    s[ty][tx] = a;
+    __syncthreads();
+    if (ty == 0 && n < N) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += s[i][tx];
+        atomicAdd(out + n, t);
+    }
+}
+int colsum(const float* X, int ld, int M, int N, float* out, cudaStream_t st) {
+    if (M <= 0 || N <= 0) return 0;
+    const int rpb = 256;
+    launch_k(colsum_kernel, dim3(cdiv(N, 32), cdiv(M, rpb)), dim3(256), 0, st, X, ld, M, N, rpb, out);
+    MV2D_CHECK_LAUNCH("train colsum");
+    return 0;
+}
+
+// out = a + b (b nullable); in-place allowed
+__global__ void __launch_bounds__(256) add_kernel(float* out, const float* a, const float* b, long long n) {
+    pdl_wait();
+    pdl_trigger();
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256)
+        out[i] = a[i] + (b ? b[i] : 0.f);
+}
+int add(float* out, const float* a, const float* b, long long n, cudaStream_t st) {
+    if (n <= 0) return 0;
+    const long long want = (n + 255) / 256;
+    const int grid = (int)(want < 148 * 8 ? want : 148 * 8);
+    launch_k(add_kernel, dim3(grid), dim3(256), 0, st, out, a, b, n);
+    MV2D_CHECK_LAUNCH("train add");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ LayerNorm
+// y = a (+ b); xhat = (y - mean) * rstd; out = [relu](xhat * g + beta).  One warp per row of 256.
+__global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                     const float* __restrict__ g, const float* __restrict__ beta,
+                                                     float* __restrict__ out, float* __restrict__ xhat, float* __restrict__ rstd,
+                                                     int N, int relu) {
+    pdl_wait();
+    pdl_trigger();
+    const int lane = threadIdx.x & 31, r = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (r >= N) return;
+    float v[8], s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const long long o = (long long)r * TC_ + lane + 32 * k;
+        v[k] = a[o] + (b ? b[o] : 0.f);
+        s += v[k];
+    }
+    const float mean = warp_sum(s) * (1.f / TC_);
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { const float d = v[k] - mean; q += d * d; }
+    const float var = warp_sum(q) * (1.f / TC_);
+    const float rs = 1.f / sqrtf(var + 1e-5f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int c = lane + 32 * k;
+        const long long o = (long long)r * TC_ + c;
+        const float xh = (v[k] - mean) * rs;
+        xhat[o] = xh;
+        float y = xh * g[c] + beta[c];
+        if (relu) y = fmaxf(y, 0.f);
+        out[o] = y;
+    }
+    if (lane == 0) rstd[r] = rs;
+}
+int ln_fwd(const float* a, const float* b, const float* g, const float* beta, float* out, float* xhat, float* rstd, int N,
+           bool relu, cudaStream_t st) {
+    if (N <= 0) return 0;
+    launch_k(ln_fwd_kernel, dim3(cdiv(N, 8)), dim3(256), 0, st, a, b, g, beta, out, xhat, rstd, N, relu ? 1 : 0);
+    MV2D_CHECK_LAUNCH("train ln_fwd");
+    return 0;
+}
+
+// dy (masked by act > 0 when act != NULL: the ReLU that followed the norm) -> dx (written, or added when accumulate),
+// dg += sum_rows dy * xhat,  db += sum_rows dy
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ act,
+                                                     const float* __restrict__ xhat, const float* __restrict__ rstd,
+                                                     const float* __restrict__ g, float* __restrict__ dx, float* __restrict__ dg,
+                                                     float* __restrict__ db, int N, int accumulate) {
+    pdl_wait();
+    pdl_trigger();
+    __shared__ float sg[8][TC_], sb[8][TC_];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float pg[8], pb[8], gg[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { pg[k] = 0.f; pb[k] = 0.f; gg[k] = g[lane + 32 * k]; }
+    for (int r = blockIdx.x * 8 + warp; r < N; r += gridDim.x * 8) {
+        float d[8], xh[8], s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const long long o = (long long)r * TC_ + lane + 32 * k;
+            d[k] = dy[o];
+            if (act && !(act[o] > 0.f)) d[k] = 0.f;
+            xh[k] = xhat[o];
+            pb[k] += d[k];
+            pg[k] += d[k] * xh[k];
+            const float t = d[k] * gg[k];
+            s1 += t;
+            s2 += t * xh[k];
+        }
+        s1 = warp_sum(s1) * (1.f / TC_);
+        s2 = warp_sum(s2) * (1.f / TC_);
+        const float rs = rstd[r];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const long long o = (long long)r * TC_ + lane + 32 * k;
+            const float v = rs * (d[k] * gg[k] - s1 - xh[k] * s2);
+            dx[o] = accumulate ? dx[o] + v : v;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { sg[warp][lane + 32 * k] = pg[k]; sb[warp][lane + 32 * k] = pb[k]; }
+    __syncthreads();
+    const int c = threadIdx.x;
+    float tg = 0.f, tb = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { tg += sg[i][c]; tb += sb[i][c]; }
+    atomicAdd(dg + c, tg);
+    atomicAdd(db + c, tb);
+}
+int ln_bwd(const float* dy, const float* act, const float* xhat, const float* rstd, const float* g, float* dx, float* dg,
+           float* db, int N, bool accumulate, cudaStream_t st) {
+    if (N <= 0) return 0;
+    launch_k(ln_bwd_kernel, dim3(std::min(cdiv(N, 8), 148)), dim3(256), 0, st, dy, act, xhat, rstd, g, dx, dg, db, N, accumulate ? 1 : 0);
+    MV2D_CHECK_LAUNCH("train ln_bwd");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ query embedding
+// pos2posemb3d (utils/pe.py:21-33): [N,3] -> [N,384], blocks (y, x, z), interleaved sin / cos of ref * 2 pi / dim_t
+__global__ void __launch_bounds__(128) posemb_fwd_kernel(const float* __restrict__ ref, const float* __restrict__ dim_t,
+                                                         float* __restrict__ out, int N) {
+    pdl_wait();
+    pdl_trigger();
+    const int n = blockIdx.x, i = threadIdx.x;
+    if (n >= N) return;
+#pragma unroll
+    for (int blk = 0; blk < 3; ++blk) {
+        const int comp = blk == 0 ? 1 : (blk == 1 ? 0 : 2);
+        const float p = ref[n * 3 + comp] * 6.283185307179586f;
+        const float arg = p / dim_t[i];
+        out[(long long)n * TPE + blk * 128 + i] = (i & 1) ? cosf(arg) : sinf(arg);
+    }
+}
+// d_ref[n][comp] += sum_i dpe[n][blk*128+i] * d/dref
+__global__ void __launch_bounds__(96) posemb_bwd_kernel(const float* __restrict__ dpe, const float* __restrict__ ref,
+                                                        const float* __restrict__ dim_t, float* __restrict__ d_ref, int N) {
+    pdl_wait();
+    pdl_trigger();
+    const int n = blockIdx.x, blk = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (n >= N) return;
+    const int comp = blk == 0 ? 1 : (blk == 1 ? 0 : 2);
+    const float p = ref[n * 3 + comp] * 6.283185307179586f;
+    float a = 0.f;
+    for (int i = lane; i < 128; i += 32) {
+        const float w = 6.283185307179586f / dim_t[i];
+        const float arg = p / dim_t[i];
+        const float d = dpe[(long long)n * TPE + blk * 128 + i];
+        a += (i & 1) ? -d * sinf(arg) * w : d * cosf(arg) * w;
+    }
+    a = warp_sum(a);
+    if (lane == 0) d_ref[n * 3 + comp] += a;
+}
+
+// ------------------------------------------------------------------------------------------------ self-attention
+// One CTA per query, one warp per head; lane = key.  qkv [N,768] = (q | k | v), q and k from x + query_pos.
+__global__ void __launch_bounds__(256) sa_fwd_kernel(const float* __restrict__ qkv, float* __restrict__ P,
+                                                     float* __restrict__ attn_o, int N) {
+    pdl_wait();
+    pdl_trigger();
+    const int i = blockIdx.x, h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float scale = 0.17677669529663687f;   // 1 / sqrt(32)
+    float q[THD];
+#pragma unroll
+    for (int c = 0; c < THD; ++c) q[c] = qkv[(long long)i * 768 + h * THD + c] * scale;
+    float* Prow = P + ((long long)h * N + i) * N;
+    float mx = -INFINITY;
+    for (int j = lane; j < N; j += 32) {
+        const float4* kr = reinterpret_cast<const float4*>(qkv + (long long)j * 768 + 256 + h * THD);
+        float s = 0.f;
+#pragma unroll
+        for (int c4 = 0; c4 < THD / 4; ++c4) {
+            const float4 k = kr[c4];
+            s += q[c4 * 4] * k.x + q[c4 * 4 + 1] * k.y + q[c4 * 4 + 2] * k.z + q[c4 * 4 + 3] * k.w;
+        }
+        Prow[j] = s;
+        mx = fmaxf(mx, s);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int j = lane; j < N; j += 32) {
+        const float e = expf(Prow[j] - mx);
+        Prow[j] = e;
+        sum += e;
+    }
+    sum = warp_sum(sum);
+    const float inv = 1.f / sum;
+    float o[THD];
+#pragma unroll
+    for (int c = 0; c < THD; ++c) o[c] = 0.f;
+    for (int j = lane; j < N; j += 32) {
+        const float p = Prow[j] * inv;
+        Prow[j] = p;
+        const float4* vr = reinterpret_cast<const float4*>(qkv + (long long)j * 768 + 512 + h * THD);
+#pragma unroll
+        for (int c4 = 0; c4 < THD / 4; ++c4) {
+            const float4 v = vr[c4];
+            o[c4 * 4] += p * v.x; o[c4 * 4 + 1] += p * v.y; o[c4 * 4 + 2] += p * v.z; o[c4 * 4 + 3] += p * v.w;
+        }
+    }
+    float mine = 0.f;
+#pragma unroll
+    for (int c = 0; c < THD; ++c) {
+        const float r = warp_sum(o[c]);
+        if (lane == c) mine = r;
+    }
+    attn_o[(long long)i * TC_ + h * THD + lane] = mine;
+}
+
+// dO [N,256] -> dS (probability-space gradient folded to logits) and dq (rows 0:256 of dqkv)
+__global__ void __launch_bounds__(256) sa_bwd_dq_kernel(const float* __restrict__ qkv, const float* __restrict__ P,
+                                                        const float* __restrict__ dO, float* __restrict__ dS,
+                                                        float* __restrict__ dqkv, int N) {
+    pdl_wait();
+    pdl_trigger();
+    const int i = blockIdx.x, h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float scale = 0.17677669529663687f;
+    float go[THD];
+#pragma unroll
+    for (int c = 0; c < THD; ++c) go[c] = dO[(long long)i * TC_ + h * THD + c];
+    const float* Prow = P + ((long long)h * N + i) * N;
+    float* Srow = dS + ((long long)h * N + i) * N;
+    float D = 0.f;
+    for (int j = lane; j < N; j += 32) {
+        const float4* vr = reinterpret_cast<const float4*>(qkv + (long long)j * 768 + 512 + h * THD);
+        float dp = 0.f;
+#pragma unroll
+        for (int c4 = 0; c4 < THD / 4; ++c4) {
+            const float4 v = vr[c4];
+            dp += go[c4 * 4] * v.x + go[c4 * 4 + 1] * v.y + go[c4 * 4 + 2] * v.z + go[c4 * 4 + 3] * v.w;
+        }
+        Srow[j] = dp;
+        D += Prow[j] * dp;
+    }
+    D = warp_sum(D);
+    float dq[THD];
+#pragma unroll
+    for (int c = 0; c < THD; ++c) dq[c] = 0.f;
+    for (int j = lane; j < N; j += 32) {
+        const float ds = Prow[j] * (Srow[j] - D);
+        Srow[j] = ds;
+        const float4* kr = reinterpret_cast<const float4*>(qkv + (long long)j * 768 + 256 + h * THD);
+#pragma unroll
+        for (int c4 = 0; c4 < THD / 4; ++c4) {
+            const float4 k = kr[c4];
+            dq[c4 * 4] += ds * k.x; dq[c4 * 4 + 1] += ds * k.y; dq[c4 * 4 + 2] += ds * k.z; dq[c4 * 4 + 3] += ds * k.w;
+        }
+    }
+    float mine = 0.f;
+#pragma unroll
+    for (int c = 0; c < THD; ++c) {
+        const float r = warp_sum(dq[c]);
+        if (lane == c) mine = r;
+    }
+    dqkv[(long long)i * 768 + h * THD + lane] = mine * scale;
+}
+
+// one CTA per key j, one warp per head; lane = query.  dk -> dqkv[:, 256:512], dv -> dqkv[:, 512:768]
+__global__ void __launch_bounds__(256) sa_bwd_dkv_kernel(const float* __restrict__ qkv, const float* __restrict__ P,
+                                                         const float* __restrict__ dS, const float* __restrict__ dO,
+                                                         float* __restrict__ dqkv, int N) {
+    pdl_wait();
+    pdl_trigger();
+    const int j = blockIdx.x, h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float scale = 0.17677669529663687f;
+    float dk[THD], dv[THD];
+#pragma unroll
+    for (int c = 0; c < THD; ++c) { dk[c] = 0.f; dv[c] = 0.f; }
+    for (int i = lane; i < N; i += 32) {
+        const long long o = ((long long)h * N + i) * N + j;
+        const float p = P[o], ds = dS[o];
+        const float4* qr = reinterpret_cast<const float4*>(qkv + (long long)i * 768 + h * THD);
+        const float4* gr = reinterpret_cast<const float4*>(dO + (long long)i * TC_ + h * THD);
+#pragma unroll
+        for (int c4 = 0; c4 < THD / 4; ++c4) {
+            const float4 q = qr[c4], g = gr[c4];
+            dk[c4 * 4] += ds * q.x; dk[c4 * 4 + 1] += ds * q.y; dk[c4 * 4 + 2] += ds * q.z; dk[c4 * 4 + 3] += ds * q.w;
+            dv[c4 * 4] += p * g.x; dv[c4 * 4 + 1] += p * g.y; dv[c4 * 4 + 2] += p * g.z; dv[c4 * 4 + 3] += p * g.w;
+        }
+    }
+    float mk = 0.f, mv = 0.f;
+#pragma unroll
+    for (int c = 0; c < THD; ++c) {
+        const float rk = warp_sum(dk[c]), rv = warp_sum(dv[c]);
+        if (lane == c) { mk = rk; mv = rv; }
+    }
+    dqkv[(long long)j * 768 + 256 + h * THD + lane] = mk * scale;
+    dqkv[(long long)j * 768 + 512 + h * THD + lane] = mv;
+}
+
+// ------------------------------------------------------------------------------------------------ cross-attention
+// query i attends to the 49 tokens of every RoI in match[i][0 .. cnt_i); Kp / Vp [N*49,256] projected tokens.
+// P [N, 8, PM] with PM = max_match * 49; slot = m * 49 + t.
+__global__ void __launch_bounds__(256) xa_fwd_kernel(const float* __restrict__ cq, const float* __restrict__ Kp,
+                                                     const float* __restrict__ Vp, const int* __restrict__ match,
+                                                     const int* __restrict__ match_cnt, int max_match,
+                                                     float* __restrict__ P, float* __restrict__ ctx, int N) {
+    pdl_wait();
+    pdl_trigger();
+    const int i = blockIdx.x, h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int PM = max_match * TTOK;
+    const int cnt = min(match_cnt[i], max_match);
+    const float scale = 0.17677669529663687f;
+    float q[THD];
+#pragma unroll
+    for (int c = 0; c < THD; ++c) q[c] = cq[(long long)i * TC_ + h * THD + c] * scale;
+    float* Prow = P + ((long long)i * TH + h) * PM;
+    float mx = -INFINITY;
+    for (int m = 0; m < cnt; ++m) {
+        const int r = match[i * max_match + m];
+        for (int t = lane; t < TTOK; t += 32) {
+            const float4* kr = reinterpret_cast<const float4*>(Kp + ((long long)r * TTOK + t) * TC_ + h * THD);
+            float s = 0.f;
+#pragma unroll
+            for (int c4 = 0; c4 < THD / 4; ++c4) {
+                const float4 k = kr[c4];
+                s += q[c4 * 4] * k.x + q[c4 * 4 + 1] * k.y + q[c4 * 4 + 2] * k.z + q[c4 * 4 + 3] * k.w;
+            }
+            Prow[m * TTOK + t] = s;
+            mx = fmaxf(mx, s);
+        }
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int m = 0; m < cnt; ++m)
+        for (int t = lane; t < TTOK; t += 32) {
+            const float e = expf(Prow[m * TTOK + t] - mx);
+            Prow[m * TTOK + t] = e;
+            sum += e;
+        }
+    sum = warp_sum(sum);
+    const float inv = cnt > 0 ? 1.f / sum : 0.f;
+    float o[THD];
+#pragma unroll
+    for (int c = 0; c < THD; ++c) o[c] = 0.f;
+    for (int m = 0; m < cnt; ++m) {
+        const int r = match[i * max_match + m];
+        for (int t = lane; t < TTOK; t += 32) {
+            const float p = Prow[m * TTOK + t] * inv;
+            Prow[m * TTOK + t] = p;
+            const float4* vr = reinterpret_cast<const float4*>(Vp + ((long long)r * TTOK + t) * TC_ + h * THD);
+#pragma unroll
+            for (int c4 = 0; c4 < THD / 4; ++c4) {
+                const float4 v = vr[c4];
+                o[c4 * 4] += p * v.x; o[c4 * 4 + 1] += p * v.y; o[c4 * 4 + 2] += p * v.z; o[c4 * 4 + 3] += p * v.w;
+            }
+        }
+    }
+    float mine = 0.f;
+#pragma unroll
+    for (int c = 0; c < THD; ++c) {
+        const float r = warp_sum(o[c]);
+        if (lane == c) mine = r;
+    }
+    ctx[(long long)i * TC_ + h * THD + lane] = mine;
+}
+
+__global__ void __launch_bounds__(256) xa_bwd_dq_kernel(const float* __restrict__ Kp, const float* __restrict__ Vp,
+                                                        const float* __restrict__ P, const float* __restrict__ dctx,
+                                                        const int* __restrict__ match, const int* __restrict__ match_cnt,
+                                                        int max_match, float* __restrict__ dS, float* __restrict__ dcq, int N) {
+    pdl_wait();
+    pdl_trigger();
+    const int i = blockIdx.x, h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int PM = max_match * TTOK;
+    const int cnt = min(match_cnt[i], max_match);
+    const float scale = 0.17677669529663687f;
+    float go[THD];
+#pragma unroll
+    for (int c = 0; c < THD; ++c) go[c] = dctx[(long long)i * TC_ + h * THD + c];
+    const float* Prow = P + ((long long)i * TH + h) * PM;
+    float* Srow = dS + ((long long)i * TH + h) * PM;
+    float D = 0.f;
+    for (int m = 0; m < cnt; ++m) {
+        const int r = match[i * max_match + m];
+        for (int t = lane; t < TTOK; t += 32) {
+            const float4* vr = reinterpret_cast<const float4*>(Vp + ((long long)r * TTOK + t) * TC_ + h * THD);
+            float dp = 0.f;
+#pragma unroll
+            for (int c4 = 0; c4 < THD / 4; ++c4) {
+                const float4 v = vr[c4];
+                dp += go[c4 * 4] * v.x + go[c4 * 4 + 1] * v.y + go[c4 * 4 + 2] * v.z + go[c4 * 4 + 3] * v.w;
+            }
+            Srow[m * TTOK + t] = dp;
+            D += Prow[m * TTOK + t] * dp;
+        }
+    }
+    D = warp_sum(D);
+    float dq[THD];
+#pragma unroll
+    for (int c = 0; c < THD; ++c) dq[c] = 0.f;
+    for (int m = 0; m < cnt; ++m) {
+        const int r = match[i * max_match + m];
+        for (int t = lane; t < TTOK; t += 32) {
+            const float ds = Prow[m * TTOK + t] * (Srow[m * TTOK + t] - D);
+            Srow[m * TTOK + t] = ds;
+            const float4* kr = reinterpret_cast<const float4*>(Kp + ((long long)r * TTOK + t) * TC_ + h * THD);
+#pragma unroll
+            for (int c4 = 0; c4 < THD / 4; ++c4) {
+                const float4 k = kr[c4];
+                dq[c4 * 4] += ds * k.x; dq[c4 * 4 + 1] += ds * k.y; dq[c4 * 4 + 2] += ds * k.z; dq[c4 * 4 + 3] += ds * k.w;
+            }
+        }
+    }
+    float mine = 0.f;
+#pragma unroll
+    for (int c = 0; c < THD; ++c) {
+        const float r = warp_sum(dq[c]);
+        if (lane == c) mine = r;
+    }
+    dcq[(long long)i * TC_ + h * THD + lane] = mine * scale;
+}
+
+// inverse of the match lists: for every RoI r the (query, list position) pairs that attend to it, in ascending
+// order (deterministic summation order in xa_bwd_dkv).  One warp per RoI.
+__global__ void __launch_bounds__(32) xa_inverse_kernel(const int* __restrict__ match, const int* __restrict__ match_cnt,
+                                                        int max_match, int N, int* __restrict__ inv_cnt, int* __restrict__ inv_list) {
+    pdl_wait();
+    pdl_trigger();
+    const int r = blockIdx.x, lane = threadIdx.x;
+    int pos = 0;
+    const int total = N * max_match;
+    for (int base = 0; base < total; base += 32) {
+        const int e = base + lane;
+        bool hit = false;
+        if (e < total) {
+            const int i = e / max_match, m = e % max_match;
+            hit = m < min(match_cnt[i], max_match) && match[e] == r;
+        }
+        const unsigned b = __ballot_sync(0xffffffffu, hit);
+        if (hit) {
+            const int at = pos + __popc(b & ((1u << lane) - 1u));
+            if (at < N) inv_list[(long long)r * N + at] = e;
+        }
+        pos += __popc(b);
+    }
+    if (lane == 0) inv_cnt[r] = min(pos, N);
+}
+
+// one CTA per key token row (r, t), one warp per head; lane = entry of the RoI's inverse list
+__global__ void __launch_bounds__(256) xa_bwd_dkv_kernel(const float* __restrict__ cq, const float* __restrict__ dctx,
+                                                         const float* __restrict__ P, const float* __restrict__ dS,
+                                                         const int* __restrict__ inv_cnt, const int* __restrict__ inv_list,
+                                                         int max_match, float* __restrict__ dKp, float* __restrict__ dVp, int N) {
+    pdl_wait();
+    pdl_trigger();
+    const int row = blockIdx.x, r = row / TTOK, t = row % TTOK;
+    const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int PM = max_match * TTOK;
+    const float scale = 0.17677669529663687f;
+    const int n = inv_cnt[r];
+    float dk[THD], dv[THD];
+#pragma unroll
+    for (int c = 0; c < THD; ++c) { dk[c] = 0.f; dv[c] = 0.f; }
+    for (int e = lane; e < n; e += 32) {
+        const int code = inv_list[(long long)r * N + e];
+        const int i = code / max_match, m = code % max_match;
+        const long long o = ((long long)i * TH + h) * PM + m * TTOK + t;
+        const float p = P[o], ds = dS[o];
+        const float4* qr = reinterpret_cast<const float4*>(cq + (long long)i * TC_ + h * THD);
+        const float4* gr = reinterpret_cast<const float4*>(dctx + (long long)i * TC_ + h * THD);
+#pragma unroll
+        for (int c4 = 0; c4 < THD / 4; ++c4) {
+            const float4 q = qr[c4], g = gr[c4];
+            dk[c4 * 4] += ds * q.x; dk[c4 * 4 + 1] += ds * q.y; dk[c4 * 4 + 2] += ds * q.z; dk[c4 * 4 + 3] += ds * q.w;
+            dv[c4 * 4] += p * g.x; dv[c4 * 4 + 1] += p * g.y; dv[c4 * 4 + 2] += p * g.z; dv[c4 * 4 + 3] += p * g.w;
+        }
+    }
+    float mk = 0.f, mv = 0.f;
+#pragma unroll
+    for (int c = 0; c < THD; ++c) {
+        const float rk = warp_sum(dk[c]), rv = warp_sum(dv[c]);
+        if (lane == c) { mk = rk; mv = rv; }
+    }
+    dKp[(long long)row * TC_ + h * THD + lane] = mk * scale;
+    dVp[(long long)row * TC_ + h * THD + lane] = mv;
+}
+
+// ------------------------------------------------------------------------------------------------ reg branch tail
+struct Range6 { float v[6]; };
+
+// cross_attention_head.py:224-237: codes 0,1 (+ inverse_sigmoid(ref) 0,1) and 4 (+ ref 2) go through a sigmoid and
+// are scaled to pc_range; sig [N,4] keeps the three sigmoid values for the backward
+__global__ void __launch_bounds__(128) reg_tail_fwd_kernel(float* __restrict__ box, const float* __restrict__ ref,
+                                                           float* __restrict__ sig, Range6 pc, int N) {
+    pdl_wait();
+    pdl_trigger();
+    const int n = blockIdx.x * 128 + threadIdx.x;
+    if (n >= N) return;
+    float* b = box + (long long)n * TCODE;
+    const float s0 = sigmoid_f(b[0] + inverse_sigmoid_f(ref[n * 3 + 0]));
+    const float s1 = sigmoid_f(b[1] + inverse_sigmoid_f(ref[n * 3 + 1]));
+    const float s4 = sigmoid_f(b[4] + inverse_sigmoid_f(ref[n * 3 + 2]));
+    b[0] = s0 * (pc.v[3] - pc.v[0]) + pc.v[0];
+    b[1] = s1 * (pc.v[4] - pc.v[1]) + pc.v[1];
+    b[4] = s4 * (pc.v[5] - pc.v[2]) + pc.v[2];
+    sig[n * 4 + 0] = s0; sig[n * 4 + 1] = s1; sig[n * 4 + 2] = s4; sig[n * 4 + 3] = 0.f;
+}
+
+// d inverse_sigmoid(x) / dx with mmdet's clamps (x in [0,1], numerator / denominator floored at 1e-5)
+__device__ __forceinline__ float inverse_sigmoid_grad(float x) {
+    if (x < 0.f || x > 1.f) return 0.f;
+    float g = 0.f;
+    if (x >= 1e-5f) g += 1.f / x;
+    if (1.f - x >= 1e-5f) g += 1.f / (1.f - x);
+    return g;
+}
+
+// dbox [N,10] -> gradient of the raw reg output in place; d_ref += through inverse_sigmoid(ref)
+__global__ void __launch_bounds__(128) reg_tail_bwd_kernel(float* __restrict__ dbox, const float* __restrict__ ref,
+                                                           const float* __restrict__ sig, float* __restrict__ d_ref, Range6 pc, int N) {
+    pdl_wait();
+    pdl_trigger();
+    const int n = blockIdx.x * 128 + threadIdx.x;
+    if (n >= N) return;
+    float* d = dbox + (long long)n * TCODE;
+    const float s0 = sig[n * 4 + 0], s1 = sig[n * 4 + 1], s4 = sig[n * 4 + 2];
+    const float g0 = d[0] * (pc.v[3] - pc.v[0]) * s0 * (1.f - s0);
+    const float g1 = d[1] * (pc.v[4] - pc.v[1]) * s1 * (1.f - s1);
+    const float g4 = d[4] * (pc.v[5] - pc.v[2]) * s4 * (1.f - s4);
+    d[0] = g0; d[1] = g1; d[4] = g4;
+    d_ref[n * 3 + 0] += g0 * inverse_sigmoid_grad(ref[n * 3 + 0]);
+    d_ref[n * 3 + 1] += g1 * inverse_sigmoid_grad(ref[n * 3 + 1]);
+    d_ref[n * 3 + 2] += g4 * inverse_sigmoid_grad(ref[n * 3 + 2]);
+}
+
+// ------------------------------------------------------------------------------------------------ loss gradient
+// d (sum_l w_l (loss_cls_l + loss_bbox_l)) / d cls_scores, bbox_preds given the assignment of mv2d_loss
+// (cross_attention_head.py:379-434; mmdet py_sigmoid_focal_loss, L1Loss; avg_factor = max(num_pos, 1) + eps).
+struct LossGradArgs {
+    const float* cls; const float* box; const int* assigned; const float* gt_boxes; const int* gt_labels;
+    float* dcls; float* dbox;
+    int N, G, num_classes;
+    float alpha, gamma, cls_lw, box_lw;
+    float code_w[TCODE];
+    float stage_w[MV2D_MAX_LAYERS];
+};
+
+__global__ void __launch_bounds__(256) loss_grad_kernel(LossGradArgs a) {
+    pdl_wait();
+    pdl_trigger();
+    const int l = blockIdx.x, tid = threadIdx.x;
+    const int* asg = a.assigned + (long long)l * a.N;
+    __shared__ int sp[256];
+    int np = 0;
+    for (int n = tid; n < a.N; n += 256) np += asg[n] >= 0;
+    sp[tid] = np;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (tid < o) sp[tid] += sp[tid + o];
+        __syncthreads();
+    }
+    const double avg = fmax((double)sp[0], 1.0) + 1.1920928955078125e-07;
+    const float kc = (float)((double)a.cls_lw * a.stage_w[l] / avg);
+    const float kb = (float)((double)a.box_lw * a.stage_w[l] / avg);
+    for (int n = tid; n < a.N; n += 256) {
+        const int g = asg[n];
+        const int label = g >= 0 ? a.gt_labels[g] : a.num_classes;
+        const long long oc = ((long long)l * a.N + n) * a.num_classes;
+        for (int c = 0; c < a.num_classes; ++c) {
+            const float x = a.cls[oc + c];
+            const float p = 1.f / (1.f + expf(-x));
+            // log p = -softplus(-x), log(1 - p) = -softplus(x), both stable
+            const float l1p = log1pf(expf(-fabsf(x)));
+            const float logp = fminf(x, 0.f) - l1p, log1mp = fminf(-x, 0.f) - l1p;
+            float d;
+            if (c == label) {
+                // a (1-p)^g (-log p):  d/dx = a [ g (1-p)^(g-1) (-p (1-p)) (-log p) - (1-p)^g (1-p) ]
+                const float om = 1.f - p;
+                d = a.alpha * (a.gamma * powf(om, a.gamma - 1.f) * p * om * logp - powf(om, a.gamma) * om);
+            } else {
+                // (1-a) p^g (-log(1-p)):  d/dx = (1-a) [ g p^(g-1) p (1-p) (-log(1-p)) + p^g p ]
+                d = (1.f - a.alpha) * (-a.gamma * powf(p, a.gamma - 1.f) * p * (1.f - p) * log1mp + powf(p, a.gamma) * p);
+            }
+            a.dcls[oc + c] = d * kc;
+        }
+        const long long ob = ((long long)l * a.N + n) * TCODE;
+        float gn[TCODE];
+        bool ok = false;
+        if (g >= 0) {
+            const float* b = a.gt_boxes + g * 9;
+            gn[0] = b[0]; gn[1] = b[1]; gn[2] = logf(b[3]); gn[3] = logf(b[4]); gn[4] = b[2]; gn[5] = logf(b[5]);
+            gn[6] = sinf(b[6]); gn[7] = cosf(b[6]); gn[8] = b[7]; gn[9] = b[8];
+            ok = true;
+#pragma unroll
+            for (int j = 0; j < TCODE; ++j) ok = ok && isfinite(gn[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < TCODE; ++j) {
+            float d = 0.f;
+            if (ok) {
+                const float e = a.box[ob + j] - gn[j];
+                d = (e > 0.f ? 1.f : (e < 0.f ? -1.f : 0.f)) * a.code_w[j] * kb;
+            }
+            a.dbox[ob + j] = d;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ workspace layout
+struct LayerAct {
+    float *x_in, *xq, *qkv, *P_sa, *attn_o, *xhat0, *rstd0, *x1, *xq1, *cq, *Kp, *Vp, *P_xa, *ctx, *xhat1, *rstd1, *x2,
+        *hdn, *xhat2, *rstd2, *x3, *xhatp, *rstdp, *inter, *xhat_c0, *rstd_c0, *c0n, *xhat_c1, *rstd_c1, *c1n, *r0, *r1, *rsig;
+};
+struct TrainWs {
+    float *posemb, *h0, *qpos, *zero;
+    LayerAct layer[MV2D_MAX_LAYERS];
+    // backward scratch
+    float *dx, *dqpos, *t1, *t2, *t3, *dinter, *dcq, *dhdn, *dqkv, *dS_sa, *dS_xa, *dKp, *dVp, *dcls, *dbox, *dposemb;
+    int *inv_cnt, *inv_list;
+    float* loss_ws;
+    size_t loss_ws_bytes;
+    size_t total_bytes;
+};
+
+TrainWs train_layout(float* base, int N, int L, int max_match, int G) {
+    TrainWs w{};
+    size_t off = 0;   // in floats
+    auto take = [&](size_t n) -> float* {
+        float* p = base ? base + off : nullptr;
+        off += (n + 63) / 64 * 64;
+        return p;
+    };
+    const size_t n = (size_t)(N > 0 ? N : 1), NC = n * TC_, PM = (size_t)max_match * TTOK, NK = n * TTOK * TC_;
+    w.posemb = take(n * TPE); w.h0 = take(NC); w.qpos = take(NC); w.zero = take(NC);
+    for (int l = 0; l < L; ++l) {
+        LayerAct& a = w.layer[l];
+        a.xq = take(NC); a.qkv = take(n * 768); a.P_sa = take(TH * n * n); a.attn_o = take(NC);
+        a.xhat0 = take(NC); a.rstd0 = take(n); a.x1 = take(NC); a.xq1 = take(NC); a.cq = take(NC);
+        a.Kp = take(NK); a.Vp = take(NK); a.P_xa = take(n * TH * PM); a.ctx = take(NC);
+        a.xhat1 = take(NC); a.rstd1 = take(n); a.x2 = take(NC); a.hdn = take(n * TFF);
+        a.xhat2 = take(NC); a.rstd2 = take(n); a.x3 = take(NC);
+        a.xhatp = take(NC); a.rstdp = take(n); a.inter = take(NC);
+        a.xhat_c0 = take(NC); a.rstd_c0 = take(n); a.c0n = take(NC);
+        a.xhat_c1 = take(NC); a.rstd_c1 = take(n); a.c1n = take(NC);
+        a.r0 = take(NC); a.r1 = take(NC); a.rsig = take(n * 4);
+        a.x_in = l == 0 ? w.zero : w.layer[l - 1].x3;
+    }
+    w.dx = take(NC); w.dqpos = take(NC); w.t1 = take(NC); w.t2 = take(NC); w.t3 = take(NC); w.dinter = take(NC);
+    w.dcq = take(NC); w.dhdn = take(n * TFF); w.dqkv = take(n * 768); w.dS_sa = take(TH * n * n); w.dS_xa = take(n * TH * PM);
+    w.dKp = take(NK); w.dVp = take(NK); w.dcls = take((size_t)L * n * TCODE); w.dbox = take((size_t)L * n * TCODE);
+    w.dposemb = take(n * TPE);
+    w.inv_cnt = reinterpret_cast<int*>(take(n));
+    w.inv_list = reinterpret_cast<int*>(take(n * n));
+    w.loss_ws_bytes = loss_workspace_bytes(N, G, L);
+    w.loss_ws = take(w.loss_ws_bytes / 4 + 1);
+    w.total_bytes = off * sizeof(float);
+    return w;
+}
+
+struct LayerPtr {   // views into a flat parameter (or gradient) buffer
+    float* t[TL_COUNT];
+};
+LayerPtr layer_ptrs(float* flat, int l) {
+    LayerPtr p{};
+    for (int t = 0; t < TL_COUNT; ++t) p.t[t] = flat + layer_off(l, t);
+    return p;
+}
+
+#define TRY(expr)                \
+    do {                         \
+        int rc__ = (expr);       \
+        if (rc__ != 0) return rc__; \
+    } while (0)
+
+int check_params(const Mv2dTrainParams& p) {
+    MV2D_CHECK_ARG(p.N >= 1 && p.L >= 1 && p.L <= MV2D_MAX_LAYERS && p.max_match >= 1 && p.G >= 0, "train: bad N=%d L=%d max_match=%d G=%d",
+                   p.N, p.L, p.max_match, p.G);
+    MV2D_CHECK_ARG(p.num_classes == TCODE, "train: num_classes must be 10 (got %d)", p.num_classes);
+    MV2D_CHECK_ARG(p.params && p.ref && p.tok_kin && p.tok_mem && p.match && p.match_cnt, "train: null input");
+    MV2D_CHECK_ARG(p.dim_t, "train: null dim_t");
+    MV2D_CHECK_ARG(p.cls_scores && p.bbox_preds && p.assigned && p.losses, "train: null output");
+    MV2D_CHECK_ARG(p.G == 0 || (p.gt_boxes && p.gt_labels), "train: null ground truth");
+    MV2D_CHECK_ARG(((uintptr_t)p.params & 15) == 0 && ((uintptr_t)p.tok_kin & 15) == 0 && ((uintptr_t)p.tok_mem & 15) == 0,
+                   "train: params / tokens must be 16-byte aligned");
+    MV2D_CHECK_ARG(p.workspace && ((uintptr_t)p.workspace & 255) == 0, "train: workspace must be 256-byte aligned");
+    const TrainWs w = train_layout(nullptr, p.N, p.L, p.max_match, p.G);
+    MV2D_CHECK_ARG(p.workspace_bytes >= w.total_bytes, "train: workspace too small (%zu < %zu)", p.workspace_bytes, w.total_bytes);
+    return 0;
+}
+
+}  // namespace
+
+// ================================================================================================ host entry points
+long long train_param_total(int L) { return global_block_floats() + (long long)L * layer_block_floats(); }
+
+int train_param_info(int L, int tensor_id, long long* offset, long long* numel) {
+    MV2D_CHECK_ARG(L >= 1 && L <= MV2D_MAX_LAYERS, "train_param_info: bad L=%d", L);
+    MV2D_CHECK_ARG(tensor_id >= 0 && tensor_id < TG_COUNT + L * TL_COUNT, "train_param_info: bad tensor id %d", tensor_id);
+    if (tensor_id < TG_COUNT) {
+        if (offset) *offset = global_off(tensor_id);
+        if (numel) *numel = kGlobalNumel[tensor_id];
+    } else {
+        const int l = (tensor_id - TG_COUNT) / TL_COUNT, t = (tensor_id - TG_COUNT) % TL_COUNT;
+        if (offset) *offset = layer_off(l, t);
+        if (numel) *numel = kLayerNumel[t];
+    }
+    return 0;
+}
+
+size_t train_workspace_bytes(int N, int L, int max_match, int G) {
+    return train_layout(nullptr, N, L, max_match, G).total_bytes;
+}
+
+// float offset of a saved activation inside the workspace (tests compare them with the oracle's intermediates):
+// which = 0 qpos [N,256] (layer ignored); 1 x1 (after norms.0), 2 x2 (after norms.1), 3 x3 (layer output),
+// 4 inter (post-normed), 5 ctx (cross-attention context), 6 attn_o (self-attention context).  -1 = unknown.
+long long train_debug_offset(int N, int L, int max_match, int G, int layer, int which) {
+    if (N < 1 || L < 1 || L > MV2D_MAX_LAYERS || layer < 0 || layer >= L) return -1;
+    float* base = reinterpret_cast<float*>(uintptr_t(1) << 20);
+    const TrainWs w = train_layout(base, N, L, max_match, G);
+    const LayerAct& a = w.layer[layer];
+    const float* t = nullptr;
+    switch (which) {
+        case 0: t = w.qpos; break;
+        case 1: t = a.x1; break;
+        case 2: t = a.x2; break;
+        case 3: t = a.x3; break;
+        case 4: t = a.inter; break;
+        case 5: t = a.ctx; break;
+        case 6: t = a.attn_o; break;
+        default: return -1;
+    }
+    return (long long)(t - base);
+}
+
+int run_train_forward(const Mv2dTrainParams& p, cudaStream_t st) {
+    TRY(check_params(p));
+    const int N = p.N, L = p.L, NK = N * TTOK;
+    const TrainWs w = train_layout(p.workspace, N, L, p.max_match, p.G);
+    float* P = const_cast<float*>(p.params);
+    Range6 pc;
+    for (int i = 0; i < 6; ++i) pc.v[i] = p.pc_range[i];
+
+    // query embedding of the reference points (cross_attention_head.py:199-206)
+    launch_k(posemb_fwd_kernel, dim3(N), dim3(128), 0, st, p.ref, p.dim_t, w.posemb, N);
+    MV2D_CHECK_LAUNCH("train posemb");
+    TRY(linear_fwd(w.posemb, TPE, P + global_off(TG_QE0_W), TPE, P + global_off(TG_QE0_B), w.h0, TC_, N, TC_, TPE, true, st));
+    TRY(linear_fwd(w.h0, TC_, P + global_off(TG_QE2_W), TC_, P + global_off(TG_QE2_B), w.qpos, TC_, N, TC_, TC_, false, st));
+    cudaError_t e = cudaMemsetAsync(w.zero, 0, (size_t)N * TC_ * sizeof(float), st);   // target = 0 (cross_attention_head.py:32)
+    if (e != cudaSuccess) { set_error("train: memset %s", cudaGetErrorString(e)); return (int)e; }
+
+    const float* post_g = P + global_off(TG_POST_G);
+    const float* post_b = P + global_off(TG_POST_B);
+    for (int l = 0; l < L; ++l) {
+        const LayerAct& a = w.layer[l];
+        const LayerPtr W = layer_ptrs(P, l);
+        // --- flattened self-attention over all N queries (petr_transformer.py:314-370)
+        TRY(add(a.xq, a.x_in, w.qpos, (long long)N * TC_, st));
+        TRY(linear_fwd(a.xq, TC_, W.t[TL_SA_IN_W], TC_, W.t[TL_SA_IN_B], a.qkv, 768, N, 512, TC_, false, st));
+        TRY(linear_fwd(a.x_in, TC_, W.t[TL_SA_IN_W] + 512 * TC_, TC_, W.t[TL_SA_IN_B] + 512, a.qkv + 512, 768, N, TC_, TC_, false, st));
+        launch_k(sa_fwd_kernel, dim3(N), dim3(256), 0, st, (const float*)a.qkv, a.P_sa, a.attn_o, N);
+        MV2D_CHECK_LAUNCH("train sa_fwd");
+        TRY(linear_fwd(a.attn_o, TC_, W.t[TL_SA_OUT_W], TC_, W.t[TL_SA_OUT_B], w.t1, TC_, N, TC_, TC_, false, st));
+        TRY(ln_fwd(a.x_in, w.t1, W.t[TL_LN0_G], W.t[TL_LN0_B], a.x1, a.xhat0, a.rstd0, N, false, st));
+        // --- sparse cross-attention over the matched RoIs' tokens (petr_transformer.py:373-513)
+        TRY(add(a.xq1, a.x1, w.qpos, (long long)N * TC_, st));
+        TRY(linear_fwd(a.xq1, TC_, W.t[TL_CA_IN_W], TC_, W.t[TL_CA_IN_B], a.cq, TC_, N, TC_, TC_, false, st));
+        TRY(linear_fwd(p.tok_kin, TC_, W.t[TL_CA_IN_W] + 256 * TC_, TC_, W.t[TL_CA_IN_B] + 256, a.Kp, TC_, NK, TC_, TC_, false, st));
+        TRY(linear_fwd(p.tok_mem, TC_, W.t[TL_CA_IN_W] + 512 * TC_, TC_, W.t[TL_CA_IN_B] + 512, a.Vp, TC_, NK, TC_, TC_, false, st));
+        launch_k(xa_fwd_kernel, dim3(N), dim3(256), 0, st, (const float*)a.cq, (const float*)a.Kp, (const float*)a.Vp, p.match,
+                 p.match_cnt, p.max_match, a.P_xa, a.ctx, N);
+        MV2D_CHECK_LAUNCH("train xa_fwd");
+        TRY(linear_fwd(a.ctx, TC_, W.t[TL_CA_OUT_W], TC_, W.t[TL_CA_OUT_B], w.t1, TC_, N, TC_, TC_, false, st));
+        TRY(ln_fwd(a.x1, w.t1, W.t[TL_LN1_G], W.t[TL_LN1_B], a.x2, a.xhat1, a.rstd1, N, false, st));
+        // --- FFN (mmcv FFN: x + W2 relu(W1 x))
+        TRY(linear_fwd(a.x2, TC_, W.t[TL_FFN_W1], TC_, W.t[TL_FFN_B1], a.hdn, TFF, N, TFF, TC_, true, st));
+        TRY(linear_fwd(a.hdn, TFF, W.t[TL_FFN_W2], TFF, W.t[TL_FFN_B2], w.t1, TC_, N, TC_, TFF, false, st));
+        TRY(ln_fwd(a.x2, w.t1, W.t[TL_LN2_G], W.t[TL_LN2_B], a.x3, a.xhat2, a.rstd2, N, false, st));
+        // --- post_norm on the intermediate, then the branches (cross_attention_head.py:216-242)
+        TRY(ln_fwd(a.x3, nullptr, post_g, post_b, a.inter, a.xhatp, a.rstdp, N, false, st));
+        TRY(linear_fwd(a.inter, TC_, W.t[TL_CLS_W0], TC_, W.t[TL_CLS_B0], w.t1, TC_, N, TC_, TC_, false, st));
+        TRY(ln_fwd(w.t1, nullptr, W.t[TL_CLS_G0], W.t[TL_CLS_BE0], a.c0n, a.xhat_c0, a.rstd_c0, N, true, st));
+        TRY(linear_fwd(a.c0n, TC_, W.t[TL_CLS_W1], TC_, W.t[TL_CLS_B1], w.t1, TC_, N, TC_, TC_, false, st));
+        TRY(ln_fwd(w.t1, nullptr, W.t[TL_CLS_G1], W.t[TL_CLS_BE1], a.c1n, a.xhat_c1, a.rstd_c1, N, true, st));
+        float* cls_l = p.cls_scores + (long long)l * N * TCODE;
+        float* box_l = p.bbox_preds + (long long)l * N * TCODE;
+        TRY(linear_fwd(a.c1n, TC_, W.t[TL_CLS_W2], TC_, W.t[TL_CLS_B2], cls_l, TCODE, N, TCODE, TC_, false, st));
+        TRY(linear_fwd(a.inter, TC_, W.t[TL_REG_W0], TC_, W.t[TL_REG_B0], a.r0, TC_, N, TC_, TC_, true, st));
+        TRY(linear_fwd(a.r0, TC_, W.t[TL_REG_W1], TC_, W.t[TL_REG_B1], a.r1, TC_, N, TC_, TC_, true, st));
+        TRY(linear_fwd(a.r1, TC_, W.t[TL_REG_W2], TC_, W.t[TL_REG_B2], box_l, TCODE, N, TCODE, TC_, false, st));
+        launch_k(reg_tail_fwd_kernel, dim3(cdiv(N, 128)), dim3(128), 0, st, box_l, p.ref, a.rsig, pc, N);
+        MV2D_CHECK_LAUNCH("train reg_tail");
+    }
+    // Hungarian targets + loss values of every layer (row f3)
+    Mv2dLossParams lp{};
+    lp.N = N; lp.G = p.G; lp.L = L; lp.num_classes = p.num_classes; lp.pad = 0; lp.neg_bbox_loss = 0;
+    lp.layer_stride = (long long)N * TCODE; lp.dn_layer_stride = 0;
+    lp.cls_cost_weight = p.cls_cost_weight; lp.reg_cost_weight = p.reg_cost_weight; lp.cls_loss_weight = p.cls_loss_weight;
+    lp.bbox_loss_weight = p.bbox_loss_weight; lp.focal_alpha = p.focal_alpha; lp.focal_gamma = p.focal_gamma; lp.dn_split = 0.f;
+    for (int j = 0; j < TCODE; ++j) lp.code_weights[j] = p.code_weights[j];
+    lp.cls_scores = p.cls_scores; lp.bbox_preds = p.bbox_preds; lp.gt_boxes = p.gt_boxes; lp.gt_labels = p.gt_labels;
+    lp.assigned = p.assigned; lp.losses = p.losses; lp.workspace = w.loss_ws; lp.workspace_bytes = w.loss_ws_bytes;
+    return run_loss(lp, st);
+}
+
+int run_train_backward(const Mv2dTrainParams& p, cudaStream_t st) {
+    TRY(check_params(p));
+    MV2D_CHECK_ARG(p.grads && p.d_ref && p.d_tok_kin && p.d_tok_mem, "train backward: null gradient output");
+    const int N = p.N, L = p.L, NK = N * TTOK;
+    const long long NC = (long long)N * TC_;
+    const TrainWs w = train_layout(p.workspace, N, L, p.max_match, p.G);
+    float* P = const_cast<float*>(p.params);
+    float* G = p.grads;
+    Range6 pc;
+    for (int i = 0; i < 6; ++i) pc.v[i] = p.pc_range[i];
+    cudaError_t e;
+#define ZERO(ptr, count)                                                                     \
+    if ((e = cudaMemsetAsync(ptr, 0, (size_t)(count) * sizeof(float), st)) != cudaSuccess) { \
+        set_error("train backward: memset %s", cudaGetErrorString(e));                       \
+        return (int)e;                                                                       \
+    }
+    ZERO(p.d_ref, N * 3);
+    ZERO(p.d_tok_kin, (long long)NK * TC_);
+    ZERO(p.d_tok_mem, (long long)NK * TC_);
+    ZERO(w.dqpos, NC);
+    ZERO(w.dx, NC);
+#undef ZERO
+
+    LossGradArgs lg{};
+    lg.cls = p.cls_scores; lg.box = p.bbox_preds; lg.assigned = p.assigned; lg.gt_boxes = p.gt_boxes; lg.gt_labels = p.gt_labels;
+    lg.dcls = w.dcls; lg.dbox = w.dbox; lg.N = N; lg.G = p.G; lg.num_classes = p.num_classes;
+    lg.alpha = p.focal_alpha; lg.gamma = p.focal_gamma; lg.cls_lw = p.cls_loss_weight; lg.box_lw = p.bbox_loss_weight;
+    for (int j = 0; j < TCODE; ++j) lg.code_w[j] = p.code_weights[j];
+    for (int l = 0; l < MV2D_MAX_LAYERS; ++l) lg.stage_w[l] = p.stage_loss_weights[l];
+    launch_k(loss_grad_kernel, dim3(L), dim3(256), 0, st, lg);
+    MV2D_CHECK_LAUNCH("train loss_grad");
+    launch_k(xa_inverse_kernel, dim3(N), dim3(32), 0, st, p.match, p.match_cnt, p.max_match, N, w.inv_cnt, w.inv_list);
+    MV2D_CHECK_LAUNCH("train xa_inverse");
+
+    float* g_post_g = G + global_off(TG_POST_G);
+    float* g_post_b = G + global_off(TG_POST_B);
+    for (int l = L - 1; l >= 0; --l) {
+        const LayerAct& a = w.layer[l];
+        const LayerPtr W = layer_ptrs(P, l);
+        const LayerPtr D = layer_ptrs(G, l);
+        float* dcls = w.dcls + (long long)l * N * TCODE;
+        float* dbox = w.dbox + (long long)l * N * TCODE;
+        // --- reg branch
+        launch_k(reg_tail_bwd_kernel, dim3(cdiv(N, 128)), dim3(128), 0, st, dbox, p.ref, (const float*)a.rsig, p.d_ref, pc, N);
+        MV2D_CHECK_LAUNCH("train reg_tail_bwd");
+        TRY(linear_wgrad(dbox, TCODE, a.r1, TC_, D.t[TL_REG_W2], TC_, N, TCODE, TC_, st));
+        TRY(colsum(dbox, TCODE, N, TCODE, D.t[TL_REG_B2], st));
+        TRY(linear_dgrad(dbox, TCODE, W.t[TL_REG_W2], TC_, w.t1, TC_, N, TCODE, TC_, a.r1, TC_, false, st));
+        TRY(linear_wgrad(w.t1, TC_, a.r0, TC_, D.t[TL_REG_W1], TC_, N, TC_, TC_, st));
+        TRY(colsum(w.t1, TC_, N, TC_, D.t[TL_REG_B1], st));
+        TRY(linear_dgrad(w.t1, TC_, W.t[TL_REG_W1], TC_, w.t2, TC_, N, TC_, TC_, a.r0, TC_, false, st));
+        TRY(linear_wgrad(w.t2, TC_, a.inter, TC_, D.t[TL_REG_W0], TC_, N, TC_, TC_, st));
+        TRY(colsum(w.t2, TC_, N, TC_, D.t[TL_REG_B0], st));
+        TRY(linear_dgrad(w.t2, TC_, W.t[TL_REG_W0], TC_, w.dinter, TC_, N, TC_, TC_, nullptr, 0, false, st));
+        // --- cls branch
+        TRY(linear_wgrad(dcls, TCODE, a.c1n, TC_, D.t[TL_CLS_W2], TC_, N, TCODE, TC_, st));
+        TRY(colsum(dcls, TCODE, N, TCODE, D.t[TL_CLS_B2], st));
+        TRY(linear_dgrad(dcls, TCODE, W.t[TL_CLS_W2], TC_, w.t1, TC_, N, TCODE, TC_, nullptr, 0, false, st));
+        TRY(ln_bwd(w.t1, a.c1n, a.xhat_c1, a.rstd_c1, W.t[TL_CLS_G1], w.t2, D.t[TL_CLS_G1], D.t[TL_CLS_BE1], N, false, st));
+        TRY(linear_wgrad(w.t2, TC_, a.c0n, TC_, D.t[TL_CLS_W1], TC_, N, TC_, TC_, st));
+        TRY(colsum(w.t2, TC_, N, TC_, D.t[TL_CLS_B1], st));
+        TRY(linear_dgrad(w.t2, TC_, W.t[TL_CLS_W1], TC_, w.t1, TC_, N, TC_, TC_, nullptr, 0, false, st));
+        TRY(ln_bwd(w.t1, a.c0n, a.xhat_c0, a.rstd_c0, W.t[TL_CLS_G0], w.t2, D.t[TL_CLS_G0], D.t[TL_CLS_BE0], N, false, st));
+        TRY(linear_wgrad(w.t2, TC_, a.inter, TC_, D.t[TL_CLS_W0], TC_, N, TC_, TC_, st));
+        TRY(colsum(w.t2, TC_, N, TC_, D.t[TL_CLS_B0], st));
+        TRY(linear_dgrad(w.t2, TC_, W.t[TL_CLS_W0], TC_, w.dinter, TC_, N, TC_, TC_, nullptr, 0, true, st));
+        // --- post_norm: dx (gradient of this layer's output) += LN'(dinter)
+        TRY(ln_bwd(w.dinter, nullptr, a.xhatp, a.rstdp, P + global_off(TG_POST_G), w.dx, g_post_g, g_post_b, N, true, st));
+        // --- norms.2 and the FFN
+        TRY(ln_bwd(w.dx, nullptr, a.xhat2, a.rstd2, W.t[TL_LN2_G], w.t1, D.t[TL_LN2_G], D.t[TL_LN2_B], N, false, st));
+        TRY(linear_wgrad(w.t1, TC_, a.hdn, TFF, D.t[TL_FFN_W2], TFF, N, TC_, TFF, st));
+        TRY(colsum(w.t1, TC_, N, TC_, D.t[TL_FFN_B2], st));
+        TRY(linear_dgrad(w.t1, TC_, W.t[TL_FFN_W2], TFF, w.dhdn, TFF, N, TC_, TFF, a.hdn, TFF, false, st));
+        TRY(linear_wgrad(w.dhdn, TFF, a.x2, TC_, D.t[TL_FFN_W1], TC_, N, TFF, TC_, st));
+        TRY(colsum(w.dhdn, TFF, N, TFF, D.t[TL_FFN_B1], st));
+        TRY(linear_dgrad(w.dhdn, TFF, W.t[TL_FFN_W1], TC_, w.t1, TC_, N, TFF, TC_, nullptr, 0, true, st));   // t1 = d x2
+        // --- norms.1 and the cross-attention
+        TRY(ln_bwd(w.t1, nullptr, a.xhat1, a.rstd1, W.t[TL_LN1_G], w.t2, D.t[TL_LN1_G], D.t[TL_LN1_B], N, false, st));
+        TRY(linear_wgrad(w.t2, TC_, a.ctx, TC_, D.t[TL_CA_OUT_W], TC_, N, TC_, TC_, st));
+        TRY(colsum(w.t2, TC_, N, TC_, D.t[TL_CA_OUT_B], st));
+        TRY(linear_dgrad(w.t2, TC_, W.t[TL_CA_OUT_W], TC_, w.t3, TC_, N, TC_, TC_, nullptr, 0, false, st));   // t3 = d ctx
+        launch_k(xa_bwd_dq_kernel, dim3(N), dim3(256), 0, st, (const float*)a.Kp, (const float*)a.Vp, (const float*)a.P_xa,
+                 (const float*)w.t3, p.match, p.match_cnt, p.max_match, w.dS_xa, w.dcq, N);
+        MV2D_CHECK_LAUNCH("train xa_bwd_dq");
+        launch_k(xa_bwd_dkv_kernel, dim3(NK), dim3(256), 0, st, (const float*)a.cq, (const float*)w.t3, (const float*)a.P_xa,
+                 (const float*)w.dS_xa, (const int*)w.inv_cnt, (const int*)w.inv_list, p.max_match, w.dKp, w.dVp, N);
+        MV2D_CHECK_LAUNCH("train xa_bwd_dkv");
+        TRY(linear_wgrad(w.dcq, TC_, a.xq1, TC_, D.t[TL_CA_IN_W], TC_, N, TC_, TC_, st));
+        TRY(colsum(w.dcq, TC_, N, TC_, D.t[TL_CA_IN_B], st));
+        TRY(linear_dgrad(w.dcq, TC_, W.t[TL_CA_IN_W], TC_, w.t3, TC_, N, TC_, TC_, nullptr, 0, false, st));   // t3 = d (x1 + qpos)
+        TRY(add(w.t2, w.t2, w.t3, NC, st));          // t2 = d x1
+        TRY(add(w.dqpos, w.dqpos, w.t3, NC, st));
+        TRY(linear_wgrad(w.dKp, TC_, p.tok_kin, TC_, D.t[TL_CA_IN_W] + 256 * TC_, TC_, NK, TC_, TC_, st));
+        TRY(colsum(w.dKp, TC_, NK, TC_, D.t[TL_CA_IN_B] + 256, st));
+        TRY(linear_dgrad(w.dKp, TC_, W.t[TL_CA_IN_W] + 256 * TC_, TC_, p.d_tok_kin, TC_, NK, TC_, TC_, nullptr, 0, true, st));
+        TRY(linear_wgrad(w.dVp, TC_, p.tok_mem, TC_, D.t[TL_CA_IN_W] + 512 * TC_, TC_, NK, TC_, TC_, st));
+        TRY(colsum(w.dVp, TC_, NK, TC_, D.t[TL_CA_IN_B] + 512, st));
+        TRY(linear_dgrad(w.dVp, TC_, W.t[TL_CA_IN_W] + 512 * TC_, TC_, p.d_tok_mem, TC_, NK, TC_, TC_, nullptr, 0, true, st));
+        // --- norms.0 and the self-attention
+        TRY(ln_bwd(w.t2, nullptr, a.xhat0, a.rstd0, W.t[TL_LN0_G], w.t1, D.t[TL_LN0_G], D.t[TL_LN0_B], N, false, st));   // t1 = d (x_in + sa)
+        TRY(linear_wgrad(w.t1, TC_, a.attn_o, TC_, D.t[TL_SA_OUT_W], TC_, N, TC_, TC_, st));
+        TRY(colsum(w.t1, TC_, N, TC_, D.t[TL_SA_OUT_B], st));
+        TRY(linear_dgrad(w.t1, TC_, W.t[TL_SA_OUT_W], TC_, w.t3, TC_, N, TC_, TC_, nullptr, 0, false, st));   // t3 = d attn_o
+        launch_k(sa_bwd_dq_kernel, dim3(N), dim3(256), 0, st, (const float*)a.qkv, (const float*)a.P_sa, (const float*)w.t3, w.dS_sa, w.dqkv, N);
+        MV2D_CHECK_LAUNCH("train sa_bwd_dq");
+        launch_k(sa_bwd_dkv_kernel, dim3(N), dim3(256), 0, st, (const float*)a.qkv, (const float*)a.P_sa, (const float*)w.dS_sa,
+                 (const float*)w.t3, w.dqkv, N);
+        MV2D_CHECK_LAUNCH("train sa_bwd_dkv");
+        TRY(linear_wgrad(w.dqkv, 768, a.xq, TC_, D.t[TL_SA_IN_W], TC_, N, 512, TC_, st));
+        TRY(linear_wgrad(w.dqkv + 512, 768, a.x_in, TC_, D.t[TL_SA_IN_W] + 512 * TC_, TC_, N, TC_, TC_, st));
+        TRY(colsum(w.dqkv, 768, N, 768, D.t[TL_SA_IN_B], st));
+        TRY(linear_dgrad(w.dqkv, 768, W.t[TL_SA_IN_W], TC_, w.t3, TC_, N, 512, TC_, nullptr, 0, false, st));   // t3 = d (x_in + qpos)
+        TRY(add(w.dqpos, w.dqpos, w.t3, NC, st));
+        TRY(add(w.dx, w.t1, w.t3, NC, st));           // dx = gradient of the previous layer's output
+        TRY(linear_dgrad(w.dqkv + 512, 768, W.t[TL_SA_IN_W] + 512 * TC_, TC_, w.dx, TC_, N, TC_, TC_, nullptr, 0, true, st));
+    }
+    // --- query embedding MLP and the sin / cos features
+    TRY(linear_wgrad(w.dqpos, TC_, w.h0, TC_, G + global_off(TG_QE2_W), TC_, N, TC_, TC_, st));
+    TRY(colsum(w.dqpos, TC_, N, TC_, G + global_off(TG_QE2_B), st));
+    TRY(linear_dgrad(w.dqpos, TC_, P + global_off(TG_QE2_W), TC_, w.t1, TC_, N, TC_, TC_, w.h0, TC_, false, st));
+    TRY(linear_wgrad(w.t1, TC_, w.posemb, TPE, G + global_off(TG_QE0_W), TPE, N, TC_, TPE, st));
+    TRY(colsum(w.t1, TC_, N, TC_, G + global_off(TG_QE0_B), st));
+    TRY(linear_dgrad(w.t1, TC_, P + global_off(TG_QE0_W), TPE, w.dposemb, TPE, N, TC_, TPE, nullptr, 0, false, st));
+    launch_k(posemb_bwd_kernel, dim3(N), dim3(96), 0, st, (const float*)w.dposemb, p.ref, p.dim_t, p.d_ref, N);
+    MV2D_CHECK_LAUNCH("train posemb_bwd");
+    return 0;
+}
+
+// ---- fused AdamW over the flat buffers (torch.optim.AdamW semantics, the exp configs' optimizer):
+// p -= lr * wd * p;  m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;  p -= lr / (1 - b1^t) * m / (sqrt(v / (1 - b2^t)) + eps)
+__global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                    float* __restrict__ v, long long n, float lr, float b1, float b2, float eps,
+                                                    float wd, float bc1, float bc2, float grad_scale) {
+    pdl_wait();
+    pdl_trigger();
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+        const float gi = g[i] * grad_scale;
+        float pi = p[i];
+        pi -= lr * wd * pi;
+        const float mi = b1 * m[i] + (1.f - b1) * gi;
+        const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+        m[i] = mi;
+        v[i] = vi;
+        const float denom = sqrtf(vi) / sqrtf(bc2) + eps;
+        p[i] = pi - (lr / bc1) * (mi / denom);
+    }
+}
+
+int run_adamw(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps, float wd,
+              int step, float grad_scale, cudaStream_t st) {
+    MV2D_CHECK_ARG(p && g && m && v && n >= 0 && step >= 1, "adamw: bad arguments");
+    if (n == 0) return 0;
+    const float bc1 = 1.f - powf(b1, (float)step), bc2 = 1.f - powf(b2, (float)step);
+    const long long want = (n + 255) / 256;
+    const int grid = (int)(want < 148 * 16 ? want : 148 * 16);
+    launch_k(adamw_kernel, dim3(grid), dim3(256), 0, st, p, g, m, v, n, lr, b1, b2, eps, wd, bc1, bc2, grad_scale);
+    MV2D_CHECK_LAUNCH("adamw");
+    return 0;
+}
+
+}  // namespace mv2d

@@ -9,7 +9,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'lib', 'libmv2d_b200.so')
-ABI_VERSION = 3
+ABI_VERSION = 4
 MAX_LAYERS = 8
 
 c_f = C.c_void_p  # device pointers travel as integers (tensor.data_ptr())
@@ -149,7 +149,25 @@ class NeckParams(C.Structure):
     ]
 
 
-_STRUCTS = [PeParams, QgParams, CorrParams, DecoderParams, LayerWeights, BranchWeights, DnParams, KvParams, LossParams, NeckParams]
+class TrainParams(C.Structure):
+    _fields_ = [
+        ('N', C.c_int), ('L', C.c_int), ('max_match', C.c_int), ('G', C.c_int),
+        ('num_classes', C.c_int), ('reserved0', C.c_int),
+        ('pc_range', C.c_float * 6),
+        ('cls_cost_weight', C.c_float), ('reg_cost_weight', C.c_float), ('cls_loss_weight', C.c_float),
+        ('bbox_loss_weight', C.c_float), ('focal_alpha', C.c_float), ('focal_gamma', C.c_float),
+        ('code_weights', C.c_float * 10),
+        ('stage_loss_weights', C.c_float * MAX_LAYERS),
+        ('params', c_f), ('grads', c_f), ('dim_t', c_f), ('ref', c_f), ('tok_kin', c_f), ('tok_mem', c_f),
+        ('match', c_f), ('match_cnt', c_f), ('gt_boxes', c_f), ('gt_labels', c_f),
+        ('cls_scores', c_f), ('bbox_preds', c_f), ('assigned', c_f), ('losses', c_f),
+        ('d_ref', c_f), ('d_tok_kin', c_f), ('d_tok_mem', c_f),
+        ('workspace', c_f), ('workspace_bytes', C.c_size_t),
+    ]
+
+
+_STRUCTS = [PeParams, QgParams, CorrParams, DecoderParams, LayerWeights, BranchWeights, DnParams, KvParams, LossParams, NeckParams,
+            TrainParams]
 
 # every symbol include/mv2d_b200.h declares: (name, restype, argtypes)
 SYMBOLS = [
@@ -178,6 +196,14 @@ SYMBOLS = [
     ('mv2d_fpn_neck_workspace_bytes', C.c_size_t, [C.c_int] * 3),
     ('mv2d_fpn_neck', C.c_int, [C.POINTER(NeckParams), c_f]),
     ('mv2d_xa_tile_prepare', C.c_int, [C.POINTER(DecoderParams), c_f]),
+    ('mv2d_train_param_total', C.c_longlong, [C.c_int]),
+    ('mv2d_train_param_info', C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
+    ('mv2d_decoder_train_workspace_bytes', C.c_size_t, [C.c_int] * 4),
+    ('mv2d_decoder_train_forward', C.c_int, [C.POINTER(TrainParams), c_f]),
+    ('mv2d_train_debug_offset', C.c_longlong, [C.c_int] * 6),
+    ('mv2d_decoder_train_backward', C.c_int, [C.POINTER(TrainParams), c_f]),
+    ('mv2d_adamw_step', C.c_int, [c_f, c_f, c_f, c_f, C.c_longlong, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
+                                  C.c_int, C.c_float, c_f]),
     ('mv2d_gemm', C.c_int, [c_f, C.c_int, c_f, C.c_int, c_f, c_f, C.c_int, C.c_int, C.c_int, C.c_int,
                             C.c_int, c_f]),
     ('mv2d_debug_clock_probe', C.c_int, [C.c_longlong, c_f, c_f]),

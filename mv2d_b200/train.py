@@ -1,0 +1,203 @@
+"""Training step of the MV2D-S decoder slice on one GPU (BASELINE configs[3]).
+
+``DecoderTrainer`` owns ONE flat fp32 parameter buffer and ONE flat gradient buffer for the parameters of
+``bbox_head`` (query embedding, six decoder layers, post norm, cls / reg branches) laid out as
+``mv2d_train_param_info`` says, and drives ``mv2d_decoder_train_forward`` / ``mv2d_decoder_train_backward``
+(csrc/train.cu): forward with saved activations, Hungarian targets and losses, then the gradients of every
+parameter and of the slice's inputs (reference points, RoI key tokens, RoI value tokens).  What the reference
+does with torch autograd over ``CrossAttentionBoxHead.forward`` + ``loss`` (cross_attention_head.py:199-242,
+379-434) as ``MV2DSHead.forward_train`` sums them (mv2d_s_head.py:262-307).
+
+Data parallelism: samples are sharded over ranks, the only collective is the sum all-reduce of the
+flat gradient buffer (``all_reduce_grads``: one NCCL call), followed by a fused AdamW pass (``adamw_step``).
+
+There is no CPU fallback: the library must be present and the tensors on a CUDA device.
+"""
+import ctypes as C
+
+import torch
+
+from . import lib
+
+GLOBAL_NAMES = ['query_embedding.0.weight', 'query_embedding.0.bias', 'query_embedding.2.weight', 'query_embedding.2.bias',
+                'transformer.decoder.post_norm.weight', 'transformer.decoder.post_norm.bias']
+_DEC = 'transformer.decoder.layers.{l}.'
+LAYER_NAMES = [
+    _DEC + 'attentions.0.attn.in_proj_weight', _DEC + 'attentions.0.attn.in_proj_bias',
+    _DEC + 'attentions.0.attn.out_proj.weight', _DEC + 'attentions.0.attn.out_proj.bias',
+    _DEC + 'attentions.1.attn.in_proj_weight', _DEC + 'attentions.1.attn.in_proj_bias',
+    _DEC + 'attentions.1.attn.out_proj.weight', _DEC + 'attentions.1.attn.out_proj.bias',
+    _DEC + 'ffns.0.layers.0.0.weight', _DEC + 'ffns.0.layers.0.0.bias',
+    _DEC + 'ffns.0.layers.1.weight', _DEC + 'ffns.0.layers.1.bias',
+    _DEC + 'norms.0.weight', _DEC + 'norms.0.bias', _DEC + 'norms.1.weight', _DEC + 'norms.1.bias',
+    _DEC + 'norms.2.weight', _DEC + 'norms.2.bias',
+    'cls_branches.{l}.0.weight', 'cls_branches.{l}.0.bias', 'cls_branches.{l}.1.weight', 'cls_branches.{l}.1.bias',
+    'cls_branches.{l}.3.weight', 'cls_branches.{l}.3.bias', 'cls_branches.{l}.4.weight', 'cls_branches.{l}.4.bias',
+    'cls_branches.{l}.6.weight', 'cls_branches.{l}.6.bias',
+    'reg_branches.{l}.0.weight', 'reg_branches.{l}.0.bias', 'reg_branches.{l}.2.weight', 'reg_branches.{l}.2.bias',
+    'reg_branches.{l}.4.weight', 'reg_branches.{l}.4.bias',
+]
+assert len(GLOBAL_NAMES) == 6 and len(LAYER_NAMES) == 34     # MV2D_TRAIN_GLOBAL_TENSORS / MV2D_TRAIN_LAYER_TENSORS
+
+LOSS_DEFAULTS = dict(   # configs/mv2d/exp/mv2d_r50_frcnn_single_frame_roi_1408x512_ep72.py:87-95,132-137
+    code_weights=[1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.5, 1.5, 2.0, 2.0],
+    cls_loss_weight=2.0, focal_gamma=2.0, focal_alpha=0.25, bbox_loss_weight=0.25,
+    cls_cost_weight=2.0, reg_cost_weight=0.25)
+PC_RANGE = [-51.2, -51.2, -5.0, 51.2, 51.2, 3.0]
+
+
+def param_table(num_layers):
+    """name (relative to ``bbox_head.``) -> (offset, numel) in the flat buffers, from the library itself."""
+    h = lib.load()
+    table = {}
+    off, num = C.c_longlong(), C.c_longlong()
+    names = list(GLOBAL_NAMES) + [n.format(l=l) for l in range(num_layers) for n in LAYER_NAMES]
+    for tid, name in enumerate(names):
+        lib.check(h.mv2d_train_param_info(num_layers, tid, C.byref(off), C.byref(num)), 'mv2d_train_param_info')
+        table[name] = (off.value, num.value)
+    return table, int(h.mv2d_train_param_total(num_layers))
+
+
+class DecoderTrainer:
+    def __init__(self, state_dict, device='cuda', num_layers=None, stage_loss_weights=None, prefix='bbox_head.',
+                 pc_range=None, **loss_cfg):
+        if not torch.cuda.is_available():
+            raise RuntimeError('mv2d_b200.DecoderTrainer needs a CUDA device (there is no CPU fallback)')
+        self.lib = lib.load()
+        self.device = torch.device(device)
+        sd = {k[len('roi_head.'):] if k.startswith('roi_head.') else k: v for k, v in state_dict.items()}
+        self.prefix = prefix
+        if num_layers is None:
+            num_layers = 1 + max(int(k.split('.')[4]) for k in sd if k.startswith(prefix + 'transformer.decoder.layers.'))
+        assert 1 <= num_layers <= lib.MAX_LAYERS
+        self.L = num_layers
+        self.table, self.total = param_table(num_layers)
+        self.shapes = {}
+        self.params = torch.zeros(self.total, dtype=torch.float32, device=self.device)
+        self.grads = torch.zeros_like(self.params)
+        self.exp_avg = self.exp_avg_sq = None
+        self.step_count = 0
+        self.load_state_dict(sd)
+        # train_cfg.rcnn.stage_loss_weights (configs/mv2d/exp/*single_frame*.py:131: 0.1 for each of the six layers)
+        self.stage_loss_weights = list(stage_loss_weights) if stage_loss_weights is not None else [0.1] * num_layers
+        assert len(self.stage_loss_weights) == num_layers
+        self.loss_cfg = dict(LOSS_DEFAULTS, **loss_cfg)
+        self.pc_range = list(pc_range or PC_RANGE)
+        dim_t = torch.arange(128, dtype=torch.float32)
+        self.dim_t = (10000 ** (2 * (dim_t // 2) / 128)).to(self.device)       # utils/pe.py:24-25
+        self._ws = None
+        self._keep = None
+        self._p = None
+
+    # ------------------------------------------------------------------ parameters
+    def view(self, name, buf=None):
+        off, num = self.table[name]
+        t = (self.params if buf is None else buf)[off:off + num]
+        return t.view(self.shapes[name]) if name in self.shapes else t
+
+    def load_state_dict(self, sd):
+        for name in self.table:
+            src = sd[self.prefix + name].detach().to(torch.float32)
+            self.shapes[name] = tuple(src.shape)
+            assert src.numel() == self.table[name][1], f'{name}: {tuple(src.shape)} does not match the library layout'
+            self.view(name).copy_(src.to(self.device))
+
+    def state_dict(self):
+        return {self.prefix + n: self.view(n).clone() for n in self.table}
+
+    def grad(self, name):
+        return self.view(name, self.grads)
+
+    def named_grads(self):
+        return {self.prefix + n: self.grad(n) for n in self.table}
+
+    def zero_grad(self):
+        self.grads.zero_()
+
+    # ------------------------------------------------------------------ one sample
+    def _params(self, ref, tok_kin, tok_mem, match, match_cnt, gt_boxes, gt_labels):
+        dev = self.device
+        N, M = match.shape
+        assert ref.shape == (N, 3) and tok_kin.shape == (N, 49, 256) and tok_mem.shape == (N, 49, 256)
+        f32 = dict(device=dev, dtype=torch.float32)
+        ref, tok_kin, tok_mem = (t.to(**f32).contiguous() for t in (ref, tok_kin, tok_mem))
+        match = match.to(dev, torch.int32).contiguous()
+        match_cnt = match_cnt.to(dev, torch.int32).contiguous()
+        gt = gt_boxes.to(**f32).contiguous().view(-1, 9)
+        lab = gt_labels.to(dev).to(torch.int32).contiguous()
+        G, L = gt.shape[0], self.L
+        out = dict(cls_scores=torch.empty((L, N, 10), **f32), bbox_preds=torch.empty((L, N, 10), **f32),
+                   assigned=torch.empty((L, N), device=dev, dtype=torch.int32), losses=torch.empty((L, 4), **f32),
+                   d_ref=torch.empty((N, 3), **f32), d_tok_kin=torch.empty((N, 49, 256), **f32),
+                   d_tok_mem=torch.empty((N, 49, 256), **f32))
+        ws_bytes = int(self.lib.mv2d_decoder_train_workspace_bytes(N, L, M, G))
+        if self._ws is None or self._ws.numel() * 4 < ws_bytes:
+            self._ws = torch.empty(ws_bytes // 4 + 64, **f32)
+        p = lib.TrainParams()
+        p.N, p.L, p.max_match, p.G, p.num_classes = N, L, M, G, 10
+        p.pc_range = (C.c_float * 6)(*self.pc_range)
+        c = self.loss_cfg
+        for k in ('cls_cost_weight', 'reg_cost_weight', 'cls_loss_weight', 'bbox_loss_weight', 'focal_alpha', 'focal_gamma'):
+            setattr(p, k, c[k])
+        p.code_weights = (C.c_float * 10)(*c['code_weights'])
+        p.stage_loss_weights = (C.c_float * lib.MAX_LAYERS)(*(self.stage_loss_weights + [0.0] * (lib.MAX_LAYERS - L)))
+        p.params, p.grads, p.dim_t = self.params.data_ptr(), self.grads.data_ptr(), self.dim_t.data_ptr()
+        p.ref, p.tok_kin, p.tok_mem = ref.data_ptr(), tok_kin.data_ptr(), tok_mem.data_ptr()
+        p.match, p.match_cnt = match.data_ptr(), match_cnt.data_ptr()
+        p.gt_boxes, p.gt_labels = (gt.data_ptr(), lab.data_ptr()) if G > 0 else (None, None)
+        for k, t in out.items():
+            setattr(p, k, t.data_ptr())
+        p.workspace, p.workspace_bytes = self._ws.data_ptr(), ws_bytes
+        self._keep = (ref, tok_kin, tok_mem, match, match_cnt, gt, lab)
+        return p, out
+
+    @torch.no_grad()
+    def forward(self, ref, tok_kin, tok_mem, match, match_cnt, gt_boxes, gt_labels):
+        """Training-mode forward of one sample.  ref [N,3], tok_kin / tok_mem [N,49,256], match [N,M] int,
+        match_cnt [N] (``HotPath`` stage tensors), gt_boxes [G,9], gt_labels [G].  Returns cls_scores / bbox_preds
+        [L,N,10], assigned [L,N], loss_cls / loss_bbox [L] (unweighted) and ``loss`` = the weighted total
+        sum_l stage_loss_weights[l] * (loss_cls[l] + loss_bbox[l])."""
+        self._p, out = self._params(ref, tok_kin, tok_mem, match, match_cnt, gt_boxes, gt_labels)
+        lib.check(self.lib.mv2d_decoder_train_forward(C.byref(self._p), lib.stream_ptr()), 'mv2d_decoder_train_forward')
+        self._out = out
+        w = torch.tensor(self.stage_loss_weights, device=self.device)
+        res = dict(cls_scores=out['cls_scores'], bbox_preds=out['bbox_preds'], assigned=out['assigned'],
+                   loss_cls=out['losses'][:, 0], loss_bbox=out['losses'][:, 1])
+        res['loss'] = (w * (out['losses'][:, 0] + out['losses'][:, 1])).sum()
+        return res
+
+    @torch.no_grad()
+    def backward(self):
+        """Gradient of the last forward's ``loss``: accumulates into the flat gradient buffer and returns the input
+        gradients d_ref [N,3], d_tok_kin [N,49,256] (gradient w.r.t. the key input feat + pe tokens) and d_tok_mem
+        [N,49,256] (gradient w.r.t. the value input)."""
+        assert self._p is not None, 'backward() needs a forward() first'
+        lib.check(self.lib.mv2d_decoder_train_backward(C.byref(self._p), lib.stream_ptr()), 'mv2d_decoder_train_backward')
+        out = self._out
+        return dict(d_ref=out['d_ref'], d_tok_kin=out['d_tok_kin'], d_tok_mem=out['d_tok_mem'])
+
+    # ------------------------------------------------------------------ data parallel + optimizer
+    def all_reduce_grads(self, group=None):
+        """The one collective of the data-parallel step: sum of the flat gradient buffer over ranks (NCCL on GPUs)."""
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(self.grads, op=dist.ReduceOp.SUM, group=group)
+            return dist.get_world_size(group)
+        return 1
+
+    @torch.no_grad()
+    def adamw_step(self, lr=2e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, grad_scale=1.0):
+        """torch.optim.AdamW semantics over the flat buffers in one launch (exp configs: AdamW lr 2e-4, wd 0.01)."""
+        if self.exp_avg is None:
+            self.exp_avg, self.exp_avg_sq = torch.zeros_like(self.params), torch.zeros_like(self.params)
+        self.step_count += 1
+        lib.check(self.lib.mv2d_adamw_step(self.params.data_ptr(), self.grads.data_ptr(), self.exp_avg.data_ptr(),
+                                           self.exp_avg_sq.data_ptr(), self.total, lr, betas[0], betas[1], eps, weight_decay,
+                                           self.step_count, grad_scale, lib.stream_ptr()), 'mv2d_adamw_step')
+
+
+def shard_samples(num_samples, rank, world_size):
+    """SURVEY 8e partitioning: rank r gets samples [r*B/G, (r+1)*B/G)."""
+    per = num_samples // world_size
+    assert per * world_size == num_samples, 'the batch must divide evenly over the ranks'
+    return range(rank * per, (rank + 1) * per)

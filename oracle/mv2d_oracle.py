@@ -713,7 +713,8 @@ def hungarian_assign(cls_pred, bbox_pred, gt_boxes, gt_labels, lc=LOSS_CFG):
     out = torch.full((N,), -1, dtype=torch.long)
     if N == 0 or G == 0:
         return out
-    rows, cols = linear_sum_assignment(match_cost(cls_pred, bbox_pred, gt_boxes, gt_labels, lc))
+    # the assigner runs under no_grad on the host (hungarian_assigner_3d.py:135-137: cost.detach().cpu())
+    rows, cols = linear_sum_assignment(match_cost(cls_pred, bbox_pred, gt_boxes, gt_labels, lc).detach())
     out[torch.from_numpy(rows)] = torch.from_numpy(cols)
     return out
 
@@ -770,6 +771,31 @@ def dn_loss_single(cls_scores, bbox_preds, known_boxes, known_labels, num_tgt, s
     else:
         loss_bbox = lc['bbox_loss_weight'] * ((bbox_preds[ok, :10] - nt[ok, :10]).abs() * w[ok]).sum() / (max(num_tgt, 1) + eps)
     return torch.nan_to_num(loss_cls), torch.nan_to_num(loss_bbox)
+
+
+def decoder_slice_loss(sd, ref, roi_feat, roi_pe, corr, mask, gt_boxes, gt_labels, cfg=None, stage_loss_weights=None, lc=LOSS_CFG):
+    """Row e (training step) of the MV2D-S head, DIFFERENTIABLE: the slice mv2d_decoder_train_forward covers --
+    bbox_head forward on the gathered RoI tokens as MV2DSHead._bbox_forward_denoise calls it without denoising
+    (mv2d_s_head.py:184-196 -> cross_attention_head.py:202-242) and the per-layer losses summed with
+    stage_loss_weights as forward_train does (mv2d_s_head.py:278-305).  ref [N,3], roi_feat / roi_pe [N,256,7,7],
+    corr [N,M] int64, mask [N,M] bool.  Returns (total, cls [L,N,10], box [L,N,10], [(loss_cls, loss_bbox, assigned)])."""
+    cfg = cfg or make_cfg('S')
+    N, M = corr.shape
+    C = roi_feat.shape[1]
+    mem = roi_feat[corr].permute(1, 3, 4, 0, 2).reshape(M * 49, N, C)
+    pos = roi_pe[corr].permute(1, 3, 4, 0, 2).reshape(M * 49, N, C)
+    kpm = (~mask)[:, :, None].expand(N, M, 49).reshape(N, M * 49)
+    qpos = query_embed(sd, ref[:, None])
+    outs = decoder(sd, qpos.permute(1, 0, 2), mem, pos, cfg, key_padding_mask=kpm).transpose(1, 2)
+    cls, box = branches(sd, outs, ref[:, None], cfg)
+    cls, box = cls.flatten(1, 2), box.flatten(1, 2)
+    w = stage_loss_weights or [0.1] * cls.shape[0]
+    total, per = 0.0, []
+    for l in range(cls.shape[0]):
+        a, b, asg = loss_single(cls[l], box[l], gt_boxes, gt_labels, lc)
+        total = total + w[l] * (a + b)
+        per.append((a, b, asg))
+    return total, cls, box, per
 
 
 # ============================================================================= neck (SURVEY.md 8f rank 4)
