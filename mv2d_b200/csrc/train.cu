@@ -21,6 +21,7 @@
 // of the forward and run one warp per (query, head) / (key, head).  Moving the wide GEMMs onto the tcgen05 path
 // of gemm_tc.cu is the next step for this row.
 #include <algorithm>
+#include <cstdlib>
 #include "common.cuh"
 #include "mv2d_internal.h"
 
@@ -83,56 +84,74 @@ struct Sg {
     int ldc, ldmask, M, N, K, klen, flags;
 };
 
-template <bool AK1, bool BN1>
+// TM x TM outputs per thread, 256 threads: TM = 4 -> 64 x 64 tile with BK = 16, TM = 8 -> 128 x 128 tile with BK = 8
+// (1024 elements of each operand per k-step either way: four per thread, prefetched into registers while the
+// previous k-step is multiplied).  AK1 / BN1 say which stride of A / B is 1, i.e. which index runs along a warp
+// when the tile is loaded (coalescing only; addressing always goes through the strides).
+template <int TM, bool AK1, bool BN1>
 __global__ void __launch_bounds__(256) sgemm_kernel(Sg g) {
     pdl_wait();
     pdl_trigger();
-    __shared__ __align__(16) float As[16][68];
-    __shared__ __align__(16) float Bs[16][68];
+    constexpr int BM = 16 * TM, BK = 1024 / BM, LD = BM + 4;
+    __shared__ __align__(16) float As[BK][LD];
+    __shared__ __align__(16) float Bs[BK][LD];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BM;
     const int kbeg = blockIdx.z * g.klen;
     const int kend = min(g.K, kbeg + g.klen);
-    float acc[4][4];
+    float acc[TM][TM];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < TM; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    for (int k0 = kbeg; k0 < kend; k0 += 16) {
+        for (int j = 0; j < TM; ++j) acc[i][j] = 0.f;
+    // element e (0..3) of this thread inside a tile: (am, ak) for A, (bn, bk) for B
+    int am[4], ak[4], bn[4], bk[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int idx = tid + i * 256;
-            int m, k;
-            if (AK1) { k = idx & 15; m = idx >> 4; } else { m = idx & 63; k = idx >> 6; }
-            float v = 0.f;
-            if (m0 + m < g.M && k0 + k < kend) v = __ldg(g.A + (long long)(m0 + m) * g.sam + (long long)(k0 + k) * g.sak);
-            As[k][m] = v;
-            int n, kb;
-            if (BN1) { n = idx & 63; kb = idx >> 6; } else { kb = idx & 15; n = idx >> 4; }
-            float w = 0.f;
-            if (n0 + n < g.N && k0 + kb < kend) w = __ldg(g.B + (long long)(k0 + kb) * g.sbk + (long long)(n0 + n) * g.sbn);
-            Bs[kb][n] = w;
+    for (int e = 0; e < 4; ++e) {
+        const int idx = tid + e * 256;
+        if (AK1) { ak[e] = idx % BK; am[e] = idx / BK; } else { am[e] = idx % BM; ak[e] = idx / BM; }
+        if (BN1) { bn[e] = idx % BM; bk[e] = idx / BM; } else { bk[e] = idx % BK; bn[e] = idx / BK; }
+    }
+    float ra[4], rb[4];
+    auto fetch = [&](int k0) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            ra[e] = (m0 + am[e] < g.M && k0 + ak[e] < kend)
+                        ? __ldg(g.A + (long long)(m0 + am[e]) * g.sam + (long long)(k0 + ak[e]) * g.sak) : 0.f;
+            rb[e] = (n0 + bn[e] < g.N && k0 + bk[e] < kend)
+                        ? __ldg(g.B + (long long)(k0 + bk[e]) * g.sbk + (long long)(n0 + bn[e]) * g.sbn) : 0.f;
         }
+    };
+    if (kbeg < kend) fetch(kbeg);
+    for (int k0 = kbeg; k0 < kend; k0 += BK) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { As[ak[e]][am[e]] = ra[e]; Bs[bk[e]][bn[e]] = rb[e]; }
         __syncthreads();
+        if (k0 + BK < kend) fetch(k0 + BK);
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
-            const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
-            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+        for (int k = 0; k < BK; ++k) {
+            float av[TM], bv[TM];
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int q = 0; q < TM / 4; ++q) {
+                const float4 a = *reinterpret_cast<const float4*>(&As[k][q * 64 + ty * 4]);
+                const float4 b = *reinterpret_cast<const float4*>(&Bs[k][q * 64 + tx * 4]);
+                av[q * 4] = a.x; av[q * 4 + 1] = a.y; av[q * 4 + 2] = a.z; av[q * 4 + 3] = a.w;
+                bv[q * 4] = b.x; bv[q * 4 + 1] = b.y; bv[q * 4 + 2] = b.z; bv[q * 4 + 3] = b.w;
+            }
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+            for (int i = 0; i < TM; ++i)
+#pragma unroll
+                for (int j = 0; j < TM; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
         }
         __syncthreads();
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int m = m0 + ty * 4 + i;
+    for (int i = 0; i < TM; ++i) {
+        const int m = m0 + (i / 4) * 64 + ty * 4 + (i % 4);
         if (m >= g.M) continue;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int n = n0 + tx * 4 + j;
+        for (int j = 0; j < TM; ++j) {
+            const int n = n0 + (j / 4) * 64 + tx * 4 + (j % 4);
             if (n >= g.N) continue;
             float v = acc[i][j];
             if (g.bias && blockIdx.z == 0) v += __ldg(g.bias + n);
@@ -146,16 +165,28 @@ __global__ void __launch_bounds__(256) sgemm_kernel(Sg g) {
     }
 }
 
-int launch_sgemm(const Sg& g, int splits, cudaStream_t st) {
-    if (g.M <= 0 || g.N <= 0 || g.K <= 0) return 0;
-    dim3 grid(cdiv(g.N, 64), cdiv(g.M, 64), splits);
+// 128 x 128 tiles once the problem fills the GPU with them, 64 x 64 otherwise
+inline int sg_tile(int M, int N) {
+    static const bool big_ok = []() { const char* e = getenv("MV2D_TRAIN_SGEMM128"); return !(e && e[0] == '0'); }();
+    return (big_ok && M >= 512 && N >= 128) ? 128 : 64;
+}
+
+template <int TM>
+int launch_sgemm_t(const Sg& g, dim3 grid, cudaStream_t st) {
     const bool ak1 = g.sak == 1, bn1 = g.sbn == 1;
-    if (ak1 && bn1) launch_k(sgemm_kernel<true, true>, grid, dim3(256), 0, st, g);
-    else if (ak1) launch_k(sgemm_kernel<true, false>, grid, dim3(256), 0, st, g);
-    else if (bn1) launch_k(sgemm_kernel<false, true>, grid, dim3(256), 0, st, g);
-    else launch_k(sgemm_kernel<false, false>, grid, dim3(256), 0, st, g);
+    if (ak1 && bn1) launch_k(sgemm_kernel<TM, true, true>, grid, dim3(256), 0, st, g);
+    else if (ak1) launch_k(sgemm_kernel<TM, true, false>, grid, dim3(256), 0, st, g);
+    else if (bn1) launch_k(sgemm_kernel<TM, false, true>, grid, dim3(256), 0, st, g);
+    else launch_k(sgemm_kernel<TM, false, false>, grid, dim3(256), 0, st, g);
     MV2D_CHECK_LAUNCH("train sgemm");
     return 0;
+}
+
+int launch_sgemm(const Sg& g, int splits, cudaStream_t st) {
+    if (g.M <= 0 || g.N <= 0 || g.K <= 0) return 0;
+    const int t = sg_tile(g.M, g.N);
+    dim3 grid(cdiv(g.N, t), cdiv(g.M, t), splits);
+    return t == 128 ? launch_sgemm_t<8>(g, grid, st) : launch_sgemm_t<4>(g, grid, st);
 }
 
 // Y[M,Nout] = act(X[M,K] W[Nout,K]^T + b)
@@ -179,7 +210,8 @@ int linear_wgrad(const float* dY, int ldy, const float* X, int ldx, float* dW, i
     Sg g{};
     g.A = dY; g.sam = 1; g.sak = ldy; g.B = X; g.sbk = ldx; g.sbn = 1; g.C = dW; g.ldc = ldw;
     g.M = Nout; g.N = K; g.K = M; g.flags = SG_ATOMIC;
-    const int tiles = cdiv(Nout, 64) * cdiv(K, 64);
+    const int t = sg_tile(Nout, K);
+    const int tiles = cdiv(Nout, t) * cdiv(K, t);
     int splits = cdiv(296, tiles);
     splits = std::max(1, std::min(splits, cdiv(M, 64)));
     g.klen = cdiv(cdiv(M, splits), 16) * 16;

@@ -1,7 +1,8 @@
 """Multi-GPU plumbing of the hot path.  The decoder is per-sample (the reference asserts B == 1,
 detectors/mv2d.py:143), so ranks are independent replicas on disjoint samples: no data-path
-collective.  torch.distributed is used only to rendezvous, to barrier around the timed region
-and to take the max over ranks of the device time (bench.py)."""
+collective in the forward.  torch.distributed is used to rendezvous, to barrier around the timed region,
+to take the max over ranks of the device time (bench.py) and -- in the training step, the one real exchange
+the path has -- to sum the flat gradient buffer over ranks (``all_reduce_sum``)."""
 import os
 
 import torch
@@ -39,6 +40,15 @@ def max_over_ranks(values, device='cpu'):
     if dist.is_available() and dist.is_initialized():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return t.tolist()
+
+
+def all_reduce_sum(flat, group=None):
+    """Sum a flat tensor over ranks in place (NCCL on GPUs, gloo in the CPU tests); returns the world size.
+    With the parameters in one flat buffer this is the whole gradient exchange of a data-parallel step."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        return dist.get_world_size(group)
+    return 1
 
 
 def aggregate_throughput(world, steps, samples_per_step, max_total_ms):

@@ -18,6 +18,7 @@ import ctypes as C
 import torch
 
 from . import lib
+from .dist import all_reduce_sum
 
 GLOBAL_NAMES = ['query_embedding.0.weight', 'query_embedding.0.bias', 'query_embedding.2.weight', 'query_embedding.2.bias',
                 'transformer.decoder.post_norm.weight', 'transformer.decoder.post_norm.bias']
@@ -61,9 +62,9 @@ def param_table(num_layers):
 class DecoderTrainer:
     def __init__(self, state_dict, device='cuda', num_layers=None, stage_loss_weights=None, prefix='bbox_head.',
                  pc_range=None, **loss_cfg):
-        if not torch.cuda.is_available():
-            raise RuntimeError('mv2d_b200.DecoderTrainer needs a CUDA device (there is no CPU fallback)')
         self.lib = lib.load()
+        # the flat buffers (layout, state_dict round trip, gradient all-reduce) also work on a CPU device, which is
+        # what the gloo tests use; forward / backward / adamw_step need CUDA -- there is no CPU fallback
         self.device = torch.device(device)
         sd = {k[len('roi_head.'):] if k.startswith('roi_head.') else k: v for k, v in state_dict.items()}
         self.prefix = prefix
@@ -115,6 +116,10 @@ class DecoderTrainer:
         self.grads.zero_()
 
     # ------------------------------------------------------------------ one sample
+    def _need_cuda(self):
+        if self.device.type != 'cuda' or not torch.cuda.is_available():
+            raise RuntimeError('mv2d_b200.DecoderTrainer: the training step runs on a CUDA device only (no CPU fallback)')
+
     def _params(self, ref, tok_kin, tok_mem, match, match_cnt, gt_boxes, gt_labels):
         dev = self.device
         N, M = match.shape
@@ -157,6 +162,7 @@ class DecoderTrainer:
         match_cnt [N] (``HotPath`` stage tensors), gt_boxes [G,9], gt_labels [G].  Returns cls_scores / bbox_preds
         [L,N,10], assigned [L,N], loss_cls / loss_bbox [L] (unweighted) and ``loss`` = the weighted total
         sum_l stage_loss_weights[l] * (loss_cls[l] + loss_bbox[l])."""
+        self._need_cuda()
         self._p, out = self._params(ref, tok_kin, tok_mem, match, match_cnt, gt_boxes, gt_labels)
         lib.check(self.lib.mv2d_decoder_train_forward(C.byref(self._p), lib.stream_ptr()), 'mv2d_decoder_train_forward')
         self._out = out
@@ -171,6 +177,7 @@ class DecoderTrainer:
         """Gradient of the last forward's ``loss``: accumulates into the flat gradient buffer and returns the input
         gradients d_ref [N,3], d_tok_kin [N,49,256] (gradient w.r.t. the key input feat + pe tokens) and d_tok_mem
         [N,49,256] (gradient w.r.t. the value input)."""
+        self._need_cuda()
         assert self._p is not None, 'backward() needs a forward() first'
         lib.check(self.lib.mv2d_decoder_train_backward(C.byref(self._p), lib.stream_ptr()), 'mv2d_decoder_train_backward')
         out = self._out
@@ -179,25 +186,15 @@ class DecoderTrainer:
     # ------------------------------------------------------------------ data parallel + optimizer
     def all_reduce_grads(self, group=None):
         """The one collective of the data-parallel step: sum of the flat gradient buffer over ranks (NCCL on GPUs)."""
-        import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-            dist.all_reduce(self.grads, op=dist.ReduceOp.SUM, group=group)
-            return dist.get_world_size(group)
-        return 1
+        return all_reduce_sum(self.grads, group)
 
     @torch.no_grad()
     def adamw_step(self, lr=2e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, grad_scale=1.0):
         """torch.optim.AdamW semantics over the flat buffers in one launch (exp configs: AdamW lr 2e-4, wd 0.01)."""
+        self._need_cuda()
         if self.exp_avg is None:
             self.exp_avg, self.exp_avg_sq = torch.zeros_like(self.params), torch.zeros_like(self.params)
         self.step_count += 1
         lib.check(self.lib.mv2d_adamw_step(self.params.data_ptr(), self.grads.data_ptr(), self.exp_avg.data_ptr(),
                                            self.exp_avg_sq.data_ptr(), self.total, lr, betas[0], betas[1], eps, weight_decay,
                                            self.step_count, grad_scale, lib.stream_ptr()), 'mv2d_adamw_step')
-
-
-def shard_samples(num_samples, rank, world_size):
-    """SURVEY 8e partitioning: rank r gets samples [r*B/G, (r+1)*B/G)."""
-    per = num_samples // world_size
-    assert per * world_size == num_samples, 'the batch must divide evenly over the ranks'
-    return range(rank * per, (rank + 1) * per)

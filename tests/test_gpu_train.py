@@ -1,0 +1,183 @@
+"""Row e on the GPU: the training step of the MV2D-S decoder slice (mv2d_decoder_train_forward / _backward, through the
+C ABI) against torch autograd over the oracle on the same seeded inputs, and against the gradients the reference's
+own Python produced (tests/golden/grad_*.npz).  Every tensor is checked and the whole report is written to
+gpurun_out/train_report_<case>.txt before anything asserts, so one GPU run shows every mismatch."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+from mv2d_b200 import synth
+from test_grad_oracle_golden import CASES, load, oracle_grads, sub
+
+pytestmark = pytest.mark.gpu
+TOL = 2e-3       # of the tensor's largest gradient entry (fp32 sums in a different order; atomics in the weight gradients)
+
+
+def tokens(t):          # [N,256,7,7] -> [N,49,256]
+    return t.permute(0, 2, 3, 1).reshape(t.shape[0], 49, 256).contiguous()
+
+
+def match_lists(corr, mask):
+    N, M = corr.shape
+    match = torch.zeros(N, M, dtype=torch.int32)
+    cnt = mask.sum(1).to(torch.int32)
+    for i in range(N):
+        sel = corr[i][mask[i]]
+        match[i, :sel.numel()] = sel.to(torch.int32)
+    return match, cnt
+
+
+class Report:
+    def __init__(self, name):
+        self.rows, self.bad, self.name = [], [], name
+
+    def check(self, what, got, want, tol=TOL, floor=1e-5):
+        got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
+        if got.shape != want.shape:
+            self.rows.append(f'{what}: SHAPE {got.shape} vs {want.shape}')
+            self.bad.append(what)
+            return
+        scale = max(float(np.abs(want).max()) if want.size else 0.0, floor)
+        err = float(np.abs(got - want).max()) / scale if want.size else 0.0
+        ok = np.isfinite(got).all() and err < tol
+        self.rows.append(f'{"ok  " if ok else "FAIL"} {what}: err {err:.3e} of max |ref| {scale:.3e}')
+        if not ok:
+            self.bad.append(what)
+
+    def finish(self):
+        out = os.path.join(ROOT, 'gpurun_out')
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, f'train_report_{self.name}.txt'), 'w') as f:
+            f.write('\n'.join(self.rows) + '\n')
+        assert not self.bad, f'{len(self.bad)} tensors off: {self.bad[:12]}'
+
+
+def run_case(name):
+    from mv2d_b200.train import DecoderTrainer
+    g, spec, gt_spec = load(name)
+    stage_w = [float(x) for x in g['stage_loss_weights']]
+    r = oracle_grads(spec, gt_spec, stage_w)
+    st = r['st']
+    sd = synth.make_state_dict(0, num_layers=spec['num_layers'])
+    gt_boxes, gt_labels, _ = synth.make_dn_inputs(gt_spec)
+    match, cnt = match_lists(st['corr'], st['corr_mask'])
+    tr = DecoderTrainer(sd, stage_loss_weights=stage_w)
+    tok_mem, tok_kin = tokens(st['roi_feat']), tokens(st['roi_feat'] + st['roi_pe'])
+    out = tr.forward(st['ref'], tok_kin, tok_mem, match, cnt, gt_boxes, gt_labels)
+    grads_in = tr.backward()
+    torch.cuda.synchronize()
+    return g, spec, r, tr, out, grads_in, match
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_training_step_matches_autograd_oracle_and_reference_golden(name):
+    g, spec, r, tr, out, gin, match = run_case(name)
+    rep = Report(name)
+    L, N = spec['num_layers'], match.shape[0]
+    M = match.shape[1]
+    # ---- forward: saved activations, predictions, assignment, losses
+    off = lambda l, which: int(tr.lib.mv2d_train_debug_offset(N, L, M, tr._p.G, l, which))      # noqa: E731
+    ws = tr._ws
+    rep.check('fwd query_pos', ws[off(0, 0):off(0, 0) + N * 256].view(N, 256).cpu(), r['st']['query_pos'].detach(), 1e-4)
+    for l in range(L):
+        o = off(l, 4)
+        rep.check(f'fwd outs_dec[{l}]', ws[o:o + N * 256].view(N, 256).cpu(), r['st']['outs_dec'][l].detach(), 1e-4)
+    rep.check('fwd cls_scores', out['cls_scores'].cpu(), r['cls'].detach(), 1e-4)
+    rep.check('fwd bbox_preds', out['bbox_preds'].cpu(), r['box'].detach(), 1e-4)
+    rep.check('fwd cls_scores vs reference', out['cls_scores'].cpu(), g['cls_scores'], 1e-4)
+    rep.check('fwd bbox_preds vs reference', out['bbox_preds'].cpu(), g['bbox_preds'], 1e-4)
+    asg = torch.stack([p[2] for p in r['per']]).numpy()
+    same = np.array_equal(out['assigned'].cpu().numpy(), asg)
+    rep.rows.append(f'{"ok  " if same else "FAIL"} assignment identical to scipy')
+    if not same:
+        rep.bad.append('assigned')
+    rep.check('loss_cls', out['loss_cls'].cpu(), g['loss_cls'], 2e-5)
+    rep.check('loss_bbox', out['loss_bbox'].cpu(), g['loss_bbox'], 2e-5)
+    rep.check('loss total', [float(out['loss'])], [float(g['loss'])], 2e-5)
+    # ---- backward: slice inputs
+    d_kin, d_mem = gin['d_tok_kin'].cpu(), gin['d_tok_mem'].cpu()
+    rep.check('d_ref', gin['d_ref'].cpu(), r['ref'].grad)
+    rep.check('d_ref vs reference', gin['d_ref'].cpu(), g['d_ref'])
+    rep.check('d_tok_kin (= d roi_pe)', d_kin, tokens(r['roi_pe'].grad))
+    rep.check('d_tok_kin + d_tok_mem (= d roi_feat)', d_kin + d_mem, tokens(r['roi_feat'].grad))
+    back = lambda t: t.view(N, 7, 7, 256).permute(0, 3, 1, 2).contiguous()        # noqa: E731
+    rep.check('d roi_pe vs reference', sub(back(d_kin), g), g['d_roi_pos_sub'])
+    rep.check('d roi_feat vs reference', sub(back(d_kin + d_mem), g), g['d_roi_feat_sub'])
+    # ---- backward: every parameter of the slice, full tensors vs autograd and the reference's subsample
+    for n in tr.table:
+        k = 'bbox_head.' + n
+        want = r['sd'][k].grad
+        want = want if want is not None else torch.zeros_like(r['sd'][k])
+        got = tr.grad(n).cpu()
+        rep.check(f'd {n}', got, want)
+        rep.check(f'd {n} vs reference', sub(got, g), g['dparam.' + k])
+    rep.finish()
+
+
+def test_training_forward_matches_inference_path(state_dicts):
+    """The training forward (plain in_proj / out_proj, saved activations) and the inference path (absorbed
+    cross-attention, tcgen05 GEMMs) are two implementations of the same function: same inputs from the engine's
+    own front end, outputs within the parity tolerance."""
+    from mv2d_b200.engine import HotPath
+    from mv2d_b200.train import DecoderTrainer
+    spec = dict(mode='S', seed=31, num_views=6, boxes_per_view=[20, 18, 22, 19, 21, 20], num_layers=6)
+    sd = state_dicts(6)
+    feat, boxes, metas = synth.case_inputs(spec)
+    eng = HotPath(sd, mode='S')
+    o = eng.forward(feat.cuda(), boxes, metas)
+    torch.cuda.synchronize()
+    gt_boxes, gt_labels, _ = synth.make_dn_inputs(dict(num_gt=25, seed=74))
+    tr = DecoderTrainer(sd)
+    out = tr.forward(o['ref'], o['tok_kin'], o['tok_feat'], o['match'], o['match_cnt'], gt_boxes, gt_labels)
+    torch.cuda.synchronize()
+    for k in ('cls_scores', 'bbox_preds'):
+        a, b = out[k].cpu(), o[k].cpu()
+        assert bool(((a - b).abs() <= 1e-3 + 1e-3 * b.abs()).all()), f'{k}: max diff {(a - b).abs().max():.2e}'
+    ref = eng.loss(o['cls_scores'], o['bbox_preds'], gt_boxes, gt_labels)
+    assert np.array_equal(out['assigned'].cpu().numpy(), ref['assigned'].cpu().numpy())
+    np.testing.assert_allclose(out['loss_cls'].cpu().numpy(), ref['loss_cls'].cpu().numpy(), rtol=1e-3)
+    tr.backward()
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(tr.grads).all())
+
+
+def test_adamw_matches_torch():
+    from mv2d_b200.train import DecoderTrainer
+    sd = synth.make_state_dict(0, num_layers=1)
+    tr = DecoderTrainer(sd)
+    gen = torch.Generator(device='cuda').manual_seed(0)
+    ref = torch.nn.Parameter(tr.params.clone())
+    opt = torch.optim.AdamW([ref], lr=2e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01)
+    for _ in range(3):
+        grad = torch.randn(tr.total, device='cuda', generator=gen) * 0.1
+        tr.grads.copy_(grad)
+        ref.grad = grad.clone()
+        tr.adamw_step(lr=2e-4, weight_decay=0.01)
+        opt.step()
+    torch.cuda.synchronize()
+    assert float((tr.params - ref.data).abs().max()) < 1e-6
+
+
+def test_loss_decreases_over_adamw_steps(state_dicts):
+    """Five optimisation steps on one fixed sample with the matching frozen by the data: the weighted loss goes down."""
+    name = 'grad_s_mid'
+    g, spec, gt_spec = load(name)
+    from mv2d_b200.train import DecoderTrainer
+    r_sd = synth.make_state_dict(0, num_layers=spec['num_layers'])
+    from test_grad_oracle_golden import slice_inputs
+    _, _, st = slice_inputs(spec)
+    gt_boxes, gt_labels, _ = synth.make_dn_inputs(gt_spec)
+    match, cnt = match_lists(st['corr'], st['corr_mask'])
+    tr = DecoderTrainer(r_sd)
+    tok_mem, tok_kin = tokens(st['roi_feat']).cuda(), tokens(st['roi_feat'] + st['roi_pe']).cuda()
+    losses = []
+    for _ in range(6):
+        tr.zero_grad()
+        out = tr.forward(st['ref'].cuda(), tok_kin, tok_mem, match, cnt, gt_boxes, gt_labels)
+        losses.append(float(out['loss']))
+        tr.backward()
+        tr.adamw_step(lr=2e-4)
+    assert losses[-1] < losses[0], losses
