@@ -40,7 +40,7 @@ MV2D_API const char* mv2d_last_error(void);
 /* number of kernel launches this library has enqueued so far in this process */
 MV2D_API unsigned long long mv2d_launch_count(void);
 /* sizeof() of the parameter structs, so a binding can verify its mirror of this header */
-MV2D_API size_t mv2d_sizeof(int which); /* 0 Pe, 1 Qg, 2 Corr, 3 Decoder, 4 LayerWeights, 5 BranchWeights, 6 Dn, 7 Kv, 8 Loss, 9 Neck, 10 Train */
+MV2D_API size_t mv2d_sizeof(int which); /* 0 Pe, 1 Qg, 2 Corr, 3 Decoder, 4 LayerWeights, 5 BranchWeights, 6 Dn, 7 Kv, 8 Loss, 9 Neck, 10 Train, 11 FrontTrain */
 
 /* ---- geometry (utils/pe.py:111; roi_heads/utils/box_correlation.py:118-122,174-178)
  * img2lidar[v] = inv(lidar2img[v]);  trans[src][dst] = lidar2img[dst] @ img2lidar[src]  (fp64) */
@@ -412,6 +412,49 @@ MV2D_API int mv2d_decoder_train_forward(const Mv2dTrainParams* p, void* stream);
  * context, 6 self-attention context (all [N,256]).  -1 = unknown */
 MV2D_API long long mv2d_train_debug_offset(int N, int L, int max_match, int G, int layer, int which);
 MV2D_API int mv2d_decoder_train_backward(const Mv2dTrainParams* p, void* stream);
+
+/* ---- row e, front end: training forward / backward of rows a1-a8 -- PE.forward (utils/pe.py:137-169), RoIAlign of the
+ * feature and the position embedding (roi_heads/mv2d_s_head.py:133-138; mmcv RoIAlign), QueryGenerator.forward
+ * (roi_heads/utils/query_generator.py:343-405) and the reference-point normalisation (mv2d_s_head.py:147-152).
+ * The forward recomputes the stage in fp32 with saved activations and emits the inputs of mv2d_decoder_train_forward;
+ * the backward consumes that call's input gradients and adds the parameter gradients to the same flat buffer
+ * (tensor ids 6 + 34 L + k, names relative to roi_head: k = 0 position_encoding.position_encoder.0.weight [1024,192]
+ * 1 .0.bias  2 .2.weight [256,1024]  3 .2.bias  4 position_encoding.adapt_pos3d.0.weight [1024,384]  5 .0.bias
+ * 6 .2.weight [256,1024]  7 .2.bias  8 position_encoding.fpe.conv_reduce.weight [256,256]  9 .bias
+ * 10 fpe.conv_expand.weight  11 .bias  12 query_generator.shared_convs.0.conv.weight stored [256, (ky,kx,c_in)]
+ * 13 .bias  14 query_generator.shared_fcs.0.weight [1024,256]  15 .bias  16 extra_enc.0.weight [512,1040]  17 .bias
+ * 18 extra_enc.2.weight [256,512]  19 .bias  20 fc_center.weight [3,256]  21 .bias [3]) and returns d loss / d feat. */
+#define MV2D_TRAIN_FRONT_TENSORS 22
+typedef struct Mv2dFrontTrainParams {
+    int N, V, h, w, L, stride;
+    int depth_num, pad_h, pad_w, reserved0;
+    double depth_start;
+    double position_range[6];
+    float pc_range[6];
+    float intrins_feat_scale, reserved1;
+    const float* params;            /* flat parameters (layout of L decoder layers) */
+    float* grads;                   /* flat gradients, accumulated */
+    const float* rois;              /* [N,5] */
+    const double* roi_intrinsics;   /* [N,16] K' from mv2d_roi_align_qg */
+    const double* extrinsics;       /* [V,16] */
+    const double* img2lidar;        /* [V,16] from mv2d_geom_prep */
+    const uint8_t* not_mask;        /* [V,h,w] */
+    const float* dim_t;             /* [128] */
+    const float* feat;              /* [V,h,w,256] channels-last */
+    float* tok_mem;                 /* forward out [N,49,256] RoI-pooled feat */
+    float* tok_kin;                 /* forward out [N,49,256] RoI-pooled feat + pe */
+    float* ref;                     /* forward out [N,3] */
+    float* pe_out;                  /* forward out, nullable [V,h,w,256] */
+    const float* d_ref;             /* backward in  (from mv2d_decoder_train_backward) */
+    const float* d_tok_kin;         /* backward in */
+    const float* d_tok_mem;         /* backward in */
+    float* d_feat;                  /* backward out [V,h,w,256] */
+    float* workspace;               /* saved activations + scratch; must survive between the two calls */
+    size_t workspace_bytes;
+} Mv2dFrontTrainParams;
+MV2D_API size_t mv2d_front_train_workspace_bytes(int N, int V, int h, int w);
+MV2D_API int mv2d_front_train_forward(const Mv2dFrontTrainParams* p, void* stream);
+MV2D_API int mv2d_front_train_backward(const Mv2dFrontTrainParams* p, void* stream);
 
 /* fused AdamW step over flat buffers (torch.optim.AdamW semantics; configs/mv2d/exp/*.py optimizer):
  * g is multiplied by grad_scale first (1 / world_size after a sum all-reduce); step counts from 1 */

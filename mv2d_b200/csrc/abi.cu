@@ -45,6 +45,7 @@ size_t mv2d_sizeof(int which) {
         case 8: return sizeof(Mv2dLossParams);
         case 9: return sizeof(Mv2dNeckParams);
         case 10: return sizeof(Mv2dTrainParams);
+        case 11: return sizeof(Mv2dFrontTrainParams);
         default: return 0;
     }
 }
@@ -156,6 +157,15 @@ int mv2d_decoder_train_forward(const Mv2dTrainParams* p, void* stream) {
 int mv2d_decoder_train_backward(const Mv2dTrainParams* p, void* stream) {
     NONNULL(p, "decoder_train_backward");
     return run_train_backward(*p, (cudaStream_t)stream);
+}
+size_t mv2d_front_train_workspace_bytes(int N, int V, int h, int w) { return front_train_workspace_bytes(N, V, h, w); }
+int mv2d_front_train_forward(const Mv2dFrontTrainParams* p, void* stream) {
+    NONNULL(p, "front_train_forward");
+    return run_front_train_forward(*p, (cudaStream_t)stream);
+}
+int mv2d_front_train_backward(const Mv2dFrontTrainParams* p, void* stream) {
+    NONNULL(p, "front_train_backward");
+    return run_front_train_backward(*p, (cudaStream_t)stream);
 }
 int mv2d_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
                     float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream) {

@@ -35,7 +35,15 @@ int run_scene_nms(const float* boxes, const float* scores, const int* labels, co
 
 int run_clock_probe(long long cycles, long long* out, cudaStream_t st);
 
+// pe.cu, for train.cu
+int run_pe_train_inputs(int V, int h, int w, int D, int pad_h, int pad_w, int stride, double depth_start, const double* pr,
+                        const double* img2lidar, const uint8_t* not_mask, const float* dim_t, float* coords, float* sine,
+                        cudaStream_t st);
+
 // train.cu
+size_t front_train_workspace_bytes(int N, int V, int h, int w);
+int run_front_train_forward(const Mv2dFrontTrainParams& p, cudaStream_t st);
+int run_front_train_backward(const Mv2dFrontTrainParams& p, cudaStream_t st);
 long long train_param_total(int L);
 int train_param_info(int L, int tensor_id, long long* offset, long long* numel);
 size_t train_workspace_bytes(int N, int L, int max_match, int G);

@@ -59,7 +59,7 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, float* __restr
 __global__ void pe_coords_kernel(const double* __restrict__ img2lidar, float* __restrict__ out,
                                  int V, int h, int w, int D, double pad_h, double pad_w,
                                  double depth_start, double pr0, double pr1, double pr2,
-                                 double pr3, double pr4, double pr5) {
+                                 double pr3, double pr4, double pr5, int tf32) {
     pdl_wait();
     pdl_trigger();
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -85,7 +85,8 @@ __global__ void pe_coords_kernel(const double* __restrict__ img2lidar, float* __
         c = (c - lo[i]) / (hi[i] - lo[i]);
         const float cf = (float)fmin(fmax(c, 0.0), 1.0);
         const float num = fmaxf(cf, 1e-5f), den = fmaxf((float)(1.0 - fmin(fmax(c, 0.0), 1.0)), 1e-5f);
-        r[i] = round_tf32(logf(num / den));                // inverse_sigmoid -> operand of a TF32 GEMM
+        const float lg = logf(num / den);                  // inverse_sigmoid
+        r[i] = tf32 ? round_tf32(lg) : lg;                 // inference: operand of a TF32 GEMM; training keeps fp32
     }
     float* o = out + p * (3 * D) + d * 3;
     o[0] = r[0]; o[1] = r[1]; o[2] = r[2];
@@ -127,7 +128,7 @@ __global__ void sine_prep_kernel(const uint8_t* __restrict__ not_mask, float* __
 
 // Step 2: [P, 384] = per embed (n, y, x): 64 sines of even dim_t then 64 cosines of odd dim_t.
 __global__ void sine_embed_kernel(const float* __restrict__ emb, const float* __restrict__ dim_t,
-                                  float* __restrict__ out, int P) {
+                                  float* __restrict__ out, int P, int tf32) {
     pdl_wait();
     pdl_trigger();
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -138,6 +139,10 @@ __global__ void sine_embed_kernel(const float* __restrict__ emb, const float* __
     const float val = emb[p * 3 + e];
     // arguments lie in [0, 2*pi]; the SFU sine/cosine (abs. error ~1e-6 there) is far inside the TF32 rounding below
     float r;
+    if (!tf32) {                // training: fp32 operands, libm sine / cosine
+        out[gid] = i < 64 ? sinf(val / __ldg(dim_t + 2 * i)) : cosf(val / __ldg(dim_t + 2 * (i - 64) + 1));
+        return;
+    }
     if (i < 64) r = __sinf(val / __ldg(dim_t + 2 * i));
     else        r = __cosf(val / __ldg(dim_t + 2 * (i - 64) + 1));
     out[gid] = round_tf32(r);   // operand of a TF32 GEMM
@@ -240,7 +245,7 @@ int run_pe3d(const Mv2dPeParams& p, cudaStream_t st) {
         launch_k(pe_coords_kernel, dim3((unsigned)cdiv((int)total, 256)), dim3(256), 0, st, 
             p.img2lidar, A1, p.V, p.h, p.w, D, (double)p.pad_h, (double)p.pad_w, p.depth_start,
             p.position_range[0], p.position_range[1], p.position_range[2], p.position_range[3],
-            p.position_range[4], p.position_range[5]);
+            p.position_range[4], p.position_range[5], 1);
         MV2D_CHECK_LAUNCH("pe_coords");
     }
     // position_encoder: 192 -> 1024 -> 256
@@ -267,7 +272,7 @@ int run_pe3d(const Mv2dPeParams& p, cudaStream_t st) {
         launch_k(sine_prep_kernel, dim3(cdiv(P, 128)), dim3(128), 0, st, p.not_mask, EM, p.V, p.h, p.w, (float)p.stride,
                                                       6.283185307179586f, 1e-6f);
         MV2D_CHECK_LAUNCH("sine_prep");
-        launch_k(sine_embed_kernel, dim3((unsigned)(((long long)P * 384 + 255) / 256)), dim3(256), 0, st, (const float*)EM, p.dim_t, S, P);
+        launch_k(sine_embed_kernel, dim3((unsigned)(((long long)P * 384 + 255) / 256)), dim3(256), 0, st, (const float*)EM, p.dim_t, S, P, 1);
         MV2D_CHECK_LAUNCH("sine_embed");
         if ((rc = gemm(S, 384, p.w_adapt0, 384, p.b_adapt0, Hd, 4 * C, P, 4 * C, 384, GEMM_RELU | GEMM_TF32_OK | GEMM_ROUND_TF32, st))) return rc;
         if ((rc = gemm(Hd, 4 * C, p.w_adapt2, 4 * C, p.b_adapt2, SB, C, P, C, 4 * C, GEMM_TF32_OK, st))) return rc;
@@ -285,6 +290,26 @@ int run_pe3d(const Mv2dPeParams& p, cudaStream_t st) {
                                         cudaMemcpyDeviceToDevice, st);
         if (e != cudaSuccess) { set_error("pe3d: memcpy %s", cudaGetErrorString(e)); return (int)e; }
     }
+    return 0;
+}
+
+// The parameter-free inputs of PE.forward for the training path (train.cu): frustum coordinates [P,3*D] after
+// inverse_sigmoid and the 384 sine features [P,384], both as plain fp32 (the inference path rounds them to TF32).
+// `sine` must have room for P*384 + 3*P floats: the three normalised embeds per cell are staged behind the features.
+int run_pe_train_inputs(int V, int h, int w, int D, int pad_h, int pad_w, int stride, double depth_start, const double* pr,
+                        const double* img2lidar, const uint8_t* not_mask, const float* dim_t, float* coords, float* sine,
+                        cudaStream_t st) {
+    const int P = V * h * w;
+    MV2D_CHECK_ARG(V >= 1 && V <= MV2D_MAXV && P > 0 && D > 0, "pe_train_inputs: bad V/h/w/D");
+    const long long total = (long long)P * D;
+    launch_k(pe_coords_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, img2lidar, coords, V, h, w, D, (double)pad_h,
+             (double)pad_w, depth_start, pr[0], pr[1], pr[2], pr[3], pr[4], pr[5], 0);
+    MV2D_CHECK_LAUNCH("pe_coords(train)");
+    float* emb = sine + (size_t)P * 384;     // the caller's `sine` buffer holds [P,384] + 3 P floats for the embeds
+    launch_k(sine_prep_kernel, dim3(cdiv(P, 128)), dim3(128), 0, st, not_mask, emb, V, h, w, (float)stride, 6.283185307179586f, 1e-6f);
+    MV2D_CHECK_LAUNCH("sine_prep(train)");
+    launch_k(sine_embed_kernel, dim3((unsigned)(((long long)P * 384 + 255) / 256)), dim3(256), 0, st, (const float*)emb, dim_t, sine, P, 0);
+    MV2D_CHECK_LAUNCH("sine_embed(train)");
     return 0;
 }
 

@@ -52,6 +52,17 @@ const long long kLayerNumel[TL_COUNT] = {
     256 * 256, 256, 256, 256, 256 * 256, 256, 256, 256, 10 * 256, 10,
     256 * 256, 256, 256 * 256, 256, 10 * 256, 10};
 
+// front end (position encoding + query generator), after the layer blocks; the 3x3 conv weight is kept as
+// [c_out, (ky, kx, c_in)] (K order of the im2col GEMM), the host permutes it from / to the state_dict layout
+enum TrainFront {
+    TF_POS0_W, TF_POS0_B, TF_POS2_W, TF_POS2_B, TF_ADAPT0_W, TF_ADAPT0_B, TF_ADAPT2_W, TF_ADAPT2_B,
+    TF_SE_R_W, TF_SE_R_B, TF_SE_E_W, TF_SE_E_B, TF_CONV_W, TF_CONV_B, TF_FC_W, TF_FC_B, TF_ENC0_W, TF_ENC0_B,
+    TF_ENC2_W, TF_ENC2_B, TF_CENTER_W, TF_CENTER_B, TF_COUNT
+};
+const long long kFrontNumel[TF_COUNT] = {
+    1024 * 192, 1024, 256 * 1024, 256, 1024 * 384, 1024, 256 * 1024, 256, 256 * 256, 256, 256 * 256, 256,
+    256 * 2304, 256, 1024 * 256, 1024, 512 * 1040, 512, 256 * 512, 256, 3 * 256, 3};
+
 inline long long pad16(long long n) { return (n + 15) / 16 * 16; }
 
 long long layer_block_floats() {
@@ -74,10 +85,20 @@ long long layer_off(int l, int t) {
     for (int i = 0; i < t; ++i) s += pad16(kLayerNumel[i]);
     return s;
 }
+long long front_block_floats() {
+    long long s = 0;
+    for (int t = 0; t < TF_COUNT; ++t) s += pad16(kFrontNumel[t]);
+    return s;
+}
+long long front_off(int L, int t) {
+    long long s = global_block_floats() + (long long)L * layer_block_floats();
+    for (int i = 0; i < t; ++i) s += pad16(kFrontNumel[i]);
+    return s;
+}
 
 // ------------------------------------------------------------------------------------------------ generic fp32 GEMM
 // C[M,N] (op)= sum_k A(m,k) B(k,n) (+ bias[n]),  A(m,k) = A[m*sam + k*sak],  B(k,n) = B[k*sbk + n*sbn].
-enum SgFlags { SG_RELU = 1, SG_ACC = 2, SG_ATOMIC = 4 };
+enum SgFlags { SG_RELU = 1, SG_ACC = 2, SG_ATOMIC = 4, SG_CLAMP5E3 = 8, SG_MASK_LT5E3 = 16 };
 struct Sg {
     const float* A; const float* B; float* C; const float* bias; const float* mask;
     long long sam, sak, sbk, sbn;
@@ -158,7 +179,11 @@ __global__ void __launch_bounds__(256) sgemm_kernel(Sg g) {
             float* c = g.C + (long long)m * g.ldc + n;
             if (g.flags & SG_ATOMIC) { atomicAdd(c, v); continue; }
             if (g.flags & SG_RELU) v = fmaxf(v, 0.f);
-            if (g.mask && !(g.mask[(long long)m * g.ldmask + n] > 0.f)) v = 0.f;
+            if (g.flags & SG_CLAMP5E3) v = fminf(v, 5e3f);
+            if (g.mask) {
+                const float a = g.mask[(long long)m * g.ldmask + n];
+                if (!(a > 0.f) || ((g.flags & SG_MASK_LT5E3) && !(a < 5e3f))) v = 0.f;
+            }
             if (g.flags & SG_ACC) v += *c;
             *c = v;
         }
@@ -191,18 +216,18 @@ int launch_sgemm(const Sg& g, int splits, cudaStream_t st) {
 
 // Y[M,Nout] = act(X[M,K] W[Nout,K]^T + b)
 int linear_fwd(const float* X, int ldx, const float* W, int ldw, const float* b, float* Y, int ldy, int M, int Nout, int K,
-               bool relu, cudaStream_t st) {
+               bool relu, cudaStream_t st, int extra_flags = 0) {
     Sg g{};
     g.A = X; g.sam = ldx; g.sak = 1; g.B = W; g.sbk = 1; g.sbn = ldw; g.C = Y; g.ldc = ldy; g.bias = b;
-    g.M = M; g.N = Nout; g.K = K; g.klen = K; g.flags = relu ? SG_RELU : 0;
+    g.M = M; g.N = Nout; g.K = K; g.klen = K; g.flags = (relu ? SG_RELU : 0) | extra_flags;
     return launch_sgemm(g, 1, st);
 }
 // dX[M,K] (+)= (dY[M,Nout] W[Nout,K]) . [mask > 0]
 int linear_dgrad(const float* dY, int ldy, const float* W, int ldw, float* dX, int ldx, int M, int Nout, int K,
-                 const float* mask, int ldmask, bool accumulate, cudaStream_t st) {
+                 const float* mask, int ldmask, bool accumulate, cudaStream_t st, int extra_flags = 0) {
     Sg g{};
     g.A = dY; g.sam = ldy; g.sak = 1; g.B = W; g.sbk = ldw; g.sbn = 1; g.C = dX; g.ldc = ldx; g.mask = mask; g.ldmask = ldmask;
-    g.M = M; g.N = K; g.K = Nout; g.klen = Nout; g.flags = accumulate ? SG_ACC : 0;
+    g.M = M; g.N = K; g.K = Nout; g.klen = Nout; g.flags = (accumulate ? SG_ACC : 0) | extra_flags;
     return launch_sgemm(g, 1, st);
 }
 // dW[Nout,K] += dY[M,Nout]^T X[M,K]   (split over the M rows, atomic accumulation)
@@ -925,17 +950,315 @@ int check_params(const Mv2dTrainParams& p) {
     return 0;
 }
 
+
+// ================================================================================================ front end
+// Training forward / backward of rows a1-a8: position encoding (pe.py:137-169), RoIAlign of feat and pe
+// (mv2d_s_head.py:133-138), query generator (query_generator.py:343-405) and the reference-point normalisation
+// (mv2d_s_head.py:147-152), all in fp32 FFMA (the inference path runs the same MLPs as single-pass TF32).
+
+// ---- RoIAlign (mmcv: avg, aligned=True, adaptive sampling grid), channels-last maps.  The bin geometry is evaluated
+// with explicitly rounded fp32 operations (no FMA contraction) so that forward, backward and csrc/roi.cu make the
+// same floor / in-range decisions.
+struct RoiBin { int v, gh, gw; float x1, y1, bw, bh, count; };
+__device__ __forceinline__ RoiBin roi_bin(const float* __restrict__ r, float spatial_scale) {
+    RoiBin b;
+    b.v = (int)r[0];
+    b.x1 = __fadd_rn(__fmul_rn(r[1], spatial_scale), -0.5f);
+    b.y1 = __fadd_rn(__fmul_rn(r[2], spatial_scale), -0.5f);
+    const float x2 = __fadd_rn(__fmul_rn(r[3], spatial_scale), -0.5f), y2 = __fadd_rn(__fmul_rn(r[4], spatial_scale), -0.5f);
+    const float rw = __fsub_rn(x2, b.x1), rh = __fsub_rn(y2, b.y1);
+    b.bw = __fdiv_rn(rw, (float)MV2D_ROI);
+    b.bh = __fdiv_rn(rh, (float)MV2D_ROI);
+    b.gh = (int)ceilf(__fdiv_rn(rh, (float)MV2D_ROI));
+    b.gw = (int)ceilf(__fdiv_rn(rw, (float)MV2D_ROI));
+    b.count = (float)max(b.gh * b.gw, 1);
+    return b;
+}
+struct RoiTap { int o1, o2, o3, o4; float w1, w2, w3, w4; bool ok; };
+// sample (iy, ix) of bin (ph, pw): the four corner offsets (in pixels) and bilinear weights
+__device__ __forceinline__ RoiTap roi_tap(const RoiBin& b, int ph, int pw, int iy, int ix, int h, int w) {
+    RoiTap t;
+    const float y = __fadd_rn(__fadd_rn(b.y1, __fmul_rn((float)ph, b.bh)), __fdiv_rn(__fmul_rn(__fadd_rn((float)iy, 0.5f), b.bh), (float)b.gh));
+    const float x = __fadd_rn(__fadd_rn(b.x1, __fmul_rn((float)pw, b.bw)), __fdiv_rn(__fmul_rn(__fadd_rn((float)ix, 0.5f), b.bw), (float)b.gw));
+    t.ok = !(y < -1.f || y > (float)h || x < -1.f || x > (float)w);
+    float yy = fmaxf(y, 0.f), xx = fmaxf(x, 0.f);
+    int yl = (int)yy, xl = (int)xx, yh, xh;
+    if (yl >= h - 1) { yh = yl = h - 1; yy = (float)yl; } else yh = yl + 1;
+    if (xl >= w - 1) { xh = xl = w - 1; xx = (float)xl; } else xh = xl + 1;
+    const float ly = __fsub_rn(yy, (float)yl), lx = __fsub_rn(xx, (float)xl), hy = __fsub_rn(1.f, ly), hx = __fsub_rn(1.f, lx);
+    t.w1 = __fmul_rn(hy, hx); t.w2 = __fmul_rn(hy, lx); t.w3 = __fmul_rn(ly, hx); t.w4 = __fmul_rn(ly, lx);
+    t.o1 = yl * w + xl; t.o2 = yl * w + xh; t.o3 = yh * w + xl; t.o4 = yh * w + xh;
+    return t;
+}
+
+// grid (49, N), 64 threads (one float4 of the 256 channels each): tok[n, bin] = pooled map (+ addend[n, bin])
+__global__ void __launch_bounds__(64) roi_align_fwd_kernel(const float* __restrict__ rois, const float* __restrict__ map, int h, int w,
+                                                           float spatial_scale, const float* __restrict__ addend, float* __restrict__ tok) {
+    pdl_wait();
+    pdl_trigger();
+    const int n = blockIdx.y, bin = blockIdx.x, ph = bin / MV2D_ROI, pw = bin % MV2D_ROI;
+    const RoiBin b = roi_bin(rois + n * 5, spatial_scale);
+    const float4* m4 = reinterpret_cast<const float4*>(map) + (long long)b.v * h * w * 64 + threadIdx.x;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int iy = 0; iy < b.gh; ++iy)
+        for (int ix = 0; ix < b.gw; ++ix) {
+            const RoiTap t = roi_tap(b, ph, pw, iy, ix, h, w);
+            if (!t.ok) continue;
+            const float4 c1 = __ldg(m4 + (long long)t.o1 * 64), c2 = __ldg(m4 + (long long)t.o2 * 64),
+                         c3 = __ldg(m4 + (long long)t.o3 * 64), c4 = __ldg(m4 + (long long)t.o4 * 64);
+            a.x += t.w1 * c1.x + t.w2 * c2.x + t.w3 * c3.x + t.w4 * c4.x;
+            a.y += t.w1 * c1.y + t.w2 * c2.y + t.w3 * c3.y + t.w4 * c4.y;
+            a.z += t.w1 * c1.z + t.w2 * c2.z + t.w3 * c3.z + t.w4 * c4.z;
+            a.w += t.w1 * c1.w + t.w2 * c2.w + t.w3 * c3.w + t.w4 * c4.w;
+        }
+    a.x /= b.count; a.y /= b.count; a.z /= b.count; a.w /= b.count;
+    const long long o = ((long long)n * MV2D_TOK + bin) * 64 + threadIdx.x;
+    if (addend) {
+        const float4 e = reinterpret_cast<const float4*>(addend)[o];
+        a.x += e.x; a.y += e.y; a.z += e.z; a.w += e.w;
+    }
+    reinterpret_cast<float4*>(tok)[o] = a;
+}
+
+// dmap[v, corner] += w * dtok[n, bin] / count   (atomic: RoIs and bins overlap on the map)
+__global__ void __launch_bounds__(64) roi_align_bwd_kernel(const float* __restrict__ rois, const float* __restrict__ dtok, int h, int w,
+                                                           float spatial_scale, float* __restrict__ dmap) {
+    pdl_wait();
+    pdl_trigger();
+    const int n = blockIdx.y, bin = blockIdx.x, ph = bin / MV2D_ROI, pw = bin % MV2D_ROI;
+    const RoiBin b = roi_bin(rois + n * 5, spatial_scale);
+    float4 g = reinterpret_cast<const float4*>(dtok)[((long long)n * MV2D_TOK + bin) * 64 + threadIdx.x];
+    g.x /= b.count; g.y /= b.count; g.z /= b.count; g.w /= b.count;
+    float* base = dmap + (long long)b.v * h * w * MV2D_C + threadIdx.x * 4;
+    for (int iy = 0; iy < b.gh; ++iy)
+        for (int ix = 0; ix < b.gw; ++ix) {
+            const RoiTap t = roi_tap(b, ph, pw, iy, ix, h, w);
+            if (!t.ok) continue;
+            const int off[4] = {t.o1, t.o2, t.o3, t.o4};
+            const float wt[4] = {t.w1, t.w2, t.w3, t.w4};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float* d = base + (long long)off[k] * MV2D_C;
+                atomicAdd(d + 0, wt[k] * g.x); atomicAdd(d + 1, wt[k] * g.y);
+                atomicAdd(d + 2, wt[k] * g.z); atomicAdd(d + 3, wt[k] * g.w);
+            }
+        }
+}
+
+// per RoI: the intrinsics feature of get_roi_feat (mv2d_head.py:95-101: flatten(K') * scale, zero when the box is
+// narrower than 4 px, clamped with the concatenation) into cat[:, 1024:1040], and float(inv(K' E^T)) of center2lidar
+__global__ void front_params_kernel(const float* __restrict__ rois, const double* __restrict__ k_roi, const double* __restrict__ extrinsics,
+                                    int N, float feat_scale, float* __restrict__ cat, float* __restrict__ m_roi) {
+    pdl_wait();
+    pdl_trigger();
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const float* r = rois + n * 5;
+    const int v = (int)r[0];
+    double K[16], E[16], L[16], Li[16];
+    for (int i = 0; i < 16; ++i) { K[i] = k_roi[n * 16 + i]; E[i] = extrinsics[v * 16 + i]; }
+    const bool invalid = (__fsub_rn(r[3], r[1]) < 4.f) || (__fsub_rn(r[4], r[2]) < 4.f);
+    for (int i = 0; i < 16; ++i) {
+        const float f = invalid ? 0.f : __fmul_rn((float)K[i], feat_scale);
+        cat[(long long)n * 1040 + 1024 + i] = fminf(fmaxf(f, -5e3f), 5e3f);
+    }
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) {
+            double s = 0.0;
+            for (int k = 0; k < 4; ++k) s += K[i * 4 + k] * E[j * 4 + k];
+            L[i * 4 + j] = s;
+        }
+    inv4x4(L, Li);
+    for (int i = 0; i < 16; ++i) m_roi[n * 16 + i] = (float)Li[i];
+}
+
+// [N,7,7,256] tokens -> [N*49, 9*256] patches of the 3x3 / padding 1 convolution, K ordered (ky, kx, c)
+__global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ tok, float* __restrict__ col, int N) {
+    pdl_wait();
+    pdl_trigger();
+    const long long total = (long long)N * MV2D_TOK * 9 * 64;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+        const int c4 = (int)(i % 64);
+        const int tap = (int)((i / 64) % 9);
+        const long long row = i / (64 * 9);
+        const int t = (int)(row % MV2D_TOK), y = t / MV2D_ROI + tap / 3 - 1, x = t % MV2D_ROI + tap % 3 - 1;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (y >= 0 && y < MV2D_ROI && x >= 0 && x < MV2D_ROI)
+            v = reinterpret_cast<const float4*>(tok)[((row / MV2D_TOK) * MV2D_TOK + y * MV2D_ROI + x) * 64 + c4];
+        reinterpret_cast<float4*>(col)[(row * 9 + tap) * 64 + c4] = v;
+    }
+}
+// dtok[n,y,x,:] = sum over taps of dcol at the output cell that read (y,x) through that tap, + a1 + a2 (nullable)
+__global__ void __launch_bounds__(256) col2im_kernel(const float* __restrict__ dcol, const float* __restrict__ a1,
+                                                     const float* __restrict__ a2, float* __restrict__ dtok, int N) {
+    pdl_wait();
+    pdl_trigger();
+    const long long total = (long long)N * MV2D_TOK * 64;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+        const int c4 = (int)(i % 64);
+        const long long row = i / 64;
+        const long long n = row / MV2D_TOK;
+        const int t = (int)(row % MV2D_TOK), y = t / MV2D_ROI, x = t % MV2D_ROI;
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a1) { const float4 e = reinterpret_cast<const float4*>(a1)[i]; s.x += e.x; s.y += e.y; s.z += e.z; s.w += e.w; }
+        if (a2) { const float4 e = reinterpret_cast<const float4*>(a2)[i]; s.x += e.x; s.y += e.y; s.z += e.z; s.w += e.w; }
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+            const int yo = y - (tap / 3 - 1), xo = x - (tap % 3 - 1);
+            if (yo < 0 || yo >= MV2D_ROI || xo < 0 || xo >= MV2D_ROI) continue;
+            const float4 e = reinterpret_cast<const float4*>(dcol)[((n * MV2D_TOK + yo * MV2D_ROI + xo) * 9 + tap) * 64 + c4];
+            s.x += e.x; s.y += e.y; s.z += e.z; s.w += e.w;
+        }
+        reinterpret_cast<float4*>(dtok)[i] = s;
+    }
+}
+
+// AvgPool2d(7) over [N,49,256] and its backward through the ReLU that precedes it
+__global__ void __launch_bounds__(256) pool49_fwd_kernel(const float* __restrict__ y, float* __restrict__ out, int N) {
+    pdl_wait();
+    pdl_trigger();
+    const int gid = blockIdx.x * 256 + threadIdx.x;
+    if (gid >= N * MV2D_C) return;
+    const int n = gid / MV2D_C, c = gid % MV2D_C;
+    float s = 0.f;
+    for (int t = 0; t < MV2D_TOK; ++t) s += y[((long long)n * MV2D_TOK + t) * MV2D_C + c];
+    out[gid] = s / 49.0f;
+}
+__global__ void __launch_bounds__(256) pool49_bwd_kernel(const float* __restrict__ y, const float* __restrict__ dpool,
+                                                         float* __restrict__ dy, int N) {
+    pdl_wait();
+    pdl_trigger();
+    const long long total = (long long)N * MV2D_TOK * MV2D_C;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+        const long long n = i / (MV2D_TOK * MV2D_C);
+        const int c = (int)(i % MV2D_C);
+        dy[i] = y[i] > 0.f ? dpool[n * MV2D_C + c] / 49.0f : 0.f;
+    }
+}
+
+// center2lidar + normalisation (query_generator.py:333-341, mv2d_s_head.py:147-152): c = (u, v, d) -> ref
+__global__ void __launch_bounds__(128) center_fwd_kernel(const float* __restrict__ c, const float* __restrict__ m_roi, Range6 pc,
+                                                         float* __restrict__ ref, int N) {
+    pdl_wait();
+    pdl_trigger();
+    const int n = blockIdx.x * 128 + threadIdx.x;
+    if (n >= N) return;
+    const float u = c[n * 3], v = c[n * 3 + 1], d = c[n * 3 + 2];
+    const float hom[4] = {u * d, v * d, d, 1.f};
+    const float* m = m_roi + n * 16;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const float xyz = m[i * 4] * hom[0] + m[i * 4 + 1] * hom[1] + m[i * 4 + 2] * hom[2] + m[i * 4 + 3] * hom[3];
+        ref[n * 3 + i] = (xyz - pc.v[i]) / (pc.v[i + 3] - pc.v[i]);
+    }
+}
+__global__ void __launch_bounds__(128) center_bwd_kernel(const float* __restrict__ c, const float* __restrict__ m_roi, Range6 pc,
+                                                         const float* __restrict__ d_ref, float* __restrict__ dc, int N) {
+    pdl_wait();
+    pdl_trigger();
+    const int n = blockIdx.x * 128 + threadIdx.x;
+    if (n >= N) return;
+    const float u = c[n * 3], v = c[n * 3 + 1], d = c[n * 3 + 2];
+    const float* m = m_roi + n * 16;
+    float dh[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const float g = d_ref[n * 3 + i] / (pc.v[i + 3] - pc.v[i]);
+        dh[0] += m[i * 4] * g; dh[1] += m[i * 4 + 1] * g; dh[2] += m[i * 4 + 2] * g;
+    }
+    dc[n * 3] = dh[0] * d;
+    dc[n * 3 + 1] = dh[1] * d;
+    dc[n * 3 + 2] = dh[0] * u + dh[1] * v + dh[2];
+}
+
+// SE gate + combine of PE.forward (pe.py:158-166): pe = x * sigmoid(g2) + sb; gate overwrites g2
+__global__ void __launch_bounds__(256) pe_gate_fwd_kernel(const float* __restrict__ x, float* __restrict__ g2, const float* __restrict__ sb,
+                                                          float* __restrict__ pe, long long n) {
+    pdl_wait();
+    pdl_trigger();
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+        const float s = sigmoid_f(g2[i]);
+        g2[i] = s;
+        pe[i] = x[i] * s + sb[i];
+    }
+}
+// dpe -> dx = dpe * gate, dg2 = dpe * x * gate (1 - gate)   (d sb = dpe itself)
+__global__ void __launch_bounds__(256) pe_gate_bwd_kernel(const float* __restrict__ dpe, const float* __restrict__ x,
+                                                          const float* __restrict__ gate, float* __restrict__ dx, float* __restrict__ dg2,
+                                                          long long n) {
+    pdl_wait();
+    pdl_trigger();
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+        const float s = gate[i], g = dpe[i];
+        dx[i] = g * s;
+        dg2[i] = g * x[i] * s * (1.f - s);
+    }
+}
+
+inline int ew_grid(long long n) {
+    const long long want = (n + 255) / 256;
+    return (int)(want < 148 * 16 ? (want > 0 ? want : 1) : 148 * 16);
+}
+
+struct FrontWs {
+    // position encoding ([P, .])
+    float *coords, *sine, *hp, *x, *hs, *sb, *g1, *gate, *pe;
+    // query generator
+    float *tok_pe, *col, *y, *pool, *cat, *e0, *e2, *c, *m_roi;
+    // backward scratch
+    float *dc, *de2, *de0, *df1, *dpool, *dy, *dcol, *dtok, *dpe_map, *dx, *dg2, *dh;
+    size_t total_bytes;
+};
+FrontWs front_layout(float* base, int N, int P) {
+    FrontWs w{};
+    size_t off = 0;
+    auto take = [&](size_t n) -> float* {
+        float* p = base ? base + off : nullptr;
+        off += (n + 63) / 64 * 64;
+        return p;
+    };
+    const size_t n = (size_t)(N > 0 ? N : 1), p = (size_t)P, NK = n * TTOK * TC_;
+    w.coords = take(p * 192); w.sine = take(p * 387); w.hp = take(p * 1024); w.x = take(p * TC_); w.hs = take(p * 1024);
+    w.sb = take(p * TC_); w.g1 = take(p * TC_); w.gate = take(p * TC_); w.pe = take(p * TC_);
+    w.tok_pe = take(NK); w.col = take(NK * 9); w.y = take(NK); w.pool = take(n * TC_); w.cat = take(n * 1040);
+    w.e0 = take(n * 512); w.e2 = take(n * TC_); w.c = take(n * 4); w.m_roi = take(n * 16);
+    w.dc = take(n * 4); w.de2 = take(n * TC_); w.de0 = take(n * 512); w.df1 = take(n * 1024); w.dpool = take(n * TC_);
+    w.dy = take(NK); w.dcol = take(NK * 9); w.dtok = take(NK); w.dpe_map = take(p * TC_); w.dx = take(p * TC_);
+    w.dg2 = take(p * TC_); w.dh = take(p * 1024);
+    w.total_bytes = off * sizeof(float);
+    return w;
+}
+
+int check_front(const Mv2dFrontTrainParams& p) {
+    MV2D_CHECK_ARG(p.N >= 1 && p.V >= 1 && p.V <= MV2D_MAXV && p.h >= 1 && p.w >= 1 && p.L >= 1 && p.L <= MV2D_MAX_LAYERS,
+                   "front train: bad N=%d V=%d h=%d w=%d L=%d", p.N, p.V, p.h, p.w, p.L);
+    MV2D_CHECK_ARG(p.depth_num == 64, "front train: depth_num must be 64 (position_encoder.0 has 192 inputs)");
+    MV2D_CHECK_ARG(p.params && p.rois && p.roi_intrinsics && p.extrinsics && p.feat && p.img2lidar && p.not_mask && p.dim_t,
+                   "front train: null input");
+    MV2D_CHECK_ARG(p.tok_mem && p.tok_kin && p.ref, "front train: null output");
+    MV2D_CHECK_ARG(((uintptr_t)p.params & 15) == 0 && ((uintptr_t)p.feat & 15) == 0 && ((uintptr_t)p.tok_mem & 15) == 0 &&
+                   ((uintptr_t)p.tok_kin & 15) == 0, "front train: buffers must be 16-byte aligned");
+    MV2D_CHECK_ARG(p.workspace && ((uintptr_t)p.workspace & 255) == 0, "front train: workspace must be 256-byte aligned");
+    const FrontWs w = front_layout(nullptr, p.N, p.V * p.h * p.w);
+    MV2D_CHECK_ARG(p.workspace_bytes >= w.total_bytes, "front train: workspace too small (%zu < %zu)", p.workspace_bytes, w.total_bytes);
+    return 0;
+}
+
 }  // namespace
 
 // ================================================================================================ host entry points
-long long train_param_total(int L) { return global_block_floats() + (long long)L * layer_block_floats(); }
+long long train_param_total(int L) { return global_block_floats() + (long long)L * layer_block_floats() + front_block_floats(); }
 
 int train_param_info(int L, int tensor_id, long long* offset, long long* numel) {
     MV2D_CHECK_ARG(L >= 1 && L <= MV2D_MAX_LAYERS, "train_param_info: bad L=%d", L);
-    MV2D_CHECK_ARG(tensor_id >= 0 && tensor_id < TG_COUNT + L * TL_COUNT, "train_param_info: bad tensor id %d", tensor_id);
+    MV2D_CHECK_ARG(tensor_id >= 0 && tensor_id < TG_COUNT + L * TL_COUNT + TF_COUNT, "train_param_info: bad tensor id %d", tensor_id);
     if (tensor_id < TG_COUNT) {
         if (offset) *offset = global_off(tensor_id);
         if (numel) *numel = kGlobalNumel[tensor_id];
+    } else if (tensor_id >= TG_COUNT + L * TL_COUNT) {
+        const int t = tensor_id - TG_COUNT - L * TL_COUNT;
+        if (offset) *offset = front_off(L, t);
+        if (numel) *numel = kFrontNumel[t];
     } else {
         const int l = (tensor_id - TG_COUNT) / TL_COUNT, t = (tensor_id - TG_COUNT) % TL_COUNT;
         if (offset) *offset = layer_off(l, t);
@@ -1165,6 +1488,128 @@ int run_train_backward(const Mv2dTrainParams& p, cudaStream_t st) {
     TRY(linear_dgrad(w.t1, TC_, P + global_off(TG_QE0_W), TPE, w.dposemb, TPE, N, TC_, TPE, nullptr, 0, false, st));
     launch_k(posemb_bwd_kernel, dim3(N), dim3(96), 0, st, (const float*)w.dposemb, p.ref, p.dim_t, p.d_ref, N);
     MV2D_CHECK_LAUNCH("train posemb_bwd");
+    return 0;
+}
+
+
+size_t front_train_workspace_bytes(int N, int V, int h, int w) { return front_layout(nullptr, N, V * h * w).total_bytes; }
+
+int run_front_train_forward(const Mv2dFrontTrainParams& p, cudaStream_t st) {
+    TRY(check_front(p));
+    const int N = p.N, P = p.V * p.h * p.w, NK = N * TTOK;
+    const FrontWs w = front_layout(p.workspace, N, P);
+    float* Wt = const_cast<float*>(p.params);
+    auto W = [&](int t) { return Wt + front_off(p.L, t); };
+    Range6 pc;
+    for (int i = 0; i < 6; ++i) pc.v[i] = p.pc_range[i];
+    const float scale = 1.0f / (float)p.stride;
+    // --- PE.forward: frustum coordinates and sine features are parameter-free inputs (un-rounded fp32 here)
+    TRY(run_pe_train_inputs(p.V, p.h, p.w, p.depth_num, p.pad_h, p.pad_w, p.stride, p.depth_start, p.position_range, p.img2lidar,
+                            p.not_mask, p.dim_t, w.coords, w.sine, st));
+    TRY(linear_fwd(w.coords, 192, W(TF_POS0_W), 192, W(TF_POS0_B), w.hp, 1024, P, 1024, 192, true, st));
+    TRY(linear_fwd(w.hp, 1024, W(TF_POS2_W), 1024, W(TF_POS2_B), w.x, TC_, P, TC_, 1024, false, st));
+    TRY(linear_fwd(w.sine, 384, W(TF_ADAPT0_W), 384, W(TF_ADAPT0_B), w.hs, 1024, P, 1024, 384, true, st));
+    TRY(linear_fwd(w.hs, 1024, W(TF_ADAPT2_W), 1024, W(TF_ADAPT2_B), w.sb, TC_, P, TC_, 1024, false, st));
+    TRY(linear_fwd(p.feat, TC_, W(TF_SE_R_W), TC_, W(TF_SE_R_B), w.g1, TC_, P, TC_, TC_, true, st));
+    TRY(linear_fwd(w.g1, TC_, W(TF_SE_E_W), TC_, W(TF_SE_E_B), w.gate, TC_, P, TC_, TC_, false, st));
+    launch_k(pe_gate_fwd_kernel, dim3(ew_grid((long long)P * TC_)), dim3(256), 0, st, (const float*)w.x, w.gate, (const float*)w.sb, w.pe,
+             (long long)P * TC_);
+    MV2D_CHECK_LAUNCH("front pe_gate");
+    if (p.pe_out) {
+        cudaError_t e = cudaMemcpyAsync(p.pe_out, w.pe, (size_t)P * TC_ * sizeof(float), cudaMemcpyDeviceToDevice, st);
+        if (e != cudaSuccess) { set_error("front train: memcpy %s", cudaGetErrorString(e)); return (int)e; }
+    }
+    // --- RoIAlign of the feature and of the position embedding (torch.cat + SingleRoIExtractor + split)
+    launch_k(roi_align_fwd_kernel, dim3(TTOK, N), dim3(64), 0, st, p.rois, p.feat, p.h, p.w, scale, (const float*)nullptr, p.tok_mem);
+    MV2D_CHECK_LAUNCH("front roi_align(feat)");
+    launch_k(roi_align_fwd_kernel, dim3(TTOK, N), dim3(64), 0, st, p.rois, (const float*)w.pe, p.h, p.w, scale, (const float*)p.tok_mem, p.tok_kin);
+    MV2D_CHECK_LAUNCH("front roi_align(pe)");
+    // --- query generator
+    launch_k(front_params_kernel, dim3(cdiv(N, 64)), dim3(64), 0, st, p.rois, p.roi_intrinsics, p.extrinsics, N, p.intrins_feat_scale,
+             w.cat, w.m_roi);
+    MV2D_CHECK_LAUNCH("front params");
+    launch_k(im2col_kernel, dim3(ew_grid((long long)NK * 9 * 64)), dim3(256), 0, st, (const float*)p.tok_mem, w.col, N);
+    MV2D_CHECK_LAUNCH("front im2col");
+    TRY(linear_fwd(w.col, 9 * TC_, W(TF_CONV_W), 9 * TC_, W(TF_CONV_B), w.y, TC_, NK, TC_, 9 * TC_, true, st));
+    launch_k(pool49_fwd_kernel, dim3(cdiv(N * TC_, 256)), dim3(256), 0, st, (const float*)w.y, w.pool, N);
+    MV2D_CHECK_LAUNCH("front pool49");
+    TRY(linear_fwd(w.pool, TC_, W(TF_FC_W), TC_, W(TF_FC_B), w.cat, 1040, N, 1024, TC_, true, st, SG_CLAMP5E3));
+    TRY(linear_fwd(w.cat, 1040, W(TF_ENC0_W), 1040, W(TF_ENC0_B), w.e0, 512, N, 512, 1040, true, st));
+    TRY(linear_fwd(w.e0, 512, W(TF_ENC2_W), 512, W(TF_ENC2_B), w.e2, TC_, N, TC_, 512, true, st));
+    TRY(linear_fwd(w.e2, TC_, W(TF_CENTER_W), TC_, W(TF_CENTER_B), w.c, 3, N, 3, TC_, false, st));
+    launch_k(center_fwd_kernel, dim3(cdiv(N, 128)), dim3(128), 0, st, (const float*)w.c, (const float*)w.m_roi, pc, p.ref, N);
+    MV2D_CHECK_LAUNCH("front center");
+    return 0;
+}
+
+int run_front_train_backward(const Mv2dFrontTrainParams& p, cudaStream_t st) {
+    TRY(check_front(p));
+    MV2D_CHECK_ARG(p.grads && p.d_ref && p.d_tok_kin && p.d_tok_mem && p.d_feat, "front train backward: null gradient pointer");
+    const int N = p.N, P = p.V * p.h * p.w, NK = N * TTOK;
+    const long long PC = (long long)P * TC_;
+    const FrontWs w = front_layout(p.workspace, N, P);
+    float* Wt = const_cast<float*>(p.params);
+    auto W = [&](int t) { return Wt + front_off(p.L, t); };
+    auto D = [&](int t) { return p.grads + front_off(p.L, t); };
+    Range6 pc;
+    for (int i = 0; i < 6; ++i) pc.v[i] = p.pc_range[i];
+    const float scale = 1.0f / (float)p.stride;
+    cudaError_t e;
+    if ((e = cudaMemsetAsync(p.d_feat, 0, (size_t)PC * sizeof(float), st)) != cudaSuccess ||
+        (e = cudaMemsetAsync(w.dpe_map, 0, (size_t)PC * sizeof(float), st)) != cudaSuccess) {
+        set_error("front train backward: memset %s", cudaGetErrorString(e));
+        return (int)e;
+    }
+    // --- reference points -> fc_center -> FC chain -> avg-pool -> conv
+    launch_k(center_bwd_kernel, dim3(cdiv(N, 128)), dim3(128), 0, st, (const float*)w.c, (const float*)w.m_roi, pc, p.d_ref, w.dc, N);
+    MV2D_CHECK_LAUNCH("front center_bwd");
+    TRY(linear_wgrad(w.dc, 3, w.e2, TC_, D(TF_CENTER_W), TC_, N, 3, TC_, st));
+    TRY(colsum(w.dc, 3, N, 3, D(TF_CENTER_B), st));
+    TRY(linear_dgrad(w.dc, 3, W(TF_CENTER_W), TC_, w.de2, TC_, N, 3, TC_, w.e2, TC_, false, st));
+    TRY(linear_wgrad(w.de2, TC_, w.e0, 512, D(TF_ENC2_W), 512, N, TC_, 512, st));
+    TRY(colsum(w.de2, TC_, N, TC_, D(TF_ENC2_B), st));
+    TRY(linear_dgrad(w.de2, TC_, W(TF_ENC2_W), 512, w.de0, 512, N, TC_, 512, w.e0, 512, false, st));
+    TRY(linear_wgrad(w.de0, 512, w.cat, 1040, D(TF_ENC0_W), 1040, N, 512, 1040, st));
+    TRY(colsum(w.de0, 512, N, 512, D(TF_ENC0_B), st));
+    // only the 1024 FC columns of the concatenation carry a gradient (the intrinsics feature is an input)
+    TRY(linear_dgrad(w.de0, 512, W(TF_ENC0_W), 1040, w.df1, 1024, N, 512, 1024, w.cat, 1040, false, st, SG_MASK_LT5E3));
+    TRY(linear_wgrad(w.df1, 1024, w.pool, TC_, D(TF_FC_W), TC_, N, 1024, TC_, st));
+    TRY(colsum(w.df1, 1024, N, 1024, D(TF_FC_B), st));
+    TRY(linear_dgrad(w.df1, 1024, W(TF_FC_W), TC_, w.dpool, TC_, N, 1024, TC_, nullptr, 0, false, st));
+    launch_k(pool49_bwd_kernel, dim3(ew_grid((long long)NK * TC_)), dim3(256), 0, st, (const float*)w.y, (const float*)w.dpool, w.dy, N);
+    MV2D_CHECK_LAUNCH("front pool49_bwd");
+    TRY(linear_wgrad(w.dy, TC_, w.col, 9 * TC_, D(TF_CONV_W), 9 * TC_, NK, TC_, 9 * TC_, st));
+    TRY(colsum(w.dy, TC_, NK, TC_, D(TF_CONV_B), st));
+    TRY(linear_dgrad(w.dy, TC_, W(TF_CONV_W), 9 * TC_, w.dcol, 9 * TC_, NK, TC_, 9 * TC_, nullptr, 0, false, st));
+    // d tok_mem = conv path + value path + key path (tok_kin = tok_mem + RoIAlign(pe)); d RoIAlign(pe) = d tok_kin
+    launch_k(col2im_kernel, dim3(ew_grid((long long)NK * 64)), dim3(256), 0, st, (const float*)w.dcol, p.d_tok_mem, p.d_tok_kin, w.dtok, N);
+    MV2D_CHECK_LAUNCH("front col2im");
+    launch_k(roi_align_bwd_kernel, dim3(TTOK, N), dim3(64), 0, st, p.rois, (const float*)w.dtok, p.h, p.w, scale, p.d_feat);
+    MV2D_CHECK_LAUNCH("front roi_align_bwd(feat)");
+    launch_k(roi_align_bwd_kernel, dim3(TTOK, N), dim3(64), 0, st, p.rois, p.d_tok_kin, p.h, p.w, scale, w.dpe_map);
+    MV2D_CHECK_LAUNCH("front roi_align_bwd(pe)");
+    // --- PE: pe = x * gate + sb
+    launch_k(pe_gate_bwd_kernel, dim3(ew_grid(PC)), dim3(256), 0, st, (const float*)w.dpe_map, (const float*)w.x, (const float*)w.gate, w.dx, w.dg2, PC);
+    MV2D_CHECK_LAUNCH("front pe_gate_bwd");
+    // sine branch (adapt_pos3d): d sb = dpe
+    TRY(linear_wgrad(w.dpe_map, TC_, w.hs, 1024, D(TF_ADAPT2_W), 1024, P, TC_, 1024, st));
+    TRY(colsum(w.dpe_map, TC_, P, TC_, D(TF_ADAPT2_B), st));
+    TRY(linear_dgrad(w.dpe_map, TC_, W(TF_ADAPT2_W), 1024, w.dh, 1024, P, TC_, 1024, w.hs, 1024, false, st));
+    TRY(linear_wgrad(w.dh, 1024, w.sine, 384, D(TF_ADAPT0_W), 384, P, 1024, 384, st));
+    TRY(colsum(w.dh, 1024, P, 1024, D(TF_ADAPT0_B), st));
+    // position MLP (position_encoder)
+    TRY(linear_wgrad(w.dx, TC_, w.hp, 1024, D(TF_POS2_W), 1024, P, TC_, 1024, st));
+    TRY(colsum(w.dx, TC_, P, TC_, D(TF_POS2_B), st));
+    TRY(linear_dgrad(w.dx, TC_, W(TF_POS2_W), 1024, w.dh, 1024, P, TC_, 1024, w.hp, 1024, false, st));
+    TRY(linear_wgrad(w.dh, 1024, w.coords, 192, D(TF_POS0_W), 192, P, 1024, 192, st));
+    TRY(colsum(w.dh, 1024, P, 1024, D(TF_POS0_B), st));
+    // SE gate (fpe): g2 = We relu(Wr feat + br) + be
+    TRY(linear_wgrad(w.dg2, TC_, w.g1, TC_, D(TF_SE_E_W), TC_, P, TC_, TC_, st));
+    TRY(colsum(w.dg2, TC_, P, TC_, D(TF_SE_E_B), st));
+    TRY(linear_dgrad(w.dg2, TC_, W(TF_SE_E_W), TC_, w.dx, TC_, P, TC_, TC_, w.g1, TC_, false, st));      // dx reused: d g1
+    TRY(linear_wgrad(w.dx, TC_, p.feat, TC_, D(TF_SE_R_W), TC_, P, TC_, TC_, st));
+    TRY(colsum(w.dx, TC_, P, TC_, D(TF_SE_R_B), st));
+    TRY(linear_dgrad(w.dx, TC_, W(TF_SE_R_W), TC_, p.d_feat, TC_, P, TC_, TC_, nullptr, 0, true, st));
     return 0;
 }
 

@@ -166,8 +166,22 @@ class TrainParams(C.Structure):
     ]
 
 
+class FrontTrainParams(C.Structure):
+    _fields_ = [
+        ('N', C.c_int), ('V', C.c_int), ('h', C.c_int), ('w', C.c_int), ('L', C.c_int), ('stride', C.c_int),
+        ('depth_num', C.c_int), ('pad_h', C.c_int), ('pad_w', C.c_int), ('reserved0', C.c_int),
+        ('depth_start', C.c_double), ('position_range', C.c_double * 6),
+        ('pc_range', C.c_float * 6), ('intrins_feat_scale', C.c_float), ('reserved1', C.c_float),
+        ('params', c_f), ('grads', c_f), ('rois', c_f), ('roi_intrinsics', c_f), ('extrinsics', c_f), ('img2lidar', c_f),
+        ('not_mask', c_f), ('dim_t', c_f), ('feat', c_f),
+        ('tok_mem', c_f), ('tok_kin', c_f), ('ref', c_f), ('pe_out', c_f),
+        ('d_ref', c_f), ('d_tok_kin', c_f), ('d_tok_mem', c_f), ('d_feat', c_f),
+        ('workspace', c_f), ('workspace_bytes', C.c_size_t),
+    ]
+
+
 _STRUCTS = [PeParams, QgParams, CorrParams, DecoderParams, LayerWeights, BranchWeights, DnParams, KvParams, LossParams, NeckParams,
-            TrainParams]
+            TrainParams, FrontTrainParams]
 
 # every symbol include/mv2d_b200.h declares: (name, restype, argtypes)
 SYMBOLS = [
@@ -202,6 +216,9 @@ SYMBOLS = [
     ('mv2d_decoder_train_forward', C.c_int, [C.POINTER(TrainParams), c_f]),
     ('mv2d_train_debug_offset', C.c_longlong, [C.c_int] * 6),
     ('mv2d_decoder_train_backward', C.c_int, [C.POINTER(TrainParams), c_f]),
+    ('mv2d_front_train_workspace_bytes', C.c_size_t, [C.c_int] * 4),
+    ('mv2d_front_train_forward', C.c_int, [C.POINTER(FrontTrainParams), c_f]),
+    ('mv2d_front_train_backward', C.c_int, [C.POINTER(FrontTrainParams), c_f]),
     ('mv2d_adamw_step', C.c_int, [c_f, c_f, c_f, c_f, C.c_longlong, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
                                   C.c_int, C.c_float, c_f]),
     ('mv2d_gemm', C.c_int, [c_f, C.c_int, c_f, C.c_int, c_f, c_f, C.c_int, C.c_int, C.c_int, C.c_int,

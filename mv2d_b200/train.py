@@ -20,10 +20,12 @@ import torch
 from . import lib
 from .dist import all_reduce_sum
 
-GLOBAL_NAMES = ['query_embedding.0.weight', 'query_embedding.0.bias', 'query_embedding.2.weight', 'query_embedding.2.bias',
-                'transformer.decoder.post_norm.weight', 'transformer.decoder.post_norm.bias']
+_BH = 'bbox_head.'
+GLOBAL_NAMES = [_BH + n for n in (
+    'query_embedding.0.weight', 'query_embedding.0.bias', 'query_embedding.2.weight', 'query_embedding.2.bias',
+    'transformer.decoder.post_norm.weight', 'transformer.decoder.post_norm.bias')]
 _DEC = 'transformer.decoder.layers.{l}.'
-LAYER_NAMES = [
+LAYER_NAMES = [_BH + n for n in (
     _DEC + 'attentions.0.attn.in_proj_weight', _DEC + 'attentions.0.attn.in_proj_bias',
     _DEC + 'attentions.0.attn.out_proj.weight', _DEC + 'attentions.0.attn.out_proj.bias',
     _DEC + 'attentions.1.attn.in_proj_weight', _DEC + 'attentions.1.attn.in_proj_bias',
@@ -36,9 +38,18 @@ LAYER_NAMES = [
     'cls_branches.{l}.3.weight', 'cls_branches.{l}.3.bias', 'cls_branches.{l}.4.weight', 'cls_branches.{l}.4.bias',
     'cls_branches.{l}.6.weight', 'cls_branches.{l}.6.bias',
     'reg_branches.{l}.0.weight', 'reg_branches.{l}.0.bias', 'reg_branches.{l}.2.weight', 'reg_branches.{l}.2.bias',
-    'reg_branches.{l}.4.weight', 'reg_branches.{l}.4.bias',
-]
-assert len(GLOBAL_NAMES) == 6 and len(LAYER_NAMES) == 34     # MV2D_TRAIN_GLOBAL_TENSORS / MV2D_TRAIN_LAYER_TENSORS
+    'reg_branches.{l}.4.weight', 'reg_branches.{l}.4.bias')]
+_PE, _QG = 'position_encoding.', 'query_generator.'
+CONV_W = _QG + 'shared_convs.0.conv.weight'    # state_dict [c_out, c_in, ky, kx]; flat buffer [c_out, ky, kx, c_in]
+FRONT_NAMES = [
+    _PE + 'position_encoder.0.weight', _PE + 'position_encoder.0.bias', _PE + 'position_encoder.2.weight', _PE + 'position_encoder.2.bias',
+    _PE + 'adapt_pos3d.0.weight', _PE + 'adapt_pos3d.0.bias', _PE + 'adapt_pos3d.2.weight', _PE + 'adapt_pos3d.2.bias',
+    _PE + 'fpe.conv_reduce.weight', _PE + 'fpe.conv_reduce.bias', _PE + 'fpe.conv_expand.weight', _PE + 'fpe.conv_expand.bias',
+    CONV_W, _QG + 'shared_convs.0.conv.bias', _QG + 'shared_fcs.0.weight', _QG + 'shared_fcs.0.bias',
+    _QG + 'extra_enc.0.weight', _QG + 'extra_enc.0.bias', _QG + 'extra_enc.2.weight', _QG + 'extra_enc.2.bias',
+    _QG + 'fc_center.weight', _QG + 'fc_center.bias']
+# MV2D_TRAIN_GLOBAL_TENSORS / MV2D_TRAIN_LAYER_TENSORS / MV2D_TRAIN_FRONT_TENSORS
+assert len(GLOBAL_NAMES) == 6 and len(LAYER_NAMES) == 34 and len(FRONT_NAMES) == 22
 
 LOSS_DEFAULTS = dict(   # configs/mv2d/exp/mv2d_r50_frcnn_single_frame_roi_1408x512_ep72.py:87-95,132-137
     code_weights=[1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.5, 1.5, 2.0, 2.0],
@@ -48,11 +59,11 @@ PC_RANGE = [-51.2, -51.2, -5.0, 51.2, 51.2, 3.0]
 
 
 def param_table(num_layers):
-    """name (relative to ``bbox_head.``) -> (offset, numel) in the flat buffers, from the library itself."""
+    """state_dict name (relative to ``roi_head.``) -> (offset, numel) in the flat buffers, from the library itself."""
     h = lib.load()
     table = {}
     off, num = C.c_longlong(), C.c_longlong()
-    names = list(GLOBAL_NAMES) + [n.format(l=l) for l in range(num_layers) for n in LAYER_NAMES]
+    names = list(GLOBAL_NAMES) + [n.format(l=l) for l in range(num_layers) for n in LAYER_NAMES] + list(FRONT_NAMES)
     for tid, name in enumerate(names):
         lib.check(h.mv2d_train_param_info(num_layers, tid, C.byref(off), C.byref(num)), 'mv2d_train_param_info')
         table[name] = (off.value, num.value)
@@ -60,16 +71,14 @@ def param_table(num_layers):
 
 
 class DecoderTrainer:
-    def __init__(self, state_dict, device='cuda', num_layers=None, stage_loss_weights=None, prefix='bbox_head.',
-                 pc_range=None, **loss_cfg):
+    def __init__(self, state_dict, device='cuda', num_layers=None, stage_loss_weights=None, pc_range=None, **loss_cfg):
         self.lib = lib.load()
         # the flat buffers (layout, state_dict round trip, gradient all-reduce) also work on a CPU device, which is
         # what the gloo tests use; forward / backward / adamw_step need CUDA -- there is no CPU fallback
         self.device = torch.device(device)
         sd = {k[len('roi_head.'):] if k.startswith('roi_head.') else k: v for k, v in state_dict.items()}
-        self.prefix = prefix
         if num_layers is None:
-            num_layers = 1 + max(int(k.split('.')[4]) for k in sd if k.startswith(prefix + 'transformer.decoder.layers.'))
+            num_layers = 1 + max(int(k.split('.')[4]) for k in sd if k.startswith(_BH + 'transformer.decoder.layers.'))
         assert 1 <= num_layers <= lib.MAX_LAYERS
         self.L = num_layers
         self.table, self.total = param_table(num_layers)
@@ -98,19 +107,27 @@ class DecoderTrainer:
 
     def load_state_dict(self, sd):
         for name in self.table:
-            src = sd[self.prefix + name].detach().to(torch.float32)
+            src = sd[name].detach().to(torch.float32)
+            if name == CONV_W:
+                src = src.permute(0, 2, 3, 1).contiguous()      # K order of the im2col GEMM: (ky, kx, c_in)
             self.shapes[name] = tuple(src.shape)
             assert src.numel() == self.table[name][1], f'{name}: {tuple(src.shape)} does not match the library layout'
             self.view(name).copy_(src.to(self.device))
 
+    def _sd_layout(self, name, t):
+        return t.permute(0, 3, 1, 2).contiguous() if name == CONV_W else t.clone()
+
     def state_dict(self):
-        return {self.prefix + n: self.view(n).clone() for n in self.table}
+        """The reference's names and shapes (relative to ``roi_head.``)."""
+        return {n: self._sd_layout(n, self.view(n)) for n in self.table}
 
     def grad(self, name):
-        return self.view(name, self.grads)
+        """Gradient of one tensor in the reference's state_dict layout (a permuted view for the conv weight)."""
+        t = self.view(name, self.grads)
+        return t.permute(0, 3, 1, 2) if name == CONV_W else t
 
     def named_grads(self):
-        return {self.prefix + n: self.grad(n) for n in self.table}
+        return {n: self.grad(n) for n in self.table}
 
     def zero_grad(self):
         self.grads.zero_()
@@ -198,3 +215,68 @@ class DecoderTrainer:
         lib.check(self.lib.mv2d_adamw_step(self.params.data_ptr(), self.grads.data_ptr(), self.exp_avg.data_ptr(),
                                            self.exp_avg_sq.data_ptr(), self.total, lr, betas[0], betas[1], eps, weight_decay,
                                            self.step_count, grad_scale, lib.stream_ptr()), 'mv2d_adamw_step')
+
+
+class HotPathTrainer(DecoderTrainer):
+    """The whole hot-path training step of MV2D-S on one GPU: position encoding -> RoIAlign -> query generator ->
+    decoder -> targets / losses, and back to the gradient of EVERY hot-path parameter (14.0 M, one flat buffer) and of
+    the FPN feature map (which the torch backbone continues from).  The stages without parameters or gradients
+    (camera geometry, per-RoI intrinsics, box correlation) come from the inference engine.
+    Reference: MV2DSHead.forward_train (roi_heads/mv2d_s_head.py:236-307) + torch autograd."""
+
+    def __init__(self, state_dict, device='cuda', **kw):
+        super().__init__(state_dict, device=device, **kw)
+        self._need_cuda()
+        from .engine import HotPath
+        sd = {k[len('roi_head.'):] if k.startswith('roi_head.') else k: v for k, v in state_dict.items()}
+        self.engine = HotPath(sd, mode='S', device=self.device)
+        self._front_ws = None
+        self._fp = None
+
+    @torch.no_grad()
+    def forward(self, feat, proposal_list, img_metas, gt_boxes, gt_labels):
+        """feat [V,256,h,w] fp32 NCHW (as the FPN emits it), proposal_list: V tensors [n_v, >=4], img_metas: V dicts."""
+        eng, dev = self.engine, self.device
+        f32 = dict(device=dev, dtype=torch.float32)
+        feat = feat.to(**f32).contiguous()
+        cams, rois, roi_start, counts, N = eng._upload_meta(proposal_list, img_metas)
+        i2l, trans = eng.geom_prep(cams)
+        feat_nhwc, _ = eng.to_nhwc(feat)
+        V, h, w, _ = feat_nhwc.shape
+        corr = eng.box_corr(rois, roi_start, trans, N, V, img_metas, h, w)
+        k_roi = eng.roi_align_qg(rois, cams, feat_nhwc, None, N, phase=1)['roi_intrinsics']      # K' (weight independent)
+        _, _, not_mask, _ = eng._masks(img_metas, h, w)
+        c = eng.cfg
+        out = dict(tok_mem=torch.empty((N, 49, 256), **f32), tok_kin=torch.empty((N, 49, 256), **f32),
+                   ref=torch.empty((N, 3), **f32), d_feat=torch.empty((V, h, w, 256), **f32))
+        ws_bytes = int(self.lib.mv2d_front_train_workspace_bytes(N, V, h, w))
+        if self._front_ws is None or self._front_ws.numel() * 4 < ws_bytes:
+            self._front_ws = torch.empty(ws_bytes // 4 + 64, **f32)
+        p = lib.FrontTrainParams()
+        p.N, p.V, p.h, p.w, p.L, p.stride = N, V, h, w, self.L, c['stride']
+        p.depth_num, p.pad_h, p.pad_w = c['depth_num'], int(img_metas[0]['pad_shape'][0]), int(img_metas[0]['pad_shape'][1])
+        p.depth_start = c['depth_start']
+        p.position_range = (C.c_double * 6)(*c['position_range'])
+        p.pc_range = (C.c_float * 6)(*self.pc_range)
+        p.intrins_feat_scale = c['intrins_feat_scale']
+        p.params, p.grads = self.params.data_ptr(), self.grads.data_ptr()
+        p.rois, p.roi_intrinsics, p.extrinsics, p.img2lidar = rois.data_ptr(), k_roi.data_ptr(), cams[2].data_ptr(), i2l.data_ptr()
+        p.not_mask, p.dim_t, p.feat = not_mask.data_ptr(), self.dim_t.data_ptr(), feat_nhwc.data_ptr()
+        p.tok_mem, p.tok_kin, p.ref, p.d_feat = (out[k].data_ptr() for k in ('tok_mem', 'tok_kin', 'ref', 'd_feat'))
+        p.workspace, p.workspace_bytes = self._front_ws.data_ptr(), ws_bytes
+        lib.check(self.lib.mv2d_front_train_forward(C.byref(p), lib.stream_ptr()), 'mv2d_front_train_forward')
+        self._fp, self._fout = p, out
+        self._fkeep = (feat_nhwc, rois, k_roi, cams, i2l, not_mask)
+        res = super().forward(out['ref'], out['tok_kin'], out['tok_mem'], corr['match'], corr['match_cnt'], gt_boxes, gt_labels)
+        res.update(ref=out['ref'], tok_mem=out['tok_mem'], tok_kin=out['tok_kin'], match=corr['match'], match_cnt=corr['match_cnt'],
+                   rois=rois, N=N)
+        return res
+
+    @torch.no_grad()
+    def backward(self):
+        """Accumulates every parameter gradient into the flat buffer; returns d loss / d feat as [V,256,h,w]."""
+        gin = super().backward()
+        p = self._fp
+        p.d_ref, p.d_tok_kin, p.d_tok_mem = (gin[k].data_ptr() for k in ('d_ref', 'd_tok_kin', 'd_tok_mem'))
+        lib.check(self.lib.mv2d_front_train_backward(C.byref(p), lib.stream_ptr()), 'mv2d_front_train_backward')
+        return dict(gin, d_feat=self._fout['d_feat'].permute(0, 3, 1, 2))

@@ -23,12 +23,12 @@ from mv2d_b200 import synth
 from mv2d_b200.train import DecoderTrainer
 tr = DecoderTrainer(synth.make_state_dict(0, num_layers=1), device='cpu')
 tr.grads.fill_(float(rank + 1))
-tr.grad('cls_branches.0.6.bias').fill_(10.0 * (rank + 1))
+tr.grad('bbox_head.cls_branches.0.6.bias').fill_(10.0 * (rank + 1))
 n = tr.all_reduce_grads()
 back = tr.state_dict()
 same = all(torch.equal(back[k], v) for k, v in synth.make_state_dict(0, num_layers=1).items() if k in back)
 print(json.dumps(dict(rank=rank, world=world, shard=shard, tmax=tmax, value=val, ar_world=n,
-                      g_first=float(tr.grads[0]), g_bias=tr.grad('cls_branches.0.6.bias').tolist(),
+                      g_first=float(tr.grads[0]), g_bias=tr.grad('bbox_head.cls_branches.0.6.bias').tolist(),
                       n_params=tr.total, roundtrip=bool(same), n_tensors=len(back))))
 '''
 
@@ -57,4 +57,4 @@ def test_two_rank_gloo_plumbing(tmp_path):
         assert abs(o['value'] - 2 * 4 / 0.015) < 1e-6
         # the data-parallel exchange of the training step: one sum over the flat gradient buffer
         assert o['ar_world'] == 2 and o['g_first'] == 3.0 and o['g_bias'] == [30.0] * 10
-        assert o['roundtrip'] and o['n_tensors'] == 6 + 34 and o['n_params'] >= 1_800_000
+        assert o['roundtrip'] and o['n_tensors'] == 6 + 34 + 22 and o['n_params'] >= 1_800_000

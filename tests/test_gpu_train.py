@@ -107,13 +107,49 @@ def test_training_step_matches_autograd_oracle_and_reference_golden(name):
     rep.check('d roi_pe vs reference', sub(back(d_kin), g), g['d_roi_pos_sub'])
     rep.check('d roi_feat vs reference', sub(back(d_kin + d_mem), g), g['d_roi_feat_sub'])
     # ---- backward: every parameter of the slice, full tensors vs autograd and the reference's subsample
-    for n in tr.table:
-        k = 'bbox_head.' + n
+    for k in tr.table:
+        if not k.startswith('bbox_head.'):
+            continue            # the slice: the front-end tensors are covered by the full-step test below
         want = r['sd'][k].grad
         want = want if want is not None else torch.zeros_like(r['sd'][k])
-        got = tr.grad(n).cpu()
-        rep.check(f'd {n}', got, want)
-        rep.check(f'd {n} vs reference', sub(got, g), g['dparam.' + k])
+        got = tr.grad(k).cpu()
+        rep.check(f'd {k}', got, want)
+        rep.check(f'd {k} vs reference', sub(got, g), g['dparam.' + k])
+    rep.finish()
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_full_hot_path_training_step_matches_reference_golden(name):
+    """Position encoding -> RoIAlign -> query generator -> decoder -> losses and all the way back: every one of the
+    96 hot-path parameter gradients and d loss / d feat against the reference's own autograd (golden subsamples)."""
+    from mv2d_b200.train import HotPathTrainer
+    g, spec, gt_spec = load(name)
+    stage_w = [float(x) for x in g['stage_loss_weights']]
+    sd = synth.make_state_dict(0, num_layers=spec['num_layers'])
+    feat, boxes, metas = synth.case_inputs(spec)
+    gt_boxes, gt_labels, _ = synth.make_dn_inputs(gt_spec)
+    tr = HotPathTrainer(sd, stage_loss_weights=stage_w)
+    out = tr.forward(feat, boxes, metas, gt_boxes, gt_labels)
+    gin = tr.backward()
+    torch.cuda.synchronize()
+    rep = Report('full_' + name)
+    # forward of the front end against the oracle's stages
+    from test_grad_oracle_golden import slice_inputs
+    _, _, st = slice_inputs(spec)
+    rep.check('fwd ref', out['ref'].cpu(), st['ref'], 1e-4)
+    rep.check('fwd tok_mem', out['tok_mem'].cpu(), tokens(st['roi_feat']), 1e-4)
+    rep.check('fwd tok_kin', out['tok_kin'].cpu(), tokens(st['roi_feat'] + st['roi_pe']), 1e-4)
+    rep.check('fwd cls_scores vs reference', out['cls_scores'].cpu(), g['cls_scores'], 1e-4)
+    rep.check('fwd bbox_preds vs reference', out['bbox_preds'].cpu(), g['bbox_preds'], 1e-4)
+    rep.check('loss_cls', out['loss_cls'].cpu(), g['loss_cls'], 5e-5)
+    rep.check('loss_bbox', out['loss_bbox'].cpu(), g['loss_bbox'], 5e-5)
+    rep.check('d_ref vs reference', gin['d_ref'].cpu(), g['d_ref'])
+    rep.check('d_feat vs reference', sub(gin['d_feat'].cpu().contiguous(), g), g['d_feat_sub'])
+    n = 0
+    for k in tr.table:
+        rep.check(f'd {k} vs reference', sub(tr.grad(k).cpu().contiguous(), g), g['dparam.' + k])
+        n += 1
+    assert n == 6 + 34 * spec['num_layers'] + 22
     rep.finish()
 
 
