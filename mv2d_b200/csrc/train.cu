@@ -100,53 +100,55 @@ long long front_off(int L, int t) {
 // C[M,N] (op)= sum_k A(m,k) B(k,n) (+ bias[n]),  A(m,k) = A[m*sam + k*sak],  B(k,n) = B[k*sbk + n*sbn].
 enum SgFlags { SG_RELU = 1, SG_ACC = 2, SG_ATOMIC = 4, SG_CLAMP5E3 = 8, SG_MASK_LT5E3 = 16 };
 struct Sg {
-    const float* A; const float* B; float* C; const float* bias; const float* mask;
+    const float* A; const float* B; float* C; const float* bias; const float* mask; float* rowsum;
     long long sam, sak, sbk, sbn;
     int ldc, ldmask, M, N, K, klen, flags;
 };
 
-// TM x TM outputs per thread, 256 threads: TM = 4 -> 64 x 64 tile with BK = 16, TM = 8 -> 128 x 128 tile with BK = 8
-// (1024 elements of each operand per k-step either way: four per thread, prefetched into registers while the
-// previous k-step is multiplied).  AK1 / BN1 say which stride of A / B is 1, i.e. which index runs along a warp
-// when the tile is loaded (coalescing only; addressing always goes through the strides).
+// TM x TM outputs per thread, 256 threads: TM = 4 -> 64 x 64 tile with BK = 32, TM = 8 -> 128 x 128 tile with BK = 16
+// (eight elements of each operand per thread and k-step, prefetched into registers while the previous k-step is
+// multiplied: the M ~ 300 problems of the decoder are short chains of k-steps on a few CTAs, so the loads in flight
+// per step set their speed).  AK1 / BN1 say which stride of A / B is 1, i.e. which index runs along a warp when the
+// tile is loaded (coalescing only; addressing always goes through the strides).
+// rowsum (weight-gradient calls): the CTAs of the first column of tiles also add sum_k A(m,k) -- the bias gradient
+// of the same layer -- so no separate column-sum launch is needed.
 template <int TM, bool AK1, bool BN1>
 __global__ void __launch_bounds__(256) sgemm_kernel(Sg g) {
     pdl_wait();
     pdl_trigger();
-    constexpr int BM = 16 * TM, BK = 1024 / BM, LD = BM + 4;
+    constexpr int BM = 16 * TM, BK = 2048 / BM, LD = BM + 4, E = 8;
     __shared__ __align__(16) float As[BK][LD];
     __shared__ __align__(16) float Bs[BK][LD];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BM;
     const int kbeg = blockIdx.z * g.klen;
     const int kend = min(g.K, kbeg + g.klen);
-    float acc[TM][TM];
+    const bool do_rowsum = g.rowsum != nullptr && blockIdx.x == 0 && tx == 0;
+    float acc[TM][TM], rs[TM];
 #pragma unroll
-    for (int i = 0; i < TM; ++i)
+    for (int i = 0; i < TM; ++i) {
+        rs[i] = 0.f;
 #pragma unroll
         for (int j = 0; j < TM; ++j) acc[i][j] = 0.f;
-    // element e (0..3) of this thread inside a tile: (am, ak) for A, (bn, bk) for B
-    int am[4], ak[4], bn[4], bk[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        const int idx = tid + e * 256;
-        if (AK1) { ak[e] = idx % BK; am[e] = idx / BK; } else { am[e] = idx % BM; ak[e] = idx / BM; }
-        if (BN1) { bn[e] = idx % BM; bk[e] = idx / BM; } else { bk[e] = idx % BK; bn[e] = idx / BK; }
     }
-    float ra[4], rb[4];
+    float ra[E], rb[E];
+    // element e of this thread inside a tile: (am, ak) for A, (bn, bk) for B
+    auto a_m = [&](int e) { const int idx = tid + e * 256; return AK1 ? idx / BK : idx % BM; };
+    auto a_k = [&](int e) { const int idx = tid + e * 256; return AK1 ? idx % BK : idx / BM; };
+    auto b_n = [&](int e) { const int idx = tid + e * 256; return BN1 ? idx % BM : idx / BK; };
+    auto b_k = [&](int e) { const int idx = tid + e * 256; return BN1 ? idx / BM : idx % BK; };
     auto fetch = [&](int k0) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            ra[e] = (m0 + am[e] < g.M && k0 + ak[e] < kend)
-                        ? __ldg(g.A + (long long)(m0 + am[e]) * g.sam + (long long)(k0 + ak[e]) * g.sak) : 0.f;
-            rb[e] = (n0 + bn[e] < g.N && k0 + bk[e] < kend)
-                        ? __ldg(g.B + (long long)(k0 + bk[e]) * g.sbk + (long long)(n0 + bn[e]) * g.sbn) : 0.f;
+        for (int e = 0; e < E; ++e) {
+            const int am = a_m(e), ak = a_k(e), bn = b_n(e), bk = b_k(e);
+            ra[e] = (m0 + am < g.M && k0 + ak < kend) ? __ldg(g.A + (long long)(m0 + am) * g.sam + (long long)(k0 + ak) * g.sak) : 0.f;
+            rb[e] = (n0 + bn < g.N && k0 + bk < kend) ? __ldg(g.B + (long long)(k0 + bk) * g.sbk + (long long)(n0 + bn) * g.sbn) : 0.f;
         }
     };
     if (kbeg < kend) fetch(kbeg);
     for (int k0 = kbeg; k0 < kend; k0 += BK) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) { As[ak[e]][am[e]] = ra[e]; Bs[bk[e]][bn[e]] = rb[e]; }
+        for (int e = 0; e < E; ++e) { As[a_k(e)][a_m(e)] = ra[e]; Bs[b_k(e)][b_n(e)] = rb[e]; }
         __syncthreads();
         if (k0 + BK < kend) fetch(k0 + BK);
 #pragma unroll
@@ -163,6 +165,10 @@ __global__ void __launch_bounds__(256) sgemm_kernel(Sg g) {
             for (int i = 0; i < TM; ++i)
 #pragma unroll
                 for (int j = 0; j < TM; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+            if (do_rowsum) {
+#pragma unroll
+                for (int i = 0; i < TM; ++i) rs[i] += av[i];
+            }
         }
         __syncthreads();
     }
@@ -170,6 +176,7 @@ __global__ void __launch_bounds__(256) sgemm_kernel(Sg g) {
     for (int i = 0; i < TM; ++i) {
         const int m = m0 + (i / 4) * 64 + ty * 4 + (i % 4);
         if (m >= g.M) continue;
+        if (do_rowsum) atomicAdd(g.rowsum + m, rs[i]);
 #pragma unroll
         for (int j = 0; j < TM; ++j) {
             const int n = n0 + (j / 4) * 64 + tx * 4 + (j % 4);
@@ -230,10 +237,11 @@ int linear_dgrad(const float* dY, int ldy, const float* W, int ldw, float* dX, i
     g.M = M; g.N = K; g.K = Nout; g.klen = Nout; g.flags = (accumulate ? SG_ACC : 0) | extra_flags;
     return launch_sgemm(g, 1, st);
 }
-// dW[Nout,K] += dY[M,Nout]^T X[M,K]   (split over the M rows, atomic accumulation)
-int linear_wgrad(const float* dY, int ldy, const float* X, int ldx, float* dW, int ldw, int M, int Nout, int K, cudaStream_t st) {
+// dW[Nout,K] += dY[M,Nout]^T X[M,K]   (split over the M rows, atomic accumulation);  db[Nout] += sum_rows dY (nullable)
+int linear_wgrad(const float* dY, int ldy, const float* X, int ldx, float* dW, int ldw, int M, int Nout, int K, cudaStream_t st,
+                 float* db = nullptr) {
     Sg g{};
-    g.A = dY; g.sam = 1; g.sak = ldy; g.B = X; g.sbk = ldx; g.sbn = 1; g.C = dW; g.ldc = ldw;
+    g.A = dY; g.sam = 1; g.sak = ldy; g.B = X; g.sbk = ldx; g.sbn = 1; g.C = dW; g.ldc = ldw; g.rowsum = db;
     g.M = Nout; g.N = K; g.K = M; g.flags = SG_ATOMIC;
     const int t = sg_tile(Nout, K);
     const int tiles = cdiv(Nout, t) * cdiv(K, t);
@@ -708,7 +716,9 @@ __global__ void __launch_bounds__(32) xa_inverse_kernel(const int* __restrict__ 
     if (lane == 0) inv_cnt[r] = min(pos, N);
 }
 
-// one CTA per key token row (r, t), one warp per head; lane = entry of the RoI's inverse list
+// one CTA per key token row (r, t), one warp per head, lane = channel of the head: the RoI's inverse list is short
+// (the RoI's own query plus the few that matched it), so the entries are walked sequentially with broadcast loads of
+// the two scalars and coalesced 128-byte loads of the query / output-gradient rows -- no shuffles
 __global__ void __launch_bounds__(256) xa_bwd_dkv_kernel(const float* __restrict__ cq, const float* __restrict__ dctx,
                                                          const float* __restrict__ P, const float* __restrict__ dS,
                                                          const int* __restrict__ inv_cnt, const int* __restrict__ inv_list,
@@ -720,31 +730,17 @@ __global__ void __launch_bounds__(256) xa_bwd_dkv_kernel(const float* __restrict
     const int PM = max_match * TTOK;
     const float scale = 0.17677669529663687f;
     const int n = inv_cnt[r];
-    float dk[THD], dv[THD];
-#pragma unroll
-    for (int c = 0; c < THD; ++c) { dk[c] = 0.f; dv[c] = 0.f; }
-    for (int e = lane; e < n; e += 32) {
-        const int code = inv_list[(long long)r * N + e];
+    float dk = 0.f, dv = 0.f;
+    for (int e = 0; e < n; ++e) {
+        const int code = __ldg(inv_list + (long long)r * N + e);
         const int i = code / max_match, m = code % max_match;
         const long long o = ((long long)i * TH + h) * PM + m * TTOK + t;
-        const float p = P[o], ds = dS[o];
-        const float4* qr = reinterpret_cast<const float4*>(cq + (long long)i * TC_ + h * THD);
-        const float4* gr = reinterpret_cast<const float4*>(dctx + (long long)i * TC_ + h * THD);
-#pragma unroll
-        for (int c4 = 0; c4 < THD / 4; ++c4) {
-            const float4 q = qr[c4], g = gr[c4];
-            dk[c4 * 4] += ds * q.x; dk[c4 * 4 + 1] += ds * q.y; dk[c4 * 4 + 2] += ds * q.z; dk[c4 * 4 + 3] += ds * q.w;
-            dv[c4 * 4] += p * g.x; dv[c4 * 4 + 1] += p * g.y; dv[c4 * 4 + 2] += p * g.z; dv[c4 * 4 + 3] += p * g.w;
-        }
+        const float p = __ldg(P + o), ds = __ldg(dS + o);
+        dk = fmaf(ds, __ldg(cq + (long long)i * TC_ + h * THD + lane), dk);
+        dv = fmaf(p, __ldg(dctx + (long long)i * TC_ + h * THD + lane), dv);
     }
-    float mk = 0.f, mv = 0.f;
-#pragma unroll
-    for (int c = 0; c < THD; ++c) {
-        const float rk = warp_sum(dk[c]), rv = warp_sum(dv[c]);
-        if (lane == c) { mk = rk; mv = rv; }
-    }
-    dKp[(long long)row * TC_ + h * THD + lane] = mk * scale;
-    dVp[(long long)row * TC_ + h * THD + lane] = mv;
+    dKp[(long long)row * TC_ + h * THD + lane] = dk * scale;
+    dVp[(long long)row * TC_ + h * THD + lane] = dv;
 }
 
 // ------------------------------------------------------------------------------------------------ reg branch tail
@@ -1408,41 +1404,32 @@ int run_train_backward(const Mv2dTrainParams& p, cudaStream_t st) {
         // --- reg branch
         launch_k(reg_tail_bwd_kernel, dim3(cdiv(N, 128)), dim3(128), 0, st, dbox, p.ref, (const float*)a.rsig, p.d_ref, pc, N);
         MV2D_CHECK_LAUNCH("train reg_tail_bwd");
-        TRY(linear_wgrad(dbox, TCODE, a.r1, TC_, D.t[TL_REG_W2], TC_, N, TCODE, TC_, st));
-        TRY(colsum(dbox, TCODE, N, TCODE, D.t[TL_REG_B2], st));
+        TRY(linear_wgrad(dbox, TCODE, a.r1, TC_, D.t[TL_REG_W2], TC_, N, TCODE, TC_, st, D.t[TL_REG_B2]));
         TRY(linear_dgrad(dbox, TCODE, W.t[TL_REG_W2], TC_, w.t1, TC_, N, TCODE, TC_, a.r1, TC_, false, st));
-        TRY(linear_wgrad(w.t1, TC_, a.r0, TC_, D.t[TL_REG_W1], TC_, N, TC_, TC_, st));
-        TRY(colsum(w.t1, TC_, N, TC_, D.t[TL_REG_B1], st));
+        TRY(linear_wgrad(w.t1, TC_, a.r0, TC_, D.t[TL_REG_W1], TC_, N, TC_, TC_, st, D.t[TL_REG_B1]));
         TRY(linear_dgrad(w.t1, TC_, W.t[TL_REG_W1], TC_, w.t2, TC_, N, TC_, TC_, a.r0, TC_, false, st));
-        TRY(linear_wgrad(w.t2, TC_, a.inter, TC_, D.t[TL_REG_W0], TC_, N, TC_, TC_, st));
-        TRY(colsum(w.t2, TC_, N, TC_, D.t[TL_REG_B0], st));
+        TRY(linear_wgrad(w.t2, TC_, a.inter, TC_, D.t[TL_REG_W0], TC_, N, TC_, TC_, st, D.t[TL_REG_B0]));
         TRY(linear_dgrad(w.t2, TC_, W.t[TL_REG_W0], TC_, w.dinter, TC_, N, TC_, TC_, nullptr, 0, false, st));
         // --- cls branch
-        TRY(linear_wgrad(dcls, TCODE, a.c1n, TC_, D.t[TL_CLS_W2], TC_, N, TCODE, TC_, st));
-        TRY(colsum(dcls, TCODE, N, TCODE, D.t[TL_CLS_B2], st));
+        TRY(linear_wgrad(dcls, TCODE, a.c1n, TC_, D.t[TL_CLS_W2], TC_, N, TCODE, TC_, st, D.t[TL_CLS_B2]));
         TRY(linear_dgrad(dcls, TCODE, W.t[TL_CLS_W2], TC_, w.t1, TC_, N, TCODE, TC_, nullptr, 0, false, st));
         TRY(ln_bwd(w.t1, a.c1n, a.xhat_c1, a.rstd_c1, W.t[TL_CLS_G1], w.t2, D.t[TL_CLS_G1], D.t[TL_CLS_BE1], N, false, st));
-        TRY(linear_wgrad(w.t2, TC_, a.c0n, TC_, D.t[TL_CLS_W1], TC_, N, TC_, TC_, st));
-        TRY(colsum(w.t2, TC_, N, TC_, D.t[TL_CLS_B1], st));
+        TRY(linear_wgrad(w.t2, TC_, a.c0n, TC_, D.t[TL_CLS_W1], TC_, N, TC_, TC_, st, D.t[TL_CLS_B1]));
         TRY(linear_dgrad(w.t2, TC_, W.t[TL_CLS_W1], TC_, w.t1, TC_, N, TC_, TC_, nullptr, 0, false, st));
         TRY(ln_bwd(w.t1, a.c0n, a.xhat_c0, a.rstd_c0, W.t[TL_CLS_G0], w.t2, D.t[TL_CLS_G0], D.t[TL_CLS_BE0], N, false, st));
-        TRY(linear_wgrad(w.t2, TC_, a.inter, TC_, D.t[TL_CLS_W0], TC_, N, TC_, TC_, st));
-        TRY(colsum(w.t2, TC_, N, TC_, D.t[TL_CLS_B0], st));
+        TRY(linear_wgrad(w.t2, TC_, a.inter, TC_, D.t[TL_CLS_W0], TC_, N, TC_, TC_, st, D.t[TL_CLS_B0]));
         TRY(linear_dgrad(w.t2, TC_, W.t[TL_CLS_W0], TC_, w.dinter, TC_, N, TC_, TC_, nullptr, 0, true, st));
         // --- post_norm: dx (gradient of this layer's output) += LN'(dinter)
         TRY(ln_bwd(w.dinter, nullptr, a.xhatp, a.rstdp, P + global_off(TG_POST_G), w.dx, g_post_g, g_post_b, N, true, st));
         // --- norms.2 and the FFN
         TRY(ln_bwd(w.dx, nullptr, a.xhat2, a.rstd2, W.t[TL_LN2_G], w.t1, D.t[TL_LN2_G], D.t[TL_LN2_B], N, false, st));
-        TRY(linear_wgrad(w.t1, TC_, a.hdn, TFF, D.t[TL_FFN_W2], TFF, N, TC_, TFF, st));
-        TRY(colsum(w.t1, TC_, N, TC_, D.t[TL_FFN_B2], st));
+        TRY(linear_wgrad(w.t1, TC_, a.hdn, TFF, D.t[TL_FFN_W2], TFF, N, TC_, TFF, st, D.t[TL_FFN_B2]));
         TRY(linear_dgrad(w.t1, TC_, W.t[TL_FFN_W2], TFF, w.dhdn, TFF, N, TC_, TFF, a.hdn, TFF, false, st));
-        TRY(linear_wgrad(w.dhdn, TFF, a.x2, TC_, D.t[TL_FFN_W1], TC_, N, TFF, TC_, st));
-        TRY(colsum(w.dhdn, TFF, N, TFF, D.t[TL_FFN_B1], st));
+        TRY(linear_wgrad(w.dhdn, TFF, a.x2, TC_, D.t[TL_FFN_W1], TC_, N, TFF, TC_, st, D.t[TL_FFN_B1]));
         TRY(linear_dgrad(w.dhdn, TFF, W.t[TL_FFN_W1], TC_, w.t1, TC_, N, TFF, TC_, nullptr, 0, true, st));   // t1 = d x2
         // --- norms.1 and the cross-attention
         TRY(ln_bwd(w.t1, nullptr, a.xhat1, a.rstd1, W.t[TL_LN1_G], w.t2, D.t[TL_LN1_G], D.t[TL_LN1_B], N, false, st));
-        TRY(linear_wgrad(w.t2, TC_, a.ctx, TC_, D.t[TL_CA_OUT_W], TC_, N, TC_, TC_, st));
-        TRY(colsum(w.t2, TC_, N, TC_, D.t[TL_CA_OUT_B], st));
+        TRY(linear_wgrad(w.t2, TC_, a.ctx, TC_, D.t[TL_CA_OUT_W], TC_, N, TC_, TC_, st, D.t[TL_CA_OUT_B]));
         TRY(linear_dgrad(w.t2, TC_, W.t[TL_CA_OUT_W], TC_, w.t3, TC_, N, TC_, TC_, nullptr, 0, false, st));   // t3 = d ctx
         launch_k(xa_bwd_dq_kernel, dim3(N), dim3(256), 0, st, (const float*)a.Kp, (const float*)a.Vp, (const float*)a.P_xa,
                  (const float*)w.t3, p.match, p.match_cnt, p.max_match, w.dS_xa, w.dcq, N);
@@ -1450,41 +1437,34 @@ int run_train_backward(const Mv2dTrainParams& p, cudaStream_t st) {
         launch_k(xa_bwd_dkv_kernel, dim3(NK), dim3(256), 0, st, (const float*)a.cq, (const float*)w.t3, (const float*)a.P_xa,
                  (const float*)w.dS_xa, (const int*)w.inv_cnt, (const int*)w.inv_list, p.max_match, w.dKp, w.dVp, N);
         MV2D_CHECK_LAUNCH("train xa_bwd_dkv");
-        TRY(linear_wgrad(w.dcq, TC_, a.xq1, TC_, D.t[TL_CA_IN_W], TC_, N, TC_, TC_, st));
-        TRY(colsum(w.dcq, TC_, N, TC_, D.t[TL_CA_IN_B], st));
+        TRY(linear_wgrad(w.dcq, TC_, a.xq1, TC_, D.t[TL_CA_IN_W], TC_, N, TC_, TC_, st, D.t[TL_CA_IN_B]));
         TRY(linear_dgrad(w.dcq, TC_, W.t[TL_CA_IN_W], TC_, w.t3, TC_, N, TC_, TC_, nullptr, 0, false, st));   // t3 = d (x1 + qpos)
         TRY(add(w.t2, w.t2, w.t3, NC, st));          // t2 = d x1
         TRY(add(w.dqpos, w.dqpos, w.t3, NC, st));
-        TRY(linear_wgrad(w.dKp, TC_, p.tok_kin, TC_, D.t[TL_CA_IN_W] + 256 * TC_, TC_, NK, TC_, TC_, st));
-        TRY(colsum(w.dKp, TC_, NK, TC_, D.t[TL_CA_IN_B] + 256, st));
+        TRY(linear_wgrad(w.dKp, TC_, p.tok_kin, TC_, D.t[TL_CA_IN_W] + 256 * TC_, TC_, NK, TC_, TC_, st, D.t[TL_CA_IN_B] + 256));
         TRY(linear_dgrad(w.dKp, TC_, W.t[TL_CA_IN_W] + 256 * TC_, TC_, p.d_tok_kin, TC_, NK, TC_, TC_, nullptr, 0, true, st));
-        TRY(linear_wgrad(w.dVp, TC_, p.tok_mem, TC_, D.t[TL_CA_IN_W] + 512 * TC_, TC_, NK, TC_, TC_, st));
-        TRY(colsum(w.dVp, TC_, NK, TC_, D.t[TL_CA_IN_B] + 512, st));
+        TRY(linear_wgrad(w.dVp, TC_, p.tok_mem, TC_, D.t[TL_CA_IN_W] + 512 * TC_, TC_, NK, TC_, TC_, st, D.t[TL_CA_IN_B] + 512));
         TRY(linear_dgrad(w.dVp, TC_, W.t[TL_CA_IN_W] + 512 * TC_, TC_, p.d_tok_mem, TC_, NK, TC_, TC_, nullptr, 0, true, st));
         // --- norms.0 and the self-attention
         TRY(ln_bwd(w.t2, nullptr, a.xhat0, a.rstd0, W.t[TL_LN0_G], w.t1, D.t[TL_LN0_G], D.t[TL_LN0_B], N, false, st));   // t1 = d (x_in + sa)
-        TRY(linear_wgrad(w.t1, TC_, a.attn_o, TC_, D.t[TL_SA_OUT_W], TC_, N, TC_, TC_, st));
-        TRY(colsum(w.t1, TC_, N, TC_, D.t[TL_SA_OUT_B], st));
+        TRY(linear_wgrad(w.t1, TC_, a.attn_o, TC_, D.t[TL_SA_OUT_W], TC_, N, TC_, TC_, st, D.t[TL_SA_OUT_B]));
         TRY(linear_dgrad(w.t1, TC_, W.t[TL_SA_OUT_W], TC_, w.t3, TC_, N, TC_, TC_, nullptr, 0, false, st));   // t3 = d attn_o
         launch_k(sa_bwd_dq_kernel, dim3(N), dim3(256), 0, st, (const float*)a.qkv, (const float*)a.P_sa, (const float*)w.t3, w.dS_sa, w.dqkv, N);
         MV2D_CHECK_LAUNCH("train sa_bwd_dq");
         launch_k(sa_bwd_dkv_kernel, dim3(N), dim3(256), 0, st, (const float*)a.qkv, (const float*)a.P_sa, (const float*)w.dS_sa,
                  (const float*)w.t3, w.dqkv, N);
         MV2D_CHECK_LAUNCH("train sa_bwd_dkv");
-        TRY(linear_wgrad(w.dqkv, 768, a.xq, TC_, D.t[TL_SA_IN_W], TC_, N, 512, TC_, st));
-        TRY(linear_wgrad(w.dqkv + 512, 768, a.x_in, TC_, D.t[TL_SA_IN_W] + 512 * TC_, TC_, N, TC_, TC_, st));
-        TRY(colsum(w.dqkv, 768, N, 768, D.t[TL_SA_IN_B], st));
+        TRY(linear_wgrad(w.dqkv, 768, a.xq, TC_, D.t[TL_SA_IN_W], TC_, N, 512, TC_, st, D.t[TL_SA_IN_B]));
+        TRY(linear_wgrad(w.dqkv + 512, 768, a.x_in, TC_, D.t[TL_SA_IN_W] + 512 * TC_, TC_, N, TC_, TC_, st, D.t[TL_SA_IN_B] + 512));
         TRY(linear_dgrad(w.dqkv, 768, W.t[TL_SA_IN_W], TC_, w.t3, TC_, N, 512, TC_, nullptr, 0, false, st));   // t3 = d (x_in + qpos)
         TRY(add(w.dqpos, w.dqpos, w.t3, NC, st));
         TRY(add(w.dx, w.t1, w.t3, NC, st));           // dx = gradient of the previous layer's output
         TRY(linear_dgrad(w.dqkv + 512, 768, W.t[TL_SA_IN_W] + 512 * TC_, TC_, w.dx, TC_, N, TC_, TC_, nullptr, 0, true, st));
     }
     // --- query embedding MLP and the sin / cos features
-    TRY(linear_wgrad(w.dqpos, TC_, w.h0, TC_, G + global_off(TG_QE2_W), TC_, N, TC_, TC_, st));
-    TRY(colsum(w.dqpos, TC_, N, TC_, G + global_off(TG_QE2_B), st));
+    TRY(linear_wgrad(w.dqpos, TC_, w.h0, TC_, G + global_off(TG_QE2_W), TC_, N, TC_, TC_, st, G + global_off(TG_QE2_B)));
     TRY(linear_dgrad(w.dqpos, TC_, P + global_off(TG_QE2_W), TC_, w.t1, TC_, N, TC_, TC_, w.h0, TC_, false, st));
-    TRY(linear_wgrad(w.t1, TC_, w.posemb, TPE, G + global_off(TG_QE0_W), TPE, N, TC_, TPE, st));
-    TRY(colsum(w.t1, TC_, N, TC_, G + global_off(TG_QE0_B), st));
+    TRY(linear_wgrad(w.t1, TC_, w.posemb, TPE, G + global_off(TG_QE0_W), TPE, N, TC_, TPE, st, G + global_off(TG_QE0_B)));
     TRY(linear_dgrad(w.t1, TC_, P + global_off(TG_QE0_W), TPE, w.dposemb, TPE, N, TC_, TPE, nullptr, 0, false, st));
     launch_k(posemb_bwd_kernel, dim3(N), dim3(96), 0, st, (const float*)w.dposemb, p.ref, p.dim_t, p.d_ref, N);
     MV2D_CHECK_LAUNCH("train posemb_bwd");
@@ -1563,23 +1543,18 @@ int run_front_train_backward(const Mv2dFrontTrainParams& p, cudaStream_t st) {
     // --- reference points -> fc_center -> FC chain -> avg-pool -> conv
     launch_k(center_bwd_kernel, dim3(cdiv(N, 128)), dim3(128), 0, st, (const float*)w.c, (const float*)w.m_roi, pc, p.d_ref, w.dc, N);
     MV2D_CHECK_LAUNCH("front center_bwd");
-    TRY(linear_wgrad(w.dc, 3, w.e2, TC_, D(TF_CENTER_W), TC_, N, 3, TC_, st));
-    TRY(colsum(w.dc, 3, N, 3, D(TF_CENTER_B), st));
+    TRY(linear_wgrad(w.dc, 3, w.e2, TC_, D(TF_CENTER_W), TC_, N, 3, TC_, st, D(TF_CENTER_B)));
     TRY(linear_dgrad(w.dc, 3, W(TF_CENTER_W), TC_, w.de2, TC_, N, 3, TC_, w.e2, TC_, false, st));
-    TRY(linear_wgrad(w.de2, TC_, w.e0, 512, D(TF_ENC2_W), 512, N, TC_, 512, st));
-    TRY(colsum(w.de2, TC_, N, TC_, D(TF_ENC2_B), st));
+    TRY(linear_wgrad(w.de2, TC_, w.e0, 512, D(TF_ENC2_W), 512, N, TC_, 512, st, D(TF_ENC2_B)));
     TRY(linear_dgrad(w.de2, TC_, W(TF_ENC2_W), 512, w.de0, 512, N, TC_, 512, w.e0, 512, false, st));
-    TRY(linear_wgrad(w.de0, 512, w.cat, 1040, D(TF_ENC0_W), 1040, N, 512, 1040, st));
-    TRY(colsum(w.de0, 512, N, 512, D(TF_ENC0_B), st));
+    TRY(linear_wgrad(w.de0, 512, w.cat, 1040, D(TF_ENC0_W), 1040, N, 512, 1040, st, D(TF_ENC0_B)));
     // only the 1024 FC columns of the concatenation carry a gradient (the intrinsics feature is an input)
     TRY(linear_dgrad(w.de0, 512, W(TF_ENC0_W), 1040, w.df1, 1024, N, 512, 1024, w.cat, 1040, false, st, SG_MASK_LT5E3));
-    TRY(linear_wgrad(w.df1, 1024, w.pool, TC_, D(TF_FC_W), TC_, N, 1024, TC_, st));
-    TRY(colsum(w.df1, 1024, N, 1024, D(TF_FC_B), st));
+    TRY(linear_wgrad(w.df1, 1024, w.pool, TC_, D(TF_FC_W), TC_, N, 1024, TC_, st, D(TF_FC_B)));
     TRY(linear_dgrad(w.df1, 1024, W(TF_FC_W), TC_, w.dpool, TC_, N, 1024, TC_, nullptr, 0, false, st));
     launch_k(pool49_bwd_kernel, dim3(ew_grid((long long)NK * TC_)), dim3(256), 0, st, (const float*)w.y, (const float*)w.dpool, w.dy, N);
     MV2D_CHECK_LAUNCH("front pool49_bwd");
-    TRY(linear_wgrad(w.dy, TC_, w.col, 9 * TC_, D(TF_CONV_W), 9 * TC_, NK, TC_, 9 * TC_, st));
-    TRY(colsum(w.dy, TC_, NK, TC_, D(TF_CONV_B), st));
+    TRY(linear_wgrad(w.dy, TC_, w.col, 9 * TC_, D(TF_CONV_W), 9 * TC_, NK, TC_, 9 * TC_, st, D(TF_CONV_B)));
     TRY(linear_dgrad(w.dy, TC_, W(TF_CONV_W), 9 * TC_, w.dcol, 9 * TC_, NK, TC_, 9 * TC_, nullptr, 0, false, st));
     // d tok_mem = conv path + value path + key path (tok_kin = tok_mem + RoIAlign(pe)); d RoIAlign(pe) = d tok_kin
     launch_k(col2im_kernel, dim3(ew_grid((long long)NK * 64)), dim3(256), 0, st, (const float*)w.dcol, p.d_tok_mem, p.d_tok_kin, w.dtok, N);
@@ -1592,23 +1567,17 @@ int run_front_train_backward(const Mv2dFrontTrainParams& p, cudaStream_t st) {
     launch_k(pe_gate_bwd_kernel, dim3(ew_grid(PC)), dim3(256), 0, st, (const float*)w.dpe_map, (const float*)w.x, (const float*)w.gate, w.dx, w.dg2, PC);
     MV2D_CHECK_LAUNCH("front pe_gate_bwd");
     // sine branch (adapt_pos3d): d sb = dpe
-    TRY(linear_wgrad(w.dpe_map, TC_, w.hs, 1024, D(TF_ADAPT2_W), 1024, P, TC_, 1024, st));
-    TRY(colsum(w.dpe_map, TC_, P, TC_, D(TF_ADAPT2_B), st));
+    TRY(linear_wgrad(w.dpe_map, TC_, w.hs, 1024, D(TF_ADAPT2_W), 1024, P, TC_, 1024, st, D(TF_ADAPT2_B)));
     TRY(linear_dgrad(w.dpe_map, TC_, W(TF_ADAPT2_W), 1024, w.dh, 1024, P, TC_, 1024, w.hs, 1024, false, st));
-    TRY(linear_wgrad(w.dh, 1024, w.sine, 384, D(TF_ADAPT0_W), 384, P, 1024, 384, st));
-    TRY(colsum(w.dh, 1024, P, 1024, D(TF_ADAPT0_B), st));
+    TRY(linear_wgrad(w.dh, 1024, w.sine, 384, D(TF_ADAPT0_W), 384, P, 1024, 384, st, D(TF_ADAPT0_B)));
     // position MLP (position_encoder)
-    TRY(linear_wgrad(w.dx, TC_, w.hp, 1024, D(TF_POS2_W), 1024, P, TC_, 1024, st));
-    TRY(colsum(w.dx, TC_, P, TC_, D(TF_POS2_B), st));
+    TRY(linear_wgrad(w.dx, TC_, w.hp, 1024, D(TF_POS2_W), 1024, P, TC_, 1024, st, D(TF_POS2_B)));
     TRY(linear_dgrad(w.dx, TC_, W(TF_POS2_W), 1024, w.dh, 1024, P, TC_, 1024, w.hp, 1024, false, st));
-    TRY(linear_wgrad(w.dh, 1024, w.coords, 192, D(TF_POS0_W), 192, P, 1024, 192, st));
-    TRY(colsum(w.dh, 1024, P, 1024, D(TF_POS0_B), st));
+    TRY(linear_wgrad(w.dh, 1024, w.coords, 192, D(TF_POS0_W), 192, P, 1024, 192, st, D(TF_POS0_B)));
     // SE gate (fpe): g2 = We relu(Wr feat + br) + be
-    TRY(linear_wgrad(w.dg2, TC_, w.g1, TC_, D(TF_SE_E_W), TC_, P, TC_, TC_, st));
-    TRY(colsum(w.dg2, TC_, P, TC_, D(TF_SE_E_B), st));
+    TRY(linear_wgrad(w.dg2, TC_, w.g1, TC_, D(TF_SE_E_W), TC_, P, TC_, TC_, st, D(TF_SE_E_B)));
     TRY(linear_dgrad(w.dg2, TC_, W(TF_SE_E_W), TC_, w.dx, TC_, P, TC_, TC_, w.g1, TC_, false, st));      // dx reused: d g1
-    TRY(linear_wgrad(w.dx, TC_, p.feat, TC_, D(TF_SE_R_W), TC_, P, TC_, TC_, st));
-    TRY(colsum(w.dx, TC_, P, TC_, D(TF_SE_R_B), st));
+    TRY(linear_wgrad(w.dx, TC_, p.feat, TC_, D(TF_SE_R_W), TC_, P, TC_, TC_, st, D(TF_SE_R_B)));
     TRY(linear_dgrad(w.dx, TC_, W(TF_SE_R_W), TC_, p.d_feat, TC_, P, TC_, TC_, nullptr, 0, true, st));
     return 0;
 }

@@ -1,10 +1,10 @@
-"""Training step of the decoder slice, timed (BASELINE configs[3] shape: MV2D-S, 300 queries, 6 layers, 2 samples per GPU):
-per step and rank  zero_grad -> for each local sample [forward with saved activations + targets / losses -> backward]
--> ONE NCCL sum all-reduce of the flat gradient buffer -> fused AdamW.  The front end (position embedding, RoIAlign,
-query generator, box correlation) runs once per sample outside the timed region: its backward is not built yet, so
-what is timed is the slice mv2d_decoder_train_* covers.
+"""Hot-path training step, timed (BASELINE configs[3] shape: MV2D-S, 300 queries, 6 layers, 2 samples per GPU):
+per step and rank  zero_grad -> for each local sample [forward with saved activations (position encoding, RoIAlign,
+query generator, decoder) + Hungarian targets / losses -> backward down to d feat] -> ONE NCCL sum all-reduce of the
+flat gradient buffer (all 14.0 M hot-path parameters) -> fused AdamW.  The torch backbone is outside (north star).
+--slice times the decoder slice alone (mv2d_decoder_train_*), its inputs prepared once outside the timed region.
 
-    python tools/train_bench.py [--per-view 50] [--samples 2] [--steps 10]
+    python tools/train_bench.py [--per-view 50] [--samples 2] [--steps 10] [--slice]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tools/train_bench.py
 """
 import argparse
@@ -19,7 +19,7 @@ sys.path.insert(0, ROOT)
 from mv2d_b200 import dist as D  # noqa: E402
 from mv2d_b200 import synth  # noqa: E402
 from mv2d_b200.engine import HotPath  # noqa: E402
-from mv2d_b200.train import DecoderTrainer  # noqa: E402
+from mv2d_b200.train import DecoderTrainer, HotPathTrainer  # noqa: E402
 
 
 def main():
@@ -28,22 +28,29 @@ def main():
     ap.add_argument('--samples', type=int, default=2, help='samples per rank and step')
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--slice', action='store_true', help='decoder slice only')
     a = ap.parse_args()
     rank, local_rank, world = D.env_rank()
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     D.init('nccl', dev)
     sd = synth.make_state_dict(0, num_layers=6)
-    eng = HotPath(sd, mode='S', device=dev)
-    tr = DecoderTrainer(sd, device=dev)
+    if a.slice:
+        eng = HotPath(sd, mode='S', device=dev)
+        tr = DecoderTrainer(sd, device=dev)
+    else:
+        tr = HotPathTrainer(sd, device=dev)
     samples = []
     for s in D.shard_samples(a.samples * world, rank, world):
         spec = dict(mode='S', seed=100 + s, num_views=6, boxes_per_view=a.per_view, num_layers=6)
         feat, boxes, metas = synth.case_inputs(spec)
-        o = eng.forward(feat.to(dev), boxes, metas)
         gt_boxes, gt_labels, _ = synth.make_dn_inputs(dict(num_gt=30, seed=200 + s))
-        samples.append(tuple(t.clone() for t in (o['ref'], o['tok_kin'], o['tok_feat'], o['match'], o['match_cnt'])) +
-                       (gt_boxes.to(dev), gt_labels.to(dev)))
+        if a.slice:
+            o = eng.forward(feat.to(dev), boxes, metas)
+            samples.append(tuple(t.clone() for t in (o['ref'], o['tok_kin'], o['tok_feat'], o['match'], o['match_cnt'])) +
+                           (gt_boxes.to(dev), gt_labels.to(dev)))
+        else:
+            samples.append((feat.to(dev), boxes, metas, gt_boxes.to(dev), gt_labels.to(dev)))
     torch.cuda.synchronize()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
     rows, losses = [], []
@@ -80,15 +87,17 @@ def main():
     total_ms = D.max_over_ranks([float(t[:, 0].sum())], device=dev)[0]
     med = t.median(0).values.tolist()
     if rank == 0:
-        line = dict(metric='samples/sec (MV2D-S decoder-slice training step: fwd + targets/losses + bwd + grad all-reduce + AdamW)',
+        what = 'decoder-slice' if a.slice else 'hot-path'
+        line = dict(metric=f'samples/sec (MV2D-S {what} training step: fwd + targets/losses + bwd + grad all-reduce + AdamW)',
                     value=world * a.samples * a.steps / (total_ms * 1e-3), unit='samples/s', n_gpus=world, steps=a.steps,
-                    warmup=a.warmup, samples_per_gpu=a.samples, N=int(samples[0][0].shape[0]), L=6,
+                    warmup=a.warmup, samples_per_gpu=a.samples, N=6 * a.per_view, L=6,
                     step_ms=med[0], fwd_ms=med[1], bwd_ms=med[2], allreduce_ms=med[3], adamw_ms=med[4],
                     grad_bytes=tr.total * 4, loss_first=losses[0], loss_last=losses[-1],
-                    scope='decoder slice only (rows a12-a18 + f3); front-end backward not built yet')
+                    scope='decoder slice only (rows a12-a18 + f3)' if a.slice else
+                    'rows a1-a18 + f3: every hot-path parameter and d feat; the torch backbone is outside')
         print(json.dumps(line))
         os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
-        with open(os.path.join(ROOT, 'gpurun_out', f'train_bench_{world}gpu.json'), 'w') as f:
+        with open(os.path.join(ROOT, 'gpurun_out', f'train_bench_{"slice_" if a.slice else ""}{world}gpu.json'), 'w') as f:
             f.write(json.dumps(line) + '\n')
 
 
