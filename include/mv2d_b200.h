@@ -375,6 +375,12 @@ MV2D_API int mv2d_fpn_neck(const Mv2dNeckParams* p, void* stream);
 #define MV2D_TRAIN_GLOBAL_TENSORS 6
 #define MV2D_TRAIN_LAYER_TENSORS 34
 MV2D_API long long mv2d_train_param_total(int L);                      /* floats in the flat buffer */
+/* Arithmetic of the training step's GPU-filling contractions (M >= 1024 rows: K/V projections, the 3x3 conv, the
+ * position-encoding MLPs): 1 (default; env MV2D_TRAIN_TC=0 turns it off) = error-compensated 3xTF32 on the tcgen05
+ * tensor cores, forward and backward; 0 = fp32 FFMA everywhere.  Both are fp32-grade, but 3xTF32 is ~16x coarser
+ * (2^-20 vs 2^-24 of sum |a||b|), so a ReLU whose input sits within ~1e-5 of zero can land on the other side than in
+ * the reference: the gradient is then exact for a forward that differs by that rounding.  Returns the previous mode. */
+MV2D_API int mv2d_train_set_tensor_cores(int on);
 MV2D_API int mv2d_train_param_info(int L, int tensor_id, long long* offset, long long* numel);
 
 typedef struct Mv2dTrainParams {

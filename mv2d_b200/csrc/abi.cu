@@ -143,6 +143,7 @@ int mv2d_fpn_neck(const Mv2dNeckParams* p, void* stream) {
 }
 
 long long mv2d_train_param_total(int L) { return train_param_total(L); }
+int mv2d_train_set_tensor_cores(int on) { return train_set_tensor_cores(on); }
 int mv2d_train_param_info(int L, int tensor_id, long long* offset, long long* numel) {
     return train_param_info(L, tensor_id, offset, numel);
 }

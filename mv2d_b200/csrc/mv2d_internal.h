@@ -45,6 +45,7 @@ size_t front_train_workspace_bytes(int N, int V, int h, int w);
 int run_front_train_forward(const Mv2dFrontTrainParams& p, cudaStream_t st);
 int run_front_train_backward(const Mv2dFrontTrainParams& p, cudaStream_t st);
 long long train_param_total(int L);
+int train_set_tensor_cores(int on);
 int train_param_info(int L, int tensor_id, long long* offset, long long* numel);
 size_t train_workspace_bytes(int N, int L, int max_match, int G);
 long long train_debug_offset(int N, int L, int max_match, int G, int layer, int which);

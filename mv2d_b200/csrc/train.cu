@@ -23,11 +23,19 @@
 #include <algorithm>
 #include <cstdlib>
 #include "common.cuh"
+#include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
 #include "mv2d_internal.h"
 
 namespace mv2d {
 
 namespace {
+
+#define TRY(expr)                \
+    do {                         \
+        int rc__ = (expr);       \
+        if (rc__ != 0) return rc__; \
+    } while (0)
 
 constexpr int TC_ = MV2D_C;        // 256
 constexpr int TH = MV2D_HEADS;     // 8
@@ -221,9 +229,136 @@ int launch_sgemm(const Sg& g, int splits, cudaStream_t st) {
     return t == 128 ? launch_sgemm_t<8>(g, grid, st) : launch_sgemm_t<4>(g, grid, st);
 }
 
+
+// ------------------------------------------------------------------------------------------------ tensor-core route
+// The GPU-filling contractions of the step (K/V projections over all RoI tokens, the 3x3 conv as an im2col GEMM, the
+// position-encoding MLPs: M = 14 700 .. 16 896 rows) run on the tcgen05 kernel of gemm_tc.cu as error-compensated
+// 3xTF32 (fp32-grade, operands split inside the kernel).  That kernel computes C = A W^T with both operands
+// K-contiguous, so the backward forms get their operands re-laid-out first:
+//   dX = dY W        -> W^T is materialised (weights are small), the ReLU mask / accumulation is a second pass;
+//   dW = dY^T X      -> dY^T and X^T are materialised with the row count zero-padded to a multiple of 32 (the GEMM's
+//                       K), the reduction is split over CTAs (raw partial sums) and one kernel folds the partials into
+//                       the flat gradient buffer and the bias gradient.
+// MV2D_TRAIN_TC=0 keeps everything on the FFMA kernel below (the tests run both).
+struct TcScratch {
+    float *at, *bt, *wt, *part, *tmp;
+    size_t at_cap, bt_cap, wt_cap, part_cap, tmp_cap;   // floats
+};
+int g_tc_mode = -1;      // -1 = not set yet: MV2D_TRAIN_TC from the environment (default on); mv2d_train_set_tensor_cores overrides
+bool tc_enabled() {
+    if (g_tc_mode < 0) { const char* e = getenv("MV2D_TRAIN_TC"); g_tc_mode = (e && e[0] == '0') ? 0 : 1; }
+    return g_tc_mode == 1;
+}
+inline bool al16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+inline int round32(int x) { return (x + 31) / 32 * 32; }
+
+int tc_gemm(const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc, int M, int N, int K, bool relu,
+            int nsplit, long long split_stride, cudaStream_t st) {
+    TcGemm t{};
+    t.A = A; t.A_lo = nullptr; t.lda = lda; t.W = W; t.W_lo = nullptr; t.ldw = ldw; t.bias = bias; t.C = C; t.ldc = ldc;
+    t.M = M; t.N = N; t.K = K; t.passes = 3; t.im2col = 0; t.flags = relu ? GEMM_RELU : 0; t.nsplit = nsplit; t.split_stride = split_stride;
+    return launch_gemm_tc(t, st);
+}
+// shape rule of launch_gemm_tc: N tiles are 64 wide for M <= 512, 128 wide otherwise
+inline bool tc_shape_ok(int M, int N, int K) { return K % 32 == 0 && N % (M <= 512 ? 64 : 128) == 0; }
+
+// out[C, Rp] = in[R, C]^T, columns r >= R zero-filled
+__global__ void __launch_bounds__(256) transpose_pad_kernel(const float* __restrict__ in, int ld, int R, int C, float* __restrict__ out, int Rp) {
+    pdl_wait();
+    pdl_trigger();
+    __shared__ float tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = r0 + ty + i * 8, c = c0 + tx;
+        tile[ty + i * 8][tx] = (r < R && c < C) ? in[(long long)r * ld + c] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int c = c0 + ty + i * 8, r = r0 + tx;
+        if (c < C && r < Rp) out[(long long)c * Rp + r] = tile[tx][ty + i * 8];
+    }
+}
+int transpose_pad(const float* in, int ld, int R, int C, float* out, int Rp, cudaStream_t st) {
+    launch_k(transpose_pad_kernel, dim3(cdiv(Rp, 32), cdiv(C, 32)), dim3(256), 0, st, in, ld, R, C, out, Rp);
+    MV2D_CHECK_LAUNCH("train transpose");
+    return 0;
+}
+
+// dW[n,k] += sum_z part[z][...]; part is [rows, cols] = [Nout, K], or [K, Nout] when `swapped`
+__global__ void __launch_bounds__(256) wgrad_fold_kernel(const float* __restrict__ part, int nsplit, long long stride, int Nout, int K,
+                                                         int swapped, float* __restrict__ dW, int ldw) {
+    pdl_wait();
+    pdl_trigger();
+    const long long total = (long long)Nout * K;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+        // walk the partial in ITS row-major order (coalesced reads), scatter into dW
+        int n, k;
+        if (swapped) { k = (int)(i / Nout); n = (int)(i % Nout); } else { n = (int)(i / K); k = (int)(i % K); }
+        float a = 0.f;
+        for (int z = 0; z < nsplit; ++z) a += part[z * stride + i];
+        dW[(long long)n * ldw + k] += a;
+    }
+}
+// db[n] += sum_r yt[n][r]  (rows of the transposed, zero-padded output gradient); one CTA per row
+__global__ void __launch_bounds__(256) rowsum_kernel(const float* __restrict__ yt, int Rp, int Nout, float* __restrict__ db) {
+    pdl_wait();
+    pdl_trigger();
+    __shared__ float red[8];
+    const int n = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float a = 0.f;
+    for (int r = threadIdx.x; r < Rp; r += 256) a += yt[(long long)n * Rp + r];
+    a = warp_sum(a);
+    if (lane == 0) red[warp] = a;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += red[i];
+        db[n] += t;
+    }
+}
+// dX = (accumulate ? dX : 0) + src . [mask > 0 (and < 5e3)]   (rows of K floats; ld per operand)
+__global__ void __launch_bounds__(256) dgrad_finish_kernel(const float* __restrict__ src, int lds, const float* __restrict__ mask, int ldmask,
+                                                           int lt5e3, int accumulate, float* __restrict__ dX, int ldx, int M, int K) {
+    pdl_wait();
+    pdl_trigger();
+    const long long total = (long long)M * K;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+        const long long m = i / K;
+        const int k = (int)(i % K);
+        float v = src[m * lds + k];
+        if (mask) {
+            const float a = mask[m * ldmask + k];
+            if (!(a > 0.f) || (lt5e3 && !(a < 5e3f))) v = 0.f;
+        }
+        float* d = dX + m * ldx + k;
+        *d = accumulate ? *d + v : v;
+    }
+}
+inline int ew_grid_n(long long n) {
+    const long long want = (n + 255) / 256;
+    return (int)(want < 148 * 16 ? (want > 0 ? want : 1) : 148 * 16);
+}
+
+// the scratch of the current call (set by the run_* entry points; the library is single-threaded per call)
+thread_local TcScratch g_tc{};
+
 // Y[M,Nout] = act(X[M,K] W[Nout,K]^T + b)
 int linear_fwd(const float* X, int ldx, const float* W, int ldw, const float* b, float* Y, int ldy, int M, int Nout, int K,
                bool relu, cudaStream_t st, int extra_flags = 0) {
+    const bool lds_ok = (ldx & 3) == 0 && (ldw & 3) == 0 && (ldy & 3) == 0 && al16(X) && al16(W) && al16(Y);
+    if (tc_enabled() && lds_ok && extra_flags == 0 && M >= 1024 && tc_shape_ok(M, Nout, K))
+        return tc_gemm(X, ldx, W, ldw, b, Y, ldy, M, Nout, K, relu, 1, 0, st);
+    if (tc_enabled() && lds_ok && M <= 512 && K % 32 == 0 && (Nout & 3) == 0 && (extra_flags & ~SG_CLAMP5E3) == 0) {
+        // the inference path's small-M kernel (in-CTA split-K): fp32 FFMA, same arithmetic class as the kernel below
+        GemmArgs a{};
+        a.A = X; a.lda = ldx; a.W = W; a.ldw = ldw; a.C = Y; a.ldc = ldy; a.bias = b; a.M = M; a.N = Nout; a.K = K;
+        a.batch = 1; a.nsplit = 1; a.flags = (relu ? GEMM_RELU : 0) | ((extra_flags & SG_CLAMP5E3) ? GEMM_CLAMP5E3 : 0);
+        return launch_gemm_small(a, nullptr, 0, st);
+    }
     Sg g{};
     g.A = X; g.sam = ldx; g.sak = 1; g.B = W; g.sbk = 1; g.sbn = ldw; g.C = Y; g.ldc = ldy; g.bias = b;
     g.M = M; g.N = Nout; g.K = K; g.klen = K; g.flags = (relu ? SG_RELU : 0) | extra_flags;
@@ -232,6 +367,37 @@ int linear_fwd(const float* X, int ldx, const float* W, int ldw, const float* b,
 // dX[M,K] (+)= (dY[M,Nout] W[Nout,K]) . [mask > 0]
 int linear_dgrad(const float* dY, int ldy, const float* W, int ldw, float* dX, int ldx, int M, int Nout, int K,
                  const float* mask, int ldmask, bool accumulate, cudaStream_t st, int extra_flags = 0) {
+    const TcScratch& sc = g_tc;
+    if (tc_enabled() && sc.wt && M >= 1024 && tc_shape_ok(M, K, Nout) && (ldy & 3) == 0 && (ldx & 3) == 0 && al16(dY) && al16(dX) &&
+        (size_t)K * Nout <= sc.wt_cap && (!accumulate || (size_t)M * K <= sc.tmp_cap)) {
+        TRY(transpose_pad(W, ldw, Nout, K, sc.wt, Nout, st));                       // W^T [K, Nout]
+        float* target = accumulate ? sc.tmp : dX;
+        const int ldt = accumulate ? K : ldx;
+        TRY(tc_gemm(dY, ldy, sc.wt, Nout, nullptr, target, ldt, M, K, Nout, false, 1, 0, st));
+        if (accumulate || mask) {
+            launch_k(dgrad_finish_kernel, dim3(ew_grid_n((long long)M * K)), dim3(256), 0, st, (const float*)target, ldt, mask, ldmask,
+                     (extra_flags & SG_MASK_LT5E3) ? 1 : 0, accumulate ? 1 : 0, dX, ldx, M, K);
+            MV2D_CHECK_LAUNCH("train dgrad_finish");
+        }
+        return 0;
+    }
+    if (tc_enabled() && sc.wt && M <= 512 && Nout % 32 == 0 && (K & 3) == 0 && (ldy & 3) == 0 && (ldx & 3) == 0 && al16(dY) && al16(dX) &&
+        (size_t)K * Nout <= sc.wt_cap && (!accumulate || (size_t)M * K <= sc.tmp_cap)) {
+        // M ~ 300 rows: W^T once, then the inference path's small-M kernel (in-CTA split-K) -- a chain of k-steps on
+        // the 20 CTAs the strided FFMA kernel would get for these shapes is latency bound
+        TRY(transpose_pad(W, ldw, Nout, K, sc.wt, Nout, st));
+        float* target = accumulate ? sc.tmp : dX;
+        const int ldt = accumulate ? K : ldx;
+        GemmArgs a{};
+        a.A = dY; a.lda = ldy; a.W = sc.wt; a.ldw = Nout; a.C = target; a.ldc = ldt; a.M = M; a.N = K; a.K = Nout; a.batch = 1; a.nsplit = 1;
+        TRY(launch_gemm_small(a, nullptr, 0, st));
+        if (accumulate || mask) {
+            launch_k(dgrad_finish_kernel, dim3(ew_grid_n((long long)M * K)), dim3(256), 0, st, (const float*)target, ldt, mask, ldmask,
+                     (extra_flags & SG_MASK_LT5E3) ? 1 : 0, accumulate ? 1 : 0, dX, ldx, M, K);
+            MV2D_CHECK_LAUNCH("train dgrad_finish");
+        }
+        return 0;
+    }
     Sg g{};
     g.A = dY; g.sam = ldy; g.sak = 1; g.B = W; g.sbk = ldw; g.sbn = 1; g.C = dX; g.ldc = ldx; g.mask = mask; g.ldmask = ldmask;
     g.M = M; g.N = K; g.K = Nout; g.klen = Nout; g.flags = (accumulate ? SG_ACC : 0) | extra_flags;
@@ -240,6 +406,33 @@ int linear_dgrad(const float* dY, int ldy, const float* W, int ldw, float* dX, i
 // dW[Nout,K] += dY[M,Nout]^T X[M,K]   (split over the M rows, atomic accumulation);  db[Nout] += sum_rows dY (nullable)
 int linear_wgrad(const float* dY, int ldy, const float* X, int ldx, float* dW, int ldw, int M, int Nout, int K, cudaStream_t st,
                  float* db = nullptr) {
+    const TcScratch& sc = g_tc;
+    if (tc_enabled() && sc.at && M >= 1024) {
+        const int Mp = round32(M);
+        const bool direct = tc_shape_ok(Nout, K, Mp), swapped = !direct && tc_shape_ok(K, Nout, Mp);
+        const int gm = direct ? Nout : K, gn = direct ? K : Nout;           // the GEMM's M and N
+        const int tiles = cdiv(gm, 128) * (gn / (gm <= 512 ? 64 : 128));
+        const int nkb = Mp / 32;
+        int nsplit = 1;
+        for (int d = 1; d <= 48 && d <= nkb; ++d)
+            if (nkb % d == 0 && nkb / d >= 4) { nsplit = d; if (tiles * d >= 148) break; }
+        if ((direct || swapped) && (size_t)Nout * Mp <= sc.at_cap && (size_t)K * Mp <= sc.bt_cap &&
+            (size_t)nsplit * Nout * K <= sc.part_cap) {
+            TRY(transpose_pad(dY, ldy, M, Nout, sc.at, Mp, st));                     // dY^T [Nout, Mp]
+            TRY(transpose_pad(X, ldx, M, K, sc.bt, Mp, st));                         // X^T  [K, Mp]
+            const float* ga = direct ? sc.at : sc.bt;
+            const float* gw = direct ? sc.bt : sc.at;
+            TRY(tc_gemm(ga, Mp, gw, Mp, nullptr, sc.part, gn, gm, gn, Mp, false, nsplit, (long long)Nout * K, st));
+            launch_k(wgrad_fold_kernel, dim3(ew_grid_n((long long)Nout * K)), dim3(256), 0, st, (const float*)sc.part, nsplit,
+                     (long long)Nout * K, Nout, K, swapped ? 1 : 0, dW, ldw);
+            MV2D_CHECK_LAUNCH("train wgrad_fold");
+            if (db) {
+                launch_k(rowsum_kernel, dim3(Nout), dim3(256), 0, st, (const float*)sc.at, Mp, Nout, db);
+                MV2D_CHECK_LAUNCH("train rowsum");
+            }
+            return 0;
+        }
+    }
     Sg g{};
     g.A = dY; g.sam = 1; g.sak = ldy; g.B = X; g.sbk = ldx; g.sbn = 1; g.C = dW; g.ldc = ldw; g.rowsum = db;
     g.M = Nout; g.N = K; g.K = M; g.flags = SG_ATOMIC;
@@ -877,6 +1070,7 @@ struct TrainWs {
     int *inv_cnt, *inv_list;
     float* loss_ws;
     size_t loss_ws_bytes;
+    TcScratch tc;
     size_t total_bytes;
 };
 
@@ -911,6 +1105,13 @@ TrainWs train_layout(float* base, int N, int L, int max_match, int G) {
     w.inv_list = reinterpret_cast<int*>(take(n * n));
     w.loss_ws_bytes = loss_workspace_bytes(N, G, L);
     w.loss_ws = take(w.loss_ws_bytes / 4 + 1);
+    {   // tensor-core route: transposed operands of the K/V weight gradients, W^T, split-K partials, accumulate temp
+        const size_t Mp = (size_t)round32((int)(n * TTOK));
+        w.tc.at_cap = TC_ * Mp; w.tc.bt_cap = TC_ * Mp; w.tc.wt_cap = (size_t)TFF * TC_; w.tc.part_cap = (size_t)48 * TC_ * TC_;
+        w.tc.tmp_cap = NK;
+        w.tc.at = take(w.tc.at_cap); w.tc.bt = take(w.tc.bt_cap); w.tc.wt = take(w.tc.wt_cap); w.tc.part = take(w.tc.part_cap);
+        w.tc.tmp = take(w.tc.tmp_cap);
+    }
     w.total_bytes = off * sizeof(float);
     return w;
 }
@@ -924,11 +1125,6 @@ LayerPtr layer_ptrs(float* flat, int l) {
     return p;
 }
 
-#define TRY(expr)                \
-    do {                         \
-        int rc__ = (expr);       \
-        if (rc__ != 0) return rc__; \
-    } while (0)
 
 int check_params(const Mv2dTrainParams& p) {
     MV2D_CHECK_ARG(p.N >= 1 && p.L >= 1 && p.L <= MV2D_MAX_LAYERS && p.max_match >= 1 && p.G >= 0, "train: bad N=%d L=%d max_match=%d G=%d",
@@ -1203,6 +1399,7 @@ struct FrontWs {
     float *tok_pe, *col, *y, *pool, *cat, *e0, *e2, *c, *m_roi;
     // backward scratch
     float *dc, *de2, *de0, *df1, *dpool, *dy, *dcol, *dtok, *dpe_map, *dx, *dg2, *dh;
+    TcScratch tc;
     size_t total_bytes;
 };
 FrontWs front_layout(float* base, int N, int P) {
@@ -1221,6 +1418,13 @@ FrontWs front_layout(float* base, int N, int P) {
     w.dc = take(n * 4); w.de2 = take(n * TC_); w.de0 = take(n * 512); w.df1 = take(n * 1024); w.dpool = take(n * TC_);
     w.dy = take(NK); w.dcol = take(NK * 9); w.dtok = take(NK); w.dpe_map = take(p * TC_); w.dx = take(p * TC_);
     w.dg2 = take(p * TC_); w.dh = take(p * 1024);
+    {   // tensor-core route (widest operands: the im2col matrix [*, 2304] and the 1024-wide MLP hidden layers)
+        const size_t rows = p > n * TTOK ? p : n * TTOK, Mp = (size_t)round32((int)rows);
+        w.tc.at_cap = 1024 * Mp; w.tc.bt_cap = 2304 * Mp; w.tc.wt_cap = (size_t)2304 * 256; w.tc.part_cap = (size_t)48 * 2304 * 256;
+        w.tc.tmp_cap = rows * TC_;
+        w.tc.at = take(w.tc.at_cap); w.tc.bt = take(w.tc.bt_cap); w.tc.wt = take(w.tc.wt_cap); w.tc.part = take(w.tc.part_cap);
+        w.tc.tmp = take(w.tc.tmp_cap);
+    }
     w.total_bytes = off * sizeof(float);
     return w;
 }
@@ -1243,6 +1447,12 @@ int check_front(const Mv2dFrontTrainParams& p) {
 }  // namespace
 
 // ================================================================================================ host entry points
+int train_set_tensor_cores(int on) {
+    const int prev = tc_enabled() ? 1 : 0;
+    g_tc_mode = on ? 1 : 0;
+    return prev;
+}
+
 long long train_param_total(int L) { return global_block_floats() + (long long)L * layer_block_floats() + front_block_floats(); }
 
 int train_param_info(int L, int tensor_id, long long* offset, long long* numel) {
@@ -1293,6 +1503,7 @@ int run_train_forward(const Mv2dTrainParams& p, cudaStream_t st) {
     TRY(check_params(p));
     const int N = p.N, L = p.L, NK = N * TTOK;
     const TrainWs w = train_layout(p.workspace, N, L, p.max_match, p.G);
+    g_tc = w.tc;
     float* P = const_cast<float*>(p.params);
     Range6 pc;
     for (int i = 0; i < 6; ++i) pc.v[i] = p.pc_range[i];
@@ -1365,6 +1576,7 @@ int run_train_backward(const Mv2dTrainParams& p, cudaStream_t st) {
     const int N = p.N, L = p.L, NK = N * TTOK;
     const long long NC = (long long)N * TC_;
     const TrainWs w = train_layout(p.workspace, N, L, p.max_match, p.G);
+    g_tc = w.tc;
     float* P = const_cast<float*>(p.params);
     float* G = p.grads;
     Range6 pc;
@@ -1478,6 +1690,7 @@ int run_front_train_forward(const Mv2dFrontTrainParams& p, cudaStream_t st) {
     TRY(check_front(p));
     const int N = p.N, P = p.V * p.h * p.w, NK = N * TTOK;
     const FrontWs w = front_layout(p.workspace, N, P);
+    g_tc = w.tc;
     float* Wt = const_cast<float*>(p.params);
     auto W = [&](int t) { return Wt + front_off(p.L, t); };
     Range6 pc;
@@ -1528,6 +1741,7 @@ int run_front_train_backward(const Mv2dFrontTrainParams& p, cudaStream_t st) {
     const int N = p.N, P = p.V * p.h * p.w, NK = N * TTOK;
     const long long PC = (long long)P * TC_;
     const FrontWs w = front_layout(p.workspace, N, P);
+    g_tc = w.tc;
     float* Wt = const_cast<float*>(p.params);
     auto W = [&](int t) { return Wt + front_off(p.L, t); };
     auto D = [&](int t) { return p.grads + front_off(p.L, t); };

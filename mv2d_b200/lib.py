@@ -211,6 +211,7 @@ SYMBOLS = [
     ('mv2d_fpn_neck', C.c_int, [C.POINTER(NeckParams), c_f]),
     ('mv2d_xa_tile_prepare', C.c_int, [C.POINTER(DecoderParams), c_f]),
     ('mv2d_train_param_total', C.c_longlong, [C.c_int]),
+    ('mv2d_train_set_tensor_cores', C.c_int, [C.c_int]),
     ('mv2d_train_param_info', C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
     ('mv2d_decoder_train_workspace_bytes', C.c_size_t, [C.c_int] * 4),
     ('mv2d_decoder_train_forward', C.c_int, [C.POINTER(TrainParams), c_f]),

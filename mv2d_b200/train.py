@@ -58,6 +58,12 @@ LOSS_DEFAULTS = dict(   # configs/mv2d/exp/mv2d_r50_frcnn_single_frame_roi_1408x
 PC_RANGE = [-51.2, -51.2, -5.0, 51.2, 51.2, 3.0]
 
 
+def set_tensor_cores(on):
+    """1 (default) = the GPU-filling contractions of the training step run as 3xTF32 on the tcgen05 tensor cores,
+    0 = fp32 FFMA everywhere (``mv2d_train_set_tensor_cores``).  Returns the previous mode."""
+    return int(lib.load().mv2d_train_set_tensor_cores(int(bool(on))))
+
+
 def param_table(num_layers):
     """state_dict name (relative to ``roi_head.``) -> (offset, numel) in the flat buffers, from the library itself."""
     h = lib.load()

@@ -14,6 +14,18 @@ from test_grad_oracle_golden import CASES, load, oracle_grads, sub
 
 pytestmark = pytest.mark.gpu
 TOL = 2e-3       # of the tensor's largest gradient entry (fp32 sums in a different order; atomics in the weight gradients)
+# Tensor-core mode (3xTF32, 2^-20 of sum |a||b| instead of 2^-24): a ReLU input within ~1e-5 of zero can fall on the
+# other side than in the reference, which moves one row of a weight gradient by a visible amount while everything
+# else stays at 1e-5.  So that mode is judged by the relative L2 error of each tensor plus a loose per-entry bound.
+TOL_TC_L2, TOL_TC_MAX = 5e-3, 5e-2
+
+
+@pytest.fixture(params=[0, 1], ids=['ffma', 'tensor-cores'])
+def tc_mode(request):
+    from mv2d_b200.train import set_tensor_cores
+    prev = set_tensor_cores(request.param)
+    yield request.param
+    set_tensor_cores(prev)
 
 
 def tokens(t):          # [N,256,7,7] -> [N,49,256]
@@ -31,10 +43,10 @@ def match_lists(corr, mask):
 
 
 class Report:
-    def __init__(self, name):
-        self.rows, self.bad, self.name = [], [], name
+    def __init__(self, name, tc=0):
+        self.rows, self.bad, self.name, self.tc = [], [], name, tc
 
-    def check(self, what, got, want, tol=TOL, floor=1e-5):
+    def check(self, what, got, want, tol=TOL, floor=1e-5, grad=False):
         got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
         if got.shape != want.shape:
             self.rows.append(f'{what}: SHAPE {got.shape} vs {want.shape}')
@@ -42,15 +54,19 @@ class Report:
             return
         scale = max(float(np.abs(want).max()) if want.size else 0.0, floor)
         err = float(np.abs(got - want).max()) / scale if want.size else 0.0
-        ok = np.isfinite(got).all() and err < tol
-        self.rows.append(f'{"ok  " if ok else "FAIL"} {what}: err {err:.3e} of max |ref| {scale:.3e}')
+        l2 = float(np.linalg.norm(got - want)) / max(float(np.linalg.norm(want)), floor * max(want.size, 1) ** 0.5) if want.size else 0.0
+        if grad and self.tc:
+            ok = np.isfinite(got).all() and l2 < TOL_TC_L2 and err < TOL_TC_MAX
+        else:
+            ok = np.isfinite(got).all() and err < tol
+        self.rows.append(f'{"ok  " if ok else "FAIL"} {what}: err {err:.3e} of max |ref| {scale:.3e}, rel L2 {l2:.3e}')
         if not ok:
             self.bad.append(what)
 
     def finish(self):
         out = os.path.join(ROOT, 'gpurun_out')
         os.makedirs(out, exist_ok=True)
-        with open(os.path.join(out, f'train_report_{self.name}.txt'), 'w') as f:
+        with open(os.path.join(out, f'train_report_{self.name}_{"tc" if self.tc else "ffma"}.txt'), 'w') as f:
             f.write('\n'.join(self.rows) + '\n')
         assert not self.bad, f'{len(self.bad)} tensors off: {self.bad[:12]}'
 
@@ -73,9 +89,9 @@ def run_case(name):
 
 
 @pytest.mark.parametrize('name', CASES)
-def test_training_step_matches_autograd_oracle_and_reference_golden(name):
+def test_training_step_matches_autograd_oracle_and_reference_golden(name, tc_mode):
     g, spec, r, tr, out, gin, match = run_case(name)
-    rep = Report(name)
+    rep = Report(name, tc_mode)
     L, N = spec['num_layers'], match.shape[0]
     M = match.shape[1]
     # ---- forward: saved activations, predictions, assignment, losses
@@ -99,13 +115,13 @@ def test_training_step_matches_autograd_oracle_and_reference_golden(name):
     rep.check('loss total', [float(out['loss'])], [float(g['loss'])], 2e-5)
     # ---- backward: slice inputs
     d_kin, d_mem = gin['d_tok_kin'].cpu(), gin['d_tok_mem'].cpu()
-    rep.check('d_ref', gin['d_ref'].cpu(), r['ref'].grad)
-    rep.check('d_ref vs reference', gin['d_ref'].cpu(), g['d_ref'])
-    rep.check('d_tok_kin (= d roi_pe)', d_kin, tokens(r['roi_pe'].grad))
-    rep.check('d_tok_kin + d_tok_mem (= d roi_feat)', d_kin + d_mem, tokens(r['roi_feat'].grad))
+    rep.check('d_ref', gin['d_ref'].cpu(), r['ref'].grad, grad=True)
+    rep.check('d_ref vs reference', gin['d_ref'].cpu(), g['d_ref'], grad=True)
+    rep.check('d_tok_kin (= d roi_pe)', d_kin, tokens(r['roi_pe'].grad), grad=True)
+    rep.check('d_tok_kin + d_tok_mem (= d roi_feat)', d_kin + d_mem, tokens(r['roi_feat'].grad), grad=True)
     back = lambda t: t.view(N, 7, 7, 256).permute(0, 3, 1, 2).contiguous()        # noqa: E731
-    rep.check('d roi_pe vs reference', sub(back(d_kin), g), g['d_roi_pos_sub'])
-    rep.check('d roi_feat vs reference', sub(back(d_kin + d_mem), g), g['d_roi_feat_sub'])
+    rep.check('d roi_pe vs reference', sub(back(d_kin), g), g['d_roi_pos_sub'], grad=True)
+    rep.check('d roi_feat vs reference', sub(back(d_kin + d_mem), g), g['d_roi_feat_sub'], grad=True)
     # ---- backward: every parameter of the slice, full tensors vs autograd and the reference's subsample
     for k in tr.table:
         if not k.startswith('bbox_head.'):
@@ -113,13 +129,13 @@ def test_training_step_matches_autograd_oracle_and_reference_golden(name):
         want = r['sd'][k].grad
         want = want if want is not None else torch.zeros_like(r['sd'][k])
         got = tr.grad(k).cpu()
-        rep.check(f'd {k}', got, want)
-        rep.check(f'd {k} vs reference', sub(got, g), g['dparam.' + k])
+        rep.check(f'd {k}', got, want, grad=True)
+        rep.check(f'd {k} vs reference', sub(got, g), g['dparam.' + k], grad=True)
     rep.finish()
 
 
 @pytest.mark.parametrize('name', CASES)
-def test_full_hot_path_training_step_matches_reference_golden(name):
+def test_full_hot_path_training_step_matches_reference_golden(name, tc_mode):
     """Position encoding -> RoIAlign -> query generator -> decoder -> losses and all the way back: every one of the
     96 hot-path parameter gradients and d loss / d feat against the reference's own autograd (golden subsamples)."""
     from mv2d_b200.train import HotPathTrainer
@@ -132,7 +148,7 @@ def test_full_hot_path_training_step_matches_reference_golden(name):
     out = tr.forward(feat, boxes, metas, gt_boxes, gt_labels)
     gin = tr.backward()
     torch.cuda.synchronize()
-    rep = Report('full_' + name)
+    rep = Report('full_' + name, tc_mode)
     # forward of the front end against the oracle's stages
     from test_grad_oracle_golden import slice_inputs
     _, _, st = slice_inputs(spec)
@@ -143,11 +159,11 @@ def test_full_hot_path_training_step_matches_reference_golden(name):
     rep.check('fwd bbox_preds vs reference', out['bbox_preds'].cpu(), g['bbox_preds'], 1e-4)
     rep.check('loss_cls', out['loss_cls'].cpu(), g['loss_cls'], 5e-5)
     rep.check('loss_bbox', out['loss_bbox'].cpu(), g['loss_bbox'], 5e-5)
-    rep.check('d_ref vs reference', gin['d_ref'].cpu(), g['d_ref'])
-    rep.check('d_feat vs reference', sub(gin['d_feat'].cpu().contiguous(), g), g['d_feat_sub'])
+    rep.check('d_ref vs reference', gin['d_ref'].cpu(), g['d_ref'], grad=True)
+    rep.check('d_feat vs reference', sub(gin['d_feat'].cpu().contiguous(), g), g['d_feat_sub'], grad=True)
     n = 0
     for k in tr.table:
-        rep.check(f'd {k} vs reference', sub(tr.grad(k).cpu().contiguous(), g), g['dparam.' + k])
+        rep.check(f'd {k} vs reference', sub(tr.grad(k).cpu().contiguous(), g), g['dparam.' + k], grad=True)
         n += 1
     assert n == 6 + 34 * spec['num_layers'] + 22
     rep.finish()
