@@ -798,6 +798,26 @@ def decoder_slice_loss(sd, ref, roi_feat, roi_pe, corr, mask, gt_boxes, gt_label
     return total, cls, box, per
 
 
+def hot_path_loss(sd, feat, proposal_list, img_metas, gt_boxes, gt_labels, cfg=None, stage_loss_weights=None, lc=LOSS_CFG):
+    """The whole MV2D-S hot path as a DIFFERENTIABLE function of the weights and of the feature map: what
+    MV2DSHead.forward_train computes (roi_heads/mv2d_s_head.py:236-307: position encoding, RoIAlign of cat(feat, pe),
+    query generator, bbox_head on the gathered RoI tokens, per-layer losses times stage_loss_weights).  The box
+    correlation and the per-RoI camera parameters are computed without gradient, as in the reference
+    (@torch.no_grad, box_correlation.py:164, mv2d_head.py:51).  Returns (total, cls, box, per-layer tuples)."""
+    cfg = cfg or make_cfg('S')
+    pe = pe_forward(sd, feat, img_metas, cfg)
+    with torch.no_grad():
+        proposal_list = guard_empty(proposal_list)
+        rois = bbox2roi(proposal_list)
+        K, E = get_box_params(proposal_list, img_metas, cfg['roi_size'])
+        ifeat = process_intrins_feat(rois, K, cfg['intrins_feat_scale'])
+        corr, mask = box_roi_correlation(rois, [len(p) for p in proposal_list], img_metas, cfg)
+    roi_feat = roi_align(feat, rois, cfg['roi_size'], 1.0 / cfg['stride'])
+    roi_pe = roi_align(pe, rois, cfg['roi_size'], 1.0 / cfg['stride'])
+    ref, _ = query_generator(sd, roi_feat, K, E, ifeat, cfg)
+    return decoder_slice_loss(sd, ref, roi_feat, roi_pe, corr, mask, gt_boxes, gt_labels, cfg, stage_loss_weights, lc)
+
+
 # ============================================================================= neck (SURVEY.md 8f rank 4)
 def fpn_neck(neck_sd, x):
     """The MV2D neck: mmdet 2.25.1 FPN with in_channels [256]*5, start_level = end_level = 2, num_outs = 1

@@ -169,6 +169,39 @@ def test_full_hot_path_training_step_matches_reference_golden(name, tc_mode):
     rep.finish()
 
 
+@pytest.mark.parametrize('case,num_gt', [('s_pad', 5), ('s_small', 0), ('s_empty', 4), ('s_cfg1', 12)])
+def test_training_edge_cases_match_full_chain_oracle(case, num_gt):
+    """Padded images (general sine branch, masked cells), no ground truth at all (every query is background), zero
+    detections (the reference's dummy box), BASELINE configs[0]'s 50 queries / 1 layer: every parameter gradient and
+    d loss / d feat, FULL tensors, against torch autograd through the restated hot path (fp32 FFMA mode)."""
+    from mv2d_b200.train import HotPathTrainer, set_tensor_cores
+    from test_grad_oracle_golden import full_oracle_grads
+    spec = dict(synth.CASES[case])
+    spec['num_layers'] = min(spec['num_layers'], 2)
+    gt_spec = dict(num_gt=num_gt, seed=75)
+    stage_w = [0.1] * spec['num_layers']
+    r = full_oracle_grads(spec, gt_spec, stage_w)
+    sd = synth.make_state_dict(0, num_layers=spec['num_layers'])
+    feat, boxes, metas = synth.case_inputs(spec)
+    prev = set_tensor_cores(0)
+    try:
+        tr = HotPathTrainer(sd, stage_loss_weights=stage_w)
+        out = tr.forward(feat, boxes, metas, *r['gt'])
+        gin = tr.backward()
+        torch.cuda.synchronize()
+    finally:
+        set_tensor_cores(prev)
+    rep = Report(f'edge_{case}_G{num_gt}')
+    rep.check('fwd cls_scores', out['cls_scores'].cpu(), r['cls'].detach(), 1e-4)
+    rep.check('fwd bbox_preds', out['bbox_preds'].cpu(), r['box'].detach(), 1e-4)
+    rep.check('loss total', [float(out['loss'])], [float(r['total'].detach())], 5e-5)
+    rep.check('d_feat', gin['d_feat'].cpu(), r['feat'].grad)
+    for k in tr.table:
+        want = r['sd'][k].grad
+        rep.check(f'd {k}', tr.grad(k).cpu(), want if want is not None else torch.zeros_like(r['sd'][k]))
+    rep.finish()
+
+
 def test_training_forward_matches_inference_path(state_dicts):
     """The training forward (plain in_proj / out_proj, saved activations) and the inference path (absorbed
     cross-attention, tcgen05 GEMMs) are two implementations of the same function: same inputs from the engine's

@@ -54,8 +54,8 @@ def test_gradient_oracle_matches_reference(name):
     r = oracle_grads(spec, gt_spec, list(g['stage_loss_weights']))
     assert np.array_equal(r['st']['corr'].numpy(), g['corr'])
     np.testing.assert_allclose(float(r['total'].detach()), float(g['loss']), rtol=2e-5)
-    np.testing.assert_allclose([float(p[0]) for p in r['per']], g['loss_cls'], rtol=2e-5)
-    np.testing.assert_allclose([float(p[1]) for p in r['per']], g['loss_bbox'], rtol=2e-5)
+    np.testing.assert_allclose([float(p[0].detach()) for p in r['per']], g['loss_cls'], rtol=2e-5)
+    np.testing.assert_allclose([float(p[1].detach()) for p in r['per']], g['loss_bbox'], rtol=2e-5)
 
     def close(a, b, what):
         # relative to the tensor's largest entry, with an absolute floor: layer 0's self-attention in_proj weight has
@@ -73,3 +73,37 @@ def test_gradient_oracle_matches_reference(name):
             close(sub(grad, g), g['dparam.' + k], k)
             n += 1
     assert n >= 6 + 34 * spec['num_layers']
+
+
+def full_oracle_grads(spec, gt_spec, stage_w, sd=None):
+    """Autograd through the whole restated hot path: gradients of all weights and of the feature map."""
+    sd = sd or synth.make_state_dict(0, num_layers=spec['num_layers'])
+    sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and k != 'bbox_head.code_weights' else v) for k, v in sd.items()}
+    feat, boxes, metas = synth.case_inputs(spec)
+    feat = feat.clone().requires_grad_(True)
+    gt_boxes, gt_labels, _ = synth.make_dn_inputs(gt_spec) if gt_spec['num_gt'] > 0 else (torch.zeros(0, 9), torch.zeros(0, dtype=torch.long), None)
+    cfg = O.make_cfg('S', num_layers=spec['num_layers'])
+    total, cls, box, per = O.hot_path_loss(sd, feat, boxes, metas, gt_boxes, gt_labels, cfg, stage_loss_weights=stage_w)
+    total.backward()
+    return dict(sd=sd, feat=feat, total=total, cls=cls, box=box, per=per, gt=(gt_boxes, gt_labels), inputs=(boxes, metas))
+
+
+@pytest.mark.parametrize('name', ['grad_s_small', 'grad_s_one'])
+def test_full_chain_gradient_oracle_matches_reference(name):
+    """All 96 hot-path parameter gradients and d loss / d feat of the restated full path vs the reference's autograd."""
+    g, spec, gt_spec = load(name)
+    r = full_oracle_grads(spec, gt_spec, list(g['stage_loss_weights']))
+    np.testing.assert_allclose(float(r['total'].detach()), float(g['loss']), rtol=2e-5)
+
+    def close(a, b, what):
+        scale = max(float(np.abs(b).max()), 1e-5)
+        err = float(np.abs(a - b).max()) / scale
+        assert err < 2e-3, f'{what}: max error {err:.2e} of the largest gradient entry'
+    close(sub(r['feat'].grad, g), g['d_feat_sub'], 'd_feat')
+    n = 0
+    for k, v in r['sd'].items():
+        if ('dparam.' + k) in g:
+            grad = v.grad if v.grad is not None else torch.zeros_like(v)
+            close(sub(grad, g), g['dparam.' + k], k)
+            n += 1
+    assert n == 6 + 34 * spec['num_layers'] + 22
