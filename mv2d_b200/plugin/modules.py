@@ -483,11 +483,89 @@ class MV2DHead(nn.Module):
         return self.bbox_head.get_bboxes({'cls_scores': [res['cls_scores'][-1]], 'bbox_preds': [res['bbox_preds'][-1]]},
                                          img_metas)
 
-    def forward_train(self, *args, **kwargs):
-        raise NotImplementedError('there are no backward kernels yet (DESIGN.md section 7).  The training-mode FORWARD incl. '
-                                  'denoising queries is _bbox_forward under .train(); the loss VALUES of that forward '
-                                  '(Hungarian targets, focal / L1, denoising) come from bbox_head.loss / dn_loss_single '
-                                  'or HotPath.forward_losses')
+    def trainer(self):
+        """The flat-buffer trainer over THIS module's parameters (mv2d_b200/train.py).  On first use every hot-path
+        Parameter's storage is re-pointed at its slice of the trainer's flat parameter buffer, so a torch optimizer
+        stepping the module's Parameters updates the buffer the kernels read -- no copy in either direction."""
+        if getattr(self, '_trainer', None) is None:
+            from ..train import HotPathTrainer
+            pe = self.position_encoding
+            dev = next(self.parameters()).device
+            kw = self.bbox_head._loss_kwargs()
+            ecfg = dict(pc_range=list(self.pc_range), position_range=list(pe.position_range), depth_num=pe.depth_num,
+                        depth_start=float(pe.depth_start), stride=pe.strides[0], intrins_feat_scale=self.intrins_feat_scale)
+            ecfg.update(self.box_corr_module.engine_cfg())
+            tr = HotPathTrainer(self.state_dict(), device=dev, stage_loss_weights=self.stage_loss_weights,
+                                pc_range=list(self.pc_range), engine_cfg=ecfg, **kw)
+            params = dict(self.named_parameters())
+            self._train_params = []
+            for name in tr.table:
+                prm = params[name]
+                prm.data = tr.grad_layout_view(name)       # a view of the flat buffer in the Parameter's own shape
+                self._train_params.append((name, prm))
+            object.__setattr__(self, '_trainer', tr)
+        return self._trainer
+
+    def forward_train(self, x, img_metas, proposal_list, gt_bboxes, gt_labels, gt_bboxes_3d, gt_labels_3d,
+                      ori_gt_bboxes_3d, ori_gt_labels_3d, attr_labels=None, gt_bboxes_ignore=None, gt_masks=None, **kwargs):
+        """MV2DSHead.forward_train (roi_heads/mv2d_s_head.py:236-307): the loss dict ``l{i}.loss_cls`` / ``l{i}.loss_bbox``
+        (each times stage_loss_weights[i]) of one sample.  The values come from the CUDA forward; their SUM carries
+        the autograd edge: calling ``.backward()`` on it (what mmdet's ``_parse_losses`` + the runner do) runs
+        ``mv2d_decoder_train_backward`` + ``mv2d_front_train_backward``, accumulates into every hot-path
+        Parameter's ``.grad`` and hands d loss / d feat back to autograd, so the torch backbone trains through it."""
+        assert len(img_metas) // img_metas[0]['num_views'] == 1      # mv2d_s_head.py:250
+        if getattr(self, 'use_denoise', False) or self.MODE != 'S':
+            raise NotImplementedError('the backward covers the single-frame head without denoising queries (the configuration '
+                                      'the reference trains MV2D-S with); the denoising / two-frame forward exists '
+                                      '(_bbox_forward under .train()) but has no backward yet')
+        feat = x[self.feat_lvl]
+        if feat.shape[1] == 2 * self.position_encoding.embed_dims:
+            feat = feat[:, :self.position_encoding.embed_dims]
+        boxes = self.bbox_head._gt_tensor(ori_gt_bboxes_3d[0])
+        tr = self.trainer()
+        self._engine = None           # the packed inference weights go stale as soon as the optimizer steps
+        anchor = self._train_params[0][1]
+        total, loss_cls, loss_bbox = _TrainStep.apply(feat, anchor, self, [p[:, :6] for p in proposal_list], img_metas, boxes,
+                                                      ori_gt_labels_3d[0])
+        w = tr.stage_loss_weights
+        losses = {}
+        for i in range(tr.L):
+            losses[f'l{i}.loss_cls'] = loss_cls[i] * w[i]
+            losses[f'l{i}.loss_bbox'] = loss_bbox[i] * w[i]
+        # the entries above are plain values; the autograd edge rides on the first one (the sum of the dict is `total`)
+        losses['l0.loss_cls'] = losses['l0.loss_cls'] + (total - total.detach())
+        return losses
+
+
+class _TrainStep(torch.autograd.Function):
+    """One sample's hot-path training step as an autograd node: forward = the CUDA forward with saved activations +
+    targets / losses, backward = the CUDA backward; parameter gradients are accumulated into ``Parameter.grad``."""
+
+    @staticmethod
+    def forward(ctx, feat, anchor, head, proposal_list, img_metas, gt_boxes, gt_labels):
+        tr = head.trainer()
+        tr.zero_grad()
+        out = tr.forward(feat.detach(), proposal_list, img_metas, gt_boxes, gt_labels)
+        ctx.head = head
+        loss_cls, loss_bbox = out['loss_cls'].clone(), out['loss_bbox'].clone()
+        ctx.mark_non_differentiable(loss_cls, loss_bbox)
+        return out['loss'].clone(), loss_cls, loss_bbox
+
+    @staticmethod
+    def backward(ctx, g_total, g_cls, g_bbox):
+        head = ctx.head
+        tr = head.trainer()
+        gin = tr.backward()
+        if float(g_total) != 1.0:      # a scaled loss (gradient accumulation, AMP scaler): scale what this step produced
+            tr.grads.mul_(g_total)
+        fresh = [(prm, tr.grad(name)) for name, prm in head._train_params]
+        have = [(prm, g) for prm, g in fresh if prm.grad is not None]
+        if have:
+            torch._foreach_add_([prm.grad for prm, _ in have], [g for _, g in have])
+        for prm, g in fresh:
+            if prm.grad is None:
+                prm.grad = g.clone()
+        return gin['d_feat'] * g_total, None, None, None, None, None, None
 
 
 @HEADS.register_module()

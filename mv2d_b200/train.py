@@ -132,6 +132,11 @@ class DecoderTrainer:
         t = self.view(name, self.grads)
         return t.permute(0, 3, 1, 2) if name == CONV_W else t
 
+    def grad_layout_view(self, name, buf=None):
+        """A view of one tensor's slice of the flat parameter (or another flat) buffer in the reference's shape."""
+        t = self.view(name, buf)
+        return t.permute(0, 3, 1, 2) if name == CONV_W else t
+
     def named_grads(self):
         return {n: self.grad(n) for n in self.table}
 
@@ -230,12 +235,12 @@ class HotPathTrainer(DecoderTrainer):
     (camera geometry, per-RoI intrinsics, box correlation) come from the inference engine.
     Reference: MV2DSHead.forward_train (roi_heads/mv2d_s_head.py:236-307) + torch autograd."""
 
-    def __init__(self, state_dict, device='cuda', **kw):
+    def __init__(self, state_dict, device='cuda', engine_cfg=None, **kw):
         super().__init__(state_dict, device=device, **kw)
         self._need_cuda()
         from .engine import HotPath
         sd = {k[len('roi_head.'):] if k.startswith('roi_head.') else k: v for k, v in state_dict.items()}
-        self.engine = HotPath(sd, mode='S', device=self.device)
+        self.engine = HotPath(sd, mode='S', device=self.device, **(engine_cfg or {}))
         self._front_ws = None
         self._fp = None
 
