@@ -48,6 +48,7 @@ def parse():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--mode', default='S', choices=['S', 'T'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-train', action='store_true', help='skip the extra training-step section')
     ap.add_argument('--depth', type=int, default=4, help='samples in flight (inter-sample pipelining); 1 = serial')
     return ap.parse_args()
 
@@ -258,6 +259,10 @@ def main():
     e2e_total_ms, _, _ = timed_pipe(True, args.steps, W)
     clocks = sampler.stop() if rank == 0 else None
 
+    train = None
+    if mode == 'S' and not args.no_train:
+        train = train_step_section(sd, dev, samples, world, barrier)
+
     # max over ranks of the device time
     total_ms, e2e_total_ms, ser_total_ms, ser_e2e_total_ms = D.max_over_ranks(
         [total_ms, e2e_total_ms, ser_total_ms, ser_e2e_total_ms], device=dev)
@@ -304,11 +309,60 @@ def main():
                  ms_per_step=e2e_total_ms / args.steps),
         gpu_launches=launches, clocks=clocks, roofline=roof['roofline'], attention_roofline=roof['attention'],
         stage_us=roof['stage_us'], peaks=peaks, serial=serial)
+    if train is not None:
+        line['train_step'] = train
     if not args.no_cpu_baseline and world == 1:
         line['cpu_baseline'] = cpu_baseline(mode)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def train_step_section(sd, dev, samples, world, barrier, per_rank=2, steps=8, warmup=3):
+    """Extra object `train_step` (BASELINE configs[3] shape: MV2D-S, 2 samples per GPU): per step and rank, for each local
+    sample the hot-path training forward (saved activations) + Hungarian targets / losses + backward down to d feat, then
+    ONE NCCL sum all-reduce of the flat gradient buffer (all 14.0 M hot-path parameters) and a fused AdamW pass.
+    Device time by CUDA events, max over ranks; the torch backbone is outside the hot path."""
+    import torch
+    from mv2d_b200 import dist as D
+    from mv2d_b200 import synth
+    from mv2d_b200.train import HotPathTrainer
+    tr = HotPathTrainer(sd, device=dev)
+    before = tr.lib.mv2d_launch_count()
+    batch = []
+    for i in range(per_rank):
+        feat, boxes, metas = samples[i % len(samples)]
+        gt_boxes, gt_labels, _ = synth.make_dn_inputs(dict(num_gt=30, seed=300 + i))
+        batch.append((feat.to(dev), boxes, metas, gt_boxes.to(dev), gt_labels.to(dev)))
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    rows, losses = [], []
+    for it in range(warmup + steps):
+        barrier()
+        tr.zero_grad()
+        ev[0].record()
+        loss = 0.0
+        for smp in batch:
+            loss = loss + tr.forward(*smp)['loss']
+            tr.backward()
+        ev[1].record()
+        tr.all_reduce_grads()
+        ev[2].record()
+        tr.adamw_step(grad_scale=1.0 / (world * per_rank))
+        ev[3].record()
+        torch.cuda.synchronize()
+        if it >= warmup:
+            rows.append([ev[0].elapsed_time(ev[3]), ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), ev[2].elapsed_time(ev[3])])
+            losses.append(float(loss) / per_rank)
+    t = torch.tensor(rows, dtype=torch.float64)
+    total_ms = D.max_over_ranks([float(t[:, 0].sum())], device=dev)[0]
+    med = t.median(0).values.tolist()
+    return dict(value=world * per_rank * steps / (total_ms * 1e-3), unit='samples/s', samples_per_gpu=per_rank, steps=steps, warmup=warmup,
+                step_ms=med[0], fwd_bwd_ms=med[1], allreduce_ms=med[2], adamw_ms=med[3], grad_bytes=tr.total * 4,
+                launches_per_step=int(tr.lib.mv2d_launch_count() - before) // (warmup + steps),
+                loss_first=losses[0], loss_last=losses[-1],
+                scope='rows a1-a18 + f3 forward and backward: every hot-path parameter gradient and d loss / d feat; 3xTF32 tcgen05 for the '
+                      'GPU-filling contractions, fp32 FFMA elsewhere; the torch backbone is outside',
+                collective='one NCCL sum all-reduce of the flat gradient buffer per step' if world > 1 else 'none (1 GPU)')
 
 
 def roofline_section(eng, out, mode, N, flush, peaks):
