@@ -760,6 +760,186 @@ __global__ void __launch_bounds__(256) sa_bwd_dkv_kernel(const float* __restrict
     dqkv[(long long)j * 768 + 512 + h * THD + lane] = mv;
 }
 
+// ---- shared-memory variants (the default whenever one head's K and V of all N queries fit: N <= 775).  The kernels
+// above read every key row from L2 once per (query, head) -- 184 MB of L2 traffic per launch at N = 300, which is what
+// bounded them (66 us).  Here a CTA owns one head and 16 queries (or 16 keys), stages the head's two [N,32] operand
+// slices in shared memory once (row stride 33 floats: lane = row reads are conflict-free) and the warps walk them.
+constexpr int SA_QB = 16;
+__device__ __forceinline__ void sa_stage(const float* __restrict__ src, int ld, int col, int N, float* __restrict__ dst) {
+    for (int idx = threadIdx.x; idx < N * 8; idx += 256) {
+        const int r = idx >> 3, c4 = idx & 7;
+        const float4 v = *reinterpret_cast<const float4*>(src + (long long)r * ld + col + c4 * 4);
+        float* d = dst + r * 33 + c4 * 4;
+        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+    }
+}
+
+__global__ void __launch_bounds__(256) sa_fwd_smem_kernel(const float* __restrict__ qkv, float* __restrict__ P,
+                                                          float* __restrict__ attn_o, int N) {
+    pdl_wait();
+    pdl_trigger();
+    extern __shared__ float sa_sm[];
+    float* Ks = sa_sm;
+    float* Vs = sa_sm + (size_t)N * 33;
+    const int h = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    sa_stage(qkv, 768, 256 + h * THD, N, Ks);
+    sa_stage(qkv, 768, 512 + h * THD, N, Vs);
+    __syncthreads();
+    const float scale = 0.17677669529663687f;
+    for (int qi = warp; qi < SA_QB; qi += 8) {
+        const int i = blockIdx.x * SA_QB + qi;
+        if (i >= N) break;
+        float q[THD];
+#pragma unroll
+        for (int c = 0; c < THD; ++c) q[c] = qkv[(long long)i * 768 + h * THD + c] * scale;
+        float* Prow = P + ((long long)h * N + i) * N;
+        float mx = -INFINITY;
+        for (int j = lane; j < N; j += 32) {
+            const float* k = Ks + j * 33;
+            float s = 0.f;
+#pragma unroll
+            for (int c = 0; c < THD; ++c) s = fmaf(q[c], k[c], s);
+            Prow[j] = s;
+            mx = fmaxf(mx, s);
+        }
+        mx = warp_max(mx);
+        float sum = 0.f;
+        for (int j = lane; j < N; j += 32) {
+            const float e = expf(Prow[j] - mx);
+            Prow[j] = e;
+            sum += e;
+        }
+        sum = warp_sum(sum);
+        const float inv = 1.f / sum;
+        float o[THD];
+#pragma unroll
+        for (int c = 0; c < THD; ++c) o[c] = 0.f;
+        for (int j = lane; j < N; j += 32) {
+            const float p = Prow[j] * inv;
+            Prow[j] = p;
+            const float* v = Vs + j * 33;
+#pragma unroll
+            for (int c = 0; c < THD; ++c) o[c] = fmaf(p, v[c], o[c]);
+        }
+        float mine = 0.f;
+#pragma unroll
+        for (int c = 0; c < THD; ++c) {
+            const float r = warp_sum(o[c]);
+            if (lane == c) mine = r;
+        }
+        attn_o[(long long)i * TC_ + h * THD + lane] = mine;
+    }
+}
+
+__global__ void __launch_bounds__(256) sa_bwd_dq_smem_kernel(const float* __restrict__ qkv, const float* __restrict__ P,
+                                                             const float* __restrict__ dO, float* __restrict__ dS,
+                                                             float* __restrict__ dqkv, int N) {
+    pdl_wait();
+    pdl_trigger();
+    extern __shared__ float sa_sm[];
+    float* Ks = sa_sm;
+    float* Vs = sa_sm + (size_t)N * 33;
+    const int h = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    sa_stage(qkv, 768, 256 + h * THD, N, Ks);
+    sa_stage(qkv, 768, 512 + h * THD, N, Vs);
+    __syncthreads();
+    const float scale = 0.17677669529663687f;
+    for (int qi = warp; qi < SA_QB; qi += 8) {
+        const int i = blockIdx.x * SA_QB + qi;
+        if (i >= N) break;
+        float go[THD];
+#pragma unroll
+        for (int c = 0; c < THD; ++c) go[c] = dO[(long long)i * TC_ + h * THD + c];
+        const float* Prow = P + ((long long)h * N + i) * N;
+        float* Srow = dS + ((long long)h * N + i) * N;
+        float D = 0.f;
+        for (int j = lane; j < N; j += 32) {
+            const float* v = Vs + j * 33;
+            float dp = 0.f;
+#pragma unroll
+            for (int c = 0; c < THD; ++c) dp = fmaf(go[c], v[c], dp);
+            Srow[j] = dp;
+            D += Prow[j] * dp;
+        }
+        D = warp_sum(D);
+        float dq[THD];
+#pragma unroll
+        for (int c = 0; c < THD; ++c) dq[c] = 0.f;
+        for (int j = lane; j < N; j += 32) {
+            const float ds = Prow[j] * (Srow[j] - D);
+            Srow[j] = ds;
+            const float* k = Ks + j * 33;
+#pragma unroll
+            for (int c = 0; c < THD; ++c) dq[c] = fmaf(ds, k[c], dq[c]);
+        }
+        float mine = 0.f;
+#pragma unroll
+        for (int c = 0; c < THD; ++c) {
+            const float r = warp_sum(dq[c]);
+            if (lane == c) mine = r;
+        }
+        dqkv[(long long)i * 768 + h * THD + lane] = mine * scale;
+    }
+}
+
+// CTA = (16 keys, head): the head's Q and dO slices of all queries are staged; one warp per key, lane = query
+__global__ void __launch_bounds__(256) sa_bwd_dkv_smem_kernel(const float* __restrict__ qkv, const float* __restrict__ P,
+                                                              const float* __restrict__ dS, const float* __restrict__ dO,
+                                                              float* __restrict__ dqkv, int N) {
+    pdl_wait();
+    pdl_trigger();
+    extern __shared__ float sa_sm[];
+    float* Qs = sa_sm;
+    float* Gs = sa_sm + (size_t)N * 33;
+    const int h = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    sa_stage(qkv, 768, h * THD, N, Qs);
+    sa_stage(dO, TC_, h * THD, N, Gs);
+    __syncthreads();
+    const float scale = 0.17677669529663687f;
+    for (int ki = warp; ki < SA_QB; ki += 8) {
+        const int j = blockIdx.x * SA_QB + ki;
+        if (j >= N) break;
+        float dk[THD], dv[THD];
+#pragma unroll
+        for (int c = 0; c < THD; ++c) { dk[c] = 0.f; dv[c] = 0.f; }
+        for (int i = lane; i < N; i += 32) {
+            const long long o = ((long long)h * N + i) * N + j;
+            const float p = P[o], ds = dS[o];
+            const float* q = Qs + i * 33;
+            const float* g = Gs + i * 33;
+#pragma unroll
+            for (int c = 0; c < THD; ++c) { dk[c] = fmaf(ds, q[c], dk[c]); dv[c] = fmaf(p, g[c], dv[c]); }
+        }
+        float mk = 0.f, mv = 0.f;
+#pragma unroll
+        for (int c = 0; c < THD; ++c) {
+            const float rk = warp_sum(dk[c]), rv = warp_sum(dv[c]);
+            if (lane == c) { mk = rk; mv = rv; }
+        }
+        dqkv[(long long)j * 768 + 256 + h * THD + lane] = mk * scale;
+        dqkv[(long long)j * 768 + 512 + h * THD + lane] = mv;
+    }
+}
+
+inline size_t sa_smem_bytes(int N) { return (size_t)2 * N * 33 * sizeof(float); }
+inline bool sa_use_smem(int N) {
+    static const bool on = []() { const char* e = getenv("MV2D_TRAIN_SA_SMEM"); return !(e && e[0] == '0'); }();
+    return on && sa_smem_bytes(N) <= 200 * 1024;
+}
+int sa_set_attr() {
+    static bool done = false;
+    if (done) return 0;
+    cudaError_t e;
+    if ((e = cudaFuncSetAttribute(sa_fwd_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(sa_bwd_dq_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(sa_bwd_dkv_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)) != cudaSuccess) {
+        set_error("train: self-attention smem attribute: %s", cudaGetErrorString(e));
+        return (int)e;
+    }
+    done = true;
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------------ cross-attention
 // query i attends to the 49 tokens of every RoI in match[i][0 .. cnt_i); Kp / Vp [N*49,256] projected tokens.
 // P [N, 8, PM] with PM = max_match * 49; slot = m * 49 + t.
@@ -1525,7 +1705,12 @@ int run_train_forward(const Mv2dTrainParams& p, cudaStream_t st) {
         TRY(add(a.xq, a.x_in, w.qpos, (long long)N * TC_, st));
         TRY(linear_fwd(a.xq, TC_, W.t[TL_SA_IN_W], TC_, W.t[TL_SA_IN_B], a.qkv, 768, N, 512, TC_, false, st));
         TRY(linear_fwd(a.x_in, TC_, W.t[TL_SA_IN_W] + 512 * TC_, TC_, W.t[TL_SA_IN_B] + 512, a.qkv + 512, 768, N, TC_, TC_, false, st));
-        launch_k(sa_fwd_kernel, dim3(N), dim3(256), 0, st, (const float*)a.qkv, a.P_sa, a.attn_o, N);
+        if (sa_use_smem(N)) {
+            TRY(sa_set_attr());
+            launch_k(sa_fwd_smem_kernel, dim3(cdiv(N, SA_QB), TH), dim3(256), sa_smem_bytes(N), st, (const float*)a.qkv, a.P_sa, a.attn_o, N);
+        } else {
+            launch_k(sa_fwd_kernel, dim3(N), dim3(256), 0, st, (const float*)a.qkv, a.P_sa, a.attn_o, N);
+        }
         MV2D_CHECK_LAUNCH("train sa_fwd");
         TRY(linear_fwd(a.attn_o, TC_, W.t[TL_SA_OUT_W], TC_, W.t[TL_SA_OUT_B], w.t1, TC_, N, TC_, TC_, false, st));
         TRY(ln_fwd(a.x_in, w.t1, W.t[TL_LN0_G], W.t[TL_LN0_B], a.x1, a.xhat0, a.rstd0, N, false, st));
@@ -1661,11 +1846,21 @@ int run_train_backward(const Mv2dTrainParams& p, cudaStream_t st) {
         TRY(ln_bwd(w.t2, nullptr, a.xhat0, a.rstd0, W.t[TL_LN0_G], w.t1, D.t[TL_LN0_G], D.t[TL_LN0_B], N, false, st));   // t1 = d (x_in + sa)
         TRY(linear_wgrad(w.t1, TC_, a.attn_o, TC_, D.t[TL_SA_OUT_W], TC_, N, TC_, TC_, st, D.t[TL_SA_OUT_B]));
         TRY(linear_dgrad(w.t1, TC_, W.t[TL_SA_OUT_W], TC_, w.t3, TC_, N, TC_, TC_, nullptr, 0, false, st));   // t3 = d attn_o
-        launch_k(sa_bwd_dq_kernel, dim3(N), dim3(256), 0, st, (const float*)a.qkv, (const float*)a.P_sa, (const float*)w.t3, w.dS_sa, w.dqkv, N);
-        MV2D_CHECK_LAUNCH("train sa_bwd_dq");
-        launch_k(sa_bwd_dkv_kernel, dim3(N), dim3(256), 0, st, (const float*)a.qkv, (const float*)a.P_sa, (const float*)w.dS_sa,
-                 (const float*)w.t3, w.dqkv, N);
-        MV2D_CHECK_LAUNCH("train sa_bwd_dkv");
+        if (sa_use_smem(N)) {
+            TRY(sa_set_attr());
+            launch_k(sa_bwd_dq_smem_kernel, dim3(cdiv(N, SA_QB), TH), dim3(256), sa_smem_bytes(N), st, (const float*)a.qkv,
+                     (const float*)a.P_sa, (const float*)w.t3, w.dS_sa, w.dqkv, N);
+            MV2D_CHECK_LAUNCH("train sa_bwd_dq");
+            launch_k(sa_bwd_dkv_smem_kernel, dim3(cdiv(N, SA_QB), TH), dim3(256), sa_smem_bytes(N), st, (const float*)a.qkv,
+                     (const float*)a.P_sa, (const float*)w.dS_sa, (const float*)w.t3, w.dqkv, N);
+            MV2D_CHECK_LAUNCH("train sa_bwd_dkv");
+        } else {
+            launch_k(sa_bwd_dq_kernel, dim3(N), dim3(256), 0, st, (const float*)a.qkv, (const float*)a.P_sa, (const float*)w.t3, w.dS_sa, w.dqkv, N);
+            MV2D_CHECK_LAUNCH("train sa_bwd_dq");
+            launch_k(sa_bwd_dkv_kernel, dim3(N), dim3(256), 0, st, (const float*)a.qkv, (const float*)a.P_sa, (const float*)w.dS_sa,
+                     (const float*)w.t3, w.dqkv, N);
+            MV2D_CHECK_LAUNCH("train sa_bwd_dkv");
+        }
         TRY(linear_wgrad(w.dqkv, 768, a.xq, TC_, D.t[TL_SA_IN_W], TC_, N, 512, TC_, st, D.t[TL_SA_IN_B]));
         TRY(linear_wgrad(w.dqkv + 512, 768, a.x_in, TC_, D.t[TL_SA_IN_W] + 512 * TC_, TC_, N, TC_, TC_, st, D.t[TL_SA_IN_B] + 512));
         TRY(linear_dgrad(w.dqkv, 768, W.t[TL_SA_IN_W], TC_, w.t3, TC_, N, 512, TC_, nullptr, 0, false, st));   // t3 = d (x_in + qpos)
