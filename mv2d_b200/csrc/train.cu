@@ -262,8 +262,9 @@ int tc_gemm(const float* A, int lda, const float* W, int ldw, const float* bias,
 // shape rule of launch_gemm_tc: N tiles are 64 wide for M <= 512, 128 wide otherwise
 inline bool tc_shape_ok(int M, int N, int K) { return K % 32 == 0 && N % (M <= 512 ? 64 : 128) == 0; }
 
-// out[C, Rp] = in[R, C]^T, columns r >= R zero-filled
-__global__ void __launch_bounds__(256) transpose_pad_kernel(const float* __restrict__ in, int ld, int R, int C, float* __restrict__ out, int Rp) {
+// out[c * ldo + r] = in[r * ld + c] for r < Rp (zero for R <= r < Rp), c < C
+__global__ void __launch_bounds__(256) transpose_pad_kernel(const float* __restrict__ in, int ld, int R, int C, float* __restrict__ out, int Rp,
+                                                            int ldo) {
     pdl_wait();
     pdl_trigger();
     __shared__ float tile[32][33];
@@ -278,18 +279,20 @@ __global__ void __launch_bounds__(256) transpose_pad_kernel(const float* __restr
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int c = c0 + ty + i * 8, r = r0 + tx;
-        if (c < C && r < Rp) out[(long long)c * Rp + r] = tile[tx][ty + i * 8];
+        if (c < C && r < Rp) out[(long long)c * ldo + r] = tile[tx][ty + i * 8];
     }
 }
-int transpose_pad(const float* in, int ld, int R, int C, float* out, int Rp, cudaStream_t st) {
-    launch_k(transpose_pad_kernel, dim3(cdiv(Rp, 32), cdiv(C, 32)), dim3(256), 0, st, in, ld, R, C, out, Rp);
+int transpose_pad(const float* in, int ld, int R, int C, float* out, int Rp, cudaStream_t st, int ldo = 0) {
+    launch_k(transpose_pad_kernel, dim3(cdiv(Rp, 32), cdiv(C, 32)), dim3(256), 0, st, in, ld, R, C, out, Rp, ldo > 0 ? ldo : Rp);
     MV2D_CHECK_LAUNCH("train transpose");
     return 0;
 }
 
 // dW[n,k] += sum_z part[z][...]; part is [rows, cols] = [Nout, K], or [K, Nout] when `swapped`
+// rows_per_blk / blk_stride: output rows n are grouped in blocks of rows_per_blk that sit blk_stride floats apart in dW (the
+// same tensor of consecutive decoder layers in the flat gradient buffer); 0 = one contiguous matrix
 __global__ void __launch_bounds__(256) wgrad_fold_kernel(const float* __restrict__ part, int nsplit, long long stride, int Nout, int K,
-                                                         int swapped, float* __restrict__ dW, int ldw) {
+                                                         int swapped, float* __restrict__ dW, int ldw, int rows_per_blk, long long blk_stride) {
     pdl_wait();
     pdl_trigger();
     const long long total = (long long)Nout * K;
@@ -299,11 +302,13 @@ __global__ void __launch_bounds__(256) wgrad_fold_kernel(const float* __restrict
         if (swapped) { k = (int)(i / Nout); n = (int)(i % Nout); } else { n = (int)(i / K); k = (int)(i % K); }
         float a = 0.f;
         for (int z = 0; z < nsplit; ++z) a += part[z * stride + i];
-        dW[(long long)n * ldw + k] += a;
+        if (rows_per_blk > 0) dW[(n / rows_per_blk) * blk_stride + (long long)(n % rows_per_blk) * ldw + k] += a;
+        else dW[(long long)n * ldw + k] += a;
     }
 }
 // db[n] += sum_r yt[n][r]  (rows of the transposed, zero-padded output gradient); one CTA per row
-__global__ void __launch_bounds__(256) rowsum_kernel(const float* __restrict__ yt, int Rp, int Nout, float* __restrict__ db) {
+__global__ void __launch_bounds__(256) rowsum_kernel(const float* __restrict__ yt, int Rp, int Nout, float* __restrict__ db, int rows_per_blk,
+                                                     long long blk_stride) {
     pdl_wait();
     pdl_trigger();
     __shared__ float red[8];
@@ -317,7 +322,8 @@ __global__ void __launch_bounds__(256) rowsum_kernel(const float* __restrict__ y
         float t = 0.f;
 #pragma unroll
         for (int i = 0; i < 8; ++i) t += red[i];
-        db[n] += t;
+        if (rows_per_blk > 0) db[(n / rows_per_blk) * blk_stride + n % rows_per_blk] += t;
+        else db[n] += t;
     }
 }
 // dX = (accumulate ? dX : 0) + src . [mask > 0 (and < 5e3)]   (rows of K floats; ld per operand)
@@ -424,10 +430,10 @@ int linear_wgrad(const float* dY, int ldy, const float* X, int ldx, float* dW, i
             const float* gw = direct ? sc.bt : sc.at;
             TRY(tc_gemm(ga, Mp, gw, Mp, nullptr, sc.part, gn, gm, gn, Mp, false, nsplit, (long long)Nout * K, st));
             launch_k(wgrad_fold_kernel, dim3(ew_grid_n((long long)Nout * K)), dim3(256), 0, st, (const float*)sc.part, nsplit,
-                     (long long)Nout * K, Nout, K, swapped ? 1 : 0, dW, ldw);
+                     (long long)Nout * K, Nout, K, swapped ? 1 : 0, dW, ldw, 0, 0LL);
             MV2D_CHECK_LAUNCH("train wgrad_fold");
             if (db) {
-                launch_k(rowsum_kernel, dim3(Nout), dim3(256), 0, st, (const float*)sc.at, Mp, Nout, db);
+                launch_k(rowsum_kernel, dim3(Nout), dim3(256), 0, st, (const float*)sc.at, Mp, Nout, db, 0, 0LL);
                 MV2D_CHECK_LAUNCH("train rowsum");
             }
             return 0;
@@ -1095,7 +1101,7 @@ __global__ void __launch_bounds__(32) xa_inverse_kernel(const int* __restrict__ 
 __global__ void __launch_bounds__(256) xa_bwd_dkv_kernel(const float* __restrict__ cq, const float* __restrict__ dctx,
                                                          const float* __restrict__ P, const float* __restrict__ dS,
                                                          const int* __restrict__ inv_cnt, const int* __restrict__ inv_list,
-                                                         int max_match, float* __restrict__ dKp, float* __restrict__ dVp, int N) {
+                                                         int max_match, float* __restrict__ dKp, float* __restrict__ dVp, int ldo, int N) {
     pdl_wait();
     pdl_trigger();
     const int row = blockIdx.x, r = row / TTOK, t = row % TTOK;
@@ -1112,8 +1118,8 @@ __global__ void __launch_bounds__(256) xa_bwd_dkv_kernel(const float* __restrict
         dk = fmaf(ds, __ldg(cq + (long long)i * TC_ + h * THD + lane), dk);
         dv = fmaf(p, __ldg(dctx + (long long)i * TC_ + h * THD + lane), dv);
     }
-    dKp[(long long)row * TC_ + h * THD + lane] = dk * scale;
-    dVp[(long long)row * TC_ + h * THD + lane] = dv;
+    dKp[(long long)row * ldo + h * THD + lane] = dk * scale;      // ldo: all layers' gradients side by side, [N*49, L*256]
+    dVp[(long long)row * ldo + h * THD + lane] = dv;
 }
 
 // ------------------------------------------------------------------------------------------------ reg branch tail
@@ -1279,7 +1285,7 @@ TrainWs train_layout(float* base, int N, int L, int max_match, int G) {
     }
     w.dx = take(NC); w.dqpos = take(NC); w.t1 = take(NC); w.t2 = take(NC); w.t3 = take(NC); w.dinter = take(NC);
     w.dcq = take(NC); w.dhdn = take(n * TFF); w.dqkv = take(n * 768); w.dS_sa = take(TH * n * n); w.dS_xa = take(n * TH * PM);
-    w.dKp = take(NK); w.dVp = take(NK); w.dcls = take((size_t)L * n * TCODE); w.dbox = take((size_t)L * n * TCODE);
+    w.dKp = take(NK * L); w.dVp = take(NK * L); w.dcls = take((size_t)L * n * TCODE); w.dbox = take((size_t)L * n * TCODE);
     w.dposemb = take(n * TPE);
     w.inv_cnt = reinterpret_cast<int*>(take(n));
     w.inv_list = reinterpret_cast<int*>(take(n * n));
@@ -1287,7 +1293,9 @@ TrainWs train_layout(float* base, int N, int L, int max_match, int G) {
     w.loss_ws = take(w.loss_ws_bytes / 4 + 1);
     {   // tensor-core route: transposed operands of the K/V weight gradients, W^T, split-K partials, accumulate temp
         const size_t Mp = (size_t)round32((int)(n * TTOK));
-        w.tc.at_cap = TC_ * Mp; w.tc.bt_cap = TC_ * Mp; w.tc.wt_cap = (size_t)TFF * TC_; w.tc.part_cap = (size_t)48 * TC_ * TC_;
+        // at: [L*256, Mp] (the K / V gradients of all layers transposed at once); part: split-K partials of a [L*256, 256] product
+        w.tc.at_cap = (size_t)L * TC_ * Mp; w.tc.bt_cap = TC_ * Mp; w.tc.wt_cap = (size_t)(L * TC_ > TFF ? L * TC_ : TFF) * TC_;
+        w.tc.part_cap = (size_t)48 * L * TC_ * TC_;
         w.tc.tmp_cap = NK;
         w.tc.at = take(w.tc.at_cap); w.tc.bt = take(w.tc.bt_cap); w.tc.wt = take(w.tc.wt_cap); w.tc.part = take(w.tc.part_cap);
         w.tc.tmp = take(w.tc.tmp_cap);
@@ -1792,6 +1800,13 @@ int run_train_backward(const Mv2dTrainParams& p, cudaStream_t st) {
 
     float* g_post_g = G + global_off(TG_POST_G);
     float* g_post_b = G + global_off(TG_POST_B);
+    const int LC = L * TC_;           // row stride of the K / V gradients of all layers side by side
+    const int Mp = round32(NK);
+    // tensor-core mode with enough RoI tokens: the K / V projection gradients of ALL layers as four GEMMs after the loop
+    // (dW_k of every layer = [dKp_0 | .. | dKp_L-1]^T tok_kin, d tok_kin = [dKp_0 | .. ] [Wk_0 ; .. ]: K = L*256 instead
+    // of L GEMMs + L accumulation passes), 24 launches instead of 16 per layer
+    const bool kv_batched = tc_enabled() && NK >= 1024 && tc_shape_ok(LC, TC_, Mp) && tc_shape_ok(NK, TC_, LC) &&
+                            (size_t)LC * Mp <= w.tc.at_cap && (size_t)TC_ * Mp <= w.tc.bt_cap && (size_t)LC * TC_ <= w.tc.wt_cap;
     for (int l = L - 1; l >= 0; --l) {
         const LayerAct& a = w.layer[l];
         const LayerPtr W = layer_ptrs(P, l);
@@ -1832,16 +1847,18 @@ int run_train_backward(const Mv2dTrainParams& p, cudaStream_t st) {
                  (const float*)w.t3, p.match, p.match_cnt, p.max_match, w.dS_xa, w.dcq, N);
         MV2D_CHECK_LAUNCH("train xa_bwd_dq");
         launch_k(xa_bwd_dkv_kernel, dim3(NK), dim3(256), 0, st, (const float*)a.cq, (const float*)w.t3, (const float*)a.P_xa,
-                 (const float*)w.dS_xa, (const int*)w.inv_cnt, (const int*)w.inv_list, p.max_match, w.dKp, w.dVp, N);
+                 (const float*)w.dS_xa, (const int*)w.inv_cnt, (const int*)w.inv_list, p.max_match, w.dKp + l * TC_, w.dVp + l * TC_, LC, N);
         MV2D_CHECK_LAUNCH("train xa_bwd_dkv");
         TRY(linear_wgrad(w.dcq, TC_, a.xq1, TC_, D.t[TL_CA_IN_W], TC_, N, TC_, TC_, st, D.t[TL_CA_IN_B]));
         TRY(linear_dgrad(w.dcq, TC_, W.t[TL_CA_IN_W], TC_, w.t3, TC_, N, TC_, TC_, nullptr, 0, false, st));   // t3 = d (x1 + qpos)
         TRY(add(w.t2, w.t2, w.t3, NC, st));          // t2 = d x1
         TRY(add(w.dqpos, w.dqpos, w.t3, NC, st));
-        TRY(linear_wgrad(w.dKp, TC_, p.tok_kin, TC_, D.t[TL_CA_IN_W] + 256 * TC_, TC_, NK, TC_, TC_, st, D.t[TL_CA_IN_B] + 256));
-        TRY(linear_dgrad(w.dKp, TC_, W.t[TL_CA_IN_W] + 256 * TC_, TC_, p.d_tok_kin, TC_, NK, TC_, TC_, nullptr, 0, true, st));
-        TRY(linear_wgrad(w.dVp, TC_, p.tok_mem, TC_, D.t[TL_CA_IN_W] + 512 * TC_, TC_, NK, TC_, TC_, st, D.t[TL_CA_IN_B] + 512));
-        TRY(linear_dgrad(w.dVp, TC_, W.t[TL_CA_IN_W] + 512 * TC_, TC_, p.d_tok_mem, TC_, NK, TC_, TC_, nullptr, 0, true, st));
+        if (!kv_batched) {     // per layer; otherwise all layers' K / V projection gradients in four GEMMs after the loop
+            TRY(linear_wgrad(w.dKp + l * TC_, LC, p.tok_kin, TC_, D.t[TL_CA_IN_W] + 256 * TC_, TC_, NK, TC_, TC_, st, D.t[TL_CA_IN_B] + 256));
+            TRY(linear_dgrad(w.dKp + l * TC_, LC, W.t[TL_CA_IN_W] + 256 * TC_, TC_, p.d_tok_kin, TC_, NK, TC_, TC_, nullptr, 0, true, st));
+            TRY(linear_wgrad(w.dVp + l * TC_, LC, p.tok_mem, TC_, D.t[TL_CA_IN_W] + 512 * TC_, TC_, NK, TC_, TC_, st, D.t[TL_CA_IN_B] + 512));
+            TRY(linear_dgrad(w.dVp + l * TC_, LC, W.t[TL_CA_IN_W] + 512 * TC_, TC_, p.d_tok_mem, TC_, NK, TC_, TC_, nullptr, 0, true, st));
+        }
         // --- norms.0 and the self-attention
         TRY(ln_bwd(w.t2, nullptr, a.xhat0, a.rstd0, W.t[TL_LN0_G], w.t1, D.t[TL_LN0_G], D.t[TL_LN0_B], N, false, st));   // t1 = d (x_in + sa)
         TRY(linear_wgrad(w.t1, TC_, a.attn_o, TC_, D.t[TL_SA_OUT_W], TC_, N, TC_, TC_, st, D.t[TL_SA_OUT_B]));
@@ -1867,6 +1884,32 @@ int run_train_backward(const Mv2dTrainParams& p, cudaStream_t st) {
         TRY(add(w.dqpos, w.dqpos, w.t3, NC, st));
         TRY(add(w.dx, w.t1, w.t3, NC, st));           // dx = gradient of the previous layer's output
         TRY(linear_dgrad(w.dqkv + 512, 768, W.t[TL_SA_IN_W] + 512 * TC_, TC_, w.dx, TC_, N, TC_, TC_, nullptr, 0, true, st));
+    }
+    if (kv_batched) {
+        const long long lstride = layer_block_floats();
+        const int tiles = cdiv(LC, 128) * (TC_ / (LC <= 512 ? 64 : 128)), nkb = Mp / 32;
+        int nsplit = 1;
+        for (int d = 1; d <= 48 && d <= nkb; ++d)
+            if (nkb % d == 0 && nkb / d >= 4 && (size_t)d * LC * TC_ <= w.tc.part_cap) { nsplit = d; if (tiles * d >= 148) break; }
+        for (int kv = 0; kv < 2; ++kv) {
+            const float* dYall = kv == 0 ? w.dKp : w.dVp;             // [NK, L*256]
+            const float* X = kv == 0 ? p.tok_kin : p.tok_mem;         // [NK, 256]
+            float* dX = kv == 0 ? p.d_tok_kin : p.d_tok_mem;
+            const int wrow = kv == 0 ? 256 : 512;                     // rows of in_proj: q | k | v
+            // weight + bias gradients of every layer
+            TRY(transpose_pad(dYall, LC, NK, LC, w.tc.at, Mp, st));
+            TRY(transpose_pad(X, TC_, NK, TC_, w.tc.bt, Mp, st));
+            TRY(tc_gemm(w.tc.at, Mp, w.tc.bt, Mp, nullptr, w.tc.part, TC_, LC, TC_, Mp, false, nsplit, (long long)LC * TC_, st));
+            launch_k(wgrad_fold_kernel, dim3(ew_grid_n((long long)LC * TC_)), dim3(256), 0, st, (const float*)w.tc.part, nsplit,
+                     (long long)LC * TC_, LC, TC_, 0, G + layer_off(0, TL_CA_IN_W) + (long long)wrow * TC_, TC_, TC_, lstride);
+            MV2D_CHECK_LAUNCH("train kv wgrad_fold");
+            launch_k(rowsum_kernel, dim3(LC), dim3(256), 0, st, (const float*)w.tc.at, Mp, LC, G + layer_off(0, TL_CA_IN_B) + wrow, TC_, lstride);
+            MV2D_CHECK_LAUNCH("train kv rowsum");
+            // input gradient: d tok = [dY_0 | .. | dY_L-1] [W_0 ; .. ; W_L-1]  (d_tok_* was zeroed above; written once here)
+            for (int l = 0; l < L; ++l)
+                TRY(transpose_pad(P + layer_off(l, TL_CA_IN_W) + (long long)wrow * TC_, TC_, TC_, TC_, w.tc.wt + l * TC_, TC_, st, LC));
+            TRY(tc_gemm(dYall, LC, w.tc.wt, LC, nullptr, dX, TC_, NK, TC_, LC, false, 1, 0, st));
+        }
     }
     // --- query embedding MLP and the sin / cos features
     TRY(linear_wgrad(w.dqpos, TC_, w.h0, TC_, G + global_off(TG_QE2_W), TC_, N, TC_, TC_, st, G + global_off(TG_QE2_B)));
