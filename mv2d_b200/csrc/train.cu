@@ -104,397 +104,7 @@ long long front_off(int L, int t) {
     return s;
 }
 
-// ------------------------------------------------------------------------------------------------ generic fp32 GEMM
-// C[M,N] (op)= sum_k A(m,k) B(k,n) (+ bias[n]),  A(m,k) = A[m*sam + k*sak],  B(k,n) = B[k*sbk + n*sbn].
-enum SgFlags { SG_RELU = 1, SG_ACC = 2, SG_ATOMIC = 4, SG_CLAMP5E3 = 8, SG_MASK_LT5E3 = 16 };
-struct Sg {
-    const float* A; const float* B; float* C; const float* bias; const float* mask; float* rowsum;
-    long long sam, sak, sbk, sbn;
-    int ldc, ldmask, M, N, K, klen, flags;
-};
-
-// TM x TM outputs per thread, 256 threads: TM = 4 -> 64 x 64 tile with BK = 32, TM = 8 -> 128 x 128 tile with BK = 16
-// (eight elements of each operand per thread and k-step, prefetched into registers while the previous k-step is
-// multiplied: the M ~ 300 problems of the decoder are short chains of k-steps on a few CTAs, so the loads in flight
-// per step set their speed).  AK1 / BN1 say which stride of A / B is 1, i.e. which index runs along a warp when the
-// tile is loaded (coalescing only; addressing always goes through the strides).
-// rowsum (weight-gradient calls): the CTAs of the first column of tiles also add sum_k A(m,k) -- the bias gradient
-// of the same layer -- so no separate column-sum launch is needed.
-template <int TM, bool AK1, bool BN1>
-__global__ void __launch_bounds__(256) sgemm_kernel(Sg g) {
-    pdl_wait();
-    pdl_trigger();
-    constexpr int BM = 16 * TM, BK = 2048 / BM, LD = BM + 4, E = 8;
-    __shared__ __align__(16) float As[BK][LD];
-    __shared__ __align__(16) float Bs[BK][LD];
-    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BM;
-    const int kbeg = blockIdx.z * g.klen;
-    const int kend = min(g.K, kbeg + g.klen);
-    const bool do_rowsum = g.rowsum != nullptr && blockIdx.x == 0 && tx == 0;
-    float acc[TM][TM], rs[TM];
-#pragma unroll
-    for (int i = 0; i < TM; ++i) {
-        rs[i] = 0.f;
-#pragma unroll
-        for (int j = 0; j < TM; ++j) acc[i][j] = 0.f;
-    }
-    float ra[E], rb[E];
-    // element e of this thread inside a tile: (am, ak) for A, (bn, bk) for B
-    auto a_m = [&](int e) { const int idx = tid + e * 256; return AK1 ? idx / BK : idx % BM; };
-    auto a_k = [&](int e) { const int idx = tid + e * 256; return AK1 ? idx % BK : idx / BM; };
-    auto b_n = [&](int e) { const int idx = tid + e * 256; return BN1 ? idx % BM : idx / BK; };
-    auto b_k = [&](int e) { const int idx = tid + e * 256; return BN1 ? idx / BM : idx % BK; };
-    auto fetch = [&](int k0) {
-#pragma unroll
-        for (int e = 0; e < E; ++e) {
-            const int am = a_m(e), ak = a_k(e), bn = b_n(e), bk = b_k(e);
-            ra[e] = (m0 + am < g.M && k0 + ak < kend) ? __ldg(g.A + (long long)(m0 + am) * g.sam + (long long)(k0 + ak) * g.sak) : 0.f;
-            rb[e] = (n0 + bn < g.N && k0 + bk < kend) ? __ldg(g.B + (long long)(k0 + bk) * g.sbk + (long long)(n0 + bn) * g.sbn) : 0.f;
-        }
-    };
-    if (kbeg < kend) fetch(kbeg);
-    for (int k0 = kbeg; k0 < kend; k0 += BK) {
-#pragma unroll
-        for (int e = 0; e < E; ++e) { As[a_k(e)][a_m(e)] = ra[e]; Bs[b_k(e)][b_n(e)] = rb[e]; }
-        __syncthreads();
-        if (k0 + BK < kend) fetch(k0 + BK);
-#pragma unroll
-        for (int k = 0; k < BK; ++k) {
-            float av[TM], bv[TM];
-#pragma unroll
-            for (int q = 0; q < TM / 4; ++q) {
-                const float4 a = *reinterpret_cast<const float4*>(&As[k][q * 64 + ty * 4]);
-                const float4 b = *reinterpret_cast<const float4*>(&Bs[k][q * 64 + tx * 4]);
-                av[q * 4] = a.x; av[q * 4 + 1] = a.y; av[q * 4 + 2] = a.z; av[q * 4 + 3] = a.w;
-                bv[q * 4] = b.x; bv[q * 4 + 1] = b.y; bv[q * 4 + 2] = b.z; bv[q * 4 + 3] = b.w;
-            }
-#pragma unroll
-            for (int i = 0; i < TM; ++i)
-#pragma unroll
-                for (int j = 0; j < TM; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
-            if (do_rowsum) {
-#pragma unroll
-                for (int i = 0; i < TM; ++i) rs[i] += av[i];
-            }
-        }
-        __syncthreads();
-    }
-#pragma unroll
-    for (int i = 0; i < TM; ++i) {
-        const int m = m0 + (i / 4) * 64 + ty * 4 + (i % 4);
-        if (m >= g.M) continue;
-        if (do_rowsum) atomicAdd(g.rowsum + m, rs[i]);
-#pragma unroll
-        for (int j = 0; j < TM; ++j) {
-            const int n = n0 + (j / 4) * 64 + tx * 4 + (j % 4);
-            if (n >= g.N) continue;
-            float v = acc[i][j];
-            if (g.bias && blockIdx.z == 0) v += __ldg(g.bias + n);
-            float* c = g.C + (long long)m * g.ldc + n;
-            if (g.flags & SG_ATOMIC) { atomicAdd(c, v); continue; }
-            if (g.flags & SG_RELU) v = fmaxf(v, 0.f);
-            if (g.flags & SG_CLAMP5E3) v = fminf(v, 5e3f);
-            if (g.mask) {
-                const float a = g.mask[(long long)m * g.ldmask + n];
-                if (!(a > 0.f) || ((g.flags & SG_MASK_LT5E3) && !(a < 5e3f))) v = 0.f;
-            }
-            if (g.flags & SG_ACC) v += *c;
-            *c = v;
-        }
-    }
-}
-
-// 128 x 128 tiles once the problem fills the GPU with them, 64 x 64 otherwise
-inline int sg_tile(int M, int N) {
-    static const bool big_ok = []() { const char* e = getenv("MV2D_TRAIN_SGEMM128"); return !(e && e[0] == '0'); }();
-    return (big_ok && M >= 512 && N >= 128) ? 128 : 64;
-}
-
-template <int TM>
-int launch_sgemm_t(const Sg& g, dim3 grid, cudaStream_t st) {
-    const bool ak1 = g.sak == 1, bn1 = g.sbn == 1;
-    if (ak1 && bn1) launch_k(sgemm_kernel<TM, true, true>, grid, dim3(256), 0, st, g);
-    else if (ak1) launch_k(sgemm_kernel<TM, true, false>, grid, dim3(256), 0, st, g);
-    else if (bn1) launch_k(sgemm_kernel<TM, false, true>, grid, dim3(256), 0, st, g);
-    else launch_k(sgemm_kernel<TM, false, false>, grid, dim3(256), 0, st, g);
-    MV2D_CHECK_LAUNCH("train sgemm");
-    return 0;
-}
-
-int launch_sgemm(const Sg& g, int splits, cudaStream_t st) {
-    if (g.M <= 0 || g.N <= 0 || g.K <= 0) return 0;
-    const int t = sg_tile(g.M, g.N);
-    dim3 grid(cdiv(g.N, t), cdiv(g.M, t), splits);
-    return t == 128 ? launch_sgemm_t<8>(g, grid, st) : launch_sgemm_t<4>(g, grid, st);
-}
-
-
-// ------------------------------------------------------------------------------------------------ tensor-core route
-// The GPU-filling contractions of the step (K/V projections over all RoI tokens, the 3x3 conv as an im2col GEMM, the
-// position-encoding MLPs: M = 14 700 .. 16 896 rows) run on the tcgen05 kernel of gemm_tc.cu as error-compensated
-// 3xTF32 (fp32-grade, operands split inside the kernel).  That kernel computes C = A W^T with both operands
-// K-contiguous, so the backward forms get their operands re-laid-out first:
-//   dX = dY W        -> W^T is materialised (weights are small), the ReLU mask / accumulation is a second pass;
-//   dW = dY^T X      -> dY^T and X^T are materialised with the row count zero-padded to a multiple of 32 (the GEMM's
-//                       K), the reduction is split over CTAs (raw partial sums) and one kernel folds the partials into
-//                       the flat gradient buffer and the bias gradient.
-// MV2D_TRAIN_TC=0 keeps everything on the FFMA kernel below (the tests run both).
-struct TcScratch {
-    float *at, *bt, *wt, *part, *tmp;
-    size_t at_cap, bt_cap, wt_cap, part_cap, tmp_cap;   // floats
-};
-int g_tc_mode = -1;      // -1 = not set yet: MV2D_TRAIN_TC from the environment (default on); mv2d_train_set_tensor_cores overrides
-bool tc_enabled() {
-    if (g_tc_mode < 0) { const char* e = getenv("MV2D_TRAIN_TC"); g_tc_mode = (e && e[0] == '0') ? 0 : 1; }
-    return g_tc_mode == 1;
-}
-inline bool al16(const void* p) { return ((uintptr_t)p & 15) == 0; }
-inline int round32(int x) { return (x + 31) / 32 * 32; }
-
-int tc_gemm(const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc, int M, int N, int K, bool relu,
-            int nsplit, long long split_stride, cudaStream_t st) {
-    TcGemm t{};
-    t.A = A; t.A_lo = nullptr; t.lda = lda; t.W = W; t.W_lo = nullptr; t.ldw = ldw; t.bias = bias; t.C = C; t.ldc = ldc;
-    t.M = M; t.N = N; t.K = K; t.passes = 3; t.im2col = 0; t.flags = relu ? GEMM_RELU : 0; t.nsplit = nsplit; t.split_stride = split_stride;
-    return launch_gemm_tc(t, st);
-}
-// shape rule of launch_gemm_tc: N tiles are 64 wide for M <= 512, 128 wide otherwise
-inline bool tc_shape_ok(int M, int N, int K) { return K % 32 == 0 && N % (M <= 512 ? 64 : 128) == 0; }
-
-// out[c * ldo + r] = in[r * ld + c] for r < Rp (zero for R <= r < Rp), c < C
-__global__ void __launch_bounds__(256) transpose_pad_kernel(const float* __restrict__ in, int ld, int R, int C, float* __restrict__ out, int Rp,
-                                                            int ldo) {
-    pdl_wait();
-    pdl_trigger();
-    __shared__ float tile[32][33];
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int r = r0 + ty + i * 8, c = c0 + tx;
-        tile[ty + i * 8][tx] = (r < R && c < C) ? in[(long long)r * ld + c] : 0.f;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int c = c0 + ty + i * 8, r = r0 + tx;
-        if (c < C && r < Rp) out[(long long)c * ldo + r] = tile[tx][ty + i * 8];
-    }
-}
-int transpose_pad(const float* in, int ld, int R, int C, float* out, int Rp, cudaStream_t st, int ldo = 0) {
-    launch_k(transpose_pad_kernel, dim3(cdiv(Rp, 32), cdiv(C, 32)), dim3(256), 0, st, in, ld, R, C, out, Rp, ldo > 0 ? ldo : Rp);
-    MV2D_CHECK_LAUNCH("train transpose");
-    return 0;
-}
-
-// dW[n,k] += sum_z part[z][...]; part is [rows, cols] = [Nout, K], or [K, Nout] when `swapped`
-// rows_per_blk / blk_stride: output rows n are grouped in blocks of rows_per_blk that sit blk_stride floats apart in dW (the
-// same tensor of consecutive decoder layers in the flat gradient buffer); 0 = one contiguous matrix
-__global__ void __launch_bounds__(256) wgrad_fold_kernel(const float* __restrict__ part, int nsplit, long long stride, int Nout, int K,
-                                                         int swapped, float* __restrict__ dW, int ldw, int rows_per_blk, long long blk_stride) {
-    pdl_wait();
-    pdl_trigger();
-    const long long total = (long long)Nout * K;
-    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
-        // walk the partial in ITS row-major order (coalesced reads), scatter into dW
-        int n, k;
-        if (swapped) { k = (int)(i / Nout); n = (int)(i % Nout); } else { n = (int)(i / K); k = (int)(i % K); }
-        float a = 0.f;
-        for (int z = 0; z < nsplit; ++z) a += part[z * stride + i];
-        if (rows_per_blk > 0) dW[(n / rows_per_blk) * blk_stride + (long long)(n % rows_per_blk) * ldw + k] += a;
-        else dW[(long long)n * ldw + k] += a;
-    }
-}
-// db[n] += sum_r yt[n][r]  (rows of the transposed, zero-padded output gradient); one CTA per row
-__global__ void __launch_bounds__(256) rowsum_kernel(const float* __restrict__ yt, int Rp, int Nout, float* __restrict__ db, int rows_per_blk,
-                                                     long long blk_stride) {
-    pdl_wait();
-    pdl_trigger();
-    __shared__ float red[8];
-    const int n = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float a = 0.f;
-    for (int r = threadIdx.x; r < Rp; r += 256) a += yt[(long long)n * Rp + r];
-    a = warp_sum(a);
-    if (lane == 0) red[warp] = a;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        float t = 0.f;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) t += red[i];
-        if (rows_per_blk > 0) db[(n / rows_per_blk) * blk_stride + n % rows_per_blk] += t;
-        else db[n] += t;
-    }
-}
-// dX = (accumulate ? dX : 0) + src . [mask > 0 (and < 5e3)]   (rows of K floats; ld per operand)
-__global__ void __launch_bounds__(256) dgrad_finish_kernel(const float* __restrict__ src, int lds, const float* __restrict__ mask, int ldmask,
-                                                           int lt5e3, int accumulate, float* __restrict__ dX, int ldx, int M, int K) {
-    pdl_wait();
-    pdl_trigger();
-    const long long total = (long long)M * K;
-    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
-        const long long m = i / K;
-        const int k = (int)(i % K);
-        float v = src[m * lds + k];
-        if (mask) {
-            const float a = mask[m * ldmask + k];
-            if (!(a > 0.f) || (lt5e3 && !(a < 5e3f))) v = 0.f;
-        }
-        float* d = dX + m * ldx + k;
-        *d = accumulate ? *d + v : v;
-    }
-}
-inline int ew_grid_n(long long n) {
-    const long long want = (n + 255) / 256;
-    return (int)(want < 148 * 16 ? (want > 0 ? want : 1) : 148 * 16);
-}
-
-// the scratch of the current call (set by the run_* entry points; the library is single-threaded per call)
-thread_local TcScratch g_tc{};
-
-// Y[M,Nout] = act(X[M,K] W[Nout,K]^T + b)
-int linear_fwd(const float* X, int ldx, const float* W, int ldw, const float* b, float* Y, int ldy, int M, int Nout, int K,
-               bool relu, cudaStream_t st, int extra_flags = 0) {
-    const bool lds_ok = (ldx & 3) == 0 && (ldw & 3) == 0 && (ldy & 3) == 0 && al16(X) && al16(W) && al16(Y);
-    if (tc_enabled() && lds_ok && extra_flags == 0 && M >= 1024 && tc_shape_ok(M, Nout, K))
-        return tc_gemm(X, ldx, W, ldw, b, Y, ldy, M, Nout, K, relu, 1, 0, st);
-    if (tc_enabled() && lds_ok && M <= 512 && K % 32 == 0 && (Nout & 3) == 0 && (extra_flags & ~SG_CLAMP5E3) == 0) {
-        // the inference path's small-M kernel (in-CTA split-K): fp32 FFMA, same arithmetic class as the kernel below
-        GemmArgs a{};
-        a.A = X; a.lda = ldx; a.W = W; a.ldw = ldw; a.C = Y; a.ldc = ldy; a.bias = b; a.M = M; a.N = Nout; a.K = K;
-        a.batch = 1; a.nsplit = 1; a.flags = (relu ? GEMM_RELU : 0) | ((extra_flags & SG_CLAMP5E3) ? GEMM_CLAMP5E3 : 0);
-        return launch_gemm_small(a, nullptr, 0, st);
-    }
-    Sg g{};
-    g.A = X; g.sam = ldx; g.sak = 1; g.B = W; g.sbk = 1; g.sbn = ldw; g.C = Y; g.ldc = ldy; g.bias = b;
-    g.M = M; g.N = Nout; g.K = K; g.klen = K; g.flags = (relu ? SG_RELU : 0) | extra_flags;
-    return launch_sgemm(g, 1, st);
-}
-// dX[M,K] (+)= (dY[M,Nout] W[Nout,K]) . [mask > 0]
-int linear_dgrad(const float* dY, int ldy, const float* W, int ldw, float* dX, int ldx, int M, int Nout, int K,
-                 const float* mask, int ldmask, bool accumulate, cudaStream_t st, int extra_flags = 0) {
-    const TcScratch& sc = g_tc;
-    if (tc_enabled() && sc.wt && M >= 1024 && tc_shape_ok(M, K, Nout) && (ldy & 3) == 0 && (ldx & 3) == 0 && al16(dY) && al16(dX) &&
-        (size_t)K * Nout <= sc.wt_cap && (!accumulate || (size_t)M * K <= sc.tmp_cap)) {
-        TRY(transpose_pad(W, ldw, Nout, K, sc.wt, Nout, st));                       // W^T [K, Nout]
-        float* target = accumulate ? sc.tmp : dX;
-        const int ldt = accumulate ? K : ldx;
-        TRY(tc_gemm(dY, ldy, sc.wt, Nout, nullptr, target, ldt, M, K, Nout, false, 1, 0, st));
-        if (accumulate || mask) {
-            launch_k(dgrad_finish_kernel, dim3(ew_grid_n((long long)M * K)), dim3(256), 0, st, (const float*)target, ldt, mask, ldmask,
-                     (extra_flags & SG_MASK_LT5E3) ? 1 : 0, accumulate ? 1 : 0, dX, ldx, M, K);
-            MV2D_CHECK_LAUNCH("train dgrad_finish");
-        }
-        return 0;
-    }
-    if (tc_enabled() && sc.wt && M <= 512 && Nout % 32 == 0 && (K & 3) == 0 && (ldy & 3) == 0 && (ldx & 3) == 0 && al16(dY) && al16(dX) &&
-        (size_t)K * Nout <= sc.wt_cap && (!accumulate || (size_t)M * K <= sc.tmp_cap)) {
-        // M ~ 300 rows: W^T once, then the inference path's small-M kernel (in-CTA split-K) -- a chain of k-steps on
-        // the 20 CTAs the strided FFMA kernel would get for these shapes is latency bound
-        TRY(transpose_pad(W, ldw, Nout, K, sc.wt, Nout, st));
-        float* target = accumulate ? sc.tmp : dX;
-        const int ldt = accumulate ? K : ldx;
-        GemmArgs a{};
-        a.A = dY; a.lda = ldy; a.W = sc.wt; a.ldw = Nout; a.C = target; a.ldc = ldt; a.M = M; a.N = K; a.K = Nout; a.batch = 1; a.nsplit = 1;
-        TRY(launch_gemm_small(a, nullptr, 0, st));
-        if (accumulate || mask) {
-            launch_k(dgrad_finish_kernel, dim3(ew_grid_n((long long)M * K)), dim3(256), 0, st, (const float*)target, ldt, mask, ldmask,
-                     (extra_flags & SG_MASK_LT5E3) ? 1 : 0, accumulate ? 1 : 0, dX, ldx, M, K);
-            MV2D_CHECK_LAUNCH("train dgrad_finish");
-        }
-        return 0;
-    }
-    Sg g{};
-    g.A = dY; g.sam = ldy; g.sak = 1; g.B = W; g.sbk = ldw; g.sbn = 1; g.C = dX; g.ldc = ldx; g.mask = mask; g.ldmask = ldmask;
-    g.M = M; g.N = K; g.K = Nout; g.klen = Nout; g.flags = (accumulate ? SG_ACC : 0) | extra_flags;
-    return launch_sgemm(g, 1, st);
-}
-// dW[Nout,K] += dY[M,Nout]^T X[M,K]   (split over the M rows, atomic accumulation);  db[Nout] += sum_rows dY (nullable)
-int linear_wgrad(const float* dY, int ldy, const float* X, int ldx, float* dW, int ldw, int M, int Nout, int K, cudaStream_t st,
-                 float* db = nullptr) {
-    const TcScratch& sc = g_tc;
-    if (tc_enabled() && sc.at && M >= 1024) {
-        const int Mp = round32(M);
-        const bool direct = tc_shape_ok(Nout, K, Mp), swapped = !direct && tc_shape_ok(K, Nout, Mp);
-        const int gm = direct ? Nout : K, gn = direct ? K : Nout;           // the GEMM's M and N
-        const int tiles = cdiv(gm, 128) * (gn / (gm <= 512 ? 64 : 128));
-        const int nkb = Mp / 32;
-        int nsplit = 1;
-        for (int d = 1; d <= 48 && d <= nkb; ++d)
-            if (nkb % d == 0 && nkb / d >= 4) { nsplit = d; if (tiles * d >= 148) break; }
-        if ((direct || swapped) && (size_t)Nout * Mp <= sc.at_cap && (size_t)K * Mp <= sc.bt_cap &&
-            (size_t)nsplit * Nout * K <= sc.part_cap) {
-            TRY(transpose_pad(dY, ldy, M, Nout, sc.at, Mp, st));                     // dY^T [Nout, Mp]
-            TRY(transpose_pad(X, ldx, M, K, sc.bt, Mp, st));                         // X^T  [K, Mp]
-            const float* ga = direct ? sc.at : sc.bt;
-            const float* gw = direct ? sc.bt : sc.at;
-            TRY(tc_gemm(ga, Mp, gw, Mp, nullptr, sc.part, gn, gm, gn, Mp, false, nsplit, (long long)Nout * K, st));
-            launch_k(wgrad_fold_kernel, dim3(ew_grid_n((long long)Nout * K)), dim3(256), 0, st, (const float*)sc.part, nsplit,
-                     (long long)Nout * K, Nout, K, swapped ? 1 : 0, dW, ldw, 0, 0LL);
-            MV2D_CHECK_LAUNCH("train wgrad_fold");
-            if (db) {
-                launch_k(rowsum_kernel, dim3(Nout), dim3(256), 0, st, (const float*)sc.at, Mp, Nout, db, 0, 0LL);
-                MV2D_CHECK_LAUNCH("train rowsum");
-            }
-            return 0;
-        }
-    }
-    Sg g{};
-    g.A = dY; g.sam = 1; g.sak = ldy; g.B = X; g.sbk = ldx; g.sbn = 1; g.C = dW; g.ldc = ldw; g.rowsum = db;
-    g.M = Nout; g.N = K; g.K = M; g.flags = SG_ATOMIC;
-    const int t = sg_tile(Nout, K);
-    const int tiles = cdiv(Nout, t) * cdiv(K, t);
-    int splits = cdiv(296, tiles);
-    splits = std::max(1, std::min(splits, cdiv(M, 64)));
-    g.klen = cdiv(cdiv(M, splits), 16) * 16;
-    splits = cdiv(M, g.klen);
-    return launch_sgemm(g, splits, st);
-}
-
-// out[n] += sum_m X[m*ld + n]   (bias gradients)
-__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ X, int ld, int M, int N, int rows_per_block,
-                                                     float* __restrict__ out) {
-    pdl_wait();
-    pdl_trigger();
-    __shared__ float s[8][33];
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const int n = blockIdx.x * 32 + tx;
-    const int r0 = blockIdx.y * rows_per_block, r1 = min(M, r0 + rows_per_block);
-    float a = 0.f;
-    if (n < N)
-        for (int r = r0 + ty; r < r1; r += 8) a += X[(long long)r * ld + n];
-    s[ty][tx] = a;
-    __syncthreads();
-    if (ty == 0 && n < N) {
-        float t = 0.f;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) t += s[i][tx];
-        atomicAdd(out + n, t);
-    }
-}
-int colsum(const float* X, int ld, int M, int N, float* out, cudaStream_t st) {
-    if (M <= 0 || N <= 0) return 0;
-    const int rpb = 256;
-    launch_k(colsum_kernel, dim3(cdiv(N, 32), cdiv(M, rpb)), dim3(256), 0, st, X, ld, M, N, rpb, out);
-    MV2D_CHECK_LAUNCH("train colsum");
-    return 0;
-}
-
-// out = a + b (b nullable); in-place allowed
-__global__ void __launch_bounds__(256) add_kernel(float* out, const float* a, const float* b, long long n) {
-    pdl_wait();
-    pdl_trigger();
-    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256)
-        out[i] = a[i] + (b ? b[i] : 0.f);
-}
-int add(float* out, const float* a, const float* b, long long n, cudaStream_t st) {
-    if (n <= 0) return 0;
-    const long long want = (n + 255) / 256;
-    const int grid = (int)(want < 148 * 8 ? want : 148 * 8);
-    launch_k(add_kernel, dim3(grid), dim3(256), 0, st, out, a, b, n);
-    MV2D_CHECK_LAUNCH("train add");
-    return 0;
-}
+#include "train_gemm.cuh"
 
 // ------------------------------------------------------------------------------------------------ LayerNorm
 // y = a (+ b); xhat = (y - mean) * rstd; out = [relu](xhat * g + beta).  One warp per row of 256.
@@ -630,497 +240,7 @@ __global__ void __launch_bounds__(96) posemb_bwd_kernel(const float* __restrict_
     if (lane == 0) d_ref[n * 3 + comp] += a;
 }
 
-// ------------------------------------------------------------------------------------------------ self-attention
-// One CTA per query, one warp per head; lane = key.  qkv [N,768] = (q | k | v), q and k from x + query_pos.
-__global__ void __launch_bounds__(256) sa_fwd_kernel(const float* __restrict__ qkv, float* __restrict__ P,
-                                                     float* __restrict__ attn_o, int N) {
-    pdl_wait();
-    pdl_trigger();
-    const int i = blockIdx.x, h = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const float scale = 0.17677669529663687f;   // 1 / sqrt(32)
-    float q[THD];
-#pragma unroll
-    for (int c = 0; c < THD; ++c) q[c] = qkv[(long long)i * 768 + h * THD + c] * scale;
-    float* Prow = P + ((long long)h * N + i) * N;
-    float mx = -INFINITY;
-    for (int j = lane; j < N; j += 32) {
-        const float4* kr = reinterpret_cast<const float4*>(qkv + (long long)j * 768 + 256 + h * THD);
-        float s = 0.f;
-#pragma unroll
-        for (int c4 = 0; c4 < THD / 4; ++c4) {
-            const float4 k = kr[c4];
-            s += q[c4 * 4] * k.x + q[c4 * 4 + 1] * k.y + q[c4 * 4 + 2] * k.z + q[c4 * 4 + 3] * k.w;
-        }
-        Prow[j] = s;
-        mx = fmaxf(mx, s);
-    }
-    mx = warp_max(mx);
-    float sum = 0.f;
-    for (int j = lane; j < N; j += 32) {
-        const float e = expf(Prow[j] - mx);
-        Prow[j] = e;
-        sum += e;
-    }
-    sum = warp_sum(sum);
-    const float inv = 1.f / sum;
-    float o[THD];
-#pragma unroll
-    for (int c = 0; c < THD; ++c) o[c] = 0.f;
-    for (int j = lane; j < N; j += 32) {
-        const float p = Prow[j] * inv;
-        Prow[j] = p;
-        const float4* vr = reinterpret_cast<const float4*>(qkv + (long long)j * 768 + 512 + h * THD);
-#pragma unroll
-        for (int c4 = 0; c4 < THD / 4; ++c4) {
-            const float4 v = vr[c4];
-            o[c4 * 4] += p * v.x; o[c4 * 4 + 1] += p * v.y; o[c4 * 4 + 2] += p * v.z; o[c4 * 4 + 3] += p * v.w;
-        }
-    }
-    float mine = 0.f;
-#pragma unroll
-    for (int c = 0; c < THD; ++c) {
-        const float r = warp_sum(o[c]);
-        if (lane == c) mine = r;
-    }
-    attn_o[(long long)i * TC_ + h * THD + lane] = mine;
-}
-
-// dO [N,256] -> dS (probability-space gradient folded to logits) and dq (rows 0:256 of dqkv)
-__global__ void __launch_bounds__(256) sa_bwd_dq_kernel(const float* __restrict__ qkv, const float* __restrict__ P,
-                                                        const float* __restrict__ dO, float* __restrict__ dS,
-                                                        float* __restrict__ dqkv, int N) {
-    pdl_wait();
-    pdl_trigger();
-    const int i = blockIdx.x, h = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const float scale = 0.17677669529663687f;
-    float go[THD];
-#pragma unroll
-    for (int c = 0; c < THD; ++c) go[c] = dO[(long long)i * TC_ + h * THD + c];
-    const float* Prow = P + ((long long)h * N + i) * N;
-    float* Srow = dS + ((long long)h * N + i) * N;
-    float D = 0.f;
-    for (int j = lane; j < N; j += 32) {
-        const float4* vr = reinterpret_cast<const float4*>(qkv + (long long)j * 768 + 512 + h * THD);
-        float dp = 0.f;
-#pragma unroll
-        for (int c4 = 0; c4 < THD / 4; ++c4) {
-            const float4 v = vr[c4];
-            dp += go[c4 * 4] * v.x + go[c4 * 4 + 1] * v.y + go[c4 * 4 + 2] * v.z + go[c4 * 4 + 3] * v.w;
-        }
-        Srow[j] = dp;
-        D += Prow[j] * dp;
-    }
-    D = warp_sum(D);
-    float dq[THD];
-#pragma unroll
-    for (int c = 0; c < THD; ++c) dq[c] = 0.f;
-    for (int j = lane; j < N; j += 32) {
-        const float ds = Prow[j] * (Srow[j] - D);
-        Srow[j] = ds;
-        const float4* kr = reinterpret_cast<const float4*>(qkv + (long long)j * 768 + 256 + h * THD);
-#pragma unroll
-        for (int c4 = 0; c4 < THD / 4; ++c4) {
-            const float4 k = kr[c4];
-            dq[c4 * 4] += ds * k.x; dq[c4 * 4 + 1] += ds * k.y; dq[c4 * 4 + 2] += ds * k.z; dq[c4 * 4 + 3] += ds * k.w;
-        }
-    }
-    float mine = 0.f;
-#pragma unroll
-    for (int c = 0; c < THD; ++c) {
-        const float r = warp_sum(dq[c]);
-        if (lane == c) mine = r;
-    }
-    dqkv[(long long)i * 768 + h * THD + lane] = mine * scale;
-}
-
-// one CTA per key j, one warp per head; lane = query.  dk -> dqkv[:, 256:512], dv -> dqkv[:, 512:768]
-__global__ void __launch_bounds__(256) sa_bwd_dkv_kernel(const float* __restrict__ qkv, const float* __restrict__ P,
-                                                         const float* __restrict__ dS, const float* __restrict__ dO,
-                                                         float* __restrict__ dqkv, int N) {
-    pdl_wait();
-    pdl_trigger();
-    const int j = blockIdx.x, h = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const float scale = 0.17677669529663687f;
-    float dk[THD], dv[THD];
-#pragma unroll
-    for (int c = 0; c < THD; ++c) { dk[c] = 0.f; dv[c] = 0.f; }
-    for (int i = lane; i < N; i += 32) {
-        const long long o = ((long long)h * N + i) * N + j;
-        const float p = P[o], ds = dS[o];
-        const float4* qr = reinterpret_cast<const float4*>(qkv + (long long)i * 768 + h * THD);
-        const float4* gr = reinterpret_cast<const float4*>(dO + (long long)i * TC_ + h * THD);
-#pragma unroll
-        for (int c4 = 0; c4 < THD / 4; ++c4) {
-            const float4 q = qr[c4], g = gr[c4];
-            dk[c4 * 4] += ds * q.x; dk[c4 * 4 + 1] += ds * q.y; dk[c4 * 4 + 2] += ds * q.z; dk[c4 * 4 + 3] += ds * q.w;
-            dv[c4 * 4] += p * g.x; dv[c4 * 4 + 1] += p * g.y; dv[c4 * 4 + 2] += p * g.z; dv[c4 * 4 + 3] += p * g.w;
-        }
-    }
-    float mk = 0.f, mv = 0.f;
-#pragma unroll
-    for (int c = 0; c < THD; ++c) {
-        const float rk = warp_sum(dk[c]), rv = warp_sum(dv[c]);
-        if (lane == c) { mk = rk; mv = rv; }
-    }
-    dqkv[(long long)j * 768 + 256 + h * THD + lane] = mk * scale;
-    dqkv[(long long)j * 768 + 512 + h * THD + lane] = mv;
-}
-
-// ---- shared-memory variants (the default whenever one head's K and V of all N queries fit: N <= 775).  The kernels
-// above read every key row from L2 once per (query, head) -- 184 MB of L2 traffic per launch at N = 300, which is what
-// bounded them (66 us).  Here a CTA owns one head and 16 queries (or 16 keys), stages the head's two [N,32] operand
-// slices in shared memory once (row stride 33 floats: lane = row reads are conflict-free) and the warps walk them.
-constexpr int SA_QB = 16;
-__device__ __forceinline__ void sa_stage(const float* __restrict__ src, int ld, int col, int N, float* __restrict__ dst) {
-    for (int idx = threadIdx.x; idx < N * 8; idx += 256) {
-        const int r = idx >> 3, c4 = idx & 7;
-        const float4 v = *reinterpret_cast<const float4*>(src + (long long)r * ld + col + c4 * 4);
-        float* d = dst + r * 33 + c4 * 4;
-        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
-    }
-}
-
-__global__ void __launch_bounds__(256) sa_fwd_smem_kernel(const float* __restrict__ qkv, float* __restrict__ P,
-                                                          float* __restrict__ attn_o, int N) {
-    pdl_wait();
-    pdl_trigger();
-    extern __shared__ float sa_sm[];
-    float* Ks = sa_sm;
-    float* Vs = sa_sm + (size_t)N * 33;
-    const int h = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    sa_stage(qkv, 768, 256 + h * THD, N, Ks);
-    sa_stage(qkv, 768, 512 + h * THD, N, Vs);
-    __syncthreads();
-    const float scale = 0.17677669529663687f;
-    for (int qi = warp; qi < SA_QB; qi += 8) {
-        const int i = blockIdx.x * SA_QB + qi;
-        if (i >= N) break;
-        float q[THD];
-#pragma unroll
-        for (int c = 0; c < THD; ++c) q[c] = qkv[(long long)i * 768 + h * THD + c] * scale;
-        float* Prow = P + ((long long)h * N + i) * N;
-        float mx = -INFINITY;
-        for (int j = lane; j < N; j += 32) {
-            const float* k = Ks + j * 33;
-            float s = 0.f;
-#pragma unroll
-            for (int c = 0; c < THD; ++c) s = fmaf(q[c], k[c], s);
-            Prow[j] = s;
-            mx = fmaxf(mx, s);
-        }
-        mx = warp_max(mx);
-        float sum = 0.f;
-        for (int j = lane; j < N; j += 32) {
-            const float e = expf(Prow[j] - mx);
-            Prow[j] = e;
-            sum += e;
-        }
-        sum = warp_sum(sum);
-        const float inv = 1.f / sum;
-        float o[THD];
-#pragma unroll
-        for (int c = 0; c < THD; ++c) o[c] = 0.f;
-        for (int j = lane; j < N; j += 32) {
-            const float p = Prow[j] * inv;
-            Prow[j] = p;
-            const float* v = Vs + j * 33;
-#pragma unroll
-            for (int c = 0; c < THD; ++c) o[c] = fmaf(p, v[c], o[c]);
-        }
-        float mine = 0.f;
-#pragma unroll
-        for (int c = 0; c < THD; ++c) {
-            const float r = warp_sum(o[c]);
-            if (lane == c) mine = r;
-        }
-        attn_o[(long long)i * TC_ + h * THD + lane] = mine;
-    }
-}
-
-__global__ void __launch_bounds__(256) sa_bwd_dq_smem_kernel(const float* __restrict__ qkv, const float* __restrict__ P,
-                                                             const float* __restrict__ dO, float* __restrict__ dS,
-                                                             float* __restrict__ dqkv, int N) {
-    pdl_wait();
-    pdl_trigger();
-    extern __shared__ float sa_sm[];
-    float* Ks = sa_sm;
-    float* Vs = sa_sm + (size_t)N * 33;
-    const int h = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    sa_stage(qkv, 768, 256 + h * THD, N, Ks);
-    sa_stage(qkv, 768, 512 + h * THD, N, Vs);
-    __syncthreads();
-    const float scale = 0.17677669529663687f;
-    for (int qi = warp; qi < SA_QB; qi += 8) {
-        const int i = blockIdx.x * SA_QB + qi;
-        if (i >= N) break;
-        float go[THD];
-#pragma unroll
-        for (int c = 0; c < THD; ++c) go[c] = dO[(long long)i * TC_ + h * THD + c];
-        const float* Prow = P + ((long long)h * N + i) * N;
-        float* Srow = dS + ((long long)h * N + i) * N;
-        float D = 0.f;
-        for (int j = lane; j < N; j += 32) {
-            const float* v = Vs + j * 33;
-            float dp = 0.f;
-#pragma unroll
-            for (int c = 0; c < THD; ++c) dp = fmaf(go[c], v[c], dp);
-            Srow[j] = dp;
-            D += Prow[j] * dp;
-        }
-        D = warp_sum(D);
-        float dq[THD];
-#pragma unroll
-        for (int c = 0; c < THD; ++c) dq[c] = 0.f;
-        for (int j = lane; j < N; j += 32) {
-            const float ds = Prow[j] * (Srow[j] - D);
-            Srow[j] = ds;
-            const float* k = Ks + j * 33;
-#pragma unroll
-            for (int c = 0; c < THD; ++c) dq[c] = fmaf(ds, k[c], dq[c]);
-        }
-        float mine = 0.f;
-#pragma unroll
-        for (int c = 0; c < THD; ++c) {
-            const float r = warp_sum(dq[c]);
-            if (lane == c) mine = r;
-        }
-        dqkv[(long long)i * 768 + h * THD + lane] = mine * scale;
-    }
-}
-
-// CTA = (16 keys, head): the head's Q and dO slices of all queries are staged; one warp per key, lane = query
-__global__ void __launch_bounds__(256) sa_bwd_dkv_smem_kernel(const float* __restrict__ qkv, const float* __restrict__ P,
-                                                              const float* __restrict__ dS, const float* __restrict__ dO,
-                                                              float* __restrict__ dqkv, int N) {
-    pdl_wait();
-    pdl_trigger();
-    extern __shared__ float sa_sm[];
-    float* Qs = sa_sm;
-    float* Gs = sa_sm + (size_t)N * 33;
-    const int h = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    sa_stage(qkv, 768, h * THD, N, Qs);
-    sa_stage(dO, TC_, h * THD, N, Gs);
-    __syncthreads();
-    const float scale = 0.17677669529663687f;
-    for (int ki = warp; ki < SA_QB; ki += 8) {
-        const int j = blockIdx.x * SA_QB + ki;
-        if (j >= N) break;
-        float dk[THD], dv[THD];
-#pragma unroll
-        for (int c = 0; c < THD; ++c) { dk[c] = 0.f; dv[c] = 0.f; }
-        for (int i = lane; i < N; i += 32) {
-            const long long o = ((long long)h * N + i) * N + j;
-            const float p = P[o], ds = dS[o];
-            const float* q = Qs + i * 33;
-            const float* g = Gs + i * 33;
-#pragma unroll
-            for (int c = 0; c < THD; ++c) { dk[c] = fmaf(ds, q[c], dk[c]); dv[c] = fmaf(p, g[c], dv[c]); }
-        }
-        float mk = 0.f, mv = 0.f;
-#pragma unroll
-        for (int c = 0; c < THD; ++c) {
-            const float rk = warp_sum(dk[c]), rv = warp_sum(dv[c]);
-            if (lane == c) { mk = rk; mv = rv; }
-        }
-        dqkv[(long long)j * 768 + 256 + h * THD + lane] = mk * scale;
-        dqkv[(long long)j * 768 + 512 + h * THD + lane] = mv;
-    }
-}
-
-inline size_t sa_smem_bytes(int N) { return (size_t)2 * N * 33 * sizeof(float); }
-inline bool sa_use_smem(int N) {
-    static const bool on = []() { const char* e = getenv("MV2D_TRAIN_SA_SMEM"); return !(e && e[0] == '0'); }();
-    return on && sa_smem_bytes(N) <= 200 * 1024;
-}
-int sa_set_attr() {
-    static bool done = false;
-    if (done) return 0;
-    cudaError_t e;
-    if ((e = cudaFuncSetAttribute(sa_fwd_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)) != cudaSuccess ||
-        (e = cudaFuncSetAttribute(sa_bwd_dq_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)) != cudaSuccess ||
-        (e = cudaFuncSetAttribute(sa_bwd_dkv_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)) != cudaSuccess) {
-        set_error("train: self-attention smem attribute: %s", cudaGetErrorString(e));
-        return (int)e;
-    }
-    done = true;
-    return 0;
-}
-
-// ------------------------------------------------------------------------------------------------ cross-attention
-// query i attends to the 49 tokens of every RoI in match[i][0 .. cnt_i); Kp / Vp [N*49,256] projected tokens.
-// P [N, 8, PM] with PM = max_match * 49; slot = m * 49 + t.
-__global__ void __launch_bounds__(256) xa_fwd_kernel(const float* __restrict__ cq, const float* __restrict__ Kp,
-                                                     const float* __restrict__ Vp, const int* __restrict__ match,
-                                                     const int* __restrict__ match_cnt, int max_match,
-                                                     float* __restrict__ P, float* __restrict__ ctx, int N) {
-    pdl_wait();
-    pdl_trigger();
-    const int i = blockIdx.x, h = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int PM = max_match * TTOK;
-    const int cnt = min(match_cnt[i], max_match);
-    const float scale = 0.17677669529663687f;
-    float q[THD];
-#pragma unroll
-    for (int c = 0; c < THD; ++c) q[c] = cq[(long long)i * TC_ + h * THD + c] * scale;
-    float* Prow = P + ((long long)i * TH + h) * PM;
-    float mx = -INFINITY;
-    for (int m = 0; m < cnt; ++m) {
-        const int r = match[i * max_match + m];
-        for (int t = lane; t < TTOK; t += 32) {
-            const float4* kr = reinterpret_cast<const float4*>(Kp + ((long long)r * TTOK + t) * TC_ + h * THD);
-            float s = 0.f;
-#pragma unroll
-            for (int c4 = 0; c4 < THD / 4; ++c4) {
-                const float4 k = kr[c4];
-                s += q[c4 * 4] * k.x + q[c4 * 4 + 1] * k.y + q[c4 * 4 + 2] * k.z + q[c4 * 4 + 3] * k.w;
-            }
-            Prow[m * TTOK + t] = s;
-            mx = fmaxf(mx, s);
-        }
-    }
-    mx = warp_max(mx);
-    float sum = 0.f;
-    for (int m = 0; m < cnt; ++m)
-        for (int t = lane; t < TTOK; t += 32) {
-            const float e = expf(Prow[m * TTOK + t] - mx);
-            Prow[m * TTOK + t] = e;
-            sum += e;
-        }
-    sum = warp_sum(sum);
-    const float inv = cnt > 0 ? 1.f / sum : 0.f;
-    float o[THD];
-#pragma unroll
-    for (int c = 0; c < THD; ++c) o[c] = 0.f;
-    for (int m = 0; m < cnt; ++m) {
-        const int r = match[i * max_match + m];
-        for (int t = lane; t < TTOK; t += 32) {
-            const float p = Prow[m * TTOK + t] * inv;
-            Prow[m * TTOK + t] = p;
-            const float4* vr = reinterpret_cast<const float4*>(Vp + ((long long)r * TTOK + t) * TC_ + h * THD);
-#pragma unroll
-            for (int c4 = 0; c4 < THD / 4; ++c4) {
-                const float4 v = vr[c4];
-                o[c4 * 4] += p * v.x; o[c4 * 4 + 1] += p * v.y; o[c4 * 4 + 2] += p * v.z; o[c4 * 4 + 3] += p * v.w;
-            }
-        }
-    }
-    float mine = 0.f;
-#pragma unroll
-    for (int c = 0; c < THD; ++c) {
-        const float r = warp_sum(o[c]);
-        if (lane == c) mine = r;
-    }
-    ctx[(long long)i * TC_ + h * THD + lane] = mine;
-}
-
-__global__ void __launch_bounds__(256) xa_bwd_dq_kernel(const float* __restrict__ Kp, const float* __restrict__ Vp,
-                                                        const float* __restrict__ P, const float* __restrict__ dctx,
-                                                        const int* __restrict__ match, const int* __restrict__ match_cnt,
-                                                        int max_match, float* __restrict__ dS, float* __restrict__ dcq, int N) {
-    pdl_wait();
-    pdl_trigger();
-    const int i = blockIdx.x, h = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int PM = max_match * TTOK;
-    const int cnt = min(match_cnt[i], max_match);
-    const float scale = 0.17677669529663687f;
-    float go[THD];
-#pragma unroll
-    for (int c = 0; c < THD; ++c) go[c] = dctx[(long long)i * TC_ + h * THD + c];
-    const float* Prow = P + ((long long)i * TH + h) * PM;
-    float* Srow = dS + ((long long)i * TH + h) * PM;
-    float D = 0.f;
-    for (int m = 0; m < cnt; ++m) {
-        const int r = match[i * max_match + m];
-        for (int t = lane; t < TTOK; t += 32) {
-            const float4* vr = reinterpret_cast<const float4*>(Vp + ((long long)r * TTOK + t) * TC_ + h * THD);
-            float dp = 0.f;
-#pragma unroll
-            for (int c4 = 0; c4 < THD / 4; ++c4) {
-                const float4 v = vr[c4];
-                dp += go[c4 * 4] * v.x + go[c4 * 4 + 1] * v.y + go[c4 * 4 + 2] * v.z + go[c4 * 4 + 3] * v.w;
-            }
-            Srow[m * TTOK + t] = dp;
-            D += Prow[m * TTOK + t] * dp;
-        }
-    }
-    D = warp_sum(D);
-    float dq[THD];
-#pragma unroll
-    for (int c = 0; c < THD; ++c) dq[c] = 0.f;
-    for (int m = 0; m < cnt; ++m) {
-        const int r = match[i * max_match + m];
-        for (int t = lane; t < TTOK; t += 32) {
-            const float ds = Prow[m * TTOK + t] * (Srow[m * TTOK + t] - D);
-            Srow[m * TTOK + t] = ds;
-            const float4* kr = reinterpret_cast<const float4*>(Kp + ((long long)r * TTOK + t) * TC_ + h * THD);
-#pragma unroll
-            for (int c4 = 0; c4 < THD / 4; ++c4) {
-                const float4 k = kr[c4];
-                dq[c4 * 4] += ds * k.x; dq[c4 * 4 + 1] += ds * k.y; dq[c4 * 4 + 2] += ds * k.z; dq[c4 * 4 + 3] += ds * k.w;
-            }
-        }
-    }
-    float mine = 0.f;
-#pragma unroll
-    for (int c = 0; c < THD; ++c) {
-        const float r = warp_sum(dq[c]);
-        if (lane == c) mine = r;
-    }
-    dcq[(long long)i * TC_ + h * THD + lane] = mine * scale;
-}
-
-// inverse of the match lists: for every RoI r the (query, list position) pairs that attend to it, in ascending
-// order (deterministic summation order in xa_bwd_dkv).  One warp per RoI.
-__global__ void __launch_bounds__(32) xa_inverse_kernel(const int* __restrict__ match, const int* __restrict__ match_cnt,
-                                                        int max_match, int N, int* __restrict__ inv_cnt, int* __restrict__ inv_list) {
-    pdl_wait();
-    pdl_trigger();
-    const int r = blockIdx.x, lane = threadIdx.x;
-    int pos = 0;
-    const int total = N * max_match;
-    for (int base = 0; base < total; base += 32) {
-        const int e = base + lane;
-        bool hit = false;
-        if (e < total) {
-            const int i = e / max_match, m = e % max_match;
-            hit = m < min(match_cnt[i], max_match) && match[e] == r;
-        }
-        const unsigned b = __ballot_sync(0xffffffffu, hit);
-        if (hit) {
-            const int at = pos + __popc(b & ((1u << lane) - 1u));
-            if (at < N) inv_list[(long long)r * N + at] = e;
-        }
-        pos += __popc(b);
-    }
-    if (lane == 0) inv_cnt[r] = min(pos, N);
-}
-
-// one CTA per key token row (r, t), one warp per head, lane = channel of the head: the RoI's inverse list is short
-// (the RoI's own query plus the few that matched it), so the entries are walked sequentially with broadcast loads of
-// the two scalars and coalesced 128-byte loads of the query / output-gradient rows -- no shuffles
-__global__ void __launch_bounds__(256) xa_bwd_dkv_kernel(const float* __restrict__ cq, const float* __restrict__ dctx,
-                                                         const float* __restrict__ P, const float* __restrict__ dS,
-                                                         const int* __restrict__ inv_cnt, const int* __restrict__ inv_list,
-                                                         int max_match, float* __restrict__ dKp, float* __restrict__ dVp, int ldo, int N) {
-    pdl_wait();
-    pdl_trigger();
-    const int row = blockIdx.x, r = row / TTOK, t = row % TTOK;
-    const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int PM = max_match * TTOK;
-    const float scale = 0.17677669529663687f;
-    const int n = inv_cnt[r];
-    float dk = 0.f, dv = 0.f;
-    for (int e = 0; e < n; ++e) {
-        const int code = __ldg(inv_list + (long long)r * N + e);
-        const int i = code / max_match, m = code % max_match;
-        const long long o = ((long long)i * TH + h) * PM + m * TTOK + t;
-        const float p = __ldg(P + o), ds = __ldg(dS + o);
-        dk = fmaf(ds, __ldg(cq + (long long)i * TC_ + h * THD + lane), dk);
-        dv = fmaf(p, __ldg(dctx + (long long)i * TC_ + h * THD + lane), dv);
-    }
-    dKp[(long long)row * ldo + h * THD + lane] = dk * scale;      // ldo: all layers' gradients side by side, [N*49, L*256]
-    dVp[(long long)row * ldo + h * THD + lane] = dv;
-}
+#include "train_attn.cuh"
 
 // ------------------------------------------------------------------------------------------------ reg branch tail
 struct Range6 { float v[6]; };
@@ -1331,254 +451,7 @@ int check_params(const Mv2dTrainParams& p) {
 }
 
 
-// ================================================================================================ front end
-// Training forward / backward of rows a1-a8: position encoding (pe.py:137-169), RoIAlign of feat and pe
-// (mv2d_s_head.py:133-138), query generator (query_generator.py:343-405) and the reference-point normalisation
-// (mv2d_s_head.py:147-152), all in fp32 FFMA (the inference path runs the same MLPs as single-pass TF32).
-
-// ---- RoIAlign (mmcv: avg, aligned=True, adaptive sampling grid), channels-last maps.  The bin geometry is evaluated
-// with explicitly rounded fp32 operations (no FMA contraction) so that forward, backward and csrc/roi.cu make the
-// same floor / in-range decisions.
-struct RoiBin { int v, gh, gw; float x1, y1, bw, bh, count; };
-__device__ __forceinline__ RoiBin roi_bin(const float* __restrict__ r, float spatial_scale) {
-    RoiBin b;
-    b.v = (int)r[0];
-    b.x1 = __fadd_rn(__fmul_rn(r[1], spatial_scale), -0.5f);
-    b.y1 = __fadd_rn(__fmul_rn(r[2], spatial_scale), -0.5f);
-    const float x2 = __fadd_rn(__fmul_rn(r[3], spatial_scale), -0.5f), y2 = __fadd_rn(__fmul_rn(r[4], spatial_scale), -0.5f);
-    const float rw = __fsub_rn(x2, b.x1), rh = __fsub_rn(y2, b.y1);
-    b.bw = __fdiv_rn(rw, (float)MV2D_ROI);
-    b.bh = __fdiv_rn(rh, (float)MV2D_ROI);
-    b.gh = (int)ceilf(__fdiv_rn(rh, (float)MV2D_ROI));
-    b.gw = (int)ceilf(__fdiv_rn(rw, (float)MV2D_ROI));
-    b.count = (float)max(b.gh * b.gw, 1);
-    return b;
-}
-struct RoiTap { int o1, o2, o3, o4; float w1, w2, w3, w4; bool ok; };
-// sample (iy, ix) of bin (ph, pw): the four corner offsets (in pixels) and bilinear weights
-__device__ __forceinline__ RoiTap roi_tap(const RoiBin& b, int ph, int pw, int iy, int ix, int h, int w) {
-    RoiTap t;
-    const float y = __fadd_rn(__fadd_rn(b.y1, __fmul_rn((float)ph, b.bh)), __fdiv_rn(__fmul_rn(__fadd_rn((float)iy, 0.5f), b.bh), (float)b.gh));
-    const float x = __fadd_rn(__fadd_rn(b.x1, __fmul_rn((float)pw, b.bw)), __fdiv_rn(__fmul_rn(__fadd_rn((float)ix, 0.5f), b.bw), (float)b.gw));
-    t.ok = !(y < -1.f || y > (float)h || x < -1.f || x > (float)w);
-    float yy = fmaxf(y, 0.f), xx = fmaxf(x, 0.f);
-    int yl = (int)yy, xl = (int)xx, yh, xh;
-    if (yl >= h - 1) { yh = yl = h - 1; yy = (float)yl; } else yh = yl + 1;
-    if (xl >= w - 1) { xh = xl = w - 1; xx = (float)xl; } else xh = xl + 1;
-    const float ly = __fsub_rn(yy, (float)yl), lx = __fsub_rn(xx, (float)xl), hy = __fsub_rn(1.f, ly), hx = __fsub_rn(1.f, lx);
-    t.w1 = __fmul_rn(hy, hx); t.w2 = __fmul_rn(hy, lx); t.w3 = __fmul_rn(ly, hx); t.w4 = __fmul_rn(ly, lx);
-    t.o1 = yl * w + xl; t.o2 = yl * w + xh; t.o3 = yh * w + xl; t.o4 = yh * w + xh;
-    return t;
-}
-
-// grid (49, N), 64 threads (one float4 of the 256 channels each): tok[n, bin] = pooled map (+ addend[n, bin])
-__global__ void __launch_bounds__(64) roi_align_fwd_kernel(const float* __restrict__ rois, const float* __restrict__ map, int h, int w,
-                                                           float spatial_scale, const float* __restrict__ addend, float* __restrict__ tok) {
-    pdl_wait();
-    pdl_trigger();
-    const int n = blockIdx.y, bin = blockIdx.x, ph = bin / MV2D_ROI, pw = bin % MV2D_ROI;
-    const RoiBin b = roi_bin(rois + n * 5, spatial_scale);
-    const float4* m4 = reinterpret_cast<const float4*>(map) + (long long)b.v * h * w * 64 + threadIdx.x;
-    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int iy = 0; iy < b.gh; ++iy)
-        for (int ix = 0; ix < b.gw; ++ix) {
-            const RoiTap t = roi_tap(b, ph, pw, iy, ix, h, w);
-            if (!t.ok) continue;
-            const float4 c1 = __ldg(m4 + (long long)t.o1 * 64), c2 = __ldg(m4 + (long long)t.o2 * 64),
-                         c3 = __ldg(m4 + (long long)t.o3 * 64), c4 = __ldg(m4 + (long long)t.o4 * 64);
-            a.x += t.w1 * c1.x + t.w2 * c2.x + t.w3 * c3.x + t.w4 * c4.x;
-            a.y += t.w1 * c1.y + t.w2 * c2.y + t.w3 * c3.y + t.w4 * c4.y;
-            a.z += t.w1 * c1.z + t.w2 * c2.z + t.w3 * c3.z + t.w4 * c4.z;
-            a.w += t.w1 * c1.w + t.w2 * c2.w + t.w3 * c3.w + t.w4 * c4.w;
-        }
-    a.x /= b.count; a.y /= b.count; a.z /= b.count; a.w /= b.count;
-    const long long o = ((long long)n * MV2D_TOK + bin) * 64 + threadIdx.x;
-    if (addend) {
-        const float4 e = reinterpret_cast<const float4*>(addend)[o];
-        a.x += e.x; a.y += e.y; a.z += e.z; a.w += e.w;
-    }
-    reinterpret_cast<float4*>(tok)[o] = a;
-}
-
-// dmap[v, corner] += w * dtok[n, bin] / count   (atomic: RoIs and bins overlap on the map)
-__global__ void __launch_bounds__(64) roi_align_bwd_kernel(const float* __restrict__ rois, const float* __restrict__ dtok, int h, int w,
-                                                           float spatial_scale, float* __restrict__ dmap) {
-    pdl_wait();
-    pdl_trigger();
-    const int n = blockIdx.y, bin = blockIdx.x, ph = bin / MV2D_ROI, pw = bin % MV2D_ROI;
-    const RoiBin b = roi_bin(rois + n * 5, spatial_scale);
-    float4 g = reinterpret_cast<const float4*>(dtok)[((long long)n * MV2D_TOK + bin) * 64 + threadIdx.x];
-    g.x /= b.count; g.y /= b.count; g.z /= b.count; g.w /= b.count;
-    float* base = dmap + (long long)b.v * h * w * MV2D_C + threadIdx.x * 4;
-    for (int iy = 0; iy < b.gh; ++iy)
-        for (int ix = 0; ix < b.gw; ++ix) {
-            const RoiTap t = roi_tap(b, ph, pw, iy, ix, h, w);
-            if (!t.ok) continue;
-            const int off[4] = {t.o1, t.o2, t.o3, t.o4};
-            const float wt[4] = {t.w1, t.w2, t.w3, t.w4};
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                float* d = base + (long long)off[k] * MV2D_C;
-                atomicAdd(d + 0, wt[k] * g.x); atomicAdd(d + 1, wt[k] * g.y);
-                atomicAdd(d + 2, wt[k] * g.z); atomicAdd(d + 3, wt[k] * g.w);
-            }
-        }
-}
-
-// per RoI: the intrinsics feature of get_roi_feat (mv2d_head.py:95-101: flatten(K') * scale, zero when the box is
-// narrower than 4 px, clamped with the concatenation) into cat[:, 1024:1040], and float(inv(K' E^T)) of center2lidar
-__global__ void front_params_kernel(const float* __restrict__ rois, const double* __restrict__ k_roi, const double* __restrict__ extrinsics,
-                                    int N, float feat_scale, float* __restrict__ cat, float* __restrict__ m_roi) {
-    pdl_wait();
-    pdl_trigger();
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= N) return;
-    const float* r = rois + n * 5;
-    const int v = (int)r[0];
-    double K[16], E[16], L[16], Li[16];
-    for (int i = 0; i < 16; ++i) { K[i] = k_roi[n * 16 + i]; E[i] = extrinsics[v * 16 + i]; }
-    const bool invalid = (__fsub_rn(r[3], r[1]) < 4.f) || (__fsub_rn(r[4], r[2]) < 4.f);
-    for (int i = 0; i < 16; ++i) {
-        const float f = invalid ? 0.f : __fmul_rn((float)K[i], feat_scale);
-        cat[(long long)n * 1040 + 1024 + i] = fminf(fmaxf(f, -5e3f), 5e3f);
-    }
-    for (int i = 0; i < 4; ++i)
-        for (int j = 0; j < 4; ++j) {
-            double s = 0.0;
-            for (int k = 0; k < 4; ++k) s += K[i * 4 + k] * E[j * 4 + k];
-            L[i * 4 + j] = s;
-        }
-    inv4x4(L, Li);
-    for (int i = 0; i < 16; ++i) m_roi[n * 16 + i] = (float)Li[i];
-}
-
-// [N,7,7,256] tokens -> [N*49, 9*256] patches of the 3x3 / padding 1 convolution, K ordered (ky, kx, c)
-__global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ tok, float* __restrict__ col, int N) {
-    pdl_wait();
-    pdl_trigger();
-    const long long total = (long long)N * MV2D_TOK * 9 * 64;
-    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
-        const int c4 = (int)(i % 64);
-        const int tap = (int)((i / 64) % 9);
-        const long long row = i / (64 * 9);
-        const int t = (int)(row % MV2D_TOK), y = t / MV2D_ROI + tap / 3 - 1, x = t % MV2D_ROI + tap % 3 - 1;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (y >= 0 && y < MV2D_ROI && x >= 0 && x < MV2D_ROI)
-            v = reinterpret_cast<const float4*>(tok)[((row / MV2D_TOK) * MV2D_TOK + y * MV2D_ROI + x) * 64 + c4];
-        reinterpret_cast<float4*>(col)[(row * 9 + tap) * 64 + c4] = v;
-    }
-}
-// dtok[n,y,x,:] = sum over taps of dcol at the output cell that read (y,x) through that tap, + a1 + a2 (nullable)
-__global__ void __launch_bounds__(256) col2im_kernel(const float* __restrict__ dcol, const float* __restrict__ a1,
-                                                     const float* __restrict__ a2, float* __restrict__ dtok, int N) {
-    pdl_wait();
-    pdl_trigger();
-    const long long total = (long long)N * MV2D_TOK * 64;
-    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
-        const int c4 = (int)(i % 64);
-        const long long row = i / 64;
-        const long long n = row / MV2D_TOK;
-        const int t = (int)(row % MV2D_TOK), y = t / MV2D_ROI, x = t % MV2D_ROI;
-        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (a1) { const float4 e = reinterpret_cast<const float4*>(a1)[i]; s.x += e.x; s.y += e.y; s.z += e.z; s.w += e.w; }
-        if (a2) { const float4 e = reinterpret_cast<const float4*>(a2)[i]; s.x += e.x; s.y += e.y; s.z += e.z; s.w += e.w; }
-#pragma unroll
-        for (int tap = 0; tap < 9; ++tap) {
-            const int yo = y - (tap / 3 - 1), xo = x - (tap % 3 - 1);
-            if (yo < 0 || yo >= MV2D_ROI || xo < 0 || xo >= MV2D_ROI) continue;
-            const float4 e = reinterpret_cast<const float4*>(dcol)[((n * MV2D_TOK + yo * MV2D_ROI + xo) * 9 + tap) * 64 + c4];
-            s.x += e.x; s.y += e.y; s.z += e.z; s.w += e.w;
-        }
-        reinterpret_cast<float4*>(dtok)[i] = s;
-    }
-}
-
-// AvgPool2d(7) over [N,49,256] and its backward through the ReLU that precedes it
-__global__ void __launch_bounds__(256) pool49_fwd_kernel(const float* __restrict__ y, float* __restrict__ out, int N) {
-    pdl_wait();
-    pdl_trigger();
-    const int gid = blockIdx.x * 256 + threadIdx.x;
-    if (gid >= N * MV2D_C) return;
-    const int n = gid / MV2D_C, c = gid % MV2D_C;
-    float s = 0.f;
-    for (int t = 0; t < MV2D_TOK; ++t) s += y[((long long)n * MV2D_TOK + t) * MV2D_C + c];
-    out[gid] = s / 49.0f;
-}
-__global__ void __launch_bounds__(256) pool49_bwd_kernel(const float* __restrict__ y, const float* __restrict__ dpool,
-                                                         float* __restrict__ dy, int N) {
-    pdl_wait();
-    pdl_trigger();
-    const long long total = (long long)N * MV2D_TOK * MV2D_C;
-    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
-        const long long n = i / (MV2D_TOK * MV2D_C);
-        const int c = (int)(i % MV2D_C);
-        dy[i] = y[i] > 0.f ? dpool[n * MV2D_C + c] / 49.0f : 0.f;
-    }
-}
-
-// center2lidar + normalisation (query_generator.py:333-341, mv2d_s_head.py:147-152): c = (u, v, d) -> ref
-__global__ void __launch_bounds__(128) center_fwd_kernel(const float* __restrict__ c, const float* __restrict__ m_roi, Range6 pc,
-                                                         float* __restrict__ ref, int N) {
-    pdl_wait();
-    pdl_trigger();
-    const int n = blockIdx.x * 128 + threadIdx.x;
-    if (n >= N) return;
-    const float u = c[n * 3], v = c[n * 3 + 1], d = c[n * 3 + 2];
-    const float hom[4] = {u * d, v * d, d, 1.f};
-    const float* m = m_roi + n * 16;
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        const float xyz = m[i * 4] * hom[0] + m[i * 4 + 1] * hom[1] + m[i * 4 + 2] * hom[2] + m[i * 4 + 3] * hom[3];
-        ref[n * 3 + i] = (xyz - pc.v[i]) / (pc.v[i + 3] - pc.v[i]);
-    }
-}
-__global__ void __launch_bounds__(128) center_bwd_kernel(const float* __restrict__ c, const float* __restrict__ m_roi, Range6 pc,
-                                                         const float* __restrict__ d_ref, float* __restrict__ dc, int N) {
-    pdl_wait();
-    pdl_trigger();
-    const int n = blockIdx.x * 128 + threadIdx.x;
-    if (n >= N) return;
-    const float u = c[n * 3], v = c[n * 3 + 1], d = c[n * 3 + 2];
-    const float* m = m_roi + n * 16;
-    float dh[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        const float g = d_ref[n * 3 + i] / (pc.v[i + 3] - pc.v[i]);
-        dh[0] += m[i * 4] * g; dh[1] += m[i * 4 + 1] * g; dh[2] += m[i * 4 + 2] * g;
-    }
-    dc[n * 3] = dh[0] * d;
-    dc[n * 3 + 1] = dh[1] * d;
-    dc[n * 3 + 2] = dh[0] * u + dh[1] * v + dh[2];
-}
-
-// SE gate + combine of PE.forward (pe.py:158-166): pe = x * sigmoid(g2) + sb; gate overwrites g2
-__global__ void __launch_bounds__(256) pe_gate_fwd_kernel(const float* __restrict__ x, float* __restrict__ g2, const float* __restrict__ sb,
-                                                          float* __restrict__ pe, long long n) {
-    pdl_wait();
-    pdl_trigger();
-    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
-        const float s = sigmoid_f(g2[i]);
-        g2[i] = s;
-        pe[i] = x[i] * s + sb[i];
-    }
-}
-// dpe -> dx = dpe * gate, dg2 = dpe * x * gate (1 - gate)   (d sb = dpe itself)
-__global__ void __launch_bounds__(256) pe_gate_bwd_kernel(const float* __restrict__ dpe, const float* __restrict__ x,
-                                                          const float* __restrict__ gate, float* __restrict__ dx, float* __restrict__ dg2,
-                                                          long long n) {
-    pdl_wait();
-    pdl_trigger();
-    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
-        const float s = gate[i], g = dpe[i];
-        dx[i] = g * s;
-        dg2[i] = g * x[i] * s * (1.f - s);
-    }
-}
-
-inline int ew_grid(long long n) {
-    const long long want = (n + 255) / 256;
-    return (int)(want < 148 * 16 ? (want > 0 ? want : 1) : 148 * 16);
-}
+#include "train_front.cuh"
 
 struct FrontWs {
     // position encoding ([P, .])
@@ -1943,7 +816,7 @@ int run_front_train_forward(const Mv2dFrontTrainParams& p, cudaStream_t st) {
     TRY(linear_fwd(w.hs, 1024, W(TF_ADAPT2_W), 1024, W(TF_ADAPT2_B), w.sb, TC_, P, TC_, 1024, false, st));
     TRY(linear_fwd(p.feat, TC_, W(TF_SE_R_W), TC_, W(TF_SE_R_B), w.g1, TC_, P, TC_, TC_, true, st));
     TRY(linear_fwd(w.g1, TC_, W(TF_SE_E_W), TC_, W(TF_SE_E_B), w.gate, TC_, P, TC_, TC_, false, st));
-    launch_k(pe_gate_fwd_kernel, dim3(ew_grid((long long)P * TC_)), dim3(256), 0, st, (const float*)w.x, w.gate, (const float*)w.sb, w.pe,
+    launch_k(pe_gate_fwd_kernel, dim3(ew_grid_n((long long)P * TC_)), dim3(256), 0, st, (const float*)w.x, w.gate, (const float*)w.sb, w.pe,
              (long long)P * TC_);
     MV2D_CHECK_LAUNCH("front pe_gate");
     if (p.pe_out) {
@@ -1959,7 +832,7 @@ int run_front_train_forward(const Mv2dFrontTrainParams& p, cudaStream_t st) {
     launch_k(front_params_kernel, dim3(cdiv(N, 64)), dim3(64), 0, st, p.rois, p.roi_intrinsics, p.extrinsics, N, p.intrins_feat_scale,
              w.cat, w.m_roi);
     MV2D_CHECK_LAUNCH("front params");
-    launch_k(im2col_kernel, dim3(ew_grid((long long)NK * 9 * 64)), dim3(256), 0, st, (const float*)p.tok_mem, w.col, N);
+    launch_k(im2col_kernel, dim3(ew_grid_n((long long)NK * 9 * 64)), dim3(256), 0, st, (const float*)p.tok_mem, w.col, N);
     MV2D_CHECK_LAUNCH("front im2col");
     TRY(linear_fwd(w.col, 9 * TC_, W(TF_CONV_W), 9 * TC_, W(TF_CONV_B), w.y, TC_, NK, TC_, 9 * TC_, true, st));
     launch_k(pool49_fwd_kernel, dim3(cdiv(N * TC_, 256)), dim3(256), 0, st, (const float*)w.y, w.pool, N);
@@ -2004,19 +877,19 @@ int run_front_train_backward(const Mv2dFrontTrainParams& p, cudaStream_t st) {
     TRY(linear_dgrad(w.de0, 512, W(TF_ENC0_W), 1040, w.df1, 1024, N, 512, 1024, w.cat, 1040, false, st, SG_MASK_LT5E3));
     TRY(linear_wgrad(w.df1, 1024, w.pool, TC_, D(TF_FC_W), TC_, N, 1024, TC_, st, D(TF_FC_B)));
     TRY(linear_dgrad(w.df1, 1024, W(TF_FC_W), TC_, w.dpool, TC_, N, 1024, TC_, nullptr, 0, false, st));
-    launch_k(pool49_bwd_kernel, dim3(ew_grid((long long)NK * TC_)), dim3(256), 0, st, (const float*)w.y, (const float*)w.dpool, w.dy, N);
+    launch_k(pool49_bwd_kernel, dim3(ew_grid_n((long long)NK * TC_)), dim3(256), 0, st, (const float*)w.y, (const float*)w.dpool, w.dy, N);
     MV2D_CHECK_LAUNCH("front pool49_bwd");
     TRY(linear_wgrad(w.dy, TC_, w.col, 9 * TC_, D(TF_CONV_W), 9 * TC_, NK, TC_, 9 * TC_, st, D(TF_CONV_B)));
     TRY(linear_dgrad(w.dy, TC_, W(TF_CONV_W), 9 * TC_, w.dcol, 9 * TC_, NK, TC_, 9 * TC_, nullptr, 0, false, st));
     // d tok_mem = conv path + value path + key path (tok_kin = tok_mem + RoIAlign(pe)); d RoIAlign(pe) = d tok_kin
-    launch_k(col2im_kernel, dim3(ew_grid((long long)NK * 64)), dim3(256), 0, st, (const float*)w.dcol, p.d_tok_mem, p.d_tok_kin, w.dtok, N);
+    launch_k(col2im_kernel, dim3(ew_grid_n((long long)NK * 64)), dim3(256), 0, st, (const float*)w.dcol, p.d_tok_mem, p.d_tok_kin, w.dtok, N);
     MV2D_CHECK_LAUNCH("front col2im");
     launch_k(roi_align_bwd_kernel, dim3(TTOK, N), dim3(64), 0, st, p.rois, (const float*)w.dtok, p.h, p.w, scale, p.d_feat);
     MV2D_CHECK_LAUNCH("front roi_align_bwd(feat)");
     launch_k(roi_align_bwd_kernel, dim3(TTOK, N), dim3(64), 0, st, p.rois, p.d_tok_kin, p.h, p.w, scale, w.dpe_map);
     MV2D_CHECK_LAUNCH("front roi_align_bwd(pe)");
     // --- PE: pe = x * gate + sb
-    launch_k(pe_gate_bwd_kernel, dim3(ew_grid(PC)), dim3(256), 0, st, (const float*)w.dpe_map, (const float*)w.x, (const float*)w.gate, w.dx, w.dg2, PC);
+    launch_k(pe_gate_bwd_kernel, dim3(ew_grid_n(PC)), dim3(256), 0, st, (const float*)w.dpe_map, (const float*)w.x, (const float*)w.gate, w.dx, w.dg2, PC);
     MV2D_CHECK_LAUNCH("front pe_gate_bwd");
     // sine branch (adapt_pos3d): d sb = dpe
     TRY(linear_wgrad(w.dpe_map, TC_, w.hs, 1024, D(TF_ADAPT2_W), 1024, P, TC_, 1024, st, D(TF_ADAPT2_B)));
