@@ -1,12 +1,12 @@
-// Training step of the MV2D-S decoder slice (SURVEY.md 8e / BASELINE configs[3]): forward WITH saved activations,
-// Hungarian targets + losses, and the BACKWARD of rows a12-a18 + f3 -- query embedding, six decoder layers
-// (flattened self-attention, sparse per-RoI cross-attention, FFN, LayerNorms), post-norm, cls / reg branches with
-// the reference-point refinement, focal + L1 losses -- down to the gradients of every parameter of that slice and of
-// its inputs (reference points, RoI key tokens, RoI value tokens).
-//   reference: roi_heads/bbox_heads/cross_attention_head.py:199-242 (forward), :379-434 (loss_single);
-//              utils/petr_transformer.py:194-370,373-513,569-593; utils/pe.py:21-33;
-//              roi_heads/mv2d_s_head.py:262-307 (forward_train: sum over layers of stage_loss_weight * loss);
-//              the backward itself is torch autograd in the reference.
+// Training step of the MV2D-S hot path (SURVEY.md 8e / BASELINE configs[3]): forward WITH saved activations, Hungarian
+// targets + losses, and the BACKWARD of rows a1-a18 + f3 -- position encoding, RoIAlign, query generator, query
+// embedding, six decoder layers (flattened self-attention, sparse per-RoI cross-attention, FFN, LayerNorms), post-norm,
+// cls / reg branches with the reference-point refinement, focal + L1 losses -- down to the gradients of every
+// hot-path parameter and of the FPN feature map.
+//   reference: roi_heads/mv2d_s_head.py:236-307 (forward_train: sum over layers of stage_loss_weight * loss);
+//              roi_heads/bbox_heads/cross_attention_head.py:199-242 (forward), :379-434 (loss_single);
+//              utils/petr_transformer.py:194-370,373-513,569-593; utils/pe.py:21-33,137-169;
+//              roi_heads/utils/query_generator.py:343-405; the backward itself is torch autograd in the reference.
 // The reference trains MV2D-S without denoising queries (configs/mv2d/exp/*single_frame*:44 use_denoise=False), so
 // every query attends to the 49 tokens of each RoI in its own match list and self-attention is unmasked.
 //
@@ -15,11 +15,11 @@
 // absorbed cross-attention weights; training uses the plain in_proj / out_proj form because those are the leaves
 // the optimizer updates.
 //
-// First correct version: every contraction runs through one bounds-checked fp32 FFMA GEMM (sgemm_kernel) that
-// takes its operands by strides (A W^T, dC W and dC^T A without materialised transposes; weight gradients use
-// split-K with atomic accumulation into the flat gradient buffer); the attention kernels keep the probabilities
-// of the forward and run one warp per (query, head) / (key, head).  Moving the wide GEMMs onto the tcgen05 path
-// of gemm_tc.cu is the next step for this row.
+// Files (one translation unit): train_gemm.cuh -- the contractions (strided fp32 FFMA GEMM; tcgen05 3xTF32 route for
+// the GPU-filling ones; linear forward / backward-data / weight-gradient helpers), train_attn.cuh -- self- and
+// cross-attention forward / backward, train_front.cuh -- RoIAlign, im2col, pooling, center2lidar, SE gate; this file:
+// parameter and workspace layouts, LayerNorm, query embedding, branch tail, loss gradient, the four entry points
+// that enqueue a step, fused AdamW.  DESIGN.md section 8 has the numbers.
 #include <algorithm>
 #include <cstdlib>
 #include "common.cuh"
