@@ -309,7 +309,7 @@ def test_plugin_forward_train_backward_through_autograd(state_dicts):
     torch.optim.AdamW([p for p in h.parameters() if p.grad is not None], lr=1e-3).step()
     assert float((tr.params - before).abs().max()) > 1e-4           # the Parameters ARE the flat buffer
     l2 = h.forward_train([x], metas, [b.cuda() for b in boxes], None, None, None, None, [gt_boxes.cuda()], [gt_labels.cuda()])
-    assert abs(float(sum(l2.values())) - float(total)) > 1e-4       # and the next forward sees the stepped weights
+    assert abs(float(sum(l2.values()).detach()) - float(total.detach())) > 1e-4       # and the next forward sees the stepped weights
     h.eval()
     res = h.simple_test([x], [b.cuda() for b in boxes], metas)      # the inference engine is re-packed from the new weights
     assert len(res) == 1

@@ -1,0 +1,43 @@
+"""CPU: the flat parameter / gradient layout of the training step (mv2d_train_param_info) against the reference's
+state_dict -- every hot-path tensor has exactly one slot, slots do not overlap, start 64-byte aligned, and the host
+mirror round-trips a state_dict bit for bit (including the re-laid-out 3x3 conv weight)."""
+import pytest
+import torch
+
+from mv2d_b200 import synth
+from mv2d_b200.train import CONV_W, FRONT_NAMES, GLOBAL_NAMES, LAYER_NAMES, DecoderTrainer, param_table
+
+
+@pytest.mark.parametrize('L', [1, 2, 6])
+def test_layout_covers_the_state_dict_once(L):
+    table, total = param_table(L)
+    sd = synth.make_state_dict(0, num_layers=L)
+    learnable = {k for k in sd if k != 'bbox_head.code_weights'}          # a constant buffer, not a Parameter
+    assert set(table) == learnable
+    assert len(table) == len(GLOBAL_NAMES) + L * len(LAYER_NAMES) + len(FRONT_NAMES)
+    spans = sorted((off, off + n, k) for k, (off, n) in table.items())
+    assert spans[0][0] == 0
+    for (a0, a1, ka), (b0, b1, kb) in zip(spans, spans[1:]):
+        assert a1 <= b0, f'{ka} overlaps {kb}'
+        assert b0 % 16 == 0, f'{kb} starts at {b0}: not a multiple of 16 floats'
+    assert spans[-1][1] <= total
+    for k, (off, n) in table.items():
+        assert n == sd[k].numel(), k
+    assert sum(n for _, n in table.values()) == sum(sd[k].numel() for k in learnable)
+
+
+def test_host_mirror_round_trips_and_grad_views_alias_the_flat_buffer():
+    sd = synth.make_state_dict(3, num_layers=2)
+    tr = DecoderTrainer(sd, device='cpu')
+    back = tr.state_dict()
+    assert all(torch.equal(back[k], sd[k].float()) for k in back)
+    # the conv weight lives as [c_out, ky, kx, c_in] in the flat buffer and is presented in the state_dict's layout
+    off, n = tr.table[CONV_W]
+    flat = tr.params[off:off + n].view(256, 3, 3, 256)
+    assert torch.equal(flat.permute(0, 3, 1, 2), sd[CONV_W].float())
+    tr.grads.zero_()
+    tr.grad(CONV_W)[5, 7, 1, 2] = 3.0
+    tr.grad('bbox_head.cls_branches.1.6.bias')[4] = 2.0
+    assert float(tr.grads.sum()) == 5.0 and float(tr.grads[off:off + n].view(256, 3, 3, 256)[5, 1, 2, 7]) == 3.0
+    with pytest.raises(RuntimeError):
+        tr.forward(None, None, None, torch.zeros(1, 1), None, None, None)        # no CPU fallback
