@@ -501,7 +501,7 @@ class MV2DHead(nn.Module):
             self._train_params = []
             for name in tr.table:
                 prm = params[name]
-                prm.data = tr.grad_layout_view(name)       # a view of the flat buffer in the Parameter's own shape
+                prm.data = tr.sd_view(name)                 # a view of the flat buffer in the Parameter's own shape
                 self._train_params.append((name, prm))
             object.__setattr__(self, '_trainer', tr)
         return self._trainer

@@ -77,6 +77,12 @@ def param_table(num_layers):
 
 
 class DecoderTrainer:
+    """Flat parameter / gradient buffers of the whole hot path plus the training step of the decoder slice
+    (``forward`` / ``backward`` on given slice inputs).  ``HotPathTrainer`` below adds the front end.
+
+    state_dict: the reference's names (with or without the ``roi_head.`` prefix).  stage_loss_weights: one weight per
+    decoder layer (train_cfg.rcnn.stage_loss_weights).  loss_cfg: overrides of ``LOSS_DEFAULTS``."""
+
     def __init__(self, state_dict, device='cuda', num_layers=None, stage_loss_weights=None, pc_range=None, **loss_cfg):
         self.lib = lib.load()
         # the flat buffers (layout, state_dict round trip, gradient all-reduce) also work on a CPU device, which is
@@ -127,15 +133,15 @@ class DecoderTrainer:
         """The reference's names and shapes (relative to ``roi_head.``)."""
         return {n: self._sd_layout(n, self.view(n)) for n in self.table}
 
-    def grad(self, name):
-        """Gradient of one tensor in the reference's state_dict layout (a permuted view for the conv weight)."""
-        t = self.view(name, self.grads)
-        return t.permute(0, 3, 1, 2) if name == CONV_W else t
-
-    def grad_layout_view(self, name, buf=None):
-        """A view of one tensor's slice of the flat parameter (or another flat) buffer in the reference's shape."""
+    def sd_view(self, name, buf=None):
+        """A view of one tensor's slice of the flat parameter (or another flat) buffer in the reference's state_dict
+        shape (a permuted, non-contiguous view for the re-laid-out conv weight)."""
         t = self.view(name, buf)
         return t.permute(0, 3, 1, 2) if name == CONV_W else t
+
+    def grad(self, name):
+        """Gradient of one tensor in the reference's state_dict layout: a view into the flat gradient buffer."""
+        return self.sd_view(name, self.grads)
 
     def named_grads(self):
         return {n: self.grad(n) for n in self.table}
