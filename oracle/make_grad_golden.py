@@ -6,8 +6,8 @@ with the config's stage_loss_weights as MV2DSHead.forward_train does (mv2d_s_hea
   * the loss values,
   * the gradients of the inputs of the decoder slice (reference points, RoI feature tokens, RoI position tokens --
     the gathered [N,M,...] gradients scattered back to the N RoIs),
-  * every parameter gradient of roi_head (bbox_head.* is what mv2d_decoder_train_backward produces today; the
-    query generator / position-encoding gradients pin the rows that come next), big tensors subsampled.
+  * every parameter gradient of roi_head (bbox_head.* from mv2d_decoder_train_backward, query_generator.* and
+    position_encoding.* from mv2d_front_train_backward) and d loss / d feat, big tensors subsampled.
 
 Run in the build container:   python -m oracle.make_grad_golden
 """
@@ -31,6 +31,8 @@ CASES = {
     'grad_s_small': (dict(synth.CASES['s_small'], num_layers=2), dict(num_gt=6, seed=71)),
     'grad_s_mid': (dict(mode='S', seed=21, num_views=6, boxes_per_view=[12, 10, 11, 9, 12, 10], num_layers=3), dict(num_gt=20, seed=72)),
     'grad_s_one': (dict(synth.CASES['s_one'], num_layers=2), dict(num_gt=3, seed=73)),
+    # padded images: masked cells in the sine branch and in the position embedding (img_shape < pad_shape)
+    'grad_s_pad': (dict(synth.CASES['s_pad'], num_layers=2), dict(num_gt=5, seed=74)),
 }
 SUB = 97          # stride of the subsample kept for tensors with more than KEEP_FULL elements
 KEEP_FULL = 4096
