@@ -320,14 +320,17 @@ def main():
 
 def train_step_section(sd, dev, samples, world, barrier, per_rank=2, steps=8, warmup=3):
     """Extra object `train_step` (BASELINE configs[3] shape: MV2D-S, 2 samples per GPU): per step and rank, for each local
-    sample the hot-path training forward (saved activations) + Hungarian targets / losses + backward down to d feat, then
-    ONE NCCL sum all-reduce of the flat gradient buffer (all 14.0 M hot-path parameters) and a fused AdamW pass.
+    sample the hot-path training forward (saved activations) + Hungarian targets / losses + backward down to d feat (the
+    two samples in flight on their own streams, `lanes`), then ONE NCCL sum all-reduce of the flat gradient buffer (all
+    14.0 M hot-path parameters) and a fused AdamW pass.
     Device time by CUDA events, max over ranks; the torch backbone is outside the hot path."""
     import torch
     from mv2d_b200 import dist as D
     from mv2d_b200 import synth
-    from mv2d_b200.train import HotPathTrainer
-    tr = HotPathTrainer(sd, device=dev)
+    from mv2d_b200.train import TrainStep
+    lanes = int(os.environ.get('MV2D_TRAIN_LANES', '2'))     # samples in flight per GPU (mv2d_b200.train.TrainStep)
+    pipe = TrainStep(sd, device=dev, lanes=lanes)
+    tr = pipe.main
     before = tr.lib.mv2d_launch_count()
     batch = []
     for i in range(per_rank):
@@ -338,6 +341,15 @@ def train_step_section(sd, dev, samples, world, barrier, per_rank=2, steps=8, wa
     rows, losses = [], []
     for it in range(warmup + steps):
         barrier()
+        if lanes > 1:
+            ev[0].record()
+            loss = pipe.step(batch, world=world) * per_rank
+            ev[1].record(); ev[2].record(); ev[3].record()
+            torch.cuda.synchronize()
+            if it >= warmup:
+                rows.append([ev[0].elapsed_time(ev[3]), ev[0].elapsed_time(ev[3]), 0.0, 0.0])
+                losses.append(float(loss) / per_rank)
+            continue
         tr.zero_grad()
         ev[0].record()
         loss = 0.0
@@ -356,7 +368,7 @@ def train_step_section(sd, dev, samples, world, barrier, per_rank=2, steps=8, wa
     t = torch.tensor(rows, dtype=torch.float64)
     total_ms = D.max_over_ranks([float(t[:, 0].sum())], device=dev)[0]
     med = t.median(0).values.tolist()
-    return dict(value=world * per_rank * steps / (total_ms * 1e-3), unit='samples/s', samples_per_gpu=per_rank, steps=steps, warmup=warmup,
+    return dict(value=world * per_rank * steps / (total_ms * 1e-3), unit='samples/s', samples_per_gpu=per_rank, lanes=lanes, steps=steps, warmup=warmup,
                 step_ms=med[0], fwd_bwd_ms=med[1], allreduce_ms=med[2], adamw_ms=med[3], grad_bytes=tr.total * 4,
                 launches_per_step=int(tr.lib.mv2d_launch_count() - before) // (warmup + steps),
                 loss_first=losses[0], loss_last=losses[-1],

@@ -297,3 +297,47 @@ class HotPathTrainer(DecoderTrainer):
         p.d_ref, p.d_tok_kin, p.d_tok_mem = (gin[k].data_ptr() for k in ('d_ref', 'd_tok_kin', 'd_tok_mem'))
         lib.check(self.lib.mv2d_front_train_backward(C.byref(p), lib.stream_ptr()), 'mv2d_front_train_backward')
         return dict(gin, d_feat=self._fout['d_feat'].permute(0, 3, 1, 2))
+
+
+class TrainStep:
+    """One data-parallel optimisation step over this rank's samples with several samples IN FLIGHT: ``lanes`` trainers
+    share the flat parameter buffer, each has its own stream, workspaces and gradient buffer, and the samples are dealt
+    round-robin.  One sample's step is a chain of ~650 mostly small kernels that leaves most of the GPU idle (DESIGN.md
+    section 8), so two chains side by side nearly overlap; the lanes' gradient buffers are summed into lane 0's before
+    the all-reduce.  lanes=1 is the plain sequential step.  Same results as running the samples one after the other
+    up to fp32 summation order."""
+
+    def __init__(self, state_dict, device='cuda', lanes=2, **kw):
+        assert lanes >= 1
+        self.main = HotPathTrainer(state_dict, device=device, **kw)
+        self.lanes = [self.main]
+        for _ in range(lanes - 1):
+            t = HotPathTrainer(state_dict, device=device, **kw)
+            t.params = self.main.params            # ONE set of weights; own gradients, workspaces, engine buffers
+            self.lanes.append(t)
+        self.streams = [torch.cuda.Stream(device=self.main.device) for _ in self.lanes]
+        self.total = self.main.total
+
+    @torch.no_grad()
+    def step(self, samples, lr=2e-4, weight_decay=0.01, world=1, optimize=True):
+        """samples: list of (feat, proposal_list, img_metas, gt_boxes, gt_labels).  Returns the mean weighted loss
+        (a device scalar).  Gradients end up summed in ``self.main.grads`` (all-reduced over ranks)."""
+        cur = torch.cuda.current_stream()
+        for t in self.lanes:
+            t.zero_grad()
+        losses = []
+        for s in self.streams:
+            s.wait_stream(cur)
+        for i, smp in enumerate(samples):
+            k = i % len(self.lanes)
+            with torch.cuda.stream(self.streams[k]):
+                losses.append(self.lanes[k].forward(*smp)['loss'])
+                self.lanes[k].backward()
+        for s in self.streams:
+            cur.wait_stream(s)
+        if len(self.lanes) > 1:
+            torch._foreach_add_([self.main.grads] * (len(self.lanes) - 1), [t.grads for t in self.lanes[1:]])
+        self.main.all_reduce_grads()
+        if optimize:
+            self.main.adamw_step(lr=lr, weight_decay=weight_decay, grad_scale=1.0 / (world * max(len(samples), 1)))
+        return torch.stack(losses).mean()

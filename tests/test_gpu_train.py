@@ -313,3 +313,32 @@ def test_plugin_forward_train_backward_through_autograd(state_dicts):
     h.eval()
     res = h.simple_test([x], [b.cuda() for b in boxes], metas)      # the inference engine is re-packed from the new weights
     assert len(res) == 1
+
+
+def test_samples_in_flight_match_the_sequential_step(state_dicts):
+    """TrainStep with two lanes (two samples' chains side by side on their own streams, gradients summed afterwards)
+    against the same two samples one after the other through one trainer."""
+    from mv2d_b200.train import HotPathTrainer, TrainStep
+    sd = state_dicts(6)
+    samples = []
+    for i in range(3):
+        spec = dict(mode='S', seed=40 + i, num_views=6, boxes_per_view=[6, 5, 7, 4, 6, 5], num_layers=6)
+        feat, boxes, metas = synth.case_inputs(spec)
+        gt_boxes, gt_labels, _ = synth.make_dn_inputs(dict(num_gt=8, seed=60 + i))
+        samples.append((feat.cuda(), boxes, metas, gt_boxes.cuda(), gt_labels.cuda()))
+    ref = HotPathTrainer(sd)
+    want_loss = 0.0
+    for smp in samples:
+        want_loss = want_loss + ref.forward(*smp)['loss']
+        ref.backward()
+    step = TrainStep(sd, lanes=2)
+    loss = step.step(samples, optimize=False)
+    torch.cuda.synchronize()
+    assert abs(float(loss) - float(want_loss) / 3) <= 1e-5 * abs(float(want_loss) / 3)
+    g, w = step.main.grads, ref.grads
+    assert float((g - w).abs().max()) <= 1e-3 * float(w.abs().max())
+    assert float((g - w).norm() / w.norm()) <= 1e-4
+    before = step.main.params.clone()
+    step.step(samples)
+    torch.cuda.synchronize()
+    assert float((step.main.params - before).abs().max()) > 0 and step.lanes[1].params.data_ptr() == step.main.params.data_ptr()

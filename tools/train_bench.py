@@ -19,7 +19,7 @@ sys.path.insert(0, ROOT)
 from mv2d_b200 import dist as D  # noqa: E402
 from mv2d_b200 import synth  # noqa: E402
 from mv2d_b200.engine import HotPath  # noqa: E402
-from mv2d_b200.train import DecoderTrainer, HotPathTrainer  # noqa: E402
+from mv2d_b200.train import DecoderTrainer, HotPathTrainer, TrainStep  # noqa: E402
 
 
 def main():
@@ -29,6 +29,7 @@ def main():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--slice', action='store_true', help='decoder slice only')
+    ap.add_argument('--lanes', type=int, default=1, help='samples in flight per GPU (TrainStep); 1 = one after the other')
     a = ap.parse_args()
     rank, local_rank, world = D.env_rank()
     torch.cuda.set_device(local_rank)
@@ -38,6 +39,9 @@ def main():
     if a.slice:
         eng = HotPath(sd, mode='S', device=dev)
         tr = DecoderTrainer(sd, device=dev)
+    elif a.lanes > 1:
+        pipe = TrainStep(sd, device=dev, lanes=a.lanes)
+        tr = pipe.main
     else:
         tr = HotPathTrainer(sd, device=dev)
     samples = []
@@ -62,6 +66,14 @@ def main():
         ev[0].record()
         loss = 0.0
         pairs = []
+        if a.lanes > 1 and not a.slice:       # samples in flight: one timed region for the whole step
+            loss = pipe.step(samples, world=world) * a.samples
+            ev[1].record(); ev[2].record(); ev[3].record()
+            torch.cuda.synchronize()
+            if it >= a.warmup:
+                rows.append([ev[0].elapsed_time(ev[3]), 0.0, 0.0, 0.0, 0.0])
+                losses.append(float(loss) / a.samples)
+            continue
         for smp in samples:
             e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
             e[0].record()
@@ -90,14 +102,14 @@ def main():
         what = 'decoder-slice' if a.slice else 'hot-path'
         line = dict(metric=f'samples/sec (MV2D-S {what} training step: fwd + targets/losses + bwd + grad all-reduce + AdamW)',
                     value=world * a.samples * a.steps / (total_ms * 1e-3), unit='samples/s', n_gpus=world, steps=a.steps,
-                    warmup=a.warmup, samples_per_gpu=a.samples, N=6 * a.per_view, L=6,
+                    warmup=a.warmup, samples_per_gpu=a.samples, lanes=a.lanes, N=6 * a.per_view, L=6,
                     step_ms=med[0], fwd_ms=med[1], bwd_ms=med[2], allreduce_ms=med[3], adamw_ms=med[4],
                     grad_bytes=tr.total * 4, loss_first=losses[0], loss_last=losses[-1],
                     scope='decoder slice only (rows a12-a18 + f3)' if a.slice else
                     'rows a1-a18 + f3: every hot-path parameter and d feat; the torch backbone is outside')
         print(json.dumps(line))
         os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
-        with open(os.path.join(ROOT, 'gpurun_out', f'train_bench_{"slice_" if a.slice else ""}{world}gpu.json'), 'w') as f:
+        with open(os.path.join(ROOT, 'gpurun_out', f'train_bench_{"slice_" if a.slice else ""}{world}gpu{"_lanes%d" % a.lanes if a.lanes > 1 else ""}.json'), 'w') as f:
             f.write(json.dumps(line) + '\n')
 
 
