@@ -150,6 +150,14 @@ class DecoderTrainer:
         self.grads.zero_()
 
     # ------------------------------------------------------------------ one sample
+    def _stage_weights(self):
+        """stage_loss_weights on the device, uploaded once (a per-call torch.tensor(list, device=...) is a pageable
+        host-to-device copy that blocks the host until the stream has drained: no running ahead, no lane overlap)."""
+        key = tuple(float(x) for x in self.stage_loss_weights)
+        if getattr(self, '_stage_w_key', None) != key:
+            self._stage_w_key, self._stage_w_dev = key, torch.tensor(key, dtype=torch.float32, device=self.device)
+        return self._stage_w_dev
+
     def _need_cuda(self):
         if self.device.type != 'cuda' or not torch.cuda.is_available():
             raise RuntimeError('mv2d_b200.DecoderTrainer: the training step runs on a CUDA device only (no CPU fallback)')
@@ -200,7 +208,7 @@ class DecoderTrainer:
         self._p, out = self._params(ref, tok_kin, tok_mem, match, match_cnt, gt_boxes, gt_labels)
         lib.check(self.lib.mv2d_decoder_train_forward(C.byref(self._p), lib.stream_ptr()), 'mv2d_decoder_train_forward')
         self._out = out
-        w = torch.tensor(self.stage_loss_weights, device=self.device)
+        w = self._stage_weights()
         res = dict(cls_scores=out['cls_scores'], bbox_preds=out['bbox_preds'], assigned=out['assigned'],
                    loss_cls=out['losses'][:, 0], loss_bbox=out['losses'][:, 1])
         res['loss'] = (w * (out['losses'][:, 0] + out['losses'][:, 1])).sum()
