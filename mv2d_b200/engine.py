@@ -149,6 +149,13 @@ class HotPath:
         if pin is None:   # fixed capacity: captured graphs bake the device address in, it must never move
             pin = torch.empty(128 * 1024, dtype=torch.uint8).pin_memory()
             self._pin['meta'] = pin
+            self._pin['meta_ev'] = None
+        elif self._pin['meta_ev'] is not None:
+            # the previous call's asynchronous copy reads this staging buffer when its stream gets there, and the host
+            # may be several samples ahead of the device (Pipeline, TrainStep): wait for THAT copy before overwriting
+            # the buffer.  It sits at the head of the previous sample's work, so this returns at once unless the host
+            # is more than a whole sample ahead on this engine.
+            self._pin['meta_ev'].synchronize()
         assert total <= pin.numel(), f'too many RoIs/views for the metadata buffer ({total} B)'
         dev = self._get('meta', (pin.numel(),), torch.uint8)
         host = pin.numpy()
@@ -167,6 +174,9 @@ class HotPath:
                 o += n
         host[st_off:st_off + st_b].view(np.int32)[:] = np.concatenate([[0], np.cumsum(counts)])
         dev[:total].copy_(pin[:total], non_blocking=True)
+        if self._pin['meta_ev'] is None:
+            self._pin['meta_ev'] = torch.cuda.Event()
+        self._pin['meta_ev'].record()
         d_cams = dev[:cam_b].view(torch.float64).view(3, V, 16)
         d_rois = dev[roi_off:roi_off + roi_b].view(torch.float32).view(N, 5)
         d_start = dev[st_off:st_off + st_b].view(torch.int32)
