@@ -88,7 +88,7 @@ def full_oracle_grads(spec, gt_spec, stage_w, sd=None):
     return dict(sd=sd, feat=feat, total=total, cls=cls, box=box, per=per, gt=(gt_boxes, gt_labels), inputs=(boxes, metas))
 
 
-@pytest.mark.parametrize('name', ['grad_s_small', 'grad_s_one', 'grad_s_pad'])
+@pytest.mark.parametrize('name', ['grad_s_small', 'grad_s_mid', 'grad_s_one', 'grad_s_pad'])
 def test_full_chain_gradient_oracle_matches_reference(name):
     """All 96 hot-path parameter gradients and d loss / d feat of the restated full path vs the reference's autograd."""
     g, spec, gt_spec = load(name)
