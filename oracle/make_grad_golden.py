@@ -127,8 +127,73 @@ def run_reference(spec, gt_spec, weight_seed=0):
     return g
 
 
+# two-frame head WITH denoising queries (the configuration the reference trains MV2D-T with): the gradients come from the
+# reference's own MV2DSHead.forward_train (inherited by MV2DTHead: mv2d_s_head.py:236-307), i.e. its loss dict summed
+# as mmdet's _parse_losses does.  Pins the oracle for the rows whose backward comes next.
+CASES_T = {'grad_t_dn': dict(synth.CASES['t_dn'], num_layers=2)}
+
+
+def run_reference_forward_train_t(spec, weight_seed=0):
+    Assigner, _ = ref_shim.install_loss_support()
+    cfg = ref_shim.load_reference_config(CFG['T'])
+    roi_head = copy.deepcopy(cfg['model']['roi_head'])
+    roi_head['bbox_head']['transformer']['decoder']['num_layers'] = spec['num_layers']
+    roi_head.update(train_cfg=None, test_cfg=ref_shim.ConfigDict(cfg['model']['test_cfg']['rcnn']))
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        head = ref_shim.build_from_cfg(roi_head, ref_shim.HEADS).eval()     # children in eval: dropout off
+    tc = cfg['model']['train_cfg']['rcnn']
+    tc = tc[0] if isinstance(tc, (list, tuple)) else tc
+    a = dict(tc['assigner'])
+    a.pop('type')
+    bh = head.bbox_head
+    bh.assigner, bh.sampler = Assigner(**a), ref_shim.PseudoSampler()
+    lc, lb = dict(roi_head['bbox_head']['loss_cls']), dict(roi_head['bbox_head']['loss_bbox'])
+    lc.pop('type'); lb.pop('type')
+    bh.loss_cls, bh.loss_bbox = ref_shim.FocalLoss(**lc), ref_shim.L1Loss(**lb)
+    head.stage_loss_weights = list(tc['stage_loss_weights'])[:spec['num_layers']]
+    head.load_state_dict(synth.make_state_dict(weight_seed, num_layers=spec['num_layers']))
+    feat, boxes, metas = synth.case_inputs(spec)
+    gt_boxes, gt_labels, rand = synth.make_dn_inputs(spec['dn'])
+    feat = feat.clone().requires_grad_(True)
+    head.training = True                      # only the head's flag: the denoising branch (mv2d_t_head.py:91-98)
+    patched = (torch.Tensor.cuda, torch.rand_like)
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    torch.rand_like = lambda t, *a, **k: rand.clone()
+    try:
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            losses = head.forward_train([feat], metas, [b.clone() for b in boxes], None, None, None, None,
+                                        [_Boxes(gt_boxes)], [gt_labels], None)
+    finally:
+        torch.Tensor.cuda, torch.rand_like = patched
+        head.training = False
+    total = sum(v for k, v in losses.items() if 'loss' in k)      # mmdet BaseDetector._parse_losses
+    total.backward()
+    g = dict(
+        spec=np.frombuffer(json.dumps(spec).encode(), dtype=np.uint8),
+        stage_loss_weights=np.array(head.stage_loss_weights, np.float64),
+        denoise_weight=np.float64(head.denoise_weight), denoise_split=np.float64(head.denoise_split),
+        neg_bbox_loss=np.int64(bool(head.neg_bbox_loss)),
+        loss=np.float64(float(total.detach())),
+        loss_names=np.frombuffer(json.dumps(sorted(losses)).encode(), dtype=np.uint8),
+        loss_values=np.array([float(losses[k].detach()) for k in sorted(losses)], np.float64),
+        d_feat_sub=sub(feat.grad), sub_stride=np.int64(SUB), keep_full=np.int64(KEEP_FULL),
+    )
+    for name, prm in head.named_parameters():
+        if prm.grad is not None:
+            g['dparam.' + name] = sub(prm.grad)
+    return g
+
+
 def main():
-    names = sys.argv[1:] or list(CASES)
+    names = sys.argv[1:] or (list(CASES) + list(CASES_T))
+    for name in [n for n in names if n in CASES_T]:
+        g = run_reference_forward_train_t(CASES_T[name])
+        path = os.path.join(ROOT, 'tests', 'golden', f'{name}.npz')
+        np.savez_compressed(path, **g)
+        print(name, 'loss', float(g['loss']), 'tensors', sum(k.startswith('dparam.') for k in g), os.path.getsize(path) // 1024, 'KiB')
+    names = [n for n in names if n in CASES]
     for name in names:
         spec, gt_spec = CASES[name]
         g = run_reference(spec, gt_spec)

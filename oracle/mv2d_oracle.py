@@ -818,6 +818,30 @@ def hot_path_loss(sd, feat, proposal_list, img_metas, gt_boxes, gt_labels, cfg=N
     return decoder_slice_loss(sd, ref, roi_feat, roi_pe, corr, mask, gt_boxes, gt_labels, cfg, stage_loss_weights, lc)
 
 
+def hot_path_loss_t(sd, feat, proposal_list, img_metas, gt_boxes, gt_labels, rand, cfg=None, stage_loss_weights=None,
+                    denoise_weight=1.0, neg_bbox_loss=True, lc=LOSS_CFG):
+    """The two-frame head's training step WITH denoising queries as a DIFFERENTIABLE function (the configuration the
+    reference trains MV2D-T with, exp/mv2d_r50_frcnn_two_frames_1408x512_ep*.py:44-47): MV2DSHead.forward_train as
+    MV2DTHead inherits it (roi_heads/mv2d_s_head.py:236-307) -- per layer loss_cls / loss_bbox of the matching queries
+    plus dn_loss_cls / dn_loss_bbox of the denoising queries times denoise_weight, each times stage_loss_weights.
+    Returns (total, dict of the named weighted losses)."""
+    cfg = cfg or make_cfg('T')
+    cls, box, st = mv2d_t_forward(sd, feat, proposal_list, img_metas, cfg, return_stages=True,
+                                  dn=dict(gt_boxes=gt_boxes, gt_labels=gt_labels, rand=rand))
+    dn = st['dn']
+    pad = dn['cls'].shape[1]
+    known_boxes = gt_boxes.repeat(pad // max(gt_boxes.shape[0], 1), 1)
+    w = stage_loss_weights or [0.1] * cls.shape[0]
+    losses = {}
+    for l in range(cls.shape[0]):
+        a, b, _ = loss_single(cls[l], box[l], gt_boxes, gt_labels, lc)
+        c, d = dn_loss_single(dn['cls'][l], dn['box'][l], known_boxes, dn['labels'], pad, cfg['denoise_split'], lc,
+                              neg_bbox_loss=neg_bbox_loss)
+        losses[f'l{l}.loss_cls'], losses[f'l{l}.loss_bbox'] = a * w[l], b * w[l]
+        losses[f'l{l}.dn_loss_cls'], losses[f'l{l}.dn_loss_bbox'] = c * denoise_weight * w[l], d * denoise_weight * w[l]
+    return sum(losses.values()), losses
+
+
 # ============================================================================= neck (SURVEY.md 8f rank 4)
 def fpn_neck(neck_sd, x):
     """The MV2D neck: mmdet 2.25.1 FPN with in_channels [256]*5, start_level = end_level = 2, num_outs = 1

@@ -107,3 +107,35 @@ def test_full_chain_gradient_oracle_matches_reference(name):
             close(sub(grad, g), g['dparam.' + k], k)
             n += 1
     assert n == 6 + 34 * spec['num_layers'] + 22
+
+
+def test_two_frame_denoising_gradient_oracle_matches_reference_forward_train():
+    """The rows whose backward comes next (two-frame head, denoising queries): the differentiable restatement against
+    the loss dict and the gradients of the reference's own MV2DTHead.forward_train + autograd (grad_t_dn.npz)."""
+    g = dict(np.load(os.path.join(ROOT, 'tests', 'golden', 'grad_t_dn.npz')))
+    spec = json.loads(bytes(g['spec']).decode())
+    names = json.loads(bytes(g['loss_names']).decode())
+    sd = synth.make_state_dict(0, num_layers=spec['num_layers'])
+    sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and k != 'bbox_head.code_weights' else v) for k, v in sd.items()}
+    feat, boxes, metas = synth.case_inputs(spec)
+    feat = feat.clone().requires_grad_(True)
+    gt_boxes, gt_labels, rand = synth.make_dn_inputs(spec['dn'])
+    cfg = O.make_cfg('T', num_layers=spec['num_layers'])
+    total, losses = O.hot_path_loss_t(sd, feat, boxes, metas, gt_boxes, gt_labels, rand, cfg,
+                                      stage_loss_weights=list(g['stage_loss_weights']), denoise_weight=float(g['denoise_weight']),
+                                      neg_bbox_loss=bool(g['neg_bbox_loss']))
+    assert sorted(losses) == names
+    np.testing.assert_allclose([float(losses[k].detach()) for k in names], g['loss_values'], rtol=5e-5)
+    total.backward()
+
+    def close(a, b, what):
+        scale = max(float(np.abs(b).max()), 1e-5)
+        err = float(np.abs(a - b).max()) / scale
+        assert err < 2e-3, f'{what}: max error {err:.2e} of the largest gradient entry'
+    close(sub(feat.grad, g), g['d_feat_sub'], 'd_feat')
+    n = 0
+    for k, v in sd.items():
+        if ('dparam.' + k) in g:
+            close(sub(v.grad if v.grad is not None else torch.zeros_like(v), g), g['dparam.' + k], k)
+            n += 1
+    assert n == 6 + 34 * spec['num_layers'] + 22
