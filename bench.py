@@ -261,7 +261,10 @@ def main():
 
     train = None
     if mode == 'S' and not args.no_train:
-        train = train_step_section(sd, dev, samples, world, barrier)
+        try:
+            train = train_step_section(sd, dev, samples, world, barrier)
+        except Exception as e:      # the auxiliary section must not take the headline line down with it; the error is reported
+            train = dict(error=f'{type(e).__name__}: {e}'[:400])
 
     # max over ranks of the device time
     total_ms, e2e_total_ms, ser_total_ms, ser_e2e_total_ms = D.max_over_ranks(
