@@ -231,6 +231,19 @@ class DecoderTrainer:
         return all_reduce_sum(self.grads, group)
 
     @torch.no_grad()
+    def clip_grad_norm_(self, max_norm=35.0, grad_scale=1.0):
+        """mmcv OptimizerHook's grad_clip (configs/mv2d/exp/*.py:172-175: max_norm 35, L2) over the hot-path parameters:
+        with the flat buffer the total norm is ONE reduction.  ``grad_scale`` is applied first (1 / (world * samples)
+        after a sum all-reduce), then the buffer is scaled in place by min(1, max_norm / (norm + 1e-6)) -- torch's
+        clip_grad_norm_ semantics, no host sync.  Returns the norm before clipping (a device scalar).  Plain torch
+        ops on the flat buffer (plumbing); pass grad_scale=1 to ``adamw_step`` afterwards."""
+        if grad_scale != 1.0:
+            self.grads.mul_(grad_scale)
+        norm = torch.linalg.vector_norm(self.grads)
+        self.grads.mul_(torch.clamp(max_norm / (norm + 1e-6), max=1.0))
+        return norm
+
+    @torch.no_grad()
     def adamw_step(self, lr=2e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, grad_scale=1.0):
         """torch.optim.AdamW semantics over the flat buffers in one launch (exp configs: AdamW lr 2e-4, wd 0.01)."""
         self._need_cuda()
@@ -327,9 +340,10 @@ class TrainStep:
         self.total = self.main.total
 
     @torch.no_grad()
-    def step(self, samples, lr=2e-4, weight_decay=0.01, world=1, optimize=True):
+    def step(self, samples, lr=2e-4, weight_decay=0.01, world=1, optimize=True, max_grad_norm=None):
         """samples: list of (feat, proposal_list, img_metas, gt_boxes, gt_labels).  Returns the mean weighted loss
-        (a device scalar).  Gradients end up summed in ``self.main.grads`` (all-reduced over ranks)."""
+        (a device scalar).  Gradients end up summed in ``self.main.grads`` (all-reduced over ranks).  max_grad_norm: the
+        reference's grad_clip (35 in the exp configs) over the hot-path parameters; None = off."""
         cur = torch.cuda.current_stream()
         for t in self.lanes:
             t.zero_grad()
@@ -346,6 +360,10 @@ class TrainStep:
         if len(self.lanes) > 1:
             torch._foreach_add_([self.main.grads] * (len(self.lanes) - 1), [t.grads for t in self.lanes[1:]])
         self.main.all_reduce_grads()
+        scale = 1.0 / (world * max(len(samples), 1))
+        if optimize and max_grad_norm is not None:
+            self.main.clip_grad_norm_(max_grad_norm, grad_scale=scale)
+            scale = 1.0
         if optimize:
-            self.main.adamw_step(lr=lr, weight_decay=weight_decay, grad_scale=1.0 / (world * max(len(samples), 1)))
+            self.main.adamw_step(lr=lr, weight_decay=weight_decay, grad_scale=scale)
         return torch.stack(losses).mean()

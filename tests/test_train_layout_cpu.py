@@ -41,3 +41,23 @@ def test_host_mirror_round_trips_and_grad_views_alias_the_flat_buffer():
     assert float(tr.grads.sum()) == 5.0 and float(tr.grads[off:off + n].view(256, 3, 3, 256)[5, 1, 2, 7]) == 3.0
     with pytest.raises(RuntimeError):
         tr.forward(None, None, None, torch.zeros(1, 1), None, None, None)        # no CPU fallback
+
+
+def test_clip_grad_norm_matches_torch_on_the_flat_buffer():
+    sd = synth.make_state_dict(0, num_layers=1)
+    tr = DecoderTrainer(sd, device='cpu')
+    g = torch.Generator().manual_seed(1)
+    for scale, max_norm in ((1.0, 35.0), (0.25, 3.0)):
+        tr.grads.zero_()                       # the padding between tensors is never written by the kernels: stays zero
+        for k in tr.table:
+            tr.grad(k).copy_(torch.randn(tr.grad(k).shape, generator=g) * 0.05)
+        ref = [tr.grad(k).clone() * scale for k in tr.table]
+        params = [torch.nn.Parameter(torch.zeros_like(r)) for r in ref]
+        for p_, r in zip(params, ref):
+            p_.grad = r.clone()
+        # the padding between tensors holds zeros, so the flat norm equals the norm over the tensors
+        want = torch.nn.utils.clip_grad_norm_(params, max_norm)
+        got = tr.clip_grad_norm_(max_norm, grad_scale=scale)
+        assert abs(float(got) - float(want)) <= 1e-5 * float(want)
+        for k, p_ in zip(tr.table, params):
+            assert torch.allclose(tr.grad(k), p_.grad, rtol=1e-5, atol=1e-8), k
