@@ -239,7 +239,7 @@ class DecoderTrainer:
         ops on the flat buffer (plumbing); pass grad_scale=1 to ``adamw_step`` afterwards."""
         if grad_scale != 1.0:
             self.grads.mul_(grad_scale)
-        norm = torch.linalg.vector_norm(self.grads)
+        norm = torch.linalg.vector_norm(self.grads, dtype=torch.float64).float()      # fp64 accumulation over 14 M entries
         self.grads.mul_(torch.clamp(max_norm / (norm + 1e-6), max=1.0))
         return norm
 
