@@ -357,8 +357,8 @@ class TrainStep:
                 self.lanes[k].backward()
         for s in self.streams:
             cur.wait_stream(s)
-        if len(self.lanes) > 1:
-            torch._foreach_add_([self.main.grads] * (len(self.lanes) - 1), [t.grads for t in self.lanes[1:]])
+        for t in self.lanes[1:]:
+            self.main.grads.add_(t.grads)
         self.main.all_reduce_grads()
         scale = 1.0 / (world * max(len(samples), 1))
         if optimize and max_grad_norm is not None:
