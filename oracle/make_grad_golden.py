@@ -9,6 +9,10 @@ with the config's stage_loss_weights as MV2DSHead.forward_train does (mv2d_s_hea
   * every parameter gradient of roi_head (bbox_head.* from mv2d_decoder_train_backward, query_generator.* and
     position_encoding.* from mv2d_front_train_backward) and d loss / d feat, big tensors subsampled.
 
+The single-frame cases assemble the loss layer by layer with bbox_head.loss (so the inputs of the decoder slice can be
+hooked); the result was checked to be identical to the reference's own head.forward_train (same total, bit-identical
+d feat).  The two-frame case calls head.forward_train itself.
+
 Run in the build container:   python -m oracle.make_grad_golden
 """
 import copy
