@@ -15,6 +15,18 @@
  *     >0 = cudaError_t of a failed launch.  Text via mv2d_last_error() (thread-local);
  *   - float tensors are fp32, geometry is fp64 where the reference uses .double();
  *   - feature maps are channels-last: [V, h, w, 256]; RoI tokens are [N, 49, 256].
+ *
+ * Batches (ABI 5).  The reference asserts one sample per call (detectors/mv2d.py:143, roi_heads/mv2d_head.py:210,251).
+ * Here B samples travel through ONE kernel chain as a segment dimension:
+ *   - the views of all samples are stacked: feature map [B*V, h, w, 256], camera matrices [B*V, 16]; a RoI's view
+ *     index (rois[n][0]) is the GLOBAL view b*V + v;
+ *   - every sample owns `rows_per_sample` consecutive query rows (row b*rows_per_sample + i); only the first
+ *     n_real[b] of them are detections, the rest are padding rows (any valid box of the sample, e.g. the reference's
+ *     dummy box) whose results the caller ignores.  Padding rows never enter another row's result: they are outside
+ *     every view's roi_start range (box correlation candidates) and outside the self-attention key range;
+ *   - self-attention, box correlation and the T head's key masks stay inside a sample; GEMMs / LayerNorms / branches
+ *     simply see B*rows_per_sample rows.  Results are those of B separate calls (same arithmetic per row).
+ * batch = 0 in a parameter struct means the single-sample layout of ABI 4.
  */
 #ifndef MV2D_B200_H_
 #define MV2D_B200_H_
@@ -32,7 +44,7 @@ extern "C" {
 #define MV2D_API
 #endif
 
-#define MV2D_ABI_VERSION 4
+#define MV2D_ABI_VERSION 5
 #define MV2D_MAX_LAYERS 8
 
 MV2D_API int mv2d_abi_version(void);
@@ -46,6 +58,8 @@ MV2D_API size_t mv2d_sizeof(int which); /* 0 Pe, 1 Qg, 2 Corr, 3 Decoder, 4 Laye
  * img2lidar[v] = inv(lidar2img[v]);  trans[src][dst] = lidar2img[dst] @ img2lidar[src]  (fp64) */
 MV2D_API int mv2d_geom_prep(const double* lidar2img /*[V,16]*/, int V, double* img2lidar /*[V,16]*/,
                    double* trans /*[V,V,16]*/, void* stream);
+/* the same for a batch: lidar2img / img2lidar [batch*V,16], trans [batch,V,V,16] (views of one sample only) */
+MV2D_API int mv2d_geom_prep_batch(const double* lidar2img, int batch, int V, double* img2lidar, double* trans, void* stream);
 
 /* NCHW [V,C,HW] -> NHWC [V,HW,C] (the FPN output layout -> this library's layout).
  * out_tf32 (nullable) receives a copy rounded to TF32 (operand of the single-pass tensor-core SE gate GEMM). */
@@ -81,7 +95,13 @@ typedef struct Mv2dPeParams {
     int sine_separable;        /* 1 = the caller guarantees not_mask is all ones (no padded cells): the first layer of
                                 * the sine branch is evaluated as W1.s(v,y,x) = Tv[v] + Ty[y] + Tx[x] from three
                                 * (V + h + w)-row tables instead of a GEMM over all V*h*w cells; 0 = general masks */
-    int reserved0;
+    int views_per_sample;      /* batch: V counts the views of all samples, this many belong to one sample (0 = V).
+                                * The view axis of SinePositionalEncoding3D (cumsum over views) is per sample. */
+    int sine_shared;           /* batch: 1 = the caller guarantees all samples have identical not_mask, so
+                                * adapt_pos3d(sine) is the same tensor for every sample: it is evaluated once, for the
+                                * first views_per_sample views, and shared (a common subexpression, not a cache: it is
+                                * recomputed on every call) */
+    int reserved3;
 } Mv2dPeParams;
 MV2D_API size_t mv2d_pe3d_workspace_bytes(int V, int h, int w, int depth_num);
 MV2D_API int mv2d_pe3d(const Mv2dPeParams* p, void* stream);
@@ -143,6 +163,11 @@ typedef struct Mv2dCorrParams {
     int* key_cnt;             /* out, nullable [N] */
     uint16_t* key_list;       /* out, nullable [N, V*h*w]: the set bits of keymask in ascending order (compacted once
                                * here instead of once per decoder layer); needs key_cnt */
+    /* ---- ABI 5: batch > 0: N = batch * rows_per_sample query rows, V = views of ONE sample, rois[n][0] = global view,
+     * roi_start [batch, V+1] global row ranges of the real detections (roi_start[b][V] = b*rows_per_sample + n_real[b]),
+     * trans [batch,V,V,16], pad_mask [batch*V,h,w]; keymask bits index the cells of the row's own sample
+     * ((v_local*h+y)*w+x) */
+    int batch, rows_per_sample;
 } Mv2dCorrParams;
 MV2D_API int mv2d_box_corr(const Mv2dCorrParams* p, void* stream);
 
@@ -222,9 +247,17 @@ typedef struct Mv2dDecoderParams {
     size_t xa_workspace_bytes;
     uint8_t* row_tile_live;     /* mv2d_xa_tile_prepare only, nullable out [ceil(num_rows/128)]: 1 = some query has a key
                                  * among rows 128 t .. 128 t + 127 (input of mv2d_kv_project) */
+    /* ---- ABI 5: batch > 0: N = batch * rows_per_sample; self-attention keys of a row are the first n_real[b] rows of
+     * its sample; mode 0: match ids are global rows; mode 1 (xa_form 1 only): num_rows = batch * V*h*w rows of
+     * kin_rows / mem_rows / kp / vp, keymask bits and mask_words refer to ONE sample's V*h*w cells */
+    int batch, rows_per_sample;
+    const int* n_real;          /* device [batch], nullable = every row is real */
+    const float* vel_dt_batch;  /* device [batch], nullable: per-sample vel_dt (replaces the scalar; 0 = off for that sample) */
 } Mv2dDecoderParams;
 MV2D_API size_t mv2d_decoder_workspace_bytes(int N, int L);
 MV2D_API size_t mv2d_xa_tile_workspace_bytes(int N, int V, int grid_h, int grid_w);
+/* batch > 0: `batch` samples of rows_per_sample query rows and V views each */
+MV2D_API size_t mv2d_xa_tile_workspace_bytes_batch(int batch, int rows_per_sample, int V, int grid_h, int grid_w);
 /* xa_form 1: per-tile query lists, per-query record lists and the tile order, built from the key masks alone
  * (so it can run right after mv2d_box_corr, beside the position embedding).  Reads N, num_rows, grid_h, grid_w,
  * keymask, mask_words, xa_workspace(_bytes) of the decoder parameters.  A decoder call with xa_prepared = 1 then

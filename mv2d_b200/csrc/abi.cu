@@ -54,7 +54,12 @@ size_t mv2d_sizeof(int which) {
 
 int mv2d_geom_prep(const double* lidar2img, int V, double* img2lidar, double* trans, void* stream) {
     MV2D_CHECK_ARG(lidar2img && img2lidar && trans, "geom_prep: null pointer");
-    return run_geom_prep(lidar2img, V, img2lidar, trans, (cudaStream_t)stream);
+    return run_geom_prep(lidar2img, V, img2lidar, trans, (cudaStream_t)stream, 1);
+}
+
+int mv2d_geom_prep_batch(const double* lidar2img, int batch, int V, double* img2lidar, double* trans, void* stream) {
+    MV2D_CHECK_ARG(lidar2img && img2lidar && trans, "geom_prep_batch: null pointer");
+    return run_geom_prep(lidar2img, V, img2lidar, trans, (cudaStream_t)stream, batch);
 }
 
 int mv2d_nchw_to_nhwc(const float* in, float* out, float* out_tf32, int V, int C, int HW, void* stream) {
@@ -110,6 +115,9 @@ int mv2d_dn_prepare(const Mv2dDnParams* p, void* stream) {
 
 size_t mv2d_decoder_workspace_bytes(int N, int L) { return decoder_workspace_bytes(N, L); }
 size_t mv2d_xa_tile_workspace_bytes(int N, int V, int grid_h, int grid_w) { return xa_tile_workspace_bytes(N, V, grid_h, grid_w); }
+size_t mv2d_xa_tile_workspace_bytes_batch(int batch, int rows_per_sample, int V, int grid_h, int grid_w) {
+    return xa_tile_workspace_bytes(rows_per_sample, V, grid_h, grid_w, batch);
+}
 int mv2d_xa_tile_prepare(const Mv2dDecoderParams* p, void* stream) {
     NONNULL(p, "xa_tile_prepare");
     MV2D_CHECK_ARG(p->N == 0 || (p->keymask && p->xa_workspace), "xa_tile_prepare: null pointer");

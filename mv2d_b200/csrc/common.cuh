@@ -10,6 +10,7 @@
 #define MV2D_ROI 7
 #define MV2D_TOK 49         // 7x7 RoI tokens
 #define MV2D_MAXV 16        // max views per sample
+#define MV2D_MAXVB 1024      // max views of a whole batch (samples x views)
 #define MV2D_CAT_LD 1056    // 1024 FC features + 16 intrinsics, K padded to a multiple of 32
 
 namespace mv2d {

@@ -153,15 +153,20 @@ __device__ __forceinline__ void sa_cp16(void* smem, const void* gmem) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
 }
 
+// A sample of a batch owns rows [seg0, seg0 + nq); its keys are the first N of them (seg0 = 0, nq = N: one sample).
 __device__ __forceinline__ void
 self_attn_body(const float* __restrict__ qkv, const uint8_t* __restrict__ mask, int N, float* __restrict__ out,
-               int vbx, int hd, float* smem_f) {
+               int vbx, int hd, float* smem_f, int seg0 = 0, int nq = -1) {
     float (*Ks)[SA_LD] = reinterpret_cast<float (*)[SA_LD]>(smem_f);
     float (*Vs)[SA_LD] = reinterpret_cast<float (*)[SA_LD]>(smem_f + SA_KT * SA_LD);
     float (*Ps)[SA_KT] = reinterpret_cast<float (*)[SA_KT]>(smem_f + 2 * SA_KT * SA_LD);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kq = lane >> 3, cq = lane & 7;
-    const int qi = vbx * 8 + warp;
+    if (nq < 0) nq = N;
+    const int ql = vbx * 8 + warp;                // query row inside the sample
+    const int qi = ql;                            // row of the (single-sample) attention mask
+    qkv += (long long)seg0 * 768;
+    out += (long long)seg0 * MV2D_C;
     float q[32], m = -INFINITY, l = 0.f;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int k0 = 0; k0 < N; k0 += SA_KT) {
@@ -180,14 +185,14 @@ self_attn_body(const float* __restrict__ qkv, const uint8_t* __restrict__ mask, 
             for (int d4 = 0; d4 < 8; ++d4) {
                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                 // ld.global.cg: inside the persistent kernel qkv was written by other CTAs a phase ago (no .nc path)
-                if (qi < N) v = __ldcg(reinterpret_cast<const float4*>(qkv + (long long)qi * 768 + hd * 32) + d4);
+                if (ql < nq) v = __ldcg(reinterpret_cast<const float4*>(qkv + (long long)ql * 768 + hd * 32) + d4);
                 q[d4 * 4 + 0] = v.x * 0.17677669529663687f; q[d4 * 4 + 1] = v.y * 0.17677669529663687f;
                 q[d4 * 4 + 2] = v.z * 0.17677669529663687f; q[d4 * 4 + 3] = v.w * 0.17677669529663687f;
             }
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
-        if (qi >= N) continue;                    // warp-uniform
+        if (ql >= nq) continue;                   // warp-uniform
         const int ngrp = (ng + 31) >> 5;
         float s[SA_KT / 32];
         float mx = -INFINITY;
@@ -243,9 +248,9 @@ self_attn_body(const float* __restrict__ qkv, const uint8_t* __restrict__ mask, 
         acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
         acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o); acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
     }
-    if (qi < N && kq == 0) {
+    if (ql < nq && kq == 0) {
         const float inv = l > 0.f ? 1.f / l : 0.f;
-        *reinterpret_cast<float4*>(out + (long long)qi * MV2D_C + hd * 32 + cq * 4) =
+        *reinterpret_cast<float4*>(out + (long long)ql * MV2D_C + hd * 32 + cq * 4) =
             make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
     }
 }
@@ -364,12 +369,20 @@ self_attn_body_v1(const float* __restrict__ qkv, const uint8_t* __restrict__ mas
     }
 }
 
+// grid (ceil(rows_per_sample / 8), heads, batch).  n_real (nullable, device [batch]): keys of sample b = its first n_real[b] rows.
 __global__ void __launch_bounds__(256)
-self_attn_kernel(const float* __restrict__ qkv, const uint8_t* __restrict__ mask, int N, float* __restrict__ out) {
+self_attn_kernel(const float* __restrict__ qkv, const uint8_t* __restrict__ mask, int N, float* __restrict__ out,
+                 int rows_per_sample, const int* __restrict__ n_real) {
     pdl_wait();
     pdl_trigger();
     extern __shared__ __align__(16) float sa_smem[];
-    self_attn_body(qkv, mask, N, out, blockIdx.x, blockIdx.y, sa_smem);
+    if (rows_per_sample > 0) {
+        const int b = blockIdx.z;
+        const int nk = n_real ? min(n_real[b], rows_per_sample) : rows_per_sample;
+        self_attn_body(qkv, nullptr, nk, out, blockIdx.x, blockIdx.y, sa_smem, b * rows_per_sample, rows_per_sample);
+    } else {
+        self_attn_body(qkv, mask, N, out, blockIdx.x, blockIdx.y, sa_smem);
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -846,10 +859,12 @@ __device__ __forceinline__ void
 head10_body(const float* __restrict__ xc, const float* __restrict__ xr, const float* __restrict__ wc,
             const float* __restrict__ bc, const float* __restrict__ wr, const float* __restrict__ br,
             const float* __restrict__ ref, int L, int N, float pc0, float pc1, float pc2, float pc3,
-            float pc4, float pc5, float vel_dt, int vel_row_start, float* __restrict__ cls, float* __restrict__ box, int vb) {
+            float pc4, float pc5, float vel_dt, int vel_row_start, float* __restrict__ cls, float* __restrict__ box, int vb,
+            const float* __restrict__ vel_dt_batch = nullptr, int rows_per_sample = 0) {
     const int row = vb * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= L * N) return;
     const int l = row / N, n = row % N;
+    if (vel_dt_batch) vel_dt = __ldg(vel_dt_batch + n / rows_per_sample);
     float a[8], b[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -882,10 +897,12 @@ __global__ void __launch_bounds__(256)
 head10_kernel(const float* __restrict__ xc, const float* __restrict__ xr, const float* __restrict__ wc,
               const float* __restrict__ bc, const float* __restrict__ wr, const float* __restrict__ br,
               const float* __restrict__ ref, int L, int N, float pc0, float pc1, float pc2, float pc3,
-              float pc4, float pc5, float vel_dt, int vel_row_start, float* __restrict__ cls, float* __restrict__ box) {
+              float pc4, float pc5, float vel_dt, int vel_row_start, float* __restrict__ cls, float* __restrict__ box,
+              const float* __restrict__ vel_dt_batch, int rows_per_sample) {
     pdl_wait();
     pdl_trigger();
-    head10_body(xc, xr, wc, bc, wr, br, ref, L, N, pc0, pc1, pc2, pc3, pc4, pc5, vel_dt, vel_row_start, cls, box, blockIdx.x);
+    head10_body(xc, xr, wc, bc, wr, br, ref, L, N, pc0, pc1, pc2, pc3, pc4, pc5, vel_dt, vel_row_start, cls, box, blockIdx.x,
+                vel_dt_batch, rows_per_sample);
 }
 
 }  // namespace mv2d
@@ -943,28 +960,32 @@ struct XtWs {
     int* qlist; int* qcnt; float* qp; float* ctx; float* rec;
     size_t bytes;
 };
-static XtWs xt_carve(void* base, int N, int ntiles) {
+// Np query rows and tiles_ps tiles per sample, batch samples (every (tile, query) pair lives inside one sample)
+static XtWs xt_carve(void* base, int Np, int tiles_ps, int batch = 1) {
     XtWs w{};
     size_t off = 0;
     auto take = [&](size_t bytes) { void* r = base ? (char*)base + off : nullptr; off += (bytes + 255) & ~(size_t)255; return r; };
-    const size_t n = (size_t)(N > 0 ? N : 1), t = (size_t)(ntiles > 0 ? ntiles : 1);
+    const size_t bb = (size_t)(batch > 0 ? batch : 1);
+    const size_t np = (size_t)(Np > 0 ? Np : 1), n = bb * np, tp = (size_t)(tiles_ps > 0 ? tiles_ps : 1), t = bb * tp;
     w.tile_cnt = (int*)take(t * sizeof(int));
     w.tile_work = (int*)take(t * sizeof(int));
     w.order = (int*)take(t * sizeof(int));
-    w.qlist = (int*)take(t * n * sizeof(int));
+    w.qlist = (int*)take(tp * n * sizeof(int));
     w.qcnt = (int*)take(n * sizeof(int));
-    w.tile_q = (uint16_t*)take(t * n * sizeof(uint16_t));
-    w.tile_mask = (unsigned long long*)take(t * n * sizeof(unsigned long long));
-    w.slot_of = (short*)take(t * n * sizeof(short));
+    w.tile_q = (uint16_t*)take(t * np * sizeof(uint16_t));
+    w.tile_mask = (unsigned long long*)take(t * np * sizeof(unsigned long long));
+    w.slot_of = (short*)take(tp * n * sizeof(short));
     w.qp = (float*)take(n * MV2D_C * sizeof(float));
     w.ctx = (float*)take(n * MV2D_C * sizeof(float));
-    w.rec = (float*)take(t * n * XT_REC * sizeof(float));
+    w.rec = (float*)take(t * np * XT_REC * sizeof(float));
     w.bytes = off;
     return w;
 }
 static int xt_ntiles(int V, int h, int w) { return V * cdiv(h, XT_TS) * cdiv(w, XT_TS); }
 
-size_t xa_tile_workspace_bytes(int N, int V, int h, int w) { return xt_carve(nullptr, N, xt_ntiles(V, h, w)).bytes; }
+size_t xa_tile_workspace_bytes(int N, int V, int h, int w, int batch) {
+    return xt_carve(nullptr, N, xt_ntiles(V, h, w), batch > 0 ? batch : 1).bytes;
+}
 
 int run_kv_project(const Mv2dKvParams& p, cudaStream_t st) {
     const int le = p.layer_end > 0 ? p.layer_end : p.L;
@@ -992,12 +1013,19 @@ static int xt_setup(const Mv2dDecoderParams& p, XtGeom& xg, XtWs& xw) {
     const int N = p.N;
     MV2D_CHECK_ARG(p.grid_h > 0 && p.grid_w > 0 && p.num_rows > 0 && p.num_rows % (p.grid_h * p.grid_w) == 0,
                    "decoder: xa_form 1 needs the feature grid (num_rows=%d, grid %dx%d)", p.num_rows, p.grid_h, p.grid_w);
-    xg.N = N; xg.h = p.grid_h; xg.w = p.grid_w; xg.V = p.num_rows / (p.grid_h * p.grid_w);
-    xg.tiles_x = cdiv(xg.w, XT_TS); xg.tiles_y = cdiv(xg.h, XT_TS); xg.ntiles = xg.V * xg.tiles_x * xg.tiles_y;
-    MV2D_CHECK_ARG(xg.ntiles <= XT_MERGE_MAXT && N <= 32767, "decoder: xa_form 1 supports <= %d tiles and <= 32767 queries", XT_MERGE_MAXT);
+    const int B = p.batch > 0 ? p.batch : 1;
+    MV2D_CHECK_ARG(p.num_rows % B == 0 && (p.batch == 0 || N == B * p.rows_per_sample), "decoder: batch=%d does not divide num_rows=%d / N=%d", B, p.num_rows, N);
+    const int rows_ps = p.num_rows / B;          // feature cells of one sample
+    MV2D_CHECK_ARG(rows_ps % (p.grid_h * p.grid_w) == 0, "decoder: rows per sample %d is not a multiple of the %dx%d grid", rows_ps, p.grid_h, p.grid_w);
+    xg.N = N; xg.h = p.grid_h; xg.w = p.grid_w; xg.V = rows_ps / (p.grid_h * p.grid_w);
+    xg.B = B; xg.Np = N / B;
+    xg.tiles_x = cdiv(xg.w, XT_TS); xg.tiles_y = cdiv(xg.h, XT_TS); xg.tiles_ps = xg.V * xg.tiles_x * xg.tiles_y;
+    xg.ntiles = B * xg.tiles_ps;
+    MV2D_CHECK_ARG(xg.tiles_ps <= XT_MERGE_MAXT && xg.ntiles <= XT_ORDER_MAXT && N <= 32767,
+                   "decoder: xa_form 1 supports <= %d tiles per sample, <= %d per batch and <= 32767 queries", XT_MERGE_MAXT, XT_ORDER_MAXT);
     MV2D_CHECK_ARG(p.keymask && p.xa_workspace, "decoder: xa_form 1 needs the key masks and xa_workspace");
-    MV2D_CHECK_ARG(p.mask_words * 32 >= p.num_rows, "decoder: keymask has %d words for %d cells", p.mask_words, p.num_rows);
-    xw = xt_carve(p.xa_workspace, N, xg.ntiles);
+    MV2D_CHECK_ARG(p.mask_words * 32 >= rows_ps, "decoder: keymask has %d words for %d cells", p.mask_words, rows_ps);
+    xw = xt_carve(p.xa_workspace, xg.Np, xg.tiles_ps, B);
     MV2D_CHECK_ARG(xw.bytes <= p.xa_workspace_bytes, "decoder: xa_workspace too small (%zu < %zu)", p.xa_workspace_bytes, xw.bytes);
     return 0;
 }
@@ -1010,10 +1038,13 @@ static int xt_prepare(const Mv2dDecoderParams& p, const XtGeom& xg, const XtWs& 
     MV2D_CHECK_LAUNCH("xt_prep");
     XtListArgs b{}; b.g = xg; b.slot_of = xw.slot_of; b.tile_work = xw.tile_work; b.qlist = xw.qlist; b.qcnt = xw.qcnt;
     b.order = xw.order;
-    launch_k(xt_list_kernel, dim3(xg.N + 1), dim3(256), 0, st, b);
+    launch_k(xt_list_kernel, dim3(xg.N + cdiv(xg.ntiles, 256)), dim3(256), 0, st, b);
     MV2D_CHECK_LAUNCH("xt_list");
     if (p.row_tile_live) {
-        launch_k(xt_rowlive_kernel, dim3(cdiv(p.num_rows, 128)), dim3(128), 0, st, p.keymask, p.mask_words, xg.N, p.num_rows, p.row_tile_live);
+        const int rows_ps = p.num_rows / xg.B;
+        MV2D_CHECK_ARG(xg.B == 1 || rows_ps % 128 == 0, "xa_tile_prepare: row_tile_live of a batch needs V*h*w %% 128 == 0 (got %d)", rows_ps);
+        launch_k(xt_rowlive_kernel, dim3(cdiv(p.num_rows, 128)), dim3(128), 0, st, p.keymask, p.mask_words, xg.N, p.num_rows, p.row_tile_live,
+                 xg.B > 1 ? rows_ps : 0, xg.Np);
         MV2D_CHECK_LAUNCH("xt_rowlive");
     }
     return 0;
@@ -1032,10 +1063,14 @@ int run_decoder(const Mv2dDecoderParams& p, cudaStream_t st) {
     const int N = p.N, L = p.L, C = MV2D_C;
     MV2D_CHECK_ARG(N >= 0 && L >= 1 && L <= MV2D_MAX_LAYERS, "decoder: bad N=%d / L=%d", N, L);
     if (N == 0) return 0;
-    MV2D_CHECK_ARG(p.num_rows > 0 && p.num_rows <= 65536, "decoder: num_rows=%d must be in (0, 65536]", p.num_rows);
+    MV2D_CHECK_ARG(p.num_rows > 0, "decoder: num_rows=%d must be positive", p.num_rows);
     MV2D_CHECK_ARG(p.layers && p.branches, "decoder: missing weights");
     MV2D_CHECK_ARG(p.mode == 0 ? (p.match && p.match_cnt && p.max_match > 0) : (p.keymask && p.mask_words > 0),
                    "decoder: key description missing for mode %d", p.mode);
+    MV2D_CHECK_ARG(p.batch == 0 || (p.batch > 0 && p.rows_per_sample > 0 && N == p.batch * p.rows_per_sample && !p.persistent &&
+                                    !p.self_attn_mask && (p.mode == 0 || p.xa_form == 1)),
+                   "decoder: batch=%d x rows_per_sample=%d must equal N=%d (staged decoder, no attention mask, T head: xa_form 1)",
+                   p.batch, p.rows_per_sample, N);
     float* ws = p.workspace;
     float* x = ws;    ws += (size_t)N * C;
     float* xq = ws;   ws += (size_t)N * C;
@@ -1110,6 +1145,8 @@ int run_decoder(const Mv2dDecoderParams& p, cudaStream_t st) {
     // S head: one CTA per (query, matched RoI) with bulk copies (xa_roi_kernel); MV2D_XA_ROI=0 keeps the per-query kernel
     static const bool xr_on = []() { const char* v = getenv("MV2D_XA_ROI"); return !(v && v[0] == '0'); }();
     const bool use_xr = xr_on && p.mode == 0 && !p.persistent && p.max_match <= XR_MAXM;
+    // the per-query kernel (and the persistent decoder) address key rows with 16-bit ids
+    MV2D_CHECK_ARG(use_xr || xt || p.num_rows <= 65536, "decoder: num_rows=%d must be <= 65536 (16-bit key ids)", p.num_rows);
     if ((e = cudaFuncSetAttribute(self_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SA_SMEM_BYTES)) != cudaSuccess) {
         set_error("decoder: self_attn smem attr %s", cudaGetErrorString(e));
         return (int)e;
@@ -1201,7 +1238,12 @@ int run_decoder(const Mv2dDecoderParams& p, cudaStream_t st) {
                 g.M = N; g.N = 768; g.K = C; g.batch = 1; g.nsplit = 1;
                 if ((rc = launch_gemm_small(g, x, 512, st))) return rc;
             }
-            launch_k(self_attn_kernel, dim3(cdiv(N, 8 * SA_QPW), MV2D_HEADS), dim3(256), SA_SMEM_BYTES, st, (const float*)qkv, p.self_attn_mask, N, sa);
+            if (p.batch > 0)
+                launch_k(self_attn_kernel, dim3(cdiv(p.rows_per_sample, 8 * SA_QPW), MV2D_HEADS, p.batch), dim3(256), SA_SMEM_BYTES, st,
+                         (const float*)qkv, (const uint8_t*)nullptr, N, sa, p.rows_per_sample, p.n_real);
+            else
+                launch_k(self_attn_kernel, dim3(cdiv(N, 8 * SA_QPW), MV2D_HEADS), dim3(256), SA_SMEM_BYTES, st, (const float*)qkv, p.self_attn_mask, N, sa,
+                         0, (const int*)nullptr);
             MV2D_CHECK_LAUNCH("self_attn");
             if ((rc = gemm(sa, C, w.sa_out_w, C, nullptr, part, C, N, C, C, 0, st))) return rc;
             {
@@ -1225,7 +1267,7 @@ int run_decoder(const Mv2dDecoderParams& p, cudaStream_t st) {
             }
             {
                 XtMergeArgs a{}; a.g = xg; a.qlist = xw.qlist; a.qcnt = xw.qcnt; a.rec = xw.rec; a.ctx = xw.ctx;
-                launch_k(xt_merge_kernel, dim3(N), dim3(XT_MERGE_THREADS), (size_t)xg.ntiles * 36, st, a);
+                launch_k(xt_merge_kernel, dim3(N), dim3(XT_MERGE_THREADS), (size_t)xg.tiles_ps * 36, st, a);
                 MV2D_CHECK_LAUNCH("xt_merge");
             }
             if ((rc = gemm(xw.ctx, C, w.xa_o_w, C, nullptr, part, C, N, C, C, 0, st))) return rc;
@@ -1286,7 +1328,8 @@ int run_decoder(const Mv2dDecoderParams& p, cudaStream_t st) {
     if ((rc = gemm(b2, C, B.reg_w1, C, B.reg_b1, b3, C, N, C, C, GEMM_RELU, st, 1, 0, L, NC, CC, NC, C))) return rc;
     launch_k(head10_kernel, dim3(cdiv(L * N, 8)), dim3(256), 0, st, (const float*)b1, (const float*)b3, B.cls_w2, B.cls_b2, B.reg_w2, B.reg_b2, p.ref, L, N,
                                                  p.pc_range[0], p.pc_range[1], p.pc_range[2], p.pc_range[3],
-                                                 p.pc_range[4], p.pc_range[5], p.vel_dt, p.vel_row_start, p.cls_scores, p.bbox_preds);
+                                                 p.pc_range[4], p.pc_range[5], p.vel_dt, p.vel_row_start, p.cls_scores, p.bbox_preds,
+                                                 p.batch > 0 ? p.vel_dt_batch : (const float*)nullptr, p.rows_per_sample);
     MV2D_CHECK_LAUNCH("head10");
     return 0;
 }

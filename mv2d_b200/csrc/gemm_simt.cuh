@@ -28,6 +28,7 @@ struct GemmArgs {
     long long splitStride;
     int flags;
     const float* gx; const float* gs; const float* gfeat; float* kin;  // GEMM_GATE extras (ld = ldc)
+    int gs_mod;           // GEMM_GATE: > 0 = gs has gs_mod rows and is read at row (m % gs_mod) (batch-shared sine branch)
 };
 
 template <int BM, int BN, int BK, int RM, int RN, int AMODE>
@@ -184,7 +185,7 @@ gemm_simt_kernel(GemmArgs g) {
                 if (!raw && (g.flags & GEMM_GATE)) {
                     // host guarantees vec for GATE
                     float4 xx = __ldg(reinterpret_cast<const float4*>(g.gx + o));
-                    float4 ss = __ldg(reinterpret_cast<const float4*>(g.gs + o));
+                    float4 ss = __ldg(reinterpret_cast<const float4*>(g.gs + (g.gs_mod > 0 ? (long long)(m % g.gs_mod) * g.ldc + n : o)));
                     v[0] = xx.x * sigmoid_f(v[0]) + ss.x;
                     v[1] = xx.y * sigmoid_f(v[1]) + ss.y;
                     v[2] = xx.z * sigmoid_f(v[2]) + ss.z;

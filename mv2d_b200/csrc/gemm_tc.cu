@@ -106,6 +106,8 @@ struct TcArgs {
     int fm_h, fm_w;                                                    // IM2COL 2: feature grid (tiles of 16 x 8 pixels)
     const uint8_t* m_tile_live;                                        // nullable [m_tiles]: 0 = nobody reads this row tile, skip it
     const float* gx; const float* gs; const float* gfeat; float* kin;  // GEMM_GATE extras
+    int gs_mod;                                                        // > 0: gs row = out row % gs_mod
+    int n_switch;                                                      // > 0: n tiles at columns >= n_switch load A through tmAlo's slot pair (see launch)
 };
 
 // RAW (PASSES == 3 only): the operands arrive as plain fp32 -- ONE copy of each tile crosses the L2->SM fabric instead
@@ -115,7 +117,8 @@ struct TcArgs {
 template <int BN, int PASSES, int IM2COL, int STAGES, bool RAW = false>
 __global__ void __launch_bounds__(TC_THREADS, (PASSES == 1 ? 2 : 1))
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
-               const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmWlo, TcArgs g) {
+               const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmWlo,
+               const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmA2lo, TcArgs g) {
     static_assert(!RAW || (PASSES == 3 && !IM2COL), "RAW is the in-kernel split of the plain 3xTF32 GEMM");
     constexpr int A_BYTES = TC_BM * TC_BK * 4;      // 16 KB
     constexpr int W_BYTES = BN * TC_BK * 4;
@@ -140,9 +143,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // CTAs that share an operand tile walk K in rotated order, so they do not all hit the same L2 lines at once
     const int rot = IM2COL ? 0 : (int)((blockIdx.x + 3 * blockIdx.y) % nkb);
 
+    // output columns >= n_switch read their A rows from the second operand (CTA-uniform)
+    const bool second_a = !IM2COL && g.n_switch > 0 && n0 >= g.n_switch;
+    const CUtensorMap* mapA = second_a ? &tmA2 : &tmA;
+    const CUtensorMap* mapAlo = second_a ? &tmA2lo : &tmAlo;
     if (warp == 0 && lane == 0) {
-        tmap_prefetch(&tmA); tmap_prefetch(&tmW);
-        if (PASSES == 3) { tmap_prefetch(&tmAlo); tmap_prefetch(&tmWlo); }
+        tmap_prefetch(mapA); tmap_prefetch(&tmW);
+        if (PASSES == 3) { tmap_prefetch(mapAlo); tmap_prefetch(&tmWlo); }
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); mbar_init(&conv_bar[s], 128); }
         mbar_init(tmem_full_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -188,8 +195,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             tma_load_4d(&tmAlo, &full_bar[s], st + A_BYTES + r * (A_BYTES / 2), c0, dx, dy, m_tile * 2 + r);
                     }
                 } else {
-                    tma_load_2d(&tmA, &full_bar[s], st, (kb0 + (kb + rot) % nkb) * TC_BK, m_tile * TC_BM);
-                    if (PASSES == 3 && !RAW) tma_load_2d(&tmAlo, &full_bar[s], st + A_BYTES, (kb0 + (kb + rot) % nkb) * TC_BK, m_tile * TC_BM);
+                    tma_load_2d(mapA, &full_bar[s], st, (kb0 + (kb + rot) % nkb) * TC_BK, m_tile * TC_BM);
+                    if (PASSES == 3 && !RAW) tma_load_2d(mapAlo, &full_bar[s], st + A_BYTES, (kb0 + (kb + rot) % nkb) * TC_BK, m_tile * TC_BM);
                 }
                 tma_load_2d(&tmW, &full_bar[s], st + NOP * A_BYTES, (kb0 + (kb + rot) % nkb) * TC_BK, n0);
                 if (PASSES == 3 && !RAW) tma_load_2d(&tmWlo, &full_bar[s], st + NOP * A_BYTES + W_BYTES, (kb0 + (kb + rot) % nkb) * TC_BK, n0);
@@ -292,14 +299,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         };
         // global -> registers (my row, 32 cols), same access pattern in reverse
-        auto load_t = [&](const float* __restrict__ src, float (&x)[32], int n) {
+        auto load_t = [&](const float* __restrict__ src, float (&x)[32], int n, int row_mod = 0) {
             __syncwarp();
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int rr = i * 4 + (lane >> 3), cc = lane & 7;
                 long long orow;
                 float4 v4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (out_row(q * 32 + rr, orow)) v4 = __ldg(reinterpret_cast<const float4*>(src + orow * g.ldc + n + cc * 4));
+                if (out_row(q * 32 + rr, orow)) v4 = __ldg(reinterpret_cast<const float4*>(src + (row_mod > 0 ? orow % row_mod : orow) * g.ldc + n + cc * 4));
                 *reinterpret_cast<float4*>(stg + rr * 32 + ((cc ^ (rr & 7)) << 2)) = v4;
             }
             __syncwarp();
@@ -334,7 +341,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 load_t(g.gx, t, n);
 #pragma unroll
                 for (int j = 0; j < 32; ++j) x[j] = t[j] * sigmoid_f(x[j]);
-                load_t(g.gs, t, n);
+                load_t(g.gs, t, n, g.gs_mod);
 #pragma unroll
                 for (int j = 0; j < 32; ++j) x[j] += t[j];
                 if (g.kin) {
@@ -617,7 +624,8 @@ static int make_map_fmap(CUtensorMap* m, const float* base, int V, int h, int w)
 
 template <int BN, int PASSES, int IM2COL, int STAGES, bool RAW = false>
 static int launch_tc(const CUtensorMap& a, const CUtensorMap& alo, const CUtensorMap& w, const CUtensorMap& wlo,
-                     const TcArgs& g, int m_tiles, int nsplit, cudaStream_t st) {
+                     const TcArgs& g, int m_tiles, int nsplit, cudaStream_t st, const CUtensorMap* a2 = nullptr,
+                     const CUtensorMap* a2lo = nullptr) {
     constexpr int NOP = PASSES == 3 ? 2 : 1;
     constexpr size_t smem = (size_t)STAGES * NOP * (TC_BM * TC_BK * 4 + BN * TC_BK * 4) + 1024 + 256;
     auto kern = gemm_tc_kernel<BN, PASSES, IM2COL, STAGES, RAW>;
@@ -628,7 +636,7 @@ static int launch_tc(const CUtensorMap& a, const CUtensorMap& alo, const CUtenso
         attr_set = true;
     }
     dim3 grid(g.N / BN, m_tiles, nsplit);
-    launch_k(kern, grid, dim3(TC_THREADS), smem, st, a, alo, w, wlo, g);
+    launch_k(kern, grid, dim3(TC_THREADS), smem, st, a, alo, w, wlo, a2 ? *a2 : a, a2lo ? *a2lo : alo, g);
     MV2D_CHECK_LAUNCH("gemm_tc");
     return 0;
 }
@@ -683,7 +691,7 @@ int launch_gemm_tc(const TcGemm& t, cudaStream_t st) {
     MV2D_CHECK_ARG(!(t.flags & GEMM_SPLIT_OUT) || t.C_lo, "gemm_tc: split output needs C_lo");
     g.C = t.C; g.C_lo = t.C_lo; g.ldc = t.ldc; g.bias = t.bias; g.M = t.M; g.N = t.N; g.K = t.K; g.flags = t.flags;
     g.nkb_per_split = t.K / TC_BK / nsplit; g.split_stride = t.split_stride;
-    g.gx = t.gx; g.gs = t.gs; g.gfeat = t.gfeat; g.kin = t.kin;
+    g.gx = t.gx; g.gs = t.gs; g.gfeat = t.gfeat; g.kin = t.kin; g.gs_mod = t.gs_mod;
     g.m_tile_live = t.m_tile_live;
     int m_tiles;
     if (t.im2col == 2) {
@@ -706,19 +714,28 @@ int launch_gemm_tc(const TcGemm& t, cudaStream_t st) {
     }
     if ((rc = make_map_2d(&w, t.W, t.N, t.K, t.ldw, bn))) return rc;
     if ((rc = make_map_2d(&wlo, (t.passes == 3 && !raw) ? t.W_lo : t.W, t.N, t.K, t.ldw, bn))) return rc;
+    CUtensorMap a2, a2lo;
+    const bool two_a = t.A2 != nullptr && t.n_switch > 0;
+    if (two_a) {
+        MV2D_CHECK_ARG(t.passes == 3 && !raw && !t.im2col && t.A2_lo && t.n_switch % bn == 0,
+                       "gemm_tc: the second A operand needs pre-split 3xTF32 operands and n_switch %% %d == 0", bn);
+        g.n_switch = t.n_switch;
+        if ((rc = make_map_2d(&a2, t.A2, t.M, t.K, t.lda, TC_BM))) return rc;
+        if ((rc = make_map_2d(&a2lo, t.A2_lo, t.M, t.K, t.lda, TC_BM))) return rc;
+    }
     if (raw && bn == 64) return launch_tc<64, 3, false, 4, true>(a, alo, w, wlo, g, m_tiles, nsplit, st);
     if (raw) return launch_tc<128, 3, false, 3, true>(a, alo, w, wlo, g, m_tiles, nsplit, st);
     if (t.im2col == 2) return launch_tc<128, 3, 2, 3>(a, alo, w, wlo, g, m_tiles, nsplit, st);
     if (t.im2col && bn == 256) return launch_tc<256, 3, 1, 2>(a, alo, w, wlo, g, m_tiles, nsplit, st);
     if (t.im2col) return launch_tc<128, 3, 1, 3>(a, alo, w, wlo, g, m_tiles, nsplit, st);
-    if (t.passes == 3 && bn == 64 && mc_enabled() && (t.N / 64) % TC_MC == 0) {
+    if (t.passes == 3 && bn == 64 && mc_enabled() && (t.N / 64) % TC_MC == 0 && !(t.A2 != nullptr && t.n_switch > 0)) {
         // A is loaded in 32-row quarters and multicast across the 4-CTA cluster that shares the M-tile
         if ((rc = make_map_2d(&a, t.A, t.M, t.K, t.lda, 32))) return rc;
         if ((rc = make_map_2d(&alo, t.A_lo, t.M, t.K, t.lda, 32))) return rc;
         return launch_tc_mc(a, alo, w, wlo, g, m_tiles, nsplit, st);
     }
-    if (t.passes == 3 && bn == 64) return launch_tc<64, 3, false, 4>(a, alo, w, wlo, g, m_tiles, nsplit, st);
-    if (t.passes == 3) return launch_tc<128, 3, false, 3>(a, alo, w, wlo, g, m_tiles, nsplit, st);
+    if (t.passes == 3 && bn == 64) return launch_tc<64, 3, false, 4>(a, alo, w, wlo, g, m_tiles, nsplit, st, two_a ? &a2 : nullptr, two_a ? &a2lo : nullptr);
+    if (t.passes == 3) return launch_tc<128, 3, false, 3>(a, alo, w, wlo, g, m_tiles, nsplit, st, two_a ? &a2 : nullptr, two_a ? &a2lo : nullptr);
     return launch_tc<128, 1, false, 3>(a, alo, w, wlo, g, m_tiles, nsplit, st);
 }
 
@@ -762,7 +779,7 @@ int launch_gemm_tc_or_simt(const GemmArgs& g, cudaStream_t stream) {
         t.M = g.M; t.N = g.N; t.K = g.K; t.passes = 1; t.im2col = 0;
         t.flags = g.flags & (GEMM_RELU | GEMM_GATE | GEMM_ROUND_TF32);
         t.nsplit = 1;
-        t.gx = g.gx; t.gs = g.gs; t.gfeat = g.gfeat; t.kin = g.kin;
+        t.gx = g.gx; t.gs = g.gs; t.gfeat = g.gfeat; t.kin = g.kin; t.gs_mod = g.gs_mod;
         return launch_gemm_tc(t, stream);
     }
     GemmArgs h = g;

@@ -31,6 +31,9 @@ struct TcGemm {
     const uint8_t* m_tile_live;   // nullable, device [ceil(M/128)]: row tiles with 0 are skipped (their C rows stay untouched)
     int flags;         // GEMM_RELU | GEMM_GATE | GEMM_ROUND_TF32
     const float* gx; const float* gs; const float* gfeat; float* kin;
+    int gs_mod;        // GEMM_GATE: > 0 = gs has gs_mod rows, read at (row % gs_mod)
+    const float* A2; const float* A2_lo; int n_switch;   // nullable: output columns >= n_switch take their A rows from A2
+                                                          // (the self-attention in_proj: q, k from x + pos, v from x)
 };
 
 int launch_gemm_tc(const TcGemm& t, cudaStream_t st);

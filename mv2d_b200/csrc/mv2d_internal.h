@@ -5,7 +5,7 @@
 
 namespace mv2d {
 
-int run_geom_prep(const double* lidar2img, int V, double* img2lidar, double* trans, cudaStream_t st);
+int run_geom_prep(const double* lidar2img, int V, double* img2lidar, double* trans, cudaStream_t st, int batch = 1);
 int run_nchw_to_nhwc(const float* in, float* out, float* out_tf32, int V, int C, int HW, cudaStream_t st);
 int run_pe3d(const Mv2dPeParams& p, cudaStream_t st);
 size_t pe3d_workspace_bytes(int V, int h, int w, int depth_num);
@@ -14,7 +14,7 @@ size_t roi_align_qg_workspace_bytes(int N);
 int run_box_corr(const Mv2dCorrParams& p, cudaStream_t st);
 int run_decoder(const Mv2dDecoderParams& p, cudaStream_t st);
 size_t decoder_workspace_bytes(int N, int L);
-size_t xa_tile_workspace_bytes(int N, int V, int h, int w);
+size_t xa_tile_workspace_bytes(int N, int V, int h, int w, int batch = 1);   // N = query rows per sample
 int run_kv_project(const Mv2dKvParams& p, cudaStream_t st);
 int run_xa_tile_prepare(const Mv2dDecoderParams& p, cudaStream_t st);
 int run_dn_prepare(const Mv2dDnParams& p, cudaStream_t st);

@@ -16,6 +16,10 @@ __global__ void geom_prep_kernel(const double* __restrict__ lidar2img, int V,
     pdl_trigger();
     __shared__ double inv_s[MV2D_MAXV][16];
     int t = threadIdx.x;
+    // one block per sample of a batch: the V views of sample blockIdx.x (trans couples views of ONE sample only)
+    lidar2img += (long long)blockIdx.x * V * 16;
+    img2lidar += (long long)blockIdx.x * V * 16;
+    trans += (long long)blockIdx.x * V * V * 16;
     if (t < V) {
         double out[16];
         inv4x4(lidar2img + t * 16, out);
@@ -95,14 +99,16 @@ __global__ void pe_coords_kernel(const double* __restrict__ img2lidar, float* __
 // ---- SinePositionalEncoding3D, normalize=True (positional_encoding.py:58-96).
 // Step 1: per pixel the three normalised embeds (view, y, x) from the not-mask cumsums.
 __global__ void sine_prep_kernel(const uint8_t* __restrict__ not_mask, float* __restrict__ emb,
-                                 int V, int h, int w, float stride, float scale, float eps) {
+                                 int V, int h, int w, float stride, float scale, float eps, int vps) {
     pdl_wait();
     pdl_trigger();
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= V * h * w) return;
     const int x = p % w, y = (p / w) % h, v = p / (w * h);
     float n = 0.f, nl = 0.f, ye = 0.f, yl = 0.f, xe = 0.f, xl = 0.f;
-    for (int i = 0; i < V; ++i) {
+    // the view cumsum runs over the views of the cell's own sample (vps views per sample; one sample: vps = V)
+    const int v0 = (v / vps) * vps;
+    for (int i = v0; i < v0 + vps; ++i) {
         float m = (float)not_mask[(i * h + y) * w + x];
         nl += m;
         if (i <= v) n += m;
@@ -179,7 +185,7 @@ __global__ void __launch_bounds__(128) sine_axis_kernel(const float* __restrict_
 
 // Step C: hidden[p, :] = tf32(relu(Tv[v] + Ty[y] + Tx[x] + b)), the A operand of the 1024 -> 256 TF32 GEMM.
 __global__ void __launch_bounds__(256) sine_hidden_kernel(const float* __restrict__ T, const float* __restrict__ bias,
-                                                          float* __restrict__ Hd, int V, int h, int w) {
+                                                          float* __restrict__ Hd, int V, int h, int w, int vps) {
     pdl_wait();
     pdl_trigger();
     const long long gid = (long long)blockIdx.x * 256 + threadIdx.x;      // one float4 of a 1024-wide row
@@ -187,10 +193,11 @@ __global__ void __launch_bounds__(256) sine_hidden_kernel(const float* __restric
     if (gid >= total) return;
     const int j4 = (int)(gid & 255);
     const long long p = gid >> 8;
-    const int x = (int)(p % w), y = (int)((p / w) % h), v = (int)(p / ((long long)w * h));
+    // tables: vps view rows (the view index inside the cell's sample), then h row rows, then w column rows
+    const int x = (int)(p % w), y = (int)((p / w) % h), v = (int)(p / ((long long)w * h)) % vps;
     const float4 a = __ldg(reinterpret_cast<const float4*>(T + (long long)v * 1024) + j4);
-    const float4 b = __ldg(reinterpret_cast<const float4*>(T + (long long)(V + y) * 1024) + j4);
-    const float4 c = __ldg(reinterpret_cast<const float4*>(T + (long long)(V + h + x) * 1024) + j4);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(T + (long long)(vps + y) * 1024) + j4);
+    const float4 c = __ldg(reinterpret_cast<const float4*>(T + (long long)(vps + h + x) * 1024) + j4);
     const float4 d = __ldg(reinterpret_cast<const float4*>(bias) + j4);
     float4 o;
     o.x = round_tf32(fmaxf(((a.x + b.x) + c.x) + d.x, 0.f)); o.y = round_tf32(fmaxf(((a.y + b.y) + c.y) + d.y, 0.f));
@@ -200,17 +207,17 @@ __global__ void __launch_bounds__(256) sine_hidden_kernel(const float* __restric
 
 static int gemm(const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc,
                 int M, int N, int K, int flags, cudaStream_t st, const float* gx = nullptr,
-                const float* gs = nullptr, const float* gfeat = nullptr, float* kin = nullptr) {
+                const float* gs = nullptr, const float* gfeat = nullptr, float* kin = nullptr, int gs_mod = 0) {
     GemmArgs g{};
     g.A = A; g.lda = lda; g.W = W; g.ldw = ldw; g.C = C; g.ldc = ldc; g.bias = bias;
     g.M = M; g.N = N; g.K = K; g.batch = 1; g.nsplit = 1; g.flags = flags;
-    g.gx = gx; g.gs = gs; g.gfeat = gfeat; g.kin = kin;
+    g.gx = gx; g.gs = gs; g.gfeat = gfeat; g.kin = kin; g.gs_mod = gs_mod;
     return launch_gemm_tc_or_simt(g, st);
 }
 
-int run_geom_prep(const double* lidar2img, int V, double* img2lidar, double* trans, cudaStream_t st) {
-    MV2D_CHECK_ARG(V >= 1 && V <= MV2D_MAXV, "geom_prep: V=%d out of range", V);
-    launch_k(geom_prep_kernel, dim3(1), dim3(V * V), 0, st, lidar2img, V, img2lidar, trans);
+int run_geom_prep(const double* lidar2img, int V, double* img2lidar, double* trans, cudaStream_t st, int batch) {
+    MV2D_CHECK_ARG(V >= 1 && V <= MV2D_MAXV && batch >= 1, "geom_prep: V=%d / batch=%d out of range", V, batch);
+    launch_k(geom_prep_kernel, dim3(batch), dim3(V * V), 0, st, lidar2img, V, img2lidar, trans);
     MV2D_CHECK_LAUNCH("geom_prep");
     return 0;
 }
@@ -225,7 +232,15 @@ int run_nchw_to_nhwc(const float* in, float* out, float* out_tf32, int V, int C,
 // PE.forward.  feat is NHWC [P,256].  Outputs pe [P,256] and (optional) kin = feat + pe.
 int run_pe3d(const Mv2dPeParams& p, cudaStream_t st) {
     const int P = p.V * p.h * p.w, D = p.depth_num, C = MV2D_C;
-    MV2D_CHECK_ARG(p.V >= 1 && p.V <= MV2D_MAXV && P > 0, "pe3d: bad V/h/w");
+    MV2D_CHECK_ARG(p.V >= 1 && p.V <= MV2D_MAXVB && P > 0, "pe3d: bad V/h/w");
+    // batch: V counts the views of ALL samples, vps = views of one sample (the sine embedding's view axis is per sample)
+    const int vps = p.views_per_sample > 0 ? p.views_per_sample : p.V;
+    MV2D_CHECK_ARG(vps <= MV2D_MAXV && p.V % vps == 0, "pe3d: V=%d is not a multiple of views_per_sample=%d", p.V, vps);
+    // sine_shared: every sample of the batch has the same padding masks, so adapt_pos3d(sine) is identical for all of
+    // them: it is evaluated for the first sample's cells only and read with the row index modulo vps*h*w
+    const int Vs = p.sine_shared ? vps : p.V;          // views the sine branch is evaluated for
+    const int Ps = Vs * p.h * p.w;
+    MV2D_CHECK_ARG(!p.sine_shared || (!p.sine_branch_cached && !p.sine_branch_out), "pe3d: sine_shared excludes the cached sine branch");
     MV2D_CHECK_ARG((3 * D) % 16 == 0, "pe3d: 3*depth_num must be a multiple of 16");
     float* ws = p.workspace;
     float* A1 = ws;                      ws += (size_t)P * 3 * D;
@@ -258,24 +273,24 @@ int run_pe3d(const Mv2dPeParams& p, cudaStream_t st) {
         // X and SB were left in the workspace by phase 1
     } else if (!p.sine_branch_cached && p.sine_separable) {
         // no padded cells: per-axis tables instead of the 384 -> 1024 GEMM over every cell
-        const int rows = p.V + p.h + p.w;
+        const int rows = vps + p.h + p.w;
         float* Fm = S;                              // [rows, 384]
         float* Tm = S + (size_t)rows * 384;         // [rows, 1024]
         MV2D_CHECK_ARG((size_t)rows * (384 + 1024) <= (size_t)P * 384, "pe3d: separable sine tables do not fit the workspace");
-        launch_k(sine_axis_kernel, dim3(rows), dim3(128), 0, st, p.dim_t, Fm, p.V, p.h, p.w, (float)p.stride, 6.283185307179586f, 1e-6f);
+        launch_k(sine_axis_kernel, dim3(rows), dim3(128), 0, st, p.dim_t, Fm, vps, p.h, p.w, (float)p.stride, 6.283185307179586f, 1e-6f);
         MV2D_CHECK_LAUNCH("sine_axis");
         if ((rc = gemm(Fm, 384, p.w_adapt0, 384, nullptr, Tm, 4 * C, rows, 4 * C, 384, 0, st))) return rc;     // fp32 FFMA
-        launch_k(sine_hidden_kernel, dim3((unsigned)(((long long)P * 256 + 255) / 256)), dim3(256), 0, st, (const float*)Tm, p.b_adapt0, Hd, p.V, p.h, p.w);
+        launch_k(sine_hidden_kernel, dim3((unsigned)(((long long)Ps * 256 + 255) / 256)), dim3(256), 0, st, (const float*)Tm, p.b_adapt0, Hd, Vs, p.h, p.w, vps);
         MV2D_CHECK_LAUNCH("sine_hidden");
-        if ((rc = gemm(Hd, 4 * C, p.w_adapt2, 4 * C, p.b_adapt2, SB, C, P, C, 4 * C, GEMM_TF32_OK, st))) return rc;
+        if ((rc = gemm(Hd, 4 * C, p.w_adapt2, 4 * C, p.b_adapt2, SB, C, Ps, C, 4 * C, GEMM_TF32_OK, st))) return rc;
     } else if (!p.sine_branch_cached) {
-        launch_k(sine_prep_kernel, dim3(cdiv(P, 128)), dim3(128), 0, st, p.not_mask, EM, p.V, p.h, p.w, (float)p.stride,
-                                                      6.283185307179586f, 1e-6f);
+        launch_k(sine_prep_kernel, dim3(cdiv(Ps, 128)), dim3(128), 0, st, p.not_mask, EM, Vs, p.h, p.w, (float)p.stride,
+                                                      6.283185307179586f, 1e-6f, vps);
         MV2D_CHECK_LAUNCH("sine_prep");
-        launch_k(sine_embed_kernel, dim3((unsigned)(((long long)P * 384 + 255) / 256)), dim3(256), 0, st, (const float*)EM, p.dim_t, S, P, 1);
+        launch_k(sine_embed_kernel, dim3((unsigned)(((long long)Ps * 384 + 255) / 256)), dim3(256), 0, st, (const float*)EM, p.dim_t, S, Ps, 1);
         MV2D_CHECK_LAUNCH("sine_embed");
-        if ((rc = gemm(S, 384, p.w_adapt0, 384, p.b_adapt0, Hd, 4 * C, P, 4 * C, 384, GEMM_RELU | GEMM_TF32_OK | GEMM_ROUND_TF32, st))) return rc;
-        if ((rc = gemm(Hd, 4 * C, p.w_adapt2, 4 * C, p.b_adapt2, SB, C, P, C, 4 * C, GEMM_TF32_OK, st))) return rc;
+        if ((rc = gemm(S, 384, p.w_adapt0, 384, p.b_adapt0, Hd, 4 * C, Ps, 4 * C, 384, GEMM_RELU | GEMM_TF32_OK | GEMM_ROUND_TF32, st))) return rc;
+        if ((rc = gemm(Hd, 4 * C, p.w_adapt2, 4 * C, p.b_adapt2, SB, C, Ps, C, 4 * C, GEMM_TF32_OK, st))) return rc;
     } else {
         SB = const_cast<float*>(p.sine_branch_cached);
     }
@@ -284,7 +299,7 @@ int run_pe3d(const Mv2dPeParams& p, cudaStream_t st) {
     if ((rc = gemm(p.feat_tf32 ? p.feat_tf32 : p.feat, C, p.w_se_reduce, C, p.b_se_reduce, G1, C, P, C, C,
                    GEMM_RELU | GEMM_TF32_OK | GEMM_ROUND_TF32, st))) return rc;
     if ((rc = gemm(G1, C, p.w_se_expand, C, p.b_se_expand, p.pe, C, P, C, C, GEMM_GATE | GEMM_TF32_OK, st, X, SB,
-                   p.feat, p.kin))) return rc;
+                   p.feat, p.kin, p.sine_shared ? Ps : 0))) return rc;
     if (p.sine_branch_out && !p.sine_branch_cached) {
         cudaError_t e = cudaMemcpyAsync(p.sine_branch_out, SB, (size_t)P * C * sizeof(float),
                                         cudaMemcpyDeviceToDevice, st);
@@ -306,7 +321,7 @@ int run_pe_train_inputs(int V, int h, int w, int D, int pad_h, int pad_w, int st
              (double)pad_w, depth_start, pr[0], pr[1], pr[2], pr[3], pr[4], pr[5], 0);
     MV2D_CHECK_LAUNCH("pe_coords(train)");
     float* emb = sine + (size_t)P * 384;     // the caller's `sine` buffer holds [P,384] + 3 P floats for the embeds
-    launch_k(sine_prep_kernel, dim3(cdiv(P, 128)), dim3(128), 0, st, not_mask, emb, V, h, w, (float)stride, 6.283185307179586f, 1e-6f);
+    launch_k(sine_prep_kernel, dim3(cdiv(P, 128)), dim3(128), 0, st, not_mask, emb, V, h, w, (float)stride, 6.283185307179586f, 1e-6f, V);
     MV2D_CHECK_LAUNCH("sine_prep(train)");
     launch_k(sine_embed_kernel, dim3((unsigned)(((long long)P * 384 + 255) / 256)), dim3(256), 0, st, (const float*)emb, dim_t, sine, P, 0);
     MV2D_CHECK_LAUNCH("sine_embed(train)");

@@ -188,7 +188,7 @@ size_t roi_align_qg_workspace_bytes(int N) {
 
 int run_roi_align_qg(const Mv2dQgParams& p, cudaStream_t st) {
     const int N = p.N, C = MV2D_C;
-    MV2D_CHECK_ARG(N >= 0 && p.V >= 1 && p.V <= MV2D_MAXV, "roi_align_qg: bad N/V");
+    MV2D_CHECK_ARG(N >= 0 && p.V >= 1 && p.V <= MV2D_MAXVB, "roi_align_qg: bad N/V");
     if (N == 0) return 0;
     MV2D_CHECK_ARG(p.phase >= 0 && p.phase <= 2, "roi_align_qg: phase must be 0, 1 or 2");
     MV2D_CHECK_ARG(p.phase == 1 || p.tok_kin == nullptr || p.pe != nullptr, "roi_align_qg: tok_kin needs pe");
@@ -279,10 +279,15 @@ box_corr_kernel(Mv2dCorrParams p) {
     int* match = p.match + (long long)n * p.max_match;
     if (t == 0) { match[0] = n; cnt_s = 1; }
     __syncthreads();
+    // batch: the RoI's sample b owns views [b*V, (b+1)*V); roi_start is [batch, V+1], trans [batch, V, V, 16]
+    const int b = p.batch > 0 ? src / p.V : 0;
+    const int src_l = src - b * p.V;
+    const int* roi_start = p.roi_start + b * (p.V + 1);
+    const double* trans = p.trans + (long long)b * p.V * p.V * 16;
     for (int v = 0; v < p.V; ++v) {
-        const int rs = p.roi_start[v], nv = p.roi_start[v + 1] - rs;
-        if (v == src || nv == 0) continue;      // block-uniform
-        const double* T = p.trans + ((long long)src * p.V + v) * 16;
+        const int rs = roi_start[v], nv = roi_start[v + 1] - rs;
+        if (v == src_l || nv == 0) continue;      // block-uniform
+        const double* T = trans + ((long long)src_l * p.V + v) * 16;
         const double cx = T[0] * hx + T[1] * hy + T[2] * dep + T[3];
         const double cy = T[4] * hx + T[5] * hy + T[6] * dep + T[7];
         const double cz = T[8] * hx + T[9] * hy + T[10] * dep + T[11];
@@ -359,7 +364,8 @@ key_mask_kernel(Mv2dCorrParams p, int words) {
     const float margin1 = 0.5f * st, margin2 = (float)p.expand_stride * st;
     for (int i = 0; i < cnt; ++i) {
         const float* q = p.rois + match[i] * 5;
-        const int v = (int)q[0];
+        const int vg = (int)q[0];                               // global view (pad_mask index)
+        const int v = p.batch > 0 ? vg % p.V : vg;              // view inside the sample (key bit index)
         // candidate cell window (generous), exact fp32 test per cell as the reference does
         int cx0 = max((int)floorf((q[1] - margin1 - margin2) / st) - 1, 0);
         int cx1 = min((int)ceilf((q[3] + margin1 + margin2) / st) + 1, p.w - 1);
@@ -373,7 +379,7 @@ key_mask_kernel(Mv2dCorrParams p, int words) {
                             (ys + margin1 + margin2 >= q[2]) && (ys - margin1 - margin2 <= q[4]);
             if (in) {
                 const int cell = (v * p.h + y) * p.w + x;
-                if (!(p.pad_mask && p.pad_mask[cell])) atomicOr(&bits[cell >> 5], 1u << (cell & 31));
+                if (!(p.pad_mask && p.pad_mask[(vg * p.h + y) * p.w + x])) atomicOr(&bits[cell >> 5], 1u << (cell & 31));
             }
         }
     }
@@ -398,6 +404,8 @@ key_mask_kernel(Mv2dCorrParams p, int words) {
 
 int run_box_corr(const Mv2dCorrParams& p, cudaStream_t st) {
     MV2D_CHECK_ARG(p.N >= 0 && p.V >= 1 && p.V <= MV2D_MAXV, "box_corr: bad N/V");
+    MV2D_CHECK_ARG(p.batch == 0 || (p.batch > 0 && p.rows_per_sample > 0 && p.N == p.batch * p.rows_per_sample),
+                   "box_corr: batch=%d x rows_per_sample=%d != N=%d", p.batch, p.rows_per_sample, p.N);
     MV2D_CHECK_ARG(p.sample_size * p.sample_size * p.num_depth == 128,
                    "box_corr: sample_size^2*num_depth must be 128 (got %d)", p.sample_size * p.sample_size * p.num_depth);
     MV2D_CHECK_ARG(p.max_match >= 1 && p.topk >= 1, "box_corr: bad max_match/topk");

@@ -24,11 +24,15 @@ namespace mv2d {
 #define XT_KEYS (XT_TS * XT_TS)
 #define XT_REC 272                     // floats per record: acc[256], m[8], l[8]
 #define XT_THREADS 512
-#define XT_MERGE_MAXT 2048             // tiles per sample the lists are sized for (V*ceil(h/8)*ceil(w/8) <= 2048)
+#define XT_MERGE_MAXT 2048             // tiles per SAMPLE the lists are sized for (V*ceil(h/8)*ceil(w/8) <= 2048)
+#define XT_ORDER_MAXT 8192             // tiles of a whole batch the heaviest-first order is sized for
 #define XT_SMEM_BYTES (2 * XT_KEYS * MV2D_C * 4 + (XT_THREADS / 32) * XT_KEYS * 8 * 4 + (XT_THREADS / 32) * 80 + 64)
 
+// Batch: B samples, each with Np query rows (row b*Np + i), V views and tiles_ps = V*tiles_y*tiles_x tiles; the tile
+// id t = b*tiles_ps + local tile, N = B*Np, ntiles = B*tiles_ps.  A tile only ever meets the queries of its own sample.
 struct XtGeom {
     int N, V, h, w, tiles_x, tiles_y, ntiles;
+    int B, Np, tiles_ps;
 };
 
 struct XtPrepArgs {
@@ -46,16 +50,17 @@ __global__ void __launch_bounds__(256) xt_prep_kernel(XtPrepArgs a) {
     pdl_wait();
     pdl_trigger();
     const int t = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int tx = t % a.g.tiles_x, ty = (t / a.g.tiles_x) % a.g.tiles_y, v = t / (a.g.tiles_x * a.g.tiles_y);
+    const int sb = t / a.g.tiles_ps, tl = t - sb * a.g.tiles_ps, q0 = sb * a.g.Np;     // sample, local tile, first query row
+    const int tx = tl % a.g.tiles_x, ty = (tl / a.g.tiles_x) % a.g.tiles_y, v = tl / (a.g.tiles_x * a.g.tiles_y);
     const int ncols = min(XT_TS, a.g.w - tx * XT_TS);
     __shared__ int wsum[8];
     __shared__ int work_s;
     if (tid == 0) work_s = 0;
     int running = 0, work = 0;
-    for (int base = 0; base < a.g.N; base += 256) {
-        const int n = base + tid;
+    for (int base = 0; base < a.g.Np; base += 256) {
+        const int nl = base + tid, n = q0 + nl;
         unsigned long long m64 = 0ull;
-        if (n < a.g.N) {
+        if (nl < a.g.Np) {
             const uint32_t* km = a.keymask + (long long)n * a.mask_words;
 #pragma unroll
             for (int r = 0; r < XT_TS; ++r) {
@@ -79,12 +84,12 @@ __global__ void __launch_bounds__(256) xt_prep_kernel(XtPrepArgs a) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) { const int c = wsum[i]; if (i < warp) before += c; total += c; }
         const int pos = running + before + __popc(bal & ((1u << lane) - 1u));
-        if (n < a.g.N) {
+        if (nl < a.g.Np) {
             if (active) {
-                a.tile_q[(long long)t * a.g.N + pos] = (uint16_t)n;
-                a.tile_mask[(long long)t * a.g.N + pos] = m64;
+                a.tile_q[(long long)t * a.g.Np + pos] = (uint16_t)n;
+                a.tile_mask[(long long)t * a.g.Np + pos] = m64;
             }
-            a.slot_of[(long long)n * a.g.ntiles + t] = active ? (short)pos : (short)-1;
+            a.slot_of[(long long)n * a.g.tiles_ps + tl] = active ? (short)pos : (short)-1;
         }
         running += total;
         __syncthreads();
@@ -105,22 +110,24 @@ struct XtListArgs {
     int* order;                        // [ntiles] tiles sorted by work, heaviest first (ties: lower id first)
 };
 
-// grid = N + 1, 256 threads.  Blocks 0..N-1: ordered compaction of slot_of[n, :]; block N: the tile order.
+// grid = N + ceil(ntiles / 256), 256 threads.  Blocks 0..N-1: ordered compaction of slot_of[n, :]; the others: the tile
+// order (each ranks 256 tiles of the batch against all of them).
 __global__ void __launch_bounds__(256) xt_list_kernel(XtListArgs a) {
     pdl_wait();
     pdl_trigger();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int nt = a.g.ntiles;
-    if ((int)blockIdx.x == a.g.N) {
-        // rank by counting out of shared memory: ntiles <= 2048, once per sample
-        __shared__ int work_s[XT_MERGE_MAXT];
-        for (int t = tid; t < nt; t += 256) work_s[t] = a.tile_work[t];
+    if ((int)blockIdx.x >= a.g.N) {
+        // rank by counting out of shared memory, once per batch
+        __shared__ int work_s[XT_ORDER_MAXT];
+        const int nall = a.g.ntiles;
+        for (int t = tid; t < nall; t += 256) work_s[t] = a.tile_work[t];
         __syncthreads();
-        for (int t = tid; t < nt; t += 256) {
+        const int t = ((int)blockIdx.x - a.g.N) * 256 + tid;
+        if (t < nall) {
             const int w = work_s[t];
             int rank = 0;
 #pragma unroll 8
-            for (int u = 0; u < nt; ++u) {
+            for (int u = 0; u < nall; ++u) {
                 const int x = work_s[u];
                 rank += (x > w) || (x == w && u < t);
             }
@@ -128,7 +135,9 @@ __global__ void __launch_bounds__(256) xt_list_kernel(XtListArgs a) {
         }
         return;
     }
+    const int nt = a.g.tiles_ps;                 // a query only meets the tiles of its own sample
     const int n = blockIdx.x;
+    const int tile0 = (n / a.g.Np) * a.g.tiles_ps;
     __shared__ int chunk_cnt[64];      // ntiles <= 2048 => <= 64 chunks of 32
     const int nchunks = (nt + 31) >> 5;
     int sv[8];
@@ -151,7 +160,7 @@ __global__ void __launch_bounds__(256) xt_list_kernel(XtListArgs a) {
         if (c < nchunks) {
             int base = 0;
             for (int i = 0; i < c; ++i) base += chunk_cnt[i];
-            if (sv[u] >= 0) a.qlist[(long long)n * nt + base + __popc(bal[u] & ((1u << lane) - 1u))] = (c * 32 + lane) * a.g.N + sv[u];
+            if (sv[u] >= 0) a.qlist[(long long)n * nt + base + __popc(bal[u] & ((1u << lane) - 1u))] = (tile0 + c * 32 + lane) * a.g.Np + sv[u];
         }
     }
     if (tid == 0) {
@@ -162,13 +171,20 @@ __global__ void __launch_bounds__(256) xt_list_kernel(XtListArgs a) {
 }
 
 // 128-row tiles of the K/V projection GEMM that hold at least one key of some query: grid = tiles, 128 threads
+// Batch (rows_ps = cells of one sample, a multiple of 128; Np query rows per sample): tile t belongs to ONE sample.
 __global__ void __launch_bounds__(128) xt_rowlive_kernel(const uint32_t* __restrict__ keymask, int mask_words, int N, int num_rows,
-                                                         uint8_t* __restrict__ live) {
+                                                         uint8_t* __restrict__ live, int rows_ps, int Np) {
     pdl_wait();
     pdl_trigger();
-    const int t = blockIdx.x, w0 = t * 4;
+    const int t = blockIdx.x;
+    int w0 = t * 4, nbeg = 0, nend = N;
+    if (rows_ps > 0) {
+        const int sb = (t * 128) / rows_ps;
+        w0 = ((t * 128) - sb * rows_ps) >> 5;
+        nbeg = sb * Np; nend = nbeg + Np;
+    }
     int any = 0;
-    for (int n = threadIdx.x; n < N; n += 128) {
+    for (int n = nbeg + threadIdx.x; n < nend; n += 128) {
         const uint32_t* km = keymask + (long long)n * mask_words;
 #pragma unroll
         for (int j = 0; j < 4; ++j)
@@ -229,7 +245,8 @@ __global__ void __launch_bounds__(XT_THREADS, 1) xt_attn_kernel(XtAttnArgs a) {
     unsigned char* klb = reinterpret_cast<unsigned char*>(scb + NW * XT_KEYS * 8);   // [NW][80] key ids of the query
     uint64_t* bar = reinterpret_cast<uint64_t*>(klb + NW * 80);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int tx = t % a.g.tiles_x, ty = (t / a.g.tiles_x) % a.g.tiles_y, v = t / (a.g.tiles_x * a.g.tiles_y);
+    const int sb = t / a.g.tiles_ps, tl = t - sb * a.g.tiles_ps;
+    const int tx = tl % a.g.tiles_x, ty = (tl / a.g.tiles_x) % a.g.tiles_y, v = sb * a.g.V + tl / (a.g.tiles_x * a.g.tiles_y);   // global view
     const int ncols = min(XT_TS, a.g.w - tx * XT_TS), nrows = min(XT_TS, a.g.h - ty * XT_TS);
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(xt_smem_u32(bar)));
@@ -258,8 +275,8 @@ __global__ void __launch_bounds__(XT_THREADS, 1) xt_attn_kernel(XtAttnArgs a) {
     // software pipeline: the next query's list entry and q slice are in flight while this one is processed
     int n_nx = 0; unsigned long long m_nx = 0ull; float4 qa_nx = make_float4(0.f, 0.f, 0.f, 0.f), qb_nx = qa_nx;
     auto fetch = [&](int ii) {
-        n_nx = a.tile_q[(long long)t * a.g.N + ii];
-        m_nx = a.tile_mask[(long long)t * a.g.N + ii];
+        n_nx = a.tile_q[(long long)t * a.g.Np + ii];
+        m_nx = a.tile_mask[(long long)t * a.g.Np + ii];
         qa_nx = __ldg(reinterpret_cast<const float4*>(a.q + (long long)n_nx * MV2D_C + offA));
         qb_nx = __ldg(reinterpret_cast<const float4*>(a.q + (long long)n_nx * MV2D_C + offB));
     };
@@ -319,7 +336,7 @@ __global__ void __launch_bounds__(XT_THREADS, 1) xt_attn_kernel(XtAttnArgs a) {
         }
         l += __shfl_xor_sync(0xffffffffu, l, 1);
         l += __shfl_xor_sync(0xffffffffu, l, 2);
-        float* r = a.rec + ((long long)t * a.g.N + i) * XT_REC;
+        float* r = a.rec + ((long long)t * a.g.Np + i) * XT_REC;
         if (part == 0) { r[256 + hd] = mx; r[264 + hd] = l; }
         __syncwarp();
         // ---- acc = sum_k p_k * V_k over the query's keys, 4 keys per step (padding slots carry p = 0)
@@ -370,12 +387,12 @@ __global__ void __launch_bounds__(XT_MERGE_THREADS) xt_merge_kernel(XtMergeArgs 
     pdl_trigger();
     const int n = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     extern __shared__ __align__(16) unsigned char xm_smem[];
-    int* list = reinterpret_cast<int*>(xm_smem);                                  // [ntiles]
-    float* wgt = reinterpret_cast<float*>(xm_smem) + a.g.ntiles;                   // [ntiles][8]
+    int* list = reinterpret_cast<int*>(xm_smem);                                  // [tiles_ps]
+    float* wgt = reinterpret_cast<float*>(xm_smem) + a.g.tiles_ps;                 // [tiles_ps][8]
     __shared__ float Ms[8][8], Mg[8], Lw[8][8];
     __shared__ float4 fold[3][64];
     const int cnt = a.qcnt[n];
-    for (int r = tid; r < cnt; r += XT_MERGE_THREADS) list[r] = a.qlist[(long long)n * a.g.ntiles + r];
+    for (int r = tid; r < cnt; r += XT_MERGE_THREADS) list[r] = a.qlist[(long long)n * a.g.tiles_ps + r];
     __syncthreads();
     const int h = tid & 7, rsub = tid >> 3;             // (record phase 0..31, head)
     // ---- global max per head (the raw maxima are parked in wgt)

@@ -73,6 +73,8 @@ class HotPath:
         self._buf = {}
         self._pin = {}
         self._graphs = {}
+        self._graphs_b = {}
+        self._batch_grid = None
         self.overlap = overlap
         if persistent_decoder is None:
             # measured on B200 (profiles/r01_persistent_decoder.md): the single-launch persistent decoder is
@@ -140,6 +142,8 @@ class HotPath:
             proposal_list = [p0] + list(proposal_list[1:])
         counts = [int(p.shape[0]) for p in proposal_list]
         N = sum(counts)
+        if max(counts) > 256:       # CORR_MAXR of csrc/roi.cu: the IoU table of box_corr_kernel
+            raise RuntimeError('box correlation handles at most 256 detections per view (include/mv2d_b200.h, limits)')
         on_device = proposal_list[0].is_cuda
         cam_b, roi_b, st_b = 3 * V * 16 * 8, N * 5 * 4, (V + 1) * 4
         roi_off = cam_b
@@ -243,13 +247,14 @@ class HotPath:
         lib.check(self.lib.mv2d_fpn_neck(C.byref(p), lib.stream_ptr()), 'mv2d_fpn_neck')
         return out, out_tf32
 
-    def pe3d(self, feat_nhwc, img2lidar, img_metas, feat_tf32=None, phase=0, dims=None):
+    def pe3d(self, feat_nhwc, img2lidar, img_metas, feat_tf32=None, phase=0, dims=None, batch=None):
         """PE.forward (utils/pe.py:137-169) -> (pe [V,h,w,256], kin = feat + pe or None).
-        phase 1 = the feature-independent part only (feat_nhwc may still be in flight), 2 = the rest."""
+        phase 1 = the feature-independent part only (feat_nhwc may still be in flight), 2 = the rest.
+        batch: the descriptor ``_upload_meta_batch`` returns (V then counts the views of all samples)."""
         V, h, w = dims if dims is not None else feat_nhwc.shape[:3]
         self._last_grid = (h, w)
         c, W = self.cfg, self.w
-        key, pad_mask, not_mask, has_pad = self._masks(img_metas, h, w)
+        key, pad_mask, not_mask, has_pad = self._masks(img_metas, h, w) if batch is None else batch['masks']
         pe = self._get('pe', (V, h, w, 256))
         kin = self._get('kin', (V, h, w, 256)) if self.mode == 'T' else None
         ws_bytes = self.lib.mv2d_pe3d_workspace_bytes(V, h, w, c['depth_num'])
@@ -259,6 +264,10 @@ class HotPath:
         p.phase = phase
         # no padded cells (img_shape == pad_shape in every view): the sine branch's first layer is separable
         p.sine_separable = int((not has_pad) and os.environ.get('MV2D_SINE_SEPARABLE', '1') != '0')
+        if batch is not None:
+            p.views_per_sample = batch['Vs']
+            p.sine_shared = int(batch['same_masks'] and os.environ.get('MV2D_SINE_SHARED', '1') != '0')
+            img_metas = batch['metas'][0]
         p.pad_h, p.pad_w = int(img_metas[0]['pad_shape'][0]), int(img_metas[0]['pad_shape'][1])
         p.stride = c['stride']
         p.depth_start = c['depth_start']
@@ -268,10 +277,10 @@ class HotPath:
         for f in ('w_pos0', 'b_pos0', 'w_pos2', 'b_pos2', 'w_adapt0', 'b_adapt0', 'w_adapt2', 'b_adapt2',
                   'w_se_reduce', 'b_se_reduce', 'w_se_expand', 'b_se_expand'):
             setattr(p, f, W.p(f))
-        cached = self._sine_cache.get(key) if (self.cache_sine_branch and phase == 0) else None
+        cached = self._sine_cache.get(key) if (self.cache_sine_branch and phase == 0 and batch is None) else None
         if cached is not None:
             p.sine_branch_cached = cached.data_ptr()
-        elif self.cache_sine_branch and phase == 0:
+        elif self.cache_sine_branch and phase == 0 and batch is None:
             self._sine_cache[key] = torch.empty((V * h * w, 256), device=self.device)
             p.sine_branch_out = self._sine_cache[key].data_ptr()
         p.pe = pe.data_ptr()
@@ -311,13 +320,19 @@ class HotPath:
         return dict(tok_feat=tok_feat, tok_kin=tok_kin, roi_intrinsics=kroi, center_lidar=center, ref=ref,
                     query_pos=qpos)
 
-    def box_corr(self, rois, roi_start, trans, N, V, img_metas, h, w):
+    def box_corr(self, rois, roi_start, trans, N, V, img_metas, h, w, batch=None):
+        """V = views of ONE sample; with ``batch`` N = B * Np rows and roi_start is [B, V+1]."""
         c = self.cfg
         max_match = 1 + (V - 1) * c['topk']
         match = self._get('match', (N, max_match), torch.int32)
         cnt = self._get('match_cnt', (N,), torch.int32)
         p = lib.CorrParams()
         p.N, p.V = N, V
+        B = 1
+        if batch is not None:
+            B = p.batch = batch['B']
+            p.rows_per_sample = batch['Np']
+            img_metas = batch['metas'][0]
         p.img_h, p.img_w = int(img_metas[0]['pad_shape'][0]), int(img_metas[0]['pad_shape'][1])
         p.topk, p.sample_size, p.num_depth, p.max_match = c['topk'], c['sample_size'], c['corr_num_depth'], max_match
         p.ratio, p.iou_thr, p.depth_start = c['ratio'], c['iou_thr'], c['corr_depth_start']
@@ -329,24 +344,29 @@ class HotPath:
             words = (V * h * w + 31) // 32
             keymask = self._get('keymask', (N, words), torch.int32)
             key_cnt = self._get('key_cnt', (N,), torch.int32)
-            _, pad_mask, _, has_pad = self._masks(img_metas, h, w)
+            _, pad_mask, _, has_pad = self._masks(img_metas, h, w) if batch is None else batch['masks']
             p.h, p.w, p.stride, p.expand_stride = h, w, c['stride'], c['expand_stride']
             p.pad_mask = pad_mask.data_ptr() if has_pad else None
-            key_list = self._get('key_list', (N, words * 32), torch.int16)
-            p.keymask, p.key_cnt, p.key_list = keymask.data_ptr(), key_cnt.data_ptr(), key_list.data_ptr()
+            # the compacted key lists feed the query-stationary form only (and the denoising prepare builds its own)
+            key_list = self._get('key_list', (N, words * 32), torch.int16) if batch is None else None
+            p.keymask, p.key_cnt = keymask.data_ptr(), key_cnt.data_ptr()
+            p.key_list = key_list.data_ptr() if key_list is not None else None
             out.update(keymask=keymask, key_cnt=key_cnt, key_list=key_list, mask_words=words)
         lib.check(self.lib.mv2d_box_corr(C.byref(p), lib.stream_ptr()), 'mv2d_box_corr')
         if self.mode == 'T' and self.xa_form == 1 and N > 0:
             # tile / record lists of the key-stationary cross-attention depend on the masks only: build them here,
             # beside the position embedding, instead of at the head of the decoder
             d = lib.DecoderParams()
-            d.N, d.num_rows, d.grid_h, d.grid_w = N, V * h * w, h, w
+            d.N, d.num_rows, d.grid_h, d.grid_w = N, B * V * h * w, h, w
             d.keymask, d.mask_words = out['keymask'].data_ptr(), out['mask_words']
-            xa_bytes = self.lib.mv2d_xa_tile_workspace_bytes(N, V, h, w)
+            if batch is not None:
+                d.batch, d.rows_per_sample = B, batch['Np']
+            xa_bytes = self.lib.mv2d_xa_tile_workspace_bytes_batch(B, N // B, V, h, w)
             xa_ws = self._get('xa_ws', (xa_bytes,), torch.uint8)
             d.xa_workspace, d.xa_workspace_bytes = xa_ws.data_ptr(), xa_bytes
-            row_live = self._get('kv_row_live', ((V * h * w + 127) // 128,), torch.uint8)
-            d.row_tile_live = row_live.data_ptr()
+            live_ok = B == 1 or (V * h * w) % 128 == 0      # a 128-row tile of the projection must lie inside one sample
+            row_live = self._get('kv_row_live', ((B * V * h * w + 127) // 128,), torch.uint8) if live_ok else None
+            d.row_tile_live = row_live.data_ptr() if live_ok else None
             lib.check(self.lib.mv2d_xa_tile_prepare(C.byref(d), lib.stream_ptr()), 'mv2d_xa_tile_prepare')
             out['xa_prepared_for'] = (out['keymask'].data_ptr(), N, xa_ws.data_ptr())
             out['row_tile_live'] = row_live     # 128-row tiles of the K/V projection some query has a key in
@@ -441,7 +461,7 @@ class HotPath:
         return kp, vp
 
     def decoder(self, qg, corr, kin_rows, mem_rows, N, vel_dt=0.0, self_attn_mask=None, vel_row_start=0,
-                kv=None, grid=None, wait_kv_events=False):
+                kv=None, grid=None, wait_kv_events=False, batch=None):
         c, W, L = self.cfg, self.w, self.L
         if self.xa_form == 1 and kv is None:    # stage-level call: project on this stream, then decode
             grid = grid or self._last_grid
@@ -470,9 +490,16 @@ class HotPath:
         p.layers, p.branches = W.layers_ptr(), W.branches_ptr()
         p.cls_scores, p.bbox_preds, p.outs_dec = cls.data_ptr(), box.data_ptr(), outs.data_ptr()
         p.workspace, p.workspace_bytes = ws.data_ptr(), ws_bytes
+        B = 1
+        if batch is not None:
+            B = p.batch = batch['B']
+            p.rows_per_sample = batch['Np']
+            p.n_real = batch['n_real'].data_ptr()
+            if batch.get('vel_dt') is not None:
+                p.vel_dt_batch = batch['vel_dt'].data_ptr()
         if kv is not None:      # two-frame head, key-stationary cross-attention over the projected K/V
-            V = kin_rows.shape[0] // (grid[0] * grid[1])
-            xa_bytes = self.lib.mv2d_xa_tile_workspace_bytes(N, V, grid[0], grid[1])
+            V = kin_rows.shape[0] // (B * grid[0] * grid[1])
+            xa_bytes = self.lib.mv2d_xa_tile_workspace_bytes_batch(B, N // B, V, grid[0], grid[1])
             xa_ws = self._get('xa_ws', (xa_bytes,), torch.uint8)
             p.xa_form, p.grid_h, p.grid_w = 1, grid[0], grid[1]
             p.kp, p.vp = kv[0].data_ptr(), kv[1].data_ptr()
@@ -505,8 +532,9 @@ class HotPath:
         return i2l, trans
 
     def _enqueue_post(self, feat_in, feat_is_nhwc, cams, rois, roi_start, counts, N, img_metas, i2l, trans, pe_phase=2,
-                      dn=None):
-        V = len(img_metas)
+                      dn=None, batch=None):
+        V = len(img_metas)          # views of ONE sample (a batch stacks B*V views in feat_in / cams)
+        assert batch is None or dn is None, 'denoising queries run one sample at a time'
         feat_tf32 = None
         if feat_is_nhwc:
             feat = feat_in
@@ -530,9 +558,9 @@ class HotPath:
                 self._ev_join.record(self._side)
             with torch.cuda.stream(self._side2):
                 self._side2.wait_event(self._ev_fork)
-                corr = self.box_corr(rois, roi_start, trans, N, V, img_metas, h, w)
+                corr = self.box_corr(rois, roi_start, trans, N, V, img_metas, h, w, batch=batch)
                 self._ev_join2.record(self._side2)
-            pe, kin = self.pe3d(feat, i2l, img_metas, feat_tf32, phase=pe_phase)
+            pe, kin = self.pe3d(feat, i2l, img_metas, feat_tf32, phase=pe_phase, batch=batch)
             if self.xa_form == 1:
                 # K/V projections of all layers on their own stream; decoder layer l waits for projection l only
                 self._ev_pe.record(main)
@@ -547,9 +575,9 @@ class HotPath:
             if self.mode == 'S':
                 self.roi_align_qg(rois, cams, feat, pe, N, phase=2)      # tok_kin = tok_feat + RoIAlign(pe)
         else:
-            pe, kin = self.pe3d(feat, i2l, img_metas, feat_tf32, phase=pe_phase)
+            pe, kin = self.pe3d(feat, i2l, img_metas, feat_tf32, phase=pe_phase, batch=batch)
             qg = self.roi_align_qg(rois, cams, feat, pe, N)
-            corr = self.box_corr(rois, roi_start, trans, N, V, img_metas, h, w)
+            corr = self.box_corr(rois, roi_start, trans, N, V, img_metas, h, w, batch=batch)
             if self.xa_form == 1:
                 kv = self.kv_project(kin.view(-1, 256), feat.view(-1, 256))
         qg_d, corr_d, T, pad, extra, sa_mask = qg, corr, N, 0, {}, None
@@ -558,7 +586,7 @@ class HotPath:
             sa_mask = extra['dn_attn_mask']
         if self.mode == 'S':
             cls, box, outs = self.decoder(qg_d, corr_d, qg['tok_kin'].view(-1, 256), qg['tok_feat'].view(-1, 256), T,
-                                          self_attn_mask=sa_mask)
+                                          self_attn_mask=sa_mask, batch=batch)
         else:
             piped = self.xa_form == 1 and self.overlap
             run_on = self._hi if (piped and os.environ.get('MV2D_DEC_PRIO', '1') != '0') else None
@@ -569,7 +597,8 @@ class HotPath:
             with torch.cuda.stream(run_on) if run_on is not None else contextlib.nullcontext():
                 cls, box, outs = self.decoder(qg_d, corr_d, kin.view(-1, 256), feat.view(-1, 256), T,
                                               vel_dt=self._vel_dt(img_metas), self_attn_mask=sa_mask, vel_row_start=pad,
-                                              kv=kv if self.xa_form == 1 else None, grid=(h, w), wait_kv_events=piped)
+                                              kv=kv if self.xa_form == 1 else None, grid=(h, w), wait_kv_events=piped,
+                                              batch=batch)
                 if run_on is not None:
                     self._ev_hi1.record(run_on)
             if run_on is not None:
@@ -594,7 +623,7 @@ class HotPath:
                                   pe_phase=0, dn=dn)
 
     @torch.no_grad()
-    def forward(self, feat, proposal_list, img_metas, feat_is_nhwc=False, use_graph=False, dn=None):
+    def forward(self, feat, proposal_list, img_metas, feat_is_nhwc=False, use_graph=False, dn=None, bucket=1):
         """feat [V,256,h,w] fp32 (NCHW as the FPN emits it; device, or pinned host memory),
         proposal_list: V tensors [n_v, >=4] (device or host), img_metas: V dicts.  Returns a dict
         with cls_scores / bbox_preds [L,N,10] and the stage tensors (views of reused buffers).
@@ -605,6 +634,15 @@ class HotPath:
         dn = dict(gt_boxes, gt_labels[, rand]) runs the training-mode forward with denoising queries
         (``dn_prepare``; eager only): the result additionally holds dn_cls_scores / dn_bbox_preds
         [L,pad,10], dn_labels, dn_attn_mask, dn_pad."""
+        if bucket > 1:
+            # a stream of samples whose detection count changes every time: the query rows are padded to a multiple of
+            # ``bucket`` (padding rows carry a dummy box, the device-side count keeps them out of every real row's
+            # result), so one captured graph serves a whole bucket of N instead of one graph per exact N
+            assert dn is None and not feat_is_nhwc
+            o = self.forward_batch(feat[None], [proposal_list], [img_metas], use_graph=use_graph, bucket=bucket)
+            out = dict(o)
+            out.update(o['samples'][0])
+            return out
         if not use_graph:
             feat = feat.to(self.device, torch.float32, non_blocking=True).contiguous()
             cams, rois, roi_start, counts, N = self._upload_meta(proposal_list, img_metas)
@@ -664,6 +702,166 @@ class HotPath:
         out = dict(ent['out'])
         out['num_per_view'] = counts
         return out
+
+    # ------------------------------------------------------------------ batches (a segment dimension through ONE kernel chain)
+    def _upload_meta_batch(self, proposal_lists, metas_list, bucket=1):
+        """Metadata of B samples in one pinned staging buffer and one H2D copy.  Layout of the rows (C ABI, "Batches"):
+        sample b owns query rows [b*Np, (b+1)*Np), Np = max_b n_b rounded up to ``bucket``; the first n_b are its
+        detections (sorted by view, view index = b*V + v), the rest padding rows carrying the reference's dummy box
+        (mv2d_s_head.py:124-127), whose results are dropped.  Returns (cams [3,B*V,16], rois [B*Np,5],
+        roi_start [B,V+1], batch descriptor)."""
+        B, V = len(metas_list), len(metas_list[0])
+        assert all(len(m) == V for m in metas_list), 'every sample of a batch needs the same number of views'
+        plists = []
+        for pl in proposal_lists:
+            if sum(len(p) for p in pl) == 0:
+                p0 = torch.tensor([[0, 50, 50, 100, 100, 0]], dtype=torch.float32, device=pl[0].device)
+                pl = [p0] + list(pl[1:])
+            plists.append(pl)
+        counts = [[int(p.shape[0]) for p in pl] for pl in plists]
+        n_b = [sum(c) for c in counts]
+        if max(max(c) for c in counts) > 256:
+            raise RuntimeError('box correlation handles at most 256 detections per view (include/mv2d_b200.h, limits)')
+        Np = (max(n_b) + bucket - 1) // bucket * bucket
+        N = B * Np
+        cam_b, roi_b, st_b, nr_b = 3 * B * V * 16 * 8, N * 5 * 4, B * (V + 1) * 4, B * 4
+        roi_off = cam_b
+        st_off = (roi_off + roi_b + 7) // 8 * 8
+        nr_off = st_off + st_b
+        vd_off = nr_off + nr_b
+        total = vd_off + B * 4
+        pin = self._pin.get('meta_b')
+        if pin is None or pin.numel() < total:
+            assert pin is None or not self._graphs_b, 'the batch metadata buffer cannot grow once graphs were captured'
+            pin = torch.empty(max(total, 1 << 20), dtype=torch.uint8).pin_memory()
+            self._pin['meta_b'] = pin
+            self._pin['meta_b_ev'] = None
+            self._buf.pop('meta_b', None)
+        elif self._pin['meta_b_ev'] is not None:
+            self._pin['meta_b_ev'].synchronize()       # the previous copy out of this staging buffer has run
+        dev = self._get('meta_b', (pin.numel(),), torch.uint8)
+        host = pin.numpy()
+        cams = host[:cam_b].view(np.float64).reshape(3, B * V, 16)
+        rh = host[roi_off:roi_off + roi_b].view(np.float32).reshape(N, 5)
+        sh = host[st_off:st_off + st_b].view(np.int32).reshape(B, V + 1)
+        on_device = plists[0][0].is_cuda
+        for b, metas in enumerate(metas_list):
+            for v, m in enumerate(metas):
+                cams[0, b * V + v] = np.asarray(m['lidar2img'], dtype=np.float64).reshape(16)
+                cams[1, b * V + v] = np.asarray(m['intrinsics'], dtype=np.float64).reshape(16)
+                cams[2, b * V + v] = np.asarray(m['extrinsics'], dtype=np.float64).reshape(16)
+            o = b * Np
+            for v, p in enumerate(plists[b]):
+                n = counts[b][v]
+                rh[o:o + n, 0] = b * V + v
+                if not on_device:
+                    rh[o:o + n, 1:] = p[:, :4].float().numpy()
+                o += n
+            rh[o:(b + 1) * Np] = (b * V, 50, 50, 100, 100)          # padding rows
+            sh[b] = b * Np + np.concatenate([[0], np.cumsum(counts[b])])
+        host[nr_off:nr_off + nr_b].view(np.int32)[:] = n_b
+        host[vd_off:vd_off + B * 4].view(np.float32)[:] = [self._vel_dt(m) for m in metas_list]
+        dev[:total].copy_(pin[:total], non_blocking=True)
+        if self._pin['meta_b_ev'] is None:
+            self._pin['meta_b_ev'] = torch.cuda.Event()
+        self._pin['meta_b_ev'].record()
+        d_cams = dev[:cam_b].view(torch.float64).view(3, B * V, 16)
+        d_rois = dev[roi_off:roi_off + roi_b].view(torch.float32).view(N, 5)
+        d_start = dev[st_off:st_off + st_b].view(torch.int32)
+        d_nreal = dev[nr_off:nr_off + nr_b].view(torch.int32)
+        d_vel = dev[vd_off:vd_off + B * 4].view(torch.float32)
+        if on_device:
+            for b in range(B):
+                d_rois[b * Np:b * Np + n_b[b], 1:] = torch.cat([p[:, :4].float() for p in plists[b]], 0)
+        h, w = self._batch_grid
+        keys = [self._masks(m, h, w)[0] for m in metas_list]
+        same = all(k == keys[0] for k in keys)
+        mk = tuple(keys)
+        ent = self._mask_cache.get(('batch', mk))
+        if ent is None:
+            per = [self._masks(m, h, w) for m in metas_list]
+            ent = (mk, torch.cat([e[1] for e in per], 0).contiguous(), torch.cat([e[2] for e in per], 0).contiguous(),
+                   any(e[3] for e in per))
+            self._mask_cache[('batch', mk)] = ent
+        batch = dict(B=B, Np=Np, Vs=V, n_b=n_b, counts=counts, n_real=d_nreal, metas=metas_list, masks=ent, same_masks=same,
+                     vel_dt=d_vel if self.mode == 'T' else None)
+        return d_cams, d_rois, d_start, batch
+
+    def _enqueue_batch(self, feat, cams, rois, roi_start, batch):
+        """All stages of a batch on the current stream (capturable)."""
+        B, V, Np = batch['B'], batch['Vs'], batch['Np']
+        i2l = self._get('img2lidar', (B * V, 16), torch.float64)
+        trans = self._get('trans', (B, V, V, 16), torch.float64)
+        lib.check(self.lib.mv2d_geom_prep_batch(cams[0].data_ptr(), B, V, i2l.data_ptr(), trans.data_ptr(), lib.stream_ptr()),
+                  'mv2d_geom_prep_batch')
+        return self._enqueue_post(feat, False, cams, rois, roi_start, batch['counts'], B * Np, batch['metas'][0], i2l, trans,
+                                  pe_phase=0, batch=batch)
+
+    @torch.no_grad()
+    def forward_batch(self, feats, proposal_lists, metas_list, use_graph=False, bucket=1):
+        """B samples through ONE kernel chain (the reference asserts B == 1: detectors/mv2d.py:143,
+        roi_heads/mv2d_head.py:210,251; here the batch is a segment dimension -- see "Batches" in include/mv2d_b200.h).
+        feats [B,V,256,h,w] fp32 (device, or pinned host memory) or a list of B [V,256,h,w] tensors; proposal_lists: B lists
+        of V tensors [n_v, >= 4]; metas_list: B lists of V dicts.  Returns a dict of batched tensors -- cls_scores /
+        bbox_preds [L, B*Np, 10] with sample b in rows [b*Np, b*Np + n_b[b]) -- plus ``samples``: per-sample dicts of views
+        (cls_scores [L,n_b,10], bbox_preds, outs_dec, ref, query_pos, rois, N).
+        ``bucket`` rounds Np up (a CUDA graph is captured per (B, Np): see ``forward(..., bucket=)``)."""
+        if isinstance(feats, (list, tuple)):
+            feats = torch.stack(list(feats), 0)
+        B, V, Cc, h, w = feats.shape
+        assert B == len(proposal_lists) == len(metas_list) and Cc == 256
+        self._batch_grid = (h, w)
+        host_input = not feats.is_cuda
+
+        def result(out, batch):
+            Np, n_b = batch['Np'], batch['n_b']
+            out = dict(out)
+            out.update(B=B, Np=Np, n_b=n_b)
+            keys = ('cls_scores', 'bbox_preds', 'outs_dec')
+            out['samples'] = [dict({k: out[k][:, b * Np:b * Np + n_b[b]] for k in keys},
+                                   **{k: out[k][b * Np:b * Np + n_b[b]] for k in ('ref', 'query_pos', 'rois', 'center_lidar',
+                                                                                  'tok_feat', 'roi_intrinsics', 'match', 'match_cnt')
+                                      if out.get(k) is not None},
+                                   N=n_b[b], num_per_view=batch['counts'][b]) for b in range(B)]
+            return out
+
+        if not use_graph:
+            feat = feats.to(self.device, torch.float32, non_blocking=True).contiguous().view(B * V, Cc, h, w)
+            cams, rois, roi_start, batch = self._upload_meta_batch(proposal_lists, metas_list, bucket)
+            return result(self._enqueue_batch(feat, cams, rois, roi_start, batch), batch)
+        n_b = [max(sum(int(p.shape[0]) for p in pl), 1) for pl in proposal_lists]
+        Np = (max(n_b) + bucket - 1) // bucket * bucket
+        mkey = tuple(self._masks(m, h, w)[0] for m in metas_list)
+        key = (B, Np, tuple(feats.shape), mkey, host_input)
+        ent = self._graphs_b.get(key)
+        if ent is None:
+            static_feat = torch.empty((B * V, Cc, h, w), dtype=torch.float32, device=self.device)
+            static_feat.copy_(feats.view(B * V, Cc, h, w), non_blocking=True)
+            cams, rois, roi_start, batch = self._upload_meta_batch(proposal_lists, metas_list, bucket)
+            self._enqueue_batch(static_feat, cams, rois, roi_start, batch)      # warm-up: sizes buffers, sets attributes
+            torch.cuda.synchronize()
+            launches0 = self.launch_count()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                out = self._enqueue_batch(static_feat, cams, rois, roi_start, batch)
+            ent = dict(graph=g, out=out, feat=static_feat, launches=self.launch_count() - launches0, keep=dict(self._buf),
+                       ev_in=torch.cuda.Event(), ev_done=torch.cuda.Event())
+            self._graphs_b[key] = ent
+        main = torch.cuda.current_stream()
+        _, _, _, batch = self._upload_meta_batch(proposal_lists, metas_list, bucket)
+        if host_input:
+            self._copy.wait_event(ent['ev_done'])
+            self._copy.wait_stream(main)
+            with torch.cuda.stream(self._copy):
+                ent['feat'].copy_(feats.view(B * V, Cc, h, w), non_blocking=True)
+                ent['ev_in'].record(self._copy)
+            main.wait_event(ent['ev_in'])
+        else:
+            ent['feat'].copy_(feats.view(B * V, Cc, h, w), non_blocking=True)
+        ent['graph'].replay()
+        ent['ev_done'].record(main)
+        self.graph_launches += ent['launches']
+        return result(ent['out'], batch)
 
     LOSS_DEFAULTS = dict(   # configs/mv2d/exp/mv2d_r50_frcnn_single_frame_roi_1408x512_ep72.py:87-95,132-137
         code_weights=[1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.5, 1.5, 2.0, 2.0],

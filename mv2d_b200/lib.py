@@ -9,7 +9,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'lib', 'libmv2d_b200.so')
-ABI_VERSION = 4
+ABI_VERSION = 5
 MAX_LAYERS = 8
 
 c_f = C.c_void_p  # device pointers travel as integers (tensor.data_ptr())
@@ -26,7 +26,7 @@ class PeParams(C.Structure):
         ('w_se_reduce', c_f), ('b_se_reduce', c_f), ('w_se_expand', c_f), ('b_se_expand', c_f),
         ('sine_branch_cached', c_f), ('sine_branch_out', c_f),
         ('pe', c_f), ('kin', c_f), ('workspace', c_f), ('workspace_bytes', C.c_size_t),
-        ('sine_separable', C.c_int), ('reserved0', C.c_int),
+        ('sine_separable', C.c_int), ('views_per_sample', C.c_int), ('sine_shared', C.c_int), ('reserved3', C.c_int),
     ]
 
 
@@ -56,6 +56,7 @@ class CorrParams(C.Structure):
         ('match', c_f), ('match_cnt', c_f),
         ('h', C.c_int), ('w', C.c_int), ('stride', C.c_int), ('expand_stride', C.c_int),
         ('pad_mask', c_f), ('keymask', c_f), ('key_cnt', c_f), ('key_list', c_f),
+        ('batch', C.c_int), ('rows_per_sample', C.c_int),
     ]
 
 
@@ -97,6 +98,7 @@ class DecoderParams(C.Structure):
         ('grid_w', C.c_int), ('xa_prepared', C.c_int),
         ('kp', c_f), ('vp', c_f), ('xa_workspace', c_f), ('xa_workspace_bytes', C.c_size_t),
         ('row_tile_live', c_f),
+        ('batch', C.c_int), ('rows_per_sample', C.c_int), ('n_real', c_f), ('vel_dt_batch', c_f),
     ]
 
 
@@ -190,6 +192,7 @@ SYMBOLS = [
     ('mv2d_launch_count', C.c_ulonglong, []),
     ('mv2d_sizeof', C.c_size_t, [C.c_int]),
     ('mv2d_geom_prep', C.c_int, [c_f, C.c_int, c_f, c_f, c_f]),
+    ('mv2d_geom_prep_batch', C.c_int, [c_f, C.c_int, C.c_int, c_f, c_f, c_f]),
     ('mv2d_nchw_to_nhwc', C.c_int, [c_f, c_f, c_f, C.c_int, C.c_int, C.c_int, c_f]),
     ('mv2d_split_tf32', C.c_int, [c_f, c_f, c_f, C.c_longlong, c_f]),
     ('mv2d_gemm_3xtf32', C.c_int, [c_f, c_f, C.c_int, c_f, c_f, C.c_int, c_f, c_f, C.c_int, C.c_int, C.c_int,
@@ -204,6 +207,7 @@ SYMBOLS = [
     ('mv2d_decoder_workspace_bytes', C.c_size_t, [C.c_int, C.c_int]),
     ('mv2d_decoder', C.c_int, [C.POINTER(DecoderParams), c_f]),
     ('mv2d_xa_tile_workspace_bytes', C.c_size_t, [C.c_int] * 4),
+    ('mv2d_xa_tile_workspace_bytes_batch', C.c_size_t, [C.c_int] * 5),
     ('mv2d_kv_project', C.c_int, [C.POINTER(KvParams), c_f]),
     ('mv2d_loss_workspace_bytes', C.c_size_t, [C.c_int] * 3),
     ('mv2d_loss', C.c_int, [C.POINTER(LossParams), c_f]),

@@ -57,6 +57,27 @@ class Pipeline:
             self.done[k].record(s)
         return k, out
 
+    def submit_batch(self, feats, proposal_lists, metas_list, to_host=False, bucket=1):
+        """Enqueue one BATCH (B samples through one kernel chain, ``HotPath.forward_batch``) on the next lane: the
+        GPU-filling front end of batch i+1 runs under the decoder tail of batch i.  Same contract as ``submit``."""
+        k = self._next % self.depth
+        self._next += 1
+        s = self.streams[k]
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            out = self.lanes[k].forward_batch(feats, proposal_lists, metas_list, use_graph=True, bucket=bucket)
+            if to_host:
+                h = self._host[k]
+                if h is None or h[0].shape != out['cls_scores'].shape:
+                    h = (torch.empty(out['cls_scores'].shape, dtype=torch.float32).pin_memory(),
+                         torch.empty(out['bbox_preds'].shape, dtype=torch.float32).pin_memory())
+                    self._host[k] = h
+                h[0].copy_(out['cls_scores'], non_blocking=True)
+                h[1].copy_(out['bbox_preds'], non_blocking=True)
+                out['host_cls'], out['host_box'] = h
+            self.done[k].record(s)
+        return k, out
+
     def wait(self, ticket):
         """Make the caller's stream wait for the sample behind ``ticket``."""
         torch.cuda.current_stream().wait_event(self.done[ticket])
