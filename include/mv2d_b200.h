@@ -195,6 +195,13 @@ typedef struct Mv2dLayerWeights {
     const float *xa_v_w, *xa_v_w_lo;    /* Wv as TF32 hi + lo : [256,256] */
     const float *xa_o_w, *xa_o_b;       /* Wo [256,256], Wo bv + bo [256] (probabilities sum to one) */
     const float *xa_k_raw, *xa_v_raw;   /* Wk, Wv as plain fp32 (= hi + lo): operands of the in-kernel-split GEMM */
+    /* ---- ABI 5: with more than 512 query rows (batches) every decoder GEMM runs as 3xTF32 on the tensor cores.
+     * sa_in_w / sa_out_w / xa_q_w / xa_o_w above stay plain fp32 (the small-M FFMA kernels read them); these are their
+     * TF32 hi / lo splits (w = hi + lo).  All nullable: NULL keeps the FFMA kernels at every size. */
+    const float *sa_in_w_hi, *sa_in_w_lo;     /* [768,256] */
+    const float *sa_out_w_hi, *sa_out_w_lo;   /* [256,256] */
+    const float *xa_q_w_hi, *xa_q_w_lo;       /* [256,256] */
+    const float *xa_o_w_hi, *xa_o_w_lo;       /* [256,256] */
 } Mv2dLayerWeights;
 
 typedef struct Mv2dBranchWeights {      /* stacked over layers: leading dim L */
@@ -204,6 +211,9 @@ typedef struct Mv2dBranchWeights {      /* stacked over layers: leading dim L */
     const float *reg_w0, *reg_b0, *reg_w1, *reg_b1;    /* [L,256,256] */
     const float *reg_w2, *reg_b2;                      /* [L,10,256] */
     const float *post_g, *post_b;                      /* decoder.post_norm */
+    /* ABI 5, nullable: TF32 hi / lo splits of the four [L,256,256] branch matrices (3xTF32 tensor-core GEMMs for
+     * batches of more than 512 query rows; NULL keeps the FFMA kernels) */
+    const float *cls_w0_hi, *cls_w0_lo, *cls_w1_hi, *cls_w1_lo, *reg_w0_hi, *reg_w0_lo, *reg_w1_hi, *reg_w1_lo;
 } Mv2dBranchWeights;
 
 typedef struct Mv2dDecoderParams {

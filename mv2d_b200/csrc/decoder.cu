@@ -31,6 +31,7 @@ struct LnArgs {
     float* out; float* out_q; float* out2;
     float* out_hi; float* out_lo;      // nullable: TF32 split of `out`   (A operand of a 3xTF32 GEMM)
     float* outq_hi; float* outq_lo;    // nullable: TF32 split of `out_q`
+    float* out2_hi; float* out2_lo;    // nullable: TF32 split of `out2`
     int rows;
     int bcast_in;     // 1: `partial` is ONE [256] row shared by every output row
 };
@@ -126,6 +127,13 @@ __device__ __forceinline__ void ln_body(const LnArgs& a, int vb) {
         for (int i = 0; i < 2; ++i) {
             const int c = i * 128 + lane * 4;
             *reinterpret_cast<float4*>(a.out2 + o + c) = make_float4(y[i * 4], y[i * 4 + 1], y[i * 4 + 2], y[i * 4 + 3]);
+            if (a.out2_hi) {
+                float hi[4], lo[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { hi[k] = round_tf32(y[i * 4 + k]); lo[k] = round_tf32(y[i * 4 + k] - hi[k]); }
+                *reinterpret_cast<float4*>(a.out2_hi + o + c) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<float4*>(a.out2_lo + o + c) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+            }
         }
     }
 }
@@ -156,7 +164,7 @@ __device__ __forceinline__ void sa_cp16(void* smem, const void* gmem) {
 // A sample of a batch owns rows [seg0, seg0 + nq); its keys are the first N of them (seg0 = 0, nq = N: one sample).
 __device__ __forceinline__ void
 self_attn_body(const float* __restrict__ qkv, const uint8_t* __restrict__ mask, int N, float* __restrict__ out,
-               int vbx, int hd, float* smem_f, int seg0 = 0, int nq = -1) {
+               int vbx, int hd, float* smem_f, int seg0 = 0, int nq = -1, float* __restrict__ out_lo = nullptr) {
     float (*Ks)[SA_LD] = reinterpret_cast<float (*)[SA_LD]>(smem_f);
     float (*Vs)[SA_LD] = reinterpret_cast<float (*)[SA_LD]>(smem_f + SA_KT * SA_LD);
     float (*Ps)[SA_KT] = reinterpret_cast<float (*)[SA_KT]>(smem_f + 2 * SA_KT * SA_LD);
@@ -250,8 +258,14 @@ self_attn_body(const float* __restrict__ qkv, const uint8_t* __restrict__ mask, 
     }
     if (ql < nq && kq == 0) {
         const float inv = l > 0.f ? 1.f / l : 0.f;
-        *reinterpret_cast<float4*>(out + (long long)ql * MV2D_C + hd * 32 + cq * 4) =
-            make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
+        float4 r = make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
+        if (out_lo) {     // TF32 hi / lo split: A operand of the 3xTF32 output projection
+            const float4 hi = make_float4(round_tf32(r.x), round_tf32(r.y), round_tf32(r.z), round_tf32(r.w));
+            *reinterpret_cast<float4*>(out_lo + (long long)(seg0 + ql) * MV2D_C + hd * 32 + cq * 4) =
+                make_float4(round_tf32(r.x - hi.x), round_tf32(r.y - hi.y), round_tf32(r.z - hi.z), round_tf32(r.w - hi.w));
+            r = hi;
+        }
+        *reinterpret_cast<float4*>(out + (long long)ql * MV2D_C + hd * 32 + cq * 4) = r;
     }
 }
 
@@ -372,16 +386,16 @@ self_attn_body_v1(const float* __restrict__ qkv, const uint8_t* __restrict__ mas
 // grid (ceil(rows_per_sample / 8), heads, batch).  n_real (nullable, device [batch]): keys of sample b = its first n_real[b] rows.
 __global__ void __launch_bounds__(256)
 self_attn_kernel(const float* __restrict__ qkv, const uint8_t* __restrict__ mask, int N, float* __restrict__ out,
-                 int rows_per_sample, const int* __restrict__ n_real) {
+                 int rows_per_sample, const int* __restrict__ n_real, float* __restrict__ out_lo) {
     pdl_wait();
     pdl_trigger();
     extern __shared__ __align__(16) float sa_smem[];
     if (rows_per_sample > 0) {
         const int b = blockIdx.z;
         const int nk = n_real ? min(n_real[b], rows_per_sample) : rows_per_sample;
-        self_attn_body(qkv, nullptr, nk, out, blockIdx.x, blockIdx.y, sa_smem, b * rows_per_sample, rows_per_sample);
+        self_attn_body(qkv, nullptr, nk, out, blockIdx.x, blockIdx.y, sa_smem, b * rows_per_sample, rows_per_sample, out_lo);
     } else {
-        self_attn_body(qkv, mask, N, out, blockIdx.x, blockIdx.y, sa_smem);
+        self_attn_body(qkv, mask, N, out, blockIdx.x, blockIdx.y, sa_smem, 0, -1, out_lo);
     }
 }
 
@@ -949,9 +963,10 @@ static size_t xa_smem_mega(int mode, int klist_cap) {
 size_t decoder_workspace_bytes(int N, int L) {
     size_t n = (size_t)(N > 0 ? N : 1), l = (size_t)(L > 0 ? L : 1);
     // x, xq, x1, x1q, x2 + 4 hi/lo copies (9*256) + qkv 768 + sa 256 + qt 2048 + ctx hi/lo + hdn hi/lo + partials
-    size_t per = 9 * MV2D_C + 768 + MV2D_C + 2048 + 2 * 2048 + 2 * 2048 + DEC_SPLIT * MV2D_C + XR_MAXM * XR_REC + 1;
-    // branches: 4 x [L,N,256]
-    return (n * per + 4 * l * n * MV2D_C) * sizeof(float) + 4096;   // + the device-wide barrier word and phase timestamps of the persistent kernel
+    // + (3xTF32 everywhere, > 512 rows) x / xq hi/lo, sa lo, xt ctx lo: 6*256
+    size_t per = 9 * MV2D_C + 768 + MV2D_C + 2048 + 2 * 2048 + 2 * 2048 + DEC_SPLIT * MV2D_C + XR_MAXM * XR_REC + 1 + 6 * MV2D_C;
+    // branches: 4 x [L,N,256] + hi/lo splits of the post-normed states and of three branch activations
+    return (n * per + (4 + 7) * l * n * MV2D_C) * sizeof(float) + 4096;   // + the device-wide barrier word and phase timestamps of the persistent kernel
 }
 
 // ---- key-stationary cross-attention of the two-frame head (xa_tile.cuh): caller-owned scratch
@@ -1095,6 +1110,20 @@ int run_decoder(const Mv2dDecoderParams& p, cudaStream_t st) {
     float* b3 = ws;   ws += (size_t)L * N * C;
     float* xr_part = ws; ws += (size_t)N * XR_MAXM * XR_REC;
     int* xr_ticket = reinterpret_cast<int*>(ws); ws += N;
+    // 3xTF32 operand splits of the GEMMs that run as FFMA below 512 rows
+    float* x_hi = ws;  ws += (size_t)N * C;
+    float* x_lo = ws;  ws += (size_t)N * C;
+    float* xq_hi = ws; ws += (size_t)N * C;
+    float* xq_lo = ws; ws += (size_t)N * C;
+    float* sa_lo = ws; ws += (size_t)N * C;
+    float* xctx_lo = ws; ws += (size_t)N * C;
+    float* in_hi = ws; ws += (size_t)L * N * C;      // post-normed states (outs_dec) split
+    float* in_lo = ws; ws += (size_t)L * N * C;
+    float* b1_lo = ws; ws += (size_t)L * N * C;
+    float* b2_lo = ws; ws += (size_t)L * N * C;
+    float* b4 = ws;    ws += (size_t)L * N * C;
+    float* b4_lo = ws; ws += (size_t)L * N * C;
+    float* b0_lo = ws; ws += (size_t)L * N * C;
     unsigned* barrier = reinterpret_cast<unsigned*>(reinterpret_cast<uintptr_t>(ws + 63) & ~(uintptr_t)63); ws += 1024;
     MV2D_CHECK_ARG((size_t)(ws - p.workspace) * sizeof(float) <= p.workspace_bytes, "decoder: workspace too small");
     const long long NC = (long long)N * C;
@@ -1222,6 +1251,16 @@ int run_decoder(const Mv2dDecoderParams& p, cudaStream_t st) {
         if (e != cudaSuccess) { set_error("decoder(persistent): launch %s", cudaGetErrorString(e)); return (int)e; }
         return 0;
     }
+    // More than 512 query rows (batches): every GEMM of the layer is a GPU-filling problem, so the ones that run as
+    // FFMA kernels at M ~ 300 (in_proj, out_proj, the T head's q / out projections, the branch MLPs) go to the 3xTF32
+    // tcgen05 kernel as well; their A operands are split by the producing kernel's epilogue.
+    static const bool tc_all_env = []() { const char* v = getenv("MV2D_DEC_TC_ALL"); return !(v && v[0] == '0'); }();
+    const bool big = tc_all_env && N > 512 && p.layers[0].sa_in_w_hi && p.layers[0].sa_out_w_hi && B.cls_w0_hi &&
+                     (!xt || (p.layers[0].xa_q_w_hi && p.layers[0].xa_o_w_hi));
+    if (big && first && !fold0) {      // layer 0 runs its self-attention: x = 0 and x + pos = pos need their splits too
+        if ((e = cudaMemsetAsync(x_hi, 0, 2 * NC * sizeof(float), st)) != cudaSuccess) { set_error("decoder: init %s", cudaGetErrorString(e)); return (int)e; }
+        if ((rc = launch_split_tf32(p.query_pos, xq_hi, xq_lo, NC, st))) return rc;
+    }
     for (int l = lb; l < le; ++l) {
         const Mv2dLayerWeights& w = p.layers[l];
         float* inter = p.outs_dec + (long long)l * NC;
@@ -1232,7 +1271,13 @@ int run_decoder(const Mv2dDecoderParams& p, cudaStream_t st) {
             if ((rc = ln(a, st))) return rc;
         } else {
             // --- self attention: q,k from (x + qpos), v from x
-            {
+            if (big) {
+                TcGemm t{};
+                t.A = xq_hi; t.A_lo = xq_lo; t.A2 = x_hi; t.A2_lo = x_lo; t.n_switch = 512; t.lda = C;
+                t.W = w.sa_in_w_hi; t.W_lo = w.sa_in_w_lo; t.ldw = C; t.bias = w.sa_in_b; t.C = qkv; t.ldc = 768;
+                t.M = N; t.N = 768; t.K = C; t.passes = 3; t.nsplit = 1;
+                if ((rc = launch_gemm_tc(t, st))) return rc;
+            } else {
                 GemmArgs g{};
                 g.A = xq; g.lda = C; g.W = w.sa_in_w; g.ldw = C; g.C = qkv; g.ldc = 768; g.bias = w.sa_in_b;
                 g.M = N; g.N = 768; g.K = C; g.batch = 1; g.nsplit = 1;
@@ -1240,12 +1285,16 @@ int run_decoder(const Mv2dDecoderParams& p, cudaStream_t st) {
             }
             if (p.batch > 0)
                 launch_k(self_attn_kernel, dim3(cdiv(p.rows_per_sample, 8 * SA_QPW), MV2D_HEADS, p.batch), dim3(256), SA_SMEM_BYTES, st,
-                         (const float*)qkv, (const uint8_t*)nullptr, N, sa, p.rows_per_sample, p.n_real);
+                         (const float*)qkv, (const uint8_t*)nullptr, N, sa, p.rows_per_sample, p.n_real, big ? sa_lo : (float*)nullptr);
             else
                 launch_k(self_attn_kernel, dim3(cdiv(N, 8 * SA_QPW), MV2D_HEADS), dim3(256), SA_SMEM_BYTES, st, (const float*)qkv, p.self_attn_mask, N, sa,
-                         0, (const int*)nullptr);
+                         0, (const int*)nullptr, big ? sa_lo : (float*)nullptr);
             MV2D_CHECK_LAUNCH("self_attn");
-            if ((rc = gemm(sa, C, w.sa_out_w, C, nullptr, part, C, N, C, C, 0, st))) return rc;
+            if (big) {
+                if ((rc = tc3(sa, sa_lo, C, w.sa_out_w_hi, w.sa_out_w_lo, C, nullptr, part, nullptr, C, N, C, C, 0, 1, 0, st))) return rc;
+            } else {
+                if ((rc = gemm(sa, C, w.sa_out_w, C, nullptr, part, C, N, C, C, 0, st))) return rc;
+            }
             {
                 LnArgs a{}; a.partial = part; a.nsplit = 1; a.bias = w.sa_out_b; a.residual = x;
                 a.gamma = w.ln_g[0]; a.beta = w.ln_b[0]; a.qpos = p.query_pos; a.out = x1; a.out_q = x1q; a.rows = N;
@@ -1256,7 +1305,11 @@ int run_decoder(const Mv2dDecoderParams& p, cudaStream_t st) {
         if (xt) {
             // --- sparse cross attention, key-stationary: q projection, per-tile partial attention, merge, output projection
             MV2D_CHECK_ARG(w.xa_q_w && w.xa_q_b && w.xa_o_w && w.xa_o_b, "decoder: layer %d has no xa_q / xa_o weights", l);
-            if ((rc = gemm(x1q, C, w.xa_q_w, C, w.xa_q_b, xw.qp, C, N, C, C, 0, st))) return rc;
+            if (big) {
+                if ((rc = tc3(x1q_hi, x1q_lo, C, w.xa_q_w_hi, w.xa_q_w_lo, C, w.xa_q_b, xw.qp, nullptr, C, N, C, C, 0, 1, 0, st))) return rc;
+            } else {
+                if ((rc = gemm(x1q, C, w.xa_q_w, C, w.xa_q_b, xw.qp, C, N, C, C, 0, st))) return rc;
+            }
             {
                 XtAttnArgs a{}; a.g = xg; a.q = xw.qp; a.kp = p.kp + (long long)l * p.num_rows * C; a.vp = p.vp + (long long)l * p.num_rows * C;
                 a.tile_cnt = xw.tile_cnt; a.tile_q = xw.tile_q; a.tile_mask = xw.tile_mask; a.rec = xw.rec; a.order = xw.order;
@@ -1267,10 +1320,15 @@ int run_decoder(const Mv2dDecoderParams& p, cudaStream_t st) {
             }
             {
                 XtMergeArgs a{}; a.g = xg; a.qlist = xw.qlist; a.qcnt = xw.qcnt; a.rec = xw.rec; a.ctx = xw.ctx;
+                a.ctx_lo = big ? xctx_lo : nullptr;
                 launch_k(xt_merge_kernel, dim3(N), dim3(XT_MERGE_THREADS), (size_t)xg.tiles_ps * 36, st, a);
                 MV2D_CHECK_LAUNCH("xt_merge");
             }
-            if ((rc = gemm(xw.ctx, C, w.xa_o_w, C, nullptr, part, C, N, C, C, 0, st))) return rc;
+            if (big) {
+                if ((rc = tc3(xw.ctx, xctx_lo, C, w.xa_o_w_hi, w.xa_o_w_lo, C, nullptr, part, nullptr, C, N, C, C, 0, 1, 0, st))) return rc;
+            } else {
+                if ((rc = gemm(xw.ctx, C, w.xa_o_w, C, nullptr, part, C, N, C, C, 0, st))) return rc;
+            }
             LnArgs a{}; a.partial = part; a.nsplit = 1; a.bias = w.xa_o_b; a.residual = x1;
             a.gamma = w.ln_g[1]; a.beta = w.ln_b[1]; a.out = x2; a.rows = N; a.out_hi = x2_hi; a.out_lo = x2_lo;
             if ((rc = ln(a, st))) return rc;
@@ -1291,27 +1349,59 @@ int run_decoder(const Mv2dDecoderParams& p, cudaStream_t st) {
             launch_k(xa_kernel, dim3(N), dim3(xa_ch == 16 ? 128 : 256), xa_smem, st, a);
             MV2D_CHECK_LAUNCH("cross_attn");
         }
-        if ((rc = tc3(ctx, ctx_lo, 2048, w.ca_o_w, w.ca_o_w_lo, 2048, nullptr, part, nullptr, C, N, C, 2048, 0, DEC_SPLIT, NC, st))) return rc;
+        // split-K only while the M tiles alone cannot fill the GPU
+        const int ksplit = big ? (N > 2048 ? 2 : 4) : DEC_SPLIT;
+        if ((rc = tc3(ctx, ctx_lo, 2048, w.ca_o_w, w.ca_o_w_lo, 2048, nullptr, part, nullptr, C, N, C, 2048, 0, ksplit, NC, st))) return rc;
         {
-            LnArgs a{}; a.partial = part; a.nsplit = DEC_SPLIT; a.split_stride = NC; a.bias = w.ca_o_b; a.residual = x1;
+            LnArgs a{}; a.partial = part; a.nsplit = ksplit; a.split_stride = NC; a.bias = w.ca_o_b; a.residual = x1;
             a.gamma = w.ln_g[1]; a.beta = w.ln_b[1]; a.out = x2; a.rows = N; a.out_hi = x2_hi; a.out_lo = x2_lo;
             if ((rc = ln(a, st))) return rc;
         }
         }
         // --- FFN
+        const int ksplit2 = big ? (N > 2048 ? 2 : 4) : DEC_SPLIT;
         if ((rc = tc3(x2_hi, x2_lo, C, w.ffn_w1, w.ffn_w1_lo, C, w.ffn_b1, hdn, hdn_lo, 2048, N, 2048, C,
                       GEMM_RELU | GEMM_SPLIT_OUT, 1, 0, st))) return rc;
-        if ((rc = tc3(hdn, hdn_lo, 2048, w.ffn_w2, w.ffn_w2_lo, 2048, nullptr, part, nullptr, C, N, C, 2048, 0, DEC_SPLIT, NC, st))) return rc;
+        if ((rc = tc3(hdn, hdn_lo, 2048, w.ffn_w2, w.ffn_w2_lo, 2048, nullptr, part, nullptr, C, N, C, 2048, 0, ksplit2, NC, st))) return rc;
         {
-            LnArgs a{}; a.partial = part; a.nsplit = DEC_SPLIT; a.split_stride = NC; a.bias = w.ffn_b2; a.residual = x2;
+            LnArgs a{}; a.partial = part; a.nsplit = ksplit2; a.split_stride = NC; a.bias = w.ffn_b2; a.residual = x2;
             a.gamma = w.ln_g[2]; a.beta = w.ln_b[2]; a.qpos = p.query_pos; a.out = x; a.out_q = xq;
             a.gamma2 = B.post_g; a.beta2 = B.post_b; a.out2 = inter; a.rows = N;
+            if (big) {
+                a.out_hi = x_hi; a.out_lo = x_lo; a.outq_hi = xq_hi; a.outq_lo = xq_lo;
+                a.out2_hi = in_hi + (long long)l * NC; a.out2_lo = in_lo + (long long)l * NC;
+            }
             if ((rc = ln(a, st))) return rc;
         }
     }
     if (!last) return 0;
     // --- branches, batched over layers (cross_attention_head.py:216-231)
     const long long CC = (long long)C * C;
+    if (big) {
+        // one grouped 3xTF32 launch per Linear: group = decoder layer (its own [256,256] matrix), M = N rows each
+        auto grouped = [&](const float* a_hi, const float* a_lo, const float* w_hi, const float* w_lo, const float* bias, float* out,
+                           float* out_lo, int flags) {
+            TcGemm t{};
+            t.A = a_hi; t.A_lo = a_lo; t.lda = C; t.W = w_hi; t.W_lo = w_lo; t.ldw = C; t.bias = bias; t.C = out; t.C_lo = out_lo; t.ldc = C;
+            t.M = N; t.N = C; t.K = C; t.passes = 3; t.nsplit = 1; t.flags = flags; t.groups = L; t.group_rows = N;
+            return launch_gemm_tc(t, st);
+        };
+        if ((rc = grouped(in_hi, in_lo, B.cls_w0_hi, B.cls_w0_lo, nullptr, b0, nullptr, 0))) return rc;
+        {
+            LnArgs a{}; a.partial = b0; a.nsplit = 1; a.bias = B.cls_b0; a.gamma = B.cls_g0; a.beta = B.cls_be0;
+            a.rows_per_group = N; a.group_stride = C; a.relu = 1; a.out = b1; a.out_hi = b4; a.out_lo = b1_lo; a.rows = L * N;
+            if ((rc = ln(a, st))) return rc;
+        }
+        if ((rc = grouped(b4, b1_lo, B.cls_w1_hi, B.cls_w1_lo, nullptr, b0, nullptr, 0))) return rc;
+        {
+            LnArgs a{}; a.partial = b0; a.nsplit = 1; a.bias = B.cls_b1; a.gamma = B.cls_g1; a.beta = B.cls_be1;
+            a.rows_per_group = N; a.group_stride = C; a.relu = 1; a.out = b1; a.rows = L * N;
+            if ((rc = ln(a, st))) return rc;
+        }
+        // reg branch: Linear-ReLU twice; the first epilogue emits the hi / lo split the second one reads (b2 = hi)
+        if ((rc = grouped(in_hi, in_lo, B.reg_w0_hi, B.reg_w0_lo, B.reg_b0, b2, b2_lo, GEMM_RELU | GEMM_SPLIT_OUT))) return rc;
+        if ((rc = grouped(b2, b2_lo, B.reg_w1_hi, B.reg_w1_lo, B.reg_b1, b3, nullptr, GEMM_RELU))) return rc;
+    } else {
     if ((rc = gemm(p.outs_dec, C, B.cls_w0, C, nullptr, b0, C, N, C, C, 0, st, 1, 0, L, NC, CC, NC, 0))) return rc;
     {
         LnArgs a{}; a.partial = b0; a.nsplit = 1; a.bias = B.cls_b0; a.gamma = B.cls_g0; a.beta = B.cls_be0;
@@ -1326,6 +1416,7 @@ int run_decoder(const Mv2dDecoderParams& p, cudaStream_t st) {
     }
     if ((rc = gemm(p.outs_dec, C, B.reg_w0, C, B.reg_b0, b2, C, N, C, C, GEMM_RELU, st, 1, 0, L, NC, CC, NC, C))) return rc;
     if ((rc = gemm(b2, C, B.reg_w1, C, B.reg_b1, b3, C, N, C, C, GEMM_RELU, st, 1, 0, L, NC, CC, NC, C))) return rc;
+    }
     launch_k(head10_kernel, dim3(cdiv(L * N, 8)), dim3(256), 0, st, (const float*)b1, (const float*)b3, B.cls_w2, B.cls_b2, B.reg_w2, B.reg_b2, p.ref, L, N,
                                                  p.pc_range[0], p.pc_range[1], p.pc_range[2], p.pc_range[3],
                                                  p.pc_range[4], p.pc_range[5], p.vel_dt, p.vel_row_start, p.cls_scores, p.bbox_preds,

@@ -107,6 +107,7 @@ struct TcArgs {
     const uint8_t* m_tile_live;                                        // nullable [m_tiles]: 0 = nobody reads this row tile, skip it
     const float* gx; const float* gs; const float* gfeat; float* kin;  // GEMM_GATE extras
     int gs_mod;                                                        // > 0: gs row = out row % gs_mod
+    int groups; int group_rows;                                        // grouped launch: blockIdx.z = group (no split-K)
     int n_switch;                                                      // > 0: n tiles at columns >= n_switch load A through tmAlo's slot pair (see launch)
 };
 
@@ -139,7 +140,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         pdl_wait();
         if (g.m_tile_live[m_tile] == 0) return;
     }
-    const int nkb = g.nkb_per_split, kb0 = blockIdx.z * g.nkb_per_split;   // this CTA's K range (split-K)
+    const bool grouped = !IM2COL && g.groups > 1;
+    const int grp = grouped ? blockIdx.z : 0;
+    const int a_row0 = grp * g.group_rows;      // first A / C row of this group
+    const int w_row0 = grp * g.N;               // first W row / bias element of this group
+    const int nkb = g.nkb_per_split, kb0 = grouped ? 0 : blockIdx.z * g.nkb_per_split;   // this CTA's K range (split-K)
     // CTAs that share an operand tile walk K in rotated order, so they do not all hit the same L2 lines at once
     const int rot = IM2COL ? 0 : (int)((blockIdx.x + 3 * blockIdx.y) % nkb);
 
@@ -195,11 +200,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             tma_load_4d(&tmAlo, &full_bar[s], st + A_BYTES + r * (A_BYTES / 2), c0, dx, dy, m_tile * 2 + r);
                     }
                 } else {
-                    tma_load_2d(mapA, &full_bar[s], st, (kb0 + (kb + rot) % nkb) * TC_BK, m_tile * TC_BM);
-                    if (PASSES == 3 && !RAW) tma_load_2d(mapAlo, &full_bar[s], st + A_BYTES, (kb0 + (kb + rot) % nkb) * TC_BK, m_tile * TC_BM);
+                    tma_load_2d(mapA, &full_bar[s], st, (kb0 + (kb + rot) % nkb) * TC_BK, a_row0 + m_tile * TC_BM);
+                    if (PASSES == 3 && !RAW) tma_load_2d(mapAlo, &full_bar[s], st + A_BYTES, (kb0 + (kb + rot) % nkb) * TC_BK, a_row0 + m_tile * TC_BM);
                 }
-                tma_load_2d(&tmW, &full_bar[s], st + NOP * A_BYTES, (kb0 + (kb + rot) % nkb) * TC_BK, n0);
-                if (PASSES == 3 && !RAW) tma_load_2d(&tmWlo, &full_bar[s], st + NOP * A_BYTES + W_BYTES, (kb0 + (kb + rot) % nkb) * TC_BK, n0);
+                tma_load_2d(&tmW, &full_bar[s], st + NOP * A_BYTES, (kb0 + (kb + rot) % nkb) * TC_BK, w_row0 + n0);
+                if (PASSES == 3 && !RAW) tma_load_2d(&tmWlo, &full_bar[s], st + NOP * A_BYTES + W_BYTES, (kb0 + (kb + rot) % nkb) * TC_BK, w_row0 + n0);
             }
         }
     } else if (warp == 1) {
@@ -279,8 +284,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 orow = ((long long)v * g.fm_h + y) * g.fm_w + x;
                 return y < g.fm_h && x < g.fm_w;
             }
-            orow = (long long)m_tile * TC_BM + r;
-            return orow < g.M;
+            orow = (long long)a_row0 + m_tile * TC_BM + r;      // rows of the tile beyond the group's M belong to the next group
+            return m_tile * TC_BM + r < g.M;
         };
         // registers (my row, 32 cols) -> global [4 rows x 128 B per instruction]
         auto store_t = [&](float* __restrict__ dst, const float (&x)[32], int n) {
@@ -324,17 +329,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             float x[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
-            if (gridDim.z > 1) {   // split-K: raw partial sums, finished by the LN/reduce kernel
+            if (gridDim.z > 1 && !grouped) {   // split-K: raw partial sums, finished by the LN/reduce kernel
                 store_t(g.C + blockIdx.z * g.split_stride, x, n);
                 continue;
             }
             if (g.bias) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) x[j] += __ldg(g.bias + n + j);
+                for (int j = 0; j < 32; ++j) x[j] += __ldg(g.bias + w_row0 + n + j);
             }
             if (g.flags & GEMM_RELU) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
+            }
+            if (g.flags & GEMM_CLAMP5E3) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) x[j] = fminf(x[j], 5e3f);
             }
             if (g.flags & GEMM_GATE) {   // pe = gx * sigmoid(acc) + gs ; kin = pe + gfeat   (pe.py:44-48,166)
                 float t[32];
@@ -635,7 +644,7 @@ static int launch_tc(const CUtensorMap& a, const CUtensorMap& alo, const CUtenso
         if (e != cudaSuccess) { set_error("gemm_tc: smem attr: %s", cudaGetErrorString(e)); return (int)e; }
         attr_set = true;
     }
-    dim3 grid(g.N / BN, m_tiles, nsplit);
+    dim3 grid(g.N / BN, m_tiles, g.groups > 1 ? g.groups : nsplit);
     launch_k(kern, grid, dim3(TC_THREADS), smem, st, a, alo, w, wlo, a2 ? *a2 : a, a2lo ? *a2lo : alo, g);
     MV2D_CHECK_LAUNCH("gemm_tc");
     return 0;
@@ -687,6 +696,10 @@ int launch_gemm_tc(const TcGemm& t, cudaStream_t st) {
     int rc;
     TcArgs g{};
     const int nsplit = t.nsplit > 1 ? t.nsplit : 1;
+    const int ngroups = t.groups > 1 ? t.groups : 1;
+    MV2D_CHECK_ARG(ngroups == 1 || (nsplit == 1 && !t.im2col && !t.A2 && t.group_rows >= t.M && !(t.flags & GEMM_GATE)),
+                   "gemm_tc: a grouped launch excludes split-K, im2col, a second A operand and the gate epilogue");
+    g.groups = ngroups; g.group_rows = (int)t.group_rows;
     MV2D_CHECK_ARG((t.K / TC_BK) % nsplit == 0, "gemm_tc: K=%d does not split %d ways into 32-wide blocks", t.K, nsplit);
     MV2D_CHECK_ARG(!(t.flags & GEMM_SPLIT_OUT) || t.C_lo, "gemm_tc: split output needs C_lo");
     g.C = t.C; g.C_lo = t.C_lo; g.ldc = t.ldc; g.bias = t.bias; g.M = t.M; g.N = t.N; g.K = t.K; g.flags = t.flags;
@@ -709,11 +722,12 @@ int launch_gemm_tc(const TcGemm& t, cudaStream_t st) {
         if ((rc = make_map_tokens(&alo, t.A_lo, g.n_rois))) return rc;
     } else {
         m_tiles = cdiv(t.M, TC_BM);
-        if ((rc = make_map_2d(&a, t.A, t.M, t.K, t.lda, TC_BM))) return rc;
-        if ((rc = make_map_2d(&alo, (t.passes == 3 && !raw) ? t.A_lo : t.A, t.M, t.K, t.lda, TC_BM))) return rc;
+        const int a_rows = ngroups > 1 ? (int)((ngroups - 1) * t.group_rows + t.M) : t.M;
+        if ((rc = make_map_2d(&a, t.A, a_rows, t.K, t.lda, TC_BM))) return rc;
+        if ((rc = make_map_2d(&alo, (t.passes == 3 && !raw) ? t.A_lo : t.A, a_rows, t.K, t.lda, TC_BM))) return rc;
     }
-    if ((rc = make_map_2d(&w, t.W, t.N, t.K, t.ldw, bn))) return rc;
-    if ((rc = make_map_2d(&wlo, (t.passes == 3 && !raw) ? t.W_lo : t.W, t.N, t.K, t.ldw, bn))) return rc;
+    if ((rc = make_map_2d(&w, t.W, ngroups * t.N, t.K, t.ldw, bn))) return rc;
+    if ((rc = make_map_2d(&wlo, (t.passes == 3 && !raw) ? t.W_lo : t.W, ngroups * t.N, t.K, t.ldw, bn))) return rc;
     CUtensorMap a2, a2lo;
     const bool two_a = t.A2 != nullptr && t.n_switch > 0;
     if (two_a) {
@@ -728,7 +742,7 @@ int launch_gemm_tc(const TcGemm& t, cudaStream_t st) {
     if (t.im2col == 2) return launch_tc<128, 3, 2, 3>(a, alo, w, wlo, g, m_tiles, nsplit, st);
     if (t.im2col && bn == 256) return launch_tc<256, 3, 1, 2>(a, alo, w, wlo, g, m_tiles, nsplit, st);
     if (t.im2col) return launch_tc<128, 3, 1, 3>(a, alo, w, wlo, g, m_tiles, nsplit, st);
-    if (t.passes == 3 && bn == 64 && mc_enabled() && (t.N / 64) % TC_MC == 0 && !(t.A2 != nullptr && t.n_switch > 0)) {
+    if (t.passes == 3 && bn == 64 && mc_enabled() && (t.N / 64) % TC_MC == 0 && !(t.A2 != nullptr && t.n_switch > 0) && ngroups == 1) {
         // A is loaded in 32-row quarters and multicast across the 4-CTA cluster that shares the M-tile
         if ((rc = make_map_2d(&a, t.A, t.M, t.K, t.lda, 32))) return rc;
         if ((rc = make_map_2d(&alo, t.A_lo, t.M, t.K, t.lda, 32))) return rc;

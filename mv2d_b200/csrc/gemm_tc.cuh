@@ -32,6 +32,10 @@ struct TcGemm {
     int flags;         // GEMM_RELU | GEMM_GATE | GEMM_ROUND_TF32
     const float* gx; const float* gs; const float* gfeat; float* kin;
     int gs_mod;        // GEMM_GATE: > 0 = gs has gs_mod rows, read at (row % gs_mod)
+    int groups;        // > 1 (plain 2-D operands, nsplit == 1): `groups` independent problems of M rows each in one launch
+                       // (blockIdx.z): A / C rows of group z start at z * group_rows, W rows at z * N, bias at z * N
+                       // (the per-layer branch MLPs: one weight matrix per decoder layer)
+    long long group_rows;
     const float* A2; const float* A2_lo; int n_switch;   // nullable: output columns >= n_switch take their A rows from A2
                                                           // (the self-attention in_proj: q, k from x + pos, v from x)
 };

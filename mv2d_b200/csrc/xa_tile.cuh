@@ -373,6 +373,7 @@ struct XtMergeArgs {
     const int* qcnt;                   // [N]
     const float* rec;
     float* ctx;                        // [N,256] softmax-weighted mean of the projected values (heads concatenated)
+    float* ctx_lo;                     // nullable: ctx then holds the TF32 hi part, this the lo part (3xTF32 output projection)
 };
 
 #define XT_MERGE_THREADS 256
@@ -455,7 +456,14 @@ __global__ void __launch_bounds__(XT_MERGE_THREADS) xt_merge_kernel(XtMergeArgs 
 #pragma unroll
         for (int w = 0; w < 8; ++w) l += Lw[w][hc];
         const float inv = l > 0.f ? 1.f / l : 0.f;
-        reinterpret_cast<float4*>(a.ctx + (long long)n * MV2D_C)[c4] = make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
+        float4 r = make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
+        if (a.ctx_lo) {
+            const float4 hi = make_float4(round_tf32(r.x), round_tf32(r.y), round_tf32(r.z), round_tf32(r.w));
+            reinterpret_cast<float4*>(a.ctx_lo + (long long)n * MV2D_C)[c4] =
+                make_float4(round_tf32(r.x - hi.x), round_tf32(r.y - hi.y), round_tf32(r.z - hi.z), round_tf32(r.w - hi.w));
+            r = hi;
+        }
+        reinterpret_cast<float4*>(a.ctx + (long long)n * MV2D_C)[c4] = r;
     }
 }
 

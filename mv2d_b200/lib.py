@@ -68,6 +68,8 @@ class LayerWeights(C.Structure):
         ('ln_g', c_f * 3), ('ln_b', c_f * 3), ('sa_const', c_f),
         ('xa_q_w', c_f), ('xa_q_b', c_f), ('xa_k_w', c_f), ('xa_k_w_lo', c_f), ('xa_v_w', c_f), ('xa_v_w_lo', c_f),
         ('xa_o_w', c_f), ('xa_o_b', c_f), ('xa_k_raw', c_f), ('xa_v_raw', c_f),
+        ('sa_in_w_hi', c_f), ('sa_in_w_lo', c_f), ('sa_out_w_hi', c_f), ('sa_out_w_lo', c_f),
+        ('xa_q_w_hi', c_f), ('xa_q_w_lo', c_f), ('xa_o_w_hi', c_f), ('xa_o_w_lo', c_f),
     ]
 
 
@@ -79,6 +81,8 @@ class BranchWeights(C.Structure):
         ('reg_w0', c_f), ('reg_b0', c_f), ('reg_w1', c_f), ('reg_b1', c_f),
         ('reg_w2', c_f), ('reg_b2', c_f),
         ('post_g', c_f), ('post_b', c_f),
+        ('cls_w0_hi', c_f), ('cls_w0_lo', c_f), ('cls_w1_hi', c_f), ('cls_w1_lo', c_f),
+        ('reg_w0_hi', c_f), ('reg_w0_lo', c_f), ('reg_w1_hi', c_f), ('reg_w1_lo', c_f),
     ]
 
 

@@ -176,6 +176,13 @@ class PackedWeights:
                 hi, lo = split_tf32(mat)
                 setattr(lw, field, put(f'l{l}.{field}', hi).data_ptr())
                 setattr(lw, field + '_lo', put(f'l{l}.{field}_lo', lo).data_ptr())
+            # hi / lo splits of the four [*,256] matrices the small-M path multiplies with FFMA: batches of more than
+            # 512 query rows run them as 3xTF32 tensor-core GEMMs as well
+            for field, mat in (('sa_in_w', sd[p + 'attentions.0.attn.in_proj_weight']),
+                               ('sa_out_w', sd[p + 'attentions.0.attn.out_proj.weight']), ('xa_q_w', xq_w), ('xa_o_w', xo_w)):
+                hi, lo = split_tf32(mat)
+                setattr(lw, field + '_hi', put(f'l{l}.{field}_hi', hi).data_ptr())
+                setattr(lw, field + '_lo', put(f'l{l}.{field}_lo', lo).data_ptr())
             lw.xa_k_raw = put(f'l{l}.xa_k_raw', xk_w).data_ptr()
             lw.xa_v_raw = put(f'l{l}.xa_v_raw', xv_w).data_ptr()
             lw.xa_o_w = put(f'l{l}.xa_o_w', xo_w).data_ptr()
@@ -206,6 +213,10 @@ class PackedWeights:
                 ('reg_w1', bh + 'reg_branches.{}.2.weight'), ('reg_b1', bh + 'reg_branches.{}.2.bias'),
                 ('reg_w2', bh + 'reg_branches.{}.4.weight'), ('reg_b2', bh + 'reg_branches.{}.4.bias')]:
             setattr(b, field, put('br.' + field, stack(fmt)).data_ptr())
+        for field in ('cls_w0', 'cls_w1', 'reg_w0', 'reg_w1'):
+            hi, lo = split_tf32(self.t['br.' + field])
+            setattr(b, field + '_hi', put(f'br.{field}_hi', hi).data_ptr())
+            setattr(b, field + '_lo', put(f'br.{field}_lo', lo).data_ptr())
         b.post_g = put('post_g', sd[bh + 'transformer.decoder.post_norm.weight']).data_ptr()
         b.post_b = put('post_b', sd[bh + 'transformer.decoder.post_norm.bias']).data_ptr()
         self.branches = b
