@@ -138,6 +138,9 @@ typedef struct Mv2dQgParams {
     float* query_pos;      /* out [N,256] */
     float* workspace;
     size_t workspace_bytes;
+    /* ---- ABI 5, all nullable: TF32 hi / lo splits of the five FC matrices.  With them, and more than 512 RoIs
+     * (batches), the FC chain runs as 3xTF32 tcgen05 GEMMs instead of the small-M FFMA kernels. */
+    const float *w_fc_hi, *w_fc_lo, *w_enc0_hi, *w_enc0_lo, *w_enc2_hi, *w_enc2_lo, *w_qe0_hi, *w_qe0_lo, *w_qe2_hi, *w_qe2_lo;
 } Mv2dQgParams;
 MV2D_API size_t mv2d_roi_align_qg_workspace_bytes(int N);
 MV2D_API int mv2d_roi_align_qg(const Mv2dQgParams* p, void* stream);

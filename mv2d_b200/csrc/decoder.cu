@@ -400,6 +400,197 @@ self_attn_kernel(const float* __restrict__ qkv, const uint8_t* __restrict__ mask
 }
 
 // ------------------------------------------------------------------------------------------
+// FlattenMHSelfAttention core, blocked form (petr_transformer.py:314-370).  One CTA = (64 queries, head, sample); the
+// head's keys stream through shared memory in tiles of 160 (K transposed, V row-major) and every staged tile serves all
+// 64 queries (the one-query-per-warp kernel above re-stages the whole K/V slice for every 8 queries).
+//   phase A  S = Q K^T: thread = 4 queries x 10 keys (register tile, 21 LDS per 80 FMA), online softmax statistics by
+//            half-warp shuffles, P^T -> shared memory;
+//   phase B  O += P V: warp = 8 queries, lane = (key phase 0..3, 4 channels), 3 LDS.128 per 32 FMA; the four key phases
+//            are folded by two shuffles at the end.
+// fp32 FFMA throughout (the parity gate rules out single-pass TF32 logits).
+#define SB_KT 160
+#define SB_KP 161          // K^T row stride
+template <int QT> struct SbCfg {
+    static constexpr int PP = QT + 4;                  // P^T row stride (conflict-free float4 stores of consecutive keys)
+    static constexpr int NQG = QT / 4;                 // phase A: groups of 4 queries
+    static constexpr int KL = 256 / NQG;               // lanes (keys) per group: 16 (QT = 64) or 32 (QT = 32)
+    static constexpr int JN = SB_KT / KL;              // keys per thread: 10 or 5
+    static constexpr int QW = QT / 8;                  // phase B: queries per warp: 8 or 4
+    static constexpr int SMEM_FLOATS = 32 * QT + 32 * SB_KP + SB_KT * 32 + SB_KT * PP + 2 * QT;
+    static constexpr int SMEM_BYTES = SMEM_FLOATS * 4;
+};
+
+// QT = 64 queries per CTA for batches; QT = 32 when the 64-query grid would leave most SMs idle (one sample)
+template <int QT>
+__global__ void __launch_bounds__(256, 2)
+self_attn_blk_kernel(const float* __restrict__ qkv, const uint8_t* __restrict__ mask, int N, float* __restrict__ out,
+                     int rows_per_sample, const int* __restrict__ n_real, float* __restrict__ out_lo) {
+    using Cf = SbCfg<QT>;
+    constexpr int PP = Cf::PP, KL = Cf::KL, JN = Cf::JN, QW = Cf::QW;
+    pdl_wait();
+    pdl_trigger();
+    extern __shared__ __align__(16) float sb_smem[];
+    float* Qt = sb_smem;                       // [32][QT]   q * scale, transposed
+    float* Kt = Qt + 32 * QT;                  // [32][161]  keys of the tile, transposed
+    float* Vs = Kt + 32 * SB_KP;               // [160][32]
+    float* Pt = Vs + SB_KT * 32;               // [160][PP]  probabilities, transposed
+    float* alpha_s = Pt + SB_KT * PP;          // [QT] rescale of the running output for this tile
+    float* l_s = alpha_s + QT;                 // [QT] softmax denominators
+    const int t = threadIdx.x, hd = blockIdx.y;
+    int seg0 = 0, nq = N, nk = N;
+    if (rows_per_sample > 0) {
+        const int b = blockIdx.z;
+        seg0 = b * rows_per_sample; nq = rows_per_sample;
+        nk = n_real ? min(n_real[b], rows_per_sample) : rows_per_sample;
+        mask = nullptr;
+    }
+    const int q0 = blockIdx.x * QT;
+    const float* base = qkv + (long long)seg0 * 768 + hd * 32;
+    // ---- Q tile, transposed: consecutive lanes take consecutive queries (conflict-free stores)
+    for (int i = t; i < QT * 8; i += 256) {
+        const int q = i % QT, d4 = i / QT;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (q0 + q < nq) v = __ldcg(reinterpret_cast<const float4*>(base + (long long)(q0 + q) * 768) + d4);
+        Qt[(d4 * 4 + 0) * QT + q] = v.x * 0.17677669529663687f; Qt[(d4 * 4 + 1) * QT + q] = v.y * 0.17677669529663687f;
+        Qt[(d4 * 4 + 2) * QT + q] = v.z * 0.17677669529663687f; Qt[(d4 * 4 + 3) * QT + q] = v.w * 0.17677669529663687f;
+    }
+    const int qg = t / KL, kl = t % KL;                 // phase A: queries 4qg..4qg+3, keys kl + KL j
+    const int warp = t >> 5, lane = t & 31;
+    const int ks = lane >> 3, dl = lane & 7;            // phase B: queries QW warp .. +QW-1, keys ks + 4 i, channels 4dl..4dl+3
+    float m_run[4], l_run[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { m_run[i] = -INFINITY; l_run[i] = 0.f; }
+    float o[QW][4];
+#pragma unroll
+    for (int i = 0; i < QW; ++i)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) o[i][c] = 0.f;
+    for (int k0 = 0; k0 < nk; k0 += SB_KT) {
+        const int ng = min(SB_KT, nk - k0);
+        __syncthreads();                                // previous tile fully consumed (and Qt written, first time)
+        for (int i = t; i < SB_KT * 8; i += 256) {      // K^T: lanes along keys
+            const int key = i % SB_KT, d4 = i / SB_KT;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (key < ng) v = __ldcg(reinterpret_cast<const float4*>(base + (long long)(k0 + key) * 768 + 256) + d4);
+            Kt[(d4 * 4 + 0) * SB_KP + key] = v.x; Kt[(d4 * 4 + 1) * SB_KP + key] = v.y;
+            Kt[(d4 * 4 + 2) * SB_KP + key] = v.z; Kt[(d4 * 4 + 3) * SB_KP + key] = v.w;
+        }
+        for (int i = t; i < SB_KT * 8; i += 256) {      // V: row-major, a quarter warp per 128-byte row
+            const int key = i >> 3, c4 = i & 7;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (key < ng) v = __ldcg(reinterpret_cast<const float4*>(base + (long long)(k0 + key) * 768 + 512) + c4);
+            *reinterpret_cast<float4*>(Vs + key * 32 + c4 * 4) = v;
+        }
+        __syncthreads();
+        // ---- phase A
+        float acc[4][JN];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < JN; ++j) acc[i][j] = 0.f;
+#pragma unroll 4
+        for (int d = 0; d < 32; ++d) {
+            const float4 q4 = *reinterpret_cast<const float4*>(Qt + d * QT + qg * 4);
+            const float* kr = Kt + d * SB_KP + kl;
+#pragma unroll
+            for (int j = 0; j < JN; ++j) {
+                const float kv = kr[KL * j];
+                acc[0][j] = fmaf(q4.x, kv, acc[0][j]); acc[1][j] = fmaf(q4.y, kv, acc[1][j]);
+                acc[2][j] = fmaf(q4.z, kv, acc[2][j]); acc[3][j] = fmaf(q4.w, kv, acc[3][j]);
+            }
+        }
+        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int j = 0; j < JN; ++j) {
+            const int key = kl + KL * j;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int q = q0 + qg * 4 + i;
+                bool off = key >= ng;
+                if (mask && !off && q < nq) off = mask[(long long)q * N + k0 + key] != 0;
+                if (off) acc[i][j] = -INFINITY;
+                mx[i] = fmaxf(mx[i], acc[i][j]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+#pragma unroll
+            for (int ofs = KL / 2; ofs > 0; ofs >>= 1) mx[i] = fmaxf(mx[i], __shfl_xor_sync(0xffffffffu, mx[i], ofs));
+            const float m_new = fmaxf(m_run[i], mx[i]);
+            const float al = (m_run[i] == -INFINITY) ? 0.f : __expf(m_run[i] - m_new);
+            float sm = 0.f;
+#pragma unroll
+            for (int j = 0; j < JN; ++j) {
+                const float pv = (m_new == -INFINITY) ? 0.f : __expf(acc[i][j] - m_new);
+                acc[i][j] = pv;
+                sm += pv;
+            }
+#pragma unroll
+            for (int ofs = KL / 2; ofs > 0; ofs >>= 1) sm += __shfl_xor_sync(0xffffffffu, sm, ofs);
+            l_run[i] = l_run[i] * al + sm;
+            m_run[i] = m_new;
+            if (kl == 0) alpha_s[qg * 4 + i] = al;
+        }
+#pragma unroll
+        for (int j = 0; j < JN; ++j)
+            *reinterpret_cast<float4*>(Pt + (kl + KL * j) * PP + qg * 4) = make_float4(acc[0][j], acc[1][j], acc[2][j], acc[3][j]);
+        __syncthreads();
+        // ---- phase B
+#pragma unroll
+        for (int i = 0; i < QW; ++i) {
+            const float al = alpha_s[warp * QW + i];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) o[i][c] *= al;
+        }
+#pragma unroll 2
+        for (int key = ks; key < ng; key += 4) {
+            const float4 v = *reinterpret_cast<const float4*>(Vs + key * 32 + dl * 4);
+            float pp[QW];
+#pragma unroll
+            for (int i4 = 0; i4 < QW / 4; ++i4) {
+                const float4 p4 = *reinterpret_cast<const float4*>(Pt + key * PP + warp * QW + i4 * 4);
+                pp[i4 * 4] = p4.x; pp[i4 * 4 + 1] = p4.y; pp[i4 * 4 + 2] = p4.z; pp[i4 * 4 + 3] = p4.w;
+            }
+#pragma unroll
+            for (int i = 0; i < QW; ++i) {
+                o[i][0] = fmaf(pp[i], v.x, o[i][0]); o[i][1] = fmaf(pp[i], v.y, o[i][1]);
+                o[i][2] = fmaf(pp[i], v.z, o[i][2]); o[i][3] = fmaf(pp[i], v.w, o[i][3]);
+            }
+        }
+    }
+    if (kl == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) l_s[qg * 4 + i] = l_run[i];
+    }
+    __syncthreads();
+    // fold the 4 key phases (lanes differing in bits 3, 4), normalise, store
+#pragma unroll
+    for (int i = 0; i < QW; ++i)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            o[i][c] += __shfl_xor_sync(0xffffffffu, o[i][c], 8);
+            o[i][c] += __shfl_xor_sync(0xffffffffu, o[i][c], 16);
+        }
+    if (ks == 0) {
+#pragma unroll
+        for (int i = 0; i < QW; ++i) {
+            const int q = q0 + warp * QW + i;
+            if (q >= nq) continue;
+            const float l = l_s[warp * QW + i], inv = l > 0.f ? 1.f / l : 0.f;
+            float4 r = make_float4(o[i][0] * inv, o[i][1] * inv, o[i][2] * inv, o[i][3] * inv);
+            const long long off = (long long)(seg0 + q) * MV2D_C + hd * 32 + dl * 4;
+            if (out_lo) {
+                const float4 hi = make_float4(round_tf32(r.x), round_tf32(r.y), round_tf32(r.z), round_tf32(r.w));
+                *reinterpret_cast<float4*>(out_lo + off) =
+                    make_float4(round_tf32(r.x - hi.x), round_tf32(r.y - hi.y), round_tf32(r.z - hi.z), round_tf32(r.w - hi.w));
+                r = hi;
+            }
+            *reinterpret_cast<float4*>(out + off) = r;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // Sparse multi-view cross-attention core, absorbed form.  One CTA (8 warps) per query.
 //   qt   [N, 8*256]   q~ per head (scale folded in)
 //   keys: mode 0 -> RoI tokens of the matched RoIs (match list); mode 1 -> set bits of keymask
@@ -1176,7 +1367,9 @@ int run_decoder(const Mv2dDecoderParams& p, cudaStream_t st) {
     const bool use_xr = xr_on && p.mode == 0 && !p.persistent && p.max_match <= XR_MAXM;
     // the per-query kernel (and the persistent decoder) address key rows with 16-bit ids
     MV2D_CHECK_ARG(use_xr || xt || p.num_rows <= 65536, "decoder: num_rows=%d must be <= 65536 (16-bit key ids)", p.num_rows);
-    if ((e = cudaFuncSetAttribute(self_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SA_SMEM_BYTES)) != cudaSuccess) {
+    if ((e = cudaFuncSetAttribute(self_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SA_SMEM_BYTES)) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(self_attn_blk_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SbCfg<64>::SMEM_BYTES)) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(self_attn_blk_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SbCfg<32>::SMEM_BYTES)) != cudaSuccess) {
         set_error("decoder: self_attn smem attr %s", cudaGetErrorString(e));
         return (int)e;
     }
@@ -1283,7 +1476,18 @@ int run_decoder(const Mv2dDecoderParams& p, cudaStream_t st) {
                 g.M = N; g.N = 768; g.K = C; g.batch = 1; g.nsplit = 1;
                 if ((rc = launch_gemm_small(g, x, 512, st))) return rc;
             }
-            if (p.batch > 0)
+            static const bool sa_blk = []() { const char* v = getenv("MV2D_SA_BLOCKED"); return !(v && v[0] == '0'); }();
+            if (sa_blk) {
+                const int rows = p.batch > 0 ? p.rows_per_sample : N, nb = p.batch > 0 ? p.batch : 1;
+                const int rps = p.batch > 0 ? p.rows_per_sample : 0;
+                const uint8_t* am = p.batch > 0 ? nullptr : p.self_attn_mask;
+                if (cdiv(rows, 64) * MV2D_HEADS * nb >= 148)
+                    launch_k(self_attn_blk_kernel<64>, dim3(cdiv(rows, 64), MV2D_HEADS, nb), dim3(256), (size_t)SbCfg<64>::SMEM_BYTES, st,
+                             (const float*)qkv, am, N, sa, rps, p.n_real, big ? sa_lo : (float*)nullptr);
+                else
+                    launch_k(self_attn_blk_kernel<32>, dim3(cdiv(rows, 32), MV2D_HEADS, nb), dim3(256), (size_t)SbCfg<32>::SMEM_BYTES, st,
+                             (const float*)qkv, am, N, sa, rps, p.n_real, big ? sa_lo : (float*)nullptr);
+            } else if (p.batch > 0)
                 launch_k(self_attn_kernel, dim3(cdiv(p.rows_per_sample, 8 * SA_QPW), MV2D_HEADS, p.batch), dim3(256), SA_SMEM_BYTES, st,
                          (const float*)qkv, (const uint8_t*)nullptr, N, sa, p.rows_per_sample, p.n_real, big ? sa_lo : (float*)nullptr);
             else

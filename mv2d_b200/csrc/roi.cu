@@ -89,7 +89,7 @@ roi_align_tokens_kernel(const float* __restrict__ rois, const float* __restrict_
 __global__ void box_params_kernel(const float* __restrict__ rois, const double* __restrict__ intrinsics,
                                   const double* __restrict__ extrinsics, int N, float feat_scale,
                                   float* __restrict__ cat /*[N,MV2D_CAT_LD]*/, float* __restrict__ m_roi /*[N,16]*/,
-                                  double* __restrict__ k_out /*nullable [N,16]*/) {
+                                  double* __restrict__ k_out /*nullable [N,16]*/, float* __restrict__ cat_lo /*nullable: cat = TF32 hi part*/) {
     pdl_wait();
     pdl_trigger();
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
@@ -106,7 +106,14 @@ __global__ void box_params_kernel(const float* __restrict__ rois, const double* 
     const bool invalid = (wx < 4.f) || (wy < 4.f);
     for (int i = 0; i < 16; ++i) {
         float f = invalid ? 0.f : (float)K[i] * feat_scale;
-        cat[(long long)n * MV2D_CAT_LD + 1024 + i] = fminf(fmaxf(f, -5e3f), 5e3f);
+        f = fminf(fmaxf(f, -5e3f), 5e3f);
+        if (cat_lo) {
+            const float hi = round_tf32(f);
+            cat_lo[(long long)n * MV2D_CAT_LD + 1024 + i] = round_tf32(f - hi);
+            cat_lo[(long long)n * MV2D_CAT_LD + 1040 + i] = 0.f;
+            f = hi;
+        }
+        cat[(long long)n * MV2D_CAT_LD + 1024 + i] = f;
         cat[(long long)n * MV2D_CAT_LD + 1040 + i] = 0.f;   // zero K-padding (weights are zero-padded too)
         if (k_out) k_out[n * 16 + i] = K[i];
     }
@@ -121,7 +128,7 @@ __global__ void box_params_kernel(const float* __restrict__ rois, const double* 
 }
 
 // AvgPool2d(7) over the ReLU'd conv output: [N,49,256] -> [N,256]
-__global__ void avgpool49_kernel(const float* __restrict__ x, float* __restrict__ out, int N) {
+__global__ void avgpool49_kernel(const float* __restrict__ x, float* __restrict__ out, int N, float* __restrict__ out_lo) {
     pdl_wait();
     pdl_trigger();
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -129,7 +136,9 @@ __global__ void avgpool49_kernel(const float* __restrict__ x, float* __restrict_
     const int n = gid / MV2D_C, c = gid % MV2D_C;
     float s = 0.f;
     for (int t = 0; t < MV2D_TOK; ++t) s += x[((long long)n * MV2D_TOK + t) * MV2D_C + c];
-    out[gid] = s / 49.0f;
+    s = s / 49.0f;
+    if (out_lo) { const float hi = round_tf32(s); out_lo[gid] = round_tf32(s - hi); s = hi; }   // 3xTF32 operand split
+    out[gid] = s;
 }
 
 // fc_center + center2lidar + normalisation + pos2posemb3d  (query_generator.py:333-341,400-403;
@@ -138,7 +147,7 @@ __global__ void qg_tail_kernel(const float* __restrict__ enc, const float* __res
                                const float* __restrict__ b_center, const float* __restrict__ m_roi,
                                const float* __restrict__ dim_t, int N, float pc0, float pc1, float pc2,
                                float pc3, float pc4, float pc5, float* __restrict__ ref,
-                               float* __restrict__ center_lidar, float* __restrict__ posemb) {
+                               float* __restrict__ center_lidar, float* __restrict__ posemb, float* __restrict__ posemb_lo) {
     pdl_wait();
     pdl_trigger();
     const int n = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
@@ -169,7 +178,9 @@ __global__ void qg_tail_kernel(const float* __restrict__ enc, const float* __res
         const int part = idx >> 7, i = idx & 127;
         const float pos = (part == 0 ? p[1] : (part == 1 ? p[0] : p[2])) * 6.283185307179586f;
         const float a = pos / __ldg(dim_t + i);
-        posemb[(long long)n * 384 + idx] = (i & 1) ? cosf(a) : sinf(a);
+        float e = (i & 1) ? cosf(a) : sinf(a);
+        if (posemb_lo) { const float hi = round_tf32(e); posemb_lo[(long long)n * 384 + idx] = round_tf32(e - hi); e = hi; }
+        posemb[(long long)n * 384 + idx] = e;
     }
 }
 
@@ -183,7 +194,9 @@ static int gemm(const float* A, int lda, const float* W, int ldw, const float* b
 
 size_t roi_align_qg_workspace_bytes(int N) {
     size_t n = (size_t)(N > 0 ? N : 1);
-    return n * ((size_t)3 * MV2D_TOK * MV2D_C + MV2D_C + MV2D_CAT_LD + 512 + MV2D_C + 16 + 384 + MV2D_C) * sizeof(float);
+    // + the lo halves of pool, cat, e0, posemb, qh (3xTF32 FC chain of a batch)
+    return n * ((size_t)3 * MV2D_TOK * MV2D_C + MV2D_C + MV2D_CAT_LD + 512 + MV2D_C + 16 + 384 + MV2D_C +
+                MV2D_C + MV2D_CAT_LD + 512 + 384 + MV2D_C) * sizeof(float);
 }
 
 int run_roi_align_qg(const Mv2dQgParams& p, cudaStream_t st) {
@@ -211,13 +224,29 @@ int run_roi_align_qg(const Mv2dQgParams& p, cudaStream_t st) {
     float* mroi = ws;   ws += (size_t)N * 16;
     float* pemb = ws;   ws += (size_t)N * 384;
     float* qh = ws;     ws += (size_t)N * C;
+    float* pool_lo = ws; ws += (size_t)N * C;
+    float* cat_lo = ws;  ws += (size_t)N * MV2D_CAT_LD;
+    float* e0_lo = ws;   ws += (size_t)N * 512;
+    float* pemb_lo = ws; ws += (size_t)N * 384;
+    float* qh_lo = ws;   ws += (size_t)N * C;
     MV2D_CHECK_ARG((size_t)(ws - p.workspace) * sizeof(float) <= p.workspace_bytes, "roi_align_qg: workspace too small");
+    // more than 512 RoIs (a batch): the FC chain is GPU-filling, it runs as 3xTF32 tcgen05 GEMMs on split operands
+    static const bool tc_fc_env = []() { const char* v = getenv("MV2D_QG_TC_FC"); return !(v && v[0] == '0'); }();
+    const bool big = tc_fc_env && N > 512 && p.w_fc_hi && p.w_fc_lo && p.w_enc0_hi && p.w_enc0_lo && p.w_enc2_hi && p.w_enc2_lo &&
+                     p.w_qe0_hi && p.w_qe0_lo && p.w_qe2_hi && p.w_qe2_lo;
+    auto tc3 = [&](const float* a_hi, const float* a_lo, int lda, const float* w_hi, const float* w_lo, int ldw, const float* bias,
+                   float* c, float* c_lo, int ldc, int n_out, int k, int flags) {
+        TcGemm t{};
+        t.A = a_hi; t.A_lo = a_lo; t.lda = lda; t.W = w_hi; t.W_lo = w_lo; t.ldw = ldw; t.bias = bias; t.C = c; t.C_lo = c_lo; t.ldc = ldc;
+        t.M = N; t.N = n_out; t.K = k; t.passes = 3; t.nsplit = 1; t.flags = flags;
+        return launch_gemm_tc(t, st);
+    };
     int rc;
     launch_k(roi_align_tokens_kernel, dim3(MV2D_TOK, N), dim3(64), 0, st, p.rois, p.feat, with_pe ? p.pe : (const float*)nullptr, p.h, p.w,
              1.0f / (float)p.stride, p.tok_feat, with_pe ? p.tok_kin : (float*)nullptr, thi, tlo);
     MV2D_CHECK_LAUNCH("roi_align_tokens");
     launch_k(box_params_kernel, dim3(cdiv(N, 64)), dim3(64), 0, st, p.rois, p.intrinsics, p.extrinsics, N, p.intrins_feat_scale, cat,
-                                                  mroi, p.roi_intrinsics);
+                                                  mroi, p.roi_intrinsics, big ? cat_lo : (float*)nullptr);
     MV2D_CHECK_LAUNCH("box_params");
     // shared conv 3x3 (+ReLU) as implicit GEMM over the tokens, avg-pool, FC chain
     {   // tcgen05 3xTF32, A staged by 4-D TMA boxes straight from the token tensor
@@ -226,18 +255,31 @@ int run_roi_align_qg(const Mv2dQgParams& p, cudaStream_t st) {
         t.C = conv; t.ldc = C; t.M = N * MV2D_TOK; t.N = C; t.K = 9 * C; t.passes = 3; t.im2col = 1; t.flags = GEMM_RELU;
         if ((rc = launch_gemm_tc(t, st))) return rc;
     }
-    launch_k(avgpool49_kernel, dim3(cdiv(N * C, 256)), dim3(256), 0, st, (const float*)conv, pool, N);
+    launch_k(avgpool49_kernel, dim3(cdiv(N * C, 256)), dim3(256), 0, st, (const float*)conv, pool, N, big ? pool_lo : (float*)nullptr);
     MV2D_CHECK_LAUNCH("avgpool49");
-    if ((rc = gemm(pool, C, p.w_fc, C, p.b_fc, cat, MV2D_CAT_LD, N, 1024, C, GEMM_RELU | GEMM_CLAMP5E3, A_PLAIN, st))) return rc;
-    if ((rc = gemm(cat, MV2D_CAT_LD, p.w_enc0, MV2D_CAT_LD, p.b_enc0, e0, 512, N, 512, MV2D_CAT_LD, GEMM_RELU, A_PLAIN, st))) return rc;
-    if ((rc = gemm(e0, 512, p.w_enc2, 512, p.b_enc2, enc, C, N, C, 512, GEMM_RELU, A_PLAIN, st))) return rc;
+    if (big) {
+        if ((rc = tc3(pool, pool_lo, C, p.w_fc_hi, p.w_fc_lo, C, p.b_fc, cat, cat_lo, MV2D_CAT_LD, 1024, C,
+                      GEMM_RELU | GEMM_CLAMP5E3 | GEMM_SPLIT_OUT))) return rc;
+        if ((rc = tc3(cat, cat_lo, MV2D_CAT_LD, p.w_enc0_hi, p.w_enc0_lo, MV2D_CAT_LD, p.b_enc0, e0, e0_lo, 512, 512, MV2D_CAT_LD,
+                      GEMM_RELU | GEMM_SPLIT_OUT))) return rc;
+        if ((rc = tc3(e0, e0_lo, 512, p.w_enc2_hi, p.w_enc2_lo, 512, p.b_enc2, enc, nullptr, C, C, 512, GEMM_RELU))) return rc;
+    } else {
+        if ((rc = gemm(pool, C, p.w_fc, C, p.b_fc, cat, MV2D_CAT_LD, N, 1024, C, GEMM_RELU | GEMM_CLAMP5E3, A_PLAIN, st))) return rc;
+        if ((rc = gemm(cat, MV2D_CAT_LD, p.w_enc0, MV2D_CAT_LD, p.b_enc0, e0, 512, N, 512, MV2D_CAT_LD, GEMM_RELU, A_PLAIN, st))) return rc;
+        if ((rc = gemm(e0, 512, p.w_enc2, 512, p.b_enc2, enc, C, N, C, 512, GEMM_RELU, A_PLAIN, st))) return rc;
+    }
     launch_k(qg_tail_kernel, dim3(cdiv(N, 4)), dim3(128), 0, st, (const float*)enc, p.w_center, p.b_center, mroi, p.dim_t, N, p.pc_range[0],
                                                p.pc_range[1], p.pc_range[2], p.pc_range[3], p.pc_range[4],
-                                               p.pc_range[5], p.ref, p.center_lidar, pemb);
+                                               p.pc_range[5], p.ref, p.center_lidar, pemb, big ? pemb_lo : (float*)nullptr);
     MV2D_CHECK_LAUNCH("qg_tail");
     // query_embedding: 384 -> 256 (ReLU) -> 256
-    if ((rc = gemm(pemb, 384, p.w_qe0, 384, p.b_qe0, qh, C, N, C, 384, GEMM_RELU, A_PLAIN, st))) return rc;
-    if ((rc = gemm(qh, C, p.w_qe2, C, p.b_qe2, p.query_pos, C, N, C, C, 0, A_PLAIN, st))) return rc;
+    if (big) {
+        if ((rc = tc3(pemb, pemb_lo, 384, p.w_qe0_hi, p.w_qe0_lo, 384, p.b_qe0, qh, qh_lo, C, C, 384, GEMM_RELU | GEMM_SPLIT_OUT))) return rc;
+        if ((rc = tc3(qh, qh_lo, C, p.w_qe2_hi, p.w_qe2_lo, C, p.b_qe2, p.query_pos, nullptr, C, C, C, 0))) return rc;
+    } else {
+        if ((rc = gemm(pemb, 384, p.w_qe0, 384, p.b_qe0, qh, C, N, C, 384, GEMM_RELU, A_PLAIN, st))) return rc;
+        if ((rc = gemm(qh, C, p.w_qe2, C, p.b_qe2, p.query_pos, C, N, C, C, 0, A_PLAIN, st))) return rc;
+    }
     return 0;
 }
 

@@ -309,7 +309,8 @@ class HotPath:
         p.pe = pe_nhwc.data_ptr() if (tok_kin is not None and pe_nhwc is not None) else None
         p.dim_t = W.p('dim_t')
         for f in ('w_conv', 'b_conv', 'w_conv_lo', 'w_fc', 'b_fc', 'w_enc0', 'b_enc0', 'w_enc2', 'b_enc2', 'w_center',
-                  'b_center', 'w_qe0', 'b_qe0', 'w_qe2', 'b_qe2'):
+                  'b_center', 'w_qe0', 'b_qe0', 'w_qe2', 'b_qe2', 'w_fc_hi', 'w_fc_lo', 'w_enc0_hi', 'w_enc0_lo', 'w_enc2_hi',
+                  'w_enc2_lo', 'w_qe0_hi', 'w_qe0_lo', 'w_qe2_hi', 'w_qe2_lo'):
             setattr(p, f, W.p(f))
         p.tok_feat = tok_feat.data_ptr()
         p.tok_kin = tok_kin.data_ptr() if tok_kin is not None else None

@@ -43,6 +43,8 @@ class QgParams(C.Structure):
         ('w_qe2', c_f), ('b_qe2', c_f),
         ('tok_feat', c_f), ('tok_kin', c_f), ('roi_intrinsics', c_f), ('center_lidar', c_f),
         ('ref', c_f), ('query_pos', c_f), ('workspace', c_f), ('workspace_bytes', C.c_size_t),
+        ('w_fc_hi', c_f), ('w_fc_lo', c_f), ('w_enc0_hi', c_f), ('w_enc0_lo', c_f), ('w_enc2_hi', c_f), ('w_enc2_lo', c_f),
+        ('w_qe0_hi', c_f), ('w_qe0_lo', c_f), ('w_qe2_hi', c_f), ('w_qe2_lo', c_f),
     ]
 
 

@@ -150,6 +150,10 @@ class PackedWeights:
         put('w_qe0', sd[bh + 'query_embedding.0.weight']); put('b_qe0', sd[bh + 'query_embedding.0.bias'])
         put('w_qe2', sd[bh + 'query_embedding.2.weight']); put('b_qe2', sd[bh + 'query_embedding.2.bias'])
 
+        for name in ('w_fc', 'w_enc0', 'w_enc2', 'w_qe0', 'w_qe2'):     # 3xTF32 operands of the FC chain for batches
+            hi, lo = split_tf32(self.t[name])
+            put(name + '_hi', hi); put(name + '_lo', lo)
+
         self.layers = (lib.LayerWeights * num_layers)()
         for l in range(num_layers):
             p = f'{bh}transformer.decoder.layers.{l}.'
