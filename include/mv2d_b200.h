@@ -101,7 +101,9 @@ typedef struct Mv2dPeParams {
                                 * adapt_pos3d(sine) is the same tensor for every sample: it is evaluated once, for the
                                 * first views_per_sample views, and shared (a common subexpression, not a cache: it is
                                 * recomputed on every call) */
-    int reserved3;
+    int unfused_mlp;           /* 1 = one GEMM per MLP layer (the 1024-wide hidden activations round-trip through HBM);
+                                * 0 = the fused two-layer kernel (csrc/mlp2.cu): hidden activations stay in TMEM / shared
+                                * memory.  Both are single-pass TF32; kept selectable for A/B tests. */
 } Mv2dPeParams;
 MV2D_API size_t mv2d_pe3d_workspace_bytes(int V, int h, int w, int depth_num);
 MV2D_API int mv2d_pe3d(const Mv2dPeParams* p, void* stream);

@@ -4,6 +4,7 @@
 #include "common.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
+#include "mlp2.cuh"
 #include "mv2d_internal.h"
 
 namespace mv2d {
@@ -205,6 +206,48 @@ __global__ void __launch_bounds__(256) sine_hidden_kernel(const float* __restric
     reinterpret_cast<float4*>(Hd)[gid] = o;
 }
 
+// ---- separable sine branch on the fused MLP kernel (mlp2.cu): the gather-add of the three table rows becomes the FIRST
+// GEMM of the fused kernel.  A = [onehot | onehot] (a one in column v, vps + y and vps + h + x of each half), W0 = the
+// transposed tables split into TF32 hi / lo halves: A . W0^T = Tv[v] + Ty[y] + Tx[x] with every product exact and fp32
+// accumulation, i.e. fp32-grade like the gather kernel.  KH = table rows rounded up to 32, K0 = 2 KH.
+__global__ void __launch_bounds__(256) sine_onehot_kernel(float* __restrict__ A, int Ps, int h, int w, int vps, int KH) {
+    pdl_wait();
+    pdl_trigger();
+    const int k4n = KH >> 1;                                    // float4s per row (K0 / 4)
+    const long long gid = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (gid >= (long long)Ps * k4n) return;
+    const int k0 = (int)(gid % k4n) * 4;
+    const long long p = gid / k4n;
+    const int x = (int)(p % w), y = (int)((p / w) % h), v = (int)(p / ((long long)w * h)) % vps;
+    const int kk = k0 >= KH ? k0 - KH : k0;                     // column inside the half
+    float o[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int c = kk + i;
+        o[i] = (c == v || c == vps + y || c == vps + h + x) ? 1.f : 0.f;
+    }
+    reinterpret_cast<float4*>(A)[gid] = make_float4(o[0], o[1], o[2], o[3]);
+}
+
+// W0s[j][r] = tf32_hi(T[r][j]), W0s[j][KH + r] = tf32_lo(T[r][j]), zero for r >= rows.  grid (1024 / 32, KH / 32), block (32, 8)
+__global__ void sine_w0_kernel(const float* __restrict__ T, float* __restrict__ W0s, int rows, int KH) {
+    pdl_wait();
+    pdl_trigger();
+    __shared__ float tile[32][33];
+    const int j0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += 8) {
+        const int r = r0 + i;
+        tile[i][threadIdx.x] = r < rows ? T[(long long)r * 1024 + j0 + threadIdx.x] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += 8) {
+        const float val = tile[threadIdx.x][i], hi = round_tf32(val);
+        float* o = W0s + (long long)(j0 + i) * (2 * KH) + r0 + threadIdx.x;
+        o[0] = hi;
+        o[KH] = round_tf32(val - hi);
+    }
+}
+
 static int gemm(const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc,
                 int M, int N, int K, int flags, cudaStream_t st, const float* gx = nullptr,
                 const float* gs = nullptr, const float* gfeat = nullptr, float* kin = nullptr, int gs_mod = 0) {
@@ -263,10 +306,21 @@ int run_pe3d(const Mv2dPeParams& p, cudaStream_t st) {
             p.position_range[4], p.position_range[5], 1);
         MV2D_CHECK_LAUNCH("pe_coords");
     }
+    // Fused MLPs (mlp2.cu): the 1024-wide hidden activations of the two branches and the SE gate's hidden stay in
+    // TMEM / shared memory.  MV2D_PE_FUSED=0 keeps one tcgen05 GEMM per layer (hidden round trip through HBM).
+    static const bool fused_env = []() { const char* v = getenv("MV2D_PE_FUSED"); return !(v && v[0] == '0'); }();
+    const bool fused = fused_env && !p.unfused_mlp && (3 * D) % 32 == 0;
     // position_encoder: 192 -> 1024 -> 256
     if (p.phase != 2) {
+        if (fused) {
+            Mlp2 m{};
+            m.A = A1; m.lda = 3 * D; m.W0 = p.w_pos0; m.b0 = p.b_pos0; m.W2 = p.w_pos2; m.b2 = p.b_pos2; m.out = X;
+            m.M = P; m.K0 = 3 * D; m.H = 4 * C;
+            if ((rc = launch_mlp2(m, st))) return rc;
+        } else {
     if ((rc = gemm(A1, 3 * D, p.w_pos0, 3 * D, p.b_pos0, Hd, 4 * C, P, 4 * C, 3 * D, GEMM_RELU | GEMM_TF32_OK | GEMM_ROUND_TF32, st))) return rc;
     if ((rc = gemm(Hd, 4 * C, p.w_pos2, 4 * C, p.b_pos2, X, C, P, C, 4 * C, GEMM_TF32_OK, st))) return rc;
+        }
     }
     // sine branch: 384 -> 1024 -> 256  (input-independent given masks + weights; recomputed here)
     if (p.phase == 2) {
@@ -280,9 +334,26 @@ int run_pe3d(const Mv2dPeParams& p, cudaStream_t st) {
         launch_k(sine_axis_kernel, dim3(rows), dim3(128), 0, st, p.dim_t, Fm, vps, p.h, p.w, (float)p.stride, 6.283185307179586f, 1e-6f);
         MV2D_CHECK_LAUNCH("sine_axis");
         if ((rc = gemm(Fm, 384, p.w_adapt0, 384, nullptr, Tm, 4 * C, rows, 4 * C, 384, 0, st))) return rc;     // fp32 FFMA
+        const int KH = (rows + 31) / 32 * 32;
+        // measured on B200 (profiles/r02_pe_fused.md): as a one-hot first GEMM the gather costs as much L2 -> SM traffic as a
+        // real layer (47 us for V = 6 against 25 + 25 for gather kernel + GEMM), so it is opt-in: MV2D_PE_FUSED_SINE=1
+        static const bool fused_sine = []() { const char* v = getenv("MV2D_PE_FUSED_SINE"); return v && v[0] == '1'; }();
+        if (fused && fused_sine && (size_t)Ps * 2 * KH + (size_t)1024 * 2 * KH <= (size_t)P * 4 * C) {
+            float* Aoh = Hd;                                 // [Ps, 2 KH] one-hot rows
+            float* W0s = Hd + (size_t)Ps * 2 * KH;           // [1024, 2 KH] transposed tables, hi | lo
+            launch_k(sine_w0_kernel, dim3(1024 / 32, KH / 32), dim3(32, 8), 0, st, (const float*)Tm, W0s, rows, KH);
+            MV2D_CHECK_LAUNCH("sine_w0");
+            launch_k(sine_onehot_kernel, dim3((unsigned)(((long long)Ps * (KH >> 1) + 255) / 256)), dim3(256), 0, st, Aoh, Ps, p.h, p.w, vps, KH);
+            MV2D_CHECK_LAUNCH("sine_onehot");
+            Mlp2 m{};
+            m.A = Aoh; m.lda = 2 * KH; m.W0 = W0s; m.b0 = p.b_adapt0; m.W2 = p.w_adapt2; m.b2 = p.b_adapt2; m.out = SB;
+            m.M = Ps; m.K0 = 2 * KH; m.H = 4 * C;
+            if ((rc = launch_mlp2(m, st))) return rc;
+        } else {
         launch_k(sine_hidden_kernel, dim3((unsigned)(((long long)Ps * 256 + 255) / 256)), dim3(256), 0, st, (const float*)Tm, p.b_adapt0, Hd, Vs, p.h, p.w, vps);
         MV2D_CHECK_LAUNCH("sine_hidden");
         if ((rc = gemm(Hd, 4 * C, p.w_adapt2, 4 * C, p.b_adapt2, SB, C, Ps, C, 4 * C, GEMM_TF32_OK, st))) return rc;
+        }
     } else if (!p.sine_branch_cached) {
         launch_k(sine_prep_kernel, dim3(cdiv(Ps, 128)), dim3(128), 0, st, p.not_mask, EM, Vs, p.h, p.w, (float)p.stride,
                                                       6.283185307179586f, 1e-6f, vps);
@@ -296,10 +367,18 @@ int run_pe3d(const Mv2dPeParams& p, cudaStream_t st) {
     }
     if (p.phase == 1) return 0;   // everything that does not read the image feature is done
     // SE gate on the image feature, fused combine: pe = X * sigmoid(gate) + SB ; kin = pe + feat
+    if (fused && (!p.sine_shared || Ps % 128 == 0)) {
+        Mlp2 m{};
+        m.A = p.feat_tf32 ? p.feat_tf32 : p.feat; m.lda = C; m.W0 = p.w_se_reduce; m.b0 = p.b_se_reduce;
+        m.W2 = p.w_se_expand; m.b2 = p.b_se_expand; m.out = p.pe; m.M = P; m.K0 = C; m.H = C;
+        m.gate = 1; m.gx = X; m.gs = SB; m.gs_mod = p.sine_shared ? Ps : 0; m.gfeat = p.feat; m.kin = p.kin;
+        if ((rc = launch_mlp2(m, st))) return rc;
+    } else {
     if ((rc = gemm(p.feat_tf32 ? p.feat_tf32 : p.feat, C, p.w_se_reduce, C, p.b_se_reduce, G1, C, P, C, C,
                    GEMM_RELU | GEMM_TF32_OK | GEMM_ROUND_TF32, st))) return rc;
     if ((rc = gemm(G1, C, p.w_se_expand, C, p.b_se_expand, p.pe, C, P, C, C, GEMM_GATE | GEMM_TF32_OK, st, X, SB,
                    p.feat, p.kin, p.sine_shared ? Ps : 0))) return rc;
+    }
     if (p.sine_branch_out && !p.sine_branch_cached) {
         cudaError_t e = cudaMemcpyAsync(p.sine_branch_out, SB, (size_t)P * C * sizeof(float),
                                         cudaMemcpyDeviceToDevice, st);

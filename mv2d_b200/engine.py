@@ -270,6 +270,7 @@ class HotPath:
             img_metas = batch['metas'][0]
         p.pad_h, p.pad_w = int(img_metas[0]['pad_shape'][0]), int(img_metas[0]['pad_shape'][1])
         p.stride = c['stride']
+        p.unfused_mlp = int(getattr(self, 'pe_unfused', False))
         p.depth_start = c['depth_start']
         p.position_range = (C.c_double * 6)(*c['position_range'])
         p.feat_tf32 = feat_tf32.data_ptr() if feat_tf32 is not None else None

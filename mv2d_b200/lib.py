@@ -26,7 +26,7 @@ class PeParams(C.Structure):
         ('w_se_reduce', c_f), ('b_se_reduce', c_f), ('w_se_expand', c_f), ('b_se_expand', c_f),
         ('sine_branch_cached', c_f), ('sine_branch_out', c_f),
         ('pe', c_f), ('kin', c_f), ('workspace', c_f), ('workspace_bytes', C.c_size_t),
-        ('sine_separable', C.c_int), ('views_per_sample', C.c_int), ('sine_shared', C.c_int), ('reserved3', C.c_int),
+        ('sine_separable', C.c_int), ('views_per_sample', C.c_int), ('sine_shared', C.c_int), ('unfused_mlp', C.c_int),
     ]
 
 

@@ -410,3 +410,26 @@ def test_two_frame_kv_projection_skips_unused_row_tiles(state_dicts):
         seg = rows_nan[t * 128:(t + 1) * 128]
         assert seg.all() if live[t] == 0 else not seg.any()
     assert_close(out['cls_scores'], g['cls_scores'], what='cls_scores')
+
+
+@pytest.mark.parametrize('name', ['s_cfg2', 's_pad', 't_small'])
+def test_fused_pe_mlps_match_the_layer_by_layer_gemms(name, state_dicts):
+    """csrc/mlp2.cu (hidden activations in TMEM / shared memory, the sine branch's gather as a one-hot GEMM) against one
+    tcgen05 GEMM per layer: both single-pass TF32, so they agree far inside the PE stage tolerance; 12 views exercise the
+    wider one-hot operand (132 table rows), the padded case the general sine branch beside the fused position MLP."""
+    spec, g = load_golden(name)
+    eng = engine(spec['mode'], spec['num_layers'], state_dicts)
+    feat, boxes, metas = synth.case_inputs(spec)
+    outs = []
+    for unfused in (False, True):
+        eng.pe_unfused = unfused
+        try:
+            o = eng.forward(feat.cuda(), boxes, metas)
+            outs.append((o['pe'].clone(), o['cls_scores'].clone(), o['bbox_preds'].clone()))
+        finally:
+            eng.pe_unfused = False
+    assert_close(outs[0][0], outs[1][0], 1e-3, 1e-3, "pe fused vs unfused")   # a ReLU / TF32 rounding flip moves single entries by ~2e-4
+    pe = outs[0][0].permute(0, 3, 1, 2).contiguous()
+    assert_close(pe.flatten()[::PE_SUB], g['pe_sub'], 3e-3, 1e-3, 'pe')
+    assert_close(outs[0][1], g['cls_scores'], what='cls_scores')
+    assert_close(outs[0][2], g['bbox_preds'], what='bbox_preds')
