@@ -9,15 +9,17 @@ Workload (BASELINE.json configs[1]): MV2D-S, R50 single frame 1408x512, 6 camera
 path -- (FPN P4 feature [6,256,32,88], per-view 2D boxes, img_metas) -> (cls_scores,
 bbox_preds) of all 6 layers -- over one sample.  Metric: samples/sec, whole job.
 
-  value  : whole-job throughput, inputs already resident in HBM.  Each step = one CUDA-graph replay of the
-           whole path for ONE sample (bs = 1); mv2d_b200.pipeline.Pipeline keeps --depth (default 4) samples in
-           flight on independent lanes, so the GPU-filling front end of sample i+1 runs under the latency-bound
-           decoder of sample i.  The K steps are bracketed by one pair of CUDA events (+ barrier and
-           synchronize on both sides); 8 distinct samples rotate (138 MB of feature maps > the 126 MB L2).
+  value  : whole-job throughput in samples/s, inputs already resident in HBM.  A step = one pass of the hot path over
+           one BATCH of --batch (default 8) samples: one CUDA-graph replay of ONE kernel chain in which the batch is a
+           segment dimension (HotPath.forward_batch; every sample's result is the one it gets at bs = 1, checked by
+           tests/test_gpu_batch.py against the per-sample goldens).  mv2d_b200.pipeline.Pipeline keeps --depth
+           (default 3) batches in flight on independent lanes.  The K steps are bracketed by one pair of CUDA events
+           (+ barrier and synchronize on both sides); 2 x batch distinct samples rotate (277 MB of feature maps at
+           batch 8 > the 126 MB L2).
   e2e    : the same through the public API with HOST (pinned) buffers: H2D of the feature map, boxes and
            camera matrices, the path, D2H of cls_scores/bbox_preds -- all inside the timed region.
-  serial : (extra object) one sample at a time, nothing else in flight, L2 flushed (256 MB memset) before every
-           step, each step timed with its own pair of CUDA events: the per-sample latency view of both numbers.
+  serial : (extra object) bs = 1, one sample at a time, nothing else in flight, L2 flushed (256 MB memset) before
+           every step, each step timed with its own pair of CUDA events: the per-sample latency view of both numbers.
   N > 1  : one process per GPU, independent replicas on different samples (the decoder is
            per-sample: no data-path collective); NCCL only for the barrier and the max-over-ranks.
   --impl reference : the CPU restatement of the reference (oracle/, kind "port": the reference's
@@ -49,8 +51,14 @@ def parse():
     ap.add_argument('--mode', default='S', choices=['S', 'T'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-train', action='store_true', help='skip the extra training-step section')
-    ap.add_argument('--depth', type=int, default=4, help='samples in flight (inter-sample pipelining); 1 = serial')
-    return ap.parse_args()
+    ap.add_argument('--batch', type=int, default=None, help='samples per step (a segment dimension through one kernel chain); default 8 (S) / 2 (T)')
+    ap.add_argument('--depth', type=int, default=3, help='batches in flight (pipelining on independent lanes); 1 = one batch at a time')
+    ap.add_argument('--no-two-frame', action='store_true', help='skip the extra MV2D-T (BASELINE configs[2]) section')
+    ap.add_argument('--no-gpu-torch-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.batch is None:
+        args.batch = 8 if args.mode == 'S' else 2
+    return args
 
 
 def measured_peaks():
@@ -102,6 +110,11 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- workload
+def workload_name(mode):
+    return (f'MV2D-{mode} R50 1408x512 V={6 if mode == "S" else 12} N=300 L=6 '
+            f'(BASELINE configs[{1 if mode == "S" else 2}])')
+
+
 def make_inputs(mode, seed):
     from mv2d_b200 import synth
     case = dict(synth.CASES['s_cfg2' if mode == 'S' else 't_cfg3'], seed=seed)
@@ -131,7 +144,7 @@ def run_reference(args, rank):
     sd = synth.make_state_dict(0)
     fn = O.mv2d_s_forward if args.mode == 'S' else O.mv2d_t_forward
     cfg = O.make_cfg(args.mode)
-    steps, warm = min(args.steps, 8), min(args.warmup, 1)
+    steps, warm = max(args.steps, 1), max(args.warmup, 0)     # ~0.45 s per S sample on 16 cores: 50 + 5 steps take ~25 s
     times = []
     with torch.no_grad():
         for i in range(warm + steps):
@@ -147,8 +160,8 @@ def run_reference(args, rank):
     line = dict(metric=METRIC if args.mode == 'S' else METRIC_T, value=val, unit=UNIT, n_gpus=args.gpus, steps=steps, warmup=warm, ms_per_step=ms,
                 higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
                 impl='reference',
-                config=dict(workload=f'MV2D-{args.mode} R50 1408x512 V={6 if args.mode == "S" else 12} N=300 L=6 bs=1',
-                            arm='CPU restatement of the reference (oracle/mv2d_oracle.py)'),
+                config=dict(workload=workload_name(args.mode),
+                            arm='CPU restatement of the reference (oracle/mv2d_oracle.py), one sample per step (the reference asserts bs = 1)'),
                 cpu_baseline=dict(value=val, unit=UNIT, cores=cores, kind='port', sample=sample),
                 e2e=dict(value=val, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
     print(json.dumps(line))
@@ -178,16 +191,22 @@ def main():
     peaks = measured_peaks()
 
     mode = args.mode
+    B = max(args.batch, 1)
     sd = synth.make_state_dict(0)
     from mv2d_b200.pipeline import Pipeline
     pipe = Pipeline(sd, mode=mode, device=dev, depth=max(args.depth, 1))
     eng = pipe.lanes[0]
-    # distinct samples per rank (different seeds per rank: replicas work on different data); 8 feature maps
-    # of the S head are 138 MB > the 126 MB L2
-    n_var = 8
+    # distinct samples per rank (different seeds per rank: replicas work on different data): 2 x B samples = two
+    # batches whose feature maps (2 x B x 17.3 MB) exceed the 126 MB L2 for B >= 4
+    n_var = max(2 * B, 8)
     samples = [make_inputs(mode, seed=i) for i in D.shard_samples(n_var * world, rank, world)]
     feats_dev = [s[0].to(dev) for s in samples]
     feats_pin = [s[0].pin_memory() for s in samples]
+    n_batches = n_var // B
+    batches_dev = [torch.stack([feats_dev[k * B + j] for j in range(B)], 0) for k in range(n_batches)]
+    batches_pin = [torch.stack([samples[k * B + j][0] for j in range(B)], 0).pin_memory() for k in range(n_batches)]
+    batch_boxes = [[samples[k * B + j][1] for j in range(B)] for k in range(n_batches)]
+    batch_metas = [[samples[k * B + j][2] for j in range(B)] for k in range(n_batches)]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
     def barrier():
@@ -231,23 +250,28 @@ def main():
         ms = [a.elapsed_time(b) for a, b in evs]
         return sum(ms), ms, eng.launch_count() - launches0, wall
 
-    def timed_pipe(host, steps, warmup):
-        """K samples through the pipeline, ONE pair of events around all of them (device time, launching stream)."""
-        src = feats_pin if host else feats_dev
-        for i in range(warmup + 2 * pipe.depth):
-            pipe.submit(src[i % n_var], samples[i % n_var][1], samples[i % n_var][2], to_host=host)
-        pipe.join()
+    def submit(pp, host, i, nb=n_batches, bd=batches_dev, bp=batches_pin, bb=batch_boxes, bm=batch_metas):
+        k = i % nb
+        if bd[k].shape[0] == 1:
+            return pp.submit((bp if host else bd)[k][0], bb[k][0], bm[k][0], to_host=host)
+        return pp.submit_batch((bp if host else bd)[k], bb[k], bm[k], to_host=host)
+
+    def timed_pipe(host, steps, warmup, pp=pipe, sub=submit):
+        """K steps (batches) through the pipeline, ONE pair of events around all of them (device time, launching stream)."""
+        for i in range(warmup + 2 * pp.depth):
+            sub(pp, host, i)
+        pp.join()
         barrier()
-        launches0 = pipe.launch_count()
+        launches0 = pp.launch_count()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t_wall = time.perf_counter()
         a.record()
         for i in range(steps):
-            pipe.submit(src[i % n_var], samples[i % n_var][1], samples[i % n_var][2], to_host=host)
-        pipe.join()
+            sub(pp, host, i)
+        pp.join()
         b.record()
         barrier()
-        return a.elapsed_time(b), pipe.launch_count() - launches0, time.perf_counter() - t_wall
+        return a.elapsed_time(b), pp.launch_count() - launches0, time.perf_counter() - t_wall
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -258,6 +282,13 @@ def main():
     total_ms, launches, wall = timed_pipe(False, args.steps, W)
     e2e_total_ms, _, _ = timed_pipe(True, args.steps, W)
     clocks = sampler.stop() if rank == 0 else None
+
+    two_frame = None
+    if mode == 'S' and not args.no_two_frame:
+        try:
+            two_frame = two_frame_section(sd, dev, world, rank, barrier, max(min(args.steps, 20), 4), W)
+        except Exception as e:
+            two_frame = dict(error=f'{type(e).__name__}: {e}'[:400])
 
     train = None
     if mode == 'S' and not args.no_train:
@@ -270,13 +301,18 @@ def main():
     total_ms, e2e_total_ms, ser_total_ms, ser_e2e_total_ms = D.max_over_ranks(
         [total_ms, e2e_total_ms, ser_total_ms, ser_e2e_total_ms], device=dev)
     ms_per_step = total_ms / args.steps
-    value = D.aggregate_throughput(world, args.steps, 1, total_ms)
-    e2e_value = D.aggregate_throughput(world, args.steps, 1, e2e_total_ms)
+    value = D.aggregate_throughput(world, args.steps, B, total_ms)
+    e2e_value = D.aggregate_throughput(world, args.steps, B, e2e_total_ms)
     serial = dict(value=D.aggregate_throughput(world, args.steps, 1, ser_total_ms), unit=UNIT,
                   ms_per_step=ser_total_ms / args.steps, ms_min=min(per_step), ms_median=statistics.median(per_step),
                   e2e_value=D.aggregate_throughput(world, args.steps, 1, ser_e2e_total_ms),
                   e2e_ms_per_step=ser_e2e_total_ms / args.steps,
-                  note='one sample at a time, L2 flushed (256 MB memset) before every step, per-step CUDA events')
+                  note='bs = 1: one sample at a time, L2 flushed (256 MB memset) before every step, per-step CUDA events')
+    if two_frame is not None and 'total_ms' in two_frame:
+        t_ms, t_e2e_ms = D.max_over_ranks([two_frame.pop('total_ms'), two_frame.pop('e2e_total_ms')], device=dev)
+        two_frame['value'] = D.aggregate_throughput(world, two_frame['steps'], two_frame['batch'], t_ms)
+        two_frame['e2e_value'] = D.aggregate_throughput(world, two_frame['steps'], two_frame['batch'], t_e2e_ms)
+        two_frame['ms_per_step'] = t_ms / two_frame['steps']
 
     if rank != 0:
         if world > 1:
@@ -285,40 +321,87 @@ def main():
 
     # ---- roofline of the attention path (the north star's named roofline) and of the dominant kernel:
     # the kernels are re-issued alone, L2 flushed, CUDA events on the launching stream.
-    out = step_resident(0)
-    torch.cuda.synchronize()
-    N = out['N']
-    out['_inputs'] = (feats_dev[0], samples[0][1], samples[0][2])
-    out['_metas'] = samples[0][2]
-    roof = roofline_section(eng, out, mode, N, flush, peaks)
+    roof = roofline_section(eng, (batches_dev[0], batch_boxes[0], batch_metas[0]), mode, flush, peaks)
+    N = roof.pop('N')
 
     feat, boxes, metas = samples[0]
-    h2d = feat.numel() * 4 + N * 5 * 4 + (len(metas) + 1) * 4 + 3 * len(metas) * 16 * 8
-    d2h = 2 * eng.L * N * 10 * 4
+    h2d = B * (feat.numel() * 4 + N * 5 * 4 + (len(metas) + 1) * 4 + 3 * len(metas) * 16 * 8)
+    d2h = B * 2 * eng.L * N * 10 * 4
     line = dict(
         metric=METRIC if mode == 'S' else METRIC_T, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
         ms_per_step=ms_per_step, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32',
         data='synthetic',
-        config=dict(workload=f'MV2D-{mode} R50 1408x512 V={len(metas)} N={N} L={eng.L} bs=1 per GPU (BASELINE configs[{1 if mode == "S" else 2}])',
-                    precision='fp32 storage; single-pass TF32 tcgen05 in the PE MLPs, 3xTF32 tcgen05 in the QG conv and the four wide decoder GEMMs, fp32 FFMA elsewhere, fp64 geometry',
-                    schedule=f'{pipe.depth} samples in flight per GPU (inter-sample pipelining on independent lanes, '
-                             'each sample processed at bs=1; mv2d_b200/pipeline.py); "serial" holds the one-at-a-time numbers',
+        config=dict(workload=workload_name(mode), batch=B, samples_per_step=B,
+                    batching=f'{B} samples per step per GPU travel through ONE kernel chain as a segment dimension (the reference asserts '
+                             'bs = 1: detectors/mv2d.py:143); every sample gets the result it gets alone (tests/test_gpu_batch.py); '
+                             '"serial" holds the bs = 1 one-at-a-time numbers',
+                    precision='fp32 storage; single-pass TF32 tcgen05 in the PE MLPs, 3xTF32 tcgen05 in the QG conv, the QG FC chain and every '
+                              'decoder GEMM (fp32 FFMA for those below 512 rows), fp32 FFMA attention, fp64 geometry',
+                    schedule=f'{pipe.depth} batches in flight per GPU (independent lanes, mv2d_b200/pipeline.py)',
                     l2=f'{n_var} distinct samples rotate: {n_var * samples[0][0].numel() * 4 / 1e6:.0f} MB of feature maps > 126 MB L2 '
                        '(weights stay L2-resident, as in serving); the serial numbers flush L2 before every step',
                     timing='one pair of CUDA events on the launching stream around the K steps, barrier + synchronize on both sides, max over ranks',
                     launch='one CUDA-graph replay of the whole path per step',
-                    sine_branch='recomputed every step (not cached)', wall_s=wall),
+                    sine_branch='recomputed every step (not cached); inside a step it is evaluated once for the whole batch when all samples '
+                                'share the padding masks (a common subexpression: it does not depend on the inputs)', wall_s=wall),
         e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                  ms_per_step=e2e_total_ms / args.steps),
-        gpu_launches=launches, clocks=clocks, roofline=roof['roofline'], attention_roofline=roof['attention'],
-        stage_us=roof['stage_us'], peaks=peaks, serial=serial)
+        gpu_launches=launches, launches_per_sample=launches / (args.steps * B), clocks=clocks, roofline=roof['roofline'],
+        attention_roofline=roof['attention'], stage_us=roof['stage_us'], peaks=peaks, serial=serial)
+    if two_frame is not None:
+        line['two_frame'] = two_frame
     if train is not None:
         line['train_step'] = train
+    if not args.no_gpu_torch_baseline and world == 1 and mode == 'S':
+        try:
+            from oracle import gpu_baseline as GB
+            line['gpu_torch_baseline'] = GB.time_s(sd, samples[:4], dev, warmup=5, iters=10)
+        except Exception as e:
+            line['gpu_torch_baseline'] = dict(error=f'{type(e).__name__}: {e}'[:400])
     if not args.no_cpu_baseline and world == 1:
         line['cpu_baseline'] = cpu_baseline(mode)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def two_frame_section(sd, dev, world, rank, barrier, steps, warmup, batch=2, depth=2):
+    """Extra object `two_frame` -- BASELINE configs[2]: MV2D-T, 12 feature views, 300 queries, bs = 2 as a real batch (both
+    samples in one kernel chain), `depth` batches in flight.  Same timing protocol as the headline."""
+    import torch
+    from mv2d_b200 import dist as D
+    from mv2d_b200.pipeline import Pipeline
+    pp = Pipeline(sd, mode='T', device=dev, depth=depth)
+    n_var = 4 * batch
+    smp = [make_inputs('T', seed=i) for i in D.shard_samples(n_var * world, rank, world)]
+    nb = n_var // batch
+    bd = [torch.stack([smp[k * batch + j][0] for j in range(batch)], 0).to(dev) for k in range(nb)]
+    bp = [torch.stack([smp[k * batch + j][0] for j in range(batch)], 0).pin_memory() for k in range(nb)]
+    bb = [[smp[k * batch + j][1] for j in range(batch)] for k in range(nb)]
+    bm = [[smp[k * batch + j][2] for j in range(batch)] for k in range(nb)]
+    res = {}
+    for host in (False, True):
+        for i in range(warmup + 2 * depth):
+            pp.submit_batch((bp if host else bd)[i % nb], bb[i % nb], bm[i % nb], to_host=host)
+        pp.join()
+        barrier()
+        l0 = pp.launch_count()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(steps):
+            pp.submit_batch((bp if host else bd)[i % nb], bb[i % nb], bm[i % nb], to_host=host)
+        pp.join()
+        b.record()
+        barrier()
+        res['e2e_total_ms' if host else 'total_ms'] = a.elapsed_time(b)
+        if not host:
+            res['gpu_launches'] = pp.launch_count() - l0
+    res.update(metric=METRIC_T, unit=UNIT, workload=workload_name('T'), batch=batch, depth=depth, steps=steps, warmup=warmup,
+               l2=f'{n_var} distinct samples rotate: {n_var * smp[0][0].numel() * 4 / 1e6:.0f} MB of feature maps > 126 MB L2',
+               note='bs = 2 in one kernel chain; K/V projections of all cells by 3xTF32 tcgen05, key-stationary cross-attention (csrc/xa_tile.cuh)')
+    del pp
+    torch.cuda.empty_cache()
+    return res
 
 
 def train_step_section(sd, dev, samples, world, barrier, per_rank=2, steps=8, warmup=3):
@@ -380,13 +463,16 @@ def train_step_section(sd, dev, samples, world, barrier, per_rank=2, steps=8, wa
                 collective='one NCCL sum all-reduce of the flat gradient buffer per step' if world > 1 else 'none (1 GPU)')
 
 
-def roofline_section(eng, out, mode, N, flush, peaks):
-    """Dominant kernel re-issued alone (L2 flushed, CUDA events on the launching stream), the
-    attention path's HBM roofline, and the device time of each stage."""
+def roofline_section(eng, batch_in, mode, flush, peaks):
+    """Dominant kernel re-issued alone (L2 flushed, CUDA events on the launching stream), the attention path's HBM
+    roofline (a whole decoder layer AND the sparse cross-attention core alone), and the device time of each stage --
+    all on one batch of the headline workload (eager launches of the stage entries)."""
     import numpy as np
     import torch
     from mv2d_b200 import lib as L
     h, W = eng.lib, eng.w
+    feats, boxes_l, metas_l = batch_in
+    B, V, _, hh, ww = feats.shape
 
     def time_fn(fn, reps=20):
         for _ in range(3):
@@ -400,7 +486,13 @@ def roofline_section(eng, out, mode, N, flush, peaks):
             ts.append(a.elapsed_time(b) * 1e3)
         return statistics.median(ts)
 
-    # --- dominant kernel: the tcgen05 3xTF32 TMA-im2col GEMM of the query-generator 3x3 conv
+    out = eng.forward_batch(feats, boxes_l, metas_l) if B > 1 else eng.forward(feats[0], boxes_l[0], metas_l[0])
+    torch.cuda.synchronize()
+    Np = out['Np'] if B > 1 else out['N']
+    N = B * Np                                    # query rows of the batch
+    n_per = out['n_b'][0] if B > 1 else out['N']
+
+    # --- dominant kernel: the tcgen05 3xTF32 TMA-im2col GEMM of the query-generator 3x3 conv (all RoIs of the batch)
     ws, n_tok = eng._buf['qg_ws'], N * 49
     conv_out, thi, tlo = ws[:n_tok * 256], ws[n_tok * 256: 2 * n_tok * 256], ws[2 * n_tok * 256: 3 * n_tok * 256]
 
@@ -411,60 +503,88 @@ def roofline_section(eng, out, mode, N, flush, peaks):
     t_conv = time_fn(conv)
     flops = 2.0 * n_tok * 256 * 2304
     achieved = flops / (t_conv * 1e-6) / 1e12
+    # dram__bytes_read.sum + dram__bytes_write.sum of this launch from the committed `ncu --set full` capture
+    # (profiles/r02_ncu_full_conv_B8.csv at B = 8, N = 300; profiles/r01_ncu_full_tc_kernels.csv at B = 1)
+    traffic = {(8, 300): None, (1, 300): 34.882816e6 + 0.07168e6}.get((B, n_per))
     roofline = dict(kernel='gemm_tc_kernel<128,3,im2col,3> (query-generator 3x3 conv, 3xTF32 tcgen05 + 4-D TMA)',
                     bound='tensor', achieved=achieved, peak=peaks['bf16_tflops'], unit='TFLOP/s',
-                    frac=achieved / peaks['bf16_tflops'],
-                    # dram__bytes_read.sum + dram__bytes_write.sum of this launch at N = 300 from the committed
-                    # `ncu --set full` capture (profiles/r01_ncu_full_tc_kernels.csv: 34.88 MB + 0.07 MB); the
-                    # algorithmic bytes are 2 x 15.05 MB of hi/lo tokens + 4.7 MB of weights + 15.05 MB out (L2-resident)
-                    traffic=(34.882816e6 + 0.07168e6) if N == 300 else None, us_per_launch=t_conv,
+                    frac=achieved / peaks['bf16_tflops'], traffic=traffic, us_per_launch=t_conv, rois_per_launch=N,
                     algorithmic_flops=flops, tf32_flops_issued=3 * flops * 128.0 / 98.0,
-                    note='achieved counts the conv flops once (17.3 GFLOP at N=300); the kernel issues 3 TF32 MMAs '
+                    note='achieved counts the conv flops once (17.3 GFLOP per 300 RoIs); the kernel issues 3 TF32 MMAs '
                          'per product (error compensation) on 128-row tiles that hold 98 real rows; peak = measured '
                          f'dense bf16 ({peaks["source"]}), the TF32 pipe is nominally half of it; kernel timed alone')
 
-    # --- attention path: one decoder layer's cross-attention, algorithmic bytes / time
+    # --- attention path: one decoder layer, algorithmic bytes (per sample x B) / time
+    bt = None
+    if B > 1:
+        cams, rois, roi_start, bt = eng._upload_meta_batch(boxes_l, metas_l)
     qg = {k: out[k] for k in ('query_pos', 'ref', 'tok_feat', 'tok_kin')}
+    grid = (hh, ww)
+    kv = None
     if mode == 'S':
         corr = dict(match=out['match'], match_cnt=out['match_cnt'], max_match=out['max_match'])
         kin_rows, mem_rows = out['tok_kin'].view(-1, 256), out['tok_feat'].view(-1, 256)
         mc = float(out['match_cnt'].float().mean())
-        bytes_layer = algorithmic_bytes_attention(N, mc, 'S')
+        bytes_layer = B * algorithmic_bytes_attention(Np, mc, 'S')
         extra = dict(matches_per_query=mc)
+        q_core = torch.randn(N, 2048, device=feats.device)
     else:
-        corr = dict(keymask=out['keymask'], mask_words=out['mask_words'], key_list=out['key_list'], key_cnt=out['key_cnt'])
+        corr = {k: out.get(k) for k in ('keymask', 'mask_words', 'key_list', 'key_cnt', 'xa_prepared_for', 'row_tile_live')}
         mem_rows = out['feat_nhwc'].view(-1, 256)
         kin_rows = eng._buf['kin'][:mem_rows.numel()].view(-1, 256)
-        km = out['keymask'].cpu().numpy().view(np.uint32)
-        n_union = int(np.unpackbits(np.bitwise_or.reduce(km, axis=0).view(np.uint8)).sum())
+        km = out['keymask'].cpu().numpy().view(np.uint32).reshape(B, Np, -1)
+        n_union = [int(np.unpackbits(np.bitwise_or.reduce(km[b], axis=0).view(np.uint8)).sum()) for b in range(B)]
         kmean = float(out['key_cnt'].float().mean())
-        bytes_layer = algorithmic_bytes_attention(N, 0, 'T', (kmean, n_union))
+        bytes_layer = sum(algorithmic_bytes_attention(Np, 0, 'T', (kmean, u)) for u in n_union)
         extra = dict(keys_per_query=kmean, union_keys=n_union)
-    vel = eng._vel_dt(out['_metas'])
-    t_dec = time_fn(lambda: eng.decoder(qg, corr, kin_rows, mem_rows, N, vel_dt=vel), reps=10)
+        kv = (eng._buf['kp'].view(eng.L, -1, 256)[:, :mem_rows.shape[0]], eng._buf['vp'].view(eng.L, -1, 256)[:, :mem_rows.shape[0]])
+        q_core = torch.randn(N, 256, device=feats.device)
+    vel = eng._vel_dt(metas_l[0])
+    t_dec = time_fn(lambda: eng.decoder(qg, corr, kin_rows, mem_rows, N, vel_dt=vel, batch=bt,
+                                        kv=kv, grid=grid if kv is not None else None), reps=10)
     per_layer = t_dec / eng.L
     ach = bytes_layer / (per_layer * 1e-6) / 1e9
     attention = dict(bound='hbm', achieved=ach, peak=peaks['hbm_gbs'], unit='GB/s', frac=ach / peaks['hbm_gbs'],
-                     algorithmic_bytes_per_layer=bytes_layer, us_per_layer=per_layer, decoder_stage_us=t_dec,
-                     note='achieved = SURVEY 8d algorithmic bytes of one cross-attention layer / (decoder stage '
-                          'time / L), i.e. a whole decoder layer (self-attn + sparse cross-attn + FFN, 11 launches) '
-                          'is charged to the attention bytes; at N=300 the layer is launch/latency bound', **extra)
+                     algorithmic_bytes_per_layer=bytes_layer, us_per_layer=per_layer, decoder_stage_us=t_dec, batch=B,
+                     note='achieved = SURVEY 8d algorithmic bytes of one cross-attention layer (x samples of the batch) / (decoder '
+                          'stage time / L), i.e. a WHOLE decoder layer (self-attn + sparse cross-attn + FFN + LayerNorms) is '
+                          'charged to the attention bytes; `core` below isolates the cross-attention kernel(s)', **extra)
+    try:    # the sparse cross-attention core alone (mv2d_cross_attention_core: xa_roi / xt_attn + xt_merge)
+        t_core = time_fn(lambda: eng.cross_attention_core(qg, corr, kin_rows, mem_rows, N, q_core, layer=0, kv=kv,
+                                                          grid=grid if kv is not None else None, batch=bt))
+        # S: every (query, matched RoI) unit streams the RoI's 49 key-input + 49 value rows; T: projected K / V of the union
+        core_bytes = (float(out['match_cnt'].sum()) * 49 * 2 * 1024) if mode == 'S' else bytes_layer
+        attention['core'] = dict(us=t_core, bytes=core_bytes, achieved=core_bytes / t_core / 1e3,
+                                 frac=core_bytes / t_core / 1e3 / peaks['hbm_gbs'],
+                                 traffic=None,
+                                 note='cross-attention kernel(s) alone, L2 flushed; bytes = key / value rows the kernel has to stream '
+                                      '(S: 100 KB per (query, RoI) unit; T: the SURVEY 8d bytes); ncu dram bytes: profiles/')
+    except Exception as e:
+        attention['core'] = dict(error=f'{type(e).__name__}: {e}'[:300])
 
-    # --- per-stage device time (eager launches, L2 flushed before each stage)
-    feat_nchw, boxes, metas = out['_inputs']
-    V, _, hh, ww = feat_nchw.shape
-    cams, rois, roi_start, counts, _ = eng._upload_meta(boxes, metas)
+    # --- per-stage device time (eager launches, L2 flushed before each stage), whole batch
+    feat_nchw = feats.view(B * V, 256, hh, ww)
     st = {}
     st['nchw_to_nhwc'] = time_fn(lambda: eng.to_nhwc(feat_nchw))
     f, f32r = eng.to_nhwc(feat_nchw)
-    st['geom_prep'] = time_fn(lambda: eng.geom_prep(cams))
-    i2l, trans = eng.geom_prep(cams)
-    st['pe3d'] = time_fn(lambda: eng.pe3d(f, i2l, metas, f32r))
-    pe, kin = eng.pe3d(f, i2l, metas, f32r)
+    if B > 1:
+        i2l = eng._get('img2lidar', (B * V, 16), torch.float64)
+        trans = eng._get('trans', (B, V, V, 16), torch.float64)
+        gp = lambda: L.check(h.mv2d_geom_prep_batch(cams[0].data_ptr(), B, V, i2l.data_ptr(), trans.data_ptr(), L.stream_ptr()), 'geom')
+        metas0 = metas_l[0]
+    else:
+        cams, rois, roi_start, counts, _ = eng._upload_meta(boxes_l[0], metas_l[0])
+        gp = lambda: eng.geom_prep(cams)
+        i2l, trans = eng.geom_prep(cams)
+        metas0 = metas_l[0]
+    st['geom_prep'] = time_fn(gp)
+    st['pe3d'] = time_fn(lambda: eng.pe3d(f, i2l, metas0, f32r, batch=bt))
+    pe, kin = eng.pe3d(f, i2l, metas0, f32r, batch=bt)
     st['roi_align_qg'] = time_fn(lambda: eng.roi_align_qg(rois, cams, f, pe, N))
-    st['box_corr'] = time_fn(lambda: eng.box_corr(rois, roi_start, trans, N, V, metas, hh, ww))
+    st['box_corr'] = time_fn(lambda: eng.box_corr(rois, roi_start, trans, N, V, metas0, hh, ww, batch=bt))
     st['decoder'] = t_dec
-    return dict(roofline=roofline, attention=attention, stage_us=st)
+    st['batch'] = B
+    return dict(roofline=roofline, attention=attention, stage_us=st, N=n_per)
 
 
 def cpu_baseline(mode):

@@ -279,6 +279,15 @@ MV2D_API size_t mv2d_xa_tile_workspace_bytes_batch(int batch, int rows_per_sampl
  * skips this step. */
 MV2D_API int mv2d_xa_tile_prepare(const Mv2dDecoderParams* p, void* stream);
 MV2D_API int mv2d_decoder(const Mv2dDecoderParams* p, void* stream);
+/* The sparse cross-attention core of decoder layer `layer` on its own -- PETRMultiheadAttention between its query and
+ * output projections (utils/petr_transformer.py:426-513) -- for stage-level bindings and the attention-only
+ * microbenchmark (BASELINE configs[4]).  Reads the key description of `p` (match lists / prepared key tiles).
+ *   mode 0: q = absorbed queries [N,2048] (scale * Wk_h^T (Wq_h x + bq_h)), ctx [N,2048] = per-head softmax-weighted
+ *           sums of the raw value rows; uses the partial-record scratch inside p->workspace;
+ *   mode 1 (xa_form 1, xa_prepared): q = projected queries [N,256], ctx [N,256] (heads concatenated).
+ * ctx_lo (nullable): ctx then receives the TF32 hi part and ctx_lo the lo part. */
+MV2D_API int mv2d_cross_attention_core(const Mv2dDecoderParams* p, int layer, const float* q, float* ctx, float* ctx_lo,
+                                       void* stream);
 
 /* ---- K/V projection of the two-frame head's keys (SURVEY.md 8b "kv_proj"; utils/petr_transformer.py:503-508 ->
  * torch.nn.MultiheadAttention in_proj on key = memory + pos and value = memory).  For every layer l in

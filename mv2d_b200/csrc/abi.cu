@@ -129,6 +129,11 @@ int mv2d_kv_project(const Mv2dKvParams* p, void* stream) {
                    "kv_project: null pointer");
     return run_kv_project(*p, (cudaStream_t)stream);
 }
+int mv2d_cross_attention_core(const Mv2dDecoderParams* p, int layer, const float* q, float* ctx, float* ctx_lo, void* stream) {
+    NONNULL(p, "cross_attention_core");
+    MV2D_CHECK_ARG(p->kin_rows && p->mem_rows, "cross_attention_core: null pointer");
+    return run_cross_attention_core(*p, layer, q, ctx, ctx_lo, (cudaStream_t)stream);
+}
 int mv2d_decoder(const Mv2dDecoderParams* p, void* stream) {
     NONNULL(p, "decoder");
     MV2D_CHECK_ARG(p->N == 0 || (p->query_pos && p->ref && p->kin_rows && p->mem_rows && p->cls_scores &&

@@ -1265,6 +1265,56 @@ int run_xa_tile_prepare(const Mv2dDecoderParams& p, cudaStream_t st) {
     return xt_prepare(p, xg, xw, st);
 }
 
+// first float of the xa_roi partial-record scratch inside the decoder workspace (must match the carve of run_decoder)
+static size_t xr_part_offset(int N, int L) {
+    return (size_t)N * (9 * MV2D_C + 768 + MV2D_C + 5 * 2048 + DEC_SPLIT * MV2D_C) + (size_t)4 * L * N * MV2D_C;
+}
+
+// The sparse cross-attention core of ONE decoder layer on its own (measurement / stage-level binding; the attention-only
+// microbenchmark of BASELINE configs[4]): exactly the launches run_decoder issues between the query projection and the
+// output projection.
+int run_cross_attention_core(const Mv2dDecoderParams& p, int layer, const float* q, float* ctx, float* ctx_lo, cudaStream_t st) {
+    const int N = p.N;
+    MV2D_CHECK_ARG(N > 0 && layer >= 0 && layer < p.L && q && ctx, "cross_attention_core: bad N / layer / pointers");
+    cudaError_t e;
+    if (p.mode == 0) {
+        MV2D_CHECK_ARG(p.match && p.match_cnt && p.max_match > 0 && p.max_match <= XR_MAXM && p.workspace,
+                       "cross_attention_core: S head needs match lists (max_match <= %d) and the decoder workspace", XR_MAXM);
+        MV2D_CHECK_ARG((xr_part_offset(N, p.L) + (size_t)N * XR_MAXM * XR_REC + N) * sizeof(float) <= p.workspace_bytes,
+                       "cross_attention_core: workspace too small");
+        float* part = p.workspace + xr_part_offset(N, p.L);
+        int* ticket = reinterpret_cast<int*>(part + (size_t)N * XR_MAXM * XR_REC);
+        if ((e = cudaFuncSetAttribute(xa_roi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XR_SMEM_BYTES)) != cudaSuccess ||
+            (e = cudaMemsetAsync(ticket, 0, (size_t)N * sizeof(int), st)) != cudaSuccess) {
+            set_error("cross_attention_core: setup %s", cudaGetErrorString(e));
+            return (int)e;
+        }
+        XrArgs a{}; a.qt = q; a.kin_rows = p.kin_rows; a.mem_rows = p.mem_rows; a.match = p.match;
+        a.match_cnt = p.match_cnt; a.max_match = p.max_match; a.ctx = ctx; a.ctx_lo = ctx_lo; a.part = part; a.ticket = ticket;
+        launch_k(xa_roi_kernel, dim3(N, p.max_match), dim3(XR_THREADS), (size_t)XR_SMEM_BYTES, st, a);
+        MV2D_CHECK_LAUNCH("xa_roi");
+        return 0;
+    }
+    MV2D_CHECK_ARG(p.xa_form == 1 && p.kp && p.vp && p.xa_prepared, "cross_attention_core: T head needs xa_form 1, kp / vp and prepared tile lists");
+    XtGeom xg{};
+    XtWs xw{};
+    int rc;
+    if ((rc = xt_setup(p, xg, xw))) return rc;
+    if ((e = cudaFuncSetAttribute(xt_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XT_SMEM_BYTES)) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(xt_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, XT_MERGE_MAXT * 36)) != cudaSuccess) {
+        set_error("cross_attention_core: xt smem attr %s", cudaGetErrorString(e));
+        return (int)e;
+    }
+    XtAttnArgs a{}; a.g = xg; a.q = q; a.kp = p.kp + (long long)layer * p.num_rows * MV2D_C; a.vp = p.vp + (long long)layer * p.num_rows * MV2D_C;
+    a.tile_cnt = xw.tile_cnt; a.tile_q = xw.tile_q; a.tile_mask = xw.tile_mask; a.rec = xw.rec; a.order = xw.order; a.qsplit = 1;
+    launch_k(xt_attn_kernel, dim3(xg.ntiles, 1), dim3(XT_THREADS), (size_t)XT_SMEM_BYTES, st, a);
+    MV2D_CHECK_LAUNCH("xt_attn");
+    XtMergeArgs m{}; m.g = xg; m.qlist = xw.qlist; m.qcnt = xw.qcnt; m.rec = xw.rec; m.ctx = ctx; m.ctx_lo = ctx_lo;
+    launch_k(xt_merge_kernel, dim3(N), dim3(XT_MERGE_THREADS), (size_t)xg.tiles_ps * 36, st, m);
+    MV2D_CHECK_LAUNCH("xt_merge");
+    return 0;
+}
+
 int run_decoder(const Mv2dDecoderParams& p, cudaStream_t st) {
     const int N = p.N, L = p.L, C = MV2D_C;
     MV2D_CHECK_ARG(N >= 0 && L >= 1 && L <= MV2D_MAX_LAYERS, "decoder: bad N=%d / L=%d", N, L);
@@ -1299,6 +1349,7 @@ int run_decoder(const Mv2dDecoderParams& p, cudaStream_t st) {
     float* b1 = ws;   ws += (size_t)L * N * C;
     float* b2 = ws;   ws += (size_t)L * N * C;
     float* b3 = ws;   ws += (size_t)L * N * C;
+    MV2D_CHECK_ARG((size_t)(ws - p.workspace) == xr_part_offset(N, L), "decoder: internal workspace layout drifted");
     float* xr_part = ws; ws += (size_t)N * XR_MAXM * XR_REC;
     int* xr_ticket = reinterpret_cast<int*>(ws); ws += N;
     // 3xTF32 operand splits of the GEMMs that run as FFMA below 512 rows

@@ -315,7 +315,7 @@ int launch_mlp2(const Mlp2& m, cudaStream_t st) {
     MV2D_CHECK_ARG(!m.gate || m.gs_mod == 0 || m.gs_mod % TC_BM == 0, "mlp2: gs_mod=%d must be a multiple of 128", m.gs_mod);
     CUtensorMap a, w0, w2, mo, mk, mgx, mgs, mgf;
     int rc;
-    static const int cl_env = []() { const char* v = getenv("MV2D_MLP2_CLUSTER"); return v ? atoi(v) : 4; }();
+    static const int cl_env = []() { const char* v = getenv("MV2D_MLP2_CLUSTER"); return v ? atoi(v) : 1; }();   // measured on B200: 2 / 4 give no gain (the ring depth, not L2 -> SM bytes, bounds the kernel)
     const int tiles = cdiv(m.M, TC_BM);
     const int cl = (cl_env == 4 && tiles >= 4) ? 4 : ((cl_env >= 2 && tiles >= 2) ? 2 : 1);
     if ((rc = tc_make_map_2d(&a, m.A, m.M, m.K0, m.lda, TC_BM))) return rc;

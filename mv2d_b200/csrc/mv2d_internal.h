@@ -13,6 +13,7 @@ int run_roi_align_qg(const Mv2dQgParams& p, cudaStream_t st);
 size_t roi_align_qg_workspace_bytes(int N);
 int run_box_corr(const Mv2dCorrParams& p, cudaStream_t st);
 int run_decoder(const Mv2dDecoderParams& p, cudaStream_t st);
+int run_cross_attention_core(const Mv2dDecoderParams& p, int layer, const float* q, float* ctx, float* ctx_lo, cudaStream_t st);
 size_t decoder_workspace_bytes(int N, int L);
 size_t xa_tile_workspace_bytes(int N, int V, int h, int w, int batch = 1);   // N = query rows per sample
 int run_kv_project(const Mv2dKvParams& p, cudaStream_t st);

@@ -462,12 +462,9 @@ class HotPath:
                 self._ev_kv[l].record(torch.cuda.current_stream())
         return kp, vp
 
-    def decoder(self, qg, corr, kin_rows, mem_rows, N, vel_dt=0.0, self_attn_mask=None, vel_row_start=0,
-                kv=None, grid=None, wait_kv_events=False, batch=None):
+    def _decoder_params(self, qg, corr, kin_rows, mem_rows, N, vel_dt=0.0, self_attn_mask=None, vel_row_start=0,
+                        kv=None, grid=None, batch=None):
         c, W, L = self.cfg, self.w, self.L
-        if self.xa_form == 1 and kv is None:    # stage-level call: project on this stream, then decode
-            grid = grid or self._last_grid
-            kv = self.kv_project(kin_rows, mem_rows)
         cls = self._get('cls_scores', (L, N, 10))
         box = self._get('bbox_preds', (L, N, 10))
         outs = self._get('outs_dec', (L, N, 256))
@@ -507,6 +504,16 @@ class HotPath:
             p.kp, p.vp = kv[0].data_ptr(), kv[1].data_ptr()
             p.xa_workspace, p.xa_workspace_bytes = xa_ws.data_ptr(), xa_bytes
             p.xa_prepared = int(corr.get('xa_prepared_for') == (corr['keymask'].data_ptr(), N, xa_ws.data_ptr()))
+        return p, cls, box, outs
+
+    def decoder(self, qg, corr, kin_rows, mem_rows, N, vel_dt=0.0, self_attn_mask=None, vel_row_start=0,
+                kv=None, grid=None, wait_kv_events=False, batch=None):
+        L = self.L
+        if self.xa_form == 1 and kv is None:    # stage-level call: project on this stream, then decode
+            grid = grid or self._last_grid
+            kv = self.kv_project(kin_rows, mem_rows)
+        p, cls, box, outs = self._decoder_params(qg, corr, kin_rows, mem_rows, N, vel_dt, self_attn_mask, vel_row_start,
+                                                 kv, grid, batch)
         if kv is not None and wait_kv_events:
             main = torch.cuda.current_stream()
             for l in range(L):          # layer l starts when its projection (on the kv stream) is done
@@ -516,6 +523,16 @@ class HotPath:
         else:
             lib.check(self.lib.mv2d_decoder(C.byref(p), lib.stream_ptr()), 'mv2d_decoder')
         return cls, box, outs
+
+    def cross_attention_core(self, qg, corr, kin_rows, mem_rows, N, q, layer=0, kv=None, grid=None, batch=None):
+        """The sparse cross-attention core of one decoder layer alone (``mv2d_cross_attention_core``): S head
+        q [N,2048] absorbed queries -> ctx [N,2048]; T head (xa_form 1, after ``box_corr`` prepared the key tiles)
+        q [N,256] -> ctx [N,256].  Used by the attention-only microbenchmark (tools/attention_sweep.py)."""
+        p, _, _, _ = self._decoder_params(qg, corr, kin_rows, mem_rows, N, kv=kv, grid=grid, batch=batch)
+        ctx = self._get('xa_core_ctx', tuple(q.shape))
+        lib.check(self.lib.mv2d_cross_attention_core(C.byref(p), layer, q.data_ptr(), ctx.data_ptr(), None, lib.stream_ptr()),
+                  'mv2d_cross_attention_core')
+        return ctx
 
     # ------------------------------------------------------------------ whole path
     def _vel_dt(self, img_metas):

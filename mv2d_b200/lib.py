@@ -212,6 +212,7 @@ SYMBOLS = [
     ('mv2d_dn_prepare', C.c_int, [C.POINTER(DnParams), c_f]),
     ('mv2d_decoder_workspace_bytes', C.c_size_t, [C.c_int, C.c_int]),
     ('mv2d_decoder', C.c_int, [C.POINTER(DecoderParams), c_f]),
+    ('mv2d_cross_attention_core', C.c_int, [C.POINTER(DecoderParams), C.c_int, c_f, c_f, c_f, c_f]),
     ('mv2d_xa_tile_workspace_bytes', C.c_size_t, [C.c_int] * 4),
     ('mv2d_xa_tile_workspace_bytes_batch', C.c_size_t, [C.c_int] * 5),
     ('mv2d_kv_project', C.c_int, [C.POINTER(KvParams), c_f]),

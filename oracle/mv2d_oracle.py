@@ -104,7 +104,7 @@ def pe_coords(img_metas, h, w, cfg):
     coords[..., :2] = coords[..., :2] * torch.maximum(coords[..., 2:3],
                                                      torch.full_like(coords[..., 2:3], 1e-3))
     img2lidar = torch.from_numpy(np.asarray(
-        [np.linalg.inv(m['lidar2img']) for m in img_metas])).double()  # host inverse, pe.py:111
+        [np.linalg.inv(m['lidar2img']) for m in img_metas])).double().to(coords.device)  # host inverse, pe.py:111
     c3 = torch.matmul(img2lidar.view(V, 1, 1, 1, 4, 4), coords.view(1, w, h, D, 4, 1))
     c3 = c3.squeeze(-1)[..., :3]  # [V,W,H,D,3]
     for i in range(3):
