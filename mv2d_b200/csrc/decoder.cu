@@ -409,14 +409,14 @@ self_attn_kernel(const float* __restrict__ qkv, const uint8_t* __restrict__ mask
 //            are folded by two shuffles at the end.
 // fp32 FFMA throughout (the parity gate rules out single-pass TF32 logits).
 #define SB_KT 160
-#define SB_KP 161          // K^T row stride
+#define SB_KP 33           // K row stride: lane = key reads of one channel are conflict-free (consecutive keys, odd stride)
 template <int QT> struct SbCfg {
     static constexpr int PP = QT + 4;                  // P^T row stride (conflict-free float4 stores of consecutive keys)
     static constexpr int NQG = QT / 4;                 // phase A: groups of 4 queries
     static constexpr int KL = 256 / NQG;               // lanes (keys) per group: 16 (QT = 64) or 32 (QT = 32)
     static constexpr int JN = SB_KT / KL;              // keys per thread: 10 or 5
     static constexpr int QW = QT / 8;                  // phase B: queries per warp: 8 or 4
-    static constexpr int SMEM_FLOATS = 32 * QT + 32 * SB_KP + SB_KT * 32 + SB_KT * PP + 2 * QT;
+    static constexpr int SMEM_FLOATS = 32 * QT + SB_KT * SB_KP + SB_KT * 32 + SB_KT * PP + 2 * QT;
     static constexpr int SMEM_BYTES = SMEM_FLOATS * 4;
 };
 
@@ -431,8 +431,8 @@ self_attn_blk_kernel(const float* __restrict__ qkv, const uint8_t* __restrict__ 
     pdl_trigger();
     extern __shared__ __align__(16) float sb_smem[];
     float* Qt = sb_smem;                       // [32][QT]   q * scale, transposed
-    float* Kt = Qt + 32 * QT;                  // [32][161]  keys of the tile, transposed
-    float* Vs = Kt + 32 * SB_KP;               // [160][32]
+    float* Kt = Qt + 32 * QT;                  // [160][33]  keys of the tile (row stride 33)
+    float* Vs = Kt + SB_KT * SB_KP;            // [160][32]
     float* Pt = Vs + SB_KT * 32;               // [160][PP]  probabilities, transposed
     float* alpha_s = Pt + SB_KT * PP;          // [QT] rescale of the running output for this tile
     float* l_s = alpha_s + QT;                 // [QT] softmax denominators
@@ -468,19 +468,25 @@ self_attn_blk_kernel(const float* __restrict__ qkv, const uint8_t* __restrict__ 
     for (int k0 = 0; k0 < nk; k0 += SB_KT) {
         const int ng = min(SB_KT, nk - k0);
         __syncthreads();                                // previous tile fully consumed (and Qt written, first time)
-        for (int i = t; i < SB_KT * 8; i += 256) {      // K^T: lanes along keys
-            const int key = i % SB_KT, d4 = i / SB_KT;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (key < ng) v = __ldcg(reinterpret_cast<const float4*>(base + (long long)(k0 + key) * 768 + 256) + d4);
-            Kt[(d4 * 4 + 0) * SB_KP + key] = v.x; Kt[(d4 * 4 + 1) * SB_KP + key] = v.y;
-            Kt[(d4 * 4 + 2) * SB_KP + key] = v.z; Kt[(d4 * 4 + 3) * SB_KP + key] = v.w;
+        // the whole tile goes to shared memory asynchronously (one memory latency per tile, not one per loop trip):
+        // K with 4-byte copies, a warp per 128-byte key row (the odd row stride rules out 16-byte copies), V with
+        // 16-byte copies, a quarter warp per row
+        for (int i = t; i < SB_KT * 32; i += 256) {
+            const int key = i >> 5, d = i & 31;
+            if (key < ng) {
+                const unsigned sa = (unsigned)__cvta_generic_to_shared(Kt + key * SB_KP + d);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(base + (long long)(k0 + key) * 768 + 256 + d) : "memory");
+            } else {
+                Kt[key * SB_KP + d] = 0.f;
+            }
         }
-        for (int i = t; i < SB_KT * 8; i += 256) {      // V: row-major, a quarter warp per 128-byte row
+        for (int i = t; i < SB_KT * 8; i += 256) {
             const int key = i >> 3, c4 = i & 7;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (key < ng) v = __ldcg(reinterpret_cast<const float4*>(base + (long long)(k0 + key) * 768 + 512) + c4);
-            *reinterpret_cast<float4*>(Vs + key * 32 + c4 * 4) = v;
+            if (key < ng) sa_cp16(Vs + key * 32 + c4 * 4, base + (long long)(k0 + key) * 768 + 512 + c4 * 4);
+            else *reinterpret_cast<float4*>(Vs + key * 32 + c4 * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
         // ---- phase A
         float acc[4][JN];
@@ -491,10 +497,10 @@ self_attn_blk_kernel(const float* __restrict__ qkv, const uint8_t* __restrict__ 
 #pragma unroll 4
         for (int d = 0; d < 32; ++d) {
             const float4 q4 = *reinterpret_cast<const float4*>(Qt + d * QT + qg * 4);
-            const float* kr = Kt + d * SB_KP + kl;
+            const float* kr = Kt + kl * SB_KP + d;
 #pragma unroll
             for (int j = 0; j < JN; ++j) {
-                const float kv = kr[KL * j];
+                const float kv = kr[KL * j * SB_KP];
                 acc[0][j] = fmaf(q4.x, kv, acc[0][j]); acc[1][j] = fmaf(q4.y, kv, acc[1][j]);
                 acc[2][j] = fmaf(q4.z, kv, acc[2][j]); acc[3][j] = fmaf(q4.w, kv, acc[3][j]);
             }
@@ -1532,7 +1538,10 @@ int run_decoder(const Mv2dDecoderParams& p, cudaStream_t st) {
                 const int rows = p.batch > 0 ? p.rows_per_sample : N, nb = p.batch > 0 ? p.batch : 1;
                 const int rps = p.batch > 0 ? p.rows_per_sample : 0;
                 const uint8_t* am = p.batch > 0 ? nullptr : p.self_attn_mask;
-                if (cdiv(rows, 64) * MV2D_HEADS * nb >= 148)
+                // 64 queries per CTA halve the K / V staging per query, 32 give twice the CTAs: take the variant with the
+                // smaller (waves x work per CTA); two CTAs fit an SM (93 KB of shared memory, 127 registers)
+                const int c64 = cdiv(rows, 64) * MV2D_HEADS * nb, c32 = cdiv(rows, 32) * MV2D_HEADS * nb;
+                if (cdiv(c64, 296) * 64 <= cdiv(c32, 296) * 32)
                     launch_k(self_attn_blk_kernel<64>, dim3(cdiv(rows, 64), MV2D_HEADS, nb), dim3(256), (size_t)SbCfg<64>::SMEM_BYTES, st,
                              (const float*)qkv, am, N, sa, rps, p.n_real, big ? sa_lo : (float*)nullptr);
                 else

@@ -606,7 +606,9 @@ static int launch_tc_mc(const CUtensorMap& a, const CUtensorMap& alo, const CUte
 
 int launch_gemm_tc(const TcGemm& t, cudaStream_t st) {
     // small-M problems (the decoder, M ~ 300) are latency bound: 64-wide N tiles double the CTA count
-    const int bn = (t.M <= 512 && !t.im2col && t.passes == 3) ? 64 : 128;   // (a 256-wide, 2-stage im2col variant measured slower than 128-wide / 3 stages)
+    // (a 256-wide, 2-stage im2col variant measured slower than 128-wide / 3 stages; 64-wide tiles for the N = 256 outputs of
+    // a batch -- 38 CTAs at 128 wide -- measured slower too: 28.5 vs 25 us per launch, the A tile is re-read by every N tile)
+    const int bn = (t.M <= 512 && !t.im2col && t.passes == 3) ? 64 : 128;
     MV2D_CHECK_ARG(t.M > 0 && t.N % bn == 0 && t.K % TC_BK == 0, "gemm_tc: need N%%%d==0 and K%%32==0 (N=%d K=%d)", bn, t.N, t.K);
     MV2D_CHECK_ARG((t.ldc & 3) == 0 && ((uintptr_t)t.C & 15) == 0, "gemm_tc: C must be 16-byte aligned");
     // 3xTF32 with both lo operands null: plain fp32 operands, split inside the kernel (RAW)
