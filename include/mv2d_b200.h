@@ -64,6 +64,13 @@ MV2D_API int mv2d_geom_prep_batch(const double* lidar2img, int batch, int V, dou
 /* NCHW [V,C,HW] -> NHWC [V,HW,C] (the FPN output layout -> this library's layout).
  * out_tf32 (nullable) receives a copy rounded to TF32 (operand of the single-pass tensor-core SE gate GEMM). */
 MV2D_API int mv2d_nchw_to_nhwc(const float* in, float* out, float* out_tf32, int V, int C, int HW, void* stream);
+/* the same with a second map added on the way: out = nhwc(in + in2)  (key = memory + key_pos of the dense interfaces) */
+MV2D_API int mv2d_nchw_add_to_nhwc(const float* in, const float* in2, float* out, int V, int C, int HW, void* stream);
+/* CrossAttentionBoxHead.position_embedding (bbox_heads/cross_attention_head.py:199-200):
+ * query_pos = query_embedding(pos2posemb3d(ref)); workspace: N * 640 floats */
+MV2D_API int mv2d_query_embedding(const float* ref /*[N,3]*/, int N, const float* w_qe0, const float* b_qe0, const float* w_qe2,
+                                  const float* b_qe2, const float* dim_t, float* query_pos /*[N,256]*/, float* workspace,
+                                  void* stream);
 
 /* ---- K1  PE.forward  (utils/pe.py:137-169 incl. position_encoding :84-135, SELayer :44-48,
  * SinePositionalEncoding3D positional_encoding.py:58-96 + adapt_pos3d) */
@@ -143,6 +150,13 @@ typedef struct Mv2dQgParams {
     /* ---- ABI 5, all nullable: TF32 hi / lo splits of the five FC matrices.  With them, and more than 512 RoIs
      * (batches), the FC chain runs as 3xTF32 tcgen05 GEMMs instead of the small-M FFMA kernels. */
     const float *w_fc_hi, *w_fc_lo, *w_enc0_hi, *w_enc0_lo, *w_enc2_hi, *w_enc2_lo, *w_qe0_hi, *w_qe0_lo, *w_qe2_hi, *w_qe2_lo;
+    /* ---- ABI 5, phase 3 = QueryGenerator.forward on its own (utils/query_generator.py:343-350): the RoI features and
+     * the per-RoI camera parameters are INPUTS -- tok_feat [N,49,256] (channels-last RoI features), roi_intrinsics
+     * [N,16] fp64 (K' of get_box_params), roi_extrinsics [N,16] fp64, intrins_feat [N,16] (extra_feats['intrinsic']);
+     * rois / feat / intrinsics / extrinsics are not read.  Outputs as in phase 0 (center_lidar, ref, query_pos). */
+    const double* roi_extrinsics;
+    const float* intrins_feat;
+    float* enc_out;            /* out, nullable (any phase but 2) [N,256]: the encoded RoI feature (return_feats['enc']) */
 } Mv2dQgParams;
 MV2D_API size_t mv2d_roi_align_qg_workspace_bytes(int N);
 MV2D_API int mv2d_roi_align_qg(const Mv2dQgParams* p, void* stream);
@@ -305,6 +319,17 @@ typedef struct Mv2dKvParams {
                                         * are never read by the attention) */
 } Mv2dKvParams;
 MV2D_API int mv2d_kv_project(const Mv2dKvParams* p, void* stream);
+
+/* ---- f2 (next row): the 2D-detections hand-off of MV2D.forward_train, boxes staying on the device
+ * (detectors/mv2d.py:60-86 process_2d_detections' min-size filter; :88-117 box_iou + complement_2d_gt).
+ * det [n,6] = (x1, y1, x2, y2, score, label) of all views, view v in rows det_start[v] .. det_start[v+1]; gt [m,6] the
+ * 2D ground truth in the same format (score 1, process_2d_gt) with gt_start.  For every view: the detections whose
+ * sides reach min_bbox_size, in input order, then -- complement_thr > 0 -- the ground-truth boxes whose best IoU with
+ * those is below complement_thr and whose sides reach min_bbox_size (all of them, unfiltered, when no detection is
+ * left: the reference's early return).  View v's result starts at row det_start[v] + gt_start[v] of `out`
+ * ([n + m, 6]) and has out_count[v] rows.  gt / gt_start may be NULL when complement_thr <= 0. */
+MV2D_API int mv2d_handoff_2d(const float* det, const int* det_start /*device [V+1]*/, const float* gt, const int* gt_start /*device [V+1]*/,
+                             int V, float min_bbox_size, float complement_thr, float* out, int* out_count /*device [V]*/, void* stream);
 
 /* ---- row a20: denoising queries of the training-mode forward -----------------------------------------------
  * Replaces MV2DSHead.prepare_for_dn (mv2d_s_head.py:39-120, training branch, batch_size 1) plus the way both

@@ -67,6 +67,17 @@ int mv2d_nchw_to_nhwc(const float* in, float* out, float* out_tf32, int V, int C
     return run_nchw_to_nhwc(in, out, out_tf32, V, C, HW, (cudaStream_t)stream);
 }
 
+int mv2d_nchw_add_to_nhwc(const float* in, const float* in2, float* out, int V, int C, int HW, void* stream) {
+    MV2D_CHECK_ARG(in && out && V > 0 && C > 0 && HW > 0, "nchw_add_to_nhwc: bad arguments");
+    return run_nchw_to_nhwc(in, out, nullptr, V, C, HW, (cudaStream_t)stream, in2);
+}
+
+int mv2d_query_embedding(const float* ref, int N, const float* w_qe0, const float* b_qe0, const float* w_qe2, const float* b_qe2,
+                         const float* dim_t, float* query_pos, float* workspace, void* stream) {
+    MV2D_CHECK_ARG(N >= 0 && (N == 0 || (ref && w_qe0 && b_qe0 && w_qe2 && b_qe2 && dim_t && query_pos && workspace)), "query_embedding: null pointer");
+    return run_query_embedding(ref, N, w_qe0, b_qe0, w_qe2, b_qe2, dim_t, query_pos, workspace, (cudaStream_t)stream);
+}
+
 int mv2d_split_tf32(const float* x, float* hi, float* lo, long long n, void* stream) {
     MV2D_CHECK_ARG(x && hi && lo && n >= 0, "split_tf32: bad arguments");
     return launch_split_tf32(x, hi, lo, n, (cudaStream_t)stream);
@@ -93,7 +104,7 @@ int mv2d_pe3d(const Mv2dPeParams* p, void* stream) {
 size_t mv2d_roi_align_qg_workspace_bytes(int N) { return roi_align_qg_workspace_bytes(N); }
 int mv2d_roi_align_qg(const Mv2dQgParams* p, void* stream) {
     NONNULL(p, "roi_align_qg");
-    MV2D_CHECK_ARG(p->N == 0 || (p->rois && p->intrinsics && p->extrinsics && p->feat && p->tok_feat && p->ref &&
+    MV2D_CHECK_ARG(p->N == 0 || ((p->phase == 3 || (p->rois && p->intrinsics && p->extrinsics && p->feat)) && p->tok_feat && p->ref &&
                                  p->query_pos && p->workspace && p->dim_t),
                    "roi_align_qg: null pointer");
     return run_roi_align_qg(*p, (cudaStream_t)stream);
@@ -104,6 +115,11 @@ int mv2d_box_corr(const Mv2dCorrParams* p, void* stream) {
     MV2D_CHECK_ARG(p->N == 0 || (p->rois && p->roi_start && p->trans && p->lin && p->depths && p->match && p->match_cnt),
                    "box_corr: null pointer");
     return run_box_corr(*p, (cudaStream_t)stream);
+}
+
+int mv2d_handoff_2d(const float* det, const int* det_start, const float* gt, const int* gt_start, int V, float min_bbox_size,
+                    float complement_thr, float* out, int* out_count, void* stream) {
+    return run_handoff_2d(det, det_start, gt, gt_start, V, min_bbox_size, complement_thr, out, out_count, (cudaStream_t)stream);
 }
 
 size_t mv2d_dn_workspace_bytes(int T, int mask_words) { return dn_workspace_bytes(T, mask_words); }

@@ -108,6 +108,41 @@ dn_keys_kernel(Mv2dDnParams p, int pad, const uint32_t* __restrict__ uni) {
     compact_key_bits(bits, words, grp_cnt, p.key_list_all + (long long)i * words * 32);
 }
 
+// pos2posemb3d (utils/pe.py:21-33) of N reference points: [N,384] = (emb(y) | emb(x) | emb(z)), interleaved sin / cos.
+// Same arithmetic as qg_tail_kernel (roi.cu) and dn_rows_kernel above.
+__global__ void __launch_bounds__(128) posemb3d_kernel(const float* __restrict__ ref, const float* __restrict__ dim_t, int N,
+                                                       float* __restrict__ posemb) {
+    pdl_wait();
+    pdl_trigger();
+    const int n = blockIdx.x;
+    if (n >= N) return;
+    const float p[3] = {ref[n * 3 + 0], ref[n * 3 + 1], ref[n * 3 + 2]};
+    for (int idx = threadIdx.x; idx < 384; idx += blockDim.x) {
+        const int part = idx >> 7, i = idx & 127;
+        const float pos = (part == 0 ? p[1] : (part == 1 ? p[0] : p[2])) * 6.283185307179586f;
+        const float a = pos / __ldg(dim_t + i);
+        posemb[(long long)n * 384 + idx] = (i & 1) ? cosf(a) : sinf(a);
+    }
+}
+
+// CrossAttentionBoxHead.position_embedding (cross_attention_head.py:199-200): query_embedding(pos2posemb3d(ref)).
+// workspace: N * (384 + 256) floats.
+int run_query_embedding(const float* ref, int N, const float* w_qe0, const float* b_qe0, const float* w_qe2, const float* b_qe2,
+                        const float* dim_t, float* query_pos, float* workspace, cudaStream_t st) {
+    if (N == 0) return 0;
+    float* pemb = workspace;
+    float* qh = workspace + (size_t)N * 384;
+    launch_k(posemb3d_kernel, dim3(N), dim3(128), 0, st, ref, dim_t, N, pemb);
+    MV2D_CHECK_LAUNCH("posemb3d");
+    GemmArgs g{};
+    g.A = pemb; g.lda = 384; g.W = w_qe0; g.ldw = 384; g.bias = b_qe0; g.C = qh; g.ldc = MV2D_C;
+    g.M = N; g.N = MV2D_C; g.K = 384; g.batch = 1; g.nsplit = 1; g.flags = GEMM_RELU;
+    int rc;
+    if ((rc = launch_gemm_simt(g, A_PLAIN, st))) return rc;
+    g.A = qh; g.lda = MV2D_C; g.W = w_qe2; g.ldw = MV2D_C; g.bias = b_qe2; g.C = query_pos; g.K = MV2D_C; g.flags = 0;
+    return launch_gemm_simt(g, A_PLAIN, st);
+}
+
 size_t dn_workspace_bytes(int T, int mask_words) {
     size_t t = (size_t)(T > 0 ? T : 1);
     return t * (384 + MV2D_C) * sizeof(float) + (size_t)(mask_words > 0 ? mask_words : 0) * sizeof(uint32_t) + 256;

@@ -6,12 +6,16 @@
 namespace mv2d {
 
 int run_geom_prep(const double* lidar2img, int V, double* img2lidar, double* trans, cudaStream_t st, int batch = 1);
-int run_nchw_to_nhwc(const float* in, float* out, float* out_tf32, int V, int C, int HW, cudaStream_t st);
+int run_nchw_to_nhwc(const float* in, float* out, float* out_tf32, int V, int C, int HW, cudaStream_t st, const float* in2 = nullptr);
+int run_query_embedding(const float* ref, int N, const float* w_qe0, const float* b_qe0, const float* w_qe2, const float* b_qe2,
+                        const float* dim_t, float* query_pos, float* workspace, cudaStream_t st);
 int run_pe3d(const Mv2dPeParams& p, cudaStream_t st);
 size_t pe3d_workspace_bytes(int V, int h, int w, int depth_num);
 int run_roi_align_qg(const Mv2dQgParams& p, cudaStream_t st);
 size_t roi_align_qg_workspace_bytes(int N);
 int run_box_corr(const Mv2dCorrParams& p, cudaStream_t st);
+int run_handoff_2d(const float* det, const int* det_start, const float* gt, const int* gt_start, int V, float min_size, float thr,
+                   float* out, int* out_count, cudaStream_t st);
 int run_decoder(const Mv2dDecoderParams& p, cudaStream_t st);
 int run_cross_attention_core(const Mv2dDecoderParams& p, int layer, const float* q, float* ctx, float* ctx_lo, cudaStream_t st);
 size_t decoder_workspace_bytes(int N, int L);

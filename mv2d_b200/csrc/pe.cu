@@ -36,17 +36,21 @@ __global__ void geom_prep_kernel(const double* __restrict__ lidar2img, int V,
 }
 
 // ---- NCHW -> NHWC (the FPN hands us NCHW; every kernel below wants C contiguous)
-__global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, float* __restrict__ out, float* __restrict__ out_tf32, int C, int HW) {
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, float* __restrict__ out, float* __restrict__ out_tf32, int C, int HW,
+                                    const float* __restrict__ in2) {
     pdl_wait();
     pdl_trigger();
     __shared__ float tile[32][33];
     const int v = blockIdx.z;
     const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
     const float* src = in + (long long)v * C * HW;
+    const float* src2 = in2 ? in2 + (long long)v * C * HW : nullptr;      // optional second map, added (key = memory + pos)
     float* dst = out + (long long)v * C * HW;
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
         int c = c0 + i, p = p0 + threadIdx.x;
-        tile[i][threadIdx.x] = (c < C && p < HW) ? src[(long long)c * HW + p] : 0.f;
+        float val = (c < C && p < HW) ? src[(long long)c * HW + p] : 0.f;
+        if (src2 && c < C && p < HW) val += src2[(long long)c * HW + p];
+        tile[i][threadIdx.x] = val;
     }
     __syncthreads();
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
@@ -265,9 +269,10 @@ int run_geom_prep(const double* lidar2img, int V, double* img2lidar, double* tra
     return 0;
 }
 
-int run_nchw_to_nhwc(const float* in, float* out, float* out_tf32, int V, int C, int HW, cudaStream_t st) {
+int run_nchw_to_nhwc(const float* in, float* out, float* out_tf32, int V, int C, int HW, cudaStream_t st, const float* in2) {
+    MV2D_CHECK_ARG(V <= 65535, "nchw_to_nhwc: at most 65535 maps per call (got %d)", V);
     dim3 grid(cdiv(HW, 32), cdiv(C, 32), V), block(32, 8);
-    launch_k(nchw_to_nhwc_kernel, grid, block, 0, st, in, out, out_tf32, C, HW);
+    launch_k(nchw_to_nhwc_kernel, grid, block, 0, st, in, out, out_tf32, C, HW, in2);
     MV2D_CHECK_LAUNCH("nchw_to_nhwc");
     return 0;
 }

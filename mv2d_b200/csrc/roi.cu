@@ -127,6 +127,37 @@ __global__ void box_params_kernel(const float* __restrict__ rois, const double* 
     for (int i = 0; i < 16; ++i) m_roi[n * 16 + i] = (float)Li[i];
 }
 
+// Stage-level QueryGenerator.forward (phase 3): the per-RoI camera inputs are given instead of derived from the boxes:
+// K' [N,16] fp64 (get_box_params), per-RoI extrinsics [N,16] fp64 and the intrinsics feature [N,16] (extra_feats).
+__global__ void qg_inputs_kernel(const double* __restrict__ k_roi, const double* __restrict__ e_roi, const float* __restrict__ ifeat,
+                                 int N, float* __restrict__ cat, float* __restrict__ m_roi, float* __restrict__ cat_lo) {
+    pdl_wait();
+    pdl_trigger();
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    double K[16], E[16], L[16], Li[16];
+    for (int i = 0; i < 16; ++i) { K[i] = k_roi[n * 16 + i]; E[i] = e_roi[n * 16 + i]; }
+    for (int i = 0; i < 16; ++i) {
+        float f = fminf(fmaxf(ifeat[n * 16 + i], -5e3f), 5e3f);
+        if (cat_lo) {
+            const float hi = round_tf32(f);
+            cat_lo[(long long)n * MV2D_CAT_LD + 1024 + i] = round_tf32(f - hi);
+            cat_lo[(long long)n * MV2D_CAT_LD + 1040 + i] = 0.f;
+            f = hi;
+        }
+        cat[(long long)n * MV2D_CAT_LD + 1024 + i] = f;
+        cat[(long long)n * MV2D_CAT_LD + 1040 + i] = 0.f;
+    }
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) {
+            double s = 0.0;
+            for (int k = 0; k < 4; ++k) s += K[i * 4 + k] * E[j * 4 + k];
+            L[i * 4 + j] = s;
+        }
+    inv4x4(L, Li);
+    for (int i = 0; i < 16; ++i) m_roi[n * 16 + i] = (float)Li[i];
+}
+
 // AvgPool2d(7) over the ReLU'd conv output: [N,49,256] -> [N,256]
 __global__ void avgpool49_kernel(const float* __restrict__ x, float* __restrict__ out, int N, float* __restrict__ out_lo) {
     pdl_wait();
@@ -203,8 +234,9 @@ int run_roi_align_qg(const Mv2dQgParams& p, cudaStream_t st) {
     const int N = p.N, C = MV2D_C;
     MV2D_CHECK_ARG(N >= 0 && p.V >= 1 && p.V <= MV2D_MAXVB, "roi_align_qg: bad N/V");
     if (N == 0) return 0;
-    MV2D_CHECK_ARG(p.phase >= 0 && p.phase <= 2, "roi_align_qg: phase must be 0, 1 or 2");
-    MV2D_CHECK_ARG(p.phase == 1 || p.tok_kin == nullptr || p.pe != nullptr, "roi_align_qg: tok_kin needs pe");
+    MV2D_CHECK_ARG(p.phase >= 0 && p.phase <= 3, "roi_align_qg: phase must be 0, 1, 2 or 3");
+    MV2D_CHECK_ARG(p.phase == 1 || p.phase == 3 || p.tok_kin == nullptr || p.pe != nullptr, "roi_align_qg: tok_kin needs pe");
+    MV2D_CHECK_ARG(p.phase != 3 || (p.roi_intrinsics && p.roi_extrinsics && p.intrins_feat), "roi_align_qg: phase 3 needs K', E and the intrinsics feature per RoI");
     if (p.phase == 2) {   // only the position-embedding tokens: tok_kin = tok_feat + RoIAlign(pe)
         if (p.tok_kin == nullptr) return 0;
         launch_k(roi_align_tokens_kernel, dim3(MV2D_TOK, N), dim3(64), 0, st, p.rois, (const float*)nullptr, p.pe, p.h, p.w,
@@ -242,12 +274,19 @@ int run_roi_align_qg(const Mv2dQgParams& p, cudaStream_t st) {
         return launch_gemm_tc(t, st);
     };
     int rc;
+    if (p.phase == 3) {     // tokens and per-RoI camera parameters are inputs (QueryGenerator.forward on its own)
+        if ((rc = launch_split_tf32(p.tok_feat, thi, tlo, (long long)N * MV2D_TOK * C, st))) return rc;
+        launch_k(qg_inputs_kernel, dim3(cdiv(N, 64)), dim3(64), 0, st, (const double*)p.roi_intrinsics, p.roi_extrinsics, p.intrins_feat, N, cat,
+                 mroi, big ? cat_lo : (float*)nullptr);
+        MV2D_CHECK_LAUNCH("qg_inputs");
+    } else {
     launch_k(roi_align_tokens_kernel, dim3(MV2D_TOK, N), dim3(64), 0, st, p.rois, p.feat, with_pe ? p.pe : (const float*)nullptr, p.h, p.w,
              1.0f / (float)p.stride, p.tok_feat, with_pe ? p.tok_kin : (float*)nullptr, thi, tlo);
     MV2D_CHECK_LAUNCH("roi_align_tokens");
     launch_k(box_params_kernel, dim3(cdiv(N, 64)), dim3(64), 0, st, p.rois, p.intrinsics, p.extrinsics, N, p.intrins_feat_scale, cat,
                                                   mroi, p.roi_intrinsics, big ? cat_lo : (float*)nullptr);
     MV2D_CHECK_LAUNCH("box_params");
+    }
     // shared conv 3x3 (+ReLU) as implicit GEMM over the tokens, avg-pool, FC chain
     {   // tcgen05 3xTF32, A staged by 4-D TMA boxes straight from the token tensor
         TcGemm t{};
@@ -267,6 +306,10 @@ int run_roi_align_qg(const Mv2dQgParams& p, cudaStream_t st) {
         if ((rc = gemm(pool, C, p.w_fc, C, p.b_fc, cat, MV2D_CAT_LD, N, 1024, C, GEMM_RELU | GEMM_CLAMP5E3, A_PLAIN, st))) return rc;
         if ((rc = gemm(cat, MV2D_CAT_LD, p.w_enc0, MV2D_CAT_LD, p.b_enc0, e0, 512, N, 512, MV2D_CAT_LD, GEMM_RELU, A_PLAIN, st))) return rc;
         if ((rc = gemm(e0, 512, p.w_enc2, 512, p.b_enc2, enc, C, N, C, 512, GEMM_RELU, A_PLAIN, st))) return rc;
+    }
+    if (p.enc_out) {
+        cudaError_t e = cudaMemcpyAsync(p.enc_out, enc, (size_t)N * C * sizeof(float), cudaMemcpyDeviceToDevice, st);
+        if (e != cudaSuccess) { set_error("roi_align_qg: enc copy %s", cudaGetErrorString(e)); return (int)e; }
     }
     launch_k(qg_tail_kernel, dim3(cdiv(N, 4)), dim3(128), 0, st, (const float*)enc, p.w_center, p.b_center, mroi, p.dim_t, N, p.pc_range[0],
                                                p.pc_range[1], p.pc_range[2], p.pc_range[3], p.pc_range[4],
@@ -442,6 +485,100 @@ key_mask_kernel(Mv2dCorrParams p, int words) {
         __shared__ int grp_cnt[128];
         compact_key_bits(bits, words, grp_cnt, p.key_list + (long long)n * words * 32);
     }
+}
+
+// ------------------------------------------------------------------------------------------
+// Next row f2: the 2D-detections hand-off of MV2D.forward_train, on the device (detectors/mv2d.py:60-117):
+// process_2d_detections' min-size filter, then complement_2d_gt -- the 2D ground-truth boxes whose best IoU with the
+// kept detections is below `thr` (and whose sides reach the minimum) are appended.  One CTA per view; both steps are
+// ORDERED compactions (the reference's boolean indexing keeps the input order).  fp32 operation order of box_iou as in
+// the reference (this unit is compiled with -fmad=false), so the `max_iou < thr` decisions are bit-identical.
+__device__ __forceinline__ int ordered_slot(bool flag, int* warp_cnt, int& running) {
+    // position of this thread's element among the flagged ones of the current 256-wide chunk (+ running), or -1
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned bal = __ballot_sync(0xffffffffu, flag);
+    if (lane == 0) warp_cnt[warp] = __popc(bal);
+    __syncthreads();
+    int before = 0, total = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { const int c = warp_cnt[i]; if (i < warp) before += c; total += c; }
+    const int pos = flag ? running + before + __popc(bal & ((1u << lane) - 1u)) : -1;
+    running += total;
+    __syncthreads();
+    return pos;
+}
+
+__global__ void __launch_bounds__(256)
+handoff_2d_kernel(const float* __restrict__ det, const int* __restrict__ det_start, const float* __restrict__ gt,
+                  const int* __restrict__ gt_start, float min_size, float thr, float* __restrict__ out, int* __restrict__ out_count) {
+    pdl_wait();
+    pdl_trigger();
+    __shared__ int warp_cnt[8];
+    const int v = blockIdx.x, t = threadIdx.x;
+    const int d0 = det_start[v], n = det_start[v + 1] - d0;
+    const int g0 = gt ? gt_start[v] : 0, m = gt ? gt_start[v + 1] - g0 : 0;
+    float* o = out + (long long)(d0 + g0) * 6;
+    int kept = 0;
+    for (int base = 0; base < n; base += 256) {
+        const int i = base + t;
+        bool keep = false;
+        float r[6];
+        if (i < n) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) r[k] = det[(long long)(d0 + i) * 6 + k];
+            keep = !(min_size > 0.f) || ((r[2] - r[0]) >= min_size && (r[3] - r[1]) >= min_size);
+        }
+        const int pos = ordered_slot(keep, warp_cnt, kept);
+        if (pos >= 0) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) o[(long long)pos * 6 + k] = r[k];
+        }
+    }
+    __syncthreads();        // the kept detections are read back below (same CTA)
+    int total = kept;
+    if (thr > 0.f && m > 0) {
+        const bool no_det = kept == 0;       // the reference returns ALL ground-truth boxes then, unfiltered
+        for (int base = 0; base < m; base += 256) {
+            const int j = base + t;
+            bool keep = false;
+            float r[6];
+            if (j < m) {
+#pragma unroll
+                for (int k = 0; k < 6; ++k) r[k] = gt[(long long)(g0 + j) * 6 + k];
+                if (no_det) {
+                    keep = true;
+                } else {
+                    const float area_a = (r[2] - r[0]) * (r[3] - r[1]);
+                    float best = -INFINITY;
+                    for (int i = 0; i < kept; ++i) {
+                        const float* b = o + (long long)i * 6;
+                        const float w = fmaxf(fminf(r[2], b[2]) - fmaxf(r[0], b[0]), 0.f);
+                        const float h = fmaxf(fminf(r[3], b[3]) - fmaxf(r[1], b[1]), 0.f);
+                        const float inter = w * h;
+                        const float area_b = (b[2] - b[0]) * (b[3] - b[1]);
+                        const float uni = area_a + area_b - inter;
+                        best = fmaxf(best, inter / (uni + 1e-4f));
+                    }
+                    keep = best < thr && (r[2] - r[0]) >= min_size && (r[3] - r[1]) >= min_size;
+                }
+            }
+            const int pos = ordered_slot(keep, warp_cnt, total);
+            if (pos >= 0) {
+#pragma unroll
+                for (int k = 0; k < 6; ++k) o[(long long)pos * 6 + k] = r[k];
+            }
+        }
+    }
+    if (t == 0) out_count[v] = total;
+}
+
+int run_handoff_2d(const float* det, const int* det_start, const float* gt, const int* gt_start, int V, float min_size, float thr,
+                   float* out, int* out_count, cudaStream_t st) {
+    MV2D_CHECK_ARG(V >= 1 && det_start && out && out_count && (thr <= 0.f || !gt || gt_start), "handoff_2d: bad arguments");
+    launch_k(handoff_2d_kernel, dim3(V), dim3(256), 0, st, det, det_start, thr > 0.f ? gt : (const float*)nullptr, gt_start, min_size, thr, out,
+             out_count);
+    MV2D_CHECK_LAUNCH("handoff_2d");
+    return 0;
 }
 
 int run_box_corr(const Mv2dCorrParams& p, cudaStream_t st) {

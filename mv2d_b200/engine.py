@@ -722,6 +722,96 @@ class HotPath:
         out['num_per_view'] = counts
         return out
 
+    # ------------------------------------------------------------------ stage-level entries (the plugin modules' own forwards)
+    def query_embedding(self, ref):
+        """CrossAttentionBoxHead.position_embedding (cross_attention_head.py:199-200): ref [N,3] -> query_pos [N,256]."""
+        ref = ref.to(self.device, torch.float32).contiguous().view(-1, 3)
+        N, W = ref.shape[0], self.w
+        qpos = self._get('se_query_pos', (N, 256))
+        ws = self._get('se_qe_ws', (max(N, 1) * 640,))
+        lib.check(self.lib.mv2d_query_embedding(ref.data_ptr(), N, W.p('w_qe0'), W.p('b_qe0'), W.p('w_qe2'), W.p('b_qe2'), W.p('dim_t'),
+                                                qpos.data_ptr(), ws.data_ptr(), lib.stream_ptr()), 'mv2d_query_embedding')
+        return qpos
+
+    def to_tokens(self, x, x2=None, name='se_tok'):
+        """[B,C,h,w] (+ a second map added on the way) -> channels-last rows [B,h*w,C] (``mv2d_nchw_add_to_nhwc``)."""
+        x = x.to(self.device, torch.float32).contiguous()
+        Bn, Cc, h, w = x.shape
+        out = self._get(name, (Bn, h * w, Cc))
+        x2p = x2.to(self.device, torch.float32).contiguous().data_ptr() if x2 is not None else None
+        lib.check(self.lib.mv2d_nchw_add_to_nhwc(x.data_ptr(), x2p, out.data_ptr(), Bn, Cc, h * w, lib.stream_ptr()), 'mv2d_nchw_add_to_nhwc')
+        return out
+
+    def query_generator(self, x, intrinsics, extrinsics, intrins_feat):
+        """QueryGenerator.forward on its own (utils/query_generator.py:343-405): x [N,256,7,7] RoI features, intrinsics
+        [N,4,4] (K' of get_box_params, fp64), extrinsics [N,4,4], intrins_feat [N,16] -> dict(center_lidar [N,3], enc
+        [N,256], ref [N,3], query_pos [N,256])."""
+        N, W, c = x.shape[0], self.w, self.cfg
+        tok = self.to_tokens(x, name='se_qg_tok')
+        kroi = intrinsics.to(self.device, torch.float64).contiguous().view(N, 16)
+        eroi = extrinsics.to(self.device, torch.float64).contiguous().view(N, 16)
+        ifeat = intrins_feat.to(self.device, torch.float32).contiguous().view(N, 16)
+        center, ref, qpos, enc = (self._get('se_center', (N, 3)), self._get('se_ref', (N, 3)), self._get('se_qpos', (N, 256)),
+                                  self._get('se_enc', (N, 256)))
+        ws_bytes = self.lib.mv2d_roi_align_qg_workspace_bytes(N)
+        ws = self._get('qg_ws', (ws_bytes // 4,))
+        p = lib.QgParams()
+        p.N, p.V, p.h, p.w, p.stride, p.phase = N, 1, 1, 1, c['stride'], 3
+        p.pc_range = (C.c_float * 6)(*c['pc_range'])
+        p.intrins_feat_scale = c['intrins_feat_scale']
+        p.dim_t = W.p('dim_t')
+        for f in ('w_conv', 'b_conv', 'w_conv_lo', 'w_fc', 'b_fc', 'w_enc0', 'b_enc0', 'w_enc2', 'b_enc2', 'w_center',
+                  'b_center', 'w_qe0', 'b_qe0', 'w_qe2', 'b_qe2', 'w_fc_hi', 'w_fc_lo', 'w_enc0_hi', 'w_enc0_lo', 'w_enc2_hi',
+                  'w_enc2_lo', 'w_qe0_hi', 'w_qe0_lo', 'w_qe2_hi', 'w_qe2_lo'):
+            setattr(p, f, W.p(f))
+        p.tok_feat, p.roi_intrinsics, p.roi_extrinsics, p.intrins_feat = tok.data_ptr(), kroi.data_ptr(), eroi.data_ptr(), ifeat.data_ptr()
+        p.center_lidar, p.ref, p.query_pos, p.enc_out = center.data_ptr(), ref.data_ptr(), qpos.data_ptr(), enc.data_ptr()
+        p.workspace, p.workspace_bytes = ws.data_ptr(), ws_bytes
+        lib.check(self.lib.mv2d_roi_align_qg(C.byref(p), lib.stream_ptr()), 'mv2d_roi_align_qg')
+        return dict(center_lidar=center, enc=enc, ref=ref, query_pos=qpos)
+
+    def transformer(self, x, mask, query_embed, pos_embed, ref=None, attn_mask=None, cross_attn_mask=None, vel_dt=0.0):
+        """MV2DTransformer.forward / CrossAttentionBoxHead.forward on the reference's dense interface
+        (cross_attention_head.py:22-49, 202-242).  x / pos_embed [bs,n,C,h,w], mask [bs,n,h,w] (True = padded key),
+        query_embed [bs,nq,C].  Two layouts, as the two heads call it:
+          S head: bs = number of queries, nq = 1, memory of query i = its n gathered RoI feature blocks (h = w = 7);
+          T head: bs = 1, memory = the n feature views, cross_attn_mask [nq,n,h,w] (True = masked).
+        Returns (outs_dec [L,nq_total,256], cls_scores [L,nq_total,10], bbox_preds [L,nq_total,10]); the branch outputs
+        need ``ref`` [nq_total,3]."""
+        bs, n, Cc, h, w = x.shape
+        dev = self.device
+        mem = self.to_tokens(x.reshape(bs * n, Cc, h, w), name='se_mem')                       # [bs*n, h*w, C]
+        kin = self.to_tokens(x.reshape(bs * n, Cc, h, w), pos_embed.reshape(bs * n, Cc, h, w), name='se_kin')
+        qpos = query_embed.to(dev, torch.float32).reshape(-1, 256).contiguous()
+        N = qpos.shape[0]
+        ref_t = (ref.to(dev, torch.float32).reshape(-1, 3).contiguous() if ref is not None else self._get('se_ref0', (N, 3)).fill_(0.5))
+        qg = dict(query_pos=qpos, ref=ref_t)
+        sa_mask = attn_mask.to(dev).to(torch.uint8).contiguous() if attn_mask is not None else None
+        if self.mode == 'S':
+            assert h * w == 49 and query_embed.shape[1] == 1, 'the single-frame head attends to gathered 7x7 RoI blocks, one query per batch entry'
+            valid = ~mask.to(dev).reshape(bs, n, h * w).all(-1)                                  # [N, n] RoI slot is real
+            cnt = valid.sum(1).to(torch.int32)
+            order = torch.argsort((~valid).to(torch.int8), dim=1, stable=True).to(torch.int32)   # real slots first, in order
+            match = (order + torch.arange(bs, device=dev, dtype=torch.int32)[:, None] * n).contiguous()
+            corr = dict(match=match, match_cnt=cnt.contiguous(), max_match=n)
+            out = self.decoder(qg, corr, kin.view(-1, 256), mem.view(-1, 256), N, self_attn_mask=sa_mask)
+        else:
+            assert bs == 1, 'the two-frame head calls the transformer with one batch entry'
+            R = n * h * w
+            words = (R + 31) // 32
+            keep = torch.ones((N, R), dtype=torch.bool, device=dev)
+            if cross_attn_mask is not None:
+                keep &= ~cross_attn_mask.to(dev).reshape(N, R)
+            keep &= ~mask.to(dev).reshape(1, R)
+            bits = torch.zeros((N, words * 32), dtype=torch.int64, device=dev)
+            bits[:, :R] = keep
+            packed = (bits.view(N, words, 32) << torch.arange(32, device=dev, dtype=torch.int64)).sum(-1)
+            keymask = packed.to(torch.int32).contiguous()                                       # bit c of word c/32 (wraps to the sign bit)
+            corr = dict(keymask=keymask, mask_words=words, key_list=None, key_cnt=None)
+            out = self.decoder(qg, corr, kin.view(-1, 256), mem.view(-1, 256), N, vel_dt=vel_dt, self_attn_mask=sa_mask, grid=(h, w))
+        cls, box, outs = out
+        return outs, cls, box
+
     # ------------------------------------------------------------------ batches (a segment dimension through ONE kernel chain)
     def _upload_meta_batch(self, proposal_lists, metas_list, bucket=1):
         """Metadata of B samples in one pinned staging buffer and one H2D copy.  Layout of the rows (C ABI, "Batches"):
@@ -982,6 +1072,38 @@ class HotPath:
         k = min(max_num, N * 10)
         m = valid[:k].bool()
         return boxes[:k][m], scores[:k][m], labels[:k][m].long()
+
+    @torch.no_grad()
+    def handoff_2d(self, detections, gts=None, min_bbox_size=0.0, complement_thr=-1.0):
+        """Next row f2 on the device (``mv2d_handoff_2d``): per view, detections [n_v,6] filtered by the minimum box size,
+        then (complement_thr > 0) the 2D ground truth ``gts`` [m_v,6] that no kept detection covers appended
+        (detectors/mv2d.py:60-117).  Lists of per-view tensors in (device or host), list of per-view DEVICE tensors out;
+        the boxes never leave the device -- only the V result counts are read back, where the reference's boolean
+        indexing synchronises as well."""
+        dev, V = self.device, len(detections)
+        dets = [d.to(dev, torch.float32).reshape(-1, 6) for d in detections]
+        det = torch.cat(dets, 0).contiguous() if V else torch.zeros((0, 6), device=dev)
+        dstart = torch.tensor(np.concatenate([[0], np.cumsum([d.shape[0] for d in dets])]), dtype=torch.int32, device=dev)
+        use_gt = complement_thr > 0 and gts is not None
+        if use_gt:
+            g = [x.to(dev, torch.float32).reshape(-1, 6) for x in gts]
+            gt = torch.cat(g, 0).contiguous()
+            gstart = torch.tensor(np.concatenate([[0], np.cumsum([x.shape[0] for x in g])]), dtype=torch.int32, device=dev)
+            gcounts = [x.shape[0] for x in g]
+        else:
+            gt, gstart, gcounts = None, torch.zeros(V + 1, dtype=torch.int32, device=dev), [0] * V
+        out = torch.empty((det.shape[0] + (gt.shape[0] if use_gt else 0) + 1, 6), device=dev)
+        cnt = torch.empty((V,), dtype=torch.int32, device=dev)
+        lib.check(self.lib.mv2d_handoff_2d(det.data_ptr() if det.numel() else None, dstart.data_ptr(),
+                                           gt.data_ptr() if (use_gt and gt.numel()) else None, gstart.data_ptr(), V,
+                                           float(min_bbox_size), float(complement_thr if use_gt else -1.0), out.data_ptr(),
+                                           cnt.data_ptr(), lib.stream_ptr()), 'mv2d_handoff_2d')
+        counts = cnt.tolist()
+        res, o = [], 0
+        for v in range(V):
+            res.append(out[o:o + counts[v]])
+            o += dets[v].shape[0] + gcounts[v]
+        return res
 
     @torch.no_grad()
     def scene_nms(self, boxes, scores, labels, score_thr=0.0, nms_thr=1.0, max_num=300):

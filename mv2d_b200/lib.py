@@ -45,6 +45,7 @@ class QgParams(C.Structure):
         ('ref', c_f), ('query_pos', c_f), ('workspace', c_f), ('workspace_bytes', C.c_size_t),
         ('w_fc_hi', c_f), ('w_fc_lo', c_f), ('w_enc0_hi', c_f), ('w_enc0_lo', c_f), ('w_enc2_hi', c_f), ('w_enc2_lo', c_f),
         ('w_qe0_hi', c_f), ('w_qe0_lo', c_f), ('w_qe2_hi', c_f), ('w_qe2_lo', c_f),
+        ('roi_extrinsics', c_f), ('intrins_feat', c_f), ('enc_out', c_f),
     ]
 
 
@@ -200,6 +201,8 @@ SYMBOLS = [
     ('mv2d_geom_prep', C.c_int, [c_f, C.c_int, c_f, c_f, c_f]),
     ('mv2d_geom_prep_batch', C.c_int, [c_f, C.c_int, C.c_int, c_f, c_f, c_f]),
     ('mv2d_nchw_to_nhwc', C.c_int, [c_f, c_f, c_f, C.c_int, C.c_int, C.c_int, c_f]),
+    ('mv2d_nchw_add_to_nhwc', C.c_int, [c_f, c_f, c_f, C.c_int, C.c_int, C.c_int, c_f]),
+    ('mv2d_query_embedding', C.c_int, [c_f, C.c_int, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f]),
     ('mv2d_split_tf32', C.c_int, [c_f, c_f, c_f, C.c_longlong, c_f]),
     ('mv2d_gemm_3xtf32', C.c_int, [c_f, c_f, C.c_int, c_f, c_f, C.c_int, c_f, c_f, C.c_int, C.c_int, C.c_int,
                                    C.c_int, C.c_int, c_f]),
@@ -208,6 +211,7 @@ SYMBOLS = [
     ('mv2d_roi_align_qg_workspace_bytes', C.c_size_t, [C.c_int]),
     ('mv2d_roi_align_qg', C.c_int, [C.POINTER(QgParams), c_f]),
     ('mv2d_box_corr', C.c_int, [C.POINTER(CorrParams), c_f]),
+    ('mv2d_handoff_2d', C.c_int, [c_f, c_f, c_f, c_f, C.c_int, C.c_float, C.c_float, c_f, c_f, c_f]),
     ('mv2d_dn_workspace_bytes', C.c_size_t, [C.c_int, C.c_int]),
     ('mv2d_dn_prepare', C.c_int, [C.POINTER(DnParams), c_f]),
     ('mv2d_decoder_workspace_bytes', C.c_size_t, [C.c_int, C.c_int]),

@@ -134,6 +134,21 @@ class QueryGenerator(nn.Module):
                                        nn.Linear(512, 256), nn.ReLU(inplace=True))
         self.fc_center = nn.Linear(256, 3)
         self.loss_cls = loss_cls
+        self.return_cfg = dict(return_cfg or {})
+        self._owner = None
+
+    @torch.no_grad()
+    def forward(self, x, intrinsics, extrinsics, extra_feats=dict()):
+        """utils/query_generator.py:343-350: x [N,256,7,7] RoI features, intrinsics [N,4,4] (per-RoI K' of
+        MV2DHead.get_box_params), extrinsics [N,4,4], extra_feats['intrinsic'] [N,16] -> (center_lidar [N,3],
+        return_feats).  One call into ``mv2d_roi_align_qg`` (phase 3: conv3x3 as a 3xTF32 tcgen05 implicit GEMM, FC chain,
+        fc_center, center2lidar)."""
+        assert self._owner is not None, 'QueryGenerator must be owned by an MV2D head'
+        out = self._owner.engine().query_generator(x, intrinsics, extrinsics, extra_feats['intrinsic'])
+        return_feats = dict()
+        if self.return_cfg.get('enc', False):
+            return_feats['enc'] = out['enc']
+        return out['center_lidar'], return_feats
 
 
 class BoxCorrelation(nn.Module):
@@ -259,6 +274,18 @@ class MV2DTransformer(nn.Module):
         assert encoder is None
         self.decoder = build_from_cfg(decoder, TRANSFORMER_LAYER_SEQUENCE)
         self.embed_dims = self.decoder.embed_dims
+        self._owner = None      # the MV2D head whose engine runs the decoder
+
+    @torch.no_grad()
+    def forward(self, x, mask, query_embed, pos_embed, attn_mask=None, cross_attn_mask=None, **kwargs):
+        """cross_attention_head.py:22-49: x / pos_embed [bs,n,c,h,w], mask [bs,n,h,w], query_embed [bs,n_query,c],
+        attn_mask [n_query,n_query], cross_attn_mask [n_query,n,h,w] -> (out_dec [num_layers,bs,n_query,c], memory).
+        The six decoder layers run in ``mv2d_decoder`` (``HotPath.transformer`` converts the dense interface: gathered
+        RoI blocks become match lists, the dense bool mask a bit-packed key mask)."""
+        assert self._owner is not None, 'MV2DTransformer must be owned by an MV2D head'
+        outs, _, _ = self._owner.engine().transformer(x, mask, query_embed, pos_embed, None, attn_mask, cross_attn_mask)
+        bs, nq = query_embed.shape[0], query_embed.shape[1]
+        return outs.view(outs.shape[0], bs, nq, -1), x
 
 
 class _Cfg:
@@ -320,6 +347,27 @@ class CrossAttentionBoxHead(nn.Module):
         self.train_cfg, self.test_cfg = train_cfg, test_cfg
         self.assigner = build_from_cfg(train_cfg['assigner'], BBOX_ASSIGNERS) if (train_cfg and train_cfg.get('assigner')) else None
         self._owner = None
+
+    @torch.no_grad()
+    def position_embedding(self, query_pos):
+        """cross_attention_head.py:199-200: query_embedding(pos2posemb3d(reference points)) -- ``mv2d_query_embedding``."""
+        q = self._owner.engine().query_embedding(query_pos)
+        return q.view(*query_pos.shape[:-1], self.embed_dims)
+
+    @torch.no_grad()
+    def forward(self, reference_points, x, masks, pos_embed, attn_mask=None, cross_attn_mask=None, force_fp32=False,
+                query_embeds=None, return_query_feats=False, **kwargs):
+        """cross_attention_head.py:202-242: reference_points [bs,n_query,3] (normalised), x / pos_embed [bs,n,c,h,w],
+        masks [bs,n,h,w] -> (all_cls_scores, all_bbox_preds) [num_layers,bs,n_query,10]: query embedding, the decoder,
+        the per-layer cls / reg branches and the reference-point refinement in one ``mv2d_decoder`` call."""
+        eng = self._owner.engine()
+        query_embeds = self.position_embedding(reference_points)
+        outs, cls, box = eng.transformer(x, masks, query_embeds, pos_embed, reference_points, attn_mask, cross_attn_mask)
+        L, bs, nq = cls.shape[0], reference_points.shape[0], reference_points.shape[1]
+        cls, box = cls.view(L, bs, nq, -1), box.view(L, bs, nq, -1)
+        if return_query_feats:
+            return cls, box, outs[-1].view(bs, nq, -1)
+        return cls, box
 
     def get_bboxes(self, preds_dicts, img_metas, rescale=False):
         """cross_attention_head.py:356-377: NMS-free decode (top-k, denormalise, range filter) + z-shift."""
@@ -397,7 +445,7 @@ class MV2DHead(nn.Module):
         self.pc_range, self.intrins_feat_scale, self.feat_lvl, self.force_fp32 = pc_range, intrins_feat_scale, feat_lvl, force_fp32
         self.roi_size = [7, 7]
         self.stage_loss_weights = train_cfg.get('stage_loss_weights') if train_cfg else None
-        for m in (self.position_encoding, self.box_corr_module, self.bbox_head):
+        for m in (self.position_encoding, self.box_corr_module, self.bbox_head, self.query_generator, self.bbox_head.transformer):
             object.__setattr__(m, '_owner', self)
         self._engine = None
         self.register_load_state_dict_post_hook(lambda module, incompatible: setattr(module, '_engine', None))
@@ -686,6 +734,84 @@ class MV2D(nn.Module):
                 det = det[(wh >= min_size).all(dim=1)]
             out.append(det)
         return out
+
+    @staticmethod
+    def process_2d_gt(gt_bboxes, gt_labels, device):
+        """detectors/mv2d.py:47-58: per view [m,4] boxes + [m] labels -> [m,6] (x1, y1, x2, y2, 1, label)."""
+        return [torch.cat([b.to(device).float(), torch.ones((len(l), 1), device=device), l.to(device).float()[:, None]], dim=-1)
+                for b, l in zip(gt_bboxes, gt_labels)]
+
+    def complement_2d_gt(self, detections, gts, thr=0.35):
+        """detectors/mv2d.py:104-117 for ONE view, on the device (``mv2d_handoff_2d``)."""
+        min_size = ((self.train_cfg or {}).get('detection_proposal') or {}).get('min_bbox_size', 0)
+        if len(gts) == 0:
+            return detections
+        if len(detections) == 0:
+            return gts
+        # the detections come size-filtered from process_2d_detections, so the kernel's filter leaves them untouched
+        return self.roi_head.engine().handoff_2d([detections], [gts], min_size, thr)[0]
+
+    def handoff(self, results, gt_bboxes=None, gt_labels=None, device=None):
+        """process_2d_detections + complement_2d_gt for all views in ONE device call (detectors/mv2d.py:196-202):
+        ``results`` = per view either the detector's per-class [n_c,5] arrays or an [n,6] tensor."""
+        device = device or next(self.roi_head.parameters()).device
+        cfg = self.train_cfg if self.train_cfg is not None else (self.test_cfg or {})
+        min_size = (cfg.get('detection_proposal') or {}).get('min_bbox_size', 0)
+        thr = (self.train_cfg or {}).get('complement_2d_gt', -1) if gt_bboxes is not None else -1
+        dets = []
+        for res in results:
+            if torch.is_tensor(res):
+                dets.append(res.to(device).float().reshape(-1, 6))
+                continue
+            per_cls = [torch.cat([torch.as_tensor(b, dtype=torch.float32).reshape(-1, 5).to(device),
+                                  torch.full((len(b), 1), float(i), device=device)], dim=1) for i, b in enumerate(res)]
+            dets.append(torch.cat(per_cls, 0) if per_cls else torch.zeros((0, 6), device=device))
+        gts = self.process_2d_gt(gt_bboxes, gt_labels, device) if thr > 0 else None
+        return self.roi_head.engine().handoff_2d(dets, gts, min_size, thr)
+
+    def forward_train(self, img, img_metas, gt_bboxes_2d, gt_labels_2d, gt_bboxes_2d_to_3d, gt_bboxes_3d, gt_labels_3d,
+                      attr_labels=None, gt_bboxes_ignore=None, detector_out=None):
+        """detectors/mv2d.py:129-213, the shell around the hot path: per-view metas and ground truth, the 2D detector's
+        losses and detections (``base_detector``: a torch callable returning (feat, results, losses); or pass
+        ``detector_out`` = that triple), the hand-off on the device, the neck, ``roi_head.forward_train``.
+        One sample per call, as the reference asserts (:143); batches of samples go through
+        ``HotPath.forward_batch`` / ``TrainStep``."""
+        batch_size, num_views = img.shape[0], img.shape[1]
+        assert batch_size == 1, 'only support batch_size 1 now'          # mv2d.py:143
+        img = img.view(batch_size * num_views, *img.shape[2:])
+        ori_img_metas, ori_gt_bboxes_3d, ori_gt_labels_3d = img_metas, gt_bboxes_3d, gt_labels_3d
+        views_meta, gt_bboxes, gt_labels, v_boxes_3d, v_labels_3d = [], [], [], [], []
+        for i in range(batch_size):
+            for j in range(num_views):                                   # mv2d.py:157-166
+                m = dict(num_views=num_views)
+                for k, v in ori_img_metas[i].items():
+                    m[k] = v[j] if isinstance(v, list) else (v[:3] if k == 'ori_shape' else v)
+                views_meta.append(m)
+            lab3d = ori_gt_labels_3d[i]
+            box3d = ori_gt_bboxes_3d[i]
+            for j in range(num_views):                                   # mv2d.py:170-174
+                ids = gt_bboxes_2d_to_3d[i][j].unique()
+                sel = ids[ids > -1].long()
+                v_boxes_3d.append(box3d[sel])
+                v_labels_3d.append(lab3d[sel])
+            gt_bboxes.extend(gt_bboxes_2d[i])
+            gt_labels.extend(gt_labels_2d[i])
+        losses = dict()
+        if detector_out is None:
+            assert self.base_detector is not None, 'inject a torch 2D detector or pass detector_out'
+            detector_out = self.base_detector(img, views_meta, gt_bboxes=gt_bboxes, gt_labels=gt_labels)
+        detector_feat, results, det_losses = detector_out
+        for k, v in (det_losses or {}).items():
+            losses['det_' + k] = v
+        detections = self.handoff(results, gt_bboxes, gt_labels, device=img.device)
+        if self.with_neck:
+            cl, _ = self.process_detector_feat(detector_feat)
+            feat = cl.permute(0, 3, 1, 2)
+        else:
+            feat = detector_feat[0] if isinstance(detector_feat, (list, tuple)) else detector_feat
+        losses.update(self.roi_head.forward_train([feat], views_meta, detections, gt_bboxes, gt_labels, v_boxes_3d, v_labels_3d,
+                                                  ori_gt_bboxes_3d, ori_gt_labels_3d, attr_labels, None))
+        return losses
 
     @torch.no_grad()
     def simple_test(self, img, img_metas, detections=None, feat=None):

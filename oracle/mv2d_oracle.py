@@ -872,3 +872,41 @@ def scene_nms(boxes, scores, labels, score_thr=0.0, max_num=300, num_classes=10)
         inds = torch.argsort(s, descending=True, stable=True)[:max_num]
         b, s, l = b[inds], s[inds], l[inds]
     return b, s, l
+
+
+# ----------------------------------------------------------------------------- f2: detections hand-off (next row)
+def process_2d_detections(results, min_bbox_size=0):
+    """MV2D.process_2d_detections (detectors/mv2d.py:60-86): per view the 2D detector's per-class [n_c,5] arrays ->
+    one [n,6] tensor (x1, y1, x2, y2, score, label); boxes with a side below ``min_bbox_size`` are dropped."""
+    out = []
+    for res in results:
+        det = torch.cat([torch.cat([torch.as_tensor(b, dtype=torch.float32).reshape(-1, 5),
+                                    torch.full((len(b), 1), float(i))], dim=1) for i, b in enumerate(res)], dim=0)
+        if min_bbox_size > 0:
+            wh = det[:, 2:4] - det[:, 0:2]
+            det = det[(wh >= min_bbox_size).all(dim=1)]
+        out.append(det)
+    return out
+
+
+def box_iou_2d(a, b, eps=1e-4):
+    """MV2D.box_iou (detectors/mv2d.py:88-102): a [n,4], b [m,4] -> [n,m]; same fp32 operation order."""
+    a, b = a[:, None, :], b[None, :, :]
+    wh = torch.maximum(torch.minimum(a[..., 2:4], b[..., 2:4]) - torch.maximum(a[..., 0:2], b[..., 0:2]), a.new_tensor(0))
+    inter = wh.prod(-1)
+    union = (a[..., 2:4] - a[..., 0:2]).prod(-1) + (b[..., 2:4] - b[..., 0:2]).prod(-1) - inter
+    return inter / (union + eps)
+
+
+def complement_2d_gt(detections, gts, thr=0.35, min_bbox_size=0):
+    """MV2D.complement_2d_gt (detectors/mv2d.py:104-117): append the 2D ground-truth boxes ([m,6], score 1) whose best
+    IoU with the detections is below ``thr`` and whose sides reach ``min_bbox_size``.  Quirks kept: no ground truth ->
+    the detections; no detections -> ALL ground-truth boxes, unfiltered."""
+    if len(gts) == 0:
+        return detections
+    if len(detections) == 0:
+        return gts
+    max_iou = box_iou_2d(gts[:, :4], detections[:, :4]).max(-1)[0]
+    wh = gts[:, 2:4] - gts[:, 0:2]
+    keep = (max_iou < thr) & (wh >= min_bbox_size).all(dim=1)
+    return torch.cat([detections, gts[keep]], dim=0)
