@@ -412,6 +412,11 @@ typedef struct Mv2dLossParams {
     float* losses;              /* out [L,4]: loss_cls, loss_bbox, dn_loss_cls, dn_loss_bbox */
     float* workspace;
     size_t workspace_bytes;
+    /* ---- ABI 5: the reference divides loss_bbox by clamp(reduce_mean(num_total_pos), min=1) taken ACROSS RANKS
+     * (cross_attention_head.py:419-420); loss_cls keeps the local count (sync_cls_avg_factor = False). */
+    float* num_pos;             /* out, nullable [L]: positive matching queries of every layer (local count, as float) */
+    const float* bbox_avg_factor; /* in, nullable [L]: replaces max(num_pos, 1) as the avg factor of loss_bbox (the caller
+                                 * all-reduces num_pos, divides by the number of samples and clamps at 1) */
 } Mv2dLossParams;
 MV2D_API size_t mv2d_loss_workspace_bytes(int N, int G, int L);
 MV2D_API int mv2d_loss(const Mv2dLossParams* p, void* stream);
@@ -492,6 +497,10 @@ typedef struct Mv2dTrainParams {
     float* workspace;           /* saved activations of the forward + scratch of the backward; must survive between the
                                  * two calls */
     size_t workspace_bytes;
+    /* ---- ABI 5: cross-rank loss normaliser (see Mv2dLossParams) */
+    float* num_pos;             /* forward out, nullable [L] */
+    const float* bbox_avg_factor; /* backward in, nullable [L]: the gradient of loss_bbox uses it instead of the local
+                                 * max(num_pos, 1), and losses[l][1] is rescaled to it in place */
 } Mv2dTrainParams;
 MV2D_API size_t mv2d_decoder_train_workspace_bytes(int N, int L, int max_match, int G);
 MV2D_API int mv2d_decoder_train_forward(const Mv2dTrainParams* p, void* stream);

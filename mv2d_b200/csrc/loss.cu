@@ -173,6 +173,8 @@ struct LossArgs {
     float alpha, gamma, cls_lw, box_lw, dn_split;
     float code_w[LOSS_CODE];
     float* losses;       // [L,4]
+    float* num_pos;                    // nullable out [L]
+    const float* bbox_avg_factor;      // nullable in [L]
 };
 
 __device__ __forceinline__ double focal_elem(float x, bool t, float alpha, float gamma) {
@@ -236,7 +238,9 @@ __global__ void __launch_bounds__(256) loss_kernel(LossArgs a) {
             box_avg = fmax((double)a.pad, 1.0);
         } else {
             cls_avg = fmax((double)sp[0], 1.0);          // bg_cls_weight = 0 with a sigmoid focal loss (cross_attention_head.py:153)
-            box_avg = fmax((double)sp[0], 1.0);
+            // clamp(reduce_mean(num_total_pos), min=1) over ranks when the caller supplies it (cross_attention_head.py:419-420)
+            box_avg = a.bbox_avg_factor ? (double)a.bbox_avg_factor[l] : fmax((double)sp[0], 1.0);
+            if (a.num_pos) a.num_pos[l] = (float)sp[0];
         }
         float lc = (float)(a.cls_lw * sf[0] / (cls_avg + eps));
         float lb = (float)(a.box_lw * sb[0] / (box_avg + eps));
@@ -293,7 +297,7 @@ int run_loss(const Mv2dLossParams& p, cudaStream_t st) {
     a.N = p.N; a.G = p.G; a.num_classes = p.num_classes; a.alpha = p.focal_alpha; a.gamma = p.focal_gamma;
     a.cls_lw = p.cls_loss_weight; a.box_lw = p.bbox_loss_weight; a.dn_split = p.dn_split;
     for (int j = 0; j < LOSS_CODE; ++j) a.code_w[j] = p.code_weights[j];
-    a.losses = p.losses;
+    a.losses = p.losses; a.num_pos = p.num_pos; a.bbox_avg_factor = p.bbox_avg_factor;
     launch_k(loss_kernel, dim3(p.L, 2), dim3(256), 0, st, a);
     MV2D_CHECK_LAUNCH("loss");
     return 0;

@@ -300,6 +300,8 @@ struct LossGradArgs {
     float alpha, gamma, cls_lw, box_lw;
     float code_w[TCODE];
     float stage_w[MV2D_MAX_LAYERS];
+    const float* bbox_avg_factor;     // nullable [L]: cross-rank avg factor of loss_bbox (cross_attention_head.py:419-420)
+    float* losses;                    // [L,4]: with bbox_avg_factor, losses[l][1] is rescaled from the local factor to it
 };
 
 __global__ void __launch_bounds__(256) loss_grad_kernel(LossGradArgs a) {
@@ -317,8 +319,10 @@ __global__ void __launch_bounds__(256) loss_grad_kernel(LossGradArgs a) {
         __syncthreads();
     }
     const double avg = fmax((double)sp[0], 1.0) + 1.1920928955078125e-07;
+    const double avg_box = a.bbox_avg_factor ? (double)a.bbox_avg_factor[l] + 1.1920928955078125e-07 : avg;
     const float kc = (float)((double)a.cls_lw * a.stage_w[l] / avg);
-    const float kb = (float)((double)a.box_lw * a.stage_w[l] / avg);
+    const float kb = (float)((double)a.box_lw * a.stage_w[l] / avg_box);
+    if (a.bbox_avg_factor && a.losses && tid == 0) a.losses[l * 4 + 1] = (float)((double)a.losses[l * 4 + 1] * avg / avg_box);
     for (int n = tid; n < a.N; n += 256) {
         const int g = asg[n];
         const int label = g >= 0 ? a.gt_labels[g] : a.num_classes;
@@ -633,6 +637,7 @@ int run_train_forward(const Mv2dTrainParams& p, cudaStream_t st) {
     for (int j = 0; j < TCODE; ++j) lp.code_weights[j] = p.code_weights[j];
     lp.cls_scores = p.cls_scores; lp.bbox_preds = p.bbox_preds; lp.gt_boxes = p.gt_boxes; lp.gt_labels = p.gt_labels;
     lp.assigned = p.assigned; lp.losses = p.losses; lp.workspace = w.loss_ws; lp.workspace_bytes = w.loss_ws_bytes;
+    lp.num_pos = p.num_pos;
     return run_loss(lp, st);
 }
 
@@ -666,6 +671,7 @@ int run_train_backward(const Mv2dTrainParams& p, cudaStream_t st) {
     lg.alpha = p.focal_alpha; lg.gamma = p.focal_gamma; lg.cls_lw = p.cls_loss_weight; lg.box_lw = p.bbox_loss_weight;
     for (int j = 0; j < TCODE; ++j) lg.code_w[j] = p.code_weights[j];
     for (int l = 0; l < MV2D_MAX_LAYERS; ++l) lg.stage_w[l] = p.stage_loss_weights[l];
+    lg.bbox_avg_factor = p.bbox_avg_factor; lg.losses = p.losses;
     launch_k(loss_grad_kernel, dim3(L), dim3(256), 0, st, lg);
     MV2D_CHECK_LAUNCH("train loss_grad");
     launch_k(xa_inverse_kernel, dim3(N), dim3(32), 0, st, p.match, p.match_cnt, p.max_match, N, w.inv_cnt, w.inv_list);

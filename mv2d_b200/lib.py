@@ -146,6 +146,7 @@ class LossParams(C.Structure):
         ('cls_scores', c_f), ('bbox_preds', c_f), ('gt_boxes', c_f), ('gt_labels', c_f),
         ('dn_cls', c_f), ('dn_box', c_f), ('dn_labels', c_f),
         ('assigned', c_f), ('losses', c_f), ('workspace', c_f), ('workspace_bytes', C.c_size_t),
+        ('num_pos', c_f), ('bbox_avg_factor', c_f),
     ]
 
 
@@ -172,6 +173,7 @@ class TrainParams(C.Structure):
         ('cls_scores', c_f), ('bbox_preds', c_f), ('assigned', c_f), ('losses', c_f),
         ('d_ref', c_f), ('d_tok_kin', c_f), ('d_tok_mem', c_f),
         ('workspace', c_f), ('workspace_bytes', C.c_size_t),
+        ('num_pos', c_f), ('bbox_avg_factor', c_f),
     ]
 
 

@@ -572,9 +572,8 @@ class MV2DHead(nn.Module):
         boxes = self.bbox_head._gt_tensor(ori_gt_bboxes_3d[0])
         tr = self.trainer()
         self._engine = None           # the packed inference weights go stale as soon as the optimizer steps
-        anchor = self._train_params[0][1]
-        total, loss_cls, loss_bbox = _TrainStep.apply(feat, anchor, self, [p[:, :6] for p in proposal_list], img_metas, boxes,
-                                                      ori_gt_labels_3d[0])
+        total, loss_cls, loss_bbox = _TrainStep.apply(feat, self, [p[:, :6] for p in proposal_list], img_metas, boxes,
+                                                      ori_gt_labels_3d[0], *[prm for _, prm in self._train_params])
         w = tr.stage_loss_weights
         losses = {}
         for i in range(tr.L):
@@ -587,33 +586,35 @@ class MV2DHead(nn.Module):
 
 class _TrainStep(torch.autograd.Function):
     """One sample's hot-path training step as an autograd node: forward = the CUDA forward with saved activations +
-    targets / losses, backward = the CUDA backward; parameter gradients are accumulated into ``Parameter.grad``."""
+    targets / losses, backward = the CUDA backward.  EVERY hot-path Parameter is an input of the node and gets its slice
+    of the flat gradient buffer back from ``backward``, so autograd's AccumulateGrad nodes -- and with them the hooks of
+    (MM)DistributedDataParallel's bucketed all-reduce -- see all of them (find_unused_parameters=False works)."""
 
     @staticmethod
-    def forward(ctx, feat, anchor, head, proposal_list, img_metas, gt_boxes, gt_labels):
+    def forward(ctx, feat, head, proposal_list, img_metas, gt_boxes, gt_labels, *params):
         tr = head.trainer()
         tr.zero_grad()
         out = tr.forward(feat.detach(), proposal_list, img_metas, gt_boxes, gt_labels)
-        ctx.head = head
+        ctx.head, ctx.num_pos = head, out['num_pos']
         loss_cls, loss_bbox = out['loss_cls'].clone(), out['loss_bbox'].clone()
         ctx.mark_non_differentiable(loss_cls, loss_bbox)
         return out['loss'].clone(), loss_cls, loss_bbox
 
     @staticmethod
     def backward(ctx, g_total, g_cls, g_bbox):
+        import torch.distributed as dist
+        from ..train import DecoderTrainer
         head = ctx.head
         tr = head.trainer()
-        gin = tr.backward()
+        factor = None
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            # the reference's loss_bbox normaliser is the mean positive count over ranks (cross_attention_head.py:419-420)
+            factor = DecoderTrainer.global_bbox_avg_factor([ctx.num_pos])
+        gin = tr.backward(factor)
         if float(g_total) != 1.0:      # a scaled loss (gradient accumulation, AMP scaler): scale what this step produced
             tr.grads.mul_(g_total)
-        fresh = [(prm, tr.grad(name)) for name, prm in head._train_params]
-        have = [(prm, g) for prm, g in fresh if prm.grad is not None]
-        if have:
-            torch._foreach_add_([prm.grad for prm, _ in have], [g for _, g in have])
-        for prm, g in fresh:
-            if prm.grad is None:
-                prm.grad = g.clone()
-        return gin['d_feat'] * g_total, None, None, None, None, None, None
+        grads = [tr.grad(name) for name, _ in head._train_params]      # views of the flat buffer; autograd copies them
+        return (gin['d_feat'] * g_total, None, None, None, None, None, *grads)
 
 
 @HEADS.register_module()

@@ -175,6 +175,7 @@ class DecoderTrainer:
         G, L = gt.shape[0], self.L
         out = dict(cls_scores=torch.empty((L, N, 10), **f32), bbox_preds=torch.empty((L, N, 10), **f32),
                    assigned=torch.empty((L, N), device=dev, dtype=torch.int32), losses=torch.empty((L, 4), **f32),
+                   num_pos=torch.empty((L,), **f32),
                    d_ref=torch.empty((N, 3), **f32), d_tok_kin=torch.empty((N, 49, 256), **f32),
                    d_tok_mem=torch.empty((N, 49, 256), **f32))
         ws_bytes = int(self.lib.mv2d_decoder_train_workspace_bytes(N, L, M, G))
@@ -210,20 +211,40 @@ class DecoderTrainer:
         self._out = out
         w = self._stage_weights()
         res = dict(cls_scores=out['cls_scores'], bbox_preds=out['bbox_preds'], assigned=out['assigned'],
-                   loss_cls=out['losses'][:, 0], loss_bbox=out['losses'][:, 1])
+                   loss_cls=out['losses'][:, 0], loss_bbox=out['losses'][:, 1], num_pos=out['num_pos'])
         res['loss'] = (w * (out['losses'][:, 0] + out['losses'][:, 1])).sum()
         return res
 
     @torch.no_grad()
-    def backward(self):
+    def backward(self, bbox_avg_factor=None):
         """Gradient of the last forward's ``loss``: accumulates into the flat gradient buffer and returns the input
         gradients d_ref [N,3], d_tok_kin [N,49,256] (gradient w.r.t. the key input feat + pe tokens) and d_tok_mem
-        [N,49,256] (gradient w.r.t. the value input)."""
+        [N,49,256] (gradient w.r.t. the value input).
+        bbox_avg_factor [L] (device): the reference divides loss_bbox by clamp(reduce_mean(num_total_pos), min=1) taken
+        across ranks (cross_attention_head.py:419-420); ``global_bbox_avg_factor`` makes it from the forwards' ``num_pos``.
+        With it the gradient (and the stored loss_bbox values) use that factor instead of the sample's own count."""
         self._need_cuda()
         assert self._p is not None, 'backward() needs a forward() first'
+        if bbox_avg_factor is not None:
+            self._baf = bbox_avg_factor.to(self.device, torch.float32).contiguous()
+            self._p.bbox_avg_factor = self._baf.data_ptr()
+        else:
+            self._p.bbox_avg_factor = None
         lib.check(self.lib.mv2d_decoder_train_backward(C.byref(self._p), lib.stream_ptr()), 'mv2d_decoder_train_backward')
         out = self._out
         return dict(d_ref=out['d_ref'], d_tok_kin=out['d_tok_kin'], d_tok_mem=out['d_tok_mem'])
+
+    @staticmethod
+    @torch.no_grad()
+    def global_bbox_avg_factor(num_pos_list, group=None):
+        """clamp(mean over ALL samples of the global batch of num_pos, min=1) per decoder layer: the local sums are
+        all-reduced in one tiny collective (the reference: reduce_mean over ranks with one sample per rank,
+        cross_attention_head.py:419-420).  num_pos_list: the ``num_pos`` [L] of this rank's forwards."""
+        s = torch.stack(list(num_pos_list), 0).sum(0)
+        n = torch.tensor([float(len(num_pos_list))], device=s.device)
+        buf = torch.cat([s, n])
+        all_reduce_sum(buf, group)
+        return torch.clamp(buf[:-1] / buf[-1], min=1.0)
 
     # ------------------------------------------------------------------ data parallel + optimizer
     def all_reduce_grads(self, group=None):
@@ -311,9 +332,9 @@ class HotPathTrainer(DecoderTrainer):
         return res
 
     @torch.no_grad()
-    def backward(self):
+    def backward(self, bbox_avg_factor=None):
         """Accumulates every parameter gradient into the flat buffer; returns d loss / d feat as [V,256,h,w]."""
-        gin = super().backward()
+        gin = super().backward(bbox_avg_factor)
         p = self._fp
         p.d_ref, p.d_tok_kin, p.d_tok_mem = (gin[k].data_ptr() for k in ('d_ref', 'd_tok_kin', 'd_tok_mem'))
         lib.check(self.lib.mv2d_front_train_backward(C.byref(p), lib.stream_ptr()), 'mv2d_front_train_backward')
@@ -328,42 +349,72 @@ class TrainStep:
     the all-reduce.  lanes=1 is the plain sequential step.  Same results as running the samples one after the other
     up to fp32 summation order."""
 
-    def __init__(self, state_dict, device='cuda', lanes=2, **kw):
+    def __init__(self, state_dict, device='cuda', lanes=2, sync_bbox_avg_factor=True, **kw):
         assert lanes >= 1
+        self._sd, self._kw = state_dict, dict(kw)
         self.main = HotPathTrainer(state_dict, device=device, **kw)
         self.lanes = [self.main]
+        self.streams = [torch.cuda.Stream(device=self.main.device)]
+        # True (the reference's objective, cross_attention_head.py:419-420): loss_bbox is divided by the mean positive count
+        # over all samples of the GLOBAL batch; False: by each sample's own count (no collective before the backward)
+        self.sync_bbox_avg_factor = sync_bbox_avg_factor
         for _ in range(lanes - 1):
-            t = HotPathTrainer(state_dict, device=device, **kw)
-            t.params = self.main.params            # ONE set of weights; own gradients, workspaces, engine buffers
-            self.lanes.append(t)
-        self.streams = [torch.cuda.Stream(device=self.main.device) for _ in self.lanes]
+            self._add_lane()
         self.total = self.main.total
+
+    def _add_lane(self):
+        t = HotPathTrainer(self._sd, device=self.main.device, **self._kw)
+        t.params = self.main.params            # ONE set of weights; own gradients, workspaces, engine buffers
+        self.lanes.append(t)
+        self.streams.append(torch.cuda.Stream(device=self.main.device))
 
     @torch.no_grad()
     def step(self, samples, lr=2e-4, weight_decay=0.01, world=1, optimize=True, max_grad_norm=None):
         """samples: list of (feat, proposal_list, img_metas, gt_boxes, gt_labels).  Returns the mean weighted loss
-        (a device scalar).  Gradients end up summed in ``self.main.grads`` (all-reduced over ranks).  max_grad_norm: the
+        (a device scalar).  Gradients end up summed in ``self.main.grads`` (all-reduced over ranks) and are scaled by
+        1 / (ranks of the process group x samples); ``world`` is only checked against the group.  max_grad_norm: the
         reference's grad_clip (35 in the exp configs) over the hot-path parameters; None = off."""
+        if not samples:
+            return torch.zeros((), device=self.main.device)
+        while len(self.lanes) < len(samples) and self.sync_bbox_avg_factor:
+            self._add_lane()          # every sample keeps its activations until the global loss normaliser is known
         cur = torch.cuda.current_stream()
         for t in self.lanes:
             t.zero_grad()
-        losses = []
+        outs = []
         for s in self.streams:
             s.wait_stream(cur)
-        for i, smp in enumerate(samples):
-            k = i % len(self.lanes)
-            with torch.cuda.stream(self.streams[k]):
-                losses.append(self.lanes[k].forward(*smp)['loss'])
-                self.lanes[k].backward()
+        if not self.sync_bbox_avg_factor:      # each sample normalised by its own count: forward + backward back to back
+            for i, smp in enumerate(samples):
+                k = i % len(self.lanes)
+                with torch.cuda.stream(self.streams[k]):
+                    outs.append(self.lanes[k].forward(*smp))
+                    self.lanes[k].backward()
+        else:
+            for i, smp in enumerate(samples):
+                with torch.cuda.stream(self.streams[i]):
+                    outs.append(self.lanes[i].forward(*smp))
+            for s in self.streams:
+                cur.wait_stream(s)
+            # loss_bbox / its gradient are divided by the mean positive count over the GLOBAL batch (one tiny all-reduce)
+            factor = DecoderTrainer.global_bbox_avg_factor([o['num_pos'] for o in outs])
+            for s in self.streams:
+                s.wait_stream(cur)
+            for i in range(len(samples)):
+                with torch.cuda.stream(self.streams[i]):
+                    self.lanes[i].backward(factor)
         for s in self.streams:
             cur.wait_stream(s)
         for t in self.lanes[1:]:
             self.main.grads.add_(t.grads)
-        self.main.all_reduce_grads()
-        scale = 1.0 / (world * max(len(samples), 1))
+        nranks = self.main.all_reduce_grads()
+        assert world in (1, nranks), f'world={world} but the process group has {nranks} ranks'
+        scale = 1.0 / (nranks * len(samples))
         if optimize and max_grad_norm is not None:
             self.main.clip_grad_norm_(max_grad_norm, grad_scale=scale)
             scale = 1.0
         if optimize:
             self.main.adamw_step(lr=lr, weight_decay=weight_decay, grad_scale=scale)
+        w = self.main._stage_weights()
+        losses = [(w * (o['loss_cls'] + o['loss_bbox'])).sum() for o in outs]      # after the backward: rescaled loss_bbox
         return torch.stack(losses).mean()
