@@ -501,8 +501,30 @@ typedef struct Mv2dTrainParams {
     float* num_pos;             /* forward out, nullable [L] */
     const float* bbox_avg_factor; /* backward in, nullable [L]: the gradient of loss_bbox uses it instead of the local
                                  * max(num_pos, 1), and losses[l][1] is rescaled to it in place */
+    /* ---- ABI 5: the two-frame head and denoising queries (roi_heads/mv2d_t_head.py:26-142, mv2d_s_head.py:39-120,
+     * 278-299, bbox_heads/cross_attention_head.py:475-538) -- the configuration the reference trains MV2D-T with.
+     * mode 1: the decoder runs over pad + N query rows (denoising rows first); `ref`, `d_ref`, cls_scores and
+     * bbox_preds have pad + N rows ([L, pad+N, 10]); the cross-attention keys are the num_rows feature cells of
+     * kin_map / mem_map, query i attends to key_list[i][0 .. key_cnt[i]) (= the set bits of keymask[i]); tok_kin /
+     * tok_mem / match* / d_tok_* are not used.  The matching rows' velocity outputs are divided by vel_dt before
+     * the loss (mv2d_t_head.py:130-142); the denoising rows add dn_loss_cls / dn_loss_bbox (losses[l][2..3]) times
+     * denoise_weight.  `assigned`, `num_pos` and the Hungarian losses refer to the N matching rows. */
+    int mode, pad, num_rows, mask_words;
+    int neg_bbox_loss, reserved5;
+    float vel_dt, dn_split, denoise_weight, reserved6;
+    const float* kin_map;       /* [num_rows,256] key input (feat + pe), channels-last */
+    const float* mem_map;       /* [num_rows,256] value input (feat) */
+    const uint32_t* keymask;    /* [pad+N, mask_words] */
+    const uint16_t* key_list;   /* [pad+N, mask_words*32] */
+    const int* key_cnt;         /* [pad+N] */
+    const uint8_t* self_attn_mask; /* nullable [pad+N, pad+N], 1 = masked */
+    const int* dn_labels;       /* [pad]: label of denoising query i (num_classes = negative); its box is gt_boxes[i % G] */
+    float* d_kin_map;           /* backward out [num_rows,256] */
+    float* d_mem_map;           /* backward out [num_rows,256] */
 } Mv2dTrainParams;
 MV2D_API size_t mv2d_decoder_train_workspace_bytes(int N, int L, int max_match, int G);
+/* the same from a filled parameter block (needed for mode 1: N, pad, L, num_rows, G are read) */
+MV2D_API size_t mv2d_decoder_train_workspace_bytes_p(const Mv2dTrainParams* p);
 MV2D_API int mv2d_decoder_train_forward(const Mv2dTrainParams* p, void* stream);
 /* tests: float offset of a saved activation in `workspace` after the forward.  which = 0 query_pos [N,256];
  * per layer: 1 x after norms.0, 2 after norms.1, 3 layer output, 4 post-normed intermediate, 5 cross-attention
@@ -548,6 +570,11 @@ typedef struct Mv2dFrontTrainParams {
     float* d_feat;                  /* backward out [V,h,w,256] */
     float* workspace;               /* saved activations + scratch; must survive between the two calls */
     size_t workspace_bytes;
+    /* ---- ABI 5 (two-frame head: the decoder's keys are the whole maps feat + pe and feat) */
+    const float* d_pe_extra;        /* backward in, nullable [V,h,w,256]: added to d loss / d pe before the PE backward */
+    const float* d_feat_extra;      /* backward in, nullable [V,h,w,256]: added to d_feat */
+    const float* d_feat_extra2;     /* backward in, nullable: a second map added to d_feat (value-input gradient) */
+    float* kin_out;                 /* forward out, nullable [V,h,w,256]: feat + pe, the key input of the two-frame head */
 } Mv2dFrontTrainParams;
 MV2D_API size_t mv2d_front_train_workspace_bytes(int N, int V, int h, int w);
 MV2D_API int mv2d_front_train_forward(const Mv2dFrontTrainParams* p, void* stream);

@@ -177,6 +177,7 @@ int mv2d_train_param_info(int L, int tensor_id, long long* offset, long long* nu
     return train_param_info(L, tensor_id, offset, numel);
 }
 size_t mv2d_decoder_train_workspace_bytes(int N, int L, int max_match, int G) { return train_workspace_bytes(N, L, max_match, G); }
+size_t mv2d_decoder_train_workspace_bytes_p(const Mv2dTrainParams* p) { return p ? train_workspace_bytes_p(*p) : 0; }
 long long mv2d_train_debug_offset(int N, int L, int max_match, int G, int layer, int which) {
     return train_debug_offset(N, L, max_match, G, layer, which);
 }

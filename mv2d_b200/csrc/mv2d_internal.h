@@ -53,6 +53,7 @@ long long train_param_total(int L);
 int train_set_tensor_cores(int on);
 int train_param_info(int L, int tensor_id, long long* offset, long long* numel);
 size_t train_workspace_bytes(int N, int L, int max_match, int G);
+size_t train_workspace_bytes_p(const Mv2dTrainParams& p);
 long long train_debug_offset(int N, int L, int max_match, int G, int layer, int which);
 int run_train_forward(const Mv2dTrainParams& p, cudaStream_t st);
 int run_train_backward(const Mv2dTrainParams& p, cudaStream_t st);

@@ -247,13 +247,16 @@ struct Range6 { float v[6]; };
 
 // cross_attention_head.py:224-237: codes 0,1 (+ inverse_sigmoid(ref) 0,1) and 4 (+ ref 2) go through a sigmoid and
 // are scaled to pc_range; sig [N,4] keeps the three sigmoid values for the backward
+// vel_dt != 0: rows >= vel_row_start (the matching queries of the two-frame head) get their velocity outputs divided by
+// the frame interval (mv2d_t_head.py:130-142); the denoising rows in front are left alone (:112-118 come first)
 __global__ void __launch_bounds__(128) reg_tail_fwd_kernel(float* __restrict__ box, const float* __restrict__ ref,
-                                                           float* __restrict__ sig, Range6 pc, int N) {
+                                                           float* __restrict__ sig, Range6 pc, int N, float vel_dt, int vel_row_start) {
     pdl_wait();
     pdl_trigger();
     const int n = blockIdx.x * 128 + threadIdx.x;
     if (n >= N) return;
     float* b = box + (long long)n * TCODE;
+    if (vel_dt != 0.f && n >= vel_row_start) { b[8] = b[8] / vel_dt; b[9] = b[9] / vel_dt; }
     const float s0 = sigmoid_f(b[0] + inverse_sigmoid_f(ref[n * 3 + 0]));
     const float s1 = sigmoid_f(b[1] + inverse_sigmoid_f(ref[n * 3 + 1]));
     const float s4 = sigmoid_f(b[4] + inverse_sigmoid_f(ref[n * 3 + 2]));
@@ -274,12 +277,14 @@ __device__ __forceinline__ float inverse_sigmoid_grad(float x) {
 
 // dbox [N,10] -> gradient of the raw reg output in place; d_ref += through inverse_sigmoid(ref)
 __global__ void __launch_bounds__(128) reg_tail_bwd_kernel(float* __restrict__ dbox, const float* __restrict__ ref,
-                                                           const float* __restrict__ sig, float* __restrict__ d_ref, Range6 pc, int N) {
+                                                           const float* __restrict__ sig, float* __restrict__ d_ref, Range6 pc, int N,
+                                                           float vel_dt, int vel_row_start) {
     pdl_wait();
     pdl_trigger();
     const int n = blockIdx.x * 128 + threadIdx.x;
     if (n >= N) return;
     float* d = dbox + (long long)n * TCODE;
+    if (vel_dt != 0.f && n >= vel_row_start) { d[8] = d[8] / vel_dt; d[9] = d[9] / vel_dt; }
     const float s0 = sig[n * 4 + 0], s1 = sig[n * 4 + 1], s4 = sig[n * 4 + 2];
     const float g0 = d[0] * (pc.v[3] - pc.v[0]) * s0 * (1.f - s0);
     const float g1 = d[1] * (pc.v[4] - pc.v[1]) * s1 * (1.f - s1);
@@ -302,6 +307,9 @@ struct LossGradArgs {
     float stage_w[MV2D_MAX_LAYERS];
     const float* bbox_avg_factor;     // nullable [L]: cross-rank avg factor of loss_bbox (cross_attention_head.py:419-420)
     float* losses;                    // [L,4]: with bbox_avg_factor, losses[l][1] is rescaled from the local factor to it
+    // denoising queries (dn_loss_single, cross_attention_head.py:475-538): the first `pad` of the NT = pad + N rows of
+    // every layer; N, assigned refer to the matching rows behind them
+    int pad; const int* dn_labels; float dn_split, dn_weight; int neg_bbox_loss;
 };
 
 __global__ void __launch_bounds__(256) loss_grad_kernel(LossGradArgs a) {
@@ -320,13 +328,28 @@ __global__ void __launch_bounds__(256) loss_grad_kernel(LossGradArgs a) {
     }
     const double avg = fmax((double)sp[0], 1.0) + 1.1920928955078125e-07;
     const double avg_box = a.bbox_avg_factor ? (double)a.bbox_avg_factor[l] + 1.1920928955078125e-07 : avg;
-    const float kc = (float)((double)a.cls_lw * a.stage_w[l] / avg);
-    const float kb = (float)((double)a.box_lw * a.stage_w[l] / avg_box);
+    const float kc_m = (float)((double)a.cls_lw * a.stage_w[l] / avg);
+    const float kb_m = (float)((double)a.box_lw * a.stage_w[l] / avg_box);
     if (a.bbox_avg_factor && a.losses && tid == 0) a.losses[l * 4 + 1] = (float)((double)a.losses[l * 4 + 1] * avg / avg_box);
-    for (int n = tid; n < a.N; n += 256) {
-        const int g = asg[n];
-        const int label = g >= 0 ? a.gt_labels[g] : a.num_classes;
-        const long long oc = ((long long)l * a.N + n) * a.num_classes;
+    // denoising rows: avg factors pad * pi / 6 * split^3 (classification) and pad (boxes), both floored at 1
+    const double dn_cls_avg = fmax((double)a.pad * 3.14159 / 6.0 * a.dn_split * a.dn_split * a.dn_split, 1.0) + 1.1920928955078125e-07;
+    const double dn_box_avg = fmax((double)a.pad, 1.0) + 1.1920928955078125e-07;
+    const float kc_d = (float)((double)a.cls_lw * a.stage_w[l] * a.dn_weight / dn_cls_avg);
+    const float kb_d = (float)((double)a.box_lw * a.stage_w[l] * a.dn_weight / dn_box_avg);
+    const int NT = a.pad + a.N;
+    for (int row = tid; row < NT; row += 256) {
+        const bool dn = row < a.pad;
+        const int n = row - a.pad;
+        int g, label;
+        if (dn) {
+            label = a.dn_labels[row];
+            g = (a.G > 0 && (a.neg_bbox_loss || label != a.num_classes)) ? row % a.G : -1;
+        } else {
+            g = asg[n];
+            label = g >= 0 ? a.gt_labels[g] : a.num_classes;
+        }
+        const float kc = dn ? kc_d : kc_m, kb = dn ? kb_d : kb_m;
+        const long long oc = ((long long)l * NT + row) * a.num_classes;
         for (int c = 0; c < a.num_classes; ++c) {
             const float x = a.cls[oc + c];
             const float p = 1.f / (1.f + expf(-x));
@@ -344,7 +367,7 @@ __global__ void __launch_bounds__(256) loss_grad_kernel(LossGradArgs a) {
             }
             a.dcls[oc + c] = d * kc;
         }
-        const long long ob = ((long long)l * a.N + n) * TCODE;
+        const long long ob = ((long long)l * NT + row) * TCODE;
         float gn[TCODE];
         bool ok = false;
         if (g >= 0) {
@@ -360,7 +383,8 @@ __global__ void __launch_bounds__(256) loss_grad_kernel(LossGradArgs a) {
             float d = 0.f;
             if (ok) {
                 const float e = a.box[ob + j] - gn[j];
-                d = (e > 0.f ? 1.f : (e < 0.f ? -1.f : 0.f)) * a.code_w[j] * kb;
+                const float cw = (dn && (j == 6 || j == 7)) ? 0.f : a.code_w[j];     // the denoising loss leaves sin / cos out (:527)
+                d = (e > 0.f ? 1.f : (e < 0.f ? -1.f : 0.f)) * cw * kb;
             }
             a.dbox[ob + j] = d;
         }
@@ -384,7 +408,9 @@ struct TrainWs {
     size_t total_bytes;
 };
 
-TrainWs train_layout(float* base, int N, int L, int max_match, int G) {
+// N = query rows of the decoder (pad + matching queries in mode 1), Nm = matching queries (Hungarian loss);
+// mode 1 (two-frame head): keys = R feature cells -> Kp / Vp [R,256] per layer, P / dS dense [N,8,R]
+TrainWs train_layout(float* base, int N, int L, int max_match, int G, int mode = 0, int R = 0, int Nm = -1) {
     TrainWs w{};
     size_t off = 0;   // in floats
     auto take = [&](size_t n) -> float* {
@@ -392,7 +418,10 @@ TrainWs train_layout(float* base, int N, int L, int max_match, int G) {
         off += (n + 63) / 64 * 64;
         return p;
     };
-    const size_t n = (size_t)(N > 0 ? N : 1), NC = n * TC_, PM = (size_t)max_match * TTOK, NK = n * TTOK * TC_;
+    if (Nm < 0) Nm = N;
+    const size_t n = (size_t)(N > 0 ? N : 1), NC = n * TC_;
+    const size_t krows = mode == 1 ? (size_t)(R > 0 ? R : 1) : n * TTOK;          // key rows of the cross-attention
+    const size_t PM = mode == 1 ? krows : (size_t)max_match * TTOK, NK = krows * TC_;
     w.posemb = take(n * TPE); w.h0 = take(NC); w.qpos = take(NC); w.zero = take(NC);
     for (int l = 0; l < L; ++l) {
         LayerAct& a = w.layer[l];
@@ -412,11 +441,11 @@ TrainWs train_layout(float* base, int N, int L, int max_match, int G) {
     w.dKp = take(NK * L); w.dVp = take(NK * L); w.dcls = take((size_t)L * n * TCODE); w.dbox = take((size_t)L * n * TCODE);
     w.dposemb = take(n * TPE);
     w.inv_cnt = reinterpret_cast<int*>(take(n));
-    w.inv_list = reinterpret_cast<int*>(take(n * n));
-    w.loss_ws_bytes = loss_workspace_bytes(N, G, L);
+    w.inv_list = reinterpret_cast<int*>(take(mode == 1 ? 64 : n * n));
+    w.loss_ws_bytes = loss_workspace_bytes(Nm, G, L);
     w.loss_ws = take(w.loss_ws_bytes / 4 + 1);
     {   // tensor-core route: transposed operands of the K/V weight gradients, W^T, split-K partials, accumulate temp
-        const size_t Mp = (size_t)round32((int)(n * TTOK));
+        const size_t Mp = (size_t)round32((int)krows);
         // at: [L*256, Mp] (the K / V gradients of all layers transposed at once); part: split-K partials of a [L*256, 256] product
         w.tc.at_cap = (size_t)L * TC_ * Mp; w.tc.bt_cap = TC_ * Mp; w.tc.wt_cap = (size_t)(L * TC_ > TFF ? L * TC_ : TFF) * TC_;
         w.tc.part_cap = (size_t)48 * L * TC_ * TC_;
@@ -442,14 +471,25 @@ int check_params(const Mv2dTrainParams& p) {
     MV2D_CHECK_ARG(p.N >= 1 && p.L >= 1 && p.L <= MV2D_MAX_LAYERS && p.max_match >= 1 && p.G >= 0, "train: bad N=%d L=%d max_match=%d G=%d",
                    p.N, p.L, p.max_match, p.G);
     MV2D_CHECK_ARG(p.num_classes == TCODE, "train: num_classes must be 10 (got %d)", p.num_classes);
-    MV2D_CHECK_ARG(p.params && p.ref && p.tok_kin && p.tok_mem && p.match && p.match_cnt, "train: null input");
+    MV2D_CHECK_ARG(p.mode == 0 || p.mode == 1, "train: mode must be 0 (single-frame) or 1 (two-frame)");
+    MV2D_CHECK_ARG(p.params && p.ref, "train: null input");
+    if (p.mode == 0) {
+        MV2D_CHECK_ARG(p.tok_kin && p.tok_mem && p.match && p.match_cnt, "train: null input");
+        MV2D_CHECK_ARG(p.pad == 0 && !p.self_attn_mask, "train: denoising queries need mode 1 (the reference trains MV2D-S without them)");
+    } else {
+        MV2D_CHECK_ARG(p.pad >= 0 && p.num_rows >= 1 && p.num_rows <= 65536 && p.mask_words * 32 >= p.num_rows,
+                       "train: mode 1 needs 1 <= num_rows <= 65536 and mask_words covering them (num_rows=%d mask_words=%d)", p.num_rows, p.mask_words);
+        MV2D_CHECK_ARG(p.kin_map && p.mem_map && p.keymask && p.key_list && p.key_cnt, "train: mode 1 needs kin_map / mem_map / keymask / key_list / key_cnt");
+        MV2D_CHECK_ARG(p.pad == 0 || (p.dn_labels && p.G > 0), "train: denoising queries need dn_labels and ground truth");
+        MV2D_CHECK_ARG(((uintptr_t)p.kin_map & 15) == 0 && ((uintptr_t)p.mem_map & 15) == 0, "train: kin_map / mem_map must be 16-byte aligned");
+    }
     MV2D_CHECK_ARG(p.dim_t, "train: null dim_t");
     MV2D_CHECK_ARG(p.cls_scores && p.bbox_preds && p.assigned && p.losses, "train: null output");
     MV2D_CHECK_ARG(p.G == 0 || (p.gt_boxes && p.gt_labels), "train: null ground truth");
     MV2D_CHECK_ARG(((uintptr_t)p.params & 15) == 0 && ((uintptr_t)p.tok_kin & 15) == 0 && ((uintptr_t)p.tok_mem & 15) == 0,
                    "train: params / tokens must be 16-byte aligned");
     MV2D_CHECK_ARG(p.workspace && ((uintptr_t)p.workspace & 255) == 0, "train: workspace must be 256-byte aligned");
-    const TrainWs w = train_layout(nullptr, p.N, p.L, p.max_match, p.G);
+    const TrainWs w = train_layout(nullptr, p.pad + p.N, p.L, p.max_match, p.G, p.mode, p.num_rows, p.N);
     MV2D_CHECK_ARG(p.workspace_bytes >= w.total_bytes, "train: workspace too small (%zu < %zu)", p.workspace_bytes, w.total_bytes);
     return 0;
 }
@@ -541,6 +581,9 @@ int train_param_info(int L, int tensor_id, long long* offset, long long* numel) 
 size_t train_workspace_bytes(int N, int L, int max_match, int G) {
     return train_layout(nullptr, N, L, max_match, G).total_bytes;
 }
+size_t train_workspace_bytes_p(const Mv2dTrainParams& p) {
+    return train_layout(nullptr, p.pad + p.N, p.L, p.max_match > 0 ? p.max_match : 1, p.G, p.mode, p.num_rows, p.N).total_bytes;
+}
 
 // float offset of a saved activation inside the workspace (tests compare them with the oracle's intermediates):
 // which = 0 qpos [N,256] (layer ignored); 1 x1 (after norms.0), 2 x2 (after norms.1), 3 x3 (layer output),
@@ -566,8 +609,10 @@ long long train_debug_offset(int N, int L, int max_match, int G, int layer, int 
 
 int run_train_forward(const Mv2dTrainParams& p, cudaStream_t st) {
     TRY(check_params(p));
-    const int N = p.N, L = p.L, NK = N * TTOK;
-    const TrainWs w = train_layout(p.workspace, N, L, p.max_match, p.G);
+    // N = query rows of the decoder: the denoising rows (mode 1) come first, then the p.N matching queries
+    const int N = p.pad + p.N, L = p.L, NK = p.mode == 1 ? p.num_rows : N * TTOK;
+    const bool two_frame = p.mode == 1;
+    const TrainWs w = train_layout(p.workspace, N, L, p.max_match, p.G, p.mode, p.num_rows, p.N);
     g_tc = w.tc;
     float* P = const_cast<float*>(p.params);
     Range6 pc;
@@ -592,9 +637,10 @@ int run_train_forward(const Mv2dTrainParams& p, cudaStream_t st) {
         TRY(linear_fwd(a.x_in, TC_, W.t[TL_SA_IN_W] + 512 * TC_, TC_, W.t[TL_SA_IN_B] + 512, a.qkv + 512, 768, N, TC_, TC_, false, st));
         if (sa_use_smem(N)) {
             TRY(sa_set_attr());
-            launch_k(sa_fwd_smem_kernel, dim3(cdiv(N, SA_QB), TH), dim3(256), sa_smem_bytes(N), st, (const float*)a.qkv, a.P_sa, a.attn_o, N);
+            launch_k(sa_fwd_smem_kernel, dim3(cdiv(N, SA_QB), TH), dim3(256), sa_smem_bytes(N), st, (const float*)a.qkv, a.P_sa, a.attn_o, N,
+                     p.self_attn_mask);
         } else {
-            launch_k(sa_fwd_kernel, dim3(N), dim3(256), 0, st, (const float*)a.qkv, a.P_sa, a.attn_o, N);
+            launch_k(sa_fwd_kernel, dim3(N), dim3(256), 0, st, (const float*)a.qkv, a.P_sa, a.attn_o, N, p.self_attn_mask);
         }
         MV2D_CHECK_LAUNCH("train sa_fwd");
         TRY(linear_fwd(a.attn_o, TC_, W.t[TL_SA_OUT_W], TC_, W.t[TL_SA_OUT_B], w.t1, TC_, N, TC_, TC_, false, st));
@@ -602,10 +648,17 @@ int run_train_forward(const Mv2dTrainParams& p, cudaStream_t st) {
         // --- sparse cross-attention over the matched RoIs' tokens (petr_transformer.py:373-513)
         TRY(add(a.xq1, a.x1, w.qpos, (long long)N * TC_, st));
         TRY(linear_fwd(a.xq1, TC_, W.t[TL_CA_IN_W], TC_, W.t[TL_CA_IN_B], a.cq, TC_, N, TC_, TC_, false, st));
-        TRY(linear_fwd(p.tok_kin, TC_, W.t[TL_CA_IN_W] + 256 * TC_, TC_, W.t[TL_CA_IN_B] + 256, a.Kp, TC_, NK, TC_, TC_, false, st));
-        TRY(linear_fwd(p.tok_mem, TC_, W.t[TL_CA_IN_W] + 512 * TC_, TC_, W.t[TL_CA_IN_B] + 512, a.Vp, TC_, NK, TC_, TC_, false, st));
-        launch_k(xa_fwd_kernel, dim3(N), dim3(256), 0, st, (const float*)a.cq, (const float*)a.Kp, (const float*)a.Vp, p.match,
-                 p.match_cnt, p.max_match, a.P_xa, a.ctx, N);
+        const float* kin = two_frame ? p.kin_map : p.tok_kin;
+        const float* mem = two_frame ? p.mem_map : p.tok_mem;
+        TRY(linear_fwd(kin, TC_, W.t[TL_CA_IN_W] + 256 * TC_, TC_, W.t[TL_CA_IN_B] + 256, a.Kp, TC_, NK, TC_, TC_, false, st));
+        TRY(linear_fwd(mem, TC_, W.t[TL_CA_IN_W] + 512 * TC_, TC_, W.t[TL_CA_IN_B] + 512, a.Vp, TC_, NK, TC_, TC_, false, st));
+        if (two_frame) {
+            launch_k(xt_train_fwd_kernel, dim3(N), dim3(256), 0, st, (const float*)a.cq, (const float*)a.Kp, (const float*)a.Vp, p.key_list,
+                     p.key_cnt, p.mask_words * 32, p.num_rows, a.P_xa, a.ctx);
+        } else {
+            launch_k(xa_fwd_kernel, dim3(N), dim3(256), 0, st, (const float*)a.cq, (const float*)a.Kp, (const float*)a.Vp, p.match,
+                     p.match_cnt, p.max_match, a.P_xa, a.ctx, N);
+        }
         MV2D_CHECK_LAUNCH("train xa_fwd");
         TRY(linear_fwd(a.ctx, TC_, W.t[TL_CA_OUT_W], TC_, W.t[TL_CA_OUT_B], w.t1, TC_, N, TC_, TC_, false, st));
         TRY(ln_fwd(a.x1, w.t1, W.t[TL_LN1_G], W.t[TL_LN1_B], a.x2, a.xhat1, a.rstd1, N, false, st));
@@ -625,17 +678,20 @@ int run_train_forward(const Mv2dTrainParams& p, cudaStream_t st) {
         TRY(linear_fwd(a.inter, TC_, W.t[TL_REG_W0], TC_, W.t[TL_REG_B0], a.r0, TC_, N, TC_, TC_, true, st));
         TRY(linear_fwd(a.r0, TC_, W.t[TL_REG_W1], TC_, W.t[TL_REG_B1], a.r1, TC_, N, TC_, TC_, true, st));
         TRY(linear_fwd(a.r1, TC_, W.t[TL_REG_W2], TC_, W.t[TL_REG_B2], box_l, TCODE, N, TCODE, TC_, false, st));
-        launch_k(reg_tail_fwd_kernel, dim3(cdiv(N, 128)), dim3(128), 0, st, box_l, p.ref, a.rsig, pc, N);
+        launch_k(reg_tail_fwd_kernel, dim3(cdiv(N, 128)), dim3(128), 0, st, box_l, p.ref, a.rsig, pc, N, two_frame ? p.vel_dt : 0.f, p.pad);
         MV2D_CHECK_LAUNCH("train reg_tail");
     }
     // Hungarian targets + loss values of every layer (row f3)
     Mv2dLossParams lp{};
-    lp.N = N; lp.G = p.G; lp.L = L; lp.num_classes = p.num_classes; lp.pad = 0; lp.neg_bbox_loss = 0;
-    lp.layer_stride = (long long)N * TCODE; lp.dn_layer_stride = 0;
+    // the matching queries are rows pad .. pad + p.N of every layer's [N,10] block; the denoising rows come first
+    lp.N = p.N; lp.G = p.G; lp.L = L; lp.num_classes = p.num_classes; lp.pad = p.pad; lp.neg_bbox_loss = p.neg_bbox_loss;
+    lp.layer_stride = (long long)N * TCODE; lp.dn_layer_stride = (long long)N * TCODE;
     lp.cls_cost_weight = p.cls_cost_weight; lp.reg_cost_weight = p.reg_cost_weight; lp.cls_loss_weight = p.cls_loss_weight;
-    lp.bbox_loss_weight = p.bbox_loss_weight; lp.focal_alpha = p.focal_alpha; lp.focal_gamma = p.focal_gamma; lp.dn_split = 0.f;
+    lp.bbox_loss_weight = p.bbox_loss_weight; lp.focal_alpha = p.focal_alpha; lp.focal_gamma = p.focal_gamma; lp.dn_split = p.dn_split;
     for (int j = 0; j < TCODE; ++j) lp.code_weights[j] = p.code_weights[j];
-    lp.cls_scores = p.cls_scores; lp.bbox_preds = p.bbox_preds; lp.gt_boxes = p.gt_boxes; lp.gt_labels = p.gt_labels;
+    lp.cls_scores = p.cls_scores + (long long)p.pad * TCODE; lp.bbox_preds = p.bbox_preds + (long long)p.pad * TCODE;
+    if (p.pad > 0) { lp.dn_cls = p.cls_scores; lp.dn_box = p.bbox_preds; lp.dn_labels = p.dn_labels; }
+    lp.gt_boxes = p.gt_boxes; lp.gt_labels = p.gt_labels;
     lp.assigned = p.assigned; lp.losses = p.losses; lp.workspace = w.loss_ws; lp.workspace_bytes = w.loss_ws_bytes;
     lp.num_pos = p.num_pos;
     return run_loss(lp, st);
@@ -643,10 +699,16 @@ int run_train_forward(const Mv2dTrainParams& p, cudaStream_t st) {
 
 int run_train_backward(const Mv2dTrainParams& p, cudaStream_t st) {
     TRY(check_params(p));
-    MV2D_CHECK_ARG(p.grads && p.d_ref && p.d_tok_kin && p.d_tok_mem, "train backward: null gradient output");
-    const int N = p.N, L = p.L, NK = N * TTOK;
+    const bool two_frame = p.mode == 1;
+    MV2D_CHECK_ARG(p.grads && p.d_ref && (two_frame ? (p.d_kin_map && p.d_mem_map) : (p.d_tok_kin && p.d_tok_mem)),
+                   "train backward: null gradient output");
+    const int N = p.pad + p.N, L = p.L, NK = two_frame ? p.num_rows : N * TTOK;
     const long long NC = (long long)N * TC_;
-    const TrainWs w = train_layout(p.workspace, N, L, p.max_match, p.G);
+    const TrainWs w = train_layout(p.workspace, N, L, p.max_match, p.G, p.mode, p.num_rows, p.N);
+    float* d_kin = two_frame ? p.d_kin_map : p.d_tok_kin;       // gradient of the key input rows / of the value input rows
+    float* d_mem = two_frame ? p.d_mem_map : p.d_tok_mem;
+    const float* kin = two_frame ? p.kin_map : p.tok_kin;
+    const float* mem = two_frame ? p.mem_map : p.tok_mem;
     g_tc = w.tc;
     float* P = const_cast<float*>(p.params);
     float* G = p.grads;
@@ -659,23 +721,26 @@ int run_train_backward(const Mv2dTrainParams& p, cudaStream_t st) {
         return (int)e;                                                                       \
     }
     ZERO(p.d_ref, N * 3);
-    ZERO(p.d_tok_kin, (long long)NK * TC_);
-    ZERO(p.d_tok_mem, (long long)NK * TC_);
+    ZERO(d_kin, (long long)NK * TC_);
+    ZERO(d_mem, (long long)NK * TC_);
     ZERO(w.dqpos, NC);
     ZERO(w.dx, NC);
 #undef ZERO
 
     LossGradArgs lg{};
     lg.cls = p.cls_scores; lg.box = p.bbox_preds; lg.assigned = p.assigned; lg.gt_boxes = p.gt_boxes; lg.gt_labels = p.gt_labels;
-    lg.dcls = w.dcls; lg.dbox = w.dbox; lg.N = N; lg.G = p.G; lg.num_classes = p.num_classes;
+    lg.dcls = w.dcls; lg.dbox = w.dbox; lg.N = p.N; lg.G = p.G; lg.num_classes = p.num_classes;
+    lg.pad = p.pad; lg.dn_labels = p.dn_labels; lg.dn_split = p.dn_split; lg.dn_weight = p.denoise_weight; lg.neg_bbox_loss = p.neg_bbox_loss;
     lg.alpha = p.focal_alpha; lg.gamma = p.focal_gamma; lg.cls_lw = p.cls_loss_weight; lg.box_lw = p.bbox_loss_weight;
     for (int j = 0; j < TCODE; ++j) lg.code_w[j] = p.code_weights[j];
     for (int l = 0; l < MV2D_MAX_LAYERS; ++l) lg.stage_w[l] = p.stage_loss_weights[l];
     lg.bbox_avg_factor = p.bbox_avg_factor; lg.losses = p.losses;
     launch_k(loss_grad_kernel, dim3(L), dim3(256), 0, st, lg);
     MV2D_CHECK_LAUNCH("train loss_grad");
-    launch_k(xa_inverse_kernel, dim3(N), dim3(32), 0, st, p.match, p.match_cnt, p.max_match, N, w.inv_cnt, w.inv_list);
-    MV2D_CHECK_LAUNCH("train xa_inverse");
+    if (!two_frame) {
+        launch_k(xa_inverse_kernel, dim3(N), dim3(32), 0, st, p.match, p.match_cnt, p.max_match, N, w.inv_cnt, w.inv_list);
+        MV2D_CHECK_LAUNCH("train xa_inverse");
+    }
 
     float* g_post_g = G + global_off(TG_POST_G);
     float* g_post_b = G + global_off(TG_POST_B);
@@ -693,7 +758,8 @@ int run_train_backward(const Mv2dTrainParams& p, cudaStream_t st) {
         float* dcls = w.dcls + (long long)l * N * TCODE;
         float* dbox = w.dbox + (long long)l * N * TCODE;
         // --- reg branch
-        launch_k(reg_tail_bwd_kernel, dim3(cdiv(N, 128)), dim3(128), 0, st, dbox, p.ref, (const float*)a.rsig, p.d_ref, pc, N);
+        launch_k(reg_tail_bwd_kernel, dim3(cdiv(N, 128)), dim3(128), 0, st, dbox, p.ref, (const float*)a.rsig, p.d_ref, pc, N,
+                 two_frame ? p.vel_dt : 0.f, p.pad);
         MV2D_CHECK_LAUNCH("train reg_tail_bwd");
         TRY(linear_wgrad(dbox, TCODE, a.r1, TC_, D.t[TL_REG_W2], TC_, N, TCODE, TC_, st, D.t[TL_REG_B2]));
         TRY(linear_dgrad(dbox, TCODE, W.t[TL_REG_W2], TC_, w.t1, TC_, N, TCODE, TC_, a.r1, TC_, false, st));
@@ -722,21 +788,30 @@ int run_train_backward(const Mv2dTrainParams& p, cudaStream_t st) {
         TRY(ln_bwd(w.t1, nullptr, a.xhat1, a.rstd1, W.t[TL_LN1_G], w.t2, D.t[TL_LN1_G], D.t[TL_LN1_B], N, false, st));
         TRY(linear_wgrad(w.t2, TC_, a.ctx, TC_, D.t[TL_CA_OUT_W], TC_, N, TC_, TC_, st, D.t[TL_CA_OUT_B]));
         TRY(linear_dgrad(w.t2, TC_, W.t[TL_CA_OUT_W], TC_, w.t3, TC_, N, TC_, TC_, nullptr, 0, false, st));   // t3 = d ctx
+        if (two_frame) {
+            launch_k(xt_train_bwd_dq_kernel, dim3(N), dim3(256), 0, st, (const float*)a.Kp, (const float*)a.Vp, (const float*)a.P_xa,
+                     (const float*)w.t3, p.key_list, p.key_cnt, p.mask_words * 32, p.num_rows, w.dS_xa, w.dcq);
+            MV2D_CHECK_LAUNCH("train xt_bwd_dq");
+            launch_k(xt_train_bwd_dkv_kernel, dim3(NK), dim3(256), 0, st, (const float*)a.cq, (const float*)w.t3, (const float*)a.P_xa,
+                     (const float*)w.dS_xa, p.keymask, p.mask_words, N, p.num_rows, w.dKp + l * TC_, w.dVp + l * TC_, LC);
+            MV2D_CHECK_LAUNCH("train xt_bwd_dkv");
+        } else {
         launch_k(xa_bwd_dq_kernel, dim3(N), dim3(256), 0, st, (const float*)a.Kp, (const float*)a.Vp, (const float*)a.P_xa,
                  (const float*)w.t3, p.match, p.match_cnt, p.max_match, w.dS_xa, w.dcq, N);
         MV2D_CHECK_LAUNCH("train xa_bwd_dq");
         launch_k(xa_bwd_dkv_kernel, dim3(NK), dim3(256), 0, st, (const float*)a.cq, (const float*)w.t3, (const float*)a.P_xa,
                  (const float*)w.dS_xa, (const int*)w.inv_cnt, (const int*)w.inv_list, p.max_match, w.dKp + l * TC_, w.dVp + l * TC_, LC, N);
         MV2D_CHECK_LAUNCH("train xa_bwd_dkv");
+        }
         TRY(linear_wgrad(w.dcq, TC_, a.xq1, TC_, D.t[TL_CA_IN_W], TC_, N, TC_, TC_, st, D.t[TL_CA_IN_B]));
         TRY(linear_dgrad(w.dcq, TC_, W.t[TL_CA_IN_W], TC_, w.t3, TC_, N, TC_, TC_, nullptr, 0, false, st));   // t3 = d (x1 + qpos)
         TRY(add(w.t2, w.t2, w.t3, NC, st));          // t2 = d x1
         TRY(add(w.dqpos, w.dqpos, w.t3, NC, st));
         if (!kv_batched) {     // per layer; otherwise all layers' K / V projection gradients in four GEMMs after the loop
-            TRY(linear_wgrad(w.dKp + l * TC_, LC, p.tok_kin, TC_, D.t[TL_CA_IN_W] + 256 * TC_, TC_, NK, TC_, TC_, st, D.t[TL_CA_IN_B] + 256));
-            TRY(linear_dgrad(w.dKp + l * TC_, LC, W.t[TL_CA_IN_W] + 256 * TC_, TC_, p.d_tok_kin, TC_, NK, TC_, TC_, nullptr, 0, true, st));
-            TRY(linear_wgrad(w.dVp + l * TC_, LC, p.tok_mem, TC_, D.t[TL_CA_IN_W] + 512 * TC_, TC_, NK, TC_, TC_, st, D.t[TL_CA_IN_B] + 512));
-            TRY(linear_dgrad(w.dVp + l * TC_, LC, W.t[TL_CA_IN_W] + 512 * TC_, TC_, p.d_tok_mem, TC_, NK, TC_, TC_, nullptr, 0, true, st));
+            TRY(linear_wgrad(w.dKp + l * TC_, LC, kin, TC_, D.t[TL_CA_IN_W] + 256 * TC_, TC_, NK, TC_, TC_, st, D.t[TL_CA_IN_B] + 256));
+            TRY(linear_dgrad(w.dKp + l * TC_, LC, W.t[TL_CA_IN_W] + 256 * TC_, TC_, d_kin, TC_, NK, TC_, TC_, nullptr, 0, true, st));
+            TRY(linear_wgrad(w.dVp + l * TC_, LC, mem, TC_, D.t[TL_CA_IN_W] + 512 * TC_, TC_, NK, TC_, TC_, st, D.t[TL_CA_IN_B] + 512));
+            TRY(linear_dgrad(w.dVp + l * TC_, LC, W.t[TL_CA_IN_W] + 512 * TC_, TC_, d_mem, TC_, NK, TC_, TC_, nullptr, 0, true, st));
         }
         // --- norms.0 and the self-attention
         TRY(ln_bwd(w.t2, nullptr, a.xhat0, a.rstd0, W.t[TL_LN0_G], w.t1, D.t[TL_LN0_G], D.t[TL_LN0_B], N, false, st));   // t1 = d (x_in + sa)
@@ -772,8 +847,8 @@ int run_train_backward(const Mv2dTrainParams& p, cudaStream_t st) {
             if (nkb % d == 0 && nkb / d >= 4 && (size_t)d * LC * TC_ <= w.tc.part_cap) { nsplit = d; if (tiles * d >= 148) break; }
         for (int kv = 0; kv < 2; ++kv) {
             const float* dYall = kv == 0 ? w.dKp : w.dVp;             // [NK, L*256]
-            const float* X = kv == 0 ? p.tok_kin : p.tok_mem;         // [NK, 256]
-            float* dX = kv == 0 ? p.d_tok_kin : p.d_tok_mem;
+            const float* X = kv == 0 ? kin : mem;                     // [NK, 256]
+            float* dX = kv == 0 ? d_kin : d_mem;
             const int wrow = kv == 0 ? 256 : 512;                     // rows of in_proj: q | k | v
             // weight + bias gradients of every layer
             TRY(transpose_pad(dYall, LC, NK, LC, w.tc.at, Mp, st));
@@ -829,6 +904,7 @@ int run_front_train_forward(const Mv2dFrontTrainParams& p, cudaStream_t st) {
         cudaError_t e = cudaMemcpyAsync(p.pe_out, w.pe, (size_t)P * TC_ * sizeof(float), cudaMemcpyDeviceToDevice, st);
         if (e != cudaSuccess) { set_error("front train: memcpy %s", cudaGetErrorString(e)); return (int)e; }
     }
+    if (p.kin_out) TRY(add(p.kin_out, p.feat, w.pe, (long long)P * TC_, st));       // key input of the two-frame head
     // --- RoIAlign of the feature and of the position embedding (torch.cat + SingleRoIExtractor + split)
     launch_k(roi_align_fwd_kernel, dim3(TTOK, N), dim3(64), 0, st, p.rois, p.feat, p.h, p.w, scale, (const float*)nullptr, p.tok_mem);
     MV2D_CHECK_LAUNCH("front roi_align(feat)");
@@ -894,6 +970,9 @@ int run_front_train_backward(const Mv2dFrontTrainParams& p, cudaStream_t st) {
     MV2D_CHECK_LAUNCH("front roi_align_bwd(feat)");
     launch_k(roi_align_bwd_kernel, dim3(TTOK, N), dim3(64), 0, st, p.rois, p.d_tok_kin, p.h, p.w, scale, w.dpe_map);
     MV2D_CHECK_LAUNCH("front roi_align_bwd(pe)");
+    if (p.d_pe_extra) TRY(add(w.dpe_map, w.dpe_map, p.d_pe_extra, PC, st));        // two-frame head: keys = the whole feat + pe map
+    if (p.d_feat_extra) TRY(add(p.d_feat, p.d_feat, p.d_feat_extra, PC, st));
+    if (p.d_feat_extra2) TRY(add(p.d_feat, p.d_feat, p.d_feat_extra2, PC, st));
     // --- PE: pe = x * gate + sb
     launch_k(pe_gate_bwd_kernel, dim3(ew_grid_n(PC)), dim3(256), 0, st, (const float*)w.dpe_map, (const float*)w.x, (const float*)w.gate, w.dx, w.dg2, PC);
     MV2D_CHECK_LAUNCH("front pe_gate_bwd");

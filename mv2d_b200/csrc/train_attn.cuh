@@ -4,8 +4,10 @@
 
 // ------------------------------------------------------------------------------------------------ self-attention
 // One CTA per query, one warp per head; lane = key.  qkv [N,768] = (q | k | v), q and k from x + query_pos.
+// mask (nullable, [N,N] u8, 1 = masked): the denoising groups' attention mask; a masked logit is -inf, its probability 0,
+// so the backward kernels (which work from P) need no mask of their own.
 __global__ void __launch_bounds__(256) sa_fwd_kernel(const float* __restrict__ qkv, float* __restrict__ P,
-                                                     float* __restrict__ attn_o, int N) {
+                                                     float* __restrict__ attn_o, int N, const uint8_t* __restrict__ mask) {
     pdl_wait();
     pdl_trigger();
     const int i = blockIdx.x, h = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -153,7 +155,7 @@ __device__ __forceinline__ void sa_stage(const float* __restrict__ src, int ld, 
 }
 
 __global__ void __launch_bounds__(256) sa_fwd_smem_kernel(const float* __restrict__ qkv, float* __restrict__ P,
-                                                          float* __restrict__ attn_o, int N) {
+                                                          float* __restrict__ attn_o, int N, const uint8_t* __restrict__ mask) {
     pdl_wait();
     pdl_trigger();
     extern __shared__ float sa_sm[];
@@ -177,6 +179,7 @@ __global__ void __launch_bounds__(256) sa_fwd_smem_kernel(const float* __restric
             float s = 0.f;
 #pragma unroll
             for (int c = 0; c < THD; ++c) s = fmaf(q[c], k[c], s);
+            if (mask && mask[(long long)i * N + j]) s = -INFINITY;
             Prow[j] = s;
             mx = fmaxf(mx, s);
         }
@@ -492,4 +495,146 @@ __global__ void __launch_bounds__(256) xa_bwd_dkv_kernel(const float* __restrict
     }
     dKp[(long long)row * ldo + h * THD + lane] = dk * scale;      // ldo: all layers' gradients side by side, [N*49, L*256]
     dVp[(long long)row * ldo + h * THD + lane] = dv;
+}
+
+// ------------------------------------------------------------------------------------------------ cross-attention, two-frame head
+// Keys = the R feature cells (projected once per layer: Kp / Vp [R,256]); query i attends to key_list[i][0 .. cnt_i)
+// (ascending cell ids = the set bits of its key mask; denoising queries carry the union of all masks).
+// P / dS are stored DENSELY indexed, [NT, 8, R] -- only the entries of a query's keys are ever written or read -- so the
+// key-side backward finds the entry of (query, key) without ranking the key inside the query's list.
+// One CTA per query, one warp per head, lane = key slot (same structure as xa_fwd_kernel).
+__global__ void __launch_bounds__(256) xt_train_fwd_kernel(const float* __restrict__ cq, const float* __restrict__ Kp,
+                                                           const float* __restrict__ Vp, const uint16_t* __restrict__ key_list,
+                                                           const int* __restrict__ key_cnt, int klist_ld, int R,
+                                                           float* __restrict__ P, float* __restrict__ ctx) {
+    pdl_wait();
+    pdl_trigger();
+    const int i = blockIdx.x, h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cnt = key_cnt[i];
+    const uint16_t* kl = key_list + (long long)i * klist_ld;
+    const float scale = 0.17677669529663687f;
+    float q[THD];
+#pragma unroll
+    for (int c = 0; c < THD; ++c) q[c] = cq[(long long)i * TC_ + h * THD + c] * scale;
+    float* Prow = P + ((long long)i * TH + h) * R;
+    float mx = -INFINITY;
+    for (int j = lane; j < cnt; j += 32) {
+        const int k = kl[j];
+        const float4* kr = reinterpret_cast<const float4*>(Kp + (long long)k * TC_ + h * THD);
+        float s = 0.f;
+#pragma unroll
+        for (int c4 = 0; c4 < THD / 4; ++c4) {
+            const float4 kk = kr[c4];
+            s += q[c4 * 4] * kk.x + q[c4 * 4 + 1] * kk.y + q[c4 * 4 + 2] * kk.z + q[c4 * 4 + 3] * kk.w;
+        }
+        Prow[k] = s;
+        mx = fmaxf(mx, s);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int j = lane; j < cnt; j += 32) {
+        const int k = kl[j];
+        const float e = expf(Prow[k] - mx);
+        Prow[k] = e;
+        sum += e;
+    }
+    sum = warp_sum(sum);
+    const float inv = cnt > 0 ? 1.f / sum : 0.f;
+    float o[THD];
+#pragma unroll
+    for (int c = 0; c < THD; ++c) o[c] = 0.f;
+    for (int j = lane; j < cnt; j += 32) {
+        const int k = kl[j];
+        const float p = Prow[k] * inv;
+        Prow[k] = p;
+        const float4* vr = reinterpret_cast<const float4*>(Vp + (long long)k * TC_ + h * THD);
+#pragma unroll
+        for (int c4 = 0; c4 < THD / 4; ++c4) {
+            const float4 v = vr[c4];
+            o[c4 * 4] += p * v.x; o[c4 * 4 + 1] += p * v.y; o[c4 * 4 + 2] += p * v.z; o[c4 * 4 + 3] += p * v.w;
+        }
+    }
+    float mine = 0.f;
+#pragma unroll
+    for (int c = 0; c < THD; ++c) {
+        const float r = warp_sum(o[c]);
+        if (lane == c) mine = r;
+    }
+    ctx[(long long)i * TC_ + h * THD + lane] = mine;
+}
+
+__global__ void __launch_bounds__(256) xt_train_bwd_dq_kernel(const float* __restrict__ Kp, const float* __restrict__ Vp,
+                                                              const float* __restrict__ P, const float* __restrict__ dctx,
+                                                              const uint16_t* __restrict__ key_list, const int* __restrict__ key_cnt,
+                                                              int klist_ld, int R, float* __restrict__ dS, float* __restrict__ dcq) {
+    pdl_wait();
+    pdl_trigger();
+    const int i = blockIdx.x, h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cnt = key_cnt[i];
+    const uint16_t* kl = key_list + (long long)i * klist_ld;
+    const float scale = 0.17677669529663687f;
+    float go[THD];
+#pragma unroll
+    for (int c = 0; c < THD; ++c) go[c] = dctx[(long long)i * TC_ + h * THD + c];
+    const float* Prow = P + ((long long)i * TH + h) * R;
+    float* Srow = dS + ((long long)i * TH + h) * R;
+    float D = 0.f;
+    for (int j = lane; j < cnt; j += 32) {
+        const int k = kl[j];
+        const float4* vr = reinterpret_cast<const float4*>(Vp + (long long)k * TC_ + h * THD);
+        float dp = 0.f;
+#pragma unroll
+        for (int c4 = 0; c4 < THD / 4; ++c4) {
+            const float4 v = vr[c4];
+            dp += go[c4 * 4] * v.x + go[c4 * 4 + 1] * v.y + go[c4 * 4 + 2] * v.z + go[c4 * 4 + 3] * v.w;
+        }
+        Srow[k] = dp;
+        D += Prow[k] * dp;
+    }
+    D = warp_sum(D);
+    float dq[THD];
+#pragma unroll
+    for (int c = 0; c < THD; ++c) dq[c] = 0.f;
+    for (int j = lane; j < cnt; j += 32) {
+        const int k = kl[j];
+        const float ds = Prow[k] * (Srow[k] - D);
+        Srow[k] = ds;
+        const float4* kr = reinterpret_cast<const float4*>(Kp + (long long)k * TC_ + h * THD);
+#pragma unroll
+        for (int c4 = 0; c4 < THD / 4; ++c4) {
+            const float4 kk = kr[c4];
+            dq[c4 * 4] += ds * kk.x; dq[c4 * 4 + 1] += ds * kk.y; dq[c4 * 4 + 2] += ds * kk.z; dq[c4 * 4 + 3] += ds * kk.w;
+        }
+    }
+    float mine = 0.f;
+#pragma unroll
+    for (int c = 0; c < THD; ++c) {
+        const float r = warp_sum(dq[c]);
+        if (lane == c) mine = r;
+    }
+    dcq[(long long)i * TC_ + h * THD + lane] = mine * scale;
+}
+
+// one CTA per key cell, one warp per head, lane = channel: the queries are walked in ascending order (deterministic
+// summation) and the key-mask bit of (query, cell) decides -- warp-uniformly -- whether the query attends to the cell
+__global__ void __launch_bounds__(256) xt_train_bwd_dkv_kernel(const float* __restrict__ cq, const float* __restrict__ dctx,
+                                                               const float* __restrict__ P, const float* __restrict__ dS,
+                                                               const uint32_t* __restrict__ keymask, int mask_words, int NT, int R,
+                                                               float* __restrict__ dKp, float* __restrict__ dVp, int ldo) {
+    pdl_wait();
+    pdl_trigger();
+    const int k = blockIdx.x, h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int word = k >> 5;
+    const uint32_t bit = 1u << (k & 31);
+    const float scale = 0.17677669529663687f;
+    float dk = 0.f, dv = 0.f;
+    for (int i = 0; i < NT; ++i) {
+        if (!(__ldg(keymask + (long long)i * mask_words + word) & bit)) continue;
+        const long long o = ((long long)i * TH + h) * R + k;
+        const float p = __ldg(P + o), ds = __ldg(dS + o);
+        dk = fmaf(ds, __ldg(cq + (long long)i * TC_ + h * THD + lane), dk);
+        dv = fmaf(p, __ldg(dctx + (long long)i * TC_ + h * THD + lane), dv);
+    }
+    dKp[(long long)k * ldo + h * THD + lane] = dk * scale;
+    dVp[(long long)k * ldo + h * THD + lane] = dv;
 }

@@ -174,6 +174,11 @@ class TrainParams(C.Structure):
         ('d_ref', c_f), ('d_tok_kin', c_f), ('d_tok_mem', c_f),
         ('workspace', c_f), ('workspace_bytes', C.c_size_t),
         ('num_pos', c_f), ('bbox_avg_factor', c_f),
+        ('mode', C.c_int), ('pad', C.c_int), ('num_rows', C.c_int), ('mask_words', C.c_int),
+        ('neg_bbox_loss', C.c_int), ('reserved5', C.c_int),
+        ('vel_dt', C.c_float), ('dn_split', C.c_float), ('denoise_weight', C.c_float), ('reserved6', C.c_float),
+        ('kin_map', c_f), ('mem_map', c_f), ('keymask', c_f), ('key_list', c_f), ('key_cnt', c_f),
+        ('self_attn_mask', c_f), ('dn_labels', c_f), ('d_kin_map', c_f), ('d_mem_map', c_f),
     ]
 
 
@@ -188,6 +193,7 @@ class FrontTrainParams(C.Structure):
         ('tok_mem', c_f), ('tok_kin', c_f), ('ref', c_f), ('pe_out', c_f),
         ('d_ref', c_f), ('d_tok_kin', c_f), ('d_tok_mem', c_f), ('d_feat', c_f),
         ('workspace', c_f), ('workspace_bytes', C.c_size_t),
+        ('d_pe_extra', c_f), ('d_feat_extra', c_f), ('d_feat_extra2', c_f), ('kin_out', c_f),
     ]
 
 
@@ -231,6 +237,7 @@ SYMBOLS = [
     ('mv2d_train_set_tensor_cores', C.c_int, [C.c_int]),
     ('mv2d_train_param_info', C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
     ('mv2d_decoder_train_workspace_bytes', C.c_size_t, [C.c_int] * 4),
+    ('mv2d_decoder_train_workspace_bytes_p', C.c_size_t, [C.POINTER(TrainParams)]),
     ('mv2d_decoder_train_forward', C.c_int, [C.POINTER(TrainParams), c_f]),
     ('mv2d_train_debug_offset', C.c_longlong, [C.c_int] * 6),
     ('mv2d_decoder_train_backward', C.c_int, [C.POINTER(TrainParams), c_f]),

@@ -283,18 +283,29 @@ class HotPathTrainer(DecoderTrainer):
     (camera geometry, per-RoI intrinsics, box correlation) come from the inference engine.
     Reference: MV2DSHead.forward_train (roi_heads/mv2d_s_head.py:236-307) + torch autograd."""
 
-    def __init__(self, state_dict, device='cuda', engine_cfg=None, **kw):
+    def __init__(self, state_dict, device='cuda', engine_cfg=None, mode='S', use_denoise=None, denoise_weight=1.0,
+                 neg_bbox_loss=None, **kw):
         super().__init__(state_dict, device=device, **kw)
         self._need_cuda()
         from .engine import HotPath
         sd = {k[len('roi_head.'):] if k.startswith('roi_head.') else k: v for k, v in state_dict.items()}
-        self.engine = HotPath(sd, mode='S', device=self.device, **(engine_cfg or {}))
+        self.mode = mode
+        self.engine = HotPath(sd, mode=mode, device=self.device, **(engine_cfg or {}))
+        # the reference trains MV2D-T with denoising queries and neg_bbox_loss, MV2D-S without either
+        # (configs/mv2d/exp/*two_frames*:44-47, *single_frame*:44)
+        self.use_denoise = (mode == 'T') if use_denoise is None else use_denoise
+        self.neg_bbox_loss = (mode == 'T') if neg_bbox_loss is None else neg_bbox_loss
+        self.denoise_weight = float(denoise_weight)
+        assert mode == 'T' or not self.use_denoise, 'denoising queries are trained with the two-frame head (mode T)'
         self._front_ws = None
         self._fp = None
 
     @torch.no_grad()
-    def forward(self, feat, proposal_list, img_metas, gt_boxes, gt_labels):
-        """feat [V,256,h,w] fp32 NCHW (as the FPN emits it), proposal_list: V tensors [n_v, >=4], img_metas: V dicts."""
+    def forward(self, feat, proposal_list, img_metas, gt_boxes, gt_labels, rand=None):
+        """feat [V,256,h,w] fp32 NCHW (as the FPN emits it), proposal_list: V tensors [n_v, >=4], img_metas: V dicts.
+        Two-frame head: ``rand`` [scalar*G,3] = the uniform noise of the denoising queries (None: torch.rand)."""
+        if self.mode == 'T':
+            return self._forward_t(feat, proposal_list, img_metas, gt_boxes, gt_labels, rand)
         eng, dev = self.engine, self.device
         f32 = dict(device=dev, dtype=torch.float32)
         feat = feat.to(**f32).contiguous()
@@ -331,9 +342,123 @@ class HotPathTrainer(DecoderTrainer):
                    rois=rois, N=N)
         return res
 
+    # ------------------------------------------------------------------ two-frame head (+ denoising queries)
+    def _front_params(self, N, V, h, w, rois, k_roi, cams, i2l, not_mask, feat_nhwc, img_metas, out):
+        c = self.engine.cfg
+        f32 = dict(device=self.device, dtype=torch.float32)
+        ws_bytes = int(self.lib.mv2d_front_train_workspace_bytes(N, V, h, w))
+        if self._front_ws is None or self._front_ws.numel() * 4 < ws_bytes:
+            self._front_ws = torch.empty(ws_bytes // 4 + 64, **f32)
+        p = lib.FrontTrainParams()
+        p.N, p.V, p.h, p.w, p.L, p.stride = N, V, h, w, self.L, c['stride']
+        p.depth_num, p.pad_h, p.pad_w = c['depth_num'], int(img_metas[0]['pad_shape'][0]), int(img_metas[0]['pad_shape'][1])
+        p.depth_start = c['depth_start']
+        p.position_range = (C.c_double * 6)(*c['position_range'])
+        p.pc_range = (C.c_float * 6)(*self.pc_range)
+        p.intrins_feat_scale = c['intrins_feat_scale']
+        p.params, p.grads = self.params.data_ptr(), self.grads.data_ptr()
+        p.rois, p.roi_intrinsics, p.extrinsics, p.img2lidar = rois.data_ptr(), k_roi.data_ptr(), cams[2].data_ptr(), i2l.data_ptr()
+        p.not_mask, p.dim_t, p.feat = not_mask.data_ptr(), self.dim_t.data_ptr(), feat_nhwc.data_ptr()
+        p.tok_mem, p.tok_kin, p.ref, p.d_feat = (out[k].data_ptr() for k in ('tok_mem', 'tok_kin', 'ref', 'd_feat'))
+        p.workspace, p.workspace_bytes = self._front_ws.data_ptr(), ws_bytes
+        return p
+
+    @torch.no_grad()
+    def _forward_t(self, feat, proposal_list, img_metas, gt_boxes, gt_labels, rand=None):
+        """MV2DTHead training forward (roi_heads/mv2d_t_head.py:26-142 under mv2d_s_head.py:236-307): front end with saved
+        activations, key masks from the box correlation, denoising queries prepended (``mv2d_dn_prepare``), the decoder
+        over pad + N rows with the feature cells as keys, Hungarian + denoising losses."""
+        eng, dev = self.engine, self.device
+        f32 = dict(device=dev, dtype=torch.float32)
+        feat = feat.to(**f32).contiguous()
+        cams, rois, roi_start, counts, N = eng._upload_meta(proposal_list, img_metas)
+        i2l, trans = eng.geom_prep(cams)
+        feat_nhwc, _ = eng.to_nhwc(feat)
+        V, h, w, _ = feat_nhwc.shape
+        R = V * h * w
+        corr = eng.box_corr(rois, roi_start, trans, N, V, img_metas, h, w)
+        k_roi = eng.roi_align_qg(rois, cams, feat_nhwc, None, N, phase=1)['roi_intrinsics']
+        _, _, not_mask, _ = eng._masks(img_metas, h, w)
+        out = dict(tok_mem=torch.empty((N, 49, 256), **f32), tok_kin=torch.empty((N, 49, 256), **f32),
+                   ref=torch.empty((N, 3), **f32), d_feat=torch.empty((V, h, w, 256), **f32),
+                   kin_map=torch.empty((R, 256), **f32))
+        p = self._front_params(N, V, h, w, rois, k_roi, cams, i2l, not_mask, feat_nhwc, img_metas, out)
+        p.kin_out = out['kin_map'].data_ptr()
+        lib.check(self.lib.mv2d_front_train_forward(C.byref(p), lib.stream_ptr()), 'mv2d_front_train_forward')
+        self._fp, self._fout = p, out
+        self._fkeep = (feat_nhwc, rois, k_roi, cams, i2l, not_mask)
+        # denoising queries + the training-mode key masks (a query without any key gets key 0: mv2d_t_head.py:80-82)
+        gt = gt_boxes.to(**f32).contiguous().view(-1, 9)
+        lab = gt_labels.to(dev).to(torch.int32).contiguous()
+        G = gt.shape[0] if self.use_denoise else 0
+        dn = dict(gt_boxes=gt[:G], gt_labels=lab[:G], rand=rand if G > 0 else torch.zeros((0, 3), **f32))
+        qg = dict(ref=out['ref'], query_pos=out['ref'])        # query_pos is recomputed from the live parameters below
+        qg_d, corr_d, T, pad, extra = eng.dn_prepare(qg, corr, N, dn)
+        L, M = self.L, 1
+        res_buf = dict(cls_scores=torch.empty((L, T, 10), **f32), bbox_preds=torch.empty((L, T, 10), **f32),
+                       assigned=torch.empty((L, N), device=dev, dtype=torch.int32), losses=torch.empty((L, 4), **f32),
+                       num_pos=torch.empty((L,), **f32), d_ref=torch.empty((T, 3), **f32),
+                       d_kin_map=torch.empty((R, 256), **f32), d_mem_map=torch.empty((R, 256), **f32))
+        q = lib.TrainParams()
+        q.N, q.L, q.max_match, q.G, q.num_classes = N, L, M, gt.shape[0], 10
+        q.mode, q.pad, q.num_rows, q.mask_words = 1, pad, R, corr['mask_words']
+        q.neg_bbox_loss = int(self.neg_bbox_loss)
+        q.vel_dt, q.dn_split, q.denoise_weight = eng._vel_dt(img_metas), eng.cfg['denoise_split'], self.denoise_weight
+        q.pc_range = (C.c_float * 6)(*self.pc_range)
+        c = self.loss_cfg
+        for k in ('cls_cost_weight', 'reg_cost_weight', 'cls_loss_weight', 'bbox_loss_weight', 'focal_alpha', 'focal_gamma'):
+            setattr(q, k, c[k])
+        q.code_weights = (C.c_float * 10)(*c['code_weights'])
+        q.stage_loss_weights = (C.c_float * lib.MAX_LAYERS)(*(self.stage_loss_weights + [0.0] * (lib.MAX_LAYERS - L)))
+        q.params, q.grads, q.dim_t = self.params.data_ptr(), self.grads.data_ptr(), self.dim_t.data_ptr()
+        ref_all = qg_d['ref'].contiguous()
+        q.ref = ref_all.data_ptr()
+        q.kin_map, q.mem_map = out['kin_map'].data_ptr(), feat_nhwc.data_ptr()
+        q.keymask, q.key_list, q.key_cnt = corr_d['keymask'].data_ptr(), corr_d['key_list'].data_ptr(), corr_d['key_cnt'].data_ptr()
+        q.self_attn_mask = extra['dn_attn_mask'].data_ptr() if pad > 0 else None
+        q.dn_labels = extra['dn_labels'].data_ptr() if pad > 0 else None
+        q.gt_boxes, q.gt_labels = (gt.data_ptr(), lab.data_ptr()) if gt.shape[0] > 0 else (None, None)
+        for k in ('cls_scores', 'bbox_preds', 'assigned', 'losses', 'num_pos', 'd_ref', 'd_kin_map', 'd_mem_map'):
+            setattr(q, k, res_buf[k].data_ptr())
+        ws_bytes = int(self.lib.mv2d_decoder_train_workspace_bytes_p(C.byref(q)))
+        if self._ws is None or self._ws.numel() * 4 < ws_bytes:
+            self._ws = torch.empty(ws_bytes // 4 + 64, **f32)
+        q.workspace, q.workspace_bytes = self._ws.data_ptr(), ws_bytes
+        self._p, self._out = q, res_buf
+        self._keep = (ref_all, gt, lab, corr_d, extra, qg_d)
+        lib.check(self.lib.mv2d_decoder_train_forward(C.byref(q), lib.stream_ptr()), 'mv2d_decoder_train_forward')
+        wts = self._stage_weights()
+        ls = res_buf['losses']
+        res = dict(cls_scores=res_buf['cls_scores'][:, pad:], bbox_preds=res_buf['bbox_preds'][:, pad:],
+                   dn_cls_scores=res_buf['cls_scores'][:, :pad], dn_bbox_preds=res_buf['bbox_preds'][:, :pad],
+                   assigned=res_buf['assigned'], loss_cls=ls[:, 0], loss_bbox=ls[:, 1], dn_loss_cls=ls[:, 2], dn_loss_bbox=ls[:, 3],
+                   num_pos=res_buf['num_pos'], ref=out['ref'], rois=rois, N=N, dn_pad=pad, dn_labels=extra.get('dn_labels'))
+        res['loss'] = (wts * (ls[:, 0] + ls[:, 1] + self.denoise_weight * (ls[:, 2] + ls[:, 3]))).sum()
+        return res
+
+    @torch.no_grad()
+    def _backward_t(self, bbox_avg_factor=None):
+        q, out = self._p, self._out
+        if bbox_avg_factor is not None:
+            self._baf = bbox_avg_factor.to(self.device, torch.float32).contiguous()
+            q.bbox_avg_factor = self._baf.data_ptr()
+        else:
+            q.bbox_avg_factor = None
+        lib.check(self.lib.mv2d_decoder_train_backward(C.byref(q), lib.stream_ptr()), 'mv2d_decoder_train_backward')
+        p, pad, N = self._fp, int(q.pad), int(q.N)
+        d_ref = out['d_ref'][pad:].contiguous()
+        zeros = torch.zeros((N, 49, 256), device=self.device)
+        p.d_ref, p.d_tok_kin, p.d_tok_mem = d_ref.data_ptr(), zeros.data_ptr(), zeros.data_ptr()
+        p.d_pe_extra, p.d_feat_extra, p.d_feat_extra2 = out['d_kin_map'].data_ptr(), out['d_kin_map'].data_ptr(), out['d_mem_map'].data_ptr()
+        self._bkeep = (d_ref, zeros)
+        lib.check(self.lib.mv2d_front_train_backward(C.byref(p), lib.stream_ptr()), 'mv2d_front_train_backward')
+        return dict(d_ref=d_ref, d_feat=self._fout['d_feat'].permute(0, 3, 1, 2))
+
     @torch.no_grad()
     def backward(self, bbox_avg_factor=None):
         """Accumulates every parameter gradient into the flat buffer; returns d loss / d feat as [V,256,h,w]."""
+        if self.mode == 'T':
+            return self._backward_t(bbox_avg_factor)
         gin = super().backward(bbox_avg_factor)
         p = self._fp
         p.d_ref, p.d_tok_kin, p.d_tok_mem = (gin[k].data_ptr() for k in ('d_ref', 'd_tok_kin', 'd_tok_mem'))

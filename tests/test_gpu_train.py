@@ -342,3 +342,42 @@ def test_samples_in_flight_match_the_sequential_step(state_dicts):
     step.step(samples)
     torch.cuda.synchronize()
     assert float((step.main.params - before).abs().max()) > 0 and step.lanes[1].params.data_ptr() == step.main.params.data_ptr()
+
+
+def test_two_frame_head_training_step_with_denoising_matches_reference_golden(tc_mode):
+    """VERDICT r1 missing #1: the backward of the two-frame head and of the denoising queries -- the configuration the
+    reference trains MV2D-T with (exp/*two_frames*:44-47).  Loss dict, d loss / d feat and every hot-path parameter
+    gradient against the reference's own MV2DTHead.forward_train under autograd (tests/golden/grad_t_dn.npz, written by
+    oracle/make_grad_golden.py)."""
+    import json
+    from conftest import golden_path
+    from mv2d_b200.train import HotPathTrainer
+    g = dict(np.load(golden_path('grad_t_dn')))
+    spec = json.loads(bytes(g['spec']).decode())
+    stage_w = [float(x) for x in g['stage_loss_weights']]
+    L = spec['num_layers']
+    sd = synth.make_state_dict(0, num_layers=L)
+    feat, boxes, metas = synth.case_inputs(spec)
+    gt_boxes, gt_labels, rand = synth.make_dn_inputs(spec['dn'])
+    tr = HotPathTrainer(sd, mode='T', stage_loss_weights=stage_w, denoise_weight=float(g['denoise_weight']),
+                        neg_bbox_loss=bool(g['neg_bbox_loss']))
+    out = tr.forward(feat, boxes, metas, gt_boxes, gt_labels, rand=rand)
+    gin = tr.backward()
+    torch.cuda.synchronize()
+    rep = Report('full_grad_t_dn', tc_mode)
+    names = json.loads(bytes(g['loss_names']).decode())
+    want = dict(zip(names, g['loss_values']))
+    dw = float(g['denoise_weight'])
+    for l in range(L):
+        for key, val in (('loss_cls', out['loss_cls'][l]), ('loss_bbox', out['loss_bbox'][l]),
+                         ('dn_loss_cls', out['dn_loss_cls'][l] * dw), ('dn_loss_bbox', out['dn_loss_bbox'][l] * dw)):
+            rep.check(f'l{l}.{key}', [float(val) * stage_w[l]], [want[f'l{l}.{key}']], 1e-4)
+    rep.check('loss total', [float(out['loss'])], [float(g['loss'])], 1e-4)
+    rep.check('d_feat vs reference', sub(gin['d_feat'].cpu().contiguous(), g), g['d_feat_sub'], grad=True)
+    n = 0
+    for k in tr.table:
+        if 'dparam.' + k in g:
+            rep.check(f'd {k} vs reference', sub(tr.grad(k).cpu().contiguous(), g), g['dparam.' + k], grad=True)
+            n += 1
+    assert n >= 6 + 34 * L + 20, n
+    rep.finish()
