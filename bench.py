@@ -290,12 +290,19 @@ def main():
         except Exception as e:
             two_frame = dict(error=f'{type(e).__name__}: {e}'[:400])
 
-    train = None
+    train = train_t = None
     if mode == 'S' and not args.no_train:
         try:
             train = train_step_section(sd, dev, samples, world, barrier)
         except Exception as e:      # the auxiliary section must not take the headline line down with it; the error is reported
             train = dict(error=f'{type(e).__name__}: {e}'[:400])
+        try:        # the two-frame head with denoising queries (the configuration the reference trains MV2D-T with)
+            smp_t = [make_inputs('T', seed=i) for i in D.shard_samples(2 * world, rank, world)]
+            train_t = train_step_section(sd, dev, smp_t, world, barrier, steps=4, warmup=2, mode='T')
+            train_t['scope'] = ('MV2D-T (12 views) with denoising queries: front end, key masks, 10 x G denoising queries, decoder over the '
+                                'feature cells as keys, Hungarian + denoising losses, backward to every parameter and d feat')
+        except Exception as e:
+            train_t = dict(error=f'{type(e).__name__}: {e}'[:400])
 
     # max over ranks of the device time
     total_ms, e2e_total_ms, ser_total_ms, ser_e2e_total_ms = D.max_over_ranks(
@@ -352,6 +359,8 @@ def main():
         line['two_frame'] = two_frame
     if train is not None:
         line['train_step'] = train
+    if train_t is not None:
+        line['train_step_two_frame'] = train_t
     if not args.no_gpu_torch_baseline and world == 1 and mode == 'S':
         try:
             from oracle import gpu_baseline as GB
@@ -404,7 +413,7 @@ def two_frame_section(sd, dev, world, rank, barrier, steps, warmup, batch=2, dep
     return res
 
 
-def train_step_section(sd, dev, samples, world, barrier, per_rank=2, steps=8, warmup=3):
+def train_step_section(sd, dev, samples, world, barrier, per_rank=2, steps=8, warmup=3, mode='S'):
     """Extra object `train_step` (BASELINE configs[3] shape: MV2D-S, 2 samples per GPU): per step and rank, for each local
     sample the hot-path training forward (saved activations) + Hungarian targets / losses + backward down to d feat (the
     two samples in flight on their own streams, `lanes`), then ONE NCCL sum all-reduce of the flat gradient buffer (all
@@ -415,7 +424,7 @@ def train_step_section(sd, dev, samples, world, barrier, per_rank=2, steps=8, wa
     from mv2d_b200 import synth
     from mv2d_b200.train import TrainStep
     lanes = int(os.environ.get('MV2D_TRAIN_LANES', '2'))     # samples in flight per GPU (mv2d_b200.train.TrainStep)
-    pipe = TrainStep(sd, device=dev, lanes=lanes)
+    pipe = TrainStep(sd, device=dev, lanes=lanes, mode=mode)
     tr = pipe.main
     before = tr.lib.mv2d_launch_count()
     batch = []

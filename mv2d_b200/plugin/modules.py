@@ -543,8 +543,13 @@ class MV2DHead(nn.Module):
             ecfg = dict(pc_range=list(self.pc_range), position_range=list(pe.position_range), depth_num=pe.depth_num,
                         depth_start=float(pe.depth_start), stride=pe.strides[0], intrins_feat_scale=self.intrins_feat_scale)
             ecfg.update(self.box_corr_module.engine_cfg())
+            ecfg.update(self._denoise_cfg())
+            ecfg['num_views_per_frame'] = getattr(self, 'num_views', 6)
             tr = HotPathTrainer(self.state_dict(), device=dev, stage_loss_weights=self.stage_loss_weights,
-                                pc_range=list(self.pc_range), engine_cfg=ecfg, **kw)
+                                pc_range=list(self.pc_range), engine_cfg=ecfg, mode=self.MODE,
+                                use_denoise=bool(getattr(self, 'use_denoise', False)),
+                                denoise_weight=float(getattr(self, 'denoise_weight', 1.0)),
+                                neg_bbox_loss=bool(getattr(self, 'neg_bbox_loss', False)), **kw)
             params = dict(self.named_parameters())
             self._train_params = []
             for name in tr.table:
@@ -562,21 +567,23 @@ class MV2DHead(nn.Module):
         ``mv2d_decoder_train_backward`` + ``mv2d_front_train_backward``, accumulates into every hot-path
         Parameter's ``.grad`` and hands d loss / d feat back to autograd, so the torch backbone trains through it."""
         assert len(img_metas) // img_metas[0]['num_views'] == 1      # mv2d_s_head.py:250
-        if getattr(self, 'use_denoise', False) or self.MODE != 'S':
-            raise NotImplementedError('the backward covers the single-frame head without denoising queries (the configuration '
-                                      'the reference trains MV2D-S with); the denoising / two-frame forward exists '
-                                      '(_bbox_forward under .train()) but has no backward yet')
+        if getattr(self, 'use_denoise', False) and self.MODE != 'T':
+            raise NotImplementedError('denoising queries are trained with the two-frame head (the reference trains MV2D-S '
+                                      'without them: configs/mv2d/exp/*single_frame*:44); their forward exists for both heads')
         feat = x[self.feat_lvl]
         if feat.shape[1] == 2 * self.position_encoding.embed_dims:
             feat = feat[:, :self.position_encoding.embed_dims]
         boxes = self.bbox_head._gt_tensor(ori_gt_bboxes_3d[0])
         tr = self.trainer()
         self._engine = None           # the packed inference weights go stale as soon as the optimizer steps
-        total, loss_cls, loss_bbox = _TrainStep.apply(feat, self, [p[:, :6] for p in proposal_list], img_metas, boxes,
-                                                      ori_gt_labels_3d[0], *[prm for _, prm in self._train_params])
+        total, loss_cls, loss_bbox, dn_cls, dn_bbox = _TrainStep.apply(feat, self, [p[:, :6] for p in proposal_list], img_metas, boxes,
+                                                                       ori_gt_labels_3d[0], *[prm for _, prm in self._train_params])
         w = tr.stage_loss_weights
         losses = {}
         for i in range(tr.L):
+            if tr.mode == 'T' and tr.use_denoise and boxes.shape[0] > 0:      # mv2d_s_head.py:288-298
+                losses[f'l{i}.dn_loss_cls'] = dn_cls[i] * tr.denoise_weight * w[i]
+                losses[f'l{i}.dn_loss_bbox'] = dn_bbox[i] * tr.denoise_weight * w[i]
             losses[f'l{i}.loss_cls'] = loss_cls[i] * w[i]
             losses[f'l{i}.loss_bbox'] = loss_bbox[i] * w[i]
         # the entries above are plain values; the autograd edge rides on the first one (the sum of the dict is `total`)
@@ -597,11 +604,13 @@ class _TrainStep(torch.autograd.Function):
         out = tr.forward(feat.detach(), proposal_list, img_metas, gt_boxes, gt_labels)
         ctx.head, ctx.num_pos = head, out['num_pos']
         loss_cls, loss_bbox = out['loss_cls'].clone(), out['loss_bbox'].clone()
-        ctx.mark_non_differentiable(loss_cls, loss_bbox)
-        return out['loss'].clone(), loss_cls, loss_bbox
+        dn_cls = out['dn_loss_cls'].clone() if 'dn_loss_cls' in out else torch.zeros_like(loss_cls)
+        dn_bbox = out['dn_loss_bbox'].clone() if 'dn_loss_bbox' in out else torch.zeros_like(loss_cls)
+        ctx.mark_non_differentiable(loss_cls, loss_bbox, dn_cls, dn_bbox)
+        return out['loss'].clone(), loss_cls, loss_bbox, dn_cls, dn_bbox
 
     @staticmethod
-    def backward(ctx, g_total, g_cls, g_bbox):
+    def backward(ctx, g_total, g_cls, g_bbox, g_dn_cls, g_dn_bbox):
         import torch.distributed as dist
         from ..train import DecoderTrainer
         head = ctx.head

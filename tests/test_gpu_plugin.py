@@ -310,3 +310,31 @@ def test_detector_forward_train_shell(state_dicts):
         h.eval()
     assert 'det_loss_rpn' in losses and all(f'l{i}.loss_cls' in losses and f'l{i}.loss_bbox' in losses for i in range(6))
     assert all(torch.isfinite(v).all() for v in losses.values())
+
+
+def test_two_frame_head_forward_train_runs_the_backward(state_dicts, monkeypatch):
+    """MV2DTHead.forward_train (mv2d_s_head.py:236-307 as the two-frame head inherits it, denoising queries on): the loss
+    dict of the reference's golden run and gradients through ``loss.backward()`` for every hot-path Parameter."""
+    import json
+    g = dict(np.load(golden_path('grad_t_dn')))
+    spec = json.loads(bytes(g['spec']).decode())
+    from mv2d_b200.plugin.build import build_roi_head
+    h = build_roi_head(CFG['T'], device='cuda')
+    sd = synth.make_state_dict(0, num_layers=6)
+    h.load_state_dict(sd, strict=True)
+    feat, boxes, metas = synth.case_inputs(spec)
+    gt_boxes, gt_labels, rand = synth.make_dn_inputs(spec['dn'])
+    monkeypatch.setattr(torch, 'rand', lambda *a, **k: rand.clone().to(k.get('device', 'cpu')))
+    h.train()
+    try:
+        f = feat.cuda().requires_grad_(True)
+        losses = h.forward_train([f], metas, [b.cuda() for b in boxes], None, None, None, None, [gt_boxes.cuda()], [gt_labels.cuda()])
+        sum(losses.values()).backward()
+    finally:
+        h.eval()
+    assert {f'l{i}.{k}' for i in range(6) for k in ('loss_cls', 'loss_bbox', 'dn_loss_cls', 'dn_loss_bbox')} == set(losses)
+    assert all(torch.isfinite(v).all() for v in losses.values())
+    assert f.grad is not None and torch.isfinite(f.grad).all() and float(f.grad.abs().max()) > 0
+    named = dict(h.named_parameters())
+    missing = [n for n in h.trainer().table if named[n].grad is None or not torch.isfinite(named[n].grad).all()]
+    assert not missing, missing
