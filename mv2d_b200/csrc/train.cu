@@ -394,7 +394,7 @@ __global__ void __launch_bounds__(256) loss_grad_kernel(LossGradArgs a) {
 // ------------------------------------------------------------------------------------------------ workspace layout
 struct LayerAct {
     float *x_in, *xq, *qkv, *P_sa, *attn_o, *xhat0, *rstd0, *x1, *xq1, *cq, *Kp, *Vp, *P_xa, *ctx, *xhat1, *rstd1, *x2,
-        *hdn, *xhat2, *rstd2, *x3, *xhatp, *rstdp, *inter, *xhat_c0, *rstd_c0, *c0n, *xhat_c1, *rstd_c1, *c1n, *r0, *r1, *rsig;
+        *hdn, *xhat2, *rstd2, *x3, *xhatp, *rstdp, *inter, *xhat_c0, *rstd_c0, *c0n, *xhat_c1, *rstd_c1, *c1n, *r0, *r1, *rsig, *xa_stats;
 };
 struct TrainWs {
     float *posemb, *h0, *qpos, *zero;
@@ -433,7 +433,7 @@ TrainWs train_layout(float* base, int N, int L, int max_match, int G, int mode =
         a.xhatp = take(NC); a.rstdp = take(n); a.inter = take(NC);
         a.xhat_c0 = take(NC); a.rstd_c0 = take(n); a.c0n = take(NC);
         a.xhat_c1 = take(NC); a.rstd_c1 = take(n); a.c1n = take(NC);
-        a.r0 = take(NC); a.r1 = take(NC); a.rsig = take(n * 4);
+        a.r0 = take(NC); a.r1 = take(NC); a.rsig = take(n * 4); a.xa_stats = take(n * TH * 2);
         a.x_in = l == 0 ? w.zero : w.layer[l - 1].x3;
     }
     w.dx = take(NC); w.dqpos = take(NC); w.t1 = take(NC); w.t2 = take(NC); w.t3 = take(NC); w.dinter = take(NC);
@@ -652,7 +652,10 @@ int run_train_forward(const Mv2dTrainParams& p, cudaStream_t st) {
         const float* mem = two_frame ? p.mem_map : p.tok_mem;
         TRY(linear_fwd(kin, TC_, W.t[TL_CA_IN_W] + 256 * TC_, TC_, W.t[TL_CA_IN_B] + 256, a.Kp, TC_, NK, TC_, TC_, false, st));
         TRY(linear_fwd(mem, TC_, W.t[TL_CA_IN_W] + 512 * TC_, TC_, W.t[TL_CA_IN_B] + 512, a.Vp, TC_, NK, TC_, TC_, false, st));
-        if (two_frame) {
+        if (two_frame && xt2_enabled()) {
+            launch_k(xt2_fwd_kernel, dim3(cdiv(N, XT2_QB), TH), dim3(256), 0, st, (const float*)a.cq, (const float*)a.Kp, (const float*)a.Vp,
+                     p.keymask, p.mask_words, N, p.num_rows, a.P_xa, a.xa_stats, a.ctx);
+        } else if (two_frame) {
             launch_k(xt_train_fwd_kernel, dim3(N), dim3(256), 0, st, (const float*)a.cq, (const float*)a.Kp, (const float*)a.Vp, p.key_list,
                      p.key_cnt, p.mask_words * 32, p.num_rows, a.P_xa, a.ctx);
         } else {
@@ -788,7 +791,14 @@ int run_train_backward(const Mv2dTrainParams& p, cudaStream_t st) {
         TRY(ln_bwd(w.t1, nullptr, a.xhat1, a.rstd1, W.t[TL_LN1_G], w.t2, D.t[TL_LN1_G], D.t[TL_LN1_B], N, false, st));
         TRY(linear_wgrad(w.t2, TC_, a.ctx, TC_, D.t[TL_CA_OUT_W], TC_, N, TC_, TC_, st, D.t[TL_CA_OUT_B]));
         TRY(linear_dgrad(w.t2, TC_, W.t[TL_CA_OUT_W], TC_, w.t3, TC_, N, TC_, TC_, nullptr, 0, false, st));   // t3 = d ctx
-        if (two_frame) {
+        if (two_frame && xt2_enabled()) {
+            launch_k(xt2_bwd_dq_kernel, dim3(cdiv(N, XT2_QB), TH), dim3(256), 0, st, (const float*)a.Kp, (const float*)a.Vp, (const float*)a.P_xa,
+                     (const float*)a.xa_stats, (const float*)w.t3, (const float*)a.ctx, p.keymask, p.mask_words, N, p.num_rows, w.dS_xa, w.dcq);
+            MV2D_CHECK_LAUNCH("train xt2_bwd_dq");
+            launch_k(xt2_bwd_dkv_kernel, dim3(cdiv(NK, XT2_KT), TH), dim3(128), 0, st, (const float*)a.cq, (const float*)w.t3, (const float*)a.P_xa,
+                     (const float*)a.xa_stats, (const float*)w.dS_xa, p.keymask, p.mask_words, N, p.num_rows, w.dKp + l * TC_, w.dVp + l * TC_, LC);
+            MV2D_CHECK_LAUNCH("train xt2_bwd_dkv");
+        } else if (two_frame) {
             launch_k(xt_train_bwd_dq_kernel, dim3(N), dim3(256), 0, st, (const float*)a.Kp, (const float*)a.Vp, (const float*)a.P_xa,
                      (const float*)w.t3, p.key_list, p.key_cnt, p.mask_words * 32, p.num_rows, w.dS_xa, w.dcq);
             MV2D_CHECK_LAUNCH("train xt_bwd_dq");

@@ -638,3 +638,283 @@ __global__ void __launch_bounds__(256) xt_train_bwd_dkv_kernel(const float* __re
     dKp[(long long)k * ldo + h * THD + lane] = dk * scale;
     dVp[(long long)k * ldo + h * THD + lane] = dv;
 }
+
+// ---- tiled variants (default).  The per-query kernels above stream every query's K / V rows from L2 on their own: with
+// denoising queries (each attends to the UNION of all key masks, ~25 k cells) that is 15 GB of L2 traffic per layer.
+// Here a tile of 128 keys of one head is staged in shared memory once per CTA and serves a block of 32 queries
+// (forward, query-side backward), or a tile of 128 keys accumulates over all queries (key-side backward); tiles / word
+// groups without a set mask bit are skipped warp-uniformly.
+#define XT2_QB 8           // queries per CTA (one per warp: the dense denoising rows need the parallelism more than the reuse)
+#define XT2_KT 128         // keys per tile
+#define XT2_LD 36          // row stride of the staged K / V tiles (16-byte aligned rows, conflict-free LDS.128 with lane = key)
+
+__device__ __forceinline__ void xt2_stage_tile(const float* __restrict__ src, int R, int row0, int h, float* __restrict__ dst) {
+    // rows row0 .. row0 + 127 of src [R,256], channels 32 h .. 32 h + 31 -> dst [128][36]
+    for (int i = threadIdx.x; i < XT2_KT * 8; i += 256) {
+        const int r = i >> 3, c4 = i & 7;
+        float* d = dst + r * XT2_LD + c4 * 4;
+        if (row0 + r < R) {
+            const unsigned sa = (unsigned)__cvta_generic_to_shared(d);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(src + (long long)(row0 + r) * TC_ + h * THD + c4 * 4) : "memory");
+        } else {
+            *reinterpret_cast<float4*>(d) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+}
+
+// grid (ceil(NT / XT2_QB), 8 heads), 256 threads.  P keeps the RAW logits of a query's keys; stats [NT, 8, 2] = (max,
+// 1 / sum) of every (query, head): the backward kernels form p = exp(s - max) / sum on the fly (a normalising sweep over
+// the 25 k keys of a denoising query would be one long dependent chain per warp).
+__global__ void __launch_bounds__(256) xt2_fwd_kernel(const float* __restrict__ cq, const float* __restrict__ Kp, const float* __restrict__ Vp,
+                                                      const uint32_t* __restrict__ keymask, int mask_words,
+                                                      int NT, int R, float* __restrict__ P, float* __restrict__ stats, float* __restrict__ ctx) {
+    pdl_wait();
+    pdl_trigger();
+    __shared__ __align__(16) float Ks[XT2_KT * XT2_LD];
+    __shared__ __align__(16) float Vs[XT2_KT * XT2_LD];
+    __shared__ __align__(16) float psm[8][32];
+    const int h = blockIdx.y, q0 = blockIdx.x * XT2_QB, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float scale = 0.17677669529663687f;
+    constexpr int QPW = XT2_QB / 8;
+    float m_i[QPW], l_i[QPW], o_i[QPW];
+#pragma unroll
+    for (int u = 0; u < QPW; ++u) { m_i[u] = -INFINITY; l_i[u] = 0.f; o_i[u] = 0.f; }
+    const int ntiles = (R + XT2_KT - 1) / XT2_KT;
+    for (int t = 0; t < ntiles; ++t) {
+        // does any query of the block have a key in this tile?
+        int any = 0;
+        if (threadIdx.x < XT2_QB * 4) {
+            const int q = q0 + (threadIdx.x >> 2), w = t * 4 + (threadIdx.x & 3);
+            if (q < NT && w < mask_words) any = keymask[(long long)q * mask_words + w] != 0u;
+        }
+        if (!__syncthreads_or(any)) continue;
+        xt2_stage_tile(Kp, R, t * XT2_KT, h, Ks);
+        xt2_stage_tile(Vp, R, t * XT2_KT, h, Vs);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < QPW; ++u) {
+            const int i = q0 + warp * QPW + u;
+            if (i >= NT) break;
+            const uint32_t* km = keymask + (long long)i * mask_words + t * 4;
+            uint32_t wd = (lane < 4 && t * 4 + lane < mask_words) ? km[lane] : 0u;
+            if (__ballot_sync(0xffffffffu, wd != 0u) == 0u) continue;
+            float q[THD];
+            const float4* qr = reinterpret_cast<const float4*>(cq + (long long)i * TC_ + h * THD);
+#pragma unroll
+            for (int c4 = 0; c4 < 8; ++c4) {
+                const float4 v = __ldg(qr + c4);
+                q[c4 * 4] = v.x * scale; q[c4 * 4 + 1] = v.y * scale; q[c4 * 4 + 2] = v.z * scale; q[c4 * 4 + 3] = v.w * scale;
+            }
+            float* Prow = P + ((long long)i * TH + h) * R + t * XT2_KT;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const uint32_t bits = __shfl_sync(0xffffffffu, wd, g);
+                if (bits == 0u) continue;
+                const bool act = (bits >> lane) & 1u;
+                float sv = -INFINITY;
+                if (act) {
+                    const float* kr = Ks + (g * 32 + lane) * XT2_LD;
+                    float a = 0.f;
+#pragma unroll
+                    for (int c4 = 0; c4 < 8; ++c4) {
+                        const float4 kk = *reinterpret_cast<const float4*>(kr + c4 * 4);
+                        a = fmaf(q[c4 * 4], kk.x, a); a = fmaf(q[c4 * 4 + 1], kk.y, a); a = fmaf(q[c4 * 4 + 2], kk.z, a); a = fmaf(q[c4 * 4 + 3], kk.w, a);
+                    }
+                    sv = a;
+                    Prow[g * 32 + lane] = a;               // raw logit (see stats)
+                }
+                const float m_new = fmaxf(m_i[u], warp_max(sv));
+                const float alpha = m_i[u] == -INFINITY ? 0.f : expf(m_i[u] - m_new);
+                const float pv = act ? expf(sv - m_new) : 0.f;
+                l_i[u] = l_i[u] * alpha + warp_sum(pv);
+                m_i[u] = m_new;
+                __syncwarp();
+                psm[warp][lane] = pv;
+                __syncwarp();
+                // all 32 keys of the group, unrolled (an inactive key carries p = 0): independent LDS, two FMA chains
+                float acc0 = o_i[u] * alpha, acc1 = 0.f;
+                const float* vcol = Vs + g * 32 * XT2_LD + lane;
+#pragma unroll
+                for (int k4 = 0; k4 < 8; ++k4) {
+                    const float4 pp = *reinterpret_cast<const float4*>(&psm[warp][k4 * 4]);
+                    acc0 = fmaf(pp.x, vcol[(k4 * 4 + 0) * XT2_LD], acc0); acc1 = fmaf(pp.y, vcol[(k4 * 4 + 1) * XT2_LD], acc1);
+                    acc0 = fmaf(pp.z, vcol[(k4 * 4 + 2) * XT2_LD], acc0); acc1 = fmaf(pp.w, vcol[(k4 * 4 + 3) * XT2_LD], acc1);
+                }
+                o_i[u] = acc0 + acc1;
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int u = 0; u < QPW; ++u) {
+        const int i = q0 + warp * QPW + u;
+        if (i >= NT) break;
+        const float inv = l_i[u] > 0.f ? 1.f / l_i[u] : 0.f;
+        ctx[(long long)i * TC_ + h * THD + lane] = o_i[u] * inv;
+        if (lane == 0) { stats[((long long)i * TH + h) * 2] = m_i[u]; stats[((long long)i * TH + h) * 2 + 1] = inv; }
+    }
+}
+
+// query-side backward, same tiling.  D = sum_k P_k dP_k = dO . ctx (head slice): no pass over the keys needed for it.
+__global__ void __launch_bounds__(256) xt2_bwd_dq_kernel(const float* __restrict__ Kp, const float* __restrict__ Vp, const float* __restrict__ P,
+                                                         const float* __restrict__ stats, const float* __restrict__ dctx, const float* __restrict__ ctx,
+                                                         const uint32_t* __restrict__ keymask, int mask_words, int NT, int R,
+                                                         float* __restrict__ dS, float* __restrict__ dcq) {
+    pdl_wait();
+    pdl_trigger();
+    __shared__ __align__(16) float Ks[XT2_KT * XT2_LD];
+    __shared__ __align__(16) float Vs[XT2_KT * XT2_LD];
+    __shared__ __align__(16) float psm[8][32];
+    const int h = blockIdx.y, q0 = blockIdx.x * XT2_QB, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float scale = 0.17677669529663687f;
+    constexpr int QPW = XT2_QB / 8;
+    float D_i[QPW], dq_i[QPW];
+#pragma unroll
+    for (int u = 0; u < QPW; ++u) {
+        const int i = q0 + warp * QPW + u;
+        dq_i[u] = 0.f;
+        float d = 0.f;
+        if (i < NT) d = dctx[(long long)i * TC_ + h * THD + lane] * ctx[(long long)i * TC_ + h * THD + lane];
+        D_i[u] = warp_sum(d);
+    }
+    const int ntiles = (R + XT2_KT - 1) / XT2_KT;
+    for (int t = 0; t < ntiles; ++t) {
+        int any = 0;
+        if (threadIdx.x < XT2_QB * 4) {
+            const int q = q0 + (threadIdx.x >> 2), w = t * 4 + (threadIdx.x & 3);
+            if (q < NT && w < mask_words) any = keymask[(long long)q * mask_words + w] != 0u;
+        }
+        if (!__syncthreads_or(any)) continue;
+        xt2_stage_tile(Kp, R, t * XT2_KT, h, Ks);
+        xt2_stage_tile(Vp, R, t * XT2_KT, h, Vs);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < QPW; ++u) {
+            const int i = q0 + warp * QPW + u;
+            if (i >= NT) break;
+            const uint32_t* km = keymask + (long long)i * mask_words + t * 4;
+            uint32_t wd = (lane < 4 && t * 4 + lane < mask_words) ? km[lane] : 0u;
+            if (__ballot_sync(0xffffffffu, wd != 0u) == 0u) continue;
+            float go[THD];
+            const float4* gr = reinterpret_cast<const float4*>(dctx + (long long)i * TC_ + h * THD);
+#pragma unroll
+            for (int c4 = 0; c4 < 8; ++c4) {
+                const float4 v = __ldg(gr + c4);
+                go[c4 * 4] = v.x; go[c4 * 4 + 1] = v.y; go[c4 * 4 + 2] = v.z; go[c4 * 4 + 3] = v.w;
+            }
+            const long long prow = ((long long)i * TH + h) * R + t * XT2_KT;
+            const float smax = __ldg(stats + ((long long)i * TH + h) * 2), sinv = __ldg(stats + ((long long)i * TH + h) * 2 + 1);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const uint32_t bits = __shfl_sync(0xffffffffu, wd, g);
+                if (bits == 0u) continue;
+                const bool act = (bits >> lane) & 1u;
+                float ds = 0.f;
+                if (act) {
+                    const float* vr = Vs + (g * 32 + lane) * XT2_LD;
+                    float dp = 0.f;
+#pragma unroll
+                    for (int c4 = 0; c4 < 8; ++c4) {
+                        const float4 vv = *reinterpret_cast<const float4*>(vr + c4 * 4);
+                        dp = fmaf(go[c4 * 4], vv.x, dp); dp = fmaf(go[c4 * 4 + 1], vv.y, dp); dp = fmaf(go[c4 * 4 + 2], vv.z, dp); dp = fmaf(go[c4 * 4 + 3], vv.w, dp);
+                    }
+                    ds = expf(P[prow + g * 32 + lane] - smax) * sinv * (dp - D_i[u]);
+                    dS[prow + g * 32 + lane] = ds;
+                }
+                __syncwarp();
+                psm[warp][lane] = ds;
+                __syncwarp();
+                float acc0 = dq_i[u], acc1 = 0.f;
+                const float* kcol = Ks + g * 32 * XT2_LD + lane;
+#pragma unroll
+                for (int k4 = 0; k4 < 8; ++k4) {
+                    const float4 pp = *reinterpret_cast<const float4*>(&psm[warp][k4 * 4]);
+                    acc0 = fmaf(pp.x, kcol[(k4 * 4 + 0) * XT2_LD], acc0); acc1 = fmaf(pp.y, kcol[(k4 * 4 + 1) * XT2_LD], acc1);
+                    acc0 = fmaf(pp.z, kcol[(k4 * 4 + 2) * XT2_LD], acc0); acc1 = fmaf(pp.w, kcol[(k4 * 4 + 3) * XT2_LD], acc1);
+                }
+                dq_i[u] = acc0 + acc1;
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int u = 0; u < QPW; ++u) {
+        const int i = q0 + warp * QPW + u;
+        if (i < NT) dcq[(long long)i * TC_ + h * THD + lane] = dq_i[u] * scale;
+    }
+}
+
+// key-side backward: CTA = (128 keys, head), 128 threads = one key each with its 2 x 32 accumulators in registers; the
+// queries are walked in ascending order in chunks of 32 whose q / dO head slices are staged in shared memory
+__global__ void __launch_bounds__(128) xt2_bwd_dkv_kernel(const float* __restrict__ cq, const float* __restrict__ dctx, const float* __restrict__ P,
+                                                          const float* __restrict__ stats,
+                                                          const float* __restrict__ dS, const uint32_t* __restrict__ keymask, int mask_words,
+                                                          int NT, int R, float* __restrict__ dKp, float* __restrict__ dVp, int ldo) {
+    pdl_wait();
+    pdl_trigger();
+    __shared__ __align__(16) float Qs[32 * THD];
+    __shared__ __align__(16) float Gs[32 * THD];
+    __shared__ float Ss[32 * 2];
+    const int t = blockIdx.x, h = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int key = t * XT2_KT + threadIdx.x, word = t * 4 + warp;
+    const float scale = 0.17677669529663687f;
+    float dk[THD], dv[THD];
+#pragma unroll
+    for (int c = 0; c < THD; ++c) { dk[c] = 0.f; dv[c] = 0.f; }
+    for (int i0 = 0; i0 < NT; i0 += 32) {
+        __syncthreads();
+        for (int e = threadIdx.x; e < 32 * 8; e += 128) {
+            const int r = e >> 3, c4 = e & 7;
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+            if (i0 + r < NT) {
+                a = __ldg(reinterpret_cast<const float4*>(cq + (long long)(i0 + r) * TC_ + h * THD) + c4);
+                b = __ldg(reinterpret_cast<const float4*>(dctx + (long long)(i0 + r) * TC_ + h * THD) + c4);
+            }
+            *reinterpret_cast<float4*>(Qs + r * THD + c4 * 4) = a;
+            *reinterpret_cast<float4*>(Gs + r * THD + c4 * 4) = b;
+        }
+        if (threadIdx.x < 64) Ss[threadIdx.x] = (i0 + (threadIdx.x >> 1) < NT) ? stats[((long long)(i0 + (threadIdx.x >> 1)) * TH + h) * 2 + (threadIdx.x & 1)] : 0.f;
+        __syncthreads();
+        // the mask word of (query i0 + lane, this warp's 32 keys): one coalesced-ish load per chunk, then shuffles
+        uint32_t mine = 0u;
+        if (i0 + lane < NT && word < mask_words) mine = __ldg(keymask + (long long)(i0 + lane) * mask_words + word);
+        if (__ballot_sync(0xffffffffu, mine != 0u) == 0u) continue;
+        const int nq = min(32, NT - i0);
+        for (int r = 0; r < nq; ++r) {
+            const uint32_t bits = __shfl_sync(0xffffffffu, mine, r);
+            if (bits == 0u) continue;
+            if (!((bits >> lane) & 1u)) continue;
+            const long long o = ((long long)(i0 + r) * TH + h) * R + key;
+            const float p = expf(__ldg(P + o) - Ss[r * 2]) * Ss[r * 2 + 1], ds = __ldg(dS + o);
+            const float* qr = Qs + r * THD;
+            const float* gr = Gs + r * THD;
+#pragma unroll
+            for (int c4 = 0; c4 < 8; ++c4) {
+                const float4 qq = *reinterpret_cast<const float4*>(qr + c4 * 4);
+                const float4 gg = *reinterpret_cast<const float4*>(gr + c4 * 4);
+                dk[c4 * 4] = fmaf(ds, qq.x, dk[c4 * 4]); dk[c4 * 4 + 1] = fmaf(ds, qq.y, dk[c4 * 4 + 1]);
+                dk[c4 * 4 + 2] = fmaf(ds, qq.z, dk[c4 * 4 + 2]); dk[c4 * 4 + 3] = fmaf(ds, qq.w, dk[c4 * 4 + 3]);
+                dv[c4 * 4] = fmaf(p, gg.x, dv[c4 * 4]); dv[c4 * 4 + 1] = fmaf(p, gg.y, dv[c4 * 4 + 1]);
+                dv[c4 * 4 + 2] = fmaf(p, gg.z, dv[c4 * 4 + 2]); dv[c4 * 4 + 3] = fmaf(p, gg.w, dv[c4 * 4 + 3]);
+            }
+        }
+    }
+    if (key < R) {
+        float4* ok = reinterpret_cast<float4*>(dKp + (long long)key * ldo + h * THD);
+        float4* ov = reinterpret_cast<float4*>(dVp + (long long)key * ldo + h * THD);
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4) {
+            ok[c4] = make_float4(dk[c4 * 4] * scale, dk[c4 * 4 + 1] * scale, dk[c4 * 4 + 2] * scale, dk[c4 * 4 + 3] * scale);
+            ov[c4] = make_float4(dv[c4 * 4], dv[c4 * 4 + 1], dv[c4 * 4 + 2], dv[c4 * 4 + 3]);
+        }
+    }
+}
+
+inline bool xt2_enabled() {
+    static const bool on = []() { const char* e = getenv("MV2D_TRAIN_XT_TILED"); return !(e && e[0] == '0'); }();
+    return on;
+}
