@@ -442,7 +442,11 @@ def train_step_section(sd, dev, samples, world, barrier, per_rank=2, steps=8, wa
             ev[1].record(); ev[2].record(); ev[3].record()
             torch.cuda.synchronize()
             if it >= warmup:
-                rows.append([ev[0].elapsed_time(ev[3]), ev[0].elapsed_time(ev[3]), 0.0, 0.0])
+                tm = pipe.timing      # CUDA events inside TrainStep.step: forward+backward | gradient all-reduce | AdamW
+                if tm is not None:
+                    rows.append([ev[0].elapsed_time(ev[3]), tm[0].elapsed_time(tm[1]), tm[1].elapsed_time(tm[2]), tm[2].elapsed_time(tm[3])])
+                else:
+                    rows.append([ev[0].elapsed_time(ev[3]), ev[0].elapsed_time(ev[3]), 0.0, 0.0])
                 losses.append(float(loss) / per_rank)
             continue
         tr.zero_grad()
@@ -466,6 +470,7 @@ def train_step_section(sd, dev, samples, world, barrier, per_rank=2, steps=8, wa
     return dict(value=world * per_rank * steps / (total_ms * 1e-3), unit='samples/s', samples_per_gpu=per_rank, lanes=lanes, steps=steps, warmup=warmup,
                 step_ms=med[0], fwd_bwd_ms=med[1], allreduce_ms=med[2], adamw_ms=med[3], grad_bytes=tr.total * 4,
                 launches_per_step=int(tr.lib.mv2d_launch_count() - before) // (warmup + steps),
+                cuda_graphs=bool(getattr(pipe, 'use_graphs', False)),
                 loss_first=losses[0], loss_last=losses[-1],
                 scope='rows a1-a18 + f3 forward and backward: every hot-path parameter gradient and d loss / d feat; 3xTF32 tcgen05 for the '
                       'GPU-filling contractions, fp32 FFMA elsewhere; the torch backbone is outside',

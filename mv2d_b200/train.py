@@ -301,15 +301,17 @@ class HotPathTrainer(DecoderTrainer):
         self._fp = None
 
     @torch.no_grad()
-    def forward(self, feat, proposal_list, img_metas, gt_boxes, gt_labels, rand=None):
+    def forward(self, feat, proposal_list, img_metas, gt_boxes, gt_labels, rand=None, uploaded=None):
         """feat [V,256,h,w] fp32 NCHW (as the FPN emits it), proposal_list: V tensors [n_v, >=4], img_metas: V dicts.
-        Two-frame head: ``rand`` [scalar*G,3] = the uniform noise of the denoising queries (None: torch.rand)."""
+        Two-frame head: ``rand`` [scalar*G,3] = the uniform noise of the denoising queries (None: torch.rand).
+        uploaded: the tuple ``engine._upload_meta`` returned for this sample (CUDA-graph replays upload the metadata
+        outside the captured region)."""
         if self.mode == 'T':
             return self._forward_t(feat, proposal_list, img_metas, gt_boxes, gt_labels, rand)
         eng, dev = self.engine, self.device
         f32 = dict(device=dev, dtype=torch.float32)
         feat = feat.to(**f32).contiguous()
-        cams, rois, roi_start, counts, N = eng._upload_meta(proposal_list, img_metas)
+        cams, rois, roi_start, counts, N = uploaded if uploaded is not None else eng._upload_meta(proposal_list, img_metas)
         i2l, trans = eng.geom_prep(cams)
         feat_nhwc, _ = eng.to_nhwc(feat)
         V, h, w, _ = feat_nhwc.shape
@@ -474,9 +476,17 @@ class TrainStep:
     the all-reduce.  lanes=1 is the plain sequential step.  Same results as running the samples one after the other
     up to fp32 summation order."""
 
-    def __init__(self, state_dict, device='cuda', lanes=2, sync_bbox_avg_factor=True, **kw):
+    def __init__(self, state_dict, device='cuda', lanes=2, sync_bbox_avg_factor=True, use_graphs=None, **kw):
         assert lanes >= 1
         self._sd, self._kw = state_dict, dict(kw)
+        # CUDA-graph replay of every sample's forward and backward (single-frame head; keyed by the sample's shapes): the
+        # step is ~650 launches per sample, which one Python thread cannot enqueue as fast as the GPU retires them
+        if use_graphs is None:
+            import os
+            use_graphs = os.environ.get('MV2D_TRAIN_GRAPHS', '1') != '0'
+        self.use_graphs = bool(use_graphs) and kw.get('mode', 'S') == 'S'
+        self._graphs = {}
+        self.timing = None
         self.main = HotPathTrainer(state_dict, device=device, **kw)
         self.lanes = [self.main]
         self.streams = [torch.cuda.Stream(device=self.main.device)]
@@ -486,6 +496,42 @@ class TrainStep:
         for _ in range(lanes - 1):
             self._add_lane()
         self.total = self.main.total
+
+    def _graph_entry(self, k, smp):
+        """The captured forward / backward of lane k for this sample's shapes; the sample's tensors are copied into the
+        graph's static inputs and its metadata uploaded (outside the graphs) before the replay."""
+        lane = self.lanes[k]
+        feat, boxes, metas, gt_boxes, gt_labels = smp[:5]
+        eng, dev = lane.engine, lane.device
+        N = max(sum(int(b.shape[0]) for b in boxes), 1)
+        key = (k, N, int(gt_boxes.shape[0]), tuple(feat.shape), eng._masks(metas, feat.shape[2], feat.shape[3])[0])
+        ent = self._graphs.get(key)
+        if ent is None:
+            st = dict(feat=torch.empty(tuple(feat.shape), dtype=torch.float32, device=dev),
+                      gt_boxes=torch.empty((gt_boxes.shape[0], 9), dtype=torch.float32, device=dev),
+                      gt_labels=torch.empty((gt_boxes.shape[0],), dtype=torch.int32, device=dev),
+                      factor=torch.ones((lane.L,), dtype=torch.float32, device=dev))
+            st['feat'].copy_(feat); st['gt_boxes'].copy_(gt_boxes.view(-1, 9)); st['gt_labels'].copy_(gt_labels)
+            up = eng._upload_meta(boxes, metas)
+            keep_grads = lane.grads.clone()
+            lane.forward(st['feat'], boxes, metas, st['gt_boxes'], st['gt_labels'], uploaded=up)     # warm-up: sizes every buffer
+            lane.backward(st['factor'])
+            torch.cuda.synchronize()
+            gf, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gf):
+                out = lane.forward(st['feat'], boxes, metas, st['gt_boxes'], st['gt_labels'], uploaded=up)
+            with torch.cuda.graph(gb, pool=gf.pool()):
+                lane.backward(st['factor'])
+            lane.grads.copy_(keep_grads)         # warm-up and capture do not count
+            torch.cuda.synchronize()
+            ent = dict(fwd=gf, bwd=gb, out=out, keep=(lane._p, lane._out, lane._keep, lane._fp, lane._fout, lane._fkeep), **st)
+            self._graphs[key] = ent
+            torch.cuda.current_stream().wait_stream(torch.cuda.default_stream(dev))
+        ent['feat'].copy_(feat, non_blocking=True)
+        ent['gt_boxes'].copy_(gt_boxes.view(-1, 9), non_blocking=True)
+        ent['gt_labels'].copy_(gt_labels, non_blocking=True)
+        eng._upload_meta(boxes, metas)
+        return ent
 
     def _add_lane(self):
         t = HotPathTrainer(self._sd, device=self.main.device, **self._kw)
@@ -516,9 +562,18 @@ class TrainStep:
                     outs.append(self.lanes[k].forward(*smp))
                     self.lanes[k].backward()
         else:
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            ev[0].record(cur)
+            ents = []
             for i, smp in enumerate(samples):
                 with torch.cuda.stream(self.streams[i]):
-                    outs.append(self.lanes[i].forward(*smp))
+                    if self.use_graphs:
+                        ent = self._graph_entry(i, smp)
+                        ents.append(ent)
+                        ent['fwd'].replay()
+                        outs.append(ent['out'])
+                    else:
+                        outs.append(self.lanes[i].forward(*smp))
             for s in self.streams:
                 cur.wait_stream(s)
             # loss_bbox / its gradient are divided by the mean positive count over the GLOBAL batch (one tiny all-reduce)
@@ -527,12 +582,20 @@ class TrainStep:
                 s.wait_stream(cur)
             for i in range(len(samples)):
                 with torch.cuda.stream(self.streams[i]):
-                    self.lanes[i].backward(factor)
+                    if self.use_graphs:
+                        ents[i]['factor'].copy_(factor)
+                        ents[i]['bwd'].replay()
+                    else:
+                        self.lanes[i].backward(factor)
         for s in self.streams:
             cur.wait_stream(s)
         for t in self.lanes[1:]:
             self.main.grads.add_(t.grads)
+        if self.sync_bbox_avg_factor:
+            ev[1].record(cur)
         nranks = self.main.all_reduce_grads()
+        if self.sync_bbox_avg_factor:
+            ev[2].record(cur)
         assert world in (1, nranks), f'world={world} but the process group has {nranks} ranks'
         scale = 1.0 / (nranks * len(samples))
         if optimize and max_grad_norm is not None:
@@ -540,6 +603,9 @@ class TrainStep:
             scale = 1.0
         if optimize:
             self.main.adamw_step(lr=lr, weight_decay=weight_decay, grad_scale=scale)
+        if self.sync_bbox_avg_factor:
+            ev[3].record(cur)
+            self.timing = ev        # fwd + bwd: ev[0] -> ev[1]; gradient all-reduce: ev[1] -> ev[2]; clip + AdamW: ev[2] -> ev[3]
         w = self.main._stage_weights()
         losses = [(w * (o['loss_cls'] + o['loss_bbox'])).sum() for o in outs]      # after the backward: rescaled loss_bbox
         return torch.stack(losses).mean()
