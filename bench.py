@@ -184,6 +184,7 @@ def main():
     assert torch.cuda.is_available(), 'bench.py needs a GPU (mv2d_b200 has no CPU fallback)'
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
+    numa = D.bind_to_gpu_numa_node(local_rank)      # before any pinned allocation
     if os.environ.get('NCCL_DEBUG', '').upper() == 'VERSION':
         os.environ['NCCL_DEBUG'] = 'WARN'       # keep stdout to the one JSON line (NCCL prints its version there)
     D.init('nccl', dev)
@@ -353,7 +354,7 @@ def main():
                                 'share the padding masks (a common subexpression: it does not depend on the inputs)', wall_s=wall),
         e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                  ms_per_step=e2e_total_ms / args.steps),
-        gpu_launches=launches, launches_per_sample=launches / (args.steps * B), clocks=clocks, roofline=roof['roofline'],
+        gpu_launches=launches, launches_per_sample=launches / (args.steps * B), clocks=clocks, numa=numa, roofline=roof['roofline'],
         attention_roofline=roof['attention'], stage_us=roof['stage_us'], peaks=peaks, serial=serial)
     if two_frame is not None:
         line['two_frame'] = two_frame
