@@ -235,6 +235,29 @@ typedef struct Mv2dBranchWeights {      /* stacked over layers: leading dim L */
     const float *cls_w0_hi, *cls_w0_lo, *cls_w1_hi, *cls_w1_lo, *reg_w0_hi, *reg_w0_lo, *reg_w1_hi, *reg_w1_lo;
 } Mv2dBranchWeights;
 
+/* ---- weight packing (host only, no CUDA calls): the one-time re-layout of the reference state_dict into the buffers
+ * the kernels read -- absorbed cross-attention matrices (fp64, rounded once), K-major 3x3 convolutions, TF32 hi / lo
+ * splits, stacked branches, layer 0's constant self-attention output.  Replaces what a reference user gets from
+ * `load_state_dict` (mmdet3d checkpoint keys; the `roi_head.` prefix is optional).
+ *   1. bytes = mv2d_pack_weights_bytes(L, fold, &n_entries); allocate a device arena (256-byte aligned) and a host image
+ *   2. mv2d_pack_weights(...): fills the host image, the directory (name -> byte offset) and the two weight structs with
+ *      DEVICE pointers (device_base + offset)
+ *   3. copy the host image to the device arena (one cudaMemcpy)
+ * Directory names are the ones the other parameter structs use (w_pos0, b_pos0, ..., w_conv, w_conv_lo, w_fc, w_fc_hi,
+ * ..., l<k>.<field>, br.<field>, post_g, post_b, dim_t). */
+typedef struct Mv2dNamedTensor { const char* name; const float* data; int64_t numel; } Mv2dNamedTensor;   /* HOST fp32 */
+typedef struct Mv2dPackedEntry { char name[48]; int64_t offset /*bytes into the arena*/; int64_t numel; } Mv2dPackedEntry;
+MV2D_API int64_t mv2d_pack_weights_bytes(int num_layers, int fold_first_self_attn, int* n_entries);
+MV2D_API int mv2d_pack_weights(const Mv2dNamedTensor* state_dict, int n_tensors, int num_layers, int fold_first_self_attn,
+                               void* host_arena, int64_t arena_bytes, const void* device_base, Mv2dPackedEntry* dir,
+                               int dir_cap, int* n_dir, struct Mv2dLayerWeights* layers /*out [num_layers]*/,
+                               struct Mv2dBranchWeights* branches /*out*/);
+/* `neck.*` (one-level FPN, configs/mv2d/exp/*.py:32-39) as the operands of mv2d_fpn_neck: lat_w / lat_w_lo / lat_b,
+ * fpn_w / fpn_w_lo (K ordered (ky, kx, c_in)) / fpn_b.  Keys with or without the `neck.` prefix. */
+MV2D_API int64_t mv2d_pack_neck_bytes(int* n_entries);
+MV2D_API int mv2d_pack_neck(const Mv2dNamedTensor* state_dict, int n_tensors, void* host_arena, int64_t arena_bytes,
+                            const void* device_base, Mv2dPackedEntry* dir, int dir_cap, int* n_dir);
+
 typedef struct Mv2dDecoderParams {
     int N, L, mode /*0 = RoI-token keys (S), 1 = feature-map keys (T)*/, num_rows;
     int max_match, mask_words;

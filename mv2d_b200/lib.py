@@ -197,6 +197,14 @@ class FrontTrainParams(C.Structure):
     ]
 
 
+class NamedTensor(C.Structure):      # Mv2dNamedTensor: a HOST fp32 tensor under its reference state_dict key
+    _fields_ = [('name', C.c_char_p), ('data', C.c_void_p), ('numel', C.c_int64)]
+
+
+class PackedEntry(C.Structure):      # Mv2dPackedEntry: one buffer of the packed arena
+    _fields_ = [('name', C.c_char * 48), ('offset', C.c_int64), ('numel', C.c_int64)]
+
+
 _STRUCTS = [PeParams, QgParams, CorrParams, DecoderParams, LayerWeights, BranchWeights, DnParams, KvParams, LossParams, NeckParams,
             TrainParams, FrontTrainParams]
 
@@ -206,6 +214,12 @@ SYMBOLS = [
     ('mv2d_last_error', C.c_char_p, []),
     ('mv2d_launch_count', C.c_ulonglong, []),
     ('mv2d_sizeof', C.c_size_t, [C.c_int]),
+    ('mv2d_pack_weights_bytes', C.c_int64, [C.c_int, C.c_int, C.POINTER(C.c_int)]),
+    ('mv2d_pack_weights', C.c_int, [C.POINTER(NamedTensor), C.c_int, C.c_int, C.c_int, c_f, C.c_int64, c_f, C.POINTER(PackedEntry),
+                                    C.c_int, C.POINTER(C.c_int), C.POINTER(LayerWeights), C.POINTER(BranchWeights)]),
+    ('mv2d_pack_neck_bytes', C.c_int64, [C.POINTER(C.c_int)]),
+    ('mv2d_pack_neck', C.c_int, [C.POINTER(NamedTensor), C.c_int, c_f, C.c_int64, c_f, C.POINTER(PackedEntry), C.c_int,
+                                 C.POINTER(C.c_int)]),
     ('mv2d_geom_prep', C.c_int, [c_f, C.c_int, c_f, c_f, c_f]),
     ('mv2d_geom_prep_batch', C.c_int, [c_f, C.c_int, C.c_int, c_f, c_f, c_f]),
     ('mv2d_nchw_to_nhwc', C.c_int, [c_f, c_f, c_f, C.c_int, C.c_int, C.c_int, c_f]),
