@@ -15,128 +15,9 @@
 #include "gemm_tc.cuh"
 #include "mv2d_internal.h"
 
+#include "ln.cuh"
+
 namespace mv2d {
-
-// ------------------------------------------------------------------------------------------
-// Row-wise: x = LN( sum_s partial[s] + bias + residual ) ; optional second LN (post_norm) and
-// optional "+ query_pos" copy.  One warp per row of 256.  Also used (relu=1, grouped gammas)
-// for the Linear-LN-ReLU blocks of the classification branch.
-struct LnArgs {
-    const float* partial; int nsplit; long long split_stride;
-    const float* bias; const float* residual;
-    const float* gamma; const float* beta; int rows_per_group; int group_stride;  // per-layer params
-    int relu;
-    const float* qpos;   // nullable
-    const float* gamma2; const float* beta2;  // nullable: post_norm
-    float* out; float* out_q; float* out2;
-    float* out_hi; float* out_lo;      // nullable: TF32 split of `out`   (A operand of a 3xTF32 GEMM)
-    float* outq_hi; float* outq_lo;    // nullable: TF32 split of `out_q`
-    float* out2_hi; float* out2_lo;    // nullable: TF32 split of `out2`
-    int rows;
-    int bcast_in;     // 1: `partial` is ONE [256] row shared by every output row
-};
-
-__device__ __forceinline__ void ln_body(const LnArgs& a, int vb) {
-    const int row = vb * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (row >= a.rows) return;
-    const int grp = a.rows_per_group > 0 ? row / a.rows_per_group : 0;
-    const long long o = (long long)row * MV2D_C;
-    const long long oi = a.bcast_in ? 0 : o;
-    float v[8];
-    // all loads of the row (up to 8 split-K partials x 2 halves) are issued before the first add: one memory
-    // latency per row instead of one per partial
-    float4 pt[2][8];
-#pragma unroll
-    for (int i = 0; i < 2; ++i)
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-            if (k < a.nsplit) pt[i][k] = *reinterpret_cast<const float4*>(a.partial + k * a.split_stride + oi + i * 128 + lane * 4);
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        const int c = i * 128 + lane * 4;
-        float4 s = pt[i][0];
-#pragma unroll
-        for (int k = 1; k < 8; ++k) {
-            if (k < a.nsplit) { s.x += pt[i][k].x; s.y += pt[i][k].y; s.z += pt[i][k].z; s.w += pt[i][k].w; }
-        }
-        if (a.bias) {
-            float4 t = __ldg(reinterpret_cast<const float4*>(a.bias + grp * a.group_stride + c));
-            s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
-        }
-        if (a.residual) {
-            float4 t = *reinterpret_cast<const float4*>(a.residual + o + c);
-            s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
-        }
-        v[i * 4 + 0] = s.x; v[i * 4 + 1] = s.y; v[i * 4 + 2] = s.z; v[i * 4 + 3] = s.w;
-    }
-    auto norm = [&](const float* g, const float* b, float* y) {
-        float s = 0.f;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) s += v[i];
-        const float mean = warp_sum(s) * (1.f / MV2D_C);
-        float q = 0.f;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { float d = v[i] - mean; q += d * d; }
-        const float rstd = rsqrtf(warp_sum(q) * (1.f / MV2D_C) + 1e-5f);
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const int c = i * 128 + lane * 4;
-            float4 gg = __ldg(reinterpret_cast<const float4*>(g + c));
-            float4 bb = __ldg(reinterpret_cast<const float4*>(b + c));
-            y[i * 4 + 0] = (v[i * 4 + 0] - mean) * rstd * gg.x + bb.x;
-            y[i * 4 + 1] = (v[i * 4 + 1] - mean) * rstd * gg.y + bb.y;
-            y[i * 4 + 2] = (v[i * 4 + 2] - mean) * rstd * gg.z + bb.z;
-            y[i * 4 + 3] = (v[i * 4 + 3] - mean) * rstd * gg.w + bb.w;
-        }
-    };
-    float y[8];
-    norm(a.gamma + grp * a.group_stride, a.beta + grp * a.group_stride, y);
-    if (a.relu) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) y[i] = fmaxf(y[i], 0.f);
-    }
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        const int c = i * 128 + lane * 4;
-        *reinterpret_cast<float4*>(a.out + o + c) = make_float4(y[i * 4], y[i * 4 + 1], y[i * 4 + 2], y[i * 4 + 3]);
-        if (a.out_hi) {
-            float hi[4], lo[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) { hi[k] = round_tf32(y[i * 4 + k]); lo[k] = round_tf32(y[i * 4 + k] - hi[k]); }
-            *reinterpret_cast<float4*>(a.out_hi + o + c) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-            *reinterpret_cast<float4*>(a.out_lo + o + c) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-        }
-        if (a.out_q) {
-            float4 qp = *reinterpret_cast<const float4*>(a.qpos + o + c);
-            const float z[4] = {y[i * 4] + qp.x, y[i * 4 + 1] + qp.y, y[i * 4 + 2] + qp.z, y[i * 4 + 3] + qp.w};
-            *reinterpret_cast<float4*>(a.out_q + o + c) = make_float4(z[0], z[1], z[2], z[3]);
-            if (a.outq_hi) {
-                float hi[4], lo[4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) { hi[k] = round_tf32(z[k]); lo[k] = round_tf32(z[k] - hi[k]); }
-                *reinterpret_cast<float4*>(a.outq_hi + o + c) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-                *reinterpret_cast<float4*>(a.outq_lo + o + c) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-            }
-        }
-    }
-    if (a.out2) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = y[i];
-        norm(a.gamma2, a.beta2, y);
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const int c = i * 128 + lane * 4;
-            *reinterpret_cast<float4*>(a.out2 + o + c) = make_float4(y[i * 4], y[i * 4 + 1], y[i * 4 + 2], y[i * 4 + 3]);
-            if (a.out2_hi) {
-                float hi[4], lo[4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) { hi[k] = round_tf32(y[i * 4 + k]); lo[k] = round_tf32(y[i * 4 + k] - hi[k]); }
-                *reinterpret_cast<float4*>(a.out2_hi + o + c) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-                *reinterpret_cast<float4*>(a.out2_lo + o + c) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-            }
-        }
-    }
-}
 
 __global__ void __launch_bounds__(256) ln_kernel(LnArgs a) {
     pdl_wait();
@@ -1163,7 +1044,7 @@ size_t decoder_workspace_bytes(int N, int L) {
     // + (3xTF32 everywhere, > 512 rows) x / xq hi/lo, sa lo, xt ctx lo: 6*256
     size_t per = 9 * MV2D_C + 768 + MV2D_C + 2048 + 2 * 2048 + 2 * 2048 + DEC_SPLIT * MV2D_C + XR_MAXM * XR_REC + 1 + 6 * MV2D_C;
     // branches: 4 x [L,N,256] + hi/lo splits of the post-normed states and of three branch activations
-    return (n * per + (4 + 7) * l * n * MV2D_C) * sizeof(float) + 4096;   // + the device-wide barrier word and phase timestamps of the persistent kernel
+    return (n * per + (4 + 7) * l * n * MV2D_C) * sizeof(float) + 4096 + 256;   // + the device-wide barrier word and phase timestamps of the persistent kernel
 }
 
 // ---- key-stationary cross-attention of the two-frame head (xa_tile.cuh): caller-owned scratch
@@ -1358,6 +1239,7 @@ int run_decoder(const Mv2dDecoderParams& p, cudaStream_t st) {
     MV2D_CHECK_ARG((size_t)(ws - p.workspace) == xr_part_offset(N, L), "decoder: internal workspace layout drifted");
     float* xr_part = ws; ws += (size_t)N * XR_MAXM * XR_REC;
     int* xr_ticket = reinterpret_cast<int*>(ws); ws += N;
+    ws = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);     // TMA operands follow
     // 3xTF32 operand splits of the GEMMs that run as FFMA below 512 rows
     float* x_hi = ws;  ws += (size_t)N * C;
     float* x_lo = ws;  ws += (size_t)N * C;
@@ -1511,6 +1393,11 @@ int run_decoder(const Mv2dDecoderParams& p, cudaStream_t st) {
         if ((e = cudaMemsetAsync(x_hi, 0, 2 * NC * sizeof(float), st)) != cudaSuccess) { set_error("decoder: init %s", cudaGetErrorString(e)); return (int)e; }
         if ((rc = launch_split_tf32(p.query_pos, xq_hi, xq_lo, NC, st))) return rc;
     }
+    // projection + residual + LayerNorm as one cluster launch (gemm_ln.cu) wherever the operands exist as TF32 hi / lo pairs
+    const bool fuse_ln = gemm_ln_enabled();
+    const bool fuse_sa = fuse_ln && p.layers[0].sa_out_w_hi && p.layers[0].sa_out_w_lo;
+    const bool fuse_xo = fuse_ln && xt && p.layers[0].xa_o_w_hi && p.layers[0].xa_o_w_lo;
+    const bool sa_split = big || fuse_sa;
     for (int l = lb; l < le; ++l) {
         const Mv2dLayerWeights& w = p.layers[l];
         float* inter = p.outs_dec + (long long)l * NC;
@@ -1543,27 +1430,31 @@ int run_decoder(const Mv2dDecoderParams& p, cudaStream_t st) {
                 const int c64 = cdiv(rows, 64) * MV2D_HEADS * nb, c32 = cdiv(rows, 32) * MV2D_HEADS * nb;
                 if (cdiv(c64, 296) * 64 <= cdiv(c32, 296) * 32)
                     launch_k(self_attn_blk_kernel<64>, dim3(cdiv(rows, 64), MV2D_HEADS, nb), dim3(256), (size_t)SbCfg<64>::SMEM_BYTES, st,
-                             (const float*)qkv, am, N, sa, rps, p.n_real, big ? sa_lo : (float*)nullptr);
+                             (const float*)qkv, am, N, sa, rps, p.n_real, sa_split ? sa_lo : (float*)nullptr);
                 else
                     launch_k(self_attn_blk_kernel<32>, dim3(cdiv(rows, 32), MV2D_HEADS, nb), dim3(256), (size_t)SbCfg<32>::SMEM_BYTES, st,
-                             (const float*)qkv, am, N, sa, rps, p.n_real, big ? sa_lo : (float*)nullptr);
+                             (const float*)qkv, am, N, sa, rps, p.n_real, sa_split ? sa_lo : (float*)nullptr);
             } else if (p.batch > 0)
                 launch_k(self_attn_kernel, dim3(cdiv(p.rows_per_sample, 8 * SA_QPW), MV2D_HEADS, p.batch), dim3(256), SA_SMEM_BYTES, st,
-                         (const float*)qkv, (const uint8_t*)nullptr, N, sa, p.rows_per_sample, p.n_real, big ? sa_lo : (float*)nullptr);
+                         (const float*)qkv, (const uint8_t*)nullptr, N, sa, p.rows_per_sample, p.n_real, sa_split ? sa_lo : (float*)nullptr);
             else
                 launch_k(self_attn_kernel, dim3(cdiv(N, 8 * SA_QPW), MV2D_HEADS), dim3(256), SA_SMEM_BYTES, st, (const float*)qkv, p.self_attn_mask, N, sa,
-                         0, (const int*)nullptr, big ? sa_lo : (float*)nullptr);
+                         0, (const int*)nullptr, sa_split ? sa_lo : (float*)nullptr);
             MV2D_CHECK_LAUNCH("self_attn");
-            if (big) {
-                if ((rc = tc3(sa, sa_lo, C, w.sa_out_w_hi, w.sa_out_w_lo, C, nullptr, part, nullptr, C, N, C, C, 0, 1, 0, st))) return rc;
-            } else {
-                if ((rc = gemm(sa, C, w.sa_out_w, C, nullptr, part, C, N, C, C, 0, st))) return rc;
-            }
             {
                 LnArgs a{}; a.partial = part; a.nsplit = 1; a.bias = w.sa_out_b; a.residual = x;
                 a.gamma = w.ln_g[0]; a.beta = w.ln_b[0]; a.qpos = p.query_pos; a.out = x1; a.out_q = x1q; a.rows = N;
                 a.outq_hi = x1q_hi; a.outq_lo = x1q_lo;
-                if ((rc = ln(a, st))) return rc;
+                if (fuse_sa) {          // out_proj + residual + LayerNorm in one cluster launch (gemm_ln.cu)
+                    if ((rc = launch_gemm_ln(sa, sa_lo, C, w.sa_out_w_hi, w.sa_out_w_lo, C, N, C, a, 0, st))) return rc;
+                } else {
+                    if (big) {
+                        if ((rc = tc3(sa, sa_lo, C, w.sa_out_w_hi, w.sa_out_w_lo, C, nullptr, part, nullptr, C, N, C, C, 0, 1, 0, st))) return rc;
+                    } else {
+                        if ((rc = gemm(sa, C, w.sa_out_w, C, nullptr, part, C, N, C, C, 0, st))) return rc;
+                    }
+                    if ((rc = ln(a, st))) return rc;
+                }
             }
         }
         if (xt) {
@@ -1584,18 +1475,22 @@ int run_decoder(const Mv2dDecoderParams& p, cudaStream_t st) {
             }
             {
                 XtMergeArgs a{}; a.g = xg; a.qlist = xw.qlist; a.qcnt = xw.qcnt; a.rec = xw.rec; a.ctx = xw.ctx;
-                a.ctx_lo = big ? xctx_lo : nullptr;
+                a.ctx_lo = (big || fuse_xo) ? xctx_lo : nullptr;
                 launch_k(xt_merge_kernel, dim3(N), dim3(XT_MERGE_THREADS), (size_t)xg.tiles_ps * 36, st, a);
                 MV2D_CHECK_LAUNCH("xt_merge");
             }
-            if (big) {
-                if ((rc = tc3(xw.ctx, xctx_lo, C, w.xa_o_w_hi, w.xa_o_w_lo, C, nullptr, part, nullptr, C, N, C, C, 0, 1, 0, st))) return rc;
-            } else {
-                if ((rc = gemm(xw.ctx, C, w.xa_o_w, C, nullptr, part, C, N, C, C, 0, st))) return rc;
-            }
             LnArgs a{}; a.partial = part; a.nsplit = 1; a.bias = w.xa_o_b; a.residual = x1;
             a.gamma = w.ln_g[1]; a.beta = w.ln_b[1]; a.out = x2; a.rows = N; a.out_hi = x2_hi; a.out_lo = x2_lo;
-            if ((rc = ln(a, st))) return rc;
+            if (fuse_xo) {
+                if ((rc = launch_gemm_ln(xw.ctx, xctx_lo, C, w.xa_o_w_hi, w.xa_o_w_lo, C, N, C, a, 0, st))) return rc;
+            } else {
+                if (big) {
+                    if ((rc = tc3(xw.ctx, xctx_lo, C, w.xa_o_w_hi, w.xa_o_w_lo, C, nullptr, part, nullptr, C, N, C, C, 0, 1, 0, st))) return rc;
+                } else {
+                    if ((rc = gemm(xw.ctx, C, w.xa_o_w, C, nullptr, part, C, N, C, C, 0, st))) return rc;
+                }
+                if ((rc = ln(a, st))) return rc;
+            }
         } else {
         // --- sparse cross attention (absorbed)
         if ((rc = tc3(x1q_hi, x1q_lo, C, w.ca_q_w, w.ca_q_w_lo, C, w.ca_q_b, qt, nullptr, 2048, N, 2048, C, 0, 1, 0, st))) return rc;
@@ -1615,18 +1510,22 @@ int run_decoder(const Mv2dDecoderParams& p, cudaStream_t st) {
         }
         // split-K only while the M tiles alone cannot fill the GPU
         const int ksplit = big ? (N > 2048 ? 2 : 4) : DEC_SPLIT;
-        if ((rc = tc3(ctx, ctx_lo, 2048, w.ca_o_w, w.ca_o_w_lo, 2048, nullptr, part, nullptr, C, N, C, 2048, 0, ksplit, NC, st))) return rc;
         {
             LnArgs a{}; a.partial = part; a.nsplit = ksplit; a.split_stride = NC; a.bias = w.ca_o_b; a.residual = x1;
             a.gamma = w.ln_g[1]; a.beta = w.ln_b[1]; a.out = x2; a.rows = N; a.out_hi = x2_hi; a.out_lo = x2_lo;
-            if ((rc = ln(a, st))) return rc;
+            if (fuse_ln) {
+                if ((rc = launch_gemm_ln(ctx, ctx_lo, 2048, w.ca_o_w, w.ca_o_w_lo, 2048, N, 2048, a, 0, st))) return rc;
+            } else {
+                if ((rc = tc3(ctx, ctx_lo, 2048, w.ca_o_w, w.ca_o_w_lo, 2048, nullptr, part, nullptr, C, N, C, 2048, 0, ksplit, NC, st))) return rc;
+                if ((rc = ln(a, st))) return rc;
+            }
         }
         }
         // --- FFN
         const int ksplit2 = big ? (N > 2048 ? 2 : 4) : DEC_SPLIT;
         if ((rc = tc3(x2_hi, x2_lo, C, w.ffn_w1, w.ffn_w1_lo, C, w.ffn_b1, hdn, hdn_lo, 2048, N, 2048, C,
                       GEMM_RELU | GEMM_SPLIT_OUT, 1, 0, st))) return rc;
-        if ((rc = tc3(hdn, hdn_lo, 2048, w.ffn_w2, w.ffn_w2_lo, 2048, nullptr, part, nullptr, C, N, C, 2048, 0, ksplit2, NC, st))) return rc;
+        if (!fuse_ln && (rc = tc3(hdn, hdn_lo, 2048, w.ffn_w2, w.ffn_w2_lo, 2048, nullptr, part, nullptr, C, N, C, 2048, 0, ksplit2, NC, st))) return rc;
         {
             LnArgs a{}; a.partial = part; a.nsplit = ksplit2; a.split_stride = NC; a.bias = w.ffn_b2; a.residual = x2;
             a.gamma = w.ln_g[2]; a.beta = w.ln_b[2]; a.qpos = p.query_pos; a.out = x; a.out_q = xq;
@@ -1635,7 +1534,9 @@ int run_decoder(const Mv2dDecoderParams& p, cudaStream_t st) {
                 a.out_hi = x_hi; a.out_lo = x_lo; a.outq_hi = xq_hi; a.outq_lo = xq_lo;
                 a.out2_hi = in_hi + (long long)l * NC; a.out2_lo = in_lo + (long long)l * NC;
             }
-            if ((rc = ln(a, st))) return rc;
+            if (fuse_ln) {
+                if ((rc = launch_gemm_ln(hdn, hdn_lo, 2048, w.ffn_w2, w.ffn_w2_lo, 2048, N, 2048, a, 0, st))) return rc;
+            } else if ((rc = ln(a, st))) return rc;
         }
     }
     if (!last) return 0;

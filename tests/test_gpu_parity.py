@@ -241,6 +241,40 @@ def test_cluster_multicast_gemm_variant():
     assert r.returncode == 0 and 'MC_OK' in r.stdout, r.stderr[-2000:]
 
 
+def test_fused_projection_layernorm_variant():
+    """MV2D_GEMM_LN=1 (opt-in, read once per process): out_proj / FFN-2 + residual + LayerNorm as ONE cluster launch --
+    split-K over the cluster, partial tiles summed over distributed shared memory (csrc/gemm_ln.cu).  Same goldens, same
+    gate, for the S head (cluster of 8 and 2), the T head's key-stationary form and a batch."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import json, numpy as np, torch\n"
+        "from mv2d_b200 import synth\n"
+        "from mv2d_b200.engine import HotPath\n"
+        "for name in ('s_cfg2', 's_small', 't_cfg3'):\n"
+        "    g = dict(np.load(f'tests/golden/{name}.npz')); spec = json.loads(bytes(g.pop('spec')).decode())\n"
+        "    eng = HotPath(synth.make_state_dict(0, num_layers=spec['num_layers']), mode=spec['mode'])\n"
+        "    feat, boxes, metas = synth.case_inputs(spec)\n"
+        "    n0 = eng.launch_count()\n"
+        "    out = eng.forward(feat.cuda(), boxes, metas); torch.cuda.synchronize()\n"
+        "    print(name, 'launches', eng.launch_count() - n0)\n"
+        "    for k in ('cls_scores', 'bbox_preds'):\n"
+        "        a, b = out[k].cpu().numpy().astype(np.float64), g[k].astype(np.float64)\n"
+        "        assert np.isfinite(a).all() and (np.abs(a - b) <= 1e-3 + 1e-3 * np.abs(b)).all(), (name, k)\n"
+        "    if name == 's_cfg2':\n"
+        "        outs = eng.forward_batch(torch.stack([feat, feat], 0).cuda(), [boxes, boxes], [metas, metas]); torch.cuda.synchronize()\n"
+        "        for o in outs['samples']:\n"
+        "            for k in ('cls_scores', 'bbox_preds'):\n"
+        "                a, b = o[k].cpu().numpy().astype(np.float64), g[k].astype(np.float64)\n"
+        "                assert (np.abs(a - b) <= 1e-3 + 1e-3 * np.abs(b)).all(), ('batch', k)\n"
+        "print('GL_OK')\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, '-c', code], cwd=root, env=dict(os.environ, MV2D_GEMM_LN='1'),
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and 'GL_OK' in r.stdout, (r.stdout[-500:], r.stderr[-2000:])
+
+
 def test_tcgen05_gemm_3xtf32_and_im2col(state_dicts):
     """Error-compensated 3xTF32: fp32-grade on arbitrary fp32 operands; and the TMA-im2col form
     against torch conv2d (fp64)."""
