@@ -11,6 +11,10 @@
 //   * IM2COL: the A operand is the implicit im2col of the [N,7,7,256] RoI tokens: a 4-D tensor
 //     map with box (32 ch, 7, 7, 1) loaded at (c0, dx-1, dy-1, roi); TMA zero-fills the halo.
 //     Two RoIs share one 128-row tile (rows 0..48 and 64..112).
+//   * IM2COL = 3: the same operand, FIVE RoIs per 256-row tile: the five 49-row boxes land back to back (rows 0..244; the
+//     128B swizzle is a function of the shared-memory address, so boxes need not start on a 1024-byte atom) and every
+//     K step issues two M = 128 MMAs (rows 0..127, 128..255) on the same W tile into two TMEM accumulators.  245 of
+//     256 MMA rows are real (98 of 128 before) and a W tile is fetched once per five RoIs instead of once per two.
 //   * IM2COL = 2: the same trick on a whole feature map [V,h,w,256] (3x3 conv, padding 1, of the FPN neck): a
 //     tile is 16 rows x 8 columns of pixels, the box (32 ch, 8, 16, 1) is loaded at (c0, x0+dx-1, y0+dy-1, v).
 // Warp roles (192 threads): warp 0 TMA producer, warp 1 TMEM alloc + MMA issue, warps 2..5
@@ -55,7 +59,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmWlo,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmA2lo, TcArgs g) {
     static_assert(!RAW || (PASSES == 3 && !IM2COL), "RAW is the in-kernel split of the plain 3xTF32 GEMM");
-    constexpr int A_BYTES = TC_BM * TC_BK * 4;      // 16 KB
+    constexpr bool PACK5 = IM2COL == 3;
+    constexpr int NACC = PACK5 ? 2 : 1;             // accumulators (M = 128 each) per CTA
+    constexpr int A_BYTES = NACC * TC_BM * TC_BK * 4;      // 16 KB per 128 rows
     constexpr int W_BYTES = BN * TC_BK * 4;
     constexpr int NOP = PASSES == 3 ? 2 : 1;        // hi (+ lo) copies of each operand
     constexpr int STAGE_BYTES = NOP * (A_BYTES + W_BYTES);
@@ -81,6 +87,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int nkb = g.nkb_per_split, kb0 = grouped ? 0 : blockIdx.z * g.nkb_per_split;   // this CTA's K range (split-K)
     // CTAs that share an operand tile walk K in rotated order, so they do not all hit the same L2 lines at once
     const int rot = IM2COL ? 0 : (int)((blockIdx.x + 3 * blockIdx.y) % nkb);
+    constexpr int ROI_BYTES = MV2D_TOK * TC_BK * 4;        // one im2col box: 49 rows x 128 B
 
     // output columns >= n_switch read their A rows from the second operand (CTA-uniform)
     const bool second_a = !IM2COL && g.n_switch > 0 && n0 >= g.n_switch;
@@ -94,7 +101,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(BN));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(NACC * BN));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -113,7 +120,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 mbar_wait(&empty_bar[s], ph ^ 1);
                 uint8_t* st = smem + s * STAGE_BYTES;
                 // bytes TMA will deliver: an im2col box is 49 rows x 128 B per RoI, not a full 64-row half tile
-                constexpr int A_TX = IM2COL == 1 ? 2 * MV2D_TOK * TC_BK * 4 : A_BYTES;
+                constexpr int A_TX = IM2COL == 1 ? 2 * ROI_BYTES : (PACK5 ? 5 * ROI_BYTES : A_BYTES);
                 mbar_expect_tx(&full_bar[s], (RAW ? 1 : NOP) * (A_TX + W_BYTES));
                 if (IM2COL == 2) {
                     const int kg = kb0 + kb;
@@ -123,6 +130,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const int x0 = tx * 8 + tap % 3 - 1, y0 = ty * 16 + tap / 3 - 1;
                     tma_load_4d(&tmA, &full_bar[s], st, c0, x0, y0, v);
                     if (PASSES == 3) tma_load_4d(&tmAlo, &full_bar[s], st + A_BYTES, c0, x0, y0, v);
+                } else if (PACK5) {
+                    const int kg = kb0 + kb;
+                    const int tap = kg / (MV2D_C / TC_BK), c0 = (kg % (MV2D_C / TC_BK)) * TC_BK;
+                    const int dx = tap % 3 - 1, dy = tap / 3 - 1;
+#pragma unroll
+                    for (int r = 0; r < 5; ++r) {   // five RoIs back to back: rows 49 r .. 49 r + 48 (RoIs past the end: zero fill)
+                        tma_load_4d(&tmA, &full_bar[s], st + r * ROI_BYTES, c0, dx, dy, m_tile * 5 + r);
+                        tma_load_4d(&tmAlo, &full_bar[s], st + A_BYTES + r * ROI_BYTES, c0, dx, dy, m_tile * 5 + r);
+                    }
                 } else if (IM2COL == 1) {
                     const int kg = kb0 + kb;
                     const int tap = kg / (MV2D_C / TC_BK), c0 = (kg % (MV2D_C / TC_BK)) * TC_BK;
@@ -156,10 +172,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                 for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
                     const uint64_t adv = (uint64_t)((k * TC_UMMA_K * 4) >> 4);   // advance start address inside the swizzle row
-                    umma_tf32(tmem_base, a_hi + adv, w_hi + adv, idesc, (kb | k) != 0);
-                    if (PASSES == 3) {
-                        umma_tf32(tmem_base, a_hi + adv, w_lo + adv, idesc, 1);
-                        umma_tf32(tmem_base, a_lo + adv, w_hi + adv, idesc, 1);
+#pragma unroll
+                    for (int acc = 0; acc < NACC; ++acc) {
+                        const uint64_t ra = adv + (uint64_t)((acc * TC_BM * TC_BK * 4) >> 4);    // rows 128 acc .. of the A tile
+                        umma_tf32(tmem_base + acc * BN, a_hi + ra, w_hi + adv, idesc, (kb | k) != 0);
+                        if (PASSES == 3) {
+                            umma_tf32(tmem_base + acc * BN, a_hi + ra, w_lo + adv, idesc, 1);
+                            umma_tf32(tmem_base + acc * BN, a_lo + ra, w_hi + adv, idesc, 1);
+                        }
                     }
                 }
                 umma_commit(&empty_bar[s]);               // frees the smem slot when these MMAs retire
@@ -205,7 +225,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int q = warp & 3;                           // TMEM lane quadrant this warp may access
         float* stg = reinterpret_cast<float*>(smem) + q * 1024;
+        int acc_row0 = 0;                                 // first tile row of the accumulator being drained
         auto out_row = [&](int r, long long& orow) -> bool {   // tile row -> output row
+            if (PACK5) {
+                orow = (long long)m_tile * 5 * MV2D_TOK + r;
+                return r < 5 * MV2D_TOK && orow < (long long)g.n_rois * MV2D_TOK;
+            }
             if (IM2COL == 1) {
                 const int roi = m_tile * 2 + (r >> 6), tok = r & 63;
                 orow = (long long)roi * MV2D_TOK + tok;
@@ -234,7 +259,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int rr = i * 4 + (lane >> 3), cc = lane & 7;
                 const float4 v4 = *reinterpret_cast<const float4*>(stg + rr * 32 + ((cc ^ (rr & 7)) << 2));
                 long long orow;
-                if (out_row(q * 32 + rr, orow)) *reinterpret_cast<float4*>(dst + orow * g.ldc + n + cc * 4) = v4;
+                if (out_row(acc_row0 + q * 32 + rr, orow)) *reinterpret_cast<float4*>(dst + orow * g.ldc + n + cc * 4) = v4;
             }
         };
         // global -> registers (my row, 32 cols), same access pattern in reverse
@@ -245,7 +270,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int rr = i * 4 + (lane >> 3), cc = lane & 7;
                 long long orow;
                 float4 v4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (out_row(q * 32 + rr, orow)) v4 = __ldg(reinterpret_cast<const float4*>(src + (row_mod > 0 ? orow % row_mod : orow) * g.ldc + n + cc * 4));
+                if (out_row(acc_row0 + q * 32 + rr, orow)) v4 = __ldg(reinterpret_cast<const float4*>(src + (row_mod > 0 ? orow % row_mod : orow) * g.ldc + n + cc * 4));
                 *reinterpret_cast<float4*>(stg + rr * 32 + ((cc ^ (rr & 7)) << 2)) = v4;
             }
             __syncwarp();
@@ -256,9 +281,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         };
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int cc2 = 0; cc2 < NACC * (BN / 32); ++cc2) {
+            const int c = cc2 % (BN / 32);
+            acc_row0 = (cc2 / (BN / 32)) * TC_BM;
             uint32_t v[32];
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cc2 * 32), v);
             const int n = n0 + c * 32;
             float x[32];
 #pragma unroll
@@ -311,7 +338,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(NACC * BN));
     }
 }
 
@@ -551,12 +578,17 @@ static int make_map_fmap(CUtensorMap* m, const float* base, int V, int h, int w)
     return 0;
 }
 
+static bool pack5_enabled() {
+    static const bool on = []() { const char* e = getenv("MV2D_CONV_PACK5"); return !(e && e[0] == '0'); }();
+    return on;
+}
+
 template <int BN, int PASSES, int IM2COL, int STAGES, bool RAW = false>
 static int launch_tc(const CUtensorMap& a, const CUtensorMap& alo, const CUtensorMap& w, const CUtensorMap& wlo,
                      const TcArgs& g, int m_tiles, int nsplit, cudaStream_t st, const CUtensorMap* a2 = nullptr,
                      const CUtensorMap* a2lo = nullptr) {
     constexpr int NOP = PASSES == 3 ? 2 : 1;
-    constexpr size_t smem = (size_t)STAGES * NOP * (TC_BM * TC_BK * 4 + BN * TC_BK * 4) + 1024 + 256;
+    constexpr size_t smem = (size_t)STAGES * NOP * ((IM2COL == 3 ? 2 : 1) * TC_BM * TC_BK * 4 + BN * TC_BK * 4) + 1024 + 256;
     auto kern = gemm_tc_kernel<BN, PASSES, IM2COL, STAGES, RAW>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -639,7 +671,7 @@ int launch_gemm_tc(const TcGemm& t, cudaStream_t st) {
     } else if (t.im2col) {
         MV2D_CHECK_ARG(t.K == 9 * MV2D_C && t.passes == 3, "gemm_tc: im2col expects K=2304, 3 passes");
         g.n_rois = t.M / MV2D_TOK;
-        m_tiles = cdiv(g.n_rois, 2);
+        m_tiles = pack5_enabled() ? cdiv(g.n_rois, 5) : cdiv(g.n_rois, 2);
         if ((rc = make_map_tokens(&a, t.A, g.n_rois))) return rc;
         if ((rc = make_map_tokens(&alo, t.A_lo, g.n_rois))) return rc;
     } else {
@@ -662,6 +694,7 @@ int launch_gemm_tc(const TcGemm& t, cudaStream_t st) {
     if (raw && bn == 64) return launch_tc<64, 3, false, 4, true>(a, alo, w, wlo, g, m_tiles, nsplit, st);
     if (raw) return launch_tc<128, 3, false, 3, true>(a, alo, w, wlo, g, m_tiles, nsplit, st);
     if (t.im2col == 2) return launch_tc<128, 3, 2, 3>(a, alo, w, wlo, g, m_tiles, nsplit, st);
+    if (t.im2col && pack5_enabled()) return launch_tc<128, 3, 3, 2>(a, alo, w, wlo, g, m_tiles, nsplit, st);
     if (t.im2col && bn == 256) return launch_tc<256, 3, 1, 2>(a, alo, w, wlo, g, m_tiles, nsplit, st);
     if (t.im2col) return launch_tc<128, 3, 1, 3>(a, alo, w, wlo, g, m_tiles, nsplit, st);
     if (t.passes == 3 && bn == 64 && mc_enabled() && (t.N / 64) % TC_MC == 0 && !(t.A2 != nullptr && t.n_switch > 0) && ngroups == 1) {
