@@ -1085,6 +1085,8 @@ int run_kv_project(const Mv2dKvParams& p, cudaStream_t st) {
     MV2D_CHECK_ARG(p.num_rows > 0 && p.L >= 1 && p.L <= MV2D_MAX_LAYERS && p.layer_begin >= 0 && p.layer_begin < le && le <= p.L,
                    "kv_project: bad num_rows=%d / layers [%d,%d) of %d", p.num_rows, p.layer_begin, le, p.L);
     const long long RC = (long long)p.num_rows * MV2D_C;
+    // pre-split rows + weights stacked by mv2d_pack_weights: one persistent launch for all the layers asked for (kvproj.cu)
+    if (kv_persistent_usable(p)) return run_kv_project_persistent(p, st);
     for (int l = p.layer_begin; l < le; ++l) {
         const Mv2dLayerWeights& w = p.layers[l];
         const bool raw = p.kin_lo == nullptr;      // plain fp32 rows: the GEMM splits rows and weights in shared memory

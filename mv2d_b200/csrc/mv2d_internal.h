@@ -21,6 +21,8 @@ int run_cross_attention_core(const Mv2dDecoderParams& p, int layer, const float*
 size_t decoder_workspace_bytes(int N, int L);
 size_t xa_tile_workspace_bytes(int N, int V, int h, int w, int batch = 1);   // N = query rows per sample
 int run_kv_project(const Mv2dKvParams& p, cudaStream_t st);
+bool kv_persistent_usable(const Mv2dKvParams& p);                       // kvproj.cu
+int run_kv_project_persistent(const Mv2dKvParams& p, cudaStream_t st);
 int run_xa_tile_prepare(const Mv2dDecoderParams& p, cudaStream_t st);
 int run_dn_prepare(const Mv2dDnParams& p, cudaStream_t st);
 size_t dn_workspace_bytes(int T, int mask_words);

@@ -86,6 +86,17 @@ struct Packer {
         }
         return arena + off / 4;
     }
+    // directory entry for a sub-range of an existing buffer (no new storage)
+    void alias(const std::string& name, int64_t offset, int64_t numel) {
+        if (dir && n_dir < dir_cap) {
+            Mv2dPackedEntry& e = dir[n_dir];
+            memset(&e, 0, sizeof(e));
+            strncpy(e.name, name.c_str(), sizeof(e.name) - 1);
+            e.offset = offset;
+            e.numel = numel;
+        }
+        ++n_dir;
+    }
     void put_copy(const std::string& name, const float* src, int64_t numel, const float** dptr) {
         float* d = put(name, numel, dptr);
         if (d && src) memcpy(d, src, numel * 4);
@@ -170,6 +181,13 @@ int pack_all(Packer& P, int L, int fold_first, Mv2dLayerWeights* layers, Mv2dBra
         if (strcmp(f.name, "center")) P.put_split(wn + "_hi", wn + "_lo", w, (int64_t)f.out * f.in_pad, &dp, &dp);   // 3xTF32 FC chain for batches
     }
     // K4 decoder layers
+    // the plain K / V projections of all layers form ONE [L*2*256, 256] operand (rows (2 l + side) * 256 ..), hi and lo:
+    // the persistent projection kernel (kvproj.cu) addresses every matrix through one tensor map
+    const float *kv_hi_dev = nullptr, *kv_lo_dev = nullptr;
+    const int64_t kv_hi_off = P.used;
+    float* kv_hi = P.put("xa_kv_w", (int64_t)L * 2 * E * E, &kv_hi_dev);
+    const int64_t kv_lo_off = P.used;
+    float* kv_lo = P.put("xa_kv_w_lo", (int64_t)L * 2 * E * E, &kv_lo_dev);
     const double scale = 1.0 / std::sqrt((double)HD);
     std::vector<float> qw((size_t)HEADS * E * E), qb((size_t)HEADS * E), ow((size_t)E * HEADS * E), ob(E), xq((size_t)E * E), xqb(E), xob(E), sac(E);
     for (int l = 0; l < L; ++l) {
@@ -227,8 +245,20 @@ int pack_all(Packer& P, int L, int fold_first, Mv2dLayerWeights* layers, Mv2dBra
         P.put_split(n + "ffn_w2", n + "ffn_w2_lo", ok ? f2->data : nullptr, (int64_t)E * FF, &lw.ffn_w2, &lw.ffn_w2_lo);
         P.put_copy(n + "xa_q_w", ok ? xq.data() : nullptr, E * E, &lw.xa_q_w);
         P.put_copy(n + "xa_q_b", ok ? xqb.data() : nullptr, E, &lw.xa_q_b);
-        P.put_split(n + "xa_k_w", n + "xa_k_w_lo", ok ? cin_w->data + E * E : nullptr, E * E, &lw.xa_k_w, &lw.xa_k_w_lo);
-        P.put_split(n + "xa_v_w", n + "xa_v_w_lo", ok ? cin_w->data + 2 * E * E : nullptr, E * E, &lw.xa_v_w, &lw.xa_v_w_lo);
+        for (int side = 0; side < 2; ++side) {
+            const int64_t sub = (int64_t)(2 * l + side) * E * E;
+            const float* src = ok ? cin_w->data + (1 + side) * E * E : nullptr;
+            if (kv_hi && kv_lo && src)
+                for (int i = 0; i < E * E; ++i) {
+                    const float hi = round_tf32_host(src[i]);
+                    kv_hi[sub + i] = hi;
+                    kv_lo[sub + i] = round_tf32_host(src[i] - hi);
+                }
+            (side ? lw.xa_v_w : lw.xa_k_w) = kv_hi_dev + sub;
+            (side ? lw.xa_v_w_lo : lw.xa_k_w_lo) = kv_lo_dev + sub;
+            P.alias(n + (side ? "xa_v_w" : "xa_k_w"), kv_hi_off + sub * 4, E * E);
+            P.alias(n + (side ? "xa_v_w_lo" : "xa_k_w_lo"), kv_lo_off + sub * 4, E * E);
+        }
         P.put_split(n + "sa_in_w_hi", n + "sa_in_w_lo", ok ? sin_w->data : nullptr, 3 * E * E, &lw.sa_in_w_hi, &lw.sa_in_w_lo);
         P.put_split(n + "sa_out_w_hi", n + "sa_out_w_lo", ok ? sout_w->data : nullptr, E * E, &lw.sa_out_w_hi, &lw.sa_out_w_lo);
         P.put_split(n + "xa_q_w_hi", n + "xa_q_w_lo", ok ? xq.data() : nullptr, E * E, &lw.xa_q_w_hi, &lw.xa_q_w_lo);

@@ -455,11 +455,16 @@ class HotPath:
         p.kp, p.vp = kp.data_ptr(), vp.data_ptr()
         if row_live is not None and os.environ.get('MV2D_KV_SKIP', '1') != '0':
             p.row_tile_live = row_live.data_ptr()
-        for l in range(L):
-            p.layer_begin, p.layer_end = l, l + 1
+        # one persistent launch for all layers (csrc/kvproj.cu; needs the pre-split rows): it holds every SM anyway, so
+        # the decoder layers could not overlap it; MV2D_KV_PER_LAYER=1 keeps one call (and one event) per layer
+        per_layer = os.environ.get('MV2D_KV_PER_LAYER', '0') == '1' or os.environ.get('MV2D_KV_RAW', '0') == '1' \
+            or os.environ.get('MV2D_KV_PERSISTENT', '1') == '0'
+        for l in (range(L) if per_layer else (0,)):
+            p.layer_begin, p.layer_end = (l, l + 1) if per_layer else (0, L)
             lib.check(self.lib.mv2d_kv_project(C.byref(p), st), 'mv2d_kv_project')
             if record_events:
-                self._ev_kv[l].record(torch.cuda.current_stream())
+                for e in (self._ev_kv[l:l + 1] if per_layer else self._ev_kv):
+                    e.record(torch.cuda.current_stream())
         return kp, vp
 
     def _decoder_params(self, qg, corr, kin_rows, mem_rows, N, vel_dt=0.0, self_attn_mask=None, vel_row_start=0,

@@ -39,7 +39,14 @@ def _close(a, b, ulps=2):
 def test_pack_matches_torch_restatement(state_dicts):
     sd = state_dicts(2)
     w = PackedWeights(sd, 'cpu')
-    assert w.num_layers == 2 and w.nbytes() == sum((v.numel() * 4 + 255) // 256 * 256 for v in w.t.values())
+    assert w.num_layers == 2 and w.nbytes() == sum((v.numel() * 4 + 255) // 256 * 256 for k, v in w.t.items()
+                                                   if not k.split('.')[-1] in ('xa_k_w', 'xa_k_w_lo', 'xa_v_w', 'xa_v_w_lo'))
+    # the plain K / V projections of all layers are stacked into one operand (rows (2 l + side) * 256 ..)
+    for l in range(2):
+        for side, nm in enumerate(('xa_k_w', 'xa_v_w')):
+            assert w.t[f'l{l}.{nm}'].data_ptr() == w.t['xa_kv_w'].data_ptr() + (2 * l + side) * 256 * 256 * 4
+            assert w.t[f'l{l}.{nm}_lo'].data_ptr() == w.t['xa_kv_w_lo'].data_ptr() + (2 * l + side) * 256 * 256 * 4
+            assert getattr(w.layers[l], nm) == w.t[f'l{l}.{nm}'].data_ptr()
     for l in range(2):
         p = f'bbox_head.transformer.decoder.layers.{l}.attentions.1.attn.'
         qw, qb, ow, ob = absorb_cross_attention(sd[p + 'in_proj_weight'], sd[p + 'in_proj_bias'], sd[p + 'out_proj.weight'],
