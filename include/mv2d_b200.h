@@ -297,8 +297,12 @@ typedef struct Mv2dDecoderParams {
     const float* vp;            /* xa_form 1: [L,num_rows,256] projected values from mv2d_kv_project */
     void* xa_workspace;         /* xa_form 1: mv2d_xa_tile_workspace_bytes(N, V, grid_h, grid_w) */
     size_t xa_workspace_bytes;
-    uint8_t* row_tile_live;     /* mv2d_xa_tile_prepare only, nullable out [ceil(num_rows/128)]: 1 = some query has a key
-                                 * among rows 128 t .. 128 t + 127 (input of mv2d_kv_project) */
+    uint8_t* row_tile_live;     /* nullable [ceil(num_rows/128)]: 1 = some query has a key among rows 128 t .. 128 t + 127.
+                                 * mv2d_xa_tile_prepare WRITES it (it is then the input of mv2d_kv_project);
+                                 * mv2d_decoder / mv2d_cross_attention_core READ it when it is passed: set it exactly when
+                                 * the projection that made kp / vp was given the same flags -- the tensor-core tile
+                                 * attention loads whole 8x8 cell tiles and zero-fills the cells of skipped row tiles
+                                 * instead of reading their stale kp / vp rows.  NULL = every row was projected. */
     /* ---- ABI 5: batch > 0: N = batch * rows_per_sample; self-attention keys of a row are the first n_real[b] rows of
      * its sample; mode 0: match ids are global rows; mode 1 (xa_form 1 only): num_rows = batch * V*h*w rows of
      * kin_rows / mem_rows / kp / vp, keymask bits and mask_words refer to ONE sample's V*h*w cells */

@@ -1074,6 +1074,28 @@ static XtWs xt_carve(void* base, int Np, int tiles_ps, int batch = 1) {
     w.bytes = off;
     return w;
 }
+static bool xt_mma_enabled() {
+    static const bool on = []() { const char* v = getenv("MV2D_XT_MMA"); return !(v && v[0] == '0'); }();
+    return on;
+}
+// per-tile attention of the key-stationary form: TF32 tensor-core kernel (16 queries per MMA row block), or the FFMA
+// kernel (a warp per query) with MV2D_XT_MMA=0
+static int launch_xt_attn(const XtAttnArgs& a, int ntiles, cudaStream_t st) {
+    if (xt_mma_enabled()) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaError_t e = cudaFuncSetAttribute(xt_attn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XTM_SMEM_BYTES);
+            if (e != cudaSuccess) { set_error("xt_attn: smem attr %s", cudaGetErrorString(e)); return (int)e; }
+            attr_set = true;
+        }
+        launch_k(xt_attn_mma_kernel, dim3(ntiles, a.qsplit), dim3(XTM_THREADS), (size_t)XTM_SMEM_BYTES, st, a);
+    } else {
+        launch_k(xt_attn_kernel, dim3(ntiles, a.qsplit), dim3(XT_THREADS), (size_t)XT_SMEM_BYTES, st, a);
+    }
+    MV2D_CHECK_LAUNCH("xt_attn");
+    return 0;
+}
+
 static int xt_ntiles(int V, int h, int w) { return V * cdiv(h, XT_TS) * cdiv(w, XT_TS); }
 
 size_t xa_tile_workspace_bytes(int N, int V, int h, int w, int batch) {
@@ -1196,8 +1218,8 @@ int run_cross_attention_core(const Mv2dDecoderParams& p, int layer, const float*
     }
     XtAttnArgs a{}; a.g = xg; a.q = q; a.kp = p.kp + (long long)layer * p.num_rows * MV2D_C; a.vp = p.vp + (long long)layer * p.num_rows * MV2D_C;
     a.tile_cnt = xw.tile_cnt; a.tile_q = xw.tile_q; a.tile_mask = xw.tile_mask; a.rec = xw.rec; a.order = xw.order; a.qsplit = 1;
-    launch_k(xt_attn_kernel, dim3(xg.ntiles, 1), dim3(XT_THREADS), (size_t)XT_SMEM_BYTES, st, a);
-    MV2D_CHECK_LAUNCH("xt_attn");
+    a.row_live = p.row_tile_live;
+    { int rc; if ((rc = launch_xt_attn(a, xg.ntiles, st))) return rc; }
     XtMergeArgs m{}; m.g = xg; m.qlist = xw.qlist; m.qcnt = xw.qcnt; m.rec = xw.rec; m.ctx = ctx; m.ctx_lo = ctx_lo;
     launch_k(xt_merge_kernel, dim3(N), dim3(XT_MERGE_THREADS), (size_t)xg.tiles_ps * 36, st, m);
     MV2D_CHECK_LAUNCH("xt_merge");
@@ -1472,8 +1494,8 @@ int run_decoder(const Mv2dDecoderParams& p, cudaStream_t st) {
                 a.tile_cnt = xw.tile_cnt; a.tile_q = xw.tile_q; a.tile_mask = xw.tile_mask; a.rec = xw.rec; a.order = xw.order;
                 static const int qs_env = []() { const char* v = getenv("MV2D_XT_QSPLIT"); return v ? atoi(v) : 0; }();
                 a.qsplit = qs_env > 0 ? qs_env : 1;
-                launch_k(xt_attn_kernel, dim3(xg.ntiles, a.qsplit), dim3(XT_THREADS), (size_t)XT_SMEM_BYTES, st, a);
-                MV2D_CHECK_LAUNCH("xt_attn");
+                a.row_live = p.row_tile_live;
+                if ((rc = launch_xt_attn(a, xg.ntiles, st))) return rc;
             }
             {
                 XtMergeArgs a{}; a.g = xg; a.qlist = xw.qlist; a.qcnt = xw.qcnt; a.rec = xw.rec; a.ctx = xw.ctx;

@@ -202,6 +202,8 @@ struct XtAttnArgs {
     const int* order;                  // [ntiles] heaviest tile first
     float* rec;                        // [ntiles*N, XT_REC]
     int qsplit;                        // gridDim.y: the tile's query list is dealt round-robin to this many CTAs
+    const uint8_t* row_live;           // nullable [ceil(rows/128)]: 0 = mv2d_kv_project skipped this 128-row tile (its kp / vp
+                                       // rows are stale): the tensor-core kernel reads whole tiles, so it zero-fills those cells
 };
 
 // transpose-reduce 4 per-lane partials over the 4 lanes of a head: 3 shuffles instead of 8.
@@ -365,6 +367,194 @@ __global__ void __launch_bounds__(XT_THREADS, 1) xt_attn_kernel(XtAttnArgs a) {
     }
     // a CTA must not exit while its bulk copies are in flight
     if (!waited) xt_wait(bar);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Tensor-core form of the per-tile attention (default; MV2D_XT_MMA=0 keeps xt_attn_kernel).
+// The FFMA kernel above re-reads a K and a V row (2 KB) from shared memory for every (query, key) pair: it is bound by
+// shared-memory bandwidth.  Here the tile's queries are taken 16 at a time as the M rows of warp-level TF32 MMAs
+// (mma.sync.m16n8k8), one warp per HEAD:
+//     S_h [16 x 64] = Q_h [16 x 32] . K_h^T          8 key blocks x 4 channel steps
+//     O_h [16 x 32] = P_h [16 x 64] . V_h            8 key steps x 4 channel blocks,  P = exp(S - rowmax) on the query's keys
+// so a K / V element is read from shared memory once per 16 queries (and only its head's 128-byte slice per warp).
+// Every product is error-compensated 3xTF32 (x = hi + lo, both TF32: hi*hi + lo*hi + hi*lo accumulated in fp32), the
+// splits made in registers on the fly, so the result is fp32-grade like the FFMA kernel's.
+// The C fragment of S (columns 2t, 2t+1 of a key block) is reused as the A fragment of the P.V product by reading V's
+// rows in the matching order (MMA k index t <-> key 2t, t+4 <-> key 2t+1): no shuffles between the two products.
+// Keys outside a query's 64-bit mask get p = 0; cells outside the feature map (edge tiles) are zero-filled.
+// K / V rows sit at a pitch of 260 floats, which makes both B-fragment access patterns bank-conflict free.
+// Record format, tile order and the merge kernel are unchanged.
+#define XTM_THREADS 256
+#define XTM_PITCH 260
+#define XTM_SMEM_BYTES (2 * XT_KEYS * XTM_PITCH * 4 + 64)
+
+__device__ __forceinline__ void split_tf32_reg(float x, uint32_t& hi, uint32_t& lo) {
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+    const float r = x - __uint_as_float(hi);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+}
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// grid = (ntiles, qsplit), XTM_THREADS threads (warp = head), XTM_SMEM_BYTES dynamic shared memory
+__global__ void __launch_bounds__(XTM_THREADS, 1) xt_attn_mma_kernel(XtAttnArgs a) {
+    pdl_wait();
+    pdl_trigger();
+    const int t = a.order[blockIdx.x];
+    const int cnt = a.tile_cnt[t];
+    const int nblk = (cnt + 15) >> 4;
+    if ((int)blockIdx.y >= nblk) return;
+    extern __shared__ __align__(128) unsigned char xt_smem[];
+    float* Ks = reinterpret_cast<float*>(xt_smem);
+    float* Vs = Ks + XT_KEYS * XTM_PITCH;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(Vs + XT_KEYS * XTM_PITCH);
+    const int tid = threadIdx.x, hd = tid >> 5, lane = tid & 31, g = lane >> 2, tg = lane & 3;
+    const int sb = t / a.g.tiles_ps, tl = t - sb * a.g.tiles_ps;
+    const int tx = tl % a.g.tiles_x, ty = (tl / a.g.tiles_x) % a.g.tiles_y, v = sb * a.g.V + tl / (a.g.tiles_x * a.g.tiles_y);
+    const int ncols = min(XT_TS, a.g.w - tx * XT_TS), nrows = min(XT_TS, a.g.h - ty * XT_TS);
+    // one 1 KB bulk copy per cell and operand, spread over 64 threads.  Cells outside the map (edge tiles) and cells whose
+    // 128-row tile the projection skipped take no copy and are zero-filled: p = 0 times stale data must stay 0.
+    __shared__ unsigned long long use_mask;
+    bool use = false;
+    long long off = 0;
+    if (tid < XT_KEYS) {
+        const int r = tid >> 3, c = tid & 7;
+        if (r < nrows && c < ncols) {
+            const long long cell = (long long)(v * a.g.h + ty * XT_TS + r) * a.g.w + tx * XT_TS + c;
+            off = cell * MV2D_C;
+            use = a.row_live == nullptr || a.row_live[cell >> 7] != 0;
+        }
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, use);
+    if (tid == 0) use_mask = 0ull;
+    __syncthreads();
+    if (tid < XT_KEYS && lane == 0 && bal) atomicOr(&use_mask, (unsigned long long)bal << (tid & 32));
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(xt_smem_u32(bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const unsigned long long um = use_mask;
+    if (tid == 0)
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(xt_smem_u32(bar)), "r"(2u * __popcll(um) * MV2D_C * 4) : "memory");
+    __syncthreads();            // barrier armed before the copies are issued and before anyone polls it
+    if (use) {
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(xt_smem_u32(Ks + tid * XTM_PITCH)), "l"(a.kp + off), "r"(MV2D_C * 4), "r"(xt_smem_u32(bar)) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(xt_smem_u32(Vs + tid * XTM_PITCH)), "l"(a.vp + off), "r"(MV2D_C * 4), "r"(xt_smem_u32(bar)) : "memory");
+    }
+    if (um != ~0ull) {
+        for (int i = tid; i < XT_KEYS * MV2D_C; i += XTM_THREADS) {
+            const int key = i >> 8;
+            if (!((um >> key) & 1ull)) { Ks[key * XTM_PITCH + (i & 255)] = 0.f; Vs[key * XTM_PITCH + (i & 255)] = 0.f; }
+        }
+        __syncthreads();
+    }
+    bool waited = false;
+    const float* Kh = Ks + hd * 32;
+    const float* Vh = Vs + hd * 32;
+    for (int b = blockIdx.y; b < nblk; b += a.qsplit) {
+        // ---- the block's 16 queries: rows g and g + 8 of this lane
+        const int i0 = b * 16 + g, i1 = i0 + 8;
+        const bool ok0 = i0 < cnt, ok1 = i1 < cnt;
+        const long long e0 = (long long)t * a.g.Np + (ok0 ? i0 : b * 16), e1 = (long long)t * a.g.Np + (ok1 ? i1 : b * 16);
+        const int n0 = a.tile_q[e0], n1 = a.tile_q[e1];
+        const unsigned long long m0 = ok0 ? a.tile_mask[e0] : 0ull, m1 = ok1 ? a.tile_mask[e1] : 0ull;
+        uint32_t qh[4][4], ql[4][4];
+        {
+            const float* q0 = a.q + (long long)n0 * MV2D_C + hd * 32 + tg;
+            const float* q1 = a.q + (long long)n1 * MV2D_C + hd * 32 + tg;
+#pragma unroll
+            for (int kc = 0; kc < 4; ++kc) {
+                split_tf32_reg(__ldg(q0 + kc * 8), qh[kc][0], ql[kc][0]);
+                split_tf32_reg(__ldg(q1 + kc * 8), qh[kc][1], ql[kc][1]);
+                split_tf32_reg(__ldg(q0 + kc * 8 + 4), qh[kc][2], ql[kc][2]);
+                split_tf32_reg(__ldg(q1 + kc * 8 + 4), qh[kc][3], ql[kc][3]);
+            }
+        }
+        if (!waited) { xt_wait(bar); waited = true; }
+        // ---- S = Q K^T
+        float s[8][4];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+            const float* krow = Kh + (j * 8 + g) * XTM_PITCH + tg;
+#pragma unroll
+            for (int kc = 0; kc < 4; ++kc) {
+                uint32_t bh0, bl0, bh1, bl1;
+                split_tf32_reg(krow[kc * 8], bh0, bl0);
+                split_tf32_reg(krow[kc * 8 + 4], bh1, bl1);
+                mma_tf32_16x8x8(s[j], qh[kc], bh0, bh1);
+                mma_tf32_16x8x8(s[j], ql[kc], bh0, bh1);
+                mma_tf32_16x8x8(s[j], qh[kc], bl0, bl1);
+            }
+        }
+        // ---- masked softmax numerators over the tile's keys: rows g (values 0, 1) and g + 8 (values 2, 3)
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int k0 = j * 8 + 2 * tg;
+            if (!((m0 >> k0) & 1ull)) s[j][0] = -INFINITY;
+            if (!((m0 >> (k0 + 1)) & 1ull)) s[j][1] = -INFINITY;
+            if (!((m1 >> k0) & 1ull)) s[j][2] = -INFINITY;
+            if (!((m1 >> (k0 + 1)) & 1ull)) s[j][3] = -INFINITY;
+            mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
+            mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
+        }
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+        const float sub0 = ok0 ? mx0 : 0.f, sub1 = ok1 ? mx1 : 0.f;      // rows past the list: all keys masked, exp(-inf - 0) = 0
+        float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            s[j][0] = __expf(s[j][0] - sub0); s[j][1] = __expf(s[j][1] - sub0);
+            s[j][2] = __expf(s[j][2] - sub1); s[j][3] = __expf(s[j][3] - sub1);
+            l0 += s[j][0] + s[j][1];
+            l1 += s[j][2] + s[j][3];
+        }
+        l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+        l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+        // ---- O = P V : MMA k index tg <-> key 8 j + 2 tg, tg + 4 <-> key 8 j + 2 tg + 1
+        float o[4][4];
+#pragma unroll
+        for (int nb = 0; nb < 4; ++nb) o[nb][0] = o[nb][1] = o[nb][2] = o[nb][3] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            uint32_t ph[4], pl[4];
+            split_tf32_reg(s[j][0], ph[0], pl[0]);      // (row g,     k = tg)
+            split_tf32_reg(s[j][2], ph[1], pl[1]);      // (row g + 8, k = tg)
+            split_tf32_reg(s[j][1], ph[2], pl[2]);      // (row g,     k = tg + 4)
+            split_tf32_reg(s[j][3], ph[3], pl[3]);      // (row g + 8, k = tg + 4)
+            const float* vrow = Vh + (j * 8 + 2 * tg) * XTM_PITCH + g;
+#pragma unroll
+            for (int nb = 0; nb < 4; ++nb) {
+                uint32_t bh0, bl0, bh1, bl1;
+                split_tf32_reg(vrow[nb * 8], bh0, bl0);
+                split_tf32_reg(vrow[XTM_PITCH + nb * 8], bh1, bl1);
+                mma_tf32_16x8x8(o[nb], ph, bh0, bh1);
+                mma_tf32_16x8x8(o[nb], pl, bh0, bh1);
+                mma_tf32_16x8x8(o[nb], ph, bl0, bl1);
+            }
+        }
+        // ---- records
+        if (ok0) {
+            float* r = a.rec + e0 * XT_REC;
+#pragma unroll
+            for (int nb = 0; nb < 4; ++nb) *reinterpret_cast<float2*>(r + hd * 32 + nb * 8 + 2 * tg) = make_float2(o[nb][0], o[nb][1]);
+            if (tg == 0) { r[256 + hd] = mx0; r[264 + hd] = l0; }
+        }
+        if (ok1) {
+            float* r = a.rec + e1 * XT_REC;
+#pragma unroll
+            for (int nb = 0; nb < 4; ++nb) *reinterpret_cast<float2*>(r + hd * 32 + nb * 8 + 2 * tg) = make_float2(o[nb][2], o[nb][3]);
+            if (tg == 0) { r[256 + hd] = mx1; r[264 + hd] = l1; }
+        }
+    }
+    if (!waited) xt_wait(bar);      // a CTA must not exit while its bulk copies are in flight
 }
 
 struct XtMergeArgs {

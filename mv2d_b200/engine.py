@@ -93,6 +93,7 @@ class HotPath:
         self._ev_hi0, self._ev_hi1 = torch.cuda.Event(), torch.cuda.Event()
         self._ev_pe = torch.cuda.Event()
         self._ev_kv = [torch.cuda.Event() for _ in range(self.L)]
+        self._kv_row_live = None      # live-tile flags the last K/V projection honoured (pointer), None = projected everything
         self._side = torch.cuda.Stream(device=self.device)
         self._side2 = torch.cuda.Stream(device=self.device)
         self._copy = torch.cuda.Stream(device=self.device)
@@ -453,8 +454,9 @@ class HotPath:
             p.kin_hi, p.kin_lo, p.mem_hi, p.mem_lo = kin_hi.data_ptr(), kin_lo.data_ptr(), mem_hi.data_ptr(), mem_lo.data_ptr()
         p.layers = self.w.layers_ptr()
         p.kp, p.vp = kp.data_ptr(), vp.data_ptr()
+        self._kv_row_live = None
         if row_live is not None and os.environ.get('MV2D_KV_SKIP', '1') != '0':
-            p.row_tile_live = row_live.data_ptr()
+            p.row_tile_live = self._kv_row_live = row_live.data_ptr()
         # one persistent launch for all layers (csrc/kvproj.cu; needs the pre-split rows): it holds every SM anyway, so
         # the decoder layers could not overlap it; MV2D_KV_PER_LAYER=1 keeps one call (and one event) per layer
         per_layer = os.environ.get('MV2D_KV_PER_LAYER', '0') == '1' or os.environ.get('MV2D_KV_RAW', '0') == '1' \
@@ -509,6 +511,8 @@ class HotPath:
             p.kp, p.vp = kv[0].data_ptr(), kv[1].data_ptr()
             p.xa_workspace, p.xa_workspace_bytes = xa_ws.data_ptr(), xa_bytes
             p.xa_prepared = int(corr.get('xa_prepared_for') == (corr['keymask'].data_ptr(), N, xa_ws.data_ptr()))
+            # the tensor-core tile attention reads whole 8x8 tiles: it must know which 128-row tiles the projection skipped
+            p.row_tile_live = self._kv_row_live
         return p, cls, box, outs
 
     def decoder(self, qg, corr, kin_rows, mem_rows, N, vel_dt=0.0, self_attn_mask=None, vel_row_start=0,
