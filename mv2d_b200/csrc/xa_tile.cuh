@@ -384,9 +384,9 @@ __global__ void __launch_bounds__(XT_THREADS, 1) xt_attn_kernel(XtAttnArgs a) {
 // Keys outside a query's 64-bit mask get p = 0; cells outside the feature map (edge tiles) are zero-filled.
 // K / V rows sit at a pitch of 260 floats, which makes both B-fragment access patterns bank-conflict free.
 // Record format, tile order and the merge kernel are unchanged.
-#define XTM_THREADS 256
+#define XTM_THREADS 512                    // 16 warps: warp = (head, row-block parity)
 #define XTM_PITCH 260
-#define XTM_SMEM_BYTES (2 * XT_KEYS * XTM_PITCH * 4 + 64)
+#define XTM_SMEM_BYTES (2 * XT_KEYS * XTM_PITCH * 4 + 64)       // K rows, V rows, two mbarriers
 
 __device__ __forceinline__ void split_tf32_reg(float x, uint32_t& hi, uint32_t& lo) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
@@ -399,19 +399,19 @@ __device__ __forceinline__ void mma_tf32_16x8x8(float (&d)[4], const uint32_t (&
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-// grid = (ntiles, qsplit), XTM_THREADS threads (warp = head), XTM_SMEM_BYTES dynamic shared memory
+// grid = (ntiles, qsplit), XTM_THREADS threads (warp = head + 8 * row-block parity), XTM_SMEM_BYTES dynamic shared memory
 __global__ void __launch_bounds__(XTM_THREADS, 1) xt_attn_mma_kernel(XtAttnArgs a) {
     pdl_wait();
     pdl_trigger();
     const int t = a.order[blockIdx.x];
     const int cnt = a.tile_cnt[t];
     const int nblk = (cnt + 15) >> 4;
-    if ((int)blockIdx.y >= nblk) return;
+    if ((int)blockIdx.y * 2 >= nblk) return;
     extern __shared__ __align__(128) unsigned char xt_smem[];
     float* Ks = reinterpret_cast<float*>(xt_smem);
     float* Vs = Ks + XT_KEYS * XTM_PITCH;
     uint64_t* bar = reinterpret_cast<uint64_t*>(Vs + XT_KEYS * XTM_PITCH);
-    const int tid = threadIdx.x, hd = tid >> 5, lane = tid & 31, g = lane >> 2, tg = lane & 3;
+    const int tid = threadIdx.x, hd = (tid >> 5) & 7, par = tid >> 8, lane = tid & 31, g = lane >> 2, tg = lane & 3;
     const int sb = t / a.g.tiles_ps, tl = t - sb * a.g.tiles_ps;
     const int tx = tl % a.g.tiles_x, ty = (tl / a.g.tiles_x) % a.g.tiles_y, v = sb * a.g.V + tl / (a.g.tiles_x * a.g.tiles_y);
     const int ncols = min(XT_TS, a.g.w - tx * XT_TS), nrows = min(XT_TS, a.g.h - ty * XT_TS);
@@ -432,20 +432,23 @@ __global__ void __launch_bounds__(XTM_THREADS, 1) xt_attn_mma_kernel(XtAttnArgs 
     if (tid == 0) use_mask = 0ull;
     __syncthreads();
     if (tid < XT_KEYS && lane == 0 && bal) atomicOr(&use_mask, (unsigned long long)bal << (tid & 32));
-    if (tid == 0) {
+    if (tid == 0) {      // bar[0]: the K rows have landed, bar[1]: the V rows
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(xt_smem_u32(bar)));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(xt_smem_u32(bar + 1)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     const unsigned long long um = use_mask;
-    if (tid == 0)
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(xt_smem_u32(bar)), "r"(2u * __popcll(um) * MV2D_C * 4) : "memory");
+    if (tid == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(xt_smem_u32(bar)), "r"((unsigned)__popcll(um) * MV2D_C * 4) : "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(xt_smem_u32(bar + 1)), "r"((unsigned)__popcll(um) * MV2D_C * 4) : "memory");
+    }
     __syncthreads();            // barrier armed before the copies are issued and before anyone polls it
     if (use) {
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                      ::"r"(xt_smem_u32(Ks + tid * XTM_PITCH)), "l"(a.kp + off), "r"(MV2D_C * 4), "r"(xt_smem_u32(bar)) : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"(xt_smem_u32(Vs + tid * XTM_PITCH)), "l"(a.vp + off), "r"(MV2D_C * 4), "r"(xt_smem_u32(bar)) : "memory");
+                     ::"r"(xt_smem_u32(Vs + tid * XTM_PITCH)), "l"(a.vp + off), "r"(MV2D_C * 4), "r"(xt_smem_u32(bar + 1)) : "memory");
     }
     if (um != ~0ull) {
         for (int i = tid; i < XT_KEYS * MV2D_C; i += XTM_THREADS) {
@@ -454,10 +457,10 @@ __global__ void __launch_bounds__(XTM_THREADS, 1) xt_attn_mma_kernel(XtAttnArgs 
         }
         __syncthreads();
     }
-    bool waited = false;
+    bool waited = false, waited_v = false;
     const float* Kh = Ks + hd * 32;
     const float* Vh = Vs + hd * 32;
-    for (int b = blockIdx.y; b < nblk; b += a.qsplit) {
+    for (int b = blockIdx.y * 2 + par; b < nblk; b += 2 * a.qsplit) {
         // ---- the block's 16 queries: rows g and g + 8 of this lane
         const int i0 = b * 16 + g, i1 = i0 + 8;
         const bool ok0 = i0 < cnt, ok1 = i1 < cnt;
@@ -518,6 +521,7 @@ __global__ void __launch_bounds__(XTM_THREADS, 1) xt_attn_mma_kernel(XtAttnArgs 
         }
         l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
         l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+        if (!waited_v) { xt_wait(bar + 1); waited_v = true; }
         // ---- O = P V : MMA k index tg <-> key 8 j + 2 tg, tg + 4 <-> key 8 j + 2 tg + 1
         float o[4][4];
 #pragma unroll
@@ -555,6 +559,7 @@ __global__ void __launch_bounds__(XTM_THREADS, 1) xt_attn_mma_kernel(XtAttnArgs 
         }
     }
     if (!waited) xt_wait(bar);      // a CTA must not exit while its bulk copies are in flight
+    if (!waited_v) xt_wait(bar + 1);
 }
 
 struct XtMergeArgs {
