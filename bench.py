@@ -375,7 +375,7 @@ def main():
         dist.destroy_process_group()
 
 
-def two_frame_section(sd, dev, world, rank, barrier, steps, warmup, batch=2, depth=2):
+def two_frame_section(sd, dev, world, rank, barrier, steps, warmup, batch=2, depth=3):
     """Extra object `two_frame` -- BASELINE configs[2]: MV2D-T, 12 feature views, 300 queries, bs = 2 as a real batch (both
     samples in one kernel chain), `depth` batches in flight.  Same timing protocol as the headline."""
     import torch

@@ -758,6 +758,14 @@ struct XrArgs {
 
 __device__ __forceinline__ uint32_t xr_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// Packed fp32 pairs (sm_100a: fma.rn.f32x2 issues two IEEE fp32 FMAs per instruction).  The two inner loops of
+// xa_roi_kernel are bound by instruction issue, not by the FMA pipe: pairing the channels halves their FMA count.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+
 __global__ void __launch_bounds__(XR_THREADS, 2)
 xa_roi_kernel(XrArgs a) {
     pdl_wait();
@@ -785,13 +793,12 @@ xa_roi_kernel(XrArgs a) {
     }
     {
         // ---- logits.  q~ slice of this lane: 8 heads x channels {lane*4..+3, 128+lane*4..+3}
-        float qv[8][8];
+        f32x2 qv[8][4];             // channel pairs (4 lane, 4 lane + 1), (+2, +3), (128 + 4 lane, ..), (.. + 2, + 3)
 #pragma unroll
         for (int h = 0; h < 8; ++h) {
-            const float4 x0 = *reinterpret_cast<const float4*>(a.qt + (long long)n * 2048 + h * 256 + lane * 4);
-            const float4 x1 = *reinterpret_cast<const float4*>(a.qt + (long long)n * 2048 + h * 256 + 128 + lane * 4);
-            qv[h][0] = x0.x; qv[h][1] = x0.y; qv[h][2] = x0.z; qv[h][3] = x0.w;
-            qv[h][4] = x1.x; qv[h][5] = x1.y; qv[h][6] = x1.z; qv[h][7] = x1.w;
+            const ulonglong2 x0 = *reinterpret_cast<const ulonglong2*>(a.qt + (long long)n * 2048 + h * 256 + lane * 4);
+            const ulonglong2 x1 = *reinterpret_cast<const ulonglong2*>(a.qt + (long long)n * 2048 + h * 256 + 128 + lane * 4);
+            qv[h][0] = x0.x; qv[h][1] = x0.y; qv[h][2] = x1.x; qv[h][3] = x1.y;
         }
         __syncthreads();            // barrier initialised before anyone polls it
         {
@@ -802,16 +809,16 @@ xa_roi_kernel(XrArgs a) {
         }
         for (int j = warp; j < MV2D_TOK; j += NW) {
             const float* row = Ks + j * MV2D_C;
-            const float4 k0 = *reinterpret_cast<const float4*>(row + lane * 4);
-            const float4 k1 = *reinterpret_cast<const float4*>(row + 128 + lane * 4);
+            const ulonglong2 k0 = *reinterpret_cast<const ulonglong2*>(row + lane * 4);
+            const ulonglong2 k1 = *reinterpret_cast<const ulonglong2*>(row + 128 + lane * 4);
             float sv[8];
 #pragma unroll
             for (int h = 0; h < 8; ++h) {
-                float x = qv[h][0] * k0.x;
-                x = fmaf(qv[h][1], k0.y, x); x = fmaf(qv[h][2], k0.z, x); x = fmaf(qv[h][3], k0.w, x);
-                x = fmaf(qv[h][4], k1.x, x); x = fmaf(qv[h][5], k1.y, x); x = fmaf(qv[h][6], k1.z, x);
-                x = fmaf(qv[h][7], k1.w, x);
-                sv[h] = x;
+                f32x2 x = mul2(qv[h][0], k0.x);
+                x = fma2(qv[h][1], k0.y, x); x = fma2(qv[h][2], k1.x, x); x = fma2(qv[h][3], k1.y, x);
+                float lo, hi;
+                unpack2(x, lo, hi);
+                sv[h] = lo + hi;
             }
             reduce8(sv, lane);
             if ((lane & 3) == 0) sc[j * 8 + (lane >> 2)] = sv[0];
@@ -832,24 +839,30 @@ xa_roi_kernel(XrArgs a) {
     __syncthreads();
     // ---- acc = sum_k p_k * mem_k
     float acc[8][8];
+    {
+        f32x2 acc2[8][4];
 #pragma unroll
-    for (int h = 0; h < 8; ++h)
+        for (int h = 0; h < 8; ++h)
 #pragma unroll
-        for (int c = 0; c < 8; ++c) acc[h][c] = 0.f;
-    for (int j = warp; j < MV2D_TOK; j += NW) {
-        const float* row = Vs + j * MV2D_C;
-        const float4 v0 = *reinterpret_cast<const float4*>(row + lane * 4);
-        const float4 v1 = *reinterpret_cast<const float4*>(row + 128 + lane * 4);
-        const float4 p0 = *reinterpret_cast<const float4*>(sc + j * 8);
-        const float4 p1 = *reinterpret_cast<const float4*>(sc + j * 8 + 4);
-        const float pp[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+            for (int c = 0; c < 4; ++c) acc2[h][c] = 0ull;
+        for (int j = warp; j < MV2D_TOK; j += NW) {
+            const float* row = Vs + j * MV2D_C;
+            const ulonglong2 v0 = *reinterpret_cast<const ulonglong2*>(row + lane * 4);
+            const ulonglong2 v1 = *reinterpret_cast<const ulonglong2*>(row + 128 + lane * 4);
+            const float4 p0 = *reinterpret_cast<const float4*>(sc + j * 8);
+            const float4 p1 = *reinterpret_cast<const float4*>(sc + j * 8 + 4);
+            const float pp[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
 #pragma unroll
-        for (int h = 0; h < 8; ++h) {
-            acc[h][0] = fmaf(pp[h], v0.x, acc[h][0]); acc[h][1] = fmaf(pp[h], v0.y, acc[h][1]);
-            acc[h][2] = fmaf(pp[h], v0.z, acc[h][2]); acc[h][3] = fmaf(pp[h], v0.w, acc[h][3]);
-            acc[h][4] = fmaf(pp[h], v1.x, acc[h][4]); acc[h][5] = fmaf(pp[h], v1.y, acc[h][5]);
-            acc[h][6] = fmaf(pp[h], v1.z, acc[h][6]); acc[h][7] = fmaf(pp[h], v1.w, acc[h][7]);
+            for (int h = 0; h < 8; ++h) {
+                const f32x2 p2 = pack2(pp[h], pp[h]);
+                acc2[h][0] = fma2(p2, v0.x, acc2[h][0]); acc2[h][1] = fma2(p2, v0.y, acc2[h][1]);
+                acc2[h][2] = fma2(p2, v1.x, acc2[h][2]); acc2[h][3] = fma2(p2, v1.y, acc2[h][3]);
+            }
         }
+#pragma unroll
+        for (int h = 0; h < 8; ++h)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) unpack2(acc2[h][c], acc[h][2 * c], acc[h][2 * c + 1]);
     }
     // ---- cross-warp tree sum through the (now free) key block, fixed order
     float4* T = reinterpret_cast<float4*>(Ks);   // [NW/2][512] float4
