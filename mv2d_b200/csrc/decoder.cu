@@ -754,7 +754,45 @@ struct XrArgs {
     const float* qt; const float* kin_rows; const float* mem_rows;
     const int* match; const int* match_cnt; int max_match;
     float* ctx; float* ctx_lo; float* part; int* ticket;
+    const int* units;            // [total] (query << 3 | slot), query-major, from xr_units_kernel; units[-1..]: see XR_UNITS_HDR
+    const int* total;            // device: number of units
 };
+
+// Work list of xa_roi_kernel: one unit per (query, matched RoI), query-major.  Built once per decoder call (the match
+// lists do not change between layers).  One block.
+#define XR_UNITS_THREADS 1024
+__global__ void __launch_bounds__(XR_UNITS_THREADS) xr_units_kernel(const int* __restrict__ match_cnt, int N, int* __restrict__ units,
+                                                                    int* __restrict__ total) {
+    pdl_wait();
+    pdl_trigger();
+    __shared__ int wsum[XR_UNITS_THREADS / 32];
+    __shared__ int base_s;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) base_s = 0;
+    __syncthreads();
+    for (int n0 = 0; n0 < N; n0 += XR_UNITS_THREADS) {
+        const int n = n0 + tid;
+        const int c = n < N ? min(match_cnt[n], 8) : 0;
+        int incl = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += y; }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int w = wsum[lane];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(0xffffffffu, w, d); if (lane >= d) w += y; }
+            wsum[lane] = w;
+        }
+        __syncthreads();
+        const int off = base_s + (warp ? wsum[warp - 1] : 0) + incl - c;
+        for (int s2 = 0; s2 < c; ++s2) units[off + s2] = (n << 3) | s2;
+        __syncthreads();
+        if (tid == 0) base_s += wsum[XR_UNITS_THREADS / 32 - 1];
+        __syncthreads();
+    }
+    if (tid == 0) *total = base_s;
+}
 
 __device__ __forceinline__ uint32_t xr_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -766,14 +804,8 @@ __device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) { asm("mo
 __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
 __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 
-__global__ void __launch_bounds__(XR_THREADS, 2)
-xa_roi_kernel(XrArgs a) {
-    pdl_wait();
-    pdl_trigger();
-    const int n = blockIdx.x, slot = blockIdx.y;
-    const int cnt = min(a.match_cnt[n], XR_MAXM);
-    if (slot >= cnt) return;
-    extern __shared__ __align__(128) unsigned char xr_smem[];
+// one (query n, match slot) unit; `phase` = parity of this use of the CTA's mbarrier
+__device__ __forceinline__ void xr_unit(const XrArgs& a, int n, int slot, int cnt, uint32_t phase, unsigned char* xr_smem) {
     float* Ks = reinterpret_cast<float*>(xr_smem);
     float* Vs = Ks + MV2D_TOK * MV2D_C;
     float* sc = Vs + MV2D_TOK * MV2D_C;          // [64][8] logits -> probabilities
@@ -783,13 +815,14 @@ xa_roi_kernel(XrArgs a) {
     constexpr int NW = XR_THREADS / 32;
     const long long blk = (long long)a.match[(long long)n * a.max_match + slot] * MV2D_TOK * MV2D_C;
     if (t == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(xr_smem_u32(bar)));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(xr_smem_u32(bar)), "r"(2 * XR_BLK_BYTES) : "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the previous unit's generic-proxy use of Ks / Vs is ordered before these copies
+        // bar[0]: the key block has landed, bar[1]: the value block (the logits do not wait for the values)
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(xr_smem_u32(bar)), "r"(XR_BLK_BYTES) : "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(xr_smem_u32(bar + 1)), "r"(XR_BLK_BYTES) : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                      ::"r"(xr_smem_u32(Ks)), "l"(a.kin_rows + blk), "r"(XR_BLK_BYTES), "r"(xr_smem_u32(bar)) : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"(xr_smem_u32(Vs)), "l"(a.mem_rows + blk), "r"(XR_BLK_BYTES), "r"(xr_smem_u32(bar)) : "memory");
+                     ::"r"(xr_smem_u32(Vs)), "l"(a.mem_rows + blk), "r"(XR_BLK_BYTES), "r"(xr_smem_u32(bar + 1)) : "memory");
     }
     {
         // ---- logits.  q~ slice of this lane: 8 heads x channels {lane*4..+3, 128+lane*4..+3}
@@ -800,12 +833,11 @@ xa_roi_kernel(XrArgs a) {
             const ulonglong2 x1 = *reinterpret_cast<const ulonglong2*>(a.qt + (long long)n * 2048 + h * 256 + 128 + lane * 4);
             qv[h][0] = x0.x; qv[h][1] = x0.y; qv[h][2] = x1.x; qv[h][3] = x1.y;
         }
-        __syncthreads();            // barrier initialised before anyone polls it
         {
             uint32_t done = 0;
             while (!done)
-                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                             : "=r"(done) : "r"(xr_smem_u32(bar)) : "memory");
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                             : "=r"(done) : "r"(xr_smem_u32(bar)), "r"(phase) : "memory");
         }
         for (int j = warp; j < MV2D_TOK; j += NW) {
             const float* row = Ks + j * MV2D_C;
@@ -838,6 +870,12 @@ xa_roi_kernel(XrArgs a) {
     }
     __syncthreads();
     // ---- acc = sum_k p_k * mem_k
+    {
+        uint32_t done = 0;
+        while (!done)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(xr_smem_u32(bar + 1)), "r"(phase) : "memory");
+    }
     float acc[8][8];
     {
         f32x2 acc2[8][4];
@@ -864,96 +902,99 @@ xa_roi_kernel(XrArgs a) {
 #pragma unroll
             for (int c = 0; c < 4; ++c) unpack2(acc2[h][c], acc[h][2 * c], acc[h][2 * c + 1]);
     }
-    // ---- cross-warp tree sum through the (now free) key block, fixed order
-    float4* T = reinterpret_cast<float4*>(Ks);   // [NW/2][512] float4
+    // ---- cross-warp sum, fixed order: every warp parks its partial (8 heads x 256) in the now free K / V blocks, then
+    // warp h adds up head h's eight partials and finishes that head (normalise, store / record, merge)
+    __syncthreads();                             // all warps are done reading Vs and sc
+    float4* T = reinterpret_cast<float4*>(Ks);   // [NW][8 heads][64] float4 = 64 KB of the 98 KB
 #pragma unroll
-    for (int stride = NW / 2; stride >= 1; stride >>= 1) {
-        if (warp >= stride && warp < 2 * stride) {
-#pragma unroll
-            for (int h = 0; h < 8; ++h) {
-                T[(warp - stride) * 512 + h * 64 + lane] = make_float4(acc[h][0], acc[h][1], acc[h][2], acc[h][3]);
-                T[(warp - stride) * 512 + h * 64 + 32 + lane] = make_float4(acc[h][4], acc[h][5], acc[h][6], acc[h][7]);
-            }
-        }
-        __syncthreads();
-        if (warp < stride) {
-#pragma unroll
-            for (int h = 0; h < 8; ++h) {
-                const float4 x0 = T[warp * 512 + h * 64 + lane], x1 = T[warp * 512 + h * 64 + 32 + lane];
-                acc[h][0] += x0.x; acc[h][1] += x0.y; acc[h][2] += x0.z; acc[h][3] += x0.w;
-                acc[h][4] += x1.x; acc[h][5] += x1.y; acc[h][6] += x1.z; acc[h][7] += x1.w;
-            }
-        }
-        __syncthreads();
+    for (int h = 0; h < 8; ++h) {
+        T[(warp * 8 + h) * 64 + lane] = make_float4(acc[h][0], acc[h][1], acc[h][2], acc[h][3]);
+        T[(warp * 8 + h) * 64 + 32 + lane] = make_float4(acc[h][4], acc[h][5], acc[h][6], acc[h][7]);
     }
-    if (warp != 0) return;
-    float inv[8];
-    if (cnt == 1) {
+    __syncthreads();
+    const int h = warp;                          // NW == 8 == heads
+    float o[8];
+    {
+        float4 x0 = T[h * 64 + lane], x1 = T[h * 64 + 32 + lane];
 #pragma unroll
-        for (int h = 0; h < 8; ++h) inv[h] = 1.f / stat[8 + h];
+        for (int w = 1; w < NW; ++w) {
+            const float4 y0 = T[(w * 8 + h) * 64 + lane], y1 = T[(w * 8 + h) * 64 + 32 + lane];
+            x0.x += y0.x; x0.y += y0.y; x0.z += y0.z; x0.w += y0.w;
+            x1.x += y1.x; x1.y += y1.y; x1.z += y1.z; x1.w += y1.w;
+        }
+        o[0] = x0.x; o[1] = x0.y; o[2] = x0.z; o[3] = x0.w; o[4] = x1.x; o[5] = x1.y; o[6] = x1.z; o[7] = x1.w;
+    }
+    float inv;
+    if (cnt == 1) {
+        inv = 1.f / stat[8 + h];
     } else {
         // leave the un-normalised record; the last CTA of this query merges all of them in slot order
         float* rec = a.part + ((long long)n * XR_MAXM + slot) * XR_REC;
-#pragma unroll
-        for (int h = 0; h < 8; ++h) {
-            *reinterpret_cast<float4*>(rec + h * 256 + lane * 4) = make_float4(acc[h][0], acc[h][1], acc[h][2], acc[h][3]);
-            *reinterpret_cast<float4*>(rec + h * 256 + 128 + lane * 4) = make_float4(acc[h][4], acc[h][5], acc[h][6], acc[h][7]);
-        }
-        if (lane < 16) rec[2048 + lane] = stat[lane];
+        *reinterpret_cast<float4*>(rec + h * 256 + lane * 4) = make_float4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<float4*>(rec + h * 256 + 128 + lane * 4) = make_float4(o[4], o[5], o[6], o[7]);
+        if (lane == 0) { rec[2048 + h] = stat[h]; rec[2056 + h] = stat[8 + h]; }
         __threadfence();
-        __syncwarp();
-        int tk = 0;
-        if (lane == 0) tk = atomicAdd(a.ticket + n, 1);
-        tk = __shfl_sync(0xffffffffu, tk, 0);
-        if (tk != cnt - 1) return;
+        __syncthreads();                         // the whole record is written (and fenced) before the ticket is taken
+        int* last = reinterpret_cast<int*>(stat + 16);
+        if (t == 0) *last = atomicAdd(a.ticket + n, 1) == cnt - 1;
+        __syncthreads();
+        if (!*last) return;                      // CTA-uniform
         __threadfence();
         const float* base = a.part + (long long)n * XR_MAXM * XR_REC;
-        float M[8], Lsum[8];
+        float M = -INFINITY, Lsum = 0.f;
+        for (int s2 = 0; s2 < cnt; ++s2) M = fmaxf(M, __ldcg(base + s2 * XR_REC + 2048 + h));
 #pragma unroll
-        for (int h = 0; h < 8; ++h) { M[h] = -INFINITY; Lsum[h] = 0.f; }
-        for (int s2 = 0; s2 < cnt; ++s2)
-#pragma unroll
-            for (int h = 0; h < 8; ++h) M[h] = fmaxf(M[h], __ldcg(base + s2 * XR_REC + 2048 + h));
-#pragma unroll
-        for (int h = 0; h < 8; ++h)
-#pragma unroll
-            for (int c = 0; c < 8; ++c) acc[h][c] = 0.f;
+        for (int c = 0; c < 8; ++c) o[c] = 0.f;
         for (int s2 = 0; s2 < cnt; ++s2) {
             const float* r2 = base + s2 * XR_REC;
-#pragma unroll
-            for (int h = 0; h < 8; ++h) {
-                const float w = __expf(__ldcg(r2 + 2048 + h) - M[h]);
-                Lsum[h] = fmaf(__ldcg(r2 + 2056 + h), w, Lsum[h]);
-                const float4 x0 = __ldcg(reinterpret_cast<const float4*>(r2 + h * 256 + lane * 4));
-                const float4 x1 = __ldcg(reinterpret_cast<const float4*>(r2 + h * 256 + 128 + lane * 4));
-                acc[h][0] = fmaf(x0.x, w, acc[h][0]); acc[h][1] = fmaf(x0.y, w, acc[h][1]);
-                acc[h][2] = fmaf(x0.z, w, acc[h][2]); acc[h][3] = fmaf(x0.w, w, acc[h][3]);
-                acc[h][4] = fmaf(x1.x, w, acc[h][4]); acc[h][5] = fmaf(x1.y, w, acc[h][5]);
-                acc[h][6] = fmaf(x1.z, w, acc[h][6]); acc[h][7] = fmaf(x1.w, w, acc[h][7]);
-            }
+            const float w = __expf(__ldcg(r2 + 2048 + h) - M);
+            Lsum = fmaf(__ldcg(r2 + 2056 + h), w, Lsum);
+            const float4 x0 = __ldcg(reinterpret_cast<const float4*>(r2 + h * 256 + lane * 4));
+            const float4 x1 = __ldcg(reinterpret_cast<const float4*>(r2 + h * 256 + 128 + lane * 4));
+            o[0] = fmaf(x0.x, w, o[0]); o[1] = fmaf(x0.y, w, o[1]); o[2] = fmaf(x0.z, w, o[2]); o[3] = fmaf(x0.w, w, o[3]);
+            o[4] = fmaf(x1.x, w, o[4]); o[5] = fmaf(x1.y, w, o[5]); o[6] = fmaf(x1.z, w, o[6]); o[7] = fmaf(x1.w, w, o[7]);
         }
-#pragma unroll
-        for (int h = 0; h < 8; ++h) inv[h] = 1.f / Lsum[h];
-        if (lane == 0) a.ticket[n] = 0;          // re-armed for the next layer (stream order)
+        inv = 1.f / Lsum;
+        if (t == 0) a.ticket[n] = 0;             // re-armed for the next layer (stream order)
     }
 #pragma unroll
-    for (int h = 0; h < 8; ++h) {
+    for (int half = 0; half < 2; ++half) {
+        float v[4];
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            float v[4];
+        for (int k = 0; k < 4; ++k) v[k] = o[half * 4 + k] * inv;
+        const long long oo = (long long)n * 2048 + h * 256 + half * 128 + lane * 4;
+        if (a.ctx_lo) {
+            float hi[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) v[k] = acc[h][half * 4 + k] * inv[h];
-            const long long o = (long long)n * 2048 + h * 256 + half * 128 + lane * 4;
-            if (a.ctx_lo) {
-                float hi[4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) { hi[k] = round_tf32(v[k]); v[k] = round_tf32(v[k] - hi[k]); }
-                *reinterpret_cast<float4*>(a.ctx + o) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-                *reinterpret_cast<float4*>(a.ctx_lo + o) = make_float4(v[0], v[1], v[2], v[3]);
-            } else {
-                *reinterpret_cast<float4*>(a.ctx + o) = make_float4(v[0], v[1], v[2], v[3]);
-            }
+            for (int k = 0; k < 4; ++k) { hi[k] = round_tf32(v[k]); v[k] = round_tf32(v[k] - hi[k]); }
+            *reinterpret_cast<float4*>(a.ctx + oo) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<float4*>(a.ctx_lo + oo) = make_float4(v[0], v[1], v[2], v[3]);
+        } else {
+            *reinterpret_cast<float4*>(a.ctx + oo) = make_float4(v[0], v[1], v[2], v[3]);
         }
+    }
+}
+
+// Persistent: 2 CTAs per SM walk the unit list (no CTA is launched for the ~80 % of (query, slot) pairs that do not
+// exist, and while one CTA of an SM computes the other one's copies are in flight).
+__global__ void __launch_bounds__(XR_THREADS, 2)
+xa_roi_kernel(XrArgs a) {
+    pdl_wait();
+    pdl_trigger();
+    extern __shared__ __align__(128) unsigned char xr_smem[];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(reinterpret_cast<float*>(xr_smem) + 2 * MV2D_TOK * MV2D_C + 64 * 8 + 32);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(xr_smem_u32(bar)));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(xr_smem_u32(bar + 1)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();            // barriers initialised before anyone arms or polls them
+    const int total = *a.total;
+    uint32_t phase = 0;
+    for (int u = blockIdx.x; u < total; u += gridDim.x, phase ^= 1u) {
+        const int code = a.units[u], n = code >> 3, slot = code & 7;
+        xr_unit(a, n, slot, min(a.match_cnt[n], XR_MAXM), phase, xr_smem);
+        __syncthreads();        // every warp is done with this unit's shared memory
     }
 }
 
@@ -1055,9 +1096,9 @@ size_t decoder_workspace_bytes(int N, int L) {
     size_t n = (size_t)(N > 0 ? N : 1), l = (size_t)(L > 0 ? L : 1);
     // x, xq, x1, x1q, x2 + 4 hi/lo copies (9*256) + qkv 768 + sa 256 + qt 2048 + ctx hi/lo + hdn hi/lo + partials
     // + (3xTF32 everywhere, > 512 rows) x / xq hi/lo, sa lo, xt ctx lo: 6*256
-    size_t per = 9 * MV2D_C + 768 + MV2D_C + 2048 + 2 * 2048 + 2 * 2048 + DEC_SPLIT * MV2D_C + XR_MAXM * XR_REC + 1 + 6 * MV2D_C;
+    size_t per = 9 * MV2D_C + 768 + MV2D_C + 2048 + 2 * 2048 + 2 * 2048 + DEC_SPLIT * MV2D_C + XR_MAXM * XR_REC + 1 + XR_MAXM + 6 * MV2D_C;   // + ticket + unit list
     // branches: 4 x [L,N,256] + hi/lo splits of the post-normed states and of three branch activations
-    return (n * per + (4 + 7) * l * n * MV2D_C) * sizeof(float) + 4096 + 256;   // + the device-wide barrier word and phase timestamps of the persistent kernel
+    return (n * per + (4 + 7) * l * n * MV2D_C) * sizeof(float) + 4096 + 512;   // + the device-wide barrier word and phase timestamps of the persistent kernel
 }
 
 // ---- key-stationary cross-attention of the two-frame head (xa_tile.cuh): caller-owned scratch
@@ -1190,6 +1231,18 @@ int run_xa_tile_prepare(const Mv2dDecoderParams& p, cudaStream_t st) {
 }
 
 // first float of the xa_roi partial-record scratch inside the decoder workspace (must match the carve of run_decoder)
+// persistent xa_roi_kernel: two CTAs per SM (or one per possible unit when that is fewer)
+static int xr_grid(int N, int max_match) {
+    static int num_sms = 0;
+    if (num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const long long cap = (long long)N * max_match;
+    return (int)(cap < 2LL * num_sms ? cap : 2LL * num_sms);
+}
+
 static size_t xr_part_offset(int N, int L) {
     return (size_t)N * (9 * MV2D_C + 768 + MV2D_C + 5 * 2048 + DEC_SPLIT * MV2D_C) + (size_t)4 * L * N * MV2D_C;
 }
@@ -1204,10 +1257,14 @@ int run_cross_attention_core(const Mv2dDecoderParams& p, int layer, const float*
     if (p.mode == 0) {
         MV2D_CHECK_ARG(p.match && p.match_cnt && p.max_match > 0 && p.max_match <= XR_MAXM && p.workspace,
                        "cross_attention_core: S head needs match lists (max_match <= %d) and the decoder workspace", XR_MAXM);
-        MV2D_CHECK_ARG((xr_part_offset(N, p.L) + (size_t)N * XR_MAXM * XR_REC + N) * sizeof(float) <= p.workspace_bytes,
+        MV2D_CHECK_ARG((xr_part_offset(N, p.L) + (size_t)N * XR_MAXM * XR_REC + N + (size_t)N * XR_MAXM + 1) * sizeof(float) <= p.workspace_bytes,
                        "cross_attention_core: workspace too small");
         float* part = p.workspace + xr_part_offset(N, p.L);
         int* ticket = reinterpret_cast<int*>(part + (size_t)N * XR_MAXM * XR_REC);
+        int* units = ticket + N;
+        int* total = units + (size_t)N * XR_MAXM;
+        launch_k(xr_units_kernel, dim3(1), dim3(XR_UNITS_THREADS), 0, st, p.match_cnt, N, units, total);
+        MV2D_CHECK_LAUNCH("xr_units");
         if ((e = cudaFuncSetAttribute(xa_roi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XR_SMEM_BYTES)) != cudaSuccess ||
             (e = cudaMemsetAsync(ticket, 0, (size_t)N * sizeof(int), st)) != cudaSuccess) {
             set_error("cross_attention_core: setup %s", cudaGetErrorString(e));
@@ -1215,7 +1272,8 @@ int run_cross_attention_core(const Mv2dDecoderParams& p, int layer, const float*
         }
         XrArgs a{}; a.qt = q; a.kin_rows = p.kin_rows; a.mem_rows = p.mem_rows; a.match = p.match;
         a.match_cnt = p.match_cnt; a.max_match = p.max_match; a.ctx = ctx; a.ctx_lo = ctx_lo; a.part = part; a.ticket = ticket;
-        launch_k(xa_roi_kernel, dim3(N, p.max_match), dim3(XR_THREADS), (size_t)XR_SMEM_BYTES, st, a);
+        a.units = units; a.total = total;
+        launch_k(xa_roi_kernel, dim3(xr_grid(N, p.max_match)), dim3(XR_THREADS), (size_t)XR_SMEM_BYTES, st, a);
         MV2D_CHECK_LAUNCH("xa_roi");
         return 0;
     }
@@ -1276,6 +1334,8 @@ int run_decoder(const Mv2dDecoderParams& p, cudaStream_t st) {
     MV2D_CHECK_ARG((size_t)(ws - p.workspace) == xr_part_offset(N, L), "decoder: internal workspace layout drifted");
     float* xr_part = ws; ws += (size_t)N * XR_MAXM * XR_REC;
     int* xr_ticket = reinterpret_cast<int*>(ws); ws += N;
+    int* xr_units = reinterpret_cast<int*>(ws); ws += (size_t)N * XR_MAXM;      // (query, slot) work list of xa_roi_kernel
+    int* xr_total = reinterpret_cast<int*>(ws); ws += 1;
     ws = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);     // TMA operands follow
     // 3xTF32 operand splits of the GEMMs that run as FFMA below 512 rows
     float* x_hi = ws;  ws += (size_t)N * C;
@@ -1354,6 +1414,10 @@ int run_decoder(const Mv2dDecoderParams& p, cudaStream_t st) {
             (first && (e = cudaMemsetAsync(xr_ticket, 0, (size_t)N * sizeof(int), st)) != cudaSuccess)) {
             set_error("decoder: xa_roi setup %s", cudaGetErrorString(e));
             return (int)e;
+        }
+        if (first) {
+            launch_k(xr_units_kernel, dim3(1), dim3(XR_UNITS_THREADS), 0, st, p.match_cnt, N, xr_units, xr_total);
+            MV2D_CHECK_LAUNCH("xr_units");
         }
     }
     int rc;
@@ -1534,8 +1598,8 @@ int run_decoder(const Mv2dDecoderParams& p, cudaStream_t st) {
         if (use_xr) {
             XrArgs a{}; a.qt = qt; a.kin_rows = p.kin_rows; a.mem_rows = p.mem_rows; a.match = p.match;
             a.match_cnt = p.match_cnt; a.max_match = p.max_match; a.ctx = ctx; a.ctx_lo = ctx_lo;
-            a.part = xr_part; a.ticket = xr_ticket;
-            launch_k(xa_roi_kernel, dim3(N, p.max_match), dim3(XR_THREADS), (size_t)XR_SMEM_BYTES, st, a);
+            a.part = xr_part; a.ticket = xr_ticket; a.units = xr_units; a.total = xr_total;
+            launch_k(xa_roi_kernel, dim3(xr_grid(N, p.max_match)), dim3(XR_THREADS), (size_t)XR_SMEM_BYTES, st, a);
             MV2D_CHECK_LAUNCH("xa_roi");
         } else {
             XaArgs a{}; a.qt = qt; a.kin_rows = p.kin_rows; a.mem_rows = p.mem_rows; a.match = p.match;
