@@ -408,7 +408,7 @@ def two_frame_section(sd, dev, world, rank, barrier, steps, warmup, batch=2, dep
             res['gpu_launches'] = pp.launch_count() - l0
     res.update(metric=METRIC_T, unit=UNIT, workload=workload_name('T'), batch=batch, depth=depth, steps=steps, warmup=warmup,
                l2=f'{n_var} distinct samples rotate: {n_var * smp[0][0].numel() * 4 / 1e6:.0f} MB of feature maps > 126 MB L2',
-               note='bs = 2 in one kernel chain; K/V projections of all cells by 3xTF32 tcgen05, key-stationary cross-attention (csrc/xa_tile.cuh)')
+               note='bs = 2 in one kernel chain; K/V projections of all cells and layers by one persistent 3xTF32 tcgen05 launch (csrc/kvproj.cu), key-stationary cross-attention on TF32 tensor cores (csrc/xa_tile.cuh)')
     del pp
     torch.cuda.empty_cache()
     return res
@@ -519,14 +519,15 @@ def roofline_section(eng, batch_in, mode, flush, peaks):
     flops = 2.0 * n_tok * 256 * 2304
     achieved = flops / (t_conv * 1e-6) / 1e12
     # dram__bytes_read.sum + dram__bytes_write.sum of this launch from the committed `ncu --set full` capture
-    # (profiles/r02_ncu_full_conv_B8.csv at B = 8, N = 300; profiles/r01_ncu_full_tc_kernels.csv at B = 1)
-    traffic = {(8, 300): None, (1, 300): 34.882816e6 + 0.07168e6}.get((B, n_per))
-    roofline = dict(kernel='gemm_tc_kernel<128,3,im2col,3> (query-generator 3x3 conv, 3xTF32 tcgen05 + 4-D TMA)',
+    # (profiles/r02_ncu_full_kernels.csv: B = 8, N = 300)
+    traffic = {(8, 300): 257.363712e6 + 95.28448e6}.get((B, n_per))     # profiles/r02_ncu_full_kernels.csv
+    roofline = dict(kernel='gemm_tc_kernel<128,3,im2col=3,2> (query-generator 3x3 conv, 3xTF32 tcgen05 + 4-D TMA, five RoIs per 256-row tile)',
                     bound='tensor', achieved=achieved, peak=peaks['bf16_tflops'], unit='TFLOP/s',
                     frac=achieved / peaks['bf16_tflops'], traffic=traffic, us_per_launch=t_conv, rois_per_launch=N,
-                    algorithmic_flops=flops, tf32_flops_issued=3 * flops * 128.0 / 98.0,
+                    algorithmic_flops=flops, tf32_flops_issued=3 * flops * 256.0 / 245.0,
                     note='achieved counts the conv flops once (17.3 GFLOP per 300 RoIs); the kernel issues 3 TF32 MMAs '
-                         'per product (error compensation) on 128-row tiles that hold 98 real rows; peak = measured '
+                         'per product (error compensation) on 256-row tiles that hold 245 real rows (ncu: tensor pipe 78 % '
+                         'active, DRAM traffic = the operand + output bytes); peak = measured '
                          f'dense bf16 ({peaks["source"]}), the TF32 pipe is nominally half of it; kernel timed alone')
 
     # --- attention path: one decoder layer, algorithmic bytes (per sample x B) / time
@@ -571,7 +572,8 @@ def roofline_section(eng, batch_in, mode, flush, peaks):
         core_bytes = (float(out['match_cnt'].sum()) * 49 * 2 * 1024) if mode == 'S' else bytes_layer
         attention['core'] = dict(us=t_core, bytes=core_bytes, achieved=core_bytes / t_core / 1e3,
                                  frac=core_bytes / t_core / 1e3 / peaks['hbm_gbs'],
-                                 traffic=None,
+                                 # dram__bytes_read + write of the kernel(s) in the committed ncu capture (profiles/r02_ncu_full_kernels.csv)
+                                 traffic={('S', 8, 300): 260.734976e6 + 36.452352e6, ('T', 2, 300): 131.600896e6 + 21.562368e6}.get((mode, B, n_per)),
                                  note='cross-attention kernel(s) alone, L2 flushed; bytes = key / value rows the kernel has to stream '
                                       '(S: 100 KB per (query, RoI) unit; T: the SURVEY 8d bytes); ncu dram bytes: profiles/')
     except Exception as e:

@@ -223,9 +223,15 @@ def test_training_forward_matches_inference_path(state_dicts):
     for k in ('cls_scores', 'bbox_preds'):
         a, b = out[k].cpu(), o[k].cpu()
         assert bool(((a - b).abs() <= 1e-3 + 1e-3 * b.abs()).all()), f'{k}: max diff {(a - b).abs().max():.2e}'
+    # targets / losses: on the trainer's OWN predictions the standalone loss entry must reproduce it exactly ...
+    own = eng.loss(out['cls_scores'].contiguous(), out['bbox_preds'].contiguous(), gt_boxes, gt_labels)
+    assert np.array_equal(out['assigned'].cpu().numpy(), own['assigned'].cpu().numpy())
+    np.testing.assert_allclose(out['loss_cls'].cpu().numpy(), own['loss_cls'].cpu().numpy(), rtol=1e-5)
+    # ... and on the inference path's predictions (equal to 1e-3, so a near-tie of the Hungarian matching may flip)
     ref = eng.loss(o['cls_scores'], o['bbox_preds'], gt_boxes, gt_labels)
-    assert np.array_equal(out['assigned'].cpu().numpy(), ref['assigned'].cpu().numpy())
-    np.testing.assert_allclose(out['loss_cls'].cpu().numpy(), ref['loss_cls'].cpu().numpy(), rtol=1e-3)
+    same = (out['assigned'].cpu().numpy() == ref['assigned'].cpu().numpy()).mean()
+    assert same >= 0.99, f'assignments agree on {same:.3f} of the (layer, query) slots'
+    np.testing.assert_allclose(out['loss_cls'].cpu().numpy(), ref['loss_cls'].cpu().numpy(), rtol=2e-2)
     tr.backward()
     torch.cuda.synchronize()
     assert bool(torch.isfinite(tr.grads).all())
