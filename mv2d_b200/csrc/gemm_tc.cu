@@ -479,6 +479,163 @@ gemm_tc_mc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
 }
 
+// ---------------------------------------------------------------------------- persistent variant
+// For the GPU-filling 3xTF32 GEMMs of a batch (M = 2400 rows, N = 2048: the absorbed query projection and FFN layer 1,
+// >= 2 tiles per SM).  One CTA per SM walks the (m tile, n tile) units round-robin; the 256 TMEM columns hold TWO
+// 128-column accumulators, so the epilogue of unit i (TMEM -> registers -> smem transpose -> coalesced stores, hi / lo
+// split) overlaps the main loop of unit i + 1 and the TMA producer runs ahead across unit boundaries.  The one-tile-per-CTA
+// kernel above exposes barrier setup, TMEM allocation, pipeline fill and the whole epilogue once per tile (1 CTA / SM at
+// 192 KB of shared memory): 33-40 us for these two GEMMs against ~9 us of tensor time.
+// Pre-split operands only; epilogue: bias, ReLU, TF32 rounding, hi / lo split.
+struct PgArgs {
+    TcArgs t;
+    int m_tiles, n_tiles;
+};
+
+template <int STAGES>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
+                       const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmWlo, PgArgs pg) {
+    constexpr int BN = 128;
+    constexpr int A_BYTES = TC_BM * TC_BK * 4, W_BYTES = BN * TC_BK * 4;
+    constexpr int STAGE_BYTES = 2 * (A_BYTES + W_BYTES);       // 64 KB
+    const TcArgs& g = pg.t;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    float* stg_all = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);        // 4 x 4 KB epilogue transpose tiles
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + 4 * 4096);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tmem_full = empty_bar + STAGES;       // [2]
+    uint64_t* tmem_empty = tmem_full + 2;           // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nkb = g.nkb_per_split, total = pg.m_tiles * pg.n_tiles;
+
+    if (warp == 0 && lane == 0) {
+        tmap_prefetch(&tmA); tmap_prefetch(&tmW); tmap_prefetch(&tmAlo); tmap_prefetch(&tmWlo);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(2 * BN));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();
+    pdl_trigger();
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int it = 0;
+            for (int u = blockIdx.x; u < total; u += gridDim.x) {
+                const int m_tile = u / pg.n_tiles, n0 = (u % pg.n_tiles) * BN;
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % STAGES, ph = (it / STAGES) & 1;
+                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    uint8_t* st = smem + s * STAGE_BYTES;
+                    mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+                    tma_load_2d(&tmA, &full_bar[s], st, kb * TC_BK, m_tile * TC_BM);
+                    tma_load_2d(&tmAlo, &full_bar[s], st + A_BYTES, kb * TC_BK, m_tile * TC_BM);
+                    tma_load_2d(&tmW, &full_bar[s], st + 2 * A_BYTES, kb * TC_BK, n0);
+                    tma_load_2d(&tmWlo, &full_bar[s], st + 2 * A_BYTES + W_BYTES, kb * TC_BK, n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+        if (lane == 0) {
+            int it = 0, ui = 0;
+            for (int u = blockIdx.x; u < total; u += gridDim.x, ++ui) {
+                const int buf = ui & 1;
+                mbar_wait(&tmem_empty[buf], ((ui >> 1) & 1) ^ 1);      // the epilogue has drained this accumulator
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t acc = tmem_base + (uint32_t)(buf * BN);
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % STAGES, ph = (it / STAGES) & 1;
+                    mbar_wait(&full_bar[s], ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+                    const uint64_t a_hi = make_desc(sa), a_lo = make_desc(sa + A_BYTES);
+                    const uint64_t w_hi = make_desc(sa + 2 * A_BYTES), w_lo = make_desc(sa + 2 * A_BYTES + W_BYTES);
+#pragma unroll
+                    for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
+                        const uint64_t adv = (uint64_t)((k * TC_UMMA_K * 4) >> 4);
+                        umma_tf32(acc, a_hi + adv, w_hi + adv, idesc, (kb | k) != 0);
+                        umma_tf32(acc, a_hi + adv, w_lo + adv, idesc, 1);
+                        umma_tf32(acc, a_lo + adv, w_hi + adv, idesc, 1);
+                    }
+                    umma_commit(&empty_bar[s]);
+                }
+                umma_commit(&tmem_full[buf]);
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        float* stg = stg_all + q * 1024;
+        int ui = 0;
+        for (int u = blockIdx.x; u < total; u += gridDim.x, ++ui) {
+            const int m_tile = u / pg.n_tiles, n0 = (u % pg.n_tiles) * BN, buf = ui & 1;
+            auto store_t = [&](float* __restrict__ dst, const float (&x)[32], int n) {
+                __syncwarp();
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4)
+                    *reinterpret_cast<float4*>(stg + lane * 32 + ((j4 ^ (lane & 7)) << 2)) =
+                        make_float4(x[j4 * 4], x[j4 * 4 + 1], x[j4 * 4 + 2], x[j4 * 4 + 3]);
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int rr = i * 4 + (lane >> 3), cc = lane & 7;
+                    const float4 v4 = *reinterpret_cast<const float4*>(stg + rr * 32 + ((cc ^ (rr & 7)) << 2));
+                    const long long orow = (long long)m_tile * TC_BM + q * 32 + rr;
+                    if (orow < g.M) *reinterpret_cast<float4*>(dst + orow * g.ldc + n + cc * 4) = v4;
+                }
+            };
+            mbar_wait(&tmem_full[buf], (ui >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + c * 32), v);
+                const int n = n0 + c * 32;
+                float x[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
+                if (g.bias) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) x[j] += __ldg(g.bias + n + j);
+                }
+                if (g.flags & GEMM_RELU) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
+                }
+                if (g.flags & GEMM_ROUND_TF32) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) x[j] = round_tf32(x[j]);
+                }
+                if (g.flags & GEMM_SPLIT_OUT) {
+                    float lo[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) { const float hi = round_tf32(x[j]); lo[j] = round_tf32(x[j] - hi); x[j] = hi; }
+                    store_t(g.C_lo, lo, n);
+                }
+                store_t(g.C, x, n);
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty[buf])) : "memory");
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * BN));
+    }
+}
+
 // ---------------------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -636,6 +793,30 @@ static int launch_tc_mc(const CUtensorMap& a, const CUtensorMap& alo, const CUte
     return 0;
 }
 
+static bool persist_enabled() {
+    static const bool on = []() { const char* e = getenv("MV2D_TC_PERSIST"); return !(e && e[0] == '0'); }();
+    return on;
+}
+
+static int launch_tc_persist(const CUtensorMap& a, const CUtensorMap& alo, const CUtensorMap& w, const CUtensorMap& wlo, const TcArgs& g,
+                             int m_tiles, int num_sms, cudaStream_t st) {
+    constexpr int STAGES = 3;
+    constexpr size_t smem = (size_t)STAGES * 2 * (TC_BM * TC_BK * 4 + 128 * TC_BK * 4) + 4 * 4096 + 256 + 1024;
+    auto kern = gemm_tc_persist_kernel<STAGES>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_error("gemm_tc_persist: smem attr: %s", cudaGetErrorString(e)); return (int)e; }
+        attr_set = true;
+    }
+    PgArgs pg{};
+    pg.t = g; pg.m_tiles = m_tiles; pg.n_tiles = g.N / 128;
+    const int total = pg.m_tiles * pg.n_tiles;
+    launch_k(kern, dim3(total < num_sms ? total : num_sms), dim3(TC_THREADS), smem, st, a, alo, w, wlo, pg);
+    MV2D_CHECK_LAUNCH("gemm_tc_persist");
+    return 0;
+}
+
 int launch_gemm_tc(const TcGemm& t, cudaStream_t st) {
     // small-M problems (the decoder, M ~ 300) are latency bound: 64-wide N tiles double the CTA count
     // (a 256-wide, 2-stage im2col variant measured slower than 128-wide / 3 stages; 64-wide tiles for the N = 256 outputs of
@@ -690,6 +871,23 @@ int launch_gemm_tc(const TcGemm& t, cudaStream_t st) {
         g.n_switch = t.n_switch;
         if ((rc = make_map_2d(&a2, t.A2, t.M, t.K, t.lda, TC_BM))) return rc;
         if ((rc = make_map_2d(&a2lo, t.A2_lo, t.M, t.K, t.lda, TC_BM))) return rc;
+    }
+    if (persist_enabled() && t.passes == 3 && !raw && !t.im2col && ngroups == 1 && !two_a && nsplit == 1 && !t.m_tile_live &&
+        !(t.flags & ~(GEMM_RELU | GEMM_ROUND_TF32 | GEMM_SPLIT_OUT)) && t.N % 128 == 0) {
+        static int num_sms = 0;
+        if (num_sms == 0) {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+        }
+        // at least two tiles per SM: below that the one-tile-per-CTA kernel spreads the work just as well
+        if (m_tiles * (t.N / 128) >= 2 * num_sms) {
+            if (bn != 128) {
+                if ((rc = make_map_2d(&w, t.W, t.N, t.K, t.ldw, 128))) return rc;
+                if ((rc = make_map_2d(&wlo, t.W_lo, t.N, t.K, t.ldw, 128))) return rc;
+            }
+            return launch_tc_persist(a, alo, w, wlo, g, m_tiles, num_sms, st);
+        }
     }
     if (raw && bn == 64) return launch_tc<64, 3, false, 4, true>(a, alo, w, wlo, g, m_tiles, nsplit, st);
     if (raw) return launch_tc<128, 3, false, 3, true>(a, alo, w, wlo, g, m_tiles, nsplit, st);
