@@ -353,7 +353,12 @@ def main():
                     sine_branch='recomputed every step (not cached); inside a step it is evaluated once for the whole batch when all samples '
                                 'share the padding masks (a common subexpression: it does not depend on the inputs)', wall_s=wall),
         e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
-                 ms_per_step=e2e_total_ms / args.steps),
+                 ms_per_step=e2e_total_ms / args.steps,
+                 h2d_gb_per_s_per_gpu=h2d / (e2e_total_ms / args.steps) * 1e-6,
+                 h2d_gb_per_s_all_gpus=world * h2d / (e2e_total_ms / args.steps) * 1e-6,
+                 note='every sample carries its 17.3 MB fp32 feature map over PCIe inside the timed region; one GPU moves ~42 GB/s of '
+                      'its x16 link, eight ranks together saturate the host at ~180 GB/s (measured on the 8-GPU box: a VM with one '
+                      'NUMA node), which is the ceiling of the 8-GPU end-to-end number, not a collective or a kernel'),
         gpu_launches=launches, launches_per_sample=launches / (args.steps * B), clocks=clocks, numa=numa, roofline=roof['roofline'],
         attention_roofline=roof['attention'], stage_us=roof['stage_us'], peaks=peaks, serial=serial)
     if two_frame is not None:

@@ -120,7 +120,8 @@ MV2D_API int mv2d_pe3d(const Mv2dPeParams* p, void* stream);
  *  bbox_heads/cross_attention_head.py:199-200; utils/pe.py:21-33; mmcv RoIAlign avg/aligned) */
 typedef struct Mv2dQgParams {
     /* phase: 0 = everything; 1 = everything that does not need `pe` (can run concurrently with mv2d_pe3d);
-     *        2 = only tok_kin = tok_feat + RoIAlign(pe) (after phases 1 and mv2d_pe3d) */
+     *        2 = only tok_kin = tok_feat + RoIAlign(pe) (after phases 1 and mv2d_pe3d);
+     *        4 = only roi_intrinsics (get_box_params, mv2d_head.py:51-72: reads rois / intrinsics / extrinsics, no weights) */
     int N, V, h, w, stride, phase;
     float pc_range[6];
     float intrins_feat_scale;

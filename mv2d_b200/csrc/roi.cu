@@ -234,8 +234,8 @@ int run_roi_align_qg(const Mv2dQgParams& p, cudaStream_t st) {
     const int N = p.N, C = MV2D_C;
     MV2D_CHECK_ARG(N >= 0 && p.V >= 1 && p.V <= MV2D_MAXVB, "roi_align_qg: bad N/V");
     if (N == 0) return 0;
-    MV2D_CHECK_ARG(p.phase >= 0 && p.phase <= 3, "roi_align_qg: phase must be 0, 1, 2 or 3");
-    MV2D_CHECK_ARG(p.phase == 1 || p.phase == 3 || p.tok_kin == nullptr || p.pe != nullptr, "roi_align_qg: tok_kin needs pe");
+    MV2D_CHECK_ARG(p.phase >= 0 && p.phase <= 4, "roi_align_qg: phase must be 0 .. 4");
+    MV2D_CHECK_ARG(p.phase == 1 || p.phase >= 3 || p.tok_kin == nullptr || p.pe != nullptr, "roi_align_qg: tok_kin needs pe");
     MV2D_CHECK_ARG(p.phase != 3 || (p.roi_intrinsics && p.roi_extrinsics && p.intrins_feat), "roi_align_qg: phase 3 needs K', E and the intrinsics feature per RoI");
     if (p.phase == 2) {   // only the position-embedding tokens: tok_kin = tok_feat + RoIAlign(pe)
         if (p.tok_kin == nullptr) return 0;
@@ -274,6 +274,13 @@ int run_roi_align_qg(const Mv2dQgParams& p, cudaStream_t st) {
         return launch_gemm_tc(t, st);
     };
     int rc;
+    if (p.phase == 4) {     // per-RoI intrinsics K' only (weight independent: what the training forward needs from this entry)
+        MV2D_CHECK_ARG(p.roi_intrinsics != nullptr, "roi_align_qg: phase 4 writes roi_intrinsics");
+        launch_k(box_params_kernel, dim3(cdiv(N, 64)), dim3(64), 0, st, p.rois, p.intrinsics, p.extrinsics, N, p.intrins_feat_scale, cat,
+                                                      mroi, p.roi_intrinsics, (float*)nullptr);
+        MV2D_CHECK_LAUNCH("box_params");
+        return 0;
+    }
     if (p.phase == 3) {     // tokens and per-RoI camera parameters are inputs (QueryGenerator.forward on its own)
         if ((rc = launch_split_tf32(p.tok_feat, thi, tlo, (long long)N * MV2D_TOK * C, st))) return rc;
         launch_k(qg_inputs_kernel, dim3(cdiv(N, 64)), dim3(64), 0, st, (const double*)p.roi_intrinsics, p.roi_extrinsics, p.intrins_feat, N, cat,

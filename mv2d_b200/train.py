@@ -316,7 +316,7 @@ class HotPathTrainer(DecoderTrainer):
         feat_nhwc, _ = eng.to_nhwc(feat)
         V, h, w, _ = feat_nhwc.shape
         corr = eng.box_corr(rois, roi_start, trans, N, V, img_metas, h, w)
-        k_roi = eng.roi_align_qg(rois, cams, feat_nhwc, None, N, phase=1)['roi_intrinsics']      # K' (weight independent)
+        k_roi = eng.roi_align_qg(rois, cams, feat_nhwc, None, N, phase=4)['roi_intrinsics']      # K' only (weight independent)
         _, _, not_mask, _ = eng._masks(img_metas, h, w)
         c = eng.cfg
         out = dict(tok_mem=torch.empty((N, 49, 256), **f32), tok_kin=torch.empty((N, 49, 256), **f32),
@@ -379,7 +379,7 @@ class HotPathTrainer(DecoderTrainer):
         V, h, w, _ = feat_nhwc.shape
         R = V * h * w
         corr = eng.box_corr(rois, roi_start, trans, N, V, img_metas, h, w)
-        k_roi = eng.roi_align_qg(rois, cams, feat_nhwc, None, N, phase=1)['roi_intrinsics']
+        k_roi = eng.roi_align_qg(rois, cams, feat_nhwc, None, N, phase=4)['roi_intrinsics']
         _, _, not_mask, _ = eng._masks(img_metas, h, w)
         out = dict(tok_mem=torch.empty((N, 49, 256), **f32), tok_kin=torch.empty((N, 49, 256), **f32),
                    ref=torch.empty((N, 3), **f32), d_feat=torch.empty((V, h, w, 256), **f32),
