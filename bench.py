@@ -52,7 +52,7 @@ def parse():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-train', action='store_true', help='skip the extra training-step section')
     ap.add_argument('--batch', type=int, default=None, help='samples per step (a segment dimension through one kernel chain); default 8 (S) / 2 (T)')
-    ap.add_argument('--depth', type=int, default=3, help='batches in flight (pipelining on independent lanes); 1 = one batch at a time')
+    ap.add_argument('--depth', type=int, default=0, help='batches in flight (pipelining on independent lanes); 1 = one batch at a time; 0 = 4 for the single-frame head, 3 for the two-frame head (tools/batch_sweep.py)')
     ap.add_argument('--no-two-frame', action='store_true', help='skip the extra MV2D-T (BASELINE configs[2]) section')
     ap.add_argument('--no-gpu-torch-baseline', action='store_true')
     args = ap.parse_args()
@@ -195,7 +195,7 @@ def main():
     B = max(args.batch, 1)
     sd = synth.make_state_dict(0)
     from mv2d_b200.pipeline import Pipeline
-    pipe = Pipeline(sd, mode=mode, device=dev, depth=max(args.depth, 1))
+    pipe = Pipeline(sd, mode=mode, device=dev, depth=args.depth if args.depth > 0 else (4 if mode == 'S' else 3))
     eng = pipe.lanes[0]
     # distinct samples per rank (different seeds per rank: replicas work on different data): 2 x B samples = two
     # batches whose feature maps (2 x B x 17.3 MB) exceed the 126 MB L2 for B >= 4

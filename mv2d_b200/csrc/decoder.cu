@@ -19,7 +19,7 @@
 
 namespace mv2d {
 
-__global__ void __launch_bounds__(256) ln_kernel(LnArgs a) {
+__global__ void __launch_bounds__(256, 3) ln_kernel(LnArgs a) {      // 3 CTAs per SM: the 300 CTAs of a batch of 8 are one wave (296 slots at 2)
     pdl_wait();
     pdl_trigger();
     ln_body(a, blockIdx.x);
@@ -303,7 +303,7 @@ template <int QT> struct SbCfg {
 
 // QT = 64 queries per CTA for batches; QT = 32 when the 64-query grid would leave most SMs idle (one sample)
 template <int QT>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, QT == 32 ? 3 : 2)
 self_attn_blk_kernel(const float* __restrict__ qkv, const uint8_t* __restrict__ mask, int N, float* __restrict__ out,
                      int rows_per_sample, const int* __restrict__ n_real, float* __restrict__ out_lo) {
     using Cf = SbCfg<QT>;
@@ -796,13 +796,8 @@ __global__ void __launch_bounds__(XR_UNITS_THREADS) xr_units_kernel(const int* _
 
 __device__ __forceinline__ uint32_t xr_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-// Packed fp32 pairs (sm_100a: fma.rn.f32x2 issues two IEEE fp32 FMAs per instruction).  The two inner loops of
-// xa_roi_kernel are bound by instruction issue, not by the FMA pipe: pairing the channels halves their FMA count.
-typedef unsigned long long f32x2;
-__device__ __forceinline__ f32x2 pack2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
-__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
-__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+// The two inner loops of xa_roi_kernel are bound by instruction issue, not by the FMA pipe: pairing the channels (f32x2,
+// common.cuh) halves their FMA count.
 
 // one (query n, match slot) unit; `phase` = parity of this use of the CTA's mbarrier
 __device__ __forceinline__ void xr_unit(const XrArgs& a, int n, int slot, int cnt, uint32_t phase, unsigned char* xr_smem) {
@@ -1527,9 +1522,10 @@ int run_decoder(const Mv2dDecoderParams& p, cudaStream_t st) {
                 const int rps = p.batch > 0 ? p.rows_per_sample : 0;
                 const uint8_t* am = p.batch > 0 ? nullptr : p.self_attn_mask;
                 // 64 queries per CTA halve the K / V staging per query, 32 give twice the CTAs: take the variant with the
-                // smaller (waves x work per CTA); two CTAs fit an SM (93 KB of shared memory, 127 registers)
+                // smaller (waves x work per CTA); two 64-query CTAs fit an SM (93 KB of shared memory, 127 registers), three
+                // 32-query ones (69 KB, 79 registers)
                 const int c64 = cdiv(rows, 64) * MV2D_HEADS * nb, c32 = cdiv(rows, 32) * MV2D_HEADS * nb;
-                if (cdiv(c64, 296) * 64 <= cdiv(c32, 296) * 32)
+                if (cdiv(c64, 296) * 64 <= cdiv(c32, 444) * 32)
                     launch_k(self_attn_blk_kernel<64>, dim3(cdiv(rows, 64), MV2D_HEADS, nb), dim3(256), (size_t)SbCfg<64>::SMEM_BYTES, st,
                              (const float*)qkv, am, N, sa, rps, p.n_real, sa_split ? sa_lo : (float*)nullptr);
                 else

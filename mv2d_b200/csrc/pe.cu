@@ -63,41 +63,83 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, float* __restr
     }
 }
 
+// C = 256 (the hot path's feature maps): one CTA moves 64 pixels x all 256 channels, so it writes 64 KB of consecutive
+// channels-last rows (the 32 x 32 tiles above write 128-byte pieces of 1 KB rows from four different CTAs) and reads
+// 256-byte runs of every channel plane.
+constexpr int NHWC_PT = 64;
+constexpr int NHWC_SMEM = 256 * (NHWC_PT + 1) * 4;
+__global__ void __launch_bounds__(256)
+nchw_to_nhwc_c256_kernel(const float* __restrict__ in, float* __restrict__ out, float* __restrict__ out_tf32, int HW,
+                         const float* __restrict__ in2) {
+    pdl_wait();
+    pdl_trigger();
+    extern __shared__ float nh_tile[];          // [256][65]
+    const int v = blockIdx.y, p0 = blockIdx.x * NHWC_PT;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float* src = in + (long long)v * 256 * HW + p0;
+    const float* src2 = in2 ? in2 + (long long)v * 256 * HW + p0 : nullptr;
+    const bool ok0 = p0 + lane < HW, ok1 = p0 + 32 + lane < HW;
+#pragma unroll 8
+    for (int c = warp; c < 256; c += 8) {
+        float a = ok0 ? __ldg(src + (long long)c * HW + lane) : 0.f;
+        float b = ok1 ? __ldg(src + (long long)c * HW + 32 + lane) : 0.f;
+        if (src2) {
+            if (ok0) a += __ldg(src2 + (long long)c * HW + lane);
+            if (ok1) b += __ldg(src2 + (long long)c * HW + 32 + lane);
+        }
+        nh_tile[c * (NHWC_PT + 1) + lane] = a;
+        nh_tile[c * (NHWC_PT + 1) + 32 + lane] = b;
+    }
+    __syncthreads();
+    for (int p = warp; p < NHWC_PT; p += 8) {
+        if (p0 + p >= HW) break;
+        const long long o = ((long long)v * HW + p0 + p) * 256;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float val = nh_tile[(k * 32 + lane) * (NHWC_PT + 1) + p];
+            out[o + k * 32 + lane] = val;
+            if (out_tf32) out_tf32[o + k * 32 + lane] = round_tf32(val);
+        }
+    }
+}
+
 // ---- frustum coordinates -> [P, 3*D] (pe.py:93-130).  fp64 geometry as in the reference.
 // thread = (pixel, depth); 3 consecutive floats per thread => a warp writes 384 contiguous bytes.
 __global__ void pe_coords_kernel(const double* __restrict__ img2lidar, float* __restrict__ out,
                                  int V, int h, int w, int D, double pad_h, double pad_w,
                                  double depth_start, double pr0, double pr1, double pr2,
-                                 double pr3, double pr4, double pr5, int tf32) {
+                                 double bin, double ir0, double ir1, double ir2, int tf32) {
+    // bin = (pr3 - depth_start) / (D (1 + D)) and ir = 1 / (hi - lo) come from the host: fp64 divisions are ~40-instruction
+    // sequences and were most of this kernel
     pdl_wait();
     pdl_trigger();
-    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long total = (long long)V * h * w * D;
+    // 32-bit index arithmetic (the launchers check V h w D < 2^31): 64-bit divisions are long instruction sequences too
+    const unsigned gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned total = (unsigned)V * h * w * D;
     if (gid >= total) return;
-    const int d = (int)(gid % D);
-    const long long p = gid / D;
-    const int x = (int)(p % w), y = (int)((p / w) % h), v = (int)(p / ((long long)w * h));
-    const double cw = ((double)x + 0.5) * pad_w / (double)w - 0.5;
-    const double ch = ((double)y + 0.5) * pad_h / (double)h - 0.5;
-    const double bin = (pr3 - depth_start) / ((double)D * (1.0 + (double)D));
+    const unsigned d = gid % (unsigned)D;
+    const unsigned p = gid / (unsigned)D;
+    const unsigned x = p % (unsigned)w, y = (p / (unsigned)w) % (unsigned)h, v = p / ((unsigned)w * h);
+    const double cw = ((double)x + 0.5) * pad_w - 0.5;        // pad_w, pad_h: already divided by w, h on the host
+    const double ch = ((double)y + 0.5) * pad_h - 0.5;
     const double cd = depth_start + bin * (double)d * ((double)d + 1.0);
     const double s = fmax(cd, 1e-3);
     const double c0 = cw * s, c1 = ch * s;
     const double* m = img2lidar + v * 16;
-    const double lo[3] = {pr0, pr1, pr2}, hi[3] = {pr3, pr4, pr5};
+    const double lo[3] = {pr0, pr1, pr2}, ir[3] = {ir0, ir1, ir2};
     float r[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
         // the frustum point and its normalisation in fp64 as the reference; the logit itself in fp32: the value is
         // rounded to TF32 (2^-11) right below because it feeds a TF32 tensor-core GEMM, fp32 log error (2^-23) is noise
         double c = m[i * 4 + 0] * c0 + m[i * 4 + 1] * c1 + m[i * 4 + 2] * cd + m[i * 4 + 3];
-        c = (c - lo[i]) / (hi[i] - lo[i]);
+        c = (c - lo[i]) * ir[i];
         const float cf = (float)fmin(fmax(c, 0.0), 1.0);
         const float num = fmaxf(cf, 1e-5f), den = fmaxf((float)(1.0 - fmin(fmax(c, 0.0), 1.0)), 1e-5f);
         const float lg = logf(num / den);                  // inverse_sigmoid
         r[i] = tf32 ? round_tf32(lg) : lg;                 // inference: operand of a TF32 GEMM; training keeps fp32
     }
-    float* o = out + p * (3 * D) + d * 3;
+    float* o = out + (size_t)p * (3 * D) + d * 3;
     o[0] = r[0]; o[1] = r[1]; o[2] = r[2];
 }
 
@@ -271,6 +313,18 @@ int run_geom_prep(const double* lidar2img, int V, double* img2lidar, double* tra
 
 int run_nchw_to_nhwc(const float* in, float* out, float* out_tf32, int V, int C, int HW, cudaStream_t st, const float* in2) {
     MV2D_CHECK_ARG(V <= 65535, "nchw_to_nhwc: at most 65535 maps per call (got %d)", V);
+    static const bool wide = []() { const char* e = getenv("MV2D_NHWC_WIDE"); return !(e && e[0] == '0'); }();
+    if (C == 256 && wide) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaError_t e = cudaFuncSetAttribute(nchw_to_nhwc_c256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NHWC_SMEM);
+            if (e != cudaSuccess) { set_error("nchw_to_nhwc: smem attr: %s", cudaGetErrorString(e)); return (int)e; }
+            attr_set = true;
+        }
+        launch_k(nchw_to_nhwc_c256_kernel, dim3(cdiv(HW, NHWC_PT), V), dim3(256), (size_t)NHWC_SMEM, st, in, out, out_tf32, HW, in2);
+        MV2D_CHECK_LAUNCH("nchw_to_nhwc");
+        return 0;
+    }
     dim3 grid(cdiv(HW, 32), cdiv(C, 32), V), block(32, 8);
     launch_k(nchw_to_nhwc_kernel, grid, block, 0, st, in, out, out_tf32, C, HW, in2);
     MV2D_CHECK_LAUNCH("nchw_to_nhwc");
@@ -305,10 +359,14 @@ int run_pe3d(const Mv2dPeParams& p, cudaStream_t st) {
     MV2D_CHECK_ARG(p.phase == 0 || !p.sine_branch_cached, "pe3d: phases cannot be combined with a cached sine branch");
     if (p.phase != 2) {
         long long total = (long long)P * D;
+        MV2D_CHECK_ARG(total < (1LL << 31), "pe3d: V h w D = %lld must be below 2^31", total);
         launch_k(pe_coords_kernel, dim3((unsigned)cdiv((int)total, 256)), dim3(256), 0, st, 
-            p.img2lidar, A1, p.V, p.h, p.w, D, (double)p.pad_h, (double)p.pad_w, p.depth_start,
-            p.position_range[0], p.position_range[1], p.position_range[2], p.position_range[3],
-            p.position_range[4], p.position_range[5], 1);
+            p.img2lidar, A1, p.V, p.h, p.w, D, (double)p.pad_h / (double)p.h, (double)p.pad_w / (double)p.w, (double)p.depth_start,
+            (double)p.position_range[0], (double)p.position_range[1], (double)p.position_range[2],
+            ((double)p.position_range[3] - (double)p.depth_start) / ((double)D * (1.0 + (double)D)),
+            1.0 / ((double)p.position_range[3] - (double)p.position_range[0]),
+            1.0 / ((double)p.position_range[4] - (double)p.position_range[1]),
+            1.0 / ((double)p.position_range[5] - (double)p.position_range[2]), 1);
         MV2D_CHECK_LAUNCH("pe_coords");
     }
     // Fused MLPs (mlp2.cu): the 1024-wide hidden activations of the two branches and the SE gate's hidden stay in
@@ -401,8 +459,11 @@ int run_pe_train_inputs(int V, int h, int w, int D, int pad_h, int pad_w, int st
     const int P = V * h * w;
     MV2D_CHECK_ARG(V >= 1 && V <= MV2D_MAXV && P > 0 && D > 0, "pe_train_inputs: bad V/h/w/D");
     const long long total = (long long)P * D;
-    launch_k(pe_coords_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, img2lidar, coords, V, h, w, D, (double)pad_h,
-             (double)pad_w, depth_start, pr[0], pr[1], pr[2], pr[3], pr[4], pr[5], 0);
+    MV2D_CHECK_ARG(total < (1LL << 31), "pe_train_inputs: V h w D = %lld must be below 2^31", total);
+    launch_k(pe_coords_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, img2lidar, coords, V, h, w, D, (double)pad_h / (double)h,
+             (double)pad_w / (double)w, (double)depth_start, (double)pr[0], (double)pr[1], (double)pr[2],
+             ((double)pr[3] - (double)depth_start) / ((double)D * (1.0 + (double)D)), 1.0 / ((double)pr[3] - (double)pr[0]),
+             1.0 / ((double)pr[4] - (double)pr[1]), 1.0 / ((double)pr[5] - (double)pr[2]), 0);
     MV2D_CHECK_LAUNCH("pe_coords(train)");
     float* emb = sine + (size_t)P * 384;     // the caller's `sine` buffer holds [P,384] + 3 P floats for the embeds
     launch_k(sine_prep_kernel, dim3(cdiv(P, 128)), dim3(128), 0, st, not_mask, emb, V, h, w, (float)stride, 6.283185307179586f, 1e-6f, V);

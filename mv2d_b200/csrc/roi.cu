@@ -34,9 +34,11 @@ roi_align_tokens_kernel(const float* __restrict__ rois, const float* __restrict_
     const float bw = rw / (float)MV2D_ROI, bh = rh / (float)MV2D_ROI;
     const int gh = (int)ceilf(rh / (float)MV2D_ROI), gw = (int)ceilf(rw / (float)MV2D_ROI);
     const float count = (float)max(gh * gw, 1);
-    const float4* f4 = feat ? reinterpret_cast<const float4*>(feat) + (long long)v * h * w * 64 + threadIdx.x : nullptr;
-    const float4* p4 = pe ? reinterpret_cast<const float4*>(pe) + (long long)v * h * w * 64 + threadIdx.x : nullptr;
-    float4 af = make_float4(0.f, 0.f, 0.f, 0.f), ap = af;
+    // channel pairs as packed f32x2 (the kernel is bound by instruction issue: 4 corners x 4 channels x 2 maps per sample
+    // point; roi.cu is compiled with -fmad=false for the box geometry, so these FMAs are spelled out)
+    const ulonglong2* f4 = feat ? reinterpret_cast<const ulonglong2*>(feat) + (long long)v * h * w * 64 + threadIdx.x : nullptr;
+    const ulonglong2* p4 = pe ? reinterpret_cast<const ulonglong2*>(pe) + (long long)v * h * w * 64 + threadIdx.x : nullptr;
+    f32x2 af0 = 0ull, af1 = 0ull, ap0 = 0ull, ap1 = 0ull;
     for (int iy = 0; iy < gh; ++iy) {
         float y = y1 + (float)ph * bh + ((float)iy + 0.5f) * bh / (float)gh;
         for (int ix = 0; ix < gw; ++ix) {
@@ -48,25 +50,28 @@ roi_align_tokens_kernel(const float* __restrict__ rois, const float* __restrict_
             if (xl >= w - 1) { xh = xl = w - 1; xx = (float)xl; } else xh = xl + 1;
             const float ly = yy - (float)yl, lx = xx - (float)xl, hy = 1.f - ly, hx = 1.f - lx;
             const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
+            const f32x2 q1 = pack2(w1, w1), q2 = pack2(w2, w2), q3 = pack2(w3, w3), q4 = pack2(w4, w4);
             const int o1 = (yl * w + xl) * 64, o2 = (yl * w + xh) * 64, o3 = (yh * w + xl) * 64,
                       o4 = (yh * w + xh) * 64;
-            float4 a, b, c, d;
             if (f4) {
-                a = __ldg(f4 + o1); b = __ldg(f4 + o2); c = __ldg(f4 + o3); d = __ldg(f4 + o4);
-                af.x += w1 * a.x + w2 * b.x + w3 * c.x + w4 * d.x;
-                af.y += w1 * a.y + w2 * b.y + w3 * c.y + w4 * d.y;
-                af.z += w1 * a.z + w2 * b.z + w3 * c.z + w4 * d.z;
-                af.w += w1 * a.w + w2 * b.w + w3 * c.w + w4 * d.w;
+                const ulonglong2 a = __ldg(f4 + o1), b = __ldg(f4 + o2), c = __ldg(f4 + o3), d = __ldg(f4 + o4);
+                af0 = fma2(q1, a.x, af0); af1 = fma2(q1, a.y, af1);
+                af0 = fma2(q2, b.x, af0); af1 = fma2(q2, b.y, af1);
+                af0 = fma2(q3, c.x, af0); af1 = fma2(q3, c.y, af1);
+                af0 = fma2(q4, d.x, af0); af1 = fma2(q4, d.y, af1);
             }
             if (p4) {
-                a = __ldg(p4 + o1); b = __ldg(p4 + o2); c = __ldg(p4 + o3); d = __ldg(p4 + o4);
-                ap.x += w1 * a.x + w2 * b.x + w3 * c.x + w4 * d.x;
-                ap.y += w1 * a.y + w2 * b.y + w3 * c.y + w4 * d.y;
-                ap.z += w1 * a.z + w2 * b.z + w3 * c.z + w4 * d.z;
-                ap.w += w1 * a.w + w2 * b.w + w3 * c.w + w4 * d.w;
+                const ulonglong2 a = __ldg(p4 + o1), b = __ldg(p4 + o2), c = __ldg(p4 + o3), d = __ldg(p4 + o4);
+                ap0 = fma2(q1, a.x, ap0); ap1 = fma2(q1, a.y, ap1);
+                ap0 = fma2(q2, b.x, ap0); ap1 = fma2(q2, b.y, ap1);
+                ap0 = fma2(q3, c.x, ap0); ap1 = fma2(q3, c.y, ap1);
+                ap0 = fma2(q4, d.x, ap0); ap1 = fma2(q4, d.y, ap1);
             }
         }
     }
+    float4 af, ap;
+    unpack2(af0, af.x, af.y); unpack2(af1, af.z, af.w);
+    unpack2(ap0, ap.x, ap.y); unpack2(ap1, ap.z, ap.w);
     const long long o = ((long long)n * MV2D_TOK + bin) * 64 + threadIdx.x;
     if (!f4) af = reinterpret_cast<const float4*>(tok_feat)[o];   // phase 2: pooled feature from phase 1
     else { af.x /= count; af.y /= count; af.z /= count; af.w /= count; }

@@ -573,7 +573,11 @@ class HotPath:
         else:
             _, _, h, w = feat_in.shape
             feat, feat_tf32 = self.to_nhwc(feat_in)
-        if self.overlap:
+        # A batch of the single-frame head runs the front end on ONE stream: PE first, then RoIAlign pools feat and
+        # feat + pe in one pass (phase 0) instead of a second pass over the RoIs after the join -- every kernel fills the
+        # GPU at B x 300 RoIs, so the fork buys nothing and the second pass costs 160 us per 8 samples
+        # (tools/batch_sweep.py --overlap 0/1: 2669 vs 2582 samples/s resident, 2578 vs 2529 end to end at B = 8 x 4 lanes)
+        if self.overlap and not (batch is not None and self.mode == 'S'):
             # fork: everything of the query generator that does not need the position embedding (RoIAlign
             # of the image feature, 3x3 conv, FC chain, reference points, query embedding) runs on a side
             # stream and the box correlation on a second one, concurrently with the position MLPs / SE gate /

@@ -17,6 +17,7 @@ def main():
     ap.add_argument('--mode', default='S')
     ap.add_argument('--steps', type=int, default=40)
     ap.add_argument('--grid', default='1x1,1x4,2x1,2x2,4x1,4x2,8x1,8x2')
+    ap.add_argument('--overlap', type=int, default=1, help='0: PE -> RoIAlign (feat and pe in one pass) -> box correlation on one stream')
     args = ap.parse_args()
     sd = synth.make_state_dict(0)
     case = synth.CASES['s_cfg2' if args.mode == 'S' else 't_cfg3']
@@ -24,7 +25,7 @@ def main():
     samples = [synth.case_inputs(dict(case, seed=i)) for i in range(n_var)]
     for cell in args.grid.split(','):
         B, depth = [int(x) for x in cell.split('x')]
-        pipe = Pipeline(sd, mode=args.mode, depth=depth)
+        pipe = Pipeline(sd, mode=args.mode, depth=depth, overlap=bool(args.overlap))
         batches = []
         for i in range(0, n_var, B):
             grp = [samples[(i + j) % n_var] for j in range(B)]
@@ -53,7 +54,7 @@ def main():
             ms = a.elapsed_time(b)
             res['e2e' if host else 'resident'] = dict(samples_per_s=args.steps * B / ms * 1e3, ms_per_sample=ms / (args.steps * B),
                                                      launches_per_sample=(pipe.launch_count() - l0) / (args.steps * B))
-        print(json.dumps(dict(mode=args.mode, batch=B, lanes=depth, **res)), flush=True)
+        print(json.dumps(dict(mode=args.mode, batch=B, lanes=depth, overlap=args.overlap, **res)), flush=True)
         del pipe
         torch.cuda.empty_cache()
 
