@@ -287,7 +287,7 @@ def main():
     two_frame = None
     if mode == 'S' and not args.no_two_frame:
         try:
-            two_frame = two_frame_section(sd, dev, world, rank, barrier, max(min(args.steps, 20), 4), W)
+            two_frame = two_frame_section(sd, dev, world, rank, barrier, max(min(args.steps, 40), 4), W)
         except Exception as e:
             two_frame = dict(error=f'{type(e).__name__}: {e}'[:400])
 
@@ -380,7 +380,7 @@ def main():
         dist.destroy_process_group()
 
 
-def two_frame_section(sd, dev, world, rank, barrier, steps, warmup, batch=2, depth=3):
+def two_frame_section(sd, dev, world, rank, barrier, steps, warmup, batch=2, depth=4):
     """Extra object `two_frame` -- BASELINE configs[2]: MV2D-T, 12 feature views, 300 queries, bs = 2 as a real batch (both
     samples in one kernel chain), `depth` batches in flight.  Same timing protocol as the headline."""
     import torch

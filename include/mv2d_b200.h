@@ -64,6 +64,9 @@ MV2D_API int mv2d_geom_prep_batch(const double* lidar2img, int batch, int V, dou
 /* NCHW [V,C,HW] -> NHWC [V,HW,C] (the FPN output layout -> this library's layout).
  * out_tf32 (nullable) receives a copy rounded to TF32 (operand of the single-pass tensor-core SE gate GEMM). */
 MV2D_API int mv2d_nchw_to_nhwc(const float* in, float* out, float* out_tf32, int V, int C, int HW, void* stream);
+/* the same, additionally writing out_lo = tf32(x - tf32(x)): with out_tf32 the hi / lo operand pair of a 3xTF32 GEMM over the map
+ * (two-frame head: the value rows of mv2d_kv_project), so no separate mv2d_split_tf32 pass over it is needed */
+MV2D_API int mv2d_nchw_to_nhwc_split(const float* in, float* out, float* out_tf32, float* out_lo, int V, int C, int HW, void* stream);
 /* the same with a second map added on the way: out = nhwc(in + in2)  (key = memory + key_pos of the dense interfaces) */
 MV2D_API int mv2d_nchw_add_to_nhwc(const float* in, const float* in2, float* out, int V, int C, int HW, void* stream);
 /* CrossAttentionBoxHead.position_embedding (bbox_heads/cross_attention_head.py:199-200):

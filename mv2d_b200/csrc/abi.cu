@@ -67,6 +67,11 @@ int mv2d_nchw_to_nhwc(const float* in, float* out, float* out_tf32, int V, int C
     return run_nchw_to_nhwc(in, out, out_tf32, V, C, HW, (cudaStream_t)stream);
 }
 
+int mv2d_nchw_to_nhwc_split(const float* in, float* out, float* out_tf32, float* out_lo, int V, int C, int HW, void* stream) {
+    MV2D_CHECK_ARG(in && out && out_tf32 && out_lo && V > 0 && C == MV2D_C && HW > 0, "nchw_to_nhwc_split: bad arguments (C must be 256)");
+    return run_nchw_to_nhwc(in, out, out_tf32, V, C, HW, (cudaStream_t)stream, nullptr, out_lo);
+}
+
 int mv2d_nchw_add_to_nhwc(const float* in, const float* in2, float* out, int V, int C, int HW, void* stream) {
     MV2D_CHECK_ARG(in && out && V > 0 && C > 0 && HW > 0, "nchw_add_to_nhwc: bad arguments");
     return run_nchw_to_nhwc(in, out, nullptr, V, C, HW, (cudaStream_t)stream, in2);

@@ -6,7 +6,8 @@
 namespace mv2d {
 
 int run_geom_prep(const double* lidar2img, int V, double* img2lidar, double* trans, cudaStream_t st, int batch = 1);
-int run_nchw_to_nhwc(const float* in, float* out, float* out_tf32, int V, int C, int HW, cudaStream_t st, const float* in2 = nullptr);
+int run_nchw_to_nhwc(const float* in, float* out, float* out_tf32, int V, int C, int HW, cudaStream_t st, const float* in2 = nullptr,
+                     float* out_lo = nullptr);
 int run_query_embedding(const float* ref, int N, const float* w_qe0, const float* b_qe0, const float* w_qe2, const float* b_qe2,
                         const float* dim_t, float* query_pos, float* workspace, cudaStream_t st);
 int run_pe3d(const Mv2dPeParams& p, cudaStream_t st);

@@ -70,7 +70,7 @@ constexpr int NHWC_PT = 64;
 constexpr int NHWC_SMEM = 256 * (NHWC_PT + 1) * 4;
 __global__ void __launch_bounds__(256)
 nchw_to_nhwc_c256_kernel(const float* __restrict__ in, float* __restrict__ out, float* __restrict__ out_tf32, int HW,
-                         const float* __restrict__ in2) {
+                         const float* __restrict__ in2, float* __restrict__ out_lo) {
     pdl_wait();
     pdl_trigger();
     extern __shared__ float nh_tile[];          // [256][65]
@@ -98,7 +98,11 @@ nchw_to_nhwc_c256_kernel(const float* __restrict__ in, float* __restrict__ out, 
         for (int k = 0; k < 8; ++k) {
             const float val = nh_tile[(k * 32 + lane) * (NHWC_PT + 1) + p];
             out[o + k * 32 + lane] = val;
-            if (out_tf32) out_tf32[o + k * 32 + lane] = round_tf32(val);
+            if (out_tf32) {
+                const float hi = round_tf32(val);
+                out_tf32[o + k * 32 + lane] = hi;
+                if (out_lo) out_lo[o + k * 32 + lane] = round_tf32(val - hi);
+            }
         }
     }
 }
@@ -311,17 +315,18 @@ int run_geom_prep(const double* lidar2img, int V, double* img2lidar, double* tra
     return 0;
 }
 
-int run_nchw_to_nhwc(const float* in, float* out, float* out_tf32, int V, int C, int HW, cudaStream_t st, const float* in2) {
+int run_nchw_to_nhwc(const float* in, float* out, float* out_tf32, int V, int C, int HW, cudaStream_t st, const float* in2, float* out_lo) {
+    MV2D_CHECK_ARG(out_lo == nullptr || (C == 256 && out_tf32 != nullptr), "nchw_to_nhwc: the lo half needs C = 256 and the TF32 copy");
     MV2D_CHECK_ARG(V <= 65535, "nchw_to_nhwc: at most 65535 maps per call (got %d)", V);
     static const bool wide = []() { const char* e = getenv("MV2D_NHWC_WIDE"); return !(e && e[0] == '0'); }();
-    if (C == 256 && wide) {
+    if (C == 256 && (wide || out_lo)) {
         static bool attr_set = false;
         if (!attr_set) {
             cudaError_t e = cudaFuncSetAttribute(nchw_to_nhwc_c256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NHWC_SMEM);
             if (e != cudaSuccess) { set_error("nchw_to_nhwc: smem attr: %s", cudaGetErrorString(e)); return (int)e; }
             attr_set = true;
         }
-        launch_k(nchw_to_nhwc_c256_kernel, dim3(cdiv(HW, NHWC_PT), V), dim3(256), (size_t)NHWC_SMEM, st, in, out, out_tf32, HW, in2);
+        launch_k(nchw_to_nhwc_c256_kernel, dim3(cdiv(HW, NHWC_PT), V), dim3(256), (size_t)NHWC_SMEM, st, in, out, out_tf32, HW, in2, out_lo);
         MV2D_CHECK_LAUNCH("nchw_to_nhwc");
         return 0;
     }

@@ -93,6 +93,7 @@ class HotPath:
         self._ev_hi0, self._ev_hi1 = torch.cuda.Event(), torch.cuda.Event()
         self._ev_pe = torch.cuda.Event()
         self._ev_kv = [torch.cuda.Event() for _ in range(self.L)]
+        self._mem_split = None        # (map pointer, hi, lo) when to_nhwc wrote the TF32 halves of the map beside it
         self._kv_row_live = None      # live-tile flags the last K/V projection honoured (pointer), None = projected everything
         self._side = torch.cuda.Stream(device=self.device)
         self._side2 = torch.cuda.Stream(device=self.device)
@@ -219,6 +220,15 @@ class HotPath:
         V, Cc, h, w = feat_nchw.shape
         out = self._get('feat_nhwc', (V, h, w, Cc))
         out_tf32 = self._get('feat_tf32', (V, h, w, Cc))
+        self._mem_split = None
+        if self.mode == 'T' and self.xa_form == 1 and Cc == 256:
+            # two-frame head: the value rows of the K/V projection are this map; its TF32 hi half is feat_tf32, the lo half
+            # comes out of the same pass (kv_project then skips its mv2d_split_tf32 over the map)
+            lo = self._get('mem_lo', (V * h * w, 256))
+            lib.check(self.lib.mv2d_nchw_to_nhwc_split(lib.ptr(feat_nchw), out.data_ptr(), out_tf32.data_ptr(), lo.data_ptr(), V, Cc,
+                                                       h * w, lib.stream_ptr()), 'mv2d_nchw_to_nhwc_split')
+            self._mem_split = (out.data_ptr(), out_tf32, lo)
+            return out, out_tf32
         lib.check(self.lib.mv2d_nchw_to_nhwc(lib.ptr(feat_nchw), out.data_ptr(), out_tf32.data_ptr(), V, Cc, h * w,
                                              lib.stream_ptr()), 'mv2d_nchw_to_nhwc')
         return out, out_tf32
@@ -448,9 +458,13 @@ class HotPath:
             p.kin_hi, p.mem_hi = kin_rows.data_ptr(), mem_rows.data_ptr()
         else:
             kin_hi, kin_lo = self._get('kin_hi', (R, 256)), self._get('kin_lo', (R, 256))
-            mem_hi, mem_lo = self._get('mem_hi', (R, 256)), self._get('mem_lo', (R, 256))
             lib.check(self.lib.mv2d_split_tf32(kin_rows.data_ptr(), kin_hi.data_ptr(), kin_lo.data_ptr(), n, st), 'mv2d_split_tf32')
-            lib.check(self.lib.mv2d_split_tf32(mem_rows.data_ptr(), mem_hi.data_ptr(), mem_lo.data_ptr(), n, st), 'mv2d_split_tf32')
+            ms = getattr(self, '_mem_split', None)
+            if ms is not None and ms[0] == mem_rows.data_ptr() and ms[2].shape[0] == R:
+                mem_hi, mem_lo = ms[1], ms[2]           # written by to_nhwc beside the map
+            else:
+                mem_hi, mem_lo = self._get('mem_hi', (R, 256)), self._get('mem_lo', (R, 256))
+                lib.check(self.lib.mv2d_split_tf32(mem_rows.data_ptr(), mem_hi.data_ptr(), mem_lo.data_ptr(), n, st), 'mv2d_split_tf32')
             p.kin_hi, p.kin_lo, p.mem_hi, p.mem_lo = kin_hi.data_ptr(), kin_lo.data_ptr(), mem_hi.data_ptr(), mem_lo.data_ptr()
         p.layers = self.w.layers_ptr()
         p.kp, p.vp = kp.data_ptr(), vp.data_ptr()
@@ -566,6 +580,7 @@ class HotPath:
         feat_tf32 = None
         if feat_is_nhwc:
             feat = feat_in
+            self._mem_split = None      # a map that did not come through to_nhwc has no lo half beside it
             _, h, w, _ = feat.shape
             own = self._buf.get('feat_nhwc')
             if own is not None and 'feat_tf32' in self._buf and feat.data_ptr() == own.data_ptr():

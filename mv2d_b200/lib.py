@@ -223,6 +223,7 @@ SYMBOLS = [
     ('mv2d_geom_prep', C.c_int, [c_f, C.c_int, c_f, c_f, c_f]),
     ('mv2d_geom_prep_batch', C.c_int, [c_f, C.c_int, C.c_int, c_f, c_f, c_f]),
     ('mv2d_nchw_to_nhwc', C.c_int, [c_f, c_f, c_f, C.c_int, C.c_int, C.c_int, c_f]),
+    ('mv2d_nchw_to_nhwc_split', C.c_int, [c_f, c_f, c_f, c_f, C.c_int, C.c_int, C.c_int, c_f]),
     ('mv2d_nchw_add_to_nhwc', C.c_int, [c_f, c_f, c_f, C.c_int, C.c_int, C.c_int, c_f]),
     ('mv2d_query_embedding', C.c_int, [c_f, C.c_int, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f]),
     ('mv2d_split_tf32', C.c_int, [c_f, c_f, c_f, C.c_longlong, c_f]),
