@@ -834,21 +834,35 @@ __device__ __forceinline__ void xr_unit(const XrArgs& a, int n, int slot, int cn
                 asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                              : "=r"(done) : "r"(xr_smem_u32(bar)), "r"(phase) : "memory");
         }
-        for (int j = warp; j < MV2D_TOK; j += NW) {
+        // two rows per trip (j and j + NW): the five dependent shuffle stages of the transpose-reduce of one row run under
+        // the FMAs / shuffles of the other (at 16 warps per SM the kernel is bound by exactly these dependent chains)
+        for (int j = warp; j < MV2D_TOK; j += 2 * NW) {
+            const bool two = j + NW < MV2D_TOK;
             const float* row = Ks + j * MV2D_C;
+            const float* rowb = Ks + (two ? j + NW : j) * MV2D_C;
             const ulonglong2 k0 = *reinterpret_cast<const ulonglong2*>(row + lane * 4);
             const ulonglong2 k1 = *reinterpret_cast<const ulonglong2*>(row + 128 + lane * 4);
-            float sv[8];
+            const ulonglong2 m0 = *reinterpret_cast<const ulonglong2*>(rowb + lane * 4);
+            const ulonglong2 m1 = *reinterpret_cast<const ulonglong2*>(rowb + 128 + lane * 4);
+            float sv[8], sw[8];
 #pragma unroll
             for (int h = 0; h < 8; ++h) {
-                f32x2 x = mul2(qv[h][0], k0.x);
-                x = fma2(qv[h][1], k0.y, x); x = fma2(qv[h][2], k1.x, x); x = fma2(qv[h][3], k1.y, x);
+                f32x2 x = mul2(qv[h][0], k0.x), y = mul2(qv[h][0], m0.x);
+                x = fma2(qv[h][1], k0.y, x); y = fma2(qv[h][1], m0.y, y);
+                x = fma2(qv[h][2], k1.x, x); y = fma2(qv[h][2], m1.x, y);
+                x = fma2(qv[h][3], k1.y, x); y = fma2(qv[h][3], m1.y, y);
                 float lo, hi;
                 unpack2(x, lo, hi);
                 sv[h] = lo + hi;
+                unpack2(y, lo, hi);
+                sw[h] = lo + hi;
             }
             reduce8(sv, lane);
-            if ((lane & 3) == 0) sc[j * 8 + (lane >> 2)] = sv[0];
+            reduce8(sw, lane);
+            if ((lane & 3) == 0) {
+                sc[j * 8 + (lane >> 2)] = sv[0];
+                if (two) sc[(j + NW) * 8 + (lane >> 2)] = sw[0];
+            }
         }
     }
     __syncthreads();
