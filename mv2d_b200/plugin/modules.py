@@ -8,6 +8,7 @@ import copy
 import numpy as np
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 from ..engine import HotPath
 from ..registry import (ATTENTION, BBOX_ASSIGNERS, BBOX_CODERS, BBOX_SAMPLERS, MATCH_COST, DETECTORS, HEADS, LOSSES, NECKS, POSITIONAL_ENCODING,
@@ -690,9 +691,20 @@ class FPN(nn.Module):
     def forward(self, inputs, engine):
         from ..pack import PackedNeck
         x = inputs[self.start_level] if isinstance(inputs, (list, tuple)) else inputs
-        if self._packed is None or self._packed[0] != x.device:
-            self._packed = (x.device, PackedNeck(self.state_dict(), x.device))
+        lat, out = self.lateral_convs[0].conv, self.fpn_convs[0].conv
+        if torch.is_grad_enabled() and (x.requires_grad or lat.weight.requires_grad or out.weight.requires_grad):
+            # training: the neck's backward is torch's -- two convolutions under autograd, so that
+            # d loss / d feat of the hot path reaches the neck's parameters and the backbone.  Channels-last VIEW of the
+            # NCHW result: ``.permute(0, 3, 1, 2)`` of it is the contiguous reference layout again.
+            y = F.conv2d(F.conv2d(x, lat.weight, lat.bias), out.weight, out.bias, padding=1)
+            return y.permute(0, 2, 3, 1), None
+        if self._packed is None or self._packed[0] != x.device or self._packed[2] != self._version_key():
+            self._packed = (x.device, PackedNeck(self.state_dict(), x.device), self._version_key())
         return engine.neck(x, self._packed[1])
+
+    def _version_key(self):
+        """Re-pack after an optimizer step changed the parameters in place."""
+        return tuple(int(p._version) for p in self.parameters())
 
 
 @DETECTORS.register_module()
@@ -715,7 +727,6 @@ class MV2D(nn.Module):
     def with_neck(self):
         return self.neck is not None
 
-    @torch.no_grad()
     def process_detector_feat(self, detector_feat):
         """detectors/mv2d.py:122-127.  Returns (feat, is_channels_last): with the neck the feature map comes out of
         mv2d_fpn_neck channels-last, which is what the roi_head's kernels read."""

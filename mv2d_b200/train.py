@@ -461,11 +461,31 @@ class HotPathTrainer(DecoderTrainer):
         """Accumulates every parameter gradient into the flat buffer; returns d loss / d feat as [V,256,h,w]."""
         if self.mode == 'T':
             return self._backward_t(bbox_avg_factor)
-        gin = super().backward(bbox_avg_factor)
-        p = self._fp
+        self.backward_decoder(bbox_avg_factor)
+        return self.backward_front()
+
+    # The single-frame backward in its two halves: the decoder half fills the decoder slice of the flat gradient buffer
+    # ([0, decoder_grad_end): 80 % of it) and is done before the front end starts, so a data-parallel step can all-reduce
+    # that slice while the front-end half (PE MLPs, RoIAlign, query generator: ~60 % of the backward) still runs.
+    @torch.no_grad()
+    def backward_decoder(self, bbox_avg_factor=None):
+        assert self.mode == 'S'
+        self._gin = super().backward(bbox_avg_factor)
+        return self._gin
+
+    @torch.no_grad()
+    def backward_front(self):
+        gin, p = self._gin, self._fp
         p.d_ref, p.d_tok_kin, p.d_tok_mem = (gin[k].data_ptr() for k in ('d_ref', 'd_tok_kin', 'd_tok_mem'))
         lib.check(self.lib.mv2d_front_train_backward(C.byref(p), lib.stream_ptr()), 'mv2d_front_train_backward')
         return dict(gin, d_feat=self._fout['d_feat'].permute(0, 3, 1, 2))
+
+    @property
+    def decoder_grad_end(self):
+        """End (in floats) of the decoder's slice of the flat buffers: every ``bbox_head.*`` tensor precedes the front end's."""
+        front = min(off for name, (off, n) in self.table.items() if not name.startswith('bbox_head.'))
+        assert all(off + n <= front for name, (off, n) in self.table.items() if name.startswith('bbox_head.'))
+        return front
 
 
 class TrainStep:
@@ -476,7 +496,7 @@ class TrainStep:
     the all-reduce.  lanes=1 is the plain sequential step.  Same results as running the samples one after the other
     up to fp32 summation order."""
 
-    def __init__(self, state_dict, device='cuda', lanes=2, sync_bbox_avg_factor=True, use_graphs=None, **kw):
+    def __init__(self, state_dict, device='cuda', lanes=2, sync_bbox_avg_factor=True, use_graphs=None, overlap_all_reduce=True, **kw):
         assert lanes >= 1
         self._sd, self._kw = state_dict, dict(kw)
         # CUDA-graph replay of every sample's forward and backward (single-frame head; keyed by the sample's shapes): the
@@ -493,6 +513,10 @@ class TrainStep:
         # True (the reference's objective, cross_attention_head.py:419-420): loss_bbox is divided by the mean positive count
         # over all samples of the GLOBAL batch; False: by each sample's own count (no collective before the backward)
         self.sync_bbox_avg_factor = sync_bbox_avg_factor
+        # the decoder slice of the gradient buffer is all-reduced under the front-end half of the backward (single-frame head)
+        self.overlap_all_reduce = overlap_all_reduce
+        self._comm = torch.cuda.Stream(device=self.main.device)
+        self._ev_dec = [torch.cuda.Event()]
         for _ in range(lanes - 1):
             self._add_lane()
         self.total = self.main.total
@@ -517,14 +541,17 @@ class TrainStep:
             lane.forward(st['feat'], boxes, metas, st['gt_boxes'], st['gt_labels'], uploaded=up)     # warm-up: sizes every buffer
             lane.backward(st['factor'])
             torch.cuda.synchronize()
-            gf, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            gf, gb, gb2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
             with torch.cuda.graph(gf):
                 out = lane.forward(st['feat'], boxes, metas, st['gt_boxes'], st['gt_labels'], uploaded=up)
             with torch.cuda.graph(gb, pool=gf.pool()):
-                lane.backward(st['factor'])
+                lane.backward_decoder(st['factor'])
+            with torch.cuda.graph(gb2, pool=gf.pool()):
+                lane.backward_front()
             lane.grads.copy_(keep_grads)         # warm-up and capture do not count
             torch.cuda.synchronize()
-            ent = dict(fwd=gf, bwd=gb, out=out, keep=(lane._p, lane._out, lane._keep, lane._fp, lane._fout, lane._fkeep), **st)
+            ent = dict(fwd=gf, bwd=gb, bwd_front=gb2, out=out,
+                       keep=(lane._p, lane._out, lane._keep, lane._fp, lane._fout, lane._fkeep, lane._gin), **st)
             self._graphs[key] = ent
             torch.cuda.current_stream().wait_stream(torch.cuda.default_stream(dev))
         ent['feat'].copy_(feat, non_blocking=True)
@@ -538,6 +565,7 @@ class TrainStep:
         t.params = self.main.params            # ONE set of weights; own gradients, workspaces, engine buffers
         self.lanes.append(t)
         self.streams.append(torch.cuda.Stream(device=self.main.device))
+        self._ev_dec.append(torch.cuda.Event())
 
     @torch.no_grad()
     def step(self, samples, lr=2e-4, weight_decay=0.01, world=1, optimize=True, max_grad_norm=None):
@@ -553,6 +581,7 @@ class TrainStep:
         for t in self.lanes:
             t.zero_grad()
         outs = []
+        split, dec_end = False, 0
         for s in self.streams:
             s.wait_stream(cur)
         if not self.sync_bbox_avg_factor:      # each sample normalised by its own count: forward + backward back to back
@@ -580,20 +609,51 @@ class TrainStep:
             factor = DecoderTrainer.global_bbox_avg_factor([o['num_pos'] for o in outs])
             for s in self.streams:
                 s.wait_stream(cur)
+            split = self.main.mode == 'S' and self.overlap_all_reduce
+            dec_end = self.main.decoder_grad_end if split else 0
             for i in range(len(samples)):
                 with torch.cuda.stream(self.streams[i]):
                     if self.use_graphs:
                         ents[i]['factor'].copy_(factor)
                         ents[i]['bwd'].replay()
+                    elif split:
+                        self.lanes[i].backward_decoder(factor)
                     else:
                         self.lanes[i].backward(factor)
+                    if split:
+                        self._ev_dec[i].record(self.streams[i])
+            if split:
+                # decoder gradients of every lane are complete: fold them and start their all-reduce (80 % of the bytes) on
+                # the communication stream while the lanes run the front-end half of the backward
+                with torch.cuda.stream(self._comm):
+                    for i in range(len(samples)):
+                        self._comm.wait_event(self._ev_dec[i])
+                    for t in self.lanes[1:len(samples)]:
+                        self.main.grads[:dec_end].add_(t.grads[:dec_end])
+                    all_reduce_sum(self.main.grads[:dec_end])
+                for i in range(len(samples)):
+                    with torch.cuda.stream(self.streams[i]):
+                        if self.use_graphs:
+                            ents[i]['bwd_front'].replay()
+                        else:
+                            self.lanes[i].backward_front()
+            elif self.use_graphs:
+                for i in range(len(samples)):
+                    with torch.cuda.stream(self.streams[i]):
+                        ents[i]['bwd_front'].replay()
         for s in self.streams:
             cur.wait_stream(s)
-        for t in self.lanes[1:]:
-            self.main.grads.add_(t.grads)
         if self.sync_bbox_avg_factor:
             ev[1].record(cur)
-        nranks = self.main.all_reduce_grads()
+        if self.sync_bbox_avg_factor and split:
+            for t in self.lanes[1:len(samples)]:
+                self.main.grads[dec_end:].add_(t.grads[dec_end:])
+            nranks = all_reduce_sum(self.main.grads[dec_end:])
+            cur.wait_stream(self._comm)
+        else:
+            for t in self.lanes[1:]:
+                self.main.grads.add_(t.grads)
+            nranks = self.main.all_reduce_grads()
         if self.sync_bbox_avg_factor:
             ev[2].record(cur)
         assert world in (1, nranks), f'world={world} but the process group has {nranks} ranks'

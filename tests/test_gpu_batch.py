@@ -16,6 +16,7 @@ pytestmark = pytest.mark.gpu
 GROUPS = {
     's2': ['s_small', 's_cfg2'],                          # ragged: 27 and 300 queries, an empty view
     's4': ['s_cfg2', 's_small', 's_small', 's_cfg2'],
+    's8': ['s_cfg2', 's_small', 's_cfg2', 's_cfg2', 's_small', 's_cfg2', 's_cfg2', 's_cfg2'],     # the benched batch size: 8 x <= 300 queries (persistent GEMMs, one-stream front end)
     's3_masks': ['s_empty', 's_pad', 's_one'],            # zero detections, padded images (general sine branch), one query
     's2_pad': ['s_pad', 's_pad'],                         # identical padding masks: shared sine branch on the general path
     't2': ['t_small', 't_cfg3'],                          # BASELINE configs[2]: the two-frame head at bs = 2

@@ -6,6 +6,7 @@ import os
 import numpy as np
 import pytest
 import torch
+import torch.nn.functional as F
 
 from conftest import ROOT, golden_path
 from mv2d_b200 import synth
@@ -310,6 +311,57 @@ def test_detector_forward_train_shell(state_dicts):
         h.eval()
     assert 'det_loss_rpn' in losses and all(f'l{i}.loss_cls' in losses and f'l{i}.loss_bbox' in losses for i in range(6))
     assert all(torch.isfinite(v).all() for v in losses.values())
+
+
+def test_detector_shell_trains_through_the_neck(state_dicts):
+    """With the one-level FPN neck in front (configs/mv2d/exp/*.py:32-39) MV2D.forward_train keeps the autograd chain:
+    d loss / d feat of the CUDA backward flows through the neck (two torch convolutions in training mode) into the neck's
+    parameters and the backbone's feature map; in eval mode the same module runs mv2d_fpn_neck and agrees with it."""
+    from mv2d_b200.plugin.modules import MV2D, FPN
+    spec = synth.CASES['s_small']
+    h = head('S', state_dicts)
+    feat, boxes, metas = synth.case_inputs(spec)
+    gt_boxes, gt_labels, _ = synth.make_dn_inputs(dict(num_gt=6, seed=5))
+    torch.manual_seed(3)
+    neck = FPN([256], 256, 1).cuda()
+    with torch.no_grad():
+        for prm in neck.parameters():
+            prm.mul_(0.5)
+    det = MV2D.__new__(MV2D)
+    torch.nn.Module.__init__(det)
+    det.roi_head, det.neck, det.base_detector = h, neck, None
+    det.train_cfg = dict(detection_proposal=dict(min_bbox_size=8), complement_2d_gt=0.4)
+    det.test_cfg = None
+    V = len(metas)
+    x = feat.cuda().clone().requires_grad_(True)            # the backbone's P4 map
+    with torch.no_grad():
+        cl_eval, _ = det.process_detector_feat(x)           # eval path: mv2d_fpn_neck
+    cl_train, _ = det.process_detector_feat(x)              # training path: autograd
+    assert cl_train.requires_grad
+    assert torch.allclose(cl_train.detach(), cl_eval, atol=1e-3, rtol=1e-3)
+    img = torch.zeros(1, V, 3, 8, 8, device='cuda')
+    meta = {k: [m[k] for m in metas] for k in metas[0] if k != 'num_views'}
+    gt2d = [[b[:2, :4].cuda() for b in boxes]]
+    gl2d = [[b[:2, 5].long().cuda() for b in boxes]]
+    to3d = [[torch.tensor([v % 6, -1]) for v in range(V)]]
+    h.train()
+    try:
+        losses = det.forward_train(img, [meta], gt2d, gl2d, to3d, [gt_boxes.cuda()], [gt_labels.cuda()],
+                                   detector_out=(x, [b.cuda() for b in boxes], None))
+        sum(v.sum() for v in losses.values()).backward()
+    finally:
+        h.eval()
+    for name, prm in neck.named_parameters():
+        assert prm.grad is not None and torch.isfinite(prm.grad).all() and prm.grad.abs().max() > 0, name
+    assert x.grad is not None and torch.isfinite(x.grad).all() and x.grad.abs().max() > 0
+    # after an in-place parameter update the eval path re-packs the neck weights
+    with torch.no_grad():
+        for prm in neck.parameters():
+            prm.add_(0.01)
+        cl2, _ = det.process_detector_feat(x)
+        ref = F.conv2d(F.conv2d(x, neck.lateral_convs[0].conv.weight, neck.lateral_convs[0].conv.bias),
+                       neck.fpn_convs[0].conv.weight, neck.fpn_convs[0].conv.bias, padding=1).permute(0, 2, 3, 1)
+    assert torch.allclose(cl2, ref, atol=1e-3, rtol=1e-3)
 
 
 def test_two_frame_head_forward_train_runs_the_backward(state_dicts, monkeypatch):

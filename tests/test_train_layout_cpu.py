@@ -62,3 +62,13 @@ def test_clip_grad_norm_matches_torch_on_the_flat_buffer():
         assert abs(float(got) - exact) <= 1e-6 * exact and abs(float(want) - exact) <= 5e-4 * exact
         for k, p_ in zip(tr.table, params):
             assert torch.allclose(tr.grad(k), p_.grad, rtol=1e-3, atol=1e-8), k
+
+
+def test_decoder_tensors_form_the_leading_slice_of_the_flat_buffers():
+    """TrainStep all-reduces the decoder's gradient slice while the front-end half of the backward still runs: every
+    ``bbox_head.*`` tensor has to end before the first front-end tensor starts."""
+    from mv2d_b200.train import param_table
+    table, total = param_table(6)
+    front = min(off for name, (off, n) in table.items() if not name.startswith('bbox_head.'))
+    assert all(off + n <= front for name, (off, n) in table.items() if name.startswith('bbox_head.'))
+    assert 0 < front < total and front % 16 == 0
