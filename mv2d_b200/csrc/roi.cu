@@ -13,10 +13,13 @@ namespace mv2d {
 
 // ------------------------------------------------------------------------------------------
 // RoIAlign (avg, aligned=True, adaptive sampling grid) on channels-last maps.
-// grid (49, N), 64 threads: thread = one float4 of the 256 channels => a warp reads 512
-// contiguous bytes per bilinear corner.  Writes tok_feat and (optionally) tok_kin = feat + pe
-// tokens (RoIAlign is linear, so pooling feat+pe equals pooling them separately).
-__global__ void __launch_bounds__(64)
+// grid (N, 1 or 4), 256 threads: one CTA per RoI (four for a single sample's few hundred RoIs), warp = bins {w, w + 8, ..}, lane = eight channels {4 lane .. 4 lane + 3,
+// 128 + 4 lane .. + 3} => a warp reads two 512-byte runs per bilinear corner and the per-point geometry (the larger part of
+// the instruction stream: the kernel is bound by instruction issue) is shared by eight channels instead of four.
+// Writes tok_feat and (optionally) tok_kin = feat + pe tokens (RoIAlign is linear, so pooling feat+pe equals pooling them
+// separately) and the TF32 hi / lo split of tok_feat.
+// Channel pairs as packed f32x2; roi.cu is compiled with -fmad=false for the box geometry, so these FMAs are spelled out.
+__global__ void __launch_bounds__(256)
 roi_align_tokens_kernel(const float* __restrict__ rois, const float* __restrict__ feat,
                         const float* __restrict__ pe, int h, int w, float spatial_scale,
                         float* __restrict__ tok_feat, float* __restrict__ tok_kin,
@@ -24,8 +27,7 @@ roi_align_tokens_kernel(const float* __restrict__ rois, const float* __restrict_
     // feat == nullptr: second phase -- pool only pe and add the already pooled tok_feat (tok_kin = tok_feat + pool(pe))
     pdl_wait();
     pdl_trigger();
-    const int n = blockIdx.y, bin = blockIdx.x;
-    const int ph = bin / MV2D_ROI, pw = bin % MV2D_ROI;
+    const int n = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float* r = rois + n * 5;
     const int v = (int)r[0];
     const float x1 = r[1] * spatial_scale - 0.5f, y1 = r[2] * spatial_scale - 0.5f;
@@ -34,57 +36,64 @@ roi_align_tokens_kernel(const float* __restrict__ rois, const float* __restrict_
     const float bw = rw / (float)MV2D_ROI, bh = rh / (float)MV2D_ROI;
     const int gh = (int)ceilf(rh / (float)MV2D_ROI), gw = (int)ceilf(rw / (float)MV2D_ROI);
     const float count = (float)max(gh * gw, 1);
-    // channel pairs as packed f32x2 (the kernel is bound by instruction issue: 4 corners x 4 channels x 2 maps per sample
-    // point; roi.cu is compiled with -fmad=false for the box geometry, so these FMAs are spelled out)
-    const ulonglong2* f4 = feat ? reinterpret_cast<const ulonglong2*>(feat) + (long long)v * h * w * 64 + threadIdx.x : nullptr;
-    const ulonglong2* p4 = pe ? reinterpret_cast<const ulonglong2*>(pe) + (long long)v * h * w * 64 + threadIdx.x : nullptr;
-    f32x2 af0 = 0ull, af1 = 0ull, ap0 = 0ull, ap1 = 0ull;
-    for (int iy = 0; iy < gh; ++iy) {
-        float y = y1 + (float)ph * bh + ((float)iy + 0.5f) * bh / (float)gh;
-        for (int ix = 0; ix < gw; ++ix) {
-            float x = x1 + (float)pw * bw + ((float)ix + 0.5f) * bw / (float)gw;
-            if (y < -1.f || y > (float)h || x < -1.f || x > (float)w) continue;
-            float yy = fmaxf(y, 0.f), xx = fmaxf(x, 0.f);
-            int yl = (int)yy, xl = (int)xx, yh, xh;
-            if (yl >= h - 1) { yh = yl = h - 1; yy = (float)yl; } else yh = yl + 1;
-            if (xl >= w - 1) { xh = xl = w - 1; xx = (float)xl; } else xh = xl + 1;
-            const float ly = yy - (float)yl, lx = xx - (float)xl, hy = 1.f - ly, hx = 1.f - lx;
-            const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
-            const f32x2 q1 = pack2(w1, w1), q2 = pack2(w2, w2), q3 = pack2(w3, w3), q4 = pack2(w4, w4);
-            const int o1 = (yl * w + xl) * 64, o2 = (yl * w + xh) * 64, o3 = (yh * w + xl) * 64,
-                      o4 = (yh * w + xh) * 64;
-            if (f4) {
-                const ulonglong2 a = __ldg(f4 + o1), b = __ldg(f4 + o2), c = __ldg(f4 + o3), d = __ldg(f4 + o4);
-                af0 = fma2(q1, a.x, af0); af1 = fma2(q1, a.y, af1);
-                af0 = fma2(q2, b.x, af0); af1 = fma2(q2, b.y, af1);
-                af0 = fma2(q3, c.x, af0); af1 = fma2(q3, c.y, af1);
-                af0 = fma2(q4, d.x, af0); af1 = fma2(q4, d.y, af1);
-            }
-            if (p4) {
-                const ulonglong2 a = __ldg(p4 + o1), b = __ldg(p4 + o2), c = __ldg(p4 + o3), d = __ldg(p4 + o4);
-                ap0 = fma2(q1, a.x, ap0); ap1 = fma2(q1, a.y, ap1);
-                ap0 = fma2(q2, b.x, ap0); ap1 = fma2(q2, b.y, ap1);
-                ap0 = fma2(q3, c.x, ap0); ap1 = fma2(q3, c.y, ap1);
-                ap0 = fma2(q4, d.x, ap0); ap1 = fma2(q4, d.y, ap1);
+    const ulonglong2* f4 = feat ? reinterpret_cast<const ulonglong2*>(feat) + (long long)v * h * w * 64 + lane : nullptr;
+    const ulonglong2* p4 = pe ? reinterpret_cast<const ulonglong2*>(pe) + (long long)v * h * w * 64 + lane : nullptr;
+    for (int bin = blockIdx.y * 8 + warp; bin < MV2D_TOK; bin += 8 * gridDim.y) {     // gridDim.y > 1: few RoIs (one sample)
+        const int ph = bin / MV2D_ROI, pw = bin % MV2D_ROI;
+        f32x2 af0 = 0ull, af1 = 0ull, af2 = 0ull, af3 = 0ull, ap0 = 0ull, ap1 = 0ull, ap2 = 0ull, ap3 = 0ull;
+        for (int iy = 0; iy < gh; ++iy) {
+            float y = y1 + (float)ph * bh + ((float)iy + 0.5f) * bh / (float)gh;
+            for (int ix = 0; ix < gw; ++ix) {
+                float x = x1 + (float)pw * bw + ((float)ix + 0.5f) * bw / (float)gw;
+                if (y < -1.f || y > (float)h || x < -1.f || x > (float)w) continue;
+                float yy = fmaxf(y, 0.f), xx = fmaxf(x, 0.f);
+                int yl = (int)yy, xl = (int)xx, yh, xh;
+                if (yl >= h - 1) { yh = yl = h - 1; yy = (float)yl; } else yh = yl + 1;
+                if (xl >= w - 1) { xh = xl = w - 1; xx = (float)xl; } else xh = xl + 1;
+                const float ly = yy - (float)yl, lx = xx - (float)xl, hy = 1.f - ly, hx = 1.f - lx;
+                const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
+                const f32x2 q1 = pack2(w1, w1), q2 = pack2(w2, w2), q3 = pack2(w3, w3), q4 = pack2(w4, w4);
+                const int o1 = (yl * w + xl) * 64, o2 = (yl * w + xh) * 64, o3 = (yh * w + xl) * 64,
+                          o4 = (yh * w + xh) * 64;
+                if (f4) {
+                    const ulonglong2 a = __ldg(f4 + o1), b = __ldg(f4 + o2), c = __ldg(f4 + o3), d = __ldg(f4 + o4);
+                    const ulonglong2 a2 = __ldg(f4 + o1 + 32), b2 = __ldg(f4 + o2 + 32), c2 = __ldg(f4 + o3 + 32), d2 = __ldg(f4 + o4 + 32);
+                    af0 = fma2(q1, a.x, af0); af1 = fma2(q1, a.y, af1); af2 = fma2(q1, a2.x, af2); af3 = fma2(q1, a2.y, af3);
+                    af0 = fma2(q2, b.x, af0); af1 = fma2(q2, b.y, af1); af2 = fma2(q2, b2.x, af2); af3 = fma2(q2, b2.y, af3);
+                    af0 = fma2(q3, c.x, af0); af1 = fma2(q3, c.y, af1); af2 = fma2(q3, c2.x, af2); af3 = fma2(q3, c2.y, af3);
+                    af0 = fma2(q4, d.x, af0); af1 = fma2(q4, d.y, af1); af2 = fma2(q4, d2.x, af2); af3 = fma2(q4, d2.y, af3);
+                }
+                if (p4) {
+                    const ulonglong2 a = __ldg(p4 + o1), b = __ldg(p4 + o2), c = __ldg(p4 + o3), d = __ldg(p4 + o4);
+                    const ulonglong2 a2 = __ldg(p4 + o1 + 32), b2 = __ldg(p4 + o2 + 32), c2 = __ldg(p4 + o3 + 32), d2 = __ldg(p4 + o4 + 32);
+                    ap0 = fma2(q1, a.x, ap0); ap1 = fma2(q1, a.y, ap1); ap2 = fma2(q1, a2.x, ap2); ap3 = fma2(q1, a2.y, ap3);
+                    ap0 = fma2(q2, b.x, ap0); ap1 = fma2(q2, b.y, ap1); ap2 = fma2(q2, b2.x, ap2); ap3 = fma2(q2, b2.y, ap3);
+                    ap0 = fma2(q3, c.x, ap0); ap1 = fma2(q3, c.y, ap1); ap2 = fma2(q3, c2.x, ap2); ap3 = fma2(q3, c2.y, ap3);
+                    ap0 = fma2(q4, d.x, ap0); ap1 = fma2(q4, d.y, ap1); ap2 = fma2(q4, d2.x, ap2); ap3 = fma2(q4, d2.y, ap3);
+                }
             }
         }
-    }
-    float4 af, ap;
-    unpack2(af0, af.x, af.y); unpack2(af1, af.z, af.w);
-    unpack2(ap0, ap.x, ap.y); unpack2(ap1, ap.z, ap.w);
-    const long long o = ((long long)n * MV2D_TOK + bin) * 64 + threadIdx.x;
-    if (!f4) af = reinterpret_cast<const float4*>(tok_feat)[o];   // phase 2: pooled feature from phase 1
-    else { af.x /= count; af.y /= count; af.z /= count; af.w /= count; }
-    if (f4) reinterpret_cast<float4*>(tok_feat)[o] = af;
-    if (f4) {   // TF32 hi/lo split of the pooled feature: operands of the 3xTF32 conv GEMM
-        float4 hi = make_float4(round_tf32(af.x), round_tf32(af.y), round_tf32(af.z), round_tf32(af.w));
-        reinterpret_cast<float4*>(tok_hi)[o] = hi;
-        reinterpret_cast<float4*>(tok_lo)[o] = make_float4(round_tf32(af.x - hi.x), round_tf32(af.y - hi.y),
-                                                          round_tf32(af.z - hi.z), round_tf32(af.w - hi.w));
-    }
-    if (tok_kin) {
-        ap.x /= count; ap.y /= count; ap.z /= count; ap.w /= count;
-        reinterpret_cast<float4*>(tok_kin)[o] = make_float4(af.x + ap.x, af.y + ap.y, af.z + ap.z, af.w + ap.w);
+        const f32x2 accf[2][2] = {{af0, af1}, {af2, af3}}, accp[2][2] = {{ap0, ap1}, {ap2, ap3}};
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            float4 af, ap;
+            unpack2(accf[half][0], af.x, af.y); unpack2(accf[half][1], af.z, af.w);
+            unpack2(accp[half][0], ap.x, ap.y); unpack2(accp[half][1], ap.z, ap.w);
+            const long long o = ((long long)n * MV2D_TOK + bin) * 64 + half * 32 + lane;
+            if (!f4) af = reinterpret_cast<const float4*>(tok_feat)[o];   // phase 2: pooled feature from phase 1
+            else { af.x /= count; af.y /= count; af.z /= count; af.w /= count; }
+            if (f4) reinterpret_cast<float4*>(tok_feat)[o] = af;
+            if (f4) {   // TF32 hi/lo split of the pooled feature: operands of the 3xTF32 conv GEMM
+                float4 hi = make_float4(round_tf32(af.x), round_tf32(af.y), round_tf32(af.z), round_tf32(af.w));
+                reinterpret_cast<float4*>(tok_hi)[o] = hi;
+                reinterpret_cast<float4*>(tok_lo)[o] = make_float4(round_tf32(af.x - hi.x), round_tf32(af.y - hi.y),
+                                                                  round_tf32(af.z - hi.z), round_tf32(af.w - hi.w));
+            }
+            if (tok_kin) {
+                ap.x /= count; ap.y /= count; ap.z /= count; ap.w /= count;
+                reinterpret_cast<float4*>(tok_kin)[o] = make_float4(af.x + ap.x, af.y + ap.y, af.z + ap.z, af.w + ap.w);
+            }
+        }
     }
 }
 
@@ -244,7 +253,7 @@ int run_roi_align_qg(const Mv2dQgParams& p, cudaStream_t st) {
     MV2D_CHECK_ARG(p.phase != 3 || (p.roi_intrinsics && p.roi_extrinsics && p.intrins_feat), "roi_align_qg: phase 3 needs K', E and the intrinsics feature per RoI");
     if (p.phase == 2) {   // only the position-embedding tokens: tok_kin = tok_feat + RoIAlign(pe)
         if (p.tok_kin == nullptr) return 0;
-        launch_k(roi_align_tokens_kernel, dim3(MV2D_TOK, N), dim3(64), 0, st, p.rois, (const float*)nullptr, p.pe, p.h, p.w,
+        launch_k(roi_align_tokens_kernel, dim3(N, N < 1024 ? 4 : 1), dim3(256), 0, st, p.rois, (const float*)nullptr, p.pe, p.h, p.w,
                  1.0f / (float)p.stride, p.tok_feat, p.tok_kin, (float*)nullptr, (float*)nullptr);
         MV2D_CHECK_LAUNCH("roi_align_tokens(pe)");
         return 0;
@@ -292,7 +301,7 @@ int run_roi_align_qg(const Mv2dQgParams& p, cudaStream_t st) {
                  mroi, big ? cat_lo : (float*)nullptr);
         MV2D_CHECK_LAUNCH("qg_inputs");
     } else {
-    launch_k(roi_align_tokens_kernel, dim3(MV2D_TOK, N), dim3(64), 0, st, p.rois, p.feat, with_pe ? p.pe : (const float*)nullptr, p.h, p.w,
+    launch_k(roi_align_tokens_kernel, dim3(N, N < 1024 ? 4 : 1), dim3(256), 0, st, p.rois, p.feat, with_pe ? p.pe : (const float*)nullptr, p.h, p.w,
              1.0f / (float)p.stride, p.tok_feat, with_pe ? p.tok_kin : (float*)nullptr, thi, tlo);
     MV2D_CHECK_LAUNCH("roi_align_tokens");
     launch_k(box_params_kernel, dim3(cdiv(N, 64)), dim3(64), 0, st, p.rois, p.intrinsics, p.extrinsics, N, p.intrins_feat_scale, cat,

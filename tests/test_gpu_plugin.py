@@ -177,8 +177,9 @@ def test_detector_shell_with_neck_matches_oracle(state_dicts):
     assert torch.equal(got['labels_3d'], rl)
     close(got['scores_3d'], rs.numpy(), 1e-3, 1e-3)
     close(got['boxes_3d'], rb.numpy(), 2e-3, 2e-3)
-    res = det.roi_head._bbox_forward([det.process_detector_feat([l.cuda() for l in levels])[0].permute(0, 3, 1, 2)],
-                                     [x.cuda() for x in boxes], metas)
+    with torch.no_grad():           # inference: mv2d_fpn_neck (with gradients enabled the neck runs as torch convolutions)
+        res = det.roi_head._bbox_forward([det.process_detector_feat([l.cuda() for l in levels])[0].permute(0, 3, 1, 2)],
+                                         [x.cuda() for x in boxes], metas)
     close(torch.stack(res['cls_scores']), cls.numpy())
     close(torch.stack(res['bbox_preds']), box.numpy())
 
@@ -334,6 +335,8 @@ def test_detector_shell_trains_through_the_neck(state_dicts):
     det.test_cfg = None
     V = len(metas)
     x = feat.cuda().clone().requires_grad_(True)            # the backbone's P4 map
+    monkey_tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False                 # fp32 torch convolutions: comparable with the 3xTF32 kernel at 1e-3
     with torch.no_grad():
         cl_eval, _ = det.process_detector_feat(x)           # eval path: mv2d_fpn_neck
     cl_train, _ = det.process_detector_feat(x)              # training path: autograd
@@ -361,6 +364,7 @@ def test_detector_shell_trains_through_the_neck(state_dicts):
         cl2, _ = det.process_detector_feat(x)
         ref = F.conv2d(F.conv2d(x, neck.lateral_convs[0].conv.weight, neck.lateral_convs[0].conv.bias),
                        neck.fpn_convs[0].conv.weight, neck.fpn_convs[0].conv.bias, padding=1).permute(0, 2, 3, 1)
+    torch.backends.cudnn.allow_tf32 = monkey_tf32
     assert torch.allclose(cl2, ref, atol=1e-3, rtol=1e-3)
 
 
