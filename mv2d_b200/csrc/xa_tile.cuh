@@ -481,19 +481,28 @@ __global__ void __launch_bounds__(XTM_THREADS, 1) xt_attn_mma_kernel(XtAttnArgs 
         }
         if (!waited) { xt_wait(bar); waited = true; }
         // ---- S = Q K^T
+        // (the MMAs are issued in groups of four independent accumulators: an mma.sync that reads the accumulator the
+        // previous one wrote stalls the warp for the MMA latency, and `asm volatile` keeps the source order)
         float s[8][4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
-            const float* krow = Kh + (j * 8 + g) * XTM_PITCH + tg;
+        for (int j = 0; j < 8; ++j) s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
 #pragma unroll
-            for (int kc = 0; kc < 4; ++kc) {
-                uint32_t bh0, bl0, bh1, bl1;
-                split_tf32_reg(krow[kc * 8], bh0, bl0);
-                split_tf32_reg(krow[kc * 8 + 4], bh1, bl1);
-                mma_tf32_16x8x8(s[j], qh[kc], bh0, bh1);
-                mma_tf32_16x8x8(s[j], ql[kc], bh0, bh1);
-                mma_tf32_16x8x8(s[j], qh[kc], bl0, bl1);
+        for (int kc = 0; kc < 4; ++kc) {
+#pragma unroll
+            for (int jh = 0; jh < 2; ++jh) {
+                uint32_t bh0[4], bl0[4], bh1[4], bl1[4];
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    const float* krow = Kh + ((jh * 4 + jj) * 8 + g) * XTM_PITCH + tg;
+                    split_tf32_reg(krow[kc * 8], bh0[jj], bl0[jj]);
+                    split_tf32_reg(krow[kc * 8 + 4], bh1[jj], bl1[jj]);
+                }
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) mma_tf32_16x8x8(s[jh * 4 + jj], qh[kc], bh0[jj], bh1[jj]);
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) mma_tf32_16x8x8(s[jh * 4 + jj], ql[kc], bh0[jj], bh1[jj]);
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) mma_tf32_16x8x8(s[jh * 4 + jj], qh[kc], bl0[jj], bl1[jj]);
             }
         }
         // ---- masked softmax numerators over the tile's keys: rows g (values 0, 1) and g + 8 (values 2, 3)
@@ -534,15 +543,18 @@ __global__ void __launch_bounds__(XTM_THREADS, 1) xt_attn_mma_kernel(XtAttnArgs 
             split_tf32_reg(s[j][1], ph[2], pl[2]);      // (row g,     k = tg + 4)
             split_tf32_reg(s[j][3], ph[3], pl[3]);      // (row g + 8, k = tg + 4)
             const float* vrow = Vh + (j * 8 + 2 * tg) * XTM_PITCH + g;
+            uint32_t bh0[4], bl0[4], bh1[4], bl1[4];
 #pragma unroll
             for (int nb = 0; nb < 4; ++nb) {
-                uint32_t bh0, bl0, bh1, bl1;
-                split_tf32_reg(vrow[nb * 8], bh0, bl0);
-                split_tf32_reg(vrow[XTM_PITCH + nb * 8], bh1, bl1);
-                mma_tf32_16x8x8(o[nb], ph, bh0, bh1);
-                mma_tf32_16x8x8(o[nb], pl, bh0, bh1);
-                mma_tf32_16x8x8(o[nb], ph, bl0, bl1);
+                split_tf32_reg(vrow[nb * 8], bh0[nb], bl0[nb]);
+                split_tf32_reg(vrow[XTM_PITCH + nb * 8], bh1[nb], bl1[nb]);
             }
+#pragma unroll
+            for (int nb = 0; nb < 4; ++nb) mma_tf32_16x8x8(o[nb], ph, bh0[nb], bh1[nb]);
+#pragma unroll
+            for (int nb = 0; nb < 4; ++nb) mma_tf32_16x8x8(o[nb], pl, bh0[nb], bh1[nb]);
+#pragma unroll
+            for (int nb = 0; nb < 4; ++nb) mma_tf32_16x8x8(o[nb], ph, bl0[nb], bl1[nb]);
         }
         // ---- records
         if (ok0) {
