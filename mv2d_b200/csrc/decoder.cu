@@ -1532,11 +1532,11 @@ int run_decoder(const Mv2dDecoderParams& p, cudaStream_t st) {
                 if ((rc = launch_gemm_small(g, x, 512, st))) return rc;
             }
             static const bool sa_blk = []() { const char* v = getenv("MV2D_SA_BLOCKED"); return !(v && v[0] == '0'); }();
-            // MV2D_SA_MMA: 0 = FFMA kernels only, 1 (default) = tensor-core kernel for batches of four samples or more (measured:
-            // 37 vs 47 us at 8 x 300 queries, 22 vs 20 us at 2 x 300), 2 = always
+            // MV2D_SA_MMA=0: FFMA kernels only.  Default: the tensor-core kernel whenever the sample's K / V slices of one head fit
+            // shared memory (measured per layer: 31 vs 47 us at 8 x 300 queries, 16 vs 22 us at 2 x 300, 11 vs 15 us at 1 x 300)
             static const int sa_mma = []() { const char* v = getenv("MV2D_SA_MMA"); return v ? atoi(v) : 1; }();
             const int sa_rows = p.batch > 0 ? p.rows_per_sample : N, sa_nb = p.batch > 0 ? p.batch : 1;
-            if (sa_mma > 0 && (sa_mma > 1 || sa_nb >= 4) && sam_smem_bytes(sa_rows) <= 200 * 1024) {
+            if (sa_mma > 0 && sam_smem_bytes(sa_rows) <= 200 * 1024) {
                 static int num_sms = 0;
                 if (num_sms == 0) {
                     int dev = 0;
@@ -1548,12 +1548,16 @@ int run_decoder(const Mv2dDecoderParams& p, cudaStream_t st) {
                 int W = 8;
                 for (int w = 2; w <= 8; ++w)
                     if (sa_nb * MV2D_HEADS * cdiv(nrb, w) <= slots) { W = w; break; }
-                const size_t smem = sam_smem_bytes(sa_rows);
-                if ((e = cudaFuncSetAttribute(self_attn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) {
+                const size_t smem = sam_smem_bytes(sa_rows, W);
+                // two warps per row block (alternate key blocks, folded at the end) while the CTA stays within 320 threads
+                static const bool ks2_env = []() { const char* v = getenv("MV2D_SA_KS2"); return !(v && v[0] == '0'); }();
+                const bool ks2 = ks2_env && W <= 5;
+                auto kern = ks2 ? self_attn_mma_kernel<2> : self_attn_mma_kernel<1>;
+                if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) {
                     set_error("decoder: self_attn_mma smem attr %s", cudaGetErrorString(e));
                     return (int)e;
                 }
-                launch_k(self_attn_mma_kernel, dim3(cdiv(nrb, W), MV2D_HEADS, sa_nb), dim3(32 * W), smem, st, (const float*)qkv,
+                launch_k(kern, dim3(cdiv(nrb, W), MV2D_HEADS, sa_nb), dim3(32 * W * (ks2 ? 2 : 1)), smem, st, (const float*)qkv,
                          p.batch > 0 ? (const uint8_t*)nullptr : p.self_attn_mask, N, sa, p.batch > 0 ? p.rows_per_sample : 0, p.n_real,
                          sa_split ? sa_lo : (float*)nullptr);
             } else if (sa_blk) {

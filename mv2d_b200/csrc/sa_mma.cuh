@@ -21,16 +21,19 @@ namespace mv2d {
 #define SAM_PITCH 36
 #define SAM_KB 64               // keys per block
 
-static inline size_t sam_smem_bytes(int nk_max) { return (size_t)2 * ((nk_max + SAM_KB - 1) / SAM_KB * SAM_KB) * SAM_PITCH * 4; }
+static inline size_t sam_smem_bytes(int nk_max, int W = 8) {      // K and V slices + the fold scratch of the two-phase form
+    return (size_t)2 * ((nk_max + SAM_KB - 1) / SAM_KB * SAM_KB) * SAM_PITCH * 4 + (size_t)W * 32 * 20 * 4;
+}
 
-__global__ void __launch_bounds__(256, 2)
+template <int KS>
+__global__ void __launch_bounds__(KS == 2 ? 320 : 256, 2)
 self_attn_mma_kernel(const float* __restrict__ qkv, const uint8_t* __restrict__ mask, int N, float* __restrict__ out,
                      int rows_per_sample, const int* __restrict__ n_real, float* __restrict__ out_lo) {
     pdl_wait();
     pdl_trigger();
     extern __shared__ __align__(16) float sam_smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tg = lane & 3;
-    const int hd = blockIdx.y, W = blockDim.x >> 5;
+    const int hd = blockIdx.y, W = (blockDim.x >> 5) / KS;      // KS = 2: two warps share a row block, each takes every other key block
     int seg0 = 0, nq = N, nk = N;
     if (rows_per_sample > 0) {
         const int b = blockIdx.z;
@@ -58,7 +61,7 @@ self_attn_mma_kernel(const float* __restrict__ qkv, const uint8_t* __restrict__ 
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
     const int nrb = (nq + 15) >> 4;
-    const int rb = blockIdx.x * W + warp;              // this warp's row block (CTA-uniform trip count: one block per warp)
+    const int rb = blockIdx.x * W + warp % W, ks = warp / W;      // this warp's row block and key-block phase
     // ---- the block's 16 queries: rows g and g + 8 of this lane, scaled by 1 / sqrt(32)
     const int i0 = rb * 16 + g, i1 = i0 + 8;
     const bool act = rb < nrb, ok0 = act && i0 < nq, ok1 = act && i1 < nq;
@@ -77,12 +80,11 @@ self_attn_mma_kernel(const float* __restrict__ qkv, const uint8_t* __restrict__ 
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
-    if (!act) return;
     float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
     float o[4][4];
 #pragma unroll
     for (int nb = 0; nb < 4; ++nb) o[nb][0] = o[nb][1] = o[nb][2] = o[nb][3] = 0.f;
-    for (int kb = 0; kb < nkb; ++kb) {
+    for (int kb = act ? ks : nkb; kb < nkb; kb += KS) {
         const float* Kb = Ks + (size_t)kb * SAM_KB * SAM_PITCH;
         const float* Vb = Vs + (size_t)kb * SAM_KB * SAM_PITCH;
         // ---- S = Q K^T
@@ -171,6 +173,29 @@ self_attn_mma_kernel(const float* __restrict__ qkv, const uint8_t* __restrict__ 
             for (int nb = 0; nb < 4; ++nb) mma_tf32_16x8x8(o[nb], ph, bl0[nb], bl1[nb]);
         }
     }
+    if (KS == 2) {
+        // ---- fold the two key phases of a row block: the odd phase parks (m, l, o) behind the K / V slices
+        float* part = Vs + (size_t)nk_pad * SAM_PITCH + ((warp % W) * 32 + lane) * 20;
+        if (ks == 1) {
+            part[0] = m0; part[1] = m1; part[2] = l0; part[3] = l1;
+#pragma unroll
+            for (int nb = 0; nb < 4; ++nb) *reinterpret_cast<float4*>(part + 4 + nb * 4) = make_float4(o[nb][0], o[nb][1], o[nb][2], o[nb][3]);
+        }
+        __syncthreads();
+        if (ks == 1) return;
+        const float pm0 = part[0], pm1 = part[1];
+        const float M0 = fmaxf(m0, pm0), M1 = fmaxf(m1, pm1);
+        const float a0 = (m0 == -INFINITY) ? 0.f : __expf(m0 - M0), a1 = (m1 == -INFINITY) ? 0.f : __expf(m1 - M1);
+        const float c0 = (pm0 == -INFINITY) ? 0.f : __expf(pm0 - M0), c1 = (pm1 == -INFINITY) ? 0.f : __expf(pm1 - M1);
+        l0 = l0 * a0 + part[2] * c0; l1 = l1 * a1 + part[3] * c1;
+#pragma unroll
+        for (int nb = 0; nb < 4; ++nb) {
+            const float4 q = *reinterpret_cast<const float4*>(part + 4 + nb * 4);
+            o[nb][0] = o[nb][0] * a0 + q.x * c0; o[nb][1] = o[nb][1] * a0 + q.y * c0;
+            o[nb][2] = o[nb][2] * a1 + q.z * c1; o[nb][3] = o[nb][3] * a1 + q.w * c1;
+        }
+    }
+    if (!act) return;
     // ---- normalise, store (and the TF32 hi / lo split for a 3xTF32 out_proj)
     const float inv0 = l0 > 0.f ? 1.f / l0 : 0.f, inv1 = l1 > 0.f ? 1.f / l1 : 0.f;
 #pragma unroll

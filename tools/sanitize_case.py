@@ -21,6 +21,15 @@ for mode, case in (('T', 't_small'), ('S', 's_small'), ('T', 't_dn'), ('S', 's_d
         b, s, l = eng.scene_nms(b, s, l)
         print(case, 'N', out['N'], 'boxes', b.shape[0])
     torch.cuda.synchronize()
+# batches as a segment dimension: the kernels only batches reach (tensor-core self-attention, persistent GEMMs, one-pass RoIAlign)
+for mode, names in (('S', ['s_small', 's_cfg2', 's_small', 's_small']), ('T', ['t_small', 't_small'])):
+    specs = [synth.CASES[n] for n in names]
+    sd = synth.make_state_dict(0, num_layers=specs[0]['num_layers'])
+    eng = HotPath(sd, mode=mode)
+    ins = [synth.case_inputs(sp) for sp in specs]
+    out = eng.forward_batch(torch.stack([i[0] for i in ins], 0).cuda(), [i[1] for i in ins], [i[2] for i in ins])
+    torch.cuda.synchronize()
+    print('batch', mode, [smp['N'] for smp in out['samples']])
 nsd = synth.make_neck_state_dict(0)
 f, _ = eng.neck(torch.randn(2, 256, 30, 85).cuda(), nsd)
 torch.cuda.synchronize()
