@@ -480,7 +480,11 @@ def train_step_section(sd, dev, samples, world, barrier, per_rank=2, steps=8, wa
                 loss_first=losses[0], loss_last=losses[-1],
                 scope='rows a1-a18 + f3 forward and backward: every hot-path parameter gradient and d loss / d feat; 3xTF32 tcgen05 for the '
                       'GPU-filling contractions, fp32 FFMA elsewhere; the torch backbone is outside',
-                collective='one NCCL sum all-reduce of the flat gradient buffer per step' if world > 1 else 'none (1 GPU)')
+                collective=('none (1 GPU)' if world == 1 else
+                            'NCCL sum all-reduce of the flat gradient buffer in two buckets: the decoder slice (80 % of the bytes) on a '
+                            'communication stream under the front-end half of the backward, the front-end slice after it; allreduce_ms is '
+                            'the exposed part' if (mode == 'S' and getattr(pipe, 'overlap_all_reduce', False)) else
+                            'one NCCL sum all-reduce of the flat gradient buffer per step'))
 
 
 def roofline_section(eng, batch_in, mode, flush, peaks):
