@@ -467,3 +467,31 @@ def test_fused_pe_mlps_match_the_layer_by_layer_gemms(name, state_dicts):
     assert_close(pe.flatten()[::PE_SUB], g['pe_sub'], 3e-3, 1e-3, 'pe')
     assert_close(outs[0][1], g['cls_scores'], what='cls_scores')
     assert_close(outs[0][2], g['bbox_preds'], what='bbox_preds')
+
+
+def test_layout_pass_with_tf32_halves_is_bit_exact():
+    """mv2d_nchw_to_nhwc_split: the channels-last copy, its TF32 hi half and lo half (operands of the 3xTF32 K / V projection)
+    against the integer rounding the host packer uses -- bit for bit, on an odd grid (ragged 64-pixel tiles)."""
+    from mv2d_b200 import lib
+    h = lib.load()
+    torch.manual_seed(11)
+    V, C, H, W = 3, 256, 30, 85
+    x = (torch.randn(V, C, H, W, device='cuda') * 3).contiguous()
+    out = torch.empty(V, H, W, C, device='cuda')
+    hi, lo = torch.empty_like(out), torch.empty_like(out)
+    lib.check(h.mv2d_nchw_to_nhwc_split(x.data_ptr(), out.data_ptr(), hi.data_ptr(), lo.data_ptr(), V, C, H * W, lib.stream_ptr()),
+              'mv2d_nchw_to_nhwc_split')
+    torch.cuda.synchronize()
+
+    def rnd(t):        # (bits + 0x1000) & ~0x1fff: cvt.rna.tf32.f32 on the bit pattern (csrc/pack.cpp, gemm_tc.cuh)
+        b = t.contiguous().view(torch.int32)
+        return ((b + 0x1000) & ~0x1FFF).view(torch.float32)
+    ref = x.permute(0, 2, 3, 1).contiguous()
+    assert torch.equal(out, ref)
+    assert torch.equal(hi, rnd(ref))
+    assert torch.equal(lo, rnd(ref - rnd(ref)))
+    # the plain entry writes the same copy and hi half
+    out2, hi2 = torch.empty_like(out), torch.empty_like(out)
+    lib.check(h.mv2d_nchw_to_nhwc(x.data_ptr(), out2.data_ptr(), hi2.data_ptr(), V, C, H * W, lib.stream_ptr()), 'mv2d_nchw_to_nhwc')
+    torch.cuda.synchronize()
+    assert torch.equal(out2, ref) and torch.equal(hi2, hi)
