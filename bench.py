@@ -202,10 +202,11 @@ def main():
     n_var = max(2 * B, 8)
     samples = [make_inputs(mode, seed=i) for i in D.shard_samples(n_var * world, rank, world)]
     feats_dev = [s[0].to(dev) for s in samples]
-    feats_pin = [s[0].pin_memory() for s in samples]
+    wc = os.environ.get('MV2D_BENCH_WC', '0') == '1'      # write-combined staging buffers (dist.pin_host): measured, no difference (tools/h2d_probe.py)
+    feats_pin = [D.pin_host(s[0], wc) for s in samples]
     n_batches = n_var // B
     batches_dev = [torch.stack([feats_dev[k * B + j] for j in range(B)], 0) for k in range(n_batches)]
-    batches_pin = [torch.stack([samples[k * B + j][0] for j in range(B)], 0).pin_memory() for k in range(n_batches)]
+    batches_pin = [D.pin_host(torch.stack([samples[k * B + j][0] for j in range(B)], 0), wc) for k in range(n_batches)]
     batch_boxes = [[samples[k * B + j][1] for j in range(B)] for k in range(n_batches)]
     batch_metas = [[samples[k * B + j][2] for j in range(B)] for k in range(n_batches)]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
@@ -357,8 +358,9 @@ def main():
                  h2d_gb_per_s_per_gpu=h2d / (e2e_total_ms / args.steps) * 1e-6,
                  h2d_gb_per_s_all_gpus=world * h2d / (e2e_total_ms / args.steps) * 1e-6,
                  note='every sample carries its 17.3 MB fp32 feature map over PCIe inside the timed region; one GPU moves ~42 GB/s of '
-                      'its x16 link, eight ranks together saturate the host at ~180 GB/s (measured on the 8-GPU box: a VM with one '
-                      'NUMA node), which is the ceiling of the 8-GPU end-to-end number, not a collective or a kernel'),
+                      'its x16 link (55 GB/s raw), eight ranks together saturate the host: plain pinned cudaMemcpyAsync from all eight '
+                      'ranks at once tops out at 186 GB/s = 23 GB/s per GPU on this box (tools/h2d_probe.py), which is the ceiling of '
+                      'the 8-GPU end-to-end number, not a collective or a kernel'),
         gpu_launches=launches, launches_per_sample=launches / (args.steps * B), clocks=clocks, numa=numa, roofline=roof['roofline'],
         attention_roofline=roof['attention'], stage_us=roof['stage_us'], peaks=peaks, serial=serial)
     if two_frame is not None:
@@ -391,7 +393,8 @@ def two_frame_section(sd, dev, world, rank, barrier, steps, warmup, batch=2, dep
     smp = [make_inputs('T', seed=i) for i in D.shard_samples(n_var * world, rank, world)]
     nb = n_var // batch
     bd = [torch.stack([smp[k * batch + j][0] for j in range(batch)], 0).to(dev) for k in range(nb)]
-    bp = [torch.stack([smp[k * batch + j][0] for j in range(batch)], 0).pin_memory() for k in range(nb)]
+    wc = os.environ.get('MV2D_BENCH_WC', '0') == '1'
+    bp = [D.pin_host(torch.stack([smp[k * batch + j][0] for j in range(batch)], 0), wc) for k in range(nb)]
     bb = [[smp[k * batch + j][1] for j in range(batch)] for k in range(nb)]
     bm = [[smp[k * batch + j][2] for j in range(batch)] for k in range(nb)]
     res = {}
