@@ -1359,8 +1359,7 @@ int run_decoder(const Mv2dDecoderParams& p, cudaStream_t st) {
     float* b1_lo = ws; ws += (size_t)L * N * C;
     float* b2_lo = ws; ws += (size_t)L * N * C;
     float* b4 = ws;    ws += (size_t)L * N * C;
-    float* b4_lo = ws; ws += (size_t)L * N * C;
-    float* b0_lo = ws; ws += (size_t)L * N * C;
+    ws += (size_t)2 * L * N * C;                     // (two more [L,N,C] slots of the layout mv2d_decoder_workspace_bytes reports; unused)
     unsigned* barrier = reinterpret_cast<unsigned*>(reinterpret_cast<uintptr_t>(ws + 63) & ~(uintptr_t)63); ws += 1024;
     MV2D_CHECK_ARG((size_t)(ws - p.workspace) * sizeof(float) <= p.workspace_bytes, "decoder: workspace too small");
     const long long NC = (long long)N * C;
