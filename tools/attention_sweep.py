@@ -62,10 +62,28 @@ for mode, V in (('S', 6), ('T', 12)):
                 run()
         torch.cuda.synchronize()
         t = time_fn(graph.replay)
+        # the sparse cross-attention kernel(s) alone (mv2d_cross_attention_core: xa_roi, or xt_attn_mma + xt_merge), L2 flushed
+        core = {}
+        try:
+            if mode == 'S':
+                q_core = torch.randn(n, 2048, device='cuda')
+                fn = lambda: eng.cross_attention_core(qg, corr, kin_rows, mem_rows, n, q_core, layer=0)
+                core_bytes = float(out['match_cnt'].sum()) * 49 * 2 * 1024        # 100 KB per (query, RoI) unit
+            else:
+                h_, w_ = out['feat_nhwc'].shape[1:3]
+                kv = (eng._buf['kp'].view(eng.L, -1, 256)[:, :mem_rows.shape[0]], eng._buf['vp'].view(eng.L, -1, 256)[:, :mem_rows.shape[0]])
+                corr_t = {k: out.get(k) for k in ('keymask', 'mask_words', 'key_list', 'key_cnt', 'xa_prepared_for', 'row_tile_live')}
+                q_core = torch.randn(n, 256, device='cuda')
+                fn = lambda: eng.cross_attention_core(qg, corr_t, kin_rows, mem_rows, n, q_core, layer=0, kv=kv, grid=(h_, w_))
+                core_bytes = 4 * 2 * n_k * C                                        # projected K and V rows of the union of keys
+            tc = time_fn(fn)
+            core = dict(core_us=tc, core_MB=core_bytes / 1e6, core_GBs=core_bytes / tc / 1e3, core_frac_hbm=core_bytes / tc / 1e3 / peaks['hbm_gbs'])
+        except Exception as e:
+            core = dict(core_error=f'{type(e).__name__}: {e}'[:200])
         # rows actually gathered by the kernel (each query streams its own key rows, 2 KB per key)
         moved = gathered * 2 * C * 4
         print(json.dumps(dict(mode=mode, V=V, N=n, unique_keys=n_k, keys_gathered=gathered, us_layer=t,
                               algorithmic_MB=alg / 1e6, achieved_GBs=alg / t / 1e3, frac_hbm=alg / t / 1e3 / peaks['hbm_gbs'],
-                              gathered_MB=moved / 1e6, gathered_GBs=moved / t / 1e3,
+                              gathered_MB=moved / 1e6, gathered_GBs=moved / t / 1e3, **core,
                               note='one full decoder layer (self-attn, cross-attn incl. its K/V projection for the two-frame head, FFN) + branches, '
                                    'replayed from a CUDA graph, charged to the attention bytes')))
