@@ -17,7 +17,7 @@ def main():
     ap.add_argument('--mode', default='S')
     ap.add_argument('--steps', type=int, default=40)
     ap.add_argument('--grid', default='1x1,1x4,2x1,2x2,4x1,4x2,8x1,8x2')
-    ap.add_argument('--overlap', type=int, default=1, help='0: PE -> RoIAlign (feat and pe in one pass) -> box correlation on one stream')
+    ap.add_argument('--overlap', type=int, default=1, help='0: the whole front end on one stream (batches of the single-frame head do that by themselves since the A/B run recorded in engine._enqueue_post; the flag still matters for bs = 1 and the two-frame head)')
     args = ap.parse_args()
     sd = synth.make_state_dict(0)
     case = synth.CASES['s_cfg2' if args.mode == 'S' else 't_cfg3']
