@@ -584,7 +584,7 @@ def roofline_section(eng, batch_in, mode, flush, peaks):
         core_bytes = (float(out['match_cnt'].sum()) * 49 * 2 * 1024) if mode == 'S' else bytes_layer
         attention['core'] = dict(us=t_core, bytes=core_bytes, achieved=core_bytes / t_core / 1e3,
                                  frac=core_bytes / t_core / 1e3 / peaks['hbm_gbs'],
-                                 # dram__bytes_read + write of the kernel(s) in the committed ncu capture (profiles/r02_ncu_full_kernels.csv)
+                                 # dram__bytes_read + write of the kernel(s) in the committed ncu captures (S: profiles/r02_ncu_full_kernels_b.csv, T: r02_ncu_full_kernels.csv)
                                  traffic={('S', 8, 300): 260.83328e6 + 37.432576e6, ('T', 2, 300): 131.600896e6 + 21.562368e6}.get((mode, B, n_per)),
                                  note='cross-attention kernel(s) alone, L2 flushed; bytes = key / value rows the kernel has to stream '
                                       '(S: 100 KB per (query, RoI) unit; T: the SURVEY 8d bytes); ncu dram bytes: profiles/')
